@@ -1,0 +1,320 @@
+/*
+ * rtxpt_b200.h — C ABI of the B200-native wavefront path tracer that drops in for RTXPT's single
+ * PathTrace dispatch.
+ *
+ * Every entry point below replaces one piece of the reference's host→GPU boundary for that path.  The
+ * citations (file:line, relative to the RTXPT source tree) name the reference interface it stands in for.
+ * Plain C: pointers and sizes only, caller owns host memory, the library owns device memory, one context per GPU,
+ * calls on one context are serialised by the caller (the reference renders from a single thread,
+ * Rtxpt/Sample.cpp:1891-2313).
+ *
+ * All entry points return RTXPT_OK (0) or a negative status; rtxpt_b200_last_error() gives the message.
+ */
+#ifndef RTXPT_B200_H_
+#define RTXPT_B200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define RTXPT_API __declspec(dllexport)
+#else
+#define RTXPT_API __attribute__((visibility("default")))
+#endif
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Status codes (the reference has no formal convention: bool returns + donut::log::error)
+ * ---------------------------------------------------------------------------------------------------------------- */
+enum {
+    RTXPT_OK                    =  0,
+    RTXPT_ERR_INVALID_ARGUMENT  = -1,
+    RTXPT_ERR_NO_DEVICE         = -2,   /* no CUDA device / driver: the library never falls back to the CPU */
+    RTXPT_ERR_CUDA              = -3,
+    RTXPT_ERR_OUT_OF_MEMORY     = -4,
+    RTXPT_ERR_NO_SCENE          = -5,
+    RTXPT_ERR_UNSUPPORTED       = -6,
+    RTXPT_ERR_INTERNAL          = -7
+};
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Scene tables.  Layouts are byte-identical to what the reference binds for the dispatch
+ * (Rtxpt/Sample.cpp:2315-2427): t1 SubInstanceData[], t2 InstanceData[], t3 GeometryData[], t5 PTMaterialData[],
+ * bindless ByteAddressBuffer[] (index + vertex) and Texture2D[].
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/* External/Donut/include/donut/shaders/bindless.h:28-46 (64 bytes) */
+typedef struct RtxptGeometryData {
+    uint32_t numIndices;
+    uint32_t numVertices;
+    int32_t  indexBufferIndex;
+    uint32_t indexOffset;           /* bytes */
+    int32_t  vertexBufferIndex;
+    uint32_t positionOffset;        /* bytes; float3 per vertex (12 B) */
+    uint32_t prevPositionOffset;    /* 0xFFFFFFFF when absent */
+    uint32_t texCoord1Offset;       /* bytes; float2 per vertex (8 B); 0xFFFFFFFF when absent */
+    uint32_t texCoord2Offset;
+    uint32_t normalOffset;          /* bytes; RGB8 snorm packed in one u32 (4 B); 0xFFFFFFFF when absent */
+    uint32_t tangentOffset;         /* bytes; RGBA8 snorm (4 B); 0xFFFFFFFF when absent */
+    uint32_t curveRadiusOffset;
+    uint32_t materialIndex;
+    uint32_t pad0, pad1, pad2;
+} RtxptGeometryData;
+
+/* External/Donut/include/donut/shaders/bindless.h:54-70 (112 bytes); transforms are row-major float3x4 */
+typedef struct RtxptInstanceData {
+    uint32_t flags;
+    uint32_t firstGeometryInstanceIndex;    /* index of this instance's first SubInstanceData */
+    uint32_t firstGeometryIndex;            /* index of this instance's first GeometryData */
+    uint32_t numGeometries;
+    float    transform[12];
+    float    prevTransform[12];
+} RtxptInstanceData;
+
+/* Rtxpt/Shaders/SubInstanceData.h:23-46 (32 bytes, SUBINSTANCEDATA_EXTENDED) */
+typedef struct RtxptSubInstanceData {
+    uint32_t FlagsAndAlphaInfo;                         /* [15:0] alpha texture index, bit16 alpha tested, bit17 exclude from NEE, [31:24] cutoff*255 */
+    uint32_t GlobalGeometryIndex_PTMaterialDataIndex;   /* [31:16] geometry index, [15:0] material index */
+    uint32_t EmissiveLightMappingOffset;                /* filled by the library's light bake; callers pass 0xFFFFFFFF */
+    uint32_t AnalyticProxyLightIndex;
+    uint32_t IndexBufferIndex_VertexBufferIndex;
+    uint32_t IndexOffset;
+    uint32_t TexCoord1Offset;
+    uint32_t padding0;
+} RtxptSubInstanceData;
+
+#define RTXPT_SUBINST_FLAG_ALPHA_TESTED     (1u << 16)
+#define RTXPT_SUBINST_FLAG_EXCLUDE_FROM_NEE (1u << 17)
+
+/* Rtxpt/Shaders/PathTracer/Materials/MaterialPT.h:23-80 (128 bytes) */
+#define RTXPT_MATFLAG_UseSpecularGlossModel          0x00000001u
+#define RTXPT_MATFLAG_UseMetalRoughOrSpecularTexture 0x00000004u
+#define RTXPT_MATFLAG_UseBaseOrDiffuseTexture        0x00000008u
+#define RTXPT_MATFLAG_UseEmissiveTexture             0x00000010u
+#define RTXPT_MATFLAG_UseNormalTexture               0x00000020u
+#define RTXPT_MATFLAG_UseTransmissionTexture         0x00000080u
+#define RTXPT_MATFLAG_MetalnessInRedChannel          0x00000100u
+#define RTXPT_MATFLAG_ThinSurface                    0x00000200u
+#define RTXPT_MATFLAG_PSDExclude                     0x00000400u
+#define RTXPT_MATFLAG_EnableAsAnalyticLightProxy     0x00000800u
+#define RTXPT_MATFLAG_IgnoreMeshTangentSpace         (1u << 12)
+#define RTXPT_MATFLAG_NestedPriorityShift            28
+
+typedef struct RtxptMaterialData {
+    float    BaseOrDiffuseColor[3];
+    uint32_t Flags;
+    float    SpecularColor[3];
+    int32_t  _padding0;
+    float    EmissiveColor[3];
+    float    ShadowNoLFadeout;
+    float    Opacity;
+    float    Roughness;
+    float    Metalness;
+    float    NormalTextureScale;
+    float    _padding1;
+    float    AlphaCutoff;
+    float    TransmissionFactor;
+    uint32_t BaseOrDiffuseTextureIndex;         /* (baseLOD<<24)|(mipLevels<<16)|bindlessIndex, Materials/MaterialsBaker.cpp:487-509 */
+    uint32_t MetalRoughOrSpecularTextureIndex;
+    uint32_t EmissiveTextureIndex;
+    uint32_t NormalTextureIndex;
+    uint32_t OcclusionTextureIndex;
+    uint32_t TransmissionTextureIndex;
+    float    IoR;
+    float    ThicknessFactor;
+    float    DiffuseTransmissionFactor;
+    float    VolumeAttenuationColor[3];
+    float    VolumeAttenuationDistance;
+} RtxptMaterialData;
+
+/* One bindless ByteAddressBuffer (index or vertex data), t_BindlessBuffers[] in Rtxpt/Shaders/Bindings/SceneBindings.hlsli */
+typedef struct RtxptBufferDesc {
+    const void* data;
+    uint64_t    sizeBytes;
+} RtxptBufferDesc;
+
+/* One bindless Texture2D.  Uncompressed only in this tier (block-compressed DDS is SURVEY §8f row 3). */
+enum {
+    RTXPT_FORMAT_RGBA8_UNORM = 0,
+    RTXPT_FORMAT_RGBA8_SRGB  = 1,   /* sRGB-decoded on fetch, like the reference's per-slot sRGB views (Materials/MaterialsBaker.cpp:63-72) */
+    RTXPT_FORMAT_RGBA32_FLOAT = 2
+};
+#define RTXPT_MAX_MIPS 16
+typedef struct RtxptTextureDesc {
+    uint32_t    width, height;
+    uint32_t    mipLevels;              /* full or partial chain, mip i is max(1,w>>i) x max(1,h>>i) */
+    uint32_t    format;
+    const void* mips[RTXPT_MAX_MIPS];   /* tightly packed rows */
+} RtxptTextureDesc;
+
+/* Environment cube (t10, Rtxpt/Shaders/Bindings/LightingBindings.hlsli; produced by Lighting/Distant/EnvMapBaker in
+ * the reference).  Faces in D3D order +X,-X,+Y,-Y,+Z,-Z, RGBA32F, square, with a mip chain. */
+typedef struct RtxptEnvCubeDesc {
+    uint32_t     faceSize;              /* 0 = no environment map */
+    uint32_t     mipLevels;
+    const float* faces[6][RTXPT_MAX_MIPS];
+} RtxptEnvCubeDesc;
+
+typedef struct RtxptSceneDesc {
+    const RtxptInstanceData*    instances;      uint32_t instanceCount;
+    const RtxptGeometryData*    geometries;     uint32_t geometryCount;
+    const RtxptSubInstanceData* subInstances;   uint32_t subInstanceCount;
+    const RtxptMaterialData*    materials;      uint32_t materialCount;
+    const RtxptBufferDesc*      buffers;        uint32_t bufferCount;
+    const RtxptTextureDesc*     textures;       uint32_t textureCount;
+    RtxptEnvCubeDesc            envCube;
+} RtxptSceneDesc;
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Per-frame constants: the slice of SampleConstants (Rtxpt/Shaders/SampleConstantBuffer.h:46-60) the reference-mode
+ * dispatch reads.
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/* Rtxpt/Shaders/PathTracer/PathTracerShared.h:24-44 (112 bytes) */
+typedef struct RtxptCameraData {
+    float    PosW[3];       float NearZ;
+    float    DirectionW[3]; float PixelConeSpreadAngle;
+    float    CameraU[3];    float FarZ;
+    float    CameraV[3];    float FocalDistance;
+    float    CameraW[3];    float AspectRatio;
+    uint32_t ViewportSize[2];
+    float    ApertureRadius;
+    float    _padding0;
+    float    Jitter[2];
+    float    _padding1, _padding2;
+} RtxptCameraData;
+
+/* Rtxpt/Shaders/PathTracer/Lighting/EnvMap.hlsli:24-31 ; transforms row-major float3x4 */
+typedef struct RtxptEnvMapSceneParams {
+    float Transform[12];
+    float InvTransform[12];
+    float ColorMultiplier[3];
+    float Enabled;
+} RtxptEnvMapSceneParams;
+
+/* Subset of PathTracerConstants (Rtxpt/Shaders/PathTracer/PathTracerShared.h:47-104) that reference mode reads,
+ * filled the way Sample::UpdatePathTracerConstants does (Rtxpt/Sample.cpp:1464-1556). */
+typedef struct RtxptPathTracerConstants {
+    uint32_t imageWidth, imageHeight;
+    uint32_t sampleBaseIndex;               /* m_sampleIndex * ActualSamplesPerPixel() (Sample.cpp:1507) */
+    float    perPixelJitterAAScale;         /* 1 in reference mode with AccumulationAA (Sample.cpp:1501) */
+    uint32_t bounceCount;
+    uint32_t diffuseBounceCount;
+    float    EnvironmentMapDiffuseSampleMIPLevel;
+    float    texLODBias;
+    float    fireflyFilterThreshold;        /* 0 disables (Sample.cpp:1518-1522) */
+    uint32_t NEEEnabled;
+    uint32_t NEEType;                       /* 0 uniform, 1 power, 2 NEE-AT (global table only in this tier) */
+    uint32_t NEECandidateSamples;
+    uint32_t NEEFullSamples;
+    uint32_t enableRussianRoulette;         /* PT_ENABLE_RUSSIAN_ROULETTE macro, Sample.cpp:988-1042 */
+    uint32_t enableLDSamplerForBSDF;        /* RTXPT_ENABLE_LOW_DISCREPANCY_SAMPLER_FOR_BSDF */
+    uint32_t nestedDielectricsQuality;      /* RTXPT_NESTED_DIELECTRICS_QUALITY: 0 off, 1 fast */
+    RtxptCameraData camera;
+    RtxptEnvMapSceneParams envMap;
+    float    distantVsLocalImportance;      /* NEEAT_Distant_vs_Local_Importance (SampleUI.h:160), scaled by 0.0002 inside like LightsBaker.cpp:1029 */
+    float    _pad[3];
+} RtxptPathTracerConstants;
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Context
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct RtxptConfig {
+    int32_t  deviceOrdinal;             /* CUDA device; -1 = current */
+    uint32_t maxWidth, maxHeight;       /* render-target allocation (Rtxpt/SampleCommon/RenderTargets.cpp:159-175) */
+    uint32_t maxSubSamplesPerLaunch;    /* how many sub-samples one path_trace call may batch into a single wavefront */
+    uint32_t tileRank, tileWorld;       /* screen-tile partition for multi-GPU: this context renders tiles t with t % world == rank; 0,1 = whole frame */
+    uint32_t tileSize;                  /* pixels, power of two, default 64 */
+    uint32_t flags;                     /* RTXPT_CFG_* */
+} RtxptConfig;
+
+#define RTXPT_CFG_COUNT_TRAVERSAL_STEPS  1u   /* instrumented traversal: per-launch node/triangle counters */
+#define RTXPT_CFG_NO_MATERIAL_SORT       2u   /* disable the per-bounce sort by material class (A/B measurement only) */
+
+typedef struct rtxpt_ctx rtxpt_ctx;
+
+/* Replaces device/pipeline creation: Sample::Init + CreateRTPipelines (Rtxpt/Sample.cpp:136-397, Rtxpt/AdvancedSample.cpp:35-46). */
+RTXPT_API int rtxpt_b200_create(const RtxptConfig* config, rtxpt_ctx** outCtx);
+RTXPT_API int rtxpt_b200_destroy(rtxpt_ctx* ctx);
+RTXPT_API const char* rtxpt_b200_last_error(void);
+
+/* Replaces scene upload + acceleration-structure build + material/light baking:
+ *   Sample::CreateBlases/BuildTLAS (Rtxpt/Sample.cpp:1061-1240), MaterialsBaker::Update (Materials/MaterialsBaker.cpp:1019-1065),
+ *   LightsBaker::UpdateBegin light list + weights + proxies (Lighting/LightsBaker.cpp:964-1327), EnvMapImportanceSamplingBaker. */
+RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* ctx, const RtxptSceneDesc* scene);
+
+/* Replaces writeBuffer(m_constantBuffer, &constants) (Rtxpt/Sample.cpp:2182).  Also re-bakes light weights when the
+ * environment parameters changed. */
+RTXPT_API int rtxpt_b200_set_constants(rtxpt_ctx* ctx, const RtxptPathTracerConstants* constants);
+
+/* Replaces the loop body of Sample::PathTrace (Rtxpt/Sample.cpp:2503-2517): setPushConstants({subSampleIndex}) +
+ * dispatchRays(width,height), for subSampleCount consecutive sub-samples starting at firstSubSampleIndex, each followed
+ * by the reference-mode accumulation (AccumulationPass::Render, Rtxpt/Sample.cpp:2770-2778) when accumulate != 0.
+ * Asynchronous on `cudaStream` (a cudaStream_t, NULL = the context's own stream). */
+RTXPT_API int rtxpt_b200_path_trace(rtxpt_ctx* ctx, uint32_t firstSubSampleIndex, uint32_t subSampleCount, int accumulate, void* cudaStream);
+
+/* Resets the accumulation counter (Sample::PreUpdatePathTracing accumulation reset, Rtxpt/Sample.cpp:1416-1450). */
+RTXPT_API int rtxpt_b200_reset_accumulation(rtxpt_ctx* ctx);
+
+enum {
+    RTXPT_BUFFER_OUTPUT_COLOR_F16   = 0,    /* u_OutputColor RGBA16F of the last sub-sample (ShaderResourceBindings.hlsli:24) */
+    RTXPT_BUFFER_ACCUMULATED_F32    = 1,    /* AccumulatedRadiance RGBA32F (RenderTargets.cpp) */
+    RTXPT_BUFFER_DEPTH_F32          = 2     /* u_Depth guide of the last sub-sample (PathTracerBridgeDonut.hlsli:1096-1153) */
+};
+/* Device→host copy of a render target; blocks until the work queued on the context has finished. */
+RTXPT_API int rtxpt_b200_readback(rtxpt_ctx* ctx, int buffer, void* dst, size_t dstBytes);
+/* Device pointer of a render target (for zero-copy interop: NCCL all-gather of radiance tiles, image diffs on device). */
+RTXPT_API int rtxpt_b200_device_ptr(rtxpt_ctx* ctx, int buffer, void** outPtr, size_t* outBytes);
+RTXPT_API int rtxpt_b200_synchronize(rtxpt_ctx* ctx);
+
+/* One-call end-to-end frame through host memory: set_constants + path_trace(accumulate) + readback of the accumulated
+ * image into `dstRGBA32F` (width*height*16 bytes). */
+RTXPT_API int rtxpt_b200_render_frame(rtxpt_ctx* ctx, const RtxptPathTracerConstants* constants,
+                                      uint32_t firstSubSampleIndex, uint32_t subSampleCount, void* dstRGBA32F, size_t dstBytes);
+
+typedef struct RtxptStats {
+    uint64_t scatterRays;           /* closest-hit queries of the last path_trace call */
+    uint64_t shadowRays;            /* any-hit (visibility) queries */
+    uint64_t paths;
+    uint64_t kernelLaunches;        /* kernels launched by the last path_trace call */
+    uint64_t traversalNodeVisits;   /* only with RTXPT_CFG_COUNT_TRAVERSAL_STEPS */
+    uint64_t traversalTriTests;
+    uint64_t raysPerBounce[16];     /* scatter rays per wavefront iteration */
+    float    msTotal;               /* CUDA-event time of the last path_trace call */
+    float    msTraceClosest, msTraceShadow, msShade, msOther;
+    uint32_t bvhNodeCount, bvhTriangleCount;
+    float    bvhBuildSeconds;
+    uint32_t lightCount, lightProxyCount;
+    uint32_t accumulatedSamples;
+} RtxptStats;
+RTXPT_API int rtxpt_b200_get_stats(rtxpt_ctx* ctx, RtxptStats* out);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Inspection hooks used by the parity tests and the traversal micro-benchmark.  They run the same device code as
+ * path_trace on caller-supplied work.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct RtxptRay  { float origin[3]; float tMin; float dir[3]; float tMax; } RtxptRay;   /* 32 bytes */
+typedef struct RtxptHit  { float t; float u, v; uint32_t instanceIndex, geometryIndex, primitiveIndex; } RtxptHit; /* t<0: miss; (u,v) = weights of vertex 1 and 2 */
+
+/* Closest-hit (anyHit=0) or first-hit (anyHit=1) queries for `count` host rays; alpha test included. */
+RTXPT_API int rtxpt_b200_trace_rays(rtxpt_ctx* ctx, const RtxptRay* rays, uint32_t count, int anyHit, RtxptHit* outHits);
+/* Same on device-resident rays, `repeat` launches back to back; returns the average kernel milliseconds (CUDA events). */
+RTXPT_API int rtxpt_b200_trace_rays_device(rtxpt_ctx* ctx, const void* dRays, uint32_t count, int anyHit, void* dHits, uint32_t repeat, float* outMsPerLaunch);
+
+/* Baked light list (PolymorphicLightInfo 32 B each), per-light proxy counters and the proxy index table. */
+RTXPT_API int rtxpt_b200_get_lights(rtxpt_ctx* ctx, void* outLightInfos, uint32_t* ioLightCount,
+                                    uint32_t* outProxyCounters, uint32_t* outProxyIndices, uint32_t* ioProxyCount);
+
+/* StandardBSDF evaluated on the device for `count` records of 32 floats in / 16 floats out; see tests/test_bsdf_parity.py. */
+RTXPT_API int rtxpt_b200_debug_bsdf(rtxpt_ctx* ctx, const float* in, uint32_t count, float* out);
+/* Stateless sample generators evaluated on the device: out[i*8..] = 4 uniform + 4 low-discrepancy draws for
+ * (pixelX,pixelY,vertexIndex,sampleIndex) tuples in `in` (4 u32 each). */
+RTXPT_API int rtxpt_b200_debug_rng(rtxpt_ctx* ctx, const uint32_t* in, uint32_t count, uint32_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTXPT_B200_H_ */

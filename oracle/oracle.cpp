@@ -1,0 +1,198 @@
+// ORACLE — test infrastructure only.  C entry points (ctypes) over the CPU restatement of RTXPT's PathTrace hot path.
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may build, load or call this library.
+// The product (rtxpt_b200/) never links it.
+//
+// Parity status: RNG / packing are pinned against the reference's own C++ halves (oracle/_ref, tests/golden/); everything that
+// depends on the DXR driver (BVH, traversal, intersection), TMU filtering or fp16 shader arithmetic is "parity unpinned" — the
+// reference ships no runnable golden data for it.
+#include "pt_path.h"
+#include <cstdio>
+#include <chrono>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+using namespace orc;
+
+struct OracleCtx
+{
+    Scene scene;
+    Bvh2 bvh;
+    LightTable lights;
+    RtxptPathTracerConstants consts;
+    bool haveConsts = false;
+    double bvhBuildSeconds = 0;
+};
+
+extern "C" {
+
+#define ORC_API __attribute__((visibility("default")))
+
+ORC_API uint32_t oracle_hash32(uint32_t x) { return Hash32(x); }
+ORC_API uint32_t oracle_hash32_combine(uint32_t s, uint32_t v) { return Hash32Combine(s, v); }
+ORC_API float    oracle_hash32_to_float(uint32_t h) { return Hash32ToFloat(h); }
+ORC_API uint32_t oracle_sobol(uint32_t index, uint32_t dim) { return bhos_sobol(index, dim); }
+ORC_API uint32_t oracle_owen_scramble(uint32_t x, uint32_t seed) { return bhos_owen_scramble(x, seed); }
+ORC_API uint32_t oracle_f32tof16(float f) { return f32tof16(f); }
+ORC_API float    oracle_f16tof32(uint32_t h) { return f16tof32(h); }
+ORC_API uint32_t oracle_pack_snorm8(float v) { return uint32_t(int(clampf(v, -1.0f, 1.0f) * 127.0f) & 0xff); }
+ORC_API float    oracle_unpack_snorm8(uint32_t v) { return Unpack_R8_SNORM(v); }
+
+// in: (pixelX, pixelY, vertexIndex, sampleIndex) ; out: 4 uniform draws (effect seed Base) then 4 LD draws (seed ScatterBSDF, raw u32 via float bits)
+ORC_API void oracle_rng(const uint32_t* in, uint32_t count, uint32_t* out)
+{
+    for (uint32_t i = 0; i < count; i++)
+    {
+        SampleGeneratorVertexBase base = SampleGeneratorVertexBase::make((in[i * 4 + 0] << 16) | in[i * 4 + 1], in[i * 4 + 2], in[i * 4 + 3]);
+        UniformSampleSequenceGenerator u = UniformSampleSequenceGenerator::make(base, SeedBase);
+        for (int k = 0; k < 4; k++) out[i * 8 + k] = u.Next();
+        float ld[4]; GenerateLD(4, base, SeedScatterBSDF, ld);
+        for (int k = 0; k < 4; k++) out[i * 8 + 4 + k] = asuint(ld[k]);
+    }
+}
+
+// Record layout shared with rtxpt_b200_debug_bsdf: 36 floats in, 16 floats out (see include/rtxpt_b200.h)
+ORC_API void oracle_bsdf(const float* in, uint32_t count, float* out)
+{
+    for (uint32_t i = 0; i < count; i++)
+    {
+        const float* r = in + size_t(i) * 36; float* o = out + size_t(i) * 16;
+        BSDFFrame f; f.V = f3(r[0], r[1], r[2]); f.N = f3(r[3], r[4], r[5]); f.T = f3(r[6], r[7], r[8]); f.B = f3(r[9], r[10], r[11]);
+        float3 wo = f3(r[12], r[13], r[14]);
+        float u[4] = { r[15], r[16], r[17], 0 };
+        StandardBSDF b;
+        b.data.diffuse = f3(r[18], r[19], r[20]); b.data.roughness = r[21]; b.data.specular = f3(r[22], r[23], r[24]); b.data.metallic = r[25];
+        b.data.transmission = f3(r[26], r[27], r[28]); b.data.diffuseTransmission = r[29]; b.data.specularTransmission = r[30]; b.data.eta = r[31];
+        f.thinSurface = r[32] != 0.0f; f.activeLobes = uint(r[33]); f.psdExclude = false;
+        float4 e = b.eval(f, wo);
+        o[0] = e.x; o[1] = e.y; o[2] = e.z; o[3] = e.w;
+        o[4] = b.evalPdf(f, wo);
+        BSDFSample s; bool valid = b.sample(f, u, s);
+        o[5] = valid ? 1.0f : 0.0f; o[6] = s.wo.x; o[7] = s.wo.y; o[8] = s.wo.z; o[9] = s.pdf; o[10] = s.weight.x; o[11] = s.weight.y; o[12] = s.weight.z;
+        o[13] = float(s.lobe); o[14] = s.lobeP; o[15] = float(b.getLobes());
+    }
+}
+
+ORC_API void* oracle_create(const RtxptSceneDesc* desc)
+{
+    OracleCtx* c = new OracleCtx();
+    c->scene.init(desc);
+    auto t0 = std::chrono::steady_clock::now();
+    c->bvh.build(c->scene);
+    c->bvhBuildSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return c;
+}
+ORC_API void oracle_destroy(void* p) { delete (OracleCtx*)p; }
+ORC_API double oracle_bvh_build_seconds(void* p) { return ((OracleCtx*)p)->bvhBuildSeconds; }
+ORC_API uint32_t oracle_triangle_count(void* p) { return uint32_t(((OracleCtx*)p)->bvh.tris.size()); }
+
+ORC_API int oracle_set_constants(void* p, const RtxptPathTracerConstants* consts)
+{
+    OracleCtx* c = (OracleCtx*)p;
+    bool rebuildEnv = !c->haveConsts;
+    c->consts = *consts; c->haveConsts = true;
+    bakeLights(c->scene, c->consts, c->lights, rebuildEnv);
+    return 0;
+}
+
+ORC_API int oracle_trace_rays(void* p, const RtxptRay* rays, uint32_t count, int anyHit, RtxptHit* out)
+{
+    OracleCtx* c = (OracleCtx*)p;
+    #pragma omp parallel for schedule(dynamic, 256)
+    for (int i = 0; i < int(count); i++)
+    {
+        const RtxptRay& r = rays[i];
+        Hit h = c->bvh.trace(c->scene, f3(r.origin[0], r.origin[1], r.origin[2]), f3(r.dir[0], r.dir[1], r.dir[2]), r.tMin, r.tMax, anyHit != 0);
+        RtxptHit& o = out[i];
+        if (h.valid()) { const Tri& t = c->bvh.tris[h.triId]; o.t = h.t; o.u = h.u; o.v = h.v; o.instanceIndex = t.instanceIndex; o.geometryIndex = t.geometryIndex; o.primitiveIndex = t.primitiveIndex; }
+        else { o.t = -1.0f; o.u = o.v = 0; o.instanceIndex = o.geometryIndex = o.primitiveIndex = 0xFFFFFFFFu; }
+    }
+    return 0;
+}
+
+ORC_API int oracle_get_lights(void* p, void* outLightInfos, uint32_t* ioLightCount, uint32_t* outProxyCounters, uint32_t* outProxyIndices, uint32_t* ioProxyCount)
+{
+    OracleCtx* c = (OracleCtx*)p;
+    uint32_t n = uint32_t(c->lights.lights.size()), m = c->lights.samplingProxyCount;
+    if (outLightInfos && *ioLightCount >= n) memcpy(outLightInfos, c->lights.lights.data(), size_t(n) * 32);
+    if (outProxyCounters && *ioLightCount >= n) memcpy(outProxyCounters, c->lights.proxyCounters.data(), size_t(n) * 4);
+    if (outProxyIndices && *ioProxyCount >= m) memcpy(outProxyIndices, c->lights.proxyIndices.data(), size_t(m) * 4);
+    *ioLightCount = n; *ioProxyCount = m;
+    return 0;
+}
+ORC_API int oracle_get_sub_instances(void* p, RtxptSubInstanceData* out, uint32_t count)
+{
+    OracleCtx* c = (OracleCtx*)p;
+    if (count < c->scene.subInstances.size()) return -1;
+    memcpy(out, c->scene.subInstances.data(), c->scene.subInstances.size() * sizeof(RtxptSubInstanceData));
+    return 0;
+}
+
+struct OracleRenderStats { uint64_t scatterRays, shadowRays, nodeVisits, triTests; double seconds; int threads; };
+
+// Renders sub-samples [first, first+count) of the pixel rectangle [x0,x1)x[y0,y1) and folds each into `accum` (RGBA32F, full image
+// pitch) with the reference accumulation (AccumulationPass.hlsl:57-65: blend = 1/(n+1), lerp; Sample.cpp:2775).
+// `lastOutput` (optional, RGB32F full image pitch) receives the per-sample u_OutputColor of the last sub-sample;
+// `primary` (optional, 4 floats per pixel: t,u,v,triId-as-bits) the primary hit of the last sub-sample.
+ORC_API int oracle_render(void* p, uint32_t firstSubSample, uint32_t subSampleCount, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1,
+                          float* accum, uint32_t* ioAccumCount, float* lastOutput, float* primary, int threads, OracleRenderStats* outStats)
+{
+    OracleCtx* c = (OracleCtx*)p;
+    if (!c->haveConsts) return -1;
+    const uint32_t W = c->consts.imageWidth;
+    auto t0 = std::chrono::steady_clock::now();
+    RenderStats total;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+    int usedThreads = (threads > 0) ? threads : omp_get_max_threads();
+#else
+    int usedThreads = 1;
+#endif
+    for (uint32_t s = 0; s < subSampleCount; s++)
+    {
+        const uint32_t n = *ioAccumCount;
+        const float blend = 1.0f / (float(n) + 1.0f);
+        #pragma omp parallel
+        {
+            RenderStats local;
+            PathTracerCtx x; x.scene = &c->scene; x.bvh = &c->bvh; x.lights = &c->lights; x.c = &c->consts; x.stats = &local;
+            x.sampleIndex = c->consts.sampleBaseIndex + firstSubSample + s;
+            #pragma omp for schedule(dynamic, 4)
+            for (int y = int(y0); y < int(y1); y++)
+                for (uint32_t px = x0; px < x1; px++)
+                {
+                    PixelResult r = tracePixel(x, px, uint32_t(y));
+                    size_t pix = size_t(y) * W + px;
+                    float sample[4] = { r.rgb[0], r.rgb[1], r.rgb[2], 1.0f };
+                    for (int k = 0; k < 4; k++)
+                    {
+                        float prev = accum[pix * 4 + k];
+                        accum[pix * 4 + k] = (blend < 1.0f) ? (prev + (sample[k] - prev) * blend) : sample[k];
+                    }
+                    if (lastOutput) { lastOutput[pix * 3 + 0] = r.rgb[0]; lastOutput[pix * 3 + 1] = r.rgb[1]; lastOutput[pix * 3 + 2] = r.rgb[2]; }
+                    if (primary) { primary[pix * 4 + 0] = r.primaryT; primary[pix * 4 + 1] = r.primaryU; primary[pix * 4 + 2] = r.primaryV; primary[pix * 4 + 3] = asfloat(r.primaryTri); }
+                }
+            #pragma omp critical
+            { total.scatterRays += local.scatterRays; total.shadowRays += local.shadowRays; total.nodeVisits += local.nodeVisits; total.triTests += local.triTests; }
+        }
+        *ioAccumCount = n + 1;
+    }
+    if (outStats)
+    {
+        outStats->scatterRays = total.scatterRays; outStats->shadowRays = total.shadowRays; outStats->nodeVisits = total.nodeVisits; outStats->triTests = total.triTests;
+        outStats->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); outStats->threads = usedThreads;
+    }
+    return 0;
+}
+
+// primary-hit triangle id -> (instance, geometry, primitive), for comparing with the product's hit records
+ORC_API int oracle_tri_info(void* p, uint32_t triId, uint32_t* out3)
+{
+    OracleCtx* c = (OracleCtx*)p;
+    if (triId >= c->bvh.tris.size()) return -1;
+    const Tri& t = c->bvh.tris[triId];
+    out3[0] = t.instanceIndex; out3[1] = t.geometryIndex; out3[2] = t.primitiveIndex;
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,478 @@
+// ORACLE — test infrastructure only (see pt_math.h).
+// pt_path.h: one reference-mode path per pixel, restated from
+//   Rtxpt/Shaders/PathTracerSample.hlsl:115-166 (nextHit), :201-256 (raygen loop)
+//   Rtxpt/Shaders/PathTracer/PathTracer.hlsli:40-45, :47-91, :139-175, :182-208, :217-380, :382-404, :407-503, :505-762
+//   Rtxpt/Shaders/PathTracer/PathTracerNEE.hlsli:41-346
+//   Rtxpt/Shaders/PathTracer/PathState.hlsli:83-268 (fp16 payload packing), PathTracerTypes.hlsli:97-200
+//   Rtxpt/Shaders/PathTracer/PathTracerHelpers.hlsli:126-153 (thin lens), :195-219 (firefly filter), :29-42
+//   Rtxpt/Shaders/PathTracer/PathTracerNestedDielectrics.hlsli:24-131, Rendering/Materials/InteriorList.hlsli:28-246
+//   Rtxpt/Shaders/PathTracerBridgeDonut.hlsli:543-564 (camera ray)
+//   Rtxpt/Shaders/PathTracer/Lighting/LightSampler.hlsli (global sampling + MIS), Lighting/EnvMap.hlsli:84-87
+#pragma once
+#include "pt_scene.h"
+#include "pt_bvh.h"
+#include "pt_lights.h"
+#include "pt_rng.h"
+
+namespace orc {
+
+enum PathFlags : uint {
+    PF_active = 1u << 0, PF_hit = 1u << 1, PF_transmission = 1u << 2, PF_specular = 1u << 3, PF_delta = 1u << 4,
+    PF_insideDielectricVolume = 1u << 5, PF_terminateAtNextBounce = 1u << 6, PF_enableThreadReorder = 1u << 9,
+    PF_deltaTransmissionPath = 1u << 11, PF_deltaOnlyPath = 1u << 12
+};
+static const uint kVertexIndexBitCount = 10, kVertexIndexBitMask = (1u << kVertexIndexBitCount) - 1u;
+enum PackedCounter { CTR_DiffuseBounces = 0, CTR_RejectedHits = 1, CTR_BouncesFromStablePlane = 2 };
+
+struct InteriorList     // InteriorList.hlsli (2 slots)
+{
+    uint slots[2] = { 0, 0 };
+    static const uint kNoMaterial = 0xffffffffu, kMaterialMask = (1u << 28) - 1u, kMaxNestedPriority = 15;
+    bool isEmpty() const { return slots[0] == 0; }
+    uint getTopNestedPriority() const { return slots[0] >> 28; }
+    uint getTopMaterialID() const { return slots[0] != 0 ? (slots[0] & kMaterialMask) : kNoMaterial; }
+    uint getNextMaterialID() const { return slots[1] != 0 ? (slots[1] & kMaterialMask) : kNoMaterial; }
+    bool isTrueIntersection(uint nestedPriority) const { return nestedPriority == 0 || nestedPriority >= getTopNestedPriority(); }
+    void handleIntersection(uint materialID, uint nestedPriority, bool entering)
+    {
+        if (nestedPriority == 0) nestedPriority = kMaxNestedPriority;
+        uint slot = (nestedPriority << 28) | (materialID & kMaterialMask);
+        if (entering && slots[0] == 0) slots[0] = slot;
+        else if (!entering && slots[0] != 0 && (slots[0] & kMaterialMask) == materialID) slots[0] = 0;
+        else if (entering && slots[1] == 0) slots[1] = slot;
+        else if (!entering && slots[1] != 0 && (slots[1] & kMaterialMask) == materialID) slots[1] = 0;
+        if (slots[0] < slots[1]) std::swap(slots[0], slots[1]);
+    }
+};
+
+struct NEEBSDFMISInfo   // PathTracerTypes.hlsli:97-160 (PT_USE_RESTIR_DI = 0)
+{
+    bool LightSamplingEnabled = false, LightSamplingIsSSC = false; uint CandidateSamples = 0, FullSamples = 0;
+    static NEEBSDFMISInfo Unpack16bit(uint p) { NEEBSDFMISInfo r; r.LightSamplingEnabled = (p & (1 << 15)) != 0; r.LightSamplingIsSSC = (p & (1 << 13)) != 0; r.CandidateSamples = (p >> 6) & 0x3F; r.FullSamples = p & 0x3F; return r; }
+    uint Pack16bit() const { return ((LightSamplingEnabled ? 1u : 0u) << 15) | ((LightSamplingIsSSC ? 1u : 0u) << 13) | ((CandidateSamples & 0x3F) << 6) | (FullSamples & 0x3F); }
+};
+
+struct PathState
+{
+    float3 origin = f3(0), dir = f3(0); uint id = 0; float sceneLength = 0;
+    uint pack23[2] = { 0, 0 };      // thp (fp16 x4)
+    uint pack45[2] = { 0, 0 };      // L   (fp16 x4)
+    InteriorList interiorList;
+    uint packedCounters = 0;
+    RayCone rayCone;
+    uint pack0 = 0, pack1 = 0, flagsAndVertexIndex = 0;
+
+    void SetThp(float3 t) { t = clamp3(t, 0, HLF_MAX); pack23[0] = Fp32ToFp16NoClamp(f2(t.x, t.y)); pack23[1] = Fp32ToFp16NoClamp(f2(t.z, 0)); }
+    float3 GetThp() const { float2 a = Fp16ToFp32(pack23[0]), b = Fp16ToFp32(pack23[1]); return f3(a.x, a.y, b.x); }
+    void SetL(float4 l) { l = f4(clampf(l.x, 0, HLF_MAX), clampf(l.y, 0, HLF_MAX), clampf(l.z, 0, HLF_MAX), clampf(l.w, 0, HLF_MAX)); pack45[0] = Fp32ToFp16NoClamp(f2(l.x, l.y)); pack45[1] = Fp32ToFp16NoClamp(f2(l.z, l.w)); }
+    float4 GetL() const { float2 a = Fp16ToFp32(pack45[0]), b = Fp16ToFp32(pack45[1]); return f4(a.x, a.y, b.x, b.y); }
+    void SetFireflyFilterK_BsdfScatterPdf(float k, float pdf) { pack0 = (f32tof16(clampf(k, 0, HLF_MAX)) << 16) | f32tof16(clampf(pdf, 0, HLF_MAX)); }
+    float GetFireflyFilterK() const { return f16tof32(pack0 >> 16); }
+    float GetBsdfScatterPdf() const { return f16tof32(pack0 & 0xFFFF); }
+    void SetPackedMISInfo_ThpRuRuCorrection(uint mis, float c) { pack1 = (mis << 16) | f32tof16(clampf(c, 0, HLF_MAX)); }
+    uint GetPackedMISInfo() const { return pack1 >> 16; }
+    float GetThpRuRuCorrection() const { return f16tof32(pack1 & 0xFFFF); }
+
+    bool hasFlag(uint f) const { return (flagsAndVertexIndex & (f << kVertexIndexBitCount)) != 0; }
+    void setFlag(uint f, bool v = true) { uint bit = f << kVertexIndexBitCount; if (v) flagsAndVertexIndex |= bit; else flagsAndVertexIndex &= ~bit; }
+    bool isActive() const { return hasFlag(PF_active); }
+    void terminate() { setFlag(PF_active, false); }
+    uint getVertexIndex() const { return flagsAndVertexIndex & kVertexIndexBitMask; }
+    uint getCounter(uint type) const { return (packedCounters >> (type << 3)) & 0xff; }
+    void incrementCounter(uint type) { packedCounters += (1u << (type << 3)); }
+    void clearScatterEventFlags() { flagsAndVertexIndex &= ~((PF_transmission | PF_specular | PF_delta) << kVertexIndexBitCount); }
+};
+
+struct RenderStats { uint64_t scatterRays = 0, shadowRays = 0, nodeVisits = 0, triTests = 0; };
+
+struct PathTracerCtx
+{
+    const Scene* scene; const Bvh2* bvh; const LightTable* lights; const RtxptPathTracerConstants* c;
+    uint sampleIndex;       // Bridge::getSampleIndex() = sampleBaseIndex + subSampleIndex (BridgeDonut:510-513)
+    RenderStats* stats;
+};
+
+inline bool HasFinishedSurfaceBounces(const PathTracerCtx& x, uint vertexIndex, uint diffuseBounces)
+{
+    if (x.c->bounceCount < vertexIndex) return true;
+    return diffuseBounces > x.c->diffuseBounceCount;
+}
+
+// ---- env map (Lighting/EnvMap.hlsli) ----------------------------------------------------------------------------------
+inline float3 envToLocal(const PathTracerCtx& x, float3 d) { return mul_vec_33of34(d, x.c->envMap.InvTransform); }
+inline float3 envToWorld(const PathTracerCtx& x, float3 d) { return mul_vec_33of34(d, x.c->envMap.Transform); }
+inline float3 envEvalLocal(const PathTracerCtx& x, float3 localDir, float lod)
+{
+    return x.scene->env.sampleLevel(localDir, lod) * f3(x.c->envMap.ColorMultiplier[0], x.c->envMap.ColorMultiplier[1], x.c->envMap.ColorMultiplier[2]);
+}
+
+// ---- light sampler (global table only) ------------------------------------------------------------------------------------
+inline float SampleGlobalPDF(const LightTable& lt, uint lightIndex) { return float(lt.proxyCounters[lightIndex]) / float(lt.samplingProxyCount); }
+inline float EvalMISBalance(float n0, float p0, float n1, float p1) { float q0 = n0 * p0, q1 = n1 * p1; return saturate(q0 / (q0 + q1)); }   // Utils/Utils.hlsli:407-437
+inline float ComputeLightVsBSDF_MIS_ForBSDF(const LightTable& lt, uint lightIndex, float bsdfPdf, float solidAnglePdf, uint fullSampleCount)
+{
+    float globalPdf = SampleGlobalPDF(lt, lightIndex);
+    float localPdf = 0;                                         // localCount == 0 in this tier
+    float lightAvgPdf = (localPdf + globalPdf) * float(fullSampleCount);
+    return EvalMISBalance(1, bsdfPdf, 1, lightAvgPdf * solidAnglePdf);
+}
+
+struct LightSample { float3 Li = f3(0); float Distance = 0; float3 Direction = f3(0); uint LightIndex = 0xFFFFFFFFu; float SelectionPdf = 0, SolidAnglePdf = 0; bool LightSampleableByBSDF = false;
+                     bool Valid() const { return Li.x > 0 || Li.y > 0 || Li.z > 0; } };
+
+// ---- firefly filter (PathTracerHelpers.hlsli:183-219) ---------------------------------------------------------------------
+inline float ComputeRayConeSpreadAngleExpansionByScatterPDF(float pdf, float growthFactor = 0.3f)
+{
+    return growthFactor * 2.0f * FastACos(std::max(-1.0f, 1.0f - (1.0f / pdf) / (2.0f * K_PI)));
+}
+inline float ComputeNewScatterFireflyFilterK(float currentK, float bouncePDF, float lobeP)
+{
+    const float minK = 0.00001f;
+    float angle = (bouncePDF == 0) ? 0 : ComputeRayConeSpreadAngleExpansionByScatterPDF(bouncePDF, 1.0f);
+    const float k = 32;
+    float p = k / (k + angle * angle);
+    p *= FastSqrt(lobeP);
+    return lp(std::max(minK, currentK * p));
+}
+inline float3 FireflyFilter(float3 signalIn, float threshold, float fireflyFilterK)
+{
+    float thr = lp(threshold * fireflyFilterK);
+    float maxR = lp(Average(signalIn));
+    if (maxR > thr) signalIn = lp(signalIn / maxR * thr);
+    return signalIn;
+}
+inline float FireflyFilterShort(float signalAverage, float threshold, float fireflyFilterK)
+{
+    float thr = threshold * fireflyFilterK;
+    return (signalAverage > thr) ? (1.0f / signalAverage * thr) : 1.0f;
+}
+
+// ---- camera (BridgeDonut:543-564, PathTracerHelpers.hlsli:126-153) ---------------------------------------------------------
+inline void computeCameraRay(const PathTracerCtx& x, uint px, uint py, float3& origin, float3& dir)
+{
+    const RtxptCameraData& cam = x.c->camera;
+    SampleSequenceGenerator sg = SampleSequenceGenerator::make(SampleGeneratorVertexBase::make((px << 16) | py, 0, x.sampleIndex));
+    float r0 = sg.Next1D(), r1 = sg.Next1D();
+    float2 subPixelOffset = f2(cam.Jitter[0] + (r0 - 0.5f) * x.c->perPixelJitterAAScale, cam.Jitter[1] + (r1 - 0.5f) * x.c->perPixelJitterAAScale);
+    float d0 = sg.Next1D(), d1 = sg.Next1D();
+    float2 p = f2((float(px) + 0.5f + (-subPixelOffset.x)) / float(cam.ViewportSize[0]), (float(py) + 0.5f + subPixelOffset.y) / float(cam.ViewportSize[1]));
+    float2 ndc = f2(2 * p.x - 1, -2 * p.y + 1);
+    float3 U = f3(cam.CameraU[0], cam.CameraU[1], cam.CameraU[2]), V = f3(cam.CameraV[0], cam.CameraV[1], cam.CameraV[2]), W = f3(cam.CameraW[0], cam.CameraW[1], cam.CameraW[2]);
+    origin = f3(cam.PosW[0], cam.PosW[1], cam.PosW[2]);
+    dir = ndc.x * U + ndc.y * V + W;
+    float2 apertureSample = sample_disk(f2(d0, d1));
+    float3 rayTarget = origin + dir;
+    origin = origin + cam.ApertureRadius * (apertureSample.x * normalize(U) + apertureSample.y * normalize(V));
+    dir = normalize(rayTarget - origin);
+    float invCos = 1.f / dot(normalize(W), dir);
+    float tMin = cam.NearZ * invCos;
+    origin = origin + dir * tMin;
+}
+
+// ---- PathTracer.hlsli:382-404 ---------------------------------------------------------------------------------------------
+inline void UpdatePathTravelled(PathState& path, float rayTCurrent)
+{
+    path.flagsAndVertexIndex += 1;
+    path.rayCone = path.rayCone.propagateDistance(rayTCurrent);
+    path.sceneLength = std::min(path.sceneLength + rayTCurrent, kMaxRayTravel);
+}
+inline void AccumulatePathRadiance(PathState& path, float3 radiance) { float4 L = path.GetL(); path.SetL(f4(L.x + radiance.x, L.y + radiance.y, L.z + radiance.z, L.w)); }
+
+// ---- miss (PathTracer.hlsli:407-503) ---------------------------------------------------------------------------------------
+inline void HandleMiss(const PathTracerCtx& x, PathState& path, float3 rayDir, float rayTCurrent)
+{
+    UpdatePathTravelled(path, rayTCurrent);
+    float3 environmentEmission = f3(0);
+    NEEBSDFMISInfo misInfo = NEEBSDFMISInfo::Unpack16bit(path.GetPackedMISInfo());
+    if (x.lights->envEnabled)
+    {
+        float mipLevel = (path.getCounter(CTR_DiffuseBounces) > 1) ? x.c->EnvironmentMapDiffuseSampleMIPLevel : 0.0f;
+        float3 localDir = envToLocal(x, rayDir);
+        float3 Le = envEvalLocal(x, localDir, mipLevel);
+        float misWeight = 1.0f;
+        float bsdfScatterPdf = path.GetBsdfScatterPdf();
+        if (misInfo.LightSamplingEnabled && bsdfScatterPdf != 0)
+        {
+            float2 uv = ndir_to_oct_equal_area_unorm(localDir);
+            uint cx = uint(uv.x * float(IMPORTANCE_MAP_DIM)), cy = uint(uv.y * float(IMPORTANCE_MAP_DIM));
+            cx = std::min(cx, IMPORTANCE_MAP_DIM - 1); cy = std::min(cy, IMPORTANCE_MAP_DIM - 1);   // Texture2D.Load out of range returns 0 in D3D; uv==1 is the only way to get there
+            uint envLightIndex = x.lights->envLookupMap[size_t(cy) * IMPORTANCE_MAP_DIM + cx];
+            EnvironmentQuadLight eq = EnvironmentQuadLight::Create(x.lights->lights[envLightIndex]);
+            misWeight = ComputeLightVsBSDF_MIS_ForBSDF(*x.lights, envLightIndex, bsdfScatterPdf, eq.SolidAnglePdf(), misInfo.FullSamples);
+        }
+        environmentEmission = lp(misWeight * Le);
+    }
+    float baseFFThreshold = lp(x.c->fireflyFilterThreshold);
+    if (baseFFThreshold != 0) environmentEmission = FireflyFilter(environmentEmission, baseFFThreshold, path.GetFireflyFilterK());
+    if (any_gt0(environmentEmission)) AccumulatePathRadiance(path, path.GetThp() * environmentEmission);
+    path.setFlag(PF_hit, false);
+    path.terminate();
+}
+
+// ---- Russian roulette (PathTracer.hlsli:182-208) ------------------------------------------------------------------------------
+inline bool HandleRussianRoulette(const PathTracerCtx& x, PathState& path, UniformSampleSequenceGenerator& sg)
+{
+    if (!x.c->enableRussianRoulette) return false;
+    const float rrVal = sqrtf(Luminance(path.GetThp()));
+    float prob = saturate(0.85f - rrVal); prob = prob * prob;
+    prob = saturate(prob + std::max(0.0f, (float(path.getVertexIndex()) / float(x.c->bounceCount) - 0.4f)));
+    if (sg.Next1D() < prob) return true;
+    float thpRuRuCorrection = lp(1.0f / (1.0f - prob));
+    path.SetPackedMISInfo_ThpRuRuCorrection(path.GetPackedMISInfo(), thpRuRuCorrection);
+    return false;
+}
+
+// ---- scatter (PathTracer.hlsli:217-380) ---------------------------------------------------------------------------------------
+inline bool GenerateScatterRay(const PathTracerCtx& x, const ShadingData& sd, const StandardBSDF& bsdf, PathState& path, const SampleGeneratorVertexBase& sgBase)
+{
+    float u[4] = { 0, 0, 0, 0 };
+    if (x.c->enableLDSamplerForBSDF && path.getCounter(CTR_DiffuseBounces) < 1) GenerateLD(3, sgBase, SeedScatterBSDF, u);
+    else GenerateUniform(3, sgBase, SeedScatterBSDF, u);
+    BSDFSample bs;
+    if (!bsdf.sample(sd.frame(), u, bs)) return false;
+
+    path.dir = bs.wo;
+    path.SetThp(path.GetThp() * bs.weight);
+    path.clearScatterEventFlags();
+    path.origin = sd.computeNewRayOrigin(bs.isLobe(Lobe_Reflection));
+    const float roughness = bsdf.data.roughness;
+    bool isDiffuse = bs.isLobe(Lobe_DiffuseReflection) || bs.isLobe(Lobe_DiffuseTransmission) || roughness > 0.25f;
+    if (isDiffuse)
+    {
+        if (!(bs.isLobe(Lobe_DiffuseTransmission) && ((path.getVertexIndex() % 2) == 1))) path.incrementCounter(CTR_DiffuseBounces);
+    }
+    else path.setFlag(PF_specular);
+    if (bs.isLobe(Lobe_Transmission))
+    {
+        path.setFlag(PF_transmission);
+        if (x.c->nestedDielectricsQuality > 0 && !sd.thinSurface)
+        {
+            path.interiorList.handleIntersection(sd.materialID, sd.nestedPriority, sd.frontFacing);
+            path.setFlag(PF_insideDielectricVolume, !path.interiorList.isEmpty());
+        }
+    }
+    if (bs.isLobe(Lobe_Delta)) path.setFlag(PF_delta);
+    else
+    {
+        path.setFlag(PF_deltaOnlyPath, false);
+        path.rayCone = RayCone::make(path.rayCone.getWidth(), std::min(path.rayCone.getSpreadAngle() + ComputeRayConeSpreadAngleExpansionByScatterPDF(bs.pdf), 2.0f * K_PI));
+    }
+    float fireflyFilterK = (x.c->fireflyFilterThreshold != 0) ? ComputeNewScatterFireflyFilterK(path.GetFireflyFilterK(), bs.pdf, bs.lobeP) : 0.0f;
+    path.SetFireflyFilterK_BsdfScatterPdf(fireflyFilterK, bs.pdf);
+    path.setFlag(PF_enableThreadReorder, true);
+    return true;
+}
+
+// ---- NEE (PathTracerNEE.hlsli) --------------------------------------------------------------------------------------------------
+struct NEEResult
+{
+    uint pkg[2]; NEEBSDFMISInfo BSDFMISInfo;
+    NEEResult() { pkg[0] = Fp32ToFp16(f2(0, 0)); pkg[1] = Fp32ToFp16(f2(0, 0)); }
+    float4 Get() const { float2 a = Fp16ToFp32(pkg[0]), b = Fp16ToFp32(pkg[1]); return f4(a.x, a.y, b.x, b.y); }
+    void Accumulate(float3 radiance, float specAvg) { float4 v = Get(); pkg[0] = Fp32ToFp16(f2(v.x + radiance.x, v.y + radiance.y)); pkg[1] = Fp32ToFp16(f2(v.z + radiance.z, v.w + specAvg)); }
+};
+
+inline NEEResult HandleNEE(const PathTracerCtx& x, const PathState& pre, const ShadingData& sd, const StandardBSDF& bsdf, UniformSampleSequenceGenerator& sg)
+{
+    NEEResult result;
+    const LightTable& lt = *x.lights;
+    if (!x.c->NEEEnabled) return result;
+    const uint fullSamples = std::min(63u, x.c->NEEFullSamples);
+    const bool hasNonDeltaLobes = (bsdf.getLobes() & Lobe_NonDelta) != 0;
+    if (!(hasNonDeltaLobes && !lt.IsEmpty() && fullSamples > 0)) return result;
+    const uint candidateSampleCount = x.c->NEECandidateSamples;
+    const BSDFFrame frame = sd.frame();
+    result.BSDFMISInfo.LightSamplingEnabled = true;
+    result.BSDFMISInfo.LightSamplingIsSSC = (pre.rayCone.getWidth() / pre.sceneLength) < 0.3f;      // IsScreenSpaceCoherentHeuristic; only packed, no effect without local samples
+    result.BSDFMISInfo.CandidateSamples = candidateSampleCount;
+    result.BSDFMISInfo.FullSamples = fullSamples;
+    const uint localCount = 0, globalCount = candidateSampleCount - localCount;
+    for (uint sampleIndex = 0; sampleIndex < fullSamples; sampleIndex++)
+    {
+        // GenerateLightSample: weighted reservoir sampling over the candidates
+        LightSample picked; float weightSum = 0, candidateWeight = 0;
+        for (uint i = 0; i < candidateSampleCount; i++)
+        {
+            float rnd = sg.Next1D();
+            uint M = lt.samplingProxyCount;
+            uint lightIndex = lt.proxyIndices[std::min(uint(rnd * float(M)), M - 1)];
+            float selectionPdf = float(lt.proxyCounters[lightIndex]) / float(M);
+            const PolymorphicLightInfo& li = lt.lights[lightIndex];
+            float2 interiorRnd; interiorRnd.x = sg.Next1D(); interiorRnd.y = sg.Next1D();
+            PolymorphicLightSample ls = {};
+            if (LightType(li) == kLightTypeTriangle) ls = TriangleLight::Create(li).CalcSample(interiorRnd, sd.posW);
+            else if (LightType(li) == kLightTypeEnvironmentQuad)
+            {
+                EnvironmentQuadLight e = EnvironmentQuadLight::Create(li);
+                float2 subTexelPos = f2((float(e.NodeX) + interiorRnd.x) / float(e.NodeDim), (float(e.NodeY) + interiorRnd.y) / float(e.NodeDim));
+                float3 worldDir = envToWorld(x, oct_to_ndir_equal_area_unorm(subTexelPos));
+                ls.Position = sd.posW + worldDir * DISTANT_LIGHT_DISTANCE;
+                ls.Normal = -worldDir; ls.Radiance = e.Radiance; ls.SolidAnglePdf = e.SolidAnglePdf(); ls.LightSampleableByBSDF = true;
+            }
+            LightSample cs;
+            const float pdf = ls.SolidAnglePdf * selectionPdf;
+            cs.Li = pdf > 0.f ? (ls.Radiance / pdf) : f3(0);
+            cs.SolidAnglePdf = ls.SolidAnglePdf;
+            float3 surfToLight = ls.Position - sd.posW;
+            cs.Distance = length(surfToLight);
+            cs.Direction = surfToLight / std::max(cs.Distance, 1e-7f);
+            cs.LightIndex = lightIndex; cs.SelectionPdf = selectionPdf; cs.LightSampleableByBSDF = ls.LightSampleableByBSDF;
+            float wrsWeight = max3(cs.Li) * bsdf.evalPdf(frame, cs.Direction);
+            float wrsRnd = sg.Next1D();
+            weightSum += wrsWeight;
+            float wrsThreshold = saturate(wrsWeight / weightSum);
+            if (wrsRnd < wrsThreshold) { picked = cs; candidateWeight = wrsWeight; }
+        }
+        picked.Li = picked.Li * (1.0f / (candidateWeight / weightSum));
+
+        // ProcessLightSample
+        bool visible = false;
+        if (picked.Valid())
+        {
+            float faceSide = dot(sd.N, picked.Direction) >= 0 ? 1.0f : -1.0f;
+            float3 o = ComputeRayOrigin(sd.posW, sd.faceNCorrected * faceSide);
+            if (x.stats) x.stats->shadowRays++;
+            Hit h = x.bvh->trace(*x.scene, o, picked.Direction, 0.0f, picked.Distance * 0.9985f, true, x.stats ? &x.stats->nodeVisits : nullptr, x.stats ? &x.stats->triTests : nullptr);
+            visible = !h.valid();
+        }
+        if (visible)
+        {
+            float fadeOut = (sd.shadowNoLFadeout > 0) ? saturate((dot(picked.Direction, sd.vertexN) - sd.shadowNoLFadeout) / (2.0f * sd.shadowNoLFadeout)) : 1.0f;
+            float thisPdf = picked.SelectionPdf, otherPdf = 0, thisCount = float(globalCount);
+            float wrsMIS = EvalMISBalance(1, thisPdf, 1, otherPdf) / thisCount;
+            float scatterPdfForDir = bsdf.evalPdf(frame, picked.Direction);
+            float lightAvgPdf = (thisPdf + otherPdf) * float(fullSamples);
+            float pathMIS = EvalMISBalance(1, lightAvgPdf * picked.SolidAnglePdf, 1, picked.LightSampleableByBSDF ? scatterPdfForDir : 0.0f);
+            float3 Li = picked.Li * (fadeOut * wrsMIS * pathMIS / float(fullSamples));
+            float4 bsdfThp = bsdf.eval(frame, picked.Direction);
+            float3 radiance = xyz(bsdfThp) * Li;
+            float radianceAvg = Average(radiance);
+            float specAvg = bsdfThp.w * Average(Li);
+            if (x.c->fireflyFilterThreshold != 0)
+            {
+                const float pdf = picked.SelectionPdf * picked.SolidAnglePdf;
+                float neeFireflyFilterK = ComputeNewScatterFireflyFilterK(pre.GetFireflyFilterK(), pdf, 1.0f);
+                radiance *= FireflyFilterShort(radianceAvg, x.c->fireflyFilterThreshold, neeFireflyFilterK);
+            }
+            float3 preScatterThp = pre.GetThp();
+            radiance *= preScatterThp;
+            specAvg *= Average(preScatterThp);
+            result.Accumulate(radiance, specAvg);
+        }
+    }
+    return result;
+}
+
+// ---- hit (PathTracer.hlsli:505-762) --------------------------------------------------------------------------------------------
+inline void HandleHit(const PathTracerCtx& x, PathState& path, float3 rayOrigin, float3 rayDir, float rayTCurrent, const Tri& tri, float2 barycentrics)
+{
+    UpdatePathTravelled(path, rayTCurrent);
+    SurfaceData surface = loadSurface(*x.scene, tri.instanceIndex, tri.geometryIndex, tri.primitiveIndex, barycentrics, rayDir, path.rayCone, x.c->texLODBias);
+    const uint ndq = x.c->nestedDielectricsQuality;
+    if (ndq > 0 && !path.interiorList.isEmpty())
+    {   // homogeneous absorption (BridgeDonut:871-887, HomogeneousVolumeSampler::evalTransmittance)
+        uint materialID = path.interiorList.getTopMaterialID();
+        float3 sigmaA = f3(0);
+        if (materialID < x.scene->desc->materialCount)
+        {
+            const RtxptMaterialData& m = x.scene->desc->materials[materialID];
+            float dist = std::max(1e-30f, m.VolumeAttenuationDistance);
+            sigmaA = f3(-logf(clampf(m.VolumeAttenuationColor[0], 1e-7f, 1)) / dist, -logf(clampf(m.VolumeAttenuationColor[1], 1e-7f, 1)) / dist, -logf(clampf(m.VolumeAttenuationColor[2], 1e-7f, 1)) / dist);
+        }
+        float3 transmittance = f3(expf(-rayTCurrent * sigmaA.x), expf(-rayTCurrent * sigmaA.y), expf(-rayTCurrent * sigmaA.z));
+        path.SetThp(path.GetThp() * transmittance);
+    }
+    if (ndq > 0 && !surface.sd.thinSurface)
+    {   // HandleNestedDielectrics, quality 1: kMaxRejectedDielectricHits = 4, NESTED_DIELECTRICS_AVOID_TERMINATION
+        uint nestedPriority = surface.sd.nestedPriority;
+        if (path.getCounter(CTR_RejectedHits) < 4 && !path.interiorList.isTrueIntersection(nestedPriority))
+        {
+            path.incrementCounter(CTR_RejectedHits);
+            path.interiorList.handleIntersection(surface.sd.materialID, nestedPriority, surface.sd.frontFacing);
+            path.origin = ComputeRayOrigin(surface.sd.posW, -surface.sd.faceNCorrected);
+            path.flagsAndVertexIndex -= 1;
+            return;     // rejected false hit: same direction continues from the far side
+        }
+        // ComputeOutsideIoR + Bridge::updateOutsideIoR
+        uint outsideMaterialID = path.interiorList.getTopMaterialID();
+        if (!surface.sd.frontFacing && outsideMaterialID == surface.sd.materialID) outsideMaterialID = path.interiorList.getNextMaterialID();
+        float outsideIoR = 1.f;
+        if (outsideMaterialID != InteriorList::kNoMaterial) outsideIoR = (outsideMaterialID >= x.scene->desc->materialCount) ? 1.0f : lp(x.scene->desc->materials[outsideMaterialID].IoR);
+        surface.sd.IoR = outsideIoR;
+        surface.bsdf.data.eta = lp(surface.sd.frontFacing ? (surface.sd.IoR / surface.interiorIoR) : (surface.interiorIoR / surface.sd.IoR));
+    }
+    const ShadingData& sd = surface.sd;
+    const StandardBSDF& bsdf = surface.bsdf;
+
+    // emissive triangle radiance with BSDF-side MIS
+    float3 surfaceEmission = f3(0);
+    NEEBSDFMISInfo misInfo = NEEBSDFMISInfo::Unpack16bit(path.GetPackedMISInfo());
+    if (any_gt0(sd.emission))
+    {
+        float misWeight = 1.0f;
+        float bsdfScatterPdf = path.GetBsdfScatterPdf();
+        if (misInfo.LightSamplingEnabled && bsdfScatterPdf != 0 && surface.neeTriangleLightIndex != RTXPT_INVALID_LIGHT_INDEX)
+        {
+            TriangleLight tl = TriangleLight::Create(x.lights->lights[surface.neeTriangleLightIndex]);
+            float solidAnglePdf = tl.CalcSolidAnglePdfForMIS(rayOrigin, sd.posW);
+            misWeight = ComputeLightVsBSDF_MIS_ForBSDF(*x.lights, surface.neeTriangleLightIndex, bsdfScatterPdf, solidAnglePdf, misInfo.FullSamples);
+        }
+        surfaceEmission = lp(sd.emission * misWeight);
+    }
+    if (any_gt0(surfaceEmission))
+    {
+        float baseFFThreshold = lp(x.c->fireflyFilterThreshold);
+        if (baseFFThreshold != 0) surfaceEmission = FireflyFilter(surfaceEmission, baseFFThreshold, path.GetFireflyFilterK());
+        if (any_gt0(surfaceEmission)) AccumulatePathRadiance(path, path.GetThp() * surfaceEmission);
+    }
+    if (path.hasFlag(PF_terminateAtNextBounce)) { path.terminate(); return; }
+
+    path.SetThp(path.GetThp() * path.GetThpRuRuCorrection());
+
+    const SampleGeneratorVertexBase sgBase = SampleGeneratorVertexBase::make(path.id, path.getVertexIndex(), x.sampleIndex);
+    UniformSampleSequenceGenerator uniformSG = UniformSampleSequenceGenerator::make(sgBase, SeedBase);
+    const PathState preScatterPath = path;
+    bool scatterValid = GenerateScatterRay(x, sd, bsdf, path, sgBase);
+    NEEResult neeResult = HandleNEE(x, preScatterPath, sd, bsdf, uniformSG);
+    path.SetPackedMISInfo_ThpRuRuCorrection(neeResult.BSDFMISInfo.Pack16bit(), path.GetThpRuRuCorrection());
+    float4 nee = neeResult.Get();
+    if (nee.x > 0 || nee.y > 0 || nee.z > 0 || nee.w > 0) AccumulatePathRadiance(path, xyz(nee));
+    if (!scatterValid) path.terminate();
+    bool shouldTerminate = HasFinishedSurfaceBounces(x, path.getVertexIndex() + 1, path.getCounter(CTR_DiffuseBounces));
+    shouldTerminate |= HandleRussianRoulette(x, path, uniformSG);
+    if (shouldTerminate) path.setFlag(PF_terminateAtNextBounce);
+}
+
+// ---- one pixel, one sample (PathTracerSample.hlsl:201-256): returns L.rgb as stored to u_OutputColor (RGBA16F) -------------------
+struct PixelResult { float rgb[3]; float primaryT; uint primaryTri; float primaryU, primaryV; };
+
+inline PixelResult tracePixel(const PathTracerCtx& x, uint px, uint py)
+{
+    PathState path;
+    path.id = (px << 16) | py;
+    path.SetThp(f3(1));
+    path.setFlag(PF_active); path.setFlag(PF_deltaOnlyPath, true);
+    path.rayCone = RayCone::make(0, x.c->camera.PixelConeSpreadAngle);
+    path.SetL(f4(0, 0, 0, 0));
+    path.SetFireflyFilterK_BsdfScatterPdf(1.0f, 0.0f);
+    path.SetPackedMISInfo_ThpRuRuCorrection(NEEBSDFMISInfo().Pack16bit(), 1.0f);
+    if (HasFinishedSurfaceBounces(x, path.getVertexIndex() + 1, path.getCounter(CTR_DiffuseBounces))) path.setFlag(PF_terminateAtNextBounce);
+    computeCameraRay(x, px, py, path.origin, path.dir);
+
+    PixelResult out = {}; out.primaryT = -1.0f; out.primaryTri = 0xFFFFFFFFu;
+    bool first = true;
+    while (path.isActive())
+    {
+        float3 o = path.origin, d = path.dir;
+        if (x.stats) x.stats->scatterRays++;
+        Hit h = x.bvh->trace(*x.scene, o, d, 0.0f, kMaxRayTravel, false, x.stats ? &x.stats->nodeVisits : nullptr, x.stats ? &x.stats->triTests : nullptr);
+        if (first) { first = false; if (h.valid()) { out.primaryT = h.t; out.primaryTri = h.triId; out.primaryU = h.u; out.primaryV = h.v; } }
+        if (!h.valid()) HandleMiss(x, path, d, kMaxRayTravel);
+        else HandleHit(x, path, o, d, h.t, x.bvh->tris[h.triId], f2(h.u, h.v));
+    }
+    float4 L = path.GetL();
+    out.rgb[0] = L.x; out.rgb[1] = L.y; out.rgb[2] = L.z;      // already fp16 values: the RGBA16F store is lossless
+    return out;
+}
+
+} // namespace orc

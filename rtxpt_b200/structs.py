@@ -1,0 +1,124 @@
+"""ctypes mirrors of include/rtxpt_b200.h (the C ABI).  Layouts are byte-identical to the reference's GPU tables:
+GeometryData / InstanceData (External/Donut/include/donut/shaders/bindless.h:28-70), SubInstanceData
+(Rtxpt/Shaders/SubInstanceData.h:23-46), PTMaterialData (Rtxpt/Shaders/PathTracer/Materials/MaterialPT.h:45-80),
+PathTracerCameraData / PathTracerConstants (Rtxpt/Shaders/PathTracer/PathTracerShared.h:24-104)."""
+import ctypes as C
+
+u32, i32, f32, u64 = C.c_uint32, C.c_int32, C.c_float, C.c_uint64
+MAX_MIPS = 16
+
+FORMAT_RGBA8_UNORM, FORMAT_RGBA8_SRGB, FORMAT_RGBA32_FLOAT = 0, 1, 2
+SUBINST_FLAG_ALPHA_TESTED = 1 << 16
+SUBINST_FLAG_EXCLUDE_FROM_NEE = 1 << 17
+
+MATFLAG_UseSpecularGlossModel = 0x1
+MATFLAG_UseMetalRoughOrSpecularTexture = 0x4
+MATFLAG_UseBaseOrDiffuseTexture = 0x8
+MATFLAG_UseEmissiveTexture = 0x10
+MATFLAG_UseNormalTexture = 0x20
+MATFLAG_UseTransmissionTexture = 0x80
+MATFLAG_MetalnessInRedChannel = 0x100
+MATFLAG_ThinSurface = 0x200
+MATFLAG_PSDExclude = 0x400
+MATFLAG_IgnoreMeshTangentSpace = 1 << 12
+MATFLAG_NestedPriorityShift = 28
+
+CFG_COUNT_TRAVERSAL_STEPS = 1
+CFG_NO_MATERIAL_SORT = 2
+
+BUFFER_OUTPUT_COLOR_F16, BUFFER_ACCUMULATED_F32, BUFFER_DEPTH_F32 = 0, 1, 2
+
+
+class GeometryData(C.Structure):
+    _fields_ = [("numIndices", u32), ("numVertices", u32), ("indexBufferIndex", i32), ("indexOffset", u32),
+                ("vertexBufferIndex", i32), ("positionOffset", u32), ("prevPositionOffset", u32), ("texCoord1Offset", u32),
+                ("texCoord2Offset", u32), ("normalOffset", u32), ("tangentOffset", u32), ("curveRadiusOffset", u32),
+                ("materialIndex", u32), ("pad0", u32), ("pad1", u32), ("pad2", u32)]
+
+
+class InstanceData(C.Structure):
+    _fields_ = [("flags", u32), ("firstGeometryInstanceIndex", u32), ("firstGeometryIndex", u32), ("numGeometries", u32),
+                ("transform", f32 * 12), ("prevTransform", f32 * 12)]
+
+
+class SubInstanceData(C.Structure):
+    _fields_ = [("FlagsAndAlphaInfo", u32), ("GlobalGeometryIndex_PTMaterialDataIndex", u32), ("EmissiveLightMappingOffset", u32),
+                ("AnalyticProxyLightIndex", u32), ("IndexBufferIndex_VertexBufferIndex", u32), ("IndexOffset", u32),
+                ("TexCoord1Offset", u32), ("padding0", u32)]
+
+
+class MaterialData(C.Structure):
+    _fields_ = [("BaseOrDiffuseColor", f32 * 3), ("Flags", u32), ("SpecularColor", f32 * 3), ("_padding0", i32),
+                ("EmissiveColor", f32 * 3), ("ShadowNoLFadeout", f32), ("Opacity", f32), ("Roughness", f32), ("Metalness", f32),
+                ("NormalTextureScale", f32), ("_padding1", f32), ("AlphaCutoff", f32), ("TransmissionFactor", f32),
+                ("BaseOrDiffuseTextureIndex", u32), ("MetalRoughOrSpecularTextureIndex", u32), ("EmissiveTextureIndex", u32),
+                ("NormalTextureIndex", u32), ("OcclusionTextureIndex", u32), ("TransmissionTextureIndex", u32), ("IoR", f32),
+                ("ThicknessFactor", f32), ("DiffuseTransmissionFactor", f32), ("VolumeAttenuationColor", f32 * 3),
+                ("VolumeAttenuationDistance", f32)]
+
+
+class BufferDesc(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("sizeBytes", u64)]
+
+
+class TextureDesc(C.Structure):
+    _fields_ = [("width", u32), ("height", u32), ("mipLevels", u32), ("format", u32), ("mips", C.c_void_p * MAX_MIPS)]
+
+
+class EnvCubeDesc(C.Structure):
+    _fields_ = [("faceSize", u32), ("mipLevels", u32), ("faces", (C.c_void_p * MAX_MIPS) * 6)]
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("instances", C.POINTER(InstanceData)), ("instanceCount", u32),
+                ("geometries", C.POINTER(GeometryData)), ("geometryCount", u32),
+                ("subInstances", C.POINTER(SubInstanceData)), ("subInstanceCount", u32),
+                ("materials", C.POINTER(MaterialData)), ("materialCount", u32),
+                ("buffers", C.POINTER(BufferDesc)), ("bufferCount", u32),
+                ("textures", C.POINTER(TextureDesc)), ("textureCount", u32),
+                ("envCube", EnvCubeDesc)]
+
+
+class CameraData(C.Structure):
+    _fields_ = [("PosW", f32 * 3), ("NearZ", f32), ("DirectionW", f32 * 3), ("PixelConeSpreadAngle", f32),
+                ("CameraU", f32 * 3), ("FarZ", f32), ("CameraV", f32 * 3), ("FocalDistance", f32),
+                ("CameraW", f32 * 3), ("AspectRatio", f32), ("ViewportSize", u32 * 2), ("ApertureRadius", f32),
+                ("_padding0", f32), ("Jitter", f32 * 2), ("_padding1", f32), ("_padding2", f32)]
+
+
+class EnvMapSceneParams(C.Structure):
+    _fields_ = [("Transform", f32 * 12), ("InvTransform", f32 * 12), ("ColorMultiplier", f32 * 3), ("Enabled", f32)]
+
+
+class PathTracerConstants(C.Structure):
+    _fields_ = [("imageWidth", u32), ("imageHeight", u32), ("sampleBaseIndex", u32), ("perPixelJitterAAScale", f32),
+                ("bounceCount", u32), ("diffuseBounceCount", u32), ("EnvironmentMapDiffuseSampleMIPLevel", f32), ("texLODBias", f32),
+                ("fireflyFilterThreshold", f32), ("NEEEnabled", u32), ("NEEType", u32), ("NEECandidateSamples", u32),
+                ("NEEFullSamples", u32), ("enableRussianRoulette", u32), ("enableLDSamplerForBSDF", u32),
+                ("nestedDielectricsQuality", u32), ("camera", CameraData), ("envMap", EnvMapSceneParams),
+                ("distantVsLocalImportance", f32), ("_pad", f32 * 3)]
+
+
+class Config(C.Structure):
+    _fields_ = [("deviceOrdinal", i32), ("maxWidth", u32), ("maxHeight", u32), ("maxSubSamplesPerLaunch", u32),
+                ("tileRank", u32), ("tileWorld", u32), ("tileSize", u32), ("flags", u32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("scatterRays", u64), ("shadowRays", u64), ("paths", u64), ("kernelLaunches", u64),
+                ("traversalNodeVisits", u64), ("traversalTriTests", u64), ("raysPerBounce", u64 * 16),
+                ("msTotal", f32), ("msTraceClosest", f32), ("msTraceShadow", f32), ("msShade", f32), ("msOther", f32),
+                ("bvhNodeCount", u32), ("bvhTriangleCount", u32), ("bvhBuildSeconds", f32),
+                ("lightCount", u32), ("lightProxyCount", u32), ("accumulatedSamples", u32)]
+
+
+class Ray(C.Structure):
+    _fields_ = [("origin", f32 * 3), ("tMin", f32), ("dir", f32 * 3), ("tMax", f32)]
+
+
+class Hit(C.Structure):
+    _fields_ = [("t", f32), ("u", f32), ("v", f32), ("instanceIndex", u32), ("geometryIndex", u32), ("primitiveIndex", u32)]
+
+
+assert C.sizeof(GeometryData) == 64 and C.sizeof(InstanceData) == 112 and C.sizeof(SubInstanceData) == 32
+assert C.sizeof(MaterialData) == 128 and C.sizeof(CameraData) == 112 and C.sizeof(Ray) == 32 and C.sizeof(Hit) == 24

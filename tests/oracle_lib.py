@@ -1,0 +1,98 @@
+"""ctypes binding of oracle/_build/liboracle.so — TEST INFRASTRUCTURE ONLY (never imported by rtxpt_b200/)."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+from rtxpt_b200 import structs as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+
+
+class RenderStats(C.Structure):
+    _fields_ = [("scatterRays", C.c_uint64), ("shadowRays", C.c_uint64), ("nodeVisits", C.c_uint64), ("triTests", C.c_uint64),
+                ("seconds", C.c_double), ("threads", C.c_int)]
+
+
+def build():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "_build/liboracle.so"], check=True)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        L = C.CDLL(LIB_PATH)
+        L.oracle_hash32.restype = C.c_uint32; L.oracle_hash32.argtypes = [C.c_uint32]
+        L.oracle_hash32_combine.restype = C.c_uint32; L.oracle_hash32_combine.argtypes = [C.c_uint32, C.c_uint32]
+        L.oracle_hash32_to_float.restype = C.c_float; L.oracle_hash32_to_float.argtypes = [C.c_uint32]
+        L.oracle_sobol.restype = C.c_uint32; L.oracle_sobol.argtypes = [C.c_uint32, C.c_uint32]
+        L.oracle_owen_scramble.restype = C.c_uint32; L.oracle_owen_scramble.argtypes = [C.c_uint32, C.c_uint32]
+        L.oracle_f32tof16.restype = C.c_uint32; L.oracle_f32tof16.argtypes = [C.c_float]
+        L.oracle_f16tof32.restype = C.c_float; L.oracle_f16tof32.argtypes = [C.c_uint32]
+        L.oracle_pack_snorm8.restype = C.c_uint32; L.oracle_pack_snorm8.argtypes = [C.c_float]
+        L.oracle_unpack_snorm8.restype = C.c_float; L.oracle_unpack_snorm8.argtypes = [C.c_uint32]
+        L.oracle_create.restype = C.c_void_p; L.oracle_create.argtypes = [C.POINTER(S.SceneDesc)]
+        L.oracle_destroy.argtypes = [C.c_void_p]
+        L.oracle_bvh_build_seconds.restype = C.c_double; L.oracle_bvh_build_seconds.argtypes = [C.c_void_p]
+        L.oracle_triangle_count.restype = C.c_uint32; L.oracle_triangle_count.argtypes = [C.c_void_p]
+        L.oracle_set_constants.argtypes = [C.c_void_p, C.POINTER(S.PathTracerConstants)]
+        L.oracle_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
+        L.oracle_get_lights.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
+        L.oracle_get_sub_instances.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.oracle_render.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                    C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.c_int, C.POINTER(RenderStats)]
+        L.oracle_tri_info.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        L.oracle_rng.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        L.oracle_bsdf.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+class Oracle:
+    def __init__(self, scene):
+        self.scene = scene          # keeps the numpy storage alive
+        self.h = lib().oracle_create(C.byref(scene.desc))
+        self.consts = None
+
+    def close(self):
+        if self.h:
+            lib().oracle_destroy(self.h); self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def set_constants(self, consts):
+        self.consts = consts
+        assert lib().oracle_set_constants(self.h, C.byref(consts)) == 0
+
+    def trace_rays(self, rays, any_hit=False):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        hits = np.zeros(len(rays), dtype=[("t", "f4"), ("u", "f4"), ("v", "f4"), ("inst", "u4"), ("geom", "u4"), ("prim", "u4")])
+        lib().oracle_trace_rays(self.h, rays.ctypes.data, len(rays), int(any_hit), hits.ctypes.data)
+        return hits
+
+    def lights(self):
+        n, m = C.c_uint32(0), C.c_uint32(0)
+        lib().oracle_get_lights(self.h, None, C.byref(n), None, None, C.byref(m))
+        infos = np.zeros((n.value, 8), np.uint32); counters = np.zeros(n.value, np.uint32); proxies = np.zeros(m.value, np.uint32)
+        lib().oracle_get_lights(self.h, infos.ctypes.data, C.byref(n), counters.ctypes.data, proxies.ctypes.data, C.byref(m))
+        return infos, counters, proxies
+
+    def render(self, first_sub_sample, count, accum=None, accum_count=0, rect=None, threads=0, want_primary=False):
+        W, H = self.consts.imageWidth, self.consts.imageHeight
+        if accum is None:
+            accum = np.zeros((H, W, 4), np.float32)
+        x0, y0, x1, y1 = rect if rect else (0, 0, W, H)
+        last = np.zeros((H, W, 3), np.float32)
+        primary = np.zeros((H, W, 4), np.float32) if want_primary else None
+        n = C.c_uint32(accum_count)
+        st = RenderStats()
+        rc = lib().oracle_render(self.h, first_sub_sample, count, x0, y0, x1, y1, accum.ctypes.data, C.byref(n), last.ctypes.data,
+                                 primary.ctypes.data if want_primary else None, threads, C.byref(st))
+        assert rc == 0
+        return accum, n.value, last, primary, st
