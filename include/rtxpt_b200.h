@@ -308,7 +308,7 @@ RTXPT_API int rtxpt_b200_trace_rays_device(rtxpt_ctx* ctx, const void* dRays, ui
 RTXPT_API int rtxpt_b200_get_lights(rtxpt_ctx* ctx, void* outLightInfos, uint32_t* ioLightCount,
                                     uint32_t* outProxyCounters, uint32_t* outProxyIndices, uint32_t* ioProxyCount);
 
-/* StandardBSDF evaluated on the device for `count` records of 32 floats in / 16 floats out; see tests/test_bsdf_parity.py. */
+/* StandardBSDF evaluated on the device for `count` records of 36 floats in / 16 floats out; see tests/test_bsdf_parity.py. */
 RTXPT_API int rtxpt_b200_debug_bsdf(rtxpt_ctx* ctx, const float* in, uint32_t count, float* out);
 /* Stateless sample generators evaluated on the device: out[i*8..] = 4 uniform + 4 low-discrepancy draws for
  * (pixelX,pixelY,vertexIndex,sampleIndex) tuples in `in` (4 u32 each). */

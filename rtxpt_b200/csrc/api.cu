@@ -1,0 +1,593 @@
+// api.cu — implementation of the C ABI declared in include/rtxpt_b200.h: context, scene upload (tables, textures, BVH, lights),
+// constants, the wavefront launch sequence, read-back and the inspection hooks.
+// Host orchestration mirrors the slice of Sample::Render that surrounds the dispatch (Rtxpt/Sample.cpp:2008-2186): acceleration
+// structure build, MaterialsBaker::Update, UpdateLighting, constant-buffer write, PathTrace, AccumulationPass.
+// There is no CPU rendering fallback anywhere in this library: without a CUDA device every entry point fails with RTXPT_ERR_NO_DEVICE.
+#include "kernels.h"
+#include "lights_bake.h"
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace pt;
+
+static_assert(sizeof(RtxptGeometryData) == 64, "GeometryData layout");
+static_assert(sizeof(RtxptInstanceData) == 112, "InstanceData layout");
+static_assert(sizeof(RtxptSubInstanceData) == 32, "SubInstanceData layout");
+static_assert(sizeof(RtxptMaterialData) == 128, "PTMaterialData layout");
+static_assert(sizeof(RtxptCameraData) == 112, "PathTracerCameraData layout");
+static_assert(sizeof(LightInfo) == 32 && sizeof(BakedLight) == 32, "PolymorphicLightInfo layout");
+static_assert(sizeof(Bvh8Node) == 80 && sizeof(Bvh8Tri) == 48, "CWBVH8 layout");
+static_assert(sizeof(LaunchParams) <= 4000, "kernel parameter block");
+
+static thread_local std::string g_lastError;
+static int fail(int code, const char* fmt, ...)
+{
+    char buf[1024]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    g_lastError = buf; return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(e_ == cudaErrorMemoryAllocation ? RTXPT_ERR_OUT_OF_MEMORY : RTXPT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+template <typename T> struct DeviceArray
+{
+    T* ptr = nullptr; size_t count = 0;
+    cudaError_t alloc(size_t n) { release(); count = n; if (n == 0) return cudaSuccess; return cudaMalloc(&ptr, n * sizeof(T)); }
+    cudaError_t upload(const T* src, size_t n, cudaStream_t s) { cudaError_t e = alloc(n); if (e != cudaSuccess || n == 0) return e; return cudaMemcpyAsync(ptr, src, n * sizeof(T), cudaMemcpyHostToDevice, s); }
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; count = 0; }
+};
+
+struct DeviceTexture { cudaMipmappedArray_t array = nullptr; cudaTextureObject_t object = 0; };
+
+struct rtxpt_ctx
+{
+    RtxptConfig cfg{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    GridConfig grid;
+    int maxSmemOptin = 0;
+    // scene
+    bool haveScene = false, haveConstants = false, lightsDirty = true;
+    DeviceArray<RtxptInstanceData> dInstances; DeviceArray<RtxptGeometryData> dGeometries; DeviceArray<RtxptSubInstanceData> dSubInstances;
+    DeviceArray<RtxptMaterialData> dMaterials; DeviceArray<uint8_t> dSubInstanceClass;
+    std::vector<uint8_t*> bufferAllocs; DeviceArray<const uint8_t*> dBufferTable;
+    std::vector<DeviceTexture> textures; DeviceArray<cudaTextureObject_t> dTextureTable;
+    DeviceTexture envCube; uint32_t envFaceSize = 0, envMipLevels = 0;
+    DeviceArray<uint4> dBvhNodes; DeviceArray<float4> dBvhTris; DeviceArray<uint4> dTriInfo;
+    uint32_t bvhNodeCount = 0, bvhTriCount = 0; float bvhBuildSeconds = 0;
+    std::vector<RtxptSubInstanceData> hSubInstances; uint32_t materialCount = 0;
+    LightBakeState lightState;
+    DeviceArray<LightInfo> dLights; DeviceArray<uint32_t> dProxyCounters, dProxyIndices, dEnvLookup;
+    // wavefront
+    DeviceArray<uint4> s0, s1, s2, s3, s4; DeviceArray<float4> hits; DeviceArray<uint32_t> rayQueue[2], shadeQueue;
+    DeviceArray<float4> shadowOriginTMax, shadowDirPath; DeviceArray<uint2> shadowRadiance;
+    DeviceArray<uint32_t> counters; DeviceArray<uint32_t> pixelOfSlot;
+    uint32_t capacity = 0, pixelCount = 0, tableWidth = 0, tableHeight = 0;
+    // render targets
+    DeviceArray<uint2> outputColor; DeviceArray<float4> accumulated; DeviceArray<float> depth;
+    uint32_t accumulatedSamples = 0;
+    RtxptPathTracerConstants consts{};
+    // stats
+    uint32_t* hCounters = nullptr;          // pinned
+    cudaEvent_t evStart = nullptr, evStop = nullptr;
+    std::vector<cudaEvent_t> evPool;
+    uint32_t lastIterations = 0, lastSubSamples = 0; uint64_t lastLaunches = 0;
+    bool statsPending = false;
+};
+
+static const uint32_t kCounterWords = (kMaxWavefrontIterations + 2) * kCountersPerIter;
+
+extern "C" RTXPT_API const char* rtxpt_b200_last_error(void) { return g_lastError.c_str(); }
+
+static void releaseScene(rtxpt_ctx* c)
+{
+    for (uint8_t* p : c->bufferAllocs) cudaFree(p);
+    c->bufferAllocs.clear();
+    for (DeviceTexture& t : c->textures) { if (t.object) cudaDestroyTextureObject(t.object); if (t.array) cudaFreeMipmappedArray(t.array); }
+    c->textures.clear();
+    if (c->envCube.object) cudaDestroyTextureObject(c->envCube.object);
+    if (c->envCube.array) cudaFreeMipmappedArray(c->envCube.array);
+    c->envCube = DeviceTexture();
+    c->haveScene = false;
+}
+
+extern "C" RTXPT_API int rtxpt_b200_create(const RtxptConfig* config, rtxpt_ctx** outCtx)
+{
+    if (!config || !outCtx) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(RTXPT_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    rtxpt_ctx* c = new rtxpt_ctx();
+    c->cfg = *config;
+    if (c->cfg.maxSubSamplesPerLaunch == 0) c->cfg.maxSubSamplesPerLaunch = 1;
+    if (c->cfg.tileWorld == 0) { c->cfg.tileWorld = 1; c->cfg.tileRank = 0; }
+    if (c->cfg.tileSize == 0) c->cfg.tileSize = 64;
+    if (c->cfg.tileRank >= c->cfg.tileWorld || (c->cfg.tileSize & (c->cfg.tileSize - 1)) != 0) { delete c; return fail(RTXPT_ERR_INVALID_ARGUMENT, "bad tile partition"); }
+    if (config->deviceOrdinal >= 0) { if (cudaSetDevice(config->deviceOrdinal) != cudaSuccess) { delete c; return fail(RTXPT_ERR_NO_DEVICE, "cudaSetDevice(%d) failed", config->deviceOrdinal); } }
+    cudaGetDevice(&c->device);
+    cudaDeviceProp prop; cudaGetDeviceProperties(&prop, c->device);
+    c->grid.smCount = prop.multiProcessorCount;
+    c->maxSmemOptin = int(prop.sharedMemPerBlockOptin);
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(RTXPT_ERR_CUDA, "stream creation failed"); }
+    cudaEventCreate(&c->evStart); cudaEventCreate(&c->evStop);
+    cudaMallocHost(&c->hCounters, kCounterWords * sizeof(uint32_t));
+    memset(c->hCounters, 0, kCounterWords * sizeof(uint32_t));
+    e = configureKernels(c->maxSmemOptin);
+    if (e != cudaSuccess) { delete c; return fail(RTXPT_ERR_CUDA, "kernel configuration failed: %s", cudaGetErrorString(e)); }
+    *outCtx = c;
+    return RTXPT_OK;
+}
+
+extern "C" RTXPT_API int rtxpt_b200_destroy(rtxpt_ctx* c)
+{
+    if (!c) return RTXPT_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    releaseScene(c);
+    c->dInstances.release(); c->dGeometries.release(); c->dSubInstances.release(); c->dMaterials.release(); c->dSubInstanceClass.release();
+    c->dBufferTable.release(); c->dTextureTable.release(); c->dBvhNodes.release(); c->dBvhTris.release(); c->dTriInfo.release();
+    c->dLights.release(); c->dProxyCounters.release(); c->dProxyIndices.release(); c->dEnvLookup.release();
+    c->s0.release(); c->s1.release(); c->s2.release(); c->s3.release(); c->s4.release(); c->hits.release();
+    c->rayQueue[0].release(); c->rayQueue[1].release(); c->shadeQueue.release();
+    c->shadowOriginTMax.release(); c->shadowDirPath.release(); c->shadowRadiance.release(); c->counters.release(); c->pixelOfSlot.release();
+    c->outputColor.release(); c->accumulated.release(); c->depth.release();
+    for (cudaEvent_t ev : c->evPool) cudaEventDestroy(ev);
+    if (c->evStart) cudaEventDestroy(c->evStart);
+    if (c->evStop) cudaEventDestroy(c->evStop);
+    if (c->hCounters) cudaFreeHost(c->hCounters);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return RTXPT_OK;
+}
+
+// ---- textures ----------------------------------------------------------------------------------------------------------------------
+static int createTexture2D(const RtxptTextureDesc& d, DeviceTexture& out)
+{
+    if (d.width == 0 || d.height == 0 || d.mipLevels == 0 || d.mipLevels > RTXPT_MAX_MIPS) return fail(RTXPT_ERR_INVALID_ARGUMENT, "bad texture description");
+    const bool isFloat = d.format == RTXPT_FORMAT_RGBA32_FLOAT;
+    cudaChannelFormatDesc fmt = isFloat ? cudaCreateChannelDesc<float4>() : cudaCreateChannelDesc<uchar4>();
+    CU(cudaMallocMipmappedArray(&out.array, &fmt, make_cudaExtent(d.width, d.height, 0), d.mipLevels));
+    const size_t texel = isFloat ? 16 : 4;
+    for (uint32_t m = 0; m < d.mipLevels; m++)
+    {
+        cudaArray_t level; CU(cudaGetMipmappedArrayLevel(&level, out.array, m));
+        const uint32_t w = std::max(1u, d.width >> m), h = std::max(1u, d.height >> m);
+        CU(cudaMemcpy2DToArray(level, 0, 0, d.mips[m], w * texel, w * texel, h, cudaMemcpyHostToDevice));
+    }
+    cudaResourceDesc res{}; res.resType = cudaResourceTypeMipmappedArray; res.res.mipmap.mipmap = out.array;
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeWrap;       // s_MaterialSampler: wrap, trilinear (CommonRenderPasses.cpp:85-86; anisotropy inert under SampleLevel)
+    td.filterMode = cudaFilterModeLinear; td.mipmapFilterMode = cudaFilterModeLinear;
+    td.readMode = isFloat ? cudaReadModeElementType : cudaReadModeNormalizedFloat;
+    td.sRGB = (d.format == RTXPT_FORMAT_RGBA8_SRGB) ? 1 : 0;
+    td.normalizedCoords = 1; td.maxAnisotropy = 1; td.minMipmapLevelClamp = 0; td.maxMipmapLevelClamp = float(d.mipLevels - 1);
+    CU(cudaCreateTextureObject(&out.object, &res, &td, nullptr));
+    return RTXPT_OK;
+}
+
+static int createEnvCube(const RtxptEnvCubeDesc& d, DeviceTexture& out)
+{
+    if (d.mipLevels == 0 || d.mipLevels > RTXPT_MAX_MIPS) return fail(RTXPT_ERR_INVALID_ARGUMENT, "bad env cube description");
+    cudaChannelFormatDesc fmt = cudaCreateChannelDesc<float4>();
+    CU(cudaMallocMipmappedArray(&out.array, &fmt, make_cudaExtent(d.faceSize, d.faceSize, 6), d.mipLevels, cudaArrayLayered));
+    for (uint32_t m = 0; m < d.mipLevels; m++)
+    {
+        cudaArray_t level; CU(cudaGetMipmappedArrayLevel(&level, out.array, m));
+        const uint32_t n = std::max(1u, d.faceSize >> m);
+        for (int f = 0; f < 6; f++)
+        {
+            cudaMemcpy3DParms cp{};
+            cp.srcPtr = make_cudaPitchedPtr(const_cast<float*>(d.faces[f][m]), n * 16, n, n);
+            cp.dstArray = level; cp.dstPos = make_cudaPos(0, 0, f); cp.extent = make_cudaExtent(n, n, 1); cp.kind = cudaMemcpyHostToDevice;
+            CU(cudaMemcpy3D(&cp));
+        }
+    }
+    cudaResourceDesc res{}; res.resType = cudaResourceTypeMipmappedArray; res.res.mipmap.mipmap = out.array;
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp; td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModeLinear; td.mipmapFilterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 1; td.maxAnisotropy = 1; td.maxMipmapLevelClamp = float(d.mipLevels - 1);
+    CU(cudaCreateTextureObject(&out.object, &res, &td, nullptr));
+    return RTXPT_OK;
+}
+
+// ---- scene upload ----------------------------------------------------------------------------------------------------------------------
+static inline void hostXformPoint(const float* m, const float* v, float* o)
+{
+    o[0] = m[0] * v[0] + m[1] * v[1] + m[2] * v[2] + m[3]; o[1] = m[4] * v[0] + m[5] * v[1] + m[6] * v[2] + m[7]; o[2] = m[8] * v[0] + m[9] * v[1] + m[10] * v[2] + m[11];
+}
+
+extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneDesc* sc)
+{
+    if (!c || !sc) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    cudaSetDevice(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    releaseScene(c);
+    if (sc->materialCount > 0xFFFF || sc->textureCount > 0xFFFF || sc->bufferCount > 0xFFFF) return fail(RTXPT_ERR_UNSUPPORTED, "table sizes exceed the 16-bit indices of SubInstanceData");
+    // validate + flatten triangles to world space (gid order: instance, geometry, primitive)
+    std::vector<BuildTriangle> tris; std::vector<uint4> triInfo;
+    for (uint32_t ii = 0; ii < sc->instanceCount; ii++)
+    {
+        const RtxptInstanceData& inst = sc->instances[ii];
+        for (uint32_t gi = 0; gi < inst.numGeometries; gi++)
+        {
+            if (inst.firstGeometryIndex + gi >= sc->geometryCount || inst.firstGeometryInstanceIndex + gi >= sc->subInstanceCount) return fail(RTXPT_ERR_INVALID_ARGUMENT, "instance %u references geometry out of range", ii);
+            const RtxptGeometryData& g = sc->geometries[inst.firstGeometryIndex + gi];
+            if (uint32_t(g.indexBufferIndex) >= sc->bufferCount || uint32_t(g.vertexBufferIndex) >= sc->bufferCount) return fail(RTXPT_ERR_INVALID_ARGUMENT, "geometry references buffer out of range");
+            const uint32_t subIndex = inst.firstGeometryInstanceIndex + gi;
+            const RtxptSubInstanceData& sub = sc->subInstances[subIndex];
+            uint32_t flags = subIndex;
+            if (sub.FlagsAndAlphaInfo & RTXPT_SUBINST_FLAG_ALPHA_TESTED) flags |= kTriFlagAlphaTested;
+            if (sub.FlagsAndAlphaInfo & RTXPT_SUBINST_FLAG_EXCLUDE_FROM_NEE) flags |= kTriFlagExcludeFromNEE;
+            const uint8_t* ib = (const uint8_t*)sc->buffers[g.indexBufferIndex].data; const uint8_t* vb = (const uint8_t*)sc->buffers[g.vertexBufferIndex].data;
+            const uint32_t triCount = g.numIndices / 3;
+            if (uint64_t(g.indexOffset) + uint64_t(triCount) * 12 > sc->buffers[g.indexBufferIndex].sizeBytes) return fail(RTXPT_ERR_INVALID_ARGUMENT, "index range exceeds buffer");
+            for (uint32_t t = 0; t < triCount; t++)
+            {
+                uint32_t idx[3]; memcpy(idx, ib + g.indexOffset + size_t(t) * 12, 12);
+                BuildTriangle bt; float* dst[3] = { bt.v0, bt.v1, bt.v2 };
+                for (int k = 0; k < 3; k++)
+                {
+                    if (uint64_t(g.positionOffset) + uint64_t(idx[k]) * 12 + 12 > sc->buffers[g.vertexBufferIndex].sizeBytes) return fail(RTXPT_ERR_INVALID_ARGUMENT, "vertex index exceeds buffer");
+                    float v[3]; memcpy(v, vb + g.positionOffset + size_t(idx[k]) * 12, 12);
+                    hostXformPoint(inst.transform, v, dst[k]);
+                }
+                bt.gid = uint32_t(tris.size()); bt.subInstanceAndFlags = flags; bt.primitiveIndex = t;
+                tris.push_back(bt);
+                triInfo.push_back(make_uint4(ii, gi, t, subIndex));
+            }
+        }
+    }
+    Bvh8 bvh;
+    buildBvh8(tris, bvh);
+    c->bvhBuildSeconds = float(bvh.buildSeconds);
+    c->bvhNodeCount = uint32_t(bvh.nodes.size()); c->bvhTriCount = uint32_t(bvh.tris.size());
+    cudaStream_t s = c->stream;
+    CU(c->dBvhNodes.upload(reinterpret_cast<const uint4*>(bvh.nodes.data()), bvh.nodes.size() * 5, s));
+    CU(c->dBvhTris.upload(reinterpret_cast<const float4*>(bvh.tris.data()), bvh.tris.size() * 3, s));
+    CU(c->dTriInfo.upload(triInfo.data(), triInfo.size(), s));
+    CU(c->dInstances.upload(sc->instances, sc->instanceCount, s));
+    CU(c->dGeometries.upload(sc->geometries, sc->geometryCount, s));
+    CU(c->dMaterials.upload(sc->materials, sc->materialCount, s));
+    c->materialCount = sc->materialCount;
+    // bindless buffers
+    std::vector<const uint8_t*> table(sc->bufferCount, nullptr);
+    for (uint32_t i = 0; i < sc->bufferCount; i++)
+    {
+        uint8_t* p = nullptr;
+        if (sc->buffers[i].sizeBytes) { CU(cudaMalloc(&p, sc->buffers[i].sizeBytes)); c->bufferAllocs.push_back(p); CU(cudaMemcpyAsync(p, sc->buffers[i].data, sc->buffers[i].sizeBytes, cudaMemcpyHostToDevice, s)); }
+        table[i] = p;
+    }
+    CU(c->dBufferTable.upload(table.data(), table.size(), s));
+    // bindless textures
+    std::vector<cudaTextureObject_t> texTable(sc->textureCount, 0);
+    c->textures.resize(sc->textureCount);
+    for (uint32_t i = 0; i < sc->textureCount; i++) { int rc = createTexture2D(sc->textures[i], c->textures[i]); if (rc != RTXPT_OK) return rc; texTable[i] = c->textures[i].object; }
+    CU(c->dTextureTable.upload(texTable.data(), texTable.size(), s));
+    c->envFaceSize = sc->envCube.faceSize; c->envMipLevels = sc->envCube.mipLevels;
+    if (sc->envCube.faceSize) { int rc = createEnvCube(sc->envCube, c->envCube); if (rc != RTXPT_OK) return rc; }
+    // sub-instances: shade-queue class (the SER sort key analogue; the reference sorts by material permutation, MaterialsBaker.cpp:1227-1285)
+    c->hSubInstances.assign(sc->subInstances, sc->subInstances + sc->subInstanceCount);
+    std::vector<uint8_t> cls(sc->subInstanceCount, 0);
+    for (uint32_t i = 0; i < sc->subInstanceCount; i++)
+    {
+        const uint32_t mi = c->hSubInstances[i].GlobalGeometryIndex_PTMaterialDataIndex & 0xFFFF;
+        if (mi >= sc->materialCount) return fail(RTXPT_ERR_INVALID_ARGUMENT, "sub-instance %u references material out of range", i);
+        const RtxptMaterialData& m = sc->materials[mi];
+        const bool transmissive = m.TransmissionFactor > 0 || m.DiffuseTransmissionFactor > 0;
+        const bool emissive = m.EmissiveColor[0] > 0 || m.EmissiveColor[1] > 0 || m.EmissiveColor[2] > 0;
+        const bool textured = (m.Flags & (RTXPT_MATFLAG_UseBaseOrDiffuseTexture | RTXPT_MATFLAG_UseMetalRoughOrSpecularTexture | RTXPT_MATFLAG_UseNormalTexture | RTXPT_MATFLAG_UseEmissiveTexture)) != 0;
+        cls[i] = transmissive ? 3 : (emissive ? 2 : (textured ? 1 : 0));
+    }
+    CU(c->dSubInstanceClass.upload(cls.data(), cls.size(), s));
+    // lights (scene part); sub-instance table goes up after EmissiveLightMappingOffset is known
+    LightBaker::prepareScene(*sc, c->hSubInstances, c->lightState);
+    CU(c->dSubInstances.upload(c->hSubInstances.data(), c->hSubInstances.size(), s));
+    CU(cudaStreamSynchronize(s));
+    c->haveScene = true; c->lightsDirty = true; c->accumulatedSamples = 0;
+    return RTXPT_OK;
+}
+
+// ---- constants -----------------------------------------------------------------------------------------------------------------------------
+static int ensureTargets(rtxpt_ctx* c, uint32_t W, uint32_t H)
+{
+    if (W == 0 || H == 0 || W > 65535 || H > 65535) return fail(RTXPT_ERR_INVALID_ARGUMENT, "image size %ux%u unsupported (path id packs x,y in 16 bits each)", W, H);
+    if (c->cfg.maxWidth && (W > c->cfg.maxWidth || H > c->cfg.maxHeight)) return fail(RTXPT_ERR_INVALID_ARGUMENT, "image larger than the configured maximum");
+    if (c->tableWidth == W && c->tableHeight == H) return RTXPT_OK;
+    CU(cudaStreamSynchronize(c->stream));
+    // pixels of this context's tiles, Morton order inside a tile: 32 consecutive path slots cover an 8x4 pixel block
+    const uint32_t T = c->cfg.tileSize, tilesX = (W + T - 1) / T, tilesY = (H + T - 1) / T;
+    std::vector<uint32_t> table;
+    for (uint32_t t = c->cfg.tileRank; t < tilesX * tilesY; t += c->cfg.tileWorld)
+    {
+        const uint32_t tx = (t % tilesX) * T, ty = (t / tilesX) * T;
+        for (uint32_t m = 0; m < T * T; m++)
+        {
+            uint32_t x = 0, y = 0;
+            for (uint32_t b = 0; b < 16; b++) { x |= ((m >> (2 * b)) & 1u) << b; y |= ((m >> (2 * b + 1)) & 1u) << b; }
+            if (tx + x < W && ty + y < H) table.push_back(((tx + x) << 16) | (ty + y));
+        }
+    }
+    c->pixelCount = uint32_t(table.size());
+    CU(c->pixelOfSlot.upload(table.data(), table.size(), c->stream));
+    const size_t P = size_t(W) * H;
+    CU(c->outputColor.alloc(P)); CU(c->accumulated.alloc(P)); CU(c->depth.alloc(P));
+    CU(cudaMemsetAsync(c->outputColor.ptr, 0, P * sizeof(uint2), c->stream)); CU(cudaMemsetAsync(c->accumulated.ptr, 0, P * sizeof(float4), c->stream)); CU(cudaMemsetAsync(c->depth.ptr, 0, P * sizeof(float), c->stream));
+    const size_t cap = size_t(c->pixelCount) * c->cfg.maxSubSamplesPerLaunch;
+    if (cap >= 0x7FFFFFFFull) return fail(RTXPT_ERR_UNSUPPORTED, "too many path slots");
+    c->capacity = uint32_t(std::max<size_t>(cap, 1));
+    CU(c->s0.alloc(c->capacity)); CU(c->s1.alloc(c->capacity)); CU(c->s2.alloc(c->capacity)); CU(c->s3.alloc(c->capacity)); CU(c->s4.alloc(c->capacity));
+    CU(c->hits.alloc(c->capacity)); CU(c->rayQueue[0].alloc(c->capacity)); CU(c->rayQueue[1].alloc(c->capacity));
+    CU(c->shadeQueue.alloc(size_t(c->capacity) * kNumShadeClasses));
+    CU(c->shadowOriginTMax.alloc(c->capacity)); CU(c->shadowDirPath.alloc(c->capacity)); CU(c->shadowRadiance.alloc(c->capacity));
+    CU(c->counters.alloc(kCounterWords));
+    c->tableWidth = W; c->tableHeight = H; c->accumulatedSamples = 0;
+    return RTXPT_OK;
+}
+
+static int uploadLights(rtxpt_ctx* c)
+{
+    LightBaker::finalize(c->consts, c->lightState);
+    const LightBakeState& st = c->lightState;
+    cudaStream_t s = c->stream;
+    CU(cudaStreamSynchronize(s));
+    CU(c->dLights.upload(reinterpret_cast<const LightInfo*>(st.lights.data()), st.lights.size(), s));
+    CU(c->dProxyCounters.upload(st.proxyCounters.data(), st.proxyCounters.size(), s));
+    CU(c->dProxyIndices.upload(st.proxyIndices.data(), st.proxyIndices.size(), s));
+    CU(c->dEnvLookup.upload(st.envLookupMap.data(), st.envLookupMap.size(), s));
+    CU(cudaStreamSynchronize(s));
+    c->lightsDirty = false;
+    return RTXPT_OK;
+}
+
+extern "C" RTXPT_API int rtxpt_b200_set_constants(rtxpt_ctx* c, const RtxptPathTracerConstants* k)
+{
+    if (!c || !k) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    cudaSetDevice(c->device);
+    if (k->NEEFullSamples > 1) return fail(RTXPT_ERR_UNSUPPORTED, "NEEFullSamples > 1 is not supported in this tier (one shadow record per vertex)");
+    if (k->bounceCount + 6 > (uint32_t)kMaxWavefrontIterations) return fail(RTXPT_ERR_UNSUPPORTED, "bounceCount above %d", kMaxWavefrontIterations - 6);
+    int rc = ensureTargets(c, k->imageWidth, k->imageHeight);
+    if (rc != RTXPT_OK) return rc;
+    const bool envChanged = !c->haveConstants || memcmp(&c->consts.envMap, &k->envMap, sizeof(k->envMap)) != 0 || c->consts.distantVsLocalImportance != k->distantVsLocalImportance || c->consts.NEEType != k->NEEType;
+    c->consts = *k; c->haveConstants = true;
+    if (envChanged) c->lightsDirty = true;
+    if (c->haveScene && c->lightsDirty) { rc = uploadLights(c); if (rc != RTXPT_OK) return rc; }
+    return RTXPT_OK;
+}
+
+// ---- launch --------------------------------------------------------------------------------------------------------------------------------
+static void fillParams(rtxpt_ctx* c, LaunchParams& p)
+{
+    memset(&p, 0, sizeof(p));
+    SceneView& v = p.scene;
+    v.instances = c->dInstances.ptr; v.geometries = c->dGeometries.ptr; v.subInstances = c->dSubInstances.ptr; v.materials = c->dMaterials.ptr;
+    v.subInstanceClass = c->dSubInstanceClass.ptr; v.materialCount = c->materialCount;
+    v.buffers = c->dBufferTable.ptr; v.textures = c->dTextureTable.ptr; v.envCube = c->envCube.object; v.envFaceSize = c->envFaceSize; v.envMipLevels = c->envMipLevels;
+    v.bvhNodes = c->dBvhNodes.ptr; v.bvhTris = c->dBvhTris.ptr; v.triInfo = c->dTriInfo.ptr; v.bvhNodeCount = c->bvhNodeCount; v.bvhTriCount = c->bvhTriCount;
+    v.lights = c->dLights.ptr; v.proxyCounters = c->dProxyCounters.ptr; v.proxyIndices = c->dProxyIndices.ptr; v.envLookupMap = c->dEnvLookup.ptr;
+    v.lightCount = uint32_t(c->lightState.lights.size()); v.samplingProxyCount = uint32_t(c->lightState.proxyIndices.size()); v.envEnabled = c->lightState.envEnabled ? 1u : 0u;
+    WavefrontBuffers& w = p.wf;
+    w.s0 = c->s0.ptr; w.s1 = c->s1.ptr; w.s2 = c->s2.ptr; w.s3 = c->s3.ptr; w.s4 = c->s4.ptr; w.hits = c->hits.ptr;
+    w.rayQueue[0] = c->rayQueue[0].ptr; w.rayQueue[1] = c->rayQueue[1].ptr; w.shadeQueue = c->shadeQueue.ptr;
+    w.shadowOriginTMax = c->shadowOriginTMax.ptr; w.shadowDirPath = c->shadowDirPath.ptr; w.shadowRadiance = c->shadowRadiance.ptr;
+    w.counters = c->counters.ptr; w.pixelOfSlot = c->pixelOfSlot.ptr; w.capacity = c->capacity; w.pixelCount = c->pixelCount;
+    p.c = c->consts;
+    p.flags = c->cfg.flags;
+    p.outputColor = c->outputColor.ptr; p.accumulated = c->accumulated.ptr; p.depth = c->depth.ptr;
+    // shared-memory BVH prefix: as many breadth-first nodes as fit next to two resident CTAs
+    const uint32_t budget = uint32_t(std::max(0, std::min(c->maxSmemOptin, 100 * 1024) - 1024));
+    p.smemNodeCount = std::min(c->bvhNodeCount, budget / 80u);
+}
+
+static int checkReady(rtxpt_ctx* c)
+{
+    if (!c) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null context");
+    if (!c->haveScene) return fail(RTXPT_ERR_NO_SCENE, "no scene uploaded");
+    if (!c->haveConstants) return fail(RTXPT_ERR_INVALID_ARGUMENT, "constants not set");
+    cudaSetDevice(c->device);
+    if (c->lightsDirty) { int rc = uploadLights(c); if (rc != RTXPT_OK) return rc; }
+    return RTXPT_OK;
+}
+
+extern "C" RTXPT_API int rtxpt_b200_path_trace(rtxpt_ctx* c, uint32_t firstSubSampleIndex, uint32_t subSampleCount, int accumulate, void* cudaStream)
+{
+    int rc = checkReady(c); if (rc != RTXPT_OK) return rc;
+    if (subSampleCount == 0) return RTXPT_OK;
+    cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
+    LaunchParams p; fillParams(c, p);
+    queryOccupancy(c->grid, 16 + size_t(p.smemNodeCount) * 80);
+    const bool countSteps = (c->cfg.flags & RTXPT_CFG_COUNT_TRAVERSAL_STEPS) != 0;
+    const bool hasRefraction = c->consts.nestedDielectricsQuality > 0;
+    const uint32_t iterations = std::min<uint32_t>(c->consts.bounceCount + 1 + (hasRefraction ? 4 : 0), kMaxWavefrontIterations);
+    CU(cudaEventRecord(c->evStart, s));
+    uint64_t launches = 0;
+    for (uint32_t done = 0; done < subSampleCount; done += c->cfg.maxSubSamplesPerLaunch)
+    {
+        const uint32_t n = std::min(c->cfg.maxSubSamplesPerLaunch, subSampleCount - done);
+        p.firstSampleIndex = c->consts.sampleBaseIndex + firstSubSampleIndex + done;
+        p.subSampleCount = n;
+        p.accumulatedSamples = c->accumulatedSamples; p.doAccumulate = accumulate ? 1u : 0u;
+        CU(cudaMemsetAsync(c->counters.ptr, 0, kCounterWords * sizeof(uint32_t), s));
+        p.iteration = 0;
+        launchGenerate(p, c->grid, s); launches++;
+        for (uint32_t it = 0; it < iterations; it++)
+        {
+            p.iteration = it;
+            launchTraceClosest(p, c->grid, countSteps, s);
+            launchShade(p, c->grid, s);
+            launchTraceShadow(p, c->grid, countSteps, s);
+            launches += 3;
+        }
+        launchCommitAccumulate(p, c->grid, s); launches++;
+        if (accumulate) c->accumulatedSamples += n;
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(c->evStop, s));
+    // statistics of the last batch (ray counts per iteration); read lazily by get_stats
+    CU(cudaMemcpyAsync(c->hCounters, c->counters.ptr, kCounterWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    c->lastIterations = iterations; c->lastSubSamples = subSampleCount; c->lastLaunches = launches; c->statsPending = true;
+    return RTXPT_OK;
+}
+
+extern "C" RTXPT_API int rtxpt_b200_reset_accumulation(rtxpt_ctx* c)
+{
+    if (!c) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null context");
+    c->accumulatedSamples = 0;
+    return RTXPT_OK;
+}
+
+extern "C" RTXPT_API int rtxpt_b200_synchronize(rtxpt_ctx* c)
+{
+    if (!c) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null context");
+    cudaSetDevice(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    return RTXPT_OK;
+}
+
+static int targetInfo(rtxpt_ctx* c, int buffer, void** ptr, size_t* bytes)
+{
+    const size_t P = size_t(c->tableWidth) * c->tableHeight;
+    switch (buffer)
+    {
+    case RTXPT_BUFFER_OUTPUT_COLOR_F16: *ptr = c->outputColor.ptr; *bytes = P * 8; return RTXPT_OK;
+    case RTXPT_BUFFER_ACCUMULATED_F32: *ptr = c->accumulated.ptr; *bytes = P * 16; return RTXPT_OK;
+    case RTXPT_BUFFER_DEPTH_F32: *ptr = c->depth.ptr; *bytes = P * 4; return RTXPT_OK;
+    default: return fail(RTXPT_ERR_INVALID_ARGUMENT, "unknown buffer %d", buffer);
+    }
+}
+
+extern "C" RTXPT_API int rtxpt_b200_device_ptr(rtxpt_ctx* c, int buffer, void** outPtr, size_t* outBytes)
+{
+    if (!c || !outPtr || !outBytes) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    return targetInfo(c, buffer, outPtr, outBytes);
+}
+
+extern "C" RTXPT_API int rtxpt_b200_readback(rtxpt_ctx* c, int buffer, void* dst, size_t dstBytes)
+{
+    if (!c || !dst) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    cudaSetDevice(c->device);
+    void* src; size_t bytes;
+    int rc = targetInfo(c, buffer, &src, &bytes); if (rc != RTXPT_OK) return rc;
+    if (dstBytes < bytes) return fail(RTXPT_ERR_INVALID_ARGUMENT, "destination too small (%zu < %zu)", dstBytes, bytes);
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return RTXPT_OK;
+}
+
+extern "C" RTXPT_API int rtxpt_b200_render_frame(rtxpt_ctx* c, const RtxptPathTracerConstants* k, uint32_t firstSubSampleIndex, uint32_t subSampleCount, void* dst, size_t dstBytes)
+{
+    int rc = rtxpt_b200_set_constants(c, k); if (rc != RTXPT_OK) return rc;
+    rc = rtxpt_b200_path_trace(c, firstSubSampleIndex, subSampleCount, 1, nullptr); if (rc != RTXPT_OK) return rc;
+    return rtxpt_b200_readback(c, RTXPT_BUFFER_ACCUMULATED_F32, dst, dstBytes);
+}
+
+extern "C" RTXPT_API int rtxpt_b200_get_stats(rtxpt_ctx* c, RtxptStats* out)
+{
+    if (!c || !out) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    cudaSetDevice(c->device);
+    memset(out, 0, sizeof(*out));
+    CU(cudaStreamSynchronize(c->stream));
+    out->bvhNodeCount = c->bvhNodeCount; out->bvhTriangleCount = c->bvhTriCount; out->bvhBuildSeconds = c->bvhBuildSeconds;
+    out->lightCount = uint32_t(c->lightState.lights.size()); out->lightProxyCount = uint32_t(c->lightState.proxyIndices.size());
+    out->accumulatedSamples = c->accumulatedSamples;
+    if (c->statsPending)
+    {
+        float ms = 0; cudaEventElapsedTime(&ms, c->evStart, c->evStop);
+        out->msTotal = ms;
+        // counters hold the LAST batch; scale ray counts to the whole call when it was split into equal batches
+        const uint32_t batches = (c->lastSubSamples + c->cfg.maxSubSamplesPerLaunch - 1) / c->cfg.maxSubSamplesPerLaunch;
+        const uint32_t lastBatch = c->lastSubSamples - (batches - 1) * c->cfg.maxSubSamplesPerLaunch;
+        const double scale = double(c->lastSubSamples) / double(lastBatch);
+        uint64_t scatter = 0, shadow = 0, nodes = 0, tests = 0;
+        for (uint32_t it = 0; it < c->lastIterations; it++)
+        {
+            const uint32_t* k = c->hCounters + it * kCountersPerIter;
+            scatter += k[kCtrRayCount]; shadow += k[kCtrShadowCount]; nodes += k[kCtrNodeVisits]; tests += k[kCtrTriTests];
+            if (it < 16) out->raysPerBounce[it] = uint64_t(k[kCtrRayCount] * scale);
+        }
+        out->scatterRays = uint64_t(scatter * scale); out->shadowRays = uint64_t(shadow * scale);
+        out->traversalNodeVisits = uint64_t(nodes * scale); out->traversalTriTests = uint64_t(tests * scale);
+        out->paths = uint64_t(c->pixelCount) * c->lastSubSamples;
+        out->kernelLaunches = c->lastLaunches;
+    }
+    return RTXPT_OK;
+}
+
+// ---- inspection hooks -------------------------------------------------------------------------------------------------------------------------
+extern "C" RTXPT_API int rtxpt_b200_trace_rays_device(rtxpt_ctx* c, const void* dRays, uint32_t count, int anyHit, void* dHits, uint32_t repeat, float* outMs)
+{
+    if (!c || !c->haveScene) return fail(RTXPT_ERR_NO_SCENE, "no scene uploaded");
+    cudaSetDevice(c->device);
+    if (c->counters.count == 0) CU(c->counters.alloc(kCounterWords));
+    LaunchParams p; fillParams(c, p);
+    queryOccupancy(c->grid, 16 + size_t(p.smemNodeCount) * 80);
+    CU(cudaMemsetAsync(c->counters.ptr, 0, 8, c->stream));
+    if (repeat == 0) repeat = 1;
+    CU(cudaEventRecord(c->evStart, c->stream));
+    for (uint32_t r = 0; r < repeat; r++)
+        launchTraceRays(p, c->grid, (const RtxptRay*)dRays, count, anyHit != 0, (RtxptHit*)dHits, (r == 0) ? c->counters.ptr : nullptr, c->stream);
+    CU(cudaEventRecord(c->evStop, c->stream));
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->hCounters, c->counters.ptr, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, c->evStart, c->evStop);
+    if (outMs) *outMs = ms / float(repeat);
+    return RTXPT_OK;
+}
+
+extern "C" RTXPT_API int rtxpt_b200_trace_rays(rtxpt_ctx* c, const RtxptRay* rays, uint32_t count, int anyHit, RtxptHit* outHits)
+{
+    if (!c || !rays || !outHits) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (!c->haveScene) return fail(RTXPT_ERR_NO_SCENE, "no scene uploaded");
+    cudaSetDevice(c->device);
+    DeviceArray<RtxptRay> dRays; DeviceArray<RtxptHit> dHits;
+    CU(dRays.upload(rays, count, c->stream)); CU(dHits.alloc(count));
+    int rc = rtxpt_b200_trace_rays_device(c, dRays.ptr, count, anyHit, dHits.ptr, 1, nullptr);
+    if (rc == RTXPT_OK) { cudaError_t e = cudaMemcpy(outHits, dHits.ptr, size_t(count) * sizeof(RtxptHit), cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = fail(RTXPT_ERR_CUDA, "readback failed: %s", cudaGetErrorString(e)); }
+    dRays.release(); dHits.release();
+    return rc;
+}
+
+extern "C" RTXPT_API int rtxpt_b200_get_lights(rtxpt_ctx* c, void* outLightInfos, uint32_t* ioLightCount, uint32_t* outProxyCounters, uint32_t* outProxyIndices, uint32_t* ioProxyCount)
+{
+    int rc = checkReady(c); if (rc != RTXPT_OK) return rc;
+    if (!ioLightCount || !ioProxyCount) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    const uint32_t n = uint32_t(c->lightState.lights.size()), m = uint32_t(c->lightState.proxyIndices.size());
+    // read back from the device: what the kernels actually sample
+    if (outLightInfos && *ioLightCount >= n) CU(cudaMemcpy(outLightInfos, c->dLights.ptr, size_t(n) * 32, cudaMemcpyDeviceToHost));
+    if (outProxyCounters && *ioLightCount >= n) CU(cudaMemcpy(outProxyCounters, c->dProxyCounters.ptr, size_t(n) * 4, cudaMemcpyDeviceToHost));
+    if (outProxyIndices && *ioProxyCount >= m && m) CU(cudaMemcpy(outProxyIndices, c->dProxyIndices.ptr, size_t(m) * 4, cudaMemcpyDeviceToHost));
+    *ioLightCount = n; *ioProxyCount = m;
+    return RTXPT_OK;
+}
+
+extern "C" RTXPT_API int rtxpt_b200_debug_bsdf(rtxpt_ctx* c, const float* in, uint32_t count, float* out)
+{
+    if (!c || !in || !out) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    cudaSetDevice(c->device);
+    DeviceArray<float> dIn, dOut;
+    CU(dIn.upload(in, size_t(count) * 36, c->stream)); CU(dOut.alloc(size_t(count) * 16));
+    launchDebugBsdf(dIn.ptr, count, dOut.ptr, c->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, dOut.ptr, size_t(count) * 16 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    dIn.release(); dOut.release();
+    return RTXPT_OK;
+}
+
+extern "C" RTXPT_API int rtxpt_b200_debug_rng(rtxpt_ctx* c, const uint32_t* in, uint32_t count, uint32_t* out)
+{
+    if (!c || !in || !out) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    cudaSetDevice(c->device);
+    DeviceArray<uint32_t> dIn, dOut;
+    CU(dIn.upload(in, size_t(count) * 4, c->stream)); CU(dOut.alloc(size_t(count) * 8));
+    launchDebugRng(dIn.ptr, count, dOut.ptr, c->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, dOut.ptr, size_t(count) * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    dIn.release(); dOut.release();
+    return RTXPT_OK;
+}

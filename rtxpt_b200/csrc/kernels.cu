@@ -1,0 +1,351 @@
+// kernels.cu — the wavefront: generate -> [ trace closest -> shade (per material class) -> trace shadow ]* -> commit + accumulate.
+//
+// One launch of this sequence replaces one DispatchRays of the reference's megakernel (Rtxpt/Sample.cpp:2503-2517,
+// Rtxpt/Shaders/PathTracerSample.hlsl:201-256), for `subSampleCount` sub-samples at once.
+//   k_generate          EmptyPathInitialize + computeCameraRay (PathTracer.hlsli:47-91, BridgeDonut:543-564, PathTracerHelpers.hlsli:126-153)
+//   k_trace_closest     Bridge::traceScatterRay (BridgeDonut:1029-1055) + the SER sort key: paths are binned by
+//                       {miss, terminating hit, material class} (PathTracerSample.hlsl:136-148, MaterialsBaker.cpp:1267-1271)
+//   k_shade             ClosestHit / miss shader bodies (shade.cuh)
+//   k_trace_shadow      Bridge::traceVisibilityRay (BridgeDonut:993-1027) + the NEE radiance accumulation
+//   k_commit_accumulate CommitPixel (PathTracer.hlsli:165-175) + AccumulationPass (ProcessingPasses/AccumulationPass.hlsl:36-66)
+// All kernels are persistent (grid = SM count x resident CTAs) and read their work counts from device memory, so a whole frame is
+// enqueued without a host round trip.  The top of the BVH (breadth-first prefix) is staged into shared memory with one TMA bulk copy
+// per CTA (cp.async.bulk + mbarrier).
+#include "shade.cuh"
+#include "traverse.cuh"
+#include "kernels.h"
+
+namespace pt {
+
+// ---- TMA bulk copy global -> shared --------------------------------------------------------------------------------------------------
+PT_DEVICE void stageNodesToShared(uint4* smemDst, const uint4* __restrict__ src, uint nodeCount, uint64_t* mbar)
+{
+    const uint bytes = nodeCount * 80u;
+    const uint mbarAddr = (uint)__cvta_generic_to_shared(mbar);
+    if (threadIdx.x == 0)
+    {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbarAddr));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (bytes == 0) return;
+    if (threadIdx.x == 0)
+    {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbarAddr), "r"(bytes) : "memory");
+        const uint chunk = 32768u;
+        for (uint off = 0; off < bytes; off += chunk)
+        {
+            const uint n = min(chunk, bytes - off);
+            const uint dst = (uint)__cvta_generic_to_shared(reinterpret_cast<char*>(smemDst) + off);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(reinterpret_cast<const char*>(src) + off), "r"(n), "r"(mbarAddr) : "memory");
+        }
+    }
+    uint done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mbarAddr) : "memory");
+}
+
+// warp-aggregated append of `value` to queue region `cls` (0xFF = nothing to append); every lane of the warp must call this
+PT_DEVICE void warpAppend(uint* queueBase, uint regionStride, uint* counters, uint cls, uint value)
+{
+    const uint lane = threadIdx.x & 31u;
+    const uint peers = __match_any_sync(0xFFFFFFFFu, cls);
+    if (cls != 0xFFu)
+    {
+        const uint leader = __ffs(peers) - 1u;
+        uint base = 0;
+        if (lane == leader) base = atomicAdd(counters + cls, __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        queueBase[size_t(cls) * regionStride + base + __popc(peers & ((1u << lane) - 1u))] = value;
+    }
+}
+
+// ---- generate --------------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_generate(const __grid_constant__ LaunchParams p)
+{
+    const uint total = p.wf.pixelCount * p.subSampleCount;
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.wf.counters[kCtrRayCount] = total;     // iteration 0 traces every path's camera ray
+    for (uint slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += gridDim.x * blockDim.x)
+    {
+        const uint sub = slot / p.wf.pixelCount, pix = slot - sub * p.wf.pixelCount;
+        const uint id = p.wf.pixelOfSlot[pix];
+        const uint px = id >> 16, py = id & 0xFFFF;
+        const uint sampleIndex = p.firstSampleIndex + sub;
+        PathRegs path;
+        path.id = id; path.sceneLength = 0.f; path.sampleIndex = sampleIndex;
+        path.flagsAndVertexIndex = 0; path.packedCounters = 0; path.interior0 = path.interior1 = 0;
+        path.setThp(mk3(1.f)); path.setL(make_float4(0.f, 0.f, 0.f, 0.f));
+        path.setFlag(kPFActive, true); path.setFlag(kPFDeltaOnlyPath, true);
+        path.setCone(0.f, p.c.camera.PixelConeSpreadAngle);
+        path.setFireflyK_BsdfPdf(1.0f, 0.0f);
+        path.setMisInfo_RuRu(0u, 1.0f);
+        if (hasFinishedSurfaceBounces(p.c, 1, 0)) path.setFlag(kPFTerminateAtNextBounce, true);
+        // Bridge::computeCameraRay + ComputeRayThinlens
+        const RtxptCameraData& cam = p.c.camera;
+        UniformSeq sg = UniformSeq::make(vertexBaseHash(id, 0), sampleIndex, 0u);
+        const float r0 = sg.next(), r1 = sg.next(), d0 = sg.next(), d1 = sg.next();
+        const float jx = cam.Jitter[0] + (r0 - 0.5f) * p.c.perPixelJitterAAScale, jy = cam.Jitter[1] + (r1 - 0.5f) * p.c.perPixelJitterAAScale;
+        const float sx = (float(px) + 0.5f + (-jx)) / float(cam.ViewportSize[0]), sy = (float(py) + 0.5f + jy) / float(cam.ViewportSize[1]);
+        const float ndcx = 2.f * sx - 1.f, ndcy = -2.f * sy + 1.f;
+        const float3 U = mk3(cam.CameraU[0], cam.CameraU[1], cam.CameraU[2]), V = mk3(cam.CameraV[0], cam.CameraV[1], cam.CameraV[2]), W = mk3(cam.CameraW[0], cam.CameraW[1], cam.CameraW[2]);
+        float3 origin = mk3(cam.PosW[0], cam.PosW[1], cam.PosW[2]);
+        float3 dir = ndcx * U + ndcy * V + W;
+        const float2 ap = sampleDiskPolar(d0, d1);
+        const float3 target = origin + dir;
+        origin = origin + cam.ApertureRadius * (ap.x * norm3(U) + ap.y * norm3(V));
+        dir = norm3(target - origin);
+        const float invCos = 1.f / dot3(norm3(W), dir);
+        origin = origin + dir * (cam.NearZ * invCos);
+        path.origin = origin; path.dir = dir;
+        path.store(p.wf, slot);
+        p.wf.rayQueue[0][slot] = slot | (path.hasFlag(kPFTerminateAtNextBounce) ? 0x80000000u : 0u);
+    }
+}
+
+// ---- closest hit ------------------------------------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(256, 2) k_trace_closest(const __grid_constant__ LaunchParams p)
+{
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    uint* ctr = p.wf.counters + p.iteration * kCountersPerIter;
+    const uint count = ctr[kCtrRayCount];
+    if (count == 0) return;                 // wavefront already drained (uniform across the grid)
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smemRaw);
+    uint4* smemNodes = reinterpret_cast<uint4*>(smemRaw + 16);
+    stageNodesToShared(smemNodes, p.scene.bvhNodes, p.smemNodeCount, mbar);
+
+    const uint* __restrict__ queue = p.wf.rayQueue[p.iteration & 1];
+    TraversalCounters tc; tc.nodeVisits = 0; tc.triTests = 0;
+    const uint warpsPerBlock = blockDim.x >> 5, lane = threadIdx.x & 31u;
+    const uint warpGlobal = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5), warpStride = gridDim.x * warpsPerBlock;
+    for (uint base = warpGlobal * 32u; base < count; base += warpStride * 32u)
+    {
+        const uint i = base + lane;
+        uint cls = 0xFFu, slot = 0;
+        if (i < count)
+        {
+            const uint entry = queue[i];
+            slot = entry & 0x7FFFFFFFu;
+            const uint4 a = p.wf.s0[slot], b = p.wf.s1[slot];
+            const float3 o = mk3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
+            const float3 d = mk3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z));
+            uint subInstance = 0;
+            const HitRecord h = traceRay<false, COUNT>(p.scene, p.scene.bvhNodes, smemNodes, p.smemNodeCount, o, d, 0.0f, kMaxRayTravel, &tc, &subInstance);
+            p.wf.hits[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.gid));
+            if (h.gid == 0xFFFFFFFFu) cls = 0;
+            else if (entry & 0x80000000u) cls = 1;
+            else cls = (p.flags & RTXPT_CFG_NO_MATERIAL_SORT) ? 2u : 2u + p.scene.subInstanceClass[subInstance];
+        }
+        warpAppend(p.wf.shadeQueue, p.wf.capacity, ctr + kCtrShadeCount, cls, slot);
+    }
+    if (COUNT) { atomicAdd(ctr + kCtrNodeVisits, tc.nodeVisits); atomicAdd(ctr + kCtrTriTests, tc.triTests); }
+}
+
+// ---- shade --------------------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_shade(const __grid_constant__ LaunchParams p)
+{
+    uint* ctr = p.wf.counters + p.iteration * kCountersPerIter;
+    uint* ctrNext = ctr + kCountersPerIter;
+    uint* nextQueue = p.wf.rayQueue[(p.iteration + 1) & 1];
+    const uint warpsPerBlock = blockDim.x >> 5, lane = threadIdx.x & 31u;
+    const uint warpGlobal = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5), warpStride = gridDim.x * warpsPerBlock;
+    for (int cls = 0; cls < kNumShadeClasses; cls++)
+    {
+        const uint count = ctr[kCtrShadeCount + cls];
+        const uint* __restrict__ queue = p.wf.shadeQueue + size_t(cls) * p.wf.capacity;
+        for (uint base = warpGlobal * 32u; base < count; base += warpStride * 32u)
+        {
+            const uint i = base + lane;
+            uint rayCls = 0xFFu, shadowCls = 0xFFu, rayEntry = 0, slot = 0;
+            HitOutputs out; out.continuePath = false; out.emitShadow = false;
+            if (i < count)
+            {
+                slot = queue[i];
+                PathRegs path; path.load(p.wf, slot, true);
+                if (cls == 0) shadeMiss(p, path);
+                else shadeHit(p, path, slot, p.wf.hits[slot], out);
+                path.store(p.wf, slot);
+                if (out.continuePath) { rayCls = 0; rayEntry = slot | (path.hasFlag(kPFTerminateAtNextBounce) ? 0x80000000u : 0u); }
+                if (out.emitShadow) shadowCls = 0;
+            }
+            warpAppend(nextQueue, 0, ctrNext + kCtrRayCount, rayCls, rayEntry);
+            // shadow records: same aggregation, three arrays
+            {
+                const uint peers = __ballot_sync(0xFFFFFFFFu, shadowCls == 0);
+                if (shadowCls == 0)
+                {
+                    const uint leader = __ffs(peers) - 1u;
+                    uint b = 0;
+                    if (lane == leader) b = atomicAdd(ctr + kCtrShadowCount, __popc(peers));
+                    b = __shfl_sync(peers, b, leader) + __popc(peers & ((1u << lane) - 1u));
+                    p.wf.shadowOriginTMax[b] = out.shadow.originTMax; p.wf.shadowDirPath[b] = out.shadow.dirPath; p.wf.shadowRadiance[b] = out.shadow.radiance;
+                }
+            }
+        }
+    }
+}
+
+// ---- shadow rays ----------------------------------------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(256, 2) k_trace_shadow(const __grid_constant__ LaunchParams p)
+{
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    uint* ctr = p.wf.counters + p.iteration * kCountersPerIter;
+    const uint count = ctr[kCtrShadowCount];
+    if (count == 0) return;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smemRaw);
+    uint4* smemNodes = reinterpret_cast<uint4*>(smemRaw + 16);
+    stageNodesToShared(smemNodes, p.scene.bvhNodes, p.smemNodeCount, mbar);
+
+    TraversalCounters tc; tc.nodeVisits = 0; tc.triTests = 0;
+    uint visibleCount = 0;
+    for (uint i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    {
+        const float4 ot = p.wf.shadowOriginTMax[i], dp = p.wf.shadowDirPath[i];
+        uint subInstance;
+        const HitRecord h = traceRay<true, COUNT>(p.scene, p.scene.bvhNodes, smemNodes, p.smemNodeCount, mk3(ot.x, ot.y, ot.z), mk3(dp.x, dp.y, dp.z), 0.0f, ot.w, &tc, &subInstance);
+        if (h.gid == 0xFFFFFFFFu)
+        {   // visible: HandleHit's "if any(neeRadianceAndSpecAvg > 0) AccumulatePathRadiance" (PathTracer.hlsli:725-746)
+            const uint2 r = p.wf.shadowRadiance[i];
+            const float rx = f16tof32(r.x), ry = f16tof32(r.x >> 16), rz = f16tof32(r.y), rw = f16tof32(r.y >> 16);
+            if (rx > 0 || ry > 0 || rz > 0 || rw > 0)
+            {
+                const uint slot = __float_as_uint(dp.w);
+                uint4 s2 = p.wf.s2[slot];
+                const float lx = f16tof32(s2.z) + rx, ly = f16tof32(s2.z >> 16) + ry, lz = f16tof32(s2.w) + rz, lw = f16tof32(s2.w >> 16);
+                s2.z = packHalf2NoClamp(clampf(lx, 0.f, kHalfMax), clampf(ly, 0.f, kHalfMax));
+                s2.w = packHalf2NoClamp(clampf(lz, 0.f, kHalfMax), clampf(lw, 0.f, kHalfMax));
+                p.wf.s2[slot] = s2;
+            }
+            visibleCount++;
+        }
+    }
+    if (COUNT) { atomicAdd(ctr + kCtrNodeVisits, tc.nodeVisits); atomicAdd(ctr + kCtrTriTests, tc.triTests); atomicAdd(ctr + kCtrShadowVisible, visibleCount); }
+}
+
+// ---- commit + accumulate ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_commit_accumulate(const __grid_constant__ LaunchParams p)
+{
+    const uint W = p.c.imageWidth;
+    for (uint pix = blockIdx.x * blockDim.x + threadIdx.x; pix < p.wf.pixelCount; pix += gridDim.x * blockDim.x)
+    {
+        const uint id = p.wf.pixelOfSlot[pix];
+        const size_t o = size_t(id & 0xFFFF) * W + (id >> 16);
+        float4 acc = p.accumulated[o];
+        uint n = p.accumulatedSamples;
+        uint2 last = make_uint2(0, 0);
+        for (uint s = 0; s < p.subSampleCount; s++)
+        {
+            const uint4 s2 = p.wf.s2[s * p.wf.pixelCount + pix];
+            const float r = f16tof32(s2.z), g = f16tof32(s2.z >> 16), b = f16tof32(s2.w);
+            last = make_uint2(s2.z, (s2.w & 0xFFFFu) | (0x3C00u << 16));          // float4(L.rgb, 1) as RGBA16F
+            if (p.doAccumulate)
+            {   // blend = 1/(n+1); lerp(prev, sample, blend) unless blend >= 1 (Sample.cpp:2775, AccumulationPass.hlsl:57-65)
+                const float blend = 1.0f / (float(n) + 1.0f);
+                if (blend < 1.0f) { acc.x = acc.x + (r - acc.x) * blend; acc.y = acc.y + (g - acc.y) * blend; acc.z = acc.z + (b - acc.z) * blend; acc.w = acc.w + (1.0f - acc.w) * blend; }
+                else acc = make_float4(r, g, b, 1.0f);
+                n++;
+            }
+        }
+        p.outputColor[o] = last;
+        if (p.doAccumulate) p.accumulated[o] = acc;
+    }
+}
+
+// ---- standalone ray queries (parity tests, traversal benchmark) ----------------------------------------------------------------------------
+template <bool ANY_HIT>
+__global__ void __launch_bounds__(256, 2) k_trace_rays(const __grid_constant__ LaunchParams p, const RtxptRay* __restrict__ rays, uint count, RtxptHit* __restrict__ out, uint* counters)
+{
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smemRaw);
+    uint4* smemNodes = reinterpret_cast<uint4*>(smemRaw + 16);
+    stageNodesToShared(smemNodes, p.scene.bvhNodes, p.smemNodeCount, mbar);
+    TraversalCounters tc; tc.nodeVisits = 0; tc.triTests = 0;
+    for (uint i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    {
+        const float4 a = reinterpret_cast<const float4*>(rays)[i * 2], b = reinterpret_cast<const float4*>(rays)[i * 2 + 1];
+        uint subInstance;
+        const HitRecord h = traceRay<ANY_HIT, true>(p.scene, p.scene.bvhNodes, smemNodes, p.smemNodeCount, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w, &tc, &subInstance);
+        RtxptHit r;
+        if (h.gid != 0xFFFFFFFFu) { const uint4 info = p.scene.triInfo[h.gid]; r.t = h.t; r.u = h.u; r.v = h.v; r.instanceIndex = info.x; r.geometryIndex = info.y; r.primitiveIndex = info.z; }
+        else { r.t = -1.0f; r.u = r.v = 0.f; r.instanceIndex = r.geometryIndex = r.primitiveIndex = 0xFFFFFFFFu; }
+        out[i] = r;
+    }
+    if (counters) { atomicAdd(counters + 0, tc.nodeVisits); atomicAdd(counters + 1, tc.triTests); }
+}
+
+// ---- debug: BSDF / RNG on the device (parity tests) -------------------------------------------------------------------------------------------
+__global__ void k_debug_bsdf(const float* __restrict__ in, uint count, float* __restrict__ out)
+{
+    const uint i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float* r = in + size_t(i) * 36; float* o = out + size_t(i) * 16;
+    BsdfParams d;
+    d.diffuse = mk3(r[18], r[19], r[20]); d.roughness = r[21]; d.specular = mk3(r[22], r[23], r[24]); d.metallic = r[25];
+    d.transmission = mk3(r[26], r[27], r[28]); d.diffuseTransmission = r[29]; d.specularTransmission = r[30]; d.eta = r[31];
+    BsdfSetup b; b.init(mk3(r[6], r[7], r[8]), mk3(r[9], r[10], r[11]), mk3(r[3], r[4], r[5]), mk3(r[0], r[1], r[2]), r[32] != 0.0f, d);
+    const float3 wo = mk3(r[12], r[13], r[14]);
+    const float4 e = b.eval(wo);
+    o[0] = e.x; o[1] = e.y; o[2] = e.z; o[3] = e.w; o[4] = b.pdf(wo);
+    BsdfSample s; const bool valid = b.sample(r[15], r[16], r[17], s);
+    o[5] = valid ? 1.0f : 0.0f; o[6] = s.wo.x; o[7] = s.wo.y; o[8] = s.wo.z; o[9] = s.pdf; o[10] = s.weight.x; o[11] = s.weight.y; o[12] = s.weight.z;
+    o[13] = float(s.lobe); o[14] = s.lobeP; o[15] = float(bsdfLobes(d));
+}
+__global__ void k_debug_rng(const uint* __restrict__ in, uint count, uint* __restrict__ out)
+{
+    const uint i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint baseHash = vertexBaseHash((in[i * 4] << 16) | in[i * 4 + 1], in[i * 4 + 2]);
+    UniformSeq u = UniformSeq::make(baseHash, in[i * 4 + 3], 0u);
+    for (int k = 0; k < 4; k++) out[i * 8 + k] = u.nextBits();
+    for (uint k = 0; k < 4; k++) out[i * 8 + 4 + k] = __float_as_uint(hashToFloat(ldSampleBits(baseHash, in[i * 4 + 3], 1u, k)));
+}
+
+// ---- launch wrappers ---------------------------------------------------------------------------------------------------------------------------
+static size_t traceSmemBytes(const LaunchParams& p) { return 16 + size_t(p.smemNodeCount) * 80; }
+
+cudaError_t configureKernels(int maxSmemOptin)
+{
+    cudaError_t e;
+    const int want = maxSmemOptin > 0 ? maxSmemOptin : 0;
+    if ((e = cudaFuncSetAttribute(k_trace_closest<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, want)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_trace_closest<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, want)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_trace_shadow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, want)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_trace_shadow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, want)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_trace_rays<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, want)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_trace_rays<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, want)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+void launchGenerate(const LaunchParams& p, const GridConfig& g, cudaStream_t s) { k_generate<<<g.smCount * 4, 256, 0, s>>>(p); }
+void launchTraceClosest(const LaunchParams& p, const GridConfig& g, bool count, cudaStream_t s)
+{
+    if (count) k_trace_closest<true><<<g.smCount * g.traceBlocksPerSM, 256, traceSmemBytes(p), s>>>(p);
+    else k_trace_closest<false><<<g.smCount * g.traceBlocksPerSM, 256, traceSmemBytes(p), s>>>(p);
+}
+void launchShade(const LaunchParams& p, const GridConfig& g, cudaStream_t s) { k_shade<<<g.smCount * g.shadeBlocksPerSM, 128, 0, s>>>(p); }
+void launchTraceShadow(const LaunchParams& p, const GridConfig& g, bool count, cudaStream_t s)
+{
+    if (count) k_trace_shadow<true><<<g.smCount * g.traceBlocksPerSM, 256, traceSmemBytes(p), s>>>(p);
+    else k_trace_shadow<false><<<g.smCount * g.traceBlocksPerSM, 256, traceSmemBytes(p), s>>>(p);
+}
+void launchCommitAccumulate(const LaunchParams& p, const GridConfig& g, cudaStream_t s) { k_commit_accumulate<<<g.smCount * 4, 256, 0, s>>>(p); }
+void launchTraceRays(const LaunchParams& p, const GridConfig& g, const RtxptRay* rays, uint32_t count, bool anyHit, RtxptHit* out, uint32_t* counters, cudaStream_t s)
+{
+    if (anyHit) k_trace_rays<true><<<g.smCount * g.traceBlocksPerSM, 256, traceSmemBytes(p), s>>>(p, rays, count, out, counters);
+    else k_trace_rays<false><<<g.smCount * g.traceBlocksPerSM, 256, traceSmemBytes(p), s>>>(p, rays, count, out, counters);
+}
+void launchDebugBsdf(const float* in, uint32_t count, float* out, cudaStream_t s) { k_debug_bsdf<<<(count + 127) / 128, 128, 0, s>>>(in, count, out); }
+void launchDebugRng(const uint32_t* in, uint32_t count, uint32_t* out, cudaStream_t s) { k_debug_rng<<<(count + 127) / 128, 128, 0, s>>>(in, count, out); }
+
+void queryOccupancy(GridConfig& g, size_t smemBytes)
+{
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_closest<false>, 256, smemBytes);
+    g.traceBlocksPerSM = n > 0 ? n : 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade, 128, 0);
+    g.shadeBlocksPerSM = n > 0 ? n : 1;
+}
+
+} // namespace pt

@@ -1,0 +1,21 @@
+// kernels.h — host-callable launchers of the wavefront kernels (kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "wavefront.cuh"
+
+namespace pt {
+
+struct GridConfig { int smCount = 1; int traceBlocksPerSM = 1; int shadeBlocksPerSM = 1; };
+
+cudaError_t configureKernels(int maxSmemOptin);
+void queryOccupancy(GridConfig& g, size_t traceSmemBytes);
+void launchGenerate(const LaunchParams& p, const GridConfig& g, cudaStream_t s);
+void launchTraceClosest(const LaunchParams& p, const GridConfig& g, bool countSteps, cudaStream_t s);
+void launchShade(const LaunchParams& p, const GridConfig& g, cudaStream_t s);
+void launchTraceShadow(const LaunchParams& p, const GridConfig& g, bool countSteps, cudaStream_t s);
+void launchCommitAccumulate(const LaunchParams& p, const GridConfig& g, cudaStream_t s);
+void launchTraceRays(const LaunchParams& p, const GridConfig& g, const RtxptRay* dRays, uint32_t count, bool anyHit, RtxptHit* dHits, uint32_t* dCounters, cudaStream_t s);
+void launchDebugBsdf(const float* dIn, uint32_t count, float* dOut, cudaStream_t s);
+void launchDebugRng(const uint32_t* dIn, uint32_t count, uint32_t* dOut, cudaStream_t s);
+
+} // namespace pt

@@ -1,0 +1,130 @@
+// wavefront.cuh — per-path state in HBM (structure of arrays), queues and launch parameters of the wavefront path tracer.
+//
+// The reference keeps an 80-byte PathState in the DXR payload of a megakernel (Rtxpt/Shaders/PathTracer/PathState.hlsli:83-121,
+// PathPayload.hlsli:19-27).  Here the same 80 bytes live in five uint4 arrays indexed by path slot, so that every kernel of the
+// wavefront reads/writes whole 16-byte words that are contiguous across a warp whenever the queue is contiguous:
+//   s0: origin.xyz, id            s1: dir.xyz, sceneLength          s2: thp(fp16 x4), L(fp16 x4)
+//   s3: interiorList[0..1], packedCounters, rayCone(fp16 x2)        s4: fireflyK|bsdfPdf, misInfo|ruRuCorrection, flagsAndVertexIndex, sampleIndex
+// (stableBranchID of the reference payload is unused in reference mode; its word carries the path's sample index instead.)
+#pragma once
+#include "device_math.cuh"
+#include "scene_device.cuh"
+
+namespace pt {
+
+constexpr int kNumShadeClasses = 6;     // 0 miss, 1 hit on a path that terminates at this vertex, 2..5 material classes (SER sort key analogue)
+constexpr int kMaxWavefrontIterations = 40;
+
+struct ShadowRecord         // 40 bytes in three arrays
+{
+    float4 originTMax;      // ComputeVisibilityRay origin, shortened tMax
+    float4 dirPath;         // direction, path slot (as bits)
+    uint2  radiance;        // NEEResult::RadianceAndSpecAvgPkg (fp16 x4): what L gains if the light is visible
+};
+
+struct WavefrontBuffers
+{
+    uint4* s0; uint4* s1; uint4* s2; uint4* s3; uint4* s4;
+    float4* hits;                   // t,u,v,gid per path slot
+    uint* rayQueue[2];              // path slots whose scatter ray is to be traced (ping-pong per iteration)
+    uint* shadeQueue;               // kNumShadeClasses regions of `capacity` entries
+    float4* shadowOriginTMax; float4* shadowDirPath; uint2* shadowRadiance;
+    uint* counters;                 // see Counter* below, one block per iteration
+    const uint* pixelOfSlot;        // packed (x<<16)|y of the pixels this context renders (tile partition), per pixel slot
+    uint capacity;                  // path slots
+    uint pixelCount;                // pixels rendered by this context
+};
+
+// counters layout: per iteration i a block of kCountersPerIter uints
+constexpr int kCtrRayCount = 0;                 // rays queued for iteration i
+constexpr int kCtrShadeCount = 1;               // + class
+constexpr int kCtrShadowCount = 1 + kNumShadeClasses;
+constexpr int kCtrNodeVisits = kCtrShadowCount + 1;
+constexpr int kCtrTriTests = kCtrNodeVisits + 1;
+constexpr int kCtrShadowVisible = kCtrTriTests + 1;
+constexpr int kCountersPerIter = 16;
+
+struct LaunchParams
+{
+    SceneView scene;
+    WavefrontBuffers wf;
+    RtxptPathTracerConstants c;
+    uint firstSampleIndex;          // sampleBaseIndex + firstSubSampleIndex
+    uint subSampleCount;
+    uint iteration;
+    uint smemNodeCount;             // BVH nodes staged in shared memory
+    uint flags;
+    // render targets
+    uint2* outputColor;             // RGBA16F, full frame, last sub-sample
+    float4* accumulated;            // RGBA32F, full frame
+    float* depth;
+    uint accumulatedSamples;        // before this call
+    uint doAccumulate;
+};
+
+// ---- packed path-state accessors (PathState.hlsli:125-200) ------------------------------------------------------------------
+enum : uint {
+    kPFActive = 1u << 0, kPFHit = 1u << 1, kPFTransmission = 1u << 2, kPFSpecular = 1u << 3, kPFDelta = 1u << 4,
+    kPFInsideDielectric = 1u << 5, kPFTerminateAtNextBounce = 1u << 6, kPFEnableThreadReorder = 1u << 9, kPFDeltaOnlyPath = 1u << 12
+};
+constexpr uint kVertexIndexBits = 10, kVertexIndexMask = (1u << kVertexIndexBits) - 1u;
+
+struct PathRegs             // one path's state in registers
+{
+    float3 origin; uint id;
+    float3 dir; float sceneLength;
+    uint thpXY, thpZ;       // fp16 pairs
+    uint lXY, lZW;
+    uint interior0, interior1, packedCounters, rayCone;
+    uint pack0, pack1, flagsAndVertexIndex, sampleIndex;
+
+    PT_DEVICE void load(const WavefrontBuffers& w, uint slot, bool needRay)
+    {
+        if (needRay)
+        {
+            const uint4 a = w.s0[slot], b = w.s1[slot];
+            origin = mk3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z)); id = a.w;
+            dir = mk3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z)); sceneLength = __uint_as_float(b.w);
+        }
+        const uint4 c = w.s2[slot], d = w.s3[slot], e = w.s4[slot];
+        thpXY = c.x; thpZ = c.y; lXY = c.z; lZW = c.w;
+        interior0 = d.x; interior1 = d.y; packedCounters = d.z; rayCone = d.w;
+        pack0 = e.x; pack1 = e.y; flagsAndVertexIndex = e.z; sampleIndex = e.w;
+    }
+    PT_DEVICE void store(const WavefrontBuffers& w, uint slot) const
+    {
+        w.s0[slot] = make_uint4(__float_as_uint(origin.x), __float_as_uint(origin.y), __float_as_uint(origin.z), id);
+        w.s1[slot] = make_uint4(__float_as_uint(dir.x), __float_as_uint(dir.y), __float_as_uint(dir.z), __float_as_uint(sceneLength));
+        w.s2[slot] = make_uint4(thpXY, thpZ, lXY, lZW);
+        w.s3[slot] = make_uint4(interior0, interior1, packedCounters, rayCone);
+        w.s4[slot] = make_uint4(pack0, pack1, flagsAndVertexIndex, sampleIndex);
+    }
+    PT_DEVICE float3 thp() const { return mk3(f16tof32(thpXY), f16tof32(thpXY >> 16), f16tof32(thpZ)); }
+    PT_DEVICE void setThp(float3 t) { thpXY = packHalf2NoClamp(clampf(t.x, 0.f, kHalfMax), clampf(t.y, 0.f, kHalfMax)); thpZ = packHalf2NoClamp(clampf(t.z, 0.f, kHalfMax), 0.f); }
+    PT_DEVICE float4 L() const { return make_float4(f16tof32(lXY), f16tof32(lXY >> 16), f16tof32(lZW), f16tof32(lZW >> 16)); }
+    PT_DEVICE void setL(float4 l) { lXY = packHalf2NoClamp(clampf(l.x, 0.f, kHalfMax), clampf(l.y, 0.f, kHalfMax)); lZW = packHalf2NoClamp(clampf(l.z, 0.f, kHalfMax), clampf(l.w, 0.f, kHalfMax)); }
+    PT_DEVICE void addRadiance(float3 r) { float4 l = L(); setL(make_float4(l.x + r.x, l.y + r.y, l.z + r.z, l.w)); }    // AccumulatePathRadiance, PathTracer.hlsli:139-143
+    PT_DEVICE float fireflyK() const { return f16tof32(pack0 >> 16); }
+    PT_DEVICE float bsdfScatterPdf() const { return f16tof32(pack0); }
+    PT_DEVICE void setFireflyK_BsdfPdf(float k, float pdf) { pack0 = (f32tof16(clampf(k, 0.f, kHalfMax)) << 16) | f32tof16(clampf(pdf, 0.f, kHalfMax)); }
+    PT_DEVICE uint misInfo() const { return pack1 >> 16; }
+    PT_DEVICE float ruRuCorrection() const { return f16tof32(pack1); }
+    PT_DEVICE void setMisInfo_RuRu(uint mis, float c) { pack1 = (mis << 16) | f32tof16(clampf(c, 0.f, kHalfMax)); }
+    PT_DEVICE bool hasFlag(uint f) const { return (flagsAndVertexIndex & (f << kVertexIndexBits)) != 0; }
+    PT_DEVICE void setFlag(uint f, bool v) { const uint bit = f << kVertexIndexBits; flagsAndVertexIndex = v ? (flagsAndVertexIndex | bit) : (flagsAndVertexIndex & ~bit); }
+    PT_DEVICE uint vertexIndex() const { return flagsAndVertexIndex & kVertexIndexMask; }
+    PT_DEVICE uint counter(uint type) const { return (packedCounters >> (type << 3)) & 0xff; }
+    PT_DEVICE void incrementCounter(uint type) { packedCounters += 1u << (type << 3); }
+    PT_DEVICE float coneWidth() const { return f16tof32(rayCone >> 16); }
+    PT_DEVICE float coneSpread() const { return f16tof32(rayCone); }
+    PT_DEVICE void setCone(float width, float spread) { rayCone = (f32tof16(width) << 16) | f32tof16(spread); }
+};
+constexpr uint kCtrDiffuseBounces = 0, kCtrRejectedHits = 1;
+
+PT_DEVICE bool hasFinishedSurfaceBounces(const RtxptPathTracerConstants& c, uint vertexIndex, uint diffuseBounces)   // PathTracer.hlsli:40-45
+{
+    if (c.bounceCount < vertexIndex) return true;
+    return diffuseBounces > c.diffuseBounceCount;
+}
+
+} // namespace pt

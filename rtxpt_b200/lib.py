@@ -1,0 +1,157 @@
+"""ctypes binding of the product library librtxpt_b200.so (C ABI: include/rtxpt_b200.h).
+
+There is no Python or CPU fallback: if the CUDA library is missing or no device is present, calls raise."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+from . import structs as S
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "_build", "librtxpt_b200.so")
+
+
+class RtxptError(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", CSRC, "-j4"], capture_output=not verbose, text=True)
+    if r.returncode != 0:
+        raise RtxptError("building librtxpt_b200.so failed:\n" + (r.stdout or "") + (r.stderr or ""))
+
+
+_lib = None
+
+_SIGNATURES = {
+    "rtxpt_b200_create": [C.POINTER(S.Config), C.POINTER(C.c_void_p)],
+    "rtxpt_b200_destroy": [C.c_void_p],
+    "rtxpt_b200_upload_scene": [C.c_void_p, C.POINTER(S.SceneDesc)],
+    "rtxpt_b200_set_constants": [C.c_void_p, C.POINTER(S.PathTracerConstants)],
+    "rtxpt_b200_path_trace": [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p],
+    "rtxpt_b200_reset_accumulation": [C.c_void_p],
+    "rtxpt_b200_readback": [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t],
+    "rtxpt_b200_device_ptr": [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)],
+    "rtxpt_b200_synchronize": [C.c_void_p],
+    "rtxpt_b200_render_frame": [C.c_void_p, C.POINTER(S.PathTracerConstants), C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t],
+    "rtxpt_b200_get_stats": [C.c_void_p, C.POINTER(S.Stats)],
+    "rtxpt_b200_trace_rays": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p],
+    "rtxpt_b200_trace_rays_device": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32, C.POINTER(C.c_float)],
+    "rtxpt_b200_get_lights": [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)],
+    "rtxpt_b200_debug_bsdf": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
+    "rtxpt_b200_debug_rng": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
+}
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["rtxpt_b200_last_error"])
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RtxptError(f"{LIB_PATH} is missing: run rtxpt_b200.lib.build() / `make -C rtxpt_b200/csrc` (no fallback path exists)")
+        L = C.CDLL(LIB_PATH)
+        for name, args in _SIGNATURES.items():
+            fn = getattr(L, name); fn.argtypes = args; fn.restype = C.c_int
+        L.rtxpt_b200_last_error.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise RtxptError(f"rtxpt_b200 error {rc}: {load().rtxpt_b200_last_error().decode()}")
+
+
+class Context:
+    def __init__(self, max_sub_samples_per_launch=1, device=-1, tile_rank=0, tile_world=1, tile_size=64, flags=0, max_width=0, max_height=0):
+        L = load()
+        cfg = S.Config(device, max_width, max_height, max_sub_samples_per_launch, tile_rank, tile_world, tile_size, flags)
+        self.h = C.c_void_p()
+        _check(L.rtxpt_b200_create(C.byref(cfg), C.byref(self.h)))
+        self.scene = None; self.consts = None
+
+    def close(self):
+        if self.h:
+            load().rtxpt_b200_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload_scene(self, scene):
+        self.scene = scene
+        _check(load().rtxpt_b200_upload_scene(self.h, C.byref(scene.desc)))
+
+    def set_constants(self, consts):
+        self.consts = consts
+        _check(load().rtxpt_b200_set_constants(self.h, C.byref(consts)))
+
+    def path_trace(self, first_sub_sample, count, accumulate=True, stream=None):
+        _check(load().rtxpt_b200_path_trace(self.h, first_sub_sample, count, int(accumulate), stream))
+
+    def reset_accumulation(self):
+        _check(load().rtxpt_b200_reset_accumulation(self.h))
+
+    def synchronize(self):
+        _check(load().rtxpt_b200_synchronize(self.h))
+
+    def readback_accumulated(self):
+        out = np.empty((self.consts.imageHeight, self.consts.imageWidth, 4), np.float32)
+        _check(load().rtxpt_b200_readback(self.h, S.BUFFER_ACCUMULATED_F32, out.ctypes.data, out.nbytes))
+        return out
+
+    def readback_output_color(self):
+        out = np.empty((self.consts.imageHeight, self.consts.imageWidth, 4), np.float16)
+        _check(load().rtxpt_b200_readback(self.h, S.BUFFER_OUTPUT_COLOR_F16, out.ctypes.data, out.nbytes))
+        return out
+
+    def device_ptr(self, buffer):
+        p, n = C.c_void_p(), C.c_size_t()
+        _check(load().rtxpt_b200_device_ptr(self.h, buffer, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def render_frame(self, consts, first_sub_sample, count, out=None):
+        self.consts = consts
+        if out is None:
+            out = np.empty((consts.imageHeight, consts.imageWidth, 4), np.float32)
+        _check(load().rtxpt_b200_render_frame(self.h, C.byref(consts), first_sub_sample, count, out.ctypes.data, out.nbytes))
+        return out
+
+    def stats(self):
+        st = S.Stats()
+        _check(load().rtxpt_b200_get_stats(self.h, C.byref(st)))
+        return st
+
+    def trace_rays(self, rays, any_hit=False):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        hits = np.zeros(len(rays), dtype=[("t", "f4"), ("u", "f4"), ("v", "f4"), ("inst", "u4"), ("geom", "u4"), ("prim", "u4")])
+        _check(load().rtxpt_b200_trace_rays(self.h, rays.ctypes.data, len(rays), int(any_hit), hits.ctypes.data))
+        return hits
+
+    def trace_rays_device(self, d_rays, count, d_hits, any_hit=False, repeat=1):
+        ms = C.c_float()
+        _check(load().rtxpt_b200_trace_rays_device(self.h, d_rays, count, int(any_hit), d_hits, repeat, C.byref(ms)))
+        return ms.value
+
+    def lights(self):
+        n, m = C.c_uint32(0), C.c_uint32(0)
+        _check(load().rtxpt_b200_get_lights(self.h, None, C.byref(n), None, None, C.byref(m)))
+        infos = np.zeros((n.value, 8), np.uint32); counters = np.zeros(n.value, np.uint32); proxies = np.zeros(max(m.value, 1), np.uint32)
+        _check(load().rtxpt_b200_get_lights(self.h, infos.ctypes.data, C.byref(n), counters.ctypes.data, proxies.ctypes.data, C.byref(m)))
+        return infos, counters, proxies[:m.value]
+
+    def debug_bsdf(self, records):
+        records = np.ascontiguousarray(records, np.float32).reshape(-1, 36)
+        out = np.zeros((len(records), 16), np.float32)
+        _check(load().rtxpt_b200_debug_bsdf(self.h, records.ctypes.data, len(records), out.ctypes.data))
+        return out
+
+    def debug_rng(self, tuples):
+        tuples = np.ascontiguousarray(tuples, np.uint32).reshape(-1, 4)
+        out = np.zeros((len(tuples), 8), np.uint32)
+        _check(load().rtxpt_b200_debug_rng(self.h, tuples.ctypes.data, len(tuples), out.ctypes.data))
+        return out
