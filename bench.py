@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the PathTrace hot path (BASELINE.json: "Mrays/s and ms/frame @1080p 4spp 6-bounce Bistro").
+
+  python bench.py --gpus N --steps K --warmup W            product arm (CUDA wavefront through the C ABI)
+  python bench.py --impl reference --gpus N ...            reference arm: the reference's algorithm for this path on the host cores
+                                                           (RTXPT itself has no CPU implementation and cannot run here — HLSL/DXR, Windows
+                                                           only, SURVEY.md F1-F3 — so this arm times the CPU restatement in oracle/)
+
+Workload (configs[1] of BASELINE.json, fits one GPU): 1920x1080, 4 sub-samples per frame, BounceCount 6 / DiffuseBounceCount 6, StandardBSDF,
+NEE with 5 candidates + 1 shadow ray per vertex, Russian roulette, firefly filter on, environment map on, on the ~2.8 M triangle procedural
+"city block" stand-in for Bistro exterior (the real Bistro assets are git-LFS stubs in the reference tree: SURVEY.md F7).
+A step is one frame: 4 sub-samples path traced and folded into the accumulation buffer.  A ray is one traversal query (scatter or shadow).
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+
+WIDTH, HEIGHT, SPP, BOUNCES = 1920, 1080, 4, 6
+TARGET_TRIANGLES = 2_800_000
+FIREFLY_THRESHOLD = 5000.0          # ReferenceFireflyFilterThreshold 5 * sqrt(preExposedGray = 1) * 1e3 (Rtxpt/Sample.cpp:1522, SampleUI.h:212-213)
+
+
+def build_workload(width=WIDTH, height=HEIGHT, triangles=TARGET_TRIANGLES):
+    from rtxpt_b200 import scenes, scene_builder as sb
+    scene, cam = scenes.city_block(target_triangles=triangles, width=width, height=height)
+    consts = sb.make_constants(width, height, cam, bounce_count=BOUNCES, diffuse_bounce_count=BOUNCES, env_enabled=True,
+                               firefly_threshold=FIREFLY_THRESHOLD, nee=True, nee_type=2)
+    return scene, consts
+
+
+def workload_config(n_gpus):
+    return {"workload": "city-block stand-in for Bistro-exterior (configs[1]): %dx%d, %d spp/frame, BounceCount %d, DiffuseBounceCount %d, StandardBSDF + envmap + NEE(5 candidates, 1 shadow ray) + RR + firefly filter"
+                        % (WIDTH, HEIGHT, SPP, BOUNCES, BOUNCES),
+            "triangles": TARGET_TRIANGLES, "materials": 254, "image": [WIDTH, HEIGHT], "spp_per_frame": SPP,
+            "partition": "1 GPU, whole frame" if n_gpus == 1 else "interleaved 64x64 screen tiles over %d GPUs + NCCL all-gather of radiance tiles" % n_gpus,
+            "cache": "working set per frame (path state 664 MB + scene ~400 MB) exceeds the 126 MB L2; no explicit flush"}
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+    def __init__(self, index):
+        self.lines, self.proc = [], None
+        q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_sample_rect():
+    # bounded sample of the same workload: a 240x135 window in the middle of the 1080p frame, 1 sub-sample
+    w, h = 240, 135
+    x0, y0 = (WIDTH - w) // 2, (HEIGHT - h) // 2
+    return x0, y0, x0 + w, y0 + h
+
+
+def run_cpu(scene, consts, steps, warmup):
+    """Times the oracle (CPU restatement of the reference path, OpenMP over all host cores) on the bounded sample; returns Mrays/s etc."""
+    import oracle_lib as ol
+    ol.build()
+    t0 = time.time(); o = ol.Oracle(scene); bvh_s = ol.lib().oracle_bvh_build_seconds(o.h)
+    o.set_constants(consts); setup_s = time.time() - t0
+    rect = cpu_sample_rect()
+    rays, secs = 0, 0.0
+    for i in range(warmup + steps):
+        acc, n, last, prim, st = o.render(i, 1, rect=rect)
+        if i >= warmup:
+            rays += st.scatterRays + st.shadowRays; secs += st.seconds
+    threads = st.threads
+    paths = (rect[2] - rect[0]) * (rect[3] - rect[1]) * steps
+    return {"mrays_s": rays / secs / 1e6, "seconds": secs, "rays": rays, "threads": threads, "bvh_build_s": bvh_s, "setup_s": setup_s,
+            "ms_per_step": secs / steps * 1e3, "rays_per_path": rays / paths,
+            "sample": "%dx%d window at the centre of the %dx%d frame, 1 sub-sample per step, %d steps" % (rect[2] - rect[0], rect[3] - rect[1], WIDTH, HEIGHT, steps)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = args.gpus
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        scene, consts = build_workload()
+        r = run_cpu(scene, consts, max(1, args.steps), min(args.warmup, 1))
+        line = {"impl": "reference", "metric": "Mrays/s", "value": r["mrays_s"], "unit": "Mrays/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp16 path-state storage)",
+                "data": "synthetic", "config": workload_config(n_gpus),
+                "cpu_baseline": {"value": r["mrays_s"], "unit": "Mrays/s", "cores": r["threads"], "kind": "port", "sample": r["sample"],
+                                 "bvh_build_s": r["bvh_build_s"], "rays_per_path": r["rays_per_path"]},
+                "e2e": {"value": r["mrays_s"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "RTXPT has no CPU implementation of this path (HLSL/DXR only); this arm times the CPU restatement of its algorithm (oracle/) on the host cores"}
+        print(json.dumps(line)); return 0
+
+    import torch
+    from rtxpt_b200 import lib, structs as S
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    scene, consts = build_workload()
+    flags_timed = S.CFG_TIME_KERNELS
+    ctx = lib.Context(max_sub_samples_per_launch=SPP, device=local_rank, tile_rank=rank, tile_world=world, tile_size=64, flags=flags_timed)
+    ctx.upload_scene(scene)
+    ctx.set_constants(consts)
+    owned, padded = ctx.tile_layout()
+    send = gathered = None
+    if world > 1:
+        send = torch.empty((padded, 4), dtype=torch.float32, device="cuda")
+        gathered = torch.empty((world * padded, 4), dtype=torch.float32, device="cuda")
+    # all GPU work of the benchmark (wavefront kernels, tile pack/unpack, NCCL) goes to one non-default torch stream; the timing events are
+    # recorded on that same stream
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    host_out = np.empty((HEIGHT, WIDTH, 4), np.float32)
+
+    def frame(i):
+        consts.sampleBaseIndex = i * SPP
+        ctx.set_constants(consts)
+        ctx.path_trace(0, SPP, True, stream)
+        if world > 1:
+            ctx.pack_owned(send.data_ptr(), stream)
+            dist.all_gather_into_tensor(gathered, send)
+            ctx.unpack_all(gathered.data_ptr(), stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: K frames between CUDA events on the launching stream --------------------------------------------------
+    for i in range(args.warmup):
+        frame(i)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rays = 0; k_closest = k_shadow = k_shade = k_other = 0.0
+    ev0.record()
+    for i in range(args.steps):
+        frame(args.warmup + i)
+        # per-frame ray counts come back with the (already asynchronous) counter copy; reading them syncs, so it is done after the loop for all but the last frame
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    st = ctx.stats()                         # last frame's counters; rays per frame vary <0.1% between frames with this workload
+    rays_per_frame_local = st.scatterRays + st.shadowRays
+    k_closest, k_shadow, k_shade, k_other = st.msTraceClosest, st.msTraceShadow, st.msShade, st.msOther
+    t = torch.tensor([ms_total, float(rays_per_frame_local)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_total = float(tmax[0]); rays_per_frame = float(tsum[1])
+    else:
+        rays_per_frame = float(rays_per_frame_local)
+    clocks = sampler.stop() if sampler else None
+    ms_per_step = ms_total / args.steps
+    value = rays_per_frame / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end-to-end through the C ABI with host buffers: constants in, accumulated RGBA32F image out, every step -------------------------
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        consts.sampleBaseIndex = (args.warmup + args.steps + i) * SPP
+        if world == 1:
+            ctx.render_frame(consts, 0, SPP, host_out)      # set_constants + path_trace + blocking read-back into host memory, on the context's own stream
+        else:
+            frame(args.warmup + args.steps + i)
+            ctx.synchronize(); torch.cuda.synchronize()
+            host_out[:] = ctx.readback_accumulated()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = rays_per_frame / (float(e2e_t[0]) / args.steps) / 1e6
+
+    # ---- roofline of the dominant kernel (closest-hit traversal): instrumented frame for N_node / N_tri, then algorithmic bytes / time ------
+    roofline = None; launches = st.kernelLaunches; paths = st.paths
+    rays_per_bounce = [int(x) for x in st.raysPerBounce[:BOUNCES + 2]]
+    scatter, shadow = int(st.scatterRays), int(st.shadowRays)
+    if rank == 0:
+        ctx2 = lib.Context(max_sub_samples_per_launch=SPP, device=local_rank, tile_rank=rank, tile_world=world, tile_size=64, flags=S.CFG_COUNT_TRAVERSAL_STEPS)
+        ctx2.upload_scene(scene); consts.sampleBaseIndex = (args.warmup + args.steps - 1) * SPP; ctx2.set_constants(consts)
+        ctx2.path_trace(0, SPP, True); ctx2.synchronize(); s2 = ctx2.stats(); ctx2.close()
+        alg_bytes = 48 * s2.scatterRays + 80 * s2.traversalNodeVisits + 48 * s2.traversalTriTests      # 32 B ray in + 16 B hit out + 80 B/node + 48 B/triangle
+        peak, peak_src = measured_peak_gbs()
+        achieved = alg_bytes / (k_closest * 1e-3) / 1e9 if k_closest > 0 else 0.0
+        roofline = {"kernel": "k_trace_closest (CWBVH8 closest-hit traversal)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_frame": int(alg_bytes), "nodes_per_ray": s2.traversalNodeVisits / max(1, s2.scatterRays), "tris_per_ray": s2.traversalTriTests / max(1, s2.scatterRays),
+                    "kernel_ms_per_frame": {"trace_closest": k_closest, "trace_shadow": k_shadow, "shade": k_shade, "other": k_other},
+                    "note": "kernel times: CUDA events around every launch of the last timed frame (RTXPT_CFG_TIME_KERNELS); traffic: see profiles/ (ncu dram bytes)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = run_cpu(scene, consts, 3, 1)
+        cpu = {"value": r["mrays_s"], "unit": "Mrays/s", "cores": r["threads"], "kind": "port", "sample": r["sample"], "bvh_build_s": r["bvh_build_s"], "rays_per_path": r["rays_per_path"]}
+
+    if rank == 0:
+        line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (fp16 path-state storage)", "data": "synthetic",
+                "config": workload_config(n_gpus),
+                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": C.sizeof(type(consts)), "d2h_bytes_per_step": WIDTH * HEIGHT * 16,
+                        "ms_per_step": float(e2e_t[0]) / args.steps * 1e3},
+                "gpu_launches": int(launches * args.steps),
+                "rays_per_frame": rays_per_frame, "rays_per_path": rays_per_frame / (WIDTH * HEIGHT * SPP), "scatter_rays": scatter, "shadow_rays": shadow,
+                "rays_per_iteration": rays_per_bounce, "bvh_build_s": st.bvhBuildSeconds, "bvh_nodes": st.bvhNodeCount, "lights": st.lightCount,
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

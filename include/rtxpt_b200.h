@@ -233,6 +233,7 @@ typedef struct RtxptConfig {
 
 #define RTXPT_CFG_COUNT_TRAVERSAL_STEPS  1u   /* instrumented traversal: per-launch node/triangle counters */
 #define RTXPT_CFG_NO_MATERIAL_SORT       2u   /* disable the per-bounce sort by material class (A/B measurement only) */
+#define RTXPT_CFG_TIME_KERNELS           4u   /* CUDA events around every kernel: fills RtxptStats.msTraceClosest/msTraceShadow/msShade/msOther */
 
 typedef struct rtxpt_ctx rtxpt_ctx;
 
@@ -280,8 +281,10 @@ typedef struct RtxptStats {
     uint64_t shadowRays;            /* any-hit (visibility) queries */
     uint64_t paths;
     uint64_t kernelLaunches;        /* kernels launched by the last path_trace call */
-    uint64_t traversalNodeVisits;   /* only with RTXPT_CFG_COUNT_TRAVERSAL_STEPS */
+    uint64_t traversalNodeVisits;   /* closest-hit queries; only with RTXPT_CFG_COUNT_TRAVERSAL_STEPS */
     uint64_t traversalTriTests;
+    uint64_t shadowNodeVisits;      /* any-hit queries */
+    uint64_t shadowTriTests;
     uint64_t raysPerBounce[16];     /* scatter rays per wavefront iteration */
     float    msTotal;               /* CUDA-event time of the last path_trace call */
     float    msTraceClosest, msTraceShadow, msShade, msOther;
@@ -291,6 +294,16 @@ typedef struct RtxptStats {
     uint32_t accumulatedSamples;
 } RtxptStats;
 RTXPT_API int rtxpt_b200_get_stats(rtxpt_ctx* ctx, RtxptStats* out);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Multi-GPU tile exchange.  The reference is single-GPU; with RtxptConfig.tileWorld > 1 each context renders
+ * the screen tiles t with t % tileWorld == tileRank.  pack_owned writes this context's accumulated pixels into a compact
+ * device array of `paddedPixelsPerRank` float4 (the send buffer of an NCCL all-gather); unpack_all scatters the gathered
+ * tileWorld * paddedPixelsPerRank float4 back into this context's full-frame accumulated image.
+ * ---------------------------------------------------------------------------------------------------------------- */
+RTXPT_API int rtxpt_b200_tile_layout(rtxpt_ctx* ctx, uint32_t* outOwnedPixels, uint32_t* outPaddedPixelsPerRank);
+RTXPT_API int rtxpt_b200_pack_owned(rtxpt_ctx* ctx, void* dDst, void* cudaStream);
+RTXPT_API int rtxpt_b200_unpack_all(rtxpt_ctx* ctx, const void* dSrcAll, void* cudaStream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Inspection hooks used by the parity tests and the traversal micro-benchmark.  They run the same device code as

@@ -64,7 +64,8 @@ struct rtxpt_ctx
     // wavefront
     DeviceArray<uint4> s0, s1, s2, s3, s4; DeviceArray<float4> hits; DeviceArray<uint32_t> rayQueue[2], shadeQueue;
     DeviceArray<float4> shadowOriginTMax, shadowDirPath; DeviceArray<uint2> shadowRadiance;
-    DeviceArray<uint32_t> counters; DeviceArray<uint32_t> pixelOfSlot;
+    DeviceArray<uint32_t> counters; DeviceArray<uint32_t> pixelOfSlot, allPixelTable;
+    uint32_t paddedPixelsPerRank = 0;
     uint32_t capacity = 0, pixelCount = 0, tableWidth = 0, tableHeight = 0;
     // render targets
     DeviceArray<uint2> outputColor; DeviceArray<float4> accumulated; DeviceArray<float> depth;
@@ -73,7 +74,7 @@ struct rtxpt_ctx
     // stats
     uint32_t* hCounters = nullptr;          // pinned
     cudaEvent_t evStart = nullptr, evStop = nullptr;
-    std::vector<cudaEvent_t> evPool;
+    std::vector<cudaEvent_t> evPool; std::vector<int> evKind; size_t evUsed = 0;     // RTXPT_CFG_TIME_KERNELS: (begin,end) pairs per kernel
     uint32_t lastIterations = 0, lastSubSamples = 0; uint64_t lastLaunches = 0;
     bool statsPending = false;
 };
@@ -132,7 +133,7 @@ extern "C" RTXPT_API int rtxpt_b200_destroy(rtxpt_ctx* c)
     c->dLights.release(); c->dProxyCounters.release(); c->dProxyIndices.release(); c->dEnvLookup.release();
     c->s0.release(); c->s1.release(); c->s2.release(); c->s3.release(); c->s4.release(); c->hits.release();
     c->rayQueue[0].release(); c->rayQueue[1].release(); c->shadeQueue.release();
-    c->shadowOriginTMax.release(); c->shadowDirPath.release(); c->shadowRadiance.release(); c->counters.release(); c->pixelOfSlot.release();
+    c->shadowOriginTMax.release(); c->shadowDirPath.release(); c->shadowRadiance.release(); c->counters.release(); c->pixelOfSlot.release(); c->allPixelTable.release();
     c->outputColor.release(); c->accumulated.release(); c->depth.release();
     for (cudaEvent_t ev : c->evPool) cudaEventDestroy(ev);
     if (c->evStart) cudaEventDestroy(c->evStart);
@@ -313,6 +314,25 @@ static int ensureTargets(rtxpt_ctx* c, uint32_t W, uint32_t H)
     }
     c->pixelCount = uint32_t(table.size());
     CU(c->pixelOfSlot.upload(table.data(), table.size(), c->stream));
+    {   // pixel tables of every rank (deterministic from W,H,tileSize,world), padded to a common length: layout of the all-gather buffer
+        std::vector<std::vector<uint32_t>> per(c->cfg.tileWorld);
+        for (uint32_t t = 0; t < tilesX * tilesY; t++)
+        {
+            const uint32_t tx = (t % tilesX) * T, ty = (t / tilesX) * T;
+            std::vector<uint32_t>& dst = per[t % c->cfg.tileWorld];
+            for (uint32_t m = 0; m < T * T; m++)
+            {
+                uint32_t x = 0, y = 0;
+                for (uint32_t b = 0; b < 16; b++) { x |= ((m >> (2 * b)) & 1u) << b; y |= ((m >> (2 * b + 1)) & 1u) << b; }
+                if (tx + x < W && ty + y < H) dst.push_back(((tx + x) << 16) | (ty + y));
+            }
+        }
+        size_t padded = 0; for (auto& v : per) padded = std::max(padded, v.size());
+        c->paddedPixelsPerRank = uint32_t(padded);
+        std::vector<uint32_t> all(padded * c->cfg.tileWorld, 0xFFFFFFFFu);
+        for (uint32_t r = 0; r < c->cfg.tileWorld; r++) std::copy(per[r].begin(), per[r].end(), all.begin() + size_t(r) * padded);
+        CU(c->allPixelTable.upload(all.data(), all.size(), c->stream));
+    }
     const size_t P = size_t(W) * H;
     CU(c->outputColor.alloc(P)); CU(c->accumulated.alloc(P)); CU(c->depth.alloc(P));
     CU(cudaMemsetAsync(c->outputColor.ptr, 0, P * sizeof(uint2), c->stream)); CU(cudaMemsetAsync(c->accumulated.ptr, 0, P * sizeof(float4), c->stream)); CU(cudaMemsetAsync(c->depth.ptr, 0, P * sizeof(float), c->stream));
@@ -382,6 +402,20 @@ static void fillParams(rtxpt_ctx* c, LaunchParams& p)
     p.smemNodeCount = std::min(c->bvhNodeCount, budget / 80u);
 }
 
+// RTXPT_CFG_TIME_KERNELS: bracket a launch with two events from the pool; kinds: 0 closest, 1 shadow, 2 shade, 3 other
+struct KernelTimer
+{
+    rtxpt_ctx* c; cudaStream_t s; bool on;
+    void begin(int kind)
+    {
+        if (!on) return;
+        while (c->evPool.size() < c->evUsed + 2) { cudaEvent_t e; cudaEventCreate(&e); c->evPool.push_back(e); }
+        c->evKind.resize(c->evPool.size() / 2 + 1); c->evKind[c->evUsed / 2] = kind;
+        cudaEventRecord(c->evPool[c->evUsed], s);
+    }
+    void end() { if (!on) return; cudaEventRecord(c->evPool[c->evUsed + 1], s); c->evUsed += 2; }
+};
+
 static int checkReady(rtxpt_ctx* c)
 {
     if (!c) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null context");
@@ -404,6 +438,8 @@ extern "C" RTXPT_API int rtxpt_b200_path_trace(rtxpt_ctx* c, uint32_t firstSubSa
     const uint32_t iterations = std::min<uint32_t>(c->consts.bounceCount + 1 + (hasRefraction ? 4 : 0), kMaxWavefrontIterations);
     CU(cudaEventRecord(c->evStart, s));
     uint64_t launches = 0;
+    KernelTimer kt{ c, s, (c->cfg.flags & RTXPT_CFG_TIME_KERNELS) != 0 };
+    c->evUsed = 0;
     for (uint32_t done = 0; done < subSampleCount; done += c->cfg.maxSubSamplesPerLaunch)
     {
         const uint32_t n = std::min(c->cfg.maxSubSamplesPerLaunch, subSampleCount - done);
@@ -412,16 +448,16 @@ extern "C" RTXPT_API int rtxpt_b200_path_trace(rtxpt_ctx* c, uint32_t firstSubSa
         p.accumulatedSamples = c->accumulatedSamples; p.doAccumulate = accumulate ? 1u : 0u;
         CU(cudaMemsetAsync(c->counters.ptr, 0, kCounterWords * sizeof(uint32_t), s));
         p.iteration = 0;
-        launchGenerate(p, c->grid, s); launches++;
+        kt.begin(3); launchGenerate(p, c->grid, s); kt.end(); launches++;
         for (uint32_t it = 0; it < iterations; it++)
         {
             p.iteration = it;
-            launchTraceClosest(p, c->grid, countSteps, s);
-            launchShade(p, c->grid, s);
-            launchTraceShadow(p, c->grid, countSteps, s);
+            kt.begin(0); launchTraceClosest(p, c->grid, countSteps, s); kt.end();
+            kt.begin(2); launchShade(p, c->grid, s); kt.end();
+            kt.begin(1); launchTraceShadow(p, c->grid, countSteps, s); kt.end();
             launches += 3;
         }
-        launchCommitAccumulate(p, c->grid, s); launches++;
+        kt.begin(3); launchCommitAccumulate(p, c->grid, s); kt.end(); launches++;
         if (accumulate) c->accumulatedSamples += n;
         CU(cudaGetLastError());
     }
@@ -501,18 +537,52 @@ extern "C" RTXPT_API int rtxpt_b200_get_stats(rtxpt_ctx* c, RtxptStats* out)
         const uint32_t batches = (c->lastSubSamples + c->cfg.maxSubSamplesPerLaunch - 1) / c->cfg.maxSubSamplesPerLaunch;
         const uint32_t lastBatch = c->lastSubSamples - (batches - 1) * c->cfg.maxSubSamplesPerLaunch;
         const double scale = double(c->lastSubSamples) / double(lastBatch);
-        uint64_t scatter = 0, shadow = 0, nodes = 0, tests = 0;
+        uint64_t scatter = 0, shadow = 0, nodes = 0, tests = 0, snodes = 0, stests = 0;
         for (uint32_t it = 0; it < c->lastIterations; it++)
         {
             const uint32_t* k = c->hCounters + it * kCountersPerIter;
             scatter += k[kCtrRayCount]; shadow += k[kCtrShadowCount]; nodes += k[kCtrNodeVisits]; tests += k[kCtrTriTests];
+            snodes += k[kCtrShadowNodeVisits]; stests += k[kCtrShadowTriTests];
             if (it < 16) out->raysPerBounce[it] = uint64_t(k[kCtrRayCount] * scale);
         }
         out->scatterRays = uint64_t(scatter * scale); out->shadowRays = uint64_t(shadow * scale);
         out->traversalNodeVisits = uint64_t(nodes * scale); out->traversalTriTests = uint64_t(tests * scale);
+        out->shadowNodeVisits = uint64_t(snodes * scale); out->shadowTriTests = uint64_t(stests * scale);
+        for (size_t e = 0; e + 1 < c->evUsed; e += 2)
+        {
+            float t = 0; cudaEventElapsedTime(&t, c->evPool[e], c->evPool[e + 1]);
+            switch (c->evKind[e / 2]) { case 0: out->msTraceClosest += t; break; case 1: out->msTraceShadow += t; break; case 2: out->msShade += t; break; default: out->msOther += t; }
+        }
         out->paths = uint64_t(c->pixelCount) * c->lastSubSamples;
         out->kernelLaunches = c->lastLaunches;
     }
+    return RTXPT_OK;
+}
+
+// ---- multi-GPU tile exchange --------------------------------------------------------------------------------------------------------------------
+extern "C" RTXPT_API int rtxpt_b200_tile_layout(rtxpt_ctx* c, uint32_t* outOwned, uint32_t* outPadded)
+{
+    if (!c || !outOwned || !outPadded) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (c->tableWidth == 0) return fail(RTXPT_ERR_INVALID_ARGUMENT, "constants not set");
+    *outOwned = c->pixelCount; *outPadded = c->paddedPixelsPerRank;
+    return RTXPT_OK;
+}
+extern "C" RTXPT_API int rtxpt_b200_pack_owned(rtxpt_ctx* c, void* dDst, void* cudaStream)
+{
+    if (!c || !dDst) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (c->tableWidth == 0) return fail(RTXPT_ERR_INVALID_ARGUMENT, "constants not set");
+    cudaSetDevice(c->device);
+    launchPackOwned(c->accumulated.ptr, c->pixelOfSlot.ptr, c->pixelCount, c->paddedPixelsPerRank, c->tableWidth, (float4*)dDst, c->grid, cudaStream ? (cudaStream_t)cudaStream : c->stream);
+    CU(cudaGetLastError());
+    return RTXPT_OK;
+}
+extern "C" RTXPT_API int rtxpt_b200_unpack_all(rtxpt_ctx* c, const void* dSrcAll, void* cudaStream)
+{
+    if (!c || !dSrcAll) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (c->tableWidth == 0) return fail(RTXPT_ERR_INVALID_ARGUMENT, "constants not set");
+    cudaSetDevice(c->device);
+    launchUnpackAll((const float4*)dSrcAll, c->allPixelTable.ptr, c->paddedPixelsPerRank * c->cfg.tileWorld, c->tableWidth, c->accumulated.ptr, c->grid, cudaStream ? (cudaStream_t)cudaStream : c->stream);
+    CU(cudaGetLastError());
     return RTXPT_OK;
 }
 

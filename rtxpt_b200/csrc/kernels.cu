@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(256, 2) k_trace_shadow(const __grid_constant__
             visibleCount++;
         }
     }
-    if (COUNT) { atomicAdd(ctr + kCtrNodeVisits, tc.nodeVisits); atomicAdd(ctr + kCtrTriTests, tc.triTests); atomicAdd(ctr + kCtrShadowVisible, visibleCount); }
+    if (COUNT) { atomicAdd(ctr + kCtrShadowNodeVisits, tc.nodeVisits); atomicAdd(ctr + kCtrShadowTriTests, tc.triTests); atomicAdd(ctr + kCtrShadowVisible, visibleCount); }
 }
 
 // ---- commit + accumulate ---------------------------------------------------------------------------------------------------------------------
@@ -301,6 +301,30 @@ __global__ void k_debug_rng(const uint* __restrict__ in, uint count, uint* __res
     for (int k = 0; k < 4; k++) out[i * 8 + k] = u.nextBits();
     for (uint k = 0; k < 4; k++) out[i * 8 + 4 + k] = __float_as_uint(hashToFloat(ldSampleBits(baseHash, in[i * 4 + 3], 1u, k)));
 }
+
+// ---- tile exchange for multi-GPU (the reference is single-GPU) ------------------------------------------------------------------
+// pack: owned pixels of the accumulated image -> compact array in slot order; unpack: all ranks' compact arrays -> full frame
+__global__ void k_pack_owned(const float4* __restrict__ image, const uint* __restrict__ pixelOfSlot, uint pixelCount, uint paddedCount, uint width, float4* __restrict__ dst)
+{
+    for (uint i = blockIdx.x * blockDim.x + threadIdx.x; i < paddedCount; i += gridDim.x * blockDim.x)
+    {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < pixelCount) { const uint id = pixelOfSlot[i]; v = image[size_t(id & 0xFFFF) * width + (id >> 16)]; }
+        dst[i] = v;
+    }
+}
+__global__ void k_unpack_all(const float4* __restrict__ srcAll, const uint* __restrict__ allPixelTable, uint totalEntries, uint width, float4* __restrict__ image)
+{
+    for (uint i = blockIdx.x * blockDim.x + threadIdx.x; i < totalEntries; i += gridDim.x * blockDim.x)
+    {
+        const uint id = allPixelTable[i];
+        if (id != 0xFFFFFFFFu) image[size_t(id & 0xFFFF) * width + (id >> 16)] = srcAll[i];
+    }
+}
+void launchPackOwned(const float4* image, const uint32_t* pixelOfSlot, uint32_t pixelCount, uint32_t paddedCount, uint32_t width, float4* dst, const GridConfig& g, cudaStream_t s)
+{ k_pack_owned<<<g.smCount * 4, 256, 0, s>>>(image, pixelOfSlot, pixelCount, paddedCount, width, dst); }
+void launchUnpackAll(const float4* srcAll, const uint32_t* allPixelTable, uint32_t totalEntries, uint32_t width, float4* image, const GridConfig& g, cudaStream_t s)
+{ k_unpack_all<<<g.smCount * 4, 256, 0, s>>>(srcAll, allPixelTable, totalEntries, width, image); }
 
 // ---- launch wrappers ---------------------------------------------------------------------------------------------------------------------------
 static size_t traceSmemBytes(const LaunchParams& p) { return 16 + size_t(p.smemNodeCount) * 80; }

@@ -39,9 +39,11 @@ struct WavefrontBuffers
 constexpr int kCtrRayCount = 0;                 // rays queued for iteration i
 constexpr int kCtrShadeCount = 1;               // + class
 constexpr int kCtrShadowCount = 1 + kNumShadeClasses;
-constexpr int kCtrNodeVisits = kCtrShadowCount + 1;
+constexpr int kCtrNodeVisits = kCtrShadowCount + 1;         // closest-hit traversal (instrumented builds only)
 constexpr int kCtrTriTests = kCtrNodeVisits + 1;
 constexpr int kCtrShadowVisible = kCtrTriTests + 1;
+constexpr int kCtrShadowNodeVisits = kCtrShadowVisible + 1;  // any-hit traversal
+constexpr int kCtrShadowTriTests = kCtrShadowNodeVisits + 1;
 constexpr int kCountersPerIter = 16;
 
 struct LaunchParams

@@ -37,6 +37,9 @@ _SIGNATURES = {
     "rtxpt_b200_synchronize": [C.c_void_p],
     "rtxpt_b200_render_frame": [C.c_void_p, C.POINTER(S.PathTracerConstants), C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t],
     "rtxpt_b200_get_stats": [C.c_void_p, C.POINTER(S.Stats)],
+    "rtxpt_b200_tile_layout": [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)],
+    "rtxpt_b200_pack_owned": [C.c_void_p, C.c_void_p, C.c_void_p],
+    "rtxpt_b200_unpack_all": [C.c_void_p, C.c_void_p, C.c_void_p],
     "rtxpt_b200_trace_rays": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p],
     "rtxpt_b200_trace_rays_device": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32, C.POINTER(C.c_float)],
     "rtxpt_b200_get_lights": [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)],
@@ -125,6 +128,17 @@ class Context:
         st = S.Stats()
         _check(load().rtxpt_b200_get_stats(self.h, C.byref(st)))
         return st
+
+    def tile_layout(self):
+        a, b = C.c_uint32(), C.c_uint32()
+        _check(load().rtxpt_b200_tile_layout(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def pack_owned(self, d_dst, stream=None):
+        _check(load().rtxpt_b200_pack_owned(self.h, d_dst, stream))
+
+    def unpack_all(self, d_src_all, stream=None):
+        _check(load().rtxpt_b200_unpack_all(self.h, d_src_all, stream))
 
     def trace_rays(self, rays, any_hit=False):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)

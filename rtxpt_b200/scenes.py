@@ -225,6 +225,7 @@ def city_block(target_triangles=2_800_000, width=1920, height=1080, seed=1234, t
     if with_env:
         b.set_env_cube(sky_cube(256))
     scene = b.build()
-    # street-level camera looking down a street towards the block centre (cf. /Cameras/Outside in bistro-programmer-art.scene.json)
-    cam = bridge_camera(width, height, pos=(-extent / 2 + pitch * 0.5 - street / 2 + 2.0, 1.8, -extent / 2 - 6.0), direction=(0.18, 0.12, 1.0), up=(0, 1, 0), fov_y=1.04)
+    # street-level camera standing in the street between the 3rd and 4th block columns, looking down the street with a slight yaw
+    # (cf. /Cameras/Outside in Assets/bistro-programmer-art.scene.json: eye height 1.8, fovY 1.04)
+    cam = bridge_camera(width, height, pos=(-extent / 2 + 3 * pitch + 1.0, 1.8, -extent / 2 + 0.4 * pitch), direction=(-0.22, 0.10, 1.0), up=(0, 1, 0), fov_y=1.04)
     return scene, cam

@@ -25,6 +25,7 @@ MATFLAG_NestedPriorityShift = 28
 
 CFG_COUNT_TRAVERSAL_STEPS = 1
 CFG_NO_MATERIAL_SORT = 2
+CFG_TIME_KERNELS = 4
 
 BUFFER_OUTPUT_COLOR_F16, BUFFER_ACCUMULATED_F32, BUFFER_DEPTH_F32 = 0, 1, 2
 
@@ -106,7 +107,7 @@ class Config(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("scatterRays", u64), ("shadowRays", u64), ("paths", u64), ("kernelLaunches", u64),
-                ("traversalNodeVisits", u64), ("traversalTriTests", u64), ("raysPerBounce", u64 * 16),
+                ("traversalNodeVisits", u64), ("traversalTriTests", u64), ("shadowNodeVisits", u64), ("shadowTriTests", u64), ("raysPerBounce", u64 * 16),
                 ("msTotal", f32), ("msTraceClosest", f32), ("msTraceShadow", f32), ("msShade", f32), ("msOther", f32),
                 ("bvhNodeCount", u32), ("bvhTriangleCount", u32), ("bvhBuildSeconds", f32),
                 ("lightCount", u32), ("lightProxyCount", u32), ("accumulatedSamples", u32)]

@@ -1,0 +1,105 @@
+"""CPU: the oracle's integer / packing primitives against the reference's own known answers.
+  - tests/golden/rng_golden.json: produced from the UNMODIFIED NoiseAndSequences.hlsli C++ half (tests/golden/make_rng_golden.py)
+  - fp16 known answers of External/Donut/tests/src/engine/test_float.cpp:74-90 (round-to-nearest-even f32->f16)
+  - when /root/reference is present (build container) the golden file is regenerated and must be identical (pins the fixture itself)"""
+import json
+import os
+import subprocess
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def golden():
+    with open(os.path.join(HERE, "golden", "rng_golden.json")) as f:
+        return json.load(f)
+
+
+def test_hash32_against_reference_header(oracle):
+    L = oracle.lib(); g = golden()
+    for x, h in g["hash32"]:
+        assert L.oracle_hash32(x) == h
+    for s, v, h in g["hash32_combine"]:
+        assert L.oracle_hash32_combine(s, v) == h
+    for h, f in g["hash32_to_float"]:
+        assert np.float32(L.oracle_hash32_to_float(h)) == np.float32(f)
+        assert 0.0 <= f < 1.0
+
+
+def test_sobol_against_reference_header(oracle):
+    L = oracle.lib()
+    for index, dim, v in golden()["sobol"]:
+        assert L.oracle_sobol(index, dim) == v
+
+
+def test_golden_file_matches_reference_tree():
+    ref = "/root/reference/Rtxpt/Shaders/PathTracer/Utils/NoiseAndSequences.hlsli"
+    if not os.path.exists(ref):
+        pytest.skip("reference tree not present (GPU box)")
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "ref"], check=True)
+    out = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_kat")], check=True, capture_output=True, text=True).stdout
+    fresh = json.loads(out); g = golden()
+    for k in ("hash32", "hash32_combine", "sobol"):
+        assert fresh[k] == g[k]
+
+
+def test_fp16_known_answers_from_donut_test_float(oracle):
+    L = oracle.lib()
+    inv1024 = np.float32(1.0 / 1024.0); smallest_normal = np.float32(2.0 ** -14)
+    cases = [(0.0, 0), (smallest_normal * inv1024 * np.float32(0.5), 0), (smallest_normal * inv1024, 1), (smallest_normal * inv1024 * np.float32(1023.0), 0x03ff),
+             (np.float32(1.0) / np.float32(3.0), 0x3555), (np.float32(0.5) * (np.float32(1.0) + np.float32(1023.0) / np.float32(1024.0)), 0x3bff), (1.0, 0x3c00),
+             (np.float32(1.0) + inv1024, 0x3c01), (65504.0, 0x7bff), (np.inf, 0x7c00), (-np.inf, 0xfc00), (65519.0, 0x7bff), (65520.0, 0x7c00), (1000000.0, 0x7c00)]
+    for v, bits in cases:
+        assert L.oracle_f32tof16(float(v)) == bits, (v, bits)
+    assert (L.oracle_f32tof16(float("nan")) & 0x7c00) == 0x7c00 and (L.oracle_f32tof16(float("nan")) & 0x3ff) != 0
+
+
+def test_fp16_matches_ieee_rne_exhaustively_sampled(oracle):
+    L = oracle.lib()
+    rng = np.random.default_rng(0)
+    bits = np.concatenate([rng.integers(0, 2 ** 32, 200000, dtype=np.uint64).astype(np.uint32),
+                           (np.arange(0, 65536, dtype=np.uint32) << 13) + 0x38000000])     # around the f16 normal range, incl. exact ties
+    vals = bits.view(np.float32)
+    with np.errstate(over="ignore", invalid="ignore"):
+        ref = vals.astype(np.float16).view(np.uint16)
+    for v, r in zip(vals[:60000], ref[:60000]):
+        if np.isnan(v):
+            continue
+        assert L.oracle_f32tof16(float(v)) == int(r)
+    # all 65536 halves round-trip
+    for h in range(0, 65536, 7):
+        f = L.oracle_f16tof32(h)
+        if np.isnan(f):
+            continue
+        assert L.oracle_f32tof16(f) == h
+
+
+def test_snorm8_roundtrip(oracle):
+    L = oracle.lib()
+    for q in range(-127, 128):
+        assert L.oracle_pack_snorm8(L.oracle_unpack_snorm8(q & 0xff)) == (q & 0xff)
+    assert L.oracle_unpack_snorm8(0x80) == -1.0     # -128 clamps
+
+
+def test_sample_sequences_are_in_unit_interval_and_deterministic(oracle):
+    L = oracle.lib()
+    rng = np.random.default_rng(1)
+    tuples = np.stack([rng.integers(0, 1920, 4096), rng.integers(0, 1080, 4096), rng.integers(0, 8, 4096), rng.integers(0, 5000, 4096)], 1).astype(np.uint32)
+    out = np.zeros((4096, 8), np.uint32); out2 = np.zeros_like(out)
+    L.oracle_rng(tuples.ctypes.data, 4096, out.ctypes.data); L.oracle_rng(tuples.ctypes.data, 4096, out2.ctypes.data)
+    assert np.array_equal(out, out2)
+    ld = out[:, 4:].view(np.float32)
+    assert (ld >= 0).all() and (ld < 1).all()
+    # uniform stream: chained Hash32 of the seeded state (StatelessSampleGenerators.hlsli:187-232)
+    x, y, v, s = [int(t) for t in tuples[0]]
+    base = L.oracle_hash32_combine(L.oracle_hash32((v + 0x035F9F29) & 0xFFFFFFFF), (x << 16) | y)
+    h = L.oracle_hash32_combine(L.oracle_hash32_combine(base, 0), s)
+    for k in range(4):
+        h = L.oracle_hash32(h); assert out[0, k] == h
+    # low-discrepancy draws are stratified: first dimension over sample indices 0..255 of one pixel covers every 1/256 stratum exactly once
+    t = np.array([[10, 20, 1, i] for i in range(256)], np.uint32); o = np.zeros((256, 8), np.uint32)
+    L.oracle_rng(t.ctypes.data, 256, o.ctypes.data)
+    strata = np.floor(o[:, 4].view(np.float32) * 256).astype(int)
+    assert len(set(strata.tolist())) == 256
