@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -396,6 +397,7 @@ static void fillParams(rtxpt_ctx* c, LaunchParams& p)
     w.counters = c->counters.ptr; w.pixelOfSlot = c->pixelOfSlot.ptr; w.capacity = c->capacity; w.pixelCount = c->pixelCount;
     p.c = c->consts;
     p.flags = c->cfg.flags;
+    { const char* e = getenv("RTXPT_REFILL_THRESHOLD"); p.refillThreshold = e ? atoi(e) : 24; }     // tuning knob; 8..24 measured equal within noise on B200
     p.outputColor = c->outputColor.ptr; p.accumulated = c->accumulated.ptr; p.depth = c->depth.ptr;
     // shared-memory BVH prefix: as many breadth-first nodes as fit next to two resident CTAs
     const uint32_t budget = uint32_t(std::max(0, std::min(c->maxSmemOptin, 100 * 1024) - 1024));
@@ -598,7 +600,7 @@ extern "C" RTXPT_API int rtxpt_b200_trace_rays_device(rtxpt_ctx* c, const void* 
     if (repeat == 0) repeat = 1;
     CU(cudaEventRecord(c->evStart, c->stream));
     for (uint32_t r = 0; r < repeat; r++)
-        launchTraceRays(p, c->grid, (const RtxptRay*)dRays, count, anyHit != 0, (RtxptHit*)dHits, (r == 0) ? c->counters.ptr : nullptr, c->stream);
+        launchTraceRays(p, c->grid, (const RtxptRay*)dRays, count, anyHit != 0, (RtxptHit*)dHits, (r == 0) ? c->counters.ptr : nullptr, c->counters.ptr + 4, c->stream);
     CU(cudaEventRecord(c->evStop, c->stream));
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->hCounters, c->counters.ptr, 8, cudaMemcpyDeviceToHost, c->stream));

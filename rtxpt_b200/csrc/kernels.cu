@@ -104,6 +104,10 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ Launch
 }
 
 // ---- closest hit ------------------------------------------------------------------------------------------------------------------------
+// Persistent warps with dynamic ray fetch: a lane whose ray has finished writes its hit, bins the path into its shade queue and pulls the
+// next ray from the queue cursor; lanes still traversing resume where they stopped.  Keeps SIMT lanes busy although ray lengths differ
+// by an order of magnitude.
+
 template <bool COUNT>
 __global__ void __launch_bounds__(256, 2) k_trace_closest(const __grid_constant__ LaunchParams p)
 {
@@ -117,27 +121,45 @@ __global__ void __launch_bounds__(256, 2) k_trace_closest(const __grid_constant_
 
     const uint* __restrict__ queue = p.wf.rayQueue[p.iteration & 1];
     TraversalCounters tc; tc.nodeVisits = 0; tc.triTests = 0;
-    const uint warpsPerBlock = blockDim.x >> 5, lane = threadIdx.x & 31u;
-    const uint warpGlobal = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5), warpStride = gridDim.x * warpsPerBlock;
-    for (uint base = warpGlobal * 32u; base < count; base += warpStride * 32u)
+    const uint lane = threadIdx.x & 31u;
+    Traverser<false, COUNT> tv; tv.done = true;
+    uint2 stack[kTraversalStackSize];
+    bool hasRay = false; uint entry = 0;
+    while (true)
     {
-        const uint i = base + lane;
-        uint cls = 0xFFu, slot = 0;
-        if (i < count)
+        if (tv.done)
         {
-            const uint entry = queue[i];
-            slot = entry & 0x7FFFFFFFu;
+            const uint active = __activemask();
+            if (hasRay)
+            {   // retire: hit record + SER-style binning by {miss, terminating hit, material class}
+                const uint slot = entry & 0x7FFFFFFFu;
+                const HitRecord h = tv.result();
+                p.wf.hits[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.gid));
+                uint cls;
+                if (h.gid == 0xFFFFFFFFu) cls = 0;
+                else if (entry & 0x80000000u) cls = 1;
+                else cls = (p.flags & RTXPT_CFG_NO_MATERIAL_SORT) ? 2u : 2u + p.scene.subInstanceClass[tv.bestSubInstance];
+                const uint peers = __match_any_sync(active, cls);
+                const uint leader = __ffs(peers) - 1u;
+                uint base = 0;
+                if (lane == leader) base = atomicAdd(ctr + kCtrShadeCount + cls, __popc(peers));
+                base = __shfl_sync(peers, base, leader);
+                p.wf.shadeQueue[size_t(cls) * p.wf.capacity + base + __popc(peers & ((1u << lane) - 1u))] = slot;
+                hasRay = false;
+            }
+            // fetch the next ray for every idle lane with one atomic per warp
+            const uint leader = __ffs(active) - 1u;
+            uint base = 0;
+            if (lane == leader) base = atomicAdd(ctr + kCtrFetchClosest, __popc(active));
+            const uint i = __shfl_sync(active, base, leader) + __popc(active & ((1u << lane) - 1u));
+            if (i >= count) break;
+            entry = queue[i];
+            const uint slot = entry & 0x7FFFFFFFu;
             const uint4 a = p.wf.s0[slot], b = p.wf.s1[slot];
-            const float3 o = mk3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
-            const float3 d = mk3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z));
-            uint subInstance = 0;
-            const HitRecord h = traceRay<false, COUNT>(p.scene, p.scene.bvhNodes, smemNodes, p.smemNodeCount, o, d, 0.0f, kMaxRayTravel, &tc, &subInstance);
-            p.wf.hits[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.gid));
-            if (h.gid == 0xFFFFFFFFu) cls = 0;
-            else if (entry & 0x80000000u) cls = 1;
-            else cls = (p.flags & RTXPT_CFG_NO_MATERIAL_SORT) ? 2u : 2u + p.scene.subInstanceClass[subInstance];
+            tv.init(p.scene, mk3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z)), mk3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z)), 0.0f, kMaxRayTravel);
+            hasRay = true;
         }
-        warpAppend(p.wf.shadeQueue, p.wf.capacity, ctr + kCtrShadeCount, cls, slot);
+        tv.run(p.scene, p.scene.bvhNodes, smemNodes, p.smemNodeCount, p.refillThreshold, &tc, stack);
     }
     if (COUNT) { atomicAdd(ctr + kCtrNodeVisits, tc.nodeVisits); atomicAdd(ctr + kCtrTriTests, tc.triTests); }
 }
@@ -200,26 +222,44 @@ __global__ void __launch_bounds__(256, 2) k_trace_shadow(const __grid_constant__
 
     TraversalCounters tc; tc.nodeVisits = 0; tc.triTests = 0;
     uint visibleCount = 0;
-    for (uint i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    const uint lane = threadIdx.x & 31u;
+    Traverser<true, COUNT> tv; tv.done = true;
+    uint2 stack[kTraversalStackSize];
+    bool hasRay = false; uint record = 0, slot = 0;
+    while (true)
     {
-        const float4 ot = p.wf.shadowOriginTMax[i], dp = p.wf.shadowDirPath[i];
-        uint subInstance;
-        const HitRecord h = traceRay<true, COUNT>(p.scene, p.scene.bvhNodes, smemNodes, p.smemNodeCount, mk3(ot.x, ot.y, ot.z), mk3(dp.x, dp.y, dp.z), 0.0f, ot.w, &tc, &subInstance);
-        if (h.gid == 0xFFFFFFFFu)
-        {   // visible: HandleHit's "if any(neeRadianceAndSpecAvg > 0) AccumulatePathRadiance" (PathTracer.hlsli:725-746)
-            const uint2 r = p.wf.shadowRadiance[i];
-            const float rx = f16tof32(r.x), ry = f16tof32(r.x >> 16), rz = f16tof32(r.y), rw = f16tof32(r.y >> 16);
-            if (rx > 0 || ry > 0 || rz > 0 || rw > 0)
+        if (tv.done)
+        {
+            const uint active = __activemask();
+            if (hasRay)
             {
-                const uint slot = __float_as_uint(dp.w);
-                uint4 s2 = p.wf.s2[slot];
-                const float lx = f16tof32(s2.z) + rx, ly = f16tof32(s2.z >> 16) + ry, lz = f16tof32(s2.w) + rz, lw = f16tof32(s2.w >> 16);
-                s2.z = packHalf2NoClamp(clampf(lx, 0.f, kHalfMax), clampf(ly, 0.f, kHalfMax));
-                s2.w = packHalf2NoClamp(clampf(lz, 0.f, kHalfMax), clampf(lw, 0.f, kHalfMax));
-                p.wf.s2[slot] = s2;
+                if (tv.best.gid == 0xFFFFFFFFu)
+                {   // visible: HandleHit's "if any(neeRadianceAndSpecAvg > 0) AccumulatePathRadiance" (PathTracer.hlsli:725-746)
+                    const uint2 r = p.wf.shadowRadiance[record];
+                    const float rx = f16tof32(r.x), ry = f16tof32(r.x >> 16), rz = f16tof32(r.y), rw = f16tof32(r.y >> 16);
+                    if (rx > 0 || ry > 0 || rz > 0 || rw > 0)
+                    {
+                        uint4 s2 = p.wf.s2[slot];
+                        const float lx = f16tof32(s2.z) + rx, ly = f16tof32(s2.z >> 16) + ry, lz = f16tof32(s2.w) + rz, lw = f16tof32(s2.w >> 16);
+                        s2.z = packHalf2NoClamp(clampf(lx, 0.f, kHalfMax), clampf(ly, 0.f, kHalfMax));
+                        s2.w = packHalf2NoClamp(clampf(lz, 0.f, kHalfMax), clampf(lw, 0.f, kHalfMax));
+                        p.wf.s2[slot] = s2;
+                    }
+                    visibleCount++;
+                }
+                hasRay = false;
             }
-            visibleCount++;
+            const uint leader = __ffs(active) - 1u;
+            uint base = 0;
+            if (lane == leader) base = atomicAdd(ctr + kCtrFetchShadow, __popc(active));
+            record = __shfl_sync(active, base, leader) + __popc(active & ((1u << lane) - 1u));
+            if (record >= count) break;
+            const float4 ot = p.wf.shadowOriginTMax[record], dp = p.wf.shadowDirPath[record];
+            slot = __float_as_uint(dp.w);
+            tv.init(p.scene, mk3(ot.x, ot.y, ot.z), mk3(dp.x, dp.y, dp.z), 0.0f, ot.w);
+            hasRay = true;
         }
+        tv.run(p.scene, p.scene.bvhNodes, smemNodes, p.smemNodeCount, p.refillThreshold, &tc, stack);
     }
     if (COUNT) { atomicAdd(ctr + kCtrShadowNodeVisits, tc.nodeVisits); atomicAdd(ctr + kCtrShadowTriTests, tc.triTests); atomicAdd(ctr + kCtrShadowVisible, visibleCount); }
 }
@@ -253,24 +293,43 @@ __global__ void __launch_bounds__(256) k_commit_accumulate(const __grid_constant
     }
 }
 
-// ---- standalone ray queries (parity tests, traversal benchmark) ----------------------------------------------------------------------------
+// ---- standalone ray queries (parity tests, traversal benchmark): same Traverser and dynamic fetch as the wavefront kernels ------------------
 template <bool ANY_HIT>
-__global__ void __launch_bounds__(256, 2) k_trace_rays(const __grid_constant__ LaunchParams p, const RtxptRay* __restrict__ rays, uint count, RtxptHit* __restrict__ out, uint* counters)
+__global__ void __launch_bounds__(256, 2) k_trace_rays(const __grid_constant__ LaunchParams p, const RtxptRay* __restrict__ rays, uint count, RtxptHit* __restrict__ out, uint* counters, uint* cursor)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smemRaw);
     uint4* smemNodes = reinterpret_cast<uint4*>(smemRaw + 16);
     stageNodesToShared(smemNodes, p.scene.bvhNodes, p.smemNodeCount, mbar);
     TraversalCounters tc; tc.nodeVisits = 0; tc.triTests = 0;
-    for (uint i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    const uint lane = threadIdx.x & 31u;
+    Traverser<ANY_HIT, true> tv; tv.done = true;
+    uint2 stack[kTraversalStackSize];
+    bool hasRay = false; uint index = 0;
+    while (true)
     {
-        const float4 a = reinterpret_cast<const float4*>(rays)[i * 2], b = reinterpret_cast<const float4*>(rays)[i * 2 + 1];
-        uint subInstance;
-        const HitRecord h = traceRay<ANY_HIT, true>(p.scene, p.scene.bvhNodes, smemNodes, p.smemNodeCount, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w, &tc, &subInstance);
-        RtxptHit r;
-        if (h.gid != 0xFFFFFFFFu) { const uint4 info = p.scene.triInfo[h.gid]; r.t = h.t; r.u = h.u; r.v = h.v; r.instanceIndex = info.x; r.geometryIndex = info.y; r.primitiveIndex = info.z; }
-        else { r.t = -1.0f; r.u = r.v = 0.f; r.instanceIndex = r.geometryIndex = r.primitiveIndex = 0xFFFFFFFFu; }
-        out[i] = r;
+        if (tv.done)
+        {
+            const uint active = __activemask();
+            if (hasRay)
+            {
+                const HitRecord h = tv.result();
+                RtxptHit r;
+                if (h.gid != 0xFFFFFFFFu) { const uint4 info = p.scene.triInfo[h.gid]; r.t = h.t; r.u = h.u; r.v = h.v; r.instanceIndex = info.x; r.geometryIndex = info.y; r.primitiveIndex = info.z; }
+                else { r.t = -1.0f; r.u = r.v = 0.f; r.instanceIndex = r.geometryIndex = r.primitiveIndex = 0xFFFFFFFFu; }
+                out[index] = r;
+                hasRay = false;
+            }
+            const uint leader = __ffs(active) - 1u;
+            uint base = 0;
+            if (lane == leader) base = atomicAdd(cursor, __popc(active));
+            index = __shfl_sync(active, base, leader) + __popc(active & ((1u << lane) - 1u));
+            if (index >= count) break;
+            const float4 a = reinterpret_cast<const float4*>(rays)[index * 2], b = reinterpret_cast<const float4*>(rays)[index * 2 + 1];
+            tv.init(p.scene, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w);
+            hasRay = true;
+        }
+        tv.run(p.scene, p.scene.bvhNodes, smemNodes, p.smemNodeCount, p.refillThreshold, &tc, stack);
     }
     if (counters) { atomicAdd(counters + 0, tc.nodeVisits); atomicAdd(counters + 1, tc.triTests); }
 }
@@ -355,10 +414,11 @@ void launchTraceShadow(const LaunchParams& p, const GridConfig& g, bool count, c
     else k_trace_shadow<false><<<g.smCount * g.traceBlocksPerSM, 256, traceSmemBytes(p), s>>>(p);
 }
 void launchCommitAccumulate(const LaunchParams& p, const GridConfig& g, cudaStream_t s) { k_commit_accumulate<<<g.smCount * 4, 256, 0, s>>>(p); }
-void launchTraceRays(const LaunchParams& p, const GridConfig& g, const RtxptRay* rays, uint32_t count, bool anyHit, RtxptHit* out, uint32_t* counters, cudaStream_t s)
+void launchTraceRays(const LaunchParams& p, const GridConfig& g, const RtxptRay* rays, uint32_t count, bool anyHit, RtxptHit* out, uint32_t* counters, uint32_t* cursor, cudaStream_t s)
 {
-    if (anyHit) k_trace_rays<true><<<g.smCount * g.traceBlocksPerSM, 256, traceSmemBytes(p), s>>>(p, rays, count, out, counters);
-    else k_trace_rays<false><<<g.smCount * g.traceBlocksPerSM, 256, traceSmemBytes(p), s>>>(p, rays, count, out, counters);
+    cudaMemsetAsync(cursor, 0, sizeof(uint32_t), s);
+    if (anyHit) k_trace_rays<true><<<g.smCount * g.traceBlocksPerSM, 256, traceSmemBytes(p), s>>>(p, rays, count, out, counters, cursor);
+    else k_trace_rays<false><<<g.smCount * g.traceBlocksPerSM, 256, traceSmemBytes(p), s>>>(p, rays, count, out, counters, cursor);
 }
 void launchDebugBsdf(const float* in, uint32_t count, float* out, cudaStream_t s) { k_debug_bsdf<<<(count + 127) / 128, 128, 0, s>>>(in, count, out); }
 void launchDebugRng(const uint32_t* in, uint32_t count, uint32_t* out, cudaStream_t s) { k_debug_rng<<<(count + 127) / 128, 128, 0, s>>>(in, count, out); }

@@ -14,7 +14,7 @@ void launchTraceClosest(const LaunchParams& p, const GridConfig& g, bool countSt
 void launchShade(const LaunchParams& p, const GridConfig& g, cudaStream_t s);
 void launchTraceShadow(const LaunchParams& p, const GridConfig& g, bool countSteps, cudaStream_t s);
 void launchCommitAccumulate(const LaunchParams& p, const GridConfig& g, cudaStream_t s);
-void launchTraceRays(const LaunchParams& p, const GridConfig& g, const RtxptRay* dRays, uint32_t count, bool anyHit, RtxptHit* dHits, uint32_t* dCounters, cudaStream_t s);
+void launchTraceRays(const LaunchParams& p, const GridConfig& g, const RtxptRay* dRays, uint32_t count, bool anyHit, RtxptHit* dHits, uint32_t* dCounters, uint32_t* dCursor, cudaStream_t s);
 void launchPackOwned(const float4* image, const uint32_t* pixelOfSlot, uint32_t pixelCount, uint32_t paddedCount, uint32_t width, float4* dst, const GridConfig& g, cudaStream_t s);
 void launchUnpackAll(const float4* srcAll, const uint32_t* allPixelTable, uint32_t totalEntries, uint32_t width, float4* image, const GridConfig& g, cudaStream_t s);
 void launchDebugBsdf(const float* dIn, uint32_t count, float* dOut, cudaStream_t s);

@@ -82,114 +82,131 @@ struct TraversalCounters { uint nodeVisits, triTests; };
 // Extracts byte j of a packed word as float
 PT_DEVICE float byteToFloat(uint w, int j) { return float((w >> (8 * j)) & 0xFFu); }
 
+// Resumable per-lane traversal state.  A persistent warp keeps one Traverser per lane; run() advances the lane's ray until it finishes
+// or until so few lanes of the warp are still working that the warp should return to its caller to fetch new rays for the idle lanes
+// (dynamic fetch, Aila & Laine HPG 2009) — the caller then re-enters run() on the unfinished lanes.
+// The traversal stack is a separate local array owned by the kernel so that the scalar state below stays in registers.
 template <bool ANY_HIT, bool COUNT>
-PT_DEVICE HitRecord traceRay(const SceneView& sc, const uint4* __restrict__ nodes, const uint4* __restrict__ smemNodes, uint smemNodeCount,
-                             float3 org, float3 dir, float tMin, float tMax, TraversalCounters* counters, uint* subInstanceOut)
+struct Traverser
 {
-    HitRecord best; best.t = tMax; best.u = 0; best.v = 0; best.gid = 0xFFFFFFFFu;
-    if (sc.bvhTriCount == 0) { best.t = -1.0f; return best; }
+    float3 org, dir;
+    float idx, idy, idz, tMin, tMax;
+    WatertightRay wr;
+    HitRecord best; uint bestSubInstance;
+    uint2 nodeGroup, triGroup;
+    uint octinv;
+    int sp;
+    bool done;
 
-    WatertightRay wr; wr.setup(dir);
-    const float eps = 1.0e-30f;
-    const float idx = 1.0f / (fabsf(dir.x) > eps ? dir.x : copysignf(eps, dir.x));
-    const float idy = 1.0f / (fabsf(dir.y) > eps ? dir.y : copysignf(eps, dir.y));
-    const float idz = 1.0f / (fabsf(dir.z) > eps ? dir.z : copysignf(eps, dir.z));
-    const uint oct = (dir.x < 0.0f ? 4u : 0u) | (dir.y < 0.0f ? 2u : 0u) | (dir.z < 0.0f ? 1u : 0u);
-    const uint octinv = 7u - oct;
-    const uint octinv4 = octinv * 0x01010101u;
-
-    uint2 stack[kTraversalStackSize];
-    int sp = 0;
-    uint2 nodeGroup = make_uint2(0u, 0x80000000u);      // virtual parent of the root: one internal child in slot 7^octinv
-    uint2 triGroup = make_uint2(0u, 0u);
-
-    while (true)
+    PT_DEVICE void init(const SceneView& sc, float3 o, float3 d, float tmin, float tmax)
     {
-        if (nodeGroup.y & 0xFF000000u)
-        {
-            const uint hits = nodeGroup.y;
-            const uint bitIndex = 31u - __clz(hits & 0xFF000000u);
-            nodeGroup.y &= ~(1u << bitIndex);
-            if (nodeGroup.y & 0xFF000000u) { if (sp < kTraversalStackSize) stack[sp++] = nodeGroup; }
-            const uint slot = (bitIndex - 24u) ^ octinv;
-            const uint rel = __popc(hits & ~(0xFFFFFFFFu << slot) & 0xFFu);
-            const uint nodeIndex = nodeGroup.x + rel;
-            const uint4* np = (nodeIndex < smemNodeCount) ? (smemNodes + nodeIndex * 5) : (nodes + size_t(nodeIndex) * 5);
-            const uint4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3], n4 = np[4];
-            if (COUNT) counters->nodeVisits++;
+        org = o; dir = d; tMin = tmin; tMax = tmax;
+        best.t = tmax; best.u = 0; best.v = 0; best.gid = 0xFFFFFFFFu; bestSubInstance = 0;
+        wr.setup(d);
+        const float eps = 1.0e-30f;
+        idx = 1.0f / (fabsf(d.x) > eps ? d.x : copysignf(eps, d.x));
+        idy = 1.0f / (fabsf(d.y) > eps ? d.y : copysignf(eps, d.y));
+        idz = 1.0f / (fabsf(d.z) > eps ? d.z : copysignf(eps, d.z));
+        octinv = 7u - ((d.x < 0.0f ? 4u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 1u : 0u));
+        sp = 0;
+        nodeGroup = make_uint2(0u, 0x80000000u);        // virtual parent of the root: one internal child in slot 7^octinv
+        triGroup = make_uint2(0u, 0u);
+        done = (sc.bvhTriCount == 0);
+    }
 
-            const float px = __uint_as_float(n0.x), py = __uint_as_float(n0.y), pz = __uint_as_float(n0.z);
-            const float sx = __uint_as_float((n0.w & 0xFFu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23), sz = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23);
-            const uint imask = n0.w >> 24;
-            nodeGroup.x = n1.x; triGroup.x = n1.y;
-            const float adx = sx * idx, ady = sy * idy, adz = sz * idz;
-            const float ox = (px - org.x) * idx, oy = (py - org.y) * idy, oz = (pz - org.z) * idz;
-            uint hitmask = 0;
-            #pragma unroll
-            for (int half = 0; half < 2; half++)
+    PT_DEVICE HitRecord result() const { HitRecord r = best; if (r.gid == 0xFFFFFFFFu) r.t = -1.0f; return r; }
+
+    PT_DEVICE void run(const SceneView& sc, const uint4* __restrict__ nodes, const uint4* __restrict__ smemNodes, uint smemNodeCount, int minActiveLanes,
+                       TraversalCounters* counters, uint2* __restrict__ stack)
+    {
+        const uint octinv4 = octinv * 0x01010101u;
+        while (!done)
+        {
+            if (nodeGroup.y & 0xFF000000u)
             {
-                const uint meta4 = half ? n1.w : n1.z;
-                const uint isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-                const uint innerMask4 = (isInner4 >> 4) * 0xFFu;
-                const uint bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1F1F1F1Fu;
-                const uint childBits4 = (meta4 >> 5) & 0x07070707u;
-                const uint qlox = half ? n2.y : n2.x, qloy = half ? n2.w : n2.z, qloz = half ? n3.y : n3.x;
-                const uint qhix = half ? n3.w : n3.z, qhiy = half ? n4.y : n4.x, qhiz = half ? n4.w : n4.z;
-                const uint nearx = (dir.x < 0.0f) ? qhix : qlox, farx = (dir.x < 0.0f) ? qlox : qhix;
-                const uint neary = (dir.y < 0.0f) ? qhiy : qloy, fary = (dir.y < 0.0f) ? qloy : qhiy;
-                const uint nearz = (dir.z < 0.0f) ? qhiz : qloz, farz = (dir.z < 0.0f) ? qloz : qhiz;
+                const uint hits = nodeGroup.y;
+                const uint bitIndex = 31u - __clz(hits & 0xFF000000u);
+                nodeGroup.y &= ~(1u << bitIndex);
+                if (nodeGroup.y & 0xFF000000u) { if (sp < kTraversalStackSize) stack[sp++] = nodeGroup; }
+                const uint slot = (bitIndex - 24u) ^ octinv;
+                const uint rel = __popc(hits & ~(0xFFFFFFFFu << slot) & 0xFFu);
+                const uint nodeIndex = nodeGroup.x + rel;
+                const uint4* np = (nodeIndex < smemNodeCount) ? (smemNodes + nodeIndex * 5) : (nodes + size_t(nodeIndex) * 5);
+                const uint4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3], n4 = np[4];
+                if (COUNT) counters->nodeVisits++;
+
+                const float px = __uint_as_float(n0.x), py = __uint_as_float(n0.y), pz = __uint_as_float(n0.z);
+                const float sx = __uint_as_float((n0.w & 0xFFu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23), sz = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23);
+                const uint imask = n0.w >> 24;
+                nodeGroup.x = n1.x; triGroup.x = n1.y;
+                const float adx = sx * idx, ady = sy * idy, adz = sz * idz;
+                const float ox = (px - org.x) * idx, oy = (py - org.y) * idy, oz = (pz - org.z) * idz;
+                uint hitmask = 0;
                 #pragma unroll
-                for (int j = 0; j < 4; j++)
+                for (int half = 0; half < 2; half++)
                 {
-                    const float t0x = byteToFloat(nearx, j) * adx + ox, t1x = byteToFloat(farx, j) * adx + ox;
-                    const float t0y = byteToFloat(neary, j) * ady + oy, t1y = byteToFloat(fary, j) * ady + oy;
-                    const float t0z = byteToFloat(nearz, j) * adz + oz, t1z = byteToFloat(farz, j) * adz + oz;
-                    float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tMin));
-                    float cmax = fminf(fminf(t1x, t1y), fminf(t1z, best.t));
-                    // conservative slack for the float rounding of the decoded planes and slab distances
-                    cmin -= fabsf(cmin) * 6.0e-7f; cmax += fabsf(cmax) * 6.0e-7f;
-                    if (cmin <= cmax)
-                        hitmask |= ((childBits4 >> (8 * j)) & 0xFFu) << ((bitIndex4 >> (8 * j)) & 0xFFu);
+                    const uint meta4 = half ? n1.w : n1.z;
+                    const uint isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+                    const uint innerMask4 = (isInner4 >> 4) * 0xFFu;
+                    const uint bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1F1F1F1Fu;
+                    const uint childBits4 = (meta4 >> 5) & 0x07070707u;
+                    const uint qlox = half ? n2.y : n2.x, qloy = half ? n2.w : n2.z, qloz = half ? n3.y : n3.x;
+                    const uint qhix = half ? n3.w : n3.z, qhiy = half ? n4.y : n4.x, qhiz = half ? n4.w : n4.z;
+                    const uint nearx = (dir.x < 0.0f) ? qhix : qlox, farx = (dir.x < 0.0f) ? qlox : qhix;
+                    const uint neary = (dir.y < 0.0f) ? qhiy : qloy, fary = (dir.y < 0.0f) ? qloy : qhiy;
+                    const uint nearz = (dir.z < 0.0f) ? qhiz : qloz, farz = (dir.z < 0.0f) ? qloz : qhiz;
+                    #pragma unroll
+                    for (int j = 0; j < 4; j++)
+                    {
+                        // slab distances with one FMA each; the box test only has to be conservative (the triangle test decides), see the slack below
+                        const float t0x = __fmaf_rn(byteToFloat(nearx, j), adx, ox), t1x = __fmaf_rn(byteToFloat(farx, j), adx, ox);
+                        const float t0y = __fmaf_rn(byteToFloat(neary, j), ady, oy), t1y = __fmaf_rn(byteToFloat(fary, j), ady, oy);
+                        const float t0z = __fmaf_rn(byteToFloat(nearz, j), adz, oz), t1z = __fmaf_rn(byteToFloat(farz, j), adz, oz);
+                        float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tMin));
+                        float cmax = fminf(fminf(t1x, t1y), fminf(t1z, best.t));
+                        cmin = __fmaf_rn(-fabsf(cmin), 6.0e-7f, cmin); cmax = __fmaf_rn(fabsf(cmax), 6.0e-7f, cmax);
+                        if (cmin <= cmax)
+                            hitmask |= ((childBits4 >> (8 * j)) & 0xFFu) << ((bitIndex4 >> (8 * j)) & 0xFFu);
+                    }
                 }
+                nodeGroup.y = (hitmask & 0xFF000000u) | imask;
+                triGroup.y = hitmask & 0x00FFFFFFu;
             }
-            nodeGroup.y = (hitmask & 0xFF000000u) | imask;
-            triGroup.y = hitmask & 0x00FFFFFFu;
-        }
-        else
-        {
-            triGroup = nodeGroup;
-            nodeGroup = make_uint2(0u, 0u);
-        }
-
-        while (triGroup.y != 0)
-        {
-            const uint k = __ffs(triGroup.y) - 1;
-            triGroup.y &= triGroup.y - 1;
-            const float4* tp = sc.bvhTris + size_t(triGroup.x + k) * 3;
-            const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-            if (COUNT) counters->triTests++;
-            float t, u, v;
-            if (!intersectTriangleWatertight(wr, org, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), tMin, tMax, t, u, v)) continue;
-            const uint gid = __float_as_uint(a.w);
-            if (best.gid != 0xFFFFFFFFu ? !(t < best.t || (t == best.t && gid < best.gid)) : !(t < best.t)) continue;
-            const uint sub = __float_as_uint(b.w);
-            if (sub & (kTriFlagAlphaTested | kTriFlagExcludeFromNEE))
-            {   // non-opaque geometry (SampleCommon/AccelerationStructureUtil.h:88-89)
-                if (ANY_HIT && (sub & kTriFlagExcludeFromNEE)) continue;
-                if ((sub & kTriFlagAlphaTested) && !alphaTestPasses(sc, sc.subInstances[sub & kTriSubInstanceMask], __float_as_uint(c.w), u, v)) continue;
+            else
+            {
+                triGroup = nodeGroup;
+                nodeGroup = make_uint2(0u, 0u);
             }
-            best.t = t; best.u = u; best.v = v; best.gid = gid; *subInstanceOut = sub & kTriSubInstanceMask;
-            if (ANY_HIT) return best;
-        }
 
-        if ((nodeGroup.y & 0xFF000000u) == 0)
-        {
-            if (sp == 0) break;
-            nodeGroup = stack[--sp];
+            while (triGroup.y != 0)
+            {
+                const uint k = __ffs(triGroup.y) - 1;
+                triGroup.y &= triGroup.y - 1;
+                const float4* tp = sc.bvhTris + size_t(triGroup.x + k) * 3;
+                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                if (COUNT) counters->triTests++;
+                float t, u, v;
+                if (!intersectTriangleWatertight(wr, org, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), tMin, tMax, t, u, v)) continue;
+                const uint gid = __float_as_uint(a.w);
+                if (best.gid != 0xFFFFFFFFu ? !(t < best.t || (t == best.t && gid < best.gid)) : !(t < best.t)) continue;
+                const uint sub = __float_as_uint(b.w);
+                if (sub & (kTriFlagAlphaTested | kTriFlagExcludeFromNEE))
+                {   // non-opaque geometry (SampleCommon/AccelerationStructureUtil.h:88-89)
+                    if (ANY_HIT && (sub & kTriFlagExcludeFromNEE)) continue;
+                    if ((sub & kTriFlagAlphaTested) && !alphaTestPasses(sc, sc.subInstances[sub & kTriSubInstanceMask], __float_as_uint(c.w), u, v)) continue;
+                }
+                best.t = t; best.u = u; best.v = v; best.gid = gid; bestSubInstance = sub & kTriSubInstanceMask;
+                if (ANY_HIT) { done = true; return; }
+            }
+
+            if ((nodeGroup.y & 0xFF000000u) == 0)
+            {
+                if (sp == 0) { done = true; return; }
+                nodeGroup = stack[--sp];
+            }
+            if (__popc(__activemask()) < minActiveLanes) return;        // let the warp refill its idle lanes
         }
     }
-    if (best.gid == 0xFFFFFFFFu) best.t = -1.0f;
-    return best;
-}
+};
 
 } // namespace pt

@@ -44,6 +44,9 @@ constexpr int kCtrTriTests = kCtrNodeVisits + 1;
 constexpr int kCtrShadowVisible = kCtrTriTests + 1;
 constexpr int kCtrShadowNodeVisits = kCtrShadowVisible + 1;  // any-hit traversal
 constexpr int kCtrShadowTriTests = kCtrShadowNodeVisits + 1;
+constexpr int kCtrFetchClosest = kCtrShadowTriTests + 1;    // dynamic ray fetch cursors of the persistent traversal warps
+constexpr int kCtrFetchShadow = kCtrFetchClosest + 1;
+static_assert(kCtrFetchShadow < 16, "counter block");
 constexpr int kCountersPerIter = 16;
 
 struct LaunchParams
@@ -56,6 +59,7 @@ struct LaunchParams
     uint iteration;
     uint smemNodeCount;             // BVH nodes staged in shared memory
     uint flags;
+    int refillThreshold;            // dynamic fetch: a warp refills its idle lanes when fewer than this many lanes are still traversing
     // render targets
     uint2* outputColor;             // RGBA16F, full frame, last sub-sample
     float4* accumulated;            // RGBA32F, full frame
