@@ -399,8 +399,13 @@ static void fillParams(rtxpt_ctx* c, LaunchParams& p)
     p.flags = c->cfg.flags;
     { const char* e = getenv("RTXPT_REFILL_THRESHOLD"); p.refillThreshold = e ? atoi(e) : 24; }     // tuning knob; 8..24 measured equal within noise on B200
     p.outputColor = c->outputColor.ptr; p.accumulated = c->accumulated.ptr; p.depth = c->depth.ptr;
-    // shared-memory BVH prefix: as many breadth-first nodes as fit next to two resident CTAs
-    const uint32_t budget = uint32_t(std::max(0, std::min(c->maxSmemOptin, 100 * 1024) - 1024));
+    // traversal occupancy and the shared-memory BVH prefix are chosen together: B resident CTAs of 256 threads per SM (register budget
+    // 65536 / (256 B): 128 / 85 / 64 registers for B = 2 / 3 / 4) share the 227 KB of shared memory
+    int blocks = 3;
+    { const char* e = getenv("RTXPT_TRACE_CTAS"); if (e) blocks = std::min(4, std::max(2, atoi(e))); }
+    c->grid.traceBlocksPerSM = blocks;
+    { int sb = 4; const char* e = getenv("RTXPT_SHADE_CTAS"); if (e) sb = std::min(5, std::max(3, atoi(e))); c->grid.shadeBlocksPerSM = sb; }
+    const uint32_t budget = uint32_t(std::max(0, std::min(c->maxSmemOptin, (227 * 1024) / blocks - 2048) - 1024));
     p.smemNodeCount = std::min(c->bvhNodeCount, budget / 80u);
 }
 

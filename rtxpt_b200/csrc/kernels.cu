@@ -108,8 +108,8 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ Launch
 // next ray from the queue cursor; lanes still traversing resume where they stopped.  Keeps SIMT lanes busy although ray lengths differ
 // by an order of magnitude.
 
-template <bool COUNT>
-__global__ void __launch_bounds__(256, 2) k_trace_closest(const __grid_constant__ LaunchParams p)
+template <bool COUNT, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_trace_closest(const __grid_constant__ LaunchParams p)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     uint* ctr = p.wf.counters + p.iteration * kCountersPerIter;
@@ -165,7 +165,8 @@ __global__ void __launch_bounds__(256, 2) k_trace_closest(const __grid_constant_
 }
 
 // ---- shade --------------------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_shade(const __grid_constant__ LaunchParams p)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_shade(const __grid_constant__ LaunchParams p)
 {
     uint* ctr = p.wf.counters + p.iteration * kCountersPerIter;
     uint* ctrNext = ctr + kCountersPerIter;
@@ -209,8 +210,8 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ LaunchPar
 }
 
 // ---- shadow rays ----------------------------------------------------------------------------------------------------------------------------
-template <bool COUNT>
-__global__ void __launch_bounds__(256, 2) k_trace_shadow(const __grid_constant__ LaunchParams p)
+template <bool COUNT, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_trace_shadow(const __grid_constant__ LaunchParams p)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     uint* ctr = p.wf.counters + p.iteration * kCountersPerIter;
@@ -388,30 +389,43 @@ void launchUnpackAll(const float4* srcAll, const uint32_t* allPixelTable, uint32
 // ---- launch wrappers ---------------------------------------------------------------------------------------------------------------------------
 static size_t traceSmemBytes(const LaunchParams& p) { return 16 + size_t(p.smemNodeCount) * 80; }
 
+template <typename K> static cudaError_t allowSmem(K kernel, int bytes) { return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); }
+
 cudaError_t configureKernels(int maxSmemOptin)
 {
     cudaError_t e;
     const int want = maxSmemOptin > 0 ? maxSmemOptin : 0;
-    if ((e = cudaFuncSetAttribute(k_trace_closest<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, want)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_trace_closest<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, want)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_trace_shadow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, want)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_trace_shadow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, want)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_trace_rays<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, want)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_trace_rays<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, want)) != cudaSuccess) return e;
+#define ALLOW(k) if ((e = allowSmem(k, want)) != cudaSuccess) return e
+    ALLOW((k_trace_closest<false, 2>)); ALLOW((k_trace_closest<false, 3>)); ALLOW((k_trace_closest<false, 4>)); ALLOW((k_trace_closest<true, 2>));
+    ALLOW((k_trace_shadow<false, 2>)); ALLOW((k_trace_shadow<false, 3>)); ALLOW((k_trace_shadow<false, 4>)); ALLOW((k_trace_shadow<true, 2>));
+    ALLOW(k_trace_rays<false>); ALLOW(k_trace_rays<true>);
+#undef ALLOW
     return cudaSuccess;
 }
 
 void launchGenerate(const LaunchParams& p, const GridConfig& g, cudaStream_t s) { k_generate<<<g.smCount * 4, 256, 0, s>>>(p); }
 void launchTraceClosest(const LaunchParams& p, const GridConfig& g, bool count, cudaStream_t s)
 {
-    if (count) k_trace_closest<true><<<g.smCount * g.traceBlocksPerSM, 256, traceSmemBytes(p), s>>>(p);
-    else k_trace_closest<false><<<g.smCount * g.traceBlocksPerSM, 256, traceSmemBytes(p), s>>>(p);
+    const int grid = g.smCount * g.traceBlocksPerSM; const size_t smem = traceSmemBytes(p);
+    if (count) k_trace_closest<true, 2><<<grid, 256, smem, s>>>(p);
+    else if (g.traceBlocksPerSM >= 4) k_trace_closest<false, 4><<<grid, 256, smem, s>>>(p);
+    else if (g.traceBlocksPerSM == 3) k_trace_closest<false, 3><<<grid, 256, smem, s>>>(p);
+    else k_trace_closest<false, 2><<<grid, 256, smem, s>>>(p);
 }
-void launchShade(const LaunchParams& p, const GridConfig& g, cudaStream_t s) { k_shade<<<g.smCount * g.shadeBlocksPerSM, 128, 0, s>>>(p); }
+void launchShade(const LaunchParams& p, const GridConfig& g, cudaStream_t s)
+{
+    const int grid = g.smCount * g.shadeBlocksPerSM;
+    if (g.shadeBlocksPerSM >= 5) k_shade<5><<<grid, 128, 0, s>>>(p);
+    else if (g.shadeBlocksPerSM == 4) k_shade<4><<<grid, 128, 0, s>>>(p);
+    else k_shade<3><<<grid, 128, 0, s>>>(p);
+}
 void launchTraceShadow(const LaunchParams& p, const GridConfig& g, bool count, cudaStream_t s)
 {
-    if (count) k_trace_shadow<true><<<g.smCount * g.traceBlocksPerSM, 256, traceSmemBytes(p), s>>>(p);
-    else k_trace_shadow<false><<<g.smCount * g.traceBlocksPerSM, 256, traceSmemBytes(p), s>>>(p);
+    const int grid = g.smCount * g.traceBlocksPerSM; const size_t smem = traceSmemBytes(p);
+    if (count) k_trace_shadow<true, 2><<<grid, 256, smem, s>>>(p);
+    else if (g.traceBlocksPerSM >= 4) k_trace_shadow<false, 4><<<grid, 256, smem, s>>>(p);
+    else if (g.traceBlocksPerSM == 3) k_trace_shadow<false, 3><<<grid, 256, smem, s>>>(p);
+    else k_trace_shadow<false, 2><<<grid, 256, smem, s>>>(p);
 }
 void launchCommitAccumulate(const LaunchParams& p, const GridConfig& g, cudaStream_t s) { k_commit_accumulate<<<g.smCount * 4, 256, 0, s>>>(p); }
 void launchTraceRays(const LaunchParams& p, const GridConfig& g, const RtxptRay* rays, uint32_t count, bool anyHit, RtxptHit* out, uint32_t* counters, uint32_t* cursor, cudaStream_t s)
@@ -425,11 +439,7 @@ void launchDebugRng(const uint32_t* in, uint32_t count, uint32_t* out, cudaStrea
 
 void queryOccupancy(GridConfig& g, size_t smemBytes)
 {
-    int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_closest<false>, 256, smemBytes);
-    g.traceBlocksPerSM = n > 0 ? n : 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade, 128, 0);
-    g.shadeBlocksPerSM = n > 0 ? n : 1;
+    (void)g; (void)smemBytes;    // traceBlocksPerSM is chosen by the caller together with the shared-memory node budget
 }
 
 } // namespace pt

@@ -477,10 +477,42 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
         float3 pickLi = mk3(0.f), pickDir = mk3(0.f); float pickDist = 0.f, pickSelPdf = 0.f, pickSolidPdf = 0.f;
         float weightSum = 0.f, pickWeight = 0.f;
         const uint M = p.scene.samplingProxyCount;
+        // The candidate loop is a chain of dependent random gathers (proxy table -> counter, light record).  The light selection draws are
+        // every 4th value of the stream, so the proxy lookups of the first 8 candidates are issued up front and their light records
+        // prefetched into L2/L1 before the loop consumes them one by one.
+        constexpr uint kPrefetch = 8;
+        uint preLight[kPrefetch];
+        {
+            UniformSeq pre = uniformSG;
+            #pragma unroll
+            for (uint i = 0; i < kPrefetch; i++)
+            {
+                preLight[i] = 0;
+                if (i < candidateCount)
+                {
+                    const float rnd = pre.next(); pre.next(); pre.next(); pre.next();
+                    preLight[i] = __ldg(p.scene.proxyIndices + min(uint(rnd * float(M)), M - 1));
+                }
+            }
+            #pragma unroll
+            for (uint i = 0; i < kPrefetch; i++)
+                if (i < candidateCount)
+                {
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(p.scene.lights + preLight[i]));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(p.scene.proxyCounters + preLight[i]));
+                }
+        }
+        #pragma unroll 1
         for (uint i = 0; i < candidateCount; i++)
         {
             const float rnd = uniformSG.next();
-            const uint lightIndex = p.scene.proxyIndices[min(uint(rnd * float(M)), M - 1)];
+            uint lightIndex;
+            switch (i)
+            {   // static indexing keeps preLight[] in registers
+            case 0: lightIndex = preLight[0]; break; case 1: lightIndex = preLight[1]; break; case 2: lightIndex = preLight[2]; break; case 3: lightIndex = preLight[3]; break;
+            case 4: lightIndex = preLight[4]; break; case 5: lightIndex = preLight[5]; break; case 6: lightIndex = preLight[6]; break; case 7: lightIndex = preLight[7]; break;
+            default: lightIndex = p.scene.proxyIndices[min(uint(rnd * float(M)), M - 1)]; break;
+            }
             const float selectionPdf = float(p.scene.proxyCounters[lightIndex]) / float(M);
             const LightInfo li = p.scene.lights[lightIndex];
             const float r0 = uniformSG.next(), r1 = uniformSG.next();
