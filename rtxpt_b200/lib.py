@@ -9,7 +9,8 @@ from . import structs as S
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "_build", "librtxpt_b200.so")
+LIB_PATH = os.path.join(CSRC, "_build", "librtxpt_b200.so")                  # default build (FMA, approximate div/sqrt)
+LIB_PATH_STRICT = os.path.join(CSRC, "_build", "librtxpt_b200_strict.so")    # IEEE-exact arithmetic build, same sources and ABI (csrc/Makefile)
 
 
 class RtxptError(RuntimeError):
@@ -23,7 +24,7 @@ def build(verbose=False):
         raise RtxptError("building librtxpt_b200.so failed:\n" + (r.stdout or "") + (r.stderr or ""))
 
 
-_lib = None
+_libs = {}
 
 _SIGNATURES = {
     "rtxpt_b200_create": [C.POINTER(S.Config), C.POINTER(C.c_void_p)],
@@ -49,27 +50,30 @@ _SIGNATURES = {
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["rtxpt_b200_last_error"])
 
 
-def load():
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise RtxptError(f"{LIB_PATH} is missing: run rtxpt_b200.lib.build() / `make -C rtxpt_b200/csrc` (no fallback path exists)")
-        L = C.CDLL(LIB_PATH)
+def load(strict=None):
+    """Loads one of the two builds of the product; `strict=None` follows the RTXPT_STRICT environment variable (default: fast build)."""
+    if strict is None:
+        strict = os.environ.get("RTXPT_STRICT", "0") == "1"
+    if strict not in _libs:
+        path = LIB_PATH_STRICT if strict else LIB_PATH
+        if not os.path.exists(path):
+            raise RtxptError(f"{path} is missing: run rtxpt_b200.lib.build() / `make -C rtxpt_b200/csrc` (no fallback path exists)")
+        L = C.CDLL(path)
         for name, args in _SIGNATURES.items():
             fn = getattr(L, name); fn.argtypes = args; fn.restype = C.c_int
         L.rtxpt_b200_last_error.restype = C.c_char_p
-        _lib = L
-    return _lib
+        _libs[strict] = L
+    return _libs[strict]
 
 
-def _check(rc):
+def _check(rc, L=None):
     if rc != 0:
-        raise RtxptError(f"rtxpt_b200 error {rc}: {load().rtxpt_b200_last_error().decode()}")
+        raise RtxptError(f"rtxpt_b200 error {rc}: {(L or load()).rtxpt_b200_last_error().decode()}")
 
 
 class Context:
-    def __init__(self, max_sub_samples_per_launch=1, device=-1, tile_rank=0, tile_world=1, tile_size=64, flags=0, max_width=0, max_height=0):
-        L = load()
+    def __init__(self, max_sub_samples_per_launch=1, device=-1, tile_rank=0, tile_world=1, tile_size=64, flags=0, max_width=0, max_height=0, strict=None):
+        L = self.L = load(strict)
         cfg = S.Config(device, max_width, max_height, max_sub_samples_per_launch, tile_rank, tile_world, tile_size, flags)
         self.h = C.c_void_p()
         _check(L.rtxpt_b200_create(C.byref(cfg), C.byref(self.h)))
@@ -77,7 +81,7 @@ class Context:
 
     def close(self):
         if self.h:
-            load().rtxpt_b200_destroy(self.h); self.h = None
+            self.L.rtxpt_b200_destroy(self.h); self.h = None
 
     def __del__(self):
         try:
@@ -87,85 +91,85 @@ class Context:
 
     def upload_scene(self, scene):
         self.scene = scene
-        _check(load().rtxpt_b200_upload_scene(self.h, C.byref(scene.desc)))
+        _check(self.L.rtxpt_b200_upload_scene(self.h, C.byref(scene.desc)), self.L)
 
     def set_constants(self, consts):
         self.consts = consts
-        _check(load().rtxpt_b200_set_constants(self.h, C.byref(consts)))
+        _check(self.L.rtxpt_b200_set_constants(self.h, C.byref(consts)), self.L)
 
     def path_trace(self, first_sub_sample, count, accumulate=True, stream=None):
-        _check(load().rtxpt_b200_path_trace(self.h, first_sub_sample, count, int(accumulate), stream))
+        _check(self.L.rtxpt_b200_path_trace(self.h, first_sub_sample, count, int(accumulate), stream), self.L)
 
     def reset_accumulation(self):
-        _check(load().rtxpt_b200_reset_accumulation(self.h))
+        _check(self.L.rtxpt_b200_reset_accumulation(self.h), self.L)
 
     def synchronize(self):
-        _check(load().rtxpt_b200_synchronize(self.h))
+        _check(self.L.rtxpt_b200_synchronize(self.h), self.L)
 
     def readback_accumulated(self):
         out = np.empty((self.consts.imageHeight, self.consts.imageWidth, 4), np.float32)
-        _check(load().rtxpt_b200_readback(self.h, S.BUFFER_ACCUMULATED_F32, out.ctypes.data, out.nbytes))
+        _check(self.L.rtxpt_b200_readback(self.h, S.BUFFER_ACCUMULATED_F32, out.ctypes.data, out.nbytes), self.L)
         return out
 
     def readback_output_color(self):
         out = np.empty((self.consts.imageHeight, self.consts.imageWidth, 4), np.float16)
-        _check(load().rtxpt_b200_readback(self.h, S.BUFFER_OUTPUT_COLOR_F16, out.ctypes.data, out.nbytes))
+        _check(self.L.rtxpt_b200_readback(self.h, S.BUFFER_OUTPUT_COLOR_F16, out.ctypes.data, out.nbytes), self.L)
         return out
 
     def device_ptr(self, buffer):
         p, n = C.c_void_p(), C.c_size_t()
-        _check(load().rtxpt_b200_device_ptr(self.h, buffer, C.byref(p), C.byref(n)))
+        _check(self.L.rtxpt_b200_device_ptr(self.h, buffer, C.byref(p), C.byref(n)), self.L)
         return p.value, n.value
 
     def render_frame(self, consts, first_sub_sample, count, out=None):
         self.consts = consts
         if out is None:
             out = np.empty((consts.imageHeight, consts.imageWidth, 4), np.float32)
-        _check(load().rtxpt_b200_render_frame(self.h, C.byref(consts), first_sub_sample, count, out.ctypes.data, out.nbytes))
+        _check(self.L.rtxpt_b200_render_frame(self.h, C.byref(consts), first_sub_sample, count, out.ctypes.data, out.nbytes), self.L)
         return out
 
     def stats(self):
         st = S.Stats()
-        _check(load().rtxpt_b200_get_stats(self.h, C.byref(st)))
+        _check(self.L.rtxpt_b200_get_stats(self.h, C.byref(st)), self.L)
         return st
 
     def tile_layout(self):
         a, b = C.c_uint32(), C.c_uint32()
-        _check(load().rtxpt_b200_tile_layout(self.h, C.byref(a), C.byref(b)))
+        _check(self.L.rtxpt_b200_tile_layout(self.h, C.byref(a), C.byref(b)), self.L)
         return a.value, b.value
 
     def pack_owned(self, d_dst, stream=None):
-        _check(load().rtxpt_b200_pack_owned(self.h, d_dst, stream))
+        _check(self.L.rtxpt_b200_pack_owned(self.h, d_dst, stream), self.L)
 
     def unpack_all(self, d_src_all, stream=None):
-        _check(load().rtxpt_b200_unpack_all(self.h, d_src_all, stream))
+        _check(self.L.rtxpt_b200_unpack_all(self.h, d_src_all, stream), self.L)
 
     def trace_rays(self, rays, any_hit=False):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
         hits = np.zeros(len(rays), dtype=[("t", "f4"), ("u", "f4"), ("v", "f4"), ("inst", "u4"), ("geom", "u4"), ("prim", "u4")])
-        _check(load().rtxpt_b200_trace_rays(self.h, rays.ctypes.data, len(rays), int(any_hit), hits.ctypes.data))
+        _check(self.L.rtxpt_b200_trace_rays(self.h, rays.ctypes.data, len(rays), int(any_hit), hits.ctypes.data), self.L)
         return hits
 
     def trace_rays_device(self, d_rays, count, d_hits, any_hit=False, repeat=1):
         ms = C.c_float()
-        _check(load().rtxpt_b200_trace_rays_device(self.h, d_rays, count, int(any_hit), d_hits, repeat, C.byref(ms)))
+        _check(self.L.rtxpt_b200_trace_rays_device(self.h, d_rays, count, int(any_hit), d_hits, repeat, C.byref(ms)), self.L)
         return ms.value
 
     def lights(self):
         n, m = C.c_uint32(0), C.c_uint32(0)
-        _check(load().rtxpt_b200_get_lights(self.h, None, C.byref(n), None, None, C.byref(m)))
+        _check(self.L.rtxpt_b200_get_lights(self.h, None, C.byref(n), None, None, C.byref(m)), self.L)
         infos = np.zeros((n.value, 8), np.uint32); counters = np.zeros(n.value, np.uint32); proxies = np.zeros(max(m.value, 1), np.uint32)
-        _check(load().rtxpt_b200_get_lights(self.h, infos.ctypes.data, C.byref(n), counters.ctypes.data, proxies.ctypes.data, C.byref(m)))
+        _check(self.L.rtxpt_b200_get_lights(self.h, infos.ctypes.data, C.byref(n), counters.ctypes.data, proxies.ctypes.data, C.byref(m)), self.L)
         return infos, counters, proxies[:m.value]
 
     def debug_bsdf(self, records):
         records = np.ascontiguousarray(records, np.float32).reshape(-1, 36)
         out = np.zeros((len(records), 16), np.float32)
-        _check(load().rtxpt_b200_debug_bsdf(self.h, records.ctypes.data, len(records), out.ctypes.data))
+        _check(self.L.rtxpt_b200_debug_bsdf(self.h, records.ctypes.data, len(records), out.ctypes.data), self.L)
         return out
 
     def debug_rng(self, tuples):
         tuples = np.ascontiguousarray(tuples, np.uint32).reshape(-1, 4)
         out = np.zeros((len(tuples), 8), np.uint32)
-        _check(load().rtxpt_b200_debug_rng(self.h, tuples.ctypes.data, len(tuples), out.ctypes.data))
+        _check(self.L.rtxpt_b200_debug_rng(self.h, tuples.ctypes.data, len(tuples), out.ctypes.data), self.L)
         return out

@@ -15,9 +15,10 @@ def declared_symbols():
 def test_library_exports_every_declared_symbol(product):
     names = declared_symbols()
     assert len(names) >= 20
-    L = C.CDLL(product.LIB_PATH)
-    for n in names:
-        assert hasattr(L, n), n
+    for path in (product.LIB_PATH, product.LIB_PATH_STRICT):
+        L = C.CDLL(path)
+        for n in names:
+            assert hasattr(L, n), (path, n)
     assert set(product.EXPORTED_SYMBOLS) == set(names)
 
 

@@ -8,9 +8,13 @@ from bsdf_records import make_records
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def ctx(product):
-    c = product.Context(max_sub_samples_per_launch=4)
+# Every test runs against both builds of the product (rtxpt_b200/csrc/Makefile): "fast" (default: FMA, approximate div/sqrt) and "strict"
+# (IEEE-exact arithmetic).  Integer / index results must be bit-exact in both; floating-point shading is held to the tolerance stated in
+# each test, and the strict build additionally has to be bit-identical to the oracle on almost every pixel.
+@pytest.fixture(scope="module", params=["fast", "strict"])
+def ctx(product, request):
+    c = product.Context(max_sub_samples_per_launch=4, strict=(request.param == "strict"))
+    c.variant = request.param
     yield c
     c.close()
 
@@ -40,17 +44,18 @@ def test_bsdf_parity(ctx, oracle):
     ref = np.zeros((len(rec), 16), np.float32)
     oracle.lib().oracle_bsdf(rec.ctypes.data, len(rec), ref.ctypes.data)
     out = ctx.debug_bsdf(rec)
+    tol = 2e-4 if ctx.variant == "strict" else 1e-3
     assert np.array_equal(out[:, 15], ref[:, 15])                                       # lobe set
     assert np.array_equal(out[:, 5], ref[:, 5]) or (out[:, 5] != ref[:, 5]).mean() < 1e-4   # sample validity (decisions at ulp boundaries)
     same_lobe = (out[:, 13] == ref[:, 13]) & (out[:, 5] == ref[:, 5])
     assert same_lobe.mean() > 0.9995
     sane = same_lobe & (ref[:, 9] < 1e4) & (ref[:, 5] > 0)
-    # eval, pdf, sampled direction, sampling pdf and weight: relative 2e-4 (pow/sin/cos ulps through the GGX terms), absolute 1e-6
+    # eval, pdf, sampled direction, sampling pdf and weight: relative 2e-4 strict / 1e-3 fast at the 99.9th percentile (pow/sin/cos ulps through the GGX terms)
     for cols, sel in (((0, 1, 2, 3, 4), ref[:, 4] < 1e4), ((6, 7, 8, 9, 10, 11, 12, 14), sane)):
         a, b = out[sel][:, cols], ref[sel][:, cols]
         err = np.abs(a - b) / (np.abs(b) + 1e-3)
-        assert np.percentile(err, 99.9) < 2e-4, (cols, np.percentile(err, 99.9))
-        assert np.median(err) < 1e-6
+        assert np.percentile(err, 99.9) < tol, (cols, np.percentile(err, 99.9))
+        assert np.median(err) < 2e-6
 
 
 @pytest.mark.parametrize("which", ["cornell", "city"])
@@ -128,10 +133,15 @@ def test_cornell_c1_image_parity(ctx, oracle, cornell):
     o = oracle.Oracle(scene); o.set_constants(consts)
     ctx.path_trace(0, 1); img = ctx.readback_accumulated(); st = ctx.stats()
     acc, n, last, prim, ost = o.render(0, 1)
-    assert st.scatterRays == ost.scatterRays and st.shadowRays == ost.shadowRays     # identical path topology
     d = np.abs(img[..., :3] - acc[..., :3])
-    assert (d.max(-1) == 0).mean() > 0.995                                           # almost every pixel is bit-identical
-    assert d.max() < 2e-2 and per_pixel_l2(img, acc) < 1e-7
+    if ctx.variant == "strict":
+        assert st.scatterRays == ost.scatterRays and st.shadowRays == ost.shadowRays     # identical path topology
+        assert (d.max(-1) == 0).mean() > 0.995                                           # almost every pixel is bit-identical
+        assert d.max() < 2e-2 and per_pixel_l2(img, acc) < 1e-7
+    else:
+        assert abs(int(st.scatterRays) - int(ost.scatterRays)) <= 1e-3 * ost.scatterRays and abs(int(st.shadowRays) - int(ost.shadowRays)) <= 1e-3 * ost.shadowRays
+        rel = d / (np.abs(acc[..., :3]) + 1e-2)
+        assert (rel.max(-1) < 2e-2).mean() > 0.998 and per_pixel_l2(img, acc) < 1e-4     # north_star tolerance is 1e-3
     out16 = ctx.readback_output_color().astype(np.float32)
     assert np.array_equal(out16[..., :3], img[..., :3]) and (out16[..., 3] == 1).all()  # u_OutputColor = float4(L.rgb, 1) in RGBA16F; first sample overwrites
     o.close()
@@ -162,7 +172,8 @@ def test_city_image_parity_and_accumulation(ctx, oracle, small_city):
     o.close()
 
 
-def test_determinism_batching_and_tiles(product, small_city):
+@pytest.mark.parametrize("strict", [False, True])
+def test_determinism_batching_and_tiles(product, small_city, strict):
     """Size-independent properties at the product level: same seed -> same bits; 4 sub-samples in one wavefront == 4 single launches;
     a 2-way tile partition (two contexts on one GPU) + pack/unpack reassembles the single-context frame bit for bit."""
     import torch
@@ -176,11 +187,11 @@ def test_determinism_batching_and_tiles(product, small_city):
         for n in batches:
             ctx.path_trace(s, n); s += n
         return ctx.readback_accumulated()
-    a = product.Context(max_sub_samples_per_launch=4); b = product.Context(max_sub_samples_per_launch=1)
+    a = product.Context(max_sub_samples_per_launch=4, strict=strict); b = product.Context(max_sub_samples_per_launch=1, strict=strict)
     ia = render(a, [4]); ia2 = render(a, [4]); ib = render(b, [1, 1, 1, 1]); ic = render(a, [2, 2])
     assert np.array_equal(ia, ia2) and np.array_equal(ia, ib) and np.array_equal(ia, ic)
     a.close(); b.close()
-    parts = [product.Context(max_sub_samples_per_launch=4, tile_rank=r, tile_world=2, tile_size=32) for r in range(2)]
+    parts = [product.Context(max_sub_samples_per_launch=4, tile_rank=r, tile_world=2, tile_size=32, strict=strict) for r in range(2)]
     for p in parts:
         render(p, [4])
     owned = [p.tile_layout() for p in parts]
