@@ -243,6 +243,7 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
             }
         }
     }
+    if (tris.size() >= (size_t(1) << pt::kTriOwnerShift)) return fail(RTXPT_ERR_INVALID_ARGUMENT, "scene has %zu triangles; the traversal kernels address at most 2^27 - 1", tris.size());
     Bvh8 bvh;
     buildBvh8(tris, bvh);
     c->bvhBuildSeconds = float(bvh.buildSeconds);
@@ -398,6 +399,7 @@ static void fillParams(rtxpt_ctx* c, LaunchParams& p)
     p.c = c->consts;
     p.flags = c->cfg.flags;
     { const char* e = getenv("RTXPT_REFILL_THRESHOLD"); p.refillThreshold = e ? atoi(e) : 24; }     // tuning knob; 8..24 measured equal within noise on B200
+    { const char* e = getenv("RTXPT_WAIT_FLUSH"); p.waitFlushLanes = e ? std::max(1, atoi(e)) : 8; }
     p.outputColor = c->outputColor.ptr; p.accumulated = c->accumulated.ptr; p.depth = c->depth.ptr;
     // traversal occupancy and the shared-memory BVH prefix are chosen together: B resident CTAs of 256 threads per SM (register budget
     // 65536 / (256 B): 128 / 85 / 64 registers for B = 2 / 3 / 4) share the 227 KB of shared memory
@@ -405,7 +407,7 @@ static void fillParams(rtxpt_ctx* c, LaunchParams& p)
     { const char* e = getenv("RTXPT_TRACE_CTAS"); if (e) blocks = std::min(4, std::max(2, atoi(e))); }
     c->grid.traceBlocksPerSM = blocks;
     { int sb = 4; const char* e = getenv("RTXPT_SHADE_CTAS"); if (e) sb = std::min(5, std::max(3, atoi(e))); c->grid.shadeBlocksPerSM = sb; }
-    const uint32_t budget = uint32_t(std::max(0, std::min(c->maxSmemOptin, (227 * 1024) / blocks - 2048) - 1024));
+    const uint32_t budget = uint32_t(std::max(0, std::min(c->maxSmemOptin, (227 * 1024) / blocks - 2048) - 1024 - 8 * 2304));     // 8 x WarpScratch (traverse.cuh)
     p.smemNodeCount = std::min(c->bvhNodeCount, budget / 80u);
 }
 

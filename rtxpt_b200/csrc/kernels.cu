@@ -108,6 +108,10 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ Launch
 // next ray from the queue cursor; lanes still traversing resume where they stopped.  Keeps SIMT lanes busy although ray lengths differ
 // by an order of magnitude.
 
+// shared memory of the traversal kernels: [mbarrier 16 B][WarpScratch x 8 warps][staged BVH nodes]
+constexpr uint kTraceWarps = 8;
+constexpr uint kTraceScratchBytes = 16 + kTraceWarps * sizeof(WarpScratch);
+
 template <bool COUNT, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_trace_closest(const __grid_constant__ LaunchParams p)
 {
@@ -116,50 +120,66 @@ __global__ void __launch_bounds__(256, MINB) k_trace_closest(const __grid_consta
     const uint count = ctr[kCtrRayCount];
     if (count == 0) return;                 // wavefront already drained (uniform across the grid)
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smemRaw);
-    uint4* smemNodes = reinterpret_cast<uint4*>(smemRaw + 16);
+    WarpScratch& ws = reinterpret_cast<WarpScratch*>(smemRaw + 16)[threadIdx.x >> 5];
+    uint4* smemNodes = reinterpret_cast<uint4*>(smemRaw + kTraceScratchBytes);
     stageNodesToShared(smemNodes, p.scene.bvhNodes, p.smemNodeCount, mbar);
 
     const uint* __restrict__ queue = p.wf.rayQueue[p.iteration & 1];
     TraversalCounters tc; tc.nodeVisits = 0; tc.triTests = 0;
-    const uint lane = threadIdx.x & 31u;
-    Traverser<false, COUNT> tv; tv.done = true;
+    const uint lane = threadIdx.x & 31u, laneLt = (1u << lane) - 1u;
+    Traverser<false, COUNT> tv; tv.done = true; tv.waiting = false;
     uint2 stack[kTraversalStackSize];
-    bool hasRay = false; uint entry = 0;
+    uint head = 0, tail = 0;
+    bool hasRay = false, exhausted = false; uint entry = 0;
     while (true)
     {
-        if (tv.done)
+        // retire finished rays: hit record + SER-style binning by {miss, terminating hit, material class}
+        const bool retire = tv.done && hasRay;
+        const uint retireMask = __ballot_sync(0xFFFFFFFFu, retire);
+        if (retire)
         {
-            const uint active = __activemask();
-            if (hasRay)
-            {   // retire: hit record + SER-style binning by {miss, terminating hit, material class}
-                const uint slot = entry & 0x7FFFFFFFu;
-                const HitRecord h = tv.result();
-                p.wf.hits[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.gid));
-                uint cls;
-                if (h.gid == 0xFFFFFFFFu) cls = 0;
-                else if (entry & 0x80000000u) cls = 1;
-                else cls = (p.flags & RTXPT_CFG_NO_MATERIAL_SORT) ? 2u : 2u + p.scene.subInstanceClass[tv.bestSubInstance];
-                const uint peers = __match_any_sync(active, cls);
-                const uint leader = __ffs(peers) - 1u;
-                uint base = 0;
-                if (lane == leader) base = atomicAdd(ctr + kCtrShadeCount + cls, __popc(peers));
-                base = __shfl_sync(peers, base, leader);
-                p.wf.shadeQueue[size_t(cls) * p.wf.capacity + base + __popc(peers & ((1u << lane) - 1u))] = slot;
-                hasRay = false;
-            }
-            // fetch the next ray for every idle lane with one atomic per warp
-            const uint leader = __ffs(active) - 1u;
-            uint base = 0;
-            if (lane == leader) base = atomicAdd(ctr + kCtrFetchClosest, __popc(active));
-            const uint i = __shfl_sync(active, base, leader) + __popc(active & ((1u << lane) - 1u));
-            if (i >= count) break;
-            entry = queue[i];
             const uint slot = entry & 0x7FFFFFFFu;
-            const uint4 a = p.wf.s0[slot], b = p.wf.s1[slot];
-            tv.init(p.scene, mk3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z)), mk3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z)), 0.0f, kMaxRayTravel);
-            hasRay = true;
+            uint subInstance; const HitRecord h = tv.result(ws, subInstance);
+            p.wf.hits[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.gid));
+            uint cls;
+            if (h.gid == 0xFFFFFFFFu) cls = 0;
+            else if (entry & 0x80000000u) cls = 1;
+            else cls = (p.flags & RTXPT_CFG_NO_MATERIAL_SORT) ? 2u : 2u + p.scene.subInstanceClass[subInstance];
+            const uint peers = __match_any_sync(retireMask, cls);
+            const uint leader = __ffs(peers) - 1u;
+            uint base = 0;
+            if (lane == leader) base = atomicAdd(ctr + kCtrShadeCount + cls, __popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            p.wf.shadeQueue[size_t(cls) * p.wf.capacity + base + __popc(peers & laneLt)] = slot;
+            hasRay = false;
         }
-        tv.run(p.scene, p.scene.bvhNodes, smemNodes, p.smemNodeCount, p.refillThreshold, &tc, stack);
+        // fetch the next ray for every idle lane with one atomic per warp
+        const bool fetch = tv.done && !exhausted;
+        const uint fetchMask = __ballot_sync(0xFFFFFFFFu, fetch);
+        if (fetchMask)
+        {
+            const uint leader = __ffs(fetchMask) - 1u;
+            uint base = 0;
+            if (lane == leader) base = atomicAdd(ctr + kCtrFetchClosest, __popc(fetchMask));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (fetch)
+            {
+                const uint i = base + __popc(fetchMask & laneLt);
+                if (i >= count) exhausted = true;
+                else
+                {
+                    entry = queue[i];
+                    const uint slot = entry & 0x7FFFFFFFu;
+                    const uint4 a = p.wf.s0[slot], b = p.wf.s1[slot];
+                    tv.init(p.scene, ws, mk3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z)), mk3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z)), 0.0f, kMaxRayTravel);
+                    hasRay = true;
+                }
+            }
+        }
+        __syncwarp();
+        if (__all_sync(0xFFFFFFFFu, tv.done && !hasRay)) break;
+        const bool drained = __any_sync(0xFFFFFFFFu, exhausted);
+        tv.run(p.scene, p.scene.bvhNodes, smemNodes, p.smemNodeCount, drained ? 1 : p.refillThreshold, p.waitFlushLanes, &tc, stack, ws, head, tail);
     }
     if (COUNT) { atomicAdd(ctr + kCtrNodeVisits, tc.nodeVisits); atomicAdd(ctr + kCtrTriTests, tc.triTests); }
 }
@@ -218,49 +238,62 @@ __global__ void __launch_bounds__(256, MINB) k_trace_shadow(const __grid_constan
     const uint count = ctr[kCtrShadowCount];
     if (count == 0) return;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smemRaw);
-    uint4* smemNodes = reinterpret_cast<uint4*>(smemRaw + 16);
+    WarpScratch& ws = reinterpret_cast<WarpScratch*>(smemRaw + 16)[threadIdx.x >> 5];
+    uint4* smemNodes = reinterpret_cast<uint4*>(smemRaw + kTraceScratchBytes);
     stageNodesToShared(smemNodes, p.scene.bvhNodes, p.smemNodeCount, mbar);
 
     TraversalCounters tc; tc.nodeVisits = 0; tc.triTests = 0;
     uint visibleCount = 0;
-    const uint lane = threadIdx.x & 31u;
-    Traverser<true, COUNT> tv; tv.done = true;
+    const uint lane = threadIdx.x & 31u, laneLt = (1u << lane) - 1u;
+    Traverser<true, COUNT> tv; tv.done = true; tv.waiting = false;
     uint2 stack[kTraversalStackSize];
-    bool hasRay = false; uint record = 0, slot = 0;
+    uint head = 0, tail = 0;
+    bool hasRay = false, exhausted = false; uint record = 0, slot = 0;
     while (true)
     {
-        if (tv.done)
+        if (tv.done && hasRay)
         {
-            const uint active = __activemask();
-            if (hasRay)
-            {
-                if (tv.best.gid == 0xFFFFFFFFu)
-                {   // visible: HandleHit's "if any(neeRadianceAndSpecAvg > 0) AccumulatePathRadiance" (PathTracer.hlsli:725-746)
-                    const uint2 r = p.wf.shadowRadiance[record];
-                    const float rx = f16tof32(r.x), ry = f16tof32(r.x >> 16), rz = f16tof32(r.y), rw = f16tof32(r.y >> 16);
-                    if (rx > 0 || ry > 0 || rz > 0 || rw > 0)
-                    {
-                        uint4 s2 = p.wf.s2[slot];
-                        const float lx = f16tof32(s2.z) + rx, ly = f16tof32(s2.z >> 16) + ry, lz = f16tof32(s2.w) + rz, lw = f16tof32(s2.w >> 16);
-                        s2.z = packHalf2NoClamp(clampf(lx, 0.f, kHalfMax), clampf(ly, 0.f, kHalfMax));
-                        s2.w = packHalf2NoClamp(clampf(lz, 0.f, kHalfMax), clampf(lw, 0.f, kHalfMax));
-                        p.wf.s2[slot] = s2;
-                    }
-                    visibleCount++;
+            if (uint(ws.bestKey[lane]) == 0xFFFFFFFFu)
+            {   // visible: HandleHit's "if any(neeRadianceAndSpecAvg > 0) AccumulatePathRadiance" (PathTracer.hlsli:725-746)
+                const uint2 r = p.wf.shadowRadiance[record];
+                const float rx = f16tof32(r.x), ry = f16tof32(r.x >> 16), rz = f16tof32(r.y), rw = f16tof32(r.y >> 16);
+                if (rx > 0 || ry > 0 || rz > 0 || rw > 0)
+                {
+                    uint4 s2 = p.wf.s2[slot];
+                    const float lx = f16tof32(s2.z) + rx, ly = f16tof32(s2.z >> 16) + ry, lz = f16tof32(s2.w) + rz, lw = f16tof32(s2.w >> 16);
+                    s2.z = packHalf2NoClamp(clampf(lx, 0.f, kHalfMax), clampf(ly, 0.f, kHalfMax));
+                    s2.w = packHalf2NoClamp(clampf(lz, 0.f, kHalfMax), clampf(lw, 0.f, kHalfMax));
+                    p.wf.s2[slot] = s2;
                 }
-                hasRay = false;
+                visibleCount++;
             }
-            const uint leader = __ffs(active) - 1u;
-            uint base = 0;
-            if (lane == leader) base = atomicAdd(ctr + kCtrFetchShadow, __popc(active));
-            record = __shfl_sync(active, base, leader) + __popc(active & ((1u << lane) - 1u));
-            if (record >= count) break;
-            const float4 ot = p.wf.shadowOriginTMax[record], dp = p.wf.shadowDirPath[record];
-            slot = __float_as_uint(dp.w);
-            tv.init(p.scene, mk3(ot.x, ot.y, ot.z), mk3(dp.x, dp.y, dp.z), 0.0f, ot.w);
-            hasRay = true;
+            hasRay = false;
         }
-        tv.run(p.scene, p.scene.bvhNodes, smemNodes, p.smemNodeCount, p.refillThreshold, &tc, stack);
+        const bool fetch = tv.done && !exhausted;
+        const uint fetchMask = __ballot_sync(0xFFFFFFFFu, fetch);
+        if (fetchMask)
+        {
+            const uint leader = __ffs(fetchMask) - 1u;
+            uint base = 0;
+            if (lane == leader) base = atomicAdd(ctr + kCtrFetchShadow, __popc(fetchMask));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (fetch)
+            {
+                record = base + __popc(fetchMask & laneLt);
+                if (record >= count) exhausted = true;
+                else
+                {
+                    const float4 ot = p.wf.shadowOriginTMax[record], dp = p.wf.shadowDirPath[record];
+                    slot = __float_as_uint(dp.w);
+                    tv.init(p.scene, ws, mk3(ot.x, ot.y, ot.z), mk3(dp.x, dp.y, dp.z), 0.0f, ot.w);
+                    hasRay = true;
+                }
+            }
+        }
+        __syncwarp();
+        if (__all_sync(0xFFFFFFFFu, tv.done && !hasRay)) break;
+        const bool drained = __any_sync(0xFFFFFFFFu, exhausted);
+        tv.run(p.scene, p.scene.bvhNodes, smemNodes, p.smemNodeCount, drained ? 1 : p.refillThreshold, p.waitFlushLanes, &tc, stack, ws, head, tail);
     }
     if (COUNT) { atomicAdd(ctr + kCtrShadowNodeVisits, tc.nodeVisits); atomicAdd(ctr + kCtrShadowTriTests, tc.triTests); atomicAdd(ctr + kCtrShadowVisible, visibleCount); }
 }
@@ -300,37 +333,50 @@ __global__ void __launch_bounds__(256, 2) k_trace_rays(const __grid_constant__ L
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smemRaw);
-    uint4* smemNodes = reinterpret_cast<uint4*>(smemRaw + 16);
+    WarpScratch& ws = reinterpret_cast<WarpScratch*>(smemRaw + 16)[threadIdx.x >> 5];
+    uint4* smemNodes = reinterpret_cast<uint4*>(smemRaw + kTraceScratchBytes);
     stageNodesToShared(smemNodes, p.scene.bvhNodes, p.smemNodeCount, mbar);
     TraversalCounters tc; tc.nodeVisits = 0; tc.triTests = 0;
-    const uint lane = threadIdx.x & 31u;
-    Traverser<ANY_HIT, true> tv; tv.done = true;
+    const uint lane = threadIdx.x & 31u, laneLt = (1u << lane) - 1u;
+    Traverser<ANY_HIT, true> tv; tv.done = true; tv.waiting = false;
     uint2 stack[kTraversalStackSize];
-    bool hasRay = false; uint index = 0;
+    uint head = 0, tail = 0;
+    bool hasRay = false, exhausted = false; uint index = 0;
     while (true)
     {
-        if (tv.done)
+        if (tv.done && hasRay)
         {
-            const uint active = __activemask();
-            if (hasRay)
-            {
-                const HitRecord h = tv.result();
-                RtxptHit r;
-                if (h.gid != 0xFFFFFFFFu) { const uint4 info = p.scene.triInfo[h.gid]; r.t = h.t; r.u = h.u; r.v = h.v; r.instanceIndex = info.x; r.geometryIndex = info.y; r.primitiveIndex = info.z; }
-                else { r.t = -1.0f; r.u = r.v = 0.f; r.instanceIndex = r.geometryIndex = r.primitiveIndex = 0xFFFFFFFFu; }
-                out[index] = r;
-                hasRay = false;
-            }
-            const uint leader = __ffs(active) - 1u;
-            uint base = 0;
-            if (lane == leader) base = atomicAdd(cursor, __popc(active));
-            index = __shfl_sync(active, base, leader) + __popc(active & ((1u << lane) - 1u));
-            if (index >= count) break;
-            const float4 a = reinterpret_cast<const float4*>(rays)[index * 2], b = reinterpret_cast<const float4*>(rays)[index * 2 + 1];
-            tv.init(p.scene, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w);
-            hasRay = true;
+            uint subInstance; const HitRecord h = tv.result(ws, subInstance);
+            RtxptHit r;
+            if (h.gid != 0xFFFFFFFFu) { const uint4 info = p.scene.triInfo[h.gid]; r.t = h.t; r.u = h.u; r.v = h.v; r.instanceIndex = info.x; r.geometryIndex = info.y; r.primitiveIndex = info.z; }
+            else { r.t = -1.0f; r.u = r.v = 0.f; r.instanceIndex = r.geometryIndex = r.primitiveIndex = 0xFFFFFFFFu; }
+            out[index] = r;
+            hasRay = false;
         }
-        tv.run(p.scene, p.scene.bvhNodes, smemNodes, p.smemNodeCount, p.refillThreshold, &tc, stack);
+        const bool fetch = tv.done && !exhausted;
+        const uint fetchMask = __ballot_sync(0xFFFFFFFFu, fetch);
+        if (fetchMask)
+        {
+            const uint leader = __ffs(fetchMask) - 1u;
+            uint base = 0;
+            if (lane == leader) base = atomicAdd(cursor, __popc(fetchMask));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (fetch)
+            {
+                index = base + __popc(fetchMask & laneLt);
+                if (index >= count) exhausted = true;
+                else
+                {
+                    const float4 a = reinterpret_cast<const float4*>(rays)[index * 2], b = reinterpret_cast<const float4*>(rays)[index * 2 + 1];
+                    tv.init(p.scene, ws, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w);
+                    hasRay = true;
+                }
+            }
+        }
+        __syncwarp();
+        if (__all_sync(0xFFFFFFFFu, tv.done && !hasRay)) break;
+        const bool drained = __any_sync(0xFFFFFFFFu, exhausted);
+        tv.run(p.scene, p.scene.bvhNodes, smemNodes, p.smemNodeCount, drained ? 1 : p.refillThreshold, p.waitFlushLanes, &tc, stack, ws, head, tail);
     }
     if (counters) { atomicAdd(counters + 0, tc.nodeVisits); atomicAdd(counters + 1, tc.triTests); }
 }
@@ -387,7 +433,7 @@ void launchUnpackAll(const float4* srcAll, const uint32_t* allPixelTable, uint32
 { k_unpack_all<<<g.smCount * 4, 256, 0, s>>>(srcAll, allPixelTable, totalEntries, width, image); }
 
 // ---- launch wrappers ---------------------------------------------------------------------------------------------------------------------------
-static size_t traceSmemBytes(const LaunchParams& p) { return 16 + size_t(p.smemNodeCount) * 80; }
+static size_t traceSmemBytes(const LaunchParams& p) { return kTraceScratchBytes + size_t(p.smemNodeCount) * 80; }
 
 template <typename K> static cudaError_t allowSmem(K kernel, int bytes) { return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); }
 

@@ -82,27 +82,51 @@ struct TraversalCounters { uint nodeVisits, triTests; };
 // Extracts byte j of a packed word as float
 PT_DEVICE float byteToFloat(uint w, int j) { return float((w >> (8 * j)) & 0xFFu); }
 
-// Resumable per-lane traversal state.  A persistent warp keeps one Traverser per lane; run() advances the lane's ray until it finishes
-// or until so few lanes of the warp are still working that the warp should return to its caller to fetch new rays for the idle lanes
-// (dynamic fetch, Aila & Laine HPG 2009) — the caller then re-enters run() on the unfinished lanes.
-// The traversal stack is a separate local array owned by the kernel so that the scalar state below stays in registers.
+// ---- warp-cooperative traversal ------------------------------------------------------------------------------------------------------
+// Node steps are per-lane work (each lane walks its own ray through the CWBVH8).  Triangle tests are NOT: a leaf holds 1..3 triangles and
+// only about a third of the lanes reach a leaf in any given step, so testing them lane-by-lane leaves the warp at ~8 % utilisation in that
+// phase (ncu, round 1: 12 of 32 threads active per instruction overall).  Instead every lane appends its (ray lane, triangle) pairs to a
+// ring buffer in shared memory that belongs to the warp, and the warp drains it 32 pairs at a time — any lane tests any ray's triangle,
+// reading that ray from shared memory.  Hits are merged into the owner's record with a 64-bit shared-memory atomicMin on the key
+// (bits(t) << 32 | gid), which is exactly the "smaller t, ties to the smaller global triangle id" rule, so the result does not depend on
+// the order in which pairs are drained (and a stale pair that is tested against a lane's next ray is only a redundant, valid test).
+constexpr uint kTriQueueSize = 128;         // ring entries per warp (power of two)
+constexpr uint kTriOwnerShift = 27;         // entry = owner lane << 27 | triangle index   (upload_scene rejects scenes with >= 2^27 triangles)
+
+struct WarpScratch
+{
+    float ray[9][32];                       // per lane: org.xyz, Sx, Sy, Sz, kx|ky<<2|kz<<4 (bits), tMin, tMax
+    unsigned long long bestKey[32];         // bits(t) << 32 | gid ; gid 0xFFFFFFFF = nothing accepted yet (t = tMax)
+    float bestU[32], bestV[32];
+    uint bestSub[32];
+    uint queue[kTriQueueSize];
+};
+static_assert(sizeof(WarpScratch) == 2304, "WarpScratch layout");
+
+// Resumable per-lane traversal state.  A persistent warp keeps one Traverser per lane; run() is called by all 32 lanes and advances every
+// unfinished ray until fewer than `minActiveLanes` of them are left, so that the caller can fetch new rays for the idle lanes (dynamic
+// fetch, Aila & Laine HPG 2009).  The traversal stack is a separate local array owned by the kernel so that the scalar state stays in
+// registers; head/tail are the warp-uniform ring cursors.
 template <bool ANY_HIT, bool COUNT>
 struct Traverser
 {
-    float3 org, dir;
-    float idx, idy, idz, tMin, tMax;
-    WatertightRay wr;
-    HitRecord best; uint bestSubInstance;
-    uint2 nodeGroup, triGroup;
-    uint octinv;
+    float3 org;
+    float idx, idy, idz, tMin, bestT;
+    uint2 nodeGroup;
+    uint octinv, lastTicket;
     int sp;
-    bool done;
+    bool done, waiting;
 
-    PT_DEVICE void init(const SceneView& sc, float3 o, float3 d, float tmin, float tmax)
+    PT_DEVICE void init(const SceneView& sc, WarpScratch& ws, float3 o, float3 d, float tmin, float tmax)
     {
-        org = o; dir = d; tMin = tmin; tMax = tmax;
-        best.t = tmax; best.u = 0; best.v = 0; best.gid = 0xFFFFFFFFu; bestSubInstance = 0;
-        wr.setup(d);
+        const uint lane = threadIdx.x & 31u;
+        org = o; tMin = tmin; bestT = tmax;
+        WatertightRay wr; wr.setup(d);
+        ws.ray[0][lane] = o.x; ws.ray[1][lane] = o.y; ws.ray[2][lane] = o.z;
+        ws.ray[3][lane] = wr.Sx; ws.ray[4][lane] = wr.Sy; ws.ray[5][lane] = wr.Sz;
+        ws.ray[6][lane] = __uint_as_float(uint(wr.kx) | (uint(wr.ky) << 2) | (uint(wr.kz) << 4));
+        ws.ray[7][lane] = tmin; ws.ray[8][lane] = tmax;
+        ws.bestKey[lane] = ((unsigned long long)__float_as_uint(tmax) << 32) | 0xFFFFFFFFull;
         const float eps = 1.0e-30f;
         idx = 1.0f / (fabsf(d.x) > eps ? d.x : copysignf(eps, d.x));
         idy = 1.0f / (fabsf(d.y) > eps ? d.y : copysignf(eps, d.y));
@@ -110,19 +134,72 @@ struct Traverser
         octinv = 7u - ((d.x < 0.0f ? 4u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 1u : 0u));
         sp = 0;
         nodeGroup = make_uint2(0u, 0x80000000u);        // virtual parent of the root: one internal child in slot 7^octinv
-        triGroup = make_uint2(0u, 0u);
-        done = (sc.bvhTriCount == 0);
+        waiting = false; lastTicket = 0;
+        done = (sc.bvhTriCount == 0) || !(tmax > tmin);
     }
 
-    PT_DEVICE HitRecord result() const { HitRecord r = best; if (r.gid == 0xFFFFFFFFu) r.t = -1.0f; return r; }
-
-    PT_DEVICE void run(const SceneView& sc, const uint4* __restrict__ nodes, const uint4* __restrict__ smemNodes, uint smemNodeCount, int minActiveLanes,
-                       TraversalCounters* counters, uint2* __restrict__ stack)
+    PT_DEVICE static HitRecord result(const WarpScratch& ws, uint& subInstance)
     {
-        const uint octinv4 = octinv * 0x01010101u;
-        while (!done)
+        const uint lane = threadIdx.x & 31u;
+        const unsigned long long key = ws.bestKey[lane];
+        HitRecord r; r.gid = uint(key); r.t = __uint_as_float(uint(key >> 32)); r.u = ws.bestU[lane]; r.v = ws.bestV[lane]; subInstance = ws.bestSub[lane];
+        if (r.gid == 0xFFFFFFFFu) { r.t = -1.0f; r.u = 0.f; r.v = 0.f; subInstance = 0; }
+        return r;
+    }
+
+    // drains `n` ring entries starting at `first`: lane L tests entries first+L, first+L+32, ...
+    PT_DEVICE static void testEntries(const SceneView& sc, WarpScratch& ws, uint first, uint n, TraversalCounters* counters)
+    {
+        const uint lane = threadIdx.x & 31u;
+        for (uint base = 0; base < n; base += 32u)
         {
-            if (nodeGroup.y & 0xFF000000u)
+            bool won = false; unsigned long long key = 0; float u = 0.f, v = 0.f; uint owner = 0, sub = 0;
+            if (base + lane < n)
+            {
+                const uint ent = ws.queue[(first + base + lane) & (kTriQueueSize - 1u)];
+                owner = ent >> kTriOwnerShift;
+                const float4* tp = sc.bvhTris + size_t(ent & ((1u << kTriOwnerShift) - 1u)) * 3;
+                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                if (COUNT) counters->triTests++;
+                WatertightRay wr; const uint kp = __float_as_uint(ws.ray[6][owner]);
+                wr.kx = int(kp & 3u); wr.ky = int((kp >> 2) & 3u); wr.kz = int(kp >> 4);
+                wr.Sx = ws.ray[3][owner]; wr.Sy = ws.ray[4][owner]; wr.Sz = ws.ray[5][owner];
+                float t;
+                if (intersectTriangleWatertight(wr, mk3(ws.ray[0][owner], ws.ray[1][owner], ws.ray[2][owner]), mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z),
+                                                ws.ray[7][owner], ws.ray[8][owner], t, u, v))
+                {
+                    key = ((unsigned long long)__float_as_uint(t) << 32) | __float_as_uint(a.w);
+                    sub = __float_as_uint(b.w);
+                    if (key < ws.bestKey[owner])
+                    {
+                        bool accept = true;
+                        if (sub & (kTriFlagAlphaTested | kTriFlagExcludeFromNEE))
+                        {   // non-opaque geometry (SampleCommon/AccelerationStructureUtil.h:88-89)
+                            if (ANY_HIT && (sub & kTriFlagExcludeFromNEE)) accept = false;
+                            else if ((sub & kTriFlagAlphaTested) && !alphaTestPasses(sc, sc.subInstances[sub & kTriSubInstanceMask], __float_as_uint(c.w), u, v)) accept = false;
+                        }
+                        if (accept) { atomicMin(&ws.bestKey[owner], key); won = true; }
+                    }
+                }
+            }
+            __syncwarp();
+            if (won && ws.bestKey[owner] == key) { ws.bestU[owner] = u; ws.bestV[owner] = v; ws.bestSub[owner] = sub & kTriSubInstanceMask; }
+            __syncwarp();
+        }
+    }
+
+    // All 32 lanes of the warp call this together.
+    PT_DEVICE void run(const SceneView& sc, const uint4* __restrict__ nodes, const uint4* __restrict__ smemNodes, uint smemNodeCount, int minActiveLanes, int waitFlushLanes,
+                       TraversalCounters* counters, uint2* __restrict__ stack, WarpScratch& ws, uint& head, uint& tail)
+    {
+        const uint lane = threadIdx.x & 31u;
+        const uint octinv4 = octinv * 0x01010101u;
+        const bool negx = !(octinv & 4u), negy = !(octinv & 2u), negz = !(octinv & 1u);
+        while (true)
+        {
+            uint triBase = 0, triBits = 0;
+            const bool traversing = !done && !waiting;
+            if (traversing)
             {
                 const uint hits = nodeGroup.y;
                 const uint bitIndex = 31u - __clz(hits & 0xFF000000u);
@@ -138,7 +215,7 @@ struct Traverser
                 const float px = __uint_as_float(n0.x), py = __uint_as_float(n0.y), pz = __uint_as_float(n0.z);
                 const float sx = __uint_as_float((n0.w & 0xFFu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23), sz = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23);
                 const uint imask = n0.w >> 24;
-                nodeGroup.x = n1.x; triGroup.x = n1.y;
+                nodeGroup.x = n1.x; triBase = n1.y;
                 const float adx = sx * idx, ady = sy * idy, adz = sz * idz;
                 const float ox = (px - org.x) * idx, oy = (py - org.y) * idy, oz = (pz - org.z) * idz;
                 uint hitmask = 0;
@@ -152,9 +229,9 @@ struct Traverser
                     const uint childBits4 = (meta4 >> 5) & 0x07070707u;
                     const uint qlox = half ? n2.y : n2.x, qloy = half ? n2.w : n2.z, qloz = half ? n3.y : n3.x;
                     const uint qhix = half ? n3.w : n3.z, qhiy = half ? n4.y : n4.x, qhiz = half ? n4.w : n4.z;
-                    const uint nearx = (dir.x < 0.0f) ? qhix : qlox, farx = (dir.x < 0.0f) ? qlox : qhix;
-                    const uint neary = (dir.y < 0.0f) ? qhiy : qloy, fary = (dir.y < 0.0f) ? qloy : qhiy;
-                    const uint nearz = (dir.z < 0.0f) ? qhiz : qloz, farz = (dir.z < 0.0f) ? qloz : qhiz;
+                    const uint nearx = negx ? qhix : qlox, farx = negx ? qlox : qhix;
+                    const uint neary = negy ? qhiy : qloy, fary = negy ? qloy : qhiy;
+                    const uint nearz = negz ? qhiz : qloz, farz = negz ? qloz : qhiz;
                     #pragma unroll
                     for (int j = 0; j < 4; j++)
                     {
@@ -163,48 +240,60 @@ struct Traverser
                         const float t0y = __fmaf_rn(byteToFloat(neary, j), ady, oy), t1y = __fmaf_rn(byteToFloat(fary, j), ady, oy);
                         const float t0z = __fmaf_rn(byteToFloat(nearz, j), adz, oz), t1z = __fmaf_rn(byteToFloat(farz, j), adz, oz);
                         float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tMin));
-                        float cmax = fminf(fminf(t1x, t1y), fminf(t1z, best.t));
+                        float cmax = fminf(fminf(t1x, t1y), fminf(t1z, bestT));
                         cmin = __fmaf_rn(-fabsf(cmin), 6.0e-7f, cmin); cmax = __fmaf_rn(fabsf(cmax), 6.0e-7f, cmax);
                         if (cmin <= cmax)
                             hitmask |= ((childBits4 >> (8 * j)) & 0xFFu) << ((bitIndex4 >> (8 * j)) & 0xFFu);
                     }
                 }
                 nodeGroup.y = (hitmask & 0xFF000000u) | imask;
-                triGroup.y = hitmask & 0x00FFFFFFu;
-            }
-            else
-            {
-                triGroup = nodeGroup;
-                nodeGroup = make_uint2(0u, 0u);
-            }
-
-            while (triGroup.y != 0)
-            {
-                const uint k = __ffs(triGroup.y) - 1;
-                triGroup.y &= triGroup.y - 1;
-                const float4* tp = sc.bvhTris + size_t(triGroup.x + k) * 3;
-                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-                if (COUNT) counters->triTests++;
-                float t, u, v;
-                if (!intersectTriangleWatertight(wr, org, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), tMin, tMax, t, u, v)) continue;
-                const uint gid = __float_as_uint(a.w);
-                if (best.gid != 0xFFFFFFFFu ? !(t < best.t || (t == best.t && gid < best.gid)) : !(t < best.t)) continue;
-                const uint sub = __float_as_uint(b.w);
-                if (sub & (kTriFlagAlphaTested | kTriFlagExcludeFromNEE))
-                {   // non-opaque geometry (SampleCommon/AccelerationStructureUtil.h:88-89)
-                    if (ANY_HIT && (sub & kTriFlagExcludeFromNEE)) continue;
-                    if ((sub & kTriFlagAlphaTested) && !alphaTestPasses(sc, sc.subInstances[sub & kTriSubInstanceMask], __float_as_uint(c.w), u, v)) continue;
+                triBits = hitmask & 0x00FFFFFFu;
+                if ((nodeGroup.y & 0xFF000000u) == 0)
+                {
+                    if (sp == 0) waiting = true; else nodeGroup = stack[--sp];
                 }
-                best.t = t; best.u = u; best.v = v; best.gid = gid; bestSubInstance = sub & kTriSubInstanceMask;
-                if (ANY_HIT) { done = true; return; }
             }
 
-            if ((nodeGroup.y & 0xFF000000u) == 0)
+            // append this step's (lane, triangle) pairs to the warp's ring; drain first whenever the ring cannot take them all
+            while (__any_sync(0xFFFFFFFFu, triBits != 0))
             {
-                if (sp == 0) { done = true; return; }
-                nodeGroup = stack[--sp];
+                const uint cnt = __popc(triBits);
+                uint incl = cnt;
+                #pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= uint(d)) incl += o; }
+                const uint total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                const uint space = kTriQueueSize - (tail - head);
+                uint off = incl - cnt;
+                while (triBits != 0 && off < space)
+                {
+                    const uint k = __ffs(triBits) - 1u; triBits &= triBits - 1u;
+                    ws.queue[(tail + off) & (kTriQueueSize - 1u)] = (lane << kTriOwnerShift) | (triBase + k);
+                    off++;
+                }
+                tail += min(total, space);
+                if (cnt) lastTicket = tail;
+                __syncwarp();
+                if (total <= space) break;
+                testEntries(sc, ws, head, tail - head, counters); head = tail;
             }
-            if (__popc(__activemask()) < minActiveLanes) return;        // let the warp refill its idle lanes
+
+            // drain: whole groups of 32 pairs as soon as they exist; a partial group only when lanes are starving for their results
+            {
+                const uint avail = tail - head;
+                const uint nWait = __popc(__ballot_sync(0xFFFFFFFFu, waiting && !done));
+                const uint nTrav = __popc(__ballot_sync(0xFFFFFFFFu, !waiting && !done));
+                const bool partial = avail != 0 && (nTrav == 0 || nWait >= uint(waitFlushLanes));
+                if (avail >= 32u || partial)
+                {
+                    const uint n = partial ? avail : (avail & ~31u);
+                    testEntries(sc, ws, head, n, counters); head += n;
+                    const unsigned long long key = ws.bestKey[lane];
+                    bestT = __uint_as_float(uint(key >> 32));
+                    if (ANY_HIT && uint(key) != 0xFFFFFFFFu) done = true;
+                }
+                if (waiting && int(head - lastTicket) >= 0) done = true;
+            }
+            if (int(__popc(__ballot_sync(0xFFFFFFFFu, !done))) < minActiveLanes) return;        // let the warp refill its idle lanes
         }
     }
 };

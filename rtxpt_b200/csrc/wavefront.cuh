@@ -60,6 +60,7 @@ struct LaunchParams
     uint smemNodeCount;             // BVH nodes staged in shared memory
     uint flags;
     int refillThreshold;            // dynamic fetch: a warp refills its idle lanes when fewer than this many lanes are still traversing
+    int waitFlushLanes;             // a partial group of triangle tests is drained once this many lanes wait for nothing but their results
     // render targets
     uint2* outputColor;             // RGBA16F, full frame, last sub-sample
     float4* accumulated;            // RGBA32F, full frame
