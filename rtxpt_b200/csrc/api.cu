@@ -243,7 +243,7 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
             }
         }
     }
-    if (tris.size() >= (size_t(1) << pt::kTriOwnerShift)) return fail(RTXPT_ERR_INVALID_ARGUMENT, "scene has %zu triangles; the traversal kernels address at most 2^27 - 1", tris.size());
+    if (tris.size() >= (size_t(1) << 27)) return fail(RTXPT_ERR_INVALID_ARGUMENT, "scene has %zu triangles; the traversal kernels address at most 2^27 - 1", tris.size());
     Bvh8 bvh;
     buildBvh8(tris, bvh);
     c->bvhBuildSeconds = float(bvh.buildSeconds);
