@@ -193,8 +193,8 @@ void buildBvh8(const std::vector<BuildTriangle>& tris, Bvh8& out)
         {
             double ext = double(nb.hi[a]) - double(nb.lo[a]);
             int e = (ext > 0.0) ? int(std::ceil(std::log2(ext / 255.0))) : -126;
-            e = std::min(std::max(e, -126), 127);
-            while (e < 127 && ext / std::ldexp(1.0, e) > 255.0) e++;
+            e = std::min(std::max(e, -126), 100);          // traverse.cuh scales by a further 2^15 and by 1/|d| <= 1e20
+            while (e < 100 && ext / std::ldexp(1.0, e) > 255.0) e++;
             ebias[a] = uint32_t(e + 127);
         }
         Bvh8Node node; memset(&node, 0, sizeof(node));

@@ -79,8 +79,8 @@ PT_DEVICE bool alphaTestPasses(const SceneView& sc, const RtxptSubInstanceData& 
 
 struct TraversalCounters { uint nodeVisits, triTests; };
 
-// Extracts byte j of a packed word as float
-PT_DEVICE float byteToFloat(uint w, int j) { return float((w >> (8 * j)) & 0xFFu); }
+// byte j of a packed word -> 1 + b * 2^-15, built by placing the byte in mantissa bits 8..15 of 1.0f (one PRMT)
+PT_DEVICE float byteToUnitFloat(uint w, int j) { return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | (uint(j) << 4))); }
 
 // ---- warp-cooperative traversal ------------------------------------------------------------------------------------------------------
 // Node steps are per-lane work (each lane walks its own ray through the CWBVH8).  Triangle tests are NOT: a leaf holds 1..3 triangles and
@@ -127,7 +127,7 @@ struct Traverser
         ws.ray[6][lane] = __uint_as_float(uint(wr.kx) | (uint(wr.ky) << 2) | (uint(wr.kz) << 4));
         ws.ray[7][lane] = tmin; ws.ray[8][lane] = tmax;
         ws.bestKey[lane] = ((unsigned long long)__float_as_uint(tmax) << 32) | 0xFFFFFFFFull;
-        const float eps = 1.0e-30f;
+        const float eps = 1.0e-20f;     // keeps s * id * 2^15 finite for every node scale the builder emits
         idx = 1.0f / (fabsf(d.x) > eps ? d.x : copysignf(eps, d.x));
         idy = 1.0f / (fabsf(d.y) > eps ? d.y : copysignf(eps, d.y));
         idz = 1.0f / (fabsf(d.z) > eps ? d.z : copysignf(eps, d.z));
@@ -213,11 +213,21 @@ struct Traverser
                 if (COUNT) counters->nodeVisits++;
 
                 const float px = __uint_as_float(n0.x), py = __uint_as_float(n0.y), pz = __uint_as_float(n0.z);
-                const float sx = __uint_as_float((n0.w & 0xFFu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23), sz = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23);
+                // quantisation scale 2^(e-127) per axis, times 2^15 (bvh_builder.cpp keeps e + 15 < 255)
+                const float sx15 = __uint_as_float(((n0.w & 0xFFu) + 15u) << 23), sy15 = __uint_as_float((((n0.w >> 8) & 0xFFu) + 15u) << 23), sz15 = __uint_as_float((((n0.w >> 16) & 0xFFu) + 15u) << 23);
                 const uint imask = n0.w >> 24;
                 nodeGroup.x = n1.x; triBase = n1.y;
-                const float adx = sx * idx, ady = sy * idy, adz = sz * idz;
-                const float ox = (px - org.x) * idx, oy = (py - org.y) * idy, oz = (pz - org.z) * idz;
+                // Slab test on the quantised child boxes.  A quantised coordinate byte b is turned into the float m = 1 + b * 2^-15 with one
+                // byte permute (ALU pipe) instead of an integer->float conversion (quarter-rate XU pipe, the top pipe of this kernel in the
+                // round-1 ncu capture); then b * (s * id) + o == m * A + (o - A) with A = s * id * 2^15.  The box test only has to be
+                // conservative (the triangle test decides): the relative slack eps and an absolute pad that covers the rounding of (o - A)
+                // (<= 2^-22 (|A| + |o|), |o| <= |t| + 2^8 |s id|) are folded into the per-node constants, near planes pulled in, far pushed out.
+                const float Ax = sx15 * idx, Ay = sy15 * idy, Az = sz15 * idz;
+                const float Ox = (px - org.x) * idx - Ax, Oy = (py - org.y) * idy - Ay, Oz = (pz - org.z) * idz - Az;
+                const float kLo = 1.0f - 6.0e-7f, kHi = 1.0f + 6.0e-7f, kPad = 4.8e-7f;
+                const float Anx = Ax * kLo, Any = Ay * kLo, Anz = Az * kLo, Afx = Ax * kHi, Afy = Ay * kHi, Afz = Az * kHi;
+                const float Onx = __fmaf_rn(Ox, kLo, -fabsf(Ax) * kPad), Ony = __fmaf_rn(Oy, kLo, -fabsf(Ay) * kPad), Onz = __fmaf_rn(Oz, kLo, -fabsf(Az) * kPad);
+                const float Ofx = __fmaf_rn(Ox, kHi, fabsf(Ax) * kPad), Ofy = __fmaf_rn(Oy, kHi, fabsf(Ay) * kPad), Ofz = __fmaf_rn(Oz, kHi, fabsf(Az) * kPad);
                 uint hitmask = 0;
                 #pragma unroll
                 for (int half = 0; half < 2; half++)
@@ -235,13 +245,11 @@ struct Traverser
                     #pragma unroll
                     for (int j = 0; j < 4; j++)
                     {
-                        // slab distances with one FMA each; the box test only has to be conservative (the triangle test decides), see the slack below
-                        const float t0x = __fmaf_rn(byteToFloat(nearx, j), adx, ox), t1x = __fmaf_rn(byteToFloat(farx, j), adx, ox);
-                        const float t0y = __fmaf_rn(byteToFloat(neary, j), ady, oy), t1y = __fmaf_rn(byteToFloat(fary, j), ady, oy);
-                        const float t0z = __fmaf_rn(byteToFloat(nearz, j), adz, oz), t1z = __fmaf_rn(byteToFloat(farz, j), adz, oz);
-                        float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tMin));
-                        float cmax = fminf(fminf(t1x, t1y), fminf(t1z, bestT));
-                        cmin = __fmaf_rn(-fabsf(cmin), 6.0e-7f, cmin); cmax = __fmaf_rn(fabsf(cmax), 6.0e-7f, cmax);
+                        const float t0x = __fmaf_rn(byteToUnitFloat(nearx, j), Anx, Onx), t1x = __fmaf_rn(byteToUnitFloat(farx, j), Afx, Ofx);
+                        const float t0y = __fmaf_rn(byteToUnitFloat(neary, j), Any, Ony), t1y = __fmaf_rn(byteToUnitFloat(fary, j), Afy, Ofy);
+                        const float t0z = __fmaf_rn(byteToUnitFloat(nearz, j), Anz, Onz), t1z = __fmaf_rn(byteToUnitFloat(farz, j), Afz, Ofz);
+                        const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tMin));
+                        const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, bestT));
                         if (cmin <= cmax)
                             hitmask |= ((childBits4 >> (8 * j)) & 0xFFu) << ((bitIndex4 >> (8 * j)) & 0xFFu);
                     }
