@@ -119,6 +119,8 @@ extern "C" RTXPT_API int rtxpt_b200_create(const RtxptConfig* config, rtxpt_ctx*
     memset(c->hCounters, 0, kCounterWords * sizeof(uint32_t));
     e = configureKernels(c->maxSmemOptin);
     if (e != cudaSuccess) { delete c; return fail(RTXPT_ERR_CUDA, "kernel configuration failed: %s", cudaGetErrorString(e)); }
+    launchInitTables(c->stream);
+    if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { delete c; return fail(RTXPT_ERR_CUDA, "table initialisation failed: %s", cudaGetErrorString(e)); }
     *outCtx = c;
     return RTXPT_OK;
 }

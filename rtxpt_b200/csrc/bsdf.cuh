@@ -26,7 +26,11 @@ struct BsdfParams           // StandardBSDFData (BxDF.hlsli:612-705); lpfloat fi
     float3 transmission; float diffuseTransmission, specularTransmission, eta;
 };
 
-PT_DEVICE float schlickPow5(float cosTheta) { return powf(fmaxf(1.0f - cosTheta, 0.0f), 5.0f); }
+#if defined(PT_FAST_MATH)
+PT_DEVICE float schlickPow5(float cosTheta) { const float x = fmaxf(1.0f - cosTheta, 0.0f), x2 = x * x; return x2 * x2 * x; }
+#else
+PT_DEVICE float schlickPow5(float cosTheta) { return powf(fmaxf(1.0f - cosTheta, 0.0f), 5.0f); }     // pow() as in the reference (and the oracle)
+#endif
 PT_DEVICE float3 fresnelSchlick3(float3 f0, float f90, float cosTheta) { return f0 + (mk3(f90) - f0) * schlickPow5(cosTheta); }
 PT_DEVICE float fresnelSchlick1(float f0, float f90, float cosTheta) { return f0 + (f90 - f0) * schlickPow5(cosTheta); }
 PT_DEVICE float fresnelDielectric(float eta, float cosThetaI, float& cosThetaT)

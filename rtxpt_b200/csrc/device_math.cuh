@@ -33,7 +33,11 @@ PT_HD float3 operator-(float3 a) { return mk3(-a.x, -a.y, -a.z); }
 PT_HD float3 operator*(float3 a, float3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
 PT_HD float3 operator*(float3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
 PT_HD float3 operator*(float s, float3 a) { return mk3(a.x * s, a.y * s, a.z * s); }
+#if defined(PT_FAST_MATH)
+PT_HD float3 operator/(float3 a, float s) { const float r = 1.0f / s; return mk3(a.x * r, a.y * r, a.z * r); }      // one MUFU.RCP instead of three scaled divisions
+#else
 PT_HD float3 operator/(float3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+#endif
 PT_HD float3 operator/(float3 a, float3 b) { return mk3(a.x / b.x, a.y / b.y, a.z / b.z); }
 PT_HD float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 PT_HD float3 cross3(float3 a, float3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
@@ -75,10 +79,10 @@ PT_DEVICE float fastACos(float inX)
 // ---- integer hashing / Owen-scrambled Sobol (NoiseAndSequences.hlsli:58-84, :130-229) --------------------------------------
 PT_HD uint hash32(uint x) { x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15; x *= 0xf35a2d97u; x ^= x >> 15; return x; }
 PT_HD uint hash32Combine(uint seed, uint value) { return seed ^ (hash32(value) + 0x9e3779b9u + (seed << 6) + (seed >> 2)); }
-PT_HD float hashToFloat(uint h) { return float(h >> 8) / 16777216.0f; }
+PT_HD float hashToFloat(uint h) { return float(h >> 8) * 5.9604644775390625e-8f; }      // / 2^24, exact
 
 // Sobol direction numbers for dimensions 1..4 (dimension 0 is bit reversal); NoiseAndSequences.hlsli:135-180
-__constant__ uint cSobolDirections[4][32] = {
+static __constant__ uint cSobolDirections[4][32] = {
     { 0x80000000, 0xc0000000, 0xa0000000, 0xf0000000, 0x88000000, 0xcc000000, 0xaa000000, 0xff000000,
       0x80800000, 0xc0c00000, 0xa0a00000, 0xf0f00000, 0x88880000, 0xcccc0000, 0xaaaa0000, 0xffff0000,
       0x80008000, 0xc000c000, 0xa000a000, 0xf000f000, 0x88008800, 0xcc00cc00, 0xaa00aa00, 0xff00ff00,
@@ -96,7 +100,7 @@ __constant__ uint cSobolDirections[4][32] = {
       0x22878000, 0xb3c9c000, 0xfb65a000, 0xddb2d000, 0x78022800, 0x9c0b3c00, 0x5a0fb600, 0x2d0ddb00,
       0xa2878080, 0xf3c9c040, 0xdb65a020, 0x6db2d0b0, 0x800228f8, 0x400b3cdc, 0x200fb67a, 0xb00ddb9d },
 };
-PT_DEVICE uint sobolDim(uint index, uint dim /*1..4*/)
+PT_DEVICE uint sobolDimBitwise(uint index, uint dim /*1..4*/)
 {
     uint X = 0;
     #pragma unroll 8
@@ -104,6 +108,18 @@ PT_DEVICE uint sobolDim(uint index, uint dim /*1..4*/)
         X ^= ((index >> bit) & 1u) ? cSobolDirections[dim - 1][bit] : 0u;
     return X;
 }
+#if defined(PT_SOBOL_TABLES)
+// The Sobol matrix product is linear over GF(2): four byte-indexed partial products replace the 32-step loop (same bits out).
+// Filled once per context by k_init_sobol_tables (shade_kernels.cu).
+static __device__ uint gSobolByte[4][4][256];
+PT_DEVICE uint sobolDim(uint index, uint dim /*1..4*/)
+{
+    const uint* T = &gSobolByte[dim - 1][0][0];
+    return __ldg(T + (index & 0xFFu)) ^ __ldg(T + 256 + ((index >> 8) & 0xFFu)) ^ __ldg(T + 512 + ((index >> 16) & 0xFFu)) ^ __ldg(T + 768 + (index >> 24));
+}
+#else
+PT_DEVICE uint sobolDim(uint index, uint dim) { return sobolDimBitwise(index, dim); }
+#endif
 PT_DEVICE uint owenHash(uint x, uint seed) { x ^= x * 0x3d20adeau; x += seed; x *= (seed >> 16) | 1u; x ^= x * 0x05526c56u; x ^= x * 0x53a22864u; return x; }
 PT_DEVICE uint owenScramble(uint x, uint seed) { return __brev(owenHash(__brev(x), seed)); }
 

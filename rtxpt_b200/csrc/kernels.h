@@ -17,6 +17,7 @@ void launchCommitAccumulate(const LaunchParams& p, const GridConfig& g, cudaStre
 void launchTraceRays(const LaunchParams& p, const GridConfig& g, const RtxptRay* dRays, uint32_t count, bool anyHit, RtxptHit* dHits, uint32_t* dCounters, uint32_t* dCursor, cudaStream_t s);
 void launchPackOwned(const float4* image, const uint32_t* pixelOfSlot, uint32_t pixelCount, uint32_t paddedCount, uint32_t width, float4* dst, const GridConfig& g, cudaStream_t s);
 void launchUnpackAll(const float4* srcAll, const uint32_t* allPixelTable, uint32_t totalEntries, uint32_t width, float4* image, const GridConfig& g, cudaStream_t s);
+void launchInitTables(cudaStream_t s);       // lookup tables of the shading unit (Sobol byte tables); once per context
 void launchDebugBsdf(const float* dIn, uint32_t count, float* dOut, cudaStream_t s);
 void launchDebugRng(const uint32_t* dIn, uint32_t count, uint32_t* dOut, cudaStream_t s);
 

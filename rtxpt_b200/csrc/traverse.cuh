@@ -17,6 +17,22 @@ struct HitRecord { float t, u, v; uint gid; };      // gid == 0xFFFFFFFF: miss
 
 constexpr int kTraversalStackSize = 32;
 
+// Round-to-nearest IEEE operations that keep subnormals whatever -ftz / -use_fast_math says (inline PTX is not rewritten by those flags):
+// the hit records have to be bit-identical to the oracle's in every build.
+PT_DEVICE float xmul(float a, float b) { float r; asm("mul.rn.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+PT_DEVICE float xadd(float a, float b) { float r; asm("add.rn.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+PT_DEVICE float xsub(float a, float b) { float r; asm("sub.rn.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+PT_DEVICE float xdiv(float a, float b) { float r; asm("div.rn.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+PT_DEVICE float xedge64(float a, float b, float c, float d)        // float(double(a) * double(b) - double(c) * double(d)), each step rounded to nearest
+{
+    float r;
+    asm("{ .reg .f64 da, db, dc, dd, p0, p1;\n\t"
+        "cvt.f64.f32 da, %1; cvt.f64.f32 db, %2; cvt.f64.f32 dc, %3; cvt.f64.f32 dd, %4;\n\t"
+        "mul.rn.f64 p0, da, db; mul.rn.f64 p1, dc, dd; sub.rn.f64 p0, p0, p1;\n\t"
+        "cvt.rn.f32.f64 %0, p0; }" : "=f"(r) : "f"(a), "f"(b), "f"(c), "f"(d));
+    return r;
+}
+
 struct WatertightRay
 {
     int kx, ky, kz; float Sx, Sy, Sz;
@@ -29,7 +45,7 @@ struct WatertightRay
         if (dk < 0.0f) { int t = kx; kx = ky; ky = t; }
         float dx = (kx == 0) ? d.x : ((kx == 1) ? d.y : d.z);
         float dy = (ky == 0) ? d.x : ((ky == 1) ? d.y : d.z);
-        Sx = __fdiv_rn(dx, dk); Sy = __fdiv_rn(dy, dk); Sz = __fdiv_rn(1.0f, dk);
+        Sx = xdiv(dx, dk); Sy = xdiv(dy, dk); Sz = xdiv(1.0f, dk);
     }
 };
 
@@ -38,30 +54,30 @@ PT_DEVICE float comp(float3 v, int k) { return (k == 0) ? v.x : ((k == 1) ? v.y 
 PT_DEVICE bool intersectTriangleWatertight(const WatertightRay& wr, float3 org, float3 v0, float3 v1, float3 v2, float tMin, float tMax,
                                            float& tOut, float& uOut, float& vOut)
 {
-    const float3 A = mk3(__fsub_rn(v0.x, org.x), __fsub_rn(v0.y, org.y), __fsub_rn(v0.z, org.z));
-    const float3 B = mk3(__fsub_rn(v1.x, org.x), __fsub_rn(v1.y, org.y), __fsub_rn(v1.z, org.z));
-    const float3 C = mk3(__fsub_rn(v2.x, org.x), __fsub_rn(v2.y, org.y), __fsub_rn(v2.z, org.z));
+    const float3 A = mk3(xsub(v0.x, org.x), xsub(v0.y, org.y), xsub(v0.z, org.z));
+    const float3 B = mk3(xsub(v1.x, org.x), xsub(v1.y, org.y), xsub(v1.z, org.z));
+    const float3 C = mk3(xsub(v2.x, org.x), xsub(v2.y, org.y), xsub(v2.z, org.z));
     const float Akz = comp(A, wr.kz), Bkz = comp(B, wr.kz), Ckz = comp(C, wr.kz);
-    const float Ax = __fsub_rn(comp(A, wr.kx), __fmul_rn(wr.Sx, Akz)), Ay = __fsub_rn(comp(A, wr.ky), __fmul_rn(wr.Sy, Akz));
-    const float Bx = __fsub_rn(comp(B, wr.kx), __fmul_rn(wr.Sx, Bkz)), By = __fsub_rn(comp(B, wr.ky), __fmul_rn(wr.Sy, Bkz));
-    const float Cx = __fsub_rn(comp(C, wr.kx), __fmul_rn(wr.Sx, Ckz)), Cy = __fsub_rn(comp(C, wr.ky), __fmul_rn(wr.Sy, Ckz));
-    float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
-    float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
-    float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
+    const float Ax = xsub(comp(A, wr.kx), xmul(wr.Sx, Akz)), Ay = xsub(comp(A, wr.ky), xmul(wr.Sy, Akz));
+    const float Bx = xsub(comp(B, wr.kx), xmul(wr.Sx, Bkz)), By = xsub(comp(B, wr.ky), xmul(wr.Sy, Bkz));
+    const float Cx = xsub(comp(C, wr.kx), xmul(wr.Sx, Ckz)), Cy = xsub(comp(C, wr.ky), xmul(wr.Sy, Ckz));
+    float U = xsub(xmul(Cx, By), xmul(Cy, Bx));
+    float V = xsub(xmul(Ax, Cy), xmul(Ay, Cx));
+    float W = xsub(xmul(Bx, Ay), xmul(By, Ax));
     if (U == 0.0f || V == 0.0f || W == 0.0f)
     {
-        U = float(__dsub_rn(__dmul_rn(double(Cx), double(By)), __dmul_rn(double(Cy), double(Bx))));
-        V = float(__dsub_rn(__dmul_rn(double(Ax), double(Cy)), __dmul_rn(double(Ay), double(Cx))));
-        W = float(__dsub_rn(__dmul_rn(double(Bx), double(Ay)), __dmul_rn(double(By), double(Ax))));
+        U = xedge64(Cx, By, Cy, Bx);
+        V = xedge64(Ax, Cy, Ay, Cx);
+        W = xedge64(Bx, Ay, By, Ax);
     }
     if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
-    const float det = __fadd_rn(__fadd_rn(U, V), W);
+    const float det = xadd(xadd(U, V), W);
     if (det == 0.0f) return false;
-    const float Az = __fmul_rn(wr.Sz, Akz), Bz = __fmul_rn(wr.Sz, Bkz), Cz = __fmul_rn(wr.Sz, Ckz);
-    const float T = __fadd_rn(__fadd_rn(__fmul_rn(U, Az), __fmul_rn(V, Bz)), __fmul_rn(W, Cz));
-    const float t = __fdiv_rn(T, det);
+    const float Az = xmul(wr.Sz, Akz), Bz = xmul(wr.Sz, Bkz), Cz = xmul(wr.Sz, Ckz);
+    const float T = xadd(xadd(xmul(U, Az), xmul(V, Bz)), xmul(W, Cz));
+    const float t = xdiv(T, det);
     if (!(t > tMin && t < tMax)) return false;
-    tOut = t; uOut = __fdiv_rn(V, det); vOut = __fdiv_rn(W, det);
+    tOut = t; uOut = xdiv(V, det); vOut = xdiv(W, det);
     return true;
 }
 
