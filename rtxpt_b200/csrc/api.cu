@@ -409,8 +409,12 @@ static void fillParams(rtxpt_ctx* c, LaunchParams& p)
     { const char* e = getenv("RTXPT_TRACE_CTAS"); if (e) blocks = std::min(4, std::max(2, atoi(e))); }
     c->grid.traceBlocksPerSM = blocks;
     { int sb = 4; const char* e = getenv("RTXPT_SHADE_CTAS"); if (e) sb = std::min(5, std::max(3, atoi(e))); c->grid.shadeBlocksPerSM = sb; }
-    const uint32_t budget = uint32_t(std::max(0, std::min(c->maxSmemOptin, (227 * 1024) / blocks - 2048) - 1024 - 8 * 2304));     // 8 x WarpScratch (traverse.cuh)
-    p.smemNodeCount = std::min(c->bvhNodeCount, budget / 80u);
+    const uint32_t budget = uint32_t(std::max(0, std::min(c->maxSmemOptin, (227 * 1024) / blocks - 2048) - 1024 - 8 * 2320));     // 8 x WarpScratch (traverse.cuh)
+    // BVH prefix (breadth-first top levels) staged into shared memory by TMA.  Measured on B200 (city workload, closest+shadow ms/frame):
+    // 0 nodes 14.04, 73 nodes 14.36, 200 nodes 14.37, as many as fit (~450) 14.71 - shared memory taken from the unified L1 costs more than the
+    // staged levels save, so the default is 0 and RTXPT_SMEM_NODES opts in.
+    p.smemNodeCount = 0;
+    { const char* e = getenv("RTXPT_SMEM_NODES"); if (e) p.smemNodeCount = std::min(std::min(c->bvhNodeCount, budget / 80u), uint32_t(std::max(0, atoi(e)))); }
 }
 
 // RTXPT_CFG_TIME_KERNELS: bracket a launch with two events from the pool; kinds: 0 closest, 1 shadow, 2 shade, 3 other

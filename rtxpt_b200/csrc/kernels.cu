@@ -115,6 +115,8 @@ __global__ void __launch_bounds__(256, MINB) k_trace_closest(const __grid_consta
     Traverser<false, COUNT> tv; tv.done = true; tv.waiting = false;
     uint2 stack[kTraversalStackSize];
     uint head = 0, tail = 0;
+    if (lane == 0) ws.tail = 0;
+    __syncwarp();
     bool hasRay = false, exhausted = false; uint entry = 0;
     while (true)
     {
@@ -188,6 +190,8 @@ __global__ void __launch_bounds__(256, MINB) k_trace_shadow(const __grid_constan
     Traverser<true, COUNT> tv; tv.done = true; tv.waiting = false;
     uint2 stack[kTraversalStackSize];
     uint head = 0, tail = 0;
+    if (lane == 0) ws.tail = 0;
+    __syncwarp();
     bool hasRay = false, exhausted = false; uint record = 0, slot = 0;
     while (true)
     {
@@ -281,6 +285,8 @@ __global__ void __launch_bounds__(256, 2) k_trace_rays(const __grid_constant__ L
     Traverser<ANY_HIT, true> tv; tv.done = true; tv.waiting = false;
     uint2 stack[kTraversalStackSize];
     uint head = 0, tail = 0;
+    if (lane == 0) ws.tail = 0;
+    __syncwarp();
     bool hasRay = false, exhausted = false; uint index = 0;
     while (true)
     {

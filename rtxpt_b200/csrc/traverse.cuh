@@ -106,6 +106,9 @@ PT_DEVICE float byteToUnitFloat(uint w, int j) { return __uint_as_float(__byte_p
 // reading that ray from shared memory.  Hits are merged into the owner's record with a 64-bit shared-memory atomicMin on the key
 // (bits(t) << 32 | gid), which is exactly the "smaller t, ties to the smaller global triangle id" rule, so the result does not depend on
 // the order in which pairs are drained (and a stale pair that is tested against a lane's next ray is only a redundant, valid test).
+#ifndef PT_PREFETCH_CHILDREN
+#define PT_PREFETCH_CHILDREN 0
+#endif
 constexpr uint kTriQueueSize = 128;         // ring entries per warp (power of two)
 constexpr uint kTriOwnerShift = 27;         // entry = owner lane << 27 | triangle index   (upload_scene rejects scenes with >= 2^27 triangles)
 
@@ -116,8 +119,9 @@ struct WarpScratch
     float bestU[32], bestV[32];
     uint bestSub[32];
     uint queue[kTriQueueSize];
+    uint tail, pad[3];                      // ring reservation cursor (the consumer cursor `head` is warp-uniform and lives in registers)
 };
-static_assert(sizeof(WarpScratch) == 2304, "WarpScratch layout");
+static_assert(sizeof(WarpScratch) == 2320, "WarpScratch layout");
 
 // Resumable per-lane traversal state.  A persistent warp keeps one Traverser per lane; run() is called by all 32 lanes and advances every
 // unfinished ray until fewer than `minActiveLanes` of them are left, so that the caller can fetch new rays for the idle lanes (dynamic
@@ -224,8 +228,17 @@ struct Traverser
                 const uint slot = (bitIndex - 24u) ^ octinv;
                 const uint rel = __popc(hits & ~(0xFFFFFFFFu << slot) & 0xFFu);
                 const uint nodeIndex = nodeGroup.x + rel;
-                const uint4* np = (nodeIndex < smemNodeCount) ? (smemNodes + nodeIndex * 5) : (nodes + size_t(nodeIndex) * 5);
-                const uint4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3], n4 = np[4];
+                uint4 n0, n1, n2, n3, n4;
+                if (smemNodeCount == 0)
+                {   // default: the whole BVH is read through L1 (read-only path); measured faster than giving L1 capacity away to a staged prefix
+                    const uint4* np = nodes + size_t(nodeIndex) * 5;
+                    n0 = __ldg(np); n1 = __ldg(np + 1); n2 = __ldg(np + 2); n3 = __ldg(np + 3); n4 = __ldg(np + 4);
+                }
+                else
+                {
+                    const uint4* np = (nodeIndex < smemNodeCount) ? (smemNodes + nodeIndex * 5) : (nodes + size_t(nodeIndex) * 5);
+                    n0 = np[0]; n1 = np[1]; n2 = np[2]; n3 = np[3]; n4 = np[4];
+                }
                 if (COUNT) counters->nodeVisits++;
 
                 const float px = __uint_as_float(n0.x), py = __uint_as_float(n0.y), pz = __uint_as_float(n0.z);
@@ -272,33 +285,55 @@ struct Traverser
                 }
                 nodeGroup.y = (hitmask & 0xFF000000u) | imask;
                 triBits = hitmask & 0x00FFFFFFu;
+                if (PT_PREFETCH_CHILDREN)
+                {   // every hit inner child will be visited (popped groups are not re-tested): pull the ones that are not next into L1/L2 now
+                    uint rest = nodeGroup.y & 0xFF000000u;
+                    rest &= ~(0x80000000u >> __clz(rest));          // all but the child the next step descends into
+                    while (rest)
+                    {
+                        const uint bi = 31u - __clz(rest); rest &= ~(1u << bi);
+                        const uint sl = (bi - 24u) ^ octinv;
+                        const uint4* cp = nodes + size_t(nodeGroup.x + __popc(imask & ~(0xFFFFFFFFu << sl))) * 5;
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(cp));
+                    }
+                }
                 if ((nodeGroup.y & 0xFF000000u) == 0)
                 {
                     if (sp == 0) waiting = true; else nodeGroup = stack[--sp];
                 }
             }
 
-            // append this step's (lane, triangle) pairs to the warp's ring; drain first whenever the ring cannot take them all
-            while (__any_sync(0xFFFFFFFFu, triBits != 0))
+            // append this step's (lane, triangle) pairs to the warp's ring: every lane reserves its span with one shared-memory atomic
+            // (order is irrelevant, see above).  Spans that would overrun the ring are given back: they are the tail of the reservation
+            // order, so the valid entries stay a prefix; the ring is drained and those lanes try again.
+            uint cnt = __popc(triBits);
+            if (__any_sync(0xFFFFFFFFu, cnt != 0))
             {
-                const uint cnt = __popc(triBits);
-                uint incl = cnt;
-                #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const uint o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= uint(d)) incl += o; }
-                const uint total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-                const uint space = kTriQueueSize - (tail - head);
-                uint off = incl - cnt;
-                while (triBits != 0 && off < space)
+                while (true)
                 {
-                    const uint k = __ffs(triBits) - 1u; triBits &= triBits - 1u;
-                    ws.queue[(tail + off) & (kTriQueueSize - 1u)] = (lane << kTriOwnerShift) | (triBase + k);
-                    off++;
+                    uint off = 0;
+                    if (cnt) off = atomicAdd(&ws.tail, cnt);
+                    __syncwarp();
+                    const uint reserved = ws.tail, limit = head + kTriQueueSize;
+                    const bool fits = cnt != 0 && int(off + cnt - limit) <= 0;
+                    if (fits)
+                    {
+                        const uint tag = (lane << kTriOwnerShift) | triBase;
+                        do
+                        {
+                            const uint k = __ffs(triBits) - 1u; triBits &= triBits - 1u;
+                            ws.queue[off & (kTriQueueSize - 1u)] = tag + k;
+                            off++;
+                        } while (triBits != 0);
+                        lastTicket = off; cnt = 0;
+                    }
+                    if (int(reserved - limit) <= 0) { tail = reserved; __syncwarp(); break; }
+                    tail = head + __reduce_min_sync(0xFFFFFFFFu, cnt ? off - head : kTriQueueSize);
+                    __syncwarp();
+                    testEntries(sc, ws, head, tail - head, counters); head = tail;
+                    if (lane == 0) ws.tail = tail;
+                    __syncwarp();
                 }
-                tail += min(total, space);
-                if (cnt) lastTicket = tail;
-                __syncwarp();
-                if (total <= space) break;
-                testEntries(sc, ws, head, tail - head, counters); head = tail;
             }
 
             // drain: whole groups of 32 pairs as soon as they exist; a partial group only when lanes are starving for their results
