@@ -56,6 +56,8 @@ def load(strict=None):
         strict = os.environ.get("RTXPT_STRICT", "0") == "1"
     if strict not in _libs:
         path = LIB_PATH_STRICT if strict else LIB_PATH
+        if os.environ.get("RTXPT_LIB_DIR"):        # tuning experiments: alternative builds of the same sources (make OUT=...)
+            path = os.path.join(os.environ["RTXPT_LIB_DIR"], os.path.basename(path))
         if not os.path.exists(path):
             raise RtxptError(f"{path} is missing: run rtxpt_b200.lib.build() / `make -C rtxpt_b200/csrc` (no fallback path exists)")
         L = C.CDLL(path)
