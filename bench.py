@@ -54,7 +54,7 @@ class ClockSampler:
         self.lines, self.proc = [], None
         q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -91,6 +91,20 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(rays_per_iteration):
+    """dram__bytes_read.sum + dram__bytes_write.sum of k_trace_closest per frame, from the committed `ncu --set full` capture (profiles/): the
+    capture holds the launches of iterations 0..2; they are scaled to the frame by this run's ray counts (same unit as `achieved`: per frame = per
+    launch x launches)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_ncu_full_summary.json")
+    try:
+        rows = [r for r in json.load(open(path)) if "k_trace_closest" in r["kernel"]]
+        captured = sum(r["dram_read_bytes"] + r["dram_write_bytes"] for r in rows)
+        frac = sum(rays_per_iteration[:len(rows)]) / max(1, sum(rays_per_iteration))
+        return captured / frac, "profiles/r1_ncu_full_summary.json: %d captured launches = %.0f %% of the frame's scatter rays, scaled to the frame" % (len(rows), 100 * frac)
+    except Exception as e:                                   # no capture committed: say so instead of guessing
+        return None, "no ncu capture found (%s)" % e
+
+
 def cpu_sample_rect():
     # bounded sample of the same workload: a 240x135 window in the middle of the 1080p frame, 1 sub-sample
     w, h = 240, 135
@@ -120,7 +134,7 @@ def run_cpu(scene, consts, steps, warmup):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -134,7 +148,7 @@ def main():
         scene, consts = build_workload()
         r = run_cpu(scene, consts, max(1, args.steps), min(args.warmup, 1))
         line = {"impl": "reference", "metric": "Mrays/s", "value": r["mrays_s"], "unit": "Mrays/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp16 path-state storage)",
+                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (fp16 path-state storage)",
                 "data": "synthetic", "config": workload_config(n_gpus),
                 "cpu_baseline": {"value": r["mrays_s"], "unit": "Mrays/s", "cores": r["threads"], "kind": "port", "sample": r["sample"],
                                  "bvh_build_s": r["bvh_build_s"], "rays_per_path": r["rays_per_path"]},
@@ -238,8 +252,9 @@ def main():
         alg_bytes = 48 * s2.scatterRays + 80 * s2.traversalNodeVisits + 48 * s2.traversalTriTests      # 32 B ray in + 16 B hit out + 80 B/node + 48 B/triangle
         peak, peak_src = measured_peak_gbs()
         achieved = alg_bytes / (k_closest * 1e-3) / 1e9 if k_closest > 0 else 0.0
+        traffic, traffic_note = ncu_traffic(rays_per_bounce)
         roofline = {"kernel": "k_trace_closest (CWBVH8 closest-hit traversal)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src,
+                    "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                     "algorithmic_bytes_per_frame": int(alg_bytes), "nodes_per_ray": s2.traversalNodeVisits / max(1, s2.scatterRays), "tris_per_ray": s2.traversalTriTests / max(1, s2.scatterRays),
                     "kernel_ms_per_frame": {"trace_closest": k_closest, "trace_shadow": k_shadow, "shade": k_shade, "other": k_other},
                     "note": "kernel times: CUDA events around every launch of the last timed frame (RTXPT_CFG_TIME_KERNELS); traffic: see profiles/ (ncu dram bytes)"}
