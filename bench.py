@@ -156,6 +156,7 @@ def main():
                 "note": "RTXPT has no CPU implementation of this path (HLSL/DXR only); this arm times the CPU restatement of its algorithm (oracle/) on the host cores"}
         print(json.dumps(line)); return 0
 
+    real_stdout = os.dup(1); os.dup2(2, 1)          # libraries that print to fd 1 (NCCL's version banner) must not pollute the one-line contract
     import torch
     from rtxpt_b200 import lib, structs as S
     torch.cuda.set_device(local_rank)
@@ -178,7 +179,7 @@ def main():
     tstream = torch.cuda.Stream()
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
-    host_out = np.empty((HEIGHT, WIDTH, 4), np.float32)
+    host_out = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.float32, pin_memory=True).numpy()      # pinned host frame the e2e leg reads back into
 
     def frame(i):
         consts.sampleBaseIndex = i * SPP
@@ -232,8 +233,8 @@ def main():
             ctx.render_frame(consts, 0, SPP, host_out)      # set_constants + path_trace + blocking read-back into host memory, on the context's own stream
         else:
             frame(args.warmup + args.steps + i)
-            ctx.synchronize(); torch.cuda.synchronize()
-            host_out[:] = ctx.readback_accumulated()
+            torch.cuda.synchronize()
+            ctx.readback_accumulated(host_out)
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -274,7 +275,7 @@ def main():
                 "rays_per_frame": rays_per_frame, "rays_per_path": rays_per_frame / (WIDTH * HEIGHT * SPP), "scatter_rays": scatter, "shadow_rays": shadow,
                 "rays_per_iteration": rays_per_bounce, "bvh_build_s": st.bvhBuildSeconds, "bvh_nodes": st.bvhNodeCount, "lights": st.lightCount,
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(line))
+        sys.stdout.flush(); os.write(real_stdout, (json.dumps(line) + "\n").encode())
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

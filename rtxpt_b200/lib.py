@@ -108,8 +108,9 @@ class Context:
     def synchronize(self):
         _check(self.L.rtxpt_b200_synchronize(self.h), self.L)
 
-    def readback_accumulated(self):
-        out = np.empty((self.consts.imageHeight, self.consts.imageWidth, 4), np.float32)
+    def readback_accumulated(self, out=None):
+        if out is None:
+            out = np.empty((self.consts.imageHeight, self.consts.imageWidth, 4), np.float32)
         _check(self.L.rtxpt_b200_readback(self.h, S.BUFFER_ACCUMULATED_F32, out.ctypes.data, out.nbytes), self.L)
         return out
 
