@@ -158,6 +158,25 @@ typedef struct RtxptEnvCubeDesc {
     const float* faces[6][RTXPT_MAX_MIPS];
 } RtxptEnvCubeDesc;
 
+/* Analytic scene lights: the fields of Donut's PointLight / SpotLight (+ RTXPT's radius extension, Rtxpt/ExtendedScene.h) that
+ * LightsBaker's ConvertLight reads (Rtxpt/Lighting/LightsBaker.cpp:456-556).  A light with radius > 0 becomes a sphere light
+ * (a spot: a sphere light with cone shaping); radius == 0 becomes a kPoint record, which the reference's shaders compile out
+ * (POLYLIGHT_POINT_ENABLE 0, PolymorphicLightPTConfig.h:18) - it occupies a slot in the light list and is never sampled.
+ * Directional lights are baked into the environment map by the reference (out of scope here). */
+#define RTXPT_LIGHT_POINT 1u
+#define RTXPT_LIGHT_SPOT  2u
+typedef struct RtxptLightDesc {
+    uint32_t type;              /* RTXPT_LIGHT_* */
+    float    position[3];
+    float    direction[3];      /* spot axis (need not be normalised) */
+    float    color[3];
+    float    intensity;
+    float    radius;
+    float    innerAngle;        /* degrees (spot) */
+    float    outerAngle;        /* degrees (spot); negative: kPolymorphicLightShapingUseMinFalloff */
+    uint32_t _pad;
+} RtxptLightDesc;               /* 64 bytes */
+
 typedef struct RtxptSceneDesc {
     const RtxptInstanceData*    instances;      uint32_t instanceCount;
     const RtxptGeometryData*    geometries;     uint32_t geometryCount;
@@ -166,6 +185,7 @@ typedef struct RtxptSceneDesc {
     const RtxptBufferDesc*      buffers;        uint32_t bufferCount;
     const RtxptTextureDesc*     textures;       uint32_t textureCount;
     RtxptEnvCubeDesc            envCube;
+    const RtxptLightDesc*       lights;         uint32_t lightCount;      /* analytic lights; may be NULL / 0 */
 } RtxptSceneDesc;
 
 /* ------------------------------------------------------------------------------------------------------------------
@@ -320,6 +340,10 @@ RTXPT_API int rtxpt_b200_trace_rays_device(rtxpt_ctx* ctx, const void* dRays, ui
 /* Baked light list (PolymorphicLightInfo 32 B each), per-light proxy counters and the proxy index table. */
 RTXPT_API int rtxpt_b200_get_lights(rtxpt_ctx* ctx, void* outLightInfos, uint32_t* ioLightCount,
                                     uint32_t* outProxyCounters, uint32_t* outProxyIndices, uint32_t* ioProxyCount);
+
+/* PolymorphicLightInfoEx (16 B each: IesProfileIndex, PrimaryAxis, CosConeAngleAndSoftness, UniqueID) of the analytic lights, which
+ * occupy light indices [5368, 5368 + count) between the environment quad-tree nodes and the emissive triangles. */
+RTXPT_API int rtxpt_b200_get_lights_ex(rtxpt_ctx* ctx, void* outLightInfoEx, uint32_t* ioAnalyticLightCount);
 
 /* StandardBSDF evaluated on the device for `count` records of 36 floats in / 16 floats out; see tests/test_bsdf_parity.py. */
 RTXPT_API int rtxpt_b200_debug_bsdf(rtxpt_ctx* ctx, const float* in, uint32_t count, float* out);

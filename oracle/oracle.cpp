@@ -120,6 +120,14 @@ ORC_API int oracle_get_lights(void* p, void* outLightInfos, uint32_t* ioLightCou
     *ioLightCount = n; *ioProxyCount = m;
     return 0;
 }
+ORC_API int oracle_get_lights_ex(void* p, void* outEx, uint32_t* ioCount)
+{
+    OracleCtx* c = (OracleCtx*)p;
+    uint32_t n = c->lights.analyticLightCount;
+    if (outEx && *ioCount >= n) memcpy(outEx, c->lights.lightsEx.data(), size_t(n) * 16);
+    *ioCount = n;
+    return 0;
+}
 ORC_API int oracle_get_sub_instances(void* p, RtxptSubInstanceData* out, uint32_t count)
 {
     OracleCtx* c = (OracleCtx*)p;

@@ -17,7 +17,9 @@
 
 namespace orc {
 
-static const uint kLightTypeTriangle = 1, kLightTypeEnvironmentQuad = 5;
+static const uint kLightTypeSphere = 0, kLightTypeTriangle = 1, kLightTypePoint = 4, kLightTypeEnvironmentQuad = 5;      // PolymorphicLight.h:28-40
+static const uint kPolymorphicLightShapingEnableBit = 1u << 28, kPolymorphicLightShapingUseMinFalloff = 1u << 30;
+static const float kMinSpotlightFalloff = 0.0001f;
 static const uint kPolymorphicLightTypeShift = 24;
 static const float kMinLog2Radiance = -8.f, kMaxLog2Radiance = 40.f;
 static const float DISTANT_LIGHT_DISTANCE = 100000.0f;
@@ -30,6 +32,7 @@ static const float LIGHTING_MIN_WEIGHT = 1e-8f;
 static const uint RTXPT_INVALID_LIGHT_INDEX = 0xFFFFFFFFu;
 
 struct PolymorphicLightInfo { float Center[3]; uint ColorTypeAndFlags; uint Direction1, Direction2, Scalars, LogRadiance; };
+struct PolymorphicLightInfoEx { uint IesProfileIndex, PrimaryAxis, CosConeAngleAndSoftness, UniqueID; };      // PolymorphicLight.h:62-71
 
 inline float UnpackRadiance(uint logRadiance)
 {
@@ -135,6 +138,173 @@ struct EnvironmentQuadLight
     float SolidAnglePdf() const { return float(NodeDim * NodeDim) / (4.0f * K_PI); }
 };
 
+
+// ---- analytic lights (sphere lights with optional spot shaping) -------------------------------------------------------------------------
+// host-side packing helpers of Rtxpt/Lighting/LightsBaker.cpp:414-454 (note the truncating fp16 conversion and the doubled [0,1] mapping
+// of the octahedral encoding, both reproduced on purpose)
+inline uint fp32ToFp16Truncating(float v)
+{
+    const float multiple = asfloat(0x07800000u);        // 2^-112
+    const uint u = asuint(v * multiple);
+    const uint sign = u & 0x80000000u, body = u & 0x0fffffffu;
+    return ((sign >> 16) | (body >> 13)) & 0xFFFFu;
+}
+inline float2 OctWrapHost(float2 v) { return f2((1.0f - fabsf(v.y)) * ((v.x >= 0.0f) ? 1.0f : -1.0f), (1.0f - fabsf(v.x)) * ((v.y >= 0.0f) ? 1.0f : -1.0f)); }
+inline uint NDirToOctUnorm32(float3 n3)
+{
+    n3 = n3 / (fabsf(n3.x) + fabsf(n3.y) + fabsf(n3.z));
+    float2 n = f2(n3.x, n3.y);
+    n = n3.z >= 0.0f ? n : OctWrapHost(n);
+    n = n * 0.5f + f2(0.5f, 0.5f);
+    float2 p = n * 0.5f + f2(0.5f, 0.5f);
+    p.x = saturate(p.x); p.y = saturate(p.y);
+    return uint(p.x * float(0xfffe)) | (uint(p.y * float(0xfffe)) << 16);
+}
+inline float3 OctToNDirUnorm32(uint pUnorm)      // Utils.hlsli:128-153
+{
+    float2 p = f2(saturate(float(pUnorm & 0xffff) / float(0xfffe)), saturate(float(pUnorm >> 16) / float(0xfffe)));
+    p = p * 2.0f - f2(1.0f, 1.0f);
+    float2 f = p * 2.0f - f2(1.0f, 1.0f);            // Decode_Oct
+    float3 n = f3(f.x, f.y, 1.0f - fabsf(f.x) - fabsf(f.y));
+    float t = saturate(-n.z);
+    n.x += (n.x >= 0.0f) ? -t : t; n.y += (n.y >= 0.0f) ? -t : t;
+    return normalize(n);
+}
+
+struct LightShaping { float cosConeAngle = 0; float3 primaryAxis = f3(0); float cosConeSoftness = 0; bool isSpot = false; float minFalloff = 0; };
+inline LightShaping unpackLightShaping(const PolymorphicLightInfo& base, const PolymorphicLightInfoEx& ex)     // LightShaping.hlsli:26-42
+{
+    LightShaping s;
+    if (base.ColorTypeAndFlags & kPolymorphicLightShapingEnableBit)
+    {
+        s.isSpot = true; s.primaryAxis = OctToNDirUnorm32(ex.PrimaryAxis);
+        s.cosConeAngle = f16tof32(ex.CosConeAngleAndSoftness & 0xffff); s.cosConeSoftness = f16tof32(ex.CosConeAngleAndSoftness >> 16);
+        s.minFalloff = (base.ColorTypeAndFlags & kPolymorphicLightShapingUseMinFalloff) ? kMinSpotlightFalloff : 0.0f;
+    }
+    return s;
+}
+inline float smoothstepf(float a, float b, float x) { float t = saturate((x - a) / (b - a)); return t * t * (3.0f - 2.0f * t); }
+inline float evaluateLightShaping(const LightShaping& s, float3 surfacePosition, float3 lightSamplePosition)   // LightShaping.hlsli:76-95
+{
+    if (!s.isSpot) return 1.0f;
+    const float3 lightToSurface = normalize(surfacePosition - lightSamplePosition);
+    const float cosTheta = dot(s.primaryAxis, lightToSurface);
+    const float smoothFalloff = smoothstepf(s.cosConeAngle, s.cosConeAngle + s.cosConeSoftness, cosTheta);
+    const float softSpotlight = std::max(s.minFalloff, smoothFalloff);
+    return softSpotlight <= 0 ? 0.0f : softSpotlight;
+}
+inline float getShapingFluxFactor(const LightShaping& s)        // LightShaping.hlsli:161-174
+{
+    if (!s.isSpot) return 1.0f;
+    float solidAngleOverTwoPi = (1.0f - s.cosConeAngle);
+    solidAngleOverTwoPi *= (1.0f + (0.5f - 1.0f) * s.cosConeSoftness);      // lerp(1, 0.5, softness)
+    return solidAngleOverTwoPi * 0.5f;
+}
+inline void BranchlessONB(float3 normal, float3& tangent, float3& bitangent)    // Utils/Geometry.hlsli:17-24
+{
+    float sign = (normal.z >= 0) ? 1.0f : -1.0f;
+    float a = -1.0f / (sign + normal.z);
+    float b = normal.x * normal.y * a;
+    tangent = f3(1.0f + sign * normal.x * normal.x * a, sign * b, -sign * normal.x);
+    bitangent = f3(b, sign + normal.y * normal.y * a, -normal.y);
+}
+
+struct SphereLight      // PolymorphicLight.hlsli:93-259
+{
+    float3 position, radiance; float radius; LightShaping shaping;
+    static SphereLight Create(const PolymorphicLightInfo& li, const PolymorphicLightInfoEx& ex)
+    {
+        SphereLight s; s.position = f3(li.Center[0], li.Center[1], li.Center[2]); s.radius = f16tof32(li.Scalars & 0xffff);
+        s.radiance = UnpackLightColor(li); s.shaping = unpackLightShaping(li, ex);
+        return s;
+    }
+    PolymorphicLightSample CalcSample(float2 random, float3 viewerPosition) const
+    {
+        PolymorphicLightSample r = {};
+        const float3 lightVector = position - viewerPosition;
+        const float lightDistance2 = dot(lightVector, lightVector), radius2 = radius * radius;
+        if (lightDistance2 < radius2)
+        {   // inside the sphere: no emission (single-sided, like emissive triangles)
+            r.Position = position; r.Normal = f3(0); r.Radiance = f3(0); r.SolidAnglePdf = 1.0f; r.LightSampleableByBSDF = false;
+            return r;
+        }
+        const float lightDistance = sqrtf(lightDistance2);
+        const float sinThetaMax2 = radius2 / lightDistance2;
+        const float cosThetaMax = sqrtf(std::max(0.0f, 1.0f - sinThetaMax2));
+        const float phi = 2.0f * K_PI * random.x;
+        const float cosTheta = cosThetaMax + (1.0f - cosThetaMax) * random.y;         // lerp(cosThetaMax, 1, u.y)
+        const float sinTheta = sqrtf(std::max(0.0f, 1.0f - cosTheta * cosTheta));
+        const float sinTheta2 = sinTheta * sinTheta;
+        const float dc = lightDistance, dc2 = lightDistance2;
+        const float ds = dc * cosTheta - sqrtf(std::max(1e-10f, radius2 - dc2 * sinTheta2));
+        const float cosAlpha = (dc2 + radius2 - ds * ds) / (2.0f * dc * radius);
+        const float sinAlpha = sqrtf(std::max(0.0f, 1.0f - cosAlpha * cosAlpha));
+        const float3 sampleSpaceNormal = normalize(lightVector);
+        float3 T, B; BranchlessONB(sampleSpaceNormal, T, B);
+        const float sinPhi = sinf(phi), cosPhi = cosf(phi);
+        const float3 radiusVector = (-T) * (sinAlpha * cosPhi) + (-B) * (sinAlpha * sinPhi) + (-sampleSpaceNormal) * cosAlpha;
+        r.Position = position + radiusVector * radius;
+        r.Normal = normalize(radiusVector);
+        r.Radiance = radiance;
+        r.SolidAnglePdf = 1.0f / (2.0f * K_PI * (1.0f - cosThetaMax));
+        r.LightSampleableByBSDF = false;
+        return r;
+    }
+    float GetPower() const { return 4 * K_PI * radius * radius * K_PI * Luminance(radiance) * getShapingFluxFactor(shaping); }
+};
+
+// Rtxpt/Lighting/LightsBaker.cpp:456-556 (ConvertLight)
+inline void ConvertLight(const RtxptLightDesc& L, PolymorphicLightInfo& base, PolymorphicLightInfoEx& ex)
+{
+    base = PolymorphicLightInfo(); ex = PolymorphicLightInfoEx();
+    const float3 color = f3(L.color[0], L.color[1], L.color[2]);
+    const float kPi = 3.14159265358979323846f;
+    auto radians = [&](float deg) { return deg * (kPi / 180.0f); };
+    if (L.type == RTXPT_LIGHT_SPOT)
+    {
+        const float3 dir = normalize(f3(L.direction[0], L.direction[1], L.direction[2]));
+        const uint minFalloff = (L.outerAngle < 0) ? kPolymorphicLightShapingUseMinFalloff : 0u;
+        if (L.radius == 0.f)
+        {
+            base.ColorTypeAndFlags = (kLightTypePoint << kPolymorphicLightTypeShift) | minFalloff;
+            PackLightColor(color * L.intensity, base);
+            base.Direction1 = NDirToOctUnorm32(dir);
+            base.Direction2 = fp32ToFp16Truncating(radians(fabsf(L.outerAngle))) | (fp32ToFp16Truncating(radians(L.innerAngle)) << 16);
+        }
+        else
+        {
+            const float projectedArea = kPi * (L.radius * L.radius);
+            const float3 radiance = color * L.intensity / projectedArea;
+            const float softness = saturate(1.f - L.innerAngle / fabsf(L.outerAngle));
+            base.ColorTypeAndFlags = (kLightTypeSphere << kPolymorphicLightTypeShift) | minFalloff | kPolymorphicLightShapingEnableBit;
+            PackLightColor(radiance, base);
+            base.Scalars = fp32ToFp16Truncating(L.radius);
+            if (fabsf(L.outerAngle) > 0)
+            {
+                ex.PrimaryAxis = NDirToOctUnorm32(dir);
+                ex.CosConeAngleAndSoftness = fp32ToFp16Truncating(cosf(radians(fabsf(L.outerAngle)))) | (fp32ToFp16Truncating(softness) << 16);
+            }
+        }
+    }
+    else
+    {
+        if (L.radius == 0.f)
+        {
+            base.ColorTypeAndFlags = kLightTypePoint << kPolymorphicLightTypeShift;
+            PackLightColor(color * L.intensity, base);
+            base.Direction2 = fp32ToFp16Truncating(kPi) | (fp32ToFp16Truncating(0.0f) << 16);
+        }
+        else
+        {
+            const float projectedArea = kPi * (L.radius * L.radius);
+            base.ColorTypeAndFlags = kLightTypeSphere << kPolymorphicLightTypeShift;
+            PackLightColor(color * L.intensity / projectedArea, base);
+            base.Scalars = fp32ToFp16Truncating(L.radius);
+        }
+    }
+    base.Center[0] = L.position[0]; base.Center[1] = L.position[1]; base.Center[2] = L.position[2];
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Bake
 // ---------------------------------------------------------------------------------------------------------------------
@@ -147,6 +317,9 @@ struct LightTable
     uint envQuadNodeCount = 0, triangleLightCount = 0, samplingProxyCount = 0;
     float weightsSum = 0;
     bool envEnabled = false;
+    std::vector<PolymorphicLightInfoEx> lightsEx;      // analytic lights only: light index - ENVQT_TOTAL
+    uint analyticLightCount = 0;
+    PolymorphicLightInfoEx exOf(uint lightIndex) const { uint k = lightIndex - ENVQT_TOTAL; return k < analyticLightCount ? lightsEx[k] : PolymorphicLightInfoEx(); }
     uint importanceMipCount = 0;
     bool IsEmpty() const { return samplingProxyCount == 0; }
 };
@@ -296,6 +469,13 @@ inline void bakeLights(Scene& sc, const RtxptPathTracerConstants& consts, LightT
         c.distantVsLocalRelativeImportance = consts.distantVsLocalImportance * 0.0002f; c.transform = consts.envMap.Transform;
         bakeEnvLights(lt, c);
     }
+    // analytic lights (LightsBaker.cpp:596-640): after the environment nodes, before the emissive triangles
+    lt.lightsEx.clear(); lt.analyticLightCount = 0;
+    for (uint i = 0; i < d.lightCount; i++)
+    {
+        PolymorphicLightInfo base; PolymorphicLightInfoEx ex; ConvertLight(d.lights[i], base, ex);
+        lt.lights.push_back(base); lt.lightsEx.push_back(ex); lt.analyticLightCount++;
+    }
     // emissive triangles, one light per triangle of every emissive geometry instance, in instance/geometry order
     lt.triangleLightCount = 0;
     for (uint ii = 0; ii < d.instanceCount; ii++)
@@ -351,6 +531,7 @@ inline void bakeLights(Scene& sc, const RtxptPathTracerConstants& consts, LightT
         float flux = 0;
         if (LightType(li) == kLightTypeTriangle) flux = TriangleLight::Create(li).GetPower();
         else if (LightType(li) == kLightTypeEnvironmentQuad) flux = asfloat(li.Scalars);
+        else if (LightType(li) == kLightTypeSphere) flux = SphereLight::Create(li, lt.exOf(i)).GetPower();
         float weight = powf(flux, 0.8f);
         if (weight < LIGHTING_MIN_WEIGHT) weight = 0;
         w[i] = weight;

@@ -301,6 +301,12 @@ inline NEEResult HandleNEE(const PathTracerCtx& x, const PathState& pre, const S
             float2 interiorRnd; interiorRnd.x = sg.Next1D(); interiorRnd.y = sg.Next1D();
             PolymorphicLightSample ls = {};
             if (LightType(li) == kLightTypeTriangle) ls = TriangleLight::Create(li).CalcSample(interiorRnd, sd.posW);
+            else if (LightType(li) == kLightTypeSphere)
+            {   // PolymorphicLight::CalcSample, kSphere + the shaping factor applied to every sample with a positive pdf (PolymorphicLight.hlsli:643-676)
+                const PolymorphicLightInfoEx ex = lt.exOf(lightIndex);
+                ls = SphereLight::Create(li, ex).CalcSample(interiorRnd, sd.posW);
+                if (ls.SolidAnglePdf > 0) ls.Radiance = ls.Radiance * evaluateLightShaping(unpackLightShaping(li, ex), sd.posW, ls.Position);
+            }
             else if (LightType(li) == kLightTypeEnvironmentQuad)
             {
                 EnvironmentQuadLight e = EnvironmentQuadLight::Create(li);

@@ -61,7 +61,7 @@ struct rtxpt_ctx
     uint32_t bvhNodeCount = 0, bvhTriCount = 0; float bvhBuildSeconds = 0;
     std::vector<RtxptSubInstanceData> hSubInstances; uint32_t materialCount = 0;
     LightBakeState lightState;
-    DeviceArray<LightInfo> dLights; DeviceArray<uint32_t> dProxyCounters, dProxyIndices, dEnvLookup;
+    DeviceArray<LightInfo> dLights; DeviceArray<uint32_t> dProxyCounters, dProxyIndices, dEnvLookup; DeviceArray<uint4> dLightsEx;
     // wavefront
     DeviceArray<uint4> s0, s1, s2, s3, s4; DeviceArray<float4> hits; DeviceArray<uint32_t> rayQueue[2], shadeQueue;
     DeviceArray<float4> shadowOriginTMax, shadowDirPath; DeviceArray<uint2> shadowRadiance;
@@ -133,7 +133,7 @@ extern "C" RTXPT_API int rtxpt_b200_destroy(rtxpt_ctx* c)
     releaseScene(c);
     c->dInstances.release(); c->dGeometries.release(); c->dSubInstances.release(); c->dMaterials.release(); c->dSubInstanceClass.release();
     c->dBufferTable.release(); c->dTextureTable.release(); c->dBvhNodes.release(); c->dBvhTris.release(); c->dTriInfo.release();
-    c->dLights.release(); c->dProxyCounters.release(); c->dProxyIndices.release(); c->dEnvLookup.release();
+    c->dLightsEx.release(); c->dLights.release(); c->dProxyCounters.release(); c->dProxyIndices.release(); c->dEnvLookup.release();
     c->s0.release(); c->s1.release(); c->s2.release(); c->s3.release(); c->s4.release(); c->hits.release();
     c->rayQueue[0].release(); c->rayQueue[1].release(); c->shadeQueue.release();
     c->shadowOriginTMax.release(); c->shadowDirPath.release(); c->shadowRadiance.release(); c->counters.release(); c->pixelOfSlot.release(); c->allPixelTable.release();
@@ -360,6 +360,7 @@ static int uploadLights(rtxpt_ctx* c)
     CU(cudaStreamSynchronize(s));
     CU(c->dLights.upload(reinterpret_cast<const LightInfo*>(st.lights.data()), st.lights.size(), s));
     CU(c->dProxyCounters.upload(st.proxyCounters.data(), st.proxyCounters.size(), s));
+    if (!st.analyticLightsEx.empty()) CU(c->dLightsEx.upload(reinterpret_cast<const uint4*>(st.analyticLightsEx.data()), st.analyticLightsEx.size(), s));
     CU(c->dProxyIndices.upload(st.proxyIndices.data(), st.proxyIndices.size(), s));
     CU(c->dEnvLookup.upload(st.envLookupMap.data(), st.envLookupMap.size(), s));
     CU(cudaStreamSynchronize(s));
@@ -391,6 +392,7 @@ static void fillParams(rtxpt_ctx* c, LaunchParams& p)
     v.subInstanceClass = c->dSubInstanceClass.ptr; v.materialCount = c->materialCount;
     v.buffers = c->dBufferTable.ptr; v.textures = c->dTextureTable.ptr; v.envCube = c->envCube.object; v.envFaceSize = c->envFaceSize; v.envMipLevels = c->envMipLevels;
     v.bvhNodes = c->dBvhNodes.ptr; v.bvhTris = c->dBvhTris.ptr; v.triInfo = c->dTriInfo.ptr; v.bvhNodeCount = c->bvhNodeCount; v.bvhTriCount = c->bvhTriCount;
+    v.lightsEx = c->dLightsEx.ptr; v.analyticLightCount = uint32_t(c->lightState.analyticLightsEx.size());
     v.lights = c->dLights.ptr; v.proxyCounters = c->dProxyCounters.ptr; v.proxyIndices = c->dProxyIndices.ptr; v.envLookupMap = c->dEnvLookup.ptr;
     v.lightCount = uint32_t(c->lightState.lights.size()); v.samplingProxyCount = uint32_t(c->lightState.proxyIndices.size()); v.envEnabled = c->lightState.envEnabled ? 1u : 0u;
     WavefrontBuffers& w = p.wf;
@@ -646,6 +648,16 @@ extern "C" RTXPT_API int rtxpt_b200_get_lights(rtxpt_ctx* c, void* outLightInfos
     if (outProxyCounters && *ioLightCount >= n) CU(cudaMemcpy(outProxyCounters, c->dProxyCounters.ptr, size_t(n) * 4, cudaMemcpyDeviceToHost));
     if (outProxyIndices && *ioProxyCount >= m && m) CU(cudaMemcpy(outProxyIndices, c->dProxyIndices.ptr, size_t(m) * 4, cudaMemcpyDeviceToHost));
     *ioLightCount = n; *ioProxyCount = m;
+    return RTXPT_OK;
+}
+
+extern "C" RTXPT_API int rtxpt_b200_get_lights_ex(rtxpt_ctx* c, void* outLightInfoEx, uint32_t* ioAnalyticLightCount)
+{
+    int rc = checkReady(c); if (rc != RTXPT_OK) return rc;
+    if (!ioAnalyticLightCount) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    const uint32_t n = uint32_t(c->lightState.analyticLightsEx.size());
+    if (outLightInfoEx && *ioAnalyticLightCount >= n && n) CU(cudaMemcpy(outLightInfoEx, c->dLightsEx.ptr, size_t(n) * 16, cudaMemcpyDeviceToHost));
+    *ioAnalyticLightCount = n;
     return RTXPT_OK;
 }
 

@@ -140,7 +140,8 @@ struct HostTexture
 };
 
 // ---- packed light helpers ------------------------------------------------------------------------------------------------------
-constexpr uint32_t kTypeTriangle = 1, kTypeEnvQuad = 5;
+constexpr uint32_t kTypeSphere = 0, kTypeTriangle = 1, kTypePoint = 4, kTypeEnvQuad = 5;
+constexpr uint32_t kShapingEnableBit = 1u << 28, kShapingUseMinFalloff = 1u << 30;
 float unpackLogRadiance(uint32_t lr) { return (lr == 0) ? 0.f : std::exp2((float(lr - 1) / 65534.0f) * 48.0f + -8.0f); }
 void packColor(V3 radiance, BakedLight& li)       // PolymorphicLight::PackColor (PolymorphicLight.hlsli:776-795)
 {
@@ -239,6 +240,77 @@ void LightBaker::buildEnvRadianceMap(const RtxptEnvCubeDesc& cube, LightBakeStat
     }
 }
 
+
+// ---- analytic scene lights -> packed records (the CPU half of the reference's light list: Rtxpt/Lighting/LightsBaker.cpp:414-556) ---------
+// The reference packs these on the host with its own helpers: a truncating float->half (multiply by 2^-112, shift the mantissa) and an
+// octahedral encoding that maps to [0,1] twice; the shader-side decoders (Utils.hlsli:128-153) undo exactly that.
+static uint32_t halfTruncating(float v)
+{
+    const uint32_t u = bitsOf(v * floatOf(0x07800000u));
+    return (((u & 0x80000000u) >> 16) | ((u & 0x0fffffffu) >> 13)) & 0xFFFFu;
+}
+static uint32_t octUnorm32(V3 n)
+{
+    const float l1 = std::fabs(n.x) + std::fabs(n.y) + std::fabs(n.z);
+    float x = n.x / l1, y = n.y / l1; const float z = n.z / l1;
+    if (!(z >= 0.0f)) { const float wx = (1.0f - std::fabs(y)) * (x >= 0.0f ? 1.0f : -1.0f), wy = (1.0f - std::fabs(x)) * (y >= 0.0f ? 1.0f : -1.0f); x = wx; y = wy; }
+    x = x * 0.5f + 0.5f; y = y * 0.5f + 0.5f;
+    const float px = satf(x * 0.5f + 0.5f), py = satf(y * 0.5f + 0.5f);
+    return uint32_t(px * float(0xfffe)) | (uint32_t(py * float(0xfffe)) << 16);
+}
+[[maybe_unused]] static V3 octUnorm32ToDir(uint32_t p)
+{
+    float fx = satf(float(p & 0xffff) / float(0xfffe)) * 2.0f - 1.0f, fy = satf(float(p >> 16) / float(0xfffe)) * 2.0f - 1.0f;
+    fx = fx * 2.0f - 1.0f; fy = fy * 2.0f - 1.0f;
+    V3 n = { fx, fy, 1.0f - std::fabs(fx) - std::fabs(fy) };
+    const float t = satf(-n.z);
+    n.x += (n.x >= 0.0f) ? -t : t; n.y += (n.y >= 0.0f) ? -t : t;
+    return n / std::sqrt(dotv(n, n));
+}
+static void convertAnalyticLight(const RtxptLightDesc& L, BakedLight& li, BakedLightEx& ex)
+{
+    memset(&li, 0, sizeof(li)); memset(&ex, 0, sizeof(ex));
+    const float pi = 3.14159265358979323846f, toRad = pi / 180.0f;
+    const V3 flux = V3{ L.color[0], L.color[1], L.color[2] } * L.intensity;
+    const bool spot = (L.type == RTXPT_LIGHT_SPOT);
+    const uint32_t falloffFlag = (spot && L.outerAngle < 0) ? kShapingUseMinFalloff : 0u;
+    V3 axis = { 0, 0, 0 };
+    if (spot) { axis = { L.direction[0], L.direction[1], L.direction[2] }; axis = axis / std::sqrt(dotv(axis, axis)); }
+    if (L.radius == 0.f)
+    {   // kPoint record: compiled out of the reference's sampling code, kept for the index layout
+        li.colorTypeAndFlags = (kTypePoint << 24) | falloffFlag;
+        packColor(flux, li);
+        if (spot) { li.direction1 = octUnorm32(axis); li.direction2 = halfTruncating(std::fabs(L.outerAngle) * toRad) | (halfTruncating(L.innerAngle * toRad) << 16); }
+        else li.direction2 = halfTruncating(pi) | (halfTruncating(0.0f) << 16);
+    }
+    else
+    {   // sphere light; radiance = flux over the projected disc
+        li.colorTypeAndFlags = (kTypeSphere << 24) | falloffFlag | (spot ? kShapingEnableBit : 0u);
+        packColor(flux / (pi * (L.radius * L.radius)), li);
+        li.scalars = halfTruncating(L.radius);
+        if (spot && std::fabs(L.outerAngle) > 0)
+        {
+            const float softness = satf(1.f - L.innerAngle / std::fabs(L.outerAngle));
+            ex.primaryAxis = octUnorm32(axis);
+            ex.cosConeAngleAndSoftness = halfTruncating(std::cos(std::fabs(L.outerAngle) * toRad)) | (halfTruncating(softness) << 16);
+        }
+    }
+    li.center[0] = L.position[0]; li.center[1] = L.position[1]; li.center[2] = L.position[2];
+}
+static float sphereLightPower(const BakedLight& l, const BakedLightEx& ex)      // SphereLight::GetPower x getShapingFluxFactor
+{
+    const float pi = 3.14159265358979323846f;
+    const float radius = fromHalf(l.scalars & 0xffff);
+    const V3 rad = unpackColor(l);
+    float shaping = 1.0f;
+    if (l.colorTypeAndFlags & kShapingEnableBit)
+    {
+        const float cosCone = fromHalf(ex.cosConeAngleAndSoftness & 0xffff), softness = fromHalf(ex.cosConeAngleAndSoftness >> 16);
+        shaping = (1.0f - cosCone) * (1.0f + (0.5f - 1.0f) * softness) * 0.5f;
+    }
+    return 4 * pi * radius * radius * pi * (rad.x * 0.2126f + rad.y * 0.7152f + rad.z * 0.0722f) * shaping;
+}
+
 void LightBaker::finalize(const RtxptPathTracerConstants& consts, LightBakeState& st)
 {
     st.envEnabled = st.hasEnvCube && consts.envMap.Enabled != 0.0f;
@@ -286,6 +358,7 @@ void LightBaker::finalize(const RtxptPathTracerConstants& consts, LightBakeState
             for (uint32_t yy = 0; yy < ds; yy++) for (uint32_t xx = 0; xx < ds; xx++) st.envLookupMap[size_t(ny * ds + yy) * kEnvImportanceMapDim + nx * ds + xx] = li;
         }
     }
+    st.lights.insert(st.lights.end(), st.analyticLights.begin(), st.analyticLights.end());
     st.lights.insert(st.lights.end(), st.triangleLights.begin(), st.triangleLights.end());
     finalizeWeightsAndProxies(consts, st);
 }
@@ -295,7 +368,15 @@ void LightBaker::prepareScene(const RtxptSceneDesc& scene, std::vector<RtxptSubI
     st.hasEnvCube = scene.envCube.faceSize != 0;
     st.envRadianceMips.clear();
     if (st.hasEnvCube) buildEnvRadianceMap(scene.envCube, st);
-    // emissive triangles: one light per triangle of every emissive geometry instance, appended after the env quad-tree slots
+    // analytic lights sit between the env quad-tree slots and the emissive triangles (LightsBaker.cpp:596-640)
+    st.analyticLights.clear(); st.analyticLightsEx.clear();
+    for (uint32_t i = 0; i < scene.lightCount && scene.lights; i++)
+    {
+        BakedLight li; BakedLightEx ex; convertAnalyticLight(scene.lights[i], li, ex);
+        st.analyticLights.push_back(li); st.analyticLightsEx.push_back(ex);
+    }
+    const uint32_t firstTriangleLight = kEnvQuadLightCount + uint32_t(st.analyticLights.size());
+    // emissive triangles: one light per triangle of every emissive geometry instance
     st.triangleLights.clear();
     st.triangleLightCount = 0;
     for (uint32_t ii = 0; ii < scene.instanceCount; ii++)
@@ -308,8 +389,8 @@ void LightBaker::prepareScene(const RtxptSceneDesc& scene, std::vector<RtxptSubI
             const RtxptMaterialData& m = scene.materials[sub.GlobalGeometryIndex_PTMaterialDataIndex & 0xFFFF];
             const uint32_t triCount = g.numIndices / 3;
             const bool emissive = m.EmissiveColor[0] > 0 || m.EmissiveColor[1] > 0 || m.EmissiveColor[2] > 0;       // PTMaterial::IsEmissive
-            if (!emissive || kEnvQuadLightCount + st.triangleLights.size() + triCount >= kMaxLights) { sub.EmissiveLightMappingOffset = 0xFFFFFFFFu; continue; }
-            sub.EmissiveLightMappingOffset = kEnvQuadLightCount + uint32_t(st.triangleLights.size());
+            if (!emissive || firstTriangleLight + st.triangleLights.size() + triCount >= kMaxLights) { sub.EmissiveLightMappingOffset = 0xFFFFFFFFu; continue; }
+            sub.EmissiveLightMappingOffset = firstTriangleLight + uint32_t(st.triangleLights.size());
             const float* xf = inst.transform;
             const float det = xf[0] * (xf[5] * xf[10] - xf[6] * xf[9]) - xf[1] * (xf[4] * xf[10] - xf[6] * xf[8]) + xf[2] * (xf[4] * xf[9] - xf[5] * xf[8]);
             const uint8_t* ib = (const uint8_t*)scene.buffers[g.indexBufferIndex].data; const uint8_t* vb = (const uint8_t*)scene.buffers[g.vertexBufferIndex].data;
@@ -372,6 +453,7 @@ void LightBaker::finalizeWeightsAndProxies(const RtxptPathTracerConstants& const
             flux = area * 3.14159265358979323846f * (rad.x * 0.2126f + rad.y * 0.7152f + rad.z * 0.0722f);
         }
         else if (type == kTypeEnvQuad) flux = floatOf(l.scalars);
+        else if (type == kTypeSphere) flux = sphereLightPower(l, st.analyticLightsEx[i - kEnvQuadLightCount]);
         float weight = std::pow(flux, 0.8f);
         if (weight < 1e-8f) weight = 0;
         w[i] = weight;

@@ -11,11 +11,14 @@ constexpr uint32_t kEnvImportanceMapDim = 1024;     // EMISB_IMPORTANCE_MAP_DIM
 constexpr uint32_t kMaxLights = 512 * 1024;         // RTXPT_LIGHTING_MAX_LIGHTS
 
 struct BakedLight { float center[3]; uint32_t colorTypeAndFlags, direction1, direction2, scalars, logRadiance; };   // PolymorphicLightInfo (32 B)
+struct BakedLightEx { uint32_t iesProfileIndex, primaryAxis, cosConeAngleAndSoftness, uniqueID; };                  // PolymorphicLightInfoEx (16 B)
 
 struct LightBakeState
 {
-    std::vector<BakedLight> lights;             // [0, kEnvQuadLightCount) env quad-tree nodes, then one light per emissive triangle
+    std::vector<BakedLight> lights;             // [0, kEnvQuadLightCount) env quad-tree nodes, analytic lights, then one light per emissive triangle
     std::vector<BakedLight> triangleLights;     // scene-only part, baked once at upload
+    std::vector<BakedLight> analyticLights;     // converted scene lights (sphere / point records), baked once at upload
+    std::vector<BakedLightEx> analyticLightsEx; // their shaping records: light index - kEnvQuadLightCount
     bool hasEnvCube = false;
     std::vector<uint32_t> proxyCounters, proxyIndices, envLookupMap;
     std::vector<std::vector<float>> envRadianceMips;    // RGBA, fp16-rounded (EnvRadianceMap RGBA16F, .a = importance)

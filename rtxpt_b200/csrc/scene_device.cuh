@@ -33,6 +33,8 @@ struct SceneView
     const uint*                 proxyIndices;
     const uint*                 envLookupMap;       // 1024 x 1024 light indices
     uint                        lightCount, samplingProxyCount, envEnabled;
+    const uint4*                lightsEx;           // PolymorphicLightInfoEx of the analytic lights: index = light index - 5368
+    uint                        analyticLightCount;
 };
 
 PT_DEVICE uint load32(const SceneView& sc, uint buffer, uint byteOffset) { return __ldg(reinterpret_cast<const uint*>(sc.buffers[buffer] + byteOffset)); }

@@ -46,7 +46,8 @@ PT_DEVICE float3 envEvalLocal(const LaunchParams& p, float3 localDir, float lod)
 }
 
 // ---- lights ----------------------------------------------------------------------------------------------------------------------
-constexpr uint kLightTypeTriangle = 1, kLightTypeEnvQuad = 5;
+constexpr uint kLightTypeSphere = 0, kLightTypeTriangle = 1, kLightTypeEnvQuad = 5;
+constexpr uint kLightShapingEnableBit = 1u << 28, kLightShapingUseMinFalloff = 1u << 30;
 constexpr float kDistantLightDistance = 100000.0f;
 constexpr uint kEnvLookupDim = 1024;
 constexpr uint kInvalidLight = 0xFFFFFFFFu;
@@ -57,6 +58,54 @@ PT_DEVICE float3 unpackLightRadiance(const LightInfo& li)           // Polymorph
     const uint lr = li.logRadiance & 0xffff;
     const float radiance = (lr == 0) ? 0.f : exp2f((float(lr - 1) / 65534.0f) * 48.0f + -8.0f);
     return mk3(unpackUnorm8(li.colorTypeAndFlags), unpackUnorm8(li.colorTypeAndFlags >> 8), unpackUnorm8(li.colorTypeAndFlags >> 16)) * radiance;
+}
+
+// OctToNDirUnorm32 (Utils.hlsli:128-153; the [0,1] mapping is applied twice on both sides, see lights_bake.cpp)
+PT_DEVICE float3 octUnorm32ToDir(uint p)
+{
+    float fx = sat(float(p & 0xffffu) / float(0xfffe)) * 2.0f - 1.0f, fy = sat(float(p >> 16) / float(0xfffe)) * 2.0f - 1.0f;
+    fx = fx * 2.0f - 1.0f; fy = fy * 2.0f - 1.0f;
+    float3 n = mk3(fx, fy, 1.0f - fabsf(fx) - fabsf(fy));
+    const float t = sat(-n.z);
+    n.x += (n.x >= 0.0f) ? -t : t; n.y += (n.y >= 0.0f) ? -t : t;
+    return norm3(n);
+}
+// SphereLight::CalcSample + evaluateLightShaping (PolymorphicLight.hlsli:107-181, :669-673; LightShaping.hlsli:26-95)
+PT_DEVICE void sampleSphereLight(const LightInfo& li, const SceneView& sc, uint lightIndex, float u0, float u1, float3 viewer, float3& outPos, float3& outRadiance, float& outSolidPdf)
+{
+    const float3 center = mk3(li.cx, li.cy, li.cz);
+    const float radius = f16tof32(li.scalars);
+    const float3 lightVector = center - viewer;
+    const float d2 = dot3(lightVector, lightVector), r2 = radius * radius;
+    if (d2 < r2) { outPos = center; outRadiance = mk3(0.f); outSolidPdf = 1.0f; return; }      // viewer inside: single-sided emitter
+    const float dc = sqrtf(d2);
+    const float cosThetaMax = sqrtf(fmaxf(0.0f, 1.0f - r2 / d2));
+    const float phi = 2.0f * kPi * u0;
+    const float cosTheta = cosThetaMax + (1.0f - cosThetaMax) * u1;
+    const float sinTheta = sqrtf(fmaxf(0.0f, 1.0f - cosTheta * cosTheta));
+    const float ds = dc * cosTheta - sqrtf(fmaxf(1e-10f, r2 - d2 * (sinTheta * sinTheta)));
+    const float cosAlpha = (d2 + r2 - ds * ds) / (2.0f * dc * radius);
+    const float sinAlpha = sqrtf(fmaxf(0.0f, 1.0f - cosAlpha * cosAlpha));
+    const float3 n = norm3(lightVector);
+    const float sign = (n.z >= 0) ? 1.0f : -1.0f;                   // BranchlessONB (Utils/Geometry.hlsli:17-24)
+    const float a = -1.0f / (sign + n.z), b = n.x * n.y * a;
+    const float3 T = mk3(1.0f + sign * n.x * n.x * a, sign * b, -sign * n.x), B = mk3(b, sign + n.y * n.y * a, -n.y);
+    const float sinPhi = sinf(phi), cosPhi = cosf(phi);
+    const float3 radiusVector = (-T) * (sinAlpha * cosPhi) + (-B) * (sinAlpha * sinPhi) + (-n) * cosAlpha;
+    outPos = center + radiusVector * radius;
+    outSolidPdf = 1.0f / (2.0f * kPi * (1.0f - cosThetaMax));
+    outRadiance = unpackLightRadiance(li);
+    if (li.colorTypeAndFlags & kLightShapingEnableBit)
+    {
+        const uint4 ex = sc.lightsEx[lightIndex - 5368u];
+        const float3 axis = octUnorm32ToDir(ex.y);
+        const float cosCone = f16tof32(ex.z), softness = f16tof32(ex.z >> 16);
+        const float minFalloff = (li.colorTypeAndFlags & kLightShapingUseMinFalloff) ? 0.0001f : 0.0f;
+        const float cosT = dot3(axis, norm3(viewer - outPos));
+        const float t = sat((cosT - cosCone) / ((cosCone + softness) - cosCone));
+        const float falloff = fmaxf(minFalloff, t * t * (3.0f - 2.0f * t));
+        outRadiance = outRadiance * (falloff <= 0 ? 0.0f : falloff);
+    }
 }
 struct TriLight
 {
@@ -475,7 +524,7 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
         const bool isSSC = (preConeWidth / preSceneLength) < 0.3f;
         neeMis = (1u << 15) | ((isSSC ? 1u : 0u) << 13) | ((candidateCount & 0x3F) << 6) | (fullSamples & 0x3F);
         float3 pickLi = mk3(0.f), pickDir = mk3(0.f); float pickDist = 0.f, pickSelPdf = 0.f, pickSolidPdf = 0.f;
-        float weightSum = 0.f, pickWeight = 0.f;
+        float weightSum = 0.f, pickWeight = 0.f; bool pickBsdfSampleable = true;
         const uint M = p.scene.samplingProxyCount;
         // The candidate loop is a chain of dependent random gathers (proxy table -> counter, light record).  The light selection draws are
         // every 4th value of the stream, so the proxy lookups of the first 8 candidates are issued up front and their light records
@@ -516,8 +565,13 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
             const float selectionPdf = float(p.scene.proxyCounters[lightIndex]) / float(M);
             const LightInfo li = p.scene.lights[lightIndex];
             const float r0 = uniformSG.next(), r1 = uniformSG.next();
-            float3 lsPos = mk3(0.f), lsRadiance = mk3(0.f); float lsSolidPdf = 0.f;
-            if (lightType(li) == kLightTypeTriangle)
+            float3 lsPos = mk3(0.f), lsRadiance = mk3(0.f); float lsSolidPdf = 0.f; bool lsBsdfSampleable = true;
+            if (lightType(li) == kLightTypeSphere)
+            {   // SphereLight::CalcSample (PolymorphicLight.hlsli:107-181): cone sampling of the visible cap; never found by BSDF rays
+                lsBsdfSampleable = false;
+                sampleSphereLight(li, p.scene, lightIndex, r0, r1, s.posW, lsPos, lsRadiance, lsSolidPdf);
+            }
+            else if (lightType(li) == kLightTypeTriangle)
             {   // TriangleLight::CalcSample (PolymorphicLight.hlsli:409-441)
                 TriLight tl; tl.decode(li);
                 const float sq = sqrtf(r0);
@@ -543,7 +597,7 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
             const float wrsWeight = maxComp(Li) * bsdf.pdf(dirToLight);
             const float wrsRnd = uniformSG.next();
             weightSum += wrsWeight;
-            if (wrsRnd < sat(wrsWeight / weightSum)) { pickLi = Li; pickDir = dirToLight; pickDist = dist; pickSelPdf = selectionPdf; pickSolidPdf = lsSolidPdf; pickWeight = wrsWeight; }
+            if (wrsRnd < sat(wrsWeight / weightSum)) { pickLi = Li; pickDir = dirToLight; pickDist = dist; pickSelPdf = selectionPdf; pickSolidPdf = lsSolidPdf; pickWeight = wrsWeight; pickBsdfSampleable = lsBsdfSampleable; }
         }
         pickLi = pickLi * (1.0f / (pickWeight / weightSum));
         if (anyPositive(pickLi))
@@ -551,7 +605,7 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
             const float fadeOut = (s.shadowNoLFadeout > 0) ? sat((dot3(pickDir, s.vertexN) - s.shadowNoLFadeout) / (2.0f * s.shadowNoLFadeout)) : 1.0f;
             const float wrsMIS = misBalance(pickSelPdf, 0.0f) / float(candidateCount);     // all candidates come from the global table in this tier
             const float scatterPdfForDir = bsdf.pdf(pickDir);
-            const float pathMIS = misBalance(pickSelPdf * float(fullSamples) * pickSolidPdf, scatterPdfForDir);    // both light types are BSDF-sampleable
+            const float pathMIS = misBalance(pickSelPdf * float(fullSamples) * pickSolidPdf, pickBsdfSampleable ? scatterPdfForDir : 0.0f);    // LightSampleableByBSDF
             const float3 Li = pickLi * (fadeOut * wrsMIS * pathMIS / float(fullSamples));
             const float4 bsdfThp = bsdf.eval(pickDir);
             float3 radiance = mk3(bsdfThp.x, bsdfThp.y, bsdfThp.z) * Li;

@@ -44,6 +44,7 @@ _SIGNATURES = {
     "rtxpt_b200_trace_rays": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p],
     "rtxpt_b200_trace_rays_device": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32, C.POINTER(C.c_float)],
     "rtxpt_b200_get_lights": [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)],
+    "rtxpt_b200_get_lights_ex": [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)],
     "rtxpt_b200_debug_bsdf": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
     "rtxpt_b200_debug_rng": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
 }
@@ -164,6 +165,14 @@ class Context:
         infos = np.zeros((n.value, 8), np.uint32); counters = np.zeros(n.value, np.uint32); proxies = np.zeros(max(m.value, 1), np.uint32)
         _check(self.L.rtxpt_b200_get_lights(self.h, infos.ctypes.data, C.byref(n), counters.ctypes.data, proxies.ctypes.data, C.byref(m)), self.L)
         return infos, counters, proxies[:m.value]
+
+    def lights_ex(self):
+        n = C.c_uint32(0)
+        _check(self.L.rtxpt_b200_get_lights_ex(self.h, None, C.byref(n)), self.L)
+        ex = np.zeros((n.value, 4), np.uint32)
+        if n.value:
+            _check(self.L.rtxpt_b200_get_lights_ex(self.h, ex.ctypes.data, C.byref(n)), self.L)
+        return ex
 
     def debug_bsdf(self, records):
         records = np.ascontiguousarray(records, np.float32).reshape(-1, 36)

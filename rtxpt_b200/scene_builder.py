@@ -113,6 +113,15 @@ class SceneBuilder:
         self.meshes = []        # list of geometries: dict(positions, uvs, normals, tangents, indices, material)
         self.instances = []     # (mesh index, 3x4 transform)
         self.env_faces = None
+        self.lights = []        # analytic lights: dicts with the RtxptLightDesc fields
+
+    def add_point_light(self, position, color, intensity, radius):
+        """Donut PointLight + RTXPT radius extension; radius > 0 makes it a sphere light (LightsBaker.cpp:528-551)."""
+        self.lights.append(dict(type=S.LIGHT_POINT, position=position, direction=(0, 0, -1), color=color, intensity=intensity, radius=radius, inner=0.0, outer=0.0))
+
+    def add_spot_light(self, position, direction, color, intensity, radius, inner_angle, outer_angle):
+        """Donut SpotLight (angles in degrees); a sphere light with cone shaping (LightsBaker.cpp:463-500)."""
+        self.lights.append(dict(type=S.LIGHT_SPOT, position=position, direction=direction, color=color, intensity=intensity, radius=radius, inner=inner_angle, outer=outer_angle))
 
     def add_texture(self, img_u8, srgb):
         self.textures.append((make_mips_u8(img_u8), S.FORMAT_RGBA8_SRGB if srgb else S.FORMAT_RGBA8_UNORM))
@@ -280,6 +289,12 @@ class Scene:
                 self._keep.append(arr)
                 for f in range(6):
                     d.envCube.faces[f][m] = arr[f].ctypes.data
+        self.lights = (S.LightDesc * max(1, len(b.lights)))()
+        for i, L in enumerate(b.lights):
+            l = self.lights[i]
+            l.type = L["type"]; l.position[:] = L["position"]; l.direction[:] = L["direction"]; l.color[:] = L["color"]
+            l.intensity, l.radius, l.innerAngle, l.outerAngle = L["intensity"], L["radius"], L["inner"], L["outer"]
+        d.lights, d.lightCount = self.lights, len(b.lights)
         self.desc = d
         self.material_count = len(b.materials)
         self.has_env = b.env_faces is not None

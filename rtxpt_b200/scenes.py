@@ -38,9 +38,14 @@ def _merge(geos, material):
     return dict(positions=np.concatenate(pos), indices=np.concatenate(idx), normals=np.concatenate(nrm), uvs=np.concatenate(uvs), material=material)
 
 
-def cornell_box(width=256, height=256):
-    """Returns (scene, camera).  Classic Cornell data in metres (x right, y up, z into the box); the camera looks down +z."""
+def cornell_box(width=256, height=256, analytic_lights=False):
+    """Returns (scene, camera).  Classic Cornell data in metres (x right, y up, z into the box); the camera looks down +z.
+    analytic_lights adds a sphere light, a spot light and a zero-radius point light (the reference never samples the last)."""
     b = SceneBuilder()
+    if analytic_lights:
+        b.add_point_light(position=(1.2, 3.9, 1.6), color=(0.4, 0.6, 1.0), intensity=14.0, radius=0.22)
+        b.add_spot_light(position=(4.4, 4.6, 1.2), direction=(-0.5, -1.0, 0.55), color=(1.0, 0.85, 0.6), intensity=60.0, radius=0.12, inner_angle=18.0, outer_angle=34.0)
+        b.add_point_light(position=(2.7, 2.0, 2.7), color=(1.0, 1.0, 1.0), intensity=5.0, radius=0.0)
     white = b.add_material(Material(base_color=(0.73, 0.73, 0.73), roughness=1.0, metalness=0.0))
     red = b.add_material(Material(base_color=(0.65, 0.05, 0.05), roughness=1.0))
     green = b.add_material(Material(base_color=(0.12, 0.45, 0.15), roughness=1.0))

@@ -70,6 +70,14 @@ class EnvCubeDesc(C.Structure):
     _fields_ = [("faceSize", u32), ("mipLevels", u32), ("faces", (C.c_void_p * MAX_MIPS) * 6)]
 
 
+LIGHT_POINT, LIGHT_SPOT = 1, 2
+
+
+class LightDesc(C.Structure):       # RtxptLightDesc, 64 bytes
+    _fields_ = [("type", u32), ("position", f32 * 3), ("direction", f32 * 3), ("color", f32 * 3), ("intensity", f32), ("radius", f32),
+                ("innerAngle", f32), ("outerAngle", f32), ("_pad", u32)]
+
+
 class SceneDesc(C.Structure):
     _fields_ = [("instances", C.POINTER(InstanceData)), ("instanceCount", u32),
                 ("geometries", C.POINTER(GeometryData)), ("geometryCount", u32),
@@ -77,7 +85,8 @@ class SceneDesc(C.Structure):
                 ("materials", C.POINTER(MaterialData)), ("materialCount", u32),
                 ("buffers", C.POINTER(BufferDesc)), ("bufferCount", u32),
                 ("textures", C.POINTER(TextureDesc)), ("textureCount", u32),
-                ("envCube", EnvCubeDesc)]
+                ("envCube", EnvCubeDesc),
+                ("lights", C.POINTER(LightDesc)), ("lightCount", u32)]
 
 
 class CameraData(C.Structure):

@@ -43,6 +43,7 @@ def lib():
         L.oracle_set_constants.argtypes = [C.c_void_p, C.POINTER(S.PathTracerConstants)]
         L.oracle_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
         L.oracle_get_lights.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
+        L.oracle_get_lights_ex.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
         L.oracle_get_sub_instances.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.oracle_render.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
                                     C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.c_int, C.POINTER(RenderStats)]
@@ -82,6 +83,14 @@ class Oracle:
         infos = np.zeros((n.value, 8), np.uint32); counters = np.zeros(n.value, np.uint32); proxies = np.zeros(m.value, np.uint32)
         lib().oracle_get_lights(self.h, infos.ctypes.data, C.byref(n), counters.ctypes.data, proxies.ctypes.data, C.byref(m))
         return infos, counters, proxies
+
+    def lights_ex(self):
+        n = C.c_uint32(0)
+        lib().oracle_get_lights_ex(self.h, None, C.byref(n))
+        ex = np.zeros((n.value, 4), np.uint32)
+        if n.value:
+            lib().oracle_get_lights_ex(self.h, ex.ctypes.data, C.byref(n))
+        return ex
 
     def render(self, first_sub_sample, count, accum=None, accum_count=0, rect=None, threads=0, want_primary=False):
         W, H = self.consts.imageWidth, self.consts.imageHeight

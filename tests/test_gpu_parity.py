@@ -123,6 +123,28 @@ def test_light_tables_bit_exact(ctx, oracle, cornell, small_city, which):
     o.close()
 
 
+def test_analytic_lights_parity(ctx, oracle):
+    """Sphere / spot lights: packed records and shaping records bit-exact, image parity with NEE over analytic + triangle lights."""
+    from rtxpt_b200 import scene_builder as sb, scenes
+    from rtxpt_b200.imageio import per_pixel_l2
+    scene, cam = scenes.cornell_box(192, 192, analytic_lights=True)
+    consts = sb.make_constants(192, 192, cam, bounce_count=3, diffuse_bounce_count=3)
+    ctx.upload_scene(scene); ctx.set_constants(consts)
+    o = oracle.Oracle(scene); o.set_constants(consts)
+    lp, cp, pp = ctx.lights(); lo_, co, po = o.lights()
+    assert lp.shape[0] == 5368 + 3 + 2
+    assert np.array_equal(lp, lo_) and np.array_equal(cp, co) and np.array_equal(pp, po) and np.array_equal(ctx.lights_ex(), o.lights_ex())
+    ctx.reset_accumulation(); ctx.path_trace(0, 4, True); ctx.synchronize()
+    img = ctx.readback_accumulated(); st = ctx.stats()
+    acc, n, _, _, ost = o.render(0, 4); o.close()
+    d = np.abs(img[..., :3] - acc[..., :3])
+    if ctx.variant == "strict":
+        assert st.scatterRays == ost.scatterRays and st.shadowRays == ost.shadowRays
+        assert (d.max(-1) == 0).mean() > 0.99 and per_pixel_l2(img, acc) < 1e-6
+    else:
+        assert abs(int(st.shadowRays) - int(ost.shadowRays)) <= 1e-3 * ost.shadowRays and per_pixel_l2(img, acc) < 1e-4
+
+
 def test_cornell_c1_image_parity(ctx, oracle, cornell):
     """BASELINE.json configs[0]: Cornell box 256x256, 1 spp, 2 bounces — per-sample parity of the whole path."""
     from rtxpt_b200 import scene_builder as sb

@@ -46,3 +46,28 @@ def test_furnace_nee_and_bsdf_sampling_agree(oracle):
     assert 0.6 < means[0] < 1.0
     assert abs(means[0] - means[1]) < 0.01 * means[0], means
     o.close()
+
+
+def test_analytic_lights_cpu(oracle):
+    """Sphere / spot / zero-radius point lights: list layout [env nodes | analytic | triangles], packed records, and their effect."""
+    from rtxpt_b200 import scene_builder as sb, scenes
+    scene, cam = scenes.cornell_box(96, 96, analytic_lights=True)
+    plain, _ = scenes.cornell_box(96, 96)
+    o = oracle.Oracle(scene); consts = sb.make_constants(96, 96, cam, bounce_count=2, diffuse_bounce_count=2); o.set_constants(consts)
+    infos, counters, proxies = o.lights(); ex = o.lights_ex()
+    assert infos.shape[0] == 5368 + 3 + 2 and ex.shape == (3, 4)
+    types = (infos[5368:5373, 3] >> 24) & 0xf
+    assert list(types) == [0, 0, 4, 1, 1]                                   # sphere, sphere(spot), point, 2 emissive triangles
+    assert (infos[5369, 3] >> 28) & 1 == 1 and (infos[5368, 3] >> 28) & 1 == 0  # shaping bit only on the spot
+    assert counters[5368] > 0 and counters[5369] > 0 and counters[5370] == 0      # kPoint records carry no weight in the reference either
+    # sphere radius packed with the truncating half conversion: 0.22 -> 0x330A (RNE would give 0x330B)
+    assert infos[5368, 6] & 0xffff == 0x330A
+    # spot axis decodes back to the authored direction within the 16-bit octahedral grid; cone = cos(34 deg), softness = 1 - 18/34
+    half = lambda h: np.frombuffer(np.uint16(h).tobytes(), np.float16)[0]
+    assert abs(half(ex[1, 2] & 0xffff) - np.cos(np.radians(34.0))) < 1e-3 and abs(half(ex[1, 2] >> 16) - (1 - 18.0 / 34.0)) < 1e-3
+    a, _, _, _, st = o.render(0, 8); o.close()
+    o2 = oracle.Oracle(plain); o2.set_constants(consts); b, _, _, _, st2 = o2.render(0, 8); o2.close()
+    assert np.isfinite(a).all() and st.shadowRays > 0
+    # the blue sphere light at (1.2, 3.9, 1.6) sits near the red wall (world x = 0 is the right side of the image): it adds blue there
+    assert a[20:60, 60:90, 2].mean() > b[20:60, 60:90, 2].mean() + 0.02
+    assert a[..., :3].mean() > b[..., :3].mean() * 1.05
