@@ -253,6 +253,7 @@ typedef struct RtxptConfig {
 
 #define RTXPT_CFG_COUNT_TRAVERSAL_STEPS  1u   /* instrumented traversal: per-launch node/triangle counters */
 #define RTXPT_CFG_NO_MATERIAL_SORT       2u   /* disable the per-bounce sort by material class (A/B measurement only) */
+#define RTXPT_CFG_EXPORT_GUIDES          8u   /* write the reference-mode guide buffers (depth, motion vectors, throughput) at every path vertex */
 #define RTXPT_CFG_TIME_KERNELS           4u   /* CUDA events around every kernel: fills RtxptStats.msTraceClosest/msTraceShadow/msShade/msOther */
 
 typedef struct rtxpt_ctx rtxpt_ctx;
@@ -283,7 +284,9 @@ RTXPT_API int rtxpt_b200_reset_accumulation(rtxpt_ctx* ctx);
 enum {
     RTXPT_BUFFER_OUTPUT_COLOR_F16   = 0,    /* u_OutputColor RGBA16F of the last sub-sample (ShaderResourceBindings.hlsli:24) */
     RTXPT_BUFFER_ACCUMULATED_F32    = 1,    /* AccumulatedRadiance RGBA32F (RenderTargets.cpp) */
-    RTXPT_BUFFER_DEPTH_F32          = 2     /* u_Depth guide of the last sub-sample (PathTracerBridgeDonut.hlsli:1096-1153) */
+    RTXPT_BUFFER_DEPTH_F32          = 2,    /* u_Depth R32F guide of the last sub-sample (PathTracerBridgeDonut.hlsli:1096-1153); 0 = nothing exported */
+    RTXPT_BUFFER_MOTION_VECTORS_F16 = 3,    /* u_MotionVectors RGBA16F; zero in reference mode (PathTracer.hlsli:487,684) */
+    RTXPT_BUFFER_THROUGHPUT_R11G11B10 = 4   /* u_Throughput R11G11B10_FLOAT: saturate(thp) at the last exported vertex, 0 on a miss */
 };
 /* Device→host copy of a render target; blocks until the work queued on the context has finished. */
 RTXPT_API int rtxpt_b200_readback(rtxpt_ctx* ctx, int buffer, void* dst, size_t dstBytes);
@@ -324,6 +327,12 @@ RTXPT_API int rtxpt_b200_get_stats(rtxpt_ctx* ctx, RtxptStats* out);
 RTXPT_API int rtxpt_b200_tile_layout(rtxpt_ctx* ctx, uint32_t* outOwnedPixels, uint32_t* outPaddedPixelsPerRank);
 RTXPT_API int rtxpt_b200_pack_owned(rtxpt_ctx* ctx, void* dDst, void* cudaStream);
 RTXPT_API int rtxpt_b200_unpack_all(rtxpt_ctx* ctx, const void* dSrcAll, void* cudaStream);
+
+/* The one matrix of SampleConstants.view (PlanarViewConstants) the reference-mode dispatch reads besides the camera block:
+ * matWorldToClip, row-major, used as row-vector x matrix (Bridge::ExportSurface, PathTracerBridgeDonut.hlsli:1113-1115).
+ * Only needed with RTXPT_CFG_EXPORT_GUIDES. */
+typedef struct RtxptViewConstants { float matWorldToClip[16]; } RtxptViewConstants;
+RTXPT_API int rtxpt_b200_set_view(rtxpt_ctx* ctx, const RtxptViewConstants* view);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Inspection hooks used by the parity tests and the traversal micro-benchmark.  They run the same device code as

@@ -20,7 +20,8 @@ struct OracleCtx
     Bvh2 bvh;
     LightTable lights;
     RtxptPathTracerConstants consts;
-    bool haveConsts = false;
+    bool haveConsts = false, haveView = false;
+    float worldToClip[16] = {};
     double bvhBuildSeconds = 0;
 };
 
@@ -110,6 +111,36 @@ ORC_API int oracle_trace_rays(void* p, const RtxptRay* rays, uint32_t count, int
     return 0;
 }
 
+ORC_API int oracle_set_view(void* p, const float* worldToClip16)
+{
+    OracleCtx* c = (OracleCtx*)p;
+    memcpy(c->worldToClip, worldToClip16, 64); c->haveView = true;
+    return 0;
+}
+// guide buffers of sub-sample `subSample` (the reference overwrites them every sub-sample: the last one stays)
+ORC_API int oracle_render_guides(void* p, uint32_t subSample, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1, float* depth, uint32_t* throughput, int threads)
+{
+    OracleCtx* c = (OracleCtx*)p;
+    if (!c->haveConsts || !c->haveView) return -1;
+    const uint32_t W = c->consts.imageWidth;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#endif
+    #pragma omp parallel
+    {
+        PathTracerCtx x; x.scene = &c->scene; x.bvh = &c->bvh; x.lights = &c->lights; x.c = &c->consts; x.stats = nullptr;
+        x.sampleIndex = c->consts.sampleBaseIndex + subSample; x.worldToClip = c->worldToClip;
+        #pragma omp for schedule(dynamic, 4)
+        for (int y = int(y0); y < int(y1); y++)
+            for (uint32_t px = x0; px < x1; px++)
+            {
+                GuideOut g; x.guide = &g;
+                tracePixel(x, px, uint32_t(y));
+                depth[size_t(y) * W + px] = g.depth; throughput[size_t(y) * W + px] = g.throughput;
+            }
+    }
+    return 0;
+}
 ORC_API int oracle_get_lights(void* p, void* outLightInfos, uint32_t* ioLightCount, uint32_t* outProxyCounters, uint32_t* outProxyIndices, uint32_t* ioProxyCount)
 {
     OracleCtx* c = (OracleCtx*)p;

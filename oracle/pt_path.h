@@ -90,7 +90,26 @@ struct PathTracerCtx
     const Scene* scene; const Bvh2* bvh; const LightTable* lights; const RtxptPathTracerConstants* c;
     uint sampleIndex;       // Bridge::getSampleIndex() = sampleBaseIndex + subSampleIndex (BridgeDonut:510-513)
     RenderStats* stats;
+    // guide export of the reference-mode path (Bridge::ExportSurfaceInit / ExportSurface / ExportNonSurface, BridgeDonut:1096-1153)
+    const float* worldToClip = nullptr;     // view.matWorldToClip, row-major, row vector x matrix
+    struct GuideOut* guide = nullptr;
 };
+struct GuideOut { float depth; uint throughput; float motion[3]; };
+
+inline uint Pack_R11G11B10_FLOAT(float3 rgb)       // Utils/Packing.hlsli:175-184
+{
+    const float top = asfloat(0x477C0000u);
+    rgb = f3(std::min(rgb.x, top), std::min(rgb.y, top), std::min(rgb.z, top));
+    uint r = ((f32tof16(rgb.x) + 8) >> 4) & 0x000007FF;
+    uint g = ((f32tof16(rgb.y) + 8) << 7) & 0x003FF800;
+    uint b = ((f32tof16(rgb.z) + 16) << 17) & 0xFFC00000;
+    return r | g | b;
+}
+inline float clipDepth(const float* M, float3 p)
+{
+    const float z = p.x * M[2] + p.y * M[6] + p.z * M[10] + M[14], w = p.x * M[3] + p.y * M[7] + p.z * M[11] + M[15];
+    return z / w;
+}
 
 inline bool HasFinishedSurfaceBounces(const PathTracerCtx& x, uint vertexIndex, uint diffuseBounces)
 {
@@ -204,6 +223,7 @@ inline void HandleMiss(const PathTracerCtx& x, PathState& path, float3 rayDir, f
     }
     float baseFFThreshold = lp(x.c->fireflyFilterThreshold);
     if (baseFFThreshold != 0) environmentEmission = FireflyFilter(environmentEmission, baseFFThreshold, path.GetFireflyFilterK());
+    if (x.guide && x.worldToClip) { x.guide->depth = clipDepth(x.worldToClip, path.origin + rayDir * rayTCurrent); x.guide->throughput = 0; x.guide->motion[0] = x.guide->motion[1] = x.guide->motion[2] = 0; }     // ExportNonSurface (PathTracer.hlsli:487)
     if (any_gt0(environmentEmission)) AccumulatePathRadiance(path, path.GetThp() * environmentEmission);
     path.setFlag(PF_hit, false);
     path.terminate();
@@ -431,6 +451,13 @@ inline void HandleHit(const PathTracerCtx& x, PathState& path, float3 rayOrigin,
         if (baseFFThreshold != 0) surfaceEmission = FireflyFilter(surfaceEmission, baseFFThreshold, path.GetFireflyFilterK());
         if (any_gt0(surfaceEmission)) AccumulatePathRadiance(path, path.GetThp() * surfaceEmission);
     }
+    if (x.guide && x.worldToClip)
+    {   // ExportSurface (PathTracer.hlsli:684, BridgeDonut:1105-1129): virtual position along the pixel's camera ray at the path's scene length
+        float3 co, cd; computeCameraRay(x, path.id >> 16, path.id & 0xFFFF, co, cd);
+        x.guide->depth = clipDepth(x.worldToClip, co + cd * path.sceneLength);
+        float3 t = path.GetThp(); x.guide->throughput = Pack_R11G11B10_FLOAT(f3(saturate(t.x), saturate(t.y), saturate(t.z)));
+        x.guide->motion[0] = x.guide->motion[1] = x.guide->motion[2] = 0;
+    }
     if (path.hasFlag(PF_terminateAtNextBounce)) { path.terminate(); return; }
 
     path.SetThp(path.GetThp() * path.GetThpRuRuCorrection());
@@ -466,6 +493,7 @@ inline PixelResult tracePixel(const PathTracerCtx& x, uint px, uint py)
     computeCameraRay(x, px, py, path.origin, path.dir);
 
     PixelResult out = {}; out.primaryT = -1.0f; out.primaryTri = 0xFFFFFFFFu;
+    if (x.guide) { x.guide->depth = 0; x.guide->throughput = 0; x.guide->motion[0] = x.guide->motion[1] = x.guide->motion[2] = 0; }      // ExportSurfaceInit
     bool first = true;
     while (path.isActive())
     {

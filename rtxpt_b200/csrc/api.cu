@@ -69,7 +69,7 @@ struct rtxpt_ctx
     uint32_t paddedPixelsPerRank = 0;
     uint32_t capacity = 0, pixelCount = 0, tableWidth = 0, tableHeight = 0;
     // render targets
-    DeviceArray<uint2> outputColor; DeviceArray<float4> accumulated; DeviceArray<float> depth;
+    DeviceArray<uint2> outputColor; DeviceArray<float4> accumulated; DeviceArray<float> depth; DeviceArray<uint2> motionVectors; DeviceArray<uint32_t> throughput; float worldToClip[16] = {}; bool haveView = false;
     uint32_t accumulatedSamples = 0;
     RtxptPathTracerConstants consts{};
     // stats
@@ -137,7 +137,7 @@ extern "C" RTXPT_API int rtxpt_b200_destroy(rtxpt_ctx* c)
     c->s0.release(); c->s1.release(); c->s2.release(); c->s3.release(); c->s4.release(); c->hits.release();
     c->rayQueue[0].release(); c->rayQueue[1].release(); c->shadeQueue.release();
     c->shadowOriginTMax.release(); c->shadowDirPath.release(); c->shadowRadiance.release(); c->counters.release(); c->pixelOfSlot.release(); c->allPixelTable.release();
-    c->outputColor.release(); c->accumulated.release(); c->depth.release();
+    c->outputColor.release(); c->accumulated.release(); c->depth.release(); c->motionVectors.release(); c->throughput.release();
     for (cudaEvent_t ev : c->evPool) cudaEventDestroy(ev);
     if (c->evStart) cudaEventDestroy(c->evStart);
     if (c->evStop) cudaEventDestroy(c->evStop);
@@ -338,7 +338,8 @@ static int ensureTargets(rtxpt_ctx* c, uint32_t W, uint32_t H)
         CU(c->allPixelTable.upload(all.data(), all.size(), c->stream));
     }
     const size_t P = size_t(W) * H;
-    CU(c->outputColor.alloc(P)); CU(c->accumulated.alloc(P)); CU(c->depth.alloc(P));
+    CU(c->outputColor.alloc(P)); CU(c->accumulated.alloc(P)); CU(c->depth.alloc(P)); CU(c->motionVectors.alloc(P)); CU(c->throughput.alloc(P));
+    CU(cudaMemsetAsync(c->motionVectors.ptr, 0, P * sizeof(uint2), c->stream)); CU(cudaMemsetAsync(c->throughput.ptr, 0, P * sizeof(uint32_t), c->stream));
     CU(cudaMemsetAsync(c->outputColor.ptr, 0, P * sizeof(uint2), c->stream)); CU(cudaMemsetAsync(c->accumulated.ptr, 0, P * sizeof(float4), c->stream)); CU(cudaMemsetAsync(c->depth.ptr, 0, P * sizeof(float), c->stream));
     const size_t cap = size_t(c->pixelCount) * c->cfg.maxSubSamplesPerLaunch;
     if (cap >= 0x7FFFFFFFull) return fail(RTXPT_ERR_UNSUPPORTED, "too many path slots");
@@ -404,7 +405,8 @@ static void fillParams(rtxpt_ctx* c, LaunchParams& p)
     p.flags = c->cfg.flags;
     { const char* e = getenv("RTXPT_REFILL_THRESHOLD"); p.refillThreshold = e ? atoi(e) : 24; }     // tuning knob; 8..24 measured equal within noise on B200
     { const char* e = getenv("RTXPT_WAIT_FLUSH"); p.waitFlushLanes = e ? std::max(1, atoi(e)) : 8; }
-    p.outputColor = c->outputColor.ptr; p.accumulated = c->accumulated.ptr; p.depth = c->depth.ptr;
+    p.outputColor = c->outputColor.ptr; p.accumulated = c->accumulated.ptr; p.depth = c->depth.ptr; p.motionVectors = c->motionVectors.ptr; p.throughput = c->throughput.ptr;
+    memcpy(p.worldToClip, c->worldToClip, sizeof(p.worldToClip)); p.exportGuides = ((c->cfg.flags & RTXPT_CFG_EXPORT_GUIDES) && c->haveView) ? 1u : 0u;
     // traversal occupancy and the shared-memory BVH prefix are chosen together: B resident CTAs of 256 threads per SM (register budget
     // 65536 / (256 B): 128 / 85 / 64 registers for B = 2 / 3 / 4) share the 227 KB of shared memory
     int blocks = 4;         // measured on B200 (city workload, ms/frame closest+shadow): 2 CTAs 28.5, 3 CTAs 21.3, 4 CTAs 19.1
@@ -508,6 +510,8 @@ static int targetInfo(rtxpt_ctx* c, int buffer, void** ptr, size_t* bytes)
     case RTXPT_BUFFER_OUTPUT_COLOR_F16: *ptr = c->outputColor.ptr; *bytes = P * 8; return RTXPT_OK;
     case RTXPT_BUFFER_ACCUMULATED_F32: *ptr = c->accumulated.ptr; *bytes = P * 16; return RTXPT_OK;
     case RTXPT_BUFFER_DEPTH_F32: *ptr = c->depth.ptr; *bytes = P * 4; return RTXPT_OK;
+    case RTXPT_BUFFER_MOTION_VECTORS_F16: *ptr = c->motionVectors.ptr; *bytes = P * 8; return RTXPT_OK;
+    case RTXPT_BUFFER_THROUGHPUT_R11G11B10: *ptr = c->throughput.ptr; *bytes = P * 4; return RTXPT_OK;
     default: return fail(RTXPT_ERR_INVALID_ARGUMENT, "unknown buffer %d", buffer);
     }
 }
@@ -636,6 +640,13 @@ extern "C" RTXPT_API int rtxpt_b200_trace_rays(rtxpt_ctx* c, const RtxptRay* ray
     if (rc == RTXPT_OK) { cudaError_t e = cudaMemcpy(outHits, dHits.ptr, size_t(count) * sizeof(RtxptHit), cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = fail(RTXPT_ERR_CUDA, "readback failed: %s", cudaGetErrorString(e)); }
     dRays.release(); dHits.release();
     return rc;
+}
+
+extern "C" RTXPT_API int rtxpt_b200_set_view(rtxpt_ctx* c, const RtxptViewConstants* view)
+{
+    if (!c || !view) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    memcpy(c->worldToClip, view->matWorldToClip, sizeof(c->worldToClip)); c->haveView = true;
+    return RTXPT_OK;
 }
 
 extern "C" RTXPT_API int rtxpt_b200_get_lights(rtxpt_ctx* c, void* outLightInfos, uint32_t* ioLightCount, uint32_t* outProxyCounters, uint32_t* outProxyIndices, uint32_t* ioProxyCount)

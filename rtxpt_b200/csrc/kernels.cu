@@ -66,22 +66,8 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ Launch
         path.setFireflyK_BsdfPdf(1.0f, 0.0f);
         path.setMisInfo_RuRu(0u, 1.0f);
         if (hasFinishedSurfaceBounces(p.c, 1, 0)) path.setFlag(kPFTerminateAtNextBounce, true);
-        // Bridge::computeCameraRay + ComputeRayThinlens
-        const RtxptCameraData& cam = p.c.camera;
-        UniformSeq sg = UniformSeq::make(vertexBaseHash(id, 0), sampleIndex, 0u);
-        const float r0 = sg.next(), r1 = sg.next(), d0 = sg.next(), d1 = sg.next();
-        const float jx = cam.Jitter[0] + (r0 - 0.5f) * p.c.perPixelJitterAAScale, jy = cam.Jitter[1] + (r1 - 0.5f) * p.c.perPixelJitterAAScale;
-        const float sx = (float(px) + 0.5f + (-jx)) / float(cam.ViewportSize[0]), sy = (float(py) + 0.5f + jy) / float(cam.ViewportSize[1]);
-        const float ndcx = 2.f * sx - 1.f, ndcy = -2.f * sy + 1.f;
-        const float3 U = mk3(cam.CameraU[0], cam.CameraU[1], cam.CameraU[2]), V = mk3(cam.CameraV[0], cam.CameraV[1], cam.CameraV[2]), W = mk3(cam.CameraW[0], cam.CameraW[1], cam.CameraW[2]);
-        float3 origin = mk3(cam.PosW[0], cam.PosW[1], cam.PosW[2]);
-        float3 dir = ndcx * U + ndcy * V + W;
-        const float2 ap = sampleDiskPolar(d0, d1);
-        const float3 target = origin + dir;
-        origin = origin + cam.ApertureRadius * (ap.x * norm3(U) + ap.y * norm3(V));
-        dir = norm3(target - origin);
-        const float invCos = 1.f / dot3(norm3(W), dir);
-        origin = origin + dir * (cam.NearZ * invCos);
+        float3 origin, dir; computeCameraRay(p.c, id, sampleIndex, origin, dir);
+        if (p.exportGuides && sub + 1 == p.subSampleCount) p.depth[size_t(py) * p.c.imageWidth + px] = 0.0f;       // Bridge::ExportSurfaceInit
         path.origin = origin; path.dir = dir;
         path.store(p.wf, slot);
         p.wf.rayQueue[0][slot] = slot | (path.hasFlag(kPFTerminateAtNextBounce) ? 0x80000000u : 0u);

@@ -385,6 +385,8 @@ PT_DEVICE void shadeMiss(const LaunchParams& p, PathRegs& path)
     }
     const float ffThreshold = lp(p.c.fireflyFilterThreshold);
     if (ffThreshold != 0) emission = fireflyFilter(emission, ffThreshold, path.fireflyK());
+    if (p.exportGuides && path.sampleIndex + 1 == p.firstSampleIndex + p.subSampleCount)
+        exportGuide(p, path.id, path.origin + path.dir * kMaxRayTravel, 0u);                 // ExportNonSurface (PathTracer.hlsli:487)
     if (anyPositive(emission)) path.addRadiance(path.thp() * emission);
     path.setFlag(kPFHit, false);
     path.setFlag(kPFActive, false);
@@ -454,6 +456,11 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
         const float ffThreshold = lp(p.c.fireflyFilterThreshold);
         if (ffThreshold != 0) surfaceEmission = fireflyFilter(surfaceEmission, ffThreshold, path.fireflyK());
         if (anyPositive(surfaceEmission)) path.addRadiance(path.thp() * surfaceEmission);
+    }
+    if (p.exportGuides && path.sampleIndex + 1 == p.firstSampleIndex + p.subSampleCount)
+    {   // ExportSurface (PathTracer.hlsli:684): virtual position along the pixel's camera ray at the path's scene length, throughput before this vertex
+        float3 co, cd; computeCameraRay(p.c, path.id, path.sampleIndex, co, cd);
+        exportGuide(p, path.id, co + cd * path.sceneLength, packR11G11B10(mk3(sat(path.thp().x), sat(path.thp().y), sat(path.thp().z))));
     }
     if (path.hasFlag(kPFTerminateAtNextBounce)) { path.setFlag(kPFActive, false); return; }
 

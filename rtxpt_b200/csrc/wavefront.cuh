@@ -64,7 +64,10 @@ struct LaunchParams
     // render targets
     uint2* outputColor;             // RGBA16F, full frame, last sub-sample
     float4* accumulated;            // RGBA32F, full frame
-    float* depth;
+    float* depth;                   // guide buffers (RTXPT_CFG_EXPORT_GUIDES): R32F depth, RGBA16F motion vectors, R11G11B10 throughput
+    uint2* motionVectors; uint* throughput;
+    float worldToClip[16];          // view.matWorldToClip, row-major, row vector x matrix
+    uint exportGuides;
     uint accumulatedSamples;        // before this call
     uint doAccumulate;
 };
@@ -127,6 +130,45 @@ struct PathRegs             // one path's state in registers
     PT_DEVICE void setCone(float width, float spread) { rayCone = (f32tof16(width) << 16) | f32tof16(spread); }
 };
 constexpr uint kCtrDiffuseBounces = 0, kCtrRejectedHits = 1;
+
+// Bridge::computeCameraRay + ComputeRayThinlens (BridgeDonut:543-564, PathTracerHelpers.hlsli:126-153): camera ray of pixel `id` for sample `sampleIndex`
+PT_DEVICE void computeCameraRay(const RtxptPathTracerConstants& c, uint id, uint sampleIndex, float3& origin, float3& dir)
+{
+    const RtxptCameraData& cam = c.camera;
+    const uint px = id >> 16, py = id & 0xFFFF;
+    UniformSeq sg = UniformSeq::make(vertexBaseHash(id, 0), sampleIndex, 0u);
+    const float r0 = sg.next(), r1 = sg.next(), d0 = sg.next(), d1 = sg.next();
+    const float jx = cam.Jitter[0] + (r0 - 0.5f) * c.perPixelJitterAAScale, jy = cam.Jitter[1] + (r1 - 0.5f) * c.perPixelJitterAAScale;
+    const float sx = (float(px) + 0.5f + (-jx)) / float(cam.ViewportSize[0]), sy = (float(py) + 0.5f + jy) / float(cam.ViewportSize[1]);
+    const float ndcx = 2.f * sx - 1.f, ndcy = -2.f * sy + 1.f;
+    const float3 U = mk3(cam.CameraU[0], cam.CameraU[1], cam.CameraU[2]), V = mk3(cam.CameraV[0], cam.CameraV[1], cam.CameraV[2]), W = mk3(cam.CameraW[0], cam.CameraW[1], cam.CameraW[2]);
+    origin = mk3(cam.PosW[0], cam.PosW[1], cam.PosW[2]);
+    dir = ndcx * U + ndcy * V + W;
+    const float2 ap = sampleDiskPolar(d0, d1);
+    const float3 target = origin + dir;
+    origin = origin + cam.ApertureRadius * (ap.x * norm3(U) + ap.y * norm3(V));
+    dir = norm3(target - origin);
+    const float invCos = 1.f / dot3(norm3(W), dir);
+    origin = origin + dir * (cam.NearZ * invCos);
+}
+
+// guide export (Bridge::ExportSurface / ExportNonSurface, BridgeDonut:1105-1146): only the last sub-sample of a launch writes, as the
+// reference's sequential sub-sample dispatches leave the last one in the buffers
+PT_DEVICE uint packR11G11B10(float3 rgb)        // Utils/Packing.hlsli:175-184
+{
+    const float top = __uint_as_float(0x477C0000u);
+    const uint r = ((f32tof16(fminf(rgb.x, top)) + 8u) >> 4) & 0x000007FFu;
+    const uint g = ((f32tof16(fminf(rgb.y, top)) + 8u) << 7) & 0x003FF800u;
+    const uint b = ((f32tof16(fminf(rgb.z, top)) + 16u) << 17) & 0xFFC00000u;
+    return r | g | b;
+}
+PT_DEVICE void exportGuide(const LaunchParams& p, uint id, float3 worldPos, uint packedThroughput)
+{
+    const float* M = p.worldToClip;
+    const float z = worldPos.x * M[2] + worldPos.y * M[6] + worldPos.z * M[10] + M[14], w = worldPos.x * M[3] + worldPos.y * M[7] + worldPos.z * M[11] + M[15];
+    const size_t o = size_t(id & 0xFFFF) * p.c.imageWidth + (id >> 16);
+    p.depth[o] = z / w; p.throughput[o] = packedThroughput; p.motionVectors[o] = make_uint2(0u, 0u);
+}
 
 PT_DEVICE bool hasFinishedSurfaceBounces(const RtxptPathTracerConstants& c, uint vertexIndex, uint diffuseBounces)   // PathTracer.hlsli:40-45
 {

@@ -44,6 +44,7 @@ _SIGNATURES = {
     "rtxpt_b200_trace_rays": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p],
     "rtxpt_b200_trace_rays_device": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32, C.POINTER(C.c_float)],
     "rtxpt_b200_get_lights": [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)],
+    "rtxpt_b200_set_view": [C.c_void_p, C.c_void_p],
     "rtxpt_b200_get_lights_ex": [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)],
     "rtxpt_b200_debug_bsdf": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
     "rtxpt_b200_debug_rng": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
@@ -114,6 +115,19 @@ class Context:
             out = np.empty((self.consts.imageHeight, self.consts.imageWidth, 4), np.float32)
         _check(self.L.rtxpt_b200_readback(self.h, S.BUFFER_ACCUMULATED_F32, out.ctypes.data, out.nbytes), self.L)
         return out
+
+    def set_view(self, world_to_clip):
+        v = S.ViewConstants(); v.matWorldToClip[:] = [float(x) for x in np.asarray(world_to_clip, np.float32).reshape(16)]
+        _check(self.L.rtxpt_b200_set_view(self.h, C.byref(v)), self.L)
+
+    def readback_guides(self):
+        """(depth f32 HxW, motion vectors f16 HxWx4, throughput u32 HxW packed R11G11B10) of the last sub-sample."""
+        h, w = self.consts.imageHeight, self.consts.imageWidth
+        depth = np.empty((h, w), np.float32); mv = np.empty((h, w, 4), np.float16); thp = np.empty((h, w), np.uint32)
+        _check(self.L.rtxpt_b200_readback(self.h, S.BUFFER_DEPTH_F32, depth.ctypes.data, depth.nbytes), self.L)
+        _check(self.L.rtxpt_b200_readback(self.h, S.BUFFER_MOTION_VECTORS_F16, mv.ctypes.data, mv.nbytes), self.L)
+        _check(self.L.rtxpt_b200_readback(self.h, S.BUFFER_THROUGHPUT_R11G11B10, thp.ctypes.data, thp.nbytes), self.L)
+        return depth, mv, thp
 
     def readback_output_color(self):
         out = np.empty((self.consts.imageHeight, self.consts.imageWidth, 4), np.float16)

@@ -304,6 +304,22 @@ class Scene:
 # Camera + constants (BridgeCamera, Rtxpt/Shaders/PathTracer/PathTracerShared.h:109-141; Sample::UpdatePathTracerConstants,
 # Rtxpt/Sample.cpp:1464-1556)
 # ----------------------------------------------------------------------------------------------------------------------
+def world_to_clip(cam):
+    """SimpleViewConstants.matWorldToClip for a BridgeCamera block: row-major, row vector x matrix, D3D clip space (z in [0, 1])."""
+    f = np.float32
+    pos = np.array(cam.PosW[:], np.float32); W = np.array(cam.CameraW[:], np.float32); U = np.array(cam.CameraU[:], np.float32); V = np.array(cam.CameraV[:], np.float32)
+    fwd = W / np.linalg.norm(W); right = U / np.linalg.norm(U); up = V / np.linalg.norm(V)
+    tan_x, tan_y = float(np.linalg.norm(U) / np.linalg.norm(W)), float(np.linalg.norm(V) / np.linalg.norm(W))
+    n, fa = float(cam.NearZ), float(cam.FarZ)
+    view = np.eye(4, dtype=np.float64)
+    view[:3, 0], view[:3, 1], view[:3, 2] = right, up, fwd
+    view[3, :3] = [-np.dot(pos, right), -np.dot(pos, up), -np.dot(pos, fwd)]
+    proj = np.zeros((4, 4), np.float64)
+    proj[0, 0], proj[1, 1] = 1.0 / tan_x, 1.0 / tan_y
+    proj[2, 2], proj[2, 3], proj[3, 2] = fa / (fa - n), 1.0, -n * fa / (fa - n)
+    return (view @ proj).astype(f)
+
+
 def bridge_camera(width, height, pos, direction, up, fov_y, near_z=0.1, far_z=1e7, focal_distance=10000.0, aperture_radius=0.0, jitter=(0.0, 0.0)):
     f = np.float32
     cam = S.CameraData()

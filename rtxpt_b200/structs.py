@@ -26,8 +26,9 @@ MATFLAG_NestedPriorityShift = 28
 CFG_COUNT_TRAVERSAL_STEPS = 1
 CFG_NO_MATERIAL_SORT = 2
 CFG_TIME_KERNELS = 4
+CFG_EXPORT_GUIDES = 8
 
-BUFFER_OUTPUT_COLOR_F16, BUFFER_ACCUMULATED_F32, BUFFER_DEPTH_F32 = 0, 1, 2
+BUFFER_OUTPUT_COLOR_F16, BUFFER_ACCUMULATED_F32, BUFFER_DEPTH_F32, BUFFER_MOTION_VECTORS_F16, BUFFER_THROUGHPUT_R11G11B10 = 0, 1, 2, 3, 4
 
 
 class GeometryData(C.Structure):
@@ -87,6 +88,10 @@ class SceneDesc(C.Structure):
                 ("textures", C.POINTER(TextureDesc)), ("textureCount", u32),
                 ("envCube", EnvCubeDesc),
                 ("lights", C.POINTER(LightDesc)), ("lightCount", u32)]
+
+
+class ViewConstants(C.Structure):
+    _fields_ = [("matWorldToClip", f32 * 16)]
 
 
 class CameraData(C.Structure):

@@ -43,6 +43,8 @@ def lib():
         L.oracle_set_constants.argtypes = [C.c_void_p, C.POINTER(S.PathTracerConstants)]
         L.oracle_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
         L.oracle_get_lights.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
+        L.oracle_set_view.argtypes = [C.c_void_p, C.c_void_p]
+        L.oracle_render_guides.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
         L.oracle_get_lights_ex.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
         L.oracle_get_sub_instances.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.oracle_render.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
@@ -70,6 +72,16 @@ class Oracle:
     def set_constants(self, consts):
         self.consts = consts
         assert lib().oracle_set_constants(self.h, C.byref(consts)) == 0
+
+    def set_view(self, world_to_clip):
+        m = np.ascontiguousarray(world_to_clip, np.float32).reshape(16)
+        assert lib().oracle_set_view(self.h, m.ctypes.data) == 0
+
+    def render_guides(self, sub_sample, threads=0):
+        W, H = self.consts.imageWidth, self.consts.imageHeight
+        depth = np.zeros((H, W), np.float32); thp = np.zeros((H, W), np.uint32)
+        assert lib().oracle_render_guides(self.h, sub_sample, 0, 0, W, H, depth.ctypes.data, thp.ctypes.data, threads) == 0
+        return depth, thp
 
     def trace_rays(self, rays, any_hit=False):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
