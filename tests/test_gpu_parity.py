@@ -165,7 +165,12 @@ def test_guide_export_parity(product, oracle, small_city, strict):
         same = (depth == od) & (thp == ot)
         assert same.mean() > 0.995
     else:
-        assert (np.abs(depth - od) <= 1e-5 * np.abs(od) + 1e-7).mean() > 0.99 and (thp == ot).mean() > 0.98
+        def unpack(v):      # Unpack_R11G11B10_FLOAT (Utils/Packing.hlsli:186-192)
+            h = lambda x: np.ascontiguousarray(x.astype(np.uint16)).view(np.float16).astype(np.float32)
+            return np.stack([h((v << 4) & 0x7FF0), h((v >> 7) & 0x7FF0), h((v >> 17) & 0x7FE0)], -1)
+        a, b = unpack(thp), unpack(ot)
+        assert (np.abs(depth - od) <= 1e-5 * np.abs(od) + 1e-7).mean() > 0.99
+        assert (np.abs(a - b).max(-1) <= 0.04 * np.abs(b).max(-1) + 1e-3).mean() > 0.98        # one step of the 5/6-bit mantissas
 
 
 def test_cornell_c1_image_parity(ctx, oracle, cornell):
