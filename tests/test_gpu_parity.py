@@ -152,28 +152,35 @@ def test_guide_export_parity(product, oracle, cornell, small_city, strict, which
     from rtxpt_b200 import scene_builder as sb, structs as S
     scene, cam = cornell if which == "cornell" else small_city
     W, H = cam.ViewportSize[0], cam.ViewportSize[1]
-    consts = sb.make_constants(W, H, cam, bounce_count=3, diffuse_bounce_count=3, env_enabled=(which == "city"))
     m = sb.world_to_clip(cam)
     c = product.Context(max_sub_samples_per_launch=2, strict=strict, flags=S.CFG_EXPORT_GUIDES)
-    c.upload_scene(scene); c.set_constants(consts); c.set_view(m)
-    c.path_trace(0, 2, True); c.synchronize()
-    depth, mv, thp = c.readback_guides(); c.close()
-    o = oracle.Oracle(scene); o.set_constants(consts); o.set_view(m)
-    od, ot = o.render_guides(1); o.close()                     # sub-sample 1 is the last of the launch
-    assert (mv == 0).all() and np.isfinite(depth).all()
-    assert (depth != 0).mean() > 0.99                           # every path exports at least once (hit or miss)
-    if strict and which == "cornell":
-        # untextured scene, IEEE build: the exported words are the oracle's
-        fd, ft = float((depth == od).mean()), float((thp == ot).mean())
-        assert fd > 0.995 and ft > 0.995, (fd, ft)
-    else:
-        # textured scene (TMU filter weights vs the oracle's software taps perturb throughput and bounce directions) and/or fast arithmetic
-        def unpack(v):      # Unpack_R11G11B10_FLOAT (Utils/Packing.hlsli:186-192)
-            h = lambda x: np.ascontiguousarray(x.astype(np.uint16)).view(np.float16).astype(np.float32)
-            return np.stack([h((v << 4) & 0x7FF0), h((v >> 7) & 0x7FF0), h((v >> 17) & 0x7FE0)], -1)
-        a, b = unpack(thp), unpack(ot)
-        assert (np.abs(depth - od) <= 1e-5 * np.abs(od) + 1e-7).mean() > 0.98
-        assert (np.abs(a - b).max(-1) <= 0.04 * np.abs(b).max(-1) + 1e-3).mean() > 0.98        # one step of the 5/6-bit mantissas
+    c.upload_scene(scene)
+    o = oracle.Oracle(scene)
+
+    def unpack(v):      # Unpack_R11G11B10_FLOAT (Utils/Packing.hlsli:186-192)
+        h = lambda x: np.ascontiguousarray(x.astype(np.uint16)).view(np.float16).astype(np.float32)
+        return np.stack([h((v << 4) & 0x7FF0), h((v >> 7) & 0x7FF0), h((v >> 17) & 0x7FE0)], -1)
+
+    for bounces in (0, 3):
+        consts = sb.make_constants(W, H, cam, bounce_count=bounces, diffuse_bounce_count=bounces, env_enabled=(which == "city"))
+        c.set_constants(consts); c.set_view(m); c.reset_accumulation()
+        c.path_trace(0, 2, True); c.synchronize()
+        depth, mv, thp = c.readback_guides()
+        o.set_constants(consts); o.set_view(m)
+        od, ot = o.render_guides(1)                                 # sub-sample 1 is the last of the launch
+        assert (mv == 0).all() and np.isfinite(depth).all()
+        assert (depth != 0).mean() > 0.99                           # every path exports at least once (hit or miss)
+        if strict and bounces == 0:
+            # camera vertex only, IEEE build: the exported words are the oracle's
+            fd, ft = float((depth == od).mean()), float((thp == ot).mean())
+            assert fd > 0.999 and ft > 0.999, (fd, ft)
+        else:
+            # deeper vertices: bounce directions go through sin/cos (libdevice vs glibc) and, in the city, TMU filter weights, so scene lengths
+            # and throughputs agree to rounding, not bit for bit
+            a, b = unpack(thp), unpack(ot)
+            assert (np.abs(depth - od) <= 1e-5 * np.abs(od) + 1e-7).mean() > 0.98
+            assert (np.abs(a - b).max(-1) <= 0.04 * np.abs(b).max(-1) + 1e-3).mean() > 0.98        # one step of the 5/6-bit mantissas
+    c.close(); o.close()
 
 
 def test_cornell_c1_image_parity(ctx, oracle, cornell):
