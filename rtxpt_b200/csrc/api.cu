@@ -52,6 +52,7 @@ struct rtxpt_ctx
     int maxSmemOptin = 0;
     // scene
     bool haveScene = false, haveConstants = false, lightsDirty = true;
+    cudaStream_t stream2 = nullptr; cudaEvent_t evShadeDone = nullptr, evShadowDone = nullptr; bool overlapShadow = true;
     DeviceArray<RtxptInstanceData> dInstances; DeviceArray<RtxptGeometryData> dGeometries; DeviceArray<RtxptSubInstanceData> dSubInstances;
     DeviceArray<RtxptMaterialData> dMaterials; DeviceArray<uint8_t> dSubInstanceClass;
     std::vector<uint8_t*> bufferAllocs; DeviceArray<const uint8_t*> dBufferTable;
@@ -115,6 +116,9 @@ extern "C" RTXPT_API int rtxpt_b200_create(const RtxptConfig* config, rtxpt_ctx*
     c->maxSmemOptin = int(prop.sharedMemPerBlockOptin);
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(RTXPT_ERR_CUDA, "stream creation failed"); }
     cudaEventCreate(&c->evStart); cudaEventCreate(&c->evStop);
+    cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&c->evShadeDone, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->evShadowDone, cudaEventDisableTiming);
+    { const char* e = getenv("RTXPT_OVERLAP_SHADOW"); if (e) c->overlapShadow = atoi(e) != 0; }
     cudaMallocHost(&c->hCounters, kCounterWords * sizeof(uint32_t));
     memset(c->hCounters, 0, kCounterWords * sizeof(uint32_t));
     e = configureKernels(c->maxSmemOptin);
@@ -142,6 +146,9 @@ extern "C" RTXPT_API int rtxpt_b200_destroy(rtxpt_ctx* c)
     if (c->evStart) cudaEventDestroy(c->evStart);
     if (c->evStop) cudaEventDestroy(c->evStop);
     if (c->hCounters) cudaFreeHost(c->hCounters);
+    if (c->evShadeDone) cudaEventDestroy(c->evShadeDone);
+    if (c->evShadowDone) cudaEventDestroy(c->evShadowDone);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return RTXPT_OK;
@@ -468,14 +475,28 @@ extern "C" RTXPT_API int rtxpt_b200_path_trace(rtxpt_ctx* c, uint32_t firstSubSa
         CU(cudaMemsetAsync(c->counters.ptr, 0, kCounterWords * sizeof(uint32_t), s));
         p.iteration = 0;
         kt.begin(3); launchGenerate(p, c->grid, s); kt.end(); launches++;
+        // Shadow rays of vertex k and scatter rays of vertex k+1 touch disjoint state (shadow: shadow records + the radiance word of the path;
+        // closest: ray words, hit records, shade queues), so k_trace_shadow(it) runs on a second stream next to k_trace_closest(it+1): the
+        // long-ray tail of one persistent kernel is filled by the other's CTAs.  k_shade(it+1) joins both.
+        const bool overlap = c->overlapShadow;
         for (uint32_t it = 0; it < iterations; it++)
         {
             p.iteration = it;
             kt.begin(0); launchTraceClosest(p, c->grid, countSteps, s); kt.end();
+            if (overlap && it > 0) CU(cudaStreamWaitEvent(s, c->evShadowDone, 0));        // shadow(it-1) has updated the radiance words
             kt.begin(2); launchShade(p, c->grid, s); kt.end();
-            kt.begin(1); launchTraceShadow(p, c->grid, countSteps, s); kt.end();
+            if (overlap)
+            {
+                CU(cudaEventRecord(c->evShadeDone, s));
+                CU(cudaStreamWaitEvent(c->stream2, c->evShadeDone, 0));
+                KernelTimer kt2{ c, c->stream2, kt.on };
+                kt2.begin(1); launchTraceShadow(p, c->grid, countSteps, c->stream2); kt2.end();
+                CU(cudaEventRecord(c->evShadowDone, c->stream2));
+            }
+            else { kt.begin(1); launchTraceShadow(p, c->grid, countSteps, s); kt.end(); }
             launches += 3;
         }
+        if (overlap) CU(cudaStreamWaitEvent(s, c->evShadowDone, 0));
         kt.begin(3); launchCommitAccumulate(p, c->grid, s); kt.end(); launches++;
         if (accumulate) c->accumulatedSamples += n;
         CU(cudaGetLastError());

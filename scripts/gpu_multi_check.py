@@ -19,7 +19,8 @@ def main():
     owned, padded = ctx.tile_layout()
     send = torch.empty((padded, 4), dtype=torch.float32, device="cuda")
     gathered = torch.empty((world * padded, 4), dtype=torch.float32, device="cuda")
-    stream = torch.cuda.current_stream().cuda_stream
+    tstream = torch.cuda.Stream(); torch.cuda.set_stream(tstream)        # one non-default stream for the kernels, the tile copies and NCCL (0 would mean "the context's own stream")
+    stream = tstream.cuda_stream
     for frame in range(2):                      # two accumulated frames
         consts.sampleBaseIndex = frame * spp; ctx.set_constants(consts)
         ctx.path_trace(0, spp, True, stream)
