@@ -478,7 +478,7 @@ extern "C" RTXPT_API int rtxpt_b200_path_trace(rtxpt_ctx* c, uint32_t firstSubSa
         // Shadow rays of vertex k and scatter rays of vertex k+1 touch disjoint state (shadow: shadow records + the radiance word of the path;
         // closest: ray words, hit records, shade queues), so k_trace_shadow(it) runs on a second stream next to k_trace_closest(it+1): the
         // long-ray tail of one persistent kernel is filled by the other's CTAs.  k_shade(it+1) joins both.
-        const bool overlap = c->overlapShadow;
+        const bool overlap = c->overlapShadow && !kt.on;      // per-kernel timing wants the kernels back to back
         for (uint32_t it = 0; it < iterations; it++)
         {
             p.iteration = it;

@@ -361,6 +361,7 @@ PT_DEVICE void updatePathTravelled(PathRegs& path, float rayT)      // PathTrace
     path.sceneLength = fminf(path.sceneLength + rayT, kMaxRayTravel);
 }
 
+template <bool EXPORT_GUIDES>
 PT_DEVICE void shadeMiss(const LaunchParams& p, PathRegs& path)
 {
     updatePathTravelled(path, kMaxRayTravel);
@@ -385,7 +386,7 @@ PT_DEVICE void shadeMiss(const LaunchParams& p, PathRegs& path)
     }
     const float ffThreshold = lp(p.c.fireflyFilterThreshold);
     if (ffThreshold != 0) emission = fireflyFilter(emission, ffThreshold, path.fireflyK());
-    if (p.exportGuides && path.sampleIndex + 1 == p.firstSampleIndex + p.subSampleCount)
+    if (EXPORT_GUIDES && path.sampleIndex + 1 == p.firstSampleIndex + p.subSampleCount)
         exportGuide(p, path.id, path.origin + path.dir * kMaxRayTravel, 0u);                 // ExportNonSurface (PathTracer.hlsli:487)
     if (anyPositive(emission)) path.addRadiance(path.thp() * emission);
     path.setFlag(kPFHit, false);
@@ -395,6 +396,7 @@ PT_DEVICE void shadeMiss(const LaunchParams& p, PathRegs& path)
 // ---- hit -----------------------------------------------------------------------------------------------------------------------------------
 struct HitOutputs { bool continuePath; bool emitShadow; ShadowRecord shadow; };
 
+template <bool EXPORT_GUIDES, bool ANALYTIC_LIGHTS>
 PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4 hit, HitOutputs& out)
 {
     out.continuePath = false; out.emitShadow = false;
@@ -457,7 +459,7 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
         if (ffThreshold != 0) surfaceEmission = fireflyFilter(surfaceEmission, ffThreshold, path.fireflyK());
         if (anyPositive(surfaceEmission)) path.addRadiance(path.thp() * surfaceEmission);
     }
-    if (p.exportGuides && path.sampleIndex + 1 == p.firstSampleIndex + p.subSampleCount)
+    if (EXPORT_GUIDES && path.sampleIndex + 1 == p.firstSampleIndex + p.subSampleCount)
     {   // ExportSurface (PathTracer.hlsli:684): virtual position along the pixel's camera ray at the path's scene length, throughput before this vertex
         float3 co, cd; computeCameraRay(p.c, path.id, path.sampleIndex, co, cd);
         exportGuide(p, path.id, co + cd * path.sceneLength, packR11G11B10(mk3(sat(path.thp().x), sat(path.thp().y), sat(path.thp().z))));
@@ -573,7 +575,7 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
             const LightInfo li = p.scene.lights[lightIndex];
             const float r0 = uniformSG.next(), r1 = uniformSG.next();
             float3 lsPos = mk3(0.f), lsRadiance = mk3(0.f); float lsSolidPdf = 0.f; bool lsBsdfSampleable = true;
-            if (lightType(li) == kLightTypeSphere)
+            if (ANALYTIC_LIGHTS && lightType(li) == kLightTypeSphere)
             {   // SphereLight::CalcSample (PolymorphicLight.hlsli:107-181): cone sampling of the visible cap; never found by BSDF rays
                 lsBsdfSampleable = false;
                 sampleSphereLight(li, p.scene, lightIndex, r0, r1, s.posW, lsPos, lsRadiance, lsSolidPdf);

@@ -38,7 +38,7 @@ __global__ void k_init_sobol_tables()
 void launchInitTables(cudaStream_t s) { k_init_sobol_tables<<<16, 256, 0, s>>>(); }
 
 // ---- shade --------------------------------------------------------------------------------------------------------------------------------
-template <int MINB>
+template <int MINB, bool EXPORT_GUIDES, bool ANALYTIC_LIGHTS>
 __global__ void __launch_bounds__(128, MINB) k_shade(const __grid_constant__ LaunchParams p)
 {
     uint* ctr = p.wf.counters + p.iteration * kCountersPerIter;
@@ -59,8 +59,8 @@ __global__ void __launch_bounds__(128, MINB) k_shade(const __grid_constant__ Lau
             {
                 slot = queue[i];
                 PathRegs path; path.load(p.wf, slot, true);
-                if (cls == 0) shadeMiss(p, path);
-                else shadeHit(p, path, slot, p.wf.hits[slot], out);
+                if (cls == 0) shadeMiss<EXPORT_GUIDES>(p, path);
+                else shadeHit<EXPORT_GUIDES, ANALYTIC_LIGHTS>(p, path, slot, p.wf.hits[slot], out);
                 path.store(p.wf, slot);
                 if (out.continuePath) { rayCls = 0; rayEntry = slot | (path.hasFlag(kPFTerminateAtNextBounce) ? 0x80000000u : 0u); }
                 if (out.emitShadow) shadowCls = 0;
@@ -112,9 +112,12 @@ __global__ void k_debug_rng(const uint* __restrict__ in, uint count, uint* __res
 void launchShade(const LaunchParams& p, const GridConfig& g, cudaStream_t s)
 {
     const int grid = g.smCount * g.shadeBlocksPerSM;
-    if (g.shadeBlocksPerSM >= 5) k_shade<5><<<grid, 128, 0, s>>>(p);
-    else if (g.shadeBlocksPerSM == 4) k_shade<4><<<grid, 128, 0, s>>>(p);
-    else k_shade<3><<<grid, 128, 0, s>>>(p);
+    // guide export and analytic (sphere) lights are separate instantiations: the default kernel carries neither
+    if (p.exportGuides) { k_shade<4, true, true><<<g.smCount * 4, 128, 0, s>>>(p); return; }
+    if (p.scene.analyticLightCount != 0) { k_shade<4, false, true><<<g.smCount * 4, 128, 0, s>>>(p); return; }
+    if (g.shadeBlocksPerSM >= 5) k_shade<5, false, false><<<grid, 128, 0, s>>>(p);
+    else if (g.shadeBlocksPerSM == 4) k_shade<4, false, false><<<grid, 128, 0, s>>>(p);
+    else k_shade<3, false, false><<<grid, 128, 0, s>>>(p);
 }
 void launchDebugBsdf(const float* in, uint32_t count, float* out, cudaStream_t s) { k_debug_bsdf<<<(count + 127) / 128, 128, 0, s>>>(in, count, out); }
 void launchDebugRng(const uint32_t* in, uint32_t count, uint32_t* out, cudaStream_t s) { k_debug_rng<<<(count + 127) / 128, 128, 0, s>>>(in, count, out); }
