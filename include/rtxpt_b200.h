@@ -175,7 +175,7 @@ typedef struct RtxptLightDesc {
     float    innerAngle;        /* degrees (spot) */
     float    outerAngle;        /* degrees (spot); negative: kPolymorphicLightShapingUseMinFalloff */
     uint32_t _pad;
-} RtxptLightDesc;               /* 64 bytes */
+} RtxptLightDesc;               /* 60 bytes */
 
 typedef struct RtxptSceneDesc {
     const RtxptInstanceData*    instances;      uint32_t instanceCount;
@@ -327,6 +327,24 @@ RTXPT_API int rtxpt_b200_get_stats(rtxpt_ctx* ctx, RtxptStats* out);
 RTXPT_API int rtxpt_b200_tile_layout(rtxpt_ctx* ctx, uint32_t* outOwnedPixels, uint32_t* outPaddedPixelsPerRank);
 RTXPT_API int rtxpt_b200_pack_owned(rtxpt_ctx* ctx, void* dDst, void* cudaStream);
 RTXPT_API int rtxpt_b200_unpack_all(rtxpt_ctx* ctx, const void* dSrcAll, void* cudaStream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Host-side glTF 2.0 loader (rtxpt_b200/csrc/gltf_loader.cpp): produces the RtxptSceneDesc tables from a .gltf / .glb
+ * the way Donut's GltfImporter + Scene::CreateMeshBuffers and RTXPT's MaterialsBaker do on the reference's host side
+ * (External/Donut/src/engine/GltfImporter.cpp:641-1430, Scene.cpp:821-1000, Rtxpt/Materials/MaterialsBaker.cpp:516-591,
+ * :660-705, :960-1017).  Needs no CUDA device.  The returned object owns everything the desc points to.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct rtxpt_host_scene rtxpt_host_scene;
+typedef struct RtxptGltfCamera {        /* perspective cameras found in the node graph, world space */
+    float position[3], direction[3], up[3];
+    float yfov, znear, zfar, aspectRatio;   /* radians; aspectRatio 0 = unspecified */
+} RtxptGltfCamera;
+RTXPT_API int rtxpt_b200_load_gltf(const char* path, rtxpt_host_scene** outScene);
+RTXPT_API const char* rtxpt_b200_load_gltf_error(void);                 /* message of the last failed load on this thread */
+RTXPT_API const RtxptSceneDesc* rtxpt_b200_host_scene_desc(const rtxpt_host_scene* scene);
+RTXPT_API int rtxpt_b200_host_scene_cameras(const rtxpt_host_scene* scene, RtxptGltfCamera* outCameras, uint32_t* ioCount);
+RTXPT_API uint32_t rtxpt_b200_host_scene_triangle_count(const rtxpt_host_scene* scene);
+RTXPT_API void rtxpt_b200_free_host_scene(rtxpt_host_scene* scene);
 
 /* The one matrix of SampleConstants.view (PlanarViewConstants) the reference-mode dispatch reads besides the camera block:
  * matWorldToClip, row-major, used as row-vector x matrix (Bridge::ExportSurface, PathTracerBridgeDonut.hlsli:1113-1115).

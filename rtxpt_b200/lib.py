@@ -49,7 +49,9 @@ _SIGNATURES = {
     "rtxpt_b200_debug_bsdf": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
     "rtxpt_b200_debug_rng": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
 }
-EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["rtxpt_b200_last_error"])
+_LOADER_SYMBOLS = ["rtxpt_b200_load_gltf", "rtxpt_b200_load_gltf_error", "rtxpt_b200_host_scene_desc", "rtxpt_b200_host_scene_cameras",
+                   "rtxpt_b200_host_scene_triangle_count", "rtxpt_b200_free_host_scene"]
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["rtxpt_b200_last_error"] + _LOADER_SYMBOLS)
 
 
 def load(strict=None):
@@ -66,6 +68,12 @@ def load(strict=None):
         for name, args in _SIGNATURES.items():
             fn = getattr(L, name); fn.argtypes = args; fn.restype = C.c_int
         L.rtxpt_b200_last_error.restype = C.c_char_p
+        L.rtxpt_b200_load_gltf.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]; L.rtxpt_b200_load_gltf.restype = C.c_int
+        L.rtxpt_b200_load_gltf_error.restype = C.c_char_p
+        L.rtxpt_b200_host_scene_desc.argtypes = [C.c_void_p]; L.rtxpt_b200_host_scene_desc.restype = C.POINTER(S.SceneDesc)
+        L.rtxpt_b200_host_scene_cameras.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]; L.rtxpt_b200_host_scene_cameras.restype = C.c_int
+        L.rtxpt_b200_host_scene_triangle_count.argtypes = [C.c_void_p]; L.rtxpt_b200_host_scene_triangle_count.restype = C.c_uint32
+        L.rtxpt_b200_free_host_scene.argtypes = [C.c_void_p]; L.rtxpt_b200_free_host_scene.restype = None
         _libs[strict] = L
     return _libs[strict]
 
@@ -73,6 +81,32 @@ def load(strict=None):
 def _check(rc, L=None):
     if rc != 0:
         raise RtxptError(f"rtxpt_b200 error {rc}: {(L or load()).rtxpt_b200_last_error().decode()}")
+
+
+class GltfScene:
+    """A scene loaded by the library's host-side glTF loader (no GPU needed).  `.desc` is the RtxptSceneDesc to hand to Context.upload_scene
+    (or to the oracle); `.cameras` lists the perspective cameras of the file."""
+    def __init__(self, path, strict=None):
+        self.L = load(strict)
+        h = C.c_void_p()
+        if self.L.rtxpt_b200_load_gltf(os.fsencode(path), C.byref(h)) != 0:
+            raise RtxptError("glTF load failed: " + self.L.rtxpt_b200_load_gltf_error().decode())
+        self.h = h
+        self.desc = self.L.rtxpt_b200_host_scene_desc(h).contents
+        n = C.c_uint32(0); self.L.rtxpt_b200_host_scene_cameras(h, None, C.byref(n))
+        cams = (S.GltfCamera * max(1, n.value))(); self.L.rtxpt_b200_host_scene_cameras(h, cams, C.byref(n))
+        self.cameras = [cams[i] for i in range(n.value)]
+        self.triangle_count = self.L.rtxpt_b200_host_scene_triangle_count(h)
+        self.material_count = self.desc.materialCount
+        self.has_env = False
+
+    def close(self):
+        if self.h:
+            self.L.rtxpt_b200_free_host_scene(self.h); self.h = None
+
+    def __del__(self):
+        try: self.close()
+        except Exception: pass
 
 
 class Context:

@@ -41,6 +41,13 @@ def _merge(geos, material):
 def cornell_box(width=256, height=256, analytic_lights=False):
     """Returns (scene, camera).  Classic Cornell data in metres (x right, y up, z into the box); the camera looks down +z.
     analytic_lights adds a sphere light, a spot light and a zero-radius point light (the reference never samples the last)."""
+    scene = cornell_builder(analytic_lights).build()
+    cam = bridge_camera(width, height, pos=(2.78, 2.73, -8.0), direction=(0, 0, 1), up=(0, 1, 0), fov_y=0.66)
+    return scene, cam
+
+
+def cornell_builder(analytic_lights=False):
+    """The SceneBuilder behind cornell_box (also written out as glTF by the loader tests)."""
     b = SceneBuilder()
     if analytic_lights:
         b.add_point_light(position=(1.2, 3.9, 1.6), color=(0.4, 0.6, 1.0), intensity=14.0, radius=0.22)
@@ -64,9 +71,7 @@ def cornell_box(width=256, height=256, analytic_lights=False):
     boxes = b.add_mesh([_merge(short, white), _merge(tall, white)])
     for m in (room, lamp, boxes):
         b.add_instance(m, identity34())
-    scene = b.build()
-    cam = bridge_camera(width, height, pos=(2.78, 2.73, -8.0), direction=(0, 0, 1), up=(0, 1, 0), fov_y=0.66)
-    return scene, cam
+    return b
 
 
 # ----------------------------------------------------------------------------------------------------------------------

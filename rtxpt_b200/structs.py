@@ -74,7 +74,7 @@ class EnvCubeDesc(C.Structure):
 LIGHT_POINT, LIGHT_SPOT = 1, 2
 
 
-class LightDesc(C.Structure):       # RtxptLightDesc, 64 bytes
+class LightDesc(C.Structure):       # RtxptLightDesc, 60 bytes
     _fields_ = [("type", u32), ("position", f32 * 3), ("direction", f32 * 3), ("color", f32 * 3), ("intensity", f32), ("radius", f32),
                 ("innerAngle", f32), ("outerAngle", f32), ("_pad", u32)]
 
@@ -88,6 +88,10 @@ class SceneDesc(C.Structure):
                 ("textures", C.POINTER(TextureDesc)), ("textureCount", u32),
                 ("envCube", EnvCubeDesc),
                 ("lights", C.POINTER(LightDesc)), ("lightCount", u32)]
+
+
+class GltfCamera(C.Structure):
+    _fields_ = [("position", f32 * 3), ("direction", f32 * 3), ("up", f32 * 3), ("yfov", f32), ("znear", f32), ("zfar", f32), ("aspectRatio", f32)]
 
 
 class ViewConstants(C.Structure):
