@@ -346,6 +346,13 @@ RTXPT_API int rtxpt_b200_host_scene_cameras(const rtxpt_host_scene* scene, Rtxpt
 RTXPT_API uint32_t rtxpt_b200_host_scene_triangle_count(const rtxpt_host_scene* scene);
 RTXPT_API void rtxpt_b200_free_host_scene(rtxpt_host_scene* scene);
 
+/* Host-side helpers every C/C++ caller needs (rtxpt_b200/csrc/host_helpers.cpp; no CUDA device required):
+ * BridgeCamera (Rtxpt/Shaders/PathTracer/PathTracerShared.h:109-141; aspect ratio = width / height, jitter in pixels) and the
+ * reference-mode defaults of Sample::UpdatePathTracerConstants with the SampleUI.h defaults (Rtxpt/Sample.cpp:1464-1556). */
+RTXPT_API int rtxpt_b200_bridge_camera(uint32_t viewportWidth, uint32_t viewportHeight, const float camPos[3], const float camDir[3], const float camUp[3],
+                                       float fovY, float nearZ, float farZ, float focalDistance, float apertureRadius, const float jitter[2], RtxptCameraData* out);
+RTXPT_API int rtxpt_b200_default_constants(const RtxptCameraData* camera, int envMapPresent, RtxptPathTracerConstants* out);
+
 /* The one matrix of SampleConstants.view (PlanarViewConstants) the reference-mode dispatch reads besides the camera block:
  * matWorldToClip, row-major, used as row-vector x matrix (Bridge::ExportSurface, PathTracerBridgeDonut.hlsli:1113-1115).
  * Only needed with RTXPT_CFG_EXPORT_GUIDES. */

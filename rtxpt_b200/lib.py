@@ -50,7 +50,7 @@ _SIGNATURES = {
     "rtxpt_b200_debug_rng": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
 }
 _LOADER_SYMBOLS = ["rtxpt_b200_load_gltf", "rtxpt_b200_load_gltf_error", "rtxpt_b200_host_scene_desc", "rtxpt_b200_host_scene_cameras",
-                   "rtxpt_b200_host_scene_triangle_count", "rtxpt_b200_free_host_scene"]
+                   "rtxpt_b200_host_scene_triangle_count", "rtxpt_b200_free_host_scene", "rtxpt_b200_bridge_camera", "rtxpt_b200_default_constants"]
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["rtxpt_b200_last_error"] + _LOADER_SYMBOLS)
 
 
@@ -74,6 +74,9 @@ def load(strict=None):
         L.rtxpt_b200_host_scene_cameras.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]; L.rtxpt_b200_host_scene_cameras.restype = C.c_int
         L.rtxpt_b200_host_scene_triangle_count.argtypes = [C.c_void_p]; L.rtxpt_b200_host_scene_triangle_count.restype = C.c_uint32
         L.rtxpt_b200_free_host_scene.argtypes = [C.c_void_p]; L.rtxpt_b200_free_host_scene.restype = None
+        L.rtxpt_b200_bridge_camera.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, C.c_float,
+                                               C.c_float, C.c_float, C.POINTER(C.c_float), C.POINTER(S.CameraData)]; L.rtxpt_b200_bridge_camera.restype = C.c_int
+        L.rtxpt_b200_default_constants.argtypes = [C.POINTER(S.CameraData), C.c_int, C.POINTER(S.PathTracerConstants)]; L.rtxpt_b200_default_constants.restype = C.c_int
         _libs[strict] = L
     return _libs[strict]
 

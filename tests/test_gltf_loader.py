@@ -130,3 +130,54 @@ def test_gltf_loader_errors(product, tmp_path):
     (tmp_path / "s_tex0.png").write_bytes(b"\xff\xd8\xff\xe0 not a png")          # a JPEG where a PNG is expected
     with pytest.raises(product.RtxptError, match="not a PNG"):
         product.GltfScene(path)
+
+
+def test_host_helpers_match_python_mirror(product):
+    """rtxpt_b200_bridge_camera / rtxpt_b200_default_constants (C++) against scene_builder.bridge_camera / make_constants."""
+    from rtxpt_b200 import scene_builder as sb, structs as S
+    L = product.load()
+    f3 = lambda v: (C.c_float * 3)(*v)
+    for (w, h, pos, d, up, fov, jit) in [(256, 256, (2.78, 2.73, -8.0), (0, 0, 1), (0, 1, 0), 0.66, (0.0, 0.0)), (1920, 1080, (-20, 1.8, 12), (0.7, -0.1, 0.7), (0, 1, 0), 1.04, (0.25, -0.5))]:
+        out = S.CameraData()
+        assert L.rtxpt_b200_bridge_camera(w, h, f3(pos), f3(d), f3(up), fov, 0.1, 1e7, 10000.0, 0.0, (C.c_float * 2)(*jit), C.byref(out)) == 0
+        ref = sb.bridge_camera(w, h, pos, d, up, fov, jitter=jit)
+        a = np.frombuffer(bytes(out), np.float32); b = np.frombuffer(bytes(ref), np.float32)
+        assert np.allclose(a, b, rtol=3e-7, atol=0) and list(out.ViewportSize) == [w, h]
+        k = S.PathTracerConstants(); assert L.rtxpt_b200_default_constants(C.byref(out), 1, C.byref(k)) == 0
+        r = sb.make_constants(w, h, out, bounce_count=20, diffuse_bounce_count=2, firefly_threshold=5000.0, env_enabled=True)
+        assert bytes(k) == bytes(r)
+
+
+def test_cpp_host_example_without_gpu(product, tmp_path):
+    """The C++ example host links against the C ABI only; without a CUDA device it must stop at create() with the no-fallback message."""
+    import subprocess, torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a GPU")
+    from rtxpt_b200 import scenes
+    exe = os.path.join(os.path.dirname(product.LIB_PATH), "render_gltf")
+    path = gltf_export.export(scenes.cornell_builder(), str(tmp_path / "cornell.gltf"), camera=dict(position=(2.78, 2.73, -8.0), direction=(0, 0, 1), up=(0, 1, 0), yfov=0.66, znear=0.1, zfar=1e7))
+    r = subprocess.run([exe, path, str(tmp_path / "o.pfm"), "32", "32", "1", "2"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_host_example_renders_cornell(product, oracle, tmp_path):
+    """glTF file -> C++ host (examples/render_gltf.cpp) -> PFM, against the oracle rendering the table-builder scene."""
+    import subprocess
+    from rtxpt_b200 import scenes, scene_builder as sb
+    from rtxpt_b200.imageio import per_pixel_l2
+    exe = os.path.join(os.path.dirname(product.LIB_PATH), "render_gltf")
+    path = gltf_export.export(scenes.cornell_builder(), str(tmp_path / "cornell.gltf"), camera=dict(position=(2.78, 2.73, -8.0), direction=(0, 0, 1), up=(0, 1, 0), yfov=0.66, znear=0.1, zfar=1e7))
+    out = str(tmp_path / "o.pfm")
+    r = subprocess.run([exe, path, out, "96", "96", "8", "2"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    with open(out, "rb") as f:
+        assert f.readline() == b"PF\n" and f.readline() == b"96 96\n" and f.readline() == b"-1.0\n"
+        img = np.frombuffer(f.read(), np.float32).reshape(96, 96, 3)[::-1]
+    scene, cam = scenes.cornell_box(96, 96)
+    consts = sb.make_constants(96, 96, cam, bounce_count=2, diffuse_bounce_count=2, firefly_threshold=5000.0)
+    o = oracle.Oracle(scene); acc = None; n = 0
+    for base in (0, 4):
+        consts.sampleBaseIndex = base; o.set_constants(consts); acc, n = o.render(0, 4, accum=acc, accum_count=n)[:2]
+    o.close()
+    assert per_pixel_l2(np.concatenate([img, np.ones((96, 96, 1), np.float32)], -1), acc) < 1e-4
