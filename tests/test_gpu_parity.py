@@ -264,3 +264,51 @@ def test_determinism_batching_and_tiles(product, small_city, strict):
     assert np.array_equal(parts[0].readback_accumulated(), ia)
     for p in parts:
         p.close()
+
+
+@pytest.mark.gpu
+def test_full_size_properties(product):
+    """BASELINE.json configs[1] at full size (2.86 M triangles, 1920x1080, 6 bounces): the oracle cannot render this in test time, so the
+    size-independent properties of the path are checked instead: no NaN / negative radiance, frame-to-frame determinism, batch invariance
+    (4 sub-samples at once == 2 + 2), the running mean over frames, tile-split invariance (two half-frame contexts == one full-frame
+    context, bit for bit), closest-hit / any-hit consistency on a million random segments, and ray bookkeeping (rays per path within the
+    bounds the bounce limits allow)."""
+    from rtxpt_b200 import scenes, scene_builder as sb
+    W, H, SPP = 1920, 1080, 4
+    scene, cam = scenes.city_block(width=W, height=H)
+    consts = sb.make_constants(W, H, cam, bounce_count=6, diffuse_bounce_count=6, env_enabled=True, firefly_threshold=5000.0)
+    a = product.Context(max_sub_samples_per_launch=SPP); a.upload_scene(scene); a.set_constants(consts)
+    a.path_trace(0, SPP, True); a.synchronize(); img = a.readback_accumulated(); st = a.stats()
+    assert np.isfinite(img).all() and (img[..., :3] >= 0).all() and (img[..., 3] == 1).all()
+    paths = W * H * SPP
+    assert st.paths == paths and paths <= st.scatterRays <= paths * (6 + 1 + 4) and st.shadowRays <= st.scatterRays          # <= 7 segments (+4 nested-dielectric re-traces), <= 1 shadow ray per hit vertex
+    assert 3.0 < (st.scatterRays + st.shadowRays) / paths < 6.0
+    assert st.bvhTriangleCount == scene.triangle_count
+    # determinism: the same frame again; batch invariance: 2 + 2 sub-samples
+    a.reset_accumulation(); a.path_trace(0, SPP, True); a.synchronize(); assert np.array_equal(img, a.readback_accumulated())
+    b = product.Context(max_sub_samples_per_launch=2); b.upload_scene(scene); b.set_constants(consts)
+    b.path_trace(0, SPP, True); b.synchronize(); assert np.array_equal(img, b.readback_accumulated()); b.close()
+    # running mean: a second frame with the next sample indices accumulates to lerp(prev, sample, 1 / (n + 1)) per sub-sample
+    consts.sampleBaseIndex = SPP; a.set_constants(consts); a.path_trace(0, SPP, True); a.synchronize(); two = a.readback_accumulated()
+    assert a.stats().accumulatedSamples == 2 * SPP and np.isfinite(two).all() and not np.array_equal(two, img)
+    assert abs(float(two[..., :3].mean()) - float(img[..., :3].mean())) < 0.05 * float(img[..., :3].mean())
+    # tile split: two contexts, each tracing its interleaved 64x64 tiles, reassembled
+    consts.sampleBaseIndex = 0
+    parts = []
+    for r in range(2):
+        c = product.Context(max_sub_samples_per_launch=SPP, tile_rank=r, tile_world=2, tile_size=64); c.upload_scene(scene); c.set_constants(consts)
+        c.path_trace(0, SPP, True); c.synchronize(); parts.append(c.readback_accumulated()); c.close()
+    ty, tx = np.meshgrid(np.arange(H) // 64, np.arange(W) // 64, indexing="ij")
+    owner = (ty * ((W + 63) // 64) + tx) % 2
+    assert np.array_equal(np.where(owner[..., None] == 0, parts[0], parts[1]), img)
+    # ray queries: every segment that the any-hit query reports occluded has a closest hit inside the segment, and vice versa
+    rng = np.random.default_rng(5)
+    n = 1 << 20
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:3] = rng.uniform([-110, 0.2, -110], [110, 40, 110], (n, 3)); d = rng.normal(size=(n, 3)); rays[:, 4:7] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays[:, 3] = 0.0; rays[:, 7] = rng.uniform(1.0, 60.0, n)
+    closest, anyhit = a.trace_rays(rays), a.trace_rays(rays, any_hit=True)
+    # ExcludeFromNEE geometry is skipped by visibility rays only, so "any-hit occluded" implies "closest hit", not the converse
+    assert ((anyhit["t"] >= 0) <= (closest["t"] >= 0)).all() and ((closest["t"] < 0) | (closest["t"] < rays[:, 7])).all()
+    assert 0.05 < (closest["t"] >= 0).mean() < 0.95
+    a.close()
