@@ -80,11 +80,15 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ Launch
 // by an order of magnitude.
 
 // shared memory of the traversal kernels: [mbarrier 16 B][WarpScratch x 8 warps][staged BVH nodes]
-constexpr uint kTraceWarps = 8;
+#ifndef PT_TRACE_THREADS
+#define PT_TRACE_THREADS 256     // threads per traversal CTA; the resident-CTA count scales so that warps per SM stay the same
+#endif
+constexpr uint kTraceThreads = PT_TRACE_THREADS, kTraceCtaScale = 256 / PT_TRACE_THREADS;
+constexpr uint kTraceWarps = kTraceThreads / 32;
 constexpr uint kTraceScratchBytes = 16 + kTraceWarps * sizeof(WarpScratch);
 
 template <bool COUNT, int MINB>
-__global__ void __launch_bounds__(256, MINB) k_trace_closest(const __grid_constant__ LaunchParams p)
+__global__ void __launch_bounds__(kTraceThreads, MINB * kTraceCtaScale) k_trace_closest(const __grid_constant__ LaunchParams p)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     uint* ctr = p.wf.counters + p.iteration * kCountersPerIter;
@@ -159,7 +163,7 @@ __global__ void __launch_bounds__(256, MINB) k_trace_closest(const __grid_consta
 
 // ---- shadow rays ----------------------------------------------------------------------------------------------------------------------------
 template <bool COUNT, int MINB>
-__global__ void __launch_bounds__(256, MINB) k_trace_shadow(const __grid_constant__ LaunchParams p)
+__global__ void __launch_bounds__(kTraceThreads, MINB * kTraceCtaScale) k_trace_shadow(const __grid_constant__ LaunchParams p)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     uint* ctr = p.wf.counters + p.iteration * kCountersPerIter;
@@ -259,7 +263,7 @@ __global__ void __launch_bounds__(256) k_commit_accumulate(const __grid_constant
 
 // ---- standalone ray queries (parity tests, traversal benchmark): same Traverser and dynamic fetch as the wavefront kernels ------------------
 template <bool ANY_HIT>
-__global__ void __launch_bounds__(256, 2) k_trace_rays(const __grid_constant__ LaunchParams p, const RtxptRay* __restrict__ rays, uint count, RtxptHit* __restrict__ out, uint* counters, uint* cursor)
+__global__ void __launch_bounds__(kTraceThreads, 2 * kTraceCtaScale) k_trace_rays(const __grid_constant__ LaunchParams p, const RtxptRay* __restrict__ rays, uint count, RtxptHit* __restrict__ out, uint* counters, uint* cursor)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smemRaw);
@@ -358,25 +362,25 @@ void launchGenerate(const LaunchParams& p, const GridConfig& g, cudaStream_t s) 
 void launchTraceClosest(const LaunchParams& p, const GridConfig& g, bool count, cudaStream_t s)
 {
     const int grid = g.smCount * g.traceBlocksPerSM; const size_t smem = traceSmemBytes(p);
-    if (count) k_trace_closest<true, 2><<<grid, 256, smem, s>>>(p);
-    else if (g.traceBlocksPerSM >= 4) k_trace_closest<false, 4><<<grid, 256, smem, s>>>(p);
-    else if (g.traceBlocksPerSM == 3) k_trace_closest<false, 3><<<grid, 256, smem, s>>>(p);
-    else k_trace_closest<false, 2><<<grid, 256, smem, s>>>(p);
+    if (count) k_trace_closest<true, 2><<<grid * kTraceCtaScale, kTraceThreads, smem, s>>>(p);
+    else if (g.traceBlocksPerSM >= 4) k_trace_closest<false, 4><<<grid * kTraceCtaScale, kTraceThreads, smem, s>>>(p);
+    else if (g.traceBlocksPerSM == 3) k_trace_closest<false, 3><<<grid * kTraceCtaScale, kTraceThreads, smem, s>>>(p);
+    else k_trace_closest<false, 2><<<grid * kTraceCtaScale, kTraceThreads, smem, s>>>(p);
 }
 void launchTraceShadow(const LaunchParams& p, const GridConfig& g, bool count, cudaStream_t s)
 {
     const int grid = g.smCount * g.traceBlocksPerSM; const size_t smem = traceSmemBytes(p);
-    if (count) k_trace_shadow<true, 2><<<grid, 256, smem, s>>>(p);
-    else if (g.traceBlocksPerSM >= 4) k_trace_shadow<false, 4><<<grid, 256, smem, s>>>(p);
-    else if (g.traceBlocksPerSM == 3) k_trace_shadow<false, 3><<<grid, 256, smem, s>>>(p);
-    else k_trace_shadow<false, 2><<<grid, 256, smem, s>>>(p);
+    if (count) k_trace_shadow<true, 2><<<grid * kTraceCtaScale, kTraceThreads, smem, s>>>(p);
+    else if (g.traceBlocksPerSM >= 4) k_trace_shadow<false, 4><<<grid * kTraceCtaScale, kTraceThreads, smem, s>>>(p);
+    else if (g.traceBlocksPerSM == 3) k_trace_shadow<false, 3><<<grid * kTraceCtaScale, kTraceThreads, smem, s>>>(p);
+    else k_trace_shadow<false, 2><<<grid * kTraceCtaScale, kTraceThreads, smem, s>>>(p);
 }
 void launchCommitAccumulate(const LaunchParams& p, const GridConfig& g, cudaStream_t s) { k_commit_accumulate<<<g.smCount * 4, 256, 0, s>>>(p); }
 void launchTraceRays(const LaunchParams& p, const GridConfig& g, const RtxptRay* rays, uint32_t count, bool anyHit, RtxptHit* out, uint32_t* counters, uint32_t* cursor, cudaStream_t s)
 {
     cudaMemsetAsync(cursor, 0, sizeof(uint32_t), s);
-    if (anyHit) k_trace_rays<true><<<g.smCount * g.traceBlocksPerSM, 256, traceSmemBytes(p), s>>>(p, rays, count, out, counters, cursor);
-    else k_trace_rays<false><<<g.smCount * g.traceBlocksPerSM, 256, traceSmemBytes(p), s>>>(p, rays, count, out, counters, cursor);
+    if (anyHit) k_trace_rays<true><<<g.smCount * g.traceBlocksPerSM * kTraceCtaScale, kTraceThreads, traceSmemBytes(p), s>>>(p, rays, count, out, counters, cursor);
+    else k_trace_rays<false><<<g.smCount * g.traceBlocksPerSM * kTraceCtaScale, kTraceThreads, traceSmemBytes(p), s>>>(p, rays, count, out, counters, cursor);
 }
 void queryOccupancy(GridConfig& g, size_t smemBytes)
 {

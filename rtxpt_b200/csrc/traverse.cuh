@@ -97,6 +97,10 @@ struct TraversalCounters { uint nodeVisits, triTests; };
 
 // byte j of a packed word -> 1 + b * 2^-15, built by placing the byte in mantissa bits 8..15 of 1.0f (one PRMT)
 PT_DEVICE float byteToUnitFloat(uint w, int j) { return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | (uint(j) << 4))); }
+#ifndef PT_I2F_AXES
+#define PT_I2F_AXES 2       // how many of the three axes convert their bytes with I2F (XU pipe) instead of PRMT (ALU pipe): closest-hit ms/frame 0 axes 9.15, 1 axis 8.98, 2 axes 8.84 (profiles/r1_history.md)
+#endif
+template <bool I2F> PT_DEVICE float byteToCoord(uint w, int j) { return I2F ? float((w >> (8 * j)) & 0xFFu) : byteToUnitFloat(w, j); }
 
 // ---- warp-cooperative traversal ------------------------------------------------------------------------------------------------------
 // Node steps are per-lane work (each lane walks its own ray through the CWBVH8).  Triangle tests are NOT: a leaf holds 1..3 triangles and
@@ -251,12 +255,16 @@ struct Traverser
                 // round-1 ncu capture); then b * (s * id) + o == m * A + (o - A) with A = s * id * 2^15.  The box test only has to be
                 // conservative (the triangle test decides): the relative slack eps and an absolute pad that covers the rounding of (o - A)
                 // (<= 2^-22 (|A| + |o|), |o| <= |t| + 2^8 |s id|) are folded into the per-node constants, near planes pulled in, far pushed out.
-                const float Ax = sx15 * idx, Ay = sy15 * idy, Az = sz15 * idz;
-                const float Ox = (px - org.x) * idx - Ax, Oy = (py - org.y) * idy - Ay, Oz = (pz - org.z) * idz - Az;
+                // PT_I2F_AXES of the three axes keep the integer->float conversion (XU pipe) so that the conversions are spread over two pipes:
+                // for those, b * (s id) + o is evaluated directly (A = s id, no offset), with the same slack.
+                const float Ax15 = sx15 * idx, Ay15 = sy15 * idy, Az15 = sz15 * idz;
+                const float Ax = (PT_I2F_AXES > 0) ? Ax15 * (1.0f / 32768.0f) : Ax15, Ay = (PT_I2F_AXES > 1) ? Ay15 * (1.0f / 32768.0f) : Ay15, Az = (PT_I2F_AXES > 2) ? Az15 * (1.0f / 32768.0f) : Az15;
+                const float ox = (px - org.x) * idx, oy = (py - org.y) * idy, oz = (pz - org.z) * idz;
+                const float Ox = (PT_I2F_AXES > 0) ? ox : ox - Ax, Oy = (PT_I2F_AXES > 1) ? oy : oy - Ay, Oz = (PT_I2F_AXES > 2) ? oz : oz - Az;
                 const float kLo = 1.0f - 6.0e-7f, kHi = 1.0f + 6.0e-7f, kPad = 4.8e-7f;
                 const float Anx = Ax * kLo, Any = Ay * kLo, Anz = Az * kLo, Afx = Ax * kHi, Afy = Ay * kHi, Afz = Az * kHi;
-                const float Onx = __fmaf_rn(Ox, kLo, -fabsf(Ax) * kPad), Ony = __fmaf_rn(Oy, kLo, -fabsf(Ay) * kPad), Onz = __fmaf_rn(Oz, kLo, -fabsf(Az) * kPad);
-                const float Ofx = __fmaf_rn(Ox, kHi, fabsf(Ax) * kPad), Ofy = __fmaf_rn(Oy, kHi, fabsf(Ay) * kPad), Ofz = __fmaf_rn(Oz, kHi, fabsf(Az) * kPad);
+                const float Onx = __fmaf_rn(Ox, kLo, -fabsf(Ax15) * kPad), Ony = __fmaf_rn(Oy, kLo, -fabsf(Ay15) * kPad), Onz = __fmaf_rn(Oz, kLo, -fabsf(Az15) * kPad);
+                const float Ofx = __fmaf_rn(Ox, kHi, fabsf(Ax15) * kPad), Ofy = __fmaf_rn(Oy, kHi, fabsf(Ay15) * kPad), Ofz = __fmaf_rn(Oz, kHi, fabsf(Az15) * kPad);
                 uint hitmask = 0;
                 #pragma unroll
                 for (int half = 0; half < 2; half++)
@@ -274,9 +282,9 @@ struct Traverser
                     #pragma unroll
                     for (int j = 0; j < 4; j++)
                     {
-                        const float t0x = __fmaf_rn(byteToUnitFloat(nearx, j), Anx, Onx), t1x = __fmaf_rn(byteToUnitFloat(farx, j), Afx, Ofx);
-                        const float t0y = __fmaf_rn(byteToUnitFloat(neary, j), Any, Ony), t1y = __fmaf_rn(byteToUnitFloat(fary, j), Afy, Ofy);
-                        const float t0z = __fmaf_rn(byteToUnitFloat(nearz, j), Anz, Onz), t1z = __fmaf_rn(byteToUnitFloat(farz, j), Afz, Ofz);
+                        const float t0x = __fmaf_rn(byteToCoord<(PT_I2F_AXES > 0)>(nearx, j), Anx, Onx), t1x = __fmaf_rn(byteToCoord<(PT_I2F_AXES > 0)>(farx, j), Afx, Ofx);
+                        const float t0y = __fmaf_rn(byteToCoord<(PT_I2F_AXES > 1)>(neary, j), Any, Ony), t1y = __fmaf_rn(byteToCoord<(PT_I2F_AXES > 1)>(fary, j), Afy, Ofy);
+                        const float t0z = __fmaf_rn(byteToCoord<(PT_I2F_AXES > 2)>(nearz, j), Anz, Onz), t1z = __fmaf_rn(byteToCoord<(PT_I2F_AXES > 2)>(farz, j), Afz, Ofz);
                         const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tMin));
                         const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, bestT));
                         if (cmin <= cmax)
