@@ -79,7 +79,8 @@ typedef struct RtxptSubInstanceData {
     uint32_t FlagsAndAlphaInfo;                         /* [15:0] alpha texture index, bit16 alpha tested, bit17 exclude from NEE, [31:24] cutoff*255 */
     uint32_t GlobalGeometryIndex_PTMaterialDataIndex;   /* [31:16] geometry index, [15:0] material index */
     uint32_t EmissiveLightMappingOffset;                /* filled by the library's light bake; callers pass 0xFFFFFFFF */
-    uint32_t AnalyticProxyLightIndex;
+    uint32_t AnalyticProxyLightIndex;                   /* index into RtxptSceneDesc.lights of the analytic light this geometry stands in for (material flag
+                                                           EnableAsAnalyticLightProxy), 0xFFFFFFFF for none; the library rebases it into its light list */
     uint32_t IndexBufferIndex_VertexBufferIndex;
     uint32_t IndexOffset;
     uint32_t TexCoord1Offset;

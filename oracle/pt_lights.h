@@ -250,6 +250,30 @@ struct SphereLight      // PolymorphicLight.hlsli:93-259
         r.LightSampleableByBSDF = false;
         return r;
     }
+    // Eval (PolymorphicLight.hlsli:190-205) with IntersectRaySphere (Utils/Geometry.hlsli:85-118): what a BSDF ray sees when it reaches the light's proxy geometry
+    bool Eval(float3 rayPos, float3 rayDir, float3& outRadiance, float3& outLightSamplePosition) const
+    {
+        const float3 lightVector = position - rayPos;
+        if (dot(lightVector, lightVector) < radius * radius) return false;
+        const float3 oc = rayPos - position;
+        const float b = 2.0f * dot(oc, rayDir), c = dot(oc, oc) - radius * radius;
+        const float discriminant = b * b - 4.0f * c;
+        if (discriminant < 0.0f) return false;
+        const float sqrtDisc = sqrtf(discriminant);
+        const float t1 = (-b - sqrtDisc) / 2.0f, t2 = (-b + sqrtDisc) / 2.0f;
+        const float t = (t1 >= 0.0f) ? t1 : ((t2 >= 0.0f) ? t2 : -1.0f);
+        if (t < 0.0f) return false;
+        outLightSamplePosition = rayPos + rayDir * t;
+        outRadiance = radiance * evaluateLightShaping(shaping, rayPos, position);
+        return true;
+    }
+    float CalcSolidAnglePdfForMIS(float3 viewerPosition) const
+    {
+        const float3 lightVector = position - viewerPosition;
+        const float sinThetaMax2 = (radius * radius) / dot(lightVector, lightVector);
+        const float cosThetaMax = sqrtf(std::max(0.0f, 1.0f - sinThetaMax2));
+        return 1.0f / (2.0f * K_PI * (1.0f - cosThetaMax));
+    }
     float GetPower() const { return 4 * K_PI * radius * radius * K_PI * Luminance(radiance) * getShapingFluxFactor(shaping); }
 };
 

@@ -445,6 +445,22 @@ inline void HandleHit(const PathTracerCtx& x, PathState& path, float3 rayOrigin,
         }
         surfaceEmission = lp(sd.emission * misWeight);
     }
+    if (surface.neeAnalyticLightIndex != RTXPT_INVALID_LIGHT_INDEX)
+    {   // LightSampler::ComputeAnalyticLightProxyContributionWithMIS (LightSampler.hlsli:363-394, PathTracer.hlsli:636-648): sphere lights only
+        const PolymorphicLightInfo& li = x.lights->lights[surface.neeAnalyticLightIndex];
+        if (LightType(li) == kLightTypeSphere)
+        {
+            const SphereLight sl = SphereLight::Create(li, x.lights->exOf(surface.neeAnalyticLightIndex));
+            float3 radiance, lightSamplePosition;
+            if (sl.Eval(rayOrigin, rayDir, radiance, lightSamplePosition))
+            {
+                float mis = 1.0f;
+                const float bsdfPdf = misInfo.LightSamplingEnabled ? path.GetBsdfScatterPdf() : 0.0f;
+                if (bsdfPdf != 0) mis = ComputeLightVsBSDF_MIS_ForBSDF(*x.lights, surface.neeAnalyticLightIndex, bsdfPdf, sl.CalcSolidAnglePdfForMIS(rayOrigin), misInfo.FullSamples);
+                surfaceEmission = surfaceEmission + lp(radiance * mis);
+            }
+        }
+    }
     if (any_gt0(surfaceEmission))
     {
         float baseFFThreshold = lp(x.c->fireflyFilterThreshold);

@@ -163,6 +163,7 @@ struct SurfaceData      // PathTracerTypes.hlsli:52-94
     StandardBSDF bsdf;
     float interiorIoR;
     uint neeTriangleLightIndex;
+    uint neeAnalyticLightIndex;     // light the hit geometry stands in for (PTMaterialFlags_EnableAsAnalyticLightProxy), else 0xFFFFFFFF
 };
 
 struct Scene
@@ -179,6 +180,8 @@ struct Scene
         for (uint i = 0; i < d->textureCount; i++) textures[i].d = &d->textures[i];
         env.d = &d->envCube;
         subInstances.assign(d->subInstances, d->subInstances + d->subInstanceCount);
+        // AnalyticProxyLightIndex arrives as an index into desc->lights; the light list puts analytic lights after the 5368 environment nodes
+        for (RtxptSubInstanceData& si : subInstances) si.AnalyticProxyLightIndex = (si.AnalyticProxyLightIndex < d->lightCount) ? si.AnalyticProxyLightIndex + 5368u : 0xFFFFFFFFu;
     }
     uint load32(int buffer, uint byteOffset) const { uint v; memcpy(&v, (const uint8_t*)desc->buffers[buffer].data + byteOffset, 4); return v; }
     float3 loadFloat3(int buffer, uint byteOffset) const { float v[3]; memcpy(v, (const uint8_t*)desc->buffers[buffer].data + byteOffset, 12); return f3(v[0], v[1], v[2]); }
@@ -416,6 +419,7 @@ inline SurfaceData loadSurface(const Scene& sc, uint instanceIndex, uint geometr
     b.eta = lp(sd.IoR / matIoR);
     if (!sd.thinSurface && !sd.frontFacing) b.eta = lp(matIoR / sd.IoR);
     out.neeTriangleLightIndex = 0xFFFFFFFFu;
+    out.neeAnalyticLightIndex = (mat.flags & RTXPT_MATFLAG_EnableAsAnalyticLightProxy) ? sc.subInstances[subInstanceDataIndex].AnalyticProxyLightIndex : 0xFFFFFFFFu;   // BridgeDonut:828-829
     sd.emission = f3(0);
     if (sd.frontFacing && any_gt0(mat.emissiveColor))
     {

@@ -283,6 +283,8 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
     if (sc->envCube.faceSize) { int rc = createEnvCube(sc->envCube, c->envCube); if (rc != RTXPT_OK) return rc; }
     // sub-instances: shade-queue class (the SER sort key analogue; the reference sorts by material permutation, MaterialsBaker.cpp:1227-1285)
     c->hSubInstances.assign(sc->subInstances, sc->subInstances + sc->subInstanceCount);
+    // AnalyticProxyLightIndex arrives as an index into sc->lights; in the light list the analytic lights follow the environment quad-tree nodes
+    for (RtxptSubInstanceData& si : c->hSubInstances) si.AnalyticProxyLightIndex = (si.AnalyticProxyLightIndex < sc->lightCount) ? si.AnalyticProxyLightIndex + kEnvQuadLightCount : 0xFFFFFFFFu;
     std::vector<uint8_t> cls(sc->subInstanceCount, 0);
     for (uint32_t i = 0; i < sc->subInstanceCount; i++)
     {

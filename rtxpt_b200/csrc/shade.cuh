@@ -70,6 +70,19 @@ PT_DEVICE float3 octUnorm32ToDir(uint p)
     n.x += (n.x >= 0.0f) ? -t : t; n.y += (n.y >= 0.0f) ? -t : t;
     return norm3(n);
 }
+// evaluateLightShaping (LightShaping.hlsli:26-95): spot falloff of a shaped light towards `surfacePos`, 1 for unshaped lights
+PT_DEVICE float lightShaping(const LightInfo& li, const SceneView& sc, uint lightIndex, float3 surfacePos, float3 lightSamplePos)
+{
+    if (!(li.colorTypeAndFlags & kLightShapingEnableBit)) return 1.0f;
+    const uint4 ex = sc.lightsEx[lightIndex - 5368u];
+    const float3 axis = octUnorm32ToDir(ex.y);
+    const float cosCone = f16tof32(ex.z), softness = f16tof32(ex.z >> 16);
+    const float minFalloff = (li.colorTypeAndFlags & kLightShapingUseMinFalloff) ? 0.0001f : 0.0f;
+    const float cosT = dot3(axis, norm3(surfacePos - lightSamplePos));
+    const float t = sat((cosT - cosCone) / ((cosCone + softness) - cosCone));
+    const float falloff = fmaxf(minFalloff, t * t * (3.0f - 2.0f * t));
+    return falloff <= 0 ? 0.0f : falloff;
+}
 // SphereLight::CalcSample + evaluateLightShaping (PolymorphicLight.hlsli:107-181, :669-673; LightShaping.hlsli:26-95)
 PT_DEVICE void sampleSphereLight(const LightInfo& li, const SceneView& sc, uint lightIndex, float u0, float u1, float3 viewer, float3& outPos, float3& outRadiance, float& outSolidPdf)
 {
@@ -94,18 +107,7 @@ PT_DEVICE void sampleSphereLight(const LightInfo& li, const SceneView& sc, uint 
     const float3 radiusVector = (-T) * (sinAlpha * cosPhi) + (-B) * (sinAlpha * sinPhi) + (-n) * cosAlpha;
     outPos = center + radiusVector * radius;
     outSolidPdf = 1.0f / (2.0f * kPi * (1.0f - cosThetaMax));
-    outRadiance = unpackLightRadiance(li);
-    if (li.colorTypeAndFlags & kLightShapingEnableBit)
-    {
-        const uint4 ex = sc.lightsEx[lightIndex - 5368u];
-        const float3 axis = octUnorm32ToDir(ex.y);
-        const float cosCone = f16tof32(ex.z), softness = f16tof32(ex.z >> 16);
-        const float minFalloff = (li.colorTypeAndFlags & kLightShapingUseMinFalloff) ? 0.0001f : 0.0f;
-        const float cosT = dot3(axis, norm3(viewer - outPos));
-        const float t = sat((cosT - cosCone) / ((cosCone + softness) - cosCone));
-        const float falloff = fmaxf(minFalloff, t * t * (3.0f - 2.0f * t));
-        outRadiance = outRadiance * (falloff <= 0 ? 0.0f : falloff);
-    }
+    outRadiance = unpackLightRadiance(li) * lightShaping(li, sc, lightIndex, viewer, outPos);
 }
 struct TriLight
 {
@@ -163,6 +165,7 @@ struct Surface
     float3 emission;
     BsdfParams bsdf;
     uint neeTriangleLightIndex;
+    uint neeAnalyticLightIndex;     // light this geometry stands in for (PTMaterialFlags_EnableAsAnalyticLightProxy), else kInvalidLight
 };
 
 PT_DEVICE float3 safeNormalize(float3 v) { return v * (1.0f / sqrtf(fmaxf(1.175494351e-38f, dot3(v, v)))); }
@@ -328,6 +331,7 @@ PT_DEVICE void loadSurface(const LaunchParams& p, uint gid, float bu, float bv, 
     s.bsdf.eta = lp(s.IoR / matIoR);
     if (!s.thin && !frontFacing) s.bsdf.eta = lp(matIoR / s.IoR);
     s.neeTriangleLightIndex = kInvalidLight;
+    s.neeAnalyticLightIndex = (mflags & RTXPT_MATFLAG_EnableAsAnalyticLightProxy) ? sc.subInstances[subIndex].AnalyticProxyLightIndex : kInvalidLight;      // BridgeDonut:828-829
     s.emission = mk3(0.f);
     if (frontFacing && anyPositive(emissiveColor))
     {
@@ -452,6 +456,33 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
             misWeight = misForBsdf(p.scene, s.neeTriangleLightIndex, bsdfPdf, tl.solidAnglePdfForMIS(rayOrigin, s.posW), misPacked & 0x3F);
         }
         surfaceEmission = lp3(s.emission * misWeight);
+    }
+    if (ANALYTIC_LIGHTS && s.neeAnalyticLightIndex != kInvalidLight)
+    {   // LightSampler::ComputeAnalyticLightProxyContributionWithMIS (LightSampler.hlsli:363-394): a BSDF ray that reached the proxy geometry
+        // of a sphere light sees the analytic sphere (SphereLight::Eval + IntersectRaySphere, Utils/Geometry.hlsli:85-118)
+        const LightInfo li = p.scene.lights[s.neeAnalyticLightIndex];
+        if (lightType(li) == kLightTypeSphere)
+        {
+            const float3 center = mk3(li.cx, li.cy, li.cz); const float radius = f16tof32(li.scalars);
+            const float3 lv = center - rayOrigin, oc = rayOrigin - center;
+            const float bq = 2.0f * dot3(oc, rayDir), cq = dot3(oc, oc) - radius * radius, disc = bq * bq - 4.0f * cq;
+            if (!(dot3(lv, lv) < radius * radius) && disc >= 0.0f)
+            {
+                const float sq = sqrtf(disc), t1 = (-bq - sq) / 2.0f, t2 = (-bq + sq) / 2.0f;
+                if (t1 >= 0.0f || t2 >= 0.0f)
+                {
+                    const float3 radiance = unpackLightRadiance(li) * lightShaping(li, p.scene, s.neeAnalyticLightIndex, rayOrigin, center);
+                    float mis = 1.0f;
+                    const float bsdfPdf = (misPacked & (1u << 15)) ? path.bsdfScatterPdf() : 0.0f;
+                    if (bsdfPdf != 0)
+                    {
+                        const float cosThetaMax = sqrtf(fmaxf(0.0f, 1.0f - (radius * radius) / dot3(lv, lv)));
+                        mis = misForBsdf(p.scene, s.neeAnalyticLightIndex, bsdfPdf, 1.0f / (2.0f * kPi * (1.0f - cosThetaMax)), misPacked & 0x3F);
+                    }
+                    surfaceEmission = surfaceEmission + lp3(radiance * mis);
+                }
+            }
+        }
     }
     if (anyPositive(surfaceEmission))
     {

@@ -98,7 +98,7 @@ class Material:
                  transmission=0.0, diffuse_transmission=0.0, ior=1.5, thin_surface=False, opacity=1.0, alpha_test=False, alpha_cutoff=0.5,
                  base_texture=None, orm_texture=None, normal_texture=None, emissive_texture=None, nested_priority=0,
                  volume_color=(1, 1, 1), volume_distance=3.4e38, shadow_nol_fadeout=0.0, exclude_from_nee=False, normal_scale=1.0,
-                 metalness_in_red=False):
+                 metalness_in_red=False, analytic_light_proxy=False):
         self.__dict__.update(locals()); del self.__dict__["self"]
 
     @property
@@ -136,8 +136,10 @@ class SceneBuilder:
         self.meshes.append(geometries)
         return len(self.meshes) - 1
 
-    def add_instance(self, mesh, transform=None):
+    def add_instance(self, mesh, transform=None, proxy_light=None):
+        """proxy_light: index (into the analytic lights added so far) of the light this instance's proxy-flagged geometry stands in for."""
         self.instances.append((mesh, identity34() if transform is None else np.asarray(transform, np.float32).reshape(3, 4)))
+        self.instance_proxy_light = getattr(self, "instance_proxy_light", {}); self.instance_proxy_light[len(self.instances) - 1] = proxy_light
 
     def set_env_cube(self, faces):
         self.env_faces = np.asarray(faces, np.float32)
@@ -182,6 +184,8 @@ class Scene:
             d.OcclusionTextureIndex = 0xFFFFFFFF
             if m.metalness_in_red:
                 flags |= S.MATFLAG_MetalnessInRedChannel
+            if m.analytic_light_proxy:
+                flags |= S.MATFLAG_EnableAsAnalyticLightProxy
             if m.thin_surface or not m.enable_transmission:      # MaterialsBaker.cpp:543-544
                 flags |= S.MATFLAG_ThinSurface
             flags |= (min(int(m.nested_priority), 14) & 0xF) << S.MATFLAG_NestedPriorityShift
@@ -270,7 +274,8 @@ class Scene:
                 s.FlagsAndAlphaInfo = fl
                 s.GlobalGeometryIndex_PTMaterialDataIndex = ((mesh_first_geo[mi] + k) << 16) | g["material"]
                 s.EmissiveLightMappingOffset = 0xFFFFFFFF
-                s.AnalyticProxyLightIndex = 0xFFFFFFFF
+                pl = getattr(b, "instance_proxy_light", {}).get(ii)
+                s.AnalyticProxyLightIndex = 0xFFFFFFFF if (pl is None or not mat.analytic_light_proxy) else pl
                 s.IndexBufferIndex_VertexBufferIndex = (geo.indexBufferIndex << 16) | geo.vertexBufferIndex
                 s.IndexOffset, s.TexCoord1Offset = geo.indexOffset, geo.texCoord1Offset
                 self.triangle_count += geo.numIndices // 3

@@ -7,7 +7,7 @@ box in its tree, so the BASELINE.json configurations are exercised on scenes aut
 """
 import math
 import numpy as np
-from .scene_builder import SceneBuilder, Material, bridge_camera, identity34
+from .scene_builder import SceneBuilder, Material, bridge_camera, identity34, translate_scale
 
 
 def _quad(p0, p1, p2, p3, material, uv_scale=1.0):
@@ -71,6 +71,12 @@ def cornell_builder(analytic_lights=False):
     boxes = b.add_mesh([_merge(short, white), _merge(tall, white)])
     for m in (room, lamp, boxes):
         b.add_instance(m, identity34())
+    if analytic_lights:
+        # proxy geometry of the first sphere light (radius 0.22): a cube inscribed in it; BSDF rays that reach it evaluate the analytic sphere
+        proxy = b.add_material(Material(base_color=(0, 0, 0), roughness=1.0, analytic_light_proxy=True))
+        h = 0.12
+        cube = b.add_mesh([_merge(_box([(-h, -h, -h), (h, -h, -h), (h, -h, h), (-h, -h, h)], 2 * h, proxy), proxy)])
+        b.add_instance(cube, translate_scale((1.2, 3.9, 1.6)), proxy_light=0)
     return b
 
 

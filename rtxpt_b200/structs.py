@@ -20,6 +20,7 @@ MATFLAG_UseTransmissionTexture = 0x80
 MATFLAG_MetalnessInRedChannel = 0x100
 MATFLAG_ThinSurface = 0x200
 MATFLAG_PSDExclude = 0x400
+MATFLAG_EnableAsAnalyticLightProxy = 0x800
 MATFLAG_IgnoreMeshTangentSpace = 1 << 12
 MATFLAG_NestedPriorityShift = 28
 

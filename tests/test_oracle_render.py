@@ -71,3 +71,6 @@ def test_analytic_lights_cpu(oracle):
     # the blue sphere light at (1.2, 3.9, 1.6) sits near the red wall (world x = 0 is the right side of the image): it adds blue there
     assert a[20:60, 60:90, 2].mean() > b[20:60, 60:90, 2].mean() + 0.02
     assert a[..., :3].mean() > b[..., :3].mean() * 1.05
+    # the proxy cube of the sphere light shows the analytic sphere's radiance to camera rays: 14 * (0.4, 0.6, 1.0) / (pi 0.22^2) through the 8-bit + log packing
+    peak = a[..., 2].max()
+    assert abs(peak - 14.0 / (np.pi * 0.22 ** 2)) < 0.02 * peak
