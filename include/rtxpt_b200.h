@@ -380,6 +380,11 @@ RTXPT_API int rtxpt_b200_get_lights(rtxpt_ctx* ctx, void* outLightInfos, uint32_
  * occupy light indices [5368, 5368 + count) between the environment quad-tree nodes and the emissive triangles. */
 RTXPT_API int rtxpt_b200_get_lights_ex(rtxpt_ctx* ctx, void* outLightInfoEx, uint32_t* ioAnalyticLightCount);
 
+/* Host-only: builds the compressed wide BVH over a triangle soup (9 floats per triangle) and reports its surface-area-heuristic statistics:
+ * expected node visits / triangle tests of a random ray that hits the root box.  Used to judge builder changes without a GPU. */
+typedef struct RtxptBvhStats { uint32_t nodeCount, triangleReferenceCount, leafCount, maxDepth; float expectedNodeVisits, expectedTriangleTests, buildSeconds, _pad; } RtxptBvhStats;
+RTXPT_API int rtxpt_b200_debug_bvh_stats(const float* triangleVertices, uint32_t triangleCount, RtxptBvhStats* outStats);
+
 /* StandardBSDF evaluated on the device for `count` records of 36 floats in / 16 floats out; see tests/test_bsdf_parity.py. */
 RTXPT_API int rtxpt_b200_debug_bsdf(rtxpt_ctx* ctx, const float* in, uint32_t count, float* out);
 /* Stateless sample generators evaluated on the device: out[i*8..] = 4 uniform + 4 low-discrepancy draws for

@@ -10,6 +10,7 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <omp.h>
@@ -48,13 +49,14 @@ struct Builder2
         for (uint32_t i = first; i < first + count; i++) { uint32_t id = order[i]; box.grow(triBox[id]); cbox.grow(&cen[id * 3]); }
         nd.box = box; nd.first = first; nd.count = 0; nd.left = nd.right = 0;
         if (count == 1) { nd.count = 1; return; }
-        const int NB = 16;
+        static const int NB = [] { const char* e = getenv("RTXPT_BVH_BINS"); return e ? std::min(64, std::max(4, atoi(e))) : 16; }();
+        static const float travCost = [] { const char* e = getenv("RTXPT_BVH_TRAVCOST"); return e ? float(atof(e)) : 1.0f; }();
         float bestCost = 3.0e38f; int bestAxis = -1, bestSplit = -1;
         for (int axis = 0; axis < 3; axis++)
         {
             float ext = cbox.hi[axis] - cbox.lo[axis];
             if (!(ext > 0.0f)) continue;
-            Box bb[NB]; uint32_t bn[NB];
+            Box bb[64]; uint32_t bn[64];
             for (int b = 0; b < NB; b++) { bb[b].reset(); bn[b] = 0; }
             const float scale = float(NB) / ext;
             for (uint32_t i = first; i < first + count; i++)
@@ -63,7 +65,7 @@ struct Builder2
                 int b = std::min(std::max(int((cen[id * 3 + axis] - cbox.lo[axis]) * scale), 0), NB - 1);
                 bb[b].grow(triBox[id]); bn[b]++;
             }
-            float rightArea[NB]; uint32_t rightN[NB];
+            float rightArea[64]; uint32_t rightN[64];
             Box acc; acc.reset(); uint32_t c = 0;
             for (int b = NB - 1; b > 0; b--) { acc.grow(bb[b]); c += bn[b]; rightArea[b] = acc.area(); rightN[b] = c; }
             acc.reset(); c = 0;
@@ -78,7 +80,7 @@ struct Builder2
         if (count <= 3)
         {   // SAH termination: a leaf slot of the wide node can hold up to 3 triangles
             float leafCost = box.area() * float(count);
-            float splitCost = (bestAxis >= 0) ? (bestCost + box.area() * 1.0f) : 3.0e38f;
+            float splitCost = (bestAxis >= 0) ? (bestCost + box.area() * travCost) : 3.0e38f;
             if (leafCost <= splitCost) { nd.count = count; return; }
         }
         uint32_t mid;
@@ -248,3 +250,48 @@ void buildBvh8(const std::vector<BuildTriangle>& tris, Bvh8& out)
 }
 
 } // namespace pt
+
+// ---- inspection hook (host only): surface-area-heuristic statistics of the tree built over a triangle soup -----------------------------------------------
+// Expected work of a random ray that hits the root box (MacDonald & Booth): a node is visited with probability area(node) / area(root);
+// the child boxes used are the quantised ones the traversal tests.
+#include "../../include/rtxpt_b200.h"
+extern "C" RTXPT_API int rtxpt_b200_debug_bvh_stats(const float* triangleVertices, uint32_t triangleCount, RtxptBvhStats* out)
+{
+    if ((!triangleVertices && triangleCount) || !out) return RTXPT_ERR_INVALID_ARGUMENT;
+    using namespace pt;
+    std::vector<BuildTriangle> tris(triangleCount);
+    for (uint32_t i = 0; i < triangleCount; i++)
+    {
+        memcpy(tris[i].v0, triangleVertices + size_t(i) * 9, 12); memcpy(tris[i].v1, triangleVertices + size_t(i) * 9 + 3, 12); memcpy(tris[i].v2, triangleVertices + size_t(i) * 9 + 6, 12);
+        tris[i].gid = i; tris[i].subInstanceAndFlags = 0; tris[i].primitiveIndex = i;
+    }
+    Bvh8 bvh; buildBvh8(tris, bvh);
+    memset(out, 0, sizeof(*out));
+    out->nodeCount = uint32_t(bvh.nodes.size()); out->triangleReferenceCount = uint32_t(bvh.tris.size()); out->buildSeconds = float(bvh.buildSeconds); out->maxDepth = bvh.maxDepth;
+    if (triangleCount == 0) return RTXPT_OK;
+    auto boxArea = [](const double* lo, const double* hi) { const double dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2]; return 2.0 * (dx * dy + dy * dz + dz * dx); };
+    double rootLo[3], rootHi[3]; for (int a = 0; a < 3; a++) { rootLo[a] = bvh.sceneLo[a]; rootHi[a] = bvh.sceneHi[a]; }
+    const double rootArea = std::max(boxArea(rootLo, rootHi), 1e-30);
+    // probability of visiting node i: carried down from the parent (quantised child box area / root area); breadth-first layout = parents first
+    std::vector<double> visitP(bvh.nodes.size(), 0.0); visitP[0] = 1.0;
+    double nodeVisits = 0, triTests = 0, leafCount = 0;
+    for (size_t ni = 0; ni < bvh.nodes.size(); ni++)
+    {
+        const Bvh8Node& n = bvh.nodes[ni];
+        nodeVisits += visitP[ni];
+        float p[3]; memcpy(p, &n.w[0], 12);
+        const uint32_t e[3] = { n.w[3] & 0xFF, (n.w[3] >> 8) & 0xFF, (n.w[3] >> 16) & 0xFF }, imask = n.w[3] >> 24, childBase = n.w[4];
+        const uint8_t* meta = reinterpret_cast<const uint8_t*>(&n.w[6]); const uint8_t* q = reinterpret_cast<const uint8_t*>(&n.w[8]);
+        for (int s = 0; s < 8; s++)
+        {
+            if (meta[s] == 0) continue;
+            double lo[3], hi[3];
+            for (int a = 0; a < 3; a++) { const double sc = std::ldexp(1.0, int(e[a]) - 127); lo[a] = p[a] + q[a * 8 + s] * sc; hi[a] = p[a] + q[(3 + a) * 8 + s] * sc; }
+            const double pr = std::min(1.0, boxArea(lo, hi) / rootArea);
+            if (imask & (1u << s)) visitP[childBase + __builtin_popcount(imask & ((1u << s) - 1u))] = pr;
+            else { const int cnt = __builtin_popcount(uint32_t(meta[s] >> 5)); triTests += pr * cnt; leafCount += 1; }
+        }
+    }
+    out->expectedNodeVisits = float(nodeVisits); out->expectedTriangleTests = float(triTests); out->leafCount = uint32_t(leafCount);
+    return RTXPT_OK;
+}

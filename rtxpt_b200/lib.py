@@ -50,7 +50,7 @@ _SIGNATURES = {
     "rtxpt_b200_debug_rng": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
 }
 _LOADER_SYMBOLS = ["rtxpt_b200_load_gltf", "rtxpt_b200_load_gltf_error", "rtxpt_b200_host_scene_desc", "rtxpt_b200_host_scene_cameras",
-                   "rtxpt_b200_host_scene_triangle_count", "rtxpt_b200_free_host_scene", "rtxpt_b200_bridge_camera", "rtxpt_b200_default_constants"]
+                   "rtxpt_b200_host_scene_triangle_count", "rtxpt_b200_free_host_scene", "rtxpt_b200_bridge_camera", "rtxpt_b200_default_constants", "rtxpt_b200_debug_bvh_stats"]
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["rtxpt_b200_last_error"] + _LOADER_SYMBOLS)
 
 
@@ -84,6 +84,16 @@ def load(strict=None):
 def _check(rc, L=None):
     if rc != 0:
         raise RtxptError(f"rtxpt_b200 error {rc}: {(L or load()).rtxpt_b200_last_error().decode()}")
+
+
+def bvh_stats(triangle_vertices, strict=None):
+    """SAH statistics of the product's BVH over an (N, 3, 3) float32 triangle soup (host only)."""
+    v = np.ascontiguousarray(triangle_vertices, np.float32).reshape(-1, 9)
+    st = S.BvhStats(); L = load(strict)
+    L.rtxpt_b200_debug_bvh_stats.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(S.BvhStats)]; L.rtxpt_b200_debug_bvh_stats.restype = C.c_int
+    if L.rtxpt_b200_debug_bvh_stats(v.ctypes.data, len(v), C.byref(st)) != 0:
+        raise RtxptError("bvh_stats failed")
+    return st
 
 
 class GltfScene:

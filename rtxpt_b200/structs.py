@@ -91,6 +91,11 @@ class SceneDesc(C.Structure):
                 ("lights", C.POINTER(LightDesc)), ("lightCount", u32)]
 
 
+class BvhStats(C.Structure):
+    _fields_ = [("nodeCount", u32), ("triangleReferenceCount", u32), ("leafCount", u32), ("maxDepth", u32), ("expectedNodeVisits", f32), ("expectedTriangleTests", f32),
+                ("buildSeconds", f32), ("_pad", f32)]
+
+
 class GltfCamera(C.Structure):
     _fields_ = [("position", f32 * 3), ("direction", f32 * 3), ("up", f32 * 3), ("yfov", f32), ("znear", f32), ("zfar", f32), ("aspectRatio", f32)]
 
