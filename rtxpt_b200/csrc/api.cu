@@ -52,6 +52,7 @@ struct rtxpt_ctx
     int maxSmemOptin = 0;
     // scene
     bool haveScene = false, haveConstants = false, lightsDirty = true;
+    size_t l2PersistBytes = 0, l2WindowMax = 0;
     cudaStream_t stream2 = nullptr; cudaEvent_t evShadeDone = nullptr, evShadowDone = nullptr; bool overlapShadow = true;
     DeviceArray<RtxptInstanceData> dInstances; DeviceArray<RtxptGeometryData> dGeometries; DeviceArray<RtxptSubInstanceData> dSubInstances;
     DeviceArray<RtxptMaterialData> dMaterials; DeviceArray<uint8_t> dSubInstanceClass;
@@ -123,6 +124,15 @@ extern "C" RTXPT_API int rtxpt_b200_create(const RtxptConfig* config, rtxpt_ctx*
     memset(c->hCounters, 0, kCounterWords * sizeof(uint32_t));
     e = configureKernels(c->maxSmemOptin);
     if (e != cudaSuccess) { delete c; return fail(RTXPT_ERR_CUDA, "kernel configuration failed: %s", cudaGetErrorString(e)); }
+    {   // L2 persistence carve-out for the BVH nodes (off unless RTXPT_L2_PERSIST_MB is set; see DESIGN.md for the measurement)
+        const char* e = getenv("RTXPT_L2_PERSIST_MB"); int maxPersist = 0, maxWindow = 0;
+        cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, c->device); cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+        if (e && atoi(e) > 0 && maxPersist > 0)
+        {
+            c->l2PersistBytes = std::min(size_t(atoi(e)) << 20, size_t(maxPersist)); c->l2WindowMax = size_t(maxWindow);
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c->l2PersistBytes);
+        }
+    }
     launchInitTables(c->stream);
     if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { delete c; return fail(RTXPT_ERR_CUDA, "table initialisation failed: %s", cudaGetErrorString(e)); }
     *outCtx = c;
@@ -427,6 +437,9 @@ static void fillParams(rtxpt_ctx* c, LaunchParams& p)
     // 0 nodes 14.04, 73 nodes 14.36, 200 nodes 14.37, as many as fit (~450) 14.71 - shared memory taken from the unified L1 costs more than the
     // staged levels save, so the default is 0 and RTXPT_SMEM_NODES opts in.
     p.smemNodeCount = 0;
+    // optional: keep the BVH nodes in the persisting part of L2 (RTXPT_L2_PERSIST_MB > 0) while path state streams through
+    c->grid.l2WindowBase = nullptr; c->grid.l2WindowBytes = 0;
+    if (c->l2PersistBytes && c->dBvhNodes.ptr) { c->grid.l2WindowBase = c->dBvhNodes.ptr; c->grid.l2WindowBytes = std::min(size_t(c->bvhNodeCount) * 80, c->l2WindowMax); c->grid.l2WindowHitRatio = std::min(1.0f, float(c->l2PersistBytes) / float(c->grid.l2WindowBytes)); }
     { const char* e = getenv("RTXPT_SMEM_NODES"); if (e) p.smemNodeCount = std::min(std::min(c->bvhNodeCount, budget / 80u), uint32_t(std::max(0, atoi(e)))); }
 }
 

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB * kTraceCtaScale) k_trace_
                 {
                     entry = queue[i];
                     const uint slot = entry & 0x7FFFFFFFu;
-                    const uint4 a = p.wf.s0[slot], b = p.wf.s1[slot];
+                    const uint4 a = ldState(p.wf.s0 + slot), b = ldState(p.wf.s1 + slot);
                     tv.init(p.scene, ws, mk3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z)), mk3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z)), 0.0f, kMaxRayTravel);
                     hasRay = true;
                 }
@@ -358,22 +358,38 @@ cudaError_t configureKernels(int maxSmemOptin)
     return cudaSuccess;
 }
 
+// launch with the optional L2 access-policy window of GridConfig attached as a per-launch attribute (no stream state is touched)
+template <typename K> static void launchTrace(K kernel, int grid, size_t smem, cudaStream_t s, const LaunchParams& p, const GridConfig& g)
+{
+    cudaLaunchConfig_t cfg = {}; cfg.gridDim = dim3(uint(grid) * kTraceCtaScale); cfg.blockDim = dim3(kTraceThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1]; cfg.attrs = attr; cfg.numAttrs = 0;
+    if (g.l2WindowBytes)
+    {
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = const_cast<void*>(g.l2WindowBase); attr[0].val.accessPolicyWindow.num_bytes = g.l2WindowBytes;
+        attr[0].val.accessPolicyWindow.hitRatio = g.l2WindowHitRatio;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting; attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.numAttrs = 1;
+    }
+    cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
 void launchGenerate(const LaunchParams& p, const GridConfig& g, cudaStream_t s) { k_generate<<<g.smCount * 4, 256, 0, s>>>(p); }
 void launchTraceClosest(const LaunchParams& p, const GridConfig& g, bool count, cudaStream_t s)
 {
     const int grid = g.smCount * g.traceBlocksPerSM; const size_t smem = traceSmemBytes(p);
-    if (count) k_trace_closest<true, 2><<<grid * kTraceCtaScale, kTraceThreads, smem, s>>>(p);
-    else if (g.traceBlocksPerSM >= 4) k_trace_closest<false, 4><<<grid * kTraceCtaScale, kTraceThreads, smem, s>>>(p);
-    else if (g.traceBlocksPerSM == 3) k_trace_closest<false, 3><<<grid * kTraceCtaScale, kTraceThreads, smem, s>>>(p);
-    else k_trace_closest<false, 2><<<grid * kTraceCtaScale, kTraceThreads, smem, s>>>(p);
+    if (count) launchTrace(k_trace_closest<true, 2>, grid, smem, s, p, g);
+    else if (g.traceBlocksPerSM >= 4) launchTrace(k_trace_closest<false, 4>, grid, smem, s, p, g);
+    else if (g.traceBlocksPerSM == 3) launchTrace(k_trace_closest<false, 3>, grid, smem, s, p, g);
+    else launchTrace(k_trace_closest<false, 2>, grid, smem, s, p, g);
 }
 void launchTraceShadow(const LaunchParams& p, const GridConfig& g, bool count, cudaStream_t s)
 {
     const int grid = g.smCount * g.traceBlocksPerSM; const size_t smem = traceSmemBytes(p);
-    if (count) k_trace_shadow<true, 2><<<grid * kTraceCtaScale, kTraceThreads, smem, s>>>(p);
-    else if (g.traceBlocksPerSM >= 4) k_trace_shadow<false, 4><<<grid * kTraceCtaScale, kTraceThreads, smem, s>>>(p);
-    else if (g.traceBlocksPerSM == 3) k_trace_shadow<false, 3><<<grid * kTraceCtaScale, kTraceThreads, smem, s>>>(p);
-    else k_trace_shadow<false, 2><<<grid * kTraceCtaScale, kTraceThreads, smem, s>>>(p);
+    if (count) launchTrace(k_trace_shadow<true, 2>, grid, smem, s, p, g);
+    else if (g.traceBlocksPerSM >= 4) launchTrace(k_trace_shadow<false, 4>, grid, smem, s, p, g);
+    else if (g.traceBlocksPerSM == 3) launchTrace(k_trace_shadow<false, 3>, grid, smem, s, p, g);
+    else launchTrace(k_trace_shadow<false, 2>, grid, smem, s, p, g);
 }
 void launchCommitAccumulate(const LaunchParams& p, const GridConfig& g, cudaStream_t s) { k_commit_accumulate<<<g.smCount * 4, 256, 0, s>>>(p); }
 void launchTraceRays(const LaunchParams& p, const GridConfig& g, const RtxptRay* rays, uint32_t count, bool anyHit, RtxptHit* out, uint32_t* counters, uint32_t* cursor, cudaStream_t s)

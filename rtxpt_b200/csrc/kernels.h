@@ -5,7 +5,12 @@
 
 namespace pt {
 
-struct GridConfig { int smCount = 1; int traceBlocksPerSM = 1; int shadeBlocksPerSM = 1; };
+struct GridConfig
+{
+    int smCount = 1; int traceBlocksPerSM = 1; int shadeBlocksPerSM = 1;
+    // optional L2 access-policy window for the traversal kernels (BVH nodes kept resident in the persisting L2 carve-out while path state streams through)
+    const void* l2WindowBase = nullptr; size_t l2WindowBytes = 0; float l2WindowHitRatio = 1.0f;
+};
 
 cudaError_t configureKernels(int maxSmemOptin);
 void queryOccupancy(GridConfig& g, size_t traceSmemBytes);

@@ -79,6 +79,19 @@ enum : uint {
 };
 constexpr uint kVertexIndexBits = 10, kVertexIndexMask = (1u << kVertexIndexBits) - 1u;
 
+// Path state is written once and read once per wavefront iteration: with PT_STREAM_STATE the accesses carry the evict-first hint so that they
+// do not displace BVH and scene data in L2.
+#ifndef PT_STREAM_STATE
+#define PT_STREAM_STATE 0
+#endif
+#if PT_STREAM_STATE
+PT_DEVICE uint4 ldState(const uint4* p) { return __ldcs(p); }
+PT_DEVICE void stState(uint4* p, uint4 v) { __stcs(p, v); }
+#else
+PT_DEVICE uint4 ldState(const uint4* p) { return *p; }
+PT_DEVICE void stState(uint4* p, uint4 v) { *p = v; }
+#endif
+
 struct PathRegs             // one path's state in registers
 {
     float3 origin; uint id;
@@ -92,22 +105,22 @@ struct PathRegs             // one path's state in registers
     {
         if (needRay)
         {
-            const uint4 a = w.s0[slot], b = w.s1[slot];
+            const uint4 a = ldState(w.s0 + slot), b = ldState(w.s1 + slot);
             origin = mk3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z)); id = a.w;
             dir = mk3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z)); sceneLength = __uint_as_float(b.w);
         }
-        const uint4 c = w.s2[slot], d = w.s3[slot], e = w.s4[slot];
+        const uint4 c = ldState(w.s2 + slot), d = ldState(w.s3 + slot), e = ldState(w.s4 + slot);
         thpXY = c.x; thpZ = c.y; lXY = c.z; lZW = c.w;
         interior0 = d.x; interior1 = d.y; packedCounters = d.z; rayCone = d.w;
         pack0 = e.x; pack1 = e.y; flagsAndVertexIndex = e.z; sampleIndex = e.w;
     }
     PT_DEVICE void store(const WavefrontBuffers& w, uint slot) const
     {
-        w.s0[slot] = make_uint4(__float_as_uint(origin.x), __float_as_uint(origin.y), __float_as_uint(origin.z), id);
-        w.s1[slot] = make_uint4(__float_as_uint(dir.x), __float_as_uint(dir.y), __float_as_uint(dir.z), __float_as_uint(sceneLength));
-        w.s2[slot] = make_uint4(thpXY, thpZ, lXY, lZW);
-        w.s3[slot] = make_uint4(interior0, interior1, packedCounters, rayCone);
-        w.s4[slot] = make_uint4(pack0, pack1, flagsAndVertexIndex, sampleIndex);
+        stState(w.s0 + slot, make_uint4(__float_as_uint(origin.x), __float_as_uint(origin.y), __float_as_uint(origin.z), id));
+        stState(w.s1 + slot, make_uint4(__float_as_uint(dir.x), __float_as_uint(dir.y), __float_as_uint(dir.z), __float_as_uint(sceneLength)));
+        stState(w.s2 + slot, make_uint4(thpXY, thpZ, lXY, lZW));
+        stState(w.s3 + slot, make_uint4(interior0, interior1, packedCounters, rayCone));
+        stState(w.s4 + slot, make_uint4(pack0, pack1, flagsAndVertexIndex, sampleIndex));
     }
     PT_DEVICE float3 thp() const { return mk3(f16tof32(thpXY), f16tof32(thpXY >> 16), f16tof32(thpZ)); }
     PT_DEVICE void setThp(float3 t) { thpXY = packHalf2NoClamp(clampf(t.x, 0.f, kHalfMax), clampf(t.y, 0.f, kHalfMax)); thpZ = packHalf2NoClamp(clampf(t.z, 0.f, kHalfMax), 0.f); }
