@@ -122,6 +122,8 @@ struct PathRegs             // one path's state in registers
         stState(w.s3 + slot, make_uint4(interior0, interior1, packedCounters, rayCone));
         stState(w.s4 + slot, make_uint4(pack0, pack1, flagsAndVertexIndex, sampleIndex));
     }
+    // a path that ends at this vertex is only read again for its radiance (shadow kernel, commit): 16 of the 80 bytes
+    PT_DEVICE void storeRadianceOnly(const WavefrontBuffers& w, uint slot) const { stState(w.s2 + slot, make_uint4(thpXY, thpZ, lXY, lZW)); }
     PT_DEVICE float3 thp() const { return mk3(f16tof32(thpXY), f16tof32(thpXY >> 16), f16tof32(thpZ)); }
     PT_DEVICE void setThp(float3 t) { thpXY = packHalf2NoClamp(clampf(t.x, 0.f, kHalfMax), clampf(t.y, 0.f, kHalfMax)); thpZ = packHalf2NoClamp(clampf(t.z, 0.f, kHalfMax), 0.f); }
     PT_DEVICE float4 L() const { return make_float4(f16tof32(lXY), f16tof32(lXY >> 16), f16tof32(lZW), f16tof32(lZW >> 16)); }
