@@ -1,0 +1,105 @@
+// ORACLE/_ref — second known-answer binary: compiles, from where they lie under /root/reference (never copied), the host-visible C++ halves of
+//   Rtxpt/Shaders/PathTracer/PathTracerShared.h   (PathTracerCameraData, PathTracerConstants, BridgeCamera :109-141)
+//   Rtxpt/Shaders/PathTracer/Materials/MaterialPT.h (PTMaterialData, PTMaterialFlags_*), Rtxpt/Shaders/SubInstanceData.h,
+//   Rtxpt/Shaders/PathTracer/Lighting/PolymorphicLight.h (PolymorphicLightInfo / Ex, type enum, flag bits),
+//   External/Donut/include/donut/shaders/bindless.h (GeometryData, InstanceData), External/Donut/src/core/math/vector.cpp (vectorToSnorm8 / snorm8ToVector)
+// and prints struct layouts, constants and function outputs as JSON.  tests/golden/make_host_golden.py commits the result as
+// tests/golden/host_golden.json, which pins the C ABI struct mirrors, the camera bridge (C++ and Python) and the vertex packing.
+#include <donut/core/math/math.h>
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+using namespace donut::math;
+typedef uint32_t uint;
+#include <donut/shaders/bindless.h>
+#include "PathTracer/PathTracerShared.h"
+#include "PathTracer/Materials/MaterialPT.h"
+#include "SubInstanceData.h"
+#include "PathTracer/Lighting/PolymorphicLight.h"
+
+static uint32_t bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+#define OFF(T, f) printf("%s\"%s\": %zu", first ? "" : ", ", #f, offsetof(T, f)), first = false
+#define LAYOUT_BEGIN(T) printf(" \"%s\": {\"size\": %zu, \"offsets\": {", #T, sizeof(T)); first = true
+#define LAYOUT_END(last) printf("}}%s\n", last ? "" : ",")
+
+int main()
+{
+    bool first;
+    printf("{\n");
+    LAYOUT_BEGIN(GeometryData);
+    OFF(GeometryData, numIndices); OFF(GeometryData, numVertices); OFF(GeometryData, indexBufferIndex); OFF(GeometryData, indexOffset); OFF(GeometryData, vertexBufferIndex);
+    OFF(GeometryData, positionOffset); OFF(GeometryData, prevPositionOffset); OFF(GeometryData, texCoord1Offset); OFF(GeometryData, texCoord2Offset); OFF(GeometryData, normalOffset);
+    OFF(GeometryData, tangentOffset); OFF(GeometryData, curveRadiusOffset); OFF(GeometryData, materialIndex);
+    LAYOUT_END(false);
+    LAYOUT_BEGIN(InstanceData);
+    OFF(InstanceData, flags); OFF(InstanceData, firstGeometryInstanceIndex); OFF(InstanceData, firstGeometryIndex); OFF(InstanceData, numGeometries); OFF(InstanceData, transform); OFF(InstanceData, prevTransform);
+    LAYOUT_END(false);
+    LAYOUT_BEGIN(SubInstanceData);
+    OFF(SubInstanceData, FlagsAndAlphaInfo); OFF(SubInstanceData, GlobalGeometryIndex_PTMaterialDataIndex); OFF(SubInstanceData, EmissiveLightMappingOffset); OFF(SubInstanceData, AnalyticProxyLightIndex);
+    OFF(SubInstanceData, IndexBufferIndex_VertexBufferIndex); OFF(SubInstanceData, IndexOffset); OFF(SubInstanceData, TexCoord1Offset);
+    LAYOUT_END(false);
+    LAYOUT_BEGIN(PTMaterialData);
+    OFF(PTMaterialData, BaseOrDiffuseColor); OFF(PTMaterialData, Flags); OFF(PTMaterialData, SpecularColor); OFF(PTMaterialData, EmissiveColor); OFF(PTMaterialData, Opacity); OFF(PTMaterialData, Roughness);
+    OFF(PTMaterialData, Metalness); OFF(PTMaterialData, NormalTextureScale); OFF(PTMaterialData, AlphaCutoff); OFF(PTMaterialData, TransmissionFactor); OFF(PTMaterialData, DiffuseTransmissionFactor);
+    OFF(PTMaterialData, BaseOrDiffuseTextureIndex); OFF(PTMaterialData, MetalRoughOrSpecularTextureIndex); OFF(PTMaterialData, EmissiveTextureIndex); OFF(PTMaterialData, NormalTextureIndex);
+    OFF(PTMaterialData, OcclusionTextureIndex); OFF(PTMaterialData, TransmissionTextureIndex); OFF(PTMaterialData, IoR); OFF(PTMaterialData, ThicknessFactor); OFF(PTMaterialData, Volume);
+    OFF(PTMaterialData, ShadowNoLFadeout);
+    LAYOUT_END(false);
+    LAYOUT_BEGIN(PolymorphicLightInfo);
+    OFF(PolymorphicLightInfo, Center); OFF(PolymorphicLightInfo, ColorTypeAndFlags); OFF(PolymorphicLightInfo, Direction1); OFF(PolymorphicLightInfo, Direction2); OFF(PolymorphicLightInfo, Scalars); OFF(PolymorphicLightInfo, LogRadiance);
+    LAYOUT_END(false);
+    LAYOUT_BEGIN(PolymorphicLightInfoEx);
+    OFF(PolymorphicLightInfoEx, IesProfileIndex); OFF(PolymorphicLightInfoEx, PrimaryAxis); OFF(PolymorphicLightInfoEx, CosConeAngleAndSoftness); OFF(PolymorphicLightInfoEx, UniqueID);
+    LAYOUT_END(false);
+    LAYOUT_BEGIN(PathTracerCameraData);
+    OFF(PathTracerCameraData, PosW); OFF(PathTracerCameraData, NearZ); OFF(PathTracerCameraData, DirectionW); OFF(PathTracerCameraData, PixelConeSpreadAngle); OFF(PathTracerCameraData, CameraU);
+    OFF(PathTracerCameraData, FarZ); OFF(PathTracerCameraData, CameraV); OFF(PathTracerCameraData, FocalDistance); OFF(PathTracerCameraData, CameraW); OFF(PathTracerCameraData, AspectRatio);
+    OFF(PathTracerCameraData, ViewportSize); OFF(PathTracerCameraData, ApertureRadius); OFF(PathTracerCameraData, Jitter);
+    LAYOUT_END(false);
+    printf(" \"constants\": {\"PTMaterialFlags_UseSpecularGlossModel\": %u, \"PTMaterialFlags_UseMetalRoughOrSpecularTexture\": %u, \"PTMaterialFlags_UseBaseOrDiffuseTexture\": %u, "
+           "\"PTMaterialFlags_UseEmissiveTexture\": %u, \"PTMaterialFlags_UseNormalTexture\": %u, \"PTMaterialFlags_UseTransmissionTexture\": %u, \"PTMaterialFlags_MetalnessInRedChannel\": %u, "
+           "\"PTMaterialFlags_ThinSurface\": %u, \"PTMaterialFlags_PSDExclude\": %u, \"PTMaterialFlags_EnableAsAnalyticLightProxy\": %u, \"PTMaterialFlags_NestedPriorityShift\": %u, "
+           "\"kPolymorphicLightTypeShift\": %u, \"kPolymorphicLightShapingEnableBit\": %u, \"kPolymorphicLightShapingUseMinFalloff\": %u, "
+           "\"kSphere\": %u, \"kTriangle\": %u, \"kPoint\": %u, \"kEnvironmentQuad\": %u, \"kPolymorphicLightMinLog2Radiance\": %g, \"kPolymorphicLightMaxLog2Radiance\": %g},\n",
+           (uint)PTMaterialFlags_UseSpecularGlossModel, (uint)PTMaterialFlags_UseMetalRoughOrSpecularTexture, (uint)PTMaterialFlags_UseBaseOrDiffuseTexture, (uint)PTMaterialFlags_UseEmissiveTexture,
+           (uint)PTMaterialFlags_UseNormalTexture, (uint)PTMaterialFlags_UseTransmissionTexture, (uint)PTMaterialFlags_MetalnessInRedChannel, (uint)PTMaterialFlags_ThinSurface, (uint)PTMaterialFlags_PSDExclude,
+           (uint)PTMaterialFlags_EnableAsAnalyticLightProxy, (uint)PTMaterialFlags_NestedPriorityShift, kPolymorphicLightTypeShift, kPolymorphicLightShapingEnableBit, kPolymorphicLightShapingUseMinFalloff,
+           (uint)PolymorphicLightType::kSphere, (uint)PolymorphicLightType::kTriangle, (uint)PolymorphicLightType::kPoint, (uint)PolymorphicLightType::kEnvironmentQuad,
+           (double)kPolymorphicLightMinLog2Radiance, (double)kPolymorphicLightMaxLog2Radiance);
+    // BridgeCamera: inputs and the 28 words of PathTracerCameraData it returns
+    struct CamIn { uint w, h; float pos[3], dir[3], up[3], fov, nearZ, farZ, focal, aperture, jitter[2]; };
+    const CamIn cams[] = {
+        { 256, 256, { 2.78f, 2.73f, -8.0f }, { 0, 0, 1 }, { 0, 1, 0 }, 0.66f, 0.1f, 1e7f, 10000.0f, 0.0f, { 0, 0 } },
+        { 1920, 1080, { -20, 1.8f, 12 }, { 0.7f, -0.1f, 0.7f }, { 0, 1, 0 }, 1.04f, 0.1f, 1e7f, 10000.0f, 0.0f, { 0.25f, -0.5f } },
+        { 3840, 2160, { 3.5f, 1.2f, -7.25f }, { -0.31f, 0.22f, 0.92f }, { 0.05f, 1, 0.02f }, 0.785398f, 0.05f, 5000.0f, 4.5f, 0.035f, { -0.125f, 0.375f } },
+        { 641, 359, { 100.5f, -3.25f, 0.001f }, { -1, -1, -1 }, { 0, 0, 1 }, 1.5f, 1.0f, 100.0f, 10.0f, 0.5f, { 0.5f, 0.5f } } };
+    printf(" \"bridge_camera\": [");
+    for (size_t i = 0; i < sizeof(cams) / sizeof(cams[0]); i++)
+    {
+        const CamIn& c = cams[i];
+        PathTracerCameraData d = BridgeCamera(c.w, c.h, float(c.w) / float(c.h), float3(c.pos[0], c.pos[1], c.pos[2]), float3(c.dir[0], c.dir[1], c.dir[2]), float3(c.up[0], c.up[1], c.up[2]),
+                                              c.fov, c.nearZ, c.farZ, c.focal, c.aperture, float2(c.jitter[0], c.jitter[1]));
+        printf("%s{\"in\": [%u, %u, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g], \"out\": [", i ? ", " : "", c.w, c.h, c.pos[0], c.pos[1], c.pos[2],
+               c.dir[0], c.dir[1], c.dir[2], c.up[0], c.up[1], c.up[2], c.fov, c.nearZ, c.farZ, c.focal, c.aperture, c.jitter[0], c.jitter[1]);
+        uint32_t w[28]; memcpy(w, &d, sizeof(w));
+        for (int k = 0; k < 28; k++) printf("%s%u", k ? ", " : "", w[k]);
+        printf("]}");
+    }
+    printf("],\n \"snorm8\": [");
+    // vectorToSnorm8<float3/float4> and the decode, on a deterministic vector set
+    uint32_t s = 12345u; first = true;
+    for (int i = 0; i < 64; i++)
+    {
+        float v[4];
+        for (int k = 0; k < 4; k++) { s = s * 1664525u + 1013904223u; v[k] = (float((s >> 8) & 0xFFFF) / 32767.5f - 1.0f) * ((i % 7 == 0) ? 3.0f : 1.0f); }
+        if (i < 3) { v[0] = (i == 0); v[1] = (i == 1); v[2] = (i == 2); v[3] = (i == 1) ? -1.0f : 1.0f; }
+        const uint p3 = vectorToSnorm8(float3(v[0], v[1], v[2])), p4 = vectorToSnorm8(float4(v[0], v[1], v[2], (v[3] >= 0 ? 1.0f : -1.0f)));
+        const float3 d3 = snorm8ToVector<3>(p3); const float4 d4 = snorm8ToVector<4>(p4);
+        printf("%s[%u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u]", first ? "" : ", ", bits(v[0]), bits(v[1]), bits(v[2]), bits(v[3] >= 0 ? 1.0f : -1.0f), p3, p4,
+               bits(d3.x), bits(d3.y), bits(d3.z), bits(d4.x), bits(d4.y), bits(d4.z), bits(d4.w));
+        first = false;
+    }
+    printf("]\n}\n");
+    return 0;
+}
