@@ -53,6 +53,8 @@ struct rtxpt_ctx
     // scene
     bool haveScene = false, haveConstants = false, lightsDirty = true;
     size_t l2PersistBytes = 0, l2WindowMax = 0;
+    // measurement knobs, read from the environment once at creation (defaults are the measured optimum on B200, profiles/r1_history.md)
+    struct Tuning { int refillThreshold = 24, waitFlushLanes = 8, traceCtas = 4, shadeCtas = 4, smemNodes = 0; } tune;
     cudaStream_t stream2 = nullptr; cudaEvent_t evShadeDone = nullptr, evShadowDone = nullptr; bool overlapShadow = true;
     DeviceArray<RtxptInstanceData> dInstances; DeviceArray<RtxptGeometryData> dGeometries; DeviceArray<RtxptSubInstanceData> dSubInstances;
     DeviceArray<RtxptMaterialData> dMaterials; DeviceArray<uint8_t> dSubInstanceClass;
@@ -120,6 +122,9 @@ extern "C" RTXPT_API int rtxpt_b200_create(const RtxptConfig* config, rtxpt_ctx*
     cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&c->evShadeDone, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->evShadowDone, cudaEventDisableTiming);
     { const char* e = getenv("RTXPT_OVERLAP_SHADOW"); if (e) c->overlapShadow = atoi(e) != 0; }
+    auto envInt = [](const char* name, int def, int lo, int hi) { const char* e = getenv(name); return e ? std::min(hi, std::max(lo, atoi(e))) : def; };
+    c->tune.refillThreshold = envInt("RTXPT_REFILL_THRESHOLD", 24, 1, 32); c->tune.waitFlushLanes = envInt("RTXPT_WAIT_FLUSH", 8, 1, 33);
+    c->tune.traceCtas = envInt("RTXPT_TRACE_CTAS", 4, 2, 4); c->tune.shadeCtas = envInt("RTXPT_SHADE_CTAS", 4, 3, 5); c->tune.smemNodes = envInt("RTXPT_SMEM_NODES", 0, 0, 1 << 20);
     cudaMallocHost(&c->hCounters, kCounterWords * sizeof(uint32_t));
     memset(c->hCounters, 0, kCounterWords * sizeof(uint32_t));
     e = configureKernels(c->maxSmemOptin);
@@ -422,25 +427,22 @@ static void fillParams(rtxpt_ctx* c, LaunchParams& p)
     w.counters = c->counters.ptr; w.pixelOfSlot = c->pixelOfSlot.ptr; w.capacity = c->capacity; w.pixelCount = c->pixelCount;
     p.c = c->consts;
     p.flags = c->cfg.flags;
-    { const char* e = getenv("RTXPT_REFILL_THRESHOLD"); p.refillThreshold = e ? atoi(e) : 24; }     // tuning knob; 8..24 measured equal within noise on B200
-    { const char* e = getenv("RTXPT_WAIT_FLUSH"); p.waitFlushLanes = e ? std::max(1, atoi(e)) : 8; }
+    p.refillThreshold = c->tune.refillThreshold; p.waitFlushLanes = c->tune.waitFlushLanes;
     p.outputColor = c->outputColor.ptr; p.accumulated = c->accumulated.ptr; p.depth = c->depth.ptr; p.motionVectors = c->motionVectors.ptr; p.throughput = c->throughput.ptr;
     memcpy(p.worldToClip, c->worldToClip, sizeof(p.worldToClip)); p.exportGuides = ((c->cfg.flags & RTXPT_CFG_EXPORT_GUIDES) && c->haveView) ? 1u : 0u;
     // traversal occupancy and the shared-memory BVH prefix are chosen together: B resident CTAs of 256 threads per SM (register budget
     // 65536 / (256 B): 128 / 85 / 64 registers for B = 2 / 3 / 4) share the 227 KB of shared memory
-    int blocks = 4;         // measured on B200 (city workload, ms/frame closest+shadow): 2 CTAs 28.5, 3 CTAs 21.3, 4 CTAs 19.1
-    { const char* e = getenv("RTXPT_TRACE_CTAS"); if (e) blocks = std::min(4, std::max(2, atoi(e))); }
+    const int blocks = c->tune.traceCtas;       // measured on B200 (city workload, ms/frame closest+shadow): 2 CTAs 28.5, 3 CTAs 21.3, 4 CTAs 19.1
     c->grid.traceBlocksPerSM = blocks;
-    { int sb = 4; const char* e = getenv("RTXPT_SHADE_CTAS"); if (e) sb = std::min(5, std::max(3, atoi(e))); c->grid.shadeBlocksPerSM = sb; }
+    c->grid.shadeBlocksPerSM = c->tune.shadeCtas;
     const uint32_t budget = uint32_t(std::max(0, std::min(c->maxSmemOptin, (227 * 1024) / blocks - 2048) - 1024 - 8 * 2320));     // 8 x WarpScratch (traverse.cuh)
     // BVH prefix (breadth-first top levels) staged into shared memory by TMA.  Measured on B200 (city workload, closest+shadow ms/frame):
     // 0 nodes 14.04, 73 nodes 14.36, 200 nodes 14.37, as many as fit (~450) 14.71 - shared memory taken from the unified L1 costs more than the
     // staged levels save, so the default is 0 and RTXPT_SMEM_NODES opts in.
-    p.smemNodeCount = 0;
     // optional: keep the BVH nodes in the persisting part of L2 (RTXPT_L2_PERSIST_MB > 0) while path state streams through
     c->grid.l2WindowBase = nullptr; c->grid.l2WindowBytes = 0;
     if (c->l2PersistBytes && c->dBvhNodes.ptr) { c->grid.l2WindowBase = c->dBvhNodes.ptr; c->grid.l2WindowBytes = std::min(size_t(c->bvhNodeCount) * 80, c->l2WindowMax); c->grid.l2WindowHitRatio = std::min(1.0f, float(c->l2PersistBytes) / float(c->grid.l2WindowBytes)); }
-    { const char* e = getenv("RTXPT_SMEM_NODES"); if (e) p.smemNodeCount = std::min(std::min(c->bvhNodeCount, budget / 80u), uint32_t(std::max(0, atoi(e)))); }
+    p.smemNodeCount = std::min(std::min(c->bvhNodeCount, budget / 80u), uint32_t(c->tune.smemNodes));
 }
 
 // RTXPT_CFG_TIME_KERNELS: bracket a launch with two events from the pool; kinds: 0 closest, 1 shadow, 2 shade, 3 other
