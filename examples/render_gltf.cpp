@@ -1,7 +1,7 @@
 // render_gltf.cpp — a complete C++ host on top of the C ABI (include/rtxpt_b200.h): load a glTF with the library's loader, bridge its camera,
 // fill the reference-mode constants, accumulate N samples on the GPU and write the RGBA32F accumulation as a PFM (and a tone-mapped PPM).
 // This is the standalone equivalent of Sample::Render -> PathTrace -> AccumulationPass for a static scene (Rtxpt/Sample.cpp:2184, :2438-2559).
-//   render_gltf scene.gltf out.pfm [width height samples bounces]
+//   render_gltf scene.gltf out.pfm [width height samples bounces [materialsDir [sceneMaterialsDir]]]      (RTXPT .material.json overrides)
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -12,12 +12,14 @@ static int fail(const char* what, rtxpt_ctx* ctx) { fprintf(stderr, "%s: %s\n", 
 
 int main(int argc, char** argv)
 {
-    if (argc < 3) { fprintf(stderr, "usage: %s scene.gltf out.pfm [width height samples bounces]\n", argv[0]); return 2; }
+    if (argc < 3) { fprintf(stderr, "usage: %s scene.gltf out.pfm [width height samples bounces [materialsDir [sceneMaterialsDir]]]\n", argv[0]); return 2; }
     const uint32_t width = argc > 3 ? uint32_t(atoi(argv[3])) : 512, height = argc > 4 ? uint32_t(atoi(argv[4])) : 512;
     const uint32_t samples = argc > 5 ? uint32_t(atoi(argv[5])) : 64, bounces = argc > 6 ? uint32_t(atoi(argv[6])) : 6;
 
     rtxpt_host_scene* scene = nullptr;
-    if (rtxpt_b200_load_gltf(argv[1], &scene) != RTXPT_OK) return fail("load_gltf", nullptr);
+    uint32_t overridden = 0;
+    if (rtxpt_b200_load_gltf_ex(argv[1], argc > 7 ? argv[7] : nullptr, argc > 8 ? argv[8] : nullptr, &scene, &overridden) != RTXPT_OK) return fail("load_gltf", nullptr);
+    if (overridden) fprintf(stderr, "%u materials taken from .material.json files\n", overridden);
     uint32_t cameraCount = 1; RtxptGltfCamera gcam = {};
     rtxpt_b200_host_scene_cameras(scene, &gcam, &cameraCount);
     if (cameraCount == 0) { fprintf(stderr, "the file has no perspective camera\n"); return 1; }

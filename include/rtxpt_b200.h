@@ -341,11 +341,28 @@ typedef struct RtxptGltfCamera {        /* perspective cameras found in the node
     float yfov, znear, zfar, aspectRatio;   /* radians; aspectRatio 0 = unspecified */
 } RtxptGltfCamera;
 RTXPT_API int rtxpt_b200_load_gltf(const char* path, rtxpt_host_scene** outScene);
+/* Same, with RTXPT's material files applied on top of the glTF materials the way MaterialsBaker does (Rtxpt/Materials/MaterialsBaker.cpp:707-747, :868-917):
+ * for a glTF material <name> of model file <model>.gltf the first existing of <sceneMaterialsDir>/<model>.<name>.material.json, <sceneMaterialsDir>/<name>.material.json,
+ * <materialsDir>/<model>.<name>.material.json, <materialsDir>/<name>.material.json replaces it (either directory may be NULL). */
+RTXPT_API int rtxpt_b200_load_gltf_ex(const char* path, const char* materialsDir, const char* sceneMaterialsDir, rtxpt_host_scene** outScene, uint32_t* outOverriddenMaterials);
 RTXPT_API const char* rtxpt_b200_load_gltf_error(void);                 /* message of the last failed load on this thread */
 RTXPT_API const RtxptSceneDesc* rtxpt_b200_host_scene_desc(const rtxpt_host_scene* scene);
 RTXPT_API int rtxpt_b200_host_scene_cameras(const rtxpt_host_scene* scene, RtxptGltfCamera* outCameras, uint32_t* ioCount);
 RTXPT_API uint32_t rtxpt_b200_host_scene_triangle_count(const rtxpt_host_scene* scene);
 RTXPT_API void rtxpt_b200_free_host_scene(rtxpt_host_scene* scene);
+
+/* RTXPT's own material files (Assets/Materials/<model>.<name>.material.json; PTMaterial::Read / FillData, Rtxpt/Materials/MaterialsBaker.cpp:160-245,
+ * :516-591) -> PTMaterialData.  Texture slots come back unbound (indices 0xFFFFFFFF, Use*Texture flags clear) together with the paths the file names;
+ * the caller (or rtxpt_b200_load_gltf_ex) binds what it can load.  In the reference these files override the glTF material of the same name. */
+typedef struct RtxptMaterialJsonInfo {
+    RtxptMaterialData data;
+    uint32_t enableAlphaTesting, excludeFromNEE, skipRender, enableTransmission;
+    uint32_t textureEnabled[5];         /* base, occlusion-roughness-metallic (or specular), normal, emissive, transmission: Enable*Texture && a path is given */
+    uint32_t textureSRGB[5];
+    char     texturePath[5][260];       /* relative to the media folder, '/' separators */
+} RtxptMaterialJsonInfo;
+RTXPT_API int rtxpt_b200_parse_material_json(const char* jsonText, RtxptMaterialJsonInfo* out);
+RTXPT_API const char* rtxpt_b200_parse_material_json_error(void);
 
 /* Host-side helpers every C/C++ caller needs (rtxpt_b200/csrc/host_helpers.cpp; no CUDA device required):
  * BridgeCamera (Rtxpt/Shaders/PathTracer/PathTracerShared.h:109-141; aspect ratio = width / height, jitter in pixels) and the

@@ -23,109 +23,12 @@
 #include <vector>
 #include <zlib.h>
 #include "../../include/rtxpt_b200.h"
+#include "json_min.h"
+
+using namespace rtxpt_host;
+namespace rtxpt_host { void materialFromJson(const JValue& j, RtxptMaterialJsonInfo& out); }      // material_json.cpp
 
 namespace {
-
-struct LoadError { std::string msg; };
-[[noreturn]] void failf(const char* fmt, ...)
-{
-    char buf[1024]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
-    throw LoadError{ buf };
-}
-
-// ---- JSON (RFC 8259 subset sufficient for glTF: no surrogate pairs beyond pass-through) ------------------------------------------------------
-struct JValue
-{
-    enum Type { Null, Bool, Number, String, Array, Object } type = Null;
-    double num = 0; bool b = false; std::string str;
-    std::vector<JValue> arr; std::vector<std::pair<std::string, JValue>> obj;
-    const JValue* find(const char* key) const { if (type != Object) return nullptr; for (auto& kv : obj) if (kv.first == key) return &kv.second; return nullptr; }
-    const JValue& at(const char* key) const { const JValue* v = find(key); if (!v) failf("glTF: missing property '%s'", key); return *v; }
-    double number(const char* key, double def) const { const JValue* v = find(key); return (v && v->type == Number) ? v->num : def; }
-    int integer(const char* key, int def) const { const JValue* v = find(key); return (v && v->type == Number) ? int(v->num) : def; }
-    std::string string(const char* key, const char* def = "") const { const JValue* v = find(key); return (v && v->type == String) ? v->str : std::string(def); }
-    size_t size() const { return type == Array ? arr.size() : 0; }
-};
-struct JParser
-{
-    const char* p; const char* end;
-    void ws() { while (p < end && (*p == ' ' || *p == '\n' || *p == '\r' || *p == '\t')) p++; }
-    JValue parse() { ws(); JValue v = value(); ws(); return v; }
-    JValue value()
-    {
-        if (p >= end) failf("JSON: unexpected end");
-        JValue v;
-        switch (*p)
-        {
-        case '{':
-            v.type = JValue::Object; p++; ws();
-            if (p < end && *p == '}') { p++; return v; }
-            while (true)
-            {
-                ws(); if (p >= end || *p != '"') failf("JSON: expected string key");
-                std::string k = str(); ws();
-                if (p >= end || *p != ':') failf("JSON: expected ':'");
-                p++; ws(); v.obj.emplace_back(std::move(k), value()); ws();
-                if (p < end && *p == ',') { p++; continue; }
-                if (p < end && *p == '}') { p++; break; }
-                failf("JSON: expected ',' or '}'");
-            }
-            return v;
-        case '[':
-            v.type = JValue::Array; p++; ws();
-            if (p < end && *p == ']') { p++; return v; }
-            while (true)
-            {
-                ws(); v.arr.push_back(value()); ws();
-                if (p < end && *p == ',') { p++; continue; }
-                if (p < end && *p == ']') { p++; break; }
-                failf("JSON: expected ',' or ']'");
-            }
-            return v;
-        case '"': v.type = JValue::String; v.str = str(); return v;
-        case 't': if (end - p >= 4 && !strncmp(p, "true", 4)) { p += 4; v.type = JValue::Bool; v.b = true; return v; } break;
-        case 'f': if (end - p >= 5 && !strncmp(p, "false", 5)) { p += 5; v.type = JValue::Bool; v.b = false; return v; } break;
-        case 'n': if (end - p >= 4 && !strncmp(p, "null", 4)) { p += 4; return v; } break;
-        default:
-        {
-            char* e = nullptr; v.num = strtod(p, &e);
-            if (e == p) break;
-            p = e; v.type = JValue::Number; return v;
-        }
-        }
-        failf("JSON: unexpected character '%c'", *p);
-    }
-    std::string str()
-    {
-        std::string s; p++;
-        while (p < end && *p != '"')
-        {
-            if (*p == '\\' && p + 1 < end)
-            {
-                p++;
-                switch (*p)
-                {
-                case 'n': s += '\n'; break; case 't': s += '\t'; break; case 'r': s += '\r'; break; case 'b': s += '\b'; break; case 'f': s += '\f'; break;
-                case 'u':
-                {
-                    if (end - p < 5) failf("JSON: bad \\u escape");
-                    unsigned cp = unsigned(strtoul(std::string(p + 1, p + 5).c_str(), nullptr, 16)); p += 4;
-                    if (cp < 0x80) s += char(cp);
-                    else if (cp < 0x800) { s += char(0xC0 | (cp >> 6)); s += char(0x80 | (cp & 0x3F)); }
-                    else { s += char(0xE0 | (cp >> 12)); s += char(0x80 | ((cp >> 6) & 0x3F)); s += char(0x80 | (cp & 0x3F)); }
-                    break;
-                }
-                default: s += *p; break;
-                }
-                p++;
-            }
-            else s += *p++;
-        }
-        if (p >= end) failf("JSON: unterminated string");
-        p++;
-        return s;
-    }
-};
 
 // ---- files, base64 ------------------------------------------------------------------------------------------------------------------------------
 std::vector<uint8_t> readFile(const std::string& path)
@@ -304,6 +207,26 @@ struct Loader
     std::string baseDir; JValue root; std::vector<std::vector<uint8_t>> bufferData; std::vector<uint8_t> glbBin;
     rtxpt_host_scene* out = nullptr;
     std::map<std::pair<int, int>, uint32_t> textureSlot;        // (glTF image, sRGB) -> RtxptTextureDesc index
+    std::string materialsDir, sceneMaterialsDir, modelName;     // RTXPT material overrides (Assets/Materials[/<scene>]); empty: none
+    std::vector<bool> excludeFromNEE, skipRender;
+    uint32_t overriddenMaterials = 0;
+
+    // MaterialsBaker::Load search order (MaterialsBaker.cpp:707-747): scene-specialised folder first, then the shared one; <model>.<name> before <name>
+    bool findMaterialFile(const std::string& name, std::string& text)
+    {
+        if (name.empty()) return false;
+        const std::string cands[4] = { sceneMaterialsDir.empty() ? std::string() : sceneMaterialsDir + modelName + "." + name + ".material.json",
+                                       sceneMaterialsDir.empty() ? std::string() : sceneMaterialsDir + name + ".material.json",
+                                       materialsDir.empty() ? std::string() : materialsDir + modelName + "." + name + ".material.json",
+                                       materialsDir.empty() ? std::string() : materialsDir + name + ".material.json" };
+        for (const std::string& c : cands)
+        {
+            if (c.empty()) continue;
+            FILE* f = fopen(c.c_str(), "rb"); if (!f) continue;
+            fclose(f); const std::vector<uint8_t> d = readFile(c); text.assign(d.begin(), d.end()); return true;
+        }
+        return false;
+    }
 
     const JValue& arrayItem(const char* name, int index)
     {
@@ -451,8 +374,24 @@ struct Loader
             d.VolumeAttenuationColor[0] = volColor[0]; d.VolumeAttenuationColor[1] = volColor[1]; d.VolumeAttenuationColor[2] = volColor[2];
             d.VolumeAttenuationDistance = volDist; d.ShadowNoLFadeout = 0.0f;
             d._padding0 = 42; d._padding1 = 42.0f;
+            bool alpha = alphaMode == "MASK", noNEE = false, skip = false;
+            std::string overrideText;
+            if (i < n && findMaterialFile(m.string("name"), overrideText))
+            {   // the RTXPT material file wins over the glTF material (MaterialsBaker.cpp:868-917); its textures are DDS files this loader cannot
+                // decode, so a slot keeps the glTF texture where the file enables that slot and drops it where the file disables it
+                JParser jp{ overrideText.data(), overrideText.data() + overrideText.size() };
+                RtxptMaterialJsonInfo info; materialFromJson(jp.parse(), info);
+                const uint32_t texIdx[5] = { d.BaseOrDiffuseTextureIndex, d.MetalRoughOrSpecularTextureIndex, d.NormalTextureIndex, d.EmissiveTextureIndex, 0xFFFFFFFFu };
+                const uint32_t texBit[5] = { RTXPT_MATFLAG_UseBaseOrDiffuseTexture, RTXPT_MATFLAG_UseMetalRoughOrSpecularTexture, RTXPT_MATFLAG_UseNormalTexture, RTXPT_MATFLAG_UseEmissiveTexture, RTXPT_MATFLAG_UseTransmissionTexture };
+                d = info.data;
+                uint32_t* slots[5] = { &d.BaseOrDiffuseTextureIndex, &d.MetalRoughOrSpecularTextureIndex, &d.NormalTextureIndex, &d.EmissiveTextureIndex, &d.TransmissionTextureIndex };
+                for (int t = 0; t < 5; t++) if (info.textureEnabled[t] && texIdx[t] != 0xFFFFFFFFu) { *slots[t] = texIdx[t]; d.Flags |= texBit[t]; }
+                alpha = info.enableAlphaTesting != 0; noNEE = info.excludeFromNEE != 0; skip = info.skipRender != 0;
+                overriddenMaterials++;
+            }
             out->materials.push_back(d);
-            alphaTested.push_back(alphaMode == "MASK" && d.BaseOrDiffuseTextureIndex != 0xFFFFFFFFu);
+            alphaTested.push_back(alpha && d.BaseOrDiffuseTextureIndex != 0xFFFFFFFFu);
+            excludeFromNEE.push_back(noNEE); skipRender.push_back(skip);
         }
     }
     std::vector<bool> alphaTested;
@@ -573,7 +512,7 @@ struct Loader
                     memcpy(&vblob[offNrm + (v0 + v) * 4], &pn, 4); memcpy(&vblob[offTan + (v0 + v) * 4], &pt, 4);
                 }
                 RtxptGeometryData g = {};
-                g.numIndices = uint32_t(p.indices.size()); g.numVertices = uint32_t(n);
+                g.numIndices = skipRender[p.material] ? 0u : uint32_t(p.indices.size()); g.numVertices = uint32_t(n);      // SkipRender materials keep their slot and draw nothing
                 g.indexBufferIndex = int32_t(2 * mi); g.indexOffset = uint32_t(i0 * 4); g.vertexBufferIndex = int32_t(2 * mi + 1);
                 g.positionOffset = uint32_t(offPos + v0 * 12); g.prevPositionOffset = 0xFFFFFFFFu;
                 g.texCoord1Offset = hasUv ? uint32_t(offUv + v0 * 8) : 0xFFFFFFFFu; g.texCoord2Offset = 0xFFFFFFFFu;
@@ -624,6 +563,7 @@ struct Loader
                 uint32_t fl = 0; float cutoff = 0.0f;
                 if (alphaTested[g.materialIndex] && g.texCoord1Offset != 0xFFFFFFFFu) { fl |= RTXPT_SUBINST_FLAG_ALPHA_TESTED | (m.BaseOrDiffuseTextureIndex & 0xFFFFu); cutoff = m.AlphaCutoff; }
                 fl |= uint32_t(int(std::min(std::max(cutoff, 0.0f), 1.0f) * 255.0f + 0.5f)) << 24;
+                if (excludeFromNEE[g.materialIndex]) fl |= RTXPT_SUBINST_FLAG_EXCLUDE_FROM_NEE;
                 s.FlagsAndAlphaInfo = fl;
                 s.GlobalGeometryIndex_PTMaterialDataIndex = (gi << 16) | g.materialIndex;
                 s.EmissiveLightMappingOffset = 0xFFFFFFFFu; s.AnalyticProxyLightIndex = 0xFFFFFFFFu;
@@ -676,6 +616,7 @@ struct Loader
     {
         const size_t slash = path.find_last_of("/\\");
         baseDir = (slash == std::string::npos) ? std::string() : path.substr(0, slash + 1);
+        modelName = path.substr(slash == std::string::npos ? 0 : slash + 1); { const size_t dot = modelName.find_last_of('.'); if (dot != std::string::npos) modelName.erase(dot); }
         std::vector<uint8_t> file = readFile(path);
         std::string jsonText;
         if (file.size() >= 12 && !memcmp(file.data(), "glTF", 4))
@@ -736,17 +677,23 @@ thread_local std::string g_loaderError;
 
 extern "C" {
 
-RTXPT_API int rtxpt_b200_load_gltf(const char* path, rtxpt_host_scene** outScene)
+RTXPT_API int rtxpt_b200_load_gltf_ex(const char* path, const char* materialsDir, const char* sceneMaterialsDir, rtxpt_host_scene** outScene, uint32_t* outOverriddenMaterials)
 {
     if (!path || !outScene) { g_loaderError = "null argument"; return RTXPT_ERR_INVALID_ARGUMENT; }
     *outScene = nullptr;
     std::unique_ptr<rtxpt_host_scene> scene(new rtxpt_host_scene());
-    try { Loader l; l.out = scene.get(); l.load(path); }
+    auto asDir = [](const char* d) { std::string s = d ? d : ""; if (!s.empty() && s.back() != '/' && s.back() != '\\') s += '/'; return s; };
+    try
+    {
+        Loader l; l.out = scene.get(); l.materialsDir = asDir(materialsDir); l.sceneMaterialsDir = asDir(sceneMaterialsDir); l.load(path);
+        if (outOverriddenMaterials) *outOverriddenMaterials = l.overriddenMaterials;
+    }
     catch (const LoadError& e) { g_loaderError = e.msg; return RTXPT_ERR_INVALID_ARGUMENT; }
     catch (const std::exception& e) { g_loaderError = e.what(); return RTXPT_ERR_INVALID_ARGUMENT; }
     *outScene = scene.release();
     return RTXPT_OK;
 }
+RTXPT_API int rtxpt_b200_load_gltf(const char* path, rtxpt_host_scene** outScene) { return rtxpt_b200_load_gltf_ex(path, nullptr, nullptr, outScene, nullptr); }
 RTXPT_API const char* rtxpt_b200_load_gltf_error(void) { return g_loaderError.c_str(); }
 RTXPT_API const RtxptSceneDesc* rtxpt_b200_host_scene_desc(const rtxpt_host_scene* scene) { return scene ? &scene->desc : nullptr; }
 RTXPT_API int rtxpt_b200_host_scene_cameras(const rtxpt_host_scene* scene, RtxptGltfCamera* outCameras, uint32_t* ioCount)

@@ -49,8 +49,8 @@ _SIGNATURES = {
     "rtxpt_b200_debug_bsdf": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
     "rtxpt_b200_debug_rng": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
 }
-_LOADER_SYMBOLS = ["rtxpt_b200_load_gltf", "rtxpt_b200_load_gltf_error", "rtxpt_b200_host_scene_desc", "rtxpt_b200_host_scene_cameras",
-                   "rtxpt_b200_host_scene_triangle_count", "rtxpt_b200_free_host_scene", "rtxpt_b200_bridge_camera", "rtxpt_b200_default_constants", "rtxpt_b200_debug_bvh_stats"]
+_LOADER_SYMBOLS = ["rtxpt_b200_load_gltf", "rtxpt_b200_load_gltf_ex", "rtxpt_b200_load_gltf_error", "rtxpt_b200_host_scene_desc", "rtxpt_b200_host_scene_cameras",
+                   "rtxpt_b200_host_scene_triangle_count", "rtxpt_b200_free_host_scene", "rtxpt_b200_bridge_camera", "rtxpt_b200_default_constants", "rtxpt_b200_debug_bvh_stats", "rtxpt_b200_parse_material_json", "rtxpt_b200_parse_material_json_error"]
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["rtxpt_b200_last_error"] + _LOADER_SYMBOLS)
 
 
@@ -96,13 +96,27 @@ def bvh_stats(triangle_vertices, strict=None):
     return st
 
 
+def parse_material_json(text, strict=None):
+    """RTXPT .material.json text -> structs.MaterialJsonInfo (host only)."""
+    L = load(strict); out = S.MaterialJsonInfo()
+    L.rtxpt_b200_parse_material_json.argtypes = [C.c_char_p, C.POINTER(S.MaterialJsonInfo)]; L.rtxpt_b200_parse_material_json.restype = C.c_int
+    L.rtxpt_b200_parse_material_json_error.restype = C.c_char_p
+    if L.rtxpt_b200_parse_material_json(text.encode() if isinstance(text, str) else text, C.byref(out)) != 0:
+        raise RtxptError("material JSON: " + L.rtxpt_b200_parse_material_json_error().decode())
+    return out
+
+
 class GltfScene:
     """A scene loaded by the library's host-side glTF loader (no GPU needed).  `.desc` is the RtxptSceneDesc to hand to Context.upload_scene
     (or to the oracle); `.cameras` lists the perspective cameras of the file."""
-    def __init__(self, path, strict=None):
+    def __init__(self, path, strict=None, materials_dir=None, scene_materials_dir=None):
         self.L = load(strict)
-        h = C.c_void_p()
-        if self.L.rtxpt_b200_load_gltf(os.fsencode(path), C.byref(h)) != 0:
+        h = C.c_void_p(); n = C.c_uint32(0)
+        self.L.rtxpt_b200_load_gltf_ex.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]; self.L.rtxpt_b200_load_gltf_ex.restype = C.c_int
+        enc = lambda p: None if p is None else os.fsencode(p)
+        rc = self.L.rtxpt_b200_load_gltf_ex(os.fsencode(path), enc(materials_dir), enc(scene_materials_dir), C.byref(h), C.byref(n))
+        self.overridden_materials = n.value
+        if rc != 0:
             raise RtxptError("glTF load failed: " + self.L.rtxpt_b200_load_gltf_error().decode())
         self.h = h
         self.desc = self.L.rtxpt_b200_host_scene_desc(h).contents

@@ -91,6 +91,11 @@ class SceneDesc(C.Structure):
                 ("lights", C.POINTER(LightDesc)), ("lightCount", u32)]
 
 
+class MaterialJsonInfo(C.Structure):
+    _fields_ = [("data", MaterialData), ("enableAlphaTesting", u32), ("excludeFromNEE", u32), ("skipRender", u32), ("enableTransmission", u32),
+                ("textureEnabled", u32 * 5), ("textureSRGB", u32 * 5), ("texturePath", (C.c_char * 260) * 5)]
+
+
 class BvhStats(C.Structure):
     _fields_ = [("nodeCount", u32), ("triangleReferenceCount", u32), ("leafCount", u32), ("maxDepth", u32), ("expectedNodeVisits", f32), ("expectedTriangleTests", f32),
                 ("buildSeconds", f32), ("_pad", f32)]

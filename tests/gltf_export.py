@@ -35,7 +35,7 @@ def export(builder, path, camera=None, glb=False):
         e = np.asarray(m.emissive, np.float32) * np.float32(m.emissive_intensity)
         g = {"pbrMetallicRoughness": {"baseColorFactor": [float(np.float32(c)) for c in m.base_color] + [float(np.float32(m.opacity))],
                                       "metallicFactor": float(np.float32(m.metalness)), "roughnessFactor": float(np.float32(m.roughness))},
-             "emissiveFactor": [float(x) for x in e]}
+             "emissiveFactor": [float(x) for x in e], "name": "mat%d" % len(materials)}
         if m.base_texture is not None: g["pbrMetallicRoughness"]["baseColorTexture"] = {"index": m.base_texture}
         if m.orm_texture is not None: g["pbrMetallicRoughness"]["metallicRoughnessTexture"] = {"index": m.orm_texture}
         if m.normal_texture is not None: g["normalTexture"] = {"index": m.normal_texture, "scale": float(np.float32(m.normal_scale))}
