@@ -312,3 +312,48 @@ def test_full_size_properties(product):
     assert ((anyhit["t"] >= 0) <= (closest["t"] >= 0)).all() and ((closest["t"] < 0) | (closest["t"] < rays[:, 7])).all()
     assert 0.05 < (closest["t"] >= 0).mean() < 0.95
     a.close()
+
+
+@pytest.mark.gpu
+def test_c5_accumulation_tolerance_gate(product, oracle, small_city):
+    """BASELINE.json configs[4] in miniature: long reference accumulation against the oracle's, identical seeds, gate = per-pixel L2 <= 1e-3
+    (north_star).  256 spp in batches of 4 sub-samples with sampleBaseIndex advancing the way Sample.cpp:1507 does."""
+    from rtxpt_b200 import scene_builder as sb
+    from rtxpt_b200.imageio import per_pixel_l2
+    scene, cam0 = small_city
+    W, H, SPP, FRAMES = 160, 90, 4, 64
+    cam = sb.bridge_camera(W, H, pos=tuple(cam0.PosW[:]), direction=tuple(cam0.DirectionW[:]), up=(0, 1, 0), fov_y=1.04)
+    consts = sb.make_constants(W, H, cam, bounce_count=6, diffuse_bounce_count=6, env_enabled=True, firefly_threshold=5000.0)
+    c = product.Context(max_sub_samples_per_launch=SPP); c.upload_scene(scene)
+    o = oracle.Oracle(scene); acc = None; n = 0
+    for f in range(FRAMES):
+        consts.sampleBaseIndex = f * SPP
+        c.set_constants(consts); c.path_trace(0, SPP, True)
+        o.set_constants(consts); acc, n = o.render(0, SPP, accum=acc, accum_count=n)[:2]
+    c.synchronize(); img = c.readback_accumulated()
+    assert c.stats().accumulatedSamples == n == FRAMES * SPP
+    l2 = per_pixel_l2(img, acc)
+    assert l2 <= 1e-3, l2
+    assert abs(float(img[..., :3].mean()) - float(acc[..., :3].mean())) < 2e-3 * float(acc[..., :3].mean())
+    c.close(); o.close()
+
+
+@pytest.mark.gpu
+def test_c4_4k_tile_split_properties(product):
+    """BASELINE.json configs[3] shape: 3840x2160, 1 spp, nested dielectrics and absorbing volumes (the city's glass), split into 8 interleaved tile
+    sets.  The eight partial frames, each traced by its own context, reassemble bit for bit into the frame of a single full-frame context."""
+    from rtxpt_b200 import scenes, scene_builder as sb
+    W, H = 3840, 2160
+    scene, cam = scenes.city_block(target_triangles=600000, width=W, height=H)
+    consts = sb.make_constants(W, H, cam, bounce_count=6, diffuse_bounce_count=6, env_enabled=True, firefly_threshold=5000.0, nested_dielectrics=1)
+    full = product.Context(max_sub_samples_per_launch=1); full.upload_scene(scene); full.set_constants(consts)
+    full.path_trace(0, 1, True); full.synchronize(); img = full.readback_accumulated(); st = full.stats(); full.close()
+    assert np.isfinite(img).all() and (img[..., :3] >= 0).all() and st.paths == W * H
+    ty, tx = np.meshgrid(np.arange(H) // 64, np.arange(W) // 64, indexing="ij")
+    owner = (ty * ((W + 63) // 64) + tx) % 8
+    out = np.zeros_like(img); rays = 0
+    for r in range(8):
+        c = product.Context(max_sub_samples_per_launch=1, tile_rank=r, tile_world=8, tile_size=64); c.upload_scene(scene); c.set_constants(consts)
+        c.path_trace(0, 1, True); c.synchronize(); part = c.readback_accumulated(); s = c.stats(); c.close()
+        out[owner == r] = part[owner == r]; rays += s.scatterRays + s.shadowRays
+    assert np.array_equal(out, img) and rays == st.scatterRays + st.shadowRays
