@@ -61,7 +61,7 @@ struct rtxpt_ctx
     std::vector<uint8_t*> bufferAllocs; DeviceArray<const uint8_t*> dBufferTable;
     std::vector<DeviceTexture> textures; DeviceArray<cudaTextureObject_t> dTextureTable;
     DeviceTexture envCube; uint32_t envFaceSize = 0, envMipLevels = 0;
-    DeviceArray<uint4> dBvhNodes; DeviceArray<float4> dBvhTris; DeviceArray<uint4> dTriInfo;
+    DeviceArray<uint4> dBvhNodes; DeviceArray<float4> dBvhTris; DeviceArray<uint4> dTriInfo, dTriShade;
     uint32_t bvhNodeCount = 0, bvhTriCount = 0; float bvhBuildSeconds = 0;
     std::vector<RtxptSubInstanceData> hSubInstances; uint32_t materialCount = 0;
     LightBakeState lightState;
@@ -151,7 +151,7 @@ extern "C" RTXPT_API int rtxpt_b200_destroy(rtxpt_ctx* c)
     cudaStreamSynchronize(c->stream);
     releaseScene(c);
     c->dInstances.release(); c->dGeometries.release(); c->dSubInstances.release(); c->dMaterials.release(); c->dSubInstanceClass.release();
-    c->dBufferTable.release(); c->dTextureTable.release(); c->dBvhNodes.release(); c->dBvhTris.release(); c->dTriInfo.release();
+    c->dBufferTable.release(); c->dTextureTable.release(); c->dBvhNodes.release(); c->dBvhTris.release(); c->dTriInfo.release(); c->dTriShade.release();
     c->dLightsEx.release(); c->dLights.release(); c->dProxyCounters.release(); c->dProxyIndices.release(); c->dEnvLookup.release();
     c->s0.release(); c->s1.release(); c->s2.release(); c->s3.release(); c->s4.release(); c->hits.release();
     c->rayQueue[0].release(); c->rayQueue[1].release(); c->shadeQueue.release();
@@ -234,7 +234,7 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
     releaseScene(c);
     if (sc->materialCount > 0xFFFF || sc->textureCount > 0xFFFF || sc->bufferCount > 0xFFFF) return fail(RTXPT_ERR_UNSUPPORTED, "table sizes exceed the 16-bit indices of SubInstanceData");
     // validate + flatten triangles to world space (gid order: instance, geometry, primitive)
-    std::vector<BuildTriangle> tris; std::vector<uint4> triInfo;
+    std::vector<BuildTriangle> tris; std::vector<uint4> triInfo, triShade;
     for (uint32_t ii = 0; ii < sc->instanceCount; ii++)
     {
         const RtxptInstanceData& inst = sc->instances[ii];
@@ -255,12 +255,28 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
             {
                 uint32_t idx[3]; memcpy(idx, ib + g.indexOffset + size_t(t) * 12, 12);
                 BuildTriangle bt; float* dst[3] = { bt.v0, bt.v1, bt.v2 };
+                const uint64_t vbSize = sc->buffers[g.vertexBufferIndex].sizeBytes;
+                uint4 rec[6]; memset(rec, 0, sizeof(rec));
+                const bool hasUV = g.texCoord1Offset != ~0u, hasN = g.normalOffset != ~0u, hasT = g.tangentOffset != ~0u;
                 for (int k = 0; k < 3; k++)
                 {
-                    if (uint64_t(g.positionOffset) + uint64_t(idx[k]) * 12 + 12 > sc->buffers[g.vertexBufferIndex].sizeBytes) return fail(RTXPT_ERR_INVALID_ARGUMENT, "vertex index exceeds buffer");
+                    if (uint64_t(g.positionOffset) + uint64_t(idx[k]) * 12 + 12 > vbSize) return fail(RTXPT_ERR_INVALID_ARGUMENT, "vertex index exceeds buffer");
+                    if ((hasUV && uint64_t(g.texCoord1Offset) + uint64_t(idx[k]) * 8 + 8 > vbSize) || (hasN && uint64_t(g.normalOffset) + uint64_t(idx[k]) * 4 + 4 > vbSize) ||
+                        (hasT && uint64_t(g.tangentOffset) + uint64_t(idx[k]) * 4 + 4 > vbSize)) return fail(RTXPT_ERR_INVALID_ARGUMENT, "vertex attribute exceeds buffer");
                     float v[3]; memcpy(v, vb + g.positionOffset + size_t(idx[k]) * 12, 12);
                     hostXformPoint(inst.transform, v, dst[k]);
+                    uint32_t w[3]; memcpy(w, v, 12); uint32_t nrm = 0, tan = 0, uv[2] = { 0, 0 };
+                    if (hasN) memcpy(&nrm, vb + g.normalOffset + size_t(idx[k]) * 4, 4);
+                    if (hasT) memcpy(&tan, vb + g.tangentOffset + size_t(idx[k]) * 4, 4);
+                    if (hasUV) memcpy(uv, vb + g.texCoord1Offset + size_t(idx[k]) * 8, 8);
+                    rec[k] = make_uint4(w[0], w[1], w[2], nrm);
+                    if (k == 0) { rec[3].x = uv[0]; rec[3].y = uv[1]; rec[4].z = tan; }
+                    if (k == 1) { rec[3].z = uv[0]; rec[3].w = uv[1]; rec[4].w = tan; }
+                    if (k == 2) { rec[4].x = uv[0]; rec[4].y = uv[1]; rec[5].x = tan; }
                 }
+                if (t >= kTriShadePrimMask) return fail(RTXPT_ERR_UNSUPPORTED, "geometry with more than 2^29 triangles");
+                rec[5].y = ii; rec[5].z = subIndex; rec[5].w = t | (hasUV ? kTriShadeHasUV : 0u) | (hasN ? kTriShadeHasNormal : 0u) | (hasT ? kTriShadeHasTangent : 0u);
+                triShade.insert(triShade.end(), rec, rec + 6);
                 bt.gid = uint32_t(tris.size()); bt.subInstanceAndFlags = flags; bt.primitiveIndex = t;
                 tris.push_back(bt);
                 triInfo.push_back(make_uint4(ii, gi, t, subIndex));
@@ -276,6 +292,7 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
     CU(c->dBvhNodes.upload(reinterpret_cast<const uint4*>(bvh.nodes.data()), bvh.nodes.size() * 5, s));
     CU(c->dBvhTris.upload(reinterpret_cast<const float4*>(bvh.tris.data()), bvh.tris.size() * 3, s));
     CU(c->dTriInfo.upload(triInfo.data(), triInfo.size(), s));
+    CU(c->dTriShade.upload(triShade.data(), triShade.size(), s));
     CU(c->dInstances.upload(sc->instances, sc->instanceCount, s));
     CU(c->dGeometries.upload(sc->geometries, sc->geometryCount, s));
     CU(c->dMaterials.upload(sc->materials, sc->materialCount, s));
@@ -416,7 +433,7 @@ static void fillParams(rtxpt_ctx* c, LaunchParams& p)
     v.instances = c->dInstances.ptr; v.geometries = c->dGeometries.ptr; v.subInstances = c->dSubInstances.ptr; v.materials = c->dMaterials.ptr;
     v.subInstanceClass = c->dSubInstanceClass.ptr; v.materialCount = c->materialCount;
     v.buffers = c->dBufferTable.ptr; v.textures = c->dTextureTable.ptr; v.envCube = c->envCube.object; v.envFaceSize = c->envFaceSize; v.envMipLevels = c->envMipLevels;
-    v.bvhNodes = c->dBvhNodes.ptr; v.bvhTris = c->dBvhTris.ptr; v.triInfo = c->dTriInfo.ptr; v.bvhNodeCount = c->bvhNodeCount; v.bvhTriCount = c->bvhTriCount;
+    v.bvhNodes = c->dBvhNodes.ptr; v.bvhTris = c->dBvhTris.ptr; v.triInfo = c->dTriInfo.ptr; v.triShade = c->dTriShade.ptr; v.bvhNodeCount = c->bvhNodeCount; v.bvhTriCount = c->bvhTriCount;
     v.lightsEx = c->dLightsEx.ptr; v.analyticLightCount = uint32_t(c->lightState.analyticLightsEx.size());
     v.lights = c->dLights.ptr; v.proxyCounters = c->dProxyCounters.ptr; v.proxyIndices = c->dProxyIndices.ptr; v.envLookupMap = c->dEnvLookup.ptr;
     v.lightCount = uint32_t(c->lightState.lights.size()); v.samplingProxyCount = uint32_t(c->lightState.proxyIndices.size()); v.envEnabled = c->lightState.envEnabled ? 1u : 0u;

@@ -26,6 +26,7 @@ struct SceneView
     const uint4*                bvhNodes;           // 5 x uint4 per node
     const float4*               bvhTris;            // 3 x float4 per triangle
     const uint4*                triInfo;            // per global triangle id: instanceIndex, geometryIndex, primitiveIndex, subInstanceIndex
+    const uint4*                triShade;           // per global triangle id, 6 x uint4 (kTriShadeWords): everything loadSurface gathers per vertex, see below
     uint                        bvhNodeCount, bvhTriCount;
     // lights
     const LightInfo*            lights;
@@ -36,6 +37,13 @@ struct SceneView
     const uint4*                lightsEx;           // PolymorphicLightInfoEx of the analytic lights: index = light index - 5368
     uint                        analyticLightCount;
 };
+
+// Per-triangle shading record (96 B), built at upload from the caller's index / vertex buffers so that a hit costs one contiguous read instead of
+// the chain triInfo -> instance / geometry -> 3 indices -> 3 x (position, texcoord, normal, tangent):
+//   q0..q2: object-space position of vertex k (xyz), its packed snorm8 normal (w)
+//   q3: uv0.xy uv1.xy        q4: uv2.xy, packed tangent 0, packed tangent 1        q5: packed tangent 2, instance index, sub-instance index, primitive index | presence bits
+constexpr uint kTriShadeWords = 6;
+constexpr uint kTriShadeHasUV = 1u << 29, kTriShadeHasNormal = 1u << 30, kTriShadeHasTangent = 1u << 31, kTriShadePrimMask = (1u << 29) - 1u;
 
 PT_DEVICE uint load32(const SceneView& sc, uint buffer, uint byteOffset) { return __ldg(reinterpret_cast<const uint*>(sc.buffers[buffer] + byteOffset)); }
 PT_DEVICE uint3 loadIndex3(const SceneView& sc, uint buffer, uint byteOffset)

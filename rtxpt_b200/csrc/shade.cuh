@@ -181,40 +181,39 @@ PT_DEVICE void computeTangentSpace(Surface& s, float4 tangentW, bool ignoreTange
 PT_DEVICE void loadSurface(const LaunchParams& p, uint gid, float bu, float bv, float3 rayDir, float coneWidth, Surface& s)
 {
     const SceneView& sc = p.scene;
-    const uint4 info = sc.triInfo[gid];
+    // one contiguous 96-byte record per triangle (scene_device.cuh) instead of the reference's chain of table and vertex fetches (BridgeDonut:152-256)
+    const uint4* rec = sc.triShade + size_t(gid) * kTriShadeWords;
+    const uint4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2), r3 = __ldg(rec + 3), r4 = __ldg(rec + 4), r5 = __ldg(rec + 5);
+    const uint4 info = make_uint4(r5.y, 0u, r5.w & kTriShadePrimMask, r5.z);          // instance, -, primitive, sub-instance
     const RtxptInstanceData& inst = sc.instances[info.x];
-    const RtxptGeometryData& g = sc.geometries[inst.firstGeometryIndex + info.y];
     const float* xf = inst.transform;
     const float b0 = 1.0f - (bu + bv);
-    const uint3 idx = loadIndex3(sc, g.indexBufferIndex, g.indexOffset + info.z * 12);
-    const float3 p0 = loadFloat3(sc, g.vertexBufferIndex, g.positionOffset + idx.x * 12);
-    const float3 p1 = loadFloat3(sc, g.vertexBufferIndex, g.positionOffset + idx.y * 12);
-    const float3 p2 = loadFloat3(sc, g.vertexBufferIndex, g.positionOffset + idx.z * 12);
+    const float3 p0 = mk3(__uint_as_float(r0.x), __uint_as_float(r0.y), __uint_as_float(r0.z));
+    const float3 p1 = mk3(__uint_as_float(r1.x), __uint_as_float(r1.y), __uint_as_float(r1.z));
+    const float3 p2 = mk3(__uint_as_float(r2.x), __uint_as_float(r2.y), __uint_as_float(r2.z));
     const float3 objPos = p0 * b0 + p1 * bu + p2 * bv;
     float2 uv = mk2(0.f, 0.f), t0 = uv, t1 = uv, t2 = uv;
-    if (g.texCoord1Offset != ~0u)
+    if (r5.w & kTriShadeHasUV)
     {
-        t0 = loadFloat2(sc, g.vertexBufferIndex, g.texCoord1Offset + idx.x * 8);
-        t1 = loadFloat2(sc, g.vertexBufferIndex, g.texCoord1Offset + idx.y * 8);
-        t2 = loadFloat2(sc, g.vertexBufferIndex, g.texCoord1Offset + idx.z * 8);
+        t0 = mk2(__uint_as_float(r3.x), __uint_as_float(r3.y)); t1 = mk2(__uint_as_float(r3.z), __uint_as_float(r3.w)); t2 = mk2(__uint_as_float(r4.x), __uint_as_float(r4.y));
         uv = mk2(t0.x * b0 + t1.x * bu + t2.x * bv, t0.y * b0 + t1.y * bu + t2.y * bv);
     }
     const float3 objFlat = safeNormalize(cross3(p1 - p0, p2 - p0));
     float3 geometryNormal = mk3(0.f);
-    if (g.normalOffset != ~0u)
+    if (r5.w & kTriShadeHasNormal)
     {
-        float3 n0 = norm3(mk3(unpackSnorm8(load32(sc, g.vertexBufferIndex, g.normalOffset + idx.x * 4)), unpackSnorm8(load32(sc, g.vertexBufferIndex, g.normalOffset + idx.x * 4) >> 8), unpackSnorm8(load32(sc, g.vertexBufferIndex, g.normalOffset + idx.x * 4) >> 16)));
-        float3 n1 = norm3(mk3(unpackSnorm8(load32(sc, g.vertexBufferIndex, g.normalOffset + idx.y * 4)), unpackSnorm8(load32(sc, g.vertexBufferIndex, g.normalOffset + idx.y * 4) >> 8), unpackSnorm8(load32(sc, g.vertexBufferIndex, g.normalOffset + idx.y * 4) >> 16)));
-        float3 n2 = norm3(mk3(unpackSnorm8(load32(sc, g.vertexBufferIndex, g.normalOffset + idx.z * 4)), unpackSnorm8(load32(sc, g.vertexBufferIndex, g.normalOffset + idx.z * 4) >> 8), unpackSnorm8(load32(sc, g.vertexBufferIndex, g.normalOffset + idx.z * 4) >> 16)));
+        float3 n0 = norm3(mk3(unpackSnorm8(r0.w), unpackSnorm8(r0.w >> 8), unpackSnorm8(r0.w >> 16)));
+        float3 n1 = norm3(mk3(unpackSnorm8(r1.w), unpackSnorm8(r1.w >> 8), unpackSnorm8(r1.w >> 16)));
+        float3 n2 = norm3(mk3(unpackSnorm8(r2.w), unpackSnorm8(r2.w >> 8), unpackSnorm8(r2.w >> 16)));
         if (dot3(n0, objFlat) < 0) n0 = -n0;
         if (dot3(n1, objFlat) < 0) n1 = -n1;
         if (dot3(n2, objFlat) < 0) n2 = -n2;
         geometryNormal = safeNormalize(xfVector(xf, n0 * b0 + n1 * bu + n2 * bv));
     }
     float4 tangent = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (g.tangentOffset != ~0u)
+    if (r5.w & kTriShadeHasTangent)
     {
-        const uint q0 = load32(sc, g.vertexBufferIndex, g.tangentOffset + idx.x * 4), q1 = load32(sc, g.vertexBufferIndex, g.tangentOffset + idx.y * 4), q2 = load32(sc, g.vertexBufferIndex, g.tangentOffset + idx.z * 4);
+        const uint q0 = r4.z, q1 = r4.w, q2 = r5.x;
         const float3 a = mk3(unpackSnorm8(q0), unpackSnorm8(q0 >> 8), unpackSnorm8(q0 >> 16));
         const float3 b = mk3(unpackSnorm8(q1), unpackSnorm8(q1 >> 8), unpackSnorm8(q1 >> 16));
         const float3 c = mk3(unpackSnorm8(q2), unpackSnorm8(q2 >> 8), unpackSnorm8(q2 >> 16));

@@ -81,12 +81,13 @@ PT_DEVICE bool intersectTriangleWatertight(const WatertightRay& wr, float3 org, 
     return true;
 }
 
-// AlphaTestImpl (BridgeDonut:929-971): true when the candidate is opaque at (u,v)
-PT_DEVICE bool alphaTestPasses(const SceneView& sc, const RtxptSubInstanceData& s, uint primitiveIndex, float u, float v)
+// AlphaTestImpl (BridgeDonut:929-971): true when the candidate is opaque at (u,v).  The three texture coordinates come from the triangle's
+// shading record (scene_device.cuh) instead of the index / vertex buffer chain.
+PT_DEVICE bool alphaTestPasses(const SceneView& sc, const RtxptSubInstanceData& s, uint gid, float u, float v)
 {
-    const uint ib = s.IndexBufferIndex_VertexBufferIndex >> 16, vb = s.IndexBufferIndex_VertexBufferIndex & 0xFFFF;
-    const uint3 idx = loadIndex3(sc, ib, s.IndexOffset + primitiveIndex * 12);
-    const float2 t0 = loadFloat2(sc, vb, s.TexCoord1Offset + idx.x * 8), t1 = loadFloat2(sc, vb, s.TexCoord1Offset + idx.y * 8), t2 = loadFloat2(sc, vb, s.TexCoord1Offset + idx.z * 8);
+    const uint4* rec = sc.triShade + size_t(gid) * kTriShadeWords;
+    const uint4 r3 = __ldg(rec + 3), r4 = __ldg(rec + 4);
+    const float2 t0 = mk2(__uint_as_float(r3.x), __uint_as_float(r3.y)), t1 = mk2(__uint_as_float(r3.z), __uint_as_float(r3.w)), t2 = mk2(__uint_as_float(r4.x), __uint_as_float(r4.y));
     const float b0 = 1.0f - (u + v);
     const float2 uv = mk2(t0.x * b0 + t1.x * u + t2.x * v, t0.y * b0 + t1.y * u + t2.y * v);
     const float opacity = tex2DLod<float4>(sc.textures[s.FlagsAndAlphaInfo & 0xFFFF], uv.x, uv.y, 0.0f).w;
@@ -200,7 +201,7 @@ struct Traverser
                         if (sub & (kTriFlagAlphaTested | kTriFlagExcludeFromNEE))
                         {   // non-opaque geometry (SampleCommon/AccelerationStructureUtil.h:88-89)
                             if (ANY_HIT && (sub & kTriFlagExcludeFromNEE)) accept = false;
-                            else if ((sub & kTriFlagAlphaTested) && !alphaTestPasses(sc, sc.subInstances[sub & kTriSubInstanceMask], __float_as_uint(c.w), u, v)) accept = false;
+                            else if ((sub & kTriFlagAlphaTested) && !alphaTestPasses(sc, sc.subInstances[sub & kTriSubInstanceMask], __float_as_uint(a.w), u, v)) accept = false;
                         }
                         if (accept) { atomicMin(&ws.bestKey[owner], key); won = true; }
                     }
