@@ -106,8 +106,9 @@ def ncu_traffic(rays_per_iteration):
 
 
 def cpu_sample_rect():
-    # bounded sample of the same workload: a 240x135 window in the middle of the 1080p frame, 1 sub-sample
-    w, h = 240, 135
+    # bounded sample of the same workload: a 960x540 window in the middle of the 1080p frame, 1 sub-sample (~2.4 M rays per step: enough rows to keep
+    # every host thread busy, about a second per step on 64 cores)
+    w, h = 960, 540
     x0, y0 = (WIDTH - w) // 2, (HEIGHT - h) // 2
     return x0, y0, x0 + w, y0 + h
 

@@ -130,7 +130,7 @@ ORC_API int oracle_render_guides(void* p, uint32_t subSample, uint32_t x0, uint3
     {
         PathTracerCtx x; x.scene = &c->scene; x.bvh = &c->bvh; x.lights = &c->lights; x.c = &c->consts; x.stats = nullptr;
         x.sampleIndex = c->consts.sampleBaseIndex + subSample; x.worldToClip = c->worldToClip;
-        #pragma omp for schedule(dynamic, 4)
+        #pragma omp for schedule(dynamic, 1)
         for (int y = int(y0); y < int(y1); y++)
             for (uint32_t px = x0; px < x1; px++)
             {
@@ -196,7 +196,7 @@ ORC_API int oracle_render(void* p, uint32_t firstSubSample, uint32_t subSampleCo
             RenderStats local;
             PathTracerCtx x; x.scene = &c->scene; x.bvh = &c->bvh; x.lights = &c->lights; x.c = &c->consts; x.stats = &local;
             x.sampleIndex = c->consts.sampleBaseIndex + firstSubSample + s;
-            #pragma omp for schedule(dynamic, 4)
+            #pragma omp for schedule(dynamic, 1)
             for (int y = int(y0); y < int(y1); y++)
                 for (uint32_t px = x0; px < x1; px++)
                 {
