@@ -67,7 +67,7 @@ struct rtxpt_ctx
     LightBakeState lightState;
     DeviceArray<LightInfo> dLights; DeviceArray<uint32_t> dProxyCounters, dProxyIndices, dEnvLookup; DeviceArray<uint4> dLightsEx;
     // wavefront
-    DeviceArray<uint4> s0, s1, s2, s3, s4, s5; DeviceArray<float4> hits; DeviceArray<uint32_t> rayQueue[2], shadeQueue;
+    DeviceArray<uint4> s0, s1, s2, s3, s4; DeviceArray<float4> hits; DeviceArray<uint32_t> rayQueue[2], shadeQueue;
     DeviceArray<float4> shadowOriginTMax, shadowDirPath; DeviceArray<uint2> shadowRadiance;
     DeviceArray<uint32_t> counters; DeviceArray<uint32_t> pixelOfSlot, allPixelTable;
     uint32_t paddedPixelsPerRank = 0;
@@ -153,7 +153,7 @@ extern "C" RTXPT_API int rtxpt_b200_destroy(rtxpt_ctx* c)
     c->dInstances.release(); c->dGeometries.release(); c->dSubInstances.release(); c->dMaterials.release(); c->dSubInstanceClass.release();
     c->dBufferTable.release(); c->dTextureTable.release(); c->dBvhNodes.release(); c->dBvhTris.release(); c->dTriInfo.release(); c->dTriShade.release();
     c->dLightsEx.release(); c->dLights.release(); c->dProxyCounters.release(); c->dProxyIndices.release(); c->dEnvLookup.release();
-    c->s0.release(); c->s1.release(); c->s2.release(); c->s3.release(); c->s4.release(); c->s5.release(); c->hits.release();
+    c->s0.release(); c->s1.release(); c->s2.release(); c->s3.release(); c->s4.release(); c->hits.release();
     c->rayQueue[0].release(); c->rayQueue[1].release(); c->shadeQueue.release();
     c->shadowOriginTMax.release(); c->shadowDirPath.release(); c->shadowRadiance.release(); c->counters.release(); c->pixelOfSlot.release(); c->allPixelTable.release();
     c->outputColor.release(); c->accumulated.release(); c->depth.release(); c->motionVectors.release(); c->throughput.release();
@@ -385,7 +385,7 @@ static int ensureTargets(rtxpt_ctx* c, uint32_t W, uint32_t H)
     const size_t cap = size_t(c->pixelCount) * c->cfg.maxSubSamplesPerLaunch;
     if (cap >= 0x7FFFFFFFull) return fail(RTXPT_ERR_UNSUPPORTED, "too many path slots");
     c->capacity = uint32_t(std::max<size_t>(cap, 1));
-    CU(c->s0.alloc(c->capacity)); CU(c->s1.alloc(c->capacity)); CU(c->s2.alloc(c->capacity)); CU(c->s3.alloc(c->capacity)); CU(c->s4.alloc(c->capacity)); CU(c->s5.alloc(c->capacity));
+    CU(c->s0.alloc(c->capacity)); CU(c->s1.alloc(c->capacity)); CU(c->s2.alloc(c->capacity)); CU(c->s3.alloc(c->capacity)); CU(c->s4.alloc(c->capacity));
     CU(c->hits.alloc(c->capacity)); CU(c->rayQueue[0].alloc(c->capacity)); CU(c->rayQueue[1].alloc(c->capacity));
     CU(c->shadeQueue.alloc(size_t(c->capacity) * kNumShadeClasses));
     CU(c->shadowOriginTMax.alloc(c->capacity)); CU(c->shadowDirPath.alloc(c->capacity)); CU(c->shadowRadiance.alloc(c->capacity));
@@ -438,7 +438,7 @@ static void fillParams(rtxpt_ctx* c, LaunchParams& p)
     v.lights = c->dLights.ptr; v.proxyCounters = c->dProxyCounters.ptr; v.proxyIndices = c->dProxyIndices.ptr; v.envLookupMap = c->dEnvLookup.ptr;
     v.lightCount = uint32_t(c->lightState.lights.size()); v.samplingProxyCount = uint32_t(c->lightState.proxyIndices.size()); v.envEnabled = c->lightState.envEnabled ? 1u : 0u;
     WavefrontBuffers& w = p.wf;
-    w.s0 = c->s0.ptr; w.s1 = c->s1.ptr; w.s2 = c->s2.ptr; w.s3 = c->s3.ptr; w.s4 = c->s4.ptr; w.s5 = c->s5.ptr; w.hits = c->hits.ptr;
+    w.s0 = c->s0.ptr; w.s1 = c->s1.ptr; w.s2 = c->s2.ptr; w.s3 = c->s3.ptr; w.s4 = c->s4.ptr; w.hits = c->hits.ptr;
     w.rayQueue[0] = c->rayQueue[0].ptr; w.rayQueue[1] = c->rayQueue[1].ptr; w.shadeQueue = c->shadeQueue.ptr;
     w.shadowOriginTMax = c->shadowOriginTMax.ptr; w.shadowDirPath = c->shadowDirPath.ptr; w.shadowRadiance = c->shadowRadiance.ptr;
     w.counters = c->counters.ptr; w.pixelOfSlot = c->pixelOfSlot.ptr; w.capacity = c->capacity; w.pixelCount = c->pixelCount;

@@ -70,7 +70,6 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ Launch
         if (p.exportGuides && sub + 1 == p.subSampleCount) p.depth[size_t(py) * p.c.imageWidth + px] = 0.0f;       // Bridge::ExportSurfaceInit
         path.origin = origin; path.dir = dir;
         path.store(p.wf, slot);
-        stState(p.wf.s5 + slot, packRaySetup(dir));
         p.wf.rayQueue[0][slot] = slot | (path.hasFlag(kPFTerminateAtNextBounce) ? 0x80000000u : 0u);
     }
 }
@@ -148,8 +147,8 @@ __global__ void __launch_bounds__(kTraceThreads, MINB * kTraceCtaScale) k_trace_
                 {
                     entry = queue[i];
                     const uint slot = entry & 0x7FFFFFFFu;
-                    const uint4 a = ldState(p.wf.s0 + slot), b = ldState(p.wf.s1 + slot), setup = ldState(p.wf.s5 + slot);
-                    tv.init(p.scene, ws, mk3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z)), mk3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z)), 0.0f, kMaxRayTravel, setup);
+                    const uint4 a = ldState(p.wf.s0 + slot), b = ldState(p.wf.s1 + slot);
+                    tv.init(p.scene, ws, mk3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z)), mk3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z)), 0.0f, kMaxRayTravel);
                     hasRay = true;
                 }
             }

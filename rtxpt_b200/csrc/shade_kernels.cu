@@ -8,7 +8,6 @@
 #endif
 #define PT_SOBOL_TABLES 1
 #include "shade.cuh"
-#include "traverse.cuh"
 #include "kernels.h"
 
 namespace pt {
@@ -62,7 +61,7 @@ __global__ void __launch_bounds__(128, MINB) k_shade(const __grid_constant__ Lau
                 PathRegs path; path.load(p.wf, slot, true);
                 if (cls == 0) shadeMiss<EXPORT_GUIDES>(p, path);
                 else shadeHit<EXPORT_GUIDES, ANALYTIC_LIGHTS>(p, path, slot, p.wf.hits[slot], out);
-                if (cls != 0 && out.continuePath) { path.store(p.wf, slot); stState(p.wf.s5 + slot, packRaySetup(path.dir)); } else path.storeRadianceOnly(p.wf, slot);
+                if (cls != 0 && out.continuePath) path.store(p.wf, slot); else path.storeRadianceOnly(p.wf, slot);
                 if (out.continuePath) { rayCls = 0; rayEntry = slot | (path.hasFlag(kPFTerminateAtNextBounce) ? 0x80000000u : 0u); }
                 if (out.emitShadow) shadowCls = 0;
             }

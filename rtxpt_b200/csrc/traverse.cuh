@@ -49,14 +49,6 @@ struct WatertightRay
     }
 };
 
-// The watertight setup of a scatter ray is computed once, where the ray is generated (k_generate / k_shade, all lanes busy), and travels with the
-// path as one 16-byte word; the traversal warps, which refill a few lanes at a time, only copy it.
-PT_DEVICE uint4 packRaySetup(float3 d)
-{
-    WatertightRay wr; wr.setup(d);
-    return make_uint4(__float_as_uint(wr.Sx), __float_as_uint(wr.Sy), __float_as_uint(wr.Sz), uint(wr.kx) | (uint(wr.ky) << 2) | (uint(wr.kz) << 4));
-}
-
 PT_DEVICE float comp(float3 v, int k) { return (k == 0) ? v.x : ((k == 1) ? v.y : v.z); }
 
 PT_DEVICE bool intersectTriangleWatertight(const WatertightRay& wr, float3 org, float3 v0, float3 v1, float3 v2, float tMin, float tMax,
@@ -150,21 +142,20 @@ struct Traverser
     int sp;
     bool done, waiting;
 
-    PT_DEVICE void init(const SceneView& sc, WarpScratch& ws, float3 o, float3 d, float tmin, float tmax) { init(sc, ws, o, d, tmin, tmax, packRaySetup(d)); }
-    PT_DEVICE void init(const SceneView& sc, WarpScratch& ws, float3 o, float3 d, float tmin, float tmax, uint4 setup)
+    PT_DEVICE void init(const SceneView& sc, WarpScratch& ws, float3 o, float3 d, float tmin, float tmax)
     {
         const uint lane = threadIdx.x & 31u;
         org = o; tMin = tmin; bestT = tmax;
+        WatertightRay wr; wr.setup(d);
         ws.ray[0][lane] = o.x; ws.ray[1][lane] = o.y; ws.ray[2][lane] = o.z;
-        ws.ray[3][lane] = __uint_as_float(setup.x); ws.ray[4][lane] = __uint_as_float(setup.y); ws.ray[5][lane] = __uint_as_float(setup.z);
-        ws.ray[6][lane] = __uint_as_float(setup.w);
+        ws.ray[3][lane] = wr.Sx; ws.ray[4][lane] = wr.Sy; ws.ray[5][lane] = wr.Sz;
+        ws.ray[6][lane] = __uint_as_float(uint(wr.kx) | (uint(wr.ky) << 2) | (uint(wr.kz) << 4));
         ws.ray[7][lane] = tmin; ws.ray[8][lane] = tmax;
         ws.bestKey[lane] = ((unsigned long long)__float_as_uint(tmax) << 32) | 0xFFFFFFFFull;
         const float eps = 1.0e-20f;     // keeps s * id * 2^15 finite for every node scale the builder emits
-        // reciprocal directions feed the conservative box test only: the 1-ulp approximation is inside its slack
-        idx = __fdividef(1.0f, fabsf(d.x) > eps ? d.x : copysignf(eps, d.x));
-        idy = __fdividef(1.0f, fabsf(d.y) > eps ? d.y : copysignf(eps, d.y));
-        idz = __fdividef(1.0f, fabsf(d.z) > eps ? d.z : copysignf(eps, d.z));
+        idx = 1.0f / (fabsf(d.x) > eps ? d.x : copysignf(eps, d.x));
+        idy = 1.0f / (fabsf(d.y) > eps ? d.y : copysignf(eps, d.y));
+        idz = 1.0f / (fabsf(d.z) > eps ? d.z : copysignf(eps, d.z));
         octinv = 7u - ((d.x < 0.0f ? 4u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 1u : 0u));
         sp = 0;
         nodeGroup = make_uint2(0u, 0x80000000u);        // virtual parent of the root: one internal child in slot 7^octinv

@@ -25,7 +25,6 @@ struct ShadowRecord         // 40 bytes in three arrays
 struct WavefrontBuffers
 {
     uint4* s0; uint4* s1; uint4* s2; uint4* s3; uint4* s4;
-    uint4* s5;                      // watertight setup of the path's current scatter ray (traverse.cuh: packRaySetup), written with the ray
     float4* hits;                   // t,u,v,gid per path slot
     uint* rayQueue[2];              // path slots whose scatter ray is to be traced (ping-pong per iteration)
     uint* shadeQueue;               // kNumShadeClasses regions of `capacity` entries
