@@ -153,9 +153,10 @@ struct Traverser
         ws.ray[7][lane] = tmin; ws.ray[8][lane] = tmax;
         ws.bestKey[lane] = ((unsigned long long)__float_as_uint(tmax) << 32) | 0xFFFFFFFFull;
         const float eps = 1.0e-20f;     // keeps s * id * 2^15 finite for every node scale the builder emits
-        idx = 1.0f / (fabsf(d.x) > eps ? d.x : copysignf(eps, d.x));
-        idy = 1.0f / (fabsf(d.y) > eps ? d.y : copysignf(eps, d.y));
-        idz = 1.0f / (fabsf(d.z) > eps ? d.z : copysignf(eps, d.z));
+        // reciprocal directions feed the conservative box test only: the 1-ulp approximation is inside its slack
+        idx = __fdividef(1.0f, fabsf(d.x) > eps ? d.x : copysignf(eps, d.x));
+        idy = __fdividef(1.0f, fabsf(d.y) > eps ? d.y : copysignf(eps, d.y));
+        idz = __fdividef(1.0f, fabsf(d.z) > eps ? d.z : copysignf(eps, d.z));
         octinv = 7u - ((d.x < 0.0f ? 4u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 1u : 0u));
         sp = 0;
         nodeGroup = make_uint2(0u, 0x80000000u);        // virtual parent of the root: one internal child in slot 7^octinv
