@@ -1,10 +1,11 @@
-// render_gltf.cpp — a complete C++ host on top of the C ABI (include/rtxpt_b200.h): load a glTF with the library's loader, bridge its camera,
+// render_gltf.cpp — a complete C++ host on top of the C ABI (include/rtxpt_b200.h): load a glTF (or an RTXPT .scene.json) with the library's loader, bridge its camera,
 // fill the reference-mode constants, accumulate N samples on the GPU and write the RGBA32F accumulation as a PFM (and a tone-mapped PPM).
 // This is the standalone equivalent of Sample::Render -> PathTrace -> AccumulationPass for a static scene (Rtxpt/Sample.cpp:2184, :2438-2559).
 //   render_gltf scene.gltf out.pfm [width height samples bounces [materialsDir [sceneMaterialsDir]]]      (RTXPT .material.json overrides)
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 #include "rtxpt_b200.h"
 
@@ -18,7 +19,9 @@ int main(int argc, char** argv)
 
     rtxpt_host_scene* scene = nullptr;
     uint32_t overridden = 0;
-    if (rtxpt_b200_load_gltf_ex(argv[1], argc > 7 ? argv[7] : nullptr, argc > 8 ? argv[8] : nullptr, &scene, &overridden) != RTXPT_OK) return fail("load_gltf", nullptr);
+    const size_t len = strlen(argv[1]); const bool sceneFile = len > 11 && !strcmp(argv[1] + len - 11, ".scene.json");
+    if (sceneFile ? rtxpt_b200_load_scene_json(argv[1], nullptr, &scene) != RTXPT_OK      // RTXPT scene file: models, graph, lights, cameras, Materials/ overrides
+                  : rtxpt_b200_load_gltf_ex(argv[1], argc > 7 ? argv[7] : nullptr, argc > 8 ? argv[8] : nullptr, &scene, &overridden) != RTXPT_OK) return fail("load", nullptr);
     if (overridden) fprintf(stderr, "%u materials taken from .material.json files\n", overridden);
     uint32_t cameraCount = 1; RtxptGltfCamera gcam = {};
     rtxpt_b200_host_scene_cameras(scene, &gcam, &cameraCount);

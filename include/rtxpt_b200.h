@@ -340,11 +340,30 @@ typedef struct RtxptGltfCamera {        /* perspective cameras found in the node
     float position[3], direction[3], up[3];
     float yfov, znear, zfar, aspectRatio;   /* radians; aspectRatio 0 = unspecified */
 } RtxptGltfCamera;
+/* What an RTXPT .scene.json carries besides geometry (Assets/*.scene.json; Donut Scene::LoadSceneGraph, External/Donut/src/engine/Scene.cpp:230-360, and the
+ * leaf types of Rtxpt/SampleCommon/ExtendedScene.cpp:44-372): the environment light and the SampleSettings node.  All zero / empty for a plain glTF. */
+typedef struct RtxptSceneFileInfo {
+    char     environmentMapPath[260];   /* EnvironmentLight.path, relative to the media folder ('/' separators); "" = none */
+    float    environmentRadianceScale[3];
+    float    environmentRotation;       /* EnvironmentLight.rotation */
+    uint32_t hasSampleSettings;
+    uint32_t realtimeMode;              /* SampleSettings.realtimeMode (default true in the reference UI) */
+    int32_t  maxBounces, maxDiffuseBounces;     /* -1 = not given */
+    float    realtimeFireflyFilter, textureMIPBias;
+    char     startingCamera[64];
+    uint32_t modelCount, directionalLightCount; /* directional lights are folded into the environment map by the reference and are not in the light list */
+} RtxptSceneFileInfo;
 RTXPT_API int rtxpt_b200_load_gltf(const char* path, rtxpt_host_scene** outScene);
 /* Same, with RTXPT's material files applied on top of the glTF materials the way MaterialsBaker does (Rtxpt/Materials/MaterialsBaker.cpp:707-747, :868-917):
  * for a glTF material <name> of model file <model>.gltf the first existing of <sceneMaterialsDir>/<model>.<name>.material.json, <sceneMaterialsDir>/<name>.material.json,
  * <materialsDir>/<model>.<name>.material.json, <materialsDir>/<name>.material.json replaces it (either directory may be NULL). */
 RTXPT_API int rtxpt_b200_load_gltf_ex(const char* path, const char* materialsDir, const char* sceneMaterialsDir, rtxpt_host_scene** outScene, uint32_t* outOverriddenMaterials);
+/* RTXPT scene file: "models" (glTF paths relative to the media folder = the scene file's folder unless given), "graph" (named nodes with
+ * translation / rotation (xyzw) | euler / scaling, "model" references - a model may be instanced several times -, children, and the leaf types PointLight,
+ * SpotLight, DirectionalLight, EnvironmentLight, PerspectiveCamera[Ex], SampleSettings).  Material files are looked up under <media>/Materials and
+ * <media>/Materials/<scene file stem> like MaterialsBaker does.  Animations, named "parent" links and game props are not read. */
+RTXPT_API int rtxpt_b200_load_scene_json(const char* path, const char* mediaDir, rtxpt_host_scene** outScene);
+RTXPT_API int rtxpt_b200_host_scene_info(const rtxpt_host_scene* scene, RtxptSceneFileInfo* outInfo);
 RTXPT_API const char* rtxpt_b200_load_gltf_error(void);                 /* message of the last failed load on this thread */
 RTXPT_API const RtxptSceneDesc* rtxpt_b200_host_scene_desc(const rtxpt_host_scene* scene);
 RTXPT_API int rtxpt_b200_host_scene_cameras(const rtxpt_host_scene* scene, RtxptGltfCamera* outCameras, uint32_t* ioCount);

@@ -196,6 +196,8 @@ struct rtxpt_host_scene
     std::vector<std::vector<uint8_t>> blobs;            // index / vertex buffers and texture mips
     std::vector<RtxptGltfCamera> cameras;
     uint32_t triangleCount = 0;
+    std::vector<bool> alphaTested, excludeFromNEE, skipRender;       // per material, beside `materials`
+    RtxptSceneFileInfo info = {};                                    // .scene.json extras (environment light, settings); zero for plain glTF
 };
 
 namespace {
@@ -208,8 +210,7 @@ struct Loader
     rtxpt_host_scene* out = nullptr;
     std::map<std::pair<int, int>, uint32_t> textureSlot;        // (glTF image, sRGB) -> RtxptTextureDesc index
     std::string materialsDir, sceneMaterialsDir, modelName;     // RTXPT material overrides (Assets/Materials[/<scene>]); empty: none
-    std::vector<bool> excludeFromNEE, skipRender;
-    uint32_t overriddenMaterials = 0;
+    uint32_t overriddenMaterials = 0, materialBase = 0, bufferBase = 0;      // where this model's materials / buffers start in the shared scene
 
     // MaterialsBaker::Load search order (MaterialsBaker.cpp:707-747): scene-specialised folder first, then the shared one; <model>.<name> before <name>
     bool findMaterialFile(const std::string& name, std::string& text)
@@ -319,6 +320,7 @@ struct Loader
     {
         const JValue* mats = root.find("materials");
         const size_t n = mats ? mats->size() : 0;
+        materialBase = uint32_t(out->materials.size());
         for (size_t i = 0; i <= n; i++)
         {   // one extra record at the end: the glTF default material for primitives that name none
             static const JValue empty;
@@ -390,11 +392,10 @@ struct Loader
                 overriddenMaterials++;
             }
             out->materials.push_back(d);
-            alphaTested.push_back(alpha && d.BaseOrDiffuseTextureIndex != 0xFFFFFFFFu);
-            excludeFromNEE.push_back(noNEE); skipRender.push_back(skip);
+            out->alphaTested.push_back(alpha && d.BaseOrDiffuseTextureIndex != 0xFFFFFFFFu);
+            out->excludeFromNEE.push_back(noNEE); out->skipRender.push_back(skip);
         }
     }
-    std::vector<bool> alphaTested;
 
     // per-vertex tangents when the asset has none (GltfImporter.cpp:1331-1421): per-triangle tangent/bitangent from the UV gradients, summed
     // per vertex (vertex slot 0 of every triangle first, then slot 1, then slot 2), normalised, handedness from the bitangent
@@ -433,7 +434,7 @@ struct Loader
     void loadMeshes()
     {
         const JValue* ms = root.find("meshes"); if (!ms) return;
-        const uint32_t defaultMaterial = uint32_t(out->materials.size() - 1);
+        const uint32_t defaultMaterial = uint32_t(out->materials.size() - 1);      // the extra record loadMaterials appended for this model
         for (size_t mi = 0; mi < ms->size(); mi++)
         {
             std::vector<Primitive> prims;
@@ -478,7 +479,7 @@ struct Loader
                     pr.tangents.resize(size_t(pos.count) * 4); for (uint32_t v = 0; v < pos.count; v++) for (uint32_t c = 0; c < 4; c++) pr.tangents[4 * v + c] = component(t, v, c);
                 }
                 const int mat = p.integer("material", -1);
-                pr.material = (mat >= 0 && uint32_t(mat) < defaultMaterial) ? uint32_t(mat) : defaultMaterial;
+                pr.material = (mat >= 0 && materialBase + uint32_t(mat) < defaultMaterial) ? materialBase + uint32_t(mat) : defaultMaterial;
                 prims.push_back(std::move(pr));
             }
             meshes.push_back(std::move(prims));
@@ -488,6 +489,7 @@ struct Loader
     std::vector<uint32_t> meshFirstGeometry; std::vector<bool> meshHasUv;
     void buildBuffers()
     {
+        bufferBase = uint32_t(out->buffers.size());
         for (size_t mi = 0; mi < meshes.size(); mi++)
         {
             std::vector<Primitive>& prims = meshes[mi];
@@ -512,8 +514,8 @@ struct Loader
                     memcpy(&vblob[offNrm + (v0 + v) * 4], &pn, 4); memcpy(&vblob[offTan + (v0 + v) * 4], &pt, 4);
                 }
                 RtxptGeometryData g = {};
-                g.numIndices = skipRender[p.material] ? 0u : uint32_t(p.indices.size()); g.numVertices = uint32_t(n);      // SkipRender materials keep their slot and draw nothing
-                g.indexBufferIndex = int32_t(2 * mi); g.indexOffset = uint32_t(i0 * 4); g.vertexBufferIndex = int32_t(2 * mi + 1);
+                g.numIndices = out->skipRender[p.material] ? 0u : uint32_t(p.indices.size()); g.numVertices = uint32_t(n);      // SkipRender materials keep their slot and draw nothing
+                g.indexBufferIndex = int32_t(bufferBase + 2 * mi); g.indexOffset = uint32_t(i0 * 4); g.vertexBufferIndex = int32_t(bufferBase + 2 * mi + 1);
                 g.positionOffset = uint32_t(offPos + v0 * 12); g.prevPositionOffset = 0xFFFFFFFFu;
                 g.texCoord1Offset = hasUv ? uint32_t(offUv + v0 * 8) : 0xFFFFFFFFu; g.texCoord2Offset = 0xFFFFFFFFu;
                 g.normalOffset = uint32_t(offNrm + v0 * 4); g.tangentOffset = uint32_t(offTan + v0 * 4); g.curveRadiusOffset = 0xFFFFFFFFu;
@@ -561,9 +563,9 @@ struct Loader
                 const RtxptMaterialData& m = out->materials[g.materialIndex];
                 RtxptSubInstanceData s = {};
                 uint32_t fl = 0; float cutoff = 0.0f;
-                if (alphaTested[g.materialIndex] && g.texCoord1Offset != 0xFFFFFFFFu) { fl |= RTXPT_SUBINST_FLAG_ALPHA_TESTED | (m.BaseOrDiffuseTextureIndex & 0xFFFFu); cutoff = m.AlphaCutoff; }
+                if (out->alphaTested[g.materialIndex] && g.texCoord1Offset != 0xFFFFFFFFu) { fl |= RTXPT_SUBINST_FLAG_ALPHA_TESTED | (m.BaseOrDiffuseTextureIndex & 0xFFFFu); cutoff = m.AlphaCutoff; }
                 fl |= uint32_t(int(std::min(std::max(cutoff, 0.0f), 1.0f) * 255.0f + 0.5f)) << 24;
-                if (excludeFromNEE[g.materialIndex]) fl |= RTXPT_SUBINST_FLAG_EXCLUDE_FROM_NEE;
+                if (out->excludeFromNEE[g.materialIndex]) fl |= RTXPT_SUBINST_FLAG_EXCLUDE_FROM_NEE;
                 s.FlagsAndAlphaInfo = fl;
                 s.GlobalGeometryIndex_PTMaterialDataIndex = (gi << 16) | g.materialIndex;
                 s.EmissiveLightMappingOffset = 0xFFFFFFFFu; s.AnalyticProxyLightIndex = 0xFFFFFFFFu;
@@ -612,7 +614,8 @@ struct Loader
         if (const JValue* ch = n.find("children")) for (const JValue& c : ch->arr) visitNode(int(c.num), world, depth + 1);
     }
 
-    void load(const std::string& path)
+    // parses one model file and appends its materials, textures, meshes and buffers to the shared scene; instantiate() then places it
+    void open(const std::string& path)
     {
         const size_t slash = path.find_last_of("/\\");
         baseDir = (slash == std::string::npos) ? std::string() : path.substr(0, slash + 1);
@@ -647,29 +650,37 @@ struct Loader
             else failf("glTF: buffer %zu has no uri", i);
         }
         loadMaterials(); loadMeshes(); buildBuffers();
+    }
+    // emits the instances (and lights / cameras) of the model's default scene under `parent`; may be called several times (scene-graph instancing)
+    void instantiate(const Mat4& parent)
+    {
         const JValue* scenes = root.find("scenes");
         if (scenes && scenes->size())
         {
             const JValue& sc = scenes->arr[size_t(std::min<int>(root.integer("scene", 0), int(scenes->size()) - 1))];
-            if (const JValue* ns = sc.find("nodes")) for (const JValue& n : ns->arr) visitNode(int(n.num), identity(), 0);
+            if (const JValue* ns = sc.find("nodes")) for (const JValue& n : ns->arr) visitNode(int(n.num), parent, 0);
         }
         else if (const JValue* nodes = root.find("nodes"))
         {   // no scene: every root node (a node that is nobody's child)
             std::vector<bool> isChild(nodes->size(), false);
             for (const JValue& n : nodes->arr) if (const JValue* ch = n.find("children")) for (const JValue& c : ch->arr) if (size_t(c.num) < isChild.size()) isChild[size_t(c.num)] = true;
-            for (size_t i = 0; i < nodes->size(); i++) if (!isChild[i]) visitNode(int(i), identity(), 0);
+            for (size_t i = 0; i < nodes->size(); i++) if (!isChild[i]) visitNode(int(i), parent, 0);
         }
-        if (out->instances.empty()) failf("glTF: '%s' contains no mesh instances", path.c_str());
-        RtxptSceneDesc& d = out->desc;
-        d.instances = out->instances.data(); d.instanceCount = uint32_t(out->instances.size());
-        d.geometries = out->geometries.data(); d.geometryCount = uint32_t(out->geometries.size());
-        d.subInstances = out->subInstances.data(); d.subInstanceCount = uint32_t(out->subInstances.size());
-        d.materials = out->materials.data(); d.materialCount = uint32_t(out->materials.size());
-        d.buffers = out->buffers.data(); d.bufferCount = uint32_t(out->buffers.size());
-        d.textures = out->textures.data(); d.textureCount = uint32_t(out->textures.size());
-        d.lights = out->lights.data(); d.lightCount = uint32_t(out->lights.size());
     }
 };
+
+void finalizeScene(rtxpt_host_scene* out, const char* what)
+{
+    if (out->instances.empty()) failf("'%s' contains no mesh instances", what);
+    RtxptSceneDesc& d = out->desc;
+    d.instances = out->instances.data(); d.instanceCount = uint32_t(out->instances.size());
+    d.geometries = out->geometries.data(); d.geometryCount = uint32_t(out->geometries.size());
+    d.subInstances = out->subInstances.data(); d.subInstanceCount = uint32_t(out->subInstances.size());
+    d.materials = out->materials.data(); d.materialCount = uint32_t(out->materials.size());
+    d.buffers = out->buffers.data(); d.bufferCount = uint32_t(out->buffers.size());
+    d.textures = out->textures.data(); d.textureCount = uint32_t(out->textures.size());
+    d.lights = out->lights.data(); d.lightCount = uint32_t(out->lights.size());
+}
 
 thread_local std::string g_loaderError;
 
@@ -685,7 +696,7 @@ RTXPT_API int rtxpt_b200_load_gltf_ex(const char* path, const char* materialsDir
     auto asDir = [](const char* d) { std::string s = d ? d : ""; if (!s.empty() && s.back() != '/' && s.back() != '\\') s += '/'; return s; };
     try
     {
-        Loader l; l.out = scene.get(); l.materialsDir = asDir(materialsDir); l.sceneMaterialsDir = asDir(sceneMaterialsDir); l.load(path);
+        Loader l; l.out = scene.get(); l.materialsDir = asDir(materialsDir); l.sceneMaterialsDir = asDir(sceneMaterialsDir); l.open(path); l.instantiate(identity()); finalizeScene(scene.get(), path);
         if (outOverriddenMaterials) *outOverriddenMaterials = l.overriddenMaterials;
     }
     catch (const LoadError& e) { g_loaderError = e.msg; return RTXPT_ERR_INVALID_ARGUMENT; }
@@ -708,3 +719,143 @@ RTXPT_API uint32_t rtxpt_b200_host_scene_triangle_count(const rtxpt_host_scene* 
 RTXPT_API void rtxpt_b200_free_host_scene(rtxpt_host_scene* scene) { delete scene; }
 
 } // extern "C"
+
+// ---- RTXPT .scene.json ----------------------------------------------------------------------------------------------------------------------------------
+namespace {
+
+// Donut's JSON readers (src/core/json.cpp:200-262): a vector is taken from an array of exactly the right length, a lone number is broadcast, anything else
+// keeps the default — e.g. a 3-element "rotation" leaves the identity quaternion
+template <int N> void readVec(const JValue* v, double (&out)[N])
+{
+    if (!v) return;
+    if (v->type == JValue::Array && v->size() == size_t(N)) { for (int k = 0; k < N; k++) out[k] = v->arr[size_t(k)].num; }
+    else if (v->type == JValue::Number) { for (int k = 0; k < N; k++) out[k] = v->num; }
+}
+Mat4 trs(const double t[3], const double q[4], const double s[3])
+{
+    Mat4 m = identity();
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    const double R[9] = { 1 - 2 * (y * y + z * z), 2 * (x * y + z * w), 2 * (x * z - y * w),   2 * (x * y - z * w), 1 - 2 * (x * x + z * z), 2 * (y * z + x * w),
+                          2 * (x * z + y * w), 2 * (y * z - x * w), 1 - 2 * (x * x + y * y) };
+    for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) m.m[c * 4 + r] = R[c * 3 + r] * s[c];
+    m.m[12] = t[0]; m.m[13] = t[1]; m.m[14] = t[2];
+    return m;
+}
+
+struct SceneFileLoader
+{
+    rtxpt_host_scene* out = nullptr; std::string mediaDir, materialsDir, sceneMaterialsDir;
+    std::vector<std::unique_ptr<Loader>> models;
+
+    void visit(const JValue& list, const Mat4& parent, int depth)
+    {
+        if (list.type != JValue::Array) return;
+        if (depth > 64) failf("scene.json: graph is deeper than 64 levels");
+        for (const JValue& src : list.arr)
+        {
+            if (src.type != JValue::Object) continue;
+            double t[3] = { 0, 0, 0 }, q[4] = { 0, 0, 0, 1 }, s[3] = { 1, 1, 1 };
+            readVec(src.find("translation"), t);
+            if (src.find("rotation")) readVec(src.find("rotation"), q);
+            else if (const JValue* e = src.find("euler"))
+            {   // rotationQuat(euler) = qZ * qY * qX (donut/core/math/quat.h:398-414)
+                double eu[3] = { 0, 0, 0 }; readVec(e, eu);
+                const double sx = std::sin(0.5 * eu[0]), cx = std::cos(0.5 * eu[0]), sy = std::sin(0.5 * eu[1]), cy = std::cos(0.5 * eu[1]), sz = std::sin(0.5 * eu[2]), cz = std::cos(0.5 * eu[2]);
+                auto qmul = [](const double a[4], const double b[4], double r[4]) {      // xyzw
+                    r[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1]; r[1] = a[3] * b[1] - a[0] * b[2] + a[1] * b[3] + a[2] * b[0];
+                    r[2] = a[3] * b[2] + a[0] * b[1] - a[1] * b[0] + a[2] * b[3]; r[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2]; };
+                const double qx[4] = { sx, 0, 0, cx }, qy[4] = { 0, sy, 0, cy }, qz[4] = { 0, 0, sz, cz }; double zy[4]; qmul(qz, qy, zy); qmul(zy, qx, q);
+            }
+            readVec(src.find("scaling"), s);
+            const Mat4 world = mul(parent, trs(t, q, s));
+            if (const JValue* mj = src.find("model"))
+            {
+                const int mi = (mj->type == JValue::Number) ? int(mj->num) : -1;
+                if (mi < 0 || size_t(mi) >= models.size()) failf("scene.json: node '%s' references model %d, which is not in the model array", src.string("name").c_str(), mi);
+                models[size_t(mi)]->instantiate(world);
+            }
+            if (const JValue* ch = src.find("children")) visit(*ch, world, depth + 1);
+            const std::string type = src.string("type");
+            if (type == "PointLight" || type == "SpotLight")
+            {
+                RtxptLightDesc d = {};
+                d.type = type == "SpotLight" ? RTXPT_LIGHT_SPOT : RTXPT_LIGHT_POINT;
+                d.position[0] = float(world.m[12]); d.position[1] = float(world.m[13]); d.position[2] = float(world.m[14]);
+                for (int k = 0; k < 3; k++) d.direction[k] = float(-world.m[8 + k]);       // Light::GetDirection = -normalize(localToWorld.row2) (SceneTypes.cpp:67-75)
+                double c[3] = { 1, 1, 1 }; readVec(src.find("color"), c); d.color[0] = float(c[0]); d.color[1] = float(c[1]); d.color[2] = float(c[2]);
+                d.intensity = float(src.number("intensity", 1.0)); d.radius = float(src.number("radius", 0.0));
+                d.innerAngle = float(src.number("innerAngle", 180.0)); d.outerAngle = float(src.number("outerAngle", 180.0));     // degrees (SceneTypes.h defaults)
+                out->lights.push_back(d);
+            }
+            else if (type == "DirectionalLight") out->info.directionalLightCount++;
+            else if (type == "EnvironmentLight")
+            {
+                std::string p = src.string("path"); for (char& ch : p) if (ch == '\\') ch = '/';
+                strncpy(out->info.environmentMapPath, p.c_str(), sizeof(out->info.environmentMapPath) - 1);
+                double rs[3] = { 1, 1, 1 }; readVec(src.find("radianceScale"), rs); for (int k = 0; k < 3; k++) out->info.environmentRadianceScale[k] = float(rs[k]);
+                double rot[1] = { 0 }; readVec(src.find("rotation"), rot); out->info.environmentRotation = float(rot[0]);
+            }
+            else if (type == "PerspectiveCamera" || type == "PerspectiveCameraEx")
+            {   // SceneCamera::GetViewToWorldMatrix flips z: the camera looks down the node's -Z with +Y up (SceneGraph.cpp:133-140, Sample.cpp:459-461)
+                RtxptGltfCamera c = {};
+                c.position[0] = float(world.m[12]); c.position[1] = float(world.m[13]); c.position[2] = float(world.m[14]);
+                for (int k = 0; k < 3; k++) { c.direction[k] = float(-world.m[8 + k]); c.up[k] = float(world.m[4 + k]); }
+                c.yfov = float(src.number("verticalFov", 1.0)); c.znear = float(src.number("zNear", 1.0)); c.zfar = float(src.number("zFar", 0.0)); c.aspectRatio = float(src.number("aspectRatio", 0.0));
+                out->cameras.push_back(c);
+            }
+            else if (type == "SampleSettings")
+            {
+                RtxptSceneFileInfo& i = out->info; i.hasSampleSettings = 1;
+                const JValue* rt = src.find("realtimeMode"); i.realtimeMode = (rt && rt->type == JValue::Bool) ? (rt->b ? 1u : 0u) : 1u;
+                i.maxBounces = src.integer("maxBounces", -1); i.maxDiffuseBounces = src.integer("maxDiffuseBounces", -1);
+                i.realtimeFireflyFilter = float(src.number("realtimeFireflyFilter", 0.0)); i.textureMIPBias = float(src.number("textureMIPBias", 0.0));
+                strncpy(i.startingCamera, src.string("startingCamera").c_str(), sizeof(i.startingCamera) - 1);
+            }
+        }
+    }
+
+    void load(const std::string& path, const char* media)
+    {
+        const size_t slash = path.find_last_of("/\\");
+        mediaDir = media && *media ? std::string(media) : (slash == std::string::npos ? std::string() : path.substr(0, slash + 1));
+        if (!mediaDir.empty() && mediaDir.back() != '/' && mediaDir.back() != '\\') mediaDir += '/';
+        std::string stem = path.substr(slash == std::string::npos ? 0 : slash + 1); { const size_t dot = stem.find_last_of('.'); if (dot != std::string::npos) stem.erase(dot); }     // "x.scene.json" -> "x.scene"
+        materialsDir = mediaDir + "Materials/"; sceneMaterialsDir = materialsDir + stem + "/";
+        const std::vector<uint8_t> file = readFile(path);
+        JParser jp{ reinterpret_cast<const char*>(file.data()), reinterpret_cast<const char*>(file.data()) + file.size() };
+        const JValue root = jp.parse();
+        if (root.type != JValue::Object) failf("scene.json: top level is not an object");
+        if (const JValue* ms = root.find("models")) for (const JValue& m : ms->arr)
+        {
+            std::string rel = m.type == JValue::String ? m.str : std::string(); for (char& ch : rel) if (ch == '\\') ch = '/';
+            std::unique_ptr<Loader> l(new Loader()); l->out = out; l->materialsDir = materialsDir; l->sceneMaterialsDir = sceneMaterialsDir;
+            l->open(mediaDir + rel);
+            models.push_back(std::move(l));
+        }
+        out->info.modelCount = uint32_t(models.size());
+        out->info.environmentRadianceScale[0] = out->info.environmentRadianceScale[1] = out->info.environmentRadianceScale[2] = 1.0f;
+        out->info.maxBounces = out->info.maxDiffuseBounces = -1;
+        if (const JValue* g = root.find("graph")) visit(*g, identity(), 0);
+        finalizeScene(out, path.c_str());
+    }
+};
+
+} // namespace
+
+extern "C" RTXPT_API int rtxpt_b200_load_scene_json(const char* path, const char* mediaDir, rtxpt_host_scene** outScene)
+{
+    if (!path || !outScene) { g_loaderError = "null argument"; return RTXPT_ERR_INVALID_ARGUMENT; }
+    *outScene = nullptr;
+    std::unique_ptr<rtxpt_host_scene> scene(new rtxpt_host_scene());
+    try { SceneFileLoader l; l.out = scene.get(); l.load(path, mediaDir); }
+    catch (const LoadError& e) { g_loaderError = e.msg; return RTXPT_ERR_INVALID_ARGUMENT; }
+    catch (const std::exception& e) { g_loaderError = e.what(); return RTXPT_ERR_INVALID_ARGUMENT; }
+    *outScene = scene.release();
+    return RTXPT_OK;
+}
+extern "C" RTXPT_API int rtxpt_b200_host_scene_info(const rtxpt_host_scene* scene, RtxptSceneFileInfo* outInfo)
+{
+    if (!scene || !outInfo) return RTXPT_ERR_INVALID_ARGUMENT;
+    *outInfo = scene->info;
+    return RTXPT_OK;
+}

@@ -49,7 +49,7 @@ _SIGNATURES = {
     "rtxpt_b200_debug_bsdf": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
     "rtxpt_b200_debug_rng": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
 }
-_LOADER_SYMBOLS = ["rtxpt_b200_load_gltf", "rtxpt_b200_load_gltf_ex", "rtxpt_b200_load_gltf_error", "rtxpt_b200_host_scene_desc", "rtxpt_b200_host_scene_cameras",
+_LOADER_SYMBOLS = ["rtxpt_b200_load_gltf", "rtxpt_b200_load_gltf_ex", "rtxpt_b200_load_scene_json", "rtxpt_b200_host_scene_info", "rtxpt_b200_load_gltf_error", "rtxpt_b200_host_scene_desc", "rtxpt_b200_host_scene_cameras",
                    "rtxpt_b200_host_scene_triangle_count", "rtxpt_b200_free_host_scene", "rtxpt_b200_bridge_camera", "rtxpt_b200_default_constants", "rtxpt_b200_debug_bvh_stats", "rtxpt_b200_parse_material_json", "rtxpt_b200_parse_material_json_error"]
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["rtxpt_b200_last_error"] + _LOADER_SYMBOLS)
 
@@ -109,12 +109,16 @@ def parse_material_json(text, strict=None):
 class GltfScene:
     """A scene loaded by the library's host-side glTF loader (no GPU needed).  `.desc` is the RtxptSceneDesc to hand to Context.upload_scene
     (or to the oracle); `.cameras` lists the perspective cameras of the file."""
-    def __init__(self, path, strict=None, materials_dir=None, scene_materials_dir=None):
+    def __init__(self, path, strict=None, materials_dir=None, scene_materials_dir=None, media_dir=None):
         self.L = load(strict)
         h = C.c_void_p(); n = C.c_uint32(0)
         self.L.rtxpt_b200_load_gltf_ex.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]; self.L.rtxpt_b200_load_gltf_ex.restype = C.c_int
         enc = lambda p: None if p is None else os.fsencode(p)
-        rc = self.L.rtxpt_b200_load_gltf_ex(os.fsencode(path), enc(materials_dir), enc(scene_materials_dir), C.byref(h), C.byref(n))
+        if str(path).endswith(".scene.json"):       # RTXPT scene file: models + graph + lights / cameras / settings; material files under <media>/Materials
+            self.L.rtxpt_b200_load_scene_json.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]; self.L.rtxpt_b200_load_scene_json.restype = C.c_int
+            rc = self.L.rtxpt_b200_load_scene_json(os.fsencode(path), enc(media_dir), C.byref(h))
+        else:
+            rc = self.L.rtxpt_b200_load_gltf_ex(os.fsencode(path), enc(materials_dir), enc(scene_materials_dir), C.byref(h), C.byref(n))
         self.overridden_materials = n.value
         if rc != 0:
             raise RtxptError("glTF load failed: " + self.L.rtxpt_b200_load_gltf_error().decode())
@@ -124,6 +128,7 @@ class GltfScene:
         cams = (S.GltfCamera * max(1, n.value))(); self.L.rtxpt_b200_host_scene_cameras(h, cams, C.byref(n))
         self.cameras = [cams[i] for i in range(n.value)]
         self.triangle_count = self.L.rtxpt_b200_host_scene_triangle_count(h)
+        self.info = S.SceneFileInfo(); self.L.rtxpt_b200_host_scene_info.argtypes = [C.c_void_p, C.POINTER(S.SceneFileInfo)]; self.L.rtxpt_b200_host_scene_info(h, C.byref(self.info))
         self.material_count = self.desc.materialCount
         self.has_env = False
 

@@ -101,6 +101,12 @@ class BvhStats(C.Structure):
                 ("buildSeconds", f32), ("_pad", f32)]
 
 
+class SceneFileInfo(C.Structure):
+    _fields_ = [("environmentMapPath", C.c_char * 260), ("environmentRadianceScale", f32 * 3), ("environmentRotation", f32), ("hasSampleSettings", u32), ("realtimeMode", u32),
+                ("maxBounces", C.c_int32), ("maxDiffuseBounces", C.c_int32), ("realtimeFireflyFilter", f32), ("textureMIPBias", f32), ("startingCamera", C.c_char * 64),
+                ("modelCount", u32), ("directionalLightCount", u32)]
+
+
 class GltfCamera(C.Structure):
     _fields_ = [("position", f32 * 3), ("direction", f32 * 3), ("up", f32 * 3), ("yfov", f32), ("znear", f32), ("zfar", f32), ("aspectRatio", f32)]
 
