@@ -340,7 +340,7 @@ typedef struct RtxptGltfCamera {        /* perspective cameras found in the node
     float position[3], direction[3], up[3];
     float yfov, znear, zfar, aspectRatio;   /* radians; aspectRatio 0 = unspecified */
 } RtxptGltfCamera;
-/* What an RTXPT .scene.json carries besides geometry (Assets/*.scene.json; Donut Scene::LoadSceneGraph, External/Donut/src/engine/Scene.cpp:230-360, and the
+/* What an RTXPT .scene.json carries besides geometry (Assets/<name>.scene.json; Donut Scene::LoadSceneGraph, External/Donut/src/engine/Scene.cpp:230-360, and the
  * leaf types of Rtxpt/SampleCommon/ExtendedScene.cpp:44-372): the environment light and the SampleSettings node.  All zero / empty for a plain glTF. */
 typedef struct RtxptSceneFileInfo {
     char     environmentMapPath[260];   /* EnvironmentLight.path, relative to the media folder ('/' separators); "" = none */
@@ -415,6 +415,12 @@ RTXPT_API int rtxpt_b200_get_lights(rtxpt_ctx* ctx, void* outLightInfos, uint32_
 /* PolymorphicLightInfoEx (16 B each: IesProfileIndex, PrimaryAxis, CosConeAngleAndSoftness, UniqueID) of the analytic lights, which
  * occupy light indices [5368, 5368 + count) between the environment quad-tree nodes and the emissive triangles. */
 RTXPT_API int rtxpt_b200_get_lights_ex(rtxpt_ctx* ctx, void* outLightInfoEx, uint32_t* ioAnalyticLightCount);
+
+/* Host-only: decodes one mip of a DDS file held in memory (BC1/2/3/4/5/7, RGBA8, BGRA8) into RGBA8 - what the loaders do with the DDS textures
+ * RTXPT's assets and material files reference.  outRGBA may be NULL to query the size. */
+RTXPT_API int rtxpt_b200_debug_decode_dds(const void* fileBytes, uint64_t fileSize, uint32_t mip, uint32_t* outWidth, uint32_t* outHeight, uint32_t* outMipCount, uint32_t* outSrgb,
+                                          uint8_t* outRGBA, uint64_t outCapacity);
+RTXPT_API const char* rtxpt_b200_debug_decode_dds_error(void);
 
 /* Host-only: builds the compressed wide BVH over a triangle soup (9 floats per triangle) and reports its surface-area-heuristic statistics:
  * expected node visits / triangle tests of a random ray that hits the root box.  Used to judge builder changes without a GPU. */

@@ -26,7 +26,11 @@
 #include "json_min.h"
 
 using namespace rtxpt_host;
-namespace rtxpt_host { void materialFromJson(const JValue& j, RtxptMaterialJsonInfo& out); }      // material_json.cpp
+namespace rtxpt_host {
+void materialFromJson(const JValue& j, RtxptMaterialJsonInfo& out);       // material_json.cpp
+struct DdsImage { uint32_t width = 0, height = 0; bool srgb = false; std::vector<std::vector<uint8_t>> mips; };
+DdsImage decodeDds(const uint8_t* data, size_t size, const char* name);   // dds.cpp
+}
 
 namespace {
 
@@ -52,6 +56,13 @@ std::vector<uint8_t> base64(const char* s, size_t n)
     }
     return out;
 }
+std::string uriToPath(const std::string& uri, const std::string& baseDir)
+{
+    std::string decoded;        // percent-decoding of file URIs
+    for (size_t i = 0; i < uri.size(); i++)
+        if (uri[i] == '%' && i + 2 < uri.size()) { decoded += char(strtoul(uri.substr(i + 1, 2).c_str(), nullptr, 16)); i += 2; } else decoded += uri[i];
+    return baseDir + decoded;
+}
 std::vector<uint8_t> resolveUri(const std::string& uri, const std::string& baseDir)
 {
     if (uri.rfind("data:", 0) == 0)
@@ -59,10 +70,19 @@ std::vector<uint8_t> resolveUri(const std::string& uri, const std::string& baseD
         const size_t comma = uri.find(','); if (comma == std::string::npos) failf("glTF: malformed data URI");
         return base64(uri.c_str() + comma + 1, uri.size() - comma - 1);
     }
-    std::string decoded;        // percent-decoding of file URIs
-    for (size_t i = 0; i < uri.size(); i++)
-        if (uri[i] == '%' && i + 2 < uri.size()) { decoded += char(strtoul(uri.substr(i + 1, 2).c_str(), nullptr, 16)); i += 2; } else decoded += uri[i];
-    return readFile(baseDir + decoded);
+    return readFile(uriToPath(uri, baseDir));
+}
+bool fileExists(const std::string& path) { FILE* f = fopen(path.c_str(), "rb"); if (f) fclose(f); return f != nullptr; }
+// "<name>.png" -> "<name>.dds" when that file exists: both the glTF importer (GltfImporter.cpp:652-654, 786-796) and the material reader
+// (MaterialsBaker.cpp:179-192) prefer a block-compressed sibling of an uncompressed image
+std::string preferDdsSibling(const std::string& path, bool pngOnly)
+{
+    const size_t dot = path.find_last_of('.'), slash = path.find_last_of("/\\");
+    if (dot == std::string::npos || (slash != std::string::npos && dot < slash)) return path;
+    std::string ext = path.substr(dot); for (char& c : ext) c = char(tolower(c));
+    if (ext == ".dds" || (pngOnly && ext != ".png")) return path;
+    const std::string dds = path.substr(0, dot) + ".dds";
+    return fileExists(dds) ? dds : path;
 }
 
 // ---- PNG (8/16-bit, colour types 0/2/3/4/6, non-interlaced) -> RGBA8 --------------------------------------------------------------------------------
@@ -208,8 +228,9 @@ struct Loader
 {
     std::string baseDir; JValue root; std::vector<std::vector<uint8_t>> bufferData; std::vector<uint8_t> glbBin;
     rtxpt_host_scene* out = nullptr;
-    std::map<std::pair<int, int>, uint32_t> textureSlot;        // (glTF image, sRGB) -> RtxptTextureDesc index
+    std::map<std::pair<std::string, int>, uint32_t> textureSlot;        // (image source, sRGB) -> RtxptTextureDesc index
     std::string materialsDir, sceneMaterialsDir, modelName;     // RTXPT material overrides (Assets/Materials[/<scene>]); empty: none
+    std::string mediaDir;                                       // what the texture paths of material files are relative to (Assets/)
     uint32_t overriddenMaterials = 0, materialBase = 0, bufferBase = 0;      // where this model's materials / buffers start in the shared scene
 
     // MaterialsBaker::Load search order (MaterialsBaker.cpp:707-747): scene-specialised folder first, then the shared one; <model>.<name> before <name>
@@ -276,44 +297,83 @@ struct Loader
         failf("glTF: index component type %u is not supported", a.componentType);
     }
 
-    // ---- textures: one RtxptTextureDesc per (image, colour space) in order of first use by the materials ---------------------------------------------
+    // ---- textures: one RtxptTextureDesc per (source, colour space) in order of first use by the materials ----------------------------------------------
+    // PNG files get a generated mip chain; DDS files (BC1-5, BC7, RGBA8) are decoded to RGBA8 with the mips they carry (dds.cpp)
+    uint32_t registerTexture(const std::string& key, bool srgb, const std::vector<uint8_t>& bytes, const std::string& name)
+    {
+        std::vector<std::vector<uint8_t>> mips; uint32_t w, h;
+        if (bytes.size() >= 4 && memcmp(bytes.data(), "DDS ", 4) == 0)
+        {
+            DdsImage dds = decodeDds(bytes.data(), bytes.size(), name.c_str());
+            w = dds.width; h = dds.height; mips = std::move(dds.mips);
+        }
+        else
+        {
+            Image img = decodePng(bytes, name.c_str());
+            std::vector<std::pair<uint32_t, uint32_t>> dims;
+            mips = makeMips(img, dims); w = img.w; h = img.h;
+        }
+        if (mips.size() > 16) failf("texture '%s' is larger than 32768 texels per side", name.c_str());
+        RtxptTextureDesc d = {};
+        d.width = w; d.height = h; d.mipLevels = uint32_t(mips.size()); d.format = srgb ? RTXPT_FORMAT_RGBA8_SRGB : RTXPT_FORMAT_RGBA8_UNORM;
+        for (size_t m = 0; m < mips.size(); m++) { out->blobs.push_back(std::move(mips[m])); d.mips[m] = out->blobs.back().data(); }
+        const uint32_t slot = uint32_t(out->textures.size()); out->textures.push_back(d); textureSlot[std::make_pair(key, srgb ? 1 : 0)] = slot;
+        return slot;
+    }
+    uint32_t packedTextureIndex(uint32_t slot) const
+    {   // the packed index of MaterialsBaker (baseLOD << 24 | mipLevels << 16 | bindless index)
+        const RtxptTextureDesc& d = out->textures[slot];
+        const uint32_t baseLod = uint32_t(std::log2(float(d.width) * float(d.height)) + 0.5f);       // MaterialsBaker.cpp:499-501
+        return (baseLod << 24) | (d.mipLevels << 16) | slot;
+    }
+    uint32_t imageTexture(int imgIndex, bool srgb, bool searchForDds)
+    {
+        const JValue& im = arrayItem("images", imgIndex);
+        std::vector<uint8_t> bytes; std::string name = im.string("uri", "<bufferView image>"), key = "image:" + std::to_string(imgIndex);
+        const bool isFile = im.find("uri") && name.rfind("data:", 0) != 0;
+        if (isFile)
+        {
+            std::string path = uriToPath(name, baseDir);
+            if (searchForDds) path = preferDdsSibling(path, false);
+            key = "file:" + path; name = path;
+        }
+        auto it = textureSlot.find(std::make_pair(key, srgb ? 1 : 0));
+        if (it != textureSlot.end()) return it->second;
+        if (isFile) bytes = readFile(name);
+        else if (im.find("uri")) { bytes = resolveUri(im.at("uri").str, baseDir); name = "<data URI>"; }
+        else
+        {
+            const JValue& bv = arrayItem("bufferViews", im.integer("bufferView", -1));
+            const std::vector<uint8_t>& buf = bufferData.at(size_t(bv.integer("buffer", 0)));
+            const size_t o = size_t(bv.number("byteOffset", 0)), n = size_t(bv.number("byteLength", 0));
+            if (o + n > buf.size()) failf("glTF: image bufferView out of range");
+            bytes.assign(buf.begin() + o, buf.begin() + o + n);
+        }
+        return registerTexture(key, srgb, bytes, name);
+    }
     uint32_t textureInfo(const JValue* texRef, bool srgb)
-    {   // returns the packed index of MaterialsBaker (baseLOD << 24 | mipLevels << 16 | bindless index), 0xFFFFFFFF when absent
+    {   // 0xFFFFFFFF when absent
         if (!texRef) return 0xFFFFFFFFu;
         const int texIndex = texRef->integer("index", -1); if (texIndex < 0) return 0xFFFFFFFFu;
         if (texRef->integer("texCoord", 0) != 0) failf("glTF: only TEXCOORD_0 is supported for material textures");
         const JValue& tex = arrayItem("textures", texIndex);
-        const int imgIndex = tex.integer("source", -1); if (imgIndex < 0) failf("glTF: texture %d has no PNG source (extension-only images are not supported)", texIndex);
-        auto key = std::make_pair(imgIndex, srgb ? 1 : 0);
-        auto it = textureSlot.find(key);
-        uint32_t slot;
-        if (it != textureSlot.end()) slot = it->second;
-        else
-        {
-            const JValue& im = arrayItem("images", imgIndex);
-            std::vector<uint8_t> bytes; std::string name = im.string("uri", "<bufferView image>");
-            if (im.find("uri")) bytes = resolveUri(im.at("uri").str, baseDir);
-            else
-            {
-                const JValue& bv = arrayItem("bufferViews", im.integer("bufferView", -1));
-                const std::vector<uint8_t>& buf = bufferData.at(size_t(bv.integer("buffer", 0)));
-                const size_t o = size_t(bv.number("byteOffset", 0)), n = size_t(bv.number("byteLength", 0));
-                if (o + n > buf.size()) failf("glTF: image bufferView out of range");
-                bytes.assign(buf.begin() + o, buf.begin() + o + n);
-            }
-            if (name.rfind("data:", 0) == 0) name = "<data URI>";
-            Image img = decodePng(bytes, name.c_str());
-            std::vector<std::pair<uint32_t, uint32_t>> dims;
-            std::vector<std::vector<uint8_t>> mips = makeMips(img, dims);
-            if (mips.size() > 16) failf("texture '%s' is larger than 32768 texels per side", name.c_str());
-            RtxptTextureDesc d = {};
-            d.width = img.w; d.height = img.h; d.mipLevels = uint32_t(mips.size()); d.format = srgb ? RTXPT_FORMAT_RGBA8_SRGB : RTXPT_FORMAT_RGBA8_UNORM;
-            for (size_t m = 0; m < mips.size(); m++) { out->blobs.push_back(std::move(mips[m])); d.mips[m] = out->blobs.back().data(); }
-            slot = uint32_t(out->textures.size()); out->textures.push_back(d); textureSlot[key] = slot;
-        }
-        const RtxptTextureDesc& d = out->textures[slot];
-        const uint32_t baseLod = uint32_t(std::log2(float(d.width) * float(d.height)) + 0.5f);       // MaterialsBaker.cpp:499-501
-        return (baseLod << 24) | (d.mipLevels << 16) | slot;
+        // an MSFT_texture_dds image wins over the plain source (GltfImporter.cpp:853-860); a plain file source is swapped for its .dds sibling when one exists
+        int ddsIndex = -1;
+        if (const JValue* e = tex.find("extensions")) if (const JValue* d = e->find("MSFT_texture_dds")) ddsIndex = d->integer("source", -1);
+        const int imgIndex = tex.integer("source", -1);
+        if (ddsIndex < 0 && imgIndex < 0) failf("glTF: texture %d has neither a PNG nor a DDS source", texIndex);
+        return packedTextureIndex(ddsIndex >= 0 ? imageTexture(ddsIndex, srgb, false) : imageTexture(imgIndex, srgb, true));
+    }
+    // a texture named by an RTXPT material file: path relative to the media folder, .png swapped for a .dds sibling (MaterialsBaker.cpp:159-195)
+    uint32_t materialFileTexture(const char* localPath, bool srgb)
+    {
+        if (mediaDir.empty() || !localPath[0]) return 0xFFFFFFFFu;
+        const std::string path = preferDdsSibling(mediaDir + localPath, true);
+        const std::string key = "file:" + path;
+        auto it = textureSlot.find(std::make_pair(key, srgb ? 1 : 0));
+        if (it != textureSlot.end()) return packedTextureIndex(it->second);
+        if (!fileExists(path)) return 0xFFFFFFFFu;
+        return packedTextureIndex(registerTexture(key, srgb, readFile(path), path));
     }
 
     void loadMaterials()
@@ -379,15 +439,21 @@ struct Loader
             bool alpha = alphaMode == "MASK", noNEE = false, skip = false;
             std::string overrideText;
             if (i < n && findMaterialFile(m.string("name"), overrideText))
-            {   // the RTXPT material file wins over the glTF material (MaterialsBaker.cpp:868-917); its textures are DDS files this loader cannot
-                // decode, so a slot keeps the glTF texture where the file enables that slot and drops it where the file disables it
+            {   // the RTXPT material file wins over the glTF material (MaterialsBaker.cpp:868-917), textures included: a slot the file enables takes
+                // the file's texture (PNG or DDS under the media folder); only when that file is absent does the slot keep the glTF texture
                 JParser jp{ overrideText.data(), overrideText.data() + overrideText.size() };
                 RtxptMaterialJsonInfo info; materialFromJson(jp.parse(), info);
                 const uint32_t texIdx[5] = { d.BaseOrDiffuseTextureIndex, d.MetalRoughOrSpecularTextureIndex, d.NormalTextureIndex, d.EmissiveTextureIndex, 0xFFFFFFFFu };
                 const uint32_t texBit[5] = { RTXPT_MATFLAG_UseBaseOrDiffuseTexture, RTXPT_MATFLAG_UseMetalRoughOrSpecularTexture, RTXPT_MATFLAG_UseNormalTexture, RTXPT_MATFLAG_UseEmissiveTexture, RTXPT_MATFLAG_UseTransmissionTexture };
                 d = info.data;
                 uint32_t* slots[5] = { &d.BaseOrDiffuseTextureIndex, &d.MetalRoughOrSpecularTextureIndex, &d.NormalTextureIndex, &d.EmissiveTextureIndex, &d.TransmissionTextureIndex };
-                for (int t = 0; t < 5; t++) if (info.textureEnabled[t] && texIdx[t] != 0xFFFFFFFFu) { *slots[t] = texIdx[t]; d.Flags |= texBit[t]; }
+                for (int t = 0; t < 5; t++)
+                {
+                    if (!info.textureEnabled[t]) continue;
+                    uint32_t idx = materialFileTexture(info.texturePath[t], info.textureSRGB[t] != 0);
+                    if (idx == 0xFFFFFFFFu) idx = texIdx[t];
+                    if (idx != 0xFFFFFFFFu) { *slots[t] = idx; d.Flags |= texBit[t]; }
+                }
                 alpha = info.enableAlphaTesting != 0; noNEE = info.excludeFromNEE != 0; skip = info.skipRender != 0;
                 overriddenMaterials++;
             }
@@ -694,9 +760,11 @@ RTXPT_API int rtxpt_b200_load_gltf_ex(const char* path, const char* materialsDir
     *outScene = nullptr;
     std::unique_ptr<rtxpt_host_scene> scene(new rtxpt_host_scene());
     auto asDir = [](const char* d) { std::string s = d ? d : ""; if (!s.empty() && s.back() != '/' && s.back() != '\\') s += '/'; return s; };
+    // ".../Assets/Materials/" -> ".../Assets/": the media folder the texture paths of material files are relative to (MaterialsBaker.cpp:857-860)
+    auto parentDir = [](const std::string& dir) { if (dir.size() < 2) return std::string(); const size_t cut = dir.find_last_of("/\\", dir.size() - 2); return cut == std::string::npos ? std::string("./") : dir.substr(0, cut + 1); };
     try
     {
-        Loader l; l.out = scene.get(); l.materialsDir = asDir(materialsDir); l.sceneMaterialsDir = asDir(sceneMaterialsDir); l.open(path); l.instantiate(identity()); finalizeScene(scene.get(), path);
+        Loader l; l.out = scene.get(); l.materialsDir = asDir(materialsDir); l.sceneMaterialsDir = asDir(sceneMaterialsDir); l.mediaDir = parentDir(l.materialsDir); l.open(path); l.instantiate(identity()); finalizeScene(scene.get(), path);
         if (outOverriddenMaterials) *outOverriddenMaterials = l.overriddenMaterials;
     }
     catch (const LoadError& e) { g_loaderError = e.msg; return RTXPT_ERR_INVALID_ARGUMENT; }
@@ -828,7 +896,7 @@ struct SceneFileLoader
         if (const JValue* ms = root.find("models")) for (const JValue& m : ms->arr)
         {
             std::string rel = m.type == JValue::String ? m.str : std::string(); for (char& ch : rel) if (ch == '\\') ch = '/';
-            std::unique_ptr<Loader> l(new Loader()); l->out = out; l->materialsDir = materialsDir; l->sceneMaterialsDir = sceneMaterialsDir;
+            std::unique_ptr<Loader> l(new Loader()); l->out = out; l->materialsDir = materialsDir; l->sceneMaterialsDir = sceneMaterialsDir; l->mediaDir = mediaDir;
             l->open(mediaDir + rel);
             models.push_back(std::move(l));
         }

@@ -50,7 +50,7 @@ _SIGNATURES = {
     "rtxpt_b200_debug_rng": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
 }
 _LOADER_SYMBOLS = ["rtxpt_b200_load_gltf", "rtxpt_b200_load_gltf_ex", "rtxpt_b200_load_scene_json", "rtxpt_b200_host_scene_info", "rtxpt_b200_load_gltf_error", "rtxpt_b200_host_scene_desc", "rtxpt_b200_host_scene_cameras",
-                   "rtxpt_b200_host_scene_triangle_count", "rtxpt_b200_free_host_scene", "rtxpt_b200_bridge_camera", "rtxpt_b200_default_constants", "rtxpt_b200_debug_bvh_stats", "rtxpt_b200_parse_material_json", "rtxpt_b200_parse_material_json_error"]
+                   "rtxpt_b200_host_scene_triangle_count", "rtxpt_b200_free_host_scene", "rtxpt_b200_bridge_camera", "rtxpt_b200_default_constants", "rtxpt_b200_debug_bvh_stats", "rtxpt_b200_parse_material_json", "rtxpt_b200_parse_material_json_error", "rtxpt_b200_debug_decode_dds", "rtxpt_b200_debug_decode_dds_error"]
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["rtxpt_b200_last_error"] + _LOADER_SYMBOLS)
 
 
@@ -94,6 +94,19 @@ def bvh_stats(triangle_vertices, strict=None):
     if L.rtxpt_b200_debug_bvh_stats(v.ctypes.data, len(v), C.byref(st)) != 0:
         raise RtxptError("bvh_stats failed")
     return st
+
+
+def decode_dds(file_bytes, mip=0, strict=None):
+    """DDS file bytes -> (HxWx4 uint8 RGBA of `mip`, mip count, srgb flag), host only."""
+    L = load(strict); w, h, n, srgb = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+    f = L.rtxpt_b200_debug_decode_dds; f.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_void_p, C.c_uint64]; f.restype = C.c_int
+    L.rtxpt_b200_debug_decode_dds_error.restype = C.c_char_p
+    if f(file_bytes, len(file_bytes), mip, C.byref(w), C.byref(h), C.byref(n), C.byref(srgb), None, 0) != 0:
+        raise RtxptError("DDS: " + L.rtxpt_b200_debug_decode_dds_error().decode())
+    out = np.empty((h.value, w.value, 4), np.uint8)
+    if f(file_bytes, len(file_bytes), mip, C.byref(w), C.byref(h), C.byref(n), C.byref(srgb), out.ctypes.data, out.nbytes) != 0:
+        raise RtxptError("DDS: " + L.rtxpt_b200_debug_decode_dds_error().decode())
+    return out, n.value, bool(srgb.value)
 
 
 def parse_material_json(text, strict=None):

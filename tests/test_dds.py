@@ -1,0 +1,162 @@
+"""DDS / block-compression decoding of the host loader against an independent decoder (Pillow's DDS plugin), block by block on random data
+(random bits exercise every BC7 mode, partition, rotation and index-selector), plus the container variants (legacy FourCC, DX10 header, mips,
+non-multiple-of-4 sizes).  Host only - no GPU, no oracle."""
+import io
+import struct
+
+import numpy as np
+import pytest
+
+from rtxpt_b200 import lib as L
+
+PIL = pytest.importorskip("PIL.Image")
+
+DXGI = {"BC1": 71, "BC2": 74, "BC3": 77, "BC4": 80, "BC5": 83, "BC7": 98, "BC7_SRGB": 99, "RGBA8": 28, "BGRA8": 87}
+BLOCK_BYTES = {"BC1": 8, "BC2": 16, "BC3": 16, "BC4": 8, "BC5": 16, "BC7": 16, "BC7_SRGB": 16}
+
+
+def dds_dx10(fmt, width, height, payload, mips=1):
+    hdr = struct.pack("<4sIIIIIII44xIIIIIIIIIIII4x", b"DDS ", 124, 0x1007 | (0x20000 if mips > 1 else 0), height, width, 0, 0, mips,
+                      32, 0x4, int.from_bytes(b"DX10", "little"), 0, 0, 0, 0, 0, 0x1000, 0, 0, 0)
+    assert len(hdr) == 128, len(hdr)
+    return hdr + struct.pack("<IIIII", DXGI[fmt], 3, 0, 1, 0) + payload
+
+
+def dds_fourcc(fourcc, width, height, payload):
+    hdr = struct.pack("<4sIIIIIII44xIIIIIIIIIIII4x", b"DDS ", 124, 0x1007, height, width, 0, 0, 1, 32, 0x4, int.from_bytes(fourcc, "little"), 0, 0, 0, 0, 0, 0x1000, 0, 0, 0)
+    return hdr + payload
+
+
+def pil_decode(file_bytes):
+    im = PIL.open(io.BytesIO(file_bytes)); im.load()
+    return im.mode, np.asarray(im)
+
+
+def compare(fmt, ours, mode, theirs):
+    if fmt in ("BC4",):
+        assert mode == "L"; np.testing.assert_array_equal(ours[..., 0], theirs); assert (ours[..., 3] == 255).all()
+    elif fmt == "BC5":
+        assert mode == "RGB"; np.testing.assert_array_equal(ours[..., :2], theirs[..., :2])
+    elif mode == "RGB":
+        np.testing.assert_array_equal(ours[..., :3], theirs); assert (ours[..., 3] == 255).all()
+    else:
+        assert mode == "RGBA"; np.testing.assert_array_equal(ours, theirs)
+
+
+@pytest.mark.parametrize("fmt", ["BC1", "BC2", "BC3", "BC4", "BC5", "BC7"])
+def test_random_blocks_match_pillow(fmt):
+    rng = np.random.default_rng(hash(fmt) & 0xFFFF); W, H = 256, 128
+    payload = rng.integers(0, 256, (W // 4) * (H // 4) * BLOCK_BYTES[fmt], dtype=np.uint8)
+    if fmt == "BC7":          # spread the modes evenly: random bytes alone make mode 0 half of all blocks and mode 7 under 1 %
+        blocks = payload.reshape(-1, 16); modes = rng.integers(0, 8, len(blocks))
+        blocks[:, 0] = (blocks[:, 0] & ~((1 << (modes + 1)) - 1).astype(np.uint8)) | (1 << modes).astype(np.uint8)
+    data = dds_dx10(fmt, W, H, payload.tobytes())
+    ours, mips, srgb = L.decode_dds(data)
+    assert ours.shape == (H, W, 4) and mips == 1 and not srgb
+    mode, theirs = pil_decode(data)
+    compare(fmt, ours, mode, theirs)
+
+
+def test_bc7_every_mode_is_covered_and_reserved_mode_is_transparent():
+    rng = np.random.default_rng(7)
+    for mode in range(8):
+        blocks = rng.integers(0, 256, (64, 16), dtype=np.uint8)
+        blocks[:, 0] = (blocks[:, 0] & ~np.uint8((1 << (mode + 1)) - 1)) | np.uint8(1 << mode)
+        data = dds_dx10("BC7", 32, 32, blocks.tobytes())
+        ours, _, _ = L.decode_dds(data); m, theirs = pil_decode(data)
+        compare("BC7", ours, m, theirs)
+        if mode < 4: assert (ours[..., 3] == 255).all()       # modes 0-3 carry no alpha
+    zero = dds_dx10("BC7", 4, 4, bytes(16))
+    ours, _, _ = L.decode_dds(zero); assert (ours == 0).all()
+
+
+def test_container_variants():
+    rng = np.random.default_rng(3)
+    # legacy FourCC headers decode like their DX10 equivalents
+    for fourcc, fmt in ((b"DXT1", "BC1"), (b"DXT3", "BC2"), (b"DXT5", "BC3"), (b"ATI1", "BC4"), (b"ATI2", "BC5")):
+        payload = rng.integers(0, 256, 4 * 4 * BLOCK_BYTES[fmt], dtype=np.uint8).tobytes()
+        a, _, _ = L.decode_dds(dds_fourcc(fourcc, 16, 16, payload)); b, _, _ = L.decode_dds(dds_dx10(fmt, 16, 16, payload))
+        np.testing.assert_array_equal(a, b)
+    # sRGB flag
+    _, _, srgb = L.decode_dds(dds_dx10("BC7_SRGB", 4, 4, bytes([0x40] + [0] * 15))); assert srgb
+    # mip chain + sizes that are not multiples of four: 10x6 -> 5x3 -> 2x1 -> 1x1
+    sizes = [(10, 6), (5, 3), (2, 1), (1, 1)]; payload = b""; chunks = []
+    for (w, h) in sizes:
+        c = rng.integers(0, 256, ((w + 3) // 4) * ((h + 3) // 4) * 16, dtype=np.uint8).tobytes(); chunks.append(c); payload += c
+    data = dds_dx10("BC3", 10, 6, payload, mips=4)
+    for m, (w, h) in enumerate(sizes):
+        img, n, _ = L.decode_dds(data, mip=m); assert n == 4 and img.shape == (h, w, 4)
+        full, _, _ = L.decode_dds(dds_dx10("BC3", (w + 3) // 4 * 4, (h + 3) // 4 * 4, chunks[m]))
+        np.testing.assert_array_equal(img, full[:h, :w])
+    # uncompressed
+    px = rng.integers(0, 256, (5, 7, 4), dtype=np.uint8)
+    a, _, _ = L.decode_dds(dds_dx10("RGBA8", 7, 5, px.tobytes())); np.testing.assert_array_equal(a, px)
+    b, _, _ = L.decode_dds(dds_dx10("BGRA8", 7, 5, px.tobytes())); np.testing.assert_array_equal(b, px[..., [2, 1, 0, 3]])
+
+
+def test_errors_are_reported():
+    with pytest.raises(L.RtxptError, match="not a DDS"): L.decode_dds(b"PNG!" + bytes(200))
+    with pytest.raises(L.RtxptError, match="truncated"): L.decode_dds(dds_dx10("BC7", 64, 64, bytes(16)))
+    bc6 = bytearray(dds_dx10("BC7", 4, 4, bytes(16))); bc6[128:132] = struct.pack("<I", 95)
+    with pytest.raises(L.RtxptError, match="BC6H"): L.decode_dds(bytes(bc6))
+
+
+def _texture_pixels(desc, slot, mip=0):
+    import ctypes as C
+    t = desc.textures[slot]; w, h = max(1, t.width >> mip), max(1, t.height >> mip)
+    return np.frombuffer(C.string_at(t.mips[mip], w * h * 4), np.uint8).reshape(h, w, 4).copy()
+
+
+def test_dds_textures_through_the_scene_loaders(tmp_path):
+    """The three ways a DDS reaches a material in the reference: a .dds sibling of a glTF PNG (GltfImporter.cpp:786-796), an MSFT_texture_dds
+    image (GltfImporter.cpp:853-860) and the texture paths of .material.json files, relative to the media folder with the same .png -> .dds
+    swap (MaterialsBaker.cpp:159-195)."""
+    import json, sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    import gltf_export
+    from test_gltf_loader import _textured_builder
+    from rtxpt_b200 import structs as S
+    rng = np.random.default_rng(11)
+    media = tmp_path / "Assets"; (media / "Models").mkdir(parents=True); (media / "Materials").mkdir(); (media / "Textures").mkdir()
+    b = _textured_builder()
+    path = gltf_export.export(b, str(media / "Models" / "scene.gltf"))
+    plain = L.GltfScene(path)
+    assert plain.desc.textureCount == 3 and plain.desc.textures[0].mipLevels > 1
+    # 1. sibling: scene_tex0.dds next to scene_tex0.png (16 wide, 32 tall) with two mips of BC7 blocks
+    sib = dds_dx10("BC7", 16, 32, rng.integers(0, 256, (4 * 8 + 2 * 4) * 16, dtype=np.uint8).tobytes(), mips=2)
+    (media / "Models" / "scene_tex0.dds").write_bytes(sib)
+    # 2. MSFT_texture_dds on the emissive texture (glTF texture 2)
+    doc = json.loads(open(path).read())
+    msft = dds_dx10("BC1", 8, 8, rng.integers(0, 256, 4 * 8, dtype=np.uint8).tobytes())
+    (media / "Models" / "glow.dds").write_bytes(msft)
+    doc["images"].append({"uri": "glow.dds"}); doc["textures"][2]["extensions"] = {"MSFT_texture_dds": {"source": len(doc["images"]) - 1}}
+    open(path, "w").write(json.dumps(doc))
+    g = L.GltfScene(path)
+    assert g.desc.textureCount == 3
+    t0 = g.desc.textures[0]; assert (t0.width, t0.height, t0.mipLevels, t0.format) == (16, 32, 2, S.FORMAT_RGBA8_SRGB)
+    for m in range(2): np.testing.assert_array_equal(_texture_pixels(g.desc, 0, m), L.decode_dds(sib, m)[0])
+    np.testing.assert_array_equal(_texture_pixels(g.desc, 1), _texture_pixels(plain.desc, 1))            # the normal map is still the PNG
+    glow_slot = g.desc.materials[3].EmissiveTextureIndex & 0xFFFF
+    np.testing.assert_array_equal(_texture_pixels(g.desc, glow_slot), L.decode_dds(msft)[0])
+    idx = g.desc.materials[0].BaseOrDiffuseTextureIndex
+    assert idx & 0xFFFF == 0 and (idx >> 16) & 0xFF == 2 and idx >> 24 == 9                             # log2(16*32) = 9, two mips (MaterialsBaker.cpp:499-501)
+    g.close()
+    # 3. material file: BaseTexture names a .png whose .dds sibling exists, NormalTexture a .png without one, the emissive file is missing (glTF texture kept)
+    mat_name = doc["materials"][0]["name"]
+    base_dds = dds_dx10("BC3", 8, 4, rng.integers(0, 256, 2 * 16, dtype=np.uint8).tobytes())
+    (media / "Textures" / "albedo.dds").write_bytes(base_dds)
+    nrm = rng.integers(0, 256, (4, 4, 4), dtype=np.uint8); nrm[..., 3] = 255
+    (media / "Textures" / "bump.png").write_bytes(gltf_export.png_bytes(nrm))
+    (media / "Materials" / ("%s.material.json" % mat_name)).write_text(json.dumps({
+        "Roughness": 0.5, "BaseTexture": {"path": "Textures\\\\albedo.png", "sRGB": True}, "NormalTexture": {"path": "Textures/bump.png", "NormalMap": True},
+        "EmissiveTexture": {"path": "Textures/missing.png", "sRGB": True}}))
+    g = L.GltfScene(path, materials_dir=str(media / "Materials"))
+    assert g.overridden_materials == 1
+    m0 = g.desc.materials[0]
+    assert m0.Flags & S.MATFLAG_UseBaseOrDiffuseTexture and m0.Flags & S.MATFLAG_UseNormalTexture and not (m0.Flags & S.MATFLAG_UseEmissiveTexture)
+    bs, ns = m0.BaseOrDiffuseTextureIndex & 0xFFFF, m0.NormalTextureIndex & 0xFFFF
+    tb = g.desc.textures[bs]; assert (tb.width, tb.height, tb.mipLevels, tb.format) == (8, 4, 1, S.FORMAT_RGBA8_SRGB)
+    np.testing.assert_array_equal(_texture_pixels(g.desc, bs), L.decode_dds(base_dds)[0])
+    tn = g.desc.textures[ns]; assert (tn.width, tn.height, tn.mipLevels, tn.format) == (4, 4, 3, S.FORMAT_RGBA8_UNORM)
+    np.testing.assert_array_equal(_texture_pixels(g.desc, ns), nrm)
+    g.close(); plain.close()
