@@ -300,6 +300,56 @@ RTXPT_API int rtxpt_b200_synchronize(rtxpt_ctx* ctx);
 RTXPT_API int rtxpt_b200_render_frame(rtxpt_ctx* ctx, const RtxptPathTracerConstants* constants,
                                       uint32_t firstSubSampleIndex, uint32_t subSampleCount, void* dstRGBA32F, size_t dstBytes);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Realtime mode: path-space decomposition into "stable planes" (SURVEY §8 row a17).  Replaces the three dispatches of
+ * Sample::PathTrace in realtime mode (Rtxpt/Sample.cpp:2455-2521): RayGen_BUILD (PATH_TRACER_MODE_BUILD_STABLE_PLANES:
+ * Whitted-style delta-only exploration, writes the planes, their guides and the stable radiance), subSampleCount x
+ * RayGen_FILL (PATH_TRACER_MODE_FILL_STABLE_PLANES: noisy path tracing restarted from plane 0, radiance deposited per
+ * plane with its specular share) and, with no denoiser, PostProcess NO_DENOISER_FINAL_MERGE
+ * (Rtxpt/ProcessingPasses/PostProcess.hlsl:692-709) into u_OutputColor.
+ * Data contract = the reference's own resources: StablePlane records (Rtxpt/Shaders/PathTracer/StablePlanes.hlsli:48-80) in
+ * GenericTS addressing (8x8 Morton tiles, Rtxpt/Shaders/PathTracer/Utils/Utils.hlsli:320-362), the 4-layer R32_UINT header,
+ * StableRadiance RGBA16F, SpecularHitT R32F (Rtxpt/SampleCommon/RenderTargets.cpp:62-141, :340-351).
+ * ---------------------------------------------------------------------------------------------------------------- */
+#define RTXPT_STABLE_PLANE_COUNT            3u              /* cStablePlaneCount */
+#define RTXPT_STABLE_PLANE_MAX_VERTEX_INDEX 15u             /* cStablePlaneMaxVertexIndex */
+#define RTXPT_STABLE_PLANE_INVALID_BRANCH   0xFFFFFFFFu     /* cStablePlaneInvalidBranchID: plane unused, its radiance is not valid */
+typedef struct RtxptStablePlane {           /* 80 B, StablePlanes.hlsli:48-80 */
+    float    RayOrigin[3];                  /* start of the last segment before the plane's surface */
+    float    LastRayTCurrent;
+    float    RayDir[3];
+    float    SceneLength;                   /* total ray travel; +inf = the plane is a miss (sky) */
+    uint32_t PackedThpAndMVs[3];            /* fp16 pairs: throughput << 16 | motion vector */
+    uint32_t VertexIndexAndRoughness;       /* vertex index << 16 | fp16 roughness */
+    uint32_t DenoiserPackedBSDFEstimate[3]; /* fp16 pairs: diffuse estimate << 16 | specular estimate */
+    uint32_t PackedNormal;                  /* octahedral, 2 x 16 bit */
+    uint32_t PackedNoisyRadianceAndSpecAvg[2]; /* fp16 x 4: radiance rgb, specular average */
+    uint32_t FlagsAndVertexIndex;
+    uint32_t PackedCounters;
+} RtxptStablePlane;
+
+typedef struct RtxptRealtimeConstants {     /* the realtime-mode fields of PathTracerConstants + the two views (Sample.cpp:1501-1540, :1464-1480) */
+    uint32_t activeStablePlaneCount;        /* _activeStablePlaneCount, 1..3 */
+    uint32_t maxStablePlaneVertexDepth;     /* min(UI value, 15, bounceCount) (Sample.cpp:1532) */
+    uint32_t allowPrimarySurfaceReplacement;
+    uint32_t subSampleCount;                /* ActualSamplesPerPixel(); invSubSampleCount = 1 / subSampleCount attenuates the noisy radiance */
+    float    matWorldToClipNoOffset[16];    /* view.matWorldToClipNoOffset, row-major, row vector x matrix */
+    float    prevMatWorldToClipNoOffset[16];/* previousView.matWorldToClipNoOffset */
+    float    clipToWindowScale[2];          /* view.clipToWindowScale = (0.5 w, -0.5 h) */
+    float    _pad[2];
+} RtxptRealtimeConstants;
+
+enum {
+    RTXPT_BUFFER_STABLE_PLANES        = 5,  /* RtxptStablePlane[3 * planeStride], GenericTS addressing */
+    RTXPT_BUFFER_STABLE_PLANES_HEADER = 6,  /* uint32 [4][height][width]: layers 0-2 branch IDs, layer 3 first-hit ray length (bits 2..31) | dominant plane index (bits 0..1) */
+    RTXPT_BUFFER_STABLE_RADIANCE_F16  = 7,  /* RGBA16F: emission / sky seen along the delta tree, no noise */
+    RTXPT_BUFFER_SPECULAR_HITT_F32    = 8   /* R32F: specular hit distance of the dominant plane (denoiser guide) */
+};
+/* GenericTS addressing of the plane buffer (host helpers; Utils.hlsli:320-362) */
+RTXPT_API uint32_t rtxpt_b200_generic_ts_line_stride(uint32_t width, uint32_t height);
+RTXPT_API uint32_t rtxpt_b200_generic_ts_plane_stride(uint32_t width, uint32_t height);
+RTXPT_API uint32_t rtxpt_b200_generic_ts_address(uint32_t x, uint32_t y, uint32_t plane, uint32_t lineStride, uint32_t planeStride);
+
 typedef struct RtxptStats {
     uint64_t scatterRays;           /* closest-hit queries of the last path_trace call */
     uint64_t shadowRays;            /* any-hit (visibility) queries */

@@ -224,6 +224,53 @@ ORC_API int oracle_render(void* p, uint32_t firstSubSample, uint32_t subSampleCo
     return 0;
 }
 
+// Realtime mode over the pixel rectangle: BUILD pass, then rt->subSampleCount FILL passes (sample index = sampleBaseIndex + sub-sample), then
+// the no-denoiser merge (stable radiance + every valid plane's noisy radiance) into `merged` (RGB32F, full image pitch, optional).
+// All targets are caller-allocated at full image size: planes[3 * planeStride] (GenericTS addressing), header[4][H][W], stableRadiance RGBA16F,
+// depth R32F, motionVectors RGBA16F, throughput R32_UINT, specularHitT R32F.
+ORC_API int oracle_render_realtime(void* p, const RtxptRealtimeConstants* rt, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1,
+                                   RtxptStablePlane* planes, uint32_t* header, uint16_t* stableRadiance, float* depth, uint16_t* motionVectors, uint32_t* throughput, float* specularHitT,
+                                   float* merged, int threads)
+{
+    OracleCtx* c = (OracleCtx*)p;
+    if (!c->haveConsts || !c->haveView || !rt || rt->subSampleCount == 0 || rt->activeStablePlaneCount == 0 || rt->activeStablePlaneCount > 3) return -1;
+    RealtimeTargets T;
+    T.width = c->consts.imageWidth; T.height = c->consts.imageHeight;
+    T.lineStride = GenericTSComputeLineStride(T.width, T.height); T.planeStride = GenericTSComputePlaneStride(T.width, T.height);
+    T.planes = planes; T.header = header; T.stableRadiance = stableRadiance; T.depth = depth; T.motionVectors = motionVectors; T.throughput = throughput; T.specularHitT = specularHitT; T.rt = rt;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#endif
+    for (uint32_t pass = 0; pass <= rt->subSampleCount; pass++)
+    {
+        #pragma omp parallel
+        {
+            PathTracerCtx x; x.scene = &c->scene; x.bvh = &c->bvh; x.lights = &c->lights; x.c = &c->consts; x.stats = nullptr; x.worldToClip = c->worldToClip; x.sp = &T;
+            x.mode = pass == 0 ? MODE_BUILD_STABLE_PLANES : MODE_FILL_STABLE_PLANES;
+            x.sampleIndex = c->consts.sampleBaseIndex + (pass == 0 ? 0u : pass - 1u);
+            #pragma omp for schedule(dynamic, 1)
+            for (int y = int(y0); y < int(y1); y++)
+                for (uint32_t px = x0; px < x1; px++)
+                    if (pass == 0) buildStablePlanesPixel(x, px, uint32_t(y)); else fillStablePlanesPixel(x, px, uint32_t(y));
+        }
+    }
+    if (merged)
+        for (uint32_t y = y0; y < y1; y++) for (uint32_t px = x0; px < x1; px++)
+        {   // u_OutputColor is RGBA16F
+            const float3 r = T.GetAllRadiance(px, y); float* o = merged + (size_t(y) * T.width + px) * 3;
+            o[0] = lp(r.x); o[1] = lp(r.y); o[2] = lp(r.z);
+        }
+    return 0;
+}
+ORC_API uint32_t oracle_branch_advance(uint32_t prev, uint32_t lobe) { return StablePlanesAdvanceBranchID(prev, lobe); }
+ORC_API uint32_t oracle_branch_vertex_index(uint32_t id) { return StablePlanesVertexIndexFromBranchID(id); }
+ORC_API uint32_t oracle_branch_on_stable_path(uint32_t planeId, uint32_t planeVertex, uint32_t vertexId, uint32_t vertexIndex) { return StablePlaneIsOnStablePath(planeId, planeVertex, vertexId, vertexIndex) ? 1u : 0u; }
+ORC_API uint32_t oracle_generic_ts_address(uint32_t x, uint32_t y, uint32_t plane, uint32_t lineStride, uint32_t planeStride) { return GenericTSPixelToAddress(x, y, plane, lineStride, planeStride); }
+ORC_API uint32_t oracle_generic_ts_line_stride(uint32_t w, uint32_t h) { return GenericTSComputeLineStride(w, h); }
+ORC_API uint32_t oracle_generic_ts_plane_stride(uint32_t w, uint32_t h) { return GenericTSComputePlaneStride(w, h); }
+ORC_API void oracle_pack_ortho(const float* m9, uint32_t* out2) { mat3 m; for (int i = 0; i < 3; i++) m.r[i] = f3(m9[3 * i], m9[3 * i + 1], m9[3 * i + 2]); PackOrthoMatrix(m, out2); }
+ORC_API void oracle_unpack_ortho(const uint32_t* in2, float* m9) { mat3 m = UnpackOrthoMatrix(in2); for (int i = 0; i < 3; i++) { m9[3 * i] = m.r[i].x; m9[3 * i + 1] = m.r[i].y; m9[3 * i + 2] = m.r[i].z; } }
+
 // primary-hit triangle id -> (instance, geometry, primitive), for comparing with the product's hit records
 ORC_API int oracle_tri_info(void* p, uint32_t triId, uint32_t* out3)
 {

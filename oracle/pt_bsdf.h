@@ -61,6 +61,25 @@ inline float evalMaskingSmithGGXCorrelated(float alpha, float cosThetaI, float c
     return 1 / (1 + evalLambdaGGX(alphaSqr, cosThetaI) + evalLambdaGGX(alphaSqr, cosThetaO));
 }
 // Bounded VNDF (Microfacet.hlsli:108-130 pdf, :187-207 sample)
+// Microfacet.hlsli:282-355, SpecularMaskingFunctionSmithGGXCorrelated coefficients (BxDFConfig.hlsli:33)
+inline float3 approxSpecularIntegralGGX(float3 specularReflectance, float alpha, float cosTheta)
+{
+    cosTheta = fabsf(cosTheta);
+    const float X[4] = { 1.f, cosTheta, cosTheta * cosTheta, cosTheta * (cosTheta * cosTheta) };
+    const float Y[4] = { 1.f, alpha, alpha * alpha, alpha * (alpha * alpha) };
+    const float M1[2][2] = { { 0.995367f, -1.38839f }, { -0.24751f, 1.97442f } };
+    const float M2[3][3] = { { 1.0f, 2.68132f, 52.366f }, { 16.0932f, -3.98452f, 59.3013f }, { -5.18731f, 255.259f, 2544.07f } };
+    const float M3[2][2] = { { -0.0564526f, 3.82901f }, { 16.91f, -11.0303f } };
+    const float M4[3][3] = { { 1.0f, 4.11118f, -1.37886f }, { 19.3254f, -28.9947f, 16.9514f }, { 0.545386f, 96.0994f, -79.4492f } };
+    auto bil2 = [](const float M[2][2], float x0, float x1, float y0, float y1) { return (M[0][0] * x0 + M[0][1] * x1) * y0 + (M[1][0] * x0 + M[1][1] * x1) * y1; };
+    auto bil3 = [](const float M[3][3], float x0, float x1, float x2, float y0, float y1, float y2) {
+        return ((M[0][0] * x0 + M[0][1] * x1) + M[0][2] * x2) * y0 + ((M[1][0] * x0 + M[1][1] * x1) + M[1][2] * x2) * y1 + ((M[2][0] * x0 + M[2][1] * x1) + M[2][2] * x2) * y2; };
+    float bias = bil2(M1, X[0], X[1], Y[0], Y[1]) * (1.0f / bil3(M2, X[0], X[1], X[3], Y[0], Y[1], Y[3]));
+    const float scale = bil2(M3, X[0], X[1], Y[0], Y[1]) * (1.0f / bil3(M4, X[0], X[2], X[3], Y[0], Y[1], Y[3]));
+    const float luma = dot(specularReflectance, f3(1.f / 3.f));
+    bias *= saturate(luma * 50.0f);
+    return specularReflectance * std::max(0.0f, scale) + f3(std::max(0.0f, bias));
+}
 inline float evalPdfGGX_BVNDF(float alpha, float3 i, float3 m)
 {
     float ndf = evalNdfGGX(alpha, m.z);
@@ -106,7 +125,11 @@ struct BSDFFrame            // the part of ShadingData the BSDF reads (Scene/Sha
     float3 fromLocal(float3 v) const { return T * v.x + B * v.y + N * v.z; }
 };
 
-struct BSDFSample { float3 wo; float pdf; float3 weight; uint lobe; float lobeP; bool isLobe(uint t) const { return (lobe & t) != 0; } };
+struct BSDFSample { float3 wo; float pdf; float3 weight; uint lobe; float lobeP; bool isLobe(uint t) const { return (lobe & t) != 0; }
+                    // IBSDF.hlsli:53-60: 0 = delta transmission, 1 = delta reflection, 0xFFFFFFFF = not a delta lobe
+                    uint getDeltaLobeIndex() const { if ((lobe & Lobe_Delta) == 0u) return 0xFFFFFFFFu; return (lobe & Lobe_Transmission) == 0u ? 1u : 0u; } };
+struct DeltaLobe { float3 thp = f3(0); float probability = 0; float3 dir = f3(0); int transmission = 0; };    // IBSDF.hlsli:24-34
+static const uint cMaxDeltaLobes = 3;       // IBSDF.hlsli:22
 
 // ---- lobes ---------------------------------------------------------------------------------------------------------------
 struct DiffuseReflectionFrostbite   // BxDF.hlsli:157-208
@@ -357,6 +380,50 @@ struct FalcorBSDF
         return b;
     }
 
+    // BxDF.hlsli:972-1053; wi in the local frame, directions returned in the local frame
+    void evalDeltaLobes(float3 wi, bool psdExclude, DeltaLobe deltaLobes[cMaxDeltaLobes], int& deltaLobeCount, float& nonDeltaPart) const
+    {
+        deltaLobeCount = 2;
+        for (uint i = 0; i < cMaxDeltaLobes; i++) deltaLobes[i] = DeltaLobe();
+        nonDeltaPart = pDiffuseReflection + pDiffuseTransmission;
+        if (specularReflection.alpha > 0) nonDeltaPart += pSpecularReflection;
+        if (specularReflectionTransmission.alpha > 0) nonDeltaPart += pSpecularReflectionTransmission;
+        if ((pSpecularReflection + pSpecularReflectionTransmission) == 0 || psdExclude) return;
+        DeltaLobe deltaReflection, deltaTransmission;
+        deltaReflection.transmission = 0; deltaTransmission.transmission = 1;
+        deltaReflection.dir = f3(-wi.x, -wi.y, wi.z);
+        if (specularReflection.alpha == 0 && specularReflection.hasLobe(Lobe_DeltaReflection))
+        {
+            deltaReflection.probability = pSpecularReflection;
+            deltaReflection.thp = (1 - pSpecularReflectionTransmission) * evalFresnelSchlick(specularReflection.albedo, 1.f, wi.z);
+        }
+        if (specularReflectionTransmission.alpha == 0.f)
+        {
+            const bool hasReflection = specularReflectionTransmission.hasLobe(Lobe_DeltaReflection), hasTransmission = specularReflectionTransmission.hasLobe(Lobe_DeltaTransmission);
+            if (hasReflection || hasTransmission)
+            {
+                float cosThetaT;
+                float F = evalFresnelDielectric(specularReflectionTransmission.eta, wi.z, cosThetaT);
+                if (hasReflection)
+                {
+                    float localProbability = pSpecularReflectionTransmission * F;
+                    deltaReflection.thp = deltaReflection.thp + f3(1) * localProbability;
+                    deltaReflection.probability += localProbability;
+                }
+                if (hasTransmission)
+                {
+                    float actualEta = specularReflectionTransmission.eta;
+                    if (specularReflectionTransmission.isThinSurface) { actualEta = 1.0f; F = evalFresnelDielectric(actualEta, wi.z, cosThetaT); }
+                    float localProbability = pSpecularReflectionTransmission * (1.0f - F);
+                    deltaTransmission.dir = f3(-wi.x * actualEta, -wi.y * actualEta, -cosThetaT);
+                    deltaTransmission.thp = specularReflectionTransmission.transmissionAlbedo * localProbability;
+                    deltaTransmission.probability = localProbability;
+                }
+            }
+        }
+        deltaLobes[0] = deltaTransmission; deltaLobes[1] = deltaReflection;
+    }
+
     static uint getLobes(const StandardBSDFData& data)
     {
         float alpha = data.roughness * data.roughness;
@@ -460,6 +527,28 @@ struct StandardBSDF
         return valid;
     }
     uint getLobes() const { return FalcorBSDF::getLobes(data); }
+    // StandardBSDF.hlsli:227-237
+    void evalDeltaLobes(const BSDFFrame& sd, DeltaLobe deltaLobes[cMaxDeltaLobes], int& deltaLobeCount, float& nonDeltaPart) const
+    {
+        FalcorBSDF::make(sd, data).evalDeltaLobes(sd.toLocal(sd.V), sd.psdExclude, deltaLobes, deltaLobeCount, nonDeltaPart);
+        for (int i = 0; i < deltaLobeCount; i++) deltaLobes[i].dir = sd.fromLocal(deltaLobes[i].dir);
+    }
+    // StandardBSDF.hlsli:93-121; albedo products are lpfloat (fp16) arithmetic in the reference
+    void estimateSpecDiffBSDF(float3& outDiffEstimate, float3& outSpecEstimate, float3 normal, float3 viewVector) const
+    {
+        const float dataRoughness = data.roughness;
+        const float alpha = dataRoughness * dataRoughness;
+        const float roughness = alpha < kMinGGXAlpha ? 0.f : dataRoughness;
+        const float dT = data.diffuseTransmission, sT = data.specularTransmission;
+        const float3 diffuseReflectionAlbedo = lp(lp(lp(1.f - dT) * lp(1.f - sT)) * data.diffuse);
+        const float3 diffuseTransmissionAlbedo = lp(lp(dT * data.transmission) * lp(1.f - sT));
+        const float3 specularReflectionAlbedo = lp(lp(1.f - sT) * data.specular);
+        const float3 specularTransmissionAlbedo = lp(sT * data.transmission);
+        outDiffEstimate = lp(diffuseReflectionAlbedo + diffuseTransmissionAlbedo);
+        const float NdotV = saturate(dot(normal, viewVector));
+        const float ggxAlpha = roughness * roughness;
+        outSpecEstimate = approxSpecularIntegralGGX(specularReflectionAlbedo, ggxAlpha, NdotV) + specularTransmissionAlbedo;
+    }
 };
 
 } // namespace orc

@@ -13,15 +13,21 @@
 #include "pt_bvh.h"
 #include "pt_lights.h"
 #include "pt_rng.h"
+#include "pt_stable_planes.h"
 
 namespace orc {
 
 enum PathFlags : uint {
     PF_active = 1u << 0, PF_hit = 1u << 1, PF_transmission = 1u << 2, PF_specular = 1u << 3, PF_delta = 1u << 4,
     PF_insideDielectricVolume = 1u << 5, PF_terminateAtNextBounce = 1u << 6, PF_enableThreadReorder = 1u << 9,
-    PF_deltaTransmissionPath = 1u << 11, PF_deltaOnlyPath = 1u << 12
+    PF_deltaTransmissionPath = 1u << 11, PF_deltaOnlyPath = 1u << 12,
+    // realtime mode (PathState.hlsli:58-64); bits 14-15 hold the stable plane index
+    PF_stablePlaneOnPlane = 1u << 16, PF_stablePlaneOnBranch = 1u << 17, PF_stablePlaneBaseScatterDiff = 1u << 18, PF_exportSpecHitTQueued = 1u << 19,
+    PF_stablePlaneOnDominantBranch = 1u << 20
 };
+enum PathTracerMode : uint { MODE_REFERENCE = 0, MODE_BUILD_STABLE_PLANES = 1, MODE_FILL_STABLE_PLANES = 2 };      // Config.h:56-59
 static const uint kVertexIndexBitCount = 10, kVertexIndexBitMask = (1u << kVertexIndexBitCount) - 1u;
+static const uint kStablePlaneIndexBitOffset = 14 + kVertexIndexBitCount, kStablePlaneIndexBitMask = 3u << kStablePlaneIndexBitOffset;
 enum PackedCounter { CTR_DiffuseBounces = 0, CTR_RejectedHits = 1, CTR_BouncesFromStablePlane = 2 };
 
 struct InteriorList     // InteriorList.hlsli (2 slots)
@@ -61,6 +67,16 @@ struct PathState
     uint packedCounters = 0;
     RayCone rayCone;
     uint pack0 = 0, pack1 = 0, flagsAndVertexIndex = 0;
+    uint stableBranchID = 0;        // PathState.hlsli:102; in the BUILD pass pack45 holds imageXformPacked and pack0 the motion-vector scene length (:91-92, :151-154)
+
+    mat3 GetImageXform() const { return UnpackOrthoMatrix(pack45); }
+    void SetImageXform(const mat3& m) { PackOrthoMatrix(m, pack45); }
+    void SetMotionVectorSceneLength(float l) { pack0 = asuint(l); }
+    float GetMotionVectorSceneLength() const { return asfloat(pack0); }
+    uint getStablePlaneIndex() const { return (flagsAndVertexIndex & kStablePlaneIndexBitMask) >> kStablePlaneIndexBitOffset; }
+    void setStablePlaneIndex(uint index) { flagsAndVertexIndex &= ~kStablePlaneIndexBitMask; flagsAndVertexIndex |= index << kStablePlaneIndexBitOffset; }
+    void setCounter(uint type, uint v) { const uint shift = type << 3; packedCounters = (packedCounters & ~(0xffu << shift)) | ((v & 0xff) << shift); }
+    void setVertexIndex(uint index) { flagsAndVertexIndex &= ~kVertexIndexBitMask; flagsAndVertexIndex |= index; }
 
     void SetThp(float3 t) { t = clamp3(t, 0, HLF_MAX); pack23[0] = Fp32ToFp16NoClamp(f2(t.x, t.y)); pack23[1] = Fp32ToFp16NoClamp(f2(t.z, 0)); }
     float3 GetThp() const { float2 a = Fp16ToFp32(pack23[0]), b = Fp16ToFp32(pack23[1]); return f3(a.x, a.y, b.x); }
@@ -93,6 +109,10 @@ struct PathTracerCtx
     // guide export of the reference-mode path (Bridge::ExportSurfaceInit / ExportSurface / ExportNonSurface, BridgeDonut:1096-1153)
     const float* worldToClip = nullptr;     // view.matWorldToClip, row-major, row vector x matrix
     struct GuideOut* guide = nullptr;
+    // realtime mode (PATH_TRACER_MODE_BUILD_STABLE_PLANES / _FILL_STABLE_PLANES)
+    uint mode = MODE_REFERENCE;
+    const RealtimeTargets* sp = nullptr;
+    float noisyRadianceAttenuation() const { return 1.0f / float(sp->rt->subSampleCount); }      // Bridge::getNoisyRadianceAttenuation = invSubSampleCount (BridgeDonut:515-523)
 };
 struct GuideOut { float depth; uint throughput; float motion[3]; };
 
@@ -195,21 +215,41 @@ inline void UpdatePathTravelled(PathState& path, float rayTCurrent)
     path.rayCone = path.rayCone.propagateDistance(rayTCurrent);
     path.sceneLength = std::min(path.sceneLength + rayTCurrent, kMaxRayTravel);
 }
-inline void AccumulatePathRadiance(PathState& path, float3 radiance) { float4 L = path.GetL(); path.SetL(f4(L.x + radiance.x, L.y + radiance.y, L.z + radiance.z, L.w)); }
+// PathTracer.hlsli:139-162
+inline void AccumulatePathRadiance(const PathTracerCtx& x, PathState& path, float3 radiance, float specularRadianceAvg, bool stablePlaneOnBranch)
+{
+    if (x.mode == MODE_REFERENCE) { float4 L = path.GetL(); path.SetL(f4(L.x + radiance.x, L.y + radiance.y, L.z + radiance.z, L.w)); }
+    else if (x.mode == MODE_BUILD_STABLE_PLANES) x.sp->AccumulateStableRadiance(path.id >> 16, path.id & 0xFFFF, radiance);
+    else if (!stablePlaneOnBranch)      // FILL: the stable part was captured by the BUILD pass
+    {
+        const float a = x.noisyRadianceAttenuation();
+        float4 L = path.GetL();
+        path.SetL(f4(L.x + radiance.x * a, L.y + radiance.y * a, L.z + radiance.z * a, L.w + specularRadianceAvg * a));
+    }
+}
+inline void StablePlanesHandleMiss(const PathTracerCtx& x, PathState& path, float3 emission, float3 rayOrigin, float3 rayDir);
+inline void ExportSpecHitTStop(const PathTracerCtx& x, const PathState& path)      // BridgeDonut:1160-1175
+{
+    float& t = x.sp->specularHitT[size_t(path.id & 0xFFFF) * x.sp->width + (path.id >> 16)];
+    if (t < 0) t = std::max(0.0f, path.sceneLength + t);
+}
 
 // ---- miss (PathTracer.hlsli:407-503) ---------------------------------------------------------------------------------------
 inline void HandleMiss(const PathTracerCtx& x, PathState& path, float3 rayDir, float rayTCurrent)
 {
+    const float3 rayOrigin = path.origin;
     UpdatePathTravelled(path, rayTCurrent);
+    const bool build = x.mode == MODE_BUILD_STABLE_PLANES;
+    if (x.mode == MODE_FILL_STABLE_PLANES && path.hasFlag(PF_exportSpecHitTQueued)) { ExportSpecHitTStop(x, path); path.setFlag(PF_exportSpecHitTQueued, false); }
     float3 environmentEmission = f3(0);
-    NEEBSDFMISInfo misInfo = NEEBSDFMISInfo::Unpack16bit(path.GetPackedMISInfo());
+    NEEBSDFMISInfo misInfo = NEEBSDFMISInfo::Unpack16bit(build ? 0u : path.GetPackedMISInfo());
     if (x.lights->envEnabled)
     {
         float mipLevel = (path.getCounter(CTR_DiffuseBounces) > 1) ? x.c->EnvironmentMapDiffuseSampleMIPLevel : 0.0f;
         float3 localDir = envToLocal(x, rayDir);
         float3 Le = envEvalLocal(x, localDir, mipLevel);
         float misWeight = 1.0f;
-        float bsdfScatterPdf = path.GetBsdfScatterPdf();
+        float bsdfScatterPdf = build ? 0.0f : path.GetBsdfScatterPdf();
         if (misInfo.LightSamplingEnabled && bsdfScatterPdf != 0)
         {
             float2 uv = ndir_to_oct_equal_area_unorm(localDir);
@@ -222,9 +262,14 @@ inline void HandleMiss(const PathTracerCtx& x, PathState& path, float3 rayDir, f
         environmentEmission = lp(misWeight * Le);
     }
     float baseFFThreshold = lp(x.c->fireflyFilterThreshold);
-    if (baseFFThreshold != 0) environmentEmission = FireflyFilter(environmentEmission, baseFFThreshold, path.GetFireflyFilterK());
-    if (x.guide && x.worldToClip) { x.guide->depth = clipDepth(x.worldToClip, path.origin + rayDir * rayTCurrent); x.guide->throughput = 0; x.guide->motion[0] = x.guide->motion[1] = x.guide->motion[2] = 0; }     // ExportNonSurface (PathTracer.hlsli:487)
-    if (any_gt0(environmentEmission)) AccumulatePathRadiance(path, path.GetThp() * environmentEmission);
+    if (baseFFThreshold != 0 && !build) environmentEmission = FireflyFilter(environmentEmission, baseFFThreshold, path.GetFireflyFilterK());
+    if (build) StablePlanesHandleMiss(x, path, environmentEmission, rayOrigin, rayDir);
+    if (x.mode == MODE_REFERENCE && x.guide && x.worldToClip) { x.guide->depth = clipDepth(x.worldToClip, path.origin + rayDir * rayTCurrent); x.guide->throughput = 0; x.guide->motion[0] = x.guide->motion[1] = x.guide->motion[2] = 0; }     // ExportNonSurface (PathTracer.hlsli:487)
+    if (any_gt0(environmentEmission))
+    {
+        const float3 radiance = path.GetThp() * environmentEmission;
+        AccumulatePathRadiance(x, path, radiance, path.hasFlag(PF_stablePlaneBaseScatterDiff) ? 0.0f : Average(radiance), path.hasFlag(PF_stablePlaneOnBranch));
+    }
     path.setFlag(PF_hit, false);
     path.terminate();
 }
@@ -243,6 +288,7 @@ inline bool HandleRussianRoulette(const PathTracerCtx& x, PathState& path, Unifo
 }
 
 // ---- scatter (PathTracer.hlsli:217-380) ---------------------------------------------------------------------------------------
+inline void StablePlanesOnScatter(const PathTracerCtx& x, PathState& path, const BSDFSample& bs);
 inline bool GenerateScatterRay(const PathTracerCtx& x, const ShadingData& sd, const StandardBSDF& bsdf, PathState& path, const SampleGeneratorVertexBase& sgBase)
 {
     float u[4] = { 0, 0, 0, 0 };
@@ -252,6 +298,7 @@ inline bool GenerateScatterRay(const PathTracerCtx& x, const ShadingData& sd, co
     if (!bsdf.sample(sd.frame(), u, bs)) return false;
 
     path.dir = bs.wo;
+    const bool onDominantDenoisingLayer = path.hasFlag(PF_stablePlaneOnPlane) && path.hasFlag(PF_stablePlaneOnDominantBranch);
     path.SetThp(path.GetThp() * bs.weight);
     path.clearScatterEventFlags();
     path.origin = sd.computeNewRayOrigin(bs.isLobe(Lobe_Reflection));
@@ -277,8 +324,26 @@ inline bool GenerateScatterRay(const PathTracerCtx& x, const ShadingData& sd, co
         path.setFlag(PF_deltaOnlyPath, false);
         path.rayCone = RayCone::make(path.rayCone.getWidth(), std::min(path.rayCone.getSpreadAngle() + ComputeRayConeSpreadAngleExpansionByScatterPDF(bs.pdf), 2.0f * K_PI));
     }
+    if (x.mode == MODE_FILL_STABLE_PLANES)
+    {   // specular hit distance of the dominant plane (PathTracer.hlsli:295-324)
+        const bool isDiffuseForSpecHitT = bs.isLobe(Lobe_DiffuseReflection) || bs.isLobe(Lobe_DiffuseTransmission) || roughness > 0.35f;
+        if (onDominantDenoisingLayer && !isDiffuseForSpecHitT)
+        {
+            if (!sd.psdBlockMotionVectorsAtSurface)
+            {
+                path.setFlag(PF_exportSpecHitTQueued, true);
+                x.sp->specularHitT[size_t(path.id & 0xFFFF) * x.sp->width + (path.id >> 16)] = -path.sceneLength;      // Bridge::ExportSpecHitTStart
+            }
+        }
+        else if (path.hasFlag(PF_exportSpecHitTQueued))
+        {
+            const bool hasNonDeltaLobes = (bsdf.getLobes() & Lobe_NonDelta) != 0;
+            if (hasNonDeltaLobes || path.getCounter(CTR_BouncesFromStablePlane) > 4) { ExportSpecHitTStop(x, path); path.setFlag(PF_exportSpecHitTQueued, false); }
+        }
+    }
     float fireflyFilterK = (x.c->fireflyFilterThreshold != 0) ? ComputeNewScatterFireflyFilterK(path.GetFireflyFilterK(), bs.pdf, bs.lobeP) : 0.0f;
     path.SetFireflyFilterK_BsdfScatterPdf(fireflyFilterK, bs.pdf);
+    if (x.mode == MODE_FILL_STABLE_PLANES) StablePlanesOnScatter(x, path, bs);
     path.setFlag(PF_enableThreadReorder, true);
     return true;
 }
@@ -390,8 +455,10 @@ inline NEEResult HandleNEE(const PathTracerCtx& x, const PathState& pre, const S
 }
 
 // ---- hit (PathTracer.hlsli:505-762) --------------------------------------------------------------------------------------------
+inline void StablePlanesHandleHit(const PathTracerCtx& x, PathState& path, float3 rayOrigin, float3 rayDir, float rayTCurrent, const SurfaceData& surfaceData, bool pathStopping);
 inline void HandleHit(const PathTracerCtx& x, PathState& path, float3 rayOrigin, float3 rayDir, float rayTCurrent, const Tri& tri, float2 barycentrics)
 {
+    const bool build = x.mode == MODE_BUILD_STABLE_PLANES;
     UpdatePathTravelled(path, rayTCurrent);
     SurfaceData surface = loadSurface(*x.scene, tri.instanceIndex, tri.geometryIndex, tri.primitiveIndex, barycentrics, rayDir, path.rayCone, x.c->texLODBias);
     const uint ndq = x.c->nestedDielectricsQuality;
@@ -432,11 +499,12 @@ inline void HandleHit(const PathTracerCtx& x, PathState& path, float3 rayOrigin,
 
     // emissive triangle radiance with BSDF-side MIS
     float3 surfaceEmission = f3(0);
-    NEEBSDFMISInfo misInfo = NEEBSDFMISInfo::Unpack16bit(path.GetPackedMISInfo());
+    NEEBSDFMISInfo misInfo = NEEBSDFMISInfo::Unpack16bit(build ? 0u : path.GetPackedMISInfo());
+    const float pathBsdfScatterPdf = build ? 0.0f : path.GetBsdfScatterPdf();     // PathState.hlsli:157-159: no NEE, no MIS while building the planes
     if (any_gt0(sd.emission))
     {
         float misWeight = 1.0f;
-        float bsdfScatterPdf = path.GetBsdfScatterPdf();
+        float bsdfScatterPdf = pathBsdfScatterPdf;
         if (misInfo.LightSamplingEnabled && bsdfScatterPdf != 0 && surface.neeTriangleLightIndex != RTXPT_INVALID_LIGHT_INDEX)
         {
             TriangleLight tl = TriangleLight::Create(x.lights->lights[surface.neeTriangleLightIndex]);
@@ -455,7 +523,7 @@ inline void HandleHit(const PathTracerCtx& x, PathState& path, float3 rayOrigin,
             if (sl.Eval(rayOrigin, rayDir, radiance, lightSamplePosition))
             {
                 float mis = 1.0f;
-                const float bsdfPdf = misInfo.LightSamplingEnabled ? path.GetBsdfScatterPdf() : 0.0f;
+                const float bsdfPdf = misInfo.LightSamplingEnabled ? pathBsdfScatterPdf : 0.0f;
                 if (bsdfPdf != 0) mis = ComputeLightVsBSDF_MIS_ForBSDF(*x.lights, surface.neeAnalyticLightIndex, bsdfPdf, sl.CalcSolidAnglePdfForMIS(rayOrigin), misInfo.FullSamples);
                 surfaceEmission = surfaceEmission + lp(radiance * mis);
             }
@@ -464,19 +532,26 @@ inline void HandleHit(const PathTracerCtx& x, PathState& path, float3 rayOrigin,
     if (any_gt0(surfaceEmission))
     {
         float baseFFThreshold = lp(x.c->fireflyFilterThreshold);
-        if (baseFFThreshold != 0) surfaceEmission = FireflyFilter(surfaceEmission, baseFFThreshold, path.GetFireflyFilterK());
-        if (any_gt0(surfaceEmission)) AccumulatePathRadiance(path, path.GetThp() * surfaceEmission);
+        if (baseFFThreshold != 0 && !build) surfaceEmission = FireflyFilter(surfaceEmission, baseFFThreshold, path.GetFireflyFilterK());
+        if (any_gt0(surfaceEmission))
+        {
+            const float3 radiance = path.GetThp() * surfaceEmission;
+            AccumulatePathRadiance(x, path, radiance, path.hasFlag(PF_stablePlaneBaseScatterDiff) ? 0.0f : Average(radiance), path.hasFlag(PF_stablePlaneOnBranch));
+        }
     }
-    if (x.guide && x.worldToClip)
+    const bool pathStopping = path.hasFlag(PF_terminateAtNextBounce);
+    if (build) StablePlanesHandleHit(x, path, rayOrigin, rayDir, rayTCurrent, surface, pathStopping);      // before the throughput update (PathTracer.hlsli:679-682)
+    if (x.mode == MODE_REFERENCE && x.guide && x.worldToClip)
     {   // ExportSurface (PathTracer.hlsli:684, BridgeDonut:1105-1129): virtual position along the pixel's camera ray at the path's scene length
         float3 co, cd; computeCameraRay(x, path.id >> 16, path.id & 0xFFFF, co, cd);
         x.guide->depth = clipDepth(x.worldToClip, co + cd * path.sceneLength);
         float3 t = path.GetThp(); x.guide->throughput = Pack_R11G11B10_FLOAT(f3(saturate(t.x), saturate(t.y), saturate(t.z)));
         x.guide->motion[0] = x.guide->motion[1] = x.guide->motion[2] = 0;
     }
-    if (path.hasFlag(PF_terminateAtNextBounce)) { path.terminate(); return; }
+    if (pathStopping) { path.terminate(); return; }
 
-    path.SetThp(path.GetThp() * path.GetThpRuRuCorrection());
+    path.SetThp(path.GetThp() * (build ? 1.0f : path.GetThpRuRuCorrection()));
+    if (build) return;      // the BUILD pass consumed the emission and either re-aimed or terminated the path itself (PathTracer.hlsli:696-699)
 
     const SampleGeneratorVertexBase sgBase = SampleGeneratorVertexBase::make(path.id, path.getVertexIndex(), x.sampleIndex);
     UniformSampleSequenceGenerator uniformSG = UniformSampleSequenceGenerator::make(sgBase, SeedBase);
@@ -485,7 +560,17 @@ inline void HandleHit(const PathTracerCtx& x, PathState& path, float3 rayOrigin,
     NEEResult neeResult = HandleNEE(x, preScatterPath, sd, bsdf, uniformSG);
     path.SetPackedMISInfo_ThpRuRuCorrection(neeResult.BSDFMISInfo.Pack16bit(), path.GetThpRuRuCorrection());
     float4 nee = neeResult.Get();
-    if (nee.x > 0 || nee.y > 0 || nee.z > 0 || nee.w > 0) AccumulatePathRadiance(path, xyz(nee));
+    if (nee.x > 0 || nee.y > 0 || nee.z > 0 || nee.w > 0)
+    {
+        float specRadianceAvg = 0;
+        if (!preScatterPath.hasFlag(PF_stablePlaneBaseScatterDiff))
+        {   // PathTracer.hlsli:731-743
+            const int bouncesFromStablePlane = int(preScatterPath.getCounter(CTR_BouncesFromStablePlane)) + 1;
+            const bool specialCondition = (bouncesFromStablePlane == 1) || (preScatterPath.hasFlag(PF_deltaOnlyPath) && bouncesFromStablePlane <= 3);
+            specRadianceAvg = specialCondition ? nee.w : Average(xyz(nee));
+        }
+        AccumulatePathRadiance(x, path, xyz(nee), specRadianceAvg, false);
+    }
     if (!scatterValid) path.terminate();
     bool shouldTerminate = HasFinishedSurfaceBounces(x, path.getVertexIndex() + 1, path.getCounter(CTR_DiffuseBounces));
     shouldTerminate |= HandleRussianRoulette(x, path, uniformSG);
@@ -523,6 +608,305 @@ inline PixelResult tracePixel(const PathTracerCtx& x, uint px, uint py)
     float4 L = path.GetL();
     out.rgb[0] = L.x; out.rgb[1] = L.y; out.rgb[2] = L.z;      // already fp16 values: the RGBA16F store is lossless
     return out;
+}
+
+
+// =====================================================================================================================================================
+// Realtime mode: PathTracerStablePlanes.hlsli (SplitDeltaPath :25-99, StablePlanesHandleHit :102-326, StablePlanesOnScatter :329-380,
+// StablePlanesHandleMiss :382-412), StablePlanes.hlsli:232-252 (CommitDenoiserRadiance), PathTracerSample.hlsl:33-93 (FirstHitFromVBuffer),
+// :96-113 (postProcessHit), :201-232 (raygen), PathTracer.hlsli:47-91 (EmptyPathInitialize), PathPayload.hlsli:29-110
+// =====================================================================================================================================================
+inline void packPayload(const PathState& path, uint out[20])
+{
+    out[0] = asuint(path.origin.x); out[1] = asuint(path.origin.y); out[2] = asuint(path.origin.z); out[3] = path.id;
+    out[4] = asuint(path.dir.x); out[5] = asuint(path.dir.y); out[6] = asuint(path.dir.z); out[7] = asuint(path.sceneLength);
+    out[8] = path.pack23[0]; out[9] = path.pack23[1]; out[10] = path.pack45[0]; out[11] = path.pack45[1];
+    out[12] = path.interiorList.slots[0]; out[13] = path.interiorList.slots[1]; out[14] = path.packedCounters; out[15] = path.stableBranchID;
+    out[16] = path.rayCone.widthSpreadAngleFP16; out[17] = path.pack0; out[18] = path.pack1; out[19] = path.flagsAndVertexIndex;
+}
+inline PathState unpackPayload(const uint in[20])
+{
+    PathState path;
+    path.origin = f3(asfloat(in[0]), asfloat(in[1]), asfloat(in[2])); path.id = in[3];
+    path.dir = f3(asfloat(in[4]), asfloat(in[5]), asfloat(in[6])); path.sceneLength = asfloat(in[7]);
+    path.pack23[0] = in[8]; path.pack23[1] = in[9]; path.pack45[0] = in[10]; path.pack45[1] = in[11];
+    path.interiorList.slots[0] = in[12]; path.interiorList.slots[1] = in[13]; path.packedCounters = in[14]; path.stableBranchID = in[15];
+    path.rayCone.widthSpreadAngleFP16 = in[16]; path.pack0 = in[17]; path.pack1 = in[18]; path.flagsAndVertexIndex = in[19];
+    return path;
+}
+
+// splits out one delta lobe: the new path leaves the surface along lobe.dir; the accumulated rotation (imageXform) gets the local mirror / refraction turn
+inline PathState SplitDeltaPath(const PathTracerCtx& x, const PathState& oldPath, float3 rayDir, const SurfaceData& surfaceData, const DeltaLobe& lobe, uint deltaLobeIndex, bool verifyDominantFlag)
+{
+    const ShadingData& sd = surfaceData.sd;
+    PathState newPath = oldPath;
+    newPath.dir = lobe.dir;
+    newPath.SetThp(newPath.GetThp() * lobe.thp);
+    newPath.origin = sd.computeNewRayOrigin(lobe.transmission == 0);
+    newPath.stableBranchID = StablePlanesAdvanceBranchID(oldPath.stableBranchID, deltaLobeIndex);
+    newPath.setFlag(PF_delta);
+    if (!lobe.transmission) newPath.setFlag(PF_specular);
+    else
+    {
+        newPath.setFlag(PF_transmission);
+        if (x.c->nestedDielectricsQuality > 0 && !sd.thinSurface)
+        {
+            newPath.interiorList.handleIntersection(sd.materialID, sd.nestedPriority, sd.frontFacing);
+            newPath.setFlag(PF_insideDielectricVolume, !newPath.interiorList.isEmpty());
+        }
+    }
+    if (newPath.GetMotionVectorSceneLength() == 0)      // transform updates stop behind a surface that blocks motion vectors
+    {
+        mat3 localT;        // lpfloat3x3: fp16 elements; products accumulated in fp32 here and rounded once per element
+        if (lobe.transmission) localT = lp(MatrixRotateFromTo(lobe.dir, rayDir));
+        else
+        {
+            mat3 toTangent; toTangent.r[0] = lp(sd.T); toTangent.r[1] = lp(sd.B); toTangent.r[2] = lp(sd.N);
+            mat3 mirror; mirror.r[0] = f3(1, 0, 0); mirror.r[1] = f3(0, 1, 0); mirror.r[2] = f3(0, 0, -1);
+            localT = lp(mul(mirror, toTangent));
+            localT = lp(mul(transpose(toTangent), localT));
+        }
+        newPath.SetImageXform(mul(newPath.GetImageXform(), localT));
+    }
+    if (verifyDominantFlag && newPath.hasFlag(PF_stablePlaneOnDominantBranch))
+    {
+        const int psdDominantDeltaLobeIndex = int(sd.psdDominantDeltaLobeP1) - 1;
+        if (int(deltaLobeIndex) != psdDominantDeltaLobeIndex) newPath.setFlag(PF_stablePlaneOnDominantBranch, false);
+    }
+    return newPath;
+}
+
+inline float3 pathThroughputGuide(float3 thp) { return f3(saturate(thp.x), saturate(thp.y), saturate(thp.z)); }
+
+inline void StablePlanesHandleHit(const PathTracerCtx& x, PathState& path, float3 rayOrigin, float3 rayDir, float rayTCurrent, const SurfaceData& surfaceData, bool pathStopping)
+{
+    const RealtimeTargets& T = *x.sp;
+    const uint vertexIndex = path.getVertexIndex(), currentSPIndex = path.getStablePlaneIndex(), px = path.id >> 16, py = path.id & 0xFFFF;
+    const ShadingData& sd = surfaceData.sd;
+    if (sd.psdBlockMotionVectorsAtSurface && path.GetMotionVectorSceneLength() == 0) path.SetMotionVectorSceneLength(path.sceneLength);
+    if (vertexIndex == 1) T.StoreFirstHitRayLengthAndClearDominantToZero(px, py, path.sceneLength);
+
+    bool setAsBase = true;
+    if (vertexIndex < T.rt->maxStablePlaneVertexDepth && !pathStopping)
+    {
+        DeltaLobe deltaLobes[cMaxDeltaLobes]; int deltaLobeCount; float nonDeltaPart;
+        surfaceData.bsdf.evalDeltaLobes(sd.frame(), deltaLobes, deltaLobeCount, nonDeltaPart);
+        deltaLobeCount = std::max(int(cMaxDeltaLobes) - 1, deltaLobeCount);
+        bool potentiallyVolumeTransmission = false;
+        const float nonDeltaIgnoreThreshold = 1e-5f, deltaIgnoreThreshold = 0.001f;
+        const bool hasNonDeltaLobes = nonDeltaPart > nonDeltaIgnoreThreshold;
+        int nonZeroDeltaLobes[cMaxDeltaLobes] = { 0, 0, 0 }; int nonZeroDeltaLobeCount = 0;
+        for (int k = 0; k < deltaLobeCount; k++)
+            if (Average(deltaLobes[k].thp) > deltaIgnoreThreshold) { nonZeroDeltaLobes[nonZeroDeltaLobeCount++] = k; potentiallyVolumeTransmission |= deltaLobes[k].transmission != 0; }
+        if (nonZeroDeltaLobeCount > 0)
+        {
+            bool allowPSR = T.rt->allowPrimarySurfaceReplacement && (nonZeroDeltaLobeCount == 1) && (currentSPIndex == 0) && !potentiallyVolumeTransmission;
+            allowPSR &= !sd.psdBlockMotionVectorsAtSurface;
+            bool canReuseExisting = (currentSPIndex != 0) && (nonZeroDeltaLobeCount > 0);
+            canReuseExisting |= allowPSR;
+            canReuseExisting &= !hasNonDeltaLobes;
+            int availablePlaneCount = 0; int availablePlanes[3];
+            T.GetAvailableEmptyPlanes(px, py, availablePlaneCount, availablePlanes);
+            canReuseExisting &= (currentSPIndex == 0) || (sd.psdDominantDeltaLobeP1 > 0);
+            nonZeroDeltaLobeCount = std::min(nonZeroDeltaLobeCount, availablePlaneCount + int(canReuseExisting));
+            int lobeForReuse = -1;
+            if (canReuseExisting) { lobeForReuse = nonZeroDeltaLobes[nonZeroDeltaLobeCount - 1]; nonZeroDeltaLobeCount--; }
+            for (int i = 0; i < nonZeroDeltaLobeCount; i++)
+            {
+                const int lobeToExplore = nonZeroDeltaLobes[i];
+                PathState splitPath = SplitDeltaPath(x, path, rayDir, surfaceData, deltaLobes[lobeToExplore], uint(lobeToExplore), true);
+                splitPath.setStablePlaneIndex(uint(availablePlanes[i]));
+                uint payload[20]; packPayload(splitPath, payload);
+                memcpy(&T.planes[T.PixelToAddress(px, py, uint(availablePlanes[i]))], payload, 80);          // StoreExplorationStart
+                T.SetBranchID(px, py, uint(availablePlanes[i]), cStablePlaneEnqueuedBranchID);
+            }
+            if (lobeForReuse != -1)
+            {
+                setAsBase = false;
+                path = SplitDeltaPath(x, path, rayDir, surfaceData, deltaLobes[lobeForReuse], uint(lobeForReuse), nonZeroDeltaLobeCount > 0);
+            }
+        }
+    }
+    if (setAsBase)
+    {
+        float3 camO, camD; computeCameraRay(x, px, py, camO, camD);
+        const mat3 imageXform = path.GetImageXform();
+        const bool blockedAtSurface = path.GetMotionVectorSceneLength() != 0;
+        const float sceneLengthForMVs = blockedAtSurface ? path.GetMotionVectorSceneLength() : path.sceneLength;
+        const float3 virtualWorldPos = camO + camD * sceneLengthForMVs;
+        const float3 worldMotion = f3(0);                  // prevPosW - posW: the scene tables carry no previous transforms (static geometry)
+        const float3 virtualWorldMotion = mul(imageXform, worldMotion);
+        const float3 motionVectors = T.computeMotionVector(virtualWorldPos, virtualWorldPos + virtualWorldMotion);
+        float roughness = saturate(surfaceData.bsdf.data.roughness);
+        const float3 worldNormal = normalize(mul(imageXform, sd.N));
+        float3 diffBSDFEstimate, specBSDFEstimate;
+        surfaceData.bsdf.estimateSpecDiffBSDF(diffBSDFEstimate, specBSDFEstimate, sd.N, sd.V);
+        if (blockedAtSurface) roughness *= 0.25f * 0.95f;      // kSpecularRoughnessThreshold * 0.95
+        const bool isDominant = path.hasFlag(PF_stablePlaneOnDominantBranch);
+        T.StoreStablePlane(px, py, currentSPIndex, vertexIndex, rayOrigin, rayDir, path.stableBranchID, path.sceneLength, rayTCurrent, path.GetThp(), motionVectors, roughness, worldNormal,
+                           diffBSDFEstimate, specBSDFEstimate, isDominant);
+        if (isDominant) T.exportGuides(px, py, clipDepth(x.worldToClip, camO + camD * sceneLengthForMVs), motionVectors, Pack_R11G11B10_FLOAT(pathThroughputGuide(path.GetThp())));   // Bridge::ExportSurface
+        path.terminate();
+    }
+}
+
+inline void StablePlanesHandleMiss(const PathTracerCtx& x, PathState& path, float3 emission, float3 rayOrigin, float3 rayDir)
+{
+    const RealtimeTargets& T = *x.sp;
+    const uint px = path.id >> 16, py = path.id & 0xFFFF, vertexIndex = path.getVertexIndex();
+    if (vertexIndex == 1) T.StoreFirstHitRayLengthAndClearDominantToZero(px, py, kMaxRayTravel);
+    float3 camO, camD; computeCameraRay(x, px, py, camO, camD);
+    const bool blockedAtSurface = path.GetMotionVectorSceneLength() != 0;
+    const float sceneLengthForMVs = blockedAtSurface ? path.GetMotionVectorSceneLength() : kEnvironmentMapSceneDistance;
+    const float3 virtualWorldPos = camO + camD * sceneLengthForMVs;
+    const float3 motionVectors = T.computeMotionVector(virtualWorldPos, virtualWorldPos);
+    const bool isDominant = path.hasFlag(PF_stablePlaneOnDominantBranch);
+    const float3 r = ReinhardMax(emission), skyAlbedo = f3(sqrtf(r.x), sqrtf(r.y), sqrtf(r.z));
+    T.StoreStablePlane(px, py, path.getStablePlaneIndex(), vertexIndex, rayOrigin, rayDir, path.stableBranchID, blockedAtSurface ? sceneLengthForMVs : INFINITY, 0.0f, path.GetThp(), motionVectors,
+                       blockedAtSurface ? 0.1f : 1.0f, -rayDir, skyAlbedo, blockedAtSurface ? f3(0.5f) : f3(0), isDominant);
+    if (isDominant) T.exportGuides(px, py, clipDepth(x.worldToClip, virtualWorldPos), motionVectors, 0u);      // Bridge::ExportNonSurface
+}
+
+inline void CommitDenoiserRadiance(const PathTracerCtx& x, PathState& path)
+{
+    RtxptStablePlane& sp = x.sp->planes[x.sp->PixelToAddress(path.id >> 16, path.id & 0xFFFF, path.getStablePlaneIndex())];
+    float4 accum = path.GetL();
+    if (sp.PackedNoisyRadianceAndSpecAvg[0] != 0 && sp.PackedNoisyRadianceAndSpecAvg[1] != 0)
+    {
+        const float2 a = Fp16ToFp32(sp.PackedNoisyRadianceAndSpecAvg[0]), b = Fp16ToFp32(sp.PackedNoisyRadianceAndSpecAvg[1]);
+        accum = accum + f4(a.x, a.y, b.x, b.y);
+    }
+    sp.PackedNoisyRadianceAndSpecAvg[0] = Fp32ToFp16(f2(accum.x, accum.y)); sp.PackedNoisyRadianceAndSpecAvg[1] = Fp32ToFp16(f2(accum.z, accum.w));
+    path.SetL(f4(0, 0, 0, 0));
+}
+
+inline void StablePlanesOnScatter(const PathTracerCtx& x, PathState& path, const BSDFSample& bs)
+{
+    const RealtimeTargets& T = *x.sp;
+    const uint px = path.id >> 16, py = path.id & 0xFFFF;
+    if (path.hasFlag(PF_stablePlaneOnPlane)) path.setFlag(PF_stablePlaneBaseScatterDiff, (bs.lobe & Lobe_Diffuse) != 0);
+    path.setFlag(PF_stablePlaneOnPlane, false);
+    const uint nextVertexIndex = path.getVertexIndex() + 1;
+    if (path.hasFlag(PF_stablePlaneOnBranch) && nextVertexIndex <= cStablePlaneMaxVertexIndex)
+    {
+        path.stableBranchID = StablePlanesAdvanceBranchID(path.stableBranchID, bs.getDeltaLobeIndex());
+        bool onStablePath = false;
+        for (uint spi = 0; spi < cStablePlaneCount; spi++)
+        {
+            const uint planeBranchID = T.GetBranchID(px, py, spi);
+            if (planeBranchID == cStablePlaneInvalidBranchID) continue;
+            if (StablePlaneIsOnPlane(planeBranchID, path.stableBranchID))
+            {
+                CommitDenoiserRadiance(x, path);
+                path.setStablePlaneIndex(spi);
+                path.setFlag(PF_stablePlaneOnDominantBranch, spi == T.LoadDominantIndex(px, py));
+                path.setFlag(PF_stablePlaneOnPlane, true);
+                path.setCounter(CTR_BouncesFromStablePlane, 0);
+                onStablePath = true;
+                break;
+            }
+            onStablePath |= StablePlaneIsOnStablePath(planeBranchID, StablePlanesVertexIndexFromBranchID(planeBranchID), path.stableBranchID, nextVertexIndex);
+        }
+        path.setFlag(PF_stablePlaneOnBranch, onStablePath);
+    }
+    else
+    {
+        path.stableBranchID = cStablePlaneInvalidBranchID;
+        path.setFlag(PF_stablePlaneOnBranch, false);
+        path.incrementCounter(CTR_BouncesFromStablePlane);
+    }
+    if (!path.hasFlag(PF_stablePlaneOnPlane)) path.incrementCounter(CTR_BouncesFromStablePlane);
+}
+
+struct RealtimeStats { uint64_t rays = 0; };
+
+// RayGen of the BUILD pass for one pixel
+inline void buildStablePlanesPixel(const PathTracerCtx& x, uint px, uint py)
+{
+    const RealtimeTargets& T = *x.sp;
+    PathState path;
+    path.id = (px << 16) | py;
+    path.SetThp(f3(1));
+    path.setFlag(PF_active); path.setFlag(PF_deltaOnlyPath, true);
+    path.rayCone = RayCone::make(0, x.c->camera.PixelConeSpreadAngle);
+    path.SetImageXform(identity3());
+    path.setFlag(PF_stablePlaneOnDominantBranch, true);
+    path.SetMotionVectorSceneLength(0);
+    path.setStablePlaneIndex(0);
+    path.stableBranchID = 1;
+    if (HasFinishedSurfaceBounces(x, path.getVertexIndex() + 1, path.getCounter(CTR_DiffuseBounces))) path.setFlag(PF_terminateAtNextBounce);
+    computeCameraRay(x, px, py, path.origin, path.dir);
+    T.StartPixel(px, py); T.ExportSurfaceInit(px, py);
+    while (path.isActive())
+    {
+        const float3 o = path.origin, d = path.dir;
+        if (x.stats) x.stats->scatterRays++;
+        Hit h = x.bvh->trace(*x.scene, o, d, 0.0f, kMaxRayTravel, false, x.stats ? &x.stats->nodeVisits : nullptr, x.stats ? &x.stats->triTests : nullptr);
+        if (!h.valid()) HandleMiss(x, path, d, kMaxRayTravel);
+        else HandleHit(x, path, o, d, h.t, x.bvh->tris[h.triId], f2(h.u, h.v));
+        // postProcessHit: continue with the next enqueued branch of this pixel
+        int next;
+        if (!path.isActive() && (next = T.FindNextToExplore(px, py, path.getStablePlaneIndex() + 1)) != -1)
+        {
+            uint payload[20]; memcpy(payload, &T.planes[T.PixelToAddress(px, py, uint(next))], 80);
+            T.SetBranchID(px, py, uint(next), cStablePlaneJustStartedID);
+            path = unpackPayload(payload);
+        }
+    }
+}
+
+// RayGen of the FILL pass for one pixel and one sub-sample (x.sampleIndex = sampleBaseIndex + subSampleIndex)
+inline void fillStablePlanesPixel(const PathTracerCtx& x, uint px, uint py)
+{
+    const RealtimeTargets& T = *x.sp;
+    PathState path;
+    path.id = (px << 16) | py;
+    path.SetThp(f3(1));
+    path.setFlag(PF_active); path.setFlag(PF_deltaOnlyPath, true);
+    path.rayCone = RayCone::make(0, x.c->camera.PixelConeSpreadAngle);
+    path.SetL(f4(0, 0, 0, 0));
+    path.SetFireflyFilterK_BsdfScatterPdf(1.0f, 0.0f);
+    path.SetPackedMISInfo_ThpRuRuCorrection(NEEBSDFMISInfo().Pack16bit(), 1.0f);
+    path.setStablePlaneIndex(0);
+    path.stableBranchID = 1;
+    if (HasFinishedSurfaceBounces(x, path.getVertexIndex() + 1, path.getCounter(CTR_DiffuseBounces))) path.setFlag(PF_terminateAtNextBounce);
+    computeCameraRay(x, px, py, path.origin, path.dir);
+
+    // FirstHitFromVBuffer(path, 0): restart from stable plane 0
+    float tMin = 0, tMax = kMaxRayTravel;
+    {
+        const RtxptStablePlane& sp = T.planes[T.PixelToAddress(px, py, 0)];
+        const uint stableBranchID = T.GetBranchID(px, py, 0);
+        float sceneLength = sp.SceneLength; const float lastRayTCurrent = sp.LastRayTCurrent;
+        const uint vertexIndex = sp.VertexIndexAndRoughness >> 16;
+        float3 thp, dummy; UnpackTwoFp32ToFp16(sp.PackedThpAndMVs, thp, dummy);
+        bool isMiss = false;
+        if (!std::isfinite(sceneLength)) { sceneLength = kMaxRayTravel; isMiss = true; }
+        else { tMin = lastRayTCurrent * 0.99f; tMax = lastRayTCurrent * 1.01f; sceneLength -= lastRayTCurrent; }
+        path.setVertexIndex(vertexIndex - 1);
+        path.dir = f3(sp.RayDir[0], sp.RayDir[1], sp.RayDir[2]); path.origin = f3(sp.RayOrigin[0], sp.RayOrigin[1], sp.RayOrigin[2]);
+        path.setFlag(PF_stablePlaneOnPlane, true); path.setFlag(PF_stablePlaneOnBranch, true);
+        path.setStablePlaneIndex(0);
+        path.stableBranchID = stableBranchID;
+        path.SetThp(thp);
+        path.SetL(f4(0, 0, 0, 0));
+        path.setFlag(PF_stablePlaneOnDominantBranch, T.LoadDominantIndex(px, py) == 0);
+        path.setCounter(CTR_BouncesFromStablePlane, 0);
+        if (HasFinishedSurfaceBounces(x, path.getVertexIndex() + 1, path.getCounter(CTR_DiffuseBounces))) path.setFlag(PF_terminateAtNextBounce);
+        path.rayCone = path.rayCone.propagateDistance(sceneLength);                      // UpdatePathTravelledLengthOnly
+        path.sceneLength = std::min(path.sceneLength + sceneLength, kMaxRayTravel);
+        if (isMiss) HandleMiss(x, path, path.dir, sceneLength);
+    }
+    while (path.isActive())
+    {
+        const float3 o = path.origin, d = path.dir;
+        if (x.stats) x.stats->scatterRays++;
+        Hit h = x.bvh->trace(*x.scene, o, d, tMin, tMax, false, x.stats ? &x.stats->nodeVisits : nullptr, x.stats ? &x.stats->triTests : nullptr);
+        if (!h.valid()) HandleMiss(x, path, d, kMaxRayTravel);
+        else HandleHit(x, path, o, d, h.t, x.bvh->tris[h.triId], f2(h.u, h.v));
+        tMin = 0; tMax = kMaxRayTravel;
+    }
+    CommitDenoiserRadiance(x, path);        // PathTracer::CommitPixel
 }
 
 } // namespace orc

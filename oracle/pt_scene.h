@@ -150,6 +150,7 @@ struct ShadingData      // Scene/ShadingData.hlsli:38-61
     float3 posW, faceNCorrected, V, N, T, B, vertexN;
     bool frontFacing;
     uint nestedPriority; bool thinSurface; uint activeLobes; bool psdExclude;   // MaterialHeader (Scene/Material/MaterialData.hlsli)
+    uint psdDominantDeltaLobeP1 = 0; bool psdBlockMotionVectorsAtSurface = false;
     uint materialID;
     float IoR, shadowNoLFadeout;
     float3 emission;
@@ -400,6 +401,8 @@ inline SurfaceData loadSurface(const Scene& sc, uint instanceIndex, uint geometr
     sd.nestedPriority = std::min(15u, 1u + (mat.flags >> RTXPT_MATFLAG_NestedPriorityShift));
     sd.thinSurface = (mat.flags & RTXPT_MATFLAG_ThinSurface) != 0;
     sd.psdExclude = (mat.flags & RTXPT_MATFLAG_PSDExclude) != 0;
+    sd.psdDominantDeltaLobeP1 = (mat.flags & 0x0F000000u) >> 24;                                    // PTMaterialFlags_PSDDominantDeltaLobeP1Mask/Shift (BridgeDonut:700)
+    sd.psdBlockMotionVectorsAtSurface = ((mat.flags >> 13) & 3u) == 3u;                              // block type 3 "Full"; the curvature heuristics of types 1/2 (BridgeDonut:704-718) are not restated: treated as Off
     adjustShadingNormal(sd, gs.tangent, true, ignoreTangent);
     sd.shadowNoLFadeout = mat.shadowNoLFadeout;
 

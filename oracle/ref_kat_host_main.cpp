@@ -17,6 +17,7 @@ typedef uint32_t uint;
 #include "PathTracer/Materials/MaterialPT.h"
 #include "SubInstanceData.h"
 #include "PathTracer/Lighting/PolymorphicLight.h"
+#include "PathTracer/StablePlanes.hlsli"       // C++ half: StablePlane layout, branch-ID helpers; pulls Utils/Utils.hlsli (Morton / GenericTS addressing)
 
 static uint32_t bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 #define OFF(T, f) printf("%s\"%s\": %zu", first ? "" : ", ", #f, offsetof(T, f)), first = false
@@ -99,6 +100,46 @@ int main()
         printf("%s[%u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u]", first ? "" : ", ", bits(v[0]), bits(v[1]), bits(v[2]), bits(v[3] >= 0 ? 1.0f : -1.0f), p3, p4,
                bits(d3.x), bits(d3.y), bits(d3.z), bits(d4.x), bits(d4.y), bits(d4.z), bits(d4.w));
         first = false;
+    }
+    printf("],\n");
+    // realtime mode: StablePlane layout, constants, branch-ID arithmetic and GenericTS addressing (StablePlanes.hlsli, Utils/Utils.hlsli)
+    LAYOUT_BEGIN(StablePlane);
+    OFF(StablePlane, RayOrigin); OFF(StablePlane, LastRayTCurrent); OFF(StablePlane, RayDir); OFF(StablePlane, SceneLength); OFF(StablePlane, PackedThpAndMVs); OFF(StablePlane, VertexIndexAndRoughness);
+    OFF(StablePlane, DenoiserPackedBSDFEstimate); OFF(StablePlane, PackedNormal); OFF(StablePlane, PackedNoisyRadianceAndSpecAvg); OFF(StablePlane, FlagsAndVertexIndex); OFF(StablePlane, PackedCounters);
+    LAYOUT_END(false);
+    printf(" \"stable_plane_constants\": {\"cStablePlaneCount\": %u, \"cStablePlaneMaxVertexIndex\": %u, \"cStablePlaneInvalidBranchID\": %u, \"cStablePlaneEnqueuedBranchID\": %u, \"cStablePlaneJustStartedID\": %u, \"cMaxDeltaLobes\": %u},\n",
+           (uint)cStablePlaneCount, cStablePlaneMaxVertexIndex, cStablePlaneInvalidBranchID, cStablePlaneEnqueuedBranchID, cStablePlaneJustStartedID, cMaxDeltaLobes);
+    printf(" \"branch_ids\": [");
+    {   // random delta-lobe walks from the camera vertex: [lobes..] -> id, vertex index, on-stable-path answers against a second walk
+        uint32_t r = 777u; first = true;
+        for (int i = 0; i < 96; i++)
+        {
+            uint ids[2], depth[2];
+            for (int w = 0; w < 2; w++)
+            {
+                r = r * 1664525u + 1013904223u; depth[w] = 1 + (r >> 28) % 15; ids[w] = 1;
+                for (uint v = 1; v < depth[w]; v++) { r = r * 1664525u + 1013904223u; ids[w] = StablePlanesAdvanceBranchID(ids[w], (i % 3 == 0 && w == 1 && v < depth[0]) ? ((ids[0] >> ((depth[0] - 1 - v) * 2)) & 3) : ((r >> 30) & 1)); }
+            }
+            printf("%s[%u, %u, %u, %u, %u, %u, %u]", first ? "" : ", ", ids[0], ids[1], StablePlanesVertexIndexFromBranchID(ids[0]), StablePlanesVertexIndexFromBranchID(ids[1]),
+                   (uint)StablePlaneIsOnStablePath(ids[0], ids[1]), (uint)StablePlaneIsOnPlane(ids[0], ids[1]), StablePlanesGetParentLobeID(ids[0]));
+            first = false;
+        }
+    }
+    printf("],\n \"generic_ts\": [");
+    {
+        const uint sizes[][2] = { { 64, 64 }, { 96, 96 }, { 1920, 1080 }, { 641, 359 }, { 3840, 2160 }, { 7, 5 } };
+        uint32_t r = 4242u; first = true;
+        for (auto& sz : sizes)
+        {
+            const uint line = GenericTSComputeLineStride(sz[0], sz[1]), plane = GenericTSComputePlaneStride(sz[0], sz[1]);
+            printf("%s{\"size\": [%u, %u], \"line\": %u, \"plane\": %u, \"count3\": %u, \"samples\": [", first ? "" : ", ", sz[0], sz[1], line, plane, GenericTSComputeStorageElementCount(sz[0], sz[1], 3));
+            for (int i = 0; i < 24; i++)
+            {
+                r = r * 1664525u + 1013904223u; const uint x = (i == 0) ? sz[0] - 1 : (r >> 8) % sz[0]; r = r * 1664525u + 1013904223u; const uint y = (i == 0) ? sz[1] - 1 : (r >> 8) % sz[1]; const uint p = i % 3;
+                printf("%s[%u, %u, %u, %u]", i ? ", " : "", x, y, p, GenericTSPixelToAddress(uint2(x, y), p, line, plane));
+            }
+            printf("]}"); first = false;
+        }
     }
     printf("]\n}\n");
     return 0;

@@ -426,6 +426,7 @@ struct Loader
             }
             const std::string alphaMode = m.string("alphaMode", "OPAQUE");
             if (!enableTransmission || thin) flags |= RTXPT_MATFLAG_ThinSurface;        // MaterialsBaker.cpp:543-544
+            flags |= RTXPT_MATFLAG_PSDExclude;       // PTMaterialBase default for a material without a .material.json (MaterialsBaker.h:173)
             if (const JValue* extras = m.find("extras")) flags |= (uint32_t(std::min(extras->integer("nestedPriority", 0), 14)) & 0xFu) << RTXPT_MATFLAG_NestedPriorityShift;
             d.Flags = flags;
             d.BaseOrDiffuseColor[0] = base[0]; d.BaseOrDiffuseColor[1] = base[1]; d.BaseOrDiffuseColor[2] = base[2];

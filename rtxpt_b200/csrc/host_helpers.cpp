@@ -60,3 +60,19 @@ RTXPT_API int rtxpt_b200_default_constants(const RtxptCameraData* camera, int en
 }
 
 } // extern "C"
+
+// ---- GenericTS addressing of the stable-plane buffer (Rtxpt/Shaders/PathTracer/Utils/Utils.hlsli:262-269 Morton16BitEncode, :320-352): 8x8 tiles,
+// Morton order inside a tile, tiles row-major, planes one after the other ------------------------------------------------------------------------
+static uint32_t morton16(uint32_t x, uint32_t y)
+{
+    uint32_t t = (x & 0xff) | ((y & 0xff) << 16);
+    t = (t ^ (t << 4)) & 0x0f0f0f0f; t = (t ^ (t << 2)) & 0x33333333; t = (t ^ (t << 1)) & 0x55555555;
+    return ((t >> 15) | t) & 0xffff;
+}
+extern "C" RTXPT_API uint32_t rtxpt_b200_generic_ts_line_stride(uint32_t width, uint32_t) { return ((width + 7u) / 8u) * 8u; }
+extern "C" RTXPT_API uint32_t rtxpt_b200_generic_ts_plane_stride(uint32_t width, uint32_t height) { return rtxpt_b200_generic_ts_line_stride(width, height) * ((height + 7u) / 8u) * 8u; }
+extern "C" RTXPT_API uint32_t rtxpt_b200_generic_ts_address(uint32_t x, uint32_t y, uint32_t plane, uint32_t lineStride, uint32_t planeStride)
+{
+    const uint32_t xi = x % 8u, yi = y % 8u;
+    return (x - xi) * 8u + (y - yi) * lineStride + morton16(xi, yi) + plane * planeStride;
+}

@@ -98,7 +98,7 @@ class Material:
                  transmission=0.0, diffuse_transmission=0.0, ior=1.5, thin_surface=False, opacity=1.0, alpha_test=False, alpha_cutoff=0.5,
                  base_texture=None, orm_texture=None, normal_texture=None, emissive_texture=None, nested_priority=0,
                  volume_color=(1, 1, 1), volume_distance=3.4e38, shadow_nol_fadeout=0.0, exclude_from_nee=False, normal_scale=1.0,
-                 metalness_in_red=False, analytic_light_proxy=False):
+                 metalness_in_red=False, analytic_light_proxy=False, psd_exclude=True, psd_dominant_delta_lobe=-1, psd_block_mvs_at_surface=0):
         self.__dict__.update(locals()); del self.__dict__["self"]
 
     @property
@@ -189,7 +189,12 @@ class Scene:
             if m.thin_surface or not m.enable_transmission:      # MaterialsBaker.cpp:543-544
                 flags |= S.MATFLAG_ThinSurface
             flags |= (min(int(m.nested_priority), 14) & 0xF) << S.MATFLAG_NestedPriorityShift
-            flags |= 0 << 24                                     # PSDDominantDeltaLobe + 1 = 0 (unused by the reference-mode path)
+            # path-space decomposition controls of realtime mode (MaterialsBaker.h:173-177 defaults: excluded, no dominant lobe, motion vectors not blocked;
+            # FillData MaterialsBaker.cpp:546-553, :586)
+            if m.psd_exclude:
+                flags |= S.MATFLAG_PSDExclude
+            flags |= (int(m.psd_block_mvs_at_surface) % 2) << 13 | (int(m.psd_block_mvs_at_surface) // 2) << 14
+            flags |= min(max(int(m.psd_dominant_delta_lobe) + 1, 0), 7) << 24
             d.Flags = flags
             d.BaseOrDiffuseColor[:] = m.base_color
             d.SpecularColor[:] = (0, 0, 0)
@@ -323,6 +328,30 @@ def world_to_clip(cam):
     proj[0, 0], proj[1, 1] = 1.0 / tan_x, 1.0 / tan_y
     proj[2, 2], proj[2, 3], proj[3, 2] = fa / (fa - n), 1.0, -n * fa / (fa - n)
     return (view @ proj).astype(f)
+
+
+def make_realtime_constants(width, height, cam, prev_cam=None, active_planes=3, max_vertex_depth=14, bounce_count=None, allow_psr=True, sub_samples=1):
+    """RtxptRealtimeConstants the way Sample::UpdatePathTracerConstants / UpdateViews fill them (Sample.cpp:1464-1480, :1529-1540): both views without
+    the sub-pixel jitter offset, clipToWindowScale = (0.5 w, -0.5 h), maxStablePlaneVertexDepth = min(UI value, 15, bounceCount)."""
+    rt = S.RealtimeConstants()
+    rt.activeStablePlaneCount = active_planes
+    rt.maxStablePlaneVertexDepth = min(max_vertex_depth, 15, bounce_count if bounce_count is not None else 15)
+    rt.allowPrimarySurfaceReplacement = 1 if allow_psr else 0
+    rt.subSampleCount = sub_samples
+    rt.matWorldToClipNoOffset[:] = world_to_clip(cam).reshape(16).tolist()
+    rt.prevMatWorldToClipNoOffset[:] = world_to_clip(prev_cam if prev_cam is not None else cam).reshape(16).tolist()
+    rt.clipToWindowScale[:] = [0.5 * width, -0.5 * height]
+    return rt
+
+
+def generic_ts_address(x, y, plane, width, height):
+    """GenericTSPixelToAddress (Utils.hlsli:337-352): 8x8 tiles, Morton order inside a tile; vectorised over numpy arrays."""
+    x = np.asarray(x, np.uint32); y = np.asarray(y, np.uint32)
+    line = ((width + 7) // 8) * 8; plane_stride = line * ((height + 7) // 8) * 8
+    xi, yi = x % 8, y % 8
+    def spread(v): v = (v | (v << 2)) & 0x33; return (v | (v << 1)) & 0x55
+    morton = spread(xi) | (spread(yi) << 1)
+    return ((x - xi) * 8 + (y - yi) * line + morton + plane * plane_stride).astype(np.uint32)
 
 
 def bridge_camera(width, height, pos, direction, up, fov_y, near_z=0.1, far_z=1e7, focal_distance=10000.0, aperture_radius=0.0, jitter=(0.0, 0.0)):

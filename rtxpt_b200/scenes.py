@@ -38,16 +38,17 @@ def _merge(geos, material):
     return dict(positions=np.concatenate(pos), indices=np.concatenate(idx), normals=np.concatenate(nrm), uvs=np.concatenate(uvs), material=material)
 
 
-def cornell_box(width=256, height=256, analytic_lights=False):
+def cornell_box(width=256, height=256, analytic_lights=False, delta_surfaces=False):
     """Returns (scene, camera).  Classic Cornell data in metres (x right, y up, z into the box); the camera looks down +z.
     analytic_lights adds a sphere light, a spot light and a zero-radius point light (the reference never samples the last)."""
-    scene = cornell_builder(analytic_lights).build()
+    scene = cornell_builder(analytic_lights, delta_surfaces).build()
     cam = bridge_camera(width, height, pos=(2.78, 2.73, -8.0), direction=(0, 0, 1), up=(0, 1, 0), fov_y=0.66)
     return scene, cam
 
 
-def cornell_builder(analytic_lights=False):
-    """The SceneBuilder behind cornell_box (also written out as glTF by the loader tests)."""
+def cornell_builder(analytic_lights=False, delta_surfaces=False):
+    """The SceneBuilder behind cornell_box (also written out as glTF by the loader tests).  delta_surfaces: the tall box becomes a perfect mirror and the
+    short box clear glass, both enabled for path-space decomposition - what realtime mode splits into stable planes."""
     b = SceneBuilder()
     if analytic_lights:
         b.add_point_light(position=(1.2, 3.9, 1.6), color=(0.4, 0.6, 1.0), intensity=14.0, radius=0.22)
@@ -68,7 +69,13 @@ def cornell_builder(analytic_lights=False):
     tall = _box([(4.23, 0, 2.47), (2.65, 0, 2.96), (3.14, 0, 4.56), (4.72, 0, 4.06)], 3.30, white)
     room = b.add_mesh([_merge([floor, ceiling, back], white), left, right])
     lamp = b.add_mesh([lq])
-    boxes = b.add_mesh([_merge(short, white), _merge(tall, white)])
+    if delta_surfaces:
+        mirror = b.add_material(Material(base_color=(0.95, 0.93, 0.88), roughness=0.0, metalness=1.0, psd_exclude=False, psd_dominant_delta_lobe=1))
+        glass = b.add_material(Material(base_color=(0.9, 0.97, 1.0), roughness=0.0, transmission=1.0, ior=1.5, thin_surface=False, nested_priority=2,
+                                        volume_color=(0.8, 0.95, 0.9), volume_distance=1.5, psd_exclude=False, psd_dominant_delta_lobe=0))
+        boxes = b.add_mesh([_merge(short, glass), _merge(tall, mirror)])
+    else:
+        boxes = b.add_mesh([_merge(short, white), _merge(tall, white)])
     for m in (room, lamp, boxes):
         b.add_instance(m, identity34())
     if analytic_lights:

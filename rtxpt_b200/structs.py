@@ -30,6 +30,8 @@ CFG_TIME_KERNELS = 4
 CFG_EXPORT_GUIDES = 8
 
 BUFFER_OUTPUT_COLOR_F16, BUFFER_ACCUMULATED_F32, BUFFER_DEPTH_F32, BUFFER_MOTION_VECTORS_F16, BUFFER_THROUGHPUT_R11G11B10 = 0, 1, 2, 3, 4
+BUFFER_STABLE_PLANES, BUFFER_STABLE_PLANES_HEADER, BUFFER_STABLE_RADIANCE_F16, BUFFER_SPECULAR_HITT_F32 = 5, 6, 7, 8
+STABLE_PLANE_COUNT, STABLE_PLANE_INVALID_BRANCH = 3, 0xFFFFFFFF
 
 
 class GeometryData(C.Structure):
@@ -113,6 +115,20 @@ class GltfCamera(C.Structure):
 
 class ViewConstants(C.Structure):
     _fields_ = [("matWorldToClip", f32 * 16)]
+
+
+class StablePlane(C.Structure):          # 80 B, StablePlanes.hlsli:48-80
+    _fields_ = [("RayOrigin", f32 * 3), ("LastRayTCurrent", f32), ("RayDir", f32 * 3), ("SceneLength", f32), ("PackedThpAndMVs", u32 * 3), ("VertexIndexAndRoughness", u32),
+                ("DenoiserPackedBSDFEstimate", u32 * 3), ("PackedNormal", u32), ("PackedNoisyRadianceAndSpecAvg", u32 * 2), ("FlagsAndVertexIndex", u32), ("PackedCounters", u32)]
+
+
+STABLE_PLANE_DTYPE = [("RayOrigin", "f4", 3), ("LastRayTCurrent", "f4"), ("RayDir", "f4", 3), ("SceneLength", "f4"), ("PackedThpAndMVs", "u4", 3), ("VertexIndexAndRoughness", "u4"),
+                      ("DenoiserPackedBSDFEstimate", "u4", 3), ("PackedNormal", "u4"), ("PackedNoisyRadianceAndSpecAvg", "u4", 2), ("FlagsAndVertexIndex", "u4"), ("PackedCounters", "u4")]
+
+
+class RealtimeConstants(C.Structure):
+    _fields_ = [("activeStablePlaneCount", u32), ("maxStablePlaneVertexDepth", u32), ("allowPrimarySurfaceReplacement", u32), ("subSampleCount", u32),
+                ("matWorldToClipNoOffset", f32 * 16), ("prevMatWorldToClipNoOffset", f32 * 16), ("clipToWindowScale", f32 * 2), ("_pad", f32 * 2)]
 
 
 class CameraData(C.Structure):

@@ -49,6 +49,14 @@ def lib():
         L.oracle_get_sub_instances.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.oracle_render.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
                                     C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.c_int, C.POINTER(RenderStats)]
+        L.oracle_render_realtime.argtypes = [C.c_void_p, C.POINTER(S.RealtimeConstants)] + [C.c_uint32] * 4 + [C.c_void_p] * 8 + [C.c_int]
+        for f in ("oracle_branch_advance", "oracle_branch_vertex_index", "oracle_generic_ts_line_stride", "oracle_generic_ts_plane_stride"):
+            getattr(L, f).restype = C.c_uint32
+        L.oracle_branch_advance.argtypes = [C.c_uint32] * 2; L.oracle_branch_vertex_index.argtypes = [C.c_uint32]
+        L.oracle_branch_on_stable_path.restype = C.c_uint32; L.oracle_branch_on_stable_path.argtypes = [C.c_uint32] * 4
+        L.oracle_generic_ts_address.restype = C.c_uint32; L.oracle_generic_ts_address.argtypes = [C.c_uint32] * 5
+        L.oracle_generic_ts_line_stride.argtypes = [C.c_uint32] * 2; L.oracle_generic_ts_plane_stride.argtypes = [C.c_uint32] * 2
+        L.oracle_pack_ortho.argtypes = [C.c_void_p, C.c_void_p]; L.oracle_unpack_ortho.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_tri_info.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.oracle_rng.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.oracle_bsdf.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
@@ -117,3 +125,16 @@ class Oracle:
                                  primary.ctypes.data if want_primary else None, threads, C.byref(st))
         assert rc == 0
         return accum, n.value, last, primary, st
+
+    def render_realtime(self, rt, rect=None, threads=0):
+        """BUILD + rt.subSampleCount x FILL + no-denoiser merge.  Returns a dict of the realtime render targets (numpy)."""
+        W, H = self.consts.imageWidth, self.consts.imageHeight
+        plane_stride = lib().oracle_generic_ts_plane_stride(W, H)
+        out = dict(planes=np.zeros(3 * plane_stride, S.STABLE_PLANE_DTYPE), header=np.zeros((4, H, W), np.uint32), stable_radiance=np.zeros((H, W, 4), np.float16),
+                   depth=np.zeros((H, W), np.float32), motion=np.zeros((H, W, 4), np.float16), throughput=np.zeros((H, W), np.uint32), spec_hit_t=np.zeros((H, W), np.float32),
+                   merged=np.zeros((H, W, 3), np.float32))
+        assert out["planes"].itemsize == 80
+        x0, y0, x1, y1 = rect if rect else (0, 0, W, H)
+        rc = lib().oracle_render_realtime(self.h, C.byref(rt), x0, y0, x1, y1, *[out[k].ctypes.data for k in ("planes", "header", "stable_radiance", "depth", "motion", "throughput", "spec_hit_t", "merged")], threads)
+        assert rc == 0
+        return out
