@@ -345,6 +345,10 @@ enum {
     RTXPT_BUFFER_STABLE_RADIANCE_F16  = 7,  /* RGBA16F: emission / sky seen along the delta tree, no noise */
     RTXPT_BUFFER_SPECULAR_HITT_F32    = 8   /* R32F: specular hit distance of the dominant plane (denoiser guide) */
 };
+RTXPT_API int rtxpt_b200_set_realtime(rtxpt_ctx* ctx, const RtxptRealtimeConstants* realtime);
+/* BUILD + subSampleCount x FILL (+ the no-denoiser merge into RTXPT_BUFFER_OUTPUT_COLOR_F16 when mergeNoDenoiser != 0); asynchronous on `cudaStream`.
+ * Depth / motion vectors / throughput guides are those of the dominant plane (PathTracerStablePlanes.hlsli:316-321, :404-408). */
+RTXPT_API int rtxpt_b200_path_trace_realtime(rtxpt_ctx* ctx, int mergeNoDenoiser, void* cudaStream);
 /* GenericTS addressing of the plane buffer (host helpers; Utils.hlsli:320-362) */
 RTXPT_API uint32_t rtxpt_b200_generic_ts_line_stride(uint32_t width, uint32_t height);
 RTXPT_API uint32_t rtxpt_b200_generic_ts_plane_stride(uint32_t width, uint32_t height);

@@ -23,6 +23,7 @@ static_assert(sizeof(RtxptMaterialData) == 128, "PTMaterialData layout");
 static_assert(sizeof(RtxptCameraData) == 112, "PathTracerCameraData layout");
 static_assert(sizeof(LightInfo) == 32 && sizeof(BakedLight) == 32, "PolymorphicLightInfo layout");
 static_assert(sizeof(Bvh8Node) == 80 && sizeof(Bvh8Tri) == 48, "CWBVH8 layout");
+static_assert(sizeof(RtxptStablePlane) == 80, "StablePlane layout (StablePlanes.hlsli:48-80)");
 static_assert(sizeof(LaunchParams) <= 4000, "kernel parameter block");
 
 static thread_local std::string g_lastError;
@@ -76,6 +77,9 @@ struct rtxpt_ctx
     DeviceArray<uint2> outputColor; DeviceArray<float4> accumulated; DeviceArray<float> depth; DeviceArray<uint2> motionVectors; DeviceArray<uint32_t> throughput; float worldToClip[16] = {}; bool haveView = false;
     uint32_t accumulatedSamples = 0;
     RtxptPathTracerConstants consts{};
+    // realtime mode (stable planes): allocated on the first set_realtime for the current image size
+    DeviceArray<RtxptStablePlane> stablePlanes; DeviceArray<uint32_t> stablePlanesHeader; DeviceArray<uint2> stableRadiance; DeviceArray<float> specularHitT;
+    RtxptRealtimeConstants realtime{}; bool haveRealtime = false; uint32_t realtimeWidth = 0, realtimeHeight = 0;
     // stats
     uint32_t* hCounters = nullptr;          // pinned
     cudaEvent_t evStart = nullptr, evStop = nullptr;
@@ -542,6 +546,80 @@ extern "C" RTXPT_API int rtxpt_b200_path_trace(rtxpt_ctx* c, uint32_t firstSubSa
     return RTXPT_OK;
 }
 
+// ---- realtime mode -----------------------------------------------------------------------------------------------------------------------------------
+extern "C" RTXPT_API int rtxpt_b200_set_realtime(rtxpt_ctx* c, const RtxptRealtimeConstants* rt)
+{
+    if (!c || !rt) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (!c->haveConstants) return fail(RTXPT_ERR_INVALID_ARGUMENT, "set the path tracer constants first (the image size sizes the plane buffers)");
+    if (rt->activeStablePlaneCount < 1 || rt->activeStablePlaneCount > RTXPT_STABLE_PLANE_COUNT) return fail(RTXPT_ERR_INVALID_ARGUMENT, "activeStablePlaneCount must be 1..3");
+    if (rt->subSampleCount < 1) return fail(RTXPT_ERR_INVALID_ARGUMENT, "subSampleCount must be at least 1");
+    if (rt->maxStablePlaneVertexDepth > RTXPT_STABLE_PLANE_MAX_VERTEX_INDEX) return fail(RTXPT_ERR_INVALID_ARGUMENT, "maxStablePlaneVertexDepth above %u", RTXPT_STABLE_PLANE_MAX_VERTEX_INDEX);
+    cudaSetDevice(c->device);
+    const uint32_t W = c->tableWidth, H = c->tableHeight;
+    if (c->realtimeWidth != W || c->realtimeHeight != H)
+    {
+        CU(cudaStreamSynchronize(c->stream));
+        const size_t P = size_t(W) * H, planeStride = rtxpt_b200_generic_ts_plane_stride(W, H);
+        CU(c->stablePlanes.alloc(planeStride * RTXPT_STABLE_PLANE_COUNT)); CU(c->stablePlanesHeader.alloc(P * 4)); CU(c->stableRadiance.alloc(P)); CU(c->specularHitT.alloc(P));
+        CU(cudaMemsetAsync(c->stablePlanes.ptr, 0, planeStride * RTXPT_STABLE_PLANE_COUNT * sizeof(RtxptStablePlane), c->stream));
+        CU(cudaMemsetAsync(c->stablePlanesHeader.ptr, 0xFF, P * 16, c->stream)); CU(cudaMemsetAsync(c->stableRadiance.ptr, 0, P * 8, c->stream)); CU(cudaMemsetAsync(c->specularHitT.ptr, 0, P * 4, c->stream));
+        c->realtimeWidth = W; c->realtimeHeight = H;
+    }
+    c->realtime = *rt; c->haveRealtime = true;
+    return RTXPT_OK;
+}
+
+extern "C" RTXPT_API int rtxpt_b200_path_trace_realtime(rtxpt_ctx* c, int mergeNoDenoiser, void* cudaStream)
+{
+    int rc = checkReady(c); if (rc != RTXPT_OK) return rc;
+    if (!c->haveRealtime || c->realtimeWidth != c->tableWidth || c->realtimeHeight != c->tableHeight) return fail(RTXPT_ERR_INVALID_ARGUMENT, "rtxpt_b200_set_realtime has not been called for this image size");
+    if (!c->haveView) return fail(RTXPT_ERR_INVALID_ARGUMENT, "rtxpt_b200_set_view has not been called (the guide depth needs view.matWorldToClip)");
+    cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
+    LaunchParams p; fillParams(c, p);
+    const RtxptRealtimeConstants& r = c->realtime;
+    p.rt.planes = c->stablePlanes.ptr; p.rt.header = c->stablePlanesHeader.ptr; p.rt.stableRadiance = c->stableRadiance.ptr; p.rt.specularHitT = c->specularHitT.ptr;
+    p.rt.lineStride = rtxpt_b200_generic_ts_line_stride(c->tableWidth, c->tableHeight); p.rt.planeStride = rtxpt_b200_generic_ts_plane_stride(c->tableWidth, c->tableHeight);
+    p.rt.activePlaneCount = r.activeStablePlaneCount; p.rt.maxVertexDepth = r.maxStablePlaneVertexDepth; p.rt.allowPSR = r.allowPrimarySurfaceReplacement;
+    p.rt.attenuation = 1.0f / float(r.subSampleCount);
+    memcpy(p.rt.worldToClipNoOffset, r.matWorldToClipNoOffset, 64); memcpy(p.rt.prevWorldToClipNoOffset, r.prevMatWorldToClipNoOffset, 64);
+    p.rt.clipToWindowScale[0] = r.clipToWindowScale[0]; p.rt.clipToWindowScale[1] = r.clipToWindowScale[1];
+    p.exportGuides = 0; p.subSampleCount = 1; p.doAccumulate = 0;
+    const bool hasRefraction = c->consts.nestedDielectricsQuality > 0;
+    // BUILD: the branches of a pixel's delta tree are explored one after the other, each at most maxVertexDepth + 1 segments long (+ rejected false hits)
+    const uint32_t buildIterations = std::min<uint32_t>(r.activeStablePlaneCount * (std::min(r.maxStablePlaneVertexDepth, c->consts.bounceCount) + 1 + (hasRefraction ? 4 : 0)), kMaxWavefrontIterations);
+    const uint32_t fillIterations = std::min<uint32_t>(c->consts.bounceCount + 1 + (hasRefraction ? 4 : 0), kMaxWavefrontIterations);
+    CU(cudaEventRecord(c->evStart, s));
+    uint64_t launches = 0;
+    p.firstSampleIndex = c->consts.sampleBaseIndex;
+    CU(cudaMemsetAsync(c->counters.ptr, 0, kCounterWords * sizeof(uint32_t), s));
+    p.iteration = 0;
+    launchRtBuildGenerate(p, c->grid, s); launches++;
+    for (uint32_t it = 0; it < buildIterations; it++)
+    {
+        p.iteration = it;
+        launchTraceClosest(p, c->grid, false, s); launchRtShade(p, c->grid, false, s); launches += 2;
+    }
+    for (uint32_t sub = 0; sub < r.subSampleCount; sub++)
+    {
+        p.firstSampleIndex = c->consts.sampleBaseIndex + sub;
+        CU(cudaMemsetAsync(c->counters.ptr, 0, kCounterWords * sizeof(uint32_t), s));
+        p.iteration = 0;
+        launchRtFillGenerate(p, c->grid, s); launches++;
+        for (uint32_t it = 0; it < fillIterations; it++)
+        {
+            p.iteration = it;
+            launchTraceClosest(p, c->grid, false, s); launchRtShade(p, c->grid, true, s); launchTraceShadowRealtime(p, c->grid, s); launches += 3;
+        }
+        launchRtFillCommit(p, c->grid, s); launches++;
+    }
+    if (mergeNoDenoiser) { launchRtMerge(p, c->grid, s); launches++; }
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->evStop, s));
+    CU(cudaMemcpyAsync(c->hCounters, c->counters.ptr, kCounterWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    c->lastIterations = fillIterations; c->lastSubSamples = 1; c->lastLaunches = launches; c->statsPending = true;
+    return RTXPT_OK;
+}
+
 extern "C" RTXPT_API int rtxpt_b200_reset_accumulation(rtxpt_ctx* c)
 {
     if (!c) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null context");
@@ -567,6 +645,13 @@ static int targetInfo(rtxpt_ctx* c, int buffer, void** ptr, size_t* bytes)
     case RTXPT_BUFFER_DEPTH_F32: *ptr = c->depth.ptr; *bytes = P * 4; return RTXPT_OK;
     case RTXPT_BUFFER_MOTION_VECTORS_F16: *ptr = c->motionVectors.ptr; *bytes = P * 8; return RTXPT_OK;
     case RTXPT_BUFFER_THROUGHPUT_R11G11B10: *ptr = c->throughput.ptr; *bytes = P * 4; return RTXPT_OK;
+    case RTXPT_BUFFER_STABLE_PLANES: case RTXPT_BUFFER_STABLE_PLANES_HEADER: case RTXPT_BUFFER_STABLE_RADIANCE_F16: case RTXPT_BUFFER_SPECULAR_HITT_F32:
+        if (!c->haveRealtime || c->realtimeWidth != c->tableWidth || c->realtimeHeight != c->tableHeight) return fail(RTXPT_ERR_INVALID_ARGUMENT, "realtime buffers do not exist before rtxpt_b200_set_realtime");
+        if (buffer == RTXPT_BUFFER_STABLE_PLANES) { *ptr = c->stablePlanes.ptr; *bytes = c->stablePlanes.count * sizeof(RtxptStablePlane); }
+        else if (buffer == RTXPT_BUFFER_STABLE_PLANES_HEADER) { *ptr = c->stablePlanesHeader.ptr; *bytes = P * 16; }
+        else if (buffer == RTXPT_BUFFER_STABLE_RADIANCE_F16) { *ptr = c->stableRadiance.ptr; *bytes = P * 8; }
+        else { *ptr = c->specularHitT.ptr; *bytes = P * 4; }
+        return RTXPT_OK;
     default: return fail(RTXPT_ERR_INVALID_ARGUMENT, "unknown buffer %d", buffer);
     }
 }

@@ -162,7 +162,9 @@ __global__ void __launch_bounds__(kTraceThreads, MINB * kTraceCtaScale) k_trace_
 }
 
 // ---- shadow rays ----------------------------------------------------------------------------------------------------------------------------
-template <bool COUNT, int MINB>
+// REALTIME (FILL pass of realtime mode): the radiance is attenuated by 1 / sub-sample count and comes with a specular average chosen by the shade
+// kernel (sign bits of the record's first word, shade.cuh) - AccumulatePathRadiance of PATH_TRACER_MODE_FILL_STABLE_PLANES (PathTracer.hlsli:145-159)
+template <bool COUNT, int MINB, bool REALTIME = false>
 __global__ void __launch_bounds__(kTraceThreads, MINB * kTraceCtaScale) k_trace_shadow(const __grid_constant__ LaunchParams p)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -190,11 +192,18 @@ __global__ void __launch_bounds__(kTraceThreads, MINB * kTraceCtaScale) k_trace_
             if (uint(ws.bestKey[lane]) == 0xFFFFFFFFu)
             {   // visible: HandleHit's "if any(neeRadianceAndSpecAvg > 0) AccumulatePathRadiance" (PathTracer.hlsli:725-746)
                 const uint2 r = p.wf.shadowRadiance[record];
-                const float rx = f16tof32(r.x), ry = f16tof32(r.x >> 16), rz = f16tof32(r.y), rw = f16tof32(r.y >> 16);
+                const float rx = f16tof32(r.x & 0x7FFFu), ry = f16tof32((r.x >> 16) & 0x7FFFu), rz = f16tof32(r.y), rw = f16tof32(r.y >> 16);
                 if (rx > 0 || ry > 0 || rz > 0 || rw > 0)
                 {
                     uint4 s2 = p.wf.s2[slot];
-                    const float lx = f16tof32(s2.z) + rx, ly = f16tof32(s2.z >> 16) + ry, lz = f16tof32(s2.w) + rz, lw = f16tof32(s2.w >> 16);
+                    float lx, ly, lz, lw;
+                    if (REALTIME)
+                    {
+                        const float a = p.rt.attenuation;
+                        const float spec = (r.x & 0x00008000u) ? rw : ((r.x & 0x80000000u) ? (rx + ry + rz) / 3.0f : 0.0f);
+                        lx = f16tof32(s2.z) + rx * a; ly = f16tof32(s2.z >> 16) + ry * a; lz = f16tof32(s2.w) + rz * a; lw = f16tof32(s2.w >> 16) + spec * a;
+                    }
+                    else { lx = f16tof32(s2.z) + rx; ly = f16tof32(s2.z >> 16) + ry; lz = f16tof32(s2.w) + rz; lw = f16tof32(s2.w >> 16); }
                     s2.z = packHalf2NoClamp(clampf(lx, 0.f, kHalfMax), clampf(ly, 0.f, kHalfMax));
                     s2.w = packHalf2NoClamp(clampf(lz, 0.f, kHalfMax), clampf(lw, 0.f, kHalfMax));
                     p.wf.s2[slot] = s2;
@@ -353,6 +362,7 @@ cudaError_t configureKernels(int maxSmemOptin)
 #define ALLOW(k) if ((e = allowSmem(k, want)) != cudaSuccess) return e
     ALLOW((k_trace_closest<false, 2>)); ALLOW((k_trace_closest<false, 3>)); ALLOW((k_trace_closest<false, 4>)); ALLOW((k_trace_closest<true, 2>));
     ALLOW((k_trace_shadow<false, 2>)); ALLOW((k_trace_shadow<false, 3>)); ALLOW((k_trace_shadow<false, 4>)); ALLOW((k_trace_shadow<true, 2>));
+    ALLOW((k_trace_shadow<false, 4, true>)); ALLOW((k_trace_shadow<false, 2, true>));
     ALLOW(k_trace_rays<false>); ALLOW(k_trace_rays<true>);
 #undef ALLOW
     return cudaSuccess;
@@ -390,6 +400,12 @@ void launchTraceShadow(const LaunchParams& p, const GridConfig& g, bool count, c
     else if (g.traceBlocksPerSM >= 4) launchTrace(k_trace_shadow<false, 4>, grid, smem, s, p, g);
     else if (g.traceBlocksPerSM == 3) launchTrace(k_trace_shadow<false, 3>, grid, smem, s, p, g);
     else launchTrace(k_trace_shadow<false, 2>, grid, smem, s, p, g);
+}
+void launchTraceShadowRealtime(const LaunchParams& p, const GridConfig& g, cudaStream_t s)
+{
+    const int grid = g.smCount * g.traceBlocksPerSM; const size_t smem = traceSmemBytes(p);
+    if (g.traceBlocksPerSM >= 4) launchTrace(k_trace_shadow<false, 4, true>, grid, smem, s, p, g);
+    else launchTrace(k_trace_shadow<false, 2, true>, g.smCount * 2, smem, s, p, g);
 }
 void launchCommitAccumulate(const LaunchParams& p, const GridConfig& g, cudaStream_t s) { k_commit_accumulate<<<g.smCount * 4, 256, 0, s>>>(p); }
 void launchTraceRays(const LaunchParams& p, const GridConfig& g, const RtxptRay* rays, uint32_t count, bool anyHit, RtxptHit* out, uint32_t* counters, uint32_t* cursor, cudaStream_t s)

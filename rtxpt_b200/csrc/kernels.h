@@ -18,6 +18,13 @@ void launchGenerate(const LaunchParams& p, const GridConfig& g, cudaStream_t s);
 void launchTraceClosest(const LaunchParams& p, const GridConfig& g, bool countSteps, cudaStream_t s);
 void launchShade(const LaunchParams& p, const GridConfig& g, cudaStream_t s);
 void launchTraceShadow(const LaunchParams& p, const GridConfig& g, bool countSteps, cudaStream_t s);
+// realtime mode (realtime_kernels.cu; the shadow kernel variant lives with the other traversal kernels)
+void launchRtBuildGenerate(const LaunchParams& p, const GridConfig& g, cudaStream_t s);
+void launchRtFillGenerate(const LaunchParams& p, const GridConfig& g, cudaStream_t s);
+void launchRtShade(const LaunchParams& p, const GridConfig& g, bool fill, cudaStream_t s);
+void launchTraceShadowRealtime(const LaunchParams& p, const GridConfig& g, cudaStream_t s);
+void launchRtFillCommit(const LaunchParams& p, const GridConfig& g, cudaStream_t s);
+void launchRtMerge(const LaunchParams& p, const GridConfig& g, cudaStream_t s);
 void launchCommitAccumulate(const LaunchParams& p, const GridConfig& g, cudaStream_t s);
 void launchTraceRays(const LaunchParams& p, const GridConfig& g, const RtxptRay* dRays, uint32_t count, bool anyHit, RtxptHit* dHits, uint32_t* dCounters, uint32_t* dCursor, cudaStream_t s);
 void launchPackOwned(const float4* image, const uint32_t* pixelOfSlot, uint32_t pixelCount, uint32_t paddedCount, uint32_t width, float4* dst, const GridConfig& g, cudaStream_t s);

@@ -166,6 +166,8 @@ struct Surface
     BsdfParams bsdf;
     uint neeTriangleLightIndex;
     uint neeAnalyticLightIndex;     // light this geometry stands in for (PTMaterialFlags_EnableAsAnalyticLightProxy), else kInvalidLight
+    // path-space decomposition controls, read by realtime mode only (MaterialHeader, BridgeDonut:699-718)
+    bool psdExclude, psdBlockMVs; uint psdDominantDeltaLobeP1;
 };
 
 PT_DEVICE float3 safeNormalize(float3 v) { return v * (1.0f / sqrtf(fmaxf(1.175494351e-38f, dot3(v, v)))); }
@@ -309,6 +311,9 @@ PT_DEVICE void loadSurface(const LaunchParams& p, uint gid, float bu, float bv, 
     s.materialID = materialIndex;
     s.nestedPriority = min(15u, 1u + (mflags >> RTXPT_MATFLAG_NestedPriorityShift));
     s.thin = (mflags & RTXPT_MATFLAG_ThinSurface) != 0;
+    s.psdExclude = (mflags & RTXPT_MATFLAG_PSDExclude) != 0;
+    s.psdDominantDeltaLobeP1 = (mflags & 0x0F000000u) >> 24;
+    s.psdBlockMVs = ((mflags >> 13) & 3u) == 3u;            // block type 3 "Full"; the curvature heuristics of types 1/2 (BridgeDonut:704-718) are treated as Off
     {   // adjustShadingNormal(recomputeTangentSpace = true)
         const float signN = dot3(s.N, s.faceN) >= 0.f ? 1.f : -1.f;
         const float3 Ns = signN * s.N;
@@ -364,19 +369,39 @@ PT_DEVICE void updatePathTravelled(PathRegs& path, float rayT)      // PathTrace
     path.sceneLength = fminf(path.sceneLength + rayT, kMaxRayTravel);
 }
 
-template <bool EXPORT_GUIDES>
+} // namespace pt
+#include "realtime.cuh"
+namespace pt {
+
+// AccumulatePathRadiance (PathTracer.hlsli:139-162)
+template <int MODE>
+PT_DEVICE void accumulatePathRadiance(const LaunchParams& p, PathRegs& path, float3 radiance)
+{
+    if constexpr (MODE == kModeReference) path.addRadiance(radiance);
+    else if constexpr (MODE == kModeBuildStablePlanes) accumulateStableRadiance(p, path.id, radiance);
+    else if (!path.hasFlag(kPFStablePlaneOnBranch))         // FILL: what lies on the stable branches was captured by the BUILD pass
+    {
+        const float specAvg = path.hasFlag(kPFStablePlaneBaseScatterDiff) ? 0.0f : average(radiance);
+        const float a = p.rt.attenuation; const float4 l = path.L();
+        path.setL(make_float4(l.x + radiance.x * a, l.y + radiance.y * a, l.z + radiance.z * a, l.w + specAvg * a));
+    }
+}
+
+template <bool EXPORT_GUIDES, int MODE = kModeReference>
 PT_DEVICE void shadeMiss(const LaunchParams& p, PathRegs& path)
 {
+    const float3 segmentOrigin = path.origin;
     updatePathTravelled(path, kMaxRayTravel);
+    if constexpr (MODE == kModeFillStablePlanes) if (path.hasFlag(kPFExportSpecHitTQueued)) { exportSpecHitTStop(p, path); path.setFlag(kPFExportSpecHitTQueued, false); }
     float3 emission = mk3(0.f);
     if (p.scene.envEnabled)
     {
-        const uint mis = path.misInfo();
+        const uint mis = (MODE == kModeBuildStablePlanes) ? 0u : path.misInfo();      // no NEE, no MIS while the planes are built (PathState.hlsli:157-159)
         const float mip = (path.counter(kCtrDiffuseBounces) > 1) ? p.c.EnvironmentMapDiffuseSampleMIPLevel : 0.0f;
         const float3 localDir = rowVecTimes3x3(path.dir, p.c.envMap.InvTransform);
         const float3 Le = envEvalLocal(p, localDir, mip);
         float misWeight = 1.0f;
-        const float bsdfPdf = path.bsdfScatterPdf();
+        const float bsdfPdf = (MODE == kModeBuildStablePlanes) ? 0.0f : path.bsdfScatterPdf();
         if ((mis & (1u << 15)) && bsdfPdf != 0)
         {
             const float2 uv = dirToOctEqualArea(localDir);
@@ -388,10 +413,11 @@ PT_DEVICE void shadeMiss(const LaunchParams& p, PathRegs& path)
         emission = lp3(misWeight * Le);
     }
     const float ffThreshold = lp(p.c.fireflyFilterThreshold);
-    if (ffThreshold != 0) emission = fireflyFilter(emission, ffThreshold, path.fireflyK());
-    if (EXPORT_GUIDES && path.sampleIndex + 1 == p.firstSampleIndex + p.subSampleCount)
+    if (MODE != kModeBuildStablePlanes && ffThreshold != 0) emission = fireflyFilter(emission, ffThreshold, path.fireflyK());
+    if constexpr (MODE == kModeBuildStablePlanes) stablePlanesHandleMiss(p, path, emission, segmentOrigin, path.dir);
+    if constexpr (MODE == kModeReference) if (EXPORT_GUIDES && path.sampleIndex + 1 == p.firstSampleIndex + p.subSampleCount)
         exportGuide(p, path.id, path.origin + path.dir * kMaxRayTravel, 0u);                 // ExportNonSurface (PathTracer.hlsli:487)
-    if (anyPositive(emission)) path.addRadiance(path.thp() * emission);
+    if (anyPositive(emission)) accumulatePathRadiance<MODE>(p, path, path.thp() * emission);
     path.setFlag(kPFHit, false);
     path.setFlag(kPFActive, false);
 }
@@ -399,10 +425,12 @@ PT_DEVICE void shadeMiss(const LaunchParams& p, PathRegs& path)
 // ---- hit -----------------------------------------------------------------------------------------------------------------------------------
 struct HitOutputs { bool continuePath; bool emitShadow; ShadowRecord shadow; };
 
-template <bool EXPORT_GUIDES, bool ANALYTIC_LIGHTS>
+template <bool EXPORT_GUIDES, bool ANALYTIC_LIGHTS, int MODE = kModeReference>
 PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4 hit, HitOutputs& out)
 {
     out.continuePath = false; out.emitShadow = false;
+    constexpr bool kBuild = MODE == kModeBuildStablePlanes, kFill = MODE == kModeFillStablePlanes;
+    const uint sampleIndex = (MODE == kModeReference) ? path.sampleIndex : p.firstSampleIndex;      // realtime passes: one sample index per launch, the word holds stableBranchID
     const float3 rayOrigin = path.origin, rayDir = path.dir;
     const float rayT = hit.x;
     updatePathTravelled(path, rayT);
@@ -443,12 +471,13 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
     }
 
     // emission + BSDF-side MIS (PathTracer.hlsli:592-674)
-    const uint misPacked = path.misInfo();
+    const uint misPacked = kBuild ? 0u : path.misInfo();
+    const float pathBsdfPdf = kBuild ? 0.0f : path.bsdfScatterPdf();
     float3 surfaceEmission = mk3(0.f);
     if (anyPositive(s.emission))
     {
         float misWeight = 1.0f;
-        const float bsdfPdf = path.bsdfScatterPdf();
+        const float bsdfPdf = pathBsdfPdf;
         if ((misPacked & (1u << 15)) && bsdfPdf != 0 && s.neeTriangleLightIndex != kInvalidLight)
         {
             TriLight tl; tl.decode(p.scene.lights[s.neeTriangleLightIndex]);
@@ -472,7 +501,7 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
                 {
                     const float3 radiance = unpackLightRadiance(li) * lightShaping(li, p.scene, s.neeAnalyticLightIndex, rayOrigin, center);
                     float mis = 1.0f;
-                    const float bsdfPdf = (misPacked & (1u << 15)) ? path.bsdfScatterPdf() : 0.0f;
+                    const float bsdfPdf = (misPacked & (1u << 15)) ? pathBsdfPdf : 0.0f;
                     if (bsdfPdf != 0)
                     {
                         const float cosThetaMax = sqrtf(fmaxf(0.0f, 1.0f - (radius * radius) / dot3(lv, lv)));
@@ -486,24 +515,35 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
     if (anyPositive(surfaceEmission))
     {
         const float ffThreshold = lp(p.c.fireflyFilterThreshold);
-        if (ffThreshold != 0) surfaceEmission = fireflyFilter(surfaceEmission, ffThreshold, path.fireflyK());
-        if (anyPositive(surfaceEmission)) path.addRadiance(path.thp() * surfaceEmission);
+        if (!kBuild && ffThreshold != 0) surfaceEmission = fireflyFilter(surfaceEmission, ffThreshold, path.fireflyK());
+        if (anyPositive(surfaceEmission)) accumulatePathRadiance<MODE>(p, path, path.thp() * surfaceEmission);
     }
-    if (EXPORT_GUIDES && path.sampleIndex + 1 == p.firstSampleIndex + p.subSampleCount)
+    if constexpr (MODE == kModeReference) if (EXPORT_GUIDES && path.sampleIndex + 1 == p.firstSampleIndex + p.subSampleCount)
     {   // ExportSurface (PathTracer.hlsli:684): virtual position along the pixel's camera ray at the path's scene length, throughput before this vertex
         float3 co, cd; computeCameraRay(p.c, path.id, path.sampleIndex, co, cd);
         exportGuide(p, path.id, co + cd * path.sceneLength, packR11G11B10(mk3(sat(path.thp().x), sat(path.thp().y), sat(path.thp().z))));
     }
-    if (path.hasFlag(kPFTerminateAtNextBounce)) { path.setFlag(kPFActive, false); return; }
+    const bool pathStopping = path.hasFlag(kPFTerminateAtNextBounce);
+    if constexpr (kBuild)
+    {   // the BUILD pass consumes the emission and either re-aims the path along a delta lobe or stores the plane and stops (PathTracer.hlsli:679-699)
+        BsdfSetup deltaBsdf; deltaBsdf.init(s.T, s.B, s.N, s.V, s.thin, s.bsdf);
+        stablePlanesHandleHit(p, path, rayOrigin, rayDir, rayT, s, deltaBsdf, pathStopping);
+        if (pathStopping) { path.setFlag(kPFActive, false); return; }
+        path.setThp(path.thp() * 1.0f);
+        out.continuePath = path.hasFlag(kPFActive);
+        return;
+    }
+    if (pathStopping) { path.setFlag(kPFActive, false); return; }
 
     path.setThp(path.thp() * path.ruRuCorrection());
 
     const uint baseHash = vertexBaseHash(path.id, path.vertexIndex());
-    UniformSeq uniformSG = UniformSeq::make(baseHash, path.sampleIndex, 0u);
+    UniformSeq uniformSG = UniformSeq::make(baseHash, sampleIndex, 0u);
     // state of the path before scattering, needed by NEE
     const float3 preThp = path.thp();
     const float preFireflyK = path.fireflyK();
     const float preConeWidth = path.coneWidth(), preSceneLength = path.sceneLength;
+    const uint preFlags = path.flagsAndVertexIndex, preCounters = path.packedCounters;          // preScatterPath's flags (realtime mode's classification of NEE radiance)
 
     BsdfSetup bsdf; bsdf.init(s.T, s.B, s.N, s.V, s.thin, s.bsdf);
 
@@ -513,13 +553,13 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
         float u0, u1, u2;
         if (p.c.enableLDSamplerForBSDF && path.counter(kCtrDiffuseBounces) < 1)
         {
-            u0 = hashToFloat(ldSampleBits(baseHash, path.sampleIndex, 1u, 0));
-            u1 = hashToFloat(ldSampleBits(baseHash, path.sampleIndex, 1u, 1));
-            u2 = hashToFloat(ldSampleBits(baseHash, path.sampleIndex, 1u, 2));
+            u0 = hashToFloat(ldSampleBits(baseHash, sampleIndex, 1u, 0));
+            u1 = hashToFloat(ldSampleBits(baseHash, sampleIndex, 1u, 1));
+            u2 = hashToFloat(ldSampleBits(baseHash, sampleIndex, 1u, 2));
         }
         else
         {
-            UniformSeq sg = UniformSeq::make(baseHash, path.sampleIndex, 1u);
+            UniformSeq sg = UniformSeq::make(baseHash, sampleIndex, 1u);
             u0 = sg.next(); u1 = sg.next(); u2 = sg.next();
         }
         BsdfSample bs;
@@ -527,6 +567,7 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
         if (scatterValid)
         {
             path.dir = bs.wo;
+            const bool onDominantDenoisingLayer = kFill && path.hasFlag(kPFStablePlaneOnPlane) && path.hasFlag(kPFStablePlaneOnDominantBranch);
             path.setThp(path.thp() * bs.weight);
             path.flagsAndVertexIndex &= ~((kPFTransmission | kPFSpecular | kPFDelta) << kVertexIndexBits);
             path.origin = offsetRayOrigin(s.posW, (bs.lobe & kLobeReflection) ? s.faceN : -s.faceN);
@@ -548,8 +589,21 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
                 path.setFlag(kPFDeltaOnlyPath, false);
                 path.setCone(path.coneWidth(), fminf(path.coneSpread() + coneSpreadFromPdf(bs.pdf, 0.3f), 2.0f * kPi));
             }
+            if constexpr (kFill)
+            {   // specular hit distance of the dominant plane for the denoiser (PathTracer.hlsli:295-324)
+                const bool isDiffuseForSpecHitT = (bs.lobe & (kLobeDiffuseReflection | kLobeDiffuseTransmission)) || s.bsdf.roughness > 0.35f;
+                if (onDominantDenoisingLayer && !isDiffuseForSpecHitT)
+                {
+                    if (!s.psdBlockMVs) { path.setFlag(kPFExportSpecHitTQueued, true); p.rt.specularHitT[pixelOffset(p, path.id)] = -path.sceneLength; }     // ExportSpecHitTStart
+                }
+                else if (path.hasFlag(kPFExportSpecHitTQueued))
+                {
+                    if ((bsdfLobes(s.bsdf) & kLobeNonDelta) != 0 || path.counter(kCtrBouncesFromStablePlane) > 4) { exportSpecHitTStop(p, path); path.setFlag(kPFExportSpecHitTQueued, false); }
+                }
+            }
             const float k = (p.c.fireflyFilterThreshold != 0) ? newFireflyK(path.fireflyK(), bs.pdf, bs.lobeP) : 0.0f;
             path.setFireflyK_BsdfPdf(k, bs.pdf);
+            if constexpr (kFill) stablePlanesOnScatter(p, path, bs.lobe);
             path.setFlag(kPFEnableThreadReorder, true);
         }
     }
@@ -664,6 +718,16 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
             out.shadow.originTMax = make_float4(o.x, o.y, o.z, pickDist * 0.9985f);
             out.shadow.dirPath = make_float4(pickDir.x, pickDir.y, pickDir.z, __uint_as_float(slot));
             out.shadow.radiance = make_uint2(packHalf2Clamp(radiance.x, radiance.y), packHalf2Clamp(radiance.z, specAvg));   // NEEResult::AccumulateRadiance(0 + x)
+            if constexpr (kFill)
+            {   // which specular average the shadow kernel adds with the radiance (PathTracer.hlsli:731-743); the halves are non-negative, so the sign bits
+                // of the first word carry the choice: 00 none (base scatter was diffuse), 01 the NEE result's own, 10 the whole radiance
+                if (!(preFlags & (kPFStablePlaneBaseScatterDiff << kVertexIndexBits)))
+                {
+                    const uint bouncesFromStablePlane = ((preCounters >> (kCtrBouncesFromStablePlane << 3)) & 0xffu) + 1u;
+                    const bool special = (bouncesFromStablePlane == 1) || ((preFlags & (kPFDeltaOnlyPath << kVertexIndexBits)) && bouncesFromStablePlane <= 3);
+                    out.shadow.radiance.x |= special ? 0x00008000u : 0x80000000u;
+                }
+            }
         }
     }
     path.setMisInfo_RuRu(neeMis, path.ruRuCorrection());

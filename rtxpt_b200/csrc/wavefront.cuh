@@ -13,7 +13,7 @@
 namespace pt {
 
 constexpr int kNumShadeClasses = 6;     // 0 miss, 1 hit on a path that terminates at this vertex, 2..5 material classes (SER sort key analogue)
-constexpr int kMaxWavefrontIterations = 40;
+constexpr int kMaxWavefrontIterations = 64;   // reference mode needs bounceCount + 5; the BUILD pass of realtime mode explores up to three delta branches per pixel one after the other
 
 struct ShadowRecord         // 40 bytes in three arrays
 {
@@ -49,6 +49,21 @@ constexpr int kCtrFetchShadow = kCtrFetchClosest + 1;
 static_assert(kCtrFetchShadow < 16, "counter block");
 constexpr int kCountersPerIter = 16;
 
+// realtime mode (stable planes): the reference's u_StablePlanesHeader / u_StablePlanesBuffer / u_StableRadiance / u_SpecularHitT and the
+// realtime fields of PathTracerConstants (StablePlanes.hlsli:82-274, PathTracerShared.h:57-80)
+struct RealtimeParams
+{
+    RtxptStablePlane* planes;       // [3 * planeStride], GenericTS addressing
+    uint* header;                   // [4][height][width]
+    uint2* stableRadiance;          // RGBA16F
+    float* specularHitT;
+    uint lineStride, planeStride;
+    uint activePlaneCount, maxVertexDepth, allowPSR;
+    float attenuation;              // invSubSampleCount
+    float worldToClipNoOffset[16], prevWorldToClipNoOffset[16];
+    float clipToWindowScale[2];
+};
+
 struct LaunchParams
 {
     SceneView scene;
@@ -70,14 +85,20 @@ struct LaunchParams
     uint exportGuides;
     uint accumulatedSamples;        // before this call
     uint doAccumulate;
+    RealtimeParams rt;
 };
 
 // ---- packed path-state accessors (PathState.hlsli:125-200) ------------------------------------------------------------------
 enum : uint {
     kPFActive = 1u << 0, kPFHit = 1u << 1, kPFTransmission = 1u << 2, kPFSpecular = 1u << 3, kPFDelta = 1u << 4,
-    kPFInsideDielectric = 1u << 5, kPFTerminateAtNextBounce = 1u << 6, kPFEnableThreadReorder = 1u << 9, kPFDeltaOnlyPath = 1u << 12
+    kPFInsideDielectric = 1u << 5, kPFTerminateAtNextBounce = 1u << 6, kPFEnableThreadReorder = 1u << 9, kPFDeltaOnlyPath = 1u << 12,
+    // realtime mode (PathState.hlsli:58-64); flag bits 14-15 hold the stable plane index
+    kPFStablePlaneOnPlane = 1u << 16, kPFStablePlaneOnBranch = 1u << 17, kPFStablePlaneBaseScatterDiff = 1u << 18, kPFExportSpecHitTQueued = 1u << 19,
+    kPFStablePlaneOnDominantBranch = 1u << 20
 };
+constexpr int kModeReference = 0, kModeBuildStablePlanes = 1, kModeFillStablePlanes = 2;      // PATH_TRACER_MODE (Config.h:56-59)
 constexpr uint kVertexIndexBits = 10, kVertexIndexMask = (1u << kVertexIndexBits) - 1u;
+constexpr uint kStablePlaneIndexShift = 14 + kVertexIndexBits, kStablePlaneIndexMask = 3u << kStablePlaneIndexShift;
 
 // Path state is written once and read once per wavefront iteration: with PT_STREAM_STATE the accesses carry the evict-first hint so that they
 // do not displace BVH and scene data in L2.
@@ -140,11 +161,18 @@ struct PathRegs             // one path's state in registers
     PT_DEVICE uint vertexIndex() const { return flagsAndVertexIndex & kVertexIndexMask; }
     PT_DEVICE uint counter(uint type) const { return (packedCounters >> (type << 3)) & 0xff; }
     PT_DEVICE void incrementCounter(uint type) { packedCounters += 1u << (type << 3); }
+    PT_DEVICE void setCounter(uint type, uint v) { const uint shift = type << 3; packedCounters = (packedCounters & ~(0xffu << shift)) | ((v & 0xffu) << shift); }
+    PT_DEVICE void setVertexIndex(uint v) { flagsAndVertexIndex = (flagsAndVertexIndex & ~kVertexIndexMask) | v; }
+    PT_DEVICE uint stablePlaneIndex() const { return (flagsAndVertexIndex & kStablePlaneIndexMask) >> kStablePlaneIndexShift; }
+    PT_DEVICE void setStablePlaneIndex(uint i) { flagsAndVertexIndex = (flagsAndVertexIndex & ~kStablePlaneIndexMask) | (i << kStablePlaneIndexShift); }
+    // realtime mode: every path of a launch has the launch's sample index, and the word carries PathState::stableBranchID as in the reference payload;
+    // in the BUILD pass lXY/lZW hold imageXformPacked and pack0 the motion-vector scene length (PathState.hlsli:91-92, :151-154)
+    PT_DEVICE uint& stableBranchID() { return sampleIndex; }
     PT_DEVICE float coneWidth() const { return f16tof32(rayCone >> 16); }
     PT_DEVICE float coneSpread() const { return f16tof32(rayCone); }
     PT_DEVICE void setCone(float width, float spread) { rayCone = (f32tof16(width) << 16) | f32tof16(spread); }
 };
-constexpr uint kCtrDiffuseBounces = 0, kCtrRejectedHits = 1;
+constexpr uint kCtrDiffuseBounces = 0, kCtrRejectedHits = 1, kCtrBouncesFromStablePlane = 2;
 
 // Bridge::computeCameraRay + ComputeRayThinlens (BridgeDonut:543-564, PathTracerHelpers.hlsli:126-153): camera ray of pixel `id` for sample `sampleIndex`
 PT_DEVICE void computeCameraRay(const RtxptPathTracerConstants& c, uint id, uint sampleIndex, float3& origin, float3& dir)

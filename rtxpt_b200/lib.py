@@ -45,6 +45,8 @@ _SIGNATURES = {
     "rtxpt_b200_trace_rays_device": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32, C.POINTER(C.c_float)],
     "rtxpt_b200_get_lights": [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)],
     "rtxpt_b200_set_view": [C.c_void_p, C.c_void_p],
+    "rtxpt_b200_set_realtime": [C.c_void_p, C.POINTER(S.RealtimeConstants)],
+    "rtxpt_b200_path_trace_realtime": [C.c_void_p, C.c_int, C.c_void_p],
     "rtxpt_b200_get_lights_ex": [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)],
     "rtxpt_b200_debug_bsdf": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
     "rtxpt_b200_debug_rng": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
@@ -208,6 +210,27 @@ class Context:
         _check(self.L.rtxpt_b200_readback(self.h, S.BUFFER_MOTION_VECTORS_F16, mv.ctypes.data, mv.nbytes), self.L)
         _check(self.L.rtxpt_b200_readback(self.h, S.BUFFER_THROUGHPUT_R11G11B10, thp.ctypes.data, thp.nbytes), self.L)
         return depth, mv, thp
+
+    # ---- realtime mode (stable planes) ----
+    def set_realtime(self, rt):
+        self.realtime = rt
+        _check(self.L.rtxpt_b200_set_realtime(self.h, C.byref(rt)), self.L)
+
+    def path_trace_realtime(self, merge_no_denoiser=True, stream=None):
+        """BUILD + rt.subSampleCount x FILL (+ the no-denoiser merge into the output colour)."""
+        _check(self.L.rtxpt_b200_path_trace_realtime(self.h, 1 if merge_no_denoiser else 0, stream), self.L)
+
+    def readback_realtime(self):
+        """The realtime render targets as a dict of numpy arrays (same keys as the oracle's render_realtime)."""
+        h, w = self.consts.imageHeight, self.consts.imageWidth
+        plane_stride = self.L.rtxpt_b200_generic_ts_plane_stride(w, h)
+        out = dict(planes=np.empty(3 * plane_stride, S.STABLE_PLANE_DTYPE), header=np.empty((4, h, w), np.uint32), stable_radiance=np.empty((h, w, 4), np.float16),
+                   spec_hit_t=np.empty((h, w), np.float32))
+        for key, buf in (("planes", S.BUFFER_STABLE_PLANES), ("header", S.BUFFER_STABLE_PLANES_HEADER), ("stable_radiance", S.BUFFER_STABLE_RADIANCE_F16), ("spec_hit_t", S.BUFFER_SPECULAR_HITT_F32)):
+            _check(self.L.rtxpt_b200_readback(self.h, buf, out[key].ctypes.data, out[key].nbytes), self.L)
+        out["depth"], out["motion"], out["throughput"] = self.readback_guides()
+        out["merged"] = self.readback_output_color()[..., :3].astype(np.float32)
+        return out
 
     def readback_output_color(self):
         out = np.empty((self.consts.imageHeight, self.consts.imageWidth, 4), np.float16)

@@ -10,6 +10,15 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+    config.addinivalue_line("markers", "gpu_unverified: GPU tests of code that has compiled but not yet run on a B200 (select with `-m gpu_unverified`); skipped without a device")
+
+
+def pytest_collection_modifyitems(config, items):
+    import shutil
+    have_gpu = shutil.which("nvidia-smi") is not None and os.path.exists("/dev/nvidia0")
+    for item in items:
+        if "gpu_unverified" in item.keywords and (not have_gpu or config.getoption("-m") != "gpu_unverified"):
+            item.add_marker(pytest.mark.skip(reason="not yet verified on a GPU; run with -m gpu_unverified on a B200"))
 
 
 @pytest.fixture(scope="session")

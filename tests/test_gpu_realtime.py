@@ -1,0 +1,125 @@
+"""GPU: realtime mode - stable-plane BUILD / FILL passes and the no-denoiser merge of the CUDA path against the oracle, through
+the C ABI (rtxpt_b200_set_realtime / rtxpt_b200_path_trace_realtime).  Integer state (branch IDs, dominant plane, vertex indices) must be identical;
+packed fp16 / float fields are the oracle's on nearly every pixel in the strict (IEEE) build and within the stated tolerances in the default build
+(libdevice vs glibc transcendentals, FMA contraction)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu_unverified       # written and compiled in round 1 without GPU time left to run them; promoted to `gpu` once they have passed on a B200
+
+INVALID = 0xFFFFFFFF
+
+
+def _halves(words):
+    hi = (words >> 16).astype(np.uint16).view(np.float16).astype(np.float32); lo = (words & 0xFFFF).astype(np.uint16).view(np.float16).astype(np.float32)
+    return hi, lo
+
+
+def _setup(product, oracle, strict, W=96, H=96, bounces=8):
+    from rtxpt_b200 import scene_builder as sb, scenes
+    scene, cam = scenes.cornell_box(W, H, delta_surfaces=True)
+    consts = sb.make_constants(W, H, cam, bounce_count=bounces, diffuse_bounce_count=3)
+    c = product.Context(max_sub_samples_per_launch=1, strict=strict); c.upload_scene(scene); c.set_constants(consts); c.set_view(sb.world_to_clip(cam))
+    o = oracle.Oracle(scene); o.set_constants(consts); o.set_view(sb.world_to_clip(cam))
+    return c, o, cam, consts
+
+
+@pytest.mark.parametrize("strict", [True, False])
+def test_build_pass_matches_oracle(product, oracle, strict):
+    from rtxpt_b200 import scene_builder as sb
+    W = H = 96
+    c, o, cam, consts = _setup(product, oracle, strict, W, H)
+    for kw in (dict(), dict(active_planes=2), dict(allow_psr=False), dict(max_vertex_depth=2)):
+        rt = sb.make_realtime_constants(W, H, cam, bounce_count=8, sub_samples=1, **kw)
+        c.set_realtime(rt); c.path_trace_realtime(True); c.synchronize()
+        g = c.readback_realtime(); r = o.render_realtime(rt)
+        same = (g["header"] == r["header"]).all(0)
+        assert same.mean() > 0.998, (kw, same.mean())                                  # decomposition decisions: thresholds on Fresnel terms can flip at silhouettes
+        ys, xs = np.nonzero(same)
+        for plane in range(3):
+            valid = r["header"][plane][ys, xs] != INVALID
+            a = g["planes"][sb.generic_ts_address(xs[valid], ys[valid], plane, W, H)]; b = r["planes"][sb.generic_ts_address(xs[valid], ys[valid], plane, W, H)]
+            if not len(a): continue
+            assert (a["VertexIndexAndRoughness"] >> 16 == b["VertexIndexAndRoughness"] >> 16).all()
+            fin = np.isfinite(b["SceneLength"])
+            assert (np.isfinite(a["SceneLength"]) == fin).all()
+            tol = 2e-6 if strict else 2e-4
+            for f in ("RayOrigin", "RayDir", "SceneLength", "LastRayTCurrent"):
+                x, y = a[f][fin], b[f][fin]
+                assert np.allclose(x, y, rtol=tol, atol=tol * 10), (kw, plane, f, np.abs(x - y).max())
+            for f in ("PackedThpAndMVs", "DenoiserPackedBSDFEstimate"):
+                for xa, xb in zip(_halves(a[f]), _halves(b[f])):
+                    assert np.allclose(xa, xb, rtol=4e-3, atol=1e-3), (kw, plane, f)
+                if strict: assert (a[f] == b[f]).mean() > 0.99, (kw, plane, f, (a[f] == b[f]).mean())
+            na = a["PackedNormal"]; nb = b["PackedNormal"]
+            assert (np.abs((na & 0xFFFF).astype(np.int64) - (nb & 0xFFFF)) <= 8).mean() > 0.999 and (np.abs((na >> 16).astype(np.int64) - (nb >> 16)) <= 8).mean() > 0.999
+        # stable radiance and the dominant plane's guides
+        sa, sb_ = g["stable_radiance"].astype(np.float32), r["stable_radiance"].astype(np.float32)
+        assert np.allclose(sa[same], sb_[same], rtol=2e-3, atol=1e-3)
+        if strict: assert (g["stable_radiance"][same] == r["stable_radiance"][same]).all(-1).mean() > 0.995
+        assert np.allclose(g["depth"][same], r["depth"][same], rtol=1e-5, atol=1e-6) and (g["throughput"][same] == r["throughput"][same]).mean() > 0.99
+        assert np.allclose(g["motion"][same].astype(np.float32), r["motion"][same].astype(np.float32), atol=2e-3)
+    c.close(); o.close()
+
+
+@pytest.mark.parametrize("strict", [True, False])
+def test_fill_pass_and_merge_match_oracle(product, oracle, strict):
+    from rtxpt_b200 import scene_builder as sb
+    W = H = 96
+    c, o, cam, consts = _setup(product, oracle, strict, W, H)
+    rt = sb.make_realtime_constants(W, H, cam, bounce_count=8, sub_samples=3)
+    c.set_realtime(rt); c.path_trace_realtime(True); c.synchronize()
+    g = c.readback_realtime(); r = o.render_realtime(rt)
+    same = (g["header"] == r["header"]).all(0)
+    assert same.mean() > 0.998
+    d = np.abs(g["merged"] - r["merged"])[same]; scale = np.maximum(r["merged"][same], 0.05)
+    if strict:
+        assert (d == 0).all(-1).mean() > 0.97, (d == 0).all(-1).mean()                # paths whose every decision agrees give the same fp16 sums
+        assert np.percentile(d / scale, 99.5) < 0.05
+    else:
+        assert (d / scale < 0.02).all(-1).mean() > 0.9 and abs(g["merged"].mean() - r["merged"].mean()) < 5e-3 * r["merged"].mean()
+    # per-plane noisy radiance words and the specular hit distance
+    ys, xs = np.nonzero(same)
+    for plane in range(3):
+        valid = r["header"][plane][ys, xs] != INVALID
+        a = g["planes"][sb.generic_ts_address(xs[valid], ys[valid], plane, W, H)]["PackedNoisyRadianceAndSpecAvg"]
+        b = r["planes"][sb.generic_ts_address(xs[valid], ys[valid], plane, W, H)]["PackedNoisyRadianceAndSpecAvg"]
+        if strict and len(a): assert (a == b).all(-1).mean() > 0.96, (plane, (a == b).all(-1).mean())
+    assert np.allclose(g["spec_hit_t"][same], r["spec_hit_t"][same], rtol=1e-3, atol=1e-3) or (np.isclose(g["spec_hit_t"][same], r["spec_hit_t"][same], rtol=1e-3, atol=1e-3).mean() > 0.995)
+    c.close(); o.close()
+
+
+def test_realtime_invariants(product):
+    """Size-independent properties at a larger frame: determinism, BUILD independent of the sub-sample count, the merged frame equals stable radiance plus
+    the planes' noisy radiance, nothing left enqueued, and realtime frames average to the reference-mode image."""
+    from rtxpt_b200 import scene_builder as sb, scenes
+    W, H = 320, 200
+    scene, cam = scenes.cornell_box(W, H, delta_surfaces=True)
+    consts = sb.make_constants(W, H, cam, bounce_count=8, diffuse_bounce_count=3)
+    c = product.Context(max_sub_samples_per_launch=4); c.upload_scene(scene); c.set_constants(consts); c.set_view(sb.world_to_clip(cam))
+    rt = sb.make_realtime_constants(W, H, cam, bounce_count=8, sub_samples=2)
+    c.set_realtime(rt); c.path_trace_realtime(True); c.synchronize(); a = c.readback_realtime()
+    c.path_trace_realtime(True); c.synchronize(); b = c.readback_realtime()
+    for k in a: assert a[k].tobytes() == b[k].tobytes(), k
+    hd = a["header"]
+    assert (hd[0] != INVALID).all() and (hd[:3] != 0xFFFFFFFE).all() and (hd[:3] != 0).all()
+    ys, xs = np.mgrid[0:H, 0:W]
+    total = a["stable_radiance"][..., :3].astype(np.float32)
+    for plane in range(3):
+        w = a["planes"][sb.generic_ts_address(xs, ys, plane, W, H)]["PackedNoisyRadianceAndSpecAvg"]
+        rgb = np.stack([(w[..., 0] & 0xFFFF), (w[..., 0] >> 16), (w[..., 1] & 0xFFFF)], -1).astype(np.uint16).view(np.float16).astype(np.float32)
+        total = total + np.where((hd[plane] != INVALID)[..., None], rgb, 0)
+    assert np.array_equal(total.astype(np.float16), a["merged"].astype(np.float16))
+    rt1 = sb.make_realtime_constants(W, H, cam, bounce_count=8, sub_samples=1)
+    c.set_realtime(rt1); c.path_trace_realtime(True); c.synchronize(); one = c.readback_realtime()
+    assert np.array_equal(one["header"], a["header"]) and np.array_equal(one["stable_radiance"], a["stable_radiance"])
+    # convergence to reference mode
+    acc = np.zeros((H, W, 3), np.float64); frames = 8
+    c.set_realtime(sb.make_realtime_constants(W, H, cam, bounce_count=8, sub_samples=4))
+    for f in range(frames):
+        consts.sampleBaseIndex = f * 4; c.set_constants(consts); c.path_trace_realtime(True); c.synchronize(); acc += c.readback_output_color()[..., :3].astype(np.float32)
+    acc /= frames
+    consts.sampleBaseIndex = 0; c.set_constants(consts); c.reset_accumulation(); c.path_trace(0, 32, True); c.synchronize()
+    ref = c.readback_accumulated()[..., :3]
+    assert abs(acc.mean() - ref.mean()) < 0.02 * ref.mean(), (acc.mean(), ref.mean())
+    c.close()
