@@ -14,8 +14,14 @@ def pytest_configure(config):
 
 
 def pytest_collection_modifyitems(config, items):
-    import shutil
-    have_gpu = shutil.which("nvidia-smi") is not None and os.path.exists("/dev/nvidia0")
+    def cuda_device_present():
+        import ctypes
+        try:
+            cu = ctypes.CDLL("libcuda.so.1"); n = ctypes.c_int(0)
+            return cu.cuInit(0) == 0 and cu.cuDeviceGetCount(ctypes.byref(n)) == 0 and n.value > 0
+        except OSError:
+            return False
+    have_gpu = cuda_device_present()
     for item in items:
         if "gpu_unverified" in item.keywords and (not have_gpu or config.getoption("-m") != "gpu_unverified"):
             item.add_marker(pytest.mark.skip(reason="not yet verified on a GPU; run with -m gpu_unverified on a B200"))

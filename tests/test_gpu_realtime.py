@@ -5,7 +5,11 @@ packed fp16 / float fields are the oracle's on nearly every pixel in the strict 
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu_unverified       # written and compiled in round 1 without GPU time left to run them; promoted to `gpu` once they have passed on a B200
+# Two tests carry the `gpu` marker: they assert, with margins, exactly what one B200 run of scripts/gpu_realtime_check.py measured on this scene and
+# configuration (profiles/r1_realtime_gpu_check.log: strict build bit-identical to the oracle in every header word, plane field and guide; default build
+# identical in the decomposition except where a ray meets the glass box's bottom face and the floor at the same distance).  The remaining tests ran out
+# of round-1 GPU budget before their first run and stay under `gpu_unverified` (select with -m gpu_unverified) until they have passed on a B200.
+unverified = pytest.mark.gpu_unverified
 
 INVALID = 0xFFFFFFFF
 
@@ -24,6 +28,63 @@ def _setup(product, oracle, strict, W=96, H=96, bounces=8):
     return c, o, cam, consts
 
 
+def _run_pair(product, oracle, strict, sub_samples=2):
+    from rtxpt_b200 import scene_builder as sb
+    W = H = 96
+    c, o, cam, consts = _setup(product, oracle, strict, W, H)
+    rt = sb.make_realtime_constants(W, H, cam, bounce_count=8, sub_samples=sub_samples)
+    c.set_realtime(rt); c.path_trace_realtime(True); c.synchronize(); g = c.readback_realtime()
+    c.path_trace_realtime(True); c.synchronize(); g2 = c.readback_realtime()
+    r = o.render_realtime(rt)
+    c.close(); o.close()
+    return g, g2, r, W, H
+
+
+@pytest.mark.gpu
+def test_realtime_strict_build_is_the_oracle(product, oracle):
+    """IEEE build: the BUILD pass (branch IDs, dominant plane, plane records, stable radiance, guides) and the specular hit distance are the oracle's bit
+    for bit; the noisy radiance the FILL pass deposits differs on a few paths in a thousand (libdevice vs glibc sin/cos/pow in the BSDF sampling)."""
+    from rtxpt_b200 import scene_builder as sb
+    g, g2, r, W, H = _run_pair(product, oracle, True)
+    assert np.array_equal(g["header"], r["header"])
+    ys, xs = np.mgrid[0:H, 0:W]
+    for plane in range(3):
+        v = r["header"][plane] != INVALID
+        a = g["planes"][sb.generic_ts_address(xs[v], ys[v], plane, W, H)]; b = r["planes"][sb.generic_ts_address(xs[v], ys[v], plane, W, H)]
+        for f in a.dtype.names:
+            if f == "PackedNoisyRadianceAndSpecAvg": assert (a[f] == b[f]).all(-1).mean() > 0.995, (plane, f)
+            elif a[f].dtype.kind == "u": assert np.array_equal(a[f], b[f]), (plane, f)             # packed words: identical
+            else: assert np.allclose(a[f], b[f], rtol=1e-6, atol=1e-6, equal_nan=True), (plane, f)  # ray origin / direction / lengths (+inf marks a miss on both sides)
+    for k in ("stable_radiance", "depth", "motion", "throughput", "spec_hit_t"): assert np.array_equal(g[k], r[k]), k
+    d = np.abs(g["merged"] - r["merged"])
+    assert (d == 0).all(-1).mean() > 0.995 and abs(g["merged"].mean() - r["merged"].mean()) < 1e-3 * r["merged"].mean()
+    assert all(g[k].tobytes() == g2[k].tobytes() for k in g)                     # replay: bit-identical
+
+
+@pytest.mark.gpu
+def test_realtime_default_build_decomposes_like_the_oracle(product, oracle):
+    """FMA / fast-math build: same decomposition (planes 0 and 2 identical, plane 1 except where the glass box's bottom face and the floor are hit at the
+    same distance and ulp-level origin differences decide which comes first), same stable radiance, same image within noise."""
+    from rtxpt_b200 import scene_builder as sb
+    g, g2, r, W, H = _run_pair(product, oracle, False)
+    assert np.array_equal(g["header"][0], r["header"][0]) and np.array_equal(g["header"][2], r["header"][2])
+    assert (g["header"][1] == r["header"][1]).mean() > 0.98
+    same = (g["header"][:3] == r["header"][:3]).all(0)
+    ys, xs = np.nonzero(same)
+    for plane in range(3):
+        v = r["header"][plane][ys, xs] != INVALID
+        a = g["planes"][sb.generic_ts_address(xs[v], ys[v], plane, W, H)]; b = r["planes"][sb.generic_ts_address(xs[v], ys[v], plane, W, H)]
+        assert np.array_equal(a["VertexIndexAndRoughness"], b["VertexIndexAndRoughness"]) and (a["DenoiserPackedBSDFEstimate"] == b["DenoiserPackedBSDFEstimate"]).mean() > 0.97
+        fin = np.isfinite(b["SceneLength"]); assert np.array_equal(np.isfinite(a["SceneLength"]), fin)
+        assert np.allclose(a["SceneLength"][fin], b["SceneLength"][fin], rtol=1e-5) and np.allclose(a["RayDir"][fin], b["RayDir"][fin], atol=1e-3)
+    assert (g["stable_radiance"] == r["stable_radiance"]).mean() > 0.999
+    assert np.isclose(g["spec_hit_t"], r["spec_hit_t"], rtol=1e-3, atol=1e-3).mean() > 0.99
+    assert np.isclose(g["depth"], r["depth"], rtol=2e-3, atol=1e-3).mean() > 0.98
+    assert abs(g["merged"].mean() - r["merged"].mean()) < 0.03 * r["merged"].mean()
+    assert all(g[k].tobytes() == g2[k].tobytes() for k in g)
+
+
+@unverified
 @pytest.mark.parametrize("strict", [True, False])
 def test_build_pass_matches_oracle(product, oracle, strict):
     from rtxpt_b200 import scene_builder as sb
@@ -62,6 +123,7 @@ def test_build_pass_matches_oracle(product, oracle, strict):
     c.close(); o.close()
 
 
+@unverified
 @pytest.mark.parametrize("strict", [True, False])
 def test_fill_pass_and_merge_match_oracle(product, oracle, strict):
     from rtxpt_b200 import scene_builder as sb
@@ -89,6 +151,7 @@ def test_fill_pass_and_merge_match_oracle(product, oracle, strict):
     c.close(); o.close()
 
 
+@unverified
 def test_realtime_invariants(product):
     """Size-independent properties at a larger frame: determinism, BUILD independent of the sub-sample count, the merged frame equals stable radiance plus
     the planes' noisy radiance, nothing left enqueued, and realtime frames average to the reference-mode image."""
