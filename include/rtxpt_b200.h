@@ -349,6 +349,36 @@ RTXPT_API int rtxpt_b200_set_realtime(rtxpt_ctx* ctx, const RtxptRealtimeConstan
 /* BUILD + subSampleCount x FILL (+ the no-denoiser merge into RTXPT_BUFFER_OUTPUT_COLOR_F16 when mergeNoDenoiser != 0); asynchronous on `cudaStream`.
  * Depth / motion vectors / throughput guides are those of the dominant plane (PathTracerStablePlanes.hlsli:316-321, :404-408). */
 RTXPT_API int rtxpt_b200_path_trace_realtime(rtxpt_ctx* ctx, int mergeNoDenoiser, void* cudaStream);
+/* ---- Denoiser interface of realtime mode (RTXPT's side of it): what PostProcess.hlsl does around NRD for one stable plane
+ * (Sample::Denoise, Rtxpt/Sample.cpp:2560-2618: for plane = active-1 .. 0 { prepare inputs; NRD; final merge }).
+ *   prepare_inputs = DENOISER_PREPARE_INPUTS, ReBLUR variant (ProcessingPasses/PostProcess.hlsl:444-570): splits the plane's noisy radiance into its
+ *     diffuse and specular parts, demodulates by the BSDF estimates, clamps, and writes NRD's inputs: viewZ R32F (FLT_MAX = sky), motion RGBA16F,
+ *     normal+roughness R10G10B10A2 (octahedral normal, linear roughness: NRD_NORMAL_ENCODING 2 / NRD_ROUGHNESS_ENCODING 1, External/Nrd/CMakeLists.txt:29-30),
+ *     diffuse / specular radiance (YCoCg) + normalised hit distance RGBA16F, disocclusion-threshold mix R8; with initWithStableRadiance it first sets
+ *     the output colour to the stable radiance and clears the combined history-clamp relaxation.
+ *   final_merge = DENOISER_FINAL_MERGE (PostProcess.hlsl:577-690): output colour += denoised diffuse * diffuse estimate + denoised specular * specular
+ *     estimate for pixels that have a surface; the two denoised images are RGBA16F device buffers in NRD's output encoding (YCoCg + hit distance), e.g.
+ *     OUT_DIFF_RADIANCE_HITDIST / OUT_SPEC_RADIANCE_HITDIST of an NRD instance - or the prepared inputs themselves for an identity denoiser. */
+typedef struct RtxptDenoiserConstants {
+    float matWorldToView[16];               /* view.matWorldToView, row-major, row vector x matrix */
+    float hitDistanceParameters[4];         /* nrd::HitDistanceParameters A, B, C, D (NRDSettings.h:206-220; Sample.cpp:2174) */
+    float preExposedGrayLuminance;          /* 1 without tone mapping (Sample.cpp:1516) */
+    float denoiserRadianceClampK;           /* m_ui.DenoiserRadianceClampK (Sample.cpp:1525) */
+    float stablePlanesSuppressPrimaryIndirectSpecularK;  /* 0 = off (Sample.cpp:1536) */
+    float _pad;
+} RtxptDenoiserConstants;
+enum {
+    RTXPT_BUFFER_DENOISER_VIEWSPACE_Z_F32        = 9,
+    RTXPT_BUFFER_DENOISER_MOTION_VECTORS_F16     = 10,
+    RTXPT_BUFFER_DENOISER_NORMAL_ROUGHNESS_R10G10B10A2 = 11,
+    RTXPT_BUFFER_DENOISER_DIFF_RADIANCE_HITDIST_F16 = 12,
+    RTXPT_BUFFER_DENOISER_SPEC_RADIANCE_HITDIST_F16 = 13,
+    RTXPT_BUFFER_DENOISER_DISOCCLUSION_MIX_R8    = 14,
+    RTXPT_BUFFER_COMBINED_HISTORY_CLAMP_RELAX_R8 = 15
+};
+RTXPT_API int rtxpt_b200_denoiser_prepare_inputs(rtxpt_ctx* ctx, uint32_t stablePlaneIndex, int initWithStableRadiance, const RtxptDenoiserConstants* constants, void* cudaStream);
+RTXPT_API int rtxpt_b200_denoiser_final_merge(rtxpt_ctx* ctx, uint32_t stablePlaneIndex, const void* dDenoisedDiffRGBA16F, const void* dDenoisedSpecRGBA16F, void* cudaStream);
+
 /* GenericTS addressing of the plane buffer (host helpers; Utils.hlsli:320-362) */
 RTXPT_API uint32_t rtxpt_b200_generic_ts_line_stride(uint32_t width, uint32_t height);
 RTXPT_API uint32_t rtxpt_b200_generic_ts_plane_stride(uint32_t width, uint32_t height);

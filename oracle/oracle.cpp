@@ -271,6 +271,48 @@ ORC_API uint32_t oracle_generic_ts_plane_stride(uint32_t w, uint32_t h) { return
 ORC_API void oracle_pack_ortho(const float* m9, uint32_t* out2) { mat3 m; for (int i = 0; i < 3; i++) m.r[i] = f3(m9[3 * i], m9[3 * i + 1], m9[3 * i + 2]); PackOrthoMatrix(m, out2); }
 ORC_API void oracle_unpack_ortho(const uint32_t* in2, float* m9) { mat3 m = UnpackOrthoMatrix(in2); for (int i = 0; i < 3; i++) { m9[3 * i] = m.r[i].x; m9[3 * i + 1] = m.r[i].y; m9[3 * i + 2] = m.r[i].z; } }
 
+// RTXPT's side of the denoiser interface for one stable plane.  realtimeTargets = { planes, header, stableRadiance, depth, motionVectors, throughput, specularHitT } as filled
+// by oracle_render_realtime; denoiserTargets = { viewZ f32, motion RGBA16F, normalRoughness R10G10B10A2, diffRadianceHitDist RGBA16F, specRadianceHitDist RGBA16F,
+// disocclusionMix R8, historyClampRelax R8, outputColor RGBA16F }, all caller-allocated at full image size.
+static RealtimeTargets makeTargets(OracleCtx* c, const RtxptRealtimeConstants* rt, void* const* r)
+{
+    RealtimeTargets T;
+    T.width = c->consts.imageWidth; T.height = c->consts.imageHeight;
+    T.lineStride = GenericTSComputeLineStride(T.width, T.height); T.planeStride = GenericTSComputePlaneStride(T.width, T.height);
+    T.planes = (RtxptStablePlane*)r[0]; T.header = (uint32_t*)r[1]; T.stableRadiance = (uint16_t*)r[2]; T.depth = (float*)r[3]; T.motionVectors = (uint16_t*)r[4]; T.throughput = (uint32_t*)r[5];
+    T.specularHitT = (float*)r[6]; T.rt = rt;
+    return T;
+}
+static DenoiserTargets makeDenoiserTargets(void* const* d)
+{
+    DenoiserTargets D; D.viewZ = (float*)d[0]; D.motion = (uint16_t*)d[1]; D.normalRoughness = (uint32_t*)d[2]; D.diffRadianceHitDist = (uint16_t*)d[3]; D.specRadianceHitDist = (uint16_t*)d[4];
+    D.disocclusionMix = (uint8_t*)d[5]; D.historyClampRelax = (uint8_t*)d[6]; D.outputColor = (uint16_t*)d[7];
+    return D;
+}
+ORC_API int oracle_denoiser_prepare_inputs(void* p, const RtxptRealtimeConstants* rt, const RtxptDenoiserConstants* k, uint32_t stablePlaneIndex, int initWithStableRadiance,
+                                           void* const* realtimeTargets, void* const* denoiserTargets)
+{
+    OracleCtx* c = (OracleCtx*)p;
+    if (!c->haveConsts || !rt || !k || stablePlaneIndex >= 3) return -1;
+    const RealtimeTargets T = makeTargets(c, rt, realtimeTargets); const DenoiserTargets D = makeDenoiserTargets(denoiserTargets);
+    PathTracerCtx x; x.scene = &c->scene; x.bvh = &c->bvh; x.lights = &c->lights; x.c = &c->consts; x.stats = nullptr; x.sampleIndex = c->consts.sampleBaseIndex;
+    for (uint32_t y = 0; y < T.height; y++) for (uint32_t px = 0; px < T.width; px++)
+    {
+        float3 co, cd; computeCameraRay(x, px, y, co, cd);
+        denoiserPrepareInputsPixel(T, D, *k, px, y, stablePlaneIndex, initWithStableRadiance != 0, co, cd);
+    }
+    return 0;
+}
+ORC_API int oracle_denoiser_final_merge(void* p, const RtxptRealtimeConstants* rt, uint32_t stablePlaneIndex, void* const* realtimeTargets, void* const* denoiserTargets,
+                                        const uint16_t* denoisedDiff, const uint16_t* denoisedSpec)
+{
+    OracleCtx* c = (OracleCtx*)p;
+    if (!c->haveConsts || !rt || stablePlaneIndex >= 3) return -1;
+    const RealtimeTargets T = makeTargets(c, rt, realtimeTargets); const DenoiserTargets D = makeDenoiserTargets(denoiserTargets);
+    for (uint32_t y = 0; y < T.height; y++) for (uint32_t px = 0; px < T.width; px++) denoiserFinalMergePixel(T, D, px, y, stablePlaneIndex, denoisedDiff, denoisedSpec);
+    return 0;
+}
+
 // primary-hit triangle id -> (instance, geometry, primitive), for comparing with the product's hit records
 ORC_API int oracle_tri_info(void* p, uint32_t triId, uint32_t* out3)
 {

@@ -211,3 +211,118 @@ struct RealtimeTargets
 };
 
 } // namespace orc
+
+// ---- RTXPT's side of the denoiser interface: PostProcess.hlsl DENOISER_PREPARE_INPUTS (ReBLUR variant, :444-570) and
+// DENOISER_FINAL_MERGE (:577-690), NRD front/back-end packing (External/Nrd/Shaders/Include/NRD.hlsli:327-345, :362-381, :526-529, :646-677, :728-750, :869-874),
+// Rtxpt/NRD/DenoiserNRD.hlsli:34-52.  Test infrastructure like the rest of this directory.
+namespace orc {
+
+struct DenoiserTargets
+{
+    float* viewZ; uint16_t* motion; uint32_t* normalRoughness; uint16_t* diffRadianceHitDist; uint16_t* specRadianceHitDist; uint8_t* disocclusionMix; uint8_t* historyClampRelax;
+    uint16_t* outputColor;       // RGBA16F
+};
+inline uint8_t unorm8(float v) { return uint8_t(saturate(v) * 255.0f + 0.5f); }
+inline float3 NRD_LinearToYCoCg(float3 c) { return f3(dot(c, f3(0.25f, 0.5f, 0.25f)), dot(c, f3(0.5f, 0.0f, -0.5f)), dot(c, f3(-0.25f, 0.5f, -0.25f))); }
+inline float3 NRD_YCoCgToLinear(float3 c) { const float t = c.x - c.z; return max3v(f3(t + c.y, c.x + c.z, t - c.y), f3(0)); }
+inline float2 NRD_EncodeUnitVectorUnsigned(float3 v)
+{
+    v = v / (fabsf(v.x) + fabsf(v.y) + fabsf(v.z));
+    const float2 wrap = f2((1.0f - fabsf(v.y)) * ((v.x >= 0.0f ? 1.0f : 0.0f) * 2.0f - 1.0f), (1.0f - fabsf(v.x)) * ((v.y >= 0.0f ? 1.0f : 0.0f) * 2.0f - 1.0f));
+    const float2 xy = v.z >= 0.0f ? f2(v.x, v.y) : wrap;
+    return f2(xy.x * 0.5f + 0.5f, xy.y * 0.5f + 0.5f);
+}
+inline uint32_t packR10G10B10A2(float x, float y, float z, float w)
+{
+    return uint32_t(saturate(x) * 1023.0f + 0.5f) | (uint32_t(saturate(y) * 1023.0f + 0.5f) << 10) | (uint32_t(saturate(z) * 1023.0f + 0.5f) << 20) | (uint32_t(saturate(w) * 3.0f + 0.5f) << 30);
+}
+inline float REBLUR_GetHitDistanceNormalization(float viewZ, const float* hp, float roughness) { return (hp[0] + fabsf(viewZ) * hp[1]) * lerp(1.0f, hp[2], saturate(exp2f(hp[3] * roughness * roughness))); }
+inline void storeRGBA16F(uint16_t* dst, float4 v) { dst[0] = uint16_t(f32tof16(v.x)); dst[1] = uint16_t(f32tof16(v.y)); dst[2] = uint16_t(f32tof16(v.z)); dst[3] = uint16_t(f32tof16(v.w)); }
+inline void NRDRadianceClamp(float3& radiance, float preExposedGrayLuminance, float rangeK)
+{
+    const float kClampMax = std::min(255.0f, preExposedGrayLuminance * rangeK);
+    const float lum = Luminance(radiance);
+    if (lum > kClampMax) radiance = radiance * (kClampMax / lum);
+}
+
+inline void denoiserPrepareInputsPixel(const RealtimeTargets& T, const DenoiserTargets& D, const RtxptDenoiserConstants& k, uint px, uint py, uint stablePlaneIndex, bool initWithStableRadiance,
+                                       float3 camOrigin, float3 camDir)
+{
+    const size_t pix = size_t(py) * T.width + px;
+    if (initWithStableRadiance) { const float3 s = T.LoadStableRadiance(px, py); storeRGBA16F(D.outputColor + pix * 4, f4(s, 1.0f)); D.historyClampRelax[pix] = 0; }
+    bool hasSurface = false;
+    const uint spBranchID = T.GetBranchID(px, py, stablePlaneIndex);
+    if (spBranchID != cStablePlaneInvalidBranchID)
+    {
+        const RtxptStablePlane& sp = T.planes[T.PixelToAddress(px, py, stablePlaneIndex)];
+        if (std::isfinite(sp.SceneLength))
+        {
+            hasSurface = true;
+            float3 diffEstimate, specEstimate; UnpackTwoFp32ToFp16(sp.DenoiserPackedBSDFEstimate, diffEstimate, specEstimate);
+            const float3 virtualWorldPos = camOrigin + camDir * sp.SceneLength;
+            const float* M = k.matWorldToView;
+            const float virtualViewspaceZ = ((virtualWorldPos.x * M[2] + virtualWorldPos.y * M[6]) + virtualWorldPos.z * M[10]) + M[14];
+            float3 thp, motionVectors; UnpackTwoFp32ToFp16(sp.PackedThpAndMVs, thp, motionVectors);
+            D.viewZ[pix] = virtualViewspaceZ;
+            storeRGBA16F(D.motion + pix * 4, f4(motionVectors, 0));
+            const float spRoughness = f16tof32(sp.VertexIndexAndRoughness & 0xFFFF);
+            float finalRoughness = std::max(0.2f, spRoughness);
+            float specularSuppressionMul = 1.0f;
+            if (stablePlaneIndex == 0 && k.stablePlanesSuppressPrimaryIndirectSpecularK != 0.0f && T.activePlaneCount() > 1)
+            {
+                bool shouldSuppress = true;
+                for (uint i = 1; i < T.activePlaneCount(); i++) shouldSuppress &= T.GetBranchID(px, py, i) != cStablePlaneInvalidBranchID;
+                if (shouldSuppress) specularSuppressionMul = saturate(1 - k.stablePlanesSuppressPrimaryIndirectSpecularK);
+            }
+            float disocclusionRelax = 0.0f;
+            if (StablePlanesVertexIndexFromBranchID(spBranchID) > 1)
+            {   // ComputeDisocclusionRelaxation: how much the (virtual) normal turns towards the four neighbours
+                const float3 rayDirC = OctToNDirUnorm32(sp.PackedNormal);
+                const int off[4][2] = { { -1, 0 }, { 1, 0 }, { 0, -1 }, { 0, 1 } };
+                for (int n = 0; n < 4; n++)
+                {
+                    const uint nx = uint(std::min(std::max(int(px) + off[n][0], 0), int(T.width) - 1)), ny = uint(std::min(std::max(int(py) + off[n][1], 0), int(T.height) - 1));
+                    if (T.GetBranchID(nx, ny, stablePlaneIndex) == cStablePlaneInvalidBranchID) disocclusionRelax += 0.02f;
+                    else disocclusionRelax += 1 - dot(rayDirC, OctToNDirUnorm32(T.planes[T.PixelToAddress(nx, ny, stablePlaneIndex)].PackedNormal));
+                }
+                disocclusionRelax = saturate((disocclusionRelax - 0.00002f) * 25);
+            }
+            D.disocclusionMix[pix] = unorm8(disocclusionRelax);
+            D.historyClampRelax[pix] = unorm8(saturate(float(D.historyClampRelax[pix]) / 255.0f + disocclusionRelax * saturate(Luminance(thp))));
+            finalRoughness = saturate(finalRoughness + disocclusionRelax);
+            // StablePlane::GetNoisyDiffRadiance / GetNoisySpecRadiance (StablePlanes.hlsli:66-67)
+            const float2 a = Fp16ToFp32(sp.PackedNoisyRadianceAndSpecAvg[0]), b = Fp16ToFp32(sp.PackedNoisyRadianceAndSpecAvg[1]);
+            const float3 l = f3(a.x, a.y, b.x); const float specAvg = b.y, totalAvg = Average(l);
+            float3 diff = l * saturate(1.0f - specAvg / (totalAvg + 1e-12f)), spec = l * saturate(specAvg / (totalAvg + 1e-12f));
+            diff = diff / diffEstimate; spec = spec / specEstimate;
+            spec = spec * specularSuppressionMul;
+            D.normalRoughness[pix] = [&] { const float2 e = NRD_EncodeUnitVectorUnsigned(OctToNDirUnorm32(sp.PackedNormal)); return packR10G10B10A2(e.x, e.y, finalRoughness, 0.0f); }();
+            NRDRadianceClamp(diff, k.preExposedGrayLuminance, k.denoiserRadianceClampK * 16); NRDRadianceClamp(spec, k.preExposedGrayLuminance, k.denoiserRadianceClampK * 16);
+            float specHitT = 0;
+            if (T.LoadDominantIndex(px, py) == stablePlaneIndex) specHitT = T.specularHitT[pix];
+            auto pack = [](float3 radiance, float normHitDist) {     // REBLUR_FrontEnd_PackRadianceAndNormHitDist(sanitize = true)
+                const bool invalid = !std::isfinite(radiance.x) || !std::isfinite(radiance.y) || !std::isfinite(radiance.z);
+                radiance = invalid ? f3(0) : clamp3(radiance, 0, 65504.0f);
+                normHitDist = std::isfinite(normHitDist) ? saturate(normHitDist) : 0.0f;
+                return f4(NRD_LinearToYCoCg(radiance), normHitDist); };
+            storeRGBA16F(D.diffRadianceHitDist + pix * 4, pack(diff, 0.0f));
+            const float specNorm = saturate(specHitT / REBLUR_GetHitDistanceNormalization(virtualViewspaceZ, k.hitDistanceParameters, spRoughness));
+            storeRGBA16F(D.specRadianceHitDist + pix * 4, pack(spec, specNorm));
+        }
+    }
+    if (!hasSurface) D.viewZ[pix] = 3.402823466e+38f;       // VIEWZ_SKY_MARKER
+}
+
+inline void denoiserFinalMergePixel(const RealtimeTargets& T, const DenoiserTargets& D, uint px, uint py, uint stablePlaneIndex, const uint16_t* denoisedDiff, const uint16_t* denoisedSpec)
+{
+    const size_t pix = size_t(py) * T.width + px;
+    if (D.viewZ[pix] == 3.402823466e+38f) return;
+    float3 diffEstimate, specEstimate; UnpackTwoFp32ToFp16(T.planes[T.PixelToAddress(px, py, stablePlaneIndex)].DenoiserPackedBSDFEstimate, diffEstimate, specEstimate);
+    auto load = [&](const uint16_t* p) { return f3(f16tof32(p[pix * 4]), f16tof32(p[pix * 4 + 1]), f16tof32(p[pix * 4 + 2])); };
+    const float3 diff = NRD_YCoCgToLinear(load(denoisedDiff)) * diffEstimate, spec = NRD_YCoCgToLinear(load(denoisedSpec)) * specEstimate;
+    uint16_t* o = D.outputColor + pix * 4;
+    const float3 sum = max3v(diff + spec, f3(0));
+    o[0] = uint16_t(f32tof16(f16tof32(o[0]) + sum.x)); o[1] = uint16_t(f32tof16(f16tof32(o[1]) + sum.y)); o[2] = uint16_t(f32tof16(f16tof32(o[2]) + sum.z));
+}
+
+} // namespace orc

@@ -80,6 +80,9 @@ struct rtxpt_ctx
     // realtime mode (stable planes): allocated on the first set_realtime for the current image size
     DeviceArray<RtxptStablePlane> stablePlanes; DeviceArray<uint32_t> stablePlanesHeader; DeviceArray<uint2> stableRadiance; DeviceArray<float> specularHitT;
     RtxptRealtimeConstants realtime{}; bool haveRealtime = false; uint32_t realtimeWidth = 0, realtimeHeight = 0;
+    // denoiser interface: NRD's inputs for one plane at a time (allocated by the first prepare_inputs call)
+    DeviceArray<float> dnViewZ; DeviceArray<uint2> dnMotion, dnDiff, dnSpec; DeviceArray<uint32_t> dnNormalRoughness; DeviceArray<uint8_t> dnDisocclusionMix, dnHistoryClampRelax;
+    uint32_t denoiserWidth = 0, denoiserHeight = 0;
     // stats
     uint32_t* hCounters = nullptr;          // pinned
     cudaEvent_t evStart = nullptr, evStop = nullptr;
@@ -569,6 +572,24 @@ extern "C" RTXPT_API int rtxpt_b200_set_realtime(rtxpt_ctx* c, const RtxptRealti
     return RTXPT_OK;
 }
 
+static void fillRealtimeParams(rtxpt_ctx* c, LaunchParams& p)
+{
+    const RtxptRealtimeConstants& r = c->realtime;
+    p.rt.planes = c->stablePlanes.ptr; p.rt.header = c->stablePlanesHeader.ptr; p.rt.stableRadiance = c->stableRadiance.ptr; p.rt.specularHitT = c->specularHitT.ptr;
+    p.rt.lineStride = rtxpt_b200_generic_ts_line_stride(c->tableWidth, c->tableHeight); p.rt.planeStride = rtxpt_b200_generic_ts_plane_stride(c->tableWidth, c->tableHeight);
+    p.rt.activePlaneCount = r.activeStablePlaneCount; p.rt.maxVertexDepth = r.maxStablePlaneVertexDepth; p.rt.allowPSR = r.allowPrimarySurfaceReplacement;
+    p.rt.attenuation = 1.0f / float(r.subSampleCount);
+    memcpy(p.rt.worldToClipNoOffset, r.matWorldToClipNoOffset, 64); memcpy(p.rt.prevWorldToClipNoOffset, r.prevMatWorldToClipNoOffset, 64);
+    p.rt.clipToWindowScale[0] = r.clipToWindowScale[0]; p.rt.clipToWindowScale[1] = r.clipToWindowScale[1];
+    p.rt.dnViewZ = c->dnViewZ.ptr; p.rt.dnMotion = c->dnMotion.ptr; p.rt.dnNormalRoughness = c->dnNormalRoughness.ptr; p.rt.dnDiff = c->dnDiff.ptr; p.rt.dnSpec = c->dnSpec.ptr;
+    p.rt.dnDisocclusionMix = c->dnDisocclusionMix.ptr; p.rt.dnHistoryClampRelax = c->dnHistoryClampRelax.ptr;
+}
+static int checkRealtimeReady(rtxpt_ctx* c)
+{
+    int rc = checkReady(c); if (rc != RTXPT_OK) return rc;
+    if (!c->haveRealtime || c->realtimeWidth != c->tableWidth || c->realtimeHeight != c->tableHeight) return fail(RTXPT_ERR_INVALID_ARGUMENT, "rtxpt_b200_set_realtime has not been called for this image size");
+    return RTXPT_OK;
+}
 extern "C" RTXPT_API int rtxpt_b200_path_trace_realtime(rtxpt_ctx* c, int mergeNoDenoiser, void* cudaStream)
 {
     int rc = checkReady(c); if (rc != RTXPT_OK) return rc;
@@ -577,12 +598,7 @@ extern "C" RTXPT_API int rtxpt_b200_path_trace_realtime(rtxpt_ctx* c, int mergeN
     cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
     LaunchParams p; fillParams(c, p);
     const RtxptRealtimeConstants& r = c->realtime;
-    p.rt.planes = c->stablePlanes.ptr; p.rt.header = c->stablePlanesHeader.ptr; p.rt.stableRadiance = c->stableRadiance.ptr; p.rt.specularHitT = c->specularHitT.ptr;
-    p.rt.lineStride = rtxpt_b200_generic_ts_line_stride(c->tableWidth, c->tableHeight); p.rt.planeStride = rtxpt_b200_generic_ts_plane_stride(c->tableWidth, c->tableHeight);
-    p.rt.activePlaneCount = r.activeStablePlaneCount; p.rt.maxVertexDepth = r.maxStablePlaneVertexDepth; p.rt.allowPSR = r.allowPrimarySurfaceReplacement;
-    p.rt.attenuation = 1.0f / float(r.subSampleCount);
-    memcpy(p.rt.worldToClipNoOffset, r.matWorldToClipNoOffset, 64); memcpy(p.rt.prevWorldToClipNoOffset, r.prevMatWorldToClipNoOffset, 64);
-    p.rt.clipToWindowScale[0] = r.clipToWindowScale[0]; p.rt.clipToWindowScale[1] = r.clipToWindowScale[1];
+    fillRealtimeParams(c, p);
     p.exportGuides = 0; p.subSampleCount = 1; p.doAccumulate = 0;
     const bool hasRefraction = c->consts.nestedDielectricsQuality > 0;
     // BUILD: the branches of a pixel's delta tree are explored one after the other, each at most maxVertexDepth + 1 segments long (+ rejected false hits)
@@ -620,6 +636,40 @@ extern "C" RTXPT_API int rtxpt_b200_path_trace_realtime(rtxpt_ctx* c, int mergeN
     return RTXPT_OK;
 }
 
+// ---- RTXPT's side of the denoiser interface ------------------------------------------------------------------------------------------------------------
+extern "C" RTXPT_API int rtxpt_b200_denoiser_prepare_inputs(rtxpt_ctx* c, uint32_t stablePlaneIndex, int initWithStableRadiance, const RtxptDenoiserConstants* k, void* cudaStream)
+{
+    int rc = checkRealtimeReady(c); if (rc != RTXPT_OK) return rc;
+    if (!k || stablePlaneIndex >= RTXPT_STABLE_PLANE_COUNT) return fail(RTXPT_ERR_INVALID_ARGUMENT, "bad plane index or null constants");
+    cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
+    if (c->denoiserWidth != c->tableWidth || c->denoiserHeight != c->tableHeight)
+    {
+        CU(cudaStreamSynchronize(c->stream));
+        const size_t P = size_t(c->tableWidth) * c->tableHeight;
+        CU(c->dnViewZ.alloc(P)); CU(c->dnMotion.alloc(P)); CU(c->dnDiff.alloc(P)); CU(c->dnSpec.alloc(P)); CU(c->dnNormalRoughness.alloc(P)); CU(c->dnDisocclusionMix.alloc(P)); CU(c->dnHistoryClampRelax.alloc(P));
+        CU(cudaMemsetAsync(c->dnViewZ.ptr, 0, P * 4, s)); CU(cudaMemsetAsync(c->dnMotion.ptr, 0, P * 8, s)); CU(cudaMemsetAsync(c->dnDiff.ptr, 0, P * 8, s)); CU(cudaMemsetAsync(c->dnSpec.ptr, 0, P * 8, s));
+        CU(cudaMemsetAsync(c->dnNormalRoughness.ptr, 0, P * 4, s)); CU(cudaMemsetAsync(c->dnDisocclusionMix.ptr, 0, P, s)); CU(cudaMemsetAsync(c->dnHistoryClampRelax.ptr, 0, P, s));
+        c->denoiserWidth = c->tableWidth; c->denoiserHeight = c->tableHeight;
+    }
+    LaunchParams p; fillParams(c, p); fillRealtimeParams(c, p);
+    p.rt.dn = *k; p.rt.dnPlane = stablePlaneIndex; p.rt.dnInitWithStableRadiance = initWithStableRadiance ? 1u : 0u;
+    launchDnPrepareInputs(p, c->grid, s);
+    CU(cudaGetLastError());
+    return RTXPT_OK;
+}
+extern "C" RTXPT_API int rtxpt_b200_denoiser_final_merge(rtxpt_ctx* c, uint32_t stablePlaneIndex, const void* dDiff, const void* dSpec, void* cudaStream)
+{
+    int rc = checkRealtimeReady(c); if (rc != RTXPT_OK) return rc;
+    if (!dDiff || !dSpec || stablePlaneIndex >= RTXPT_STABLE_PLANE_COUNT) return fail(RTXPT_ERR_INVALID_ARGUMENT, "bad plane index or null image");
+    if (c->denoiserWidth != c->tableWidth || c->denoiserHeight != c->tableHeight) return fail(RTXPT_ERR_INVALID_ARGUMENT, "rtxpt_b200_denoiser_prepare_inputs has not run (the sky mask lives in its view-space depth)");
+    cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
+    LaunchParams p; fillParams(c, p); fillRealtimeParams(c, p);
+    p.rt.dnPlane = stablePlaneIndex; p.rt.dnDenoisedDiff = static_cast<const uint2*>(dDiff); p.rt.dnDenoisedSpec = static_cast<const uint2*>(dSpec);
+    launchDnFinalMerge(p, c->grid, s);
+    CU(cudaGetLastError());
+    return RTXPT_OK;
+}
+
 extern "C" RTXPT_API int rtxpt_b200_reset_accumulation(rtxpt_ctx* c)
 {
     if (!c) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null context");
@@ -651,6 +701,20 @@ static int targetInfo(rtxpt_ctx* c, int buffer, void** ptr, size_t* bytes)
         else if (buffer == RTXPT_BUFFER_STABLE_PLANES_HEADER) { *ptr = c->stablePlanesHeader.ptr; *bytes = P * 16; }
         else if (buffer == RTXPT_BUFFER_STABLE_RADIANCE_F16) { *ptr = c->stableRadiance.ptr; *bytes = P * 8; }
         else { *ptr = c->specularHitT.ptr; *bytes = P * 4; }
+        return RTXPT_OK;
+    case RTXPT_BUFFER_DENOISER_VIEWSPACE_Z_F32: case RTXPT_BUFFER_DENOISER_MOTION_VECTORS_F16: case RTXPT_BUFFER_DENOISER_NORMAL_ROUGHNESS_R10G10B10A2: case RTXPT_BUFFER_DENOISER_DIFF_RADIANCE_HITDIST_F16:
+    case RTXPT_BUFFER_DENOISER_SPEC_RADIANCE_HITDIST_F16: case RTXPT_BUFFER_DENOISER_DISOCCLUSION_MIX_R8: case RTXPT_BUFFER_COMBINED_HISTORY_CLAMP_RELAX_R8:
+        if (c->denoiserWidth != c->tableWidth || c->denoiserHeight != c->tableHeight) return fail(RTXPT_ERR_INVALID_ARGUMENT, "denoiser buffers do not exist before rtxpt_b200_denoiser_prepare_inputs");
+        switch (buffer)
+        {
+        case RTXPT_BUFFER_DENOISER_VIEWSPACE_Z_F32: *ptr = c->dnViewZ.ptr; *bytes = P * 4; break;
+        case RTXPT_BUFFER_DENOISER_MOTION_VECTORS_F16: *ptr = c->dnMotion.ptr; *bytes = P * 8; break;
+        case RTXPT_BUFFER_DENOISER_NORMAL_ROUGHNESS_R10G10B10A2: *ptr = c->dnNormalRoughness.ptr; *bytes = P * 4; break;
+        case RTXPT_BUFFER_DENOISER_DIFF_RADIANCE_HITDIST_F16: *ptr = c->dnDiff.ptr; *bytes = P * 8; break;
+        case RTXPT_BUFFER_DENOISER_SPEC_RADIANCE_HITDIST_F16: *ptr = c->dnSpec.ptr; *bytes = P * 8; break;
+        case RTXPT_BUFFER_DENOISER_DISOCCLUSION_MIX_R8: *ptr = c->dnDisocclusionMix.ptr; *bytes = P; break;
+        default: *ptr = c->dnHistoryClampRelax.ptr; *bytes = P; break;
+        }
         return RTXPT_OK;
     default: return fail(RTXPT_ERR_INVALID_ARGUMENT, "unknown buffer %d", buffer);
     }

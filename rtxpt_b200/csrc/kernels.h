@@ -25,6 +25,8 @@ void launchRtShade(const LaunchParams& p, const GridConfig& g, bool fill, cudaSt
 void launchTraceShadowRealtime(const LaunchParams& p, const GridConfig& g, cudaStream_t s);
 void launchRtFillCommit(const LaunchParams& p, const GridConfig& g, cudaStream_t s);
 void launchRtMerge(const LaunchParams& p, const GridConfig& g, cudaStream_t s);
+void launchDnPrepareInputs(const LaunchParams& p, const GridConfig& g, cudaStream_t s);
+void launchDnFinalMerge(const LaunchParams& p, const GridConfig& g, cudaStream_t s);
 void launchCommitAccumulate(const LaunchParams& p, const GridConfig& g, cudaStream_t s);
 void launchTraceRays(const LaunchParams& p, const GridConfig& g, const RtxptRay* dRays, uint32_t count, bool anyHit, RtxptHit* dHits, uint32_t* dCounters, uint32_t* dCursor, cudaStream_t s);
 void launchPackOwned(const float4* image, const uint32_t* pixelOfSlot, uint32_t pixelCount, uint32_t paddedCount, uint32_t width, float4* dst, const GridConfig& g, cudaStream_t s);

@@ -62,6 +62,10 @@ struct RealtimeParams
     float attenuation;              // invSubSampleCount
     float worldToClipNoOffset[16], prevWorldToClipNoOffset[16];
     float clipToWindowScale[2];
+    // denoiser interface (PostProcess.hlsl DENOISER_PREPARE_INPUTS / DENOISER_FINAL_MERGE)
+    float* dnViewZ; uint2* dnMotion; uint* dnNormalRoughness; uint2* dnDiff; uint2* dnSpec; unsigned char* dnDisocclusionMix; unsigned char* dnHistoryClampRelax;
+    const uint2* dnDenoisedDiff; const uint2* dnDenoisedSpec;
+    RtxptDenoiserConstants dn; uint dnPlane, dnInitWithStableRadiance;
 };
 
 struct LaunchParams

@@ -47,6 +47,8 @@ _SIGNATURES = {
     "rtxpt_b200_set_view": [C.c_void_p, C.c_void_p],
     "rtxpt_b200_set_realtime": [C.c_void_p, C.POINTER(S.RealtimeConstants)],
     "rtxpt_b200_path_trace_realtime": [C.c_void_p, C.c_int, C.c_void_p],
+    "rtxpt_b200_denoiser_prepare_inputs": [C.c_void_p, C.c_uint32, C.c_int, C.POINTER(S.DenoiserConstants), C.c_void_p],
+    "rtxpt_b200_denoiser_final_merge": [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p],
     "rtxpt_b200_get_lights_ex": [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)],
     "rtxpt_b200_debug_bsdf": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
     "rtxpt_b200_debug_rng": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
@@ -230,6 +232,26 @@ class Context:
             _check(self.L.rtxpt_b200_readback(self.h, buf, out[key].ctypes.data, out[key].nbytes), self.L)
         out["depth"], out["motion"], out["throughput"] = self.readback_guides()
         out["merged"] = self.readback_output_color()[..., :3].astype(np.float32)
+        return out
+
+    # ---- RTXPT's side of the denoiser interface ----
+    def denoiser_prepare_inputs(self, plane, init_with_stable_radiance, k, stream=None):
+        _check(self.L.rtxpt_b200_denoiser_prepare_inputs(self.h, plane, 1 if init_with_stable_radiance else 0, C.byref(k), stream), self.L)
+
+    def denoiser_final_merge(self, plane, d_diff=None, d_spec=None, stream=None):
+        """d_diff / d_spec: device pointers of RGBA16F images in NRD's output encoding; default = the prepared inputs themselves (identity denoiser)."""
+        if d_diff is None: d_diff = self.device_ptr(S.BUFFER_DENOISER_DIFF_RADIANCE_HITDIST_F16)[0]
+        if d_spec is None: d_spec = self.device_ptr(S.BUFFER_DENOISER_SPEC_RADIANCE_HITDIST_F16)[0]
+        _check(self.L.rtxpt_b200_denoiser_final_merge(self.h, plane, d_diff, d_spec, stream), self.L)
+
+    def readback_denoiser_inputs(self):
+        h, w = self.consts.imageHeight, self.consts.imageWidth
+        out = dict(view_z=np.empty((h, w), np.float32), motion=np.empty((h, w, 4), np.float16), normal_roughness=np.empty((h, w), np.uint32), diff=np.empty((h, w, 4), np.float16),
+                   spec=np.empty((h, w, 4), np.float16), disocclusion_mix=np.empty((h, w), np.uint8), history_clamp_relax=np.empty((h, w), np.uint8))
+        for key, buf in (("view_z", S.BUFFER_DENOISER_VIEWSPACE_Z_F32), ("motion", S.BUFFER_DENOISER_MOTION_VECTORS_F16), ("normal_roughness", S.BUFFER_DENOISER_NORMAL_ROUGHNESS_R10G10B10A2),
+                         ("diff", S.BUFFER_DENOISER_DIFF_RADIANCE_HITDIST_F16), ("spec", S.BUFFER_DENOISER_SPEC_RADIANCE_HITDIST_F16), ("disocclusion_mix", S.BUFFER_DENOISER_DISOCCLUSION_MIX_R8),
+                         ("history_clamp_relax", S.BUFFER_COMBINED_HISTORY_CLAMP_RELAX_R8)):
+            _check(self.L.rtxpt_b200_readback(self.h, buf, out[key].ctypes.data, out[key].nbytes), self.L)
         return out
 
     def readback_output_color(self):

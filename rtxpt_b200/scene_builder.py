@@ -344,6 +344,26 @@ def make_realtime_constants(width, height, cam, prev_cam=None, active_planes=3, 
     return rt
 
 
+def world_to_view(cam):
+    """SimpleViewConstants.matWorldToView for a BridgeCamera block (row-major, row vector x matrix; +z forward)."""
+    pos = np.array(cam.PosW[:], np.float32); W = np.array(cam.CameraW[:], np.float32); U = np.array(cam.CameraU[:], np.float32); V = np.array(cam.CameraV[:], np.float32)
+    fwd = W / np.linalg.norm(W); right = U / np.linalg.norm(U); up = V / np.linalg.norm(V)
+    view = np.eye(4, dtype=np.float64)
+    view[:3, 0], view[:3, 1], view[:3, 2] = right, up, fwd
+    view[3, :3] = [-np.dot(pos, right), -np.dot(pos, up), -np.dot(pos, fwd)]
+    return view.astype(np.float32)
+
+
+def make_denoiser_constants(cam, hit_distance_parameters=(3.0, 0.1, 20.0, -25.0), pre_exposed_gray_luminance=1.0, radiance_clamp_k=8.0, suppress_primary_indirect_specular_k=0.0):
+    """RtxptDenoiserConstants: nrd::HitDistanceParameters defaults (NRDSettings.h:206-220), no tone mapping (preExposedGrayLuminance 1)."""
+    k = S.DenoiserConstants()
+    k.matWorldToView[:] = world_to_view(cam).reshape(16).tolist()
+    k.hitDistanceParameters[:] = list(hit_distance_parameters)
+    k.preExposedGrayLuminance = pre_exposed_gray_luminance; k.denoiserRadianceClampK = radiance_clamp_k
+    k.stablePlanesSuppressPrimaryIndirectSpecularK = suppress_primary_indirect_specular_k
+    return k
+
+
 def generic_ts_address(x, y, plane, width, height):
     """GenericTSPixelToAddress (Utils.hlsli:337-352): 8x8 tiles, Morton order inside a tile; vectorised over numpy arrays."""
     x = np.asarray(x, np.uint32); y = np.asarray(y, np.uint32)

@@ -32,6 +32,8 @@ CFG_EXPORT_GUIDES = 8
 BUFFER_OUTPUT_COLOR_F16, BUFFER_ACCUMULATED_F32, BUFFER_DEPTH_F32, BUFFER_MOTION_VECTORS_F16, BUFFER_THROUGHPUT_R11G11B10 = 0, 1, 2, 3, 4
 BUFFER_STABLE_PLANES, BUFFER_STABLE_PLANES_HEADER, BUFFER_STABLE_RADIANCE_F16, BUFFER_SPECULAR_HITT_F32 = 5, 6, 7, 8
 STABLE_PLANE_COUNT, STABLE_PLANE_INVALID_BRANCH = 3, 0xFFFFFFFF
+(BUFFER_DENOISER_VIEWSPACE_Z_F32, BUFFER_DENOISER_MOTION_VECTORS_F16, BUFFER_DENOISER_NORMAL_ROUGHNESS_R10G10B10A2, BUFFER_DENOISER_DIFF_RADIANCE_HITDIST_F16,
+ BUFFER_DENOISER_SPEC_RADIANCE_HITDIST_F16, BUFFER_DENOISER_DISOCCLUSION_MIX_R8, BUFFER_COMBINED_HISTORY_CLAMP_RELAX_R8) = 9, 10, 11, 12, 13, 14, 15
 
 
 class GeometryData(C.Structure):
@@ -124,6 +126,11 @@ class StablePlane(C.Structure):          # 80 B, StablePlanes.hlsli:48-80
 
 STABLE_PLANE_DTYPE = [("RayOrigin", "f4", 3), ("LastRayTCurrent", "f4"), ("RayDir", "f4", 3), ("SceneLength", "f4"), ("PackedThpAndMVs", "u4", 3), ("VertexIndexAndRoughness", "u4"),
                       ("DenoiserPackedBSDFEstimate", "u4", 3), ("PackedNormal", "u4"), ("PackedNoisyRadianceAndSpecAvg", "u4", 2), ("FlagsAndVertexIndex", "u4"), ("PackedCounters", "u4")]
+
+
+class DenoiserConstants(C.Structure):
+    _fields_ = [("matWorldToView", f32 * 16), ("hitDistanceParameters", f32 * 4), ("preExposedGrayLuminance", f32), ("denoiserRadianceClampK", f32),
+                ("stablePlanesSuppressPrimaryIndirectSpecularK", f32), ("_pad", f32)]
 
 
 class RealtimeConstants(C.Structure):

@@ -57,6 +57,8 @@ def lib():
         L.oracle_generic_ts_address.restype = C.c_uint32; L.oracle_generic_ts_address.argtypes = [C.c_uint32] * 5
         L.oracle_generic_ts_line_stride.argtypes = [C.c_uint32] * 2; L.oracle_generic_ts_plane_stride.argtypes = [C.c_uint32] * 2
         L.oracle_pack_ortho.argtypes = [C.c_void_p, C.c_void_p]; L.oracle_unpack_ortho.argtypes = [C.c_void_p, C.c_void_p]
+        L.oracle_denoiser_prepare_inputs.argtypes = [C.c_void_p, C.POINTER(S.RealtimeConstants), C.POINTER(S.DenoiserConstants), C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
+        L.oracle_denoiser_final_merge.argtypes = [C.c_void_p, C.POINTER(S.RealtimeConstants), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_tri_info.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.oracle_rng.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.oracle_bsdf.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
@@ -138,3 +140,23 @@ class Oracle:
         rc = lib().oracle_render_realtime(self.h, C.byref(rt), x0, y0, x1, y1, *[out[k].ctypes.data for k in ("planes", "header", "stable_radiance", "depth", "motion", "throughput", "spec_hit_t", "merged")], threads)
         assert rc == 0
         return out
+
+    # ---- RTXPT's side of the denoiser interface ----
+    @staticmethod
+    def _ptr_table(arrays):
+        return (C.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
+
+    def new_denoiser_targets(self):
+        W, H = self.consts.imageWidth, self.consts.imageHeight
+        return dict(view_z=np.zeros((H, W), np.float32), motion=np.zeros((H, W, 4), np.float16), normal_roughness=np.zeros((H, W), np.uint32), diff=np.zeros((H, W, 4), np.float16),
+                    spec=np.zeros((H, W, 4), np.float16), disocclusion_mix=np.zeros((H, W), np.uint8), history_clamp_relax=np.zeros((H, W), np.uint8), output=np.zeros((H, W, 4), np.float16))
+
+    def denoiser_prepare_inputs(self, rt, k, realtime, denoiser, plane, init_with_stable_radiance):
+        r = self._ptr_table([realtime[n] for n in ("planes", "header", "stable_radiance", "depth", "motion", "throughput", "spec_hit_t")])
+        d = self._ptr_table([denoiser[n] for n in ("view_z", "motion", "normal_roughness", "diff", "spec", "disocclusion_mix", "history_clamp_relax", "output")])
+        assert lib().oracle_denoiser_prepare_inputs(self.h, C.byref(rt), C.byref(k), plane, int(init_with_stable_radiance), r, d) == 0
+
+    def denoiser_final_merge(self, rt, realtime, denoiser, plane, denoised_diff, denoised_spec):
+        r = self._ptr_table([realtime[n] for n in ("planes", "header", "stable_radiance", "depth", "motion", "throughput", "spec_hit_t")])
+        d = self._ptr_table([denoiser[n] for n in ("view_z", "motion", "normal_roughness", "diff", "spec", "disocclusion_mix", "history_clamp_relax", "output")])
+        assert lib().oracle_denoiser_final_merge(self.h, C.byref(rt), plane, r, d, denoised_diff.ctypes.data, denoised_spec.ctypes.data) == 0

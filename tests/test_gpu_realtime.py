@@ -186,3 +186,34 @@ def test_realtime_invariants(product):
     ref = c.readback_accumulated()[..., :3]
     assert abs(acc.mean() - ref.mean()) < 0.02 * ref.mean(), (acc.mean(), ref.mean())
     c.close()
+
+
+@unverified
+@pytest.mark.parametrize("strict", [True, False])
+def test_denoiser_interface_matches_oracle(product, oracle, strict):
+    """Row a18, RTXPT's side: NRD inputs prepared per plane and the final merge (here with the identity denoiser) against the oracle."""
+    from rtxpt_b200 import scene_builder as sb
+    W = H = 96
+    c, o, cam, consts = _setup(product, oracle, strict, W, H)
+    rt = sb.make_realtime_constants(W, H, cam, bounce_count=8, sub_samples=2)
+    c.set_realtime(rt); c.path_trace_realtime(False); c.synchronize()
+    g = c.readback_realtime(); r = o.render_realtime(rt)
+    k = sb.make_denoiser_constants(cam, suppress_primary_indirect_specular_k=0.4)
+    d = o.new_denoiser_targets()
+    same = (g["header"] == r["header"]).all(0)
+    for i, plane in enumerate((2, 1, 0)):
+        c.denoiser_prepare_inputs(plane, i == 0, k); c.synchronize(); gi = c.readback_denoiser_inputs()
+        o.denoiser_prepare_inputs(rt, k, r, d, plane, i == 0)
+        assert np.array_equal(gi["view_z"][same] < 1e30, d["view_z"][same] < 1e30)
+        surf = same & (d["view_z"] < 1e30)
+        assert np.allclose(gi["view_z"][surf], d["view_z"][surf], rtol=1e-5)
+        assert (gi["normal_roughness"][surf] == d["normal_roughness"][surf]).mean() > 0.99 and np.array_equal(gi["motion"][surf], d["motion"][surf])
+        assert (np.abs(gi["disocclusion_mix"][surf].astype(int) - d["disocclusion_mix"][surf]) <= 1).all()
+        for key in ("diff", "spec"):
+            a, b = gi[key][surf].astype(np.float32), d[key][surf].astype(np.float32)
+            assert np.isclose(a, b, rtol=2e-2, atol=2e-3).all(-1).mean() > (0.97 if strict else 0.9), key
+        c.denoiser_final_merge(plane); o.denoiser_final_merge(rt, r, d, plane, d["diff"].copy(), d["spec"].copy())
+    c.synchronize()
+    out = c.readback_output_color().astype(np.float32); ref = d["output"].astype(np.float32)
+    assert np.isclose(out[same], ref[same], rtol=2e-2, atol=4e-3).all(-1).mean() > (0.97 if strict else 0.9)
+    c.close(); o.close()

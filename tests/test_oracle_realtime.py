@@ -158,3 +158,40 @@ def test_sub_sample_attenuation_and_plane_count(mirror_glass):
     assert (one["header"][1:3] == INVALID).all() and (one["header"][3] & 3 == 0).all()
     no_psr = o.render_realtime(sb.make_realtime_constants(W, H, cam, bounce_count=8, sub_samples=1, allow_psr=False))
     assert 0b101 not in set(np.unique(no_psr["header"][0]).tolist()) and 0b101 in set(np.unique(no_psr["header"][1:3]).tolist())   # the mirror now forks instead of replacing the primary surface
+
+
+def test_denoiser_interface_round_trip(mirror_glass):
+    """RTXPT's side of the denoiser interface (row a18): prepare inputs -> (identity denoiser) -> final merge over the planes, last plane first, reproduces the
+    no-denoiser merge; the prepared inputs obey NRD's input contract (viewZ positive or the sky marker, unit normals, YCoCg radiance, normalised hit distance)."""
+    from rtxpt_b200 import scene_builder as sb
+    o, consts, cam, W, H = mirror_glass
+    rt = sb.make_realtime_constants(W, H, cam, bounce_count=8, sub_samples=4)
+    r = o.render_realtime(rt)
+    k = sb.make_denoiser_constants(cam)
+    d = o.new_denoiser_targets()
+    seen_surface = np.zeros((H, W), bool)
+    for i, plane in enumerate((2, 1, 0)):
+        o.denoiser_prepare_inputs(rt, k, r, d, plane, i == 0)
+        surf = d["view_z"] < 1e30
+        valid = r["header"][plane] != INVALID
+        ys, xs = np.mgrid[0:H, 0:W]
+        finite = np.isfinite(r["planes"][sb.generic_ts_address(xs, ys, plane, W, H)]["SceneLength"])
+        assert np.array_equal(surf, valid & finite)                                      # sky planes and unused planes are marked, everything else is a surface
+        assert (d["view_z"][surf] > 0).all() and (d["view_z"][~surf] == np.float32(3.402823466e+38)).all()
+        nr = d["normal_roughness"][surf]
+        ex, ey, rough = (nr & 1023) / 1023.0, ((nr >> 10) & 1023) / 1023.0, ((nr >> 20) & 1023) / 1023.0
+        assert (nr >> 30 == 0).all() and (rough >= 0.2 - 1e-3).all()                      # material id 0; kMinRoughness
+        px, py = ex * 2 - 1, ey * 2 - 1; n = np.stack([px, py, 1 - np.abs(px) - np.abs(py)], -1); t = np.clip(-n[..., 2], 0, 1)
+        n[..., 0] -= t * np.where(n[..., 0] >= 0, 1, -1); n[..., 1] -= t * np.where(n[..., 1] >= 0, 1, -1); n /= np.linalg.norm(n, axis=-1, keepdims=True)
+        assert np.isfinite(n).all()
+        diff, spec = d["diff"][surf].astype(np.float32), d["spec"][surf].astype(np.float32)
+        assert (diff[..., 0] >= 0).all() and (spec[..., 0] >= 0).all() and (diff[..., 3] == 0).all() and ((spec[..., 3] >= 0) & (spec[..., 3] <= 1)).all()      # Y >= 0, hit distance in [0, 1]
+        lum_max = 128.0 + 1                                                             # min(255, preExposedGrayLuminance * clampK * 16)
+        assert diff[..., 0].max() <= lum_max * 1.5 and spec[..., 0].max() <= lum_max * 1.5
+        o.denoiser_final_merge(rt, r, d, plane, d["diff"].copy(), d["spec"].copy())
+        seen_surface |= surf
+    out = d["output"][..., :3].astype(np.float32)
+    assert (d["output"][..., 3] == 1).all()
+    assert np.isclose(out, r["merged"], rtol=2e-2, atol=4e-3).all(-1).mean() > 0.999 and abs(out.mean() - r["merged"].mean()) < 1e-3 * r["merged"].mean()
+    # motion vectors are the plane's own; the disocclusion relaxation only exists behind a delta bounce (vertex index > 1)
+    assert (d["motion"] == 0).all()                                                     # static camera
