@@ -155,6 +155,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-realtime", action="store_true", help="skip the realtime-mode (stable planes) timing that runs in a child process after the headline measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_gpus = args.gpus
@@ -288,6 +289,15 @@ def main():
         r = run_cpu(scene, consts, 3, 1)
         cpu = {"value": r["mrays_s"], "unit": "Mrays/s", "cores": r["threads"], "kind": "port", "sample": r["sample"], "bvh_build_s": r["bvh_build_s"], "rays_per_path": r["rays_per_path"]}
 
+    realtime = None
+    if rank == 0 and world == 1 and not args.no_realtime:
+        # realtime mode (row a17) timed in a child process on the same workload: a fault there cannot take the headline line with it
+        try:
+            r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts", "bench_realtime.py")], capture_output=True, text=True, timeout=300)
+            realtime = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 and r.stdout.strip() else {"error": "exit %d: %s" % (r.returncode, r.stderr.strip()[-300:])}
+        except Exception as e:        # timeout, malformed output
+            realtime = {"error": repr(e)[:300]}
+
     if rank == 0:
         line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (fp16 path-state storage)", "data": "synthetic",
@@ -297,7 +307,7 @@ def main():
                 "gpu_launches": int(launches * args.steps),
                 "rays_per_frame": rays_per_frame, "rays_per_path": rays_per_frame / (WIDTH * HEIGHT * SPP), "scatter_rays": scatter, "shadow_rays": shadow,
                 "rays_per_iteration": rays_per_bounce, "bvh_build_s": st.bvhBuildSeconds, "bvh_nodes": st.bvhNodeCount, "lights": st.lightCount,
-                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "realtime": realtime}
         sys.stdout.flush(); os.write(real_stdout, (json.dumps(line) + "\n").encode())
     ctx.close()
     if world > 1:

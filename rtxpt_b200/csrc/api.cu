@@ -606,6 +606,7 @@ extern "C" RTXPT_API int rtxpt_b200_path_trace_realtime(rtxpt_ctx* c, int mergeN
     const uint32_t fillIterations = std::min<uint32_t>(c->consts.bounceCount + 1 + (hasRefraction ? 4 : 0), kMaxWavefrontIterations);
     CU(cudaEventRecord(c->evStart, s));
     uint64_t launches = 0;
+    c->evUsed = 0;
     p.firstSampleIndex = c->consts.sampleBaseIndex;
     CU(cudaMemsetAsync(c->counters.ptr, 0, kCounterWords * sizeof(uint32_t), s));
     p.iteration = 0;

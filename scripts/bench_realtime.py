@@ -1,0 +1,51 @@
+"""Times realtime mode (stable-plane BUILD pass + FILL pass + no-denoiser merge) on bench.py's city workload and prints ONE JSON object.
+Run by bench.py in a child process after the headline measurement (a failure here must not cost the headline line), or by hand on a GPU box:
+    python scripts/bench_realtime.py [--frames 10] [--sub-samples 1]
+Clear glass (roughness below the delta threshold) is opted into the path-space decomposition the way a .material.json with PSDExclude = false does, so the BUILD pass
+has real forks to explore; everything else keeps RTXPT's default (excluded)."""
+import argparse, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=10); ap.add_argument("--warmup", type=int, default=3); ap.add_argument("--sub-samples", type=int, default=1)
+    ap.add_argument("--width", type=int, default=1920); ap.add_argument("--height", type=int, default=1080); ap.add_argument("--triangles", type=int, default=2_800_000)
+    args = ap.parse_args()
+    real_stdout = os.dup(1); os.dup2(2, 1)
+    from rtxpt_b200 import lib, scenes, scene_builder as sb, structs as S
+    W, H = args.width, args.height
+    scene, cam = scenes.city_block(target_triangles=args.triangles, width=W, height=H)
+    opted = 0
+    for i in range(scene.desc.materialCount):
+        m = scene.desc.materials[i]
+        if m.TransmissionFactor > 0 and m.Roughness * m.Roughness < 0.0064:
+            m.Flags = (m.Flags & ~S.MATFLAG_PSDExclude & ~0x0F000000) | (1 << 24); opted += 1          # PSDExclude off, dominant delta lobe = transmission
+    consts = sb.make_constants(W, H, cam, bounce_count=6, diffuse_bounce_count=6, env_enabled=True, firefly_threshold=5000.0, nee=True, nee_type=2)
+    ctx = lib.Context(max_sub_samples_per_launch=1)
+    ctx.upload_scene(scene); ctx.set_constants(consts); ctx.set_view(sb.world_to_clip(cam))
+    rt = sb.make_realtime_constants(W, H, cam, bounce_count=6, sub_samples=args.sub_samples)
+    ctx.set_realtime(rt)
+    ms = []
+    for f in range(args.warmup + args.frames):
+        consts.sampleBaseIndex = f * args.sub_samples; ctx.set_constants(consts)
+        ctx.path_trace_realtime(True); ctx.synchronize()
+        st = ctx.stats()
+        if f >= args.warmup: ms.append(float(st.msTotal))
+    r = ctx.readback_realtime()
+    hd = r["header"]
+    out = {"ms_per_frame": float(np.median(ms)), "ms_min": float(np.min(ms)), "ms_max": float(np.max(ms)), "frames": args.frames, "warmup": args.warmup,
+           "image": [W, H], "sub_samples": args.sub_samples, "active_planes": 3, "max_vertex_depth": int(rt.maxStablePlaneVertexDepth), "kernel_launches_per_frame": int(st.kernelLaunches),
+           "materials_opted_into_decomposition": opted, "fill_pass_scatter_rays": int(st.scatterRays), "fill_pass_shadow_rays": int(st.shadowRays),
+           "pixels_with_plane": [float((hd[p] != 0xFFFFFFFF).mean()) for p in range(3)], "pixels_with_non_primary_dominant_plane": float(((hd[3] & 3) != 0).mean()),
+           "mean_radiance": float(r["merged"].mean()), "timing": "CUDA events around the whole rtxpt_b200_path_trace_realtime call (BUILD + FILL x sub_samples + merge), median over frames",
+           "workload": "bench.py city workload, clear glass opted into path-space decomposition"}
+    ctx.close()
+    os.write(real_stdout, (json.dumps(out) + "\n").encode())
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
