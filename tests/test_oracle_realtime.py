@@ -195,3 +195,45 @@ def test_denoiser_interface_round_trip(mirror_glass):
     assert np.isclose(out, r["merged"], rtol=2e-2, atol=4e-3).all(-1).mean() > 0.999 and abs(out.mean() - r["merged"].mean()) < 1e-3 * r["merged"].mean()
     # motion vectors are the plane's own; the disocclusion relaxation only exists behind a delta bounce (vertex index > 1)
     assert (d["motion"] == 0).all()                                                     # static camera
+
+
+def _opt_glass_into_decomposition(scene):
+    """What a .material.json with PSDExclude = false, PSDDominantDeltaLobe = 0 does for clear glass (roughness below the delta threshold)."""
+    from rtxpt_b200 import structs as S
+    n = 0
+    for i in range(scene.desc.materialCount):
+        m = scene.desc.materials[i]
+        if m.TransmissionFactor > 0 and m.Roughness * m.Roughness < 0.0064:
+            m.Flags = (m.Flags & ~S.MATFLAG_PSDExclude & ~0x0F000000) | (1 << 24); n += 1
+    return n
+
+
+def test_realtime_on_textured_env_lit_scene(oracle):
+    """Realtime mode on the city stand-in (textures, environment map + NEE-AT proxies, alpha-tested foliage, thin and solid glass): same expectation as
+    reference mode, the specular hit distance is exported where the dominant plane scatters off glossy surfaces, sky planes carry no noisy radiance."""
+    from rtxpt_b200 import scene_builder as sb, scenes
+    W, H = 160, 90
+    scene, cam = scenes.city_block(target_triangles=120000, width=W, height=H, texture_size=128, n_textures=6, n_materials=64)
+    assert _opt_glass_into_decomposition(scene) > 0
+    o = oracle.Oracle(scene)
+    consts = sb.make_constants(W, H, cam, bounce_count=6, diffuse_bounce_count=6, env_enabled=True, firefly_threshold=5000.0, nee=True, nee_type=2)
+    o.set_view(sb.world_to_clip(cam))
+    acc = np.zeros((H, W, 3)); frames = 6
+    for f in range(frames):
+        consts.sampleBaseIndex = f * 4; o.set_constants(consts)
+        r = o.render_realtime(sb.make_realtime_constants(W, H, cam, bounce_count=6, sub_samples=4)); acc += r["merged"]
+    acc /= frames
+    consts.sampleBaseIndex = 0; o.set_constants(consts)
+    ref = o.render(0, 48)[0][..., :3]
+    assert np.isfinite(acc).all() and abs(acc.mean() - ref.mean()) < 0.03 * ref.mean(), (acc.mean(), ref.mean())
+    hd = r["header"]
+    assert (hd[0] != INVALID).all() and 0 < (hd[1] != INVALID).mean() < 0.2
+    # a path that ends at a hit while the distance is still being measured leaves the negative "started" marker behind, as in the reference (the
+    # denoiser front end saturates it to 0); most measurements complete
+    assert 0.02 < (r["spec_hit_t"] > 0).mean() < 0.9 and (r["spec_hit_t"] < 0).mean() < 0.25 * (r["spec_hit_t"] > 0).mean()
+    ys, xs = np.mgrid[0:H, 0:W]
+    p0 = r["planes"][sb.generic_ts_address(xs, ys, 0, W, H)]
+    sky = ~np.isfinite(p0["SceneLength"])
+    assert sky.any() and (p0["PackedNoisyRadianceAndSpecAvg"][sky] == 0).all()
+    assert (r["stable_radiance"][..., :3][sky & (hd[1] == INVALID)] > 0).any()                     # the sky seen directly is stable radiance
+    o.close()
