@@ -6,6 +6,7 @@
 // depends on the DXR driver (BVH, traversal, intersection), TMU filtering or fp16 shader arithmetic is "parity unpinned" — the
 // reference ships no runnable golden data for it.
 #include "pt_path.h"
+#include "reblur.h"
 #include <cstdio>
 #include <chrono>
 #ifdef _OPENMP
@@ -310,6 +311,33 @@ ORC_API int oracle_denoiser_final_merge(void* p, const RtxptRealtimeConstants* r
     if (!c->haveConsts || !rt || stablePlaneIndex >= 3) return -1;
     const RealtimeTargets T = makeTargets(c, rt, realtimeTargets); const DenoiserTargets D = makeDenoiserTargets(denoiserTargets);
     for (uint32_t y = 0; y < T.height; y++) for (uint32_t px = 0; px < T.width; px++) denoiserFinalMergePixel(T, D, px, y, stablePlaneIndex, denoisedDiff, denoisedSpec);
+    return 0;
+}
+
+// ReBLUR, spatial half (oracle/reblur.h): ClassifyTiles -> [HitDistReconstruction 5x5] -> PrePass -> Blur -> PostBlur on NRD's inputs as rtxpt_b200_denoiser_prepare_inputs /
+// oracle_denoiser_prepare_inputs write them.  accumulatedFrames (2 floats per pixel: diffuse, specular; may be NULL = 0) stands in for the history lengths the temporal passes
+// would hand to Blur / PostBlur.  stages: bit 0 hit-distance reconstruction, bit 1 pre-pass, bit 2 blur, bit 3 post-blur.  Images are RGBA16F; matrices row-major, row vector x matrix.
+ORC_API int oracle_reblur_spatial(uint32_t W, uint32_t H, const float* worldToView16, const float* viewToClip16, uint32_t frameIndex, const float* viewZ, const uint32_t* normalRoughness,
+                                  const uint16_t* inDiff, const uint16_t* inSpec, const float* accumulatedFrames, uint32_t stages, uint16_t* outDiff, uint16_t* outSpec, float* outSpecHitDistForTracking,
+                                  uint8_t* outTiles)
+{
+    using namespace orc::reblur;
+    Settings settings; const Constants c = makeConstants(settings, W, H, worldToView16, viewToClip16, frameIndex);
+    Inputs in; in.W = W; in.H = H; in.viewZ = viewZ; in.normalRoughness = normalRoughness;
+    auto load = [&](const uint16_t* src, Image4& img) { img.init(W, H); for (size_t i = 0; i < size_t(W) * H; i++) img.v[i] = f4(f16tof32(src[4 * i]), f16tof32(src[4 * i + 1]), f16tof32(src[4 * i + 2]), f16tof32(src[4 * i + 3])); };
+    auto save = [&](const Image4& img, uint16_t* dst) { for (size_t i = 0; i < size_t(W) * H; i++) { dst[4 * i] = uint16_t(f32tof16(img.v[i].x)); dst[4 * i + 1] = uint16_t(f32tof16(img.v[i].y)); dst[4 * i + 2] = uint16_t(f32tof16(img.v[i].z)); dst[4 * i + 3] = uint16_t(f32tof16(img.v[i].w)); } };
+    Image4 diffA, specA, diffB, specB; load(inDiff, diffA); load(inSpec, specA); diffB = diffA; specB = specA;
+    const std::vector<uint8_t> tiles = classifyTiles(c, in);
+    if (outTiles) memcpy(outTiles, tiles.data(), tiles.size());
+    std::vector<float2> data1(size_t(W) * H, f2(0, 0));
+    if (accumulatedFrames) for (size_t i = 0; i < size_t(W) * H; i++) data1[i] = f2(accumulatedFrames[2 * i], accumulatedFrames[2 * i + 1]);
+    std::vector<float> tracking(size_t(W) * H, 0.0f);
+    if (stages & 1u) { hitDistReconstruction(c, in, tiles, diffA, specA, diffB, specB); diffA = diffB; specA = specB; }
+    if (stages & 2u) { SpatialOutputs o{ &diffB, &specB, &tracking }; spatialPass(c, in, tiles, PRE_BLUR, diffA, specA, nullptr, o); diffA = diffB; specA = specB; }
+    if (stages & 4u) { SpatialOutputs o{ &diffB, &specB, nullptr }; spatialPass(c, in, tiles, BLUR, diffA, specA, &data1, o); diffA = diffB; specA = specB; }
+    if (stages & 8u) { SpatialOutputs o{ &diffB, &specB, nullptr }; spatialPass(c, in, tiles, POST_BLUR, diffA, specA, &data1, o); diffA = diffB; specA = specB; }
+    save(diffA, outDiff); save(specA, outSpec);
+    if (outSpecHitDistForTracking) memcpy(outSpecHitDistForTracking, tracking.data(), tracking.size() * 4);
     return 0;
 }
 

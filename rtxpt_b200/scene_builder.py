@@ -354,6 +354,17 @@ def world_to_view(cam):
     return view.astype(np.float32)
 
 
+def view_to_clip(cam):
+    """SimpleViewConstants.matViewToClip of a BridgeCamera block (D3D, left-handed, z in [0, 1]); world_to_clip(cam) = world_to_view(cam) @ view_to_clip(cam)."""
+    W = np.array(cam.CameraW[:], np.float32); U = np.array(cam.CameraU[:], np.float32); V = np.array(cam.CameraV[:], np.float32)
+    tan_x, tan_y = float(np.linalg.norm(U) / np.linalg.norm(W)), float(np.linalg.norm(V) / np.linalg.norm(W))
+    n, fa = float(cam.NearZ), float(cam.FarZ)
+    proj = np.zeros((4, 4), np.float64)
+    proj[0, 0], proj[1, 1] = 1.0 / tan_x, 1.0 / tan_y
+    proj[2, 2], proj[2, 3], proj[3, 2] = fa / (fa - n), 1.0, -n * fa / (fa - n)
+    return proj.astype(np.float32)
+
+
 def make_denoiser_constants(cam, hit_distance_parameters=(3.0, 0.1, 20.0, -25.0), pre_exposed_gray_luminance=1.0, radiance_clamp_k=8.0, suppress_primary_indirect_specular_k=0.0):
     """RtxptDenoiserConstants: nrd::HitDistanceParameters defaults (NRDSettings.h:206-220), no tone mapping (preExposedGrayLuminance 1)."""
     k = S.DenoiserConstants()

@@ -59,6 +59,7 @@ def lib():
         L.oracle_pack_ortho.argtypes = [C.c_void_p, C.c_void_p]; L.oracle_unpack_ortho.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_denoiser_prepare_inputs.argtypes = [C.c_void_p, C.POINTER(S.RealtimeConstants), C.POINTER(S.DenoiserConstants), C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
         L.oracle_denoiser_final_merge.argtypes = [C.c_void_p, C.POINTER(S.RealtimeConstants), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_reblur_spatial.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32] + [C.c_void_p] * 5 + [C.c_uint32] + [C.c_void_p] * 4
         L.oracle_tri_info.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.oracle_rng.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.oracle_bsdf.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
@@ -160,3 +161,16 @@ class Oracle:
         r = self._ptr_table([realtime[n] for n in ("planes", "header", "stable_radiance", "depth", "motion", "throughput", "spec_hit_t")])
         d = self._ptr_table([denoiser[n] for n in ("view_z", "motion", "normal_roughness", "diff", "spec", "disocclusion_mix", "history_clamp_relax", "output")])
         assert lib().oracle_denoiser_final_merge(self.h, C.byref(rt), plane, r, d, denoised_diff.ctypes.data, denoised_spec.ctypes.data) == 0
+
+
+def reblur_spatial(world_to_view, view_to_clip, frame_index, view_z, normal_roughness, diff, spec, accumulated_frames=None, stages=0b1111):
+    """oracle/reblur.h spatial chain on NRD inputs (numpy: view_z f32 HxW, normal_roughness u32 HxW, diff / spec f16 HxWx4).  Returns (diff, spec, hit distance for tracking, tiles)."""
+    H, W = view_z.shape
+    out_d = np.zeros((H, W, 4), np.float16); out_s = np.zeros((H, W, 4), np.float16); track = np.zeros((H, W), np.float32); tiles = np.zeros(((H + 15) // 16, (W + 15) // 16), np.uint8)
+    m0 = np.ascontiguousarray(world_to_view, np.float32); m1 = np.ascontiguousarray(view_to_clip, np.float32)
+    vz = np.ascontiguousarray(view_z, np.float32); nr = np.ascontiguousarray(normal_roughness, np.uint32); d = np.ascontiguousarray(diff, np.float16); s = np.ascontiguousarray(spec, np.float16)
+    af = None if accumulated_frames is None else np.ascontiguousarray(accumulated_frames, np.float32)
+    rc = lib().oracle_reblur_spatial(W, H, m0.ctypes.data, m1.ctypes.data, frame_index, vz.ctypes.data, nr.ctypes.data, d.ctypes.data, s.ctypes.data, None if af is None else af.ctypes.data,
+                                     stages, out_d.ctypes.data, out_s.ctypes.data, track.ctypes.data, tiles.ctypes.data)
+    assert rc == 0
+    return out_d, out_s, track, tiles
