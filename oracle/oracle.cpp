@@ -341,6 +341,34 @@ ORC_API int oracle_reblur_spatial(uint32_t W, uint32_t H, const float* worldToVi
     return 0;
 }
 
+// Full ReBLUR frame (oracle/reblur.h: denoiseFrame) with a persistent history per instance - RTXPT keeps one NRD instance per stable plane (Sample.h:327).
+struct ReblurInstance { orc::reblur::History history; orc::reblur::FrameOutputs last; };
+ORC_API void* oracle_reblur_create() { return new ReblurInstance(); }
+ORC_API void oracle_reblur_destroy(void* p) { delete (ReblurInstance*)p; }
+// matrices: row-major, row vector x matrix; motion: IN_MV RGBA16F (pixels, view-depth delta) or NULL; disocclusionMix: R8 or NULL; outputs RGBA16F; outAccumFrames: 2 floats per pixel (optional)
+ORC_API int oracle_reblur_denoise(void* p, uint32_t W, uint32_t H, const float* worldToView16, const float* viewToClip16, const float* worldToViewPrev16, const float* viewToClipPrev16, uint32_t frameIndex,
+                                  int resetHistory, const float* viewZ, const uint32_t* normalRoughness, const uint16_t* motion, const uint8_t* disocclusionMix, const uint16_t* inDiff, const uint16_t* inSpec,
+                                  uint16_t* outDiff, uint16_t* outSpec, float* outAccumFrames)
+{
+    using namespace orc::reblur;
+    ReblurInstance* inst = (ReblurInstance*)p;
+    Inputs in; in.W = W; in.H = H; in.viewZ = viewZ; in.normalRoughness = normalRoughness;
+    TemporalParams tp; tp.motion = motion; tp.disocclusionThresholdMix = disocclusionMix; tp.resetHistory = resetHistory != 0;
+    tp.disocclusionThreshold = 0.03f + 1.0f / float(H); tp.disocclusionThresholdAlternate = 0.2f + 1.0f / float(H);      // + ( 1 + jitterDelta ) / rectH, no jitter
+    const size_t n = size_t(W) * H;
+    Image4 d, s; d.init(W, H); s.init(W, H);
+    for (size_t i = 0; i < n; i++) { d.v[i] = f4(f16tof32(inDiff[4 * i]), f16tof32(inDiff[4 * i + 1]), f16tof32(inDiff[4 * i + 2]), f16tof32(inDiff[4 * i + 3])); s.v[i] = f4(f16tof32(inSpec[4 * i]), f16tof32(inSpec[4 * i + 1]), f16tof32(inSpec[4 * i + 2]), f16tof32(inSpec[4 * i + 3])); }
+    denoiseFrame(Settings(), W, H, worldToView16, viewToClip16, worldToViewPrev16, viewToClipPrev16, frameIndex, tp, in, d, s, inst->history, inst->last);
+    for (size_t i = 0; i < n; i++)
+    {
+        const float4 a = inst->last.diff.v[i], b = inst->last.spec.v[i];
+        outDiff[4 * i] = uint16_t(f32tof16(a.x)); outDiff[4 * i + 1] = uint16_t(f32tof16(a.y)); outDiff[4 * i + 2] = uint16_t(f32tof16(a.z)); outDiff[4 * i + 3] = uint16_t(f32tof16(a.w));
+        outSpec[4 * i] = uint16_t(f32tof16(b.x)); outSpec[4 * i + 1] = uint16_t(f32tof16(b.y)); outSpec[4 * i + 2] = uint16_t(f32tof16(b.z)); outSpec[4 * i + 3] = uint16_t(f32tof16(b.w));
+        if (outAccumFrames) { outAccumFrames[2 * i] = float(inst->last.data1[2 * i]) / 255.0f * 63.0f; outAccumFrames[2 * i + 1] = float(inst->last.data1[2 * i + 1]) / 255.0f * 63.0f; }
+    }
+    return 0;
+}
+
 // primary-hit triangle id -> (instance, geometry, primitive), for comparing with the product's hit records
 ORC_API int oracle_tri_info(void* p, uint32_t triId, uint32_t* out3)
 {

@@ -60,6 +60,8 @@ def lib():
         L.oracle_denoiser_prepare_inputs.argtypes = [C.c_void_p, C.POINTER(S.RealtimeConstants), C.POINTER(S.DenoiserConstants), C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
         L.oracle_denoiser_final_merge.argtypes = [C.c_void_p, C.POINTER(S.RealtimeConstants), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_reblur_spatial.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32] + [C.c_void_p] * 5 + [C.c_uint32] + [C.c_void_p] * 4
+        L.oracle_reblur_create.restype = C.c_void_p; L.oracle_reblur_destroy.argtypes = [C.c_void_p]
+        L.oracle_reblur_denoise.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32] + [C.c_void_p] * 4 + [C.c_uint32, C.c_int] + [C.c_void_p] * 9
         L.oracle_tri_info.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.oracle_rng.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.oracle_bsdf.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
@@ -174,3 +176,27 @@ def reblur_spatial(world_to_view, view_to_clip, frame_index, view_z, normal_roug
                                      stages, out_d.ctypes.data, out_s.ctypes.data, track.ctypes.data, tiles.ctypes.data)
     assert rc == 0
     return out_d, out_s, track, tiles
+
+
+class Reblur:
+    """One REBLUR_DIFFUSE_SPECULAR instance of the oracle (history persists between denoise calls)."""
+    def __init__(self):
+        self.h = lib().oracle_reblur_create()
+
+    def close(self):
+        if self.h: lib().oracle_reblur_destroy(self.h); self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def denoise(self, world_to_view, view_to_clip, frame_index, view_z, normal_roughness, diff, spec, prev_world_to_view=None, prev_view_to_clip=None, motion=None, disocclusion_mix=None, reset=False):
+        H, W = view_z.shape
+        c = lambda a, t: None if a is None else np.ascontiguousarray(a, t)
+        m0, m1 = c(world_to_view, np.float32), c(view_to_clip, np.float32)
+        p0 = m0 if prev_world_to_view is None else c(prev_world_to_view, np.float32); p1 = m1 if prev_view_to_clip is None else c(prev_view_to_clip, np.float32)
+        vz, nr, d, s, mv, mix = c(view_z, np.float32), c(normal_roughness, np.uint32), c(diff, np.float16), c(spec, np.float16), c(motion, np.float16), c(disocclusion_mix, np.uint8)
+        od = np.zeros((H, W, 4), np.float16); os_ = np.zeros((H, W, 4), np.float16); frames = np.zeros((H, W, 2), np.float32)
+        ptr = lambda a: None if a is None else a.ctypes.data
+        rc = lib().oracle_reblur_denoise(self.h, W, H, ptr(m0), ptr(m1), ptr(p0), ptr(p1), frame_index, int(reset), ptr(vz), ptr(nr), ptr(mv), ptr(mix), ptr(d), ptr(s), ptr(od), ptr(os_), ptr(frames))
+        assert rc == 0
+        return od, os_, frames

@@ -106,3 +106,78 @@ def test_hit_distance_reconstruction(oracle):
     d2 = d.copy(); d2[..., 3] = np.where(np.mgrid[0:H, 0:W][1] < 32, 0.9, 0.0).astype(np.float16)
     od2, _, _, _ = oracle.reblur_spatial(wv, vc, 0, vz2, nr, d2, d2.copy(), None, 0b0001)
     assert (od2[..., 3][:, 34:] == 0).all() and np.allclose(od2[..., 3][:, :32].astype(np.float32), 0.9, atol=2e-3)
+
+
+def _cornell_frames(oracle, W=96, H=96, bounces=4):
+    from rtxpt_b200 import scene_builder as sb, scenes
+    scene, cam = scenes.cornell_box(W, H)
+    o = oracle.Oracle(scene)
+    consts = sb.make_constants(W, H, cam, bounce_count=bounces, diffuse_bounce_count=3)
+
+    def frame(index, camera=cam, prev_camera=None):
+        c = sb.make_constants(W, H, camera, bounce_count=bounces, diffuse_bounce_count=3); c.sampleBaseIndex = index
+        o.set_constants(c); o.set_view(sb.world_to_clip(camera))
+        rt = sb.make_realtime_constants(W, H, camera, prev_cam=prev_camera, bounce_count=bounces, sub_samples=1)
+        r = o.render_realtime(rt); d = o.new_denoiser_targets()
+        o.denoiser_prepare_inputs(rt, sb.make_denoiser_constants(camera), r, d, 0, True)
+        return d
+    return o, cam, frame
+
+
+def test_full_chain_converges_on_a_static_view(oracle):
+    """Eight passes per frame with history: the accumulated-frame counters grow by one per frame, the error against a converged image of the same demodulated signal keeps
+    falling well below what one frame of spatial filtering reaches, and the mean energy stays put."""
+    from rtxpt_b200 import scene_builder as sb
+    W = H = 96
+    o, cam, frame = _cornell_frames(oracle, W, H)
+    ref_d = np.zeros((H, W, 4)); ref_s = np.zeros((H, W, 4)); N = 48
+    for f in range(N):
+        d = frame(1000 + f); ref_d += d["diff"]; ref_s += d["spec"]
+    ref_d /= N; ref_s /= N
+    rb = oracle.Reblur(); wv, vc = sb.world_to_view(cam), sb.view_to_clip(cam)
+    errs = []
+    for f in range(16):
+        d = frame(f)
+        od, os_, frames = rb.denoise(wv, vc, f, d["view_z"], d["normal_roughness"], d["diff"], d["spec"], motion=d["motion"], disocclusion_mix=d["disocclusion_mix"])
+        surf = d["view_z"] < 1e30
+        assert np.isfinite(od.astype(np.float32)).all() and np.isfinite(os_.astype(np.float32)).all()
+        assert abs(frames[surf].mean() - f) < 0.08 * f + 0.01                      # one more frame of history everywhere: nothing moved
+        errs.append((np.abs(od[..., 0].astype(np.float32) - ref_d[..., 0])[surf].mean(), np.abs(os_[..., 0].astype(np.float32) - ref_s[..., 0])[surf].mean(),
+                     np.abs(d["diff"][..., 0].astype(np.float32) - ref_d[..., 0])[surf].mean(), np.abs(d["spec"][..., 0].astype(np.float32) - ref_s[..., 0])[surf].mean()))
+    e = np.float32(errs)
+    assert (e[:, 0] < e[:, 2]).all() and (e[:, 1] < e[:, 3]).all()                 # better than the input on every frame
+    assert e[15, 0] < 0.55 * e[0, 0] and e[15, 1] < 0.75 * e[0, 1] and e[15, 0] < 0.35 * e[15, 2]
+    assert abs(od[..., 0][surf].astype(np.float32).mean() - ref_d[..., 0][surf].mean()) < 0.02 * ref_d[..., 0][surf].mean()
+    rb.close(); o.close()
+
+
+def test_history_follows_a_moving_camera_and_resets_on_a_cut(oracle):
+    """A slow dolly: surface-motion reprojection (motion vectors exported with the stable planes, previous view matrices) keeps most of the history; a camera cut
+    far away fails the disocclusion tests and the counters restart, as they do when the caller asks for a reset."""
+    from rtxpt_b200 import scene_builder as sb
+    W = H = 96
+    o, cam0, frame = _cornell_frames(oracle, W, H)
+    def cam_at(dx, dz=0.0):
+        return sb.bridge_camera(W, H, pos=(2.78 + dx, 2.73, -8.0 + dz), direction=(0, 0, 1), up=(0, 1, 0), fov_y=0.66)
+    rb = oracle.Reblur(); prev = None
+    for f in range(10):
+        cam = cam_at(0.02 * f)
+        d = frame(f, cam, prev)
+        od, os_, frames = rb.denoise(sb.world_to_view(cam), sb.view_to_clip(cam), f, d["view_z"], d["normal_roughness"], d["diff"], d["spec"],
+                                     prev_world_to_view=None if prev is None else sb.world_to_view(prev), prev_view_to_clip=None if prev is None else sb.view_to_clip(prev),
+                                     motion=d["motion"], disocclusion_mix=d["disocclusion_mix"])
+        prev = cam
+    surf = d["view_z"] < 1e30
+    assert (np.abs(d["motion"][..., 0].astype(np.float32))[surf] > 0).mean() > 0.9                           # the dolly produces screen-space motion
+    assert np.median(frames[..., 0][surf]) > 6.0 and (frames[..., 0][surf] > 4.0).mean() > 0.8              # history survives the motion
+    # a cut the application does not describe (no motion vectors, previous view = current view): reprojection lands on other surfaces, the plane-distance /
+    # normal tests reject them and the counters restart for most of the image
+    cut = sb.bridge_camera(W, H, pos=(4.2, 1.2, -6.0), direction=(-0.25, 0.1, 1), up=(0, 1, 0), fov_y=0.66)
+    d = frame(20, cut, cut)
+    _, _, frames_cut = rb.denoise(sb.world_to_view(cut), sb.view_to_clip(cut), 10, d["view_z"], d["normal_roughness"], d["diff"], d["spec"], motion=None, disocclusion_mix=d["disocclusion_mix"])
+    surf = d["view_z"] < 1e30
+    assert np.median(frames_cut[..., 0][surf]) < 3.0 and np.median(frames[..., 0]) > 2 * np.median(frames_cut[..., 0][surf])
+    d = frame(21, cut, cut)
+    _, _, frames_reset = rb.denoise(sb.world_to_view(cut), sb.view_to_clip(cut), 11, d["view_z"], d["normal_roughness"], d["diff"], d["spec"], motion=d["motion"], reset=True)
+    assert (frames_reset == 0).all()
+    rb.close(); o.close()
