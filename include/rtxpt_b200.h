@@ -377,7 +377,30 @@ enum {
     RTXPT_BUFFER_COMBINED_HISTORY_CLAMP_RELAX_R8 = 15
 };
 RTXPT_API int rtxpt_b200_denoiser_prepare_inputs(rtxpt_ctx* ctx, uint32_t stablePlaneIndex, int initWithStableRadiance, const RtxptDenoiserConstants* constants, void* cudaStream);
-RTXPT_API int rtxpt_b200_denoiser_final_merge(rtxpt_ctx* ctx, uint32_t stablePlaneIndex, const void* dDenoisedDiffRGBA16F, const void* dDenoisedSpecRGBA16F, void* cudaStream);
+RTXPT_API int rtxpt_b200_denoiser_final_merge(rtxpt_ctx* ctx, uint32_t stablePlaneIndex, const void* dDenoisedDiffRGBA16F, const void* dDenoisedSpecRGBA16F, void* cudaStream);    /* NULL, NULL = the images rtxpt_b200_reblur_denoise wrote */
+
+/* ---- ReBLUR: NRD's REBLUR_DIFFUSE_SPECULAR denoiser (External/Nrd, NRD 4.15.2) for one stable plane, in RTXPT's configuration
+ * (Rtxpt/NRD/NrdConfig.cpp:49-61 settings, NrdIntegration.cpp:375-408 common settings).  Replaces NrdIntegration::RunDenoiserPasses (NrdIntegration.cpp:360-520) for the
+ * ReBLUR method: reads RTXPT_BUFFER_DENOISER_* as rtxpt_b200_denoiser_prepare_inputs wrote them, keeps one history per plane inside the context (RTXPT: one NRD instance per
+ * plane), writes RTXPT_BUFFER_DENOISED_{DIFF,SPEC}_RADIANCE_HITDIST_F16 (NRD's OUT_DIFF/SPEC_RADIANCE_HITDIST), which rtxpt_b200_denoiser_final_merge( .., NULL, NULL ) consumes. */
+typedef struct RtxptReblurFrame {
+    float matWorldToView[16], matViewToClip[16];           /* this frame, un-jittered; row-major, row vector x matrix; left-handed view space, +z forward (nrd::CommonSettings::worldToViewMatrix / viewToClipMatrix) */
+    float prevMatWorldToView[16], prevMatViewToClip[16];   /* previous frame (…MatrixPrev); equal to the current ones on the first frame */
+    uint32_t frameIndex;                                    /* CommonSettings::frameIndex */
+    uint32_t resetHistory;                                  /* AccumulationMode::CLEAR_AND_RESTART */
+    uint32_t ignoreMotionVectors;                           /* 1: treat IN_MV as zero (static camera tests) */
+    float frameTimeMs;                                      /* 0 = 1/60 s */
+    float disocclusionThreshold, disocclusionThresholdAlternate;   /* 0 = RTXPT's UI defaults 0.03 / 0.2 (SampleUI.h:294-296) */
+    float _pad[2];
+} RtxptReblurFrame;
+enum {
+    RTXPT_BUFFER_DENOISED_DIFF_RADIANCE_HITDIST_F16 = 16,
+    RTXPT_BUFFER_DENOISED_SPEC_RADIANCE_HITDIST_F16 = 17,
+    RTXPT_BUFFER_REBLUR_ACCUMULATED_FRAMES_RG8      = 18   /* NRD's DATA1 after TemporalAccumulation: accumulated frames / 63 (diffuse, specular) */
+};
+RTXPT_API int rtxpt_b200_reblur_denoise(rtxpt_ctx* ctx, uint32_t stablePlaneIndex, const RtxptReblurFrame* frame, void* cudaStream);
+/* Sample::Denoise for the ReBLUR method (Rtxpt/Sample.cpp:2560-2618): for plane = active-1 .. 0 { prepare_inputs (first: init with stable radiance); reblur_denoise; final_merge } */
+RTXPT_API int rtxpt_b200_denoise_realtime(rtxpt_ctx* ctx, const RtxptDenoiserConstants* constants, const RtxptReblurFrame* frame, void* cudaStream);
 
 /* GenericTS addressing of the plane buffer (host helpers; Utils.hlsli:320-362) */
 RTXPT_API uint32_t rtxpt_b200_generic_ts_line_stride(uint32_t width, uint32_t height);

@@ -345,6 +345,16 @@ ORC_API int oracle_reblur_spatial(uint32_t W, uint32_t H, const float* worldToVi
 struct ReblurInstance { orc::reblur::History history; orc::reblur::FrameOutputs last; };
 ORC_API void* oracle_reblur_create() { return new ReblurInstance(); }
 ORC_API void oracle_reblur_destroy(void* p) { delete (ReblurInstance*)p; }
+// debugging aid: keep / fetch the images after pass `stage` of the last frame (0 HitDistReconstruction, 1 PrePass, 2 TemporalAccumulation, 3 HistoryFix, 4 Blur, 5 PostBlur)
+ORC_API void oracle_reblur_keep_stages(void* p, int on) { ((ReblurInstance*)p)->last.keepStages = on != 0; }
+ORC_API int oracle_reblur_stage(void* p, uint32_t stage, uint16_t* outDiff, uint16_t* outSpec)
+{
+    ReblurInstance* inst = (ReblurInstance*)p;
+    if (stage >= inst->last.stageDiff.size()) return -1;
+    const orc::reblur::Image4& d = inst->last.stageDiff[stage]; const orc::reblur::Image4& s = inst->last.stageSpec[stage];
+    for (size_t i = 0; i < d.v.size(); i++) for (int k = 0; k < 4; k++) { outDiff[4 * i + k] = uint16_t(f32tof16((&d.v[i].x)[k])); outSpec[4 * i + k] = uint16_t(f32tof16((&s.v[i].x)[k])); }
+    return 0;
+}
 // matrices: row-major, row vector x matrix; motion: IN_MV RGBA16F (pixels, view-depth delta) or NULL; disocclusionMix: R8 or NULL; outputs RGBA16F; outAccumFrames: 2 floats per pixel (optional)
 ORC_API int oracle_reblur_denoise(void* p, uint32_t W, uint32_t H, const float* worldToView16, const float* viewToClip16, const float* worldToViewPrev16, const float* viewToClipPrev16, uint32_t frameIndex,
                                   int resetHistory, const float* viewZ, const uint32_t* normalRoughness, const uint16_t* motion, const uint8_t* disocclusionMix, const uint16_t* inDiff, const uint16_t* inSpec,

@@ -206,7 +206,8 @@ inline void hitDistReconstruction(const Constants& c, const Inputs& in, const st
         if (viewZ > c.s.denoisingRange) continue;
         float mid; const float4 nr = in.unpackNormalRoughness(x, y, mid);
         const float3 N = xyz(nr); const float roughness = nr.w;
-        const float2 pixelUv = f2((float(x) + 0.5f) / float(c.W), (float(y) + 0.5f) / float(c.H));
+        const float2 rectSizeInv = f2(1.0f / float(c.W), 1.0f / float(c.H));
+        const float2 pixelUv = f2((float(x) + 0.5f) * rectSizeInv.x, (float(y) + 0.5f) * rectSizeInv.y);          // ( pixelPos + 0.5 ) * gRectSizeInv
         const float3 Xv = ReconstructViewPosition(pixelUv, c, viewZ), Nv = worldToViewRotate(c, N);
         const float frustumSize = GetFrustumSize(c, viewZ);
         const float2 gw = GetGeometryWeightParams(c.s.planeDistanceSensitivity, frustumSize, Xv, Nv), rw = GetRelaxedRoughnessWeightParams(roughness * roughness);
@@ -218,7 +219,7 @@ inline void hitDistReconstruction(const Constants& c, const Inputs& in, const st
         {
             if (i == 0 && j == 0) continue;
             const int sx = std::min(std::max(x + i, 0), int(c.W) - 1), sy = std::min(std::max(y + j, 0), int(c.H) - 1);        // Preload clamps to the rect
-            const float2 uv = f2(pixelUv.x + float(i) / float(c.W), pixelUv.y + float(j) / float(c.H));
+            const float2 uv = f2(pixelUv.x + float(i) * rectSizeInv.x, pixelUv.y + float(j) * rectSizeInv.y);
             float w = (uv.x > 0.0f && uv.y > 0.0f && uv.x < 1.0f && uv.y < 1.0f) ? 1.0f : 0.0f;
             w *= GetGaussianWeight(sqrtf(float(i * i + j * j)) * 0.5f);
             const float zs = in.unpackViewZ(sx, sy, c);
@@ -1037,7 +1038,7 @@ inline void temporalStabilization(const Constants& c, const FrameMatrices& m, co
 // One frame of REBLUR_DIFFUSE_SPECULAR as RTXPT configures it (Reblur_DiffuseSpecular.hpp:71-270, Reblur.cpp:98-200): ClassifyTiles -> HitDistReconstruction 5x5 ->
 // PrePass -> TemporalAccumulation -> HistoryFix -> Blur -> PostBlur -> TemporalStabilization, with the resource routing of the dispatch graph.
 // =====================================================================================================================================================
-struct FrameOutputs { Image4 diff, spec; std::vector<uint8_t> data1; std::vector<uint32_t> data2; };
+struct FrameOutputs { Image4 diff, spec; std::vector<uint8_t> data1; std::vector<uint32_t> data2; bool keepStages = false; std::vector<Image4> stageDiff, stageSpec; };      // stage*: the images after each of the six middle passes (debugging aid for tests/test_reblur_port.py)
 inline void denoiseFrame(const Settings& settings, uint W, uint H, const float* worldToView16, const float* viewToClip16, const float* worldToViewPrev16, const float* viewToClipPrev16, uint frameIndex,
                          const TemporalParams& tp, const Inputs& in, const Image4& inDiff, const Image4& inSpec, History& h, FrameOutputs& out)
 {
@@ -1061,19 +1062,22 @@ inline void denoiseFrame(const Settings& settings, uint W, uint H, const float* 
     const size_t n = size_t(W) * H;
     const std::vector<uint8_t> tiles = classifyTiles(c, in);
     Image4 t1d = inDiff, t1s = inSpec, t2d = inDiff, t2s = inSpec;
-    hitDistReconstruction(c, in, tiles, inDiff, inSpec, t2d, t2s);
+    auto keep = [&](const Image4& d, const Image4& s) { if (out.keepStages) { out.stageDiff.push_back(d); out.stageSpec.push_back(s); } };
+    out.stageDiff.clear(); out.stageSpec.clear();
+    hitDistReconstruction(c, in, tiles, inDiff, inSpec, t2d, t2s); keep(t2d, t2s);
     std::vector<float> prepassTracking(n, 0.0f);
-    { SpatialOutputs o{ &t1d, &t1s, &prepassTracking }; spatialPass(c, in, tiles, PRE_BLUR, t2d, t2s, nullptr, o); }
+    { SpatialOutputs o{ &t1d, &t1s, &prepassTracking }; spatialPass(c, in, tiles, PRE_BLUR, t2d, t2s, nullptr, o); keep(t1d, t1s); }
     std::vector<float> diffFastT(n, 0.0f), specFastT(n, 0.0f), trackingPong(n, 0.0f);
     out.data1.assign(n * 2, 0); out.data2.assign(n, 0u);
-    { TemporalOutputs o{ &t2d, &t2s, &diffFastT, &specFastT, &trackingPong, &out.data1, &out.data2 }; temporalAccumulation(c, m, tp, in, tiles, t1d, t1s, prepassTracking, h, o); }
-    historyFix(c, in, tiles, out.data1, t2d, t2s, diffFastT, specFastT, true, 14.0f, h.valid && !tp.resetHistory, t1d, t1s, h.diffFast, h.specFast);
+    { TemporalOutputs o{ &t2d, &t2s, &diffFastT, &specFastT, &trackingPong, &out.data1, &out.data2 }; temporalAccumulation(c, m, tp, in, tiles, t1d, t1s, prepassTracking, h, o); keep(t2d, t2s); }
+    historyFix(c, in, tiles, out.data1, t2d, t2s, diffFastT, specFastT, true, 14.0f, h.valid && !tp.resetHistory, t1d, t1s, h.diffFast, h.specFast); keep(t1d, t1s);
     std::vector<float2> frames(n);
     for (size_t i = 0; i < n; i++) frames[i] = f2(float(out.data1[2 * i]) / 255.0f * 63.0f, float(out.data1[2 * i + 1]) / 255.0f * 63.0f);
-    { SpatialOutputs o{ &t2d, &t2s, nullptr }; spatialPass(c, in, tiles, BLUR, t1d, t1s, &frames, o); }
+    { SpatialOutputs o{ &t2d, &t2s, nullptr }; spatialPass(c, in, tiles, BLUR, t1d, t1s, &frames, o); keep(t2d, t2s); }
     for (size_t i = 0; i < n; i++) h.prevViewZ[i] = in.viewZ[i];                     // Blur copies viewZ (sky included)
     { SpatialOutputs o{ &h.diff, &h.spec, nullptr }; Image4 keepD = h.diff, keepS = h.spec; spatialPass(c, in, tiles, POST_BLUR, t2d, t2s, &frames, o); (void)keepD; (void)keepS; }
     for (size_t i = 0; i < n; i++) h.prevNormalRoughness[i] = in.normalRoughness[i];  // PostBlur copies the packed normal / roughness (written for non-sky pixels; sky texels are rejected by viewZ)
+    keep(h.diff, h.spec);
     out.diff = h.diff; out.spec = h.spec;
     std::vector<float> lumaD = h.diffLumaStabilized, lumaS = h.specLumaStabilized;
     temporalStabilization(c, m, tp, StabilizationParams(), in, tiles, out.data1, out.data2, h.diff, h.spec, trackingPong, h, out.diff, out.spec, lumaD, lumaS, h.prevInternalData);

@@ -4,6 +4,7 @@
 // structure build, MaterialsBaker::Update, UpdateLighting, constant-buffer write, PathTrace, AccumulationPass.
 // There is no CPU rendering fallback anywhere in this library: without a CUDA device every entry point fails with RTXPT_ERR_NO_DEVICE.
 #include "kernels.h"
+#include "reblur_host.h"
 #include "lights_bake.h"
 #include <algorithm>
 #include <chrono>
@@ -83,6 +84,16 @@ struct rtxpt_ctx
     // denoiser interface: NRD's inputs for one plane at a time (allocated by the first prepare_inputs call)
     DeviceArray<float> dnViewZ; DeviceArray<uint2> dnMotion, dnDiff, dnSpec; DeviceArray<uint32_t> dnNormalRoughness; DeviceArray<uint8_t> dnDisocclusionMix, dnHistoryClampRelax;
     uint32_t denoiserWidth = 0, denoiserHeight = 0;
+    // ReBLUR: one permanent pool per stable plane (RTXPT keeps one NRD instance per plane, Sample.cpp:2560-2618), one transient pool and one pair of outputs shared by all
+    struct ReblurHistory
+    {
+        DeviceArray<float> prevViewZ; DeviceArray<uint32_t> prevNormalRoughness; DeviceArray<uint16_t> prevInternalData, diffFast, specFast, tracking[2], diffLuma[2], specLuma[2];
+        DeviceArray<uint2> diffHistory, specHistory; bool valid = false; uint32_t pingPong = 0;
+        void release() { prevViewZ.release(); prevNormalRoughness.release(); prevInternalData.release(); diffFast.release(); specFast.release(); diffHistory.release(); specHistory.release();
+                         for (int i = 0; i < 2; i++) { tracking[i].release(); diffLuma[i].release(); specLuma[i].release(); } valid = false; }
+    } reblur[RTXPT_STABLE_PLANE_COUNT];
+    DeviceArray<uint8_t> rbTiles; DeviceArray<uint2> rbTmp1Diff, rbTmp1Spec, rbTmp2Diff, rbTmp2Spec, rbOutDiff, rbOutSpec; DeviceArray<uint16_t> rbTrackingT, rbDiffFastT, rbSpecFastT; DeviceArray<uchar2> rbData1; DeviceArray<uint32_t> rbData2;
+    uint32_t reblurWidth = 0, reblurHeight = 0;
     // stats
     uint32_t* hCounters = nullptr;          // pinned
     cudaEvent_t evStart = nullptr, evStop = nullptr;
@@ -164,6 +175,11 @@ extern "C" RTXPT_API int rtxpt_b200_destroy(rtxpt_ctx* c)
     c->rayQueue[0].release(); c->rayQueue[1].release(); c->shadeQueue.release();
     c->shadowOriginTMax.release(); c->shadowDirPath.release(); c->shadowRadiance.release(); c->counters.release(); c->pixelOfSlot.release(); c->allPixelTable.release();
     c->outputColor.release(); c->accumulated.release(); c->depth.release(); c->motionVectors.release(); c->throughput.release();
+    c->stablePlanes.release(); c->stablePlanesHeader.release(); c->stableRadiance.release(); c->specularHitT.release();
+    c->dnViewZ.release(); c->dnMotion.release(); c->dnDiff.release(); c->dnSpec.release(); c->dnNormalRoughness.release(); c->dnDisocclusionMix.release(); c->dnHistoryClampRelax.release();
+    for (auto& h : c->reblur) h.release();
+    c->rbTiles.release(); c->rbTmp1Diff.release(); c->rbTmp1Spec.release(); c->rbTmp2Diff.release(); c->rbTmp2Spec.release(); c->rbOutDiff.release(); c->rbOutSpec.release();
+    c->rbTrackingT.release(); c->rbDiffFastT.release(); c->rbSpecFastT.release(); c->rbData1.release(); c->rbData2.release();
     for (cudaEvent_t ev : c->evPool) cudaEventDestroy(ev);
     if (c->evStart) cudaEventDestroy(c->evStart);
     if (c->evStop) cudaEventDestroy(c->evStop);
@@ -661,13 +677,89 @@ extern "C" RTXPT_API int rtxpt_b200_denoiser_prepare_inputs(rtxpt_ctx* c, uint32
 extern "C" RTXPT_API int rtxpt_b200_denoiser_final_merge(rtxpt_ctx* c, uint32_t stablePlaneIndex, const void* dDiff, const void* dSpec, void* cudaStream)
 {
     int rc = checkRealtimeReady(c); if (rc != RTXPT_OK) return rc;
-    if (!dDiff || !dSpec || stablePlaneIndex >= RTXPT_STABLE_PLANE_COUNT) return fail(RTXPT_ERR_INVALID_ARGUMENT, "bad plane index or null image");
+    if (stablePlaneIndex >= RTXPT_STABLE_PLANE_COUNT) return fail(RTXPT_ERR_INVALID_ARGUMENT, "bad plane index");
+    if (!dDiff && !dSpec)
+    {   // NULL, NULL: the images rtxpt_b200_reblur_denoise wrote last
+        if (c->reblurWidth != c->tableWidth || c->reblurHeight != c->tableHeight) return fail(RTXPT_ERR_INVALID_ARGUMENT, "no denoised images: rtxpt_b200_reblur_denoise has not run");
+        dDiff = c->rbOutDiff.ptr; dSpec = c->rbOutSpec.ptr;
+    }
+    if (!dDiff || !dSpec) return fail(RTXPT_ERR_INVALID_ARGUMENT, "one denoised image is null");
     if (c->denoiserWidth != c->tableWidth || c->denoiserHeight != c->tableHeight) return fail(RTXPT_ERR_INVALID_ARGUMENT, "rtxpt_b200_denoiser_prepare_inputs has not run (the sky mask lives in its view-space depth)");
     cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
     LaunchParams p; fillParams(c, p); fillRealtimeParams(c, p);
     p.rt.dnPlane = stablePlaneIndex; p.rt.dnDenoisedDiff = static_cast<const uint2*>(dDiff); p.rt.dnDenoisedSpec = static_cast<const uint2*>(dSpec);
     launchDnFinalMerge(p, c->grid, s);
     CU(cudaGetLastError());
+    return RTXPT_OK;
+}
+
+// ---- ReBLUR (NRD) for one stable plane ------------------------------------------------------------------------------------------------------------------
+// settings and per-frame constants: reblur_host.h
+static int ensureReblurPools(rtxpt_ctx* c, cudaStream_t s)
+{
+    if (c->reblurWidth == c->tableWidth && c->reblurHeight == c->tableHeight) return RTXPT_OK;
+    CU(cudaStreamSynchronize(c->stream)); CU(cudaStreamSynchronize(s));
+    const size_t P = size_t(c->tableWidth) * c->tableHeight, T = size_t((c->tableWidth + 15) / 16) * ((c->tableHeight + 15) / 16);
+    for (auto& h : c->reblur)
+    {
+        CU(h.prevViewZ.alloc(P)); CU(h.prevNormalRoughness.alloc(P)); CU(h.prevInternalData.alloc(P)); CU(h.diffFast.alloc(P)); CU(h.specFast.alloc(P)); CU(h.diffHistory.alloc(P)); CU(h.specHistory.alloc(P));
+        CU(cudaMemsetAsync(h.prevViewZ.ptr, 0, P * 4, s)); CU(cudaMemsetAsync(h.prevNormalRoughness.ptr, 0, P * 4, s)); CU(cudaMemsetAsync(h.prevInternalData.ptr, 0, P * 2, s)); CU(cudaMemsetAsync(h.diffFast.ptr, 0, P * 2, s));
+        CU(cudaMemsetAsync(h.specFast.ptr, 0, P * 2, s)); CU(cudaMemsetAsync(h.diffHistory.ptr, 0, P * 8, s)); CU(cudaMemsetAsync(h.specHistory.ptr, 0, P * 8, s));
+        for (int i = 0; i < 2; i++)
+        {
+            CU(h.tracking[i].alloc(P)); CU(h.diffLuma[i].alloc(P)); CU(h.specLuma[i].alloc(P));
+            CU(cudaMemsetAsync(h.tracking[i].ptr, 0, P * 2, s)); CU(cudaMemsetAsync(h.diffLuma[i].ptr, 0, P * 2, s)); CU(cudaMemsetAsync(h.specLuma[i].ptr, 0, P * 2, s));
+        }
+        h.valid = false; h.pingPong = 0;
+    }
+    CU(c->rbTiles.alloc(T)); CU(c->rbTmp1Diff.alloc(P)); CU(c->rbTmp1Spec.alloc(P)); CU(c->rbTmp2Diff.alloc(P)); CU(c->rbTmp2Spec.alloc(P)); CU(c->rbOutDiff.alloc(P)); CU(c->rbOutSpec.alloc(P));
+    CU(c->rbTrackingT.alloc(P)); CU(c->rbDiffFastT.alloc(P)); CU(c->rbSpecFastT.alloc(P)); CU(c->rbData1.alloc(P)); CU(c->rbData2.alloc(P));
+    CU(cudaMemsetAsync(c->rbTmp1Diff.ptr, 0, P * 8, s)); CU(cudaMemsetAsync(c->rbTmp1Spec.ptr, 0, P * 8, s)); CU(cudaMemsetAsync(c->rbTmp2Diff.ptr, 0, P * 8, s)); CU(cudaMemsetAsync(c->rbTmp2Spec.ptr, 0, P * 8, s));
+    CU(cudaMemsetAsync(c->rbOutDiff.ptr, 0, P * 8, s)); CU(cudaMemsetAsync(c->rbOutSpec.ptr, 0, P * 8, s)); CU(cudaMemsetAsync(c->rbTrackingT.ptr, 0, P * 2, s)); CU(cudaMemsetAsync(c->rbDiffFastT.ptr, 0, P * 2, s));
+    CU(cudaMemsetAsync(c->rbSpecFastT.ptr, 0, P * 2, s)); CU(cudaMemsetAsync(c->rbData1.ptr, 0, P * 2, s)); CU(cudaMemsetAsync(c->rbData2.ptr, 0, P * 4, s));
+    c->reblurWidth = c->tableWidth; c->reblurHeight = c->tableHeight;
+    return RTXPT_OK;
+}
+
+extern "C" RTXPT_API int rtxpt_b200_reblur_denoise(rtxpt_ctx* c, uint32_t stablePlaneIndex, const RtxptReblurFrame* f, void* cudaStream)
+{
+    if (!c || !f) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (stablePlaneIndex >= RTXPT_STABLE_PLANE_COUNT) return fail(RTXPT_ERR_INVALID_ARGUMENT, "bad plane index");
+    if (c->denoiserWidth != c->tableWidth || c->denoiserHeight != c->tableHeight || c->denoiserWidth == 0) return fail(RTXPT_ERR_INVALID_ARGUMENT, "rtxpt_b200_denoiser_prepare_inputs has not run: ReBLUR reads RTXPT_BUFFER_DENOISER_*");
+    cudaSetDevice(c->device);
+    cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
+    int rc = ensureReblurPools(c, s); if (rc != RTXPT_OK) return rc;
+    rtxpt_ctx::ReblurHistory& h = c->reblur[stablePlaneIndex];
+    const uint32_t W = c->tableWidth, H = c->tableHeight;
+    rb::Params p{}; rb::fillFrameParams(p, W, H, f, h.valid);
+    // resources
+    p.viewZ = c->dnViewZ.ptr; p.normalRoughness = c->dnNormalRoughness.ptr; p.motion = f->ignoreMotionVectors ? nullptr : c->dnMotion.ptr; p.disocclusionMix = c->dnDisocclusionMix.ptr; p.inDiff = c->dnDiff.ptr; p.inSpec = c->dnSpec.ptr;
+    p.tiles = c->rbTiles.ptr; p.tmp1Diff = c->rbTmp1Diff.ptr; p.tmp1Spec = c->rbTmp1Spec.ptr; p.tmp2Diff = c->rbTmp2Diff.ptr; p.tmp2Spec = c->rbTmp2Spec.ptr;
+    p.trackingTransient = c->rbTrackingT.ptr; p.diffFastTransient = c->rbDiffFastT.ptr; p.specFastTransient = c->rbSpecFastT.ptr; p.data1 = c->rbData1.ptr; p.data2 = c->rbData2.ptr;
+    p.prevViewZ = h.prevViewZ.ptr; p.prevNormalRoughness = h.prevNormalRoughness.ptr; p.prevInternalData = h.prevInternalData.ptr; p.diffHistory = h.diffHistory.ptr; p.specHistory = h.specHistory.ptr;
+    p.diffFast = h.diffFast.ptr; p.specFast = h.specFast.ptr;
+    const uint32_t prev = h.pingPong, curr = prev ^ 1u;
+    p.trackingPrev = h.tracking[prev].ptr; p.trackingCurr = h.tracking[curr].ptr; p.diffLumaPrev = h.diffLuma[prev].ptr; p.diffLumaCurr = h.diffLuma[curr].ptr; p.specLumaPrev = h.specLuma[prev].ptr; p.specLumaCurr = h.specLuma[curr].ptr;
+    p.outDiff = c->rbOutDiff.ptr; p.outSpec = c->rbOutSpec.ptr;
+    launchReblurFrame(p, s);
+    CU(cudaGetLastError());
+    h.pingPong = curr; h.valid = true;
+    return RTXPT_OK;
+}
+
+// Sample::Denoise (Rtxpt/Sample.cpp:2560-2618): for plane = active - 1 .. 0 { prepare inputs (the first one also seeds the output with the stable radiance); NRD; final merge }
+extern "C" RTXPT_API int rtxpt_b200_denoise_realtime(rtxpt_ctx* c, const RtxptDenoiserConstants* k, const RtxptReblurFrame* f, void* cudaStream)
+{
+    int rc = checkRealtimeReady(c); if (rc != RTXPT_OK) return rc;
+    if (!k || !f) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null constants");
+    bool first = true;
+    for (int plane = int(c->realtime.activeStablePlaneCount) - 1; plane >= 0; plane--)
+    {
+        rc = rtxpt_b200_denoiser_prepare_inputs(c, uint32_t(plane), first ? 1 : 0, k, cudaStream); if (rc != RTXPT_OK) return rc;
+        rc = rtxpt_b200_reblur_denoise(c, uint32_t(plane), f, cudaStream); if (rc != RTXPT_OK) return rc;
+        rc = rtxpt_b200_denoiser_final_merge(c, uint32_t(plane), nullptr, nullptr, cudaStream); if (rc != RTXPT_OK) return rc;
+        first = false;
+    }
     return RTXPT_OK;
 }
 
@@ -716,6 +808,12 @@ static int targetInfo(rtxpt_ctx* c, int buffer, void** ptr, size_t* bytes)
         case RTXPT_BUFFER_DENOISER_DISOCCLUSION_MIX_R8: *ptr = c->dnDisocclusionMix.ptr; *bytes = P; break;
         default: *ptr = c->dnHistoryClampRelax.ptr; *bytes = P; break;
         }
+        return RTXPT_OK;
+    case RTXPT_BUFFER_DENOISED_DIFF_RADIANCE_HITDIST_F16: case RTXPT_BUFFER_DENOISED_SPEC_RADIANCE_HITDIST_F16: case RTXPT_BUFFER_REBLUR_ACCUMULATED_FRAMES_RG8:
+        if (c->reblurWidth != c->tableWidth || c->reblurHeight != c->tableHeight) return fail(RTXPT_ERR_INVALID_ARGUMENT, "ReBLUR buffers do not exist before rtxpt_b200_reblur_denoise");
+        if (buffer == RTXPT_BUFFER_DENOISED_DIFF_RADIANCE_HITDIST_F16) { *ptr = c->rbOutDiff.ptr; *bytes = P * 8; }
+        else if (buffer == RTXPT_BUFFER_DENOISED_SPEC_RADIANCE_HITDIST_F16) { *ptr = c->rbOutSpec.ptr; *bytes = P * 8; }
+        else { *ptr = c->rbData1.ptr; *bytes = P * 2; }
         return RTXPT_OK;
     default: return fail(RTXPT_ERR_INVALID_ARGUMENT, "unknown buffer %d", buffer);
     }

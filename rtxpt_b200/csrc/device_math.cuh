@@ -56,8 +56,8 @@ PT_HD float average(float3 c) { return (c.x + c.y + c.z) / 3.0f; }              
 PT_HD float maxComp(float3 c) { return fmaxf(fmaxf(c.x, c.y), c.z); }                   // Utils/ColorHelpers.hlsli:19-27
 
 // ---- fp16 storage (RNE; equals the oracle's f32tof16) ---------------------------------------------------------------------
-PT_DEVICE uint f32tof16(float v) { return (uint)__half_as_ushort(__float2half_rn(v)); }
-PT_DEVICE float f16tof32(uint h) { return __half2float(__ushort_as_half((unsigned short)(h & 0xFFFF))); }
+PT_HD uint f32tof16(float v) { return (uint)__half_as_ushort(__float2half_rn(v)); }
+PT_HD float f16tof32(uint h) { return __half2float(__ushort_as_half((unsigned short)(h & 0xFFFF))); }
 PT_DEVICE float lp(float v) { return __half2float(__float2half_rn(v)); }                 // one "lpfloat" store
 PT_DEVICE float3 lp3(float3 v) { return mk3(lp(v.x), lp(v.y), lp(v.z)); }
 PT_DEVICE uint packHalf2NoClamp(float a, float b) { return f32tof16(a) | (f32tof16(b) << 16); }          // Fp32ToFp16NoClamp, Packing.hlsli:212

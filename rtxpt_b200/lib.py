@@ -49,6 +49,8 @@ _SIGNATURES = {
     "rtxpt_b200_path_trace_realtime": [C.c_void_p, C.c_int, C.c_void_p],
     "rtxpt_b200_denoiser_prepare_inputs": [C.c_void_p, C.c_uint32, C.c_int, C.POINTER(S.DenoiserConstants), C.c_void_p],
     "rtxpt_b200_denoiser_final_merge": [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p],
+    "rtxpt_b200_reblur_denoise": [C.c_void_p, C.c_uint32, C.POINTER(S.ReblurFrame), C.c_void_p],
+    "rtxpt_b200_denoise_realtime": [C.c_void_p, C.POINTER(S.DenoiserConstants), C.POINTER(S.ReblurFrame), C.c_void_p],
     "rtxpt_b200_get_lights_ex": [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)],
     "rtxpt_b200_debug_bsdf": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
     "rtxpt_b200_debug_rng": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
@@ -238,11 +240,29 @@ class Context:
     def denoiser_prepare_inputs(self, plane, init_with_stable_radiance, k, stream=None):
         _check(self.L.rtxpt_b200_denoiser_prepare_inputs(self.h, plane, 1 if init_with_stable_radiance else 0, C.byref(k), stream), self.L)
 
-    def denoiser_final_merge(self, plane, d_diff=None, d_spec=None, stream=None):
-        """d_diff / d_spec: device pointers of RGBA16F images in NRD's output encoding; default = the prepared inputs themselves (identity denoiser)."""
-        if d_diff is None: d_diff = self.device_ptr(S.BUFFER_DENOISER_DIFF_RADIANCE_HITDIST_F16)[0]
-        if d_spec is None: d_spec = self.device_ptr(S.BUFFER_DENOISER_SPEC_RADIANCE_HITDIST_F16)[0]
+    def denoiser_final_merge(self, plane, d_diff=None, d_spec=None, stream=None, identity=True):
+        """d_diff / d_spec: device pointers of RGBA16F images in NRD's output encoding.  Default (identity=True): the prepared inputs themselves (identity denoiser);
+        identity=False passes NULL, NULL = the images reblur_denoise wrote."""
+        if identity:
+            if d_diff is None: d_diff = self.device_ptr(S.BUFFER_DENOISER_DIFF_RADIANCE_HITDIST_F16)[0]
+            if d_spec is None: d_spec = self.device_ptr(S.BUFFER_DENOISER_SPEC_RADIANCE_HITDIST_F16)[0]
         _check(self.L.rtxpt_b200_denoiser_final_merge(self.h, plane, d_diff, d_spec, stream), self.L)
+
+    # ---- ReBLUR ----
+    def reblur_denoise(self, plane, frame, stream=None):
+        _check(self.L.rtxpt_b200_reblur_denoise(self.h, plane, C.byref(frame), stream), self.L)
+
+    def denoise_realtime(self, k, frame, stream=None):
+        """Sample::Denoise: for plane = active-1..0 { prepare inputs; ReBLUR; final merge } into the output colour."""
+        _check(self.L.rtxpt_b200_denoise_realtime(self.h, C.byref(k), C.byref(frame), stream), self.L)
+
+    def readback_reblur(self):
+        h, w = self.consts.imageHeight, self.consts.imageWidth
+        out = dict(diff=np.empty((h, w, 4), np.float16), spec=np.empty((h, w, 4), np.float16), frames=np.empty((h, w, 2), np.uint8))
+        for key, buf in (("diff", S.BUFFER_DENOISED_DIFF_RADIANCE_HITDIST_F16), ("spec", S.BUFFER_DENOISED_SPEC_RADIANCE_HITDIST_F16), ("frames", S.BUFFER_REBLUR_ACCUMULATED_FRAMES_RG8)):
+            _check(self.L.rtxpt_b200_readback(self.h, buf, out[key].ctypes.data, out[key].nbytes), self.L)
+        out["frames"] = out["frames"].astype(np.float32) / 255.0 * 63.0
+        return out
 
     def readback_denoiser_inputs(self):
         h, w = self.consts.imageHeight, self.consts.imageWidth

@@ -375,6 +375,15 @@ def make_denoiser_constants(cam, hit_distance_parameters=(3.0, 0.1, 20.0, -25.0)
     return k
 
 
+def make_reblur_frame(cam, prev_cam=None, frame_index=0, reset=False, ignore_motion_vectors=False, frame_time_ms=0.0):
+    """RtxptReblurFrame from the current and the previous camera (un-jittered matrices, as NrdIntegration.cpp:375-408 passes them)."""
+    f = S.ReblurFrame(); prev_cam = cam if prev_cam is None else prev_cam
+    f.matWorldToView[:] = world_to_view(cam).reshape(16).tolist(); f.matViewToClip[:] = view_to_clip(cam).reshape(16).tolist()
+    f.prevMatWorldToView[:] = world_to_view(prev_cam).reshape(16).tolist(); f.prevMatViewToClip[:] = view_to_clip(prev_cam).reshape(16).tolist()
+    f.frameIndex = frame_index; f.resetHistory = 1 if reset else 0; f.ignoreMotionVectors = 1 if ignore_motion_vectors else 0; f.frameTimeMs = frame_time_ms
+    return f
+
+
 def generic_ts_address(x, y, plane, width, height):
     """GenericTSPixelToAddress (Utils.hlsli:337-352): 8x8 tiles, Morton order inside a tile; vectorised over numpy arrays."""
     x = np.asarray(x, np.uint32); y = np.asarray(y, np.uint32)

@@ -34,6 +34,7 @@ BUFFER_STABLE_PLANES, BUFFER_STABLE_PLANES_HEADER, BUFFER_STABLE_RADIANCE_F16, B
 STABLE_PLANE_COUNT, STABLE_PLANE_INVALID_BRANCH = 3, 0xFFFFFFFF
 (BUFFER_DENOISER_VIEWSPACE_Z_F32, BUFFER_DENOISER_MOTION_VECTORS_F16, BUFFER_DENOISER_NORMAL_ROUGHNESS_R10G10B10A2, BUFFER_DENOISER_DIFF_RADIANCE_HITDIST_F16,
  BUFFER_DENOISER_SPEC_RADIANCE_HITDIST_F16, BUFFER_DENOISER_DISOCCLUSION_MIX_R8, BUFFER_COMBINED_HISTORY_CLAMP_RELAX_R8) = 9, 10, 11, 12, 13, 14, 15
+BUFFER_DENOISED_DIFF_RADIANCE_HITDIST_F16, BUFFER_DENOISED_SPEC_RADIANCE_HITDIST_F16, BUFFER_REBLUR_ACCUMULATED_FRAMES_RG8 = 16, 17, 18
 
 
 class GeometryData(C.Structure):
@@ -131,6 +132,12 @@ STABLE_PLANE_DTYPE = [("RayOrigin", "f4", 3), ("LastRayTCurrent", "f4"), ("RayDi
 class DenoiserConstants(C.Structure):
     _fields_ = [("matWorldToView", f32 * 16), ("hitDistanceParameters", f32 * 4), ("preExposedGrayLuminance", f32), ("denoiserRadianceClampK", f32),
                 ("stablePlanesSuppressPrimaryIndirectSpecularK", f32), ("_pad", f32)]
+
+
+class ReblurFrame(C.Structure):
+    _fields_ = [("matWorldToView", f32 * 16), ("matViewToClip", f32 * 16), ("prevMatWorldToView", f32 * 16), ("prevMatViewToClip", f32 * 16),
+                ("frameIndex", u32), ("resetHistory", u32), ("ignoreMotionVectors", u32), ("frameTimeMs", f32),
+                ("disocclusionThreshold", f32), ("disocclusionThresholdAlternate", f32), ("_pad", f32 * 2)]
 
 
 class RealtimeConstants(C.Structure):

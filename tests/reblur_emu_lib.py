@@ -1,0 +1,46 @@
+"""ctypes binding of tests/emu/_build/libreblur_emu.so - TEST INFRASTRUCTURE ONLY: the product's ReBLUR pass bodies (rtxpt_b200/csrc/reblur_passes.cuh) compiled for the host."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+from rtxpt_b200 import structs as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(ROOT, "tests", "emu", "_build", "libreblur_emu.so")
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "emu"), "-s", "_build/libreblur_emu.so"], check=True)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB_PATH)
+        L.rb_emu_create.restype = C.c_void_p; L.rb_emu_destroy.argtypes = [C.c_void_p]
+        L.rb_emu_denoise.restype = C.c_int
+        L.rb_emu_denoise.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(S.ReblurFrame)] + [C.c_void_p] * 9
+        _lib = L
+    return _lib
+
+
+class ReblurPort:
+    """One instance (history persists between calls) of the host-compiled product passes; same call shape as oracle_lib.Reblur.denoise."""
+    def __init__(self): self.h = lib().rb_emu_create()
+
+    def close(self):
+        if self.h: lib().rb_emu_destroy(self.h); self.h = None
+
+    def __del__(self): self.close()
+
+    def denoise(self, frame, view_z, normal_roughness, diff, spec, motion=None, disocclusion_mix=None):
+        H, W = view_z.shape
+        c = lambda a, t: None if a is None else np.ascontiguousarray(a, t)
+        vz, nr, d, s, mv, mix = c(view_z, np.float32), c(normal_roughness, np.uint32), c(diff, np.float16), c(spec, np.float16), c(motion, np.float16), c(disocclusion_mix, np.uint8)
+        od = np.zeros((H, W, 4), np.float16); os_ = np.zeros((H, W, 4), np.float16); frames = np.zeros((H, W, 2), np.float32)
+        ptr = lambda a: None if a is None else a.ctypes.data
+        rc = lib().rb_emu_denoise(self.h, W, H, C.byref(frame), ptr(vz), ptr(nr), ptr(mv), ptr(mix), ptr(d), ptr(s), ptr(od), ptr(os_), ptr(frames))
+        assert rc == 0
+        return od, os_, frames
