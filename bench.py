@@ -294,7 +294,9 @@ def main():
         # realtime mode (row a17) timed in a child process on the same workload: a fault there cannot take the headline line with it
         try:
             r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts", "bench_realtime.py")], capture_output=True, text=True, timeout=300)
-            realtime = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 and r.stdout.strip() else {"error": "exit %d: %s" % (r.returncode, r.stderr.strip()[-300:])}
+            # the child prints its line before tearing the context down, so a fault in its last (never-before-run) stage still leaves the measurements
+            realtime = json.loads(r.stdout.strip().splitlines()[-1]) if r.stdout.strip() else {"error": "exit %d: %s" % (r.returncode, r.stderr.strip()[-300:])}
+            if r.returncode != 0: realtime["child_exit"] = r.returncode
         except Exception as e:        # timeout, malformed output
             realtime = {"error": repr(e)[:300]}
 

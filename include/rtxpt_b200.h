@@ -401,6 +401,8 @@ enum {
 RTXPT_API int rtxpt_b200_reblur_denoise(rtxpt_ctx* ctx, uint32_t stablePlaneIndex, const RtxptReblurFrame* frame, void* cudaStream);
 /* Sample::Denoise for the ReBLUR method (Rtxpt/Sample.cpp:2560-2618): for plane = active-1 .. 0 { prepare_inputs (first: init with stable radiance); reblur_denoise; final_merge } */
 RTXPT_API int rtxpt_b200_denoise_realtime(rtxpt_ctx* ctx, const RtxptDenoiserConstants* constants, const RtxptReblurFrame* frame, void* cudaStream);
+/* device time (CUDA events on the call's stream) of the last rtxpt_b200_denoise_realtime; waits for it to finish */
+RTXPT_API int rtxpt_b200_last_denoise_ms(rtxpt_ctx* ctx, float* outMs);
 
 /* GenericTS addressing of the plane buffer (host helpers; Utils.hlsli:320-362) */
 RTXPT_API uint32_t rtxpt_b200_generic_ts_line_stride(uint32_t width, uint32_t height);

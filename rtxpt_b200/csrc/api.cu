@@ -94,6 +94,7 @@ struct rtxpt_ctx
     } reblur[RTXPT_STABLE_PLANE_COUNT];
     DeviceArray<uint8_t> rbTiles; DeviceArray<uint2> rbTmp1Diff, rbTmp1Spec, rbTmp2Diff, rbTmp2Spec, rbOutDiff, rbOutSpec; DeviceArray<uint16_t> rbTrackingT, rbDiffFastT, rbSpecFastT; DeviceArray<uchar2> rbData1; DeviceArray<uint32_t> rbData2;
     uint32_t reblurWidth = 0, reblurHeight = 0;
+    cudaEvent_t evDnStart = nullptr, evDnStop = nullptr; bool denoiseTimed = false;       // around the last rtxpt_b200_denoise_realtime
     // stats
     uint32_t* hCounters = nullptr;          // pinned
     cudaEvent_t evStart = nullptr, evStop = nullptr;
@@ -184,6 +185,8 @@ extern "C" RTXPT_API int rtxpt_b200_destroy(rtxpt_ctx* c)
     if (c->evStart) cudaEventDestroy(c->evStart);
     if (c->evStop) cudaEventDestroy(c->evStop);
     if (c->hCounters) cudaFreeHost(c->hCounters);
+    if (c->evDnStart) cudaEventDestroy(c->evDnStart);
+    if (c->evDnStop) cudaEventDestroy(c->evDnStop);
     if (c->evShadeDone) cudaEventDestroy(c->evShadeDone);
     if (c->evShadowDone) cudaEventDestroy(c->evShadowDone);
     if (c->stream2) cudaStreamDestroy(c->stream2);
@@ -752,6 +755,9 @@ extern "C" RTXPT_API int rtxpt_b200_denoise_realtime(rtxpt_ctx* c, const RtxptDe
 {
     int rc = checkRealtimeReady(c); if (rc != RTXPT_OK) return rc;
     if (!k || !f) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null constants");
+    cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
+    if (!c->evDnStart) { CU(cudaEventCreate(&c->evDnStart)); CU(cudaEventCreate(&c->evDnStop)); }
+    CU(cudaEventRecord(c->evDnStart, s));
     bool first = true;
     for (int plane = int(c->realtime.activeStablePlaneCount) - 1; plane >= 0; plane--)
     {
@@ -760,6 +766,17 @@ extern "C" RTXPT_API int rtxpt_b200_denoise_realtime(rtxpt_ctx* c, const RtxptDe
         rc = rtxpt_b200_denoiser_final_merge(c, uint32_t(plane), nullptr, nullptr, cudaStream); if (rc != RTXPT_OK) return rc;
         first = false;
     }
+    CU(cudaEventRecord(c->evDnStop, s)); c->denoiseTimed = true;
+    return RTXPT_OK;
+}
+// device time of the last rtxpt_b200_denoise_realtime call (CUDA events on its stream); waits for it to finish
+extern "C" RTXPT_API int rtxpt_b200_last_denoise_ms(rtxpt_ctx* c, float* outMs)
+{
+    if (!c || !outMs) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (!c->denoiseTimed) return fail(RTXPT_ERR_INVALID_ARGUMENT, "rtxpt_b200_denoise_realtime has not run");
+    cudaSetDevice(c->device);
+    CU(cudaEventSynchronize(c->evDnStop));
+    CU(cudaEventElapsedTime(outMs, c->evDnStart, c->evDnStop));
     return RTXPT_OK;
 }
 

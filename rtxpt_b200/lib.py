@@ -51,6 +51,7 @@ _SIGNATURES = {
     "rtxpt_b200_denoiser_final_merge": [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p],
     "rtxpt_b200_reblur_denoise": [C.c_void_p, C.c_uint32, C.POINTER(S.ReblurFrame), C.c_void_p],
     "rtxpt_b200_denoise_realtime": [C.c_void_p, C.POINTER(S.DenoiserConstants), C.POINTER(S.ReblurFrame), C.c_void_p],
+    "rtxpt_b200_last_denoise_ms": [C.c_void_p, C.POINTER(C.c_float)],
     "rtxpt_b200_get_lights_ex": [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)],
     "rtxpt_b200_debug_bsdf": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
     "rtxpt_b200_debug_rng": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
@@ -255,6 +256,11 @@ class Context:
     def denoise_realtime(self, k, frame, stream=None):
         """Sample::Denoise: for plane = active-1..0 { prepare inputs; ReBLUR; final merge } into the output colour."""
         _check(self.L.rtxpt_b200_denoise_realtime(self.h, C.byref(k), C.byref(frame), stream), self.L)
+
+    def last_denoise_ms(self):
+        ms = C.c_float()
+        _check(self.L.rtxpt_b200_last_denoise_ms(self.h, C.byref(ms)), self.L)
+        return float(ms.value)
 
     def readback_reblur(self):
         h, w = self.consts.imageHeight, self.consts.imageWidth
