@@ -376,6 +376,9 @@ enum {
     RTXPT_BUFFER_DENOISER_DISOCCLUSION_MIX_R8    = 14,
     RTXPT_BUFFER_COMBINED_HISTORY_CLAMP_RELAX_R8 = 15
 };
+/* DenoisingGuidesBaker::DenoiseSpecHitT (ProcessingPasses/DenoisingGuidesBaker.hlsl:53-115; Sample.cpp:2541-2543): 5x5 depth-aware spread of RTXPT_BUFFER_SPECULAR_HITT_F32, in place,
+ * after rtxpt_b200_path_trace_realtime and before the denoiser reads the guide (rtxpt_b200_denoise_realtime runs it itself). */
+RTXPT_API int rtxpt_b200_denoise_spec_hit_t(rtxpt_ctx* ctx, void* cudaStream);
 RTXPT_API int rtxpt_b200_denoiser_prepare_inputs(rtxpt_ctx* ctx, uint32_t stablePlaneIndex, int initWithStableRadiance, const RtxptDenoiserConstants* constants, void* cudaStream);
 RTXPT_API int rtxpt_b200_denoiser_final_merge(rtxpt_ctx* ctx, uint32_t stablePlaneIndex, const void* dDenoisedDiffRGBA16F, const void* dDenoisedSpecRGBA16F, void* cudaStream);    /* NULL, NULL = the images rtxpt_b200_reblur_denoise wrote */
 

@@ -314,6 +314,9 @@ ORC_API int oracle_denoiser_final_merge(void* p, const RtxptRealtimeConstants* r
     return 0;
 }
 
+// DenoisingGuidesBaker::DenoiseSpecHitT: in place on the R32F specular hit distance guide, with the R32F depth guide
+ORC_API int oracle_denoise_spec_hit_t(uint32_t W, uint32_t H, const float* depth, float* specHitT) { if (!depth || !specHitT) return -1; denoiseSpecHitT(specHitT, depth, int(W), int(H)); return 0; }
+
 // ReBLUR, spatial half (oracle/reblur.h): ClassifyTiles -> [HitDistReconstruction 5x5] -> PrePass -> Blur -> PostBlur on NRD's inputs as rtxpt_b200_denoiser_prepare_inputs /
 // oracle_denoiser_prepare_inputs write them.  accumulatedFrames (2 floats per pixel: diffuse, specular; may be NULL = 0) stands in for the history lengths the temporal passes
 // would hand to Blur / PostBlur.  stages: bit 0 hit-distance reconstruction, bit 1 pre-pass, bit 2 blur, bit 3 post-blur.  Images are RGBA16F; matrices row-major, row vector x matrix.

@@ -8,6 +8,7 @@
 // Branch-ID helpers and GenericTS addressing are pinned against the reference's own C++ halves of the same headers (oracle/_ref/ref_kat_host,
 // tests/golden/host_golden.json); everything else here is "parity unpinned" like the rest of the shading path.
 #pragma once
+#include <vector>
 #include "pt_math.h"
 #include "pt_lights.h"
 #include "../include/rtxpt_b200.h"
@@ -323,6 +324,37 @@ inline void denoiserFinalMergePixel(const RealtimeTargets& T, const DenoiserTarg
     uint16_t* o = D.outputColor + pix * 4;
     const float3 sum = max3v(diff + spec, f3(0));
     o[0] = uint16_t(f32tof16(f16tof32(o[0]) + sum.x)); o[1] = uint16_t(f32tof16(f16tof32(o[1]) + sum.y)); o[2] = uint16_t(f32tof16(f16tof32(o[2]) + sum.z));
+}
+
+
+// DenoisingGuidesBaker::DenoiseSpecHitT (Rtxpt/ProcessingPasses/DenoisingGuidesBaker.hlsl:53-97, .cpp:62-84; run by Sample::PathTrace after the FILL pass, Sample.cpp:2541-2543):
+// the specular hit distance guide is spread over a 5x5 neighbourhood of similar depth - pixels without a value borrow the neighbours' mean, pixels with one are capped at
+// 1.5 x + 0.5 of their own.  One ping (guide -> scratch) and one pong (scratch -> guide).
+inline float SpecHitTNeighbourhood(const float* src, const float* depth, int W, int H, int px, int py)
+{
+    const float centerD = depth[size_t(py) * W + px];
+    float prevHitT = std::max(0.0f, src[size_t(py) * W + px]);
+    if (prevHitT < 5e-2f) prevHitT = 0;
+    float vAvg = prevHitT, sumW = prevHitT > 0 ? 1.0f : 0.0f;
+    for (int x = -2; x <= 2; x++) for (int y = -2; y <= 2; y++)
+    {
+        if (x == 0 && y == 0) continue;
+        const int nx = px + x, ny = py + y;
+        if (nx < 0 || ny < 0 || nx >= W || ny >= H) continue;
+        const float v = std::min(src[size_t(ny) * W + nx], 65504.0f), d = std::max(0.0f, depth[size_t(ny) * W + nx]);
+        float weight = v > 0 ? 1.0f : 0.0f;
+        weight *= fabsf(d - centerD) <= (d + centerD + 1e-5f) * 0.025f ? 1.0f : 0.0f;
+        if (weight > 0) { vAvg += v * weight; sumW += weight; }
+    }
+    if (sumW == 0) return prevHitT;
+    vAvg /= sumW;
+    return prevHitT <= 0 ? vAvg : std::min(prevHitT * 1.5f + 0.5f, vAvg);
+}
+inline void denoiseSpecHitT(float* specHitT, const float* depth, int W, int H)
+{
+    std::vector<float> scratch(size_t(W) * H);
+    for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) scratch[size_t(y) * W + x] = SpecHitTNeighbourhood(specHitT, depth, W, H, x, y);
+    for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) specHitT[size_t(y) * W + x] = SpecHitTNeighbourhood(scratch.data(), depth, W, H, x, y);
 }
 
 } // namespace orc

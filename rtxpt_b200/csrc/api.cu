@@ -84,6 +84,7 @@ struct rtxpt_ctx
     // denoiser interface: NRD's inputs for one plane at a time (allocated by the first prepare_inputs call)
     DeviceArray<float> dnViewZ; DeviceArray<uint2> dnMotion, dnDiff, dnSpec; DeviceArray<uint32_t> dnNormalRoughness; DeviceArray<uint8_t> dnDisocclusionMix, dnHistoryClampRelax;
     uint32_t denoiserWidth = 0, denoiserHeight = 0;
+    DeviceArray<float> dnScratchFloat;          // ping-pong partner of the specular hit distance guide (DenoiseSpecHitT)
     // ReBLUR: one permanent pool per stable plane (RTXPT keeps one NRD instance per plane, Sample.cpp:2560-2618), one transient pool and one pair of outputs shared by all
     struct ReblurHistory
     {
@@ -177,7 +178,7 @@ extern "C" RTXPT_API int rtxpt_b200_destroy(rtxpt_ctx* c)
     c->shadowOriginTMax.release(); c->shadowDirPath.release(); c->shadowRadiance.release(); c->counters.release(); c->pixelOfSlot.release(); c->allPixelTable.release();
     c->outputColor.release(); c->accumulated.release(); c->depth.release(); c->motionVectors.release(); c->throughput.release();
     c->stablePlanes.release(); c->stablePlanesHeader.release(); c->stableRadiance.release(); c->specularHitT.release();
-    c->dnViewZ.release(); c->dnMotion.release(); c->dnDiff.release(); c->dnSpec.release(); c->dnNormalRoughness.release(); c->dnDisocclusionMix.release(); c->dnHistoryClampRelax.release();
+    c->dnScratchFloat.release(); c->dnViewZ.release(); c->dnMotion.release(); c->dnDiff.release(); c->dnSpec.release(); c->dnNormalRoughness.release(); c->dnDisocclusionMix.release(); c->dnHistoryClampRelax.release();
     for (auto& h : c->reblur) h.release();
     c->rbTiles.release(); c->rbTmp1Diff.release(); c->rbTmp1Spec.release(); c->rbTmp2Diff.release(); c->rbTmp2Spec.release(); c->rbOutDiff.release(); c->rbOutSpec.release();
     c->rbTrackingT.release(); c->rbDiffFastT.release(); c->rbSpecFastT.release(); c->rbData1.release(); c->rbData2.release();
@@ -656,6 +657,19 @@ extern "C" RTXPT_API int rtxpt_b200_path_trace_realtime(rtxpt_ctx* c, int mergeN
     return RTXPT_OK;
 }
 
+// DenoisingGuidesBaker::DenoiseSpecHitT (Sample::PathTrace's "Denoising Guides Bake", Sample.cpp:2541-2543): ping guide -> scratch, pong scratch -> guide
+extern "C" RTXPT_API int rtxpt_b200_denoise_spec_hit_t(rtxpt_ctx* c, void* cudaStream)
+{
+    int rc = checkRealtimeReady(c); if (rc != RTXPT_OK) return rc;
+    cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
+    const size_t P = size_t(c->tableWidth) * c->tableHeight;
+    if (c->dnScratchFloat.count != P) { CU(cudaStreamSynchronize(c->stream)); CU(c->dnScratchFloat.alloc(P)); }
+    launchDnSpecHitT(c->specularHitT.ptr, c->depth.ptr, c->dnScratchFloat.ptr, int(c->tableWidth), int(c->tableHeight), s);
+    launchDnSpecHitT(c->dnScratchFloat.ptr, c->depth.ptr, c->specularHitT.ptr, int(c->tableWidth), int(c->tableHeight), s);
+    CU(cudaGetLastError());
+    return RTXPT_OK;
+}
+
 // ---- RTXPT's side of the denoiser interface ------------------------------------------------------------------------------------------------------------
 extern "C" RTXPT_API int rtxpt_b200_denoiser_prepare_inputs(rtxpt_ctx* c, uint32_t stablePlaneIndex, int initWithStableRadiance, const RtxptDenoiserConstants* k, void* cudaStream)
 {
@@ -758,6 +772,7 @@ extern "C" RTXPT_API int rtxpt_b200_denoise_realtime(rtxpt_ctx* c, const RtxptDe
     cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
     if (!c->evDnStart) { CU(cudaEventCreate(&c->evDnStart)); CU(cudaEventCreate(&c->evDnStop)); }
     CU(cudaEventRecord(c->evDnStart, s));
+    rc = rtxpt_b200_denoise_spec_hit_t(c, cudaStream); if (rc != RTXPT_OK) return rc;          // "Denoising Guides Bake" precedes Sample::Denoise in the frame
     bool first = true;
     for (int plane = int(c->realtime.activeStablePlaneCount) - 1; plane >= 0; plane--)
     {

@@ -35,6 +35,7 @@ void launchInitTables(cudaStream_t s);       // lookup tables of the shading uni
 void launchDebugBsdf(const float* dIn, uint32_t count, float* dOut, cudaStream_t s);
 void launchDebugRng(const uint32_t* dIn, uint32_t count, uint32_t* dOut, cudaStream_t s);
 
+void launchDnSpecHitT(const float* src, const float* depth, float* dst, int W, int H, cudaStream_t s);      // DenoisingGuidesBaker::DenoiseSpecHitT, one pass
 namespace rb { struct Params; }
 void launchReblurFrame(const rb::Params& p, cudaStream_t s);       // reblur_kernels.cu: the eight ReBLUR passes of one stable plane
 

@@ -12,6 +12,7 @@
 #endif
 // (the Sobol byte tables of shade_kernels.cu are private to that unit; this one evaluates the direction numbers bit by bit - same values)
 #include "shade.cuh"
+#include "guides_filter.cuh"
 #include "kernels.h"
 
 namespace pt {
@@ -320,6 +321,13 @@ __global__ void __launch_bounds__(256) k_dn_final_merge(const __grid_constant__ 
         p.outputColor[o] = make_uint2(f32tof16(f16tof32(c.x) + sum.x) | (f32tof16(f16tof32(c.x >> 16) + sum.y) << 16), f32tof16(f16tof32(c.y) + sum.z) | (c.y & 0xFFFF0000u));
     }
 }
+// DenoiseSpecHitT: one thread per pixel over the full frame (row-major guides); src / dst alternate between the guide and a scratch image
+__global__ void __launch_bounds__(256) k_dn_spec_hitt(const float* __restrict__ src, const float* __restrict__ depth, float* __restrict__ dst, int W, int H)
+{
+    const int x = int(blockIdx.x * 16 + threadIdx.x), y = int(blockIdx.y * 16 + threadIdx.y);
+    if (x < W && y < H) dst[size_t(y) * W + x] = specHitTNeighbourhood(src, depth, W, H, x, y);
+}
+void launchDnSpecHitT(const float* src, const float* depth, float* dst, int W, int H, cudaStream_t s) { k_dn_spec_hitt<<<dim3((W + 15) / 16, (H + 15) / 16), dim3(16, 16), 0, s>>>(src, depth, dst, W, H); }
 void launchDnPrepareInputs(const LaunchParams& p, const GridConfig& g, cudaStream_t s) { k_dn_prepare_inputs<<<g.smCount * 4, 256, 0, s>>>(p); }
 void launchDnFinalMerge(const LaunchParams& p, const GridConfig& g, cudaStream_t s) { k_dn_final_merge<<<g.smCount * 4, 256, 0, s>>>(p); }
 

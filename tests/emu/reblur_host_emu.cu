@@ -5,6 +5,7 @@
 // (libdevice maths, fast-math flags, launch configuration) - that stays with tests/test_gpu_reblur.py.
 #include "../../rtxpt_b200/csrc/reblur_passes.cuh"
 #include "../../rtxpt_b200/csrc/reblur_host.h"
+#include "../../rtxpt_b200/csrc/guides_filter.cuh"
 #include <vector>
 #include <cstdint>
 
@@ -80,5 +81,14 @@ extern "C" int rb_emu_denoise(void* instance, uint32_t W, uint32_t H, const Rtxp
     forEachPixel(p, [&](int x, int y) { rb::temporalStabilizationPixel(p, x, y); });
     h.pingPong = curr; h.valid = true;
     memcpy(outDiff, oDiff.data(), n * 8); memcpy(outSpec, oSpec.data(), n * 8);
+    return 0;
+}
+
+// DenoiseSpecHitT: the product's pixel function (guides_filter.cuh), ping then pong as rtxpt_b200_denoise_spec_hit_t launches it
+extern "C" int emu_denoise_spec_hit_t(uint32_t W, uint32_t H, const float* depth, float* specHitT)
+{
+    std::vector<float> scratch(size_t(W) * H);
+    for (int y = 0; y < int(H); y++) for (int x = 0; x < int(W); x++) scratch[size_t(y) * W + x] = pt::specHitTNeighbourhood(specHitT, depth, int(W), int(H), x, y);
+    for (int y = 0; y < int(H); y++) for (int x = 0; x < int(W); x++) specHitT[size_t(y) * W + x] = pt::specHitTNeighbourhood(scratch.data(), depth, int(W), int(H), x, y);
     return 0;
 }

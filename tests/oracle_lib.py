@@ -165,6 +165,15 @@ class Oracle:
         assert lib().oracle_denoiser_final_merge(self.h, C.byref(rt), plane, r, d, denoised_diff.ctypes.data, denoised_spec.ctypes.data) == 0
 
 
+def denoise_spec_hit_t(depth, spec_hit_t):
+    """DenoisingGuidesBaker::DenoiseSpecHitT of the oracle; returns the filtered guide."""
+    H, W = depth.shape
+    d = np.ascontiguousarray(depth, np.float32); out = np.array(spec_hit_t, np.float32, copy=True, order="C")
+    L = lib(); L.oracle_denoise_spec_hit_t.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+    assert L.oracle_denoise_spec_hit_t(W, H, d.ctypes.data, out.ctypes.data) == 0
+    return out
+
+
 def reblur_spatial(world_to_view, view_to_clip, frame_index, view_z, normal_roughness, diff, spec, accumulated_frames=None, stages=0b1111):
     """oracle/reblur.h spatial chain on NRD inputs (numpy: view_z f32 HxW, normal_roughness u32 HxW, diff / spec f16 HxWx4).  Returns (diff, spec, hit distance for tracking, tiles)."""
     H, W = view_z.shape

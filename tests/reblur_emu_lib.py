@@ -44,3 +44,12 @@ class ReblurPort:
         rc = lib().rb_emu_denoise(self.h, W, H, C.byref(frame), ptr(vz), ptr(nr), ptr(mv), ptr(mix), ptr(d), ptr(s), ptr(od), ptr(os_), ptr(frames))
         assert rc == 0
         return od, os_, frames
+
+
+def denoise_spec_hit_t(depth, spec_hit_t):
+    """The product's DenoiseSpecHitT pixel function (rtxpt_b200/csrc/guides_filter.cuh) compiled for the host, ping + pong."""
+    H, W = depth.shape
+    d = np.ascontiguousarray(depth, np.float32); out = np.array(spec_hit_t, np.float32, copy=True, order="C")
+    L = lib(); L.emu_denoise_spec_hit_t.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+    assert L.emu_denoise_spec_hit_t(W, H, d.ctypes.data, out.ctypes.data) == 0
+    return out

@@ -128,3 +128,17 @@ def test_denoise_realtime_reduces_error_and_keeps_energy(product):
     assert e_den < 0.5 * e_noisy, (e_den, e_noisy)
     assert abs(den.mean() - ref.mean()) < 0.1 * ref.mean(), (den.mean(), ref.mean())
     c.close()
+
+
+@unverified
+def test_spec_hit_t_guide_filter_matches_oracle(product, oracle):
+    """rtxpt_b200_denoise_spec_hit_t (DenoisingGuidesBaker::DenoiseSpecHitT) on the guide a realtime frame left behind: compare / add / divide only, so bit-identical."""
+    from rtxpt_b200 import scene_builder as sb
+    W, H = 96, 80
+    c, cam, consts = _scene(product, True, W, H)
+    c.set_realtime(sb.make_realtime_constants(W, H, cam, bounce_count=6, sub_samples=1)); c.path_trace_realtime(False); c.synchronize()
+    before = c.readback_realtime()
+    c.denoise_spec_hit_t(); c.synchronize()
+    after = c.readback_realtime()["spec_hit_t"]
+    assert np.array_equal(after, oracle.denoise_spec_hit_t(before["depth"], before["spec_hit_t"]))
+    c.close()

@@ -89,3 +89,31 @@ def test_port_equals_oracle_with_sky_roughness_and_missing_hits(oracle):
         a, b = _both(rb, port, sb, cam, cam, f, dd)
         _assert_identical(a, b, vz < 1e30, ("synthetic", f))
     rb.close(); port.close()
+
+
+def test_spec_hit_t_guide_filter(oracle):
+    """DenoisingGuidesBaker::DenoiseSpecHitT: oracle properties (holes filled from neighbours of similar depth only, values capped at 1.5 x + 0.5, tiny values dropped) and the
+    product's pixel function compiled for the host equal to the oracle bit for bit, on synthetic guides and on the guide of a rendered frame."""
+    from rtxpt_b200 import scene_builder as sb, scenes
+    import reblur_emu_lib as emu
+    rng = np.random.default_rng(3)
+    H, W = 37, 53
+    depth = np.where(np.mgrid[0:H, 0:W][1] < 30, 5.0, 50.0).astype(np.float32) * (1 + 0.002 * rng.standard_normal((H, W)).astype(np.float32))
+    hit = np.where(rng.random((H, W)) < 0.4, 0.0, rng.gamma(2.0, 3.0, (H, W))).astype(np.float32)
+    hit[5, 5] = 1e-3; hit[10, 40] = 1e6; hit[20:24, 10:14] = -1.0
+    out = oracle.denoise_spec_hit_t(depth, hit)
+    assert np.isfinite(out).all() and (out >= 0).all()
+    had = hit >= 5e-2
+    assert (out[had] <= (hit[had] * 1.5 + 0.5) * 1.5 + 0.5 + 1e-3).all()                       # two passes of the cap
+    assert (out[~had] > 0).mean() > 0.95                                                       # holes get a value
+    near = np.zeros((H, W), np.float32); near[:, :30] = 2.0; far = np.zeros((H, W), np.float32); far[:, 30:] = 40.0
+    o2 = oracle.denoise_spec_hit_t(depth, near + far)
+    assert np.allclose(o2[:, :30], 2.0) and np.allclose(o2[:, 30:], 40.0)                      # nothing crosses the depth edge
+    assert np.array_equal(emu.denoise_spec_hit_t(depth, hit), out) and np.array_equal(emu.denoise_spec_hit_t(depth, near + far), o2)
+    # a rendered frame's guide
+    Wr, Hr = 80, 64
+    scene, cam = scenes.cornell_box(Wr, Hr, delta_surfaces=True)
+    o = oracle.Oracle(scene); c = sb.make_constants(Wr, Hr, cam, bounce_count=4, diffuse_bounce_count=3); o.set_constants(c); o.set_view(sb.world_to_clip(cam))
+    r = o.render_realtime(sb.make_realtime_constants(Wr, Hr, cam, bounce_count=4, sub_samples=1)); o.close()
+    a = oracle.denoise_spec_hit_t(r["depth"], r["spec_hit_t"]); b = emu.denoise_spec_hit_t(r["depth"], r["spec_hit_t"])
+    assert np.array_equal(a, b) and (a > 0).sum() >= (r["spec_hit_t"] > 0).sum()
