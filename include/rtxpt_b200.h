@@ -228,7 +228,7 @@ typedef struct RtxptPathTracerConstants {
     float    texLODBias;
     float    fireflyFilterThreshold;        /* 0 disables (Sample.cpp:1518-1522) */
     uint32_t NEEEnabled;
-    uint32_t NEEType;                       /* 0 uniform, 1 power, 2 NEE-AT (global table only in this tier) */
+    uint32_t NEEType;                       /* 0 uniform, 1 power, 2 NEE-AT (see NEEATFeedback) */
     uint32_t NEECandidateSamples;
     uint32_t NEEFullSamples;
     uint32_t enableRussianRoulette;         /* PT_ENABLE_RUSSIAN_ROULETTE macro, Sample.cpp:988-1042 */
@@ -237,7 +237,9 @@ typedef struct RtxptPathTracerConstants {
     RtxptCameraData camera;
     RtxptEnvMapSceneParams envMap;
     float    distantVsLocalImportance;      /* NEEAT_Distant_vs_Local_Importance (SampleUI.h:160), scaled by 0.0002 inside like LightsBaker.cpp:1029 */
-    float    _pad[3];
+    uint32_t NEEATFeedback;                 /* with NEEType 2: 0 = power-based global table only (what LightsBaker gives a first frame); 1 = temporal feedback: per-pixel light reservoirs filled by
+                                             * NEE, usage-weighted global table and per-tile local samplers, advanced once per frame by rtxpt_b200_neeat_update_begin / _end */
+    float    _pad[2];
 } RtxptPathTracerConstants;
 
 /* ------------------------------------------------------------------------------------------------------------------

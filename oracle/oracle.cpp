@@ -24,6 +24,8 @@ struct OracleCtx
     bool haveConsts = false, haveView = false;
     float worldToClip[16] = {};
     double bvhBuildSeconds = 0;
+    NeeatState neeat;              // NEE-AT temporal feedback (pt_neeat.h); used when consts.NEEATFeedback != 0
+    NeeatState* neeatPtr() { return (haveConsts && consts.NEEATFeedback != 0 && consts.NEEType == 2 && neeat.W == consts.imageWidth && neeat.H == consts.imageHeight) ? &neeat : nullptr; }
 };
 
 extern "C" {
@@ -97,6 +99,58 @@ ORC_API int oracle_set_constants(void* p, const RtxptPathTracerConstants* consts
     return 0;
 }
 
+// ---- NEE-AT temporal feedback (pt_neeat.h).  Frame order as in Sample.cpp: set_constants; neeat_update_begin; [BUILD pass -> depth, motion]; neeat_update_end( depth, motion ); render.
+ORC_API int oracle_neeat_reset(void* p)
+{
+    OracleCtx* c = (OracleCtx*)p; if (!c->haveConsts) return -1;
+    c->neeat.init(c->consts.imageWidth, c->consts.imageHeight);
+    return 0;
+}
+ORC_API int oracle_neeat_update_begin(void* p)
+{
+    OracleCtx* c = (OracleCtx*)p; if (!c->neeatPtr() || c->lights.IsEmpty()) return -1;
+    NeeatUpdateBegin(c->neeat, c->lights, c->consts.NEEType);
+    return 0;
+}
+// depth: R32F guide; motion: RGBA16F guide (pixels) or NULL
+ORC_API int oracle_neeat_update_end(void* p, const float* depth, const uint16_t* motion)
+{
+    OracleCtx* c = (OracleCtx*)p; if (!c->neeatPtr() || !depth) return -1;
+    NeeatUpdateEnd(c->neeat, c->lights, depth, motion);
+    return 0;
+}
+// what: 0 feedback weight (f32 WxH), 1 feedback candidate (u32 WxH), 2 scratch weight, 3 scratch candidate, 4 blended weight, 5 blended candidate (ceil(W/2) x ceil(H/2)),
+//       6 local sampling buffer (u32 tilesX*tilesY*128), 7 proxy counters (u32 lightCount), 8 control { tilesX, tilesY, jitterX, jitterY, samplingProxyCount, updateCounter, available, validFeedbackCount }
+ORC_API int oracle_neeat_get(void* p, int what, void* out, size_t bytes)
+{
+    OracleCtx* c = (OracleCtx*)p; const NeeatState& s = c->neeat;
+    const void* src = nullptr; size_t n = 0; uint32_t ctl[8];
+    switch (what)
+    {
+    case 0: src = s.feedback.weight.data(); n = s.feedback.weight.size() * 4; break;
+    case 1: src = s.feedback.candidate.data(); n = s.feedback.candidate.size() * 4; break;
+    case 2: src = s.scratch.weight.data(); n = s.scratch.weight.size() * 4; break;
+    case 3: src = s.scratch.candidate.data(); n = s.scratch.candidate.size() * 4; break;
+    case 4: src = s.blended.weight.data(); n = s.blended.weight.size() * 4; break;
+    case 5: src = s.blended.candidate.data(); n = s.blended.candidate.size() * 4; break;
+    case 6: src = s.localSamplingBuffer.data(); n = s.localSamplingBuffer.size() * 4; break;
+    case 7: src = c->lights.proxyCounters.data(); n = c->lights.proxyCounters.size() * 4; break;
+    case 8: ctl[0] = s.tilesX; ctl[1] = s.tilesY; ctl[2] = s.jitter[0]; ctl[3] = s.jitter[1]; ctl[4] = c->lights.samplingProxyCount; ctl[5] = s.updateCounter; ctl[6] = s.lastFrameTemporalFeedbackAvailable; ctl[7] = s.validFeedbackCount; src = ctl; n = sizeof(ctl); break;
+    default: return -1;
+    }
+    if (bytes < n) return -2;
+    memcpy(out, src, n);
+    return int(n);
+}
+// test hook: overwrite the feedback reservoirs (same layouts as `what` 0 / 1)
+ORC_API int oracle_neeat_set_feedback(void* p, const float* weight, const uint32_t* candidate)
+{
+    OracleCtx* c = (OracleCtx*)p; NeeatState& s = c->neeat; if (s.W == 0) return -1;
+    memcpy(s.feedback.weight.data(), weight, s.feedback.weight.size() * 4); memcpy(s.feedback.candidate.data(), candidate, s.feedback.candidate.size() * 4);
+    s.feedbackBufferFilled = true;
+    return 0;
+}
+
 ORC_API int oracle_trace_rays(void* p, const RtxptRay* rays, uint32_t count, int anyHit, RtxptHit* out)
 {
     OracleCtx* c = (OracleCtx*)p;
@@ -129,7 +183,7 @@ ORC_API int oracle_render_guides(void* p, uint32_t subSample, uint32_t x0, uint3
 #endif
     #pragma omp parallel
     {
-        PathTracerCtx x; x.scene = &c->scene; x.bvh = &c->bvh; x.lights = &c->lights; x.c = &c->consts; x.stats = nullptr;
+        PathTracerCtx x; x.scene = &c->scene; x.bvh = &c->bvh; x.lights = &c->lights; x.c = &c->consts; x.stats = nullptr; x.neeat = c->neeatPtr();
         x.sampleIndex = c->consts.sampleBaseIndex + subSample; x.worldToClip = c->worldToClip;
         #pragma omp for schedule(dynamic, 1)
         for (int y = int(y0); y < int(y1); y++)
@@ -195,7 +249,7 @@ ORC_API int oracle_render(void* p, uint32_t firstSubSample, uint32_t subSampleCo
         #pragma omp parallel
         {
             RenderStats local;
-            PathTracerCtx x; x.scene = &c->scene; x.bvh = &c->bvh; x.lights = &c->lights; x.c = &c->consts; x.stats = &local;
+            PathTracerCtx x; x.scene = &c->scene; x.bvh = &c->bvh; x.lights = &c->lights; x.c = &c->consts; x.stats = &local; x.neeat = c->neeatPtr();
             x.sampleIndex = c->consts.sampleBaseIndex + firstSubSample + s;
             #pragma omp for schedule(dynamic, 1)
             for (int y = int(y0); y < int(y1); y++)
@@ -246,7 +300,7 @@ ORC_API int oracle_render_realtime(void* p, const RtxptRealtimeConstants* rt, ui
     {
         #pragma omp parallel
         {
-            PathTracerCtx x; x.scene = &c->scene; x.bvh = &c->bvh; x.lights = &c->lights; x.c = &c->consts; x.stats = nullptr; x.worldToClip = c->worldToClip; x.sp = &T;
+            PathTracerCtx x; x.scene = &c->scene; x.bvh = &c->bvh; x.lights = &c->lights; x.c = &c->consts; x.stats = nullptr; x.worldToClip = c->worldToClip; x.sp = &T; x.neeat = c->neeatPtr();
             x.mode = pass == 0 ? MODE_BUILD_STABLE_PLANES : MODE_FILL_STABLE_PLANES;
             x.sampleIndex = c->consts.sampleBaseIndex + (pass == 0 ? 0u : pass - 1u);
             #pragma omp for schedule(dynamic, 1)
@@ -254,6 +308,8 @@ ORC_API int oracle_render_realtime(void* p, const RtxptRealtimeConstants* rt, ui
                 for (uint32_t px = x0; px < x1; px++)
                     if (pass == 0) buildStablePlanesPixel(x, px, uint32_t(y)); else fillStablePlanesPixel(x, px, uint32_t(y));
         }
+        // LightsBaker::UpdateEnd sits between the BUILD pass and the radiance passes (Sample.cpp:2495): it needs this frame's depth and motion vectors
+        if (pass == 0 && c->neeatPtr() && x0 == 0 && y0 == 0 && x1 == T.width && y1 == T.height) NeeatUpdateEnd(c->neeat, c->lights, depth, motionVectors);
     }
     if (merged)
         for (uint32_t y = y0; y < y1; y++) for (uint32_t px = x0; px < x1; px++)
@@ -296,7 +352,7 @@ ORC_API int oracle_denoiser_prepare_inputs(void* p, const RtxptRealtimeConstants
     OracleCtx* c = (OracleCtx*)p;
     if (!c->haveConsts || !rt || !k || stablePlaneIndex >= 3) return -1;
     const RealtimeTargets T = makeTargets(c, rt, realtimeTargets); const DenoiserTargets D = makeDenoiserTargets(denoiserTargets);
-    PathTracerCtx x; x.scene = &c->scene; x.bvh = &c->bvh; x.lights = &c->lights; x.c = &c->consts; x.stats = nullptr; x.sampleIndex = c->consts.sampleBaseIndex;
+    PathTracerCtx x; x.scene = &c->scene; x.bvh = &c->bvh; x.lights = &c->lights; x.c = &c->consts; x.stats = nullptr; x.sampleIndex = c->consts.sampleBaseIndex; x.neeat = c->neeatPtr();
     for (uint32_t y = 0; y < T.height; y++) for (uint32_t px = 0; px < T.width; px++)
     {
         float3 co, cd; computeCameraRay(x, px, y, co, cd);

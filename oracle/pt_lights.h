@@ -340,6 +340,7 @@ struct LightTable
     std::vector<std::vector<float>> radianceMips;           // RGBA (rgb radiance, a importance), fp16-rounded like the RGBA16F texture
     uint envQuadNodeCount = 0, triangleLightCount = 0, samplingProxyCount = 0;
     float weightsSum = 0;
+    std::vector<float> weights;                             // per light, power-based (ComputeWeight), what ComputeProxyCounts blends the usage feedback into (pt_neeat.h)
     bool envEnabled = false;
     std::vector<PolymorphicLightInfoEx> lightsEx;      // analytic lights only: light index - ENVQT_TOTAL
     uint analyticLightCount = 0;
@@ -572,7 +573,7 @@ inline void bakeLights(Scene& sc, const RtxptPathTracerConstants& consts, LightT
         }
         total += groupSum;
     }
-    lt.weightsSum = total;
+    lt.weightsSum = total; lt.weights = w;
     // proxy counts + table (ComputeProxyCounts / ExecuteProxyJobs)
     const uint budget = LIGHTING_PROXY_RATIO * std::max(n, LIGHTING_MAX_LIGHTS / 10);
     lt.proxyCounters.assign(n, 0);

@@ -12,6 +12,7 @@
 #include "pt_scene.h"
 #include "pt_bvh.h"
 #include "pt_lights.h"
+#include "pt_neeat.h"
 #include "pt_rng.h"
 #include "pt_stable_planes.h"
 
@@ -112,6 +113,8 @@ struct PathTracerCtx
     // realtime mode (PATH_TRACER_MODE_BUILD_STABLE_PLANES / _FILL_STABLE_PLANES)
     uint mode = MODE_REFERENCE;
     const RealtimeTargets* sp = nullptr;
+    // NEE-AT temporal feedback + local samplers (pt_neeat.h); null = the global-table-only tier (RtxptPathTracerConstants::NEEATFeedback == 0)
+    NeeatState* neeat = nullptr;
     float noisyRadianceAttenuation() const { return 1.0f / float(sp->rt->subSampleCount); }      // Bridge::getNoisyRadianceAttenuation = invSubSampleCount (BridgeDonut:515-523)
 };
 struct GuideOut { float depth; uint throughput; float motion[3]; };
@@ -148,15 +151,19 @@ inline float3 envEvalLocal(const PathTracerCtx& x, float3 localDir, float lod)
 // ---- light sampler (global table only) ------------------------------------------------------------------------------------
 inline float SampleGlobalPDF(const LightTable& lt, uint lightIndex) { return float(lt.proxyCounters[lightIndex]) / float(lt.samplingProxyCount); }
 inline float EvalMISBalance(float n0, float p0, float n1, float p1) { float q0 = n0 * p0, q1 = n1 * p1; return saturate(q0 / (q0 + q1)); }   // Utils/Utils.hlsli:407-437
-inline float ComputeLightVsBSDF_MIS_ForBSDF(const LightTable& lt, uint lightIndex, float bsdfPdf, float solidAnglePdf, uint fullSampleCount)
+// neeat / pixel / misInfo: the local sampler the previous vertex drew from (LightSampler.hlsli:318-333: localCount > 0 only for screen-space-coherent vertices)
+inline float ComputeLightVsBSDF_MIS_ForBSDF(const LightTable& lt, uint lightIndex, float bsdfPdf, float solidAnglePdf, uint fullSampleCount, const NeeatState* neeat = nullptr, uint pathId = 0,
+                                            bool isSSC = false, uint candidateSampleCount = 0)
 {
     float globalPdf = SampleGlobalPDF(lt, lightIndex);
-    float localPdf = 0;                                         // localCount == 0 in this tier
+    float localPdf = 0;
+    if (neeat && isSSC && ComputeCandidateSampleLocalCount(neeat->localToGlobalSampleRatio, candidateSampleCount) > 0)
+        localPdf = SampleLocalPDF(*neeat, LocalSamplingTilePos(*neeat, pathId >> 16, pathId & 0xFFFFu), lightIndex);
     float lightAvgPdf = (localPdf + globalPdf) * float(fullSampleCount);
     return EvalMISBalance(1, bsdfPdf, 1, lightAvgPdf * solidAnglePdf);
 }
 
-struct LightSample { float3 Li = f3(0); float Distance = 0; float3 Direction = f3(0); uint LightIndex = 0xFFFFFFFFu; float SelectionPdf = 0, SolidAnglePdf = 0; bool LightSampleableByBSDF = false;
+struct LightSample { float3 Li = f3(0); float Distance = 0; float3 Direction = f3(0); uint LightIndex = 0xFFFFFFFFu; float SelectionPdf = 0, SolidAnglePdf = 0; bool LightSampleableByBSDF = false, FromLocalDistribution = false;
                      bool Valid() const { return Li.x > 0 || Li.y > 0 || Li.z > 0; } };
 
 // ---- firefly filter (PathTracerHelpers.hlsli:183-219) ---------------------------------------------------------------------
@@ -257,7 +264,7 @@ inline void HandleMiss(const PathTracerCtx& x, PathState& path, float3 rayDir, f
             cx = std::min(cx, IMPORTANCE_MAP_DIM - 1); cy = std::min(cy, IMPORTANCE_MAP_DIM - 1);   // Texture2D.Load out of range returns 0 in D3D; uv==1 is the only way to get there
             uint envLightIndex = x.lights->envLookupMap[size_t(cy) * IMPORTANCE_MAP_DIM + cx];
             EnvironmentQuadLight eq = EnvironmentQuadLight::Create(x.lights->lights[envLightIndex]);
-            misWeight = ComputeLightVsBSDF_MIS_ForBSDF(*x.lights, envLightIndex, bsdfScatterPdf, eq.SolidAnglePdf(), misInfo.FullSamples);
+            misWeight = ComputeLightVsBSDF_MIS_ForBSDF(*x.lights, envLightIndex, bsdfScatterPdf, eq.SolidAnglePdf(), misInfo.FullSamples, x.neeat, path.id, misInfo.LightSamplingIsSSC, misInfo.CandidateSamples);
         }
         environmentEmission = lp(misWeight * Le);
     }
@@ -368,20 +375,26 @@ inline NEEResult HandleNEE(const PathTracerCtx& x, const PathState& pre, const S
     const uint candidateSampleCount = x.c->NEECandidateSamples;
     const BSDFFrame frame = sd.frame();
     result.BSDFMISInfo.LightSamplingEnabled = true;
-    result.BSDFMISInfo.LightSamplingIsSSC = (pre.rayCone.getWidth() / pre.sceneLength) < 0.3f;      // IsScreenSpaceCoherentHeuristic; only packed, no effect without local samples
+    const bool isSSC = (pre.rayCone.getWidth() / pre.sceneLength) < (x.neeat ? x.neeat->settings.screenSpaceVsWorldSpaceThreshold : 0.3f);      // IsScreenSpaceCoherentHeuristic
+    result.BSDFMISInfo.LightSamplingIsSSC = isSSC;
     result.BSDFMISInfo.CandidateSamples = candidateSampleCount;
     result.BSDFMISInfo.FullSamples = fullSamples;
-    const uint localCount = 0, globalCount = candidateSampleCount - localCount;
+    // GetCandidateSampleCounts: local candidates only for screen-space-coherent vertices and only once last frame's feedback has built the tile samplers
+    const uint localCount = (x.neeat && isSSC) ? ComputeCandidateSampleLocalCount(x.neeat->localToGlobalSampleRatio, candidateSampleCount) : 0u, globalCount = candidateSampleCount - localCount;
+    const uint pixelX = pre.id >> 16, pixelY = pre.id & 0xFFFFu;
+    const uint tileAddress = x.neeat ? LocalSamplingTilePos(*x.neeat, pixelX, pixelY) : 0u;
     for (uint sampleIndex = 0; sampleIndex < fullSamples; sampleIndex++)
     {
         // GenerateLightSample: weighted reservoir sampling over the candidates
         LightSample picked; float weightSum = 0, candidateWeight = 0;
         for (uint i = 0; i < candidateSampleCount; i++)
         {
+            const bool sampleIsLocal = i >= globalCount;
             float rnd = sg.Next1D();
             uint M = lt.samplingProxyCount;
-            uint lightIndex = lt.proxyIndices[std::min(uint(rnd * float(M)), M - 1)];
-            float selectionPdf = float(lt.proxyCounters[lightIndex]) / float(M);
+            uint lightIndex; float selectionPdf;
+            if (sampleIsLocal) lightIndex = SampleLocal(*x.neeat, tileAddress, rnd, selectionPdf);
+            else { lightIndex = lt.proxyIndices[std::min(uint(rnd * float(M)), M - 1)]; selectionPdf = float(lt.proxyCounters[lightIndex]) / float(M); }
             const PolymorphicLightInfo& li = lt.lights[lightIndex];
             float2 interiorRnd; interiorRnd.x = sg.Next1D(); interiorRnd.y = sg.Next1D();
             PolymorphicLightSample ls = {};
@@ -407,7 +420,7 @@ inline NEEResult HandleNEE(const PathTracerCtx& x, const PathState& pre, const S
             float3 surfToLight = ls.Position - sd.posW;
             cs.Distance = length(surfToLight);
             cs.Direction = surfToLight / std::max(cs.Distance, 1e-7f);
-            cs.LightIndex = lightIndex; cs.SelectionPdf = selectionPdf; cs.LightSampleableByBSDF = ls.LightSampleableByBSDF;
+            cs.LightIndex = lightIndex; cs.SelectionPdf = selectionPdf; cs.LightSampleableByBSDF = ls.LightSampleableByBSDF; cs.FromLocalDistribution = sampleIsLocal;
             float wrsWeight = max3(cs.Li) * bsdf.evalPdf(frame, cs.Direction);
             float wrsRnd = sg.Next1D();
             weightSum += wrsWeight;
@@ -429,7 +442,10 @@ inline NEEResult HandleNEE(const PathTracerCtx& x, const PathState& pre, const S
         if (visible)
         {
             float fadeOut = (sd.shadowNoLFadeout > 0) ? saturate((dot(picked.Direction, sd.vertexN) - sd.shadowNoLFadeout) / (2.0f * sd.shadowNoLFadeout)) : 1.0f;
+            // ComputeLightSelectionPdfs: the pdf the other sampler would have picked this light with
             float thisPdf = picked.SelectionPdf, otherPdf = 0, thisCount = float(globalCount);
+            if (picked.FromLocalDistribution) { otherPdf = SampleGlobalPDF(lt, picked.LightIndex); thisCount = float(localCount); }
+            else if (localCount != 0) otherPdf = SampleLocalPDF(*x.neeat, tileAddress, picked.LightIndex);
             float wrsMIS = EvalMISBalance(1, thisPdf, 1, otherPdf) / thisCount;
             float scatterPdfForDir = bsdf.evalPdf(frame, picked.Direction);
             float lightAvgPdf = (thisPdf + otherPdf) * float(fullSamples);
@@ -448,7 +464,11 @@ inline NEEResult HandleNEE(const PathTracerCtx& x, const PathState& pre, const S
             float3 preScatterThp = pre.GetThp();
             radiance *= preScatterThp;
             specAvg *= Average(preScatterThp);
+            radianceAvg *= Average(preScatterThp);
             result.Accumulate(radiance, specAvg);
+            // temporal feedback for NEE-AT: how much this pixel wanted this light (path throughput x BSDF x light, un-filtered), PathTracerNEE.hlsli:276-283
+            if (x.neeat && picked.LightIndex != RTXPT_INVALID_LIGHT_INDEX && x.neeat->temporalFeedbackRequired)
+                InsertFeedbackFromNEE(*x.neeat, lt, pixelX, pixelY, isSSC, picked.LightIndex, radianceAvg, sg.Next1D());
         }
     }
     return result;
@@ -509,7 +529,7 @@ inline void HandleHit(const PathTracerCtx& x, PathState& path, float3 rayOrigin,
         {
             TriangleLight tl = TriangleLight::Create(x.lights->lights[surface.neeTriangleLightIndex]);
             float solidAnglePdf = tl.CalcSolidAnglePdfForMIS(rayOrigin, sd.posW);
-            misWeight = ComputeLightVsBSDF_MIS_ForBSDF(*x.lights, surface.neeTriangleLightIndex, bsdfScatterPdf, solidAnglePdf, misInfo.FullSamples);
+            misWeight = ComputeLightVsBSDF_MIS_ForBSDF(*x.lights, surface.neeTriangleLightIndex, bsdfScatterPdf, solidAnglePdf, misInfo.FullSamples, x.neeat, path.id, misInfo.LightSamplingIsSSC, misInfo.CandidateSamples);
         }
         surfaceEmission = lp(sd.emission * misWeight);
     }
@@ -524,7 +544,7 @@ inline void HandleHit(const PathTracerCtx& x, PathState& path, float3 rayOrigin,
             {
                 float mis = 1.0f;
                 const float bsdfPdf = misInfo.LightSamplingEnabled ? pathBsdfScatterPdf : 0.0f;
-                if (bsdfPdf != 0) mis = ComputeLightVsBSDF_MIS_ForBSDF(*x.lights, surface.neeAnalyticLightIndex, bsdfPdf, sl.CalcSolidAnglePdfForMIS(rayOrigin), misInfo.FullSamples);
+                if (bsdfPdf != 0) mis = ComputeLightVsBSDF_MIS_ForBSDF(*x.lights, surface.neeAnalyticLightIndex, bsdfPdf, sl.CalcSolidAnglePdfForMIS(rayOrigin), misInfo.FullSamples, x.neeat, path.id, misInfo.LightSamplingIsSSC, misInfo.CandidateSamples);
                 surfaceEmission = surfaceEmission + lp(radiance * mis);
             }
         }

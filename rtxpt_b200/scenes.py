@@ -87,6 +87,36 @@ def cornell_builder(analytic_lights=False, delta_surfaces=False):
     return b
 
 
+def light_gallery(width=128, height=96, bays=6, lamps_per_bay=2):
+    """A corridor of `bays` alcoves seen from the side, each lit by its own small ceiling lamps of a different colour and separated from its neighbours by full-height
+    partitions: every screen region is lit by a handful of the scene's emissive triangles and shadowed from all others - the case NEE-AT's per-tile samplers exist for.
+    Returns (Scene, CameraData)."""
+    b = SceneBuilder()
+    white = b.add_material(Material(base_color=(0.7, 0.7, 0.7), roughness=1.0))
+    bw, depth, hgt = 2.0, 3.0, 2.6
+    L = bays * bw
+    geos = [_quad((0, 0, 0), (0, 0, depth), (L, 0, depth), (L, 0, 0), white),                 # floor, +y
+            _quad((0, hgt, 0), (L, hgt, 0), (L, hgt, depth), (0, hgt, depth), white),         # ceiling, -y
+            _quad((0, 0, depth), (0, hgt, depth), (L, hgt, depth), (L, 0, depth), white)]     # back wall, -z
+    for k in range(bays + 1):                                                                 # partitions (two-sided: one quad per side), leaving the front open
+        x = k * bw
+        geos.append(_quad((x + 0.01, 0, 0.6), (x + 0.01, hgt, 0.6), (x + 0.01, hgt, depth), (x + 0.01, 0, depth), white))
+        geos.append(_quad((x - 0.01, 0, 0.6), (x - 0.01, 0, depth), (x - 0.01, hgt, depth), (x - 0.01, hgt, 0.6), white))
+    room = b.add_mesh([_merge(geos, white)])
+    lamps = []
+    rng = np.random.default_rng(7)
+    for k in range(bays):
+        col = 0.3 + 0.7 * rng.random(3)
+        m = b.add_material(Material(base_color=(0.8, 0.8, 0.8), roughness=1.0, emissive=tuple((col * (6.0 + 10.0 * rng.random())).tolist())))
+        for j in range(lamps_per_bay):
+            cx = k * bw + bw * (j + 1) / (lamps_per_bay + 1); cz = 1.2 + 0.9 * rng.random(); r = 0.12
+            lamps.append(_quad((cx - r, hgt - 0.02, cz - r), (cx + r, hgt - 0.02, cz - r), (cx + r, hgt - 0.02, cz + r), (cx - r, hgt - 0.02, cz + r), m))
+    lamp_mesh = b.add_mesh(lamps)
+    b.add_instance(room, identity34()); b.add_instance(lamp_mesh, identity34())
+    cam = bridge_camera(width, height, pos=(L * 0.5, 1.3, -7.5), direction=(0, -0.02, 1), up=(0, 1, 0), fov_y=0.8)
+    return b.build(), cam
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 def _value_noise(rng, size, octaves=5):
     img = np.zeros((size, size), np.float32)

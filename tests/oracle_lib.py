@@ -131,6 +131,36 @@ class Oracle:
         assert rc == 0
         return accum, n.value, last, primary, st
 
+    # ---- NEE-AT temporal feedback (oracle/pt_neeat.h); frame order: set_constants; neeat_update_begin; [render_realtime does update_end after its BUILD pass] or neeat_update_end; render
+    def neeat_reset(self): assert lib().oracle_neeat_reset(C.c_void_p(self.h)) == 0
+
+    def neeat_update_begin(self): assert lib().oracle_neeat_update_begin(C.c_void_p(self.h)) == 0
+
+    def neeat_update_end(self, depth, motion=None):
+        d = np.ascontiguousarray(depth, np.float32); m = None if motion is None else np.ascontiguousarray(motion, np.float16)
+        assert lib().oracle_neeat_update_end(C.c_void_p(self.h), C.c_void_p(d.ctypes.data), C.c_void_p(None if m is None else m.ctypes.data)) == 0
+
+    def neeat_get(self):
+        """All NEE-AT state as numpy arrays."""
+        W, H = self.consts.imageWidth, self.consts.imageHeight
+        L = lib(); L.oracle_neeat_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]; L.oracle_neeat_get.restype = C.c_int
+        ctl = np.zeros(8, np.uint32); assert L.oracle_neeat_get(self.h, 8, ctl.ctypes.data, ctl.nbytes) > 0
+        bw, bh = (W + 1) // 2, (H + 1) // 2
+        out = dict(tiles=(int(ctl[0]), int(ctl[1])), jitter=(int(ctl[2]), int(ctl[3])), sampling_proxy_count=int(ctl[4]), update_counter=int(ctl[5]), available=bool(ctl[6]), valid_feedback=int(ctl[7]))
+        for key, what, shape, dt in (("weight", 0, (H, W), np.float32), ("candidate", 1, (H, W), np.uint32), ("scratch_weight", 2, (H, W), np.float32), ("scratch_candidate", 3, (H, W), np.uint32),
+                                     ("blended_weight", 4, (bh, bw), np.float32), ("blended_candidate", 5, (bh, bw), np.uint32), ("local", 6, (int(ctl[1]), int(ctl[0]), 128), np.uint32)):
+            a = np.zeros(shape, dt); assert L.oracle_neeat_get(self.h, what, a.ctypes.data, a.nbytes) == a.nbytes, key; out[key] = a
+        return out
+
+    def neeat_proxy_counters(self, light_count):
+        L = lib(); L.oracle_neeat_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]; L.oracle_neeat_get.restype = C.c_int
+        a = np.zeros(light_count, np.uint32); assert L.oracle_neeat_get(self.h, 7, a.ctypes.data, a.nbytes) == a.nbytes
+        return a
+
+    def neeat_set_feedback(self, weight, candidate):
+        w = np.ascontiguousarray(weight, np.float32); c = np.ascontiguousarray(candidate, np.uint32)
+        assert lib().oracle_neeat_set_feedback(C.c_void_p(self.h), C.c_void_p(w.ctypes.data), C.c_void_p(c.ctypes.data)) == 0
+
     def render_realtime(self, rt, rect=None, threads=0):
         """BUILD + rt.subSampleCount x FILL + no-denoiser merge.  Returns a dict of the realtime render targets (numpy)."""
         W, H = self.consts.imageWidth, self.consts.imageHeight

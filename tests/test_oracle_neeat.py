@@ -1,0 +1,89 @@
+"""CPU: NEE-AT temporal feedback in the oracle (oracle/pt_neeat.h): feedback reservoirs -> usage-weighted global proxy table + per-tile local samplers ->
+local / global candidate mix with MIS in NEE.  The reference has no golden vectors for this loop (its float atomics and cross-group races make a frame's state order-dependent),
+so the restatement is held to what the algorithm guarantees: structural invariants of the tile lists, the response of both samplers to a known feedback image, an unbiased
+estimator (same mean as global-only sampling) and lower error once the loop has warmed up."""
+import numpy as np
+import pytest
+
+INVALID = 0xFFFFFFFF
+SSC = 0x80000000
+
+
+def _setup(oracle, W, H, bays=8, feedback=True, bounces=2):
+    from rtxpt_b200 import scene_builder as sb, scenes
+    scene, cam = scenes.light_gallery(W, H, bays=bays)
+    o = oracle.Oracle(scene)
+    c = sb.make_constants(W, H, cam, bounce_count=bounces, diffuse_bounce_count=bounces); c.NEEATFeedback = 1 if feedback else 0
+    o.set_constants(c); o.set_view(sb.world_to_clip(cam))
+    if feedback: o.neeat_reset()
+    return o, c, cam, sb.make_realtime_constants(W, H, cam, bounce_count=bounces, sub_samples=1)
+
+
+def _frames(o, c, rt, n, feedback, first=0):
+    out = []
+    for f in range(first, first + n):
+        c.sampleBaseIndex = f; o.set_constants(c)
+        if feedback: o.neeat_update_begin()
+        out.append(o.render_realtime(rt)["merged"].copy())
+    return np.stack(out)
+
+
+def test_tile_lists_and_counters_are_well_formed(oracle):
+    W, H = 96, 64
+    o, c, cam, rt = _setup(oracle, W, H)
+    _frames(o, c, rt, 4, True)
+    st = o.neeat_get()
+    assert st["tiles"] == ((W + 7) // 8 + 1, (H + 7) // 8 + 1) and st["available"] and 0 < st["valid_feedback"] <= W * H
+    assert all(0 <= j < 8 for j in st["jitter"])
+    light_count = 5368 + 8 * 2 * 2                                                     # environment quad-tree slots + two triangles per lamp
+    lists = st["local"].reshape(-1, 128); lights = lists >> 9; counts = (lists & 0x1FF) + 1
+    assert (np.diff(lights.astype(np.int64), axis=1) >= 0).all()                       # sorted ascending: SampleLocalPDF binary-searches them
+    assert lights.max() < light_count and lights.min() >= 5368                         # only real (emissive triangle) lights: the environment map is off
+    for row_l, row_c in zip(lights[::7], counts[::7]):
+        u, n = np.unique(row_l, return_counts=True)
+        assert n.sum() == 128 and all((row_c[row_l == k] == m).all() for k, m in zip(u, n))     # every entry carries the run length of its light: pdf = count / 128
+    cand = st["candidate"]; has = st["weight"] > 0
+    assert ((cand[has] & np.uint32(0x7FFFFFFF)) < light_count).all()                                     # reservoirs the next frame starts from hold valid lights
+    assert (st["scratch_candidate"] != INVALID).all() and (st["blended_candidate"] != INVALID).all()      # P1a / P1b never leave a hole for FillTile
+    o.close()
+
+
+def test_samplers_follow_a_known_feedback_image(oracle):
+    """All left-half pixels report lamp A, all right-half pixels lamp B: the global table shifts its proxies to A and B (75 % usage weight), left tiles hold mostly A, right
+    tiles mostly B, and nothing else gets more than the power-based remainder."""
+    W, H = 96, 64
+    o, c, cam, rt = _setup(oracle, W, H)
+    c.sampleBaseIndex = 0; o.set_constants(c); o.neeat_update_begin()
+    base = o.neeat_proxy_counters(5368 + 32).astype(np.int64)
+    r = o.render_realtime(rt)
+    A, B = 5368 + 3, 5368 + 20
+    cand = np.full((H, W), A | SSC, np.uint32); cand[:, W // 2:] = B | SSC
+    o.neeat_set_feedback(np.ones((H, W), np.float32), cand)
+    c.sampleBaseIndex = 1; o.set_constants(c); o.neeat_update_begin()
+    cnt = o.neeat_proxy_counters(5368 + 32).astype(np.int64)
+    total = cnt.sum(); others = np.delete(cnt, [A, B])
+    assert abs(cnt[A] / total - (0.25 * base[A] / base.sum() + 0.375)) < 0.01 and abs(cnt[B] / total - (0.25 * base[B] / base.sum() + 0.375)) < 0.01
+    assert np.allclose(others / total, 0.25 * np.delete(base, [A, B]) / base.sum(), atol=2e-3)
+    o.neeat_update_end(r["depth"], r["motion"])
+    st = o.neeat_get()
+    lights = st["local"] >> 9
+    tx = st["tiles"][0]; jx = st["jitter"][0]
+    left = lights[:, : (W // 2 - 16 + jx) // 8]; right = lights[:, (W // 2 + 16 + jx) // 8 + 1: tx - 1]
+    assert (left == A).mean() > 0.9 and (right == B).mean() > 0.9                       # 64 window pixels + 64 top-up picks from the blended image around the tile
+    assert st["valid_feedback"] == W * H
+    o.close()
+
+
+def test_feedback_is_unbiased_and_reduces_error(oracle):
+    W, H = 112, 72
+    o, c, cam, rt = _setup(oracle, W, H, bays=10, feedback=True)
+    a = _frames(o, c, rt, 72, True); o.close()
+    o, c, cam, rt = _setup(oracle, W, H, bays=10, feedback=False)
+    b = _frames(o, c, rt, 144, False); o.close()
+    ref = b.mean(0); warm = a[12:]
+    assert abs(warm.mean() / b.mean() - 1) < 0.03                                       # same estimator mean as global-only sampling
+    noise = np.abs(b[:72].mean(0) - b[72:].mean(0)).mean()
+    assert np.abs(warm.mean(0) - ref).mean() < 1.6 * noise                              # and per pixel, within the noise of the comparison itself
+    e_fb, e_gl = np.abs(warm - ref).mean(), np.abs(b - ref).mean()
+    assert e_fb < 0.93 * e_gl, (e_fb, e_gl)                                             # local candidates find the bay's own lamps: lower per-frame error
+    assert np.isfinite(a).all()
