@@ -136,6 +136,10 @@ ORC_API int oracle_neeat_get(void* p, int what, void* out, size_t bytes)
     case 6: src = s.localSamplingBuffer.data(); n = s.localSamplingBuffer.size() * 4; break;
     case 7: src = c->lights.proxyCounters.data(); n = c->lights.proxyCounters.size() * 4; break;
     case 8: ctl[0] = s.tilesX; ctl[1] = s.tilesY; ctl[2] = s.jitter[0]; ctl[3] = s.jitter[1]; ctl[4] = c->lights.samplingProxyCount; ctl[5] = s.updateCounter; ctl[6] = s.lastFrameTemporalFeedbackAvailable; ctl[7] = s.validFeedbackCount; src = ctl; n = sizeof(ctl); break;
+    case 9: src = c->lights.weights.data(); n = c->lights.weights.size() * 4; break;            // power-based light weights (f32 lightCount)
+    case 10: src = &c->lights.weightsSum; n = 4; break;
+    case 11: src = c->lights.proxyIndices.data(); n = c->lights.proxyIndices.size() * 4; break;
+    case 12: { static uint32_t cnt; cnt = uint32_t(c->lights.lights.size()); src = &cnt; n = 4; break; }
     default: return -1;
     }
     if (bytes < n) return -2;

@@ -152,6 +152,11 @@ class Oracle:
             a = np.zeros(shape, dt); assert L.oracle_neeat_get(self.h, what, a.ctypes.data, a.nbytes) == a.nbytes, key; out[key] = a
         return out
 
+    def neeat_raw(self, what, dtype, count):
+        L = lib(); L.oracle_neeat_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]; L.oracle_neeat_get.restype = C.c_int
+        a = np.zeros(count, dtype); n = L.oracle_neeat_get(self.h, what, a.ctypes.data, a.nbytes); assert n >= 0, (what, n)
+        return a[: n // a.itemsize]
+
     def neeat_proxy_counters(self, light_count):
         L = lib(); L.oracle_neeat_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]; L.oracle_neeat_get.restype = C.c_int
         a = np.zeros(light_count, np.uint32); assert L.oracle_neeat_get(self.h, 7, a.ctypes.data, a.nbytes) == a.nbytes

@@ -53,3 +53,31 @@ def denoise_spec_hit_t(depth, spec_hit_t):
     L = lib(); L.emu_denoise_spec_hit_t.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
     assert L.emu_denoise_spec_hit_t(W, H, d.ctypes.data, out.ctypes.data) == 0
     return out
+
+
+class NeeatPort:
+    """The product's NEE-AT feedback passes (rtxpt_b200/csrc/neeat.cuh + neeat_host.h) compiled for the host; state persists between frames like the context's does."""
+    def __init__(self, W, H, weights, weights_sum, nee_type=2):
+        L = lib(); L.neeat_emu_create.restype = C.c_void_p; L.neeat_emu_create.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_float, C.c_uint32]
+        L.neeat_emu_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]; L.neeat_emu_update_begin.argtypes = [C.c_void_p]; L.neeat_emu_update_end.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.neeat_emu_set_feedback.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]; L.neeat_emu_destroy.argtypes = [C.c_void_p]
+        w = np.ascontiguousarray(weights, np.float32); self.W, self.H, self.n = W, H, len(w)
+        self.h = L.neeat_emu_create(W, H, len(w), w.ctypes.data, float(weights_sum), nee_type)
+
+    def close(self):
+        if self.h: lib().neeat_emu_destroy(self.h); self.h = None
+
+    def __del__(self): self.close()
+
+    def set_feedback(self, weight, candidate):
+        w = np.ascontiguousarray(weight, np.float32); c = np.ascontiguousarray(candidate, np.uint32); assert lib().neeat_emu_set_feedback(self.h, w.ctypes.data, c.ctypes.data) == 0
+
+    def update_begin(self): assert lib().neeat_emu_update_begin(self.h) == 0
+
+    def update_end(self, depth, motion=None):
+        d = np.ascontiguousarray(depth, np.float32); m = None if motion is None else np.ascontiguousarray(motion, np.float16)
+        assert lib().neeat_emu_update_end(self.h, d.ctypes.data, None if m is None else m.ctypes.data) == 0
+
+    def raw(self, what, dtype, count):
+        a = np.zeros(count, dtype); n = lib().neeat_emu_get(self.h, what, a.ctypes.data, a.nbytes); assert n >= 0, (what, n)
+        return a[: n // a.itemsize]

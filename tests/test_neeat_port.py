@@ -1,0 +1,48 @@
+"""CPU: the product's NEE-AT feedback passes held to the oracle without a GPU.  rtxpt_b200/csrc/neeat.cuh keeps the bodies of LightsBaker's feedback passes as __host__ __device__
+functions and neeat_host.h the per-frame bookkeeping; tests/emu compiles both for the host and runs them in the order the C ABI launches the kernels.  The oracle's path tracer
+fills the feedback reservoirs (the product's path-tracer side needs a GPU); every frame both sides process the same reservoirs and must agree bit for bit on everything the
+passes produce: reservoirs after PreFilter + P0, proxy counts and table, blended and processed reservoirs, sorted tile lists, the seeded reservoirs of the next frame."""
+import numpy as np
+import pytest
+
+
+def _compare(o, port, W, H, n_lights, stage):
+    P, B = W * H, ((W + 1) // 2) * ((H + 1) // 2)
+    ctl_o, ctl_p = o.neeat_raw(8, np.uint32, 8), port.raw(8, np.uint32, 8)
+    assert np.array_equal(ctl_o, ctl_p), (stage, ctl_o, ctl_p)                              # tiles, jitter, proxy total, counter, availability, valid feedback count
+    T = int(ctl_o[0]) * int(ctl_o[1]) * 128
+    for what, dt, n, name in ((0, np.uint32, P, "feedback weight"), (1, np.uint32, P, "feedback candidate"), (7, np.uint32, n_lights, "proxy counters"), (11, np.uint32, int(ctl_o[4]), "proxy table")) + \
+                             (((2, np.uint32, P, "processed weight"), (3, np.uint32, P, "processed candidate"), (4, np.uint32, B, "blended weight"), (5, np.uint32, B, "blended candidate"),
+                               (6, np.uint32, T, "tile lists")) if stage == "end" else ()):
+        a, b = o.neeat_raw(what, dt, n), port.raw(what, dt, n)                              # floats compared by bit pattern
+        assert len(a) == len(b) == n and np.array_equal(a, b), (stage, name, int((a != b).sum()))
+
+
+@pytest.mark.parametrize("moving", [False, True])
+def test_feedback_passes_equal_the_oracle(oracle, moving):
+    from rtxpt_b200 import scene_builder as sb, scenes
+    import reblur_emu_lib as emu
+    W, H = 90, 58                                                                            # neither a multiple of the 8-pixel tile nor of the 2-pixel blend
+    scene, cam0 = scenes.light_gallery(W, H, bays=7)
+    guide = oracle.Oracle(scene)                                                             # depth / motion guides of every frame (no feedback involved)
+    o = oracle.Oracle(scene)
+    c = sb.make_constants(W, H, cam0, bounce_count=2, diffuse_bounce_count=2); c.NEEATFeedback = 1
+    o.set_constants(c); o.set_view(sb.world_to_clip(cam0)); o.neeat_reset()
+    n_lights = int(o.neeat_raw(12, np.uint32, 1)[0])
+    port = emu.NeeatPort(W, H, o.neeat_raw(9, np.float32, n_lights), float(o.neeat_raw(10, np.float32, 1)[0]))
+    prev = None
+    for f in range(6):
+        cam = sb.bridge_camera(W, H, pos=(7.0 + (0.4 * f if moving else 0.0), 1.3, -7.5), direction=(0, -0.02, 1), up=(0, 1, 0), fov_y=0.8)
+        cg = sb.make_constants(W, H, cam, bounce_count=2, diffuse_bounce_count=2); guide.set_constants(cg); guide.set_view(sb.world_to_clip(cam))
+        g = guide.render_realtime(sb.make_realtime_constants(W, H, cam, prev_cam=prev, bounce_count=2, sub_samples=1))
+        c = sb.make_constants(W, H, cam, bounce_count=2, diffuse_bounce_count=2, sample_base_index=f); c.NEEATFeedback = 1
+        o.set_constants(c); o.set_view(sb.world_to_clip(cam))
+        if f > 0: port.set_feedback(o.neeat_raw(0, np.float32, W * H), o.neeat_raw(1, np.uint32, W * H))        # what the path tracer left in the reservoirs last frame
+        o.neeat_update_begin(); port.update_begin(); _compare(o, port, W, H, n_lights, "begin")
+        o.neeat_update_end(g["depth"], g["motion"]); port.update_end(g["depth"], g["motion"]); _compare(o, port, W, H, n_lights, "end")
+        o.render(0, 1)                                                                       # reference-mode radiance pass: NEE draws local + global candidates and inserts feedback
+        prev = cam
+    st = o.neeat_get()
+    assert st["available"] and st["valid_feedback"] > 0.3 * W * H
+    if moving: assert np.abs(g["motion"][..., 0].astype(np.float32)).mean() > 1.0                # the dolly really exercised reprojection (whole-pixel shifts)
+    port.close(); o.close(); guide.close()
