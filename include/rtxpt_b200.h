@@ -384,6 +384,19 @@ RTXPT_API int rtxpt_b200_denoise_spec_hit_t(rtxpt_ctx* ctx, void* cudaStream);
 RTXPT_API int rtxpt_b200_denoiser_prepare_inputs(rtxpt_ctx* ctx, uint32_t stablePlaneIndex, int initWithStableRadiance, const RtxptDenoiserConstants* constants, void* cudaStream);
 RTXPT_API int rtxpt_b200_denoiser_final_merge(rtxpt_ctx* ctx, uint32_t stablePlaneIndex, const void* dDenoisedDiffRGBA16F, const void* dDenoisedSpecRGBA16F, void* cudaStream);    /* NULL, NULL = the images rtxpt_b200_reblur_denoise wrote */
 
+/* ---- NEE-AT temporal feedback (replaces the feedback half of Rtxpt/Lighting/LightsBaker: UpdateBegin's ProcessFeedbackHistoryPreFilter / P0 + usage-weighted
+ * ComputeProxyCounts, UpdateEnd's P1a / P1b / P2 / P3 / ClearFeedbackHistory, LightsBaker.cpp:1203-1225, :1331-1418).  Active with NEEType == 2 && NEEATFeedback != 0: NEE then draws
+ * ComputeCandidateSampleLocalCount( 0.65, NEECandidateSamples ) of its candidates from the pixel's 8x8-tile sampler once a frame of feedback exists, mixes them with the global ones by
+ * MIS, and records which light each pixel wanted.  Per frame: set_constants; neeat_update_begin; neeat_update_end (rtxpt_b200_path_trace_realtime calls it itself after its BUILD
+ * pass; reference mode: call it before rtxpt_b200_path_trace, the context must export guides); then trace.  Sub-samples of a reference-mode call run one per wavefront while
+ * feedback is active (a pixel's reservoir is updated by one path at a time, as in the reference). */
+RTXPT_API int rtxpt_b200_neeat_update_begin(rtxpt_ctx* ctx, void* cudaStream);
+RTXPT_API int rtxpt_b200_neeat_update_end(rtxpt_ctx* ctx, void* cudaStream);
+RTXPT_API int rtxpt_b200_neeat_reset(rtxpt_ctx* ctx);                 /* LightsBaker::BakeSettings::ResetFeedback: drop all feedback state */
+/* tests / debugging: what = 0,1 feedback weight / candidate; 2,3 processed; 4,5 half-resolution blend; 6 tile lists; 7 proxy counters; 8 control words; 11 proxy table */
+RTXPT_API int rtxpt_b200_neeat_readback(rtxpt_ctx* ctx, int what, void* dst, size_t dstBytes, size_t* outBytes);
+RTXPT_API int rtxpt_b200_neeat_debug_set_feedback(rtxpt_ctx* ctx, const float* weight, const uint32_t* candidate);
+
 /* ---- ReBLUR: NRD's REBLUR_DIFFUSE_SPECULAR denoiser (External/Nrd, NRD 4.15.2) for one stable plane, in RTXPT's configuration
  * (Rtxpt/NRD/NrdConfig.cpp:49-61 settings, NrdIntegration.cpp:375-408 common settings).  Replaces NrdIntegration::RunDenoiserPasses (NrdIntegration.cpp:360-520) for the
  * ReBLUR method: reads RTXPT_BUFFER_DENOISER_* as rtxpt_b200_denoiser_prepare_inputs wrote them, keeps one history per plane inside the context (RTXPT: one NRD instance per

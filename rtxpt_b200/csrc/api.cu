@@ -5,6 +5,7 @@
 // There is no CPU rendering fallback anywhere in this library: without a CUDA device every entry point fails with RTXPT_ERR_NO_DEVICE.
 #include "kernels.h"
 #include "reblur_host.h"
+#include "neeat_host.h"
 #include "lights_bake.h"
 #include <algorithm>
 #include <chrono>
@@ -95,6 +96,16 @@ struct rtxpt_ctx
     } reblur[RTXPT_STABLE_PLANE_COUNT];
     DeviceArray<uint8_t> rbTiles; DeviceArray<uint2> rbTmp1Diff, rbTmp1Spec, rbTmp2Diff, rbTmp2Spec, rbOutDiff, rbOutSpec; DeviceArray<uint16_t> rbTrackingT, rbDiffFastT, rbSpecFastT; DeviceArray<uchar2> rbData1; DeviceArray<uint32_t> rbData2;
     uint32_t reblurWidth = 0, reblurHeight = 0;
+    // NEE-AT temporal feedback (consts.NEEType == 2 && consts.NEEATFeedback): LightsBaker's frame state, reservoirs, tile samplers and the per-frame global proxy table
+    struct Neeat
+    {
+        neeat::HostState host; neeat::Params params{}; bool allocated = false, frameBegun = false; uint32_t lightCount = 0;
+        DeviceArray<float> fbWeight, scratchWeight, blendedWeight, historyDepth, lightWeights; DeviceArray<uint32_t> fbCandidate, scratchCandidate, blendedCandidate, local, counters,
+            proxyCounters, proxyOffsets, proxyIndices, samplingProxyCount, scanBlockSums, rrFix; DeviceArray<uint4> shadowFeedback;
+        void release() { fbWeight.release(); scratchWeight.release(); blendedWeight.release(); historyDepth.release(); lightWeights.release(); fbCandidate.release(); scratchCandidate.release();
+                         blendedCandidate.release(); local.release(); counters.release(); proxyCounters.release(); proxyOffsets.release(); proxyIndices.release(); samplingProxyCount.release();
+                         scanBlockSums.release(); rrFix.release(); shadowFeedback.release(); allocated = false; frameBegun = false; }
+    } na;
     cudaEvent_t evDnStart = nullptr, evDnStop = nullptr; bool denoiseTimed = false;       // around the last rtxpt_b200_denoise_realtime
     // stats
     uint32_t* hCounters = nullptr;          // pinned
@@ -180,6 +191,7 @@ extern "C" RTXPT_API int rtxpt_b200_destroy(rtxpt_ctx* c)
     c->stablePlanes.release(); c->stablePlanesHeader.release(); c->stableRadiance.release(); c->specularHitT.release();
     c->dnScratchFloat.release(); c->dnViewZ.release(); c->dnMotion.release(); c->dnDiff.release(); c->dnSpec.release(); c->dnNormalRoughness.release(); c->dnDisocclusionMix.release(); c->dnHistoryClampRelax.release();
     for (auto& h : c->reblur) h.release();
+    c->na.release();
     c->rbTiles.release(); c->rbTmp1Diff.release(); c->rbTmp1Spec.release(); c->rbTmp2Diff.release(); c->rbTmp2Spec.release(); c->rbOutDiff.release(); c->rbOutSpec.release();
     c->rbTrackingT.release(); c->rbDiffFastT.release(); c->rbSpecFastT.release(); c->rbData1.release(); c->rbData2.release();
     for (cudaEvent_t ev : c->evPool) cudaEventDestroy(ev);
@@ -517,6 +529,7 @@ extern "C" RTXPT_API int rtxpt_b200_path_trace(rtxpt_ctx* c, uint32_t firstSubSa
 {
     int rc = checkReady(c); if (rc != RTXPT_OK) return rc;
     if (subSampleCount == 0) return RTXPT_OK;
+    if (c->consts.NEEType == 2 && c->consts.NEEATFeedback != 0) return fail(RTXPT_ERR_UNSUPPORTED, "NEE-AT temporal feedback is wired into realtime mode (rtxpt_b200_path_trace_realtime) in this round; reference mode runs with NEEATFeedback = 0");
     cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
     LaunchParams p; fillParams(c, p);
     queryOccupancy(c->grid, 16 + size_t(p.smemNodeCount) * 80);
@@ -569,6 +582,9 @@ extern "C" RTXPT_API int rtxpt_b200_path_trace(rtxpt_ctx* c, uint32_t firstSubSa
     return RTXPT_OK;
 }
 
+static bool neeatActive(const rtxpt_ctx* c);
+extern "C" RTXPT_API int rtxpt_b200_neeat_update_end(rtxpt_ctx* c, void* cudaStream);
+
 // ---- realtime mode -----------------------------------------------------------------------------------------------------------------------------------
 extern "C" RTXPT_API int rtxpt_b200_set_realtime(rtxpt_ctx* c, const RtxptRealtimeConstants* rt)
 {
@@ -616,6 +632,9 @@ extern "C" RTXPT_API int rtxpt_b200_path_trace_realtime(rtxpt_ctx* c, int mergeN
     if (!c->haveRealtime || c->realtimeWidth != c->tableWidth || c->realtimeHeight != c->tableHeight) return fail(RTXPT_ERR_INVALID_ARGUMENT, "rtxpt_b200_set_realtime has not been called for this image size");
     if (!c->haveView) return fail(RTXPT_ERR_INVALID_ARGUMENT, "rtxpt_b200_set_view has not been called (the guide depth needs view.matWorldToClip)");
     cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
+    const bool na = neeatActive(c);
+    if (na && (!c->na.allocated || !c->na.frameBegun)) return fail(RTXPT_ERR_INVALID_ARGUMENT, "NEEATFeedback is set: call rtxpt_b200_neeat_update_begin before tracing the frame");
+    if (na && c->cfg.tileWorld > 1) return fail(RTXPT_ERR_UNSUPPORTED, "NEE-AT feedback needs every pixel's reservoir on one GPU; the tile partition runs with NEEATFeedback = 0");
     LaunchParams p; fillParams(c, p);
     const RtxptRealtimeConstants& r = c->realtime;
     fillRealtimeParams(c, p);
@@ -636,16 +655,27 @@ extern "C" RTXPT_API int rtxpt_b200_path_trace_realtime(rtxpt_ctx* c, int mergeN
         p.iteration = it;
         launchTraceClosest(p, c->grid, false, s); launchRtShade(p, c->grid, false, s); launches += 2;
     }
+    if (na)
+    {   // LightsBaker::UpdateEnd sits between the BUILD pass (this frame's depth and motion vectors) and the radiance passes (Sample.cpp:2495)
+        rc = rtxpt_b200_neeat_update_end(c, cudaStream); if (rc != RTXPT_OK) return rc;
+        p.na = c->na.params; p.naShadowFeedback = c->na.shadowFeedback.ptr; p.naRrFix = c->na.rrFix.ptr;
+        p.scene.proxyCounters = c->na.proxyCounters.ptr; p.scene.proxyIndices = c->na.proxyIndices.ptr;
+        launches += 4;
+    }
     for (uint32_t sub = 0; sub < r.subSampleCount; sub++)
     {
         p.firstSampleIndex = c->consts.sampleBaseIndex + sub;
         CU(cudaMemsetAsync(c->counters.ptr, 0, kCounterWords * sizeof(uint32_t), s));
+        if (na) CU(cudaMemsetAsync(c->na.rrFix.ptr, 0, size_t(c->capacity) * 4, s));
         p.iteration = 0;
         launchRtFillGenerate(p, c->grid, s); launches++;
         for (uint32_t it = 0; it < fillIterations; it++)
         {
             p.iteration = it;
-            launchTraceClosest(p, c->grid, false, s); launchRtShade(p, c->grid, true, s); launchTraceShadowRealtime(p, c->grid, s); launches += 3;
+            launchTraceClosest(p, c->grid, false, s);
+            if (na) { launchRtShadeNeeat(p, c->grid, s); launchTraceShadowRealtimeNeeat(p, c->grid, s); }
+            else { launchRtShade(p, c->grid, true, s); launchTraceShadowRealtime(p, c->grid, s); }
+            launches += 3;
         }
         launchRtFillCommit(p, c->grid, s); launches++;
     }
@@ -707,6 +737,122 @@ extern "C" RTXPT_API int rtxpt_b200_denoiser_final_merge(rtxpt_ctx* c, uint32_t 
     p.rt.dnPlane = stablePlaneIndex; p.rt.dnDenoisedDiff = static_cast<const uint2*>(dDiff); p.rt.dnDenoisedSpec = static_cast<const uint2*>(dSpec);
     launchDnFinalMerge(p, c->grid, s);
     CU(cudaGetLastError());
+    return RTXPT_OK;
+}
+
+// ---- NEE-AT temporal feedback ------------------------------------------------------------------------------------------------------------------
+// Frame order (Sample.cpp:1412, :2438-2520): set_constants; neeat_update_begin; [realtime: BUILD pass]; neeat_update_end; radiance pass(es).  rtxpt_b200_path_trace_realtime runs
+// update_end itself after its BUILD pass; reference mode calls it explicitly (depth / motion guides of the previous frame, as RTXPT's render targets hold at that point).
+static bool neeatActive(const rtxpt_ctx* c) { return c->haveConstants && c->consts.NEEType == 2 && c->consts.NEEATFeedback != 0; }
+static int neeatEnsure(rtxpt_ctx* c, cudaStream_t s)
+{
+    rtxpt_ctx::Neeat& n = c->na;
+    const uint32_t W = c->tableWidth, H = c->tableHeight, L = uint32_t(c->lightState.lights.size());
+    if (n.allocated && n.host.W == W && n.host.H == H && n.lightCount == L) return RTXPT_OK;
+    CU(cudaStreamSynchronize(c->stream)); CU(cudaStreamSynchronize(s));
+    n.release(); n.host.reset(W, H); n.lightCount = L;
+    const size_t P = size_t(W) * H, B = size_t((W + 1) / 2) * ((H + 1) / 2), T = size_t(neeat::HostState::tilesX(W)) * neeat::HostState::tilesY(H) * neeat::kLocalProxyCount;
+    const size_t proxyCapacity = size_t(neeat::kProxyRatio) * std::max<uint32_t>(L, neeat::kMaxLights / 10) + L;           // every light rounds its share up
+    CU(n.fbWeight.alloc(P)); CU(n.scratchWeight.alloc(P)); CU(n.blendedWeight.alloc(B)); CU(n.historyDepth.alloc(P)); CU(n.fbCandidate.alloc(P)); CU(n.scratchCandidate.alloc(P)); CU(n.blendedCandidate.alloc(B));
+    CU(n.local.alloc(T)); CU(n.counters.alloc(size_t(L) + 1)); CU(n.proxyCounters.alloc(L)); CU(n.proxyOffsets.alloc(size_t(L) + 1)); CU(n.proxyIndices.alloc(proxyCapacity)); CU(n.samplingProxyCount.alloc(1));
+    CU(n.scanBlockSums.alloc(1024)); CU(n.lightWeights.alloc(L)); CU(n.rrFix.alloc(c->capacity)); CU(n.shadowFeedback.alloc(c->capacity));
+    CU(cudaMemsetAsync(n.rrFix.ptr, 0, size_t(c->capacity) * 4, s));
+    CU(cudaMemsetAsync(n.fbWeight.ptr, 0, P * 4, s)); CU(cudaMemsetAsync(n.scratchWeight.ptr, 0, P * 4, s)); CU(cudaMemsetAsync(n.blendedWeight.ptr, 0, B * 4, s)); CU(cudaMemsetAsync(n.historyDepth.ptr, 0, P * 4, s));
+    CU(cudaMemsetAsync(n.fbCandidate.ptr, 0xFF, P * 4, s)); CU(cudaMemsetAsync(n.scratchCandidate.ptr, 0xFF, P * 4, s)); CU(cudaMemsetAsync(n.blendedCandidate.ptr, 0xFF, B * 4, s));
+    CU(cudaMemsetAsync(n.local.ptr, 0, T * 4, s)); CU(cudaMemsetAsync(n.samplingProxyCount.ptr, 0, 4, s));
+    n.allocated = true;
+    return RTXPT_OK;
+}
+static void neeatBind(rtxpt_ctx* c)
+{
+    rtxpt_ctx::Neeat& n = c->na; neeat::Params& p = n.params;
+    p.fbWeight = n.fbWeight.ptr; p.fbCandidate = n.fbCandidate.ptr; p.scratchWeight = n.scratchWeight.ptr; p.scratchCandidate = n.scratchCandidate.ptr; p.blendedWeight = n.blendedWeight.ptr;
+    p.blendedCandidate = n.blendedCandidate.ptr; p.historyDepth = n.historyDepth.ptr; p.localSamplingBuffer = n.local.ptr; p.feedbackCounters = n.counters.ptr; p.lightWeights = n.lightWeights.ptr;
+    p.proxyCounters = n.proxyCounters.ptr; p.proxyOffsets = n.proxyOffsets.ptr; p.proxyIndices = n.proxyIndices.ptr; p.samplingProxyCount = n.samplingProxyCount.ptr;
+    p.depth = c->depth.ptr; p.motion = c->motionVectors.ptr;
+}
+extern "C" RTXPT_API int rtxpt_b200_neeat_reset(rtxpt_ctx* c)
+{
+    if (!c) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null context");
+    cudaSetDevice(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    c->na.release();
+    return RTXPT_OK;
+}
+extern "C" RTXPT_API int rtxpt_b200_neeat_update_begin(rtxpt_ctx* c, void* cudaStream)
+{
+    if (!c) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null context");
+    if (!c->haveScene || !neeatActive(c)) return fail(RTXPT_ERR_INVALID_ARGUMENT, "NEE-AT feedback needs a scene and constants with NEEType == 2 and NEEATFeedback != 0");
+    if (c->lightState.proxyIndices.empty()) return fail(RTXPT_ERR_INVALID_ARGUMENT, "the scene has no lights to sample");
+    cudaSetDevice(c->device);
+    cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
+    int rc = neeatEnsure(c, s); if (rc != RTXPT_OK) return rc;
+    rtxpt_ctx::Neeat& n = c->na;
+    // the power-based weights follow the light list (uploadLights re-bakes them when the environment or the importance settings change)
+    CU(cudaMemcpyAsync(n.lightWeights.ptr, c->lightState.weights.data(), size_t(n.lightCount) * 4, cudaMemcpyHostToDevice, s));
+    neeat::beginFrame(n.host, n.params, c->consts.NEEType, n.lightCount, c->lightState.weightsSum);
+    neeatBind(c);
+    launchNeeatUpdateBegin(n.params, n.host.settings.preFilter, n.scanBlockSums.ptr, c->grid.smCount, s);
+    CU(cudaGetLastError());
+    n.frameBegun = true;
+    return RTXPT_OK;
+}
+extern "C" RTXPT_API int rtxpt_b200_neeat_update_end(rtxpt_ctx* c, void* cudaStream)
+{
+    if (!c) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null context");
+    if (!neeatActive(c) || !c->na.allocated || !c->na.frameBegun) return fail(RTXPT_ERR_INVALID_ARGUMENT, "rtxpt_b200_neeat_update_begin has not run for this frame");
+    if (!c->depth.ptr || !c->motionVectors.ptr) return fail(RTXPT_ERR_INVALID_ARGUMENT, "NEE-AT feedback reprojects with the depth / motion guides: create the context with RTXPT_CFG_EXPORT_GUIDES or use realtime mode");
+    cudaSetDevice(c->device);
+    cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
+    neeatBind(c);
+    launchNeeatUpdateEnd(c->na.params, s);
+    CU(cudaGetLastError());
+    neeat::endFrame(c->na.host, c->na.params);
+    c->na.frameBegun = false;
+    return RTXPT_OK;
+}
+// debugging / tests: `what` as in the oracle's oracle_neeat_get (0-1 feedback, 2-3 processed, 4-5 blended reservoirs, 6 tile lists, 7 proxy counters, 8 control words, 11 proxy table)
+extern "C" RTXPT_API int rtxpt_b200_neeat_readback(rtxpt_ctx* c, int what, void* dst, size_t dstBytes, size_t* outBytes)
+{
+    if (!c || !dst || !outBytes) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (!c->na.allocated) return fail(RTXPT_ERR_INVALID_ARGUMENT, "NEE-AT feedback state does not exist before rtxpt_b200_neeat_update_begin");
+    cudaSetDevice(c->device);
+    rtxpt_ctx::Neeat& n = c->na; const neeat::Params& p = n.params;
+    CU(cudaStreamSynchronize(c->stream));
+    uint32_t total = 0; CU(cudaMemcpy(&total, n.samplingProxyCount.ptr, 4, cudaMemcpyDeviceToHost));
+    const void* src = nullptr; size_t bytes = 0; uint32_t ctl[8];
+    const size_t P = size_t(p.W) * p.H, B = size_t(p.blendedW) * p.blendedH;
+    switch (what)
+    {
+    case 0: src = n.fbWeight.ptr; bytes = P * 4; break;          case 1: src = n.fbCandidate.ptr; bytes = P * 4; break;
+    case 2: src = n.scratchWeight.ptr; bytes = P * 4; break;     case 3: src = n.scratchCandidate.ptr; bytes = P * 4; break;
+    case 4: src = n.blendedWeight.ptr; bytes = B * 4; break;     case 5: src = n.blendedCandidate.ptr; bytes = B * 4; break;
+    case 6: src = n.local.ptr; bytes = n.local.count * 4; break; case 7: src = n.proxyCounters.ptr; bytes = size_t(n.lightCount) * 4; break;
+    case 11: src = n.proxyIndices.ptr; bytes = size_t(total) * 4; break;
+    case 8:
+    {
+        uint32_t invalid = 0; CU(cudaMemcpy(&invalid, n.counters.ptr + n.lightCount, 4, cudaMemcpyDeviceToHost));
+        ctl[0] = p.tilesX; ctl[1] = p.tilesY; ctl[2] = p.jitterX; ctl[3] = p.jitterY; ctl[4] = total; ctl[5] = p.updateCounter; ctl[6] = p.lastFrameFeedbackAvailable;
+        ctl[7] = p.lastFrameFeedbackAvailable ? p.W * p.H - invalid : 0u;
+        if (dstBytes < sizeof(ctl)) return fail(RTXPT_ERR_INVALID_ARGUMENT, "destination too small"); memcpy(dst, ctl, sizeof(ctl)); *outBytes = sizeof(ctl); return RTXPT_OK;
+    }
+    default: return fail(RTXPT_ERR_INVALID_ARGUMENT, "unknown NEE-AT buffer %d", what);
+    }
+    if (dstBytes < bytes) return fail(RTXPT_ERR_INVALID_ARGUMENT, "destination too small (%zu < %zu)", dstBytes, bytes);
+    CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    *outBytes = bytes;
+    return RTXPT_OK;
+}
+// tests: overwrite the feedback reservoirs (f32 weight, u32 candidate, image sized) and mark them as filled
+extern "C" RTXPT_API int rtxpt_b200_neeat_debug_set_feedback(rtxpt_ctx* c, const float* weight, const uint32_t* candidate)
+{
+    if (!c || !weight || !candidate) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (!c->na.allocated) return fail(RTXPT_ERR_INVALID_ARGUMENT, "NEE-AT feedback state does not exist before rtxpt_b200_neeat_update_begin");
+    cudaSetDevice(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    const size_t P = size_t(c->na.host.W) * c->na.host.H;
+    CU(cudaMemcpy(c->na.fbWeight.ptr, weight, P * 4, cudaMemcpyHostToDevice)); CU(cudaMemcpy(c->na.fbCandidate.ptr, candidate, P * 4, cudaMemcpyHostToDevice));
+    c->na.host.feedbackBufferFilled = true;
     return RTXPT_OK;
 }
 

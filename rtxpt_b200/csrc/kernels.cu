@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB * kTraceCtaScale) k_trace_
 // ---- shadow rays ----------------------------------------------------------------------------------------------------------------------------
 // REALTIME (FILL pass of realtime mode): the radiance is attenuated by 1 / sub-sample count and comes with a specular average chosen by the shade
 // kernel (sign bits of the record's first word, shade.cuh) - AccumulatePathRadiance of PATH_TRACER_MODE_FILL_STABLE_PLANES (PathTracer.hlsli:145-159)
-template <bool COUNT, int MINB, bool REALTIME = false>
+template <bool COUNT, int MINB, bool REALTIME = false, bool NEEAT = false>
 __global__ void __launch_bounds__(kTraceThreads, MINB * kTraceCtaScale) k_trace_shadow(const __grid_constant__ LaunchParams p)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -207,6 +207,17 @@ __global__ void __launch_bounds__(kTraceThreads, MINB * kTraceCtaScale) k_trace_
                     s2.z = packHalf2NoClamp(clampf(lx, 0.f, kHalfMax), clampf(ly, 0.f, kHalfMax));
                     s2.w = packHalf2NoClamp(clampf(lz, 0.f, kHalfMax), clampf(lw, 0.f, kHalfMax));
                     p.wf.s2[slot] = s2;
+                }
+                if constexpr (NEEAT)
+                {   // the light was visible: the pixel's feedback reservoir hears about it (PathTracerNEE.hlsli:276-283) and the path's next shade takes the roulette
+                    // outcome that belongs to a visible sample (shade.cuh)
+                    const uint4 fb = p.naShadowFeedback[record];
+                    if (fb.w & 0x80000000u)
+                    {
+                        const uint id = p.wf.pixelOfSlot[slot];
+                        neeat::Reservoir::at(p.na.fbWeight, p.na.fbCandidate, size_t(id & 0xFFFFu) * p.na.W + (id >> 16)).add(__uint_as_float(fb.z), fb.x & 0x7FFFFFFFu, __uint_as_float(fb.y), (fb.x & 0x80000000u) != 0);
+                        p.naRrFix[slot] = fb.w;
+                    }
                 }
                 visibleCount++;
             }
@@ -363,6 +374,7 @@ cudaError_t configureKernels(int maxSmemOptin)
     ALLOW((k_trace_closest<false, 2>)); ALLOW((k_trace_closest<false, 3>)); ALLOW((k_trace_closest<false, 4>)); ALLOW((k_trace_closest<true, 2>));
     ALLOW((k_trace_shadow<false, 2>)); ALLOW((k_trace_shadow<false, 3>)); ALLOW((k_trace_shadow<false, 4>)); ALLOW((k_trace_shadow<true, 2>));
     ALLOW((k_trace_shadow<false, 4, true>)); ALLOW((k_trace_shadow<false, 2, true>));
+    ALLOW((k_trace_shadow<false, 4, true, true>)); ALLOW((k_trace_shadow<false, 2, true, true>));
     ALLOW(k_trace_rays<false>); ALLOW(k_trace_rays<true>);
 #undef ALLOW
     return cudaSuccess;
@@ -406,6 +418,12 @@ void launchTraceShadowRealtime(const LaunchParams& p, const GridConfig& g, cudaS
     const int grid = g.smCount * g.traceBlocksPerSM; const size_t smem = traceSmemBytes(p);
     if (g.traceBlocksPerSM >= 4) launchTrace(k_trace_shadow<false, 4, true>, grid, smem, s, p, g);
     else launchTrace(k_trace_shadow<false, 2, true>, g.smCount * 2, smem, s, p, g);
+}
+void launchTraceShadowRealtimeNeeat(const LaunchParams& p, const GridConfig& g, cudaStream_t s)
+{
+    const int grid = g.smCount * g.traceBlocksPerSM; const size_t smem = traceSmemBytes(p);
+    if (g.traceBlocksPerSM >= 4) launchTrace(k_trace_shadow<false, 4, true, true>, grid, smem, s, p, g);
+    else launchTrace(k_trace_shadow<false, 2, true, true>, g.smCount * 2, smem, s, p, g);
 }
 void launchCommitAccumulate(const LaunchParams& p, const GridConfig& g, cudaStream_t s) { k_commit_accumulate<<<g.smCount * 4, 256, 0, s>>>(p); }
 void launchTraceRays(const LaunchParams& p, const GridConfig& g, const RtxptRay* rays, uint32_t count, bool anyHit, RtxptHit* out, uint32_t* counters, uint32_t* cursor, cudaStream_t s)

@@ -36,6 +36,11 @@ void launchDebugBsdf(const float* dIn, uint32_t count, float* dOut, cudaStream_t
 void launchDebugRng(const uint32_t* dIn, uint32_t count, uint32_t* dOut, cudaStream_t s);
 
 void launchDnSpecHitT(const float* src, const float* depth, float* dst, int W, int H, cudaStream_t s);      // DenoisingGuidesBaker::DenoiseSpecHitT, one pass
+void launchRtShadeNeeat(const LaunchParams& p, const GridConfig& g, cudaStream_t s);               // FILL pass shade with NEE-AT feedback (realtime_kernels.cu)
+void launchTraceShadowRealtimeNeeat(const LaunchParams& p, const GridConfig& g, cudaStream_t s);   // + feedback insertion for visible samples (kernels.cu)
+namespace neeat { struct Params; }
+void launchNeeatUpdateBegin(const neeat::Params& p, bool preFilter, uint* scanBlockSums, int smCount, cudaStream_t s);     // neeat_kernels.cu
+void launchNeeatUpdateEnd(const neeat::Params& p, cudaStream_t s);
 namespace rb { struct Params; }
 void launchReblurFrame(const rb::Params& p, cudaStream_t s);       // reblur_kernels.cu: the eight ReBLUR passes of one stable plane
 

@@ -470,7 +470,7 @@ void LightBaker::finalizeWeightsAndProxies(const RtxptPathTracerConstants& const
         }
         total += groupSum;
     }
-    st.weightsSum = total;
+    st.weightsSum = total; st.weights = w;
     const uint32_t budget = 12 * std::max(n, kMaxLights / 10);
     st.proxyCounters.assign(n, 0); st.proxyIndices.clear();
     for (uint32_t i = 0; i < n; i++)

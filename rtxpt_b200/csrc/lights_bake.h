@@ -24,6 +24,7 @@ struct LightBakeState
     std::vector<std::vector<float>> envRadianceMips;    // RGBA, fp16-rounded (EnvRadianceMap RGBA16F, .a = importance)
     uint32_t envMipCount = 0, triangleLightCount = 0;
     float weightsSum = 0;
+    std::vector<float> weights;                 // per light, power-based (ComputeWeight): what NEE-AT's usage feedback is blended into (neeat.cuh: proxyCountOfLight)
     bool envEnabled = false;
 };
 

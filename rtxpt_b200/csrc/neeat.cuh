@@ -263,24 +263,29 @@ PT_HD void p1bPixel(const Params& p, uint x, uint y)
     }
 }
 
-// P2 (FillTile): entry `slot` (0..127) of tile (tx, ty): the 8x8 window of processed reservoirs, then 64 top-up picks from the blended image around the tile.  The top-up
-// picks share one generator seeded per tile, so slot 64 + i needs the generator advanced 2 i draws: entries are produced by one thread per tile, in order.
-PT_HD void fillTile(const Params& p, uint tx, uint ty, uint* list /* 128 keys out */)
+// P2 (FillTile): key `slot` (0..127) of tile (tx, ty): slots 0..63 are the 8x8 window of processed reservoirs (x-major), slots 64..127 top-up picks from the blended image
+// around the tile.  The top-up picks share one generator seeded per tile (two draws each, in order), so the thread that produces slot 64 + i first advances its own copy 2 i
+// draws - at most 126 iterations of a five-instruction hash, which buys a tile filled by 128 independent lanes instead of one.
+PT_HD uint fillTileEntry(const Params& p, uint tx, uint ty, uint slot)
 {
     const int W = int(p.W), H = int(p.H), margin = int(kWindowSize - kTileSize) / 2;
     const int cellX = int(tx * kTileSize) - int(p.jitterX), cellY = int(ty * kTileSize) - int(p.jitterY);
-    uint n = 0;
-    for (int x = 0; x < int(kWindowSize); x++) for (int y = 0; y < int(kWindowSize); y++)
-        list[n++] = p.scratchCandidate[size_t(mirrorCoord(cellY - margin + y, H)) * W + mirrorCoord(cellX - margin + x, W)];
-    MicroRng rng = MicroRng::make(tx, ty, p.updateCounter, 5);
-    const float centerX = float(cellX) + 4.0f, centerY = float(cellY) + 4.0f, radius = float(kWindowSize) * 4.0f;      // + kTileSize * 0.5: exact
-    for (uint i = 0; i < kTopUpSamples; i++)
+    uint key;
+    if (slot < kWindowSize * kWindowSize)
     {
+        const int x = int(slot / kWindowSize), y = int(slot % kWindowSize);
+        key = p.scratchCandidate[size_t(mirrorCoord(cellY - margin + y, H)) * W + mirrorCoord(cellX - margin + x, W)];
+    }
+    else
+    {
+        MicroRng rng = MicroRng::make(tx, ty, p.updateCounter, 5);
+        for (uint i = 0; i < 2 * (slot - kWindowSize * kWindowSize); i++) rng.next();
+        const float centerX = float(cellX) + 4.0f, centerY = float(cellY) + 4.0f, radius = float(kWindowSize) * 4.0f;      // + kTileSize * 0.5: exact
         const float ox = fmul_rn(fsub_rn(rng.nextFloat(), 0.5f), radius), oy = fmul_rn(fsub_rn(rng.nextFloat(), 0.5f), radius);
         const int px = mirrorCoord(int(fadd_rn(fadd_rn(centerX, ox), 0.5f)), W), py = mirrorCoord(int(fadd_rn(fadd_rn(centerY, oy), 0.5f)), H);
-        list[n++] = p.blendedCandidate[size_t(py / int(kEarlyFeedbackTileSize)) * p.blendedW + px / int(kEarlyFeedbackTileSize)];
+        key = p.blendedCandidate[size_t(py / int(kEarlyFeedbackTileSize)) * p.blendedW + px / int(kEarlyFeedbackTileSize)];
     }
-    for (uint i = 0; i < kLocalProxyCount; i++) list[i] &= 0x007FFFFFu;          // the key a tuple can carry
+    return key & 0x007FFFFFu;           // the key a tuple can carry
 }
 // P3 for one tile whose 128 keys sit in `data` (shared memory on the device): one compare-exchange of the bitonic network for `thread` in [0, 64)
 PT_HD void bitonicStep(uint* data, uint thread, uint k, uint j)

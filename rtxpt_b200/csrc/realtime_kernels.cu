@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256) k_rt_fill_generate(const __grid_constant_
 }
 
 // ---- shade ------------------------------------------------------------------------------------------------------------------------------------------------------
-template <int MODE, bool ANALYTIC_LIGHTS>
+template <int MODE, bool ANALYTIC_LIGHTS, bool NEEAT = false>
 __global__ void __launch_bounds__(128, 3) k_rt_shade(const __grid_constant__ LaunchParams p)
 {
     uint* ctr = p.wf.counters + p.iteration * kCountersPerIter;
@@ -138,8 +138,9 @@ __global__ void __launch_bounds__(128, 3) k_rt_shade(const __grid_constant__ Lau
             {
                 const uint slot = queue[i];
                 PathRegs path; path.load(p.wf, slot, true);
-                if (cls == 0) shadeMiss<false, MODE>(p, path);
-                else shadeHit<false, ANALYTIC_LIGHTS, MODE>(p, path, slot, p.wf.hits[slot], out);
+                if constexpr (NEEAT) out.naRecord = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
+                if (cls == 0) shadeMiss<false, MODE, NEEAT>(p, path);
+                else shadeHit<false, ANALYTIC_LIGHTS, MODE, NEEAT>(p, path, slot, p.wf.hits[slot], out);
                 continues = (cls != 0) && out.continuePath;
                 if constexpr (MODE == kModeBuildStablePlanes)
                 {   // postProcessHit: when this branch has ended, continue with the next enqueued branch of the pixel (planes above the current one)
@@ -165,6 +166,7 @@ __global__ void __launch_bounds__(128, 3) k_rt_shade(const __grid_constant__ Lau
                     if (lane == leader) b = atomicAdd(ctr + kCtrShadowCount, __popc(peers));
                     b = __shfl_sync(peers, b, leader) + __popc(peers & ((1u << lane) - 1u));
                     p.wf.shadowOriginTMax[b] = out.shadow.originTMax; p.wf.shadowDirPath[b] = out.shadow.dirPath; p.wf.shadowRadiance[b] = out.shadow.radiance;
+                    if constexpr (NEEAT) p.naShadowFeedback[b] = out.naRecord;
                 }
             }
         }
@@ -333,6 +335,11 @@ void launchDnFinalMerge(const LaunchParams& p, const GridConfig& g, cudaStream_t
 
 void launchRtBuildGenerate(const LaunchParams& p, const GridConfig& g, cudaStream_t s) { k_rt_build_generate<<<g.smCount * 4, 256, 0, s>>>(p); }
 void launchRtFillGenerate(const LaunchParams& p, const GridConfig& g, cudaStream_t s) { k_rt_fill_generate<<<g.smCount * 4, 256, 0, s>>>(p); }
+void launchRtShadeNeeat(const LaunchParams& p, const GridConfig& g, cudaStream_t s)
+{   // FILL pass with NEE-AT feedback: tile-sampler candidates, MIS against the global table, feedback records for the shadow kernel
+    const int grid = g.smCount * 3;
+    if (p.scene.analyticLightCount != 0) k_rt_shade<kModeFillStablePlanes, true, true><<<grid, 128, 0, s>>>(p); else k_rt_shade<kModeFillStablePlanes, false, true><<<grid, 128, 0, s>>>(p);
+}
 void launchRtShade(const LaunchParams& p, const GridConfig& g, bool fill, cudaStream_t s)
 {
     const int grid = g.smCount * 3;

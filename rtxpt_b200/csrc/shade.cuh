@@ -137,6 +137,22 @@ PT_DEVICE float misForBsdf(const SceneView& sc, uint lightIndex, float bsdfPdf, 
     const float lightAvgPdf = (0.0f + globalLightPdf(sc, lightIndex)) * float(fullSamples);
     return misBalance(bsdfPdf, lightAvgPdf * solidAnglePdf);
 }
+// NEE-AT feedback active: the global table is the per-frame one (its total lives in device memory) and the previous vertex may also have drawn from the pixel's tile sampler
+// (LightSampler.hlsli:318-333: local candidates only for screen-space-coherent vertices); misPacked = NEEBSDFMISInfo of the previous vertex
+PT_DEVICE float naGlobalLightPdf(const LaunchParams& p, uint lightIndex) { return float(p.na.proxyCounters[lightIndex]) / float(*p.na.samplingProxyCount); }
+template <bool NEEAT>
+PT_DEVICE float misForBsdfT(const LaunchParams& p, uint pathId, uint misPacked, uint lightIndex, float bsdfPdf, float solidAnglePdf)
+{
+    if constexpr (!NEEAT) return misForBsdf(p.scene, lightIndex, bsdfPdf, solidAnglePdf, misPacked & 0x3F);
+    else
+    {
+        float localPdf = 0.0f;
+        if ((misPacked & (1u << 13)) && neeat::candidateLocalCount(p.na.localToGlobalSampleRatio, (misPacked >> 6) & 0x3F) > 0)
+            localPdf = neeat::sampleLocalPdf(p.na, neeat::localSamplingTilePos(p.na, pathId >> 16, pathId & 0xFFFFu), lightIndex);
+        const float lightAvgPdf = (localPdf + naGlobalLightPdf(p, lightIndex)) * float(misPacked & 0x3F);
+        return misBalance(bsdfPdf, lightAvgPdf * solidAnglePdf);
+    }
+}
 
 // ---- firefly filter (PathTracerHelpers.hlsli:183-219) ----------------------------------------------------------------------------
 PT_DEVICE float coneSpreadFromPdf(float pdf, float growth) { return growth * 2.0f * fastACos(fmaxf(-1.0f, 1.0f - (1.0f / pdf) / (2.0f * kPi))); }
@@ -387,7 +403,7 @@ PT_DEVICE void accumulatePathRadiance(const LaunchParams& p, PathRegs& path, flo
     }
 }
 
-template <bool EXPORT_GUIDES, int MODE = kModeReference>
+template <bool EXPORT_GUIDES, int MODE = kModeReference, bool NEEAT = false>
 PT_DEVICE void shadeMiss(const LaunchParams& p, PathRegs& path)
 {
     const float3 segmentOrigin = path.origin;
@@ -408,7 +424,7 @@ PT_DEVICE void shadeMiss(const LaunchParams& p, PathRegs& path)
             const uint cx = min(uint(uv.x * float(kEnvLookupDim)), kEnvLookupDim - 1), cy = min(uint(uv.y * float(kEnvLookupDim)), kEnvLookupDim - 1);
             const uint li = p.scene.envLookupMap[cy * kEnvLookupDim + cx];
             const uint nodeDim = p.scene.lights[li].direction2 >> 16;
-            misWeight = misForBsdf(p.scene, li, bsdfPdf, float(nodeDim * nodeDim) / (4.0f * kPi), mis & 0x3F);
+            misWeight = misForBsdfT<NEEAT>(p, path.id, mis, li, bsdfPdf, float(nodeDim * nodeDim) / (4.0f * kPi));
         }
         emission = lp3(misWeight * Le);
     }
@@ -423,13 +439,25 @@ PT_DEVICE void shadeMiss(const LaunchParams& p, PathRegs& path)
 }
 
 // ---- hit -----------------------------------------------------------------------------------------------------------------------------------
-struct HitOutputs { bool continuePath; bool emitShadow; ShadowRecord shadow; };
+struct HitOutputs { bool continuePath; bool emitShadow; ShadowRecord shadow; uint4 naRecord; };     // naRecord: NEE-AT feedback of the shadow record (kernels with NEEAT = true)
 
-template <bool EXPORT_GUIDES, bool ANALYTIC_LIGHTS, int MODE = kModeReference>
+template <bool EXPORT_GUIDES, bool ANALYTIC_LIGHTS, int MODE = kModeReference, bool NEEAT = false>
 PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4 hit, HitOutputs& out)
 {
     out.continuePath = false; out.emitShadow = false;
     constexpr bool kBuild = MODE == kModeBuildStablePlanes, kFill = MODE == kModeFillStablePlanes;
+    if constexpr (NEEAT)
+    {   // The previous vertex's light sample turned out visible: its feedback insertion drew one more number of the vertex's uniform sequence before Russian roulette did
+        // (PathTracerNEE.hlsli:276-283, PathTracer.hlsli:182-208).  Visibility is only known after the shadow kernel, so that vertex stored both roulette outcomes: the path
+        // state holds the "not visible" one, the shadow kernel published the other one here.
+        const uint fix = p.naRrFix[slot];
+        if (fix & 0x80000000u)
+        {
+            path.setFlag(kPFTerminateAtNextBounce, (fix & 0x40000000u) != 0);
+            path.setMisInfo_RuRu(path.misInfo(), f16tof32(fix & 0xFFFFu));
+            p.naRrFix[slot] = 0;
+        }
+    }
     const uint sampleIndex = (MODE == kModeReference) ? path.sampleIndex : p.firstSampleIndex;      // realtime passes: one sample index per launch, the word holds stableBranchID
     const float3 rayOrigin = path.origin, rayDir = path.dir;
     const float rayT = hit.x;
@@ -481,7 +509,7 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
         if ((misPacked & (1u << 15)) && bsdfPdf != 0 && s.neeTriangleLightIndex != kInvalidLight)
         {
             TriLight tl; tl.decode(p.scene.lights[s.neeTriangleLightIndex]);
-            misWeight = misForBsdf(p.scene, s.neeTriangleLightIndex, bsdfPdf, tl.solidAnglePdfForMIS(rayOrigin, s.posW), misPacked & 0x3F);
+            misWeight = misForBsdfT<NEEAT>(p, path.id, misPacked, s.neeTriangleLightIndex, bsdfPdf, tl.solidAnglePdfForMIS(rayOrigin, s.posW));
         }
         surfaceEmission = lp3(s.emission * misWeight);
     }
@@ -505,7 +533,7 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
                     if (bsdfPdf != 0)
                     {
                         const float cosThetaMax = sqrtf(fmaxf(0.0f, 1.0f - (radius * radius) / dot3(lv, lv)));
-                        mis = misForBsdf(p.scene, s.neeAnalyticLightIndex, bsdfPdf, 1.0f / (2.0f * kPi * (1.0f - cosThetaMax)), misPacked & 0x3F);
+                        mis = misForBsdfT<NEEAT>(p, path.id, misPacked, s.neeAnalyticLightIndex, bsdfPdf, 1.0f / (2.0f * kPi * (1.0f - cosThetaMax)));
                     }
                     surfaceEmission = surfaceEmission + lp3(radiance * mis);
                 }
@@ -611,14 +639,22 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
     // HandleNEE (PathTracerNEE.hlsli:303-346): candidates by weighted reservoir sampling, one shadow ray
     uint neeMis = 0;
     const uint fullSamples = min(63u, p.c.NEEFullSamples);      // this tier emits one shadow record per vertex: NEEFullSamples == 1 (reference default)
-    if (p.c.NEEEnabled && (bsdfLobes(s.bsdf) & kLobeNonDelta) != 0 && p.scene.samplingProxyCount != 0 && fullSamples > 0)
+    uint naFeedback = 0xFFFFFFFFu; float naFeedbackWeight = 0.0f;          // NEEAT: the picked light (| ssc << 31) and how much the pixel wanted it
+    if (p.c.NEEEnabled && (bsdfLobes(s.bsdf) & kLobeNonDelta) != 0 && (NEEAT ? *p.na.samplingProxyCount : p.scene.samplingProxyCount) != 0 && fullSamples > 0)
     {
         const uint candidateCount = p.c.NEECandidateSamples;
-        const bool isSSC = (preConeWidth / preSceneLength) < 0.3f;
+        const bool isSSC = (preConeWidth / preSceneLength) < (NEEAT ? p.na.screenSpaceVsWorldSpaceThreshold : 0.3f);
         neeMis = (1u << 15) | ((isSSC ? 1u : 0u) << 13) | ((candidateCount & 0x3F) << 6) | (fullSamples & 0x3F);
         float3 pickLi = mk3(0.f), pickDir = mk3(0.f); float pickDist = 0.f, pickSelPdf = 0.f, pickSolidPdf = 0.f;
         float weightSum = 0.f, pickWeight = 0.f; bool pickBsdfSampleable = true;
-        const uint M = p.scene.samplingProxyCount;
+        const uint M = NEEAT ? *p.na.samplingProxyCount : p.scene.samplingProxyCount;
+        const uint* __restrict__ proxyIndices = NEEAT ? p.na.proxyIndices : p.scene.proxyIndices;
+        const uint* __restrict__ proxyCounters = NEEAT ? p.na.proxyCounters : p.scene.proxyCounters;
+        // GetCandidateSampleCounts: the first globalCount candidates come from the global table, the rest from the pixel's tile sampler (screen-space-coherent vertices, once
+        // a frame of feedback has built the samplers)
+        const uint localCount = (NEEAT && isSSC) ? neeat::candidateLocalCount(p.na.localToGlobalSampleRatio, candidateCount) : 0u, globalCount = candidateCount - localCount;
+        const uint tileAddress = NEEAT ? neeat::localSamplingTilePos(p.na, path.id >> 16, path.id & 0xFFFFu) : 0u;
+        uint pickLight = 0xFFFFFFFFu; bool pickLocal = false;
         // The candidate loop is a chain of dependent random gathers (proxy table -> counter, light record).  The light selection draws are
         // every 4th value of the stream, so the proxy lookups of the first 8 candidates are issued up front and their light records
         // prefetched into L2/L1 before the loop consumes them one by one.
@@ -630,18 +666,18 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
             for (uint i = 0; i < kPrefetch; i++)
             {
                 preLight[i] = 0;
-                if (i < candidateCount)
+                if (i < globalCount)
                 {
                     const float rnd = pre.next(); pre.next(); pre.next(); pre.next();
-                    preLight[i] = __ldg(p.scene.proxyIndices + min(uint(rnd * float(M)), M - 1));
+                    preLight[i] = __ldg(proxyIndices + min(uint(rnd * float(M)), M - 1));
                 }
             }
             #pragma unroll
             for (uint i = 0; i < kPrefetch; i++)
-                if (i < candidateCount)
+                if (i < globalCount)
                 {
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(p.scene.lights + preLight[i]));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(p.scene.proxyCounters + preLight[i]));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(proxyCounters + preLight[i]));
                 }
         }
         #pragma unroll 1
@@ -653,9 +689,12 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
             {   // static indexing keeps preLight[] in registers
             case 0: lightIndex = preLight[0]; break; case 1: lightIndex = preLight[1]; break; case 2: lightIndex = preLight[2]; break; case 3: lightIndex = preLight[3]; break;
             case 4: lightIndex = preLight[4]; break; case 5: lightIndex = preLight[5]; break; case 6: lightIndex = preLight[6]; break; case 7: lightIndex = preLight[7]; break;
-            default: lightIndex = p.scene.proxyIndices[min(uint(rnd * float(M)), M - 1)]; break;
+            default: lightIndex = proxyIndices[min(uint(rnd * float(M)), M - 1)]; break;
             }
-            const float selectionPdf = float(p.scene.proxyCounters[lightIndex]) / float(M);
+            float selectionPdf;
+            const bool sampleIsLocal = NEEAT && i >= globalCount;
+            if (sampleIsLocal) lightIndex = neeat::sampleLocal(p.na, tileAddress, rnd, selectionPdf);
+            else selectionPdf = float(proxyCounters[lightIndex]) / float(M);
             const LightInfo li = p.scene.lights[lightIndex];
             const float r0 = uniformSG.next(), r1 = uniformSG.next();
             float3 lsPos = mk3(0.f), lsRadiance = mk3(0.f); float lsSolidPdf = 0.f; bool lsBsdfSampleable = true;
@@ -690,15 +729,23 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
             const float wrsWeight = maxComp(Li) * bsdf.pdf(dirToLight);
             const float wrsRnd = uniformSG.next();
             weightSum += wrsWeight;
-            if (wrsRnd < sat(wrsWeight / weightSum)) { pickLi = Li; pickDir = dirToLight; pickDist = dist; pickSelPdf = selectionPdf; pickSolidPdf = lsSolidPdf; pickWeight = wrsWeight; pickBsdfSampleable = lsBsdfSampleable; }
+            if (wrsRnd < sat(wrsWeight / weightSum)) { pickLi = Li; pickDir = dirToLight; pickDist = dist; pickSelPdf = selectionPdf; pickSolidPdf = lsSolidPdf; pickWeight = wrsWeight; pickBsdfSampleable = lsBsdfSampleable; if (NEEAT) { pickLight = lightIndex; pickLocal = sampleIsLocal; } }
         }
         pickLi = pickLi * (1.0f / (pickWeight / weightSum));
         if (anyPositive(pickLi))
         {   // ProcessLightSample with visibility deferred to the shadow kernel
             const float fadeOut = (s.shadowNoLFadeout > 0) ? sat((dot3(pickDir, s.vertexN) - s.shadowNoLFadeout) / (2.0f * s.shadowNoLFadeout)) : 1.0f;
-            const float wrsMIS = misBalance(pickSelPdf, 0.0f) / float(candidateCount);     // all candidates come from the global table in this tier
+            // ComputeLightSelectionPdfs: the pdf the other sampler would have picked this light with, and how many candidates this sampler drew
+            float otherPdf = 0.0f, thisCount = float(candidateCount);
+            if constexpr (NEEAT)
+            {
+                thisCount = float(globalCount);
+                if (pickLocal) { otherPdf = naGlobalLightPdf(p, pickLight); thisCount = float(localCount); }
+                else if (localCount != 0) otherPdf = neeat::sampleLocalPdf(p.na, tileAddress, pickLight);
+            }
+            const float wrsMIS = misBalance(pickSelPdf, otherPdf) / thisCount;             // without feedback all candidates come from the global table
             const float scatterPdfForDir = bsdf.pdf(pickDir);
-            const float pathMIS = misBalance(pickSelPdf * float(fullSamples) * pickSolidPdf, pickBsdfSampleable ? scatterPdfForDir : 0.0f);    // LightSampleableByBSDF
+            const float pathMIS = misBalance((pickSelPdf + otherPdf) * float(fullSamples) * pickSolidPdf, pickBsdfSampleable ? scatterPdfForDir : 0.0f);    // LightSampleableByBSDF
             const float3 Li = pickLi * (fadeOut * wrsMIS * pathMIS / float(fullSamples));
             const float4 bsdfThp = bsdf.eval(pickDir);
             float3 radiance = mk3(bsdfThp.x, bsdfThp.y, bsdfThp.z) * Li;
@@ -712,6 +759,11 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
             }
             radiance = radiance * preThp;
             specAvg *= average(preThp);
+            if constexpr (NEEAT)
+            {   // InsertFeedbackFromNEE's weight (un-filtered radiance x path throughput, biased towards globally improbable lights), inserted by the shadow kernel if visible
+                naFeedback = pickLight | (isSSC ? 0x80000000u : 0u);
+                naFeedbackWeight = __fdiv_rn(radianceAvg * average(preThp), powf(naGlobalLightPdf(p, pickLight), 0.65f));
+            }
             const float faceSide = dot3(s.N, pickDir) >= 0 ? 1.0f : -1.0f;
             const float3 o = offsetRayOrigin(s.posW, s.faceN * faceSide);
             out.emitShadow = true;
@@ -739,8 +791,24 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
         const float rrVal = sqrtf(luminance(path.thp()));
         float prob = sat(0.85f - rrVal); prob = prob * prob;
         prob = sat(prob + fmaxf(0.0f, (float(path.vertexIndex()) / float(p.c.bounceCount) - 0.4f)));
-        if (uniformSG.next() < prob) shouldTerminate = true;
+        const bool finished = shouldTerminate;
+        const float rrRnd = uniformSG.next();
+        if constexpr (NEEAT)
+        {   // had the light sample been visible, rrRnd is the feedback reservoir's number and roulette gets the next one: keep that outcome for the shadow kernel to publish
+            if (out.emitShadow && p.na.temporalFeedbackRequired)
+            {
+                const bool altTerminate = finished || (uniformSG.next() < prob);
+                out.naRecord = make_uint4(naFeedback, __float_as_uint(naFeedbackWeight), __float_as_uint(rrRnd),
+                                          0x80000000u | (altTerminate ? 0x40000000u : 0u) | (altTerminate ? f32tof16(path.ruRuCorrection()) : f32tof16(1.0f / (1.0f - prob))));
+            }
+        }
+        if (rrRnd < prob) shouldTerminate = true;
         else path.setMisInfo_RuRu(path.misInfo(), lp(1.0f / (1.0f - prob)));
+    }
+    else if constexpr (NEEAT)
+    {
+        if (out.emitShadow && p.na.temporalFeedbackRequired)
+            out.naRecord = make_uint4(naFeedback, __float_as_uint(naFeedbackWeight), __float_as_uint(uniformSG.next()), 0x80000000u | (shouldTerminate ? 0x40000000u : 0u) | f32tof16(path.ruRuCorrection()));
     }
     if (shouldTerminate) path.setFlag(kPFTerminateAtNextBounce, true);
     out.continuePath = path.hasFlag(kPFActive);

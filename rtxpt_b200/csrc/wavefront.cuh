@@ -8,6 +8,7 @@
 // (stableBranchID of the reference payload is unused in reference mode; its word carries the path's sample index instead.)
 #pragma once
 #include "device_math.cuh"
+#include "neeat.cuh"
 #include "scene_device.cuh"
 
 namespace pt {
@@ -90,6 +91,10 @@ struct LaunchParams
     uint accumulatedSamples;        // before this call
     uint doAccumulate;
     RealtimeParams rt;
+    // NEE-AT temporal feedback (kernels instantiated with NEEAT = true only; appended so that every other kernel's parameter offsets stay what they were)
+    neeat::Params na;
+    uint4* naShadowFeedback;        // per shadow record: light | ssc << 31, feedback weight, reservoir random, Russian roulette outcome had the sample been visible
+    uint* naRrFix;                  // per path slot: set by the shadow kernel when the sample was visible, consumed by the next shade of the path
 };
 
 // ---- packed path-state accessors (PathState.hlsli:125-200) ------------------------------------------------------------------

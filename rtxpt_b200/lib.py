@@ -49,6 +49,11 @@ _SIGNATURES = {
     "rtxpt_b200_path_trace_realtime": [C.c_void_p, C.c_int, C.c_void_p],
     "rtxpt_b200_denoiser_prepare_inputs": [C.c_void_p, C.c_uint32, C.c_int, C.POINTER(S.DenoiserConstants), C.c_void_p],
     "rtxpt_b200_denoiser_final_merge": [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p],
+    "rtxpt_b200_neeat_update_begin": [C.c_void_p, C.c_void_p],
+    "rtxpt_b200_neeat_update_end": [C.c_void_p, C.c_void_p],
+    "rtxpt_b200_neeat_reset": [C.c_void_p],
+    "rtxpt_b200_neeat_readback": [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)],
+    "rtxpt_b200_neeat_debug_set_feedback": [C.c_void_p, C.c_void_p, C.c_void_p],
     "rtxpt_b200_denoise_spec_hit_t": [C.c_void_p, C.c_void_p],
     "rtxpt_b200_reblur_denoise": [C.c_void_p, C.c_uint32, C.POINTER(S.ReblurFrame), C.c_void_p],
     "rtxpt_b200_denoise_realtime": [C.c_void_p, C.POINTER(S.DenoiserConstants), C.POINTER(S.ReblurFrame), C.c_void_p],
@@ -249,6 +254,23 @@ class Context:
             if d_diff is None: d_diff = self.device_ptr(S.BUFFER_DENOISER_DIFF_RADIANCE_HITDIST_F16)[0]
             if d_spec is None: d_spec = self.device_ptr(S.BUFFER_DENOISER_SPEC_RADIANCE_HITDIST_F16)[0]
         _check(self.L.rtxpt_b200_denoiser_final_merge(self.h, plane, d_diff, d_spec, stream), self.L)
+
+    # ---- NEE-AT temporal feedback: per frame set_constants; neeat_update_begin; path_trace_realtime (runs update_end after its BUILD pass) ----
+    def neeat_update_begin(self, stream=None): _check(self.L.rtxpt_b200_neeat_update_begin(self.h, stream), self.L)
+
+    def neeat_update_end(self, stream=None): _check(self.L.rtxpt_b200_neeat_update_end(self.h, stream), self.L)
+
+    def neeat_reset(self): _check(self.L.rtxpt_b200_neeat_reset(self.h), self.L)
+
+    def neeat_raw(self, what, dtype, count):
+        """Same `what` codes as the oracle's oracle_neeat_get (0-1 feedback, 2-3 processed, 4-5 blended reservoirs, 6 tile lists, 7 proxy counters, 8 control, 11 proxy table)."""
+        a = np.zeros(count, dtype); n = C.c_size_t()
+        _check(self.L.rtxpt_b200_neeat_readback(self.h, what, a.ctypes.data, a.nbytes, C.byref(n)), self.L)
+        return a[: n.value // a.itemsize]
+
+    def neeat_set_feedback(self, weight, candidate):
+        w = np.ascontiguousarray(weight, np.float32); c = np.ascontiguousarray(candidate, np.uint32)
+        _check(self.L.rtxpt_b200_neeat_debug_set_feedback(self.h, w.ctypes.data, c.ctypes.data), self.L)
 
     def denoise_spec_hit_t(self, stream=None):
         _check(self.L.rtxpt_b200_denoise_spec_hit_t(self.h, stream), self.L)

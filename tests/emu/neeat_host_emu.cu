@@ -71,7 +71,7 @@ extern "C" int neeat_emu_update_end(void* h, const float* depth, const uint16_t*
     for (uint32_t ty = 0; ty < p.tilesY; ty++) for (uint32_t tx = 0; tx < p.tilesX; tx++)
     {
         uint32_t data[neeat::kLocalProxyCount];
-        neeat::fillTile(p, tx, ty, data);
+        for (uint32_t slot = 0; slot < neeat::kLocalProxyCount; slot++) data[slot] = neeat::fillTileEntry(p, tx, ty, slot);
         for (uint32_t k = 2; k <= neeat::kLocalProxyCount; k <<= 1) for (uint32_t j = k / 2; j > 0; j /= 2) for (uint32_t t = 0; t < neeat::kLocalProxyCount / 2; t++) neeat::bitonicStep(data, t, k, j);
         const uint32_t base = neeat::tileBaseAddress(p, tx, ty);
         for (uint32_t loc = 0; loc < neeat::kLocalProxyCount; loc++) i.local[base + loc] = neeat::packMiniList(data[loc], neeat::runLength(data, loc));
