@@ -146,6 +146,15 @@ ORC_API int oracle_neeat_get(void* p, int what, void* out, size_t bytes)
     memcpy(out, src, n);
     return int(n);
 }
+// sampler-side functions of the local tile sampler for pixel (px, py): out = { SampleLocal's light, its pdf, SampleLocalPDF( lightForPdf ) }
+ORC_API int oracle_neeat_sample_local(void* p, uint32_t px, uint32_t py, float rnd, uint32_t lightForPdf, float* out)
+{
+    OracleCtx* c = (OracleCtx*)p; const NeeatState& s = c->neeat; if (s.W == 0) return -1;
+    const uint tile = LocalSamplingTilePos(s, px, py); float pdf = 0;
+    const uint light = SampleLocal(s, tile, rnd, pdf);
+    out[0] = float(light); out[1] = pdf; out[2] = SampleLocalPDF(s, tile, lightForPdf);
+    return 0;
+}
 // test hook: overwrite the feedback reservoirs (same layouts as `what` 0 / 1)
 ORC_API int oracle_neeat_set_feedback(void* p, const float* weight, const uint32_t* candidate)
 {

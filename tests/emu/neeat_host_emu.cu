@@ -99,3 +99,13 @@ extern "C" int neeat_emu_get(void* h, int what, void* out, size_t bytes)
     memcpy(out, src, n);
     return int(n);
 }
+
+// sampler-side functions (what the NEEAT shade kernel calls) for pixel (px, py): out = { sampleLocal's light, its pdf, sampleLocalPdf( lightForPdf ) }
+extern "C" int neeat_emu_sample_local(void* h, uint32_t px, uint32_t py, float rnd, uint32_t lightForPdf, float* out)
+{
+    Instance& i = *static_cast<Instance*>(h); i.bind();
+    const uint32_t tile = neeat::localSamplingTilePos(i.p, px, py); float pdf = 0;
+    const uint32_t light = neeat::sampleLocal(i.p, tile, rnd, pdf);
+    out[0] = float(light); out[1] = pdf; out[2] = neeat::sampleLocalPdf(i.p, tile, lightForPdf);
+    return 0;
+}

@@ -42,6 +42,18 @@ def test_feedback_passes_equal_the_oracle(oracle, moving):
         o.neeat_update_end(g["depth"], g["motion"]); port.update_end(g["depth"], g["motion"]); _compare(o, port, W, H, n_lights, "end")
         o.render(0, 1)                                                                       # reference-mode radiance pass: NEE draws local + global candidates and inserts feedback
         prev = cam
+    # the sampler-side functions the NEEAT shade kernel calls, on the tile lists both sides now hold: same light, same pdfs, for lights inside and outside the tile
+    import ctypes as C
+    Lo, Le = oracle.lib(), emu.lib()
+    for L_, fn in ((Lo, "oracle_neeat_sample_local"), (Le, "neeat_emu_sample_local")): getattr(L_, fn).argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_uint32, C.c_void_p]
+    rng = np.random.default_rng(9); hits = 0
+    for _ in range(400):
+        px, py, rnd = int(rng.integers(0, W)), int(rng.integers(0, H)), float(rng.random()); a = np.zeros(3, np.float32); b = np.zeros(3, np.float32)
+        probe = int(rng.integers(n_lights - 28, n_lights))
+        assert Lo.oracle_neeat_sample_local(o.h, px, py, rnd, probe, a.ctypes.data) == 0 and Le.neeat_emu_sample_local(port.h, px, py, rnd, probe, b.ctypes.data) == 0
+        assert np.array_equal(a, b) and 0 < a[1] <= 1 and a[0] < n_lights, (px, py, a, b)
+        hits += a[2] > 0
+    assert 0 < hits < 400                                                                   # the binary search both finds and misses
     st = o.neeat_get()
     assert st["available"] and st["valid_feedback"] > 0.3 * W * H
     if moving: assert np.abs(g["motion"][..., 0].astype(np.float32)).mean() > 1.0                # the dolly really exercised reprojection (whole-pixel shifts)
