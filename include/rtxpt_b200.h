@@ -388,8 +388,9 @@ RTXPT_API int rtxpt_b200_denoiser_final_merge(rtxpt_ctx* ctx, uint32_t stablePla
  * ComputeProxyCounts, UpdateEnd's P1a / P1b / P2 / P3 / ClearFeedbackHistory, LightsBaker.cpp:1203-1225, :1331-1418).  Active with NEEType == 2 && NEEATFeedback != 0: NEE then draws
  * ComputeCandidateSampleLocalCount( 0.65, NEECandidateSamples ) of its candidates from the pixel's 8x8-tile sampler once a frame of feedback exists, mixes them with the global ones by
  * MIS, and records which light each pixel wanted.  Per frame: set_constants; neeat_update_begin; neeat_update_end (rtxpt_b200_path_trace_realtime calls it itself after its BUILD
- * pass; reference mode: call it before rtxpt_b200_path_trace, the context must export guides); then trace.  Sub-samples of a reference-mode call run one per wavefront while
- * feedback is active (a pixel's reservoir is updated by one path at a time, as in the reference). */
+ * pass; reference mode: call it before rtxpt_b200_path_trace - it reprojects with the guides the previous frame exported, so the context needs RTXPT_CFG_EXPORT_GUIDES); then
+ * trace.  Sub-samples of a reference-mode call run one per wavefront while feedback is active (a pixel's reservoir is updated by one path at a time, as in the reference).
+ * Single GPU: the tile partition does not carry the reservoirs. */
 RTXPT_API int rtxpt_b200_neeat_update_begin(rtxpt_ctx* ctx, void* cudaStream);
 RTXPT_API int rtxpt_b200_neeat_update_end(rtxpt_ctx* ctx, void* cudaStream);
 RTXPT_API int rtxpt_b200_neeat_reset(rtxpt_ctx* ctx);                 /* LightsBaker::BakeSettings::ResetFeedback: drop all feedback state */

@@ -99,12 +99,12 @@ struct rtxpt_ctx
     // NEE-AT temporal feedback (consts.NEEType == 2 && consts.NEEATFeedback): LightsBaker's frame state, reservoirs, tile samplers and the per-frame global proxy table
     struct Neeat
     {
-        neeat::HostState host; neeat::Params params{}; bool allocated = false, frameBegun = false; uint32_t lightCount = 0;
+        neeat::HostState host; neeat::Params params{}; bool allocated = false, frameBegun = false, frameEnded = false; uint32_t lightCount = 0;      // begun: update_begin ran, update_end pending; ended: both ran
         DeviceArray<float> fbWeight, scratchWeight, blendedWeight, historyDepth, lightWeights; DeviceArray<uint32_t> fbCandidate, scratchCandidate, blendedCandidate, local, counters,
             proxyCounters, proxyOffsets, proxyIndices, samplingProxyCount, scanBlockSums, rrFix; DeviceArray<uint4> shadowFeedback;
         void release() { fbWeight.release(); scratchWeight.release(); blendedWeight.release(); historyDepth.release(); lightWeights.release(); fbCandidate.release(); scratchCandidate.release();
                          blendedCandidate.release(); local.release(); counters.release(); proxyCounters.release(); proxyOffsets.release(); proxyIndices.release(); samplingProxyCount.release();
-                         scanBlockSums.release(); rrFix.release(); shadowFeedback.release(); allocated = false; frameBegun = false; }
+                         scanBlockSums.release(); rrFix.release(); shadowFeedback.release(); allocated = false; frameBegun = false; frameEnded = false; }
     } na;
     cudaEvent_t evDnStart = nullptr, evDnStop = nullptr; bool denoiseTimed = false;       // around the last rtxpt_b200_denoise_realtime
     // stats
@@ -525,13 +525,24 @@ static int checkReady(rtxpt_ctx* c)
     return RTXPT_OK;
 }
 
+static bool neeatActive(const rtxpt_ctx* c);
 extern "C" RTXPT_API int rtxpt_b200_path_trace(rtxpt_ctx* c, uint32_t firstSubSampleIndex, uint32_t subSampleCount, int accumulate, void* cudaStream)
 {
     int rc = checkReady(c); if (rc != RTXPT_OK) return rc;
     if (subSampleCount == 0) return RTXPT_OK;
-    if (c->consts.NEEType == 2 && c->consts.NEEATFeedback != 0) return fail(RTXPT_ERR_UNSUPPORTED, "NEE-AT temporal feedback is wired into realtime mode (rtxpt_b200_path_trace_realtime) in this round; reference mode runs with NEEATFeedback = 0");
+    const bool na = neeatActive(c);
+    if (na && (!c->na.allocated || !c->na.frameEnded)) return fail(RTXPT_ERR_INVALID_ARGUMENT, "NEEATFeedback is set: call rtxpt_b200_neeat_update_begin and rtxpt_b200_neeat_update_end before tracing the frame");
+    if (na && c->cfg.tileWorld > 1) return fail(RTXPT_ERR_UNSUPPORTED, "NEE-AT feedback needs every pixel's reservoir on one GPU; the tile partition runs with NEEATFeedback = 0");
+    if (na && !(c->cfg.flags & RTXPT_CFG_EXPORT_GUIDES)) return fail(RTXPT_ERR_INVALID_ARGUMENT, "NEE-AT feedback in reference mode reprojects with the exported guides: create the context with RTXPT_CFG_EXPORT_GUIDES");
     cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
     LaunchParams p; fillParams(c, p);
+    if (na)
+    {
+        p.na = c->na.params; p.naShadowFeedback = c->na.shadowFeedback.ptr; p.naRrFix = c->na.rrFix.ptr;
+        p.scene.proxyCounters = c->na.proxyCounters.ptr; p.scene.proxyIndices = c->na.proxyIndices.ptr;
+    }
+    // a pixel's feedback reservoir is updated by one path at a time, as in the reference's sequential sub-sample dispatches: no batching while feedback is active
+    const uint32_t subSamplesPerLaunch = na ? 1u : c->cfg.maxSubSamplesPerLaunch;
     queryOccupancy(c->grid, 16 + size_t(p.smemNodeCount) * 80);
     const bool countSteps = (c->cfg.flags & RTXPT_CFG_COUNT_TRAVERSAL_STEPS) != 0;
     const bool hasRefraction = c->consts.nestedDielectricsQuality > 0;
@@ -540,9 +551,10 @@ extern "C" RTXPT_API int rtxpt_b200_path_trace(rtxpt_ctx* c, uint32_t firstSubSa
     uint64_t launches = 0;
     KernelTimer kt{ c, s, (c->cfg.flags & RTXPT_CFG_TIME_KERNELS) != 0 };
     c->evUsed = 0;
-    for (uint32_t done = 0; done < subSampleCount; done += c->cfg.maxSubSamplesPerLaunch)
+    for (uint32_t done = 0; done < subSampleCount; done += subSamplesPerLaunch)
     {
-        const uint32_t n = std::min(c->cfg.maxSubSamplesPerLaunch, subSampleCount - done);
+        const uint32_t n = std::min(subSamplesPerLaunch, subSampleCount - done);
+        if (na) CU(cudaMemsetAsync(c->na.rrFix.ptr, 0, size_t(c->capacity) * 4, s));
         p.firstSampleIndex = c->consts.sampleBaseIndex + firstSubSampleIndex + done;
         p.subSampleCount = n;
         p.accumulatedSamples = c->accumulatedSamples; p.doAccumulate = accumulate ? 1u : 0u;
@@ -558,16 +570,16 @@ extern "C" RTXPT_API int rtxpt_b200_path_trace(rtxpt_ctx* c, uint32_t firstSubSa
             p.iteration = it;
             kt.begin(0); launchTraceClosest(p, c->grid, countSteps, s); kt.end();
             if (overlap && it > 0) CU(cudaStreamWaitEvent(s, c->evShadowDone, 0));        // shadow(it-1) has updated the radiance words
-            kt.begin(2); launchShade(p, c->grid, s); kt.end();
+            kt.begin(2); if (na) launchShadeNeeat(p, c->grid, s); else launchShade(p, c->grid, s); kt.end();
             if (overlap)
             {
                 CU(cudaEventRecord(c->evShadeDone, s));
                 CU(cudaStreamWaitEvent(c->stream2, c->evShadeDone, 0));
                 KernelTimer kt2{ c, c->stream2, kt.on };
-                kt2.begin(1); launchTraceShadow(p, c->grid, countSteps, c->stream2); kt2.end();
+                kt2.begin(1); if (na) launchTraceShadowNeeat(p, c->grid, c->stream2); else launchTraceShadow(p, c->grid, countSteps, c->stream2); kt2.end();
                 CU(cudaEventRecord(c->evShadowDone, c->stream2));
             }
-            else { kt.begin(1); launchTraceShadow(p, c->grid, countSteps, s); kt.end(); }
+            else { kt.begin(1); if (na) launchTraceShadowNeeat(p, c->grid, s); else launchTraceShadow(p, c->grid, countSteps, s); kt.end(); }
             launches += 3;
         }
         if (overlap) CU(cudaStreamWaitEvent(s, c->evShadowDone, 0));
@@ -794,7 +806,7 @@ extern "C" RTXPT_API int rtxpt_b200_neeat_update_begin(rtxpt_ctx* c, void* cudaS
     neeatBind(c);
     launchNeeatUpdateBegin(n.params, n.host.settings.preFilter, n.scanBlockSums.ptr, c->grid.smCount, s);
     CU(cudaGetLastError());
-    n.frameBegun = true;
+    n.frameBegun = true; n.frameEnded = false;
     return RTXPT_OK;
 }
 extern "C" RTXPT_API int rtxpt_b200_neeat_update_end(rtxpt_ctx* c, void* cudaStream)
@@ -808,7 +820,7 @@ extern "C" RTXPT_API int rtxpt_b200_neeat_update_end(rtxpt_ctx* c, void* cudaStr
     launchNeeatUpdateEnd(c->na.params, s);
     CU(cudaGetLastError());
     neeat::endFrame(c->na.host, c->na.params);
-    c->na.frameBegun = false;
+    c->na.frameBegun = false; c->na.frameEnded = true;
     return RTXPT_OK;
 }
 // debugging / tests: `what` as in the oracle's oracle_neeat_get (0-1 feedback, 2-3 processed, 4-5 blended reservoirs, 6 tile lists, 7 proxy counters, 8 control words, 11 proxy table)

@@ -374,7 +374,7 @@ cudaError_t configureKernels(int maxSmemOptin)
     ALLOW((k_trace_closest<false, 2>)); ALLOW((k_trace_closest<false, 3>)); ALLOW((k_trace_closest<false, 4>)); ALLOW((k_trace_closest<true, 2>));
     ALLOW((k_trace_shadow<false, 2>)); ALLOW((k_trace_shadow<false, 3>)); ALLOW((k_trace_shadow<false, 4>)); ALLOW((k_trace_shadow<true, 2>));
     ALLOW((k_trace_shadow<false, 4, true>)); ALLOW((k_trace_shadow<false, 2, true>));
-    ALLOW((k_trace_shadow<false, 4, true, true>)); ALLOW((k_trace_shadow<false, 2, true, true>));
+    ALLOW((k_trace_shadow<false, 4, true, true>)); ALLOW((k_trace_shadow<false, 2, true, true>)); ALLOW((k_trace_shadow<false, 4, false, true>)); ALLOW((k_trace_shadow<false, 2, false, true>));
     ALLOW(k_trace_rays<false>); ALLOW(k_trace_rays<true>);
 #undef ALLOW
     return cudaSuccess;
@@ -418,6 +418,12 @@ void launchTraceShadowRealtime(const LaunchParams& p, const GridConfig& g, cudaS
     const int grid = g.smCount * g.traceBlocksPerSM; const size_t smem = traceSmemBytes(p);
     if (g.traceBlocksPerSM >= 4) launchTrace(k_trace_shadow<false, 4, true>, grid, smem, s, p, g);
     else launchTrace(k_trace_shadow<false, 2, true>, g.smCount * 2, smem, s, p, g);
+}
+void launchTraceShadowNeeat(const LaunchParams& p, const GridConfig& g, cudaStream_t s)
+{
+    const int grid = g.smCount * g.traceBlocksPerSM; const size_t smem = traceSmemBytes(p);
+    if (g.traceBlocksPerSM >= 4) launchTrace(k_trace_shadow<false, 4, false, true>, grid, smem, s, p, g);
+    else launchTrace(k_trace_shadow<false, 2, false, true>, g.smCount * 2, smem, s, p, g);
 }
 void launchTraceShadowRealtimeNeeat(const LaunchParams& p, const GridConfig& g, cudaStream_t s)
 {

@@ -36,6 +36,8 @@ void launchDebugBsdf(const float* dIn, uint32_t count, float* dOut, cudaStream_t
 void launchDebugRng(const uint32_t* dIn, uint32_t count, uint32_t* dOut, cudaStream_t s);
 
 void launchDnSpecHitT(const float* src, const float* depth, float* dst, int W, int H, cudaStream_t s);      // DenoisingGuidesBaker::DenoiseSpecHitT, one pass
+void launchShadeNeeat(const LaunchParams& p, const GridConfig& g, cudaStream_t s);                 // reference-mode shade with NEE-AT feedback (shade_kernels.cu)
+void launchTraceShadowNeeat(const LaunchParams& p, const GridConfig& g, cudaStream_t s);
 void launchRtShadeNeeat(const LaunchParams& p, const GridConfig& g, cudaStream_t s);               // FILL pass shade with NEE-AT feedback (realtime_kernels.cu)
 void launchTraceShadowRealtimeNeeat(const LaunchParams& p, const GridConfig& g, cudaStream_t s);   // + feedback insertion for visible samples (kernels.cu)
 namespace neeat { struct Params; }

@@ -38,7 +38,7 @@ __global__ void k_init_sobol_tables()
 void launchInitTables(cudaStream_t s) { k_init_sobol_tables<<<16, 256, 0, s>>>(); }
 
 // ---- shade --------------------------------------------------------------------------------------------------------------------------------
-template <int MINB, bool EXPORT_GUIDES, bool ANALYTIC_LIGHTS>
+template <int MINB, bool EXPORT_GUIDES, bool ANALYTIC_LIGHTS, bool NEEAT = false>
 __global__ void __launch_bounds__(128, MINB) k_shade(const __grid_constant__ LaunchParams p)
 {
     uint* ctr = p.wf.counters + p.iteration * kCountersPerIter;
@@ -59,8 +59,9 @@ __global__ void __launch_bounds__(128, MINB) k_shade(const __grid_constant__ Lau
             {
                 slot = queue[i];
                 PathRegs path; path.load(p.wf, slot, true);
-                if (cls == 0) shadeMiss<EXPORT_GUIDES>(p, path);
-                else shadeHit<EXPORT_GUIDES, ANALYTIC_LIGHTS>(p, path, slot, p.wf.hits[slot], out);
+                if constexpr (NEEAT) out.naRecord = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
+                if (cls == 0) shadeMiss<EXPORT_GUIDES, kModeReference, NEEAT>(p, path);
+                else shadeHit<EXPORT_GUIDES, ANALYTIC_LIGHTS, kModeReference, NEEAT>(p, path, slot, p.wf.hits[slot], out);
                 if (cls != 0 && out.continuePath) path.store(p.wf, slot); else path.storeRadianceOnly(p.wf, slot);
                 if (out.continuePath) { rayCls = 0; rayEntry = slot | (path.hasFlag(kPFTerminateAtNextBounce) ? 0x80000000u : 0u); }
                 if (out.emitShadow) shadowCls = 0;
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(128, MINB) k_shade(const __grid_constant__ Lau
                     if (lane == leader) b = atomicAdd(ctr + kCtrShadowCount, __popc(peers));
                     b = __shfl_sync(peers, b, leader) + __popc(peers & ((1u << lane) - 1u));
                     p.wf.shadowOriginTMax[b] = out.shadow.originTMax; p.wf.shadowDirPath[b] = out.shadow.dirPath; p.wf.shadowRadiance[b] = out.shadow.radiance;
+                    if constexpr (NEEAT) p.naShadowFeedback[b] = out.naRecord;
                 }
             }
         }
@@ -109,6 +111,8 @@ __global__ void k_debug_rng(const uint* __restrict__ in, uint count, uint* __res
     for (uint k = 0; k < 4; k++) out[i * 8 + 4 + k] = __float_as_uint(hashToFloat(ldSampleBits(baseHash, in[i * 4 + 3], 1u, k)));
 }
 
+// reference mode with NEE-AT feedback: one instantiation (guides on: the feedback passes reproject with them; analytic lights compiled in, gated by the light type at run time)
+void launchShadeNeeat(const LaunchParams& p, const GridConfig& g, cudaStream_t s) { k_shade<3, true, true, true><<<g.smCount * 3, 128, 0, s>>>(p); }      // 3 CTAs per SM: 155 registers, no spills
 void launchShade(const LaunchParams& p, const GridConfig& g, cudaStream_t s)
 {
     const int grid = g.smCount * g.shadeBlocksPerSM;

@@ -59,6 +59,22 @@ def main():
                            "note": "denoise_ms = CUDA events around rtxpt_b200_denoise_realtime (3 x { prepare inputs, 8 ReBLUR passes, final merge }); first GPU execution of these kernels"}
     except Exception as e:  # noqa: BLE001
         out["denoised"] = {"error": repr(e)[:300]}
+    # realtime mode with NEE-AT temporal feedback (per-tile light samplers): first GPU execution of those kernels too; same containment as above
+    try:
+        consts.NEEATFeedback = 1; fb_ms, upd = [], []
+        for f in range(args.warmup + args.frames + 8):                     # + 8: the loop needs a few frames before the tile samplers carry real feedback
+            consts.sampleBaseIndex = 2000 + f * args.sub_samples; ctx.set_constants(consts)
+            t0 = time.perf_counter(); ctx.neeat_update_begin(); ctx.synchronize(); t1 = time.perf_counter()
+            ctx.path_trace_realtime(True); ctx.synchronize()
+            if f >= args.warmup + 8: fb_ms.append(float(ctx.stats().msTotal)); upd.append((t1 - t0) * 1e3)
+        ctl = ctx.neeat_raw(8, np.uint32, 8)
+        img = ctx.readback_output_color()[..., :3].astype(np.float32)
+        out["neeat_feedback"] = {"ms_per_frame": float(np.median(fb_ms)), "update_begin_ms_host_clock": float(np.median(upd)), "finite": bool(np.isfinite(img).all()), "mean_radiance": float(img.mean()),
+                                 "pixels_with_feedback": float(ctl[7]) / float(W * H), "sampling_proxies": int(ctl[4]),
+                                 "note": "ms_per_frame = CUDA events around rtxpt_b200_path_trace_realtime (BUILD + update_end's 4 passes + FILL with local candidates + merge); update_begin timed by the host clock around a synchronize"}
+        consts.NEEATFeedback = 0; ctx.set_constants(consts)
+    except Exception as e:  # noqa: BLE001
+        out["neeat_feedback"] = {"error": repr(e)[:300]}
     os.write(real_stdout, (json.dumps(out) + "\n").encode())         # before teardown: a device fault in the untested stage must not cost the line
     try: ctx.close()
     except Exception: pass  # noqa: BLE001

@@ -94,8 +94,35 @@ def test_neeat_api_errors(product):
     c = product.Context(max_sub_samples_per_launch=1); c.upload_scene(scene); c.set_constants(consts); c.set_view(sb.world_to_clip(cam))
     c.set_realtime(sb.make_realtime_constants(W, H, cam, bounce_count=2, sub_samples=1))
     with pytest.raises(Exception): c.path_trace_realtime(True)               # update_begin missing
-    with pytest.raises(Exception): c.path_trace(0, 1, False)                 # reference mode: feedback not wired in this round
+    with pytest.raises(Exception): c.path_trace(0, 1, False)                 # reference mode: update_begin / update_end missing (and this context exports no guides)
     c.neeat_update_begin(); c.path_trace_realtime(True); c.synchronize()
     with pytest.raises(Exception): c.neeat_update_end()                      # the frame's update_end already ran inside path_trace_realtime
     c.neeat_reset(); c.neeat_update_begin(); c.path_trace_realtime(True); c.synchronize()
+    c.close()
+
+
+@unverified
+def test_reference_mode_feedback_loop(product, oracle):
+    """Reference mode with feedback (RTXPT's default NEEType 2): update_begin, update_end on the guides the previous frame exported, one sub-sample per wavefront.  Unbiased
+    against feedback-free sampling, lower error once warm, tile lists well formed."""
+    from rtxpt_b200 import scene_builder as sb, scenes, structs as S
+    W, H = 112, 72
+    scene, cam = scenes.light_gallery(W, H, bays=10)
+    consts = sb.make_constants(W, H, cam, bounce_count=2, diffuse_bounce_count=2)
+    c = product.Context(max_sub_samples_per_launch=4, flags=S.CFG_EXPORT_GUIDES); c.upload_scene(scene); c.set_constants(consts); c.set_view(sb.world_to_clip(cam))
+    def frames(n, feedback):
+        out = []
+        consts.NEEATFeedback = 1 if feedback else 0
+        for f in range(n):
+            consts.sampleBaseIndex = 2 * f; c.set_constants(consts)
+            if feedback: c.neeat_update_begin(); c.neeat_update_end()
+            c.path_trace(0, 2, False); c.synchronize(); out.append(c.readback_output_color()[..., :3].astype(np.float32))
+        return np.stack(out)
+    consts.NEEATFeedback = 0; c.set_constants(consts); c.path_trace(0, 1, False); c.synchronize()        # a first frame leaves depth / motion guides behind
+    fb = frames(48, True); gl = frames(96, False)
+    ref = gl.mean(0); warm = fb[10:]
+    assert np.isfinite(fb).all() and abs(warm.mean() / gl.mean() - 1) < 0.03
+    assert np.abs(warm - ref).mean() < 0.95 * np.abs(gl - ref).mean()
+    lists = c.neeat_raw(6, np.uint32, 1 << 22).reshape(-1, 128)
+    assert (np.diff((lists >> 9).astype(np.int64), axis=1) >= 0).all()
     c.close()
