@@ -384,6 +384,24 @@ RTXPT_API int rtxpt_b200_denoise_spec_hit_t(rtxpt_ctx* ctx, void* cudaStream);
 RTXPT_API int rtxpt_b200_denoiser_prepare_inputs(rtxpt_ctx* ctx, uint32_t stablePlaneIndex, int initWithStableRadiance, const RtxptDenoiserConstants* constants, void* cudaStream);
 RTXPT_API int rtxpt_b200_denoiser_final_merge(rtxpt_ctx* ctx, uint32_t stablePlaneIndex, const void* dDenoisedDiffRGBA16F, const void* dDenoisedSpecRGBA16F, void* cudaStream);    /* NULL, NULL = the images rtxpt_b200_reblur_denoise wrote */
 
+/* ---- Environment-map baking (replaces EnvMapBaker::Update's BaseLayerCS / MIPReduceCS passes, Rtxpt/Lighting/Distant/EnvMapBaker.cpp:425-600, .hlsl:64-356): an
+ * equirectangular or cube source and up to 16 directional lights (Sample.cpp collects the scene's DirectionalLights for it) are baked on the GPU into the RGBA16F cube the path tracer
+ * samples, with the MIP chain's solid-angle weights.  The result is returned in host memory in the layout RtxptEnvCubeDesc takes (MIP m: 6 faces of (cubeDim >> m)^2 RGBA32F texels,
+ * faces +x -x +y -y +z -z, values fp16-representable), ready for rtxpt_b200_upload_scene.  Not built: the procedural sky and the BC6U compression of the baked cube. */
+typedef struct RtxptEnvBakeLight { float colorIntensity[4]; float direction[3]; float angularSize; } RtxptEnvBakeLight;   /* colour, W/sr; incoming direction; radians */
+typedef struct RtxptEnvBakeDesc {
+    uint32_t cubeDim;                   /* power of two, 2..4096 (EnvMapBaker: 2048, 1024 with the procedural sky) */
+    uint32_t sourceType;                /* 0 none, 1 equirectangular, 2 cube */
+    uint32_t sourceWidth, sourceHeight; /* cube: face size in sourceWidth */
+    const float* source;                /* host, RGBA32F; cube: 6 faces back to back */
+    float scaleColor[3];                /* BakeSettings::EnvMapRadianceScale */
+    uint32_t directionalLightCount;
+    RtxptEnvBakeLight lights[16];
+} RtxptEnvBakeDesc;
+RTXPT_API uint32_t rtxpt_b200_env_bake_mip_count(uint32_t cubeDim);
+RTXPT_API size_t   rtxpt_b200_env_bake_floats(uint32_t cubeDim);          /* all MIPs back to back */
+RTXPT_API int      rtxpt_b200_bake_env_map(rtxpt_ctx* ctx, const RtxptEnvBakeDesc* desc, float* outAllMips, size_t outFloats);
+
 /* ---- NEE-AT temporal feedback (replaces the feedback half of Rtxpt/Lighting/LightsBaker: UpdateBegin's ProcessFeedbackHistoryPreFilter / P0 + usage-weighted
  * ComputeProxyCounts, UpdateEnd's P1a / P1b / P2 / P3 / ClearFeedbackHistory, LightsBaker.cpp:1203-1225, :1331-1418).  Active with NEEType == 2 && NEEATFeedback != 0: NEE then draws
  * ComputeCandidateSampleLocalCount( 0.65, NEECandidateSamples ) of its candidates from the pixel's 8x8-tile sampler once a frame of feedback exists, mixes them with the global ones by

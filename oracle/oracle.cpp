@@ -7,6 +7,7 @@
 // reference ships no runnable golden data for it.
 #include "pt_path.h"
 #include "reblur.h"
+#include "pt_envbake.h"
 #include <cstdio>
 #include <chrono>
 #ifdef _OPENMP
@@ -380,6 +381,20 @@ ORC_API int oracle_denoiser_final_merge(void* p, const RtxptRealtimeConstants* r
     if (!c->haveConsts || !rt || stablePlaneIndex >= 3) return -1;
     const RealtimeTargets T = makeTargets(c, rt, realtimeTargets); const DenoiserTargets D = makeDenoiserTargets(denoiserTargets);
     for (uint32_t y = 0; y < T.height; y++) for (uint32_t px = 0; px < T.width; px++) denoiserFinalMergePixel(T, D, px, y, stablePlaneIndex, denoisedDiff, denoisedSpec);
+    return 0;
+}
+
+// EnvMapBaker (pt_envbake.h): source + directional lights -> cube MIP chain.  lights: 8 floats each (colour rgb, intensity W/sr, incoming direction xyz, angular size rad);
+// out: all MIPs back to back, MIP m = 6 faces of (cubeDim >> m)^2 RGBA32F texels (fp16 values)
+ORC_API int oracle_bake_env_map(uint32_t cubeDim, uint32_t sourceType, uint32_t sourceWidth, uint32_t sourceHeight, const float* source, const float* scaleColor, uint32_t lightCount, const float* lights, float* out)
+{
+    if (cubeDim < 2 || (cubeDim & (cubeDim - 1)) || lightCount > 16) return -1;
+    envbake::Desc d; d.cubeDim = cubeDim; d.sourceType = sourceType; d.sourceWidth = sourceWidth; d.sourceHeight = sourceHeight; d.source = source;
+    for (int k = 0; k < 3; k++) d.scaleColor[k] = scaleColor[k];
+    d.directionalLightCount = lightCount;
+    for (uint32_t i = 0; i < lightCount; i++) { memcpy(d.lights[i].colorIntensity, lights + 8 * i, 16); memcpy(d.lights[i].direction, lights + 8 * i + 4, 12); d.lights[i].angularSize = lights[8 * i + 7]; }
+    std::vector<std::vector<float>> mips; envbake::bake(d, mips);
+    for (auto& m : mips) { memcpy(out, m.data(), m.size() * 4); out += m.size(); }
     return 0;
 }
 

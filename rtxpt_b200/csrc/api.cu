@@ -6,6 +6,7 @@
 #include "kernels.h"
 #include "reblur_host.h"
 #include "neeat_host.h"
+#include "envbake.cuh"
 #include "lights_bake.h"
 #include <algorithm>
 #include <chrono>
@@ -749,6 +750,39 @@ extern "C" RTXPT_API int rtxpt_b200_denoiser_final_merge(rtxpt_ctx* c, uint32_t 
     p.rt.dnPlane = stablePlaneIndex; p.rt.dnDenoisedDiff = static_cast<const uint2*>(dDiff); p.rt.dnDenoisedSpec = static_cast<const uint2*>(dSpec);
     launchDnFinalMerge(p, c->grid, s);
     CU(cudaGetLastError());
+    return RTXPT_OK;
+}
+
+// ---- environment-map baking ---------------------------------------------------------------------------------------------------------------------
+extern "C" RTXPT_API uint32_t rtxpt_b200_env_bake_mip_count(uint32_t cubeDim) { uint32_t l = 0; while ((cubeDim >> l) > 0) l++; return l; }
+extern "C" RTXPT_API size_t rtxpt_b200_env_bake_floats(uint32_t cubeDim) { size_t n = 0; for (uint32_t m = 0; (cubeDim >> m) > 0; m++) n += size_t(6) * (cubeDim >> m) * (cubeDim >> m) * 4; return n; }
+extern "C" RTXPT_API int rtxpt_b200_bake_env_map(rtxpt_ctx* c, const RtxptEnvBakeDesc* d, float* out, size_t outFloats)
+{
+    if (!c || !d || !out) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (d->cubeDim < 2 || d->cubeDim > 4096 || (d->cubeDim & (d->cubeDim - 1))) return fail(RTXPT_ERR_INVALID_ARGUMENT, "cubeDim must be a power of two in 2..4096");
+    if (d->directionalLightCount > 16) return fail(RTXPT_ERR_INVALID_ARGUMENT, "at most 16 directional lights (EMB_MAXDIRLIGHTS)");
+    if (d->sourceType > 2 || (d->sourceType != 0 && (!d->source || d->sourceWidth == 0 || (d->sourceType == 1 && d->sourceHeight == 0)))) return fail(RTXPT_ERR_INVALID_ARGUMENT, "bad source description");
+    const size_t total = rtxpt_b200_env_bake_floats(d->cubeDim);
+    if (outFloats < total) return fail(RTXPT_ERR_INVALID_ARGUMENT, "output too small (%zu < %zu floats)", outFloats, total);
+    cudaSetDevice(c->device);
+    cudaStream_t s = c->stream;
+    const uint32_t levels = rtxpt_b200_env_bake_mip_count(d->cubeDim);
+    DeviceArray<float> src, dst;
+    const size_t srcFloats = d->sourceType == 1 ? size_t(d->sourceWidth) * d->sourceHeight * 4 : (d->sourceType == 2 ? size_t(6) * d->sourceWidth * d->sourceWidth * 4 : 0);
+    cudaError_t e = srcFloats ? src.upload(d->source, srcFloats, s) : cudaSuccess;
+    if (e == cudaSuccess) e = dst.alloc(total);
+    if (e != cudaSuccess) { src.release(); dst.release(); CU(e); }
+    envbake::Params p{};
+    p.cubeDim = d->cubeDim; p.sourceType = d->sourceType; p.sourceWidth = d->sourceWidth; p.sourceHeight = d->sourceHeight; p.source = src.ptr;
+    memcpy(p.scaleColor, d->scaleColor, 12); p.lightCount = d->directionalLightCount;
+    for (uint32_t i = 0; i < d->directionalLightCount; i++) { memcpy(p.lights[i].colorIntensity, d->lights[i].colorIntensity, 16); memcpy(p.lights[i].direction, d->lights[i].direction, 12); p.lights[i].angularSize = d->lights[i].angularSize; }
+    size_t off = 0; for (uint32_t m = 0; m < levels; m++) { p.mips[m] = dst.ptr + off; off += size_t(6) * (d->cubeDim >> m) * (d->cubeDim >> m) * 4; }
+    launchEnvBake(p, levels, s);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dst.ptr, total * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    src.release(); dst.release();
+    CU(e);
     return RTXPT_OK;
 }
 

@@ -49,6 +49,7 @@ _SIGNATURES = {
     "rtxpt_b200_path_trace_realtime": [C.c_void_p, C.c_int, C.c_void_p],
     "rtxpt_b200_denoiser_prepare_inputs": [C.c_void_p, C.c_uint32, C.c_int, C.POINTER(S.DenoiserConstants), C.c_void_p],
     "rtxpt_b200_denoiser_final_merge": [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p],
+    "rtxpt_b200_bake_env_map": [C.c_void_p, C.POINTER(S.EnvBakeDesc), C.c_void_p, C.c_size_t],
     "rtxpt_b200_neeat_update_begin": [C.c_void_p, C.c_void_p],
     "rtxpt_b200_neeat_update_end": [C.c_void_p, C.c_void_p],
     "rtxpt_b200_neeat_reset": [C.c_void_p],
@@ -62,7 +63,7 @@ _SIGNATURES = {
     "rtxpt_b200_debug_bsdf": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
     "rtxpt_b200_debug_rng": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
 }
-_LOADER_SYMBOLS = ["rtxpt_b200_load_gltf", "rtxpt_b200_load_gltf_ex", "rtxpt_b200_load_scene_json", "rtxpt_b200_host_scene_info", "rtxpt_b200_load_gltf_error", "rtxpt_b200_host_scene_desc", "rtxpt_b200_host_scene_cameras",
+_LOADER_SYMBOLS = ["rtxpt_b200_env_bake_mip_count", "rtxpt_b200_env_bake_floats", "rtxpt_b200_load_gltf", "rtxpt_b200_load_gltf_ex", "rtxpt_b200_load_scene_json", "rtxpt_b200_host_scene_info", "rtxpt_b200_load_gltf_error", "rtxpt_b200_host_scene_desc", "rtxpt_b200_host_scene_cameras",
                    "rtxpt_b200_host_scene_triangle_count", "rtxpt_b200_free_host_scene", "rtxpt_b200_bridge_camera", "rtxpt_b200_default_constants", "rtxpt_b200_debug_bvh_stats", "rtxpt_b200_parse_material_json", "rtxpt_b200_parse_material_json_error", "rtxpt_b200_debug_decode_dds", "rtxpt_b200_debug_decode_dds_error",
                     "rtxpt_b200_generic_ts_line_stride", "rtxpt_b200_generic_ts_plane_stride", "rtxpt_b200_generic_ts_address"]
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["rtxpt_b200_last_error"] + _LOADER_SYMBOLS)
@@ -168,6 +169,36 @@ class GltfScene:
         except Exception: pass
 
 
+def env_bake_arguments(cube_dim, source, source_type, scale_color, lights):
+    """Shared by Context.bake_env_map and the test harnesses of the oracle / the host build: (source array or None, type, width, height, light table 8 floats each)."""
+    src = None if source is None else np.ascontiguousarray(source, np.float32)
+    if src is None: st, w, h = 0, 0, 0
+    elif src.ndim == 4: st, w, h = 2, src.shape[1], src.shape[1]
+    else: st, w, h = 1, src.shape[1], src.shape[0]
+    if source_type is not None: st = source_type
+    lt = np.zeros((len(lights), 8), np.float32)
+    for i, (col, inten, direction, ang) in enumerate(lights): lt[i, :3] = col; lt[i, 3] = inten; lt[i, 4:7] = direction; lt[i, 7] = ang
+    return src, st, w, h, lt
+
+
+def split_env_mips(flat, cube_dim):
+    out = []; off = 0; n = cube_dim
+    while n > 0:
+        cnt = 6 * n * n * 4; out.append(flat[off: off + cnt].reshape(6, n, n, 4)); off += cnt; n //= 2
+    return out
+
+
+def _bake_env_map(call, cube_dim, source, source_type, scale_color, lights):
+    src, st, w, h, lt = env_bake_arguments(cube_dim, source, source_type, scale_color, lights)
+    d = S.EnvBakeDesc(); d.cubeDim = cube_dim; d.sourceType = st; d.sourceWidth = w; d.sourceHeight = h; d.source = None if src is None else src.ctypes.data
+    d.scaleColor[:] = list(scale_color); d.directionalLightCount = len(lt)
+    for i in range(len(lt)): d.lights[i].colorIntensity[:] = lt[i, :4].tolist(); d.lights[i].direction[:] = lt[i, 4:7].tolist(); d.lights[i].angularSize = float(lt[i, 7])
+    total = sum(6 * (cube_dim >> m) ** 2 * 4 for m in range(cube_dim.bit_length()))
+    out = np.zeros(total, np.float32)
+    call(d, out)
+    return split_env_mips(out, cube_dim)
+
+
 class Context:
     def __init__(self, max_sub_samples_per_launch=1, device=-1, tile_rank=0, tile_world=1, tile_size=64, flags=0, max_width=0, max_height=0, strict=None):
         L = self.L = load(strict)
@@ -254,6 +285,11 @@ class Context:
             if d_diff is None: d_diff = self.device_ptr(S.BUFFER_DENOISER_DIFF_RADIANCE_HITDIST_F16)[0]
             if d_spec is None: d_spec = self.device_ptr(S.BUFFER_DENOISER_SPEC_RADIANCE_HITDIST_F16)[0]
         _check(self.L.rtxpt_b200_denoiser_final_merge(self.h, plane, d_diff, d_spec, stream), self.L)
+
+    def bake_env_map(self, cube_dim, source=None, source_type=None, scale_color=(1.0, 1.0, 1.0), lights=()):
+        """EnvMapBaker on the GPU.  source: HxWx4 float32 equirectangular image or 6xNxNx4 cube (None = lights only); lights: (colour rgb, intensity W/sr, incoming direction,
+        angular size rad) tuples.  Returns the MIP chain as a list of 6 x n x n x 4 float32 arrays (what SceneBuilder.set_env_cube / RtxptEnvCubeDesc take)."""
+        return _bake_env_map(lambda d, out: _check(self.L.rtxpt_b200_bake_env_map(self.h, C.byref(d), out.ctypes.data, out.size), self.L), cube_dim, source, source_type, scale_color, lights)
 
     # ---- NEE-AT temporal feedback: per frame set_constants; neeat_update_begin; path_trace_realtime (runs update_end after its BUILD pass) ----
     def neeat_update_begin(self, stream=None): _check(self.L.rtxpt_b200_neeat_update_begin(self.h, stream), self.L)

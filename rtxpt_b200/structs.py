@@ -134,6 +134,15 @@ class DenoiserConstants(C.Structure):
                 ("stablePlanesSuppressPrimaryIndirectSpecularK", f32), ("_pad", f32)]
 
 
+class EnvBakeLight(C.Structure):
+    _fields_ = [("colorIntensity", f32 * 4), ("direction", f32 * 3), ("angularSize", f32)]
+
+
+class EnvBakeDesc(C.Structure):
+    _fields_ = [("cubeDim", u32), ("sourceType", u32), ("sourceWidth", u32), ("sourceHeight", u32), ("source", C.c_void_p), ("scaleColor", f32 * 3), ("directionalLightCount", u32),
+                ("lights", EnvBakeLight * 16)]
+
+
 class ReblurFrame(C.Structure):
     _fields_ = [("matWorldToView", f32 * 16), ("matViewToClip", f32 * 16), ("prevMatWorldToView", f32 * 16), ("prevMatViewToClip", f32 * 16),
                 ("frameIndex", u32), ("resetHistory", u32), ("ignoreMotionVectors", u32), ("frameTimeMs", f32),

@@ -6,6 +6,7 @@
 #include "../../rtxpt_b200/csrc/reblur_passes.cuh"
 #include "../../rtxpt_b200/csrc/reblur_host.h"
 #include "../../rtxpt_b200/csrc/guides_filter.cuh"
+#include "../../rtxpt_b200/csrc/envbake.cuh"
 #include <vector>
 #include <cstdint>
 
@@ -90,5 +91,23 @@ extern "C" int emu_denoise_spec_hit_t(uint32_t W, uint32_t H, const float* depth
     std::vector<float> scratch(size_t(W) * H);
     for (int y = 0; y < int(H); y++) for (int x = 0; x < int(W); x++) scratch[size_t(y) * W + x] = pt::specHitTNeighbourhood(specHitT, depth, int(W), int(H), x, y);
     for (int y = 0; y < int(H); y++) for (int x = 0; x < int(W); x++) specHitT[size_t(y) * W + x] = pt::specHitTNeighbourhood(scratch.data(), depth, int(W), int(H), x, y);
+    return 0;
+}
+
+// EnvMapBaker: the product's BaseLayer / MIPReduce bodies (envbake.cuh) in launchEnvBake's order; lights: 8 floats each; out: all MIPs back to back
+extern "C" int emu_bake_env_map(uint32_t cubeDim, uint32_t sourceType, uint32_t sourceWidth, uint32_t sourceHeight, const float* source, const float* scaleColor, uint32_t lightCount, const float* lights, float* out)
+{
+    pt::envbake::Params p{};
+    p.cubeDim = cubeDim; p.sourceType = sourceType; p.sourceWidth = sourceWidth; p.sourceHeight = sourceHeight; p.source = source; memcpy(p.scaleColor, scaleColor, 12); p.lightCount = lightCount;
+    for (uint32_t i = 0; i < lightCount; i++) { memcpy(p.lights[i].colorIntensity, lights + 8 * i, 16); memcpy(p.lights[i].direction, lights + 8 * i + 4, 12); p.lights[i].angularSize = lights[8 * i + 7]; }
+    uint32_t levels = 0; while ((cubeDim >> levels) > 0) levels++;
+    size_t off = 0; for (uint32_t m = 0; m < levels; m++) { p.mips[m] = out + off; off += size_t(6) * (cubeDim >> m) * (cubeDim >> m) * 4; }
+    const uint32_t half = cubeDim / 2;
+    for (uint32_t f = 0; f < 6; f++)
+    {
+        #pragma omp parallel for schedule(dynamic, 4)
+        for (int y = 0; y < int(half); y++) for (uint32_t x = 0; x < half; x++) pt::envbake::baseLayerTexel(p, x, uint32_t(y), f, levels > 1);
+    }
+    for (uint32_t m = 2; m < levels; m++) { const uint32_t n = cubeDim >> m; for (uint32_t f = 0; f < 6; f++) for (uint32_t y = 0; y < n; y++) for (uint32_t x = 0; x < n; x++) pt::envbake::mipReduceTexel(p, m, x, y, f); }
     return 0;
 }
