@@ -384,6 +384,16 @@ RTXPT_API int rtxpt_b200_denoise_spec_hit_t(rtxpt_ctx* ctx, void* cudaStream);
 RTXPT_API int rtxpt_b200_denoiser_prepare_inputs(rtxpt_ctx* ctx, uint32_t stablePlaneIndex, int initWithStableRadiance, const RtxptDenoiserConstants* constants, void* cudaStream);
 RTXPT_API int rtxpt_b200_denoiser_final_merge(rtxpt_ctx* ctx, uint32_t stablePlaneIndex, const void* dDenoisedDiffRGBA16F, const void* dDenoisedSpecRGBA16F, void* cudaStream);    /* NULL, NULL = the images rtxpt_b200_reblur_denoise wrote */
 
+/* ---- Rigid-instance animation (stands in for the per-frame BLAS / TLAS update behind Sample::UpdateAccelStructs and BuildTLAS, Rtxpt/Sample.cpp:1170-1240): new
+ * row-major 3x4 matrices for every instance of the uploaded scene; on the stream, the leaf triangles are re-transformed (one thread each) and the 8-wide BVH is refitted bottom-up,
+ * level by level, with the builder's own quantisation - unmoved geometry gives back the built nodes bit for bit, topology never changes (quality degrades with large deformation,
+ * re-upload then).  The instance table keeps the previous matrices for the BUILD pass's motion vectors.  Emissive triangles are baked into the light list at upload: instances that
+ * carry them stay put (or re-upload).  Skinning / vertex animation: not built. */
+RTXPT_API int rtxpt_b200_update_instance_transforms(rtxpt_ctx* ctx, const float* transforms3x4, uint32_t instanceCount, void* cudaStream);
+/* host-only inspection of the builder: the compressed BVH over a triangle soup (nodes 80 B, leaf triangles 48 B with gid = soup index, level ranges); call with NULL outputs for sizes */
+RTXPT_API int rtxpt_b200_debug_build_bvh(const float* triangleVertices, uint32_t triangleCount, void* outNodes, void* outTris, uint32_t* outLevelStart,
+                                         uint32_t* outNodeCount, uint32_t* outTriCount, uint32_t* outLevelCount);
+
 /* ---- Environment-map baking (replaces EnvMapBaker::Update's BaseLayerCS / MIPReduceCS passes, Rtxpt/Lighting/Distant/EnvMapBaker.cpp:425-600, .hlsl:64-356): an
  * equirectangular or cube source and up to 16 directional lights (Sample.cpp collects the scene's DirectionalLights for it) are baked on the GPU into the RGBA16F cube the path tracer
  * samples, with the MIP chain's solid-angle weights.  The result is returned in host memory in the layout RtxptEnvCubeDesc takes (MIP m: 6 faces of (cubeDim >> m)^2 RGBA32F texels,

@@ -7,6 +7,7 @@
 #include "reblur_host.h"
 #include "neeat_host.h"
 #include "envbake.cuh"
+#include "refit.cuh"
 #include "lights_bake.h"
 #include <algorithm>
 #include <chrono>
@@ -66,6 +67,7 @@ struct rtxpt_ctx
     std::vector<DeviceTexture> textures; DeviceArray<cudaTextureObject_t> dTextureTable;
     DeviceTexture envCube; uint32_t envFaceSize = 0, envMipLevels = 0;
     DeviceArray<uint4> dBvhNodes; DeviceArray<float4> dBvhTris; DeviceArray<uint4> dTriInfo, dTriShade;
+    std::vector<RtxptInstanceData> hInstances; std::vector<uint32_t> bvhLevelStart; DeviceArray<float> dNodeBox;      // rigid-instance animation (refit.cuh)
     uint32_t bvhNodeCount = 0, bvhTriCount = 0; float bvhBuildSeconds = 0;
     std::vector<RtxptSubInstanceData> hSubInstances; uint32_t materialCount = 0;
     LightBakeState lightState;
@@ -183,7 +185,7 @@ extern "C" RTXPT_API int rtxpt_b200_destroy(rtxpt_ctx* c)
     cudaStreamSynchronize(c->stream);
     releaseScene(c);
     c->dInstances.release(); c->dGeometries.release(); c->dSubInstances.release(); c->dMaterials.release(); c->dSubInstanceClass.release();
-    c->dBufferTable.release(); c->dTextureTable.release(); c->dBvhNodes.release(); c->dBvhTris.release(); c->dTriInfo.release(); c->dTriShade.release();
+    c->dBufferTable.release(); c->dTextureTable.release(); c->dBvhNodes.release(); c->dBvhTris.release(); c->dTriInfo.release(); c->dTriShade.release(); c->dNodeBox.release();
     c->dLightsEx.release(); c->dLights.release(); c->dProxyCounters.release(); c->dProxyIndices.release(); c->dEnvLookup.release();
     c->s0.release(); c->s1.release(); c->s2.release(); c->s3.release(); c->s4.release(); c->hits.release();
     c->rayQueue[0].release(); c->rayQueue[1].release(); c->shadeQueue.release();
@@ -334,6 +336,7 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
     CU(c->dTriInfo.upload(triInfo.data(), triInfo.size(), s));
     CU(c->dTriShade.upload(triShade.data(), triShade.size(), s));
     CU(c->dInstances.upload(sc->instances, sc->instanceCount, s));
+    c->hInstances.assign(sc->instances, sc->instances + sc->instanceCount); c->bvhLevelStart = bvh.levelStart; c->dNodeBox.release();
     CU(c->dGeometries.upload(sc->geometries, sc->geometryCount, s));
     CU(c->dMaterials.upload(sc->materials, sc->materialCount, s));
     c->materialCount = sc->materialCount;
@@ -749,6 +752,28 @@ extern "C" RTXPT_API int rtxpt_b200_denoiser_final_merge(rtxpt_ctx* c, uint32_t 
     LaunchParams p; fillParams(c, p); fillRealtimeParams(c, p);
     p.rt.dnPlane = stablePlaneIndex; p.rt.dnDenoisedDiff = static_cast<const uint2*>(dDiff); p.rt.dnDenoisedSpec = static_cast<const uint2*>(dSpec);
     launchDnFinalMerge(p, c->grid, s);
+    CU(cudaGetLastError());
+    return RTXPT_OK;
+}
+
+// ---- rigid-instance animation: new instance matrices -> leaf triangles re-transformed, BVH refitted bottom-up (Sample.cpp:1170-1240) --------------------------
+extern "C" RTXPT_API int rtxpt_b200_update_instance_transforms(rtxpt_ctx* c, const float* transforms3x4, uint32_t instanceCount, void* cudaStream)
+{
+    if (!c || !transforms3x4) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (!c->haveScene) return fail(RTXPT_ERR_NO_SCENE, "no scene uploaded");
+    if (instanceCount != c->hInstances.size()) return fail(RTXPT_ERR_INVALID_ARGUMENT, "expected %zu instance transforms, got %u", c->hInstances.size(), instanceCount);
+    if (c->bvhTriCount == 0) return RTXPT_OK;
+    cudaSetDevice(c->device);
+    cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
+    if (c->dNodeBox.count != size_t(c->bvhNodeCount) * 6) { CU(cudaStreamSynchronize(c->stream)); CU(c->dNodeBox.alloc(size_t(c->bvhNodeCount) * 6)); }
+    for (uint32_t i = 0; i < instanceCount; i++)
+    {   // Donut's InstanceData keeps last frame's matrix next to the current one (motion vectors of the BUILD pass read it)
+        memcpy(c->hInstances[i].prevTransform, c->hInstances[i].transform, 48); memcpy(c->hInstances[i].transform, transforms3x4 + size_t(i) * 12, 48);
+    }
+    CU(cudaMemcpyAsync(c->dInstances.ptr, c->hInstances.data(), c->hInstances.size() * sizeof(RtxptInstanceData), cudaMemcpyHostToDevice, s));
+    refit::Params p{};
+    p.nodes = c->dBvhNodes.ptr; p.tris = c->dBvhTris.ptr; p.triShade = c->dTriShade.ptr; p.instances = c->dInstances.ptr; p.nodeBox = c->dNodeBox.ptr; p.nodeCount = c->bvhNodeCount; p.triCount = c->bvhTriCount;
+    launchRefit(p, c->bvhLevelStart.data(), uint32_t(c->bvhLevelStart.size()) - 1, c->grid.smCount, s);
     CU(cudaGetLastError());
     return RTXPT_OK;
 }

@@ -137,11 +137,11 @@ inline float biasedExpToFloat(uint32_t e) { uint32_t u = e << 23; float f; memcp
 void buildBvh8(const std::vector<BuildTriangle>& tris, Bvh8& out)
 {
     auto t0 = std::chrono::steady_clock::now();
-    out.nodes.clear(); out.tris.clear(); out.maxDepth = 0;
+    out.nodes.clear(); out.tris.clear(); out.levelStart.clear(); out.maxDepth = 0;
     for (int a = 0; a < 3; a++) { out.sceneLo[a] = 0; out.sceneHi[a] = 0; }
     if (tris.empty())
     {
-        Bvh8Node n; memset(&n, 0, sizeof(n)); out.nodes.push_back(n);
+        Bvh8Node n; memset(&n, 0, sizeof(n)); out.nodes.push_back(n); out.levelStart = { 0u, 1u };
         return;
     }
     Builder2 b2(tris);
@@ -158,6 +158,7 @@ void buildBvh8(const std::vector<BuildTriangle>& tris, Bvh8& out)
     {
         const uint32_t rootIdx = queue[qi].node2; const uint32_t depth = queue[qi].depth;
         out.maxDepth = std::max(out.maxDepth, depth);
+        if (out.levelStart.size() < depth) out.levelStart.push_back(uint32_t(qi));       // breadth-first: depths never decrease along the queue
         // 1. gather up to 8 children
         uint32_t child[8]; int nChild = 0;
         if (N[rootIdx].count > 0) child[nChild++] = rootIdx;       // degenerate: the whole (sub)tree is one leaf
@@ -193,10 +194,7 @@ void buildBvh8(const std::vector<BuildTriangle>& tris, Bvh8& out)
         uint32_t ebias[3];
         for (int a = 0; a < 3; a++)
         {
-            double ext = double(nb.hi[a]) - double(nb.lo[a]);
-            int e = (ext > 0.0) ? int(std::ceil(std::log2(ext / 255.0))) : -126;
-            e = std::min(std::max(e, -126), 100);          // traverse.cuh scales by a further 2^15 and by 1/|d| <= 1e20
-            while (e < 100 && ext / std::ldexp(1.0, e) > 255.0) e++;
+            const int e = bvh8FrameExponent(double(nb.hi[a]) - double(nb.lo[a]));
             ebias[a] = uint32_t(e + 127);
         }
         Bvh8Node node; memset(&node, 0, sizeof(node));
@@ -211,13 +209,7 @@ void buildBvh8(const std::vector<BuildTriangle>& tris, Bvh8& out)
             int ci = childInSlot[s];
             if (ci < 0) continue;
             const Node2& c = N[child[ci]];
-            for (int a = 0; a < 3; a++)
-            {
-                double scale = std::ldexp(1.0, int(ebias[a]) - 127);
-                double lo = std::floor((double(c.box.lo[a]) - double(nb.lo[a])) / scale), hi = std::ceil((double(c.box.hi[a]) - double(nb.lo[a])) / scale);
-                q[a][s] = uint8_t(std::min(std::max(lo, 0.0), 255.0));
-                q[3 + a][s] = uint8_t(std::min(std::max(hi, 0.0), 255.0));
-            }
+            { uint8_t ql[3], qh[3]; bvh8QuantizeChild(nb.lo, ebias, c.box.lo, c.box.hi, ql, qh); for (int a = 0; a < 3; a++) { q[a][s] = ql[a]; q[3 + a][s] = qh[a]; } }
             if (c.count == 0)
             {
                 imask |= 1u << s;
@@ -246,6 +238,7 @@ void buildBvh8(const std::vector<BuildTriangle>& tris, Bvh8& out)
         memcpy(&node.w[16], q[4], 8); memcpy(&node.w[18], q[5], 8);     // qhi.y | qhi.z
         out.nodes.push_back(node);
     }
+    out.levelStart.push_back(uint32_t(out.nodes.size()));
     out.buildSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
@@ -293,5 +286,24 @@ extern "C" RTXPT_API int rtxpt_b200_debug_bvh_stats(const float* triangleVertice
         }
     }
     out->expectedNodeVisits = float(nodeVisits); out->expectedTriangleTests = float(triTests); out->leafCount = uint32_t(leafCount);
+    return RTXPT_OK;
+}
+
+extern "C" RTXPT_API int rtxpt_b200_debug_build_bvh(const float* triangleVertices, uint32_t triangleCount, void* outNodes, void* outTris, uint32_t* outLevelStart, uint32_t* outNodeCount, uint32_t* outTriCount,
+                                                    uint32_t* outLevelCount)
+{
+    if ((!triangleVertices && triangleCount) || !outNodeCount || !outTriCount || !outLevelCount) return RTXPT_ERR_INVALID_ARGUMENT;
+    using namespace pt;
+    std::vector<BuildTriangle> tris(triangleCount);
+    for (uint32_t i = 0; i < triangleCount; i++)
+    {
+        memcpy(tris[i].v0, triangleVertices + size_t(i) * 9, 12); memcpy(tris[i].v1, triangleVertices + size_t(i) * 9 + 3, 12); memcpy(tris[i].v2, triangleVertices + size_t(i) * 9 + 6, 12);
+        tris[i].gid = i; tris[i].subInstanceAndFlags = 0; tris[i].primitiveIndex = i;
+    }
+    Bvh8 bvh; buildBvh8(tris, bvh);
+    *outNodeCount = uint32_t(bvh.nodes.size()); *outTriCount = uint32_t(bvh.tris.size()); *outLevelCount = uint32_t(bvh.levelStart.size()) - 1;
+    if (outNodes) memcpy(outNodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(Bvh8Node));
+    if (outTris) memcpy(outTris, bvh.tris.data(), bvh.tris.size() * sizeof(Bvh8Tri));
+    if (outLevelStart) memcpy(outLevelStart, bvh.levelStart.data(), bvh.levelStart.size() * 4);
     return RTXPT_OK;
 }

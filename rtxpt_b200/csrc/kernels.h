@@ -40,6 +40,8 @@ void launchShadeNeeat(const LaunchParams& p, const GridConfig& g, cudaStream_t s
 void launchTraceShadowNeeat(const LaunchParams& p, const GridConfig& g, cudaStream_t s);
 void launchRtShadeNeeat(const LaunchParams& p, const GridConfig& g, cudaStream_t s);               // FILL pass shade with NEE-AT feedback (realtime_kernels.cu)
 void launchTraceShadowRealtimeNeeat(const LaunchParams& p, const GridConfig& g, cudaStream_t s);   // + feedback insertion for visible samples (kernels.cu)
+namespace refit { struct Params; }
+void launchRefit(const refit::Params& p, const uint32_t* levelStart, uint32_t levelCount, int smCount, cudaStream_t s);      // refit_kernels.cu
 namespace envbake { struct Params; }
 void launchEnvBake(const envbake::Params& p, uint32_t mipLevels, cudaStream_t s);                  // envbake_kernels.cu: EnvMapBaker BaseLayerCS + MIPReduceCS
 namespace neeat { struct Params; }

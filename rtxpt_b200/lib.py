@@ -49,6 +49,7 @@ _SIGNATURES = {
     "rtxpt_b200_path_trace_realtime": [C.c_void_p, C.c_int, C.c_void_p],
     "rtxpt_b200_denoiser_prepare_inputs": [C.c_void_p, C.c_uint32, C.c_int, C.POINTER(S.DenoiserConstants), C.c_void_p],
     "rtxpt_b200_denoiser_final_merge": [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p],
+    "rtxpt_b200_update_instance_transforms": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
     "rtxpt_b200_bake_env_map": [C.c_void_p, C.POINTER(S.EnvBakeDesc), C.c_void_p, C.c_size_t],
     "rtxpt_b200_neeat_update_begin": [C.c_void_p, C.c_void_p],
     "rtxpt_b200_neeat_update_end": [C.c_void_p, C.c_void_p],
@@ -63,7 +64,7 @@ _SIGNATURES = {
     "rtxpt_b200_debug_bsdf": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
     "rtxpt_b200_debug_rng": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
 }
-_LOADER_SYMBOLS = ["rtxpt_b200_env_bake_mip_count", "rtxpt_b200_env_bake_floats", "rtxpt_b200_load_gltf", "rtxpt_b200_load_gltf_ex", "rtxpt_b200_load_scene_json", "rtxpt_b200_host_scene_info", "rtxpt_b200_load_gltf_error", "rtxpt_b200_host_scene_desc", "rtxpt_b200_host_scene_cameras",
+_LOADER_SYMBOLS = ["rtxpt_b200_debug_build_bvh", "rtxpt_b200_env_bake_mip_count", "rtxpt_b200_env_bake_floats", "rtxpt_b200_load_gltf", "rtxpt_b200_load_gltf_ex", "rtxpt_b200_load_scene_json", "rtxpt_b200_host_scene_info", "rtxpt_b200_load_gltf_error", "rtxpt_b200_host_scene_desc", "rtxpt_b200_host_scene_cameras",
                    "rtxpt_b200_host_scene_triangle_count", "rtxpt_b200_free_host_scene", "rtxpt_b200_bridge_camera", "rtxpt_b200_default_constants", "rtxpt_b200_debug_bvh_stats", "rtxpt_b200_parse_material_json", "rtxpt_b200_parse_material_json_error", "rtxpt_b200_debug_decode_dds", "rtxpt_b200_debug_decode_dds_error",
                     "rtxpt_b200_generic_ts_line_stride", "rtxpt_b200_generic_ts_plane_stride", "rtxpt_b200_generic_ts_address"]
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["rtxpt_b200_last_error"] + _LOADER_SYMBOLS)
@@ -167,6 +168,17 @@ class GltfScene:
     def __del__(self):
         try: self.close()
         except Exception: pass
+
+
+def debug_build_bvh(triangle_vertices):
+    """Host-only: the builder's BVH over a triangle soup (n x 9 float32).  Returns (nodes n x 20 u32, tris m x 12 u32 [v0 gid v1 flags v2 prim], levelStart)."""
+    L = load(); v = np.ascontiguousarray(triangle_vertices, np.float32).reshape(-1, 9)
+    f = L.rtxpt_b200_debug_build_bvh; f.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p] + [C.POINTER(C.c_uint32)] * 3; f.restype = C.c_int
+    nn, nt, nl = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    assert f(v.ctypes.data, len(v), None, None, None, C.byref(nn), C.byref(nt), C.byref(nl)) == 0
+    nodes = np.zeros((nn.value, 20), np.uint32); tris = np.zeros((nt.value, 12), np.uint32); levels = np.zeros(nl.value + 1, np.uint32)
+    assert f(v.ctypes.data, len(v), nodes.ctypes.data, tris.ctypes.data, levels.ctypes.data, C.byref(nn), C.byref(nt), C.byref(nl)) == 0
+    return nodes, tris, levels
 
 
 def env_bake_arguments(cube_dim, source, source_type, scale_color, lights):
@@ -285,6 +297,11 @@ class Context:
             if d_diff is None: d_diff = self.device_ptr(S.BUFFER_DENOISER_DIFF_RADIANCE_HITDIST_F16)[0]
             if d_spec is None: d_spec = self.device_ptr(S.BUFFER_DENOISER_SPEC_RADIANCE_HITDIST_F16)[0]
         _check(self.L.rtxpt_b200_denoiser_final_merge(self.h, plane, d_diff, d_spec, stream), self.L)
+
+    def update_instance_transforms(self, transforms, stream=None):
+        """transforms: instanceCount x 3 x 4 float32 (row-major): re-transforms the leaf triangles and refits the BVH on the stream."""
+        t = np.ascontiguousarray(transforms, np.float32).reshape(-1, 12)
+        _check(self.L.rtxpt_b200_update_instance_transforms(self.h, t.ctypes.data, len(t), stream), self.L)
 
     def bake_env_map(self, cube_dim, source=None, source_type=None, scale_color=(1.0, 1.0, 1.0), lights=()):
         """EnvMapBaker on the GPU.  source: HxWx4 float32 equirectangular image or 6xNxNx4 cube (None = lights only); lights: (colour rgb, intensity W/sr, incoming direction,

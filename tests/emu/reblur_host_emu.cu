@@ -7,6 +7,7 @@
 #include "../../rtxpt_b200/csrc/reblur_host.h"
 #include "../../rtxpt_b200/csrc/guides_filter.cuh"
 #include "../../rtxpt_b200/csrc/envbake.cuh"
+#include "../../rtxpt_b200/csrc/refit.cuh"
 #include <vector>
 #include <cstdint>
 
@@ -109,5 +110,15 @@ extern "C" int emu_bake_env_map(uint32_t cubeDim, uint32_t sourceType, uint32_t 
         for (int y = 0; y < int(half); y++) for (uint32_t x = 0; x < half; x++) pt::envbake::baseLayerTexel(p, x, uint32_t(y), f, levels > 1);
     }
     for (uint32_t m = 2; m < levels; m++) { const uint32_t n = cubeDim >> m; for (uint32_t f = 0; f < 6; f++) for (uint32_t y = 0; y < n; y++) for (uint32_t x = 0; x < n; x++) pt::envbake::mipReduceTexel(p, m, x, y, f); }
+    return 0;
+}
+
+// BVH refit: the product's bodies (refit.cuh) in launchRefit's order - every leaf triangle, then the levels deepest first; nodes / tris are updated in place, nodeBox is scratch
+extern "C" int emu_refit(uint32_t* nodes, float* tris, const uint32_t* triShade, const RtxptInstanceData* instances, float* nodeBox, uint32_t nodeCount, uint32_t triCount, const uint32_t* levelStart, uint32_t levelCount)
+{
+    pt::refit::Params p{};
+    p.nodes = reinterpret_cast<uint4*>(nodes); p.tris = reinterpret_cast<float4*>(tris); p.triShade = reinterpret_cast<const uint4*>(triShade); p.instances = instances; p.nodeBox = nodeBox; p.nodeCount = nodeCount; p.triCount = triCount;
+    for (uint32_t i = 0; i < triCount; i++) pt::refit::refitTriangle(p, i);
+    for (uint32_t d = levelCount; d-- > 0;) for (uint32_t ni = levelStart[d]; ni < levelStart[d + 1]; ni++) pt::refit::refitNode(p, ni);
     return 0;
 }
