@@ -384,6 +384,24 @@ RTXPT_API int rtxpt_b200_denoise_spec_hit_t(rtxpt_ctx* ctx, void* cudaStream);
 RTXPT_API int rtxpt_b200_denoiser_prepare_inputs(rtxpt_ctx* ctx, uint32_t stablePlaneIndex, int initWithStableRadiance, const RtxptDenoiserConstants* constants, void* cudaStream);
 RTXPT_API int rtxpt_b200_denoiser_final_merge(rtxpt_ctx* ctx, uint32_t stablePlaneIndex, const void* dDenoisedDiffRGBA16F, const void* dDenoisedSpecRGBA16F, void* cudaStream);    /* NULL, NULL = the images rtxpt_b200_reblur_denoise wrote */
 
+/* ---- Tone mapping / auto exposure (replaces ToneMappingPass::Render, Rtxpt/ToneMapper/ToneMappingPasses.cpp:230-360): log-luminance mean of the frame (auto exposure),
+ * exposure, white balance / exposure-compensation colour transform, operator, clamp, sRGB encode into RTXPT_BUFFER_LDR_COLOR_RGBA8 (RTXPT's LdrColor, SRGBA8).  Field meanings and
+ * defaults: ToneMappingParameters (ToneMappingPasses.h:36-60).  Unlike the reference, the luminance is that of the frame being mapped (no read-back latency, exact mean instead of a MIP chain). */
+typedef struct RtxptToneMappingParams {
+    uint32_t toneMapOperator;           /* 0 Linear, 1 Reinhard, 2 ReinhardModified, 3 HejiHableAlu, 4 HableUc2, 5 Aces */
+    uint32_t clamped, autoExposure, enabled, whiteBalance;
+    float exposureCompensation, exposureValueMin, exposureValueMax;   /* stops; min / max bound the auto-exposure factor */
+    float whiteScale, whiteMaxLuminance, whitePoint;                   /* HableUc2 white; ReinhardModified white; colour temperature in K (1667..25000) */
+    float filmSpeed, fNumber, shutter;                                 /* manual exposure (used when autoExposure == 0): ISO, f-number, reciprocal shutter time */
+    float _pad[2];
+} RtxptToneMappingParams;
+enum { RTXPT_BUFFER_LDR_COLOR_RGBA8 = 19 };
+/* sourceBuffer: RTXPT_BUFFER_OUTPUT_COLOR_F16 (a frame) or RTXPT_BUFFER_ACCUMULATED_F32 (the reference-mode accumulation) */
+RTXPT_API int rtxpt_b200_tone_map(rtxpt_ctx* ctx, const RtxptToneMappingParams* params, int sourceBuffer, void* cudaStream);
+RTXPT_API int rtxpt_b200_tone_map_average_luminance(rtxpt_ctx* ctx, float* outAvgLuminance);        /* of the last rtxpt_b200_tone_map; waits for it */
+/* host helper: ToneMappingPass::GetPreExposedGray (what RtxptDenoiserConstants::preExposedGrayLuminance is the luminance of, Sample.cpp:1516) */
+RTXPT_API int rtxpt_b200_tone_map_pre_exposed_gray(const RtxptToneMappingParams* params, float avgLuminance, float* outRgb);
+
 /* ---- Rigid-instance animation (stands in for the per-frame BLAS / TLAS update behind Sample::UpdateAccelStructs and BuildTLAS, Rtxpt/Sample.cpp:1170-1240): new
  * row-major 3x4 matrices for every instance of the uploaded scene; on the stream, the leaf triangles are re-transformed (one thread each) and the 8-wide BVH is refitted bottom-up,
  * level by level, with the builder's own quantisation - unmoved geometry gives back the built nodes bit for bit, topology never changes (quality degrades with large deformation,

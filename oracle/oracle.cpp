@@ -8,6 +8,7 @@
 #include "pt_path.h"
 #include "reblur.h"
 #include "pt_envbake.h"
+#include "pt_tonemap.h"
 #include <cstdio>
 #include <chrono>
 #ifdef _OPENMP
@@ -381,6 +382,24 @@ ORC_API int oracle_denoiser_final_merge(void* p, const RtxptRealtimeConstants* r
     if (!c->haveConsts || !rt || stablePlaneIndex >= 3) return -1;
     const RealtimeTargets T = makeTargets(c, rt, realtimeTargets); const DenoiserTargets D = makeDenoiserTargets(denoiserTargets);
     for (uint32_t y = 0; y < T.height; y++) for (uint32_t px = 0; px < T.width; px++) denoiserFinalMergePixel(T, D, px, y, stablePlaneIndex, denoisedDiff, denoisedSpec);
+    return 0;
+}
+
+// ToneMappingPass (pt_tonemap.h): RGBA32F frame -> SRGBA8; params as RtxptToneMappingParams; outAux = { average luminance, pre-exposed gray r, g, b }
+ORC_API int oracle_tone_map(const RtxptToneMappingParams* u, const float* rgba, uint32_t pixelCount, uint8_t* outRGBA8, float* outAux)
+{
+    if (!u || !rgba || !outRGBA8) return -1;
+    tonemap::Params p; p.op = u->toneMapOperator; p.clamped = u->clamped; p.autoExposure = u->autoExposure; p.enabled = u->enabled; p.whiteBalance = u->whiteBalance;
+    p.exposureCompensation = u->exposureCompensation; p.exposureValueMin = u->exposureValueMin; p.exposureValueMax = u->exposureValueMax; p.whiteScale = u->whiteScale; p.whiteMaxLuminance = u->whiteMaxLuminance;
+    p.whitePoint = u->whitePoint; p.filmSpeed = u->filmSpeed; p.fNumber = u->fNumber; p.shutter = u->shutter;
+    const tonemap::M3 ct = tonemap::colorTransform(p);
+    const float avg = tonemap::averageLuminance(rgba, pixelCount);
+    for (uint32_t i = 0; i < pixelCount; i++)
+    {
+        const float3 c = tonemap::apply(p, ct, p.autoExposure ? avg : 1.0f, f3(rgba[4 * i], rgba[4 * i + 1], rgba[4 * i + 2]));
+        outRGBA8[4 * i] = tonemap::srgb8(c.x); outRGBA8[4 * i + 1] = tonemap::srgb8(c.y); outRGBA8[4 * i + 2] = tonemap::srgb8(c.z); outRGBA8[4 * i + 3] = uint8_t(saturate(rgba[4 * i + 3]) * 255.0f + 0.5f);
+    }
+    if (outAux) { outAux[0] = avg; const float3 g = tonemap::preExposedGray(p, avg); outAux[1] = g.x; outAux[2] = g.y; outAux[3] = g.z; }
     return 0;
 }
 

@@ -8,6 +8,7 @@
 #include "neeat_host.h"
 #include "envbake.cuh"
 #include "refit.cuh"
+#include "tonemap.cuh"
 #include "lights_bake.h"
 #include <algorithm>
 #include <chrono>
@@ -109,6 +110,7 @@ struct rtxpt_ctx
                          blendedCandidate.release(); local.release(); counters.release(); proxyCounters.release(); proxyOffsets.release(); proxyIndices.release(); samplingProxyCount.release();
                          scanBlockSums.release(); rrFix.release(); shadowFeedback.release(); allocated = false; frameBegun = false; frameEnded = false; }
     } na;
+    DeviceArray<double> tmPartials; DeviceArray<float> tmAvgLuminance; DeviceArray<uint32_t> ldrColor; bool toneMapped = false;      // tone mapping (tonemap.cuh)
     cudaEvent_t evDnStart = nullptr, evDnStop = nullptr; bool denoiseTimed = false;       // around the last rtxpt_b200_denoise_realtime
     // stats
     uint32_t* hCounters = nullptr;          // pinned
@@ -194,7 +196,7 @@ extern "C" RTXPT_API int rtxpt_b200_destroy(rtxpt_ctx* c)
     c->stablePlanes.release(); c->stablePlanesHeader.release(); c->stableRadiance.release(); c->specularHitT.release();
     c->dnScratchFloat.release(); c->dnViewZ.release(); c->dnMotion.release(); c->dnDiff.release(); c->dnSpec.release(); c->dnNormalRoughness.release(); c->dnDisocclusionMix.release(); c->dnHistoryClampRelax.release();
     for (auto& h : c->reblur) h.release();
-    c->na.release();
+    c->na.release(); c->tmPartials.release(); c->tmAvgLuminance.release(); c->ldrColor.release();
     c->rbTiles.release(); c->rbTmp1Diff.release(); c->rbTmp1Spec.release(); c->rbTmp2Diff.release(); c->rbTmp2Spec.release(); c->rbOutDiff.release(); c->rbOutSpec.release();
     c->rbTrackingT.release(); c->rbDiffFastT.release(); c->rbSpecFastT.release(); c->rbData1.release(); c->rbData2.release();
     for (cudaEvent_t ev : c->evPool) cudaEventDestroy(ev);
@@ -756,6 +758,40 @@ extern "C" RTXPT_API int rtxpt_b200_denoiser_final_merge(rtxpt_ctx* c, uint32_t 
     return RTXPT_OK;
 }
 
+// ---- tone mapping -------------------------------------------------------------------------------------------------------------------------------------
+extern "C" RTXPT_API int rtxpt_b200_tone_map(rtxpt_ctx* c, const RtxptToneMappingParams* u, int sourceBuffer, void* cudaStream)
+{
+    if (!c || !u) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (!c->haveConstants) return fail(RTXPT_ERR_INVALID_ARGUMENT, "constants not set (the image size comes from them)");
+    if (u->toneMapOperator > 5) return fail(RTXPT_ERR_INVALID_ARGUMENT, "unknown tone-mapping operator %u", u->toneMapOperator);
+    if (sourceBuffer != RTXPT_BUFFER_OUTPUT_COLOR_F16 && sourceBuffer != RTXPT_BUFFER_ACCUMULATED_F32) return fail(RTXPT_ERR_INVALID_ARGUMENT, "tone mapping reads the output colour or the accumulation buffer");
+    cudaSetDevice(c->device);
+    cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
+    const size_t P = size_t(c->tableWidth) * c->tableHeight;
+    if (c->ldrColor.count != P) { CU(cudaStreamSynchronize(c->stream)); CU(c->ldrColor.alloc(P)); CU(c->tmPartials.alloc(1024)); CU(c->tmAvgLuminance.alloc(1)); }
+    const void* src = sourceBuffer == RTXPT_BUFFER_ACCUMULATED_F32 ? static_cast<const void*>(c->accumulated.ptr) : static_cast<const void*>(c->outputColor.ptr);
+    if (!src) return fail(RTXPT_ERR_INVALID_ARGUMENT, "the source buffer does not exist yet");
+    launchToneMap(tonemap::makeParams(*u), src, sourceBuffer == RTXPT_BUFFER_ACCUMULATED_F32, uint32_t(P), c->tmPartials.ptr, c->tmAvgLuminance.ptr, c->ldrColor.ptr, s);
+    CU(cudaGetLastError());
+    c->toneMapped = true;
+    return RTXPT_OK;
+}
+extern "C" RTXPT_API int rtxpt_b200_tone_map_average_luminance(rtxpt_ctx* c, float* out)
+{
+    if (!c || !out) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (!c->toneMapped) return fail(RTXPT_ERR_INVALID_ARGUMENT, "rtxpt_b200_tone_map has not run");
+    cudaSetDevice(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(out, c->tmAvgLuminance.ptr, 4, cudaMemcpyDeviceToHost));
+    return RTXPT_OK;
+}
+extern "C" RTXPT_API int rtxpt_b200_tone_map_pre_exposed_gray(const RtxptToneMappingParams* u, float avgLuminance, float* outRgb)
+{
+    if (!u || !outRgb) return RTXPT_ERR_INVALID_ARGUMENT;
+    tonemap::preExposedGray(*u, avgLuminance, outRgb);
+    return RTXPT_OK;
+}
+
 // ---- rigid-instance animation: new instance matrices -> leaf triangles re-transformed, BVH refitted bottom-up (Sample.cpp:1170-1240) --------------------------
 extern "C" RTXPT_API int rtxpt_b200_update_instance_transforms(rtxpt_ctx* c, const float* transforms3x4, uint32_t instanceCount, void* cudaStream)
 {
@@ -1058,6 +1094,9 @@ static int targetInfo(rtxpt_ctx* c, int buffer, void** ptr, size_t* bytes)
         default: *ptr = c->dnHistoryClampRelax.ptr; *bytes = P; break;
         }
         return RTXPT_OK;
+    case RTXPT_BUFFER_LDR_COLOR_RGBA8:
+        if (!c->toneMapped || c->ldrColor.count != P) return fail(RTXPT_ERR_INVALID_ARGUMENT, "the LDR colour does not exist before rtxpt_b200_tone_map");
+        *ptr = c->ldrColor.ptr; *bytes = P * 4; return RTXPT_OK;
     case RTXPT_BUFFER_DENOISED_DIFF_RADIANCE_HITDIST_F16: case RTXPT_BUFFER_DENOISED_SPEC_RADIANCE_HITDIST_F16: case RTXPT_BUFFER_REBLUR_ACCUMULATED_FRAMES_RG8:
         if (c->reblurWidth != c->tableWidth || c->reblurHeight != c->tableHeight) return fail(RTXPT_ERR_INVALID_ARGUMENT, "ReBLUR buffers do not exist before rtxpt_b200_reblur_denoise");
         if (buffer == RTXPT_BUFFER_DENOISED_DIFF_RADIANCE_HITDIST_F16) { *ptr = c->rbOutDiff.ptr; *bytes = P * 8; }

@@ -35,6 +35,7 @@ STABLE_PLANE_COUNT, STABLE_PLANE_INVALID_BRANCH = 3, 0xFFFFFFFF
 (BUFFER_DENOISER_VIEWSPACE_Z_F32, BUFFER_DENOISER_MOTION_VECTORS_F16, BUFFER_DENOISER_NORMAL_ROUGHNESS_R10G10B10A2, BUFFER_DENOISER_DIFF_RADIANCE_HITDIST_F16,
  BUFFER_DENOISER_SPEC_RADIANCE_HITDIST_F16, BUFFER_DENOISER_DISOCCLUSION_MIX_R8, BUFFER_COMBINED_HISTORY_CLAMP_RELAX_R8) = 9, 10, 11, 12, 13, 14, 15
 BUFFER_DENOISED_DIFF_RADIANCE_HITDIST_F16, BUFFER_DENOISED_SPEC_RADIANCE_HITDIST_F16, BUFFER_REBLUR_ACCUMULATED_FRAMES_RG8 = 16, 17, 18
+BUFFER_LDR_COLOR_RGBA8 = 19
 
 
 class GeometryData(C.Structure):
@@ -132,6 +133,20 @@ STABLE_PLANE_DTYPE = [("RayOrigin", "f4", 3), ("LastRayTCurrent", "f4"), ("RayDi
 class DenoiserConstants(C.Structure):
     _fields_ = [("matWorldToView", f32 * 16), ("hitDistanceParameters", f32 * 4), ("preExposedGrayLuminance", f32), ("denoiserRadianceClampK", f32),
                 ("stablePlanesSuppressPrimaryIndirectSpecularK", f32), ("_pad", f32)]
+
+
+class ToneMappingParams(C.Structure):
+    _fields_ = [("toneMapOperator", u32), ("clamped", u32), ("autoExposure", u32), ("enabled", u32), ("whiteBalance", u32), ("exposureCompensation", f32), ("exposureValueMin", f32),
+                ("exposureValueMax", f32), ("whiteScale", f32), ("whiteMaxLuminance", f32), ("whitePoint", f32), ("filmSpeed", f32), ("fNumber", f32), ("shutter", f32), ("_pad", f32 * 2)]
+
+
+def make_tone_mapping_params(op=5, clamped=True, auto_exposure=False, enabled=True, white_balance=False, exposure_compensation=0.0, exposure_value_min=-16.0, exposure_value_max=16.0,
+                             white_scale=11.2, white_max_luminance=1.0, white_point=6500.0, film_speed=100.0, f_number=1.0, shutter=1.0):
+    """ToneMappingParameters with the defaults of ToneMappingPasses.h:36-60 (Aces, clamped, manual exposure that scales by 1)."""
+    p = ToneMappingParams(); p.toneMapOperator = op; p.clamped = int(clamped); p.autoExposure = int(auto_exposure); p.enabled = int(enabled); p.whiteBalance = int(white_balance)
+    p.exposureCompensation = exposure_compensation; p.exposureValueMin = exposure_value_min; p.exposureValueMax = exposure_value_max; p.whiteScale = white_scale
+    p.whiteMaxLuminance = white_max_luminance; p.whitePoint = white_point; p.filmSpeed = film_speed; p.fNumber = f_number; p.shutter = shutter
+    return p
 
 
 class EnvBakeLight(C.Structure):

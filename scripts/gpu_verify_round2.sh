@@ -11,6 +11,7 @@ PY="python -m pytest -x -q -m gpu_unverified"
 run verified      python -m pytest tests -x -q -m gpu                                   # the round-1 bar first: nothing regressed
 run guide_filter  $PY tests/test_gpu_reblur.py -k spec_hit_t
 run envbake       $PY tests/test_gpu_envbake.py
+run tonemap       $PY tests/test_gpu_tonemap.py
 run refit         $PY tests/test_gpu_refit.py
 run reblur        $PY tests/test_gpu_reblur.py -k "static_camera or moving_camera or reset"
 run realtime_rest $PY tests/test_gpu_realtime.py

@@ -8,6 +8,7 @@
 #include "../../rtxpt_b200/csrc/guides_filter.cuh"
 #include "../../rtxpt_b200/csrc/envbake.cuh"
 #include "../../rtxpt_b200/csrc/refit.cuh"
+#include "../../rtxpt_b200/csrc/tonemap.cuh"
 #include <vector>
 #include <cstdint>
 
@@ -120,5 +121,20 @@ extern "C" int emu_refit(uint32_t* nodes, float* tris, const uint32_t* triShade,
     p.nodes = reinterpret_cast<uint4*>(nodes); p.tris = reinterpret_cast<float4*>(tris); p.triShade = reinterpret_cast<const uint4*>(triShade); p.instances = instances; p.nodeBox = nodeBox; p.nodeCount = nodeCount; p.triCount = triCount;
     for (uint32_t i = 0; i < triCount; i++) pt::refit::refitTriangle(p, i);
     for (uint32_t d = levelCount; d-- > 0;) for (uint32_t ni = levelStart[d]; ni < levelStart[d + 1]; ni++) pt::refit::refitNode(p, ni);
+    return 0;
+}
+
+// tone mapping: the product's host constants (makeParams / preExposedGray) and pixel bodies (tonemap.cuh); the log-luminance mean in double like the kernels' reduction
+extern "C" int emu_tone_map(const RtxptToneMappingParams* u, const float* rgba, uint32_t pixelCount, uint8_t* outRGBA8, float* outAux)
+{
+    const pt::tonemap::Params p = pt::tonemap::makeParams(*u);
+    double s = 0; for (uint32_t i = 0; i < pixelCount; i++) s += double(pt::tonemap::logLuminance(pt::mk3(rgba[4 * i], rgba[4 * i + 1], rgba[4 * i + 2])));
+    const float avg = exp2f(float(s / double(pixelCount)));
+    for (uint32_t i = 0; i < pixelCount; i++)
+    {
+        const uint32_t v = pt::tonemap::packLdr(pt::tonemap::applyToneMapping(p, p.autoExposure ? avg : 1.0f, pt::mk3(rgba[4 * i], rgba[4 * i + 1], rgba[4 * i + 2])), rgba[4 * i + 3]);
+        memcpy(outRGBA8 + 4 * size_t(i), &v, 4);
+    }
+    if (outAux) { outAux[0] = avg; pt::tonemap::preExposedGray(*u, avg, outAux + 1); }
     return 0;
 }
