@@ -42,11 +42,11 @@ def test_oracle_tone_mapping_properties(oracle):
     assert np.isclose(aux1[0], np.exp2(np.log2(np.maximum(lum, 1e-4)).mean()), rtol=1e-4) and np.isclose(aux4[0], 4 * aux1[0], rtol=1e-4)
     assert np.abs(o1.astype(int) - o4.astype(int)).max() <= 1
     # white balance: D65 is the identity; a warm white point pushes a grey towards blue (the transform undoes the illuminant), pre-exposed grey inverts the transform
-    grey = np.full((4, 4, 4), 0.4, np.float32)
+    grey = np.full((4, 4, 4), 0.05, np.float32)
     d65, _ = _run(L, "oracle_tone_map", S.make_tone_mapping_params(op=0, white_balance=True, white_point=6500.0), grey)
     warm, auxw = _run(L, "oracle_tone_map", S.make_tone_mapping_params(op=0, white_balance=True, white_point=3200.0), grey)
     assert np.array_equal(d65[..., 0], d65[..., 2]) and abs(int(d65[0, 0, 0]) - int(d65[0, 0, 1])) <= 1
-    assert int(warm[0, 0, 2]) > int(warm[0, 0, 0]) + 20
+    lin = _srgb_decode(warm[0, 0, :3]); assert lin[2] > 1.3 * lin[0] and lin.max() < 1.0, lin
     _, aux0 = _run(L, "oracle_tone_map", S.make_tone_mapping_params(op=0, exposure_compensation=2.0), grey)
     assert np.allclose(aux0[1:], 0.18 / 4, rtol=1e-5)
 
