@@ -2,6 +2,7 @@
 // Follows Rtxpt/Shaders/PathTracer/Utils/{Packing,Utils,NoiseAndSequences,StatelessSampleGenerators,SampleGenerators}.hlsli and
 // Utils/Math/MathHelpers.hlsli, Utils/Geometry.hlsli (citations at each function).
 #pragma once
+#include <string.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
@@ -54,6 +55,25 @@ PT_HD bool anyPositive(float3 v) { return v.x > 0 || v.y > 0 || v.z > 0; }
 PT_HD float luminance(float3 c) { return dot3(c, mk3(0.2126f, 0.7152f, 0.0722f)); }      // Utils/Utils.hlsli:51
 PT_HD float average(float3 c) { return (c.x + c.y + c.z) / 3.0f; }                      // Utils/Utils.hlsli:57
 PT_HD float maxComp(float3 c) { return fmaxf(fmaxf(c.x, c.y), c.z); }                   // Utils/ColorHelpers.hlsli:19-27
+
+// bit casts usable from __host__ __device__ bodies (the host builds of tests/emu)
+#ifdef __CUDA_ARCH__
+PT_HD uint floatBits(float f) { return __float_as_uint(f); }
+PT_HD float bitsToFloat(uint u) { return __uint_as_float(u); }
+#else
+PT_HD uint floatBits(float f) { uint u; memcpy(&u, &f, 4); return u; }
+PT_HD float bitsToFloat(uint u) { float f; memcpy(&f, &u, 4); return f; }
+#endif
+// OctToNDirUnorm32 (Utils.hlsli:128-153; the [0,1] mapping is applied twice on both sides, see lights_bake.cpp)
+PT_HD float3 octUnorm32ToDir(uint p)
+{
+    float fx = sat(float(p & 0xffffu) / float(0xfffe)) * 2.0f - 1.0f, fy = sat(float(p >> 16) / float(0xfffe)) * 2.0f - 1.0f;
+    fx = fx * 2.0f - 1.0f; fy = fy * 2.0f - 1.0f;
+    float3 n = mk3(fx, fy, 1.0f - fabsf(fx) - fabsf(fy));
+    const float t = sat(-n.z);
+    n.x += (n.x >= 0.0f) ? -t : t; n.y += (n.y >= 0.0f) ? -t : t;
+    return norm3(n);
+}
 
 // ---- fp16 storage (RNE; equals the oracle's f32tof16) ---------------------------------------------------------------------
 PT_HD uint f32tof16(float v) { return (uint)__half_as_ushort(__float2half_rn(v)); }
@@ -130,11 +150,11 @@ PT_HD uint vertexBaseHash(uint packedPixel, uint vertexIndex) { return hash32Com
 struct UniformSeq
 {
     uint h;
-    PT_DEVICE static UniformSeq make(uint baseHash, uint sampleIndex, uint effectSeed)
+    PT_HD static UniformSeq make(uint baseHash, uint sampleIndex, uint effectSeed)
     {
         UniformSeq s; s.h = hash32Combine(hash32Combine(baseHash, effectSeed), sampleIndex); return s;
     }
-    PT_DEVICE float next() { h = hash32(h); return hashToFloat(h); }
+    PT_HD float next() { h = hash32(h); return hashToFloat(h); }
     PT_DEVICE uint nextBits() { h = hash32(h); return h; }
 };
 // SampleSequenceGenerator::Generate, low-discrepancy branch (StatelessSampleGenerators.hlsli:150-181), dimension `dim` of sample `sampleIndex`
@@ -168,7 +188,7 @@ PT_DEVICE float3 octEqualAreaToDir(float2 p)      // oct_to_ndir_equal_area_unor
     float f = r * sqrtf(2.f - r * r);
     return mk3(f * sgn(px) * cosf(phi), f * sgn(py) * sinf(phi), sgn(d) * (1.f - r * r));
 }
-PT_DEVICE float2 sampleDiskPolar(float u0, float u1) { float r = sqrtf(u0); float phi = k2Pi * u1; return mk2(r * cosf(phi), r * sinf(phi)); }   // MathHelpers.hlsli:238
+PT_HD float2 sampleDiskPolar(float u0, float u1) { float r = sqrtf(u0); float phi = k2Pi * u1; return mk2(r * cosf(phi), r * sinf(phi)); }   // MathHelpers.hlsli:238
 PT_DEVICE float3 sampleCosineHemisphereConcentric(float u0, float u1, float& pdf)       // MathHelpers.hlsli:288-320
 {
     float ux = 2.f * u0 - 1.f, uy = 2.f * u1 - 1.f;

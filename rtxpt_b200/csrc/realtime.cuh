@@ -12,11 +12,10 @@
 namespace pt {
 
 constexpr uint kStablePlaneCount = 3, kStablePlaneMaxVertexIndex = 15, kMaxDeltaLobes = 3;
-constexpr uint kInvalidBranchID = 0xFFFFFFFFu, kEnqueuedBranchID = 0xFFFFFFFEu, kJustStartedBranchID = 0u;
+constexpr uint kEnqueuedBranchID = 0xFFFFFFFEu, kJustStartedBranchID = 0u;          // kInvalidBranchID, vertexIndexFromBranchID: wavefront.cuh (shared with the denoiser interface's host+device bodies)
 constexpr float kEnvironmentMapSceneDistance = 50000.0f * 100.0f;           // Config.h:84-85
 
 PT_DEVICE uint advanceBranchID(uint prev, uint deltaLobe) { return (prev << 2) | deltaLobe; }
-PT_DEVICE uint vertexIndexFromBranchID(uint id) { return (31u - __clz(id)) / 2u + 1u; }       // firstbithigh(id)/2 + 1
 PT_DEVICE bool isOnStablePath(uint planeBranchID, uint planeVertexIndex, uint vertexBranchID, uint vertexIndex)
 {
     if (vertexIndex > planeVertexIndex) return false;
@@ -24,23 +23,6 @@ PT_DEVICE bool isOnStablePath(uint planeBranchID, uint planeVertexIndex, uint ve
 }
 
 // ---- addressing -------------------------------------------------------------------------------------------------------------------------------
-PT_DEVICE uint morton16(uint x, uint y)
-{
-    uint t = (x & 0xffu) | ((y & 0xffu) << 16);
-    t = (t ^ (t << 4)) & 0x0f0f0f0fu; t = (t ^ (t << 2)) & 0x33333333u; t = (t ^ (t << 1)) & 0x55555555u;
-    return ((t >> 15) | t) & 0xffffu;
-}
-PT_DEVICE uint planeAddress(const RealtimeParams& rt, uint id, uint plane)
-{
-    const uint px = id >> 16, py = id & 0xFFFFu, xi = px & 7u, yi = py & 7u;
-    return (px - xi) * 8u + (py - yi) * rt.lineStride + morton16(xi, yi) + plane * rt.planeStride;
-}
-PT_DEVICE uint& headerWord(const LaunchParams& p, uint id, uint layer)
-{
-    return p.rt.header[(size_t(layer) * p.c.imageHeight + (id & 0xFFFFu)) * p.c.imageWidth + (id >> 16)];
-}
-PT_DEVICE size_t pixelOffset(const LaunchParams& p, uint id) { return size_t(id & 0xFFFFu) * p.c.imageWidth + (id >> 16); }
-
 // ---- packing ------------------------------------------------------------------------------------------------------------------------------------
 PT_DEVICE uint packTwoHalf(float hi, float lo) { return (f32tof16(clampf(hi, -kHalfMax, kHalfMax)) << 16) | f32tof16(clampf(lo, -kHalfMax, kHalfMax)); }     // PackTwoFp32ToFp16
 PT_DEVICE float2 encodeOct(float3 n)

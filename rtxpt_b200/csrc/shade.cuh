@@ -60,16 +60,6 @@ PT_DEVICE float3 unpackLightRadiance(const LightInfo& li)           // Polymorph
     return mk3(unpackUnorm8(li.colorTypeAndFlags), unpackUnorm8(li.colorTypeAndFlags >> 8), unpackUnorm8(li.colorTypeAndFlags >> 16)) * radiance;
 }
 
-// OctToNDirUnorm32 (Utils.hlsli:128-153; the [0,1] mapping is applied twice on both sides, see lights_bake.cpp)
-PT_DEVICE float3 octUnorm32ToDir(uint p)
-{
-    float fx = sat(float(p & 0xffffu) / float(0xfffe)) * 2.0f - 1.0f, fy = sat(float(p >> 16) / float(0xfffe)) * 2.0f - 1.0f;
-    fx = fx * 2.0f - 1.0f; fy = fy * 2.0f - 1.0f;
-    float3 n = mk3(fx, fy, 1.0f - fabsf(fx) - fabsf(fy));
-    const float t = sat(-n.z);
-    n.x += (n.x >= 0.0f) ? -t : t; n.y += (n.y >= 0.0f) ? -t : t;
-    return norm3(n);
-}
 // evaluateLightShaping (LightShaping.hlsli:26-95): spot falloff of a shaped light towards `surfacePos`, 1 for unshaped lights
 PT_DEVICE float lightShaping(const LightInfo& li, const SceneView& sc, uint lightIndex, float3 surfacePos, float3 lightSamplePos)
 {

@@ -97,6 +97,30 @@ struct LaunchParams
     uint* naRrFix;                  // per path slot: set by the shadow kernel when the sample was visible, consumed by the next shade of the path
 };
 
+// ---- stable-plane addressing (GenericTS, Utils.hlsli:320-362; StablePlanes.hlsli:120-140): host+device so that the denoiser interface's pixel bodies also build for the host ----
+constexpr uint kInvalidBranchID = 0xFFFFFFFFu;
+#ifdef __CUDA_ARCH__
+PT_HD uint vertexIndexFromBranchID(uint id) { return (31u - __clz(id)) / 2u + 1u; }       // firstbithigh(id)/2 + 1
+#else
+PT_HD uint vertexIndexFromBranchID(uint id) { return (31u - uint(__builtin_clz(id))) / 2u + 1u; }
+#endif
+PT_HD uint morton16(uint x, uint y)
+{
+    uint t = (x & 0xffu) | ((y & 0xffu) << 16);
+    t = (t ^ (t << 4)) & 0x0f0f0f0fu; t = (t ^ (t << 2)) & 0x33333333u; t = (t ^ (t << 1)) & 0x55555555u;
+    return ((t >> 15) | t) & 0xffffu;
+}
+PT_HD uint planeAddress(const RealtimeParams& rt, uint id, uint plane)
+{
+    const uint px = id >> 16, py = id & 0xFFFFu, xi = px & 7u, yi = py & 7u;
+    return (px - xi) * 8u + (py - yi) * rt.lineStride + morton16(xi, yi) + plane * rt.planeStride;
+}
+PT_HD uint& headerWord(const LaunchParams& p, uint id, uint layer)
+{
+    return p.rt.header[(size_t(layer) * p.c.imageHeight + (id & 0xFFFFu)) * p.c.imageWidth + (id >> 16)];
+}
+PT_HD size_t pixelOffset(const LaunchParams& p, uint id) { return size_t(id & 0xFFFFu) * p.c.imageWidth + (id >> 16); }
+
 // ---- packed path-state accessors (PathState.hlsli:125-200) ------------------------------------------------------------------
 enum : uint {
     kPFActive = 1u << 0, kPFHit = 1u << 1, kPFTransmission = 1u << 2, kPFSpecular = 1u << 3, kPFDelta = 1u << 4,
@@ -184,7 +208,7 @@ struct PathRegs             // one path's state in registers
 constexpr uint kCtrDiffuseBounces = 0, kCtrRejectedHits = 1, kCtrBouncesFromStablePlane = 2;
 
 // Bridge::computeCameraRay + ComputeRayThinlens (BridgeDonut:543-564, PathTracerHelpers.hlsli:126-153): camera ray of pixel `id` for sample `sampleIndex`
-PT_DEVICE void computeCameraRay(const RtxptPathTracerConstants& c, uint id, uint sampleIndex, float3& origin, float3& dir)
+PT_HD void computeCameraRay(const RtxptPathTracerConstants& c, uint id, uint sampleIndex, float3& origin, float3& dir)
 {
     const RtxptCameraData& cam = c.camera;
     const uint px = id >> 16, py = id & 0xFFFF;

@@ -9,6 +9,7 @@
 #include "../../rtxpt_b200/csrc/envbake.cuh"
 #include "../../rtxpt_b200/csrc/refit.cuh"
 #include "../../rtxpt_b200/csrc/tonemap.cuh"
+#include "../../rtxpt_b200/csrc/denoiser_iface.cuh"
 #include <vector>
 #include <cstdint>
 
@@ -136,5 +137,27 @@ extern "C" int emu_tone_map(const RtxptToneMappingParams* u, const float* rgba, 
         memcpy(outRGBA8 + 4 * size_t(i), &v, 4);
     }
     if (outAux) { outAux[0] = avg; pt::tonemap::preExposedGray(*u, avg, outAux + 1); }
+    return 0;
+}
+
+// RTXPT's side of the denoiser interface: the product's pixel bodies (denoiser_iface.cuh) over host copies of the realtime targets.  realtimeTargets = { planes, header, stableRadiance,
+// depth, motion, throughput, specularHitT }, denoiserTargets = { viewZ, motion, normalRoughness, diff, spec, disocclusionMix, historyClampRelax, outputColor } - the layouts of
+// oracle_denoiser_prepare_inputs.  mode 0: prepare inputs; 1: final merge with the given denoised images.
+extern "C" int emu_denoiser_interface(const RtxptPathTracerConstants* consts, const RtxptRealtimeConstants* rt, const RtxptDenoiserConstants* k, uint32_t plane, int initWithStableRadiance, int mode,
+                                      void* const* realtimeTargets, void* const* denoiserTargets, const void* denoisedDiff, const void* denoisedSpec)
+{
+    pt::LaunchParams p; memset(&p, 0, sizeof(p));
+    p.c = *consts;
+    const uint32_t W = consts->imageWidth, H = consts->imageHeight;
+    p.rt.planes = static_cast<RtxptStablePlane*>(realtimeTargets[0]); p.rt.header = static_cast<uint32_t*>(realtimeTargets[1]); p.rt.stableRadiance = static_cast<uint2*>(realtimeTargets[2]);
+    p.rt.specularHitT = static_cast<float*>(realtimeTargets[6]);
+    p.rt.lineStride = rtxpt_b200_generic_ts_line_stride(W, H); p.rt.planeStride = rtxpt_b200_generic_ts_plane_stride(W, H); p.rt.activePlaneCount = rt->activeStablePlaneCount;
+    p.rt.dnViewZ = static_cast<float*>(denoiserTargets[0]); p.rt.dnMotion = static_cast<uint2*>(denoiserTargets[1]); p.rt.dnNormalRoughness = static_cast<uint32_t*>(denoiserTargets[2]);
+    p.rt.dnDiff = static_cast<uint2*>(denoiserTargets[3]); p.rt.dnSpec = static_cast<uint2*>(denoiserTargets[4]); p.rt.dnDisocclusionMix = static_cast<unsigned char*>(denoiserTargets[5]);
+    p.rt.dnHistoryClampRelax = static_cast<unsigned char*>(denoiserTargets[6]); p.outputColor = static_cast<uint2*>(denoiserTargets[7]);
+    p.rt.dnDenoisedDiff = static_cast<const uint2*>(denoisedDiff); p.rt.dnDenoisedSpec = static_cast<const uint2*>(denoisedSpec);
+    if (k) p.rt.dn = *k;
+    p.rt.dnPlane = plane; p.rt.dnInitWithStableRadiance = initWithStableRadiance ? 1u : 0u;
+    for (uint32_t y = 0; y < H; y++) for (uint32_t x = 0; x < W; x++) { const uint32_t id = (x << 16) | y; if (mode == 0) pt::dnPrepareInputsPixel(p, id); else pt::dnFinalMergePixel(p, id); }
     return 0;
 }
