@@ -75,6 +75,28 @@ def main():
         consts.NEEATFeedback = 0; ctx.set_constants(consts)
     except Exception as e:  # noqa: BLE001
         out["neeat_feedback"] = {"error": repr(e)[:300]}
+    # the callers either side of the path (§8f rows 3-4), first GPU executions as well: tone mapping, environment bake, BVH refit (last: a wrong refit would spoil what follows)
+    try:
+        tm = S.make_tone_mapping_params(op=5, auto_exposure=True); ctx.tone_map(tm); ctx.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10): ctx.tone_map(tm)
+        ctx.synchronize(); tone_ms = (time.perf_counter() - t0) * 100.0
+        ldr = ctx.readback_ldr()
+        eq = np.random.default_rng(1).gamma(2.0, 0.5, (256, 512, 4)).astype(np.float32)
+        t0 = time.perf_counter(); mips = ctx.bake_env_map(512, eq, lights=[((1.0, 0.9, 0.8), 10.0, (0.3, -0.8, 0.52), 0.05)]); bake_ms = (time.perf_counter() - t0) * 1e3
+        n_inst = scene.desc.instanceCount
+        xf = np.stack([np.array(scene.desc.instances[i].transform[:], np.float32).reshape(3, 4) for i in range(n_inst)])
+        ctx.update_instance_transforms(xf); ctx.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5): ctx.update_instance_transforms(xf)
+        ctx.synchronize(); refit_ms = (time.perf_counter() - t0) * 200.0
+        consts.sampleBaseIndex = 0; ctx.set_constants(consts); ctx.path_trace_realtime(True); ctx.synchronize()
+        after = float(ctx.readback_output_color()[..., :3].astype(np.float32).mean())
+        out["callers"] = {"tone_map_ms_host_clock": tone_ms, "tone_map_avg_luminance": ctx.tone_map_average_luminance(), "ldr_mean": float(ldr[..., :3].mean()),
+                          "env_bake_512_ms_host_clock_incl_copies": bake_ms, "env_bake_finite": bool(np.isfinite(mips[0]).all()),
+                          "bvh_refit_ms_host_clock": refit_ms, "instances": int(n_inst), "bvh_intact_after_identity_refit": bool(abs(after - out["mean_radiance"]) < 0.25 * abs(out["mean_radiance"]) + 1e-6)}
+    except Exception as e:  # noqa: BLE001
+        out["callers"] = {"error": repr(e)[:300]}
     os.write(real_stdout, (json.dumps(out) + "\n").encode())         # before teardown: a device fault in the untested stage must not cost the line
     try: ctx.close()
     except Exception: pass  # noqa: BLE001
