@@ -87,3 +87,28 @@ def test_feedback_is_unbiased_and_reduces_error(oracle):
     e_fb, e_gl = np.abs(warm - ref).mean(), np.abs(b - ref).mean()
     assert e_fb < 0.93 * e_gl, (e_fb, e_gl)                                             # local candidates find the bay's own lamps: lower per-frame error
     assert np.isfinite(a).all()
+
+
+def test_reference_mode_loop_is_unbiased(oracle):
+    """Reference mode (RTXPT's default NEEType 2): update_begin, update_end on the previous frame's guides, then the radiance pass.  Same mean as feedback-free sampling."""
+    from rtxpt_b200 import scene_builder as sb, scenes
+    W, H = 96, 64
+    scene, cam = scenes.light_gallery(W, H, bays=8)
+    guide = oracle.Oracle(scene); cg = sb.make_constants(W, H, cam, bounce_count=2, diffuse_bounce_count=2); guide.set_constants(cg); guide.set_view(sb.world_to_clip(cam))
+    g = guide.render_realtime(sb.make_realtime_constants(W, H, cam, bounce_count=2, sub_samples=1)); guide.close()          # static camera: one set of depth / motion guides
+    def frames(n, feedback):
+        o = oracle.Oracle(scene); c = sb.make_constants(W, H, cam, bounce_count=2, diffuse_bounce_count=2); c.NEEATFeedback = 1 if feedback else 0
+        o.set_constants(c); o.set_view(sb.world_to_clip(cam))
+        if feedback: o.neeat_reset()
+        out = []
+        for f in range(n):
+            c.sampleBaseIndex = 2 * f; o.set_constants(c)
+            if feedback: o.neeat_update_begin(); o.neeat_update_end(g["depth"], g["motion"])
+            acc = o.render(0, 2)[0]; out.append(acc[..., :3].copy())
+        st = o.neeat_get() if feedback else None
+        o.close(); return np.stack(out), st
+    fb, st = frames(60, True); gl, _ = frames(120, False)
+    assert st["available"] and st["valid_feedback"] > 0.3 * W * H
+    assert abs(fb[10:].mean() / gl.mean() - 1) < 0.03
+    ref = gl.mean(0)
+    assert np.abs(fb[10:] - ref).mean() < 0.97 * np.abs(gl - ref).mean()
