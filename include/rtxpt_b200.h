@@ -239,7 +239,9 @@ typedef struct RtxptPathTracerConstants {
     float    distantVsLocalImportance;      /* NEEAT_Distant_vs_Local_Importance (SampleUI.h:160), scaled by 0.0002 inside like LightsBaker.cpp:1029 */
     uint32_t NEEATFeedback;                 /* with NEEType 2: 0 = power-based global table only (what LightsBaker gives a first frame); 1 = temporal feedback: per-pixel light reservoirs filled by
                                              * NEE, usage-weighted global table and per-tile local samplers, advanced once per frame by rtxpt_b200_neeat_update_begin / _end */
-    float    _pad[2];
+    uint32_t NEEATImportanceBoost;          /* with NEEATFeedback: LightsBaker's importance boosters (LightsBaker.h:245-249, both on in RTXPT's UI): bit 0 lights in / near the view frustum (needs
+                                             * rtxpt_b200_set_view), bit 1 lights that got brighter since the last frame; 0 = neither */
+    float    _pad[1];
 } RtxptPathTracerConstants;
 
 /* ------------------------------------------------------------------------------------------------------------------

@@ -111,7 +111,7 @@ ORC_API int oracle_neeat_reset(void* p)
 ORC_API int oracle_neeat_update_begin(void* p)
 {
     OracleCtx* c = (OracleCtx*)p; if (!c->neeatPtr() || c->lights.IsEmpty()) return -1;
-    NeeatUpdateBegin(c->neeat, c->lights, c->consts.NEEType);
+    NeeatUpdateBegin(c->neeat, c->lights, c->consts.NEEType, c->consts.NEEATImportanceBoost, c->haveView ? c->worldToClip : nullptr);
     return 0;
 }
 // depth: R32F guide; motion: RGBA16F guide (pixels) or NULL
@@ -138,6 +138,9 @@ ORC_API int oracle_neeat_get(void* p, int what, void* out, size_t bytes)
     case 6: src = s.localSamplingBuffer.data(); n = s.localSamplingBuffer.size() * 4; break;
     case 7: src = c->lights.proxyCounters.data(); n = c->lights.proxyCounters.size() * 4; break;
     case 8: ctl[0] = s.tilesX; ctl[1] = s.tilesY; ctl[2] = s.jitter[0]; ctl[3] = s.jitter[1]; ctl[4] = c->lights.samplingProxyCount; ctl[5] = s.updateCounter; ctl[6] = s.lastFrameTemporalFeedbackAvailable; ctl[7] = s.validFeedbackCount; src = ctl; n = sizeof(ctl); break;
+    case 13: src = s.currentWeights.data(); n = s.currentWeights.size() * 4; break;          // boosted weights of the frame (f32 lightCount)
+    case 14: src = &s.currentWeightsSum; n = 4; break;
+    case 15: src = c->lights.lights.data(); n = c->lights.lights.size() * sizeof(PolymorphicLightInfo); break;      // the light records (32 B each)
     case 9: src = c->lights.weights.data(); n = c->lights.weights.size() * 4; break;            // power-based light weights (f32 lightCount)
     case 10: src = &c->lights.weightsSum; n = 4; break;
     case 11: src = c->lights.proxyIndices.data(); n = c->lights.proxyIndices.size() * 4; break;

@@ -48,6 +48,8 @@ struct NeeatSettings
     float globalTemporalFeedbackWeight = 0.75f, localToGlobalSampleRatio = 0.65f;          // LightsBaker::BakeSettings
     float reservoirHistoryDropoff = 0.005f, depthDisocclusionThreshold = 1.5f, screenSpaceVsWorldSpaceThreshold = 0.3f;
     bool preFilter = true, enableMotionReprojection = true;
+    // importance boosters (LightsBaker.h:245-249; both on by default in RTXPT, selected here by RtxptPathTracerConstants::NEEATImportanceBoost: bit 0 frustum, bit 1 intensity delta)
+    float importanceBoostFrustumMul = 8.0f, importanceBoostFrustumFadeDistance = 5.0f, importanceBoostIntensityDeltaMul = 64.0f;
 };
 
 // one reservoir image pair (RWTexture2D<float> total weight + RWTexture2D<uint> candidate)
@@ -106,12 +108,15 @@ struct NeeatState
     // LightingControlData of the current frame
     bool lastFrameTemporalFeedbackAvailable = false, lastFrameLocalSamplesAvailable = false, temporalFeedbackRequired = true;
     float globalFeedbackUseWeight = 0, localToGlobalSampleRatio = 0; uint historicTotalLightCount = 0, validFeedbackCount = 0;
+    // boosted light weights of this frame (what ComputeWeights stores) and of the last one (u_lightWeights' historic half), their sum in ComputeWeights' order
+    std::vector<float> currentWeights, historicWeights; float currentWeightsSum = 0; float frustumPlanes[5][4] = {};
 
     void init(uint w, uint h)
     {
         W = w; H = h; tilesX = (w + NEEAT_TILE_SIZE - 1) / NEEAT_TILE_SIZE + 1; tilesY = (h + NEEAT_TILE_SIZE - 1) / NEEAT_TILE_SIZE + 1;       // + 1: border for the jitter offset
         feedback.init(w, h); scratch.init(w, h); blended.init((w + 1) / 2, (h + 1) / 2); historyDepth.assign(size_t(w) * h, 0.0f);
         localSamplingBuffer.assign(size_t(tilesX) * tilesY * NEEAT_LOCAL_PROXY_COUNT, 0u);
+        currentWeights.clear(); historicWeights.clear(); currentWeightsSum = 0;
         updateCounter = 0; jitterF[0] = jitterF[1] = 0; jitter[0] = jitter[1] = jitterPrev[0] = jitterPrev[1] = 0; feedbackBufferFilled = false;
         lastFrameTemporalFeedbackAvailable = lastFrameLocalSamplesAvailable = false; globalFeedbackUseWeight = localToGlobalSampleRatio = 0; historicTotalLightCount = 0;
     }
@@ -217,6 +222,61 @@ inline void ProcessFeedbackHistoryP0(NeeatState& s, uint totalLightCount)
     s.validFeedbackCount = valid;                   // = TotalMaxFeedbackCount - counters[ TotalLightCount ] (threads of the padded dispatch count as invalid)
 }
 
+// LightsBaker::UpdateFrustumConsts (LightsBaker.cpp:884-924): the five bounding planes of the view frustum (left, right, top, bottom, near) from view.matWorldToClip
+// (row-major, row vector x matrix), normalised; dist = dot( p, plane.xyz ) - plane.w is positive inside
+inline void ComputeFrustumPlanes(const float* M, float planes[5][4])
+{
+    auto vp = [&](int row, int col) { return M[row * 4 + col]; };
+    const int colOf[5] = { 0, 0, 1, 1, 2 }; const float sign[5] = { 1.0f, -1.0f, -1.0f, 1.0f, -1.0f };
+    for (int i = 0; i < 5; i++)
+    {
+        float pl[4] = { vp(0, 3) + sign[i] * vp(0, colOf[i]), vp(1, 3) + sign[i] * vp(1, colOf[i]), vp(2, 3) + sign[i] * vp(2, colOf[i]), -(vp(3, 3) + sign[i] * vp(3, colOf[i])) };
+        const float lengthSq = pl[0] * pl[0] + pl[1] * pl[1] + pl[2] * pl[2], scale = lengthSq > 0.f ? 1.0f / sqrtf(lengthSq) : 0.0f;
+        for (int k = 0; k < 4; k++) planes[i][k] = pl[k] * scale;
+    }
+}
+// ComputeWeights (LightsBaker.hlsl:835-877) with ImportanceBooster (:118-165): lights in or near the view frustum count up to 9x (the environment 5x), lights that got
+// brighter than 1.1x their last weight count 64x the increase.  Sum order: 32-light blocks, 128-block groups, groups in index order (pt_lights.h).
+inline void ComputeBoostedWeights(NeeatState& s, const LightTable& lt, uint boostFlags, const float* worldToClip)
+{
+    const uint n = uint(lt.lights.size());
+    s.historicWeights.swap(s.currentWeights); s.currentWeights.assign(n, 0.0f);
+    const bool frustum = (boostFlags & 1u) != 0 && worldToClip != nullptr && s.settings.importanceBoostFrustumMul > 0;
+    const bool delta = (boostFlags & 2u) != 0 && s.lastFrameTemporalFeedbackAvailable && s.settings.importanceBoostIntensityDeltaMul > 0;
+    if (frustum) ComputeFrustumPlanes(worldToClip, s.frustumPlanes);
+    for (uint i = 0; i < n; i++)
+    {
+        float w = lt.weights[i];
+        if (frustum)
+        {
+            float boostK;
+            if (LightType(lt.lights[i]) == kLightTypeEnvironmentQuad) boostK = 0.5f;
+            else
+            {
+                float distMin = 0;
+                for (int k = 0; k < 5; k++) distMin = std::min(distMin, (lt.lights[i].Center[0] * s.frustumPlanes[k][0] + lt.lights[i].Center[1] * s.frustumPlanes[k][1] + lt.lights[i].Center[2] * s.frustumPlanes[k][2]) - s.frustumPlanes[k][3]);
+                boostK = saturate(1 - std::max(0.0f, -distMin) / std::max(1e-5f, s.settings.importanceBoostFrustumFadeDistance));
+            }
+            w *= 1 + s.settings.importanceBoostFrustumMul * boostK;
+        }
+        if (delta)
+        {
+            const float historic = i < s.historicWeights.size() ? s.historicWeights[i] : 0.0f;          // identity remap of a static light list
+            const float d = w - historic * 1.1f;
+            if (d > 0) w += s.settings.importanceBoostIntensityDeltaMul * d;
+        }
+        s.currentWeights[i] = w;
+    }
+    float total = 0;
+    for (uint g0 = 0; g0 < n; g0 += 32 * 128)
+    {
+        float groupSum = 0;
+        for (uint b0 = g0; b0 < std::min(n, g0 + 32 * 128); b0 += 32) { float blockSum = 0; for (uint i = b0; i < std::min(n, b0 + 32); i++) blockSum += s.currentWeights[i]; groupSum += blockSum; }
+        total += groupSum;
+    }
+    s.currentWeightsSum = total;
+}
+
 // ComputeProxyCounts + proxy fill with the usage feedback blended into the power-based weights
 inline void RebuildGlobalProxies(const NeeatState& s, LightTable& lt, uint neeType)
 {
@@ -225,14 +285,14 @@ inline void RebuildGlobalProxies(const NeeatState& s, LightTable& lt, uint neeTy
     lt.proxyIndices.clear();
     for (uint i = 0; i < n; i++)
     {
-        float lightWeight = lt.weights[i];
+        float lightWeight = s.currentWeights[i];
         if (s.lastFrameTemporalFeedbackAvailable)
         {
-            const float feedbackWeight = float(s.feedbackCounters[i]) * lt.weightsSum / std::max(1.0f, float(s.validFeedbackCount));
+            const float feedbackWeight = float(s.feedbackCounters[i]) * s.currentWeightsSum / std::max(1.0f, float(s.validFeedbackCount));
             lightWeight = lerp(lightWeight, feedbackWeight, s.globalFeedbackUseWeight);
         }
         uint proxies = 0;
-        if (lightWeight > 0) proxies = (neeType == 0) ? 1u : uint(ceilf((float(budget - n) * lightWeight) / lt.weightsSum));
+        if (lightWeight > 0) proxies = (neeType == 0) ? 1u : uint(ceilf((float(budget - n) * lightWeight) / s.currentWeightsSum));
         proxies = std::min(proxies, LIGHTING_MAX_PROXIES_PER_LIGHT - 1);
         lt.proxyCounters[i] = proxies;
         lt.proxyIndices.insert(lt.proxyIndices.end(), proxies, i);
@@ -386,7 +446,7 @@ inline void ClearFeedbackHistory(NeeatState& s, const float* depth)
 
 // ---- one frame of LightsBaker around the path tracer -----------------------------------------------------------------------------------------------------------------------------
 // UpdateBegin: before anything of the frame is traced.  Rebuilds lt's global proxy table from the base weights and last frame's feedback.
-inline void NeeatUpdateBegin(NeeatState& s, LightTable& lt, uint neeType)
+inline void NeeatUpdateBegin(NeeatState& s, LightTable& lt, uint neeType, uint boostFlags = 0, const float* worldToClip = nullptr)
 {
     UpdateLocalJitter(s);
     s.updateCounter++;
@@ -404,6 +464,7 @@ inline void NeeatUpdateBegin(NeeatState& s, LightTable& lt, uint neeType)
         if (s.settings.preFilter) ProcessFeedbackHistoryPreFilter(s);
         ProcessFeedbackHistoryP0(s, n);
     }
+    ComputeBoostedWeights(s, lt, boostFlags, worldToClip);
     RebuildGlobalProxies(s, lt, neeType);
     s.historicTotalLightCount = n;                   // next frame's HistoricTotalLightCount
 }

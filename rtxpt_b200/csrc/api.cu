@@ -106,9 +106,10 @@ struct rtxpt_ctx
         neeat::HostState host; neeat::Params params{}; bool allocated = false, frameBegun = false, frameEnded = false; uint32_t lightCount = 0;      // begun: update_begin ran, update_end pending; ended: both ran
         DeviceArray<float> fbWeight, scratchWeight, blendedWeight, historyDepth, lightWeights; DeviceArray<uint32_t> fbCandidate, scratchCandidate, blendedCandidate, local, counters,
             proxyCounters, proxyOffsets, proxyIndices, samplingProxyCount, scanBlockSums, rrFix; DeviceArray<uint4> shadowFeedback;
+        DeviceArray<float> weights[2], weightGroupSums, weightsSum; uint32_t weightPingPong = 0;      // boosted weights: this frame / last frame
         void release() { fbWeight.release(); scratchWeight.release(); blendedWeight.release(); historyDepth.release(); lightWeights.release(); fbCandidate.release(); scratchCandidate.release();
                          blendedCandidate.release(); local.release(); counters.release(); proxyCounters.release(); proxyOffsets.release(); proxyIndices.release(); samplingProxyCount.release();
-                         scanBlockSums.release(); rrFix.release(); shadowFeedback.release(); allocated = false; frameBegun = false; frameEnded = false; }
+                         scanBlockSums.release(); rrFix.release(); shadowFeedback.release(); weights[0].release(); weights[1].release(); weightGroupSums.release(); weightsSum.release(); allocated = false; frameBegun = false; frameEnded = false; }
     } na;
     DeviceArray<double> tmPartials; DeviceArray<float> tmAvgLuminance; DeviceArray<uint32_t> ldrColor; bool toneMapped = false;      // tone mapping (tonemap.cuh)
     cudaEvent_t evDnStart = nullptr, evDnStop = nullptr; bool denoiseTimed = false;       // around the last rtxpt_b200_denoise_realtime
@@ -864,6 +865,8 @@ static int neeatEnsure(rtxpt_ctx* c, cudaStream_t s)
     CU(n.local.alloc(T)); CU(n.counters.alloc(size_t(L) + 1)); CU(n.proxyCounters.alloc(L)); CU(n.proxyOffsets.alloc(size_t(L) + 1)); CU(n.proxyIndices.alloc(proxyCapacity)); CU(n.samplingProxyCount.alloc(1));
     CU(n.scanBlockSums.alloc(1024)); CU(n.lightWeights.alloc(L)); CU(n.rrFix.alloc(c->capacity)); CU(n.shadowFeedback.alloc(c->capacity));
     CU(cudaMemsetAsync(n.rrFix.ptr, 0, size_t(c->capacity) * 4, s));
+    CU(n.weights[0].alloc(L)); CU(n.weights[1].alloc(L)); CU(n.weightGroupSums.alloc((L + 4095) / 4096 + 1)); CU(n.weightsSum.alloc(1)); n.weightPingPong = 0;
+    CU(cudaMemsetAsync(n.weights[0].ptr, 0, size_t(L) * 4, s)); CU(cudaMemsetAsync(n.weights[1].ptr, 0, size_t(L) * 4, s));
     CU(cudaMemsetAsync(n.fbWeight.ptr, 0, P * 4, s)); CU(cudaMemsetAsync(n.scratchWeight.ptr, 0, P * 4, s)); CU(cudaMemsetAsync(n.blendedWeight.ptr, 0, B * 4, s)); CU(cudaMemsetAsync(n.historyDepth.ptr, 0, P * 4, s));
     CU(cudaMemsetAsync(n.fbCandidate.ptr, 0xFF, P * 4, s)); CU(cudaMemsetAsync(n.scratchCandidate.ptr, 0xFF, P * 4, s)); CU(cudaMemsetAsync(n.blendedCandidate.ptr, 0xFF, B * 4, s));
     CU(cudaMemsetAsync(n.local.ptr, 0, T * 4, s)); CU(cudaMemsetAsync(n.samplingProxyCount.ptr, 0, 4, s));
@@ -877,6 +880,8 @@ static void neeatBind(rtxpt_ctx* c)
     p.blendedCandidate = n.blendedCandidate.ptr; p.historyDepth = n.historyDepth.ptr; p.localSamplingBuffer = n.local.ptr; p.feedbackCounters = n.counters.ptr; p.lightWeights = n.lightWeights.ptr;
     p.proxyCounters = n.proxyCounters.ptr; p.proxyOffsets = n.proxyOffsets.ptr; p.proxyIndices = n.proxyIndices.ptr; p.samplingProxyCount = n.samplingProxyCount.ptr;
     p.depth = c->depth.ptr; p.motion = c->motionVectors.ptr;
+    p.lightRecords = reinterpret_cast<const uint4*>(c->dLights.ptr); p.curWeights = n.weights[n.weightPingPong].ptr; p.histWeights = n.weights[n.weightPingPong ^ 1u].ptr;
+    p.weightGroupSums = n.weightGroupSums.ptr; p.weightsSumDev = n.weightsSum.ptr;
 }
 extern "C" RTXPT_API int rtxpt_b200_neeat_reset(rtxpt_ctx* c)
 {
@@ -897,7 +902,8 @@ extern "C" RTXPT_API int rtxpt_b200_neeat_update_begin(rtxpt_ctx* c, void* cudaS
     rtxpt_ctx::Neeat& n = c->na;
     // the power-based weights follow the light list (uploadLights re-bakes them when the environment or the importance settings change)
     CU(cudaMemcpyAsync(n.lightWeights.ptr, c->lightState.weights.data(), size_t(n.lightCount) * 4, cudaMemcpyHostToDevice, s));
-    neeat::beginFrame(n.host, n.params, c->consts.NEEType, n.lightCount, c->lightState.weightsSum);
+    neeat::beginFrame(n.host, n.params, c->consts.NEEType, n.lightCount, c->lightState.weightsSum, c->consts.NEEATImportanceBoost, c->haveView ? c->worldToClip : nullptr);
+    n.weightPingPong ^= 1u;                 // last frame's boosted weights become the historic ones
     neeatBind(c);
     launchNeeatUpdateBegin(n.params, n.host.settings.preFilter, n.scanBlockSums.ptr, c->grid.smCount, s);
     CU(cudaGetLastError());

@@ -29,6 +29,10 @@ struct Params
     float* fbWeight; uint* fbCandidate; float* scratchWeight; uint* scratchCandidate; float* blendedWeight; uint* blendedCandidate; float* historyDepth;
     uint* localSamplingBuffer;          // tilesX * tilesY * 128 (light << 9 | count - 1), sorted by light inside a tile
     uint* feedbackCounters;             // [lightCount + 1]: reservoirs per light; last = reservoirs without a light
+    // importance boosters (LightsBaker.hlsl:107-165): bit 0 of boostFlags frustum, bit 1 intensity delta
+    uint boostFlags; float boostFrustumMul, boostFrustumFadeDistance, boostIntensityDeltaMul; float frustumPlanes[5][4];
+    const uint4* lightRecords;          // PolymorphicLightInfo, 2 x uint4 each: [2 i] = centre.xyz, colorTypeAndFlags
+    float* curWeights; const float* histWeights; float* weightGroupSums; float* weightsSumDev;      // boosted weights of this / the last frame, partial sums, their total
     // global proxy table
     const float* lightWeights; uint* proxyCounters; uint* proxyOffsets; uint* proxyIndices; uint* samplingProxyCount;
     // guides of the frame: depth R32F, screen motion RGBA16F (pixels)
@@ -169,19 +173,54 @@ PT_HD uint p0Pixel(const Params& p, int x, int y)
     return minu(lightIndexAll, p.lightCount);
 }
 
+// ComputeWeights + ImportanceBooster for the 32 lights of block `block` (the reference gives each thread LLB_LOCAL_BLOCK_SIZE = 32 lights, summed in index order): stores the boosted
+// weights, returns the block's sum.  Single IEEE operations throughout: the sum feeds integer proxy counts that must equal the oracle's.
+PT_HD float weightBlock(const Params& p, uint block)
+{
+    float blockSum = 0.0f;
+    const uint end = minu(block * 32u + 32u, p.lightCount);
+    for (uint i = block * 32u; i < end; i++)
+    {
+        float w = p.lightWeights[i];
+        if (p.boostFlags & 1u)
+        {
+            const uint4 rec = p.lightRecords[size_t(i) * 2];
+            float boostK;
+            if (((rec.w >> 24) & 0xFu) == 5u) boostK = 0.5f;                 // kEnvironmentQuad: no position, half boost
+            else
+            {
+                const float cx = bitsToFloat(rec.x), cy = bitsToFloat(rec.y), cz = bitsToFloat(rec.z);
+                float distMin = 0.0f;
+                for (int k = 0; k < 5; k++) distMin = fminf(distMin, fsub_rn(fadd_rn(fadd_rn(fmul_rn(cx, p.frustumPlanes[k][0]), fmul_rn(cy, p.frustumPlanes[k][1])), fmul_rn(cz, p.frustumPlanes[k][2])), p.frustumPlanes[k][3]));
+                boostK = sat(fsub_rn(1.0f, fdiv_rn(fmaxf(0.0f, -distMin), fmaxf(1e-5f, p.boostFrustumFadeDistance))));
+            }
+            w = fmul_rn(w, fadd_rn(1.0f, fmul_rn(p.boostFrustumMul, boostK)));
+        }
+        if ((p.boostFlags & 2u) && p.lastFrameFeedbackAvailable)
+        {
+            const float d = fsub_rn(w, fmul_rn(p.histWeights[i], 1.1f));
+            if (d > 0.0f) w = fadd_rn(w, fmul_rn(p.boostIntensityDeltaMul, d));
+        }
+        p.curWeights[i] = w;
+        blockSum = fadd_rn(blockSum, w);
+    }
+    return blockSum;
+}
+
 // ComputeProxyCounts: proxies of one light from its power-based weight blended with last frame's usage; validFeedbackCount = W * H - feedbackCounters[ lightCount ]
 PT_HD uint proxyCountOfLight(const Params& p, uint lightIndex)
 {
-    float lightWeight = p.lightWeights[lightIndex];
+    const float weightsSum = *p.weightsSumDev;
+    float lightWeight = p.curWeights[lightIndex];
     if (p.lastFrameFeedbackAvailable)
     {
         const uint valid = p.W * p.H - p.feedbackCounters[p.lightCount];
-        const float feedbackWeight = fdiv_rn(fmul_rn(float(p.feedbackCounters[lightIndex]), p.weightsSum), fmaxf(1.0f, float(valid)));
+        const float feedbackWeight = fdiv_rn(fmul_rn(float(p.feedbackCounters[lightIndex]), weightsSum), fmaxf(1.0f, float(valid)));
         lightWeight = fadd_rn(lightWeight, fmul_rn(fsub_rn(feedbackWeight, lightWeight), p.globalFeedbackUseWeight));
     }
     const uint budget = kProxyRatio * (p.lightCount > kMaxLights / 10 ? p.lightCount : kMaxLights / 10);
     uint proxies = 0;
-    if (lightWeight > 0.0f) proxies = p.neeType == 0 ? 1u : uint(ceilf(fdiv_rn(fmul_rn(float(budget - p.lightCount), lightWeight), p.weightsSum)));
+    if (lightWeight > 0.0f) proxies = p.neeType == 0 ? 1u : uint(ceilf(fdiv_rn(fmul_rn(float(budget - p.lightCount), lightWeight), weightsSum)));
     return minu(proxies, kMaxProxiesPerLight - 1);
 }
 // proxy fill: the light that owns slot `slot` = the last light whose exclusive offset is <= slot (lights without proxies share their successor's offset and are skipped)

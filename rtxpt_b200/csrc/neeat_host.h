@@ -13,6 +13,7 @@ struct Settings
     float globalTemporalFeedbackWeight = 0.75f, localToGlobalSampleRatio = 0.65f;
     float reservoirHistoryDropoff = 0.005f, depthDisocclusionThreshold = 1.5f, screenSpaceVsWorldSpaceThreshold = 0.3f;
     bool preFilter = true, enableMotionReprojection = true;
+    float importanceBoostFrustumMul = 8.0f, importanceBoostFrustumFadeDistance = 5.0f, importanceBoostIntensityDeltaMul = 64.0f;       // LightsBaker.h:245-249
 };
 struct HostState
 {
@@ -25,7 +26,19 @@ struct HostState
 };
 
 // LightsBaker::UpdateBegin's bookkeeping: advances the jitter and the counter, decides what of last frame is usable, fills the control part of `p` (not the pointers)
-inline void beginFrame(HostState& s, Params& p, uint32_t neeType, uint32_t lightCount, float weightsSum)
+// LightsBaker::UpdateFrustumConsts (LightsBaker.cpp:884-924): left, right, top, bottom, near planes of view.matWorldToClip (row-major, row vector x matrix), normalised
+inline void frustumPlanes(const float* M, float planes[5][4])
+{
+    const int colOf[5] = { 0, 0, 1, 1, 2 }; const float sign[5] = { 1.0f, -1.0f, -1.0f, 1.0f, -1.0f };
+    for (int i = 0; i < 5; i++)
+    {
+        float pl[4] = { M[0 * 4 + 3] + sign[i] * M[0 * 4 + colOf[i]], M[1 * 4 + 3] + sign[i] * M[1 * 4 + colOf[i]], M[2 * 4 + 3] + sign[i] * M[2 * 4 + colOf[i]], -(M[3 * 4 + 3] + sign[i] * M[3 * 4 + colOf[i]]) };
+        const float lengthSq = pl[0] * pl[0] + pl[1] * pl[1] + pl[2] * pl[2], scale = lengthSq > 0.f ? 1.0f / sqrtf(lengthSq) : 0.0f;
+        for (int k = 0; k < 4; k++) planes[i][k] = pl[k] * scale;
+    }
+}
+// boostFlags: RtxptPathTracerConstants::NEEATImportanceBoost; worldToClip: null when no view has been set (the frustum booster is then off)
+inline void beginFrame(HostState& s, Params& p, uint32_t neeType, uint32_t lightCount, float weightsSum, uint32_t boostFlags = 0, const float* worldToClip = nullptr)
 {
     s.jitterPrev[0] = s.jitter[0]; s.jitterPrev[1] = s.jitter[1];
     if ((s.updateCounter % 1024) == 0) { s.jitterF[0] = 0; s.jitterF[1] = 0; }
@@ -45,6 +58,9 @@ inline void beginFrame(HostState& s, Params& p, uint32_t neeType, uint32_t light
     p.globalFeedbackUseWeight = available ? std::min(std::max(s.settings.globalTemporalFeedbackWeight, 0.0f), 0.95f) : 0.0f;
     p.localToGlobalSampleRatio = available ? std::min(std::max(s.settings.localToGlobalSampleRatio, 0.0f), 1.0f) : 0.0f;
     p.screenSpaceVsWorldSpaceThreshold = s.settings.screenSpaceVsWorldSpaceThreshold; p.weightsSum = weightsSum;
+    p.boostFlags = (boostFlags & 2u) | ((boostFlags & 1u) && worldToClip && s.settings.importanceBoostFrustumMul > 0 ? 1u : 0u);
+    p.boostFrustumMul = s.settings.importanceBoostFrustumMul; p.boostFrustumFadeDistance = s.settings.importanceBoostFrustumFadeDistance; p.boostIntensityDeltaMul = s.settings.importanceBoostIntensityDeltaMul;
+    if (p.boostFlags & 1u) frustumPlanes(worldToClip, p.frustumPlanes);
     s.historicLightCount = lightCount;
 }
 // after UpdateEnd's passes: ClearFeedbackHistory ran, so the path tracer's feedback of this frame is what next frame processes

@@ -26,6 +26,17 @@ __global__ void __launch_bounds__(256) k_na_p0(const __grid_constant__ Params p)
     if ((__ffs(peers) - 1) == int(threadIdx.x + threadIdx.y * 16) % 32) atomicAdd(p.feedbackCounters + slot, uint(__popc(peers)));
 }
 
+// ComputeWeights: thread = one 32-light block (as the reference), CTA = 128 blocks whose sums thread 0 adds in index order; k_na_weight_total adds the CTAs' sums in index order
+__global__ void __launch_bounds__(128) k_na_weights(const __grid_constant__ Params p)
+{
+    __shared__ float blockSums[128];
+    const uint block = blockIdx.x * 128 + threadIdx.x;
+    blockSums[threadIdx.x] = block * 32u < p.lightCount ? weightBlock(p, block) : 0.0f;
+    __syncthreads();
+    if (threadIdx.x == 0) { float g = 0.0f; for (int i = 0; i < 128; i++) if ((blockIdx.x * 128 + i) * 32u < p.lightCount) g = __fadd_rn(g, blockSums[i]); p.weightGroupSums[blockIdx.x] = g; }
+}
+__global__ void k_na_weight_total(const __grid_constant__ Params p, uint groups) { float t = 0.0f; for (uint g = 0; g < groups; g++) t = __fadd_rn(t, p.weightGroupSums[g]); *p.weightsSumDev = t; }
+
 __global__ void __launch_bounds__(256) k_na_proxy_counts(const __grid_constant__ Params p)
 {
     const uint i = blockIdx.x * 256 + threadIdx.x;
@@ -117,6 +128,9 @@ void launchNeeatUpdateBegin(const neeat::Params& p, bool preFilter, uint* scanBl
         }
         k_na_p0<<<grid, block, 0, s>>>(p);
     }
+    const uint weightGroups = (p.lightCount + 32 * 128 - 1) / (32 * 128);
+    k_na_weights<<<weightGroups, 128, 0, s>>>(p);
+    k_na_weight_total<<<1, 1, 0, s>>>(p, weightGroups);
     const uint lightBlocks = (p.lightCount + 255) / 256, scanBlocks = (p.lightCount + kScanBlock - 1) / kScanBlock;
     k_na_proxy_counts<<<lightBlocks, 256, 0, s>>>(p);
     k_na_scan_reduce<<<scanBlocks, kScanBlock, 0, s>>>(p, scanBlockSums);

@@ -13,12 +13,13 @@ struct Instance
 {
     neeat::HostState host; neeat::Params p{};
     uint32_t neeType = 2, lightCount = 0; float weightsSum = 0;
-    std::vector<float> fbW, scW, blW, historyDepth, weights; std::vector<uint32_t> fbC, scC, blC, local, counters, proxyCounters, proxyOffsets, proxyIndices; uint32_t samplingProxyCount = 0;
+    std::vector<float> fbW, scW, blW, historyDepth, weights, bw[2], groupSums; float weightsSumDev = 0; uint32_t pingPong = 0, boostFlags = 0; std::vector<uint32_t> lightRecords; float worldToClip[16]; bool haveView = false; std::vector<uint32_t> fbC, scC, blC, local, counters, proxyCounters, proxyOffsets, proxyIndices; uint32_t samplingProxyCount = 0;
     void bind()
     {
         p.fbWeight = fbW.data(); p.fbCandidate = fbC.data(); p.scratchWeight = scW.data(); p.scratchCandidate = scC.data(); p.blendedWeight = blW.data(); p.blendedCandidate = blC.data();
         p.historyDepth = historyDepth.data(); p.localSamplingBuffer = local.data(); p.feedbackCounters = counters.data(); p.lightWeights = weights.data(); p.proxyCounters = proxyCounters.data();
         p.proxyOffsets = proxyOffsets.data(); p.proxyIndices = proxyIndices.data(); p.samplingProxyCount = &samplingProxyCount;
+        p.lightRecords = reinterpret_cast<const uint4*>(lightRecords.data()); p.curWeights = bw[pingPong].data(); p.histWeights = bw[pingPong ^ 1u].data(); p.weightGroupSums = groupSums.data(); p.weightsSumDev = &weightsSumDev;
     }
 };
 }
@@ -31,7 +32,16 @@ extern "C" void* neeat_emu_create(uint32_t W, uint32_t H, uint32_t lightCount, c
     i->local.assign(T, 0u); i->counters.assign(size_t(lightCount) + 1, 0u); i->weights.assign(weights, weights + lightCount); i->proxyCounters.assign(lightCount, 0u); i->proxyOffsets.assign(size_t(lightCount) + 1, 0u);
     const uint32_t budget = neeat::kProxyRatio * std::max(lightCount, neeat::kMaxLights / 10);
     i->proxyIndices.assign(size_t(budget) + lightCount, 0u);
+    i->bw[0].assign(lightCount, 0.f); i->bw[1].assign(lightCount, 0.f); i->groupSums.assign((lightCount + 4095) / 4096 + 1, 0.f); i->lightRecords.assign(size_t(lightCount) * 8, 0u);
     return i;
+}
+// importance boosters: the light records (32 B each, for the centres and types), the flags of RtxptPathTracerConstants::NEEATImportanceBoost and view.matWorldToClip
+extern "C" int neeat_emu_set_boost(void* h, uint32_t flags, const uint32_t* lightRecords, const float* worldToClip)
+{
+    Instance& i = *static_cast<Instance*>(h); i.boostFlags = flags;
+    if (lightRecords) memcpy(i.lightRecords.data(), lightRecords, i.lightRecords.size() * 4);
+    i.haveView = worldToClip != nullptr; if (worldToClip) memcpy(i.worldToClip, worldToClip, 64);
+    return 0;
 }
 extern "C" void neeat_emu_destroy(void* h) { delete static_cast<Instance*>(h); }
 extern "C" int neeat_emu_set_feedback(void* h, const float* weight, const uint32_t* candidate)
@@ -44,7 +54,7 @@ extern "C" int neeat_emu_set_feedback(void* h, const float* weight, const uint32
 extern "C" int neeat_emu_update_begin(void* h)
 {
     Instance& i = *static_cast<Instance*>(h); neeat::Params& p = i.p;
-    neeat::beginFrame(i.host, p, i.neeType, i.lightCount, i.weightsSum); i.bind();
+    neeat::beginFrame(i.host, p, i.neeType, i.lightCount, i.weightsSum, i.boostFlags, i.haveView ? i.worldToClip : nullptr); i.pingPong ^= 1u; i.bind();
     std::fill(i.counters.begin(), i.counters.end(), 0u);
     if (p.lastFrameFeedbackAvailable)
     {
@@ -54,6 +64,11 @@ extern "C" int neeat_emu_update_begin(void* h)
             for (int y = 0; y < int(p.H); y++) for (int x = 0; x < int(p.W); x++) neeat::preFilterPixel(p, x, y);
         }
         for (int y = 0; y < int(p.H); y++) for (int x = 0; x < int(p.W); x++) i.counters[neeat::p0Pixel(p, x, y)]++;
+    }
+    {   // k_na_weights / k_na_weight_total: 32-light blocks, 128-block groups, groups in index order
+        const uint32_t blocks = (p.lightCount + 31) / 32, groups = (p.lightCount + 4095) / 4096; float total = 0.0f;
+        for (uint32_t g = 0; g < groups; g++) { float gs = 0.0f; for (uint32_t b = g * 128; b < std::min(blocks, g * 128 + 128); b++) gs = gs + neeat::weightBlock(p, b); i.groupSums[g] = gs; total = total + gs; }
+        i.weightsSumDev = total;
     }
     for (uint32_t l = 0; l < p.lightCount; l++) i.proxyCounters[l] = neeat::proxyCountOfLight(p, l);
     uint32_t total = 0; for (uint32_t l = 0; l < p.lightCount; l++) { i.proxyOffsets[l] = total; total += i.proxyCounters[l]; } i.proxyOffsets[p.lightCount] = total;
@@ -93,6 +108,8 @@ extern "C" int neeat_emu_get(void* h, int what, void* out, size_t bytes)
     case 8: ctl[0] = i.p.tilesX; ctl[1] = i.p.tilesY; ctl[2] = i.p.jitterX; ctl[3] = i.p.jitterY; ctl[4] = i.samplingProxyCount; ctl[5] = i.p.updateCounter; ctl[6] = i.p.lastFrameFeedbackAvailable;
             ctl[7] = i.p.lastFrameFeedbackAvailable ? i.p.W * i.p.H - i.counters[i.p.lightCount] : 0u; src = ctl; n = sizeof(ctl); break;
     case 11: src = i.proxyIndices.data(); n = size_t(i.samplingProxyCount) * 4; break;
+    case 13: src = i.bw[i.pingPong].data(); n = i.bw[i.pingPong].size() * 4; break;
+    case 14: src = &i.weightsSumDev; n = 4; break;
     default: return -1;
     }
     if (bytes < n) return -2;

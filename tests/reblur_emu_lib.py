@@ -69,6 +69,11 @@ class NeeatPort:
 
     def __del__(self): self.close()
 
+    def set_boost(self, flags, light_records, world_to_clip):
+        L = lib(); L.neeat_emu_set_boost.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        r = np.ascontiguousarray(light_records, np.uint32); m = None if world_to_clip is None else np.ascontiguousarray(world_to_clip, np.float32)
+        assert L.neeat_emu_set_boost(self.h, flags, r.ctypes.data, None if m is None else m.ctypes.data) == 0
+
     def set_feedback(self, weight, candidate):
         w = np.ascontiguousarray(weight, np.float32); c = np.ascontiguousarray(candidate, np.uint32); assert lib().neeat_emu_set_feedback(self.h, w.ctypes.data, c.ctypes.data) == 0
 

@@ -13,7 +13,7 @@ unverified = pytest.mark.gpu_unverified
 def _pair(product, oracle, W, H, bays=7, strict=True, bounces=2):
     from rtxpt_b200 import scene_builder as sb, scenes
     scene, cam = scenes.light_gallery(W, H, bays=bays)
-    consts = sb.make_constants(W, H, cam, bounce_count=bounces, diffuse_bounce_count=bounces); consts.NEEATFeedback = 1
+    consts = sb.make_constants(W, H, cam, bounce_count=bounces, diffuse_bounce_count=bounces); consts.NEEATFeedback = 1; consts.NEEATImportanceBoost = 3       # both importance boosters, as in RTXPT's UI
     c = product.Context(max_sub_samples_per_launch=1, strict=strict); c.upload_scene(scene); c.set_constants(consts); c.set_view(sb.world_to_clip(cam))
     o = oracle.Oracle(scene); o.set_constants(consts); o.set_view(sb.world_to_clip(cam)); o.neeat_reset()
     rt = sb.make_realtime_constants(W, H, cam, bounce_count=bounces, sub_samples=1); c.set_realtime(rt)

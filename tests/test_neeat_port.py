@@ -18,15 +18,15 @@ def _compare(o, port, W, H, n_lights, stage):
         assert len(a) == len(b) == n and np.array_equal(a, b), (stage, name, int((a != b).sum()))
 
 
-@pytest.mark.parametrize("moving", [False, True])
-def test_feedback_passes_equal_the_oracle(oracle, moving):
+@pytest.mark.parametrize("moving,boost", [(False, 0), (True, 0), (True, 3), (False, 1)])
+def test_feedback_passes_equal_the_oracle(oracle, moving, boost):
     from rtxpt_b200 import scene_builder as sb, scenes
     import reblur_emu_lib as emu
     W, H = 90, 58                                                                            # neither a multiple of the 8-pixel tile nor of the 2-pixel blend
     scene, cam0 = scenes.light_gallery(W, H, bays=7)
     guide = oracle.Oracle(scene)                                                             # depth / motion guides of every frame (no feedback involved)
     o = oracle.Oracle(scene)
-    c = sb.make_constants(W, H, cam0, bounce_count=2, diffuse_bounce_count=2); c.NEEATFeedback = 1
+    c = sb.make_constants(W, H, cam0, bounce_count=2, diffuse_bounce_count=2); c.NEEATFeedback = 1; c.NEEATImportanceBoost = boost
     o.set_constants(c); o.set_view(sb.world_to_clip(cam0)); o.neeat_reset()
     n_lights = int(o.neeat_raw(12, np.uint32, 1)[0])
     port = emu.NeeatPort(W, H, o.neeat_raw(9, np.float32, n_lights), float(o.neeat_raw(10, np.float32, 1)[0]))
@@ -35,10 +35,13 @@ def test_feedback_passes_equal_the_oracle(oracle, moving):
         cam = sb.bridge_camera(W, H, pos=(7.0 + (0.4 * f if moving else 0.0), 1.3, -7.5), direction=(0, -0.02, 1), up=(0, 1, 0), fov_y=0.8)
         cg = sb.make_constants(W, H, cam, bounce_count=2, diffuse_bounce_count=2); guide.set_constants(cg); guide.set_view(sb.world_to_clip(cam))
         g = guide.render_realtime(sb.make_realtime_constants(W, H, cam, prev_cam=prev, bounce_count=2, sub_samples=1))
-        c = sb.make_constants(W, H, cam, bounce_count=2, diffuse_bounce_count=2, sample_base_index=f); c.NEEATFeedback = 1
+        c = sb.make_constants(W, H, cam, bounce_count=2, diffuse_bounce_count=2, sample_base_index=f); c.NEEATFeedback = 1; c.NEEATImportanceBoost = boost
         o.set_constants(c); o.set_view(sb.world_to_clip(cam))
+        port.set_boost(boost, o.neeat_raw(15, np.uint32, n_lights * 8), sb.world_to_clip(cam))
         if f > 0: port.set_feedback(o.neeat_raw(0, np.float32, W * H), o.neeat_raw(1, np.uint32, W * H))        # what the path tracer left in the reservoirs last frame
         o.neeat_update_begin(); port.update_begin(); _compare(o, port, W, H, n_lights, "begin")
+        assert np.array_equal(o.neeat_raw(13, np.uint32, n_lights), port.raw(13, np.uint32, n_lights)) and np.array_equal(o.neeat_raw(14, np.uint32, 1), port.raw(14, np.uint32, 1))      # boosted weights, their sum
+        if boost & 1: base = o.neeat_raw(9, np.float32, n_lights); bw = o.neeat_raw(13, np.float32, n_lights); assert (bw[base > 0] > base[base > 0] * 0.999).all() and bw.max() > base.max() * 1.5
         o.neeat_update_end(g["depth"], g["motion"]); port.update_end(g["depth"], g["motion"]); _compare(o, port, W, H, n_lights, "end")
         o.render(0, 1)                                                                       # reference-mode radiance pass: NEE draws local + global candidates and inserts feedback
         prev = cam

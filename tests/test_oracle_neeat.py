@@ -112,3 +112,22 @@ def test_reference_mode_loop_is_unbiased(oracle):
     assert abs(fb[10:].mean() / gl.mean() - 1) < 0.03
     ref = gl.mean(0)
     assert np.abs(fb[10:] - ref).mean() < 0.97 * np.abs(gl - ref).mean()
+
+
+def test_frustum_booster_moves_proxies_into_view(oracle):
+    """ImportanceBooster: with the frustum booster on, lamps in (or within 5 units of) the view frustum take proxies from those far outside it."""
+    from rtxpt_b200 import scene_builder as sb, scenes
+    W, H = 64, 48
+    scene, _ = scenes.light_gallery(W, H, bays=12)
+    cam = sb.bridge_camera(W, H, pos=(3.0, 1.3, -2.0), direction=(0, 0, 1), up=(0, 1, 0), fov_y=0.5)          # close up on the leftmost bays; the right end is ~20 units off
+    def counters(boost):
+        o = oracle.Oracle(scene); c = sb.make_constants(W, H, cam, bounce_count=2, diffuse_bounce_count=2); c.NEEATFeedback = 1; c.NEEATImportanceBoost = boost
+        o.set_constants(c); o.set_view(sb.world_to_clip(cam)); o.neeat_reset(); o.neeat_update_begin()
+        n = int(o.neeat_raw(12, np.uint32, 1)[0]); cnt = o.neeat_proxy_counters(n).astype(np.float64); rec = o.neeat_raw(15, np.uint32, n * 8).reshape(n, 8); o.close()
+        return cnt, rec[:, 0].view(np.float32)
+    plain, x = counters(0); boosted, _ = counters(1)
+    tri = np.arange(len(x)) >= 5368                                                      # the lamps' triangles
+    near, far = tri & (x < 6.0), tri & (x > 16.0)
+    assert near.any() and far.any()
+    share = lambda c, m: c[m].sum() / c[tri].sum()
+    assert share(boosted, near) > 1.5 * share(plain, near) and share(boosted, far) < 0.7 * share(plain, far)
