@@ -1,4 +1,4 @@
-"""ctypes binding of tests/emu/_build/libreblur_emu.so - TEST INFRASTRUCTURE ONLY: the product's ReBLUR pass bodies (rtxpt_b200/csrc/reblur_passes.cuh) compiled for the host."""
+"""ctypes binding of tests/emu/_build/libreblur_emu.so - TEST INFRASTRUCTURE ONLY: host builds of the product's __host__ __device__ kernel bodies (ReBLUR passes, guide filter, denoiser interface, NEE-AT feedback passes, environment bake, BVH refit, tone mapping)."""
 import ctypes as C
 import os
 import subprocess

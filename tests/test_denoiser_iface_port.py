@@ -15,7 +15,7 @@ def _tables(realtime, denoiser):
 @pytest.mark.parametrize("suppress", [0.0, 0.6])
 def test_prepare_inputs_and_final_merge_equal_the_oracle(oracle, suppress):
     from rtxpt_b200 import scene_builder as sb, scenes
-    import reblur_emu_lib as emu
+    import host_build_lib as emu
     W, H = 88, 72
     scene, cam = scenes.cornell_box(W, H, delta_surfaces=True)
     consts = sb.make_constants(W, H, cam, bounce_count=6, diffuse_bounce_count=3)

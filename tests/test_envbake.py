@@ -68,7 +68,7 @@ def test_oracle_bake_properties(oracle):
 
 def test_product_bodies_equal_the_oracle(oracle):
     """Equirectangular and cube sources, lights, scale: the host build of envbake.cuh reproduces the oracle bit for bit (same libm, no contraction on either side)."""
-    import reblur_emu_lib as emu
+    import host_build_lib as emu
     Lo, Le = oracle.lib(), emu.lib()
     rng = np.random.default_rng(4)
     eq = rng.gamma(2.0, 0.5, (48, 96, 4)).astype(np.float32)

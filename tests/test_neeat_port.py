@@ -21,7 +21,7 @@ def _compare(o, port, W, H, n_lights, stage):
 @pytest.mark.parametrize("moving,boost", [(False, 0), (True, 0), (True, 3), (False, 1)])
 def test_feedback_passes_equal_the_oracle(oracle, moving, boost):
     from rtxpt_b200 import scene_builder as sb, scenes
-    import reblur_emu_lib as emu
+    import host_build_lib as emu
     W, H = 90, 58                                                                            # neither a multiple of the 8-pixel tile nor of the 2-pixel blend
     scene, cam0 = scenes.light_gallery(W, H, bays=7)
     guide = oracle.Oracle(scene)                                                             # depth / motion guides of every frame (no feedback involved)

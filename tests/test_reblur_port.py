@@ -43,7 +43,7 @@ def test_port_equals_oracle_on_a_dolly(oracle, delta, plane):
     """Six frames of a slow dolly (motion vectors, previous matrices, growing history), then an undescribed cut and a reset: all eight passes, both reprojection paths, the
     disocclusion tests and the history bookkeeping, bit for bit."""
     from rtxpt_b200 import scene_builder as sb
-    import reblur_emu_lib as emu
+    import host_build_lib as emu
     W, H = 80, 64
     o, cam0, frame = _frames(oracle, W, H, delta)
     cam_at = lambda dx: sb.bridge_camera(W, H, pos=(2.78 + dx, 2.73, -8.0), direction=(0, 0, 1), up=(0, 1, 0), fov_y=0.66)
@@ -69,7 +69,7 @@ def test_port_equals_oracle_with_sky_roughness_and_missing_hits(oracle):
     """Synthetic NRD inputs that the Cornell box lacks: sky tiles and a ragged sky border, a roughness ramp from mirror to diffuse, two material ids, pixels without a hit distance,
     an image size that is not a multiple of the 16x16 tile."""
     from rtxpt_b200 import scene_builder as sb
-    import reblur_emu_lib as emu
+    import host_build_lib as emu
     from test_oracle_reblur import pack_normal_roughness
     W, H = 90, 52
     cam = sb.bridge_camera(W, H, pos=(0, 0, 0), direction=(0, 0, 1), up=(0, 1, 0), fov_y=0.9)
@@ -95,7 +95,7 @@ def test_spec_hit_t_guide_filter(oracle):
     """DenoisingGuidesBaker::DenoiseSpecHitT: oracle properties (holes filled from neighbours of similar depth only, values capped at 1.5 x + 0.5, tiny values dropped) and the
     product's pixel function compiled for the host equal to the oracle bit for bit, on synthetic guides and on the guide of a rendered frame."""
     from rtxpt_b200 import scene_builder as sb, scenes
-    import reblur_emu_lib as emu
+    import host_build_lib as emu
     rng = np.random.default_rng(3)
     H, W = 37, 53
     depth = np.where(np.mgrid[0:H, 0:W][1] < 30, 5.0, 50.0).astype(np.float32) * (1 + 0.002 * rng.standard_normal((H, W)).astype(np.float32))

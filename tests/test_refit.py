@@ -67,7 +67,7 @@ def _check_tree(nodes, tris, box):
 
 
 def test_refit_contract(product):
-    import reblur_emu_lib as emu
+    import host_build_lib as emu
     rng = np.random.default_rng(5)
     soup, inst = _soup(6000, rng)
     nodes, tris, levels = product.debug_build_bvh(soup)
@@ -96,7 +96,7 @@ def test_refit_contract(product):
 
 
 def test_refit_edge_cases(product):
-    import reblur_emu_lib as emu
+    import host_build_lib as emu
     rng = np.random.default_rng(8)
     for n in (1, 2, 9, 70):
         soup, inst = _soup(n, rng, clusters=2)

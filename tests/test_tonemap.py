@@ -52,7 +52,7 @@ def test_oracle_tone_mapping_properties(oracle):
 
 
 def test_product_bodies_equal_the_oracle(oracle):
-    import reblur_emu_lib as emu
+    import host_build_lib as emu
     Lo, Le = oracle.lib(), emu.lib()
     rng = np.random.default_rng(6)
     img = np.concatenate([rng.gamma(1.2, 0.9, (50, 70, 3)), rng.random((50, 70, 1))], -1).astype(np.float32); img[0, 0, :3] = 0; img[1, 1, :3] = 1e4
