@@ -388,6 +388,13 @@ ORC_API int oracle_denoiser_final_merge(void* p, const RtxptRealtimeConstants* r
     return 0;
 }
 
+// pins against tests/golden/host_golden.json (reference headers compiled in place): MicroRng, candidate counts, white balance
+ORC_API void oracle_micro_rng(uint32_t x, uint32_t y, uint32_t a, uint32_t b, uint32_t n, uint32_t* outNext, float* outFloats)
+{ MicroRng r = MicroRng::make(x, y, a, b); for (uint32_t i = 0; i < n; i++) outNext[i] = r.Next(); for (uint32_t i = 0; i < n; i++) outFloats[i] = r.NextFloat(); }
+ORC_API uint32_t oracle_candidate_local_count(float ratio, uint32_t total) { return ComputeCandidateSampleLocalCount(ratio, total); }
+ORC_API void oracle_white_balance(float T, float* outM9, float* outXyz3)
+{ const tonemap::M3 m = tonemap::whiteBalanceTransform(T); for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) outM9[i * 3 + j] = m.m[i][j]; const float3 x = tonemap::colorTemperatureToXYZ(T); outXyz3[0] = x.x; outXyz3[1] = x.y; outXyz3[2] = x.z; }
+
 // ToneMappingPass (pt_tonemap.h): RGBA32F frame -> SRGBA8; params as RtxptToneMappingParams; outAux = { average luminance, pre-exposed gray r, g, b }
 ORC_API int oracle_tone_map(const RtxptToneMappingParams* u, const float* rgba, uint32_t pixelCount, uint8_t* outRGBA8, float* outAux)
 {

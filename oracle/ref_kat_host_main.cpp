@@ -17,6 +17,10 @@ typedef uint32_t uint;
 #include "PathTracer/Materials/MaterialPT.h"
 #include "SubInstanceData.h"
 #include "PathTracer/Lighting/PolymorphicLight.h"
+#include "PathTracer/Lighting/LightingTypes.hlsli"    // C++ half: LightingControlData, candidate sample counts; pulls LightingConfig.h (tile size, local proxy count ...)
+#include "Libraries/MicroRng.hlsli"                    // plain struct code: compiles as C++ with donut's uint2 / float2
+#include "../ToneMapper/ColorUtils.h"                  // colour temperature, white balance transform
+#include "../ToneMapper/ToneMapping_cb.h"
 #include "PathTracer/StablePlanes.hlsli"       // C++ half: StablePlane layout, branch-ID helpers; pulls Utils/Utils.hlsli (Morton / GenericTS addressing)
 
 static uint32_t bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
@@ -141,6 +145,37 @@ int main()
             printf("]}"); first = false;
         }
     }
-    printf("]\n}\n");
+    printf("],\n \"neeat\": {\"tile\": %d, \"window\": %d, \"local_proxies\": %d, \"search_steps\": %d, \"top_up\": %d, \"early_tile\": %d, \"proxy_ratio\": %d, \"max_lights\": %d, \"max_proxies_per_light\": %d, \"control_size\": %zu, \"local_counts\": [",
+           RTXPT_LIGHTING_SAMPLING_BUFFER_TILE_SIZE, RTXPT_LIGHTING_SAMPLING_BUFFER_WINDOW_SIZE, RTXPT_LIGHTING_LOCAL_PROXY_COUNT, RTXPT_LIGHTING_LOCAL_PROXY_BINARY_SEARCH_STEPS, RTXPT_LIGHTING_TOP_UP_SAMPLES,
+           RTXPT_NEEAT_EARLY_FEEDBACK_TILE_SIZE, RTXPT_LIGHTING_SAMPLING_PROXY_RATIO, RTXPT_LIGHTING_MAX_LIGHTS, RTXPT_LIGHTING_MAX_SAMPLING_PROXIES_PER_LIGHT, sizeof(LightingControlData));
+    {
+        const float ratios[] = { 0.0f, 0.25f, 0.5f, 0.65f, 0.9f, 1.0f }; first = true;
+        for (float r : ratios) for (uint n = 1; n <= 12; n++) { printf("%s[%u, %u, %u]", first ? "" : ", ", bits(r), n, ComputeCandidateSampleLocalCount(r, n)); first = false; }
+    }
+    printf("]},\n \"micro_rng\": [");
+    {
+        const uint seeds[][4] = { { 0, 0, 1, 1 }, { 17, 5, 2, 3 }, { 1919, 1079, 977, 4 }, { 240, 135, 65535, 5 }, { 3, 700, 123456, 7 } }; first = true;
+        for (auto& sd : seeds)
+        {
+            MicroRng r = MicroRng::make(uint2(sd[0], sd[1]), sd[2], sd[3]);
+            printf("%s{\"seed\": [%u, %u, %u, %u], \"next\": [", first ? "" : ", ", sd[0], sd[1], sd[2], sd[3]);
+            for (int i = 0; i < 6; i++) printf("%s%u", i ? ", " : "", r.Next());
+            printf("], \"floats\": ["); for (int i = 0; i < 6; i++) printf("%s%u", i ? ", " : "", bits(r.NextFloat()));
+            printf("]}"); first = false;
+        }
+    }
+    printf("],\n \"tone_mapping\": {\"exposure_key\": %u, \"cb_size\": %zu, \"white_balance\": [", bits((float)TONEMAPPING_EXPOSURE_KEY), sizeof(ToneMappingConstants));
+    {
+        const float temps[] = { 1000.f, 1667.f, 2000.f, 3200.f, 4000.f, 5000.f, 6500.f, 9000.f, 20000.f }; first = true;
+        for (float T : temps)
+        {
+            const float3 xyz = colorTemperatureToXYZ(T); const float3x3 m = calculateWhiteBalanceTransformRGB_Rec709(T);
+            printf("%s{\"T\": %u, \"xyz\": [%u, %u, %u], \"m\": [", first ? "" : ", ", bits(T), bits(xyz.x), bits(xyz.y), bits(xyz.z));
+            for (int i = 0; i < 9; i++) printf("%s%u", i ? ", " : "", bits(m.m_data[i]));
+            const float3 g = m * float3(0.25f, 0.5f, 0.75f);
+            printf("], \"m_times_v\": [%u, %u, %u]}", bits(g.x), bits(g.y), bits(g.z)); first = false;
+        }
+    }
+    printf("]}\n}\n");
     return 0;
 }

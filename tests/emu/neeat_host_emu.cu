@@ -126,3 +126,8 @@ extern "C" int neeat_emu_sample_local(void* h, uint32_t px, uint32_t py, float r
     out[0] = float(light); out[1] = pdf; out[2] = neeat::sampleLocalPdf(i.p, tile, lightForPdf);
     return 0;
 }
+
+// pins against tests/golden/host_golden.json: the product's MicroRng and candidate counts
+extern "C" void emu_micro_rng(uint32_t x, uint32_t y, uint32_t a, uint32_t b, uint32_t n, uint32_t* outNext, float* outFloats)
+{ neeat::MicroRng r = neeat::MicroRng::make(x, y, a, b); for (uint32_t i = 0; i < n; i++) outNext[i] = r.next(); for (uint32_t i = 0; i < n; i++) outFloats[i] = r.nextFloat(); }
+extern "C" uint32_t emu_candidate_local_count(float ratio, uint32_t total) { return neeat::candidateLocalCount(ratio, total); }

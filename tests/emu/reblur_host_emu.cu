@@ -161,3 +161,7 @@ extern "C" int emu_denoiser_interface(const RtxptPathTracerConstants* consts, co
     for (uint32_t y = 0; y < H; y++) for (uint32_t x = 0; x < W; x++) { const uint32_t id = (x << 16) | y; if (mode == 0) pt::dnPrepareInputsPixel(p, id); else pt::dnFinalMergePixel(p, id); }
     return 0;
 }
+
+// pin against tests/golden/host_golden.json: the product's white balance transform (tonemap.cuh host half)
+extern "C" void emu_white_balance(float T, float* outM9, float* outXyz3)
+{ const pt::tonemap::M3 m = pt::tonemap::whiteBalanceTransform(T); for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) outM9[i * 3 + j] = m.m[i][j]; pt::tonemap::colorTemperatureToXYZ(T, outXyz3); }
