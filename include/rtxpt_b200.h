@@ -410,6 +410,17 @@ RTXPT_API int rtxpt_b200_tone_map_pre_exposed_gray(const RtxptToneMappingParams*
  * re-upload then).  The instance table keeps the previous matrices for the BUILD pass's motion vectors.  Emissive triangles are baked into the light list at upload: instances that
  * carry them stay put (or re-upload).  Skinning / vertex animation: not built. */
 RTXPT_API int rtxpt_b200_update_instance_transforms(rtxpt_ctx* ctx, const float* transforms3x4, uint32_t instanceCount, void* cudaStream);
+/* Skinned meshes (Donut's skinning pass, External/Donut/shaders/skinning_cs.hlsl, which RTXPT runs before its BLAS updates, Sample.cpp:1170-1198): register a geometry's bind pose once
+ * (vertex order = the geometry's vertex buffer; normals / tangents snorm8 x 4 as in the vertex buffer, may be NULL; four uint16 joint indices and four float weights per vertex), then per
+ * frame hand the joint matrices (row-major 4x4, row vector x matrix, as Donut's t_JointMatrices): the vertices are blended on the stream and the path tracer's per-triangle shade
+ * records (object-space positions, normals, tangents) rewritten from them.  Follow with rtxpt_b200_update_instance_transforms to refit the BVH.  Motion vectors of skinned surfaces
+ * see the instance motion only (no previous-position stream). */
+typedef struct RtxptSkinDesc {
+    uint32_t instanceIndex, geometryIndexInInstance, numVertices, _pad;
+    const float* positions; const uint32_t* normals; const uint32_t* tangents; const uint16_t* jointIndices; const float* jointWeights;
+} RtxptSkinDesc;
+RTXPT_API int rtxpt_b200_skin_register(rtxpt_ctx* ctx, const RtxptSkinDesc* desc, uint32_t* outSkinId);
+RTXPT_API int rtxpt_b200_skin_update(rtxpt_ctx* ctx, uint32_t skinId, const float* jointMatrices4x4, uint32_t numJoints, void* cudaStream);
 /* host-only inspection of the builder: the compressed BVH over a triangle soup (nodes 80 B, leaf triangles 48 B with gid = soup index, level ranges); call with NULL outputs for sizes */
 RTXPT_API int rtxpt_b200_debug_build_bvh(const float* triangleVertices, uint32_t triangleCount, void* outNodes, void* outTris, uint32_t* outLevelStart,
                                          uint32_t* outNodeCount, uint32_t* outTriCount, uint32_t* outLevelCount);

@@ -9,6 +9,7 @@
 #include "reblur.h"
 #include "pt_envbake.h"
 #include "pt_tonemap.h"
+#include "pt_skinning.h"
 #include <cstdio>
 #include <chrono>
 #ifdef _OPENMP
@@ -385,6 +386,15 @@ ORC_API int oracle_denoiser_final_merge(void* p, const RtxptRealtimeConstants* r
     if (!c->haveConsts || !rt || stablePlaneIndex >= 3) return -1;
     const RealtimeTargets T = makeTargets(c, rt, realtimeTargets); const DenoiserTargets D = makeDenoiserTargets(denoiserTargets);
     for (uint32_t y = 0; y < T.height; y++) for (uint32_t px = 0; px < T.width; px++) denoiserFinalMergePixel(T, D, px, y, stablePlaneIndex, denoisedDiff, denoisedSpec);
+    return 0;
+}
+
+// Donut's skinning pass + the shade-record rewrite (pt_skinning.h); normals / tangents may be NULL; triShade: 24 words per source triangle, updated in place
+ORC_API int oracle_skin(uint32_t numVertices, uint32_t numTriangles, uint32_t firstGid, const float* positions, const uint32_t* normals, const uint32_t* tangents, const uint16_t* jointIndices,
+                        const float* jointWeights, const float* jointMatrices, const uint32_t* indices, float* outPositions, uint32_t* outNormals, uint32_t* outTangents, uint32_t* triShade)
+{
+    skinning::skinVertices(numVertices, positions, normals, tangents, jointIndices, jointWeights, jointMatrices, outPositions, outNormals, outTangents);
+    if (triShade) skinning::gatherShadeRecords(numTriangles, firstGid, indices, outPositions, normals ? outNormals : nullptr, tangents ? outTangents : nullptr, triShade);
     return 0;
 }
 

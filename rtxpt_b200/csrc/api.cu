@@ -9,6 +9,7 @@
 #include "envbake.cuh"
 #include "refit.cuh"
 #include "tonemap.cuh"
+#include "skinning.cuh"
 #include "lights_bake.h"
 #include <algorithm>
 #include <chrono>
@@ -69,6 +70,11 @@ struct rtxpt_ctx
     DeviceTexture envCube; uint32_t envFaceSize = 0, envMipLevels = 0;
     DeviceArray<uint4> dBvhNodes; DeviceArray<float4> dBvhTris; DeviceArray<uint4> dTriInfo, dTriShade;
     std::vector<RtxptInstanceData> hInstances; std::vector<uint32_t> bvhLevelStart; DeviceArray<float> dNodeBox;      // rigid-instance animation (refit.cuh)
+    // skinned meshes (skinning.cuh): where each (instance, geometry)'s triangles start in gid order, its index range on the device, and the registered bind poses
+    std::vector<RtxptGeometryData> hGeometries; std::vector<uint32_t> firstGidOfSubInstance; std::vector<const uint8_t*> hBufferTable;
+    struct Skin { uint32_t numVertices = 0, numTriangles = 0, firstGid = 0, flags = 0, numJoints = 0; const uint32_t* dIndices = nullptr;
+                  DeviceArray<float> positions, weights, outPositions, jointMatrices; DeviceArray<uint32_t> normals, tangents, outNormals, outTangents; DeviceArray<unsigned short> jointIndices; };
+    std::vector<Skin*> skins;
     uint32_t bvhNodeCount = 0, bvhTriCount = 0; float bvhBuildSeconds = 0;
     std::vector<RtxptSubInstanceData> hSubInstances; uint32_t materialCount = 0;
     LightBakeState lightState;
@@ -127,6 +133,8 @@ extern "C" RTXPT_API const char* rtxpt_b200_last_error(void) { return g_lastErro
 
 static void releaseScene(rtxpt_ctx* c)
 {
+    for (rtxpt_ctx::Skin* sk : c->skins) { sk->positions.release(); sk->weights.release(); sk->outPositions.release(); sk->jointMatrices.release(); sk->normals.release(); sk->tangents.release(); sk->outNormals.release(); sk->outTangents.release(); sk->jointIndices.release(); delete sk; }
+    c->skins.clear();
     for (uint8_t* p : c->bufferAllocs) cudaFree(p);
     c->bufferAllocs.clear();
     for (DeviceTexture& t : c->textures) { if (t.object) cudaDestroyTextureObject(t.object); if (t.array) cudaFreeMipmappedArray(t.array); }
@@ -279,7 +287,7 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
     releaseScene(c);
     if (sc->materialCount > 0xFFFF || sc->textureCount > 0xFFFF || sc->bufferCount > 0xFFFF) return fail(RTXPT_ERR_UNSUPPORTED, "table sizes exceed the 16-bit indices of SubInstanceData");
     // validate + flatten triangles to world space (gid order: instance, geometry, primitive)
-    std::vector<BuildTriangle> tris; std::vector<uint4> triInfo, triShade;
+    std::vector<BuildTriangle> tris; std::vector<uint4> triInfo, triShade; std::vector<uint32_t> firstGid;
     for (uint32_t ii = 0; ii < sc->instanceCount; ii++)
     {
         const RtxptInstanceData& inst = sc->instances[ii];
@@ -289,6 +297,8 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
             const RtxptGeometryData& g = sc->geometries[inst.firstGeometryIndex + gi];
             if (uint32_t(g.indexBufferIndex) >= sc->bufferCount || uint32_t(g.vertexBufferIndex) >= sc->bufferCount) return fail(RTXPT_ERR_INVALID_ARGUMENT, "geometry references buffer out of range");
             const uint32_t subIndex = inst.firstGeometryInstanceIndex + gi;
+            if (firstGid.size() <= subIndex) firstGid.resize(size_t(subIndex) + 1, 0u);
+            firstGid[subIndex] = uint32_t(tris.size());
             const RtxptSubInstanceData& sub = sc->subInstances[subIndex];
             uint32_t flags = subIndex;
             if (sub.FlagsAndAlphaInfo & RTXPT_SUBINST_FLAG_ALPHA_TESTED) flags |= kTriFlagAlphaTested;
@@ -340,6 +350,7 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
     CU(c->dTriShade.upload(triShade.data(), triShade.size(), s));
     CU(c->dInstances.upload(sc->instances, sc->instanceCount, s));
     c->hInstances.assign(sc->instances, sc->instances + sc->instanceCount); c->bvhLevelStart = bvh.levelStart; c->dNodeBox.release();
+    c->hGeometries.assign(sc->geometries, sc->geometries + sc->geometryCount); c->firstGidOfSubInstance = firstGid;
     CU(c->dGeometries.upload(sc->geometries, sc->geometryCount, s));
     CU(c->dMaterials.upload(sc->materials, sc->materialCount, s));
     c->materialCount = sc->materialCount;
@@ -352,6 +363,7 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
         table[i] = p;
     }
     CU(c->dBufferTable.upload(table.data(), table.size(), s));
+    c->hBufferTable = table;
     // bindless textures
     std::vector<cudaTextureObject_t> texTable(sc->textureCount, 0);
     c->textures.resize(sc->textureCount);
@@ -811,6 +823,54 @@ extern "C" RTXPT_API int rtxpt_b200_update_instance_transforms(rtxpt_ctx* c, con
     refit::Params p{};
     p.nodes = c->dBvhNodes.ptr; p.tris = c->dBvhTris.ptr; p.triShade = c->dTriShade.ptr; p.instances = c->dInstances.ptr; p.nodeBox = c->dNodeBox.ptr; p.nodeCount = c->bvhNodeCount; p.triCount = c->bvhTriCount;
     launchRefit(p, c->bvhLevelStart.data(), uint32_t(c->bvhLevelStart.size()) - 1, c->grid.smCount, s);
+    CU(cudaGetLastError());
+    return RTXPT_OK;
+}
+
+// ---- skinned meshes: Donut's skinning pass + the rewrite of the path tracer's per-triangle shade records; the caller refits afterwards -----------------------
+extern "C" RTXPT_API int rtxpt_b200_skin_register(rtxpt_ctx* c, const RtxptSkinDesc* d, uint32_t* outSkinId)
+{
+    if (!c || !d || !outSkinId) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (!c->haveScene) return fail(RTXPT_ERR_NO_SCENE, "no scene uploaded");
+    if (d->instanceIndex >= c->hInstances.size() || d->geometryIndexInInstance >= c->hInstances[d->instanceIndex].numGeometries) return fail(RTXPT_ERR_INVALID_ARGUMENT, "instance / geometry out of range");
+    if (!d->positions || !d->jointIndices || !d->jointWeights || d->numVertices == 0) return fail(RTXPT_ERR_INVALID_ARGUMENT, "bind pose needs positions, joint indices and weights");
+    const RtxptInstanceData& inst = c->hInstances[d->instanceIndex];
+    const RtxptGeometryData& g = c->hGeometries[inst.firstGeometryIndex + d->geometryIndexInInstance];
+    if (d->numVertices != g.numVertices && g.numVertices != 0) return fail(RTXPT_ERR_INVALID_ARGUMENT, "geometry has %u vertices, bind pose %u", g.numVertices, d->numVertices);
+    cudaSetDevice(c->device);
+    cudaStream_t s = c->stream;
+    rtxpt_ctx::Skin* sk = new rtxpt_ctx::Skin();
+    sk->numVertices = d->numVertices; sk->numTriangles = g.numIndices / 3; sk->firstGid = c->firstGidOfSubInstance[inst.firstGeometryInstanceIndex + d->geometryIndexInInstance];
+    sk->flags = (d->normals ? 2u : 0u) | (d->tangents ? 4u : 0u);
+    sk->dIndices = reinterpret_cast<const uint32_t*>(c->hBufferTable[g.indexBufferIndex] + g.indexOffset);
+    cudaError_t e = sk->positions.upload(d->positions, size_t(d->numVertices) * 3, s);
+    if (e == cudaSuccess) e = sk->jointIndices.upload(d->jointIndices, size_t(d->numVertices) * 4, s);
+    if (e == cudaSuccess) e = sk->weights.upload(d->jointWeights, size_t(d->numVertices) * 4, s);
+    if (e == cudaSuccess && d->normals) e = sk->normals.upload(d->normals, d->numVertices, s);
+    if (e == cudaSuccess && d->tangents) e = sk->tangents.upload(d->tangents, d->numVertices, s);
+    if (e == cudaSuccess) e = sk->outPositions.alloc(size_t(d->numVertices) * 3);
+    if (e == cudaSuccess) e = sk->outNormals.alloc(d->numVertices);
+    if (e == cudaSuccess) e = sk->outTangents.alloc(d->numVertices);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { delete sk; CU(e); }
+    c->skins.push_back(sk); *outSkinId = uint32_t(c->skins.size() - 1);
+    return RTXPT_OK;
+}
+extern "C" RTXPT_API int rtxpt_b200_skin_update(rtxpt_ctx* c, uint32_t skinId, const float* jointMatrices4x4, uint32_t numJoints, void* cudaStream)
+{
+    if (!c || !jointMatrices4x4) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (skinId >= c->skins.size()) return fail(RTXPT_ERR_INVALID_ARGUMENT, "unknown skin %u", skinId);
+    cudaSetDevice(c->device);
+    cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
+    rtxpt_ctx::Skin& sk = *c->skins[skinId];
+    if (sk.jointMatrices.count != size_t(numJoints) * 16) { CU(cudaStreamSynchronize(s)); CU(sk.jointMatrices.alloc(size_t(numJoints) * 16)); }
+    CU(cudaMemcpyAsync(sk.jointMatrices.ptr, jointMatrices4x4, size_t(numJoints) * 64, cudaMemcpyHostToDevice, s));
+    sk.numJoints = numJoints;
+    skin::Params p{};
+    p.numVertices = sk.numVertices; p.numTriangles = sk.numTriangles; p.firstGid = sk.firstGid; p.flags = sk.flags;
+    p.positions = sk.positions.ptr; p.normals = sk.normals.ptr; p.tangents = sk.tangents.ptr; p.jointIndices = sk.jointIndices.ptr; p.jointWeights = sk.weights.ptr; p.jointMatrices = sk.jointMatrices.ptr;
+    p.outPositions = sk.outPositions.ptr; p.outNormals = sk.outNormals.ptr; p.outTangents = sk.outTangents.ptr; p.indices = sk.dIndices; p.triShade = c->dTriShade.ptr;
+    launchSkin(p, s);
     CU(cudaGetLastError());
     return RTXPT_OK;
 }

@@ -40,6 +40,8 @@ void launchShadeNeeat(const LaunchParams& p, const GridConfig& g, cudaStream_t s
 void launchTraceShadowNeeat(const LaunchParams& p, const GridConfig& g, cudaStream_t s);
 void launchRtShadeNeeat(const LaunchParams& p, const GridConfig& g, cudaStream_t s);               // FILL pass shade with NEE-AT feedback (realtime_kernels.cu)
 void launchTraceShadowRealtimeNeeat(const LaunchParams& p, const GridConfig& g, cudaStream_t s);   // + feedback insertion for visible samples (kernels.cu)
+namespace skin { struct Params; }
+void launchSkin(const skin::Params& p, cudaStream_t s);                 // skinning_kernels.cu
 namespace tonemap { struct Params; }
 void launchToneMap(const tonemap::Params& p, const void* src, bool srcIsF32, uint32_t pixelCount, double* partials, float* avgLuminance, uint32_t* dst, cudaStream_t s);      // tonemap_kernels.cu
 namespace refit { struct Params; }

@@ -49,6 +49,8 @@ _SIGNATURES = {
     "rtxpt_b200_path_trace_realtime": [C.c_void_p, C.c_int, C.c_void_p],
     "rtxpt_b200_denoiser_prepare_inputs": [C.c_void_p, C.c_uint32, C.c_int, C.POINTER(S.DenoiserConstants), C.c_void_p],
     "rtxpt_b200_denoiser_final_merge": [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p],
+    "rtxpt_b200_skin_register": [C.c_void_p, C.POINTER(S.SkinDesc), C.POINTER(C.c_uint32)],
+    "rtxpt_b200_skin_update": [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p],
     "rtxpt_b200_tone_map": [C.c_void_p, C.POINTER(S.ToneMappingParams), C.c_int, C.c_void_p],
     "rtxpt_b200_tone_map_average_luminance": [C.c_void_p, C.POINTER(C.c_float)],
     "rtxpt_b200_update_instance_transforms": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
@@ -299,6 +301,19 @@ class Context:
             if d_diff is None: d_diff = self.device_ptr(S.BUFFER_DENOISER_DIFF_RADIANCE_HITDIST_F16)[0]
             if d_spec is None: d_spec = self.device_ptr(S.BUFFER_DENOISER_SPEC_RADIANCE_HITDIST_F16)[0]
         _check(self.L.rtxpt_b200_denoiser_final_merge(self.h, plane, d_diff, d_spec, stream), self.L)
+
+    def skin_register(self, instance, geometry, positions, joint_indices, joint_weights, normals=None, tangents=None):
+        """Bind pose of one geometry (vertex order of its vertex buffer); returns the skin id for skin_update."""
+        c = lambda a, t: None if a is None else np.ascontiguousarray(a, t)
+        pos, ji, jw, nr, tg = c(positions, np.float32).reshape(-1, 3), c(joint_indices, np.uint16).reshape(-1, 4), c(joint_weights, np.float32).reshape(-1, 4), c(normals, np.uint32), c(tangents, np.uint32)
+        d = S.SkinDesc(); d.instanceIndex = instance; d.geometryIndexInInstance = geometry; d.numVertices = len(pos)
+        d.positions = pos.ctypes.data; d.jointIndices = ji.ctypes.data; d.jointWeights = jw.ctypes.data; d.normals = None if nr is None else nr.ctypes.data; d.tangents = None if tg is None else tg.ctypes.data
+        sid = C.c_uint32(); _check(self.L.rtxpt_b200_skin_register(self.h, C.byref(d), C.byref(sid)), self.L)
+        return int(sid.value)
+
+    def skin_update(self, skin_id, joint_matrices, stream=None):
+        m = np.ascontiguousarray(joint_matrices, np.float32).reshape(-1, 16)
+        _check(self.L.rtxpt_b200_skin_update(self.h, skin_id, m.ctypes.data, len(m), stream), self.L)
 
     def tone_map(self, params, source=None, stream=None):
         """ToneMappingPass on the output colour (default) or the accumulation buffer; returns nothing - read the SRGBA8 result with readback_ldr()."""

@@ -135,6 +135,11 @@ class DenoiserConstants(C.Structure):
                 ("stablePlanesSuppressPrimaryIndirectSpecularK", f32), ("_pad", f32)]
 
 
+class SkinDesc(C.Structure):
+    _fields_ = [("instanceIndex", u32), ("geometryIndexInInstance", u32), ("numVertices", u32), ("_pad", u32), ("positions", C.c_void_p), ("normals", C.c_void_p), ("tangents", C.c_void_p),
+                ("jointIndices", C.c_void_p), ("jointWeights", C.c_void_p)]
+
+
 class ToneMappingParams(C.Structure):
     _fields_ = [("toneMapOperator", u32), ("clamped", u32), ("autoExposure", u32), ("enabled", u32), ("whiteBalance", u32), ("exposureCompensation", f32), ("exposureValueMin", f32),
                 ("exposureValueMax", f32), ("whiteScale", f32), ("whiteMaxLuminance", f32), ("whitePoint", f32), ("filmSpeed", f32), ("fNumber", f32), ("shutter", f32), ("_pad", f32 * 2)]

@@ -13,6 +13,7 @@ run guide_filter  $PY tests/test_gpu_reblur.py -k spec_hit_t
 run envbake       $PY tests/test_gpu_envbake.py
 run tonemap       $PY tests/test_gpu_tonemap.py
 run refit         $PY tests/test_gpu_refit.py
+run skinning      $PY tests/test_gpu_skinning.py
 run reblur        $PY tests/test_gpu_reblur.py -k "static_camera or moving_camera or reset"
 run realtime_rest $PY tests/test_gpu_realtime.py
 run denoise_e2e   $PY tests/test_gpu_reblur.py -k denoise_realtime

@@ -10,6 +10,7 @@
 #include "../../rtxpt_b200/csrc/refit.cuh"
 #include "../../rtxpt_b200/csrc/tonemap.cuh"
 #include "../../rtxpt_b200/csrc/denoiser_iface.cuh"
+#include "../../rtxpt_b200/csrc/skinning.cuh"
 #include <vector>
 #include <cstdint>
 
@@ -165,3 +166,16 @@ extern "C" int emu_denoiser_interface(const RtxptPathTracerConstants* consts, co
 // pin against tests/golden/host_golden.json: the product's white balance transform (tonemap.cuh host half)
 extern "C" void emu_white_balance(float T, float* outM9, float* outXyz3)
 { const pt::tonemap::M3 m = pt::tonemap::whiteBalanceTransform(T); for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) outM9[i * 3 + j] = m.m[i][j]; pt::tonemap::colorTemperatureToXYZ(T, outXyz3); }
+
+// skinning: the product's bodies (skinning.cuh) in launchSkin's order; same argument list as oracle_skin
+extern "C" int emu_skin(uint32_t numVertices, uint32_t numTriangles, uint32_t firstGid, const float* positions, const uint32_t* normals, const uint32_t* tangents, const uint16_t* jointIndices,
+                        const float* jointWeights, const float* jointMatrices, const uint32_t* indices, float* outPositions, uint32_t* outNormals, uint32_t* outTangents, uint32_t* triShade)
+{
+    pt::skin::Params p{};
+    p.numVertices = numVertices; p.numTriangles = triShade ? numTriangles : 0; p.firstGid = firstGid; p.flags = (normals ? 2u : 0u) | (tangents ? 4u : 0u);
+    p.positions = positions; p.normals = normals; p.tangents = tangents; p.jointIndices = jointIndices; p.jointWeights = jointWeights; p.jointMatrices = jointMatrices;
+    p.outPositions = outPositions; p.outNormals = outNormals; p.outTangents = outTangents; p.indices = indices; p.triShade = reinterpret_cast<uint4*>(triShade);
+    for (uint32_t i = 0; i < p.numVertices; i++) pt::skin::skinVertex(p, i);
+    for (uint32_t t = 0; t < p.numTriangles; t++) pt::skin::gatherTriangle(p, t);
+    return 0;
+}
