@@ -181,3 +181,37 @@ def test_history_follows_a_moving_camera_and_resets_on_a_cut(oracle):
     _, _, frames_reset = rb.denoise(sb.world_to_view(cut), sb.view_to_clip(cut), 11, d["view_z"], d["normal_roughness"], d["diff"], d["spec"], motion=d["motion"], reset=True)
     assert (frames_reset == 0).all()
     rb.close(); o.close()
+
+
+def test_whole_denoised_frame_beats_the_noisy_one(oracle):
+    """Sample::Denoise end to end in the oracle, as rtxpt_b200_denoise_realtime composes it: realtime frame -> specular hit distance guide filter -> for plane = 2..0 { prepare inputs,
+    that plane's ReBLUR instance, final merge }.  After a few frames the merged colour is closer to a converged reference-mode image than the no-denoiser merge, at equal energy."""
+    from rtxpt_b200 import scene_builder as sb, scenes
+    W, H = 80, 64
+    scene, cam = scenes.cornell_box(W, H, delta_surfaces=True)
+    o = oracle.Oracle(scene)
+    c = sb.make_constants(W, H, cam, bounce_count=5, diffuse_bounce_count=3); o.set_constants(c); o.set_view(sb.world_to_clip(cam))
+    acc, n = None, 0
+    for base in range(0, 192, 8):
+        c.sampleBaseIndex = 5000 + base; o.set_constants(c); acc, n = o.render(0, 8, accum=acc, accum_count=n)[:2]
+    ref = acc[..., :3]
+    rt = sb.make_realtime_constants(W, H, cam, bounce_count=5, sub_samples=1); k = sb.make_denoiser_constants(cam)
+    wv, vc = sb.world_to_view(cam), sb.view_to_clip(cam)
+    rbs = [oracle.Reblur() for _ in range(3)]
+    for f in range(10):
+        c.sampleBaseIndex = f; o.set_constants(c)
+        r = o.render_realtime(rt)
+        r["spec_hit_t"] = oracle.denoise_spec_hit_t(r["depth"], r["spec_hit_t"])
+        d = o.new_denoiser_targets()
+        for i, plane in enumerate((2, 1, 0)):
+            o.denoiser_prepare_inputs(rt, k, r, d, plane, i == 0)
+            od, os_, _ = rbs[plane].denoise(wv, vc, f, d["view_z"], d["normal_roughness"], d["diff"], d["spec"], motion=d["motion"], disocclusion_mix=d["disocclusion_mix"])
+            o.denoiser_final_merge(rt, r, d, plane, od, os_)
+    den = d["output"][..., :3].astype(np.float32); noisy = r["merged"]
+    assert np.isfinite(den).all()
+    clip = lambda x: np.minimum(x, 4.0)
+    e_den, e_noisy = np.abs(clip(den) - clip(ref)).mean(), np.abs(clip(noisy) - clip(ref)).mean()
+    assert e_den < 0.8 * e_noisy, (e_den, e_noisy)                           # the reference image itself still carries noise: the ratio understates the gain
+    assert abs(den.mean() - ref.mean()) < 0.12 * ref.mean(), (den.mean(), ref.mean())
+    for rb in rbs: rb.close()
+    o.close()
