@@ -580,6 +580,9 @@ RTXPT_API int rtxpt_b200_default_constants(const RtxptCameraData* camera, int en
 /* The one matrix of SampleConstants.view (PlanarViewConstants) the reference-mode dispatch reads besides the camera block:
  * matWorldToClip, row-major, used as row-vector x matrix (Bridge::ExportSurface, PathTracerBridgeDonut.hlsli:1113-1115).
  * Only needed with RTXPT_CFG_EXPORT_GUIDES. */
+/* host helper: the planar view's matrices of a BridgeCamera block (row-major, row vector x matrix; left-handed view space, +z forward; D3D clip space, z in [0, 1]) - what a host
+ * without Donut's PlanarView needs for rtxpt_b200_set_view, RtxptRealtimeConstants, RtxptDenoiserConstants and RtxptReblurFrame.  Any output may be NULL. */
+RTXPT_API int rtxpt_b200_camera_matrices(const RtxptCameraData* camera, float* outWorldToView16, float* outViewToClip16, float* outWorldToClip16);
 typedef struct RtxptViewConstants { float matWorldToClip[16]; } RtxptViewConstants;
 RTXPT_API int rtxpt_b200_set_view(rtxpt_ctx* ctx, const RtxptViewConstants* view);
 

@@ -76,3 +76,22 @@ extern "C" RTXPT_API uint32_t rtxpt_b200_generic_ts_address(uint32_t x, uint32_t
     const uint32_t xi = x % 8u, yi = y % 8u;
     return (x - xi) * 8u + (y - yi) * lineStride + morton16(xi, yi) + plane * planeStride;
 }
+
+// planar view of a BridgeCamera block: view axes = normalised CameraU / V / W, field of view from their lengths, reverse-free D3D projection (z in [0, 1]); computed in double,
+// stored as float - the arithmetic of rtxpt_b200/scene_builder.py (world_to_view, view_to_clip, world_to_clip), which the parity tests feed to both sides
+extern "C" RTXPT_API int rtxpt_b200_camera_matrices(const RtxptCameraData* cam, float* outWorldToView, float* outViewToClip, float* outWorldToClip)
+{
+    if (!cam) return RTXPT_ERR_INVALID_ARGUMENT;
+    auto len = [](const float* v) { return std::sqrt(double(v[0]) * v[0] + double(v[1]) * v[1] + double(v[2]) * v[2]); };
+    const double lu = len(cam->CameraU), lv = len(cam->CameraV), lw = len(cam->CameraW);
+    double right[3], up[3], fwd[3];
+    for (int k = 0; k < 3; k++) { right[k] = double(float(cam->CameraU[k] / float(lu))); up[k] = double(float(cam->CameraV[k] / float(lv))); fwd[k] = double(float(cam->CameraW[k] / float(lw))); }
+    auto dotp = [&](const double* a) { return double(float(cam->PosW[0])) * a[0] + double(float(cam->PosW[1])) * a[1] + double(float(cam->PosW[2])) * a[2]; };
+    double view[16] = { right[0], up[0], fwd[0], 0, right[1], up[1], fwd[1], 0, right[2], up[2], fwd[2], 0, -dotp(right), -dotp(up), -dotp(fwd), 1 };
+    const double tanX = double(float(float(lu) / float(lw))), tanY = double(float(float(lv) / float(lw))), n = cam->NearZ, f = cam->FarZ;
+    double proj[16] = { 1.0 / tanX, 0, 0, 0, 0, 1.0 / tanY, 0, 0, 0, 0, f / (f - n), 1.0, 0, 0, -n * f / (f - n), 0 };
+    if (outWorldToView) for (int i = 0; i < 16; i++) outWorldToView[i] = float(view[i]);
+    if (outViewToClip) for (int i = 0; i < 16; i++) outViewToClip[i] = float(proj[i]);
+    if (outWorldToClip) for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) { double a = 0; for (int k = 0; k < 4; k++) a += view[r * 4 + k] * proj[k * 4 + c]; outWorldToClip[r * 4 + c] = float(a); }
+    return RTXPT_OK;
+}

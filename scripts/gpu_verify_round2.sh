@@ -20,6 +20,7 @@ run denoise_e2e   $PY tests/test_gpu_reblur.py -k denoise_realtime
 run neeat_baker   $PY tests/test_gpu_neeat.py -k baker_passes
 run neeat_api     $PY tests/test_gpu_neeat.py -k api_errors
 run neeat_loop    $PY tests/test_gpu_neeat.py -k "unbiased or reference_mode"
+run cpp_example   $PY tests/test_gltf_loader.py -k realtime_example
 run bench         python bench.py --steps 4 --warmup 3                                   # its realtime child times realtime mode, the denoised frame and the NEE-AT loop
 run sanitizer     compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest -x -q -m gpu_unverified tests/test_gpu_reblur.py -k "static_camera and True" tests/test_gpu_neeat.py -k baker_passes
 echo "=== done"; grep -h "^rc=" /dev/null; ls -la gpurun_out | head -40

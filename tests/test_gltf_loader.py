@@ -158,6 +158,26 @@ def test_cpp_host_example_without_gpu(product, tmp_path):
     path = gltf_export.export(scenes.cornell_builder(), str(tmp_path / "cornell.gltf"), camera=dict(position=(2.78, 2.73, -8.0), direction=(0, 0, 1), up=(0, 1, 0), yfov=0.66, znear=0.1, zfar=1e7))
     r = subprocess.run([exe, path, str(tmp_path / "o.pfm"), "32", "32", "1", "2"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 1 and "no CPU fallback" in r.stderr
+    exe = os.path.join(os.path.dirname(product.LIB_PATH), "realtime_gltf")
+    r = subprocess.run([exe, path, str(tmp_path / "o.ppm"), "32", "32", "2", "2"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu_unverified
+def test_cpp_realtime_example_writes_a_tone_mapped_frame(product, tmp_path):
+    """glTF file -> examples/realtime_gltf.cpp (NEE-AT update, stable-plane BUILD/FILL, ReBLUR, tone mapping through the C ABI only) -> PPM: the box is lit, not saturated, and the
+    image differs from a flat fill.  Written after the round's GPU budget ran out - never run on a GPU (scripts/gpu_verify_round2.sh)."""
+    import subprocess
+    from rtxpt_b200 import scenes
+    exe = os.path.join(os.path.dirname(product.LIB_PATH), "realtime_gltf")
+    path = gltf_export.export(scenes.cornell_builder(), str(tmp_path / "cornell.gltf"), camera=dict(position=(2.78, 2.73, -8.0), direction=(0, 0, 1), up=(0, 1, 0), yfov=0.66, znear=0.1, zfar=1e7))
+    out = str(tmp_path / "o.ppm")
+    r = subprocess.run([exe, path, out, "128", "128", "8", "4"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    with open(out, "rb") as f:
+        assert f.readline() == b"P6\n" and f.readline() == b"128 128\n" and f.readline() == b"255\n"
+        img = np.frombuffer(f.read(), np.uint8).reshape(128, 128, 3)
+    assert 20 < img.mean() < 235 and img.std() > 10
 
 
 @pytest.mark.gpu
