@@ -139,8 +139,9 @@ inline float SampleLocalPDF(const NeeatState& s, uint tileAddress, uint lightInd
     {
         const uint mid = (left + right) >> 1; const uint v = s.localSamplingBuffer[mid], key = UnpackMiniListLight(v);
         if (key < lightIndex) left = mid + 1;
-        else if (key > lightIndex) right = mid - 1;
+        else if (key > lightIndex) { if (mid == left) return 0.0f; right = mid - 1; }   // empty range: LightingAlgorithms.hlsli:677 would step below the tile (tile 0: index 0xFFFFFFFF, which D3D reads as 0); "not found" is the answer the search means
         else return float(UnpackMiniListCount(v)) / float(NEEAT_LOCAL_PROXY_COUNT);
+        if (left > right) return 0.0f;
     }
     return 0.0f;
 }

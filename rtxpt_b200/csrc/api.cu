@@ -71,8 +71,8 @@ struct rtxpt_ctx
     DeviceArray<uint4> dBvhNodes; DeviceArray<float4> dBvhTris; DeviceArray<uint4> dTriInfo, dTriShade;
     std::vector<RtxptInstanceData> hInstances; std::vector<uint32_t> bvhLevelStart; DeviceArray<float> dNodeBox;      // rigid-instance animation (refit.cuh)
     // skinned meshes (skinning.cuh): where each (instance, geometry)'s triangles start in gid order, its index range on the device, and the registered bind poses
-    std::vector<RtxptGeometryData> hGeometries; std::vector<uint32_t> firstGidOfSubInstance; std::vector<const uint8_t*> hBufferTable;
-    struct Skin { uint32_t numVertices = 0, numTriangles = 0, firstGid = 0, flags = 0, numJoints = 0; const uint32_t* dIndices = nullptr;
+    std::vector<RtxptGeometryData> hGeometries; std::vector<uint32_t> firstGidOfSubInstance; std::vector<const uint8_t*> hBufferTable; std::vector<uint32_t> maxVertexOfSubInstance;      // largest vertex index each sub-instance's triangles name (skin registration validates against it)
+    struct Skin { uint32_t numVertices = 0, numTriangles = 0, firstGid = 0, flags = 0, numJoints = 0, maxJoint = 0; const uint32_t* dIndices = nullptr;
                   DeviceArray<float> positions, weights, outPositions, jointMatrices; DeviceArray<uint32_t> normals, tangents, outNormals, outTangents; DeviceArray<unsigned short> jointIndices; };
     std::vector<Skin*> skins;
     uint32_t bvhNodeCount = 0, bvhTriCount = 0; float bvhBuildSeconds = 0;
@@ -125,9 +125,30 @@ struct rtxpt_ctx
     std::vector<cudaEvent_t> evPool; std::vector<int> evKind; size_t evUsed = 0;     // RTXPT_CFG_TIME_KERNELS: (begin,end) pairs per kernel
     uint32_t lastIterations = 0, lastSubSamples = 0; uint64_t lastLaunches = 0;
     bool statsPending = false;
+    // the caller's stream that last received work through this context (null: everything went to `stream`); host reads join it first
+    cudaStream_t lastCallerStream = nullptr; cudaEvent_t evCallerJoin = nullptr;
 };
 
 static const uint32_t kCounterWords = (kMaxWavefrontIterations + 2) * kCountersPerIter;
+
+// Work goes to the caller's stream when one is passed, otherwise to the context's own (non-blocking) stream; there is no implicit ordering between the two.  Every entry point
+// that hands results to the host (readback, synchronize, get_stats, the NEE-AT / tone-map getters) therefore first makes the context stream wait for what the caller's stream
+// has been given: an event recorded there, waited on here.  One caller stream at a time (calls on a context are serialised by the caller, include/rtxpt_b200.h).
+static cudaStream_t pickStream(rtxpt_ctx* c, void* cudaStream)
+{
+    if (!cudaStream || (cudaStream_t)cudaStream == c->stream) return c->stream;
+    c->lastCallerStream = (cudaStream_t)cudaStream;
+    return c->lastCallerStream;
+}
+static cudaError_t joinCallerStream(rtxpt_ctx* c)
+{
+    if (!c->lastCallerStream) return cudaSuccess;
+    cudaError_t e;
+    if (!c->evCallerJoin && (e = cudaEventCreateWithFlags(&c->evCallerJoin, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(c->evCallerJoin, c->lastCallerStream)) != cudaSuccess) return e;
+    return cudaStreamWaitEvent(c->stream, c->evCallerJoin, 0);
+}
+static cudaError_t syncContext(rtxpt_ctx* c) { cudaError_t e = joinCallerStream(c); return e != cudaSuccess ? e : cudaStreamSynchronize(c->stream); }
 
 extern "C" RTXPT_API const char* rtxpt_b200_last_error(void) { return g_lastError.c_str(); }
 
@@ -193,7 +214,7 @@ extern "C" RTXPT_API int rtxpt_b200_destroy(rtxpt_ctx* c)
 {
     if (!c) return RTXPT_OK;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    syncContext(c);
     releaseScene(c);
     c->dInstances.release(); c->dGeometries.release(); c->dSubInstances.release(); c->dMaterials.release(); c->dSubInstanceClass.release();
     c->dBufferTable.release(); c->dTextureTable.release(); c->dBvhNodes.release(); c->dBvhTris.release(); c->dTriInfo.release(); c->dTriShade.release(); c->dNodeBox.release();
@@ -209,6 +230,7 @@ extern "C" RTXPT_API int rtxpt_b200_destroy(rtxpt_ctx* c)
     c->rbTiles.release(); c->rbTmp1Diff.release(); c->rbTmp1Spec.release(); c->rbTmp2Diff.release(); c->rbTmp2Spec.release(); c->rbOutDiff.release(); c->rbOutSpec.release();
     c->rbTrackingT.release(); c->rbDiffFastT.release(); c->rbSpecFastT.release(); c->rbData1.release(); c->rbData2.release();
     for (cudaEvent_t ev : c->evPool) cudaEventDestroy(ev);
+    if (c->evCallerJoin) cudaEventDestroy(c->evCallerJoin);
     if (c->evStart) cudaEventDestroy(c->evStart);
     if (c->evStop) cudaEventDestroy(c->evStop);
     if (c->hCounters) cudaFreeHost(c->hCounters);
@@ -234,6 +256,7 @@ static int createTexture2D(const RtxptTextureDesc& d, DeviceTexture& out)
     {
         cudaArray_t level; CU(cudaGetMipmappedArrayLevel(&level, out.array, m));
         const uint32_t w = std::max(1u, d.width >> m), h = std::max(1u, d.height >> m);
+        if (!d.mips[m]) return fail(RTXPT_ERR_INVALID_ARGUMENT, "texture mip %u has no data", m);
         CU(cudaMemcpy2DToArray(level, 0, 0, d.mips[m], w * texel, w * texel, h, cudaMemcpyHostToDevice));
     }
     cudaResourceDesc res{}; res.resType = cudaResourceTypeMipmappedArray; res.res.mipmap.mipmap = out.array;
@@ -258,6 +281,7 @@ static int createEnvCube(const RtxptEnvCubeDesc& d, DeviceTexture& out)
         const uint32_t n = std::max(1u, d.faceSize >> m);
         for (int f = 0; f < 6; f++)
         {
+            if (!d.faces[f][m]) return fail(RTXPT_ERR_INVALID_ARGUMENT, "env cube face %d mip %u has no data", f, m);
             cudaMemcpy3DParms cp{};
             cp.srcPtr = make_cudaPitchedPtr(const_cast<float*>(d.faces[f][m]), n * 16, n, n);
             cp.dstArray = level; cp.dstPos = make_cudaPos(0, 0, f); cp.extent = make_cudaExtent(n, n, 1); cp.kind = cudaMemcpyHostToDevice;
@@ -283,11 +307,11 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
 {
     if (!c || !sc) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
     cudaSetDevice(c->device);
-    CU(cudaStreamSynchronize(c->stream));
+    CU(syncContext(c));
     releaseScene(c);
     if (sc->materialCount > 0xFFFF || sc->textureCount > 0xFFFF || sc->bufferCount > 0xFFFF) return fail(RTXPT_ERR_UNSUPPORTED, "table sizes exceed the 16-bit indices of SubInstanceData");
     // validate + flatten triangles to world space (gid order: instance, geometry, primitive)
-    std::vector<BuildTriangle> tris; std::vector<uint4> triInfo, triShade; std::vector<uint32_t> firstGid;
+    std::vector<BuildTriangle> tris; std::vector<uint4> triInfo, triShade; std::vector<uint32_t> firstGid, maxVertex;
     for (uint32_t ii = 0; ii < sc->instanceCount; ii++)
     {
         const RtxptInstanceData& inst = sc->instances[ii];
@@ -299,6 +323,7 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
             const uint32_t subIndex = inst.firstGeometryInstanceIndex + gi;
             if (firstGid.size() <= subIndex) firstGid.resize(size_t(subIndex) + 1, 0u);
             firstGid[subIndex] = uint32_t(tris.size());
+            if (maxVertex.size() <= subIndex) maxVertex.resize(size_t(subIndex) + 1, 0u);
             const RtxptSubInstanceData& sub = sc->subInstances[subIndex];
             uint32_t flags = subIndex;
             if (sub.FlagsAndAlphaInfo & RTXPT_SUBINST_FLAG_ALPHA_TESTED) flags |= kTriFlagAlphaTested;
@@ -309,6 +334,7 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
             for (uint32_t t = 0; t < triCount; t++)
             {
                 uint32_t idx[3]; memcpy(idx, ib + g.indexOffset + size_t(t) * 12, 12);
+                maxVertex[subIndex] = std::max(maxVertex[subIndex], std::max(idx[0], std::max(idx[1], idx[2])));
                 BuildTriangle bt; float* dst[3] = { bt.v0, bt.v1, bt.v2 };
                 const uint64_t vbSize = sc->buffers[g.vertexBufferIndex].sizeBytes;
                 uint4 rec[6]; memset(rec, 0, sizeof(rec));
@@ -350,7 +376,7 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
     CU(c->dTriShade.upload(triShade.data(), triShade.size(), s));
     CU(c->dInstances.upload(sc->instances, sc->instanceCount, s));
     c->hInstances.assign(sc->instances, sc->instances + sc->instanceCount); c->bvhLevelStart = bvh.levelStart; c->dNodeBox.release();
-    c->hGeometries.assign(sc->geometries, sc->geometries + sc->geometryCount); c->firstGidOfSubInstance = firstGid;
+    c->hGeometries.assign(sc->geometries, sc->geometries + sc->geometryCount); c->firstGidOfSubInstance = firstGid; c->maxVertexOfSubInstance = maxVertex;
     CU(c->dGeometries.upload(sc->geometries, sc->geometryCount, s));
     CU(c->dMaterials.upload(sc->materials, sc->materialCount, s));
     c->materialCount = sc->materialCount;
@@ -375,12 +401,25 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
     c->hSubInstances.assign(sc->subInstances, sc->subInstances + sc->subInstanceCount);
     // AnalyticProxyLightIndex arrives as an index into sc->lights; in the light list the analytic lights follow the environment quad-tree nodes
     for (RtxptSubInstanceData& si : c->hSubInstances) si.AnalyticProxyLightIndex = (si.AnalyticProxyLightIndex < sc->lightCount) ? si.AnalyticProxyLightIndex + kEnvQuadLightCount : 0xFFFFFFFFu;
+    // every enabled texture slot of every material must name an uploaded texture (the kernels index the bindless table without a bounds check, shade.cuh)
+    for (uint32_t mi = 0; mi < sc->materialCount; mi++)
+    {
+        const RtxptMaterialData& m = sc->materials[mi];
+        const struct { uint32_t flag, packed; const char* name; } slots[] = {
+            { RTXPT_MATFLAG_UseBaseOrDiffuseTexture, m.BaseOrDiffuseTextureIndex, "base/diffuse" }, { RTXPT_MATFLAG_UseMetalRoughOrSpecularTexture, m.MetalRoughOrSpecularTextureIndex, "metal-rough/specular" },
+            { RTXPT_MATFLAG_UseEmissiveTexture, m.EmissiveTextureIndex, "emissive" }, { RTXPT_MATFLAG_UseNormalTexture, m.NormalTextureIndex, "normal" },
+            { RTXPT_MATFLAG_UseTransmissionTexture, m.TransmissionTextureIndex, "transmission" } };
+        for (const auto& sl : slots)
+            if ((m.Flags & sl.flag) && (sl.packed & 0xFFFFu) >= sc->textureCount) return fail(RTXPT_ERR_INVALID_ARGUMENT, "material %u: %s texture index %u out of range (%u textures)", mi, sl.name, sl.packed & 0xFFFFu, sc->textureCount);
+    }
     std::vector<uint8_t> cls(sc->subInstanceCount, 0);
     for (uint32_t i = 0; i < sc->subInstanceCount; i++)
     {
         const uint32_t mi = c->hSubInstances[i].GlobalGeometryIndex_PTMaterialDataIndex & 0xFFFF;
         if (mi >= sc->materialCount) return fail(RTXPT_ERR_INVALID_ARGUMENT, "sub-instance %u references material out of range", i);
         const RtxptMaterialData& m = sc->materials[mi];
+        if ((c->hSubInstances[i].FlagsAndAlphaInfo & RTXPT_SUBINST_FLAG_ALPHA_TESTED) && (c->hSubInstances[i].FlagsAndAlphaInfo & 0xFFFFu) >= sc->textureCount)
+            return fail(RTXPT_ERR_INVALID_ARGUMENT, "alpha-tested sub-instance %u references texture %u of %u", i, c->hSubInstances[i].FlagsAndAlphaInfo & 0xFFFFu, sc->textureCount);
         const bool transmissive = m.TransmissionFactor > 0 || m.DiffuseTransmissionFactor > 0;
         const bool emissive = m.EmissiveColor[0] > 0 || m.EmissiveColor[1] > 0 || m.EmissiveColor[2] > 0;
         const bool textured = (m.Flags & (RTXPT_MATFLAG_UseBaseOrDiffuseTexture | RTXPT_MATFLAG_UseMetalRoughOrSpecularTexture | RTXPT_MATFLAG_UseNormalTexture | RTXPT_MATFLAG_UseEmissiveTexture)) != 0;
@@ -401,7 +440,7 @@ static int ensureTargets(rtxpt_ctx* c, uint32_t W, uint32_t H)
     if (W == 0 || H == 0 || W > 65535 || H > 65535) return fail(RTXPT_ERR_INVALID_ARGUMENT, "image size %ux%u unsupported (path id packs x,y in 16 bits each)", W, H);
     if (c->cfg.maxWidth && (W > c->cfg.maxWidth || H > c->cfg.maxHeight)) return fail(RTXPT_ERR_INVALID_ARGUMENT, "image larger than the configured maximum");
     if (c->tableWidth == W && c->tableHeight == H) return RTXPT_OK;
-    CU(cudaStreamSynchronize(c->stream));
+    CU(syncContext(c));
     // pixels of this context's tiles, Morton order inside a tile: 32 consecutive path slots cover an 8x4 pixel block
     const uint32_t T = c->cfg.tileSize, tilesX = (W + T - 1) / T, tilesY = (H + T - 1) / T;
     std::vector<uint32_t> table;
@@ -553,7 +592,7 @@ extern "C" RTXPT_API int rtxpt_b200_path_trace(rtxpt_ctx* c, uint32_t firstSubSa
     if (na && (!c->na.allocated || !c->na.frameEnded)) return fail(RTXPT_ERR_INVALID_ARGUMENT, "NEEATFeedback is set: call rtxpt_b200_neeat_update_begin and rtxpt_b200_neeat_update_end before tracing the frame");
     if (na && c->cfg.tileWorld > 1) return fail(RTXPT_ERR_UNSUPPORTED, "NEE-AT feedback needs every pixel's reservoir on one GPU; the tile partition runs with NEEATFeedback = 0");
     if (na && !(c->cfg.flags & RTXPT_CFG_EXPORT_GUIDES)) return fail(RTXPT_ERR_INVALID_ARGUMENT, "NEE-AT feedback in reference mode reprojects with the exported guides: create the context with RTXPT_CFG_EXPORT_GUIDES");
-    cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
+    cudaStream_t s = pickStream(c, cudaStream);
     LaunchParams p; fillParams(c, p);
     if (na)
     {
@@ -628,7 +667,7 @@ extern "C" RTXPT_API int rtxpt_b200_set_realtime(rtxpt_ctx* c, const RtxptRealti
     const uint32_t W = c->tableWidth, H = c->tableHeight;
     if (c->realtimeWidth != W || c->realtimeHeight != H)
     {
-        CU(cudaStreamSynchronize(c->stream));
+        CU(syncContext(c));
         const size_t P = size_t(W) * H, planeStride = rtxpt_b200_generic_ts_plane_stride(W, H);
         CU(c->stablePlanes.alloc(planeStride * RTXPT_STABLE_PLANE_COUNT)); CU(c->stablePlanesHeader.alloc(P * 4)); CU(c->stableRadiance.alloc(P)); CU(c->specularHitT.alloc(P));
         CU(cudaMemsetAsync(c->stablePlanes.ptr, 0, planeStride * RTXPT_STABLE_PLANE_COUNT * sizeof(RtxptStablePlane), c->stream));
@@ -662,7 +701,7 @@ extern "C" RTXPT_API int rtxpt_b200_path_trace_realtime(rtxpt_ctx* c, int mergeN
     int rc = checkReady(c); if (rc != RTXPT_OK) return rc;
     if (!c->haveRealtime || c->realtimeWidth != c->tableWidth || c->realtimeHeight != c->tableHeight) return fail(RTXPT_ERR_INVALID_ARGUMENT, "rtxpt_b200_set_realtime has not been called for this image size");
     if (!c->haveView) return fail(RTXPT_ERR_INVALID_ARGUMENT, "rtxpt_b200_set_view has not been called (the guide depth needs view.matWorldToClip)");
-    cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
+    cudaStream_t s = pickStream(c, cudaStream);
     const bool na = neeatActive(c);
     if (na && (!c->na.allocated || !c->na.frameBegun)) return fail(RTXPT_ERR_INVALID_ARGUMENT, "NEEATFeedback is set: call rtxpt_b200_neeat_update_begin before tracing the frame");
     if (na && c->cfg.tileWorld > 1) return fail(RTXPT_ERR_UNSUPPORTED, "NEE-AT feedback needs every pixel's reservoir on one GPU; the tile partition runs with NEEATFeedback = 0");
@@ -722,9 +761,9 @@ extern "C" RTXPT_API int rtxpt_b200_path_trace_realtime(rtxpt_ctx* c, int mergeN
 extern "C" RTXPT_API int rtxpt_b200_denoise_spec_hit_t(rtxpt_ctx* c, void* cudaStream)
 {
     int rc = checkRealtimeReady(c); if (rc != RTXPT_OK) return rc;
-    cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
+    cudaStream_t s = pickStream(c, cudaStream);
     const size_t P = size_t(c->tableWidth) * c->tableHeight;
-    if (c->dnScratchFloat.count != P) { CU(cudaStreamSynchronize(c->stream)); CU(c->dnScratchFloat.alloc(P)); }
+    if (c->dnScratchFloat.count != P) { CU(syncContext(c)); CU(c->dnScratchFloat.alloc(P)); }
     launchDnSpecHitT(c->specularHitT.ptr, c->depth.ptr, c->dnScratchFloat.ptr, int(c->tableWidth), int(c->tableHeight), s);
     launchDnSpecHitT(c->dnScratchFloat.ptr, c->depth.ptr, c->specularHitT.ptr, int(c->tableWidth), int(c->tableHeight), s);
     CU(cudaGetLastError());
@@ -736,10 +775,10 @@ extern "C" RTXPT_API int rtxpt_b200_denoiser_prepare_inputs(rtxpt_ctx* c, uint32
 {
     int rc = checkRealtimeReady(c); if (rc != RTXPT_OK) return rc;
     if (!k || stablePlaneIndex >= RTXPT_STABLE_PLANE_COUNT) return fail(RTXPT_ERR_INVALID_ARGUMENT, "bad plane index or null constants");
-    cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
+    cudaStream_t s = pickStream(c, cudaStream);
     if (c->denoiserWidth != c->tableWidth || c->denoiserHeight != c->tableHeight)
     {
-        CU(cudaStreamSynchronize(c->stream));
+        CU(syncContext(c));
         const size_t P = size_t(c->tableWidth) * c->tableHeight;
         CU(c->dnViewZ.alloc(P)); CU(c->dnMotion.alloc(P)); CU(c->dnDiff.alloc(P)); CU(c->dnSpec.alloc(P)); CU(c->dnNormalRoughness.alloc(P)); CU(c->dnDisocclusionMix.alloc(P)); CU(c->dnHistoryClampRelax.alloc(P));
         CU(cudaMemsetAsync(c->dnViewZ.ptr, 0, P * 4, s)); CU(cudaMemsetAsync(c->dnMotion.ptr, 0, P * 8, s)); CU(cudaMemsetAsync(c->dnDiff.ptr, 0, P * 8, s)); CU(cudaMemsetAsync(c->dnSpec.ptr, 0, P * 8, s));
@@ -763,7 +802,7 @@ extern "C" RTXPT_API int rtxpt_b200_denoiser_final_merge(rtxpt_ctx* c, uint32_t 
     }
     if (!dDiff || !dSpec) return fail(RTXPT_ERR_INVALID_ARGUMENT, "one denoised image is null");
     if (c->denoiserWidth != c->tableWidth || c->denoiserHeight != c->tableHeight) return fail(RTXPT_ERR_INVALID_ARGUMENT, "rtxpt_b200_denoiser_prepare_inputs has not run (the sky mask lives in its view-space depth)");
-    cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
+    cudaStream_t s = pickStream(c, cudaStream);
     LaunchParams p; fillParams(c, p); fillRealtimeParams(c, p);
     p.rt.dnPlane = stablePlaneIndex; p.rt.dnDenoisedDiff = static_cast<const uint2*>(dDiff); p.rt.dnDenoisedSpec = static_cast<const uint2*>(dSpec);
     launchDnFinalMerge(p, c->grid, s);
@@ -779,9 +818,9 @@ extern "C" RTXPT_API int rtxpt_b200_tone_map(rtxpt_ctx* c, const RtxptToneMappin
     if (u->toneMapOperator > 5) return fail(RTXPT_ERR_INVALID_ARGUMENT, "unknown tone-mapping operator %u", u->toneMapOperator);
     if (sourceBuffer != RTXPT_BUFFER_OUTPUT_COLOR_F16 && sourceBuffer != RTXPT_BUFFER_ACCUMULATED_F32) return fail(RTXPT_ERR_INVALID_ARGUMENT, "tone mapping reads the output colour or the accumulation buffer");
     cudaSetDevice(c->device);
-    cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
+    cudaStream_t s = pickStream(c, cudaStream);
     const size_t P = size_t(c->tableWidth) * c->tableHeight;
-    if (c->ldrColor.count != P) { CU(cudaStreamSynchronize(c->stream)); CU(c->ldrColor.alloc(P)); CU(c->tmPartials.alloc(1024)); CU(c->tmAvgLuminance.alloc(1)); }
+    if (c->ldrColor.count != P) { CU(syncContext(c)); CU(c->ldrColor.alloc(P)); CU(c->tmPartials.alloc(1024)); CU(c->tmAvgLuminance.alloc(1)); }
     const void* src = sourceBuffer == RTXPT_BUFFER_ACCUMULATED_F32 ? static_cast<const void*>(c->accumulated.ptr) : static_cast<const void*>(c->outputColor.ptr);
     if (!src) return fail(RTXPT_ERR_INVALID_ARGUMENT, "the source buffer does not exist yet");
     launchToneMap(tonemap::makeParams(*u), src, sourceBuffer == RTXPT_BUFFER_ACCUMULATED_F32, uint32_t(P), c->tmPartials.ptr, c->tmAvgLuminance.ptr, c->ldrColor.ptr, s);
@@ -794,7 +833,7 @@ extern "C" RTXPT_API int rtxpt_b200_tone_map_average_luminance(rtxpt_ctx* c, flo
     if (!c || !out) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
     if (!c->toneMapped) return fail(RTXPT_ERR_INVALID_ARGUMENT, "rtxpt_b200_tone_map has not run");
     cudaSetDevice(c->device);
-    CU(cudaStreamSynchronize(c->stream));
+    CU(syncContext(c));
     CU(cudaMemcpy(out, c->tmAvgLuminance.ptr, 4, cudaMemcpyDeviceToHost));
     return RTXPT_OK;
 }
@@ -813,8 +852,8 @@ extern "C" RTXPT_API int rtxpt_b200_update_instance_transforms(rtxpt_ctx* c, con
     if (instanceCount != c->hInstances.size()) return fail(RTXPT_ERR_INVALID_ARGUMENT, "expected %zu instance transforms, got %u", c->hInstances.size(), instanceCount);
     if (c->bvhTriCount == 0) return RTXPT_OK;
     cudaSetDevice(c->device);
-    cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
-    if (c->dNodeBox.count != size_t(c->bvhNodeCount) * 6) { CU(cudaStreamSynchronize(c->stream)); CU(c->dNodeBox.alloc(size_t(c->bvhNodeCount) * 6)); }
+    cudaStream_t s = pickStream(c, cudaStream);
+    if (c->dNodeBox.count != size_t(c->bvhNodeCount) * 6) { CU(syncContext(c)); CU(c->dNodeBox.alloc(size_t(c->bvhNodeCount) * 6)); }
     for (uint32_t i = 0; i < instanceCount; i++)
     {   // Donut's InstanceData keeps last frame's matrix next to the current one (motion vectors of the BUILD pass read it)
         memcpy(c->hInstances[i].prevTransform, c->hInstances[i].transform, 48); memcpy(c->hInstances[i].transform, transforms3x4 + size_t(i) * 12, 48);
@@ -837,9 +876,15 @@ extern "C" RTXPT_API int rtxpt_b200_skin_register(rtxpt_ctx* c, const RtxptSkinD
     const RtxptInstanceData& inst = c->hInstances[d->instanceIndex];
     const RtxptGeometryData& g = c->hGeometries[inst.firstGeometryIndex + d->geometryIndexInInstance];
     if (d->numVertices != g.numVertices && g.numVertices != 0) return fail(RTXPT_ERR_INVALID_ARGUMENT, "geometry has %u vertices, bind pose %u", g.numVertices, d->numVertices);
+    // the bind pose must cover every vertex the geometry's triangles name and every joint a non-zero weight names (the kernels index without bounds checks, skinning.cuh)
+    uint32_t maxJoint = 0, maxIndex = 0;
+    for (size_t v = 0; v < size_t(d->numVertices) * 4; v++) if (d->jointWeights[v] > 0.0f) maxJoint = std::max<uint32_t>(maxJoint, d->jointIndices[v]);
+    maxIndex = c->maxVertexOfSubInstance[inst.firstGeometryInstanceIndex + d->geometryIndexInInstance];
+    if (g.numIndices && maxIndex >= d->numVertices) return fail(RTXPT_ERR_INVALID_ARGUMENT, "geometry indexes vertex %u, bind pose has %u vertices", maxIndex, d->numVertices);
     cudaSetDevice(c->device);
     cudaStream_t s = c->stream;
     rtxpt_ctx::Skin* sk = new rtxpt_ctx::Skin();
+    sk->maxJoint = maxJoint;
     sk->numVertices = d->numVertices; sk->numTriangles = g.numIndices / 3; sk->firstGid = c->firstGidOfSubInstance[inst.firstGeometryInstanceIndex + d->geometryIndexInInstance];
     sk->flags = (d->normals ? 2u : 0u) | (d->tangents ? 4u : 0u);
     sk->dIndices = reinterpret_cast<const uint32_t*>(c->hBufferTable[g.indexBufferIndex] + g.indexOffset);
@@ -861,8 +906,9 @@ extern "C" RTXPT_API int rtxpt_b200_skin_update(rtxpt_ctx* c, uint32_t skinId, c
     if (!c || !jointMatrices4x4) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
     if (skinId >= c->skins.size()) return fail(RTXPT_ERR_INVALID_ARGUMENT, "unknown skin %u", skinId);
     cudaSetDevice(c->device);
-    cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
+    cudaStream_t s = pickStream(c, cudaStream);
     rtxpt_ctx::Skin& sk = *c->skins[skinId];
+    if (numJoints <= sk.maxJoint) return fail(RTXPT_ERR_INVALID_ARGUMENT, "skin %u uses joint %u, %u joint matrices given", skinId, sk.maxJoint, numJoints);
     if (sk.jointMatrices.count != size_t(numJoints) * 16) { CU(cudaStreamSynchronize(s)); CU(sk.jointMatrices.alloc(size_t(numJoints) * 16)); }
     CU(cudaMemcpyAsync(sk.jointMatrices.ptr, jointMatrices4x4, size_t(numJoints) * 64, cudaMemcpyHostToDevice, s));
     sk.numJoints = numJoints;
@@ -917,7 +963,7 @@ static int neeatEnsure(rtxpt_ctx* c, cudaStream_t s)
     rtxpt_ctx::Neeat& n = c->na;
     const uint32_t W = c->tableWidth, H = c->tableHeight, L = uint32_t(c->lightState.lights.size());
     if (n.allocated && n.host.W == W && n.host.H == H && n.lightCount == L) return RTXPT_OK;
-    CU(cudaStreamSynchronize(c->stream)); CU(cudaStreamSynchronize(s));
+    CU(syncContext(c)); CU(cudaStreamSynchronize(s));
     n.release(); n.host.reset(W, H); n.lightCount = L;
     const size_t P = size_t(W) * H, B = size_t((W + 1) / 2) * ((H + 1) / 2), T = size_t(neeat::HostState::tilesX(W)) * neeat::HostState::tilesY(H) * neeat::kLocalProxyCount;
     const size_t proxyCapacity = size_t(neeat::kProxyRatio) * std::max<uint32_t>(L, neeat::kMaxLights / 10) + L;           // every light rounds its share up
@@ -947,7 +993,7 @@ extern "C" RTXPT_API int rtxpt_b200_neeat_reset(rtxpt_ctx* c)
 {
     if (!c) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null context");
     cudaSetDevice(c->device);
-    CU(cudaStreamSynchronize(c->stream));
+    CU(syncContext(c));
     c->na.release();
     return RTXPT_OK;
 }
@@ -957,7 +1003,7 @@ extern "C" RTXPT_API int rtxpt_b200_neeat_update_begin(rtxpt_ctx* c, void* cudaS
     if (!c->haveScene || !neeatActive(c)) return fail(RTXPT_ERR_INVALID_ARGUMENT, "NEE-AT feedback needs a scene and constants with NEEType == 2 and NEEATFeedback != 0");
     if (c->lightState.proxyIndices.empty()) return fail(RTXPT_ERR_INVALID_ARGUMENT, "the scene has no lights to sample");
     cudaSetDevice(c->device);
-    cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
+    cudaStream_t s = pickStream(c, cudaStream);
     int rc = neeatEnsure(c, s); if (rc != RTXPT_OK) return rc;
     rtxpt_ctx::Neeat& n = c->na;
     // the power-based weights follow the light list (uploadLights re-bakes them when the environment or the importance settings change)
@@ -976,7 +1022,7 @@ extern "C" RTXPT_API int rtxpt_b200_neeat_update_end(rtxpt_ctx* c, void* cudaStr
     if (!neeatActive(c) || !c->na.allocated || !c->na.frameBegun) return fail(RTXPT_ERR_INVALID_ARGUMENT, "rtxpt_b200_neeat_update_begin has not run for this frame");
     if (!c->depth.ptr || !c->motionVectors.ptr) return fail(RTXPT_ERR_INVALID_ARGUMENT, "NEE-AT feedback reprojects with the depth / motion guides: create the context with RTXPT_CFG_EXPORT_GUIDES or use realtime mode");
     cudaSetDevice(c->device);
-    cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
+    cudaStream_t s = pickStream(c, cudaStream);
     neeatBind(c);
     launchNeeatUpdateEnd(c->na.params, s);
     CU(cudaGetLastError());
@@ -991,7 +1037,7 @@ extern "C" RTXPT_API int rtxpt_b200_neeat_readback(rtxpt_ctx* c, int what, void*
     if (!c->na.allocated) return fail(RTXPT_ERR_INVALID_ARGUMENT, "NEE-AT feedback state does not exist before rtxpt_b200_neeat_update_begin");
     cudaSetDevice(c->device);
     rtxpt_ctx::Neeat& n = c->na; const neeat::Params& p = n.params;
-    CU(cudaStreamSynchronize(c->stream));
+    CU(syncContext(c));
     uint32_t total = 0; CU(cudaMemcpy(&total, n.samplingProxyCount.ptr, 4, cudaMemcpyDeviceToHost));
     const void* src = nullptr; size_t bytes = 0; uint32_t ctl[8];
     const size_t P = size_t(p.W) * p.H, B = size_t(p.blendedW) * p.blendedH;
@@ -1022,7 +1068,7 @@ extern "C" RTXPT_API int rtxpt_b200_neeat_debug_set_feedback(rtxpt_ctx* c, const
     if (!c || !weight || !candidate) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
     if (!c->na.allocated) return fail(RTXPT_ERR_INVALID_ARGUMENT, "NEE-AT feedback state does not exist before rtxpt_b200_neeat_update_begin");
     cudaSetDevice(c->device);
-    CU(cudaStreamSynchronize(c->stream));
+    CU(syncContext(c));
     const size_t P = size_t(c->na.host.W) * c->na.host.H;
     CU(cudaMemcpy(c->na.fbWeight.ptr, weight, P * 4, cudaMemcpyHostToDevice)); CU(cudaMemcpy(c->na.fbCandidate.ptr, candidate, P * 4, cudaMemcpyHostToDevice));
     c->na.host.feedbackBufferFilled = true;
@@ -1034,7 +1080,7 @@ extern "C" RTXPT_API int rtxpt_b200_neeat_debug_set_feedback(rtxpt_ctx* c, const
 static int ensureReblurPools(rtxpt_ctx* c, cudaStream_t s)
 {
     if (c->reblurWidth == c->tableWidth && c->reblurHeight == c->tableHeight) return RTXPT_OK;
-    CU(cudaStreamSynchronize(c->stream)); CU(cudaStreamSynchronize(s));
+    CU(syncContext(c)); CU(cudaStreamSynchronize(s));
     const size_t P = size_t(c->tableWidth) * c->tableHeight, T = size_t((c->tableWidth + 15) / 16) * ((c->tableHeight + 15) / 16);
     for (auto& h : c->reblur)
     {
@@ -1063,7 +1109,7 @@ extern "C" RTXPT_API int rtxpt_b200_reblur_denoise(rtxpt_ctx* c, uint32_t stable
     if (stablePlaneIndex >= RTXPT_STABLE_PLANE_COUNT) return fail(RTXPT_ERR_INVALID_ARGUMENT, "bad plane index");
     if (c->denoiserWidth != c->tableWidth || c->denoiserHeight != c->tableHeight || c->denoiserWidth == 0) return fail(RTXPT_ERR_INVALID_ARGUMENT, "rtxpt_b200_denoiser_prepare_inputs has not run: ReBLUR reads RTXPT_BUFFER_DENOISER_*");
     cudaSetDevice(c->device);
-    cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
+    cudaStream_t s = pickStream(c, cudaStream);
     int rc = ensureReblurPools(c, s); if (rc != RTXPT_OK) return rc;
     rtxpt_ctx::ReblurHistory& h = c->reblur[stablePlaneIndex];
     const uint32_t W = c->tableWidth, H = c->tableHeight;
@@ -1088,7 +1134,7 @@ extern "C" RTXPT_API int rtxpt_b200_denoise_realtime(rtxpt_ctx* c, const RtxptDe
 {
     int rc = checkRealtimeReady(c); if (rc != RTXPT_OK) return rc;
     if (!k || !f) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null constants");
-    cudaStream_t s = cudaStream ? (cudaStream_t)cudaStream : c->stream;
+    cudaStream_t s = pickStream(c, cudaStream);
     if (!c->evDnStart) { CU(cudaEventCreate(&c->evDnStart)); CU(cudaEventCreate(&c->evDnStop)); }
     CU(cudaEventRecord(c->evDnStart, s));
     rc = rtxpt_b200_denoise_spec_hit_t(c, cudaStream); if (rc != RTXPT_OK) return rc;          // "Denoising Guides Bake" precedes Sample::Denoise in the frame
@@ -1125,7 +1171,7 @@ extern "C" RTXPT_API int rtxpt_b200_synchronize(rtxpt_ctx* c)
 {
     if (!c) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null context");
     cudaSetDevice(c->device);
-    CU(cudaStreamSynchronize(c->stream));
+    CU(syncContext(c));
     return RTXPT_OK;
 }
 
@@ -1186,6 +1232,7 @@ extern "C" RTXPT_API int rtxpt_b200_readback(rtxpt_ctx* c, int buffer, void* dst
     void* src; size_t bytes;
     int rc = targetInfo(c, buffer, &src, &bytes); if (rc != RTXPT_OK) return rc;
     if (dstBytes < bytes) return fail(RTXPT_ERR_INVALID_ARGUMENT, "destination too small (%zu < %zu)", dstBytes, bytes);
+    CU(joinCallerStream(c));                // the frame may have been queued on the caller's stream: the copy on the context stream is ordered after it
     CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return RTXPT_OK;
@@ -1203,13 +1250,13 @@ extern "C" RTXPT_API int rtxpt_b200_get_stats(rtxpt_ctx* c, RtxptStats* out)
     if (!c || !out) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
     cudaSetDevice(c->device);
     memset(out, 0, sizeof(*out));
-    CU(cudaStreamSynchronize(c->stream));
+    CU(syncContext(c));
     out->bvhNodeCount = c->bvhNodeCount; out->bvhTriangleCount = c->bvhTriCount; out->bvhBuildSeconds = c->bvhBuildSeconds;
     out->lightCount = uint32_t(c->lightState.lights.size()); out->lightProxyCount = uint32_t(c->lightState.proxyIndices.size());
     out->accumulatedSamples = c->accumulatedSamples;
     if (c->statsPending)
     {
-        float ms = 0; cudaEventElapsedTime(&ms, c->evStart, c->evStop);
+        float ms = 0; CU(cudaEventElapsedTime(&ms, c->evStart, c->evStop));
         out->msTotal = ms;
         // counters hold the LAST batch; scale ray counts to the whole call when it was split into equal batches
         const uint32_t batches = (c->lastSubSamples + c->cfg.maxSubSamplesPerLaunch - 1) / c->cfg.maxSubSamplesPerLaunch;
@@ -1228,7 +1275,7 @@ extern "C" RTXPT_API int rtxpt_b200_get_stats(rtxpt_ctx* c, RtxptStats* out)
         out->shadowNodeVisits = uint64_t(snodes * scale); out->shadowTriTests = uint64_t(stests * scale);
         for (size_t e = 0; e + 1 < c->evUsed; e += 2)
         {
-            float t = 0; cudaEventElapsedTime(&t, c->evPool[e], c->evPool[e + 1]);
+            float t = 0; CU(cudaEventElapsedTime(&t, c->evPool[e], c->evPool[e + 1]));
             switch (c->evKind[e / 2]) { case 0: out->msTraceClosest += t; break; case 1: out->msTraceShadow += t; break; case 2: out->msShade += t; break; default: out->msOther += t; }
         }
         out->paths = uint64_t(c->pixelCount) * c->lastSubSamples;
@@ -1250,7 +1297,7 @@ extern "C" RTXPT_API int rtxpt_b200_pack_owned(rtxpt_ctx* c, void* dDst, void* c
     if (!c || !dDst) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
     if (c->tableWidth == 0) return fail(RTXPT_ERR_INVALID_ARGUMENT, "constants not set");
     cudaSetDevice(c->device);
-    launchPackOwned(c->accumulated.ptr, c->pixelOfSlot.ptr, c->pixelCount, c->paddedPixelsPerRank, c->tableWidth, (float4*)dDst, c->grid, cudaStream ? (cudaStream_t)cudaStream : c->stream);
+    launchPackOwned(c->accumulated.ptr, c->pixelOfSlot.ptr, c->pixelCount, c->paddedPixelsPerRank, c->tableWidth, (float4*)dDst, c->grid, pickStream(c, cudaStream));
     CU(cudaGetLastError());
     return RTXPT_OK;
 }
@@ -1259,7 +1306,7 @@ extern "C" RTXPT_API int rtxpt_b200_unpack_all(rtxpt_ctx* c, const void* dSrcAll
     if (!c || !dSrcAll) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
     if (c->tableWidth == 0) return fail(RTXPT_ERR_INVALID_ARGUMENT, "constants not set");
     cudaSetDevice(c->device);
-    launchUnpackAll((const float4*)dSrcAll, c->allPixelTable.ptr, c->paddedPixelsPerRank * c->cfg.tileWorld, c->tableWidth, c->accumulated.ptr, c->grid, cudaStream ? (cudaStream_t)cudaStream : c->stream);
+    launchUnpackAll((const float4*)dSrcAll, c->allPixelTable.ptr, c->paddedPixelsPerRank * c->cfg.tileWorld, c->tableWidth, c->accumulated.ptr, c->grid, pickStream(c, cudaStream));
     CU(cudaGetLastError());
     return RTXPT_OK;
 }
@@ -1280,7 +1327,7 @@ extern "C" RTXPT_API int rtxpt_b200_trace_rays_device(rtxpt_ctx* c, const void* 
     CU(cudaEventRecord(c->evStop, c->stream));
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->hCounters, c->counters.ptr, 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    CU(syncContext(c));
     float ms = 0; cudaEventElapsedTime(&ms, c->evStart, c->evStop);
     if (outMs) *outMs = ms / float(repeat);
     return RTXPT_OK;
@@ -1338,7 +1385,7 @@ extern "C" RTXPT_API int rtxpt_b200_debug_bsdf(rtxpt_ctx* c, const float* in, ui
     launchDebugBsdf(dIn.ptr, count, dOut.ptr, c->stream);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, dOut.ptr, size_t(count) * 16 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    CU(syncContext(c));
     dIn.release(); dOut.release();
     return RTXPT_OK;
 }
@@ -1352,7 +1399,7 @@ extern "C" RTXPT_API int rtxpt_b200_debug_rng(rtxpt_ctx* c, const uint32_t* in, 
     launchDebugRng(dIn.ptr, count, dOut.ptr, c->stream);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, dOut.ptr, size_t(count) * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    CU(syncContext(c));
     dIn.release(); dOut.release();
     return RTXPT_OK;
 }

@@ -109,8 +109,9 @@ PT_HD float sampleLocalPdf(const Params& p, uint tileAddress, uint lightIndex)
     {
         const uint mid = (left + right) >> 1; const uint v = p.localSamplingBuffer[mid], key = miniListLight(v);
         if (key < lightIndex) left = mid + 1;
-        else if (key > lightIndex) right = mid - 1;
+        else if (key > lightIndex) { if (mid == left) return 0.0f; right = mid - 1; }   // empty range: the reference's `mid - 1` would step below the tile (for tile 0: wrap to 0xFFFFFFFF; D3D returns 0 for that read, a raw pointer faults)
         else return float(miniListCount(v)) / float(kLocalProxyCount);
+        if (left > right) return 0.0f;
     }
     return 0.0f;
 }

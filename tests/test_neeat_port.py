@@ -58,6 +58,15 @@ def test_feedback_passes_equal_the_oracle(oracle, moving, boost):
         hits += a[2] > 0
     assert 0 < hits < 400                                                                   # the binary search both finds and misses
     st = o.neeat_get()
+    # a light below every key of the tile (light 0 is an environment slot; the lists hold emissive triangles only): the search must stop at the tile's first entry instead of
+    # stepping to `tileAddress - 1` - for tile (0,0) that index wraps to 0xFFFFFFFF, the round-1 GPU fault.  Every tile, both sides, against a brute-force count.
+    lists = st["local"].reshape(st["tiles"][1], st["tiles"][0], 128); jx, jy = st["jitter"]
+    for px, py in [(0, 0), (7 - jx, 0), (0, 7 - jy), (W - 1, H - 1), (W // 2, H // 2), (8, 0), (0, 8)]:
+        tile = lists[(py + jy) // 8, (px + jx) // 8]; keys = tile >> 9
+        for probe in (0, 1, int(keys.min()) - 1, int(keys.min()), int(keys.max()), int(keys.max()) + 1, n_lights - 1):
+            a = np.zeros(3, np.float32); b = np.zeros(3, np.float32)
+            assert Lo.oracle_neeat_sample_local(o.h, px, py, 0.5, probe, a.ctypes.data) == 0 and Le.neeat_emu_sample_local(port.h, px, py, 0.5, probe, b.ctypes.data) == 0
+            assert a[2] == b[2] == np.float32((keys == probe).sum() / 128.0), (px, py, probe, a, b)
     assert st["available"] and st["valid_feedback"] > 0.3 * W * H
     if moving: assert np.abs(g["motion"][..., 0].astype(np.float32)).mean() > 1.0                # the dolly really exercised reprojection (whole-pixel shifts)
     port.close(); o.close(); guide.close()
