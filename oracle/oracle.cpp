@@ -80,6 +80,56 @@ ORC_API void oracle_bsdf(const float* in, uint32_t count, float* out)
     }
 }
 
+// oracle_bsdf's 16 floats followed by evalDeltaLobes and estimateSpecDiffBSDF: the 40-float layout of oracle/ref_kat_bsdf_main.cpp's "bsdf" mode
+ORC_API void oracle_bsdf_ex(const float* in, uint32_t count, float* out)
+{
+    for (uint32_t i = 0; i < count; i++)
+    {
+        const float* r = in + size_t(i) * 36; float* o = out + size_t(i) * 40;
+        oracle_bsdf(r, 1, o);
+        BSDFFrame f; f.V = f3(r[0], r[1], r[2]); f.N = f3(r[3], r[4], r[5]); f.T = f3(r[6], r[7], r[8]); f.B = f3(r[9], r[10], r[11]);
+        StandardBSDF b;
+        b.data.diffuse = f3(r[18], r[19], r[20]); b.data.roughness = r[21]; b.data.specular = f3(r[22], r[23], r[24]); b.data.metallic = r[25];
+        b.data.transmission = f3(r[26], r[27], r[28]); b.data.diffuseTransmission = r[29]; b.data.specularTransmission = r[30]; b.data.eta = r[31];
+        f.thinSurface = r[32] != 0.0f; f.activeLobes = uint(r[33]); f.psdExclude = false;
+        DeltaLobe lobes[cMaxDeltaLobes]; int n = 0; float nonDelta = 0;
+        b.evalDeltaLobes(f, lobes, n, nonDelta);
+        for (int k = 0; k < 2; k++) { float* d = o + 16 + k * 8; d[0] = lobes[k].thp.x; d[1] = lobes[k].thp.y; d[2] = lobes[k].thp.z; d[3] = lobes[k].probability; d[4] = lobes[k].dir.x; d[5] = lobes[k].dir.y; d[6] = lobes[k].dir.z; d[7] = float(lobes[k].transmission); }
+        o[32] = nonDelta; o[33] = float(n);
+        float3 de, se; b.estimateSpecDiffBSDF(de, se, f.N, f.V);
+        o[34] = de.x; o[35] = de.y; o[36] = de.z; o[37] = se.x; o[38] = se.y; o[39] = se.z;
+    }
+}
+
+// the scalar building blocks of the material model on the inputs oracle/ref_kat_bsdf_main.cpp derives from 8 uniforms per record; same 40-float output layout.  Slots of functions
+// the live path does not use (and the oracle therefore does not restate: G1, separable masking, the unbounded VNDF) are left as NaN.
+ORC_API void oracle_bsdf_funcs(const float* in, uint32_t count, float* out)
+{
+    const float nan = std::nanf("");
+    for (uint32_t i = 0; i < count; i++)
+    {
+        const float* u = in + size_t(i) * 8; float* o = out + size_t(i) * 40;
+        for (int k = 0; k < 40; k++) o[k] = nan;
+        const float alpha = 0.0064f + u[0] * u[0] * 0.99f, cosI = 0.001f + 0.999f * u[1], cosO = 0.001f + 0.999f * u[2], eta = u[3] < 0.5f ? 1.0f / (1.0f + 1.2f * u[4]) : 1.0f + 1.2f * u[4];
+        const float phi = 6.2831853f * u[5], sI = sqrtf(std::max(0.0f, 1.0f - cosI * cosI));
+        const float3 wi = f3(sI * cosf(phi), sI * sinf(phi), cosI);
+        o[0] = evalFresnelSchlick(u[6], 1.0f, cosI);
+        const float3 fs = evalFresnelSchlick(f3(u[6], u[7], u[0]), 1.0f, cosO); o[1] = fs.x; o[2] = fs.y; o[3] = fs.z;
+        float cosT = -1.0f; o[4] = evalFresnelDielectric(eta, cosI, cosT); o[5] = cosT;
+        float cosT2 = -1.0f; o[6] = evalFresnelDielectric(eta, -cosI, cosT2); o[7] = cosT2;
+        o[8] = evalNdfGGX(alpha, cosO); o[9] = evalLambdaGGX(alpha * alpha, cosI);
+        o[11] = evalMaskingSmithGGXCorrelated(alpha, cosI, cosO);
+        const float3 h = sampleGGX_BVNDF(alpha, wi, f2(u[6], u[7])); o[13] = h.x; o[14] = h.y; o[15] = h.z;
+        o[16] = evalPdfGGX_BVNDF(alpha, wi, h);
+        const float3 asi = approxSpecularIntegralGGX(f3(u[6], u[7], u[0]), alpha, cosI); o[21] = asi.x; o[22] = asi.y; o[23] = asi.z;
+        float pdf = 0; const float3 ch = sample_cosine_hemisphere_concentric(f2(u[6], u[7]), pdf); o[24] = ch.x; o[25] = ch.y; o[26] = ch.z; o[27] = pdf;
+        const float2 dk = sample_disk_concentric(f2(u[0], u[1])); o[28] = dk.x; o[29] = dk.y;
+        const float3 ps = perp_stark(wi); o[30] = ps.x; o[31] = ps.y; o[32] = ps.z;
+        const float2 oc = ndir_to_oct_equal_area_unorm(wi); o[33] = oc.x; o[34] = oc.y; const float3 od = oct_to_ndir_equal_area_unorm(f2(u[2], u[3])); o[35] = od.x; o[36] = od.y; o[37] = od.z;
+        o[38] = Luminance(f3(u[0], u[1], u[2])); o[39] = Average(f3(u[0], u[1], u[2]));
+    }
+}
+
 ORC_API void* oracle_create(const RtxptSceneDesc* desc)
 {
     OracleCtx* c = new OracleCtx();

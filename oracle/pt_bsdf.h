@@ -253,7 +253,7 @@ struct SpecularReflectionTransmissionMicrofacet     // BxDF.hlsli:385-607
         if (isReflection) return f3(F * D * G * 0.25f / wi.z);
         float sqrtDenom = woDotH + actualEta * wiDotH;
         float t = actualEta * actualEta * wiDotH * woDotH / (wi.z * sqrtDenom * sqrtDenom);
-        return transmissionAlbedo * ((1.f - F) * D * G * fabsf(t));
+        return transmissionAlbedo * (1.f - F) * D * G * fabsf(t);      // left to right as written in BxDF.hlsli:436 (pinned by tests/golden/bsdf_golden.npz)
     }
     float evalPdf(float3 wi, float3 wo) const
     {

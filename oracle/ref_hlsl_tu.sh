@@ -1,0 +1,50 @@
+#!/usr/bin/env bash
+# ORACLE/_ref — TEST INFRASTRUCTURE.  Writes ONE C++ translation unit to stdout: the HLSL shim, then the UNMODIFIED reference material headers read from where they lie under
+# $REF (default /root/reference) through a stream filter, then the known-answer generator given as $1.  The Makefile pipes this into `g++ -x c++ -`; nothing of the reference is
+# written to disk or into this repository.  The filter only rewrites spellings C++ has no equivalent for (it does not touch arithmetic):
+#   out / inout T name        -> T& name                      (HLSL output parameters)
+#   scalar.xx / scalar.x      -> float2( s, s ) / s            (swizzles of scalars)
+#   0.xxx                     -> float3( 0, 0, 0 )
+#   (e).xxx as the argument of float3( )                      -> (e)   (the constructor splats);  v.xyzw -> v
+#   1.5 (unsuffixed literal)  -> 1.5f                          (an HLSL floating literal takes the type of the expression it meets - binary32 here - where C++ would make it a double
+#                                                               and carry the whole expression in binary64)
+#   c ? 0.f : dataRoughness  -> c ? 0.f : (float)dataRoughness (StandardBSDF.hlsli:98; HLSL promotes the float16_t arm, C++ finds the two arms ambiguous)
+#   [unroll] [loop] [branch] [flatten] [mutating]              (attributes: dropped)
+#   #include "local header"                                    (dropped: the files are emitted here in dependency order)
+#   #if !defined(__cplusplus)                                  -> #if 1   (the shader half is what is being compiled)
+set -euo pipefail
+REF=${REF:-/root/reference}
+PT=$REF/Rtxpt/Shaders/PathTracer
+MAIN=$1
+filter() {
+  sed -E \
+    -e 's/^[[:space:]]*#include[[:space:]]+".*$//' \
+    -e 's/#if[[:space:]]+!defined\(__cplusplus\)/#if 1/' \
+    -e 's/#ifndef[[:space:]]+__cplusplus/#if 1/' \
+    -e 's/\b(in)?out[[:space:]]+([A-Za-z_][A-Za-z0-9_]*)[[:space:]]+([A-Za-z_][A-Za-z0-9_]*)\[/\2 \3[/g' \
+    -e 's/\b(in)?out[[:space:]]+([A-Za-z_][A-Za-z0-9_]*)[[:space:]]+([A-Za-z_][A-Za-z0-9_]*)/\2\& \3/g' \
+    -e 's/\b0\.xxx\b/float3(0,0,0)/g' \
+    -e 's/\b1\.xxx\b/float3(1,1,1)/g' \
+    -e 's/\b_alpha\.xx\b/float2(_alpha, _alpha)/g' \
+    -e 's/\bpackedData\.x\b/packedData/g' \
+    -e 's/\)\.xxx\b/)/g' \
+    -e 's/\.xyzw\b//g' \
+    -e 's/\? 0\.f : dataRoughness/? 0.f : (float)dataRoughness/' \
+    -e 's/(^|[^A-Za-z0-9_.])([0-9]+\.[0-9]*([eE][-+]?[0-9]+)?|\.[0-9]+([eE][-+]?[0-9]+)?)([^0-9A-Za-z_.]|$)/\1\2f\5/g' \
+    -e 's/(^|[^A-Za-z0-9_.])([0-9]+\.[0-9]*([eE][-+]?[0-9]+)?|\.[0-9]+([eE][-+]?[0-9]+)?)([^0-9A-Za-z_.]|$)/\1\2f\5/g' \
+    -e 's/\[(unroll|loop|branch|flatten|mutating)\]//g' \
+    "$1"
+}
+echo '#include "ref_hlsl_shim.h"'
+echo '#define RTXPT_LP_TYPES_USE_16BIT_PRECISION 1      /* Sample.cpp:1017, the default */'
+echo 'float3 ComputeRayOrigin(float3 pos, float3 normal);      /* PathTracerHelpers.hlsli:29-42; declared only: ShadingData::computeNewRayOrigin is not called by anything pinned here */'
+for f in Config.h Utils/Math/MathConstants.hlsli Utils/Utils.hlsli:28-67 Rendering/Materials/BxDFConfig.hlsli Rendering/Materials/LobeType.hlsli Scene/Material/MaterialData.hlsli \
+         Utils/ColorHelpers.hlsli Utils/Math/MathHelpers.hlsli Rendering/Materials/Fresnel.hlsli Rendering/Materials/Microfacet.hlsli Rendering/Materials/IBSDF.hlsli \
+         Scene/ShadingData.hlsli Rendering/Materials/BxDF.hlsli Rendering/Materials/StandardBSDF.hlsli; do
+  case "$f" in
+    *:*) range=${f#*:}; f=${f%%:*}; echo; echo "#line ${range%-*} \"$PT/$f\""; filter "$PT/$f" | sed -n "${range%-*},${range#*-}p" ;;       # a line range of a header whose other parts resist (Utils.hlsli: only the lpfloat typedefs, Luminance and Average)
+    *)   echo; echo "#line 1 \"$PT/$f\""; filter "$PT/$f" ;;
+  esac
+done
+echo; echo "#line 1 \"$MAIN\""
+cat "$MAIN"

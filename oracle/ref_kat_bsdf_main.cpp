@@ -1,0 +1,87 @@
+// ORACLE/_ref — TEST INFRASTRUCTURE: known-answer generator for the floating-point material model, built from the UNMODIFIED reference headers
+//   Rtxpt/Shaders/PathTracer/Rendering/Materials/{Fresnel,Microfacet,BxDF,StandardBSDF,IBSDF}.hlsli, Utils/Math/MathHelpers.hlsli, Scene/{ShadingData,Material/MaterialData}.hlsli
+// compiled in place through oracle/ref_hlsl_shim.h (oracle/ref_hlsl_tu.sh appends this file to the stream it feeds g++; it is not compiled on its own).
+//   ref_kat_bsdf bsdf  in.f32 out.f32     in: N x 36 floats (tests/bsdf_records.py layout, the one oracle_bsdf and rtxpt_b200_debug_bsdf take)
+//                                         out: N x 40 floats: [0..15] eval.xyzw, evalPdf, sample{valid, wo, pdf, weight, lobe, lobeP}, getLobes (= oracle_bsdf's layout),
+//                                              [16..31] evalDeltaLobes: 2 x {thp.xyz, probability, dir.xyz, transmission}, [32] nonDeltaPart, [33] deltaLobeCount,
+//                                              [34..39] estimateSpecDiffBSDF( N, V ): diffuse estimate, specular estimate
+//   ref_kat_bsdf funcs in.f32 out.f32     in: N x 8 uniform floats; out: N x 40 floats, the scalar building blocks (see below)
+// tests/golden/make_bsdf_golden.py runs it on seeded inputs and commits the vectors; tests/test_oracle_golden.py holds the oracle's restatement to them.
+#include <cstdio>
+#include <vector>
+
+static std::vector<float> readAll(const char* path)
+{
+    FILE* f = fopen(path, "rb"); if (!f) { perror(path); exit(2); }
+    fseek(f, 0, SEEK_END); const long n = ftell(f); fseek(f, 0, SEEK_SET);
+    std::vector<float> v(size_t(n) / 4); if (fread(v.data(), 4, v.size(), f) != v.size()) { perror("read"); exit(2); }
+    fclose(f); return v;
+}
+static void writeAll(const char* path, const std::vector<float>& v)
+{
+    FILE* f = fopen(path, "wb"); if (!f) { perror(path); exit(2); }
+    fwrite(v.data(), 4, v.size(), f); fclose(f);
+}
+
+int main(int argc, char** argv)
+{
+    if (argc != 4) { fprintf(stderr, "usage: %s bsdf|funcs in.f32 out.f32\n", argv[0]); return 2; }
+    const std::vector<float> in = readAll(argv[2]); std::vector<float> out;
+    if (std::string(argv[1]) == "bsdf")
+    {
+        const size_t n = in.size() / 36; out.assign(n * 40, 0.0f);
+        for (size_t i = 0; i < n; i++)
+        {
+            const float* r = &in[i * 36]; float* o = &out[i * 40];
+            ShadingData sd = ShadingData::make();
+            sd.V = float3(r[0], r[1], r[2]); sd.N = float3(r[3], r[4], r[5]); sd.T = float3(r[6], r[7], r[8]); sd.B = float3(r[9], r[10], r[11]);
+            const float3 wo(r[12], r[13], r[14]);
+            sd.mtl = MaterialHeader::make(); sd.mtl.setActiveLobes(uint(r[33])); sd.mtl.setThinSurface(r[32] != 0.0f); sd.mtl.setPSDExclude(false);
+            StandardBSDF b = StandardBSDF::make(StandardBSDFData::make(lpfloat3(lpfloat(r[18]), lpfloat(r[19]), lpfloat(r[20])), lpfloat3(lpfloat(r[22]), lpfloat(r[23]), lpfloat(r[24])), lpfloat(r[21]), lpfloat(r[25]),
+                                                                         lpfloat(r[31]), lpfloat3(lpfloat(r[26]), lpfloat(r[27]), lpfloat(r[28])), lpfloat(r[29]), lpfloat(r[30])));
+            const float4 e = b.eval(sd, wo);
+            o[0] = e.x; o[1] = e.y; o[2] = e.z; o[3] = e.w;
+            o[4] = b.evalPdf(sd, wo, true);
+            BSDFSample s; s.wo = float3(0, 0, 0); s.pdf = 0; s.weight = float3(0, 0, 0); s.lobe = 0; s.lobeP = 0;
+            const bool valid = b.sample(sd, float4(r[15], r[16], r[17], 0.0f), s, true);
+            o[5] = valid ? 1.0f : 0.0f; o[6] = s.wo.x; o[7] = s.wo.y; o[8] = s.wo.z; o[9] = s.pdf; o[10] = s.weight.x; o[11] = s.weight.y; o[12] = s.weight.z;
+            o[13] = float(s.lobe); o[14] = s.lobeP; o[15] = float(b.getLobes(sd));
+            DeltaLobe lobes[cMaxDeltaLobes]; int count = 0; float nonDelta = 0;
+            b.evalDeltaLobes(sd, lobes, count, nonDelta);
+            for (int k = 0; k < 2; k++) { float* d = o + 16 + k * 8; d[0] = lobes[k].thp.x; d[1] = lobes[k].thp.y; d[2] = lobes[k].thp.z; d[3] = lobes[k].probability; d[4] = lobes[k].dir.x; d[5] = lobes[k].dir.y; d[6] = lobes[k].dir.z; d[7] = float(lobes[k].transmission); }
+            o[32] = nonDelta; o[33] = float(count);
+            float3 de, se; b.estimateSpecDiffBSDF(de, se, sd.N, sd.V);
+            o[34] = de.x; o[35] = de.y; o[36] = de.z; o[37] = se.x; o[38] = se.y; o[39] = se.z;
+        }
+    }
+    else
+    {
+        const size_t n = in.size() / 8; out.assign(n * 40, 0.0f);
+        for (size_t i = 0; i < n; i++)
+        {
+            const float* u = &in[i * 8]; float* o = &out[i * 40];
+            // inputs derived from the uniforms the same way on both sides (tests/golden/make_bsdf_golden.py documents them)
+            const float alpha = 0.0064f + u[0] * u[0] * 0.99f, cosI = 0.001f + 0.999f * u[1], cosO = 0.001f + 0.999f * u[2], eta = u[3] < 0.5f ? 1.0f / (1.0f + 1.2f * u[4]) : 1.0f + 1.2f * u[4];
+            const float phi = 6.2831853f * u[5], sI = sqrt(max(0.0f, 1.0f - cosI * cosI));
+            const float3 wi(sI * cos(phi), sI * sin(phi), cosI);
+            o[0] = evalFresnelSchlick(u[6], 1.0f, cosI);
+            const float3 fs = evalFresnelSchlick(float3(u[6], u[7], u[0]), float3(1.0f, 1.0f, 1.0f), cosO); o[1] = fs.x; o[2] = fs.y; o[3] = fs.z;
+            float cosT = -1.0f; o[4] = evalFresnelDielectric(eta, cosI, cosT); o[5] = cosT;
+            float cosT2 = -1.0f; o[6] = evalFresnelDielectric(eta, -cosI, cosT2); o[7] = cosT2;
+            o[8] = evalNdfGGX(alpha, cosO); o[9] = evalLambdaGGX(alpha * alpha, cosI); o[10] = evalG1GGX(alpha * alpha, cosI);
+            o[11] = evalMaskingSmithGGXCorrelated(alpha, cosI, cosO); o[12] = evalMaskingSmithGGXSeparable(alpha, cosI, cosO);
+            const float3 h = sampleGGX_BVNDF(alpha, wi, float2(u[6], u[7])); o[13] = h.x; o[14] = h.y; o[15] = h.z;
+            o[16] = evalPdfGGX_BVNDF(alpha, wi, h);
+            const float3 hv = sampleGGX_VNDF(alpha, wi, float2(u[6], u[7])); o[17] = hv.x; o[18] = hv.y; o[19] = hv.z;
+            o[20] = evalPdfGGX_VNDF(alpha, wi, hv);
+            const float3 asi = approxSpecularIntegralGGX(float3(u[6], u[7], u[0]), alpha, cosI); o[21] = asi.x; o[22] = asi.y; o[23] = asi.z;
+            float pdf = 0; const float3 ch = sample_cosine_hemisphere_concentric(float2(u[6], u[7]), pdf); o[24] = ch.x; o[25] = ch.y; o[26] = ch.z; o[27] = pdf;
+            const float2 dk = sample_disk_concentric(float2(u[0], u[1])); o[28] = dk.x; o[29] = dk.y;
+            const float3 ps = perp_stark(wi); o[30] = ps.x; o[31] = ps.y; o[32] = ps.z;
+            const float2 oc = ndir_to_oct_equal_area_unorm(wi); o[33] = oc.x; o[34] = oc.y; const float3 od = oct_to_ndir_equal_area_unorm(float2(u[2], u[3])); o[35] = od.x; o[36] = od.y; o[37] = od.z;
+            o[38] = Luminance(float3(u[0], u[1], u[2])); o[39] = Average(float3(u[0], u[1], u[2]));
+        }
+    }
+    writeAll(argv[3], out);
+    return 0;
+}

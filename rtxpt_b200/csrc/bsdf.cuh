@@ -173,7 +173,7 @@ struct BsdfSetup
         if (isReflection) return mk3(F * D * G * 0.25f / wi.z);
         const float sqrtDenom = woDotH + actualEta * wiDotH;
         const float t = actualEta * actualEta * wiDotH * woDotH / (wi.z * sqrtDenom * sqrtDenom);
-        return transAlbedo * ((1.f - F) * D * G * fabsf(t));
+        return transAlbedo * (1.f - F) * D * G * fabsf(t);        // left to right, BxDF.hlsli:436
     }
     PT_DEVICE float srtPdf(float3 wo) const
     {
