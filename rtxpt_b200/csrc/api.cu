@@ -61,8 +61,13 @@ struct rtxpt_ctx
     bool haveScene = false, haveConstants = false, lightsDirty = true;
     size_t l2PersistBytes = 0, l2WindowMax = 0;
     // measurement knobs, read from the environment once at creation (defaults are the measured optimum on B200, profiles/r1_history.md)
-    struct Tuning { int refillThreshold = 24, waitFlushLanes = 8, traceCtas = 4, shadeCtas = 4, smemNodes = 0; } tune;
+    struct Tuning { int refillThreshold = 24, waitFlushLanes = 8, traceCtas = 4, shadeCtas = 4, smemNodes = 0, lanes = 2; } tune;
     cudaStream_t stream2 = nullptr; cudaEvent_t evShadeDone = nullptr, evShadowDone = nullptr; bool overlapShadow = true;
+    // pipeline lanes: the sub-samples of one launch are split into independent wavefronts, each on its own pair of streams, so that the latency-bound tail of every
+    // persistent kernel of one lane (its last, longest rays) is filled by the CTAs of the other lanes.  Lane 0 is (caller stream, stream2).
+    static const int kMaxLanes = 8;
+    struct Lane { cudaStream_t s = nullptr, s2 = nullptr; cudaEvent_t evShadeDone = nullptr, evShadowDone = nullptr, evCommitted = nullptr; } lanes[kMaxLanes];
+    cudaEvent_t evFork = nullptr; uint32_t lastLanes = 1, lastSubSamplesPerLaunch = 1;
     DeviceArray<RtxptInstanceData> dInstances; DeviceArray<RtxptGeometryData> dGeometries; DeviceArray<RtxptSubInstanceData> dSubInstances;
     DeviceArray<RtxptMaterialData> dMaterials; DeviceArray<uint8_t> dSubInstanceClass;
     std::vector<uint8_t*> bufferAllocs; DeviceArray<const uint8_t*> dBufferTable;
@@ -191,8 +196,12 @@ extern "C" RTXPT_API int rtxpt_b200_create(const RtxptConfig* config, rtxpt_ctx*
     auto envInt = [](const char* name, int def, int lo, int hi) { const char* e = getenv(name); return e ? std::min(hi, std::max(lo, atoi(e))) : def; };
     c->tune.refillThreshold = envInt("RTXPT_REFILL_THRESHOLD", 24, 1, 32); c->tune.waitFlushLanes = envInt("RTXPT_WAIT_FLUSH", 8, 1, 33);
     c->tune.traceCtas = envInt("RTXPT_TRACE_CTAS", 4, 2, 4); c->tune.shadeCtas = envInt("RTXPT_SHADE_CTAS", 4, 3, 5); c->tune.smemNodes = envInt("RTXPT_SMEM_NODES", 0, 0, 1 << 20);
-    cudaMallocHost(&c->hCounters, kCounterWords * sizeof(uint32_t));
-    memset(c->hCounters, 0, kCounterWords * sizeof(uint32_t));
+    c->tune.lanes = envInt("RTXPT_LANES", 2, 1, rtxpt_ctx::kMaxLanes);
+    cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming);
+    for (int l = 1; l < rtxpt_ctx::kMaxLanes; l++) { cudaStreamCreateWithFlags(&c->lanes[l].s, cudaStreamNonBlocking); cudaStreamCreateWithFlags(&c->lanes[l].s2, cudaStreamNonBlocking); }
+    for (int l = 0; l < rtxpt_ctx::kMaxLanes; l++) { cudaEventCreateWithFlags(&c->lanes[l].evShadeDone, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->lanes[l].evShadowDone, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->lanes[l].evCommitted, cudaEventDisableTiming); }
+    cudaMallocHost(&c->hCounters, kCounterWords * rtxpt_ctx::kMaxLanes * sizeof(uint32_t));
+    memset(c->hCounters, 0, kCounterWords * rtxpt_ctx::kMaxLanes * sizeof(uint32_t));
     e = configureKernels(c->maxSmemOptin);
     if (e != cudaSuccess) { delete c; return fail(RTXPT_ERR_CUDA, "kernel configuration failed: %s", cudaGetErrorString(e)); }
     {   // L2 persistence carve-out for the BVH nodes (off unless RTXPT_L2_PERSIST_MB is set; see DESIGN.md for the measurement)
@@ -236,6 +245,12 @@ extern "C" RTXPT_API int rtxpt_b200_destroy(rtxpt_ctx* c)
     if (c->hCounters) cudaFreeHost(c->hCounters);
     if (c->evDnStart) cudaEventDestroy(c->evDnStart);
     if (c->evDnStop) cudaEventDestroy(c->evDnStop);
+    if (c->evFork) cudaEventDestroy(c->evFork);
+    for (int l = 0; l < rtxpt_ctx::kMaxLanes; l++)
+    {
+        if (c->lanes[l].evShadeDone) cudaEventDestroy(c->lanes[l].evShadeDone); if (c->lanes[l].evShadowDone) cudaEventDestroy(c->lanes[l].evShadowDone); if (c->lanes[l].evCommitted) cudaEventDestroy(c->lanes[l].evCommitted);
+        if (l > 0 && c->lanes[l].s) cudaStreamDestroy(c->lanes[l].s); if (l > 0 && c->lanes[l].s2) cudaStreamDestroy(c->lanes[l].s2);
+    }
     if (c->evShadeDone) cudaEventDestroy(c->evShadeDone);
     if (c->evShadowDone) cudaEventDestroy(c->evShadowDone);
     if (c->stream2) cudaStreamDestroy(c->stream2);
@@ -486,7 +501,7 @@ static int ensureTargets(rtxpt_ctx* c, uint32_t W, uint32_t H)
     CU(c->hits.alloc(c->capacity)); CU(c->rayQueue[0].alloc(c->capacity)); CU(c->rayQueue[1].alloc(c->capacity));
     CU(c->shadeQueue.alloc(size_t(c->capacity) * kNumShadeClasses));
     CU(c->shadowOriginTMax.alloc(c->capacity)); CU(c->shadowDirPath.alloc(c->capacity)); CU(c->shadowRadiance.alloc(c->capacity));
-    CU(c->counters.alloc(kCounterWords));
+    CU(c->counters.alloc(size_t(kCounterWords) * rtxpt_ctx::kMaxLanes));
     c->tableWidth = W; c->tableHeight = H; c->accumulatedSamples = 0;
     return RTXPT_OK;
 }
@@ -609,46 +624,69 @@ extern "C" RTXPT_API int rtxpt_b200_path_trace(rtxpt_ctx* c, uint32_t firstSubSa
     uint64_t launches = 0;
     KernelTimer kt{ c, s, (c->cfg.flags & RTXPT_CFG_TIME_KERNELS) != 0 };
     c->evUsed = 0;
+    const bool overlap = c->overlapShadow && !kt.on;      // per-kernel timing wants the kernels back to back
+    uint32_t lanesUsed = 1;
     for (uint32_t done = 0; done < subSampleCount; done += subSamplesPerLaunch)
     {
         const uint32_t n = std::min(subSamplesPerLaunch, subSampleCount - done);
         if (na) CU(cudaMemsetAsync(c->na.rrFix.ptr, 0, size_t(c->capacity) * 4, s));
-        p.firstSampleIndex = c->consts.sampleBaseIndex + firstSubSampleIndex + done;
-        p.subSampleCount = n;
-        p.accumulatedSamples = c->accumulatedSamples; p.doAccumulate = accumulate ? 1u : 0u;
-        CU(cudaMemsetAsync(c->counters.ptr, 0, kCounterWords * sizeof(uint32_t), s));
-        p.iteration = 0;
-        kt.begin(3); launchGenerate(p, c->grid, s); kt.end(); launches++;
-        // Shadow rays of vertex k and scatter rays of vertex k+1 touch disjoint state (shadow: shadow records + the radiance word of the path;
-        // closest: ray words, hit records, shade queues), so k_trace_shadow(it) runs on a second stream next to k_trace_closest(it+1): the
-        // long-ray tail of one persistent kernel is filled by the other's CTAs.  k_shade(it+1) joins both.
-        const bool overlap = c->overlapShadow && !kt.on;      // per-kernel timing wants the kernels back to back
-        for (uint32_t it = 0; it < iterations; it++)
+        // pipeline lanes (see rtxpt_ctx::Lane): sub-samples [ first, first + count ) of this batch per lane; feedback (one path per pixel at a time) and per-kernel timing run one lane
+        const uint32_t lanes = (na || kt.on) ? 1u : std::min<uint32_t>(uint32_t(c->tune.lanes), n);
+        lanesUsed = lanes;
+        CU(cudaMemsetAsync(c->counters.ptr, 0, size_t(kCounterWords) * lanes * sizeof(uint32_t), s));
+        if (lanes > 1) CU(cudaEventRecord(c->evFork, s));
+        for (uint32_t l = 0; l < lanes; l++)
         {
-            p.iteration = it;
-            kt.begin(0); launchTraceClosest(p, c->grid, countSteps, s); kt.end();
-            if (overlap && it > 0) CU(cudaStreamWaitEvent(s, c->evShadowDone, 0));        // shadow(it-1) has updated the radiance words
-            kt.begin(2); if (na) launchShadeNeeat(p, c->grid, s); else launchShade(p, c->grid, s); kt.end();
-            if (overlap)
-            {
-                CU(cudaEventRecord(c->evShadeDone, s));
-                CU(cudaStreamWaitEvent(c->stream2, c->evShadeDone, 0));
-                KernelTimer kt2{ c, c->stream2, kt.on };
-                kt2.begin(1); if (na) launchTraceShadowNeeat(p, c->grid, c->stream2); else launchTraceShadow(p, c->grid, countSteps, c->stream2); kt2.end();
-                CU(cudaEventRecord(c->evShadowDone, c->stream2));
+            const uint32_t firstSub = (l * n) / lanes, count = ((l + 1) * n) / lanes - firstSub;
+            rtxpt_ctx::Lane& L = c->lanes[l];
+            cudaStream_t ls = l == 0 ? s : L.s, ls2 = l == 0 ? c->stream2 : L.s2;
+            if (l > 0) CU(cudaStreamWaitEvent(ls, c->evFork, 0));
+            LaunchParams q = p;
+            {   // the lane's slice of every per-path array: slots are lane-relative, pixel = slot mod pixelCount as before
+                const size_t o = size_t(firstSub) * c->pixelCount; WavefrontBuffers& w = q.wf;
+                w.s0 += o; w.s1 += o; w.s2 += o; w.s3 += o; w.s4 += o; w.hits += o; w.rayQueue[0] += o; w.rayQueue[1] += o; w.shadeQueue += o * kNumShadeClasses;
+                w.shadowOriginTMax += o; w.shadowDirPath += o; w.shadowRadiance += o; w.counters += size_t(l) * kCounterWords; w.capacity = uint32_t(std::max<size_t>(size_t(count) * c->pixelCount, 1));
+                if (na) { q.naShadowFeedback += o; q.naRrFix += o; }
             }
-            else { kt.begin(1); if (na) launchTraceShadowNeeat(p, c->grid, s); else launchTraceShadow(p, c->grid, countSteps, s); kt.end(); }
-            launches += 3;
+            q.firstSampleIndex = c->consts.sampleBaseIndex + firstSubSampleIndex + done + firstSub;
+            q.subSampleCount = count;
+            q.accumulatedSamples = c->accumulatedSamples + firstSub; q.doAccumulate = accumulate ? 1u : 0u;
+            if (l + 1 != lanes) q.exportGuides = 0;     // the guides hold the launch's last sub-sample, as after the reference's sequential dispatches
+            q.iteration = 0;
+            KernelTimer ktl{ c, ls, kt.on };
+            ktl.begin(3); launchGenerate(q, c->grid, ls); ktl.end(); launches++;
+            // Shadow rays of vertex k and scatter rays of vertex k+1 touch disjoint state (shadow: shadow records + the radiance word of the path;
+            // closest: ray words, hit records, shade queues), so k_trace_shadow(it) runs on a second stream next to k_trace_closest(it+1): the
+            // long-ray tail of one persistent kernel is filled by the other's CTAs.  k_shade(it+1) joins both.
+            for (uint32_t it = 0; it < iterations; it++)
+            {
+                q.iteration = it;
+                ktl.begin(0); launchTraceClosest(q, c->grid, countSteps, ls); ktl.end();
+                if (overlap && it > 0) CU(cudaStreamWaitEvent(ls, L.evShadowDone, 0));        // shadow(it-1) has updated the radiance words
+                ktl.begin(2); if (na) launchShadeNeeat(q, c->grid, ls); else launchShade(q, c->grid, ls); ktl.end();
+                if (overlap)
+                {
+                    CU(cudaEventRecord(L.evShadeDone, ls));
+                    CU(cudaStreamWaitEvent(ls2, L.evShadeDone, 0));
+                    if (na) launchTraceShadowNeeat(q, c->grid, ls2); else launchTraceShadow(q, c->grid, countSteps, ls2);
+                    CU(cudaEventRecord(L.evShadowDone, ls2));
+                }
+                else { ktl.begin(1); if (na) launchTraceShadowNeeat(q, c->grid, ls); else launchTraceShadow(q, c->grid, countSteps, ls); ktl.end(); }
+                launches += 3;
+            }
+            if (overlap) CU(cudaStreamWaitEvent(ls, L.evShadowDone, 0));
+            if (l > 0) CU(cudaStreamWaitEvent(ls, c->lanes[l - 1].evCommitted, 0));       // the running mean takes the sub-samples in order
+            ktl.begin(3); launchCommitAccumulate(q, c->grid, ls); ktl.end(); launches++;
+            if (lanes > 1) CU(cudaEventRecord(L.evCommitted, ls));
         }
-        if (overlap) CU(cudaStreamWaitEvent(s, c->evShadowDone, 0));
-        kt.begin(3); launchCommitAccumulate(p, c->grid, s); kt.end(); launches++;
+        if (lanes > 1) CU(cudaStreamWaitEvent(s, c->lanes[lanes - 1].evCommitted, 0));     // every lane has committed (the commits are chained): the caller's stream joins
         if (accumulate) c->accumulatedSamples += n;
         CU(cudaGetLastError());
     }
     CU(cudaEventRecord(c->evStop, s));
     // statistics of the last batch (ray counts per iteration); read lazily by get_stats
-    CU(cudaMemcpyAsync(c->hCounters, c->counters.ptr, kCounterWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    c->lastIterations = iterations; c->lastSubSamples = subSampleCount; c->lastLaunches = launches; c->statsPending = true;
+    CU(cudaMemcpyAsync(c->hCounters, c->counters.ptr, size_t(kCounterWords) * lanesUsed * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    c->lastIterations = iterations; c->lastSubSamples = subSampleCount; c->lastLaunches = launches; c->lastLanes = lanesUsed; c->lastSubSamplesPerLaunch = subSamplesPerLaunch; c->statsPending = true;
     return RTXPT_OK;
 }
 
@@ -753,7 +791,7 @@ extern "C" RTXPT_API int rtxpt_b200_path_trace_realtime(rtxpt_ctx* c, int mergeN
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->evStop, s));
     CU(cudaMemcpyAsync(c->hCounters, c->counters.ptr, kCounterWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    c->lastIterations = fillIterations; c->lastSubSamples = 1; c->lastLaunches = launches; c->statsPending = true;
+    c->lastIterations = fillIterations; c->lastSubSamples = 1; c->lastLaunches = launches; c->lastLanes = 1; c->lastSubSamplesPerLaunch = 1; c->statsPending = true;
     return RTXPT_OK;
 }
 
@@ -1259,16 +1297,21 @@ extern "C" RTXPT_API int rtxpt_b200_get_stats(rtxpt_ctx* c, RtxptStats* out)
         float ms = 0; CU(cudaEventElapsedTime(&ms, c->evStart, c->evStop));
         out->msTotal = ms;
         // counters hold the LAST batch; scale ray counts to the whole call when it was split into equal batches
-        const uint32_t batches = (c->lastSubSamples + c->cfg.maxSubSamplesPerLaunch - 1) / c->cfg.maxSubSamplesPerLaunch;
-        const uint32_t lastBatch = c->lastSubSamples - (batches - 1) * c->cfg.maxSubSamplesPerLaunch;
+        const uint32_t perLaunch = std::max(1u, c->lastSubSamplesPerLaunch);        // 1 while NEE-AT feedback is active, cfg.maxSubSamplesPerLaunch otherwise
+        const uint32_t batches = (c->lastSubSamples + perLaunch - 1) / perLaunch;
+        const uint32_t lastBatch = c->lastSubSamples - (batches - 1) * perLaunch;
         const double scale = double(c->lastSubSamples) / double(lastBatch);
         uint64_t scatter = 0, shadow = 0, nodes = 0, tests = 0, snodes = 0, stests = 0;
         for (uint32_t it = 0; it < c->lastIterations; it++)
         {
-            const uint32_t* k = c->hCounters + it * kCountersPerIter;
-            scatter += k[kCtrRayCount]; shadow += k[kCtrShadowCount]; nodes += k[kCtrNodeVisits]; tests += k[kCtrTriTests];
-            snodes += k[kCtrShadowNodeVisits]; stests += k[kCtrShadowTriTests];
-            if (it < 16) out->raysPerBounce[it] = uint64_t(k[kCtrRayCount] * scale);
+            uint64_t raysThisIteration = 0;
+            for (uint32_t l = 0; l < c->lastLanes; l++)        // the lanes of the last batch each counted their own wavefront
+            {
+                const uint32_t* k = c->hCounters + size_t(l) * kCounterWords + it * kCountersPerIter;
+                scatter += k[kCtrRayCount]; shadow += k[kCtrShadowCount]; nodes += k[kCtrNodeVisits]; tests += k[kCtrTriTests];
+                snodes += k[kCtrShadowNodeVisits]; stests += k[kCtrShadowTriTests]; raysThisIteration += k[kCtrRayCount];
+            }
+            if (it < 16) out->raysPerBounce[it] = uint64_t(raysThisIteration * scale);
         }
         out->scatterRays = uint64_t(scatter * scale); out->shadowRays = uint64_t(shadow * scale);
         out->traversalNodeVisits = uint64_t(nodes * scale); out->traversalTriTests = uint64_t(tests * scale);
@@ -1316,7 +1359,7 @@ extern "C" RTXPT_API int rtxpt_b200_trace_rays_device(rtxpt_ctx* c, const void* 
 {
     if (!c || !c->haveScene) return fail(RTXPT_ERR_NO_SCENE, "no scene uploaded");
     cudaSetDevice(c->device);
-    if (c->counters.count == 0) CU(c->counters.alloc(kCounterWords));
+    if (c->counters.count == 0) CU(c->counters.alloc(size_t(kCounterWords) * rtxpt_ctx::kMaxLanes));
     LaunchParams p; fillParams(c, p);
     queryOccupancy(c->grid, 16 + size_t(p.smemNodeCount) * 80);
     CU(cudaMemsetAsync(c->counters.ptr, 0, 8, c->stream));

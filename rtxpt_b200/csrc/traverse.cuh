@@ -101,7 +101,27 @@ PT_DEVICE float byteToUnitFloat(uint w, int j) { return __uint_as_float(__byte_p
 #ifndef PT_I2F_AXES
 #define PT_I2F_AXES 2       // how many of the three axes convert their bytes with I2F (XU pipe) instead of PRMT (ALU pipe): closest-hit ms/frame 0 axes 9.15, 1 axis 8.98, 2 axes 8.84 (profiles/r1_history.md)
 #endif
-template <bool I2F> PT_DEVICE float byteToCoord(uint w, int j) { return I2F ? float((w >> (8 * j)) & 0xFFu) : byteToUnitFloat(w, j); }
+// the same permute with the selector as an immediate: `one` is 0x3F800000 held in a register the compiler cannot see through (otherwise ptxas folds it into the
+// instruction's only immediate slot and spends a second instruction per byte on moving the selector into a register - 16 per node visit in the round-1 SASS)
+PT_DEVICE float byteToUnitFloatImm(uint w, int j, uint one)
+{
+    uint r;
+    switch (j)
+    {
+    case 0: asm("prmt.b32 %0, %1, %2, 0x7604;" : "=r"(r) : "r"(w), "r"(one)); break;
+    case 1: asm("prmt.b32 %0, %1, %2, 0x7614;" : "=r"(r) : "r"(w), "r"(one)); break;
+    case 2: asm("prmt.b32 %0, %1, %2, 0x7624;" : "=r"(r) : "r"(w), "r"(one)); break;
+    default: asm("prmt.b32 %0, %1, %2, 0x7634;" : "=r"(r) : "r"(w), "r"(one)); break;
+    }
+    return __uint_as_float(r);
+}
+#ifndef PT_PRMT_IMM
+#define PT_PRMT_IMM 1
+#endif
+#ifndef PT_FFMA2
+#define PT_FFMA2 1      // slab test of two children per FFMA2 (Blackwell packed fp32 FMA): 24 instead of 48 FMA issues per node visit
+#endif
+template <bool I2F> PT_DEVICE float byteToCoord(uint w, int j, uint one) { return I2F ? float((w >> (8 * j)) & 0xFFu) : (PT_PRMT_IMM ? byteToUnitFloatImm(w, j, one) : byteToUnitFloat(w, j)); }
 
 // ---- warp-cooperative traversal ------------------------------------------------------------------------------------------------------
 // Node steps are per-lane work (each lane walks its own ray through the CWBVH8).  Triangle tests are NOT: a leaf holds 1..3 triangles and
@@ -221,6 +241,7 @@ struct Traverser
         const uint lane = threadIdx.x & 31u;
         const uint octinv4 = octinv * 0x01010101u;
         const bool negx = !(octinv & 4u), negy = !(octinv & 2u), negz = !(octinv & 1u);
+        uint one; asm volatile("mov.b32 %0, 0x3F800000;" : "=r"(one));        // see byteToUnitFloatImm
         while (true)
         {
             uint triBase = 0, triBits = 0;
@@ -281,17 +302,34 @@ struct Traverser
                     const uint nearx = negx ? qhix : qlox, farx = negx ? qlox : qhix;
                     const uint neary = negy ? qhiy : qloy, fary = negy ? qloy : qhiy;
                     const uint nearz = negz ? qhiz : qloz, farz = negz ? qloz : qhiz;
+#if PT_FFMA2
+                    #pragma unroll
+                    for (int jj = 0; jj < 4; jj += 2)
+                    {   // children jj and jj + 1 in the two halves of each packed FMA; every lane of a pair computes exactly what the scalar form computes (fma.rn per half)
+                        const float2 t0x = __ffma2_rn(make_float2(byteToCoord<(PT_I2F_AXES > 0)>(nearx, jj, one), byteToCoord<(PT_I2F_AXES > 0)>(nearx, jj + 1, one)), make_float2(Anx, Anx), make_float2(Onx, Onx));
+                        const float2 t1x = __ffma2_rn(make_float2(byteToCoord<(PT_I2F_AXES > 0)>(farx, jj, one), byteToCoord<(PT_I2F_AXES > 0)>(farx, jj + 1, one)), make_float2(Afx, Afx), make_float2(Ofx, Ofx));
+                        const float2 t0y = __ffma2_rn(make_float2(byteToCoord<(PT_I2F_AXES > 1)>(neary, jj, one), byteToCoord<(PT_I2F_AXES > 1)>(neary, jj + 1, one)), make_float2(Any, Any), make_float2(Ony, Ony));
+                        const float2 t1y = __ffma2_rn(make_float2(byteToCoord<(PT_I2F_AXES > 1)>(fary, jj, one), byteToCoord<(PT_I2F_AXES > 1)>(fary, jj + 1, one)), make_float2(Afy, Afy), make_float2(Ofy, Ofy));
+                        const float2 t0z = __ffma2_rn(make_float2(byteToCoord<(PT_I2F_AXES > 2)>(nearz, jj, one), byteToCoord<(PT_I2F_AXES > 2)>(nearz, jj + 1, one)), make_float2(Anz, Anz), make_float2(Onz, Onz));
+                        const float2 t1z = __ffma2_rn(make_float2(byteToCoord<(PT_I2F_AXES > 2)>(farz, jj, one), byteToCoord<(PT_I2F_AXES > 2)>(farz, jj + 1, one)), make_float2(Afz, Afz), make_float2(Ofz, Ofz));
+                        if (fmaxf(fmaxf(t0x.x, t0y.x), fmaxf(t0z.x, tMin)) <= fminf(fminf(t1x.x, t1y.x), fminf(t1z.x, bestT)))
+                            hitmask |= ((childBits4 >> (8 * jj)) & 0xFFu) << ((bitIndex4 >> (8 * jj)) & 0xFFu);
+                        if (fmaxf(fmaxf(t0x.y, t0y.y), fmaxf(t0z.y, tMin)) <= fminf(fminf(t1x.y, t1y.y), fminf(t1z.y, bestT)))
+                            hitmask |= ((childBits4 >> (8 * jj + 8)) & 0xFFu) << ((bitIndex4 >> (8 * jj + 8)) & 0xFFu);
+                    }
+#else
                     #pragma unroll
                     for (int j = 0; j < 4; j++)
                     {
-                        const float t0x = __fmaf_rn(byteToCoord<(PT_I2F_AXES > 0)>(nearx, j), Anx, Onx), t1x = __fmaf_rn(byteToCoord<(PT_I2F_AXES > 0)>(farx, j), Afx, Ofx);
-                        const float t0y = __fmaf_rn(byteToCoord<(PT_I2F_AXES > 1)>(neary, j), Any, Ony), t1y = __fmaf_rn(byteToCoord<(PT_I2F_AXES > 1)>(fary, j), Afy, Ofy);
-                        const float t0z = __fmaf_rn(byteToCoord<(PT_I2F_AXES > 2)>(nearz, j), Anz, Onz), t1z = __fmaf_rn(byteToCoord<(PT_I2F_AXES > 2)>(farz, j), Afz, Ofz);
+                        const float t0x = __fmaf_rn(byteToCoord<(PT_I2F_AXES > 0)>(nearx, j, one), Anx, Onx), t1x = __fmaf_rn(byteToCoord<(PT_I2F_AXES > 0)>(farx, j, one), Afx, Ofx);
+                        const float t0y = __fmaf_rn(byteToCoord<(PT_I2F_AXES > 1)>(neary, j, one), Any, Ony), t1y = __fmaf_rn(byteToCoord<(PT_I2F_AXES > 1)>(fary, j, one), Afy, Ofy);
+                        const float t0z = __fmaf_rn(byteToCoord<(PT_I2F_AXES > 2)>(nearz, j, one), Anz, Onz), t1z = __fmaf_rn(byteToCoord<(PT_I2F_AXES > 2)>(farz, j, one), Afz, Ofz);
                         const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tMin));
                         const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, bestT));
                         if (cmin <= cmax)
                             hitmask |= ((childBits4 >> (8 * j)) & 0xFFu) << ((bitIndex4 >> (8 * j)) & 0xFFu);
                     }
+#endif
                 }
                 nodeGroup.y = (hitmask & 0xFF000000u) | imask;
                 triBits = hitmask & 0x00FFFFFFu;
