@@ -91,18 +91,33 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(rays_per_iteration):
-    """dram__bytes_read.sum + dram__bytes_write.sum of k_trace_closest per frame, from the committed `ncu --set full` capture (profiles/): the
-    capture holds the launches of iterations 0..2; they are scaled to the frame by this run's ray counts (same unit as `achieved`: per frame = per
-    launch x launches)."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_ncu_full_summary.json")
-    try:
-        rows = [r for r in json.load(open(path)) if "k_trace_closest" in r["kernel"]]
-        captured = sum(r["dram_read_bytes"] + r["dram_write_bytes"] for r in rows)
-        frac = sum(rays_per_iteration[:len(rows)]) / max(1, sum(rays_per_iteration))
-        return captured / frac, "profiles/r1_ncu_full_summary.json: %d captured launches = %.0f %% of the frame's scatter rays, scaled to the frame" % (len(rows), 100 * frac)
-    except Exception as e:                                   # no capture committed: say so instead of guessing
-        return None, "no ncu capture found (%s)" % e
+def ncu_capture(rays_per_iteration):
+    """Counters of k_trace_closest from the committed `ncu --set full` capture (profiles/r2_ncu_full_summary.json, else round 1's): DRAM bytes per frame, the share of issue
+    slots in use and the executed thread-instructions per ray.  The capture holds the launches of the first iterations of one frame; byte and instruction totals are scaled to
+    the frame by this run's ray counts (same unit as `achieved`: per frame = per launch x launches).  The numbers describe the build the capture was taken from: its commit is
+    reported next to them, and a capture older than the kernels goes stale - `traffic_note` says which file was read."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    for name in ("r2_ncu_full_summary.json", "r1_ncu_full_summary.json"):
+        path = os.path.join(here, "profiles", name)
+        if not os.path.exists(path):
+            continue
+        try:
+            data = json.load(open(path)); rows_all = data["rows"] if isinstance(data, dict) else data
+            rows = [r for r in rows_all if "k_trace_closest" in r["kernel"]]
+            captured = sum(r["dram_read_bytes"] + r["dram_write_bytes"] for r in rows)
+            frac = sum(rays_per_iteration[:len(rows)]) / max(1, sum(rays_per_iteration))
+            rays_captured = sum(rays_per_iteration[:len(rows)])
+            ms = sum(r["time_ms"] for r in rows)
+            out = {"traffic": captured / frac, "capture_ms": ms, "capture_dram_bytes": captured,
+                   "issue_active": float(np.mean([r["issue_active_pct"] for r in rows])) / 100.0 if "issue_active_pct" in rows[0] else None,
+                   "threads_per_inst": float(np.mean([r["threads_per_inst"] for r in rows])) if "threads_per_inst" in rows[0] else None,
+                   "thread_inst_per_ray": (sum(r["warp_insts"] * r["threads_per_inst"] for r in rows) / max(1, rays_captured)) if "warp_insts" in rows[0] else None,
+                   "commit": data.get("commit") if isinstance(data, dict) else "round 1 (e38f795 or earlier)",
+                   "note": "profiles/%s: %d captured launches = %.0f %% of the frame's scatter rays, scaled to the frame" % (name, len(rows), 100 * frac)}
+            return out
+        except Exception as e:  # malformed capture: say so instead of guessing
+            return {"traffic": None, "note": "capture %s unreadable (%s)" % (name, e)}
+    return {"traffic": None, "note": "no ncu capture committed under profiles/"}
 
 
 def cpu_sample_rect():
@@ -136,15 +151,19 @@ def run_cpu(scene, consts, steps, warmup):
     t0 = time.time(); o = ol.Oracle(scene); bvh_s = ol.lib().oracle_bvh_build_seconds(o.h)
     o.set_constants(consts); setup_s = time.time() - t0
     rect = cpu_sample_rect()
-    rays, secs = 0, 0.0
+    rays, secs, cpu_s, wall_s = 0, 0.0, 0.0, 0.0
     for i in range(warmup + steps):
+        t_cpu, t_wall = time.process_time(), time.perf_counter()
         acc, n, last, prim, st = o.render(i, 1, rect=rect, threads=physical_cores())
         if i >= warmup:
             rays += st.scatterRays + st.shadowRays; secs += st.seconds
+            cpu_s += time.process_time() - t_cpu; wall_s += time.perf_counter() - t_wall
     threads = st.threads
     paths = (rect[2] - rect[0]) * (rect[3] - rect[1]) * steps
     return {"mrays_s": rays / secs / 1e6, "seconds": secs, "rays": rays, "threads": threads, "bvh_build_s": bvh_s, "setup_s": setup_s,
             "ms_per_step": secs / steps * 1e3, "rays_per_path": rays / paths,
+            # user+system CPU seconds of this process over the wall time of the timed steps: how many cores the arm really got (a cgroup quota or a noisy neighbour shows here)
+            "cpu_seconds": cpu_s, "wall_seconds": wall_s, "cores_busy": cpu_s / max(wall_s, 1e-9), "host_cpus": os.cpu_count(), "loadavg": list(os.getloadavg()),
             "sample": "%dx%d window at the centre of the %dx%d frame, 1 sub-sample per step, %d steps" % (rect[2] - rect[0], rect[3] - rect[1], WIDTH, HEIGHT, steps)}
 
 
@@ -169,7 +188,8 @@ def main():
                 "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (fp16 path-state storage)",
                 "data": "synthetic", "config": workload_config(n_gpus),
                 "cpu_baseline": {"value": r["mrays_s"], "unit": "Mrays/s", "cores": r["threads"], "kind": "port", "sample": r["sample"],
-                                 "bvh_build_s": r["bvh_build_s"], "rays_per_path": r["rays_per_path"]},
+                                 "bvh_build_s": r["bvh_build_s"], "rays_per_path": r["rays_per_path"], "cores_busy": r["cores_busy"], "cpu_seconds": r["cpu_seconds"], "wall_seconds": r["wall_seconds"],
+                                 "host_cpus": r["host_cpus"], "loadavg": r["loadavg"]},
                 "e2e": {"value": r["mrays_s"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "note": "RTXPT has no CPU implementation of this path (HLSL/DXR only); this arm times the CPU restatement of its algorithm (oracle/) on the host cores"}
         print(json.dumps(line)); return 0
@@ -240,6 +260,25 @@ def main():
     ms_per_step = ms_total / args.steps
     value = rays_per_frame / (ms_per_step * 1e-3) / 1e6
 
+    # ---- where a frame's time goes on this rank (N > 1: the scaling curve's explanation): CUDA events between the phases of 6 further frames, max over ranks per phase ------
+    phases = None
+    if world > 1:
+        names = ["set_constants+path_trace", "pack", "all_gather", "unpack"]
+        acc = np.zeros(len(names)); frames_p = 6
+        for i in range(frames_p):
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+            consts.sampleBaseIndex = (args.warmup + args.steps + i) * SPP
+            evs[0].record(); ctx.set_constants(consts); ctx.path_trace(0, SPP, True, stream)
+            evs[1].record(); ctx.pack_owned(send.data_ptr(), stream)
+            evs[2].record(); dist.all_gather_into_tensor(gathered, send)
+            evs[3].record(); ctx.unpack_all(gathered.data_ptr(), stream)
+            evs[4].record(); torch.cuda.synchronize()
+            if i > 0: acc += np.array([evs[j].elapsed_time(evs[j + 1]) for j in range(len(names))])
+        pt = torch.tensor(acc / (frames_p - 1), dtype=torch.float64, device="cuda")
+        pmax = pt.clone(); dist.all_reduce(pmax, op=dist.ReduceOp.MAX); pmin = pt.clone(); dist.all_reduce(pmin, op=dist.ReduceOp.MIN)
+        phases = {"ms_max_over_ranks": dict(zip(names, [float(x) for x in pmax])), "ms_min_over_ranks": dict(zip(names, [float(x) for x in pmin])),
+                  "note": "CUDA events on the launching stream between the phases of one frame, mean of 5 frames, each frame followed by a synchronize (so `all_gather` includes waiting for the slowest rank's path_trace)"}
+
     # ---- end-to-end through the C ABI with host buffers: constants in, accumulated RGBA32F image out, every step -------------------------
     barrier()
     t0 = time.perf_counter()
@@ -277,17 +316,26 @@ def main():
         alg_bytes = 48 * s2.scatterRays + 80 * s2.traversalNodeVisits + 48 * s2.traversalTriTests      # 32 B ray in + 16 B hit out + 80 B/node + 48 B/triangle
         peak, peak_src = measured_peak_gbs()
         achieved = alg_bytes / (k_closest * 1e-3) / 1e9 if k_closest > 0 else 0.0
-        traffic, traffic_note = ncu_traffic(rays_per_bounce)
-        roofline = {"kernel": "k_trace_closest (CWBVH8 closest-hit traversal)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
+        cap = ncu_capture(rays_per_bounce)
+        dram_gbs = (cap["capture_dram_bytes"] / (cap["capture_ms"] * 1e-3) / 1e9) if cap.get("capture_ms") else None
+        # The traversal kernel is bound by instruction issue, not by HBM (profiles/): `frac` stays the contract's algorithmic-bytes figure (what the kernel would
+        # have to move if nothing were cached, over its time and the measured HBM peak); `frac_dram` is what ncu saw cross the DRAM interface, `issue_active` the share of
+        # issue slots in use - the number the kernel is actually limited by - and `thread_inst_per_ray` the quantity to drive down.
+        roofline = {"kernel": "k_trace_closest (CWBVH8 closest-hit traversal)", "bound": "issue", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "frac_basis": "algorithmic bytes (48 B/ray + 80 B/node visit + 48 B/triangle test) / kernel time / measured HBM peak",
+                    "traffic": cap.get("traffic"), "traffic_note": cap.get("note"), "traffic_capture_commit": cap.get("commit"),
+                    "frac_dram": (dram_gbs / peak) if dram_gbs else None, "dram_gbs": dram_gbs,
+                    "issue_active": cap.get("issue_active"), "threads_per_inst": cap.get("threads_per_inst"), "thread_inst_per_ray": cap.get("thread_inst_per_ray"),
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_frame": int(alg_bytes), "nodes_per_ray": s2.traversalNodeVisits / max(1, s2.scatterRays), "tris_per_ray": s2.traversalTriTests / max(1, s2.scatterRays),
                     "kernel_ms_per_frame": {"trace_closest": k_closest, "trace_shadow": k_shadow, "shade": k_shade, "other": k_other},
-                    "note": "kernel times: CUDA events around every launch of one frame in a separate RTXPT_CFG_TIME_KERNELS context (kernels serialised; the measured configuration overlaps k_trace_shadow(i) with k_trace_closest(i+1))"}
+                    "note": "kernel times: CUDA events around every launch of one frame in a separate RTXPT_CFG_TIME_KERNELS context (kernels serialised, one pipeline lane; the measured configuration overlaps k_trace_shadow(i) with k_trace_closest(i+1) and runs the frame's sub-samples as pipeline lanes)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = run_cpu(scene, consts, 3, 1)
-        cpu = {"value": r["mrays_s"], "unit": "Mrays/s", "cores": r["threads"], "kind": "port", "sample": r["sample"], "bvh_build_s": r["bvh_build_s"], "rays_per_path": r["rays_per_path"]}
+        cpu = {"value": r["mrays_s"], "unit": "Mrays/s", "cores": r["threads"], "kind": "port", "sample": r["sample"], "bvh_build_s": r["bvh_build_s"], "rays_per_path": r["rays_per_path"],
+               "cores_busy": r["cores_busy"], "host_cpus": r["host_cpus"], "loadavg": r["loadavg"]}
 
     realtime = None
     if rank == 0 and world == 1 and not args.no_realtime:
@@ -309,7 +357,8 @@ def main():
                 "gpu_launches": int(launches * args.steps),
                 "rays_per_frame": rays_per_frame, "rays_per_path": rays_per_frame / (WIDTH * HEIGHT * SPP), "scatter_rays": scatter, "shadow_rays": shadow,
                 "rays_per_iteration": rays_per_bounce, "bvh_build_s": st.bvhBuildSeconds, "bvh_nodes": st.bvhNodeCount, "lights": st.lightCount,
-                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "realtime": realtime}
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "phases": phases,
+                "config3": (realtime or {}).get("config3") if isinstance(realtime, dict) else None, "realtime": realtime}
         sys.stdout.flush(); os.write(real_stdout, (json.dumps(line) + "\n").encode())
     ctx.close()
     if world > 1:

@@ -191,8 +191,11 @@ def sky_cube(size=256, sun_dir=(0.35, 0.55, -0.75), sun_intensity=60.0):
 
 
 def city_block(target_triangles=2_800_000, width=1920, height=1080, seed=1234, texture_size=512, n_textures=24, n_materials=254,
-               with_env=True, emissive=True):
-    """Procedural stand-in for Bistro exterior.  Returns (scene, camera)."""
+               with_env=True, emissive=True, delta_surfaces=False):
+    """Procedural stand-in for Bistro exterior.  Returns (scene, camera).
+    delta_surfaces (BASELINE configs[2], realtime mode): shop fronts glazed over four storeys with clear glass and a wet street, both opted into the path-space decomposition
+    (PSDExclude off, the way Bistro's .material.json files opt glass and puddles in), so that stable planes 1 and 2 cover a real share of the frame.  Geometry, triangle count
+    and every other material are the same as without it."""
     rng = np.random.default_rng(seed)
     b = SceneBuilder()
     # textures: albedo (sRGB), ORM (linear, G = roughness, B = metalness), alpha-noise (for foliage)
@@ -217,9 +220,11 @@ def city_block(target_triangles=2_800_000, width=1920, height=1080, seed=1234, t
     for i in range(n_materials):
         r = rng.random()
         if i < 35 * n_materials // 254:
-            glass.append(b.add_material(Material(base_color=tuple(0.85 + 0.15 * rng.random(3)), roughness=float(0.02 + 0.1 * rng.random()), transmission=1.0,
+            rough = float(0.02 + 0.1 * rng.random())
+            glass.append(b.add_material(Material(base_color=tuple(0.85 + 0.15 * rng.random(3)), roughness=min(rough, 0.06) if delta_surfaces else rough, transmission=1.0,
                                                  ior=1.5, thin_surface=bool(rng.random() < 0.7), nested_priority=2,
-                                                 volume_color=(0.8, 0.9, 0.85), volume_distance=0.5)))
+                                                 volume_color=(0.8, 0.9, 0.85), volume_distance=0.5,
+                                                 psd_exclude=not delta_surfaces, psd_dominant_delta_lobe=0 if delta_surfaces else -1)))
         elif i < (35 + 22) * n_materials // 254:
             foliage.append(b.add_material(Material(base_color=(1, 1, 1), roughness=0.8, base_texture=leaf_tex, alpha_test=True, alpha_cutoff=0.5,
                                                    diffuse_transmission=0.0)))
@@ -255,12 +260,14 @@ def city_block(target_triangles=2_800_000, width=1920, height=1080, seed=1234, t
             f.append(_quad(o + np.array([0, h, 0], np.float32), o + np.array([0, h, d], np.float32), o + np.array([w, h, d], np.float32), o + np.array([w, h, 0], np.float32), mats[0], uv_scale=4.0))
             # shop-front glass panes in front of the street-facing facade
             gm = glass[int(rng.integers(0, len(glass)))] if glass else mats[0]
-            f.append(_quad(o + np.array([w * 0.1, 0.3, -0.05], np.float32), o + np.array([w * 0.1, 3.0, -0.05], np.float32), o + np.array([w * 0.9, 3.0, -0.05], np.float32), o + np.array([w * 0.9, 0.3, -0.05], np.float32), gm))
+            gh = min(12.0, h - 0.5) if delta_surfaces else 3.0
+            f.append(_quad(o + np.array([w * 0.1, 0.3, -0.05], np.float32), o + np.array([w * 0.1, gh, -0.05], np.float32), o + np.array([w * 0.9, gh, -0.05], np.float32), o + np.array([w * 0.9, 0.3, -0.05], np.float32), gm))
             geos_by_mesh.append(f)
     # ground: tessellated, slightly noisy
     ng = max(8, int(math.sqrt(target_triangles * 0.06 / 2)))
     gnd = _facade(np.array([-extent / 2 - 20, 0, -extent / 2 - 20], np.float32), np.array([0, 0, extent + 40], np.float32), np.array([extent + 40, 0, 0], np.float32),
-                  ng, ng, np.array([0, 1, 0], np.float32), rng, opaque[0], depth=0.02)
+                  ng, ng, np.array([0, 1, 0], np.float32), rng,
+                  b.add_material(Material(base_color=(0.25, 0.25, 0.27), roughness=0.05, psd_exclude=False, psd_dominant_delta_lobe=1)) if delta_surfaces else opaque[0], depth=0.02)
     geos_by_mesh.append([gnd])
     # trees (alpha-tested canopies) and street lamps (emissive spheres) along the streets
     trees, lamp_geos = [], []

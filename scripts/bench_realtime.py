@@ -9,6 +9,53 @@ sys.path.insert(0, ROOT)
 import numpy as np
 
 
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f: return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def config3(args, lib, scenes, sb, S):
+    W, H, SPP, WARM = args.width, args.height, 4, 32
+    scene, cam = scenes.city_block(target_triangles=args.triangles, width=W, height=H, delta_surfaces=True)
+    consts = sb.make_constants(W, H, cam, bounce_count=6, diffuse_bounce_count=6, env_enabled=True, firefly_threshold=5000.0, nee=True, nee_type=2)
+    consts.NEEATFeedback = 1
+    ctx = lib.Context(max_sub_samples_per_launch=1)
+    ctx.upload_scene(scene); ctx.set_constants(consts); ctx.set_view(sb.world_to_clip(cam))
+    rt = sb.make_realtime_constants(W, H, cam, bounce_count=6, sub_samples=SPP); ctx.set_realtime(rt)
+    k = sb.make_denoiser_constants(cam); tm = S.make_tone_mapping_params(op=5, auto_exposure=True)
+    ev = {key: [] for key in ("update_begin_ms", "trace_ms", "denoise_ms", "frame_ms")}
+    for f in range(WARM + args.frames):
+        consts.sampleBaseIndex = f * SPP; ctx.set_constants(consts)
+        ctx.synchronize(); t0 = time.perf_counter()
+        ctx.neeat_update_begin(); ctx.synchronize(); t1 = time.perf_counter()
+        ctx.path_trace_realtime(False); ctx.synchronize(); trace = float(ctx.stats().msTotal)
+        ctx.denoise_spec_hit_t()
+        ctx.denoise_realtime(k, sb.make_reblur_frame(cam, cam, frame_index=f, frame_time_ms=16.0)); dn = ctx.last_denoise_ms()
+        ctx.tone_map(tm); ctx.synchronize(); t2 = time.perf_counter()
+        if f >= WARM:
+            ev["update_begin_ms"].append((t1 - t0) * 1e3); ev["trace_ms"].append(trace); ev["denoise_ms"].append(dn); ev["frame_ms"].append((t2 - t0) * 1e3)
+    st = ctx.stats(); r = ctx.readback_realtime(); hd = r["header"]
+    img = ctx.readback_output_color()[..., :3].astype(np.float32); ctl = ctx.neeat_raw(8, np.uint32, 8)
+    planes = [float((hd[p] != 0xFFFFFFFF).mean()) for p in range(3)]
+    med = {key: float(np.median(v)) for key, v in ev.items()}
+    peak, peak_src = measured_peak_gbs()
+    px = W * H; bytes_per_plane = 190 * px                      # inputs 33 + permanent pool r/w 2 x 42 + transient r/w 2 x 28 + outputs 16 B per pixel, taps assumed cached
+    rays = int(st.scatterRays + st.shadowRays)                  # the last FILL sub-sample's counters
+    out = dict(med)
+    out.update({"image": [W, H], "spp": SPP, "warmup_frames": WARM, "frames": args.frames, "emissive_triangle_lights": int(st.lightCount) - 5368, "planes_denoised": 3,
+                "pixels_with_plane": planes, "pixels_with_feedback": float(ctl[7]) / float(px), "sampling_proxies": int(ctl[4]), "finite": bool(np.isfinite(img).all()), "mean_radiance": float(img.mean()),
+                "kernel_launches_trace": int(st.kernelLaunches), "fill_rays_last_sub_sample": rays,
+                "reblur_roofline": {"bound": "hbm (compulsory bytes; the passes are ALU-heavy, see profiles/)", "algorithmic_bytes_per_plane": int(bytes_per_plane), "planes": 3,
+                                    "achieved": 3 * bytes_per_plane / (med["denoise_ms"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": 3 * bytes_per_plane / (med["denoise_ms"] * 1e-3) / 1e9 / peak,
+                                    "peak_source": peak_src, "note": "denoise_ms covers, per plane, prepare inputs + 8 ReBLUR passes + final merge; every plane is charged the full frame although planes 1-2 cover only pixels_with_plane[1..2] of it"},
+                "timing": "update_begin_ms, frame_ms: host clock between synchronizes; trace_ms (BUILD + UpdateEnd + 4 x FILL), denoise_ms: CUDA events on the context stream; medians over the timed frames"})
+    ctx.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=10); ap.add_argument("--warmup", type=int, default=3); ap.add_argument("--sub-samples", type=int, default=1)
@@ -42,39 +89,14 @@ def main():
            "pixels_with_plane": [float((hd[p] != 0xFFFFFFFF).mean()) for p in range(3)], "pixels_with_non_primary_dominant_plane": float(((hd[3] & 3) != 0).mean()),
            "mean_radiance": float(r["merged"].mean()), "timing": "CUDA events around the whole rtxpt_b200_path_trace_realtime call (BUILD + FILL x sub_samples + merge), median over frames",
            "workload": "bench.py city workload, clear glass opted into path-space decomposition"}
-    # realtime mode WITH the denoiser (BASELINE config 3's shape: stable planes + ReBLUR per plane + final merge).  The ReBLUR kernels had not run on a GPU when this was written:
-    # any failure is reported in place and leaves the numbers above intact.
+    # ---- BASELINE configs[2]: "1080p, 4 spp, NEE-AT + 10k emissive triangles + ReBLUR denoise" --------------------------------------------------------------------------------
+    # One frame = what Sample::Render does in realtime mode: LightsBaker::UpdateBegin -> BUILD -> LightsBaker::UpdateEnd -> 4 x FILL (NEE with local + global candidates, feedback)
+    # -> DenoiseSpecHitT -> per plane { prepare inputs, ReBLUR (8 passes), final merge } -> tone map.  32 warm-up frames prime the NEE-AT caches (Sample.cpp:1423) and the ReBLUR
+    # history.  Scene: the city workload with delta surfaces (glazed shop fronts, wet street) so that stable planes 1 and 2 are populated; >= 10 k emissive triangles (street lamps).
     try:
-        k = sb.make_denoiser_constants(cam); trace_ms, dn_ms = [], []
-        for f in range(args.warmup + args.frames):
-            consts.sampleBaseIndex = 1000 + f * args.sub_samples; ctx.set_constants(consts)
-            ctx.path_trace_realtime(False); ctx.synchronize(); t = float(ctx.stats().msTotal)
-            ctx.denoise_realtime(k, sb.make_reblur_frame(cam, cam, frame_index=f)); d = ctx.last_denoise_ms()
-            if f >= args.warmup: trace_ms.append(t); dn_ms.append(d)
-        img = ctx.readback_output_color()[..., :3].astype(np.float32)
-        px = W * H
-        out["denoised"] = {"trace_ms": float(np.median(trace_ms)), "denoise_ms": float(np.median(dn_ms)), "denoise_ms_min": float(np.min(dn_ms)), "planes_denoised": 3,
-                           "reblur_passes_per_plane": 8, "finite": bool(np.isfinite(img).all()), "mean_radiance": float(img.mean()),
-                           "algorithmic_bytes_per_plane": int(px * (4 + 4 + 8 + 1 + 8 + 8 + 8 + 8 + 42 * 2)),
-                           "note": "denoise_ms = CUDA events around rtxpt_b200_denoise_realtime (3 x { prepare inputs, 8 ReBLUR passes, final merge }); first GPU execution of these kernels"}
+        out["config3"] = config3(args, lib, scenes, sb, S)
     except Exception as e:  # noqa: BLE001
-        out["denoised"] = {"error": repr(e)[:300]}
-    # realtime mode with NEE-AT temporal feedback (per-tile light samplers): first GPU execution of those kernels too; same containment as above
-    try:
-        consts.NEEATFeedback = 1; fb_ms, upd = [], []
-        for f in range(args.warmup + args.frames + 8):                     # + 8: the loop needs a few frames before the tile samplers carry real feedback
-            consts.sampleBaseIndex = 2000 + f * args.sub_samples; ctx.set_constants(consts)
-            t0 = time.perf_counter(); ctx.neeat_update_begin(); ctx.synchronize(); t1 = time.perf_counter()
-            ctx.path_trace_realtime(True); ctx.synchronize()
-            if f >= args.warmup + 8: fb_ms.append(float(ctx.stats().msTotal)); upd.append((t1 - t0) * 1e3)
-        ctl = ctx.neeat_raw(8, np.uint32, 8)
-        img = ctx.readback_output_color()[..., :3].astype(np.float32)
-        out["neeat_feedback"] = {"ms_per_frame": float(np.median(fb_ms)), "update_begin_ms_host_clock": float(np.median(upd)), "finite": bool(np.isfinite(img).all()), "mean_radiance": float(img.mean()),
-                                 "pixels_with_feedback": float(ctl[7]) / float(W * H), "sampling_proxies": int(ctl[4]),
-                                 "note": "ms_per_frame = CUDA events around rtxpt_b200_path_trace_realtime (BUILD + update_end's 4 passes + FILL with local candidates + merge); update_begin timed by the host clock around a synchronize"}
-        consts.NEEATFeedback = 0; ctx.set_constants(consts)
-    except Exception as e:  # noqa: BLE001
-        out["neeat_feedback"] = {"error": repr(e)[:300]}
+        out["config3"] = {"error": repr(e)[:400]}
     # the callers either side of the path (§8f rows 3-4), first GPU executions as well: tone mapping, environment bake, BVH refit (last: a wrong refit would spoil what follows)
     try:
         tm = S.make_tone_mapping_params(op=5, auto_exposure=True); ctx.tone_map(tm); ctx.synchronize()
