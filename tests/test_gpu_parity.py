@@ -377,3 +377,88 @@ def test_c4_4k_tile_split_properties(product):
         c.path_trace(0, 1, True); c.synchronize(); part = c.readback_accumulated(); s = c.stats(); c.close()
         out[owner == r] = part[owner == r]; rays += s.scatterRays + s.shadowRays
     assert np.array_equal(out, img) and rays == st.scatterRays + st.shadowRays
+
+
+# ---- full-size parity: windows of the BENCH workload rendered by the oracle (its `rect`), compared with the same pixels of the product's full frame --------------------------
+@pytest.fixture(scope="module")
+def bench_city():
+    """bench.py's scene and camera (BASELINE configs[1]: 2.8 M-triangle city, 1920x1080), built once for the tests below."""
+    from rtxpt_b200 import scenes
+    return scenes.city_block(width=1920, height=1080)
+
+
+def _window(img, rect):
+    x0, y0, x1, y1 = rect
+    return img[y0:y1, x0:x1]
+
+
+@pytest.mark.gpu
+def test_config2_full_scene_window_per_sample(product, oracle, bench_city):
+    """BASELINE configs[1] at full size, one sample: a 256x256 window in the middle of the 1080p frame of the 2.8 M-triangle scene, oracle vs product, same seed.  Same ray counts,
+    >99 % of the window's pixels within 5 % and per-pixel L2 <= 1e-3 (the fast build's ulp differences flip a path decision on a fraction of a percent of the pixels)."""
+    from rtxpt_b200 import scene_builder as sb
+    from rtxpt_b200.imageio import per_pixel_l2
+    scene, cam = bench_city; W, H = 1920, 1080
+    consts = sb.make_constants(W, H, cam, bounce_count=6, diffuse_bounce_count=6, env_enabled=True, firefly_threshold=5000.0, nee=True, nee_type=2)
+    rect = (832, 412, 1088, 668)
+    c = product.Context(max_sub_samples_per_launch=4); c.upload_scene(scene); c.set_constants(consts)
+    c.path_trace(0, 1, True); c.synchronize(); img = c.readback_accumulated(); c.close()
+    o = oracle.Oracle(scene); o.set_constants(consts)
+    acc, n, _, _, ost = o.render(0, 1, rect=rect); o.close()
+    a, b = _window(img, rect), _window(acc, rect)
+    rel = np.abs(a[..., :3] - b[..., :3]) / (np.abs(b[..., :3]) + 1e-2)
+    assert (rel.max(-1) < 5e-2).mean() > 0.99, (rel.max(-1) < 5e-2).mean()
+    assert per_pixel_l2(a, b) < 1e-3
+    assert b[..., :3].mean() > 1e-3 and ost.scatterRays > 256 * 256            # the window is not sky
+
+
+@pytest.mark.gpu
+def test_config5_1024spp_accumulation_gate_full_scene(product, oracle, bench_city):
+    """BASELINE configs[4], the north_star's gate at its real size: 1024 spp reference accumulation of the full 1080p frame on the 2.8 M-triangle scene (256 frames of 4 sub-samples,
+    sampleBaseIndex advancing as Sample.cpp:1507), against the oracle's 1024 spp over a 128x128 window; identical seeds; per-pixel L2 <= 1e-3."""
+    from rtxpt_b200 import scene_builder as sb
+    from rtxpt_b200.imageio import per_pixel_l2
+    scene, cam = bench_city; W, H, SPP, FRAMES = 1920, 1080, 4, 256
+    consts = sb.make_constants(W, H, cam, bounce_count=6, diffuse_bounce_count=6, env_enabled=True, firefly_threshold=5000.0, nee=True, nee_type=2)
+    rect = (896, 476, 1024, 604)
+    c = product.Context(max_sub_samples_per_launch=SPP); c.upload_scene(scene)
+    o = oracle.Oracle(scene); acc = None; n = 0
+    for f in range(FRAMES):
+        consts.sampleBaseIndex = f * SPP
+        c.set_constants(consts); c.path_trace(0, SPP, True)
+    c.synchronize(); img = c.readback_accumulated(); assert c.stats().accumulatedSamples == FRAMES * SPP; c.close()
+    for f in range(FRAMES):                                                      # the oracle takes its sub-samples in the same order, frame by frame
+        consts.sampleBaseIndex = f * SPP; o.set_constants(consts)
+        acc, n = o.render(0, SPP, accum=acc, accum_count=n, rect=rect)[:2]
+    o.close()
+    assert n == FRAMES * SPP
+    a, b = _window(img, rect), _window(acc, rect)
+    l2 = per_pixel_l2(a, b)
+    assert l2 <= 1e-3, l2
+    assert abs(float(a[..., :3].mean()) - float(b[..., :3].mean())) < 5e-3 * float(b[..., :3].mean())
+
+
+@pytest.mark.gpu
+def test_config4_4k_window_nested_dielectrics(product, oracle):
+    """BASELINE configs[3] shape: 3840x2160, 1 spp, nested dielectrics + absorbing volumes, tile-split 8 ways: a 256x256 window that looks at the glazed shop fronts, product
+    (eight tile contexts reassembled) against the oracle, same tolerances as config 2."""
+    from rtxpt_b200 import scenes, scene_builder as sb
+    from rtxpt_b200.imageio import per_pixel_l2
+    W, H = 3840, 2160
+    scene, cam = scenes.city_block(target_triangles=600000, width=W, height=H, delta_surfaces=True)
+    consts = sb.make_constants(W, H, cam, bounce_count=6, diffuse_bounce_count=6, env_enabled=True, firefly_threshold=5000.0, nested_dielectrics=1)
+    rect = (2432, 800, 2688, 1056)          # glazed shop fronts fill most of this window (checked against the oracle's primary hits)
+    ty, tx = np.meshgrid(np.arange(H) // 64, np.arange(W) // 64, indexing="ij")
+    owner = (ty * ((W + 63) // 64) + tx) % 8
+    out = np.zeros((H, W, 4), np.float32)
+    for r in range(8):
+        c = product.Context(max_sub_samples_per_launch=1, tile_rank=r, tile_world=8, tile_size=64); c.upload_scene(scene); c.set_constants(consts)
+        c.path_trace(0, 1, True); c.synchronize(); part = c.readback_accumulated(); c.close()
+        out[owner == r] = part[owner == r]
+    o = oracle.Oracle(scene); o.set_constants(consts)
+    acc, n, _, _, ost = o.render(0, 1, rect=rect); o.close()
+    a, b = _window(out, rect), _window(acc, rect)
+    rel = np.abs(a[..., :3] - b[..., :3]) / (np.abs(b[..., :3]) + 1e-2)
+    assert (rel.max(-1) < 5e-2).mean() > 0.99, (rel.max(-1) < 5e-2).mean()
+    assert per_pixel_l2(a, b) < 1e-3
+    assert b[..., :3].mean() > 1e-3
