@@ -259,6 +259,7 @@ typedef struct RtxptConfig {
 #define RTXPT_CFG_COUNT_TRAVERSAL_STEPS  1u   /* instrumented traversal: per-launch node/triangle counters */
 #define RTXPT_CFG_NO_MATERIAL_SORT       2u   /* disable the per-bounce sort by material class (A/B measurement only) */
 #define RTXPT_CFG_EXPORT_GUIDES          8u   /* write the reference-mode guide buffers (depth, motion vectors, throughput) at every path vertex */
+#define RTXPT_CFG_NO_OPACITY_MASKS     16u   /* do not bake per-triangle opacity masks for alpha-tested geometry (A/B measurement; results are identical either way) */
 #define RTXPT_CFG_TIME_KERNELS           4u   /* CUDA events around every kernel: fills RtxptStats.msTraceClosest/msTraceShadow/msShade/msOther */
 
 typedef struct rtxpt_ctx rtxpt_ctx;
@@ -505,6 +506,22 @@ typedef struct RtxptStats {
     uint32_t accumulatedSamples;
 } RtxptStats;
 RTXPT_API int rtxpt_b200_get_stats(rtxpt_ctx* ctx, RtxptStats* out);
+
+/* Opacity masks: this implementation's equivalent of the reference's Opacity Micro-Maps (Rtxpt/OpacityMicroMap/: OC1_4_State OMMs baked per alpha-tested mesh and attached to
+ * the BLAS, Rtxpt/SampleCommon/AccelerationStructureUtil.h:60-84).  upload_scene bakes 64 two-bit states (transparent / opaque / unknown) per alpha-tested triangle from mip 0 of
+ * its alpha texture; the traversal kernels resolve candidates on known micro-triangles without the texture fetch of AlphaTestImpl (PathTracerBridgeDonut.hlsli:929-971).  A state is
+ * "known" only where every possible bilinear tap agrees, so hits are bit-identical with RTXPT_CFG_NO_OPACITY_MASKS. */
+typedef struct RtxptOpacityMaskStats {
+    uint32_t triangles;                 /* alpha-tested triangles that carry a mask */
+    uint32_t microTrianglesPerTriangle; /* 64 */
+    uint64_t transparent, opaque, unknown;   /* micro-triangle states over the scene */
+    float    bakeSeconds;
+} RtxptOpacityMaskStats;
+RTXPT_API int rtxpt_b200_get_opacity_mask_stats(rtxpt_ctx* ctx, RtxptOpacityMaskStats* out);
+/* Host-only hooks of the baker (no CUDA device needed): the mask of one triangle with texture coordinates uv[3][2] over mip 0 (`format` RTXPT_FORMAT_*) of an alpha texture, and
+ * the micro-triangle a barycentric hit (u, v) falls into (rtxpt_b200/csrc/opacity_masks.h). */
+RTXPT_API int rtxpt_b200_host_bake_opacity_mask(const void* mip0, uint32_t width, uint32_t height, uint32_t format, uint32_t alphaCutoffByte, const float uv[6], uint32_t outMask[4]);
+RTXPT_API uint32_t rtxpt_b200_host_opacity_micro_index(float u, float v);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Multi-GPU tile exchange.  The reference is single-GPU; with RtxptConfig.tileWorld > 1 each context renders

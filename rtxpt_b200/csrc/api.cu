@@ -4,6 +4,7 @@
 // structure build, MaterialsBaker::Update, UpdateLighting, constant-buffer write, PathTrace, AccumulationPass.
 // There is no CPU rendering fallback anywhere in this library: without a CUDA device every entry point fails with RTXPT_ERR_NO_DEVICE.
 #include "kernels.h"
+#include "opacity_masks.h"
 #include "reblur_host.h"
 #include "neeat_host.h"
 #include "envbake.cuh"
@@ -73,7 +74,8 @@ struct rtxpt_ctx
     std::vector<uint8_t*> bufferAllocs; DeviceArray<const uint8_t*> dBufferTable;
     std::vector<DeviceTexture> textures; DeviceArray<cudaTextureObject_t> dTextureTable;
     DeviceTexture envCube; uint32_t envFaceSize = 0, envMipLevels = 0;
-    DeviceArray<uint4> dBvhNodes; DeviceArray<float4> dBvhTris; DeviceArray<uint4> dTriInfo, dTriShade;
+    DeviceArray<uint4> dBvhNodes; DeviceArray<float4> dBvhTris; DeviceArray<uint4> dTriInfo, dTriShade, dOpacityMasks;
+    uint32_t opacityMaskTriangles = 0; uint64_t opacityMaskStates[3] = { 0, 0, 0 }; float opacityMaskBakeSeconds = 0;
     std::vector<RtxptInstanceData> hInstances; std::vector<uint32_t> bvhLevelStart; DeviceArray<float> dNodeBox;      // rigid-instance animation (refit.cuh)
     // skinned meshes (skinning.cuh): where each (instance, geometry)'s triangles start in gid order, its index range on the device, and the registered bind poses
     std::vector<RtxptGeometryData> hGeometries; std::vector<uint32_t> firstGidOfSubInstance; std::vector<const uint8_t*> hBufferTable; std::vector<uint32_t> maxVertexOfSubInstance;      // largest vertex index each sub-instance's triangles name (skin registration validates against it)
@@ -327,6 +329,8 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
     if (sc->materialCount > 0xFFFF || sc->textureCount > 0xFFFF || sc->bufferCount > 0xFFFF) return fail(RTXPT_ERR_UNSUPPORTED, "table sizes exceed the 16-bit indices of SubInstanceData");
     // validate + flatten triangles to world space (gid order: instance, geometry, primitive)
     std::vector<BuildTriangle> tris; std::vector<uint4> triInfo, triShade; std::vector<uint32_t> firstGid, maxVertex;
+    struct MaskJob { uint32_t tri, texture, cutoff; float uv[3][2]; }; std::vector<MaskJob> maskJobs;         // alpha-tested triangles that get an opacity mask (opacity_masks.h)
+    const bool bakeMasks = !(c->cfg.flags & RTXPT_CFG_NO_OPACITY_MASKS);
     for (uint32_t ii = 0; ii < sc->instanceCount; ii++)
     {
         const RtxptInstanceData& inst = sc->instances[ii];
@@ -373,13 +377,47 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
                 if (t >= kTriShadePrimMask) return fail(RTXPT_ERR_UNSUPPORTED, "geometry with more than 2^29 triangles");
                 rec[5].y = ii; rec[5].z = subIndex; rec[5].w = t | (hasUV ? kTriShadeHasUV : 0u) | (hasN ? kTriShadeHasNormal : 0u) | (hasT ? kTriShadeHasTangent : 0u);
                 triShade.insert(triShade.end(), rec, rec + 6);
-                bt.gid = uint32_t(tris.size()); bt.subInstanceAndFlags = flags; bt.primitiveIndex = t;
+                bt.gid = uint32_t(tris.size()); bt.subInstanceAndFlags = flags; bt.primitiveIndex = om::kNoMask;       // third w word of the BVH triangle: opacity-mask slot
+                if (bakeMasks && (flags & kTriFlagAlphaTested) && (sub.FlagsAndAlphaInfo & 0xFFFFu) < sc->textureCount)
+                {
+                    MaskJob j; j.tri = uint32_t(tris.size()); j.texture = sub.FlagsAndAlphaInfo & 0xFFFFu; j.cutoff = sub.FlagsAndAlphaInfo >> 24;
+                    const uint32_t w[6] = { rec[3].x, rec[3].y, rec[3].z, rec[3].w, rec[4].x, rec[4].y }; memcpy(j.uv, w, 24);
+                    maskJobs.push_back(j);
+                }
                 tris.push_back(bt);
                 triInfo.push_back(make_uint4(ii, gi, t, subIndex));
             }
         }
     }
     if (tris.size() >= (size_t(1) << 27)) return fail(RTXPT_ERR_INVALID_ARGUMENT, "scene has %zu triangles; the traversal kernels address at most 2^27 - 1", tris.size());
+    // opacity masks: 64 two-bit states per alpha-tested triangle, baked from mip 0 of the alpha texture (the reference bakes OMMs for the same geometries, OmmBuildQueue.cpp:30-60)
+    std::vector<uint4> masks(maskJobs.size()); uint64_t maskStates[3] = { 0, 0, 0 };
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        #pragma omp parallel
+        {
+            uint32_t local[3] = { 0, 0, 0 };
+            #pragma omp for schedule(dynamic, 256)
+            for (int64_t i = 0; i < int64_t(maskJobs.size()); i++)
+            {
+                const MaskJob& j = maskJobs[size_t(i)]; const RtxptTextureDesc& td = sc->textures[j.texture];
+                uint32_t m[4] = { 0xAAAAAAAAu, 0xAAAAAAAAu, 0xAAAAAAAAu, 0xAAAAAAAAu };            // all unknown
+                if (td.mips[0] && td.width && td.height)
+                {
+                    om::AlphaSource a; a.rgba8 = td.format == RTXPT_FORMAT_RGBA32_FLOAT ? nullptr : static_cast<const uint8_t*>(td.mips[0]);
+                    a.rgba32f = td.format == RTXPT_FORMAT_RGBA32_FLOAT ? static_cast<const float*>(td.mips[0]) : nullptr; a.width = int(td.width); a.height = int(td.height);
+                    om::bakeTriangle(a, j.cutoff, j.uv, m, local);
+                }
+                else local[om::kUnknown] += om::kMicroTriangles;
+                masks[size_t(i)] = make_uint4(m[0], m[1], m[2], m[3]);
+                tris[j.tri].primitiveIndex = uint32_t(i);
+            }
+            #pragma omp critical
+            for (int k = 0; k < 3; k++) maskStates[k] += local[k];
+        }
+        c->opacityMaskTriangles = uint32_t(maskJobs.size()); for (int k = 0; k < 3; k++) c->opacityMaskStates[k] = maskStates[k];
+        c->opacityMaskBakeSeconds = float(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
     Bvh8 bvh;
     buildBvh8(tris, bvh);
     c->bvhBuildSeconds = float(bvh.buildSeconds);
@@ -389,6 +427,7 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
     CU(c->dBvhTris.upload(reinterpret_cast<const float4*>(bvh.tris.data()), bvh.tris.size() * 3, s));
     CU(c->dTriInfo.upload(triInfo.data(), triInfo.size(), s));
     CU(c->dTriShade.upload(triShade.data(), triShade.size(), s));
+    if (!masks.empty()) CU(c->dOpacityMasks.upload(masks.data(), masks.size(), s)); else c->dOpacityMasks.release();
     CU(c->dInstances.upload(sc->instances, sc->instanceCount, s));
     c->hInstances.assign(sc->instances, sc->instances + sc->instanceCount); c->bvhLevelStart = bvh.levelStart; c->dNodeBox.release();
     c->hGeometries.assign(sc->geometries, sc->geometries + sc->geometryCount); c->firstGidOfSubInstance = firstGid; c->maxVertexOfSubInstance = maxVertex;
@@ -545,7 +584,7 @@ static void fillParams(rtxpt_ctx* c, LaunchParams& p)
     v.instances = c->dInstances.ptr; v.geometries = c->dGeometries.ptr; v.subInstances = c->dSubInstances.ptr; v.materials = c->dMaterials.ptr;
     v.subInstanceClass = c->dSubInstanceClass.ptr; v.materialCount = c->materialCount;
     v.buffers = c->dBufferTable.ptr; v.textures = c->dTextureTable.ptr; v.envCube = c->envCube.object; v.envFaceSize = c->envFaceSize; v.envMipLevels = c->envMipLevels;
-    v.bvhNodes = c->dBvhNodes.ptr; v.bvhTris = c->dBvhTris.ptr; v.triInfo = c->dTriInfo.ptr; v.triShade = c->dTriShade.ptr; v.bvhNodeCount = c->bvhNodeCount; v.bvhTriCount = c->bvhTriCount;
+    v.bvhNodes = c->dBvhNodes.ptr; v.bvhTris = c->dBvhTris.ptr; v.triInfo = c->dTriInfo.ptr; v.triShade = c->dTriShade.ptr; v.opacityMasks = c->dOpacityMasks.ptr; v.bvhNodeCount = c->bvhNodeCount; v.bvhTriCount = c->bvhTriCount;
     v.lightsEx = c->dLightsEx.ptr; v.analyticLightCount = uint32_t(c->lightState.analyticLightsEx.size());
     v.lights = c->dLights.ptr; v.proxyCounters = c->dProxyCounters.ptr; v.proxyIndices = c->dProxyIndices.ptr; v.envLookupMap = c->dEnvLookup.ptr;
     v.lightCount = uint32_t(c->lightState.lights.size()); v.samplingProxyCount = uint32_t(c->lightState.proxyIndices.size()); v.envEnabled = c->lightState.envEnabled ? 1u : 0u;
@@ -1324,6 +1363,15 @@ extern "C" RTXPT_API int rtxpt_b200_get_stats(rtxpt_ctx* c, RtxptStats* out)
         out->paths = uint64_t(c->pixelCount) * c->lastSubSamples;
         out->kernelLaunches = c->lastLaunches;
     }
+    return RTXPT_OK;
+}
+
+extern "C" RTXPT_API int rtxpt_b200_get_opacity_mask_stats(rtxpt_ctx* c, RtxptOpacityMaskStats* out)
+{
+    if (!c || !out) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (!c->haveScene) return fail(RTXPT_ERR_NO_SCENE, "no scene uploaded");
+    out->triangles = c->opacityMaskTriangles; out->microTrianglesPerTriangle = om::kMicroTriangles; out->transparent = c->opacityMaskStates[om::kTransparent];
+    out->opaque = c->opacityMaskStates[om::kOpaque]; out->unknown = c->opacityMaskStates[om::kUnknown]; out->bakeSeconds = c->opacityMaskBakeSeconds;
     return RTXPT_OK;
 }
 

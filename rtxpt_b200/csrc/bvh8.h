@@ -16,7 +16,7 @@
 //   q4: qhi.y[0..7] | qhi.z[0..7]
 //   Slot s holds the child lying towards direction (s&4 ? +x : -x, s&2 ? +y : -y, s&1 ? +z : -z) so that visiting slots in the
 //   order (s XOR octant) gives front-to-back traversal for every ray octant.
-// Triangle (48 B): v0.xyz gid | v1.xyz subInstanceAndFlags | v2.xyz primitiveIndex
+// Triangle (48 B): v0.xyz gid | v1.xyz subInstanceAndFlags | v2.xyz opacity-mask slot (0xFFFFFFFF: none; field `primitiveIndex` of BuildTriangle / Bvh8Tri)
 //   gid  = global triangle id (instance order, geometry order, primitive order) — the tie-break key for equal-t hits
 //   subInstanceAndFlags = subInstanceIndex | (alphaTested << 30) | (excludeFromNEE << 31)
 #pragma once

@@ -27,6 +27,7 @@ struct SceneView
     const float4*               bvhTris;            // 3 x float4 per triangle
     const uint4*                triInfo;            // per global triangle id: instanceIndex, geometryIndex, primitiveIndex, subInstanceIndex
     const uint4*                triShade;           // per global triangle id, 6 x uint4 (kTriShadeWords): everything loadSurface gathers per vertex, see below
+    const uint4*                opacityMasks;       // per alpha-tested triangle (slot = third w word of its BVH triangle): 64 x 2-bit states, opacity_masks.h
     uint                        bvhNodeCount, bvhTriCount;
     // lights
     const LightInfo*            lights;

@@ -10,6 +10,7 @@
 #pragma once
 #include "device_math.cuh"
 #include "scene_device.cuh"
+#include "opacity_masks.h"
 
 namespace pt {
 
@@ -92,6 +93,20 @@ PT_DEVICE bool alphaTestPasses(const SceneView& sc, const RtxptSubInstanceData& 
     const float2 uv = mk2(t0.x * b0 + t1.x * u + t2.x * v, t0.y * b0 + t1.y * u + t2.y * v);
     const float opacity = tex2DLod<float4>(sc.textures[s.FlagsAndAlphaInfo & 0xFFFF], uv.x, uv.y, 0.0f).w;
     return opacity >= float(s.FlagsAndAlphaInfo >> 24) / 255.0f;
+}
+
+// Candidate hit on an alpha-tested triangle: the opacity mask first (the OMM analogue, opacity_masks.h) - a known micro-triangle decides without the texture fetch - then
+// AlphaTestImpl.  Kept out of line: alpha-tested candidates are rare, and inlined this body costs the traversal loop registers it does not have (64 at 4 CTAs per SM).
+__device__ __noinline__ bool alphaCandidateIsOpaque(const SceneView& sc, uint sub, uint gid, uint maskSlot, float u, float v)
+{
+    if (maskSlot != om::kNoMask)
+    {
+        const uint m = om::microIndex(u, v);
+        const uint state = (__ldg(reinterpret_cast<const uint*>(sc.opacityMasks + maskSlot) + (m >> 4)) >> ((m & 15u) * 2u)) & 3u;
+        if (state == om::kTransparent) return false;
+        if (state == om::kOpaque) return true;
+    }
+    return alphaTestPasses(sc, sc.subInstances[sub & kTriSubInstanceMask], gid, u, v);
 }
 
 struct TraversalCounters { uint nodeVisits, triTests; };
@@ -222,7 +237,7 @@ struct Traverser
                         if (sub & (kTriFlagAlphaTested | kTriFlagExcludeFromNEE))
                         {   // non-opaque geometry (SampleCommon/AccelerationStructureUtil.h:88-89)
                             if (ANY_HIT && (sub & kTriFlagExcludeFromNEE)) accept = false;
-                            else if ((sub & kTriFlagAlphaTested) && !alphaTestPasses(sc, sc.subInstances[sub & kTriSubInstanceMask], __float_as_uint(a.w), u, v)) accept = false;
+                            else if ((sub & kTriFlagAlphaTested) && !alphaCandidateIsOpaque(sc, sub, __float_as_uint(a.w), __float_as_uint(c.w), u, v)) accept = false;
                         }
                         if (accept) { atomicMin(&ws.bestKey[owner], key); won = true; }
                     }

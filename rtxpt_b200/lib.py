@@ -57,6 +57,8 @@ _SIGNATURES = {
     "rtxpt_b200_bake_env_map": [C.c_void_p, C.POINTER(S.EnvBakeDesc), C.c_void_p, C.c_size_t],
     "rtxpt_b200_neeat_update_begin": [C.c_void_p, C.c_void_p],
     "rtxpt_b200_neeat_update_end": [C.c_void_p, C.c_void_p],
+    "rtxpt_b200_get_opacity_mask_stats": [C.c_void_p, C.POINTER(S.OpacityMaskStats)],
+    "rtxpt_b200_host_bake_opacity_mask": [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p],
     "rtxpt_b200_neeat_reset": [C.c_void_p],
     "rtxpt_b200_neeat_readback": [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)],
     "rtxpt_b200_neeat_debug_set_feedback": [C.c_void_p, C.c_void_p, C.c_void_p],
@@ -68,7 +70,7 @@ _SIGNATURES = {
     "rtxpt_b200_debug_bsdf": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
     "rtxpt_b200_debug_rng": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
 }
-_LOADER_SYMBOLS = ["rtxpt_b200_camera_matrices", "rtxpt_b200_tone_map_pre_exposed_gray", "rtxpt_b200_debug_build_bvh", "rtxpt_b200_env_bake_mip_count", "rtxpt_b200_env_bake_floats", "rtxpt_b200_load_gltf", "rtxpt_b200_load_gltf_ex", "rtxpt_b200_load_scene_json", "rtxpt_b200_host_scene_info", "rtxpt_b200_load_gltf_error", "rtxpt_b200_host_scene_desc", "rtxpt_b200_host_scene_cameras",
+_LOADER_SYMBOLS = ["rtxpt_b200_host_opacity_micro_index", "rtxpt_b200_camera_matrices", "rtxpt_b200_tone_map_pre_exposed_gray", "rtxpt_b200_debug_build_bvh", "rtxpt_b200_env_bake_mip_count", "rtxpt_b200_env_bake_floats", "rtxpt_b200_load_gltf", "rtxpt_b200_load_gltf_ex", "rtxpt_b200_load_scene_json", "rtxpt_b200_host_scene_info", "rtxpt_b200_load_gltf_error", "rtxpt_b200_host_scene_desc", "rtxpt_b200_host_scene_cameras",
                    "rtxpt_b200_host_scene_triangle_count", "rtxpt_b200_free_host_scene", "rtxpt_b200_bridge_camera", "rtxpt_b200_default_constants", "rtxpt_b200_debug_bvh_stats", "rtxpt_b200_parse_material_json", "rtxpt_b200_parse_material_json_error", "rtxpt_b200_debug_decode_dds", "rtxpt_b200_debug_decode_dds_error",
                     "rtxpt_b200_generic_ts_line_stride", "rtxpt_b200_generic_ts_plane_stride", "rtxpt_b200_generic_ts_address"]
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["rtxpt_b200_last_error"] + _LOADER_SYMBOLS)
@@ -82,6 +84,8 @@ def load(strict=None):
         path = LIB_PATH_STRICT if strict else LIB_PATH
         if os.environ.get("RTXPT_LIB_DIR"):        # tuning experiments: alternative builds of the same sources (make OUT=...)
             path = os.path.join(os.environ["RTXPT_LIB_DIR"], os.path.basename(path))
+        if os.environ.get("RTXPT_LIB") and not strict:      # A/B measurement builds (csrc/Makefile `variant`)
+            path = os.environ["RTXPT_LIB"]
         if not os.path.exists(path):
             raise RtxptError(f"{path} is missing: run rtxpt_b200.lib.build() / `make -C rtxpt_b200/csrc` (no fallback path exists)")
         L = C.CDLL(path)
@@ -338,6 +342,10 @@ class Context:
         return _bake_env_map(lambda d, out: _check(self.L.rtxpt_b200_bake_env_map(self.h, C.byref(d), out.ctypes.data, out.size), self.L), cube_dim, source, source_type, scale_color, lights)
 
     # ---- NEE-AT temporal feedback: per frame set_constants; neeat_update_begin; path_trace_realtime (runs update_end after its BUILD pass) ----
+    def opacity_mask_stats(self):
+        st = S.OpacityMaskStats(); _check(self.L.rtxpt_b200_get_opacity_mask_stats(self.h, C.byref(st)), self.L)
+        return st
+
     def neeat_update_begin(self, stream=None): _check(self.L.rtxpt_b200_neeat_update_begin(self.h, stream), self.L)
 
     def neeat_update_end(self, stream=None): _check(self.L.rtxpt_b200_neeat_update_end(self.h, stream), self.L)

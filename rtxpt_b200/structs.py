@@ -28,6 +28,7 @@ CFG_COUNT_TRAVERSAL_STEPS = 1
 CFG_NO_MATERIAL_SORT = 2
 CFG_TIME_KERNELS = 4
 CFG_EXPORT_GUIDES = 8
+CFG_NO_OPACITY_MASKS = 16
 
 BUFFER_OUTPUT_COLOR_F16, BUFFER_ACCUMULATED_F32, BUFFER_DEPTH_F32, BUFFER_MOTION_VECTORS_F16, BUFFER_THROUGHPUT_R11G11B10 = 0, 1, 2, 3, 4
 BUFFER_STABLE_PLANES, BUFFER_STABLE_PLANES_HEADER, BUFFER_STABLE_RADIANCE_F16, BUFFER_SPECULAR_HITT_F32 = 5, 6, 7, 8
@@ -205,6 +206,10 @@ class Stats(C.Structure):
                 ("msTotal", f32), ("msTraceClosest", f32), ("msTraceShadow", f32), ("msShade", f32), ("msOther", f32),
                 ("bvhNodeCount", u32), ("bvhTriangleCount", u32), ("bvhBuildSeconds", f32),
                 ("lightCount", u32), ("lightProxyCount", u32), ("accumulatedSamples", u32)]
+
+
+class OpacityMaskStats(C.Structure):
+    _fields_ = [("triangles", u32), ("microTrianglesPerTriangle", u32), ("transparent", u64), ("opaque", u64), ("unknown", u64), ("bakeSeconds", f32)]
 
 
 class Ray(C.Structure):

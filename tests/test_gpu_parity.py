@@ -92,6 +92,8 @@ def test_bsdf_against_reference_header_golden(ctx):
     import os
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bsdf_golden.npz"))
     rec, ref = np.ascontiguousarray(g["bsdf_in"], np.float32), g["bsdf_out"]
+    live = rec[:, 33] == 255.0                  # the path always runs with LobeType::All (PathTracerBridgeDonut.hlsli:723), which is what the CUDA BSDF is specialised for; the
+    rec, ref = np.ascontiguousarray(rec[live]), ref[live]      # restricted-lobe records of the fixture pin the oracle only (tests/test_oracle_golden.py)
     out = ctx.debug_bsdf(rec)
     tol = 2e-4 if ctx.variant == "strict" else 1e-3
     assert np.array_equal(out[:, 15], ref[:, 15])
@@ -462,3 +464,25 @@ def test_config4_4k_window_nested_dielectrics(product, oracle):
     assert (rel.max(-1) < 5e-2).mean() > 0.99, (rel.max(-1) < 5e-2).mean()
     assert per_pixel_l2(a, b) < 1e-3
     assert b[..., :3].mean() > 1e-3
+
+
+@pytest.mark.gpu
+def test_opacity_masks_do_not_change_hits(product, small_city):
+    """The opacity masks (the OMM analogue, rtxpt_b200/csrc/opacity_masks.h) only replace texture fetches whose outcome is certain: closest-hit and any-hit queries through the
+    alpha-tested tree canopies, and a whole frame, are bit-identical with the masks baked and with RTXPT_CFG_NO_OPACITY_MASKS; a real share of the micro-triangles is decided."""
+    from rtxpt_b200 import scene_builder as sb, structs as S
+    scene, cam = small_city
+    W, H = cam.ViewportSize[0], cam.ViewportSize[1]
+    consts = sb.make_constants(W, H, cam, bounce_count=4, diffuse_bounce_count=4, env_enabled=True)
+    rng = np.random.default_rng(21)
+    rays = random_rays(rng, 400000, [-60, 0.5, -60], [60, 9, 60], tmax=80.0)          # the canopies sit 2-7 m above the streets
+    out = []
+    for flags in (0, S.CFG_NO_OPACITY_MASKS):
+        c = product.Context(max_sub_samples_per_launch=2, flags=flags); c.upload_scene(scene); c.set_constants(consts)
+        st = c.opacity_mask_stats()
+        c.path_trace(0, 2, True); c.synchronize()
+        out.append((c.trace_rays(rays), c.trace_rays(rays, any_hit=True), c.readback_accumulated(), st.triangles, st.opaque + st.transparent, st.unknown))
+        c.close()
+    (ca, aa, ia, ta, ka, ua), (cb, ab, ib, tb, kb, ub) = out
+    assert ta > 1000 and tb == 0 and ka > 0.3 * (ka + ua), (ta, ka, ua)
+    assert hits_bit_equal(ca, cb).all() and np.array_equal(aa["t"] >= 0, ab["t"] >= 0) and np.array_equal(ia, ib)

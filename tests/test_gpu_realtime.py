@@ -84,6 +84,14 @@ def test_realtime_default_build_decomposes_like_the_oracle(product, oracle):
     assert all(g[k].tobytes() == g2[k].tobytes() for k in g)
 
 
+def _same_headers(g, r, strict):
+    """Pixels whose decomposition agrees.  Header words 0..2 are branch IDs (integers); word 3 is the first hit's ray length as float bits with the dominant plane index in its two
+    low bits (StablePlanes.hlsli StoreFirstHitRayLengthAndClearDominantToZero): identical bits in the strict build, the length within a few ulp in the fast one."""
+    if strict: return (g["header"] == r["header"]).all(0)
+    la, lb = (g["header"][3] & 0xFFFFFFFC).view(np.float32), (r["header"][3] & 0xFFFFFFFC).view(np.float32)
+    return (g["header"][:3] == r["header"][:3]).all(0) & ((g["header"][3] & 3) == (r["header"][3] & 3)) & np.isclose(la, lb, rtol=1e-5, atol=0)
+
+
 @unverified
 @pytest.mark.parametrize("strict", [True, False])
 def test_build_pass_matches_oracle(product, oracle, strict):
@@ -94,7 +102,7 @@ def test_build_pass_matches_oracle(product, oracle, strict):
         rt = sb.make_realtime_constants(W, H, cam, bounce_count=8, sub_samples=1, **kw)
         c.set_realtime(rt); c.path_trace_realtime(True); c.synchronize()
         g = c.readback_realtime(); r = o.render_realtime(rt)
-        same = (g["header"] == r["header"]).all(0)
+        same = _same_headers(g, r, strict)
         assert same.mean() > 0.998, (kw, same.mean())                                  # decomposition decisions: thresholds on Fresnel terms can flip at silhouettes
         ys, xs = np.nonzero(same)
         for plane in range(3):
@@ -132,7 +140,7 @@ def test_fill_pass_and_merge_match_oracle(product, oracle, strict):
     rt = sb.make_realtime_constants(W, H, cam, bounce_count=8, sub_samples=3)
     c.set_realtime(rt); c.path_trace_realtime(True); c.synchronize()
     g = c.readback_realtime(); r = o.render_realtime(rt)
-    same = (g["header"] == r["header"]).all(0)
+    same = _same_headers(g, r, strict)
     assert same.mean() > 0.998
     d = np.abs(g["merged"] - r["merged"])[same]; scale = np.maximum(r["merged"][same], 0.05)
     if strict:
@@ -200,7 +208,7 @@ def test_denoiser_interface_matches_oracle(product, oracle, strict):
     g = c.readback_realtime(); r = o.render_realtime(rt)
     k = sb.make_denoiser_constants(cam, suppress_primary_indirect_specular_k=0.4)
     d = o.new_denoiser_targets()
-    same = (g["header"] == r["header"]).all(0)
+    same = _same_headers(g, r, strict)
     for i, plane in enumerate((2, 1, 0)):
         c.denoiser_prepare_inputs(plane, i == 0, k); c.synchronize(); gi = c.readback_denoiser_inputs()
         o.denoiser_prepare_inputs(rt, k, r, d, plane, i == 0)
