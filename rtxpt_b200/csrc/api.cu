@@ -62,7 +62,7 @@ struct rtxpt_ctx
     bool haveScene = false, haveConstants = false, lightsDirty = true;
     size_t l2PersistBytes = 0, l2WindowMax = 0;
     // measurement knobs, read from the environment once at creation (defaults are the measured optimum on B200, profiles/r1_history.md)
-    struct Tuning { int refillThreshold = 24, waitFlushLanes = 8, traceCtas = 4, shadeCtas = 4, smemNodes = 0, lanes = 2; } tune;
+    struct Tuning { int refillThreshold = 24, waitFlushLanes = 8, traceCtas = 4, shadeCtas = 4, smemNodes = 0, lanes = 1; } tune;
     cudaStream_t stream2 = nullptr; cudaEvent_t evShadeDone = nullptr, evShadowDone = nullptr; bool overlapShadow = true;
     // pipeline lanes: the sub-samples of one launch are split into independent wavefronts, each on its own pair of streams, so that the latency-bound tail of every
     // persistent kernel of one lane (its last, longest rays) is filled by the CTAs of the other lanes.  Lane 0 is (caller stream, stream2).
@@ -198,7 +198,7 @@ extern "C" RTXPT_API int rtxpt_b200_create(const RtxptConfig* config, rtxpt_ctx*
     auto envInt = [](const char* name, int def, int lo, int hi) { const char* e = getenv(name); return e ? std::min(hi, std::max(lo, atoi(e))) : def; };
     c->tune.refillThreshold = envInt("RTXPT_REFILL_THRESHOLD", 24, 1, 32); c->tune.waitFlushLanes = envInt("RTXPT_WAIT_FLUSH", 8, 1, 33);
     c->tune.traceCtas = envInt("RTXPT_TRACE_CTAS", 4, 2, 4); c->tune.shadeCtas = envInt("RTXPT_SHADE_CTAS", 4, 3, 5); c->tune.smemNodes = envInt("RTXPT_SMEM_NODES", 0, 0, 1 << 20);
-    c->tune.lanes = envInt("RTXPT_LANES", 2, 1, rtxpt_ctx::kMaxLanes);
+    c->tune.lanes = envInt("RTXPT_LANES", 1, 1, rtxpt_ctx::kMaxLanes);          // measured on a B200, 1080p 4 spp: 1 lane 18.61 ms, 2 lanes 18.79, 4 lanes 19.51 (one GPU has enough rays per wavefront; lanes are for small per-rank tile sets)
     cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming);
     for (int l = 1; l < rtxpt_ctx::kMaxLanes; l++) { cudaStreamCreateWithFlags(&c->lanes[l].s, cudaStreamNonBlocking); cudaStreamCreateWithFlags(&c->lanes[l].s2, cudaStreamNonBlocking); }
     for (int l = 0; l < rtxpt_ctx::kMaxLanes; l++) { cudaEventCreateWithFlags(&c->lanes[l].evShadeDone, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->lanes[l].evShadowDone, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->lanes[l].evCommitted, cudaEventDisableTiming); }

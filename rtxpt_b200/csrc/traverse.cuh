@@ -131,10 +131,11 @@ PT_DEVICE float byteToUnitFloatImm(uint w, int j, uint one)
     return __uint_as_float(r);
 }
 #ifndef PT_PRMT_IMM
-#define PT_PRMT_IMM 1
+#define PT_PRMT_IMM 0      // measured on a B200 (closest-hit ms/frame): 8.85 with, 8.81 without - the saved selector moves are re-spent on re-materialising the constant
 #endif
 #ifndef PT_FFMA2
-#define PT_FFMA2 1      // slab test of two children per FFMA2 (Blackwell packed fp32 FMA): 24 instead of 48 FMA issues per node visit
+#define PT_FFMA2 0      // slab test of two children per FFMA2 (Blackwell packed fp32 FMA): 24 instead of 48 FMA issues per node visit, but ptxas pays for the register pairs with
+                        // re-materialised per-node constants at 64 registers: measured on a B200 9.50 ms/frame closest-hit with, 8.81 without (profiles/r2_history.md)
 #endif
 template <bool I2F> PT_DEVICE float byteToCoord(uint w, int j, uint one) { return I2F ? float((w >> (8 * j)) & 0xFFu) : (PT_PRMT_IMM ? byteToUnitFloatImm(w, j, one) : byteToUnitFloat(w, j)); }
 
