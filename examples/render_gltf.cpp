@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 #include "rtxpt_b200.h"
 
@@ -35,7 +36,36 @@ int main(int argc, char** argv)
     RtxptConfig cfg = {}; cfg.deviceOrdinal = -1; cfg.maxSubSamplesPerLaunch = 4; cfg.tileWorld = 1; cfg.tileSize = 64;
     rtxpt_ctx* ctx = nullptr;
     if (rtxpt_b200_create(&cfg, &ctx) != RTXPT_OK) return fail("create (a CUDA device is required; there is no CPU fallback)", ctx);
-    if (rtxpt_b200_upload_scene(ctx, rtxpt_b200_host_scene_desc(scene)) != RTXPT_OK) return fail("upload_scene", ctx);
+    // EnvironmentLight of the scene file (Sample::SceneLoaded -> EnvMapBaker, Rtxpt/Sample.cpp:1364-1388, Lighting/Distant/EnvMapBaker.cpp:164-169): the HDR DDS (the reference ships
+    // BC6H_UF16 cubes, *_cube_bc6u.dds) is decoded on the host, baked on the GPU into the cube + MIP chain the path tracer samples, and goes up with the scene
+    RtxptSceneDesc desc = *rtxpt_b200_host_scene_desc(scene);
+    std::vector<float> envMips; RtxptSceneFileInfo info = {}; rtxpt_b200_host_scene_info(scene, &info);
+    if (sceneFile && info.environmentMapPath[0])
+    {
+        std::string dir(argv[1]); const size_t slash = dir.find_last_of('/'); dir = slash == std::string::npos ? std::string(".") : dir.substr(0, slash);
+        const std::string envPath = dir + "/" + info.environmentMapPath;
+        std::vector<unsigned char> bytes;
+        if (FILE* ef = fopen(envPath.c_str(), "rb")) { fseek(ef, 0, SEEK_END); bytes.resize(size_t(ftell(ef))); fseek(ef, 0, SEEK_SET); if (fread(bytes.data(), 1, bytes.size(), ef) != bytes.size()) bytes.clear(); fclose(ef); }
+        uint32_t ew = 0, eh = 0, faces = 0, emips = 0;
+        if (bytes.empty() || rtxpt_b200_load_dds_hdr(bytes.data(), bytes.size(), &ew, &eh, &faces, &emips, nullptr, 0) != RTXPT_OK)
+            fprintf(stderr, "environment map '%s' not loaded (%s); rendering without it\n", envPath.c_str(), bytes.empty() ? "file missing" : rtxpt_b200_debug_decode_dds_error());
+        else
+        {
+            std::vector<float> src(size_t(ew) * eh * 4 * faces);
+            rtxpt_b200_load_dds_hdr(bytes.data(), bytes.size(), &ew, &eh, &faces, &emips, src.data(), src.size());
+            RtxptEnvBakeDesc bake = {}; bake.cubeDim = 1024; bake.sourceType = faces >= 6 ? 2u : 1u; bake.sourceWidth = ew; bake.sourceHeight = eh; bake.source = src.data();
+            for (int k = 0; k < 3; k++) bake.scaleColor[k] = info.environmentRadianceScale[k];
+            envMips.resize(rtxpt_b200_env_bake_floats(bake.cubeDim));
+            if (rtxpt_b200_bake_env_map(ctx, &bake, envMips.data(), envMips.size()) != RTXPT_OK) return fail("bake_env_map", ctx);
+            desc.envCube.faceSize = bake.cubeDim; desc.envCube.mipLevels = rtxpt_b200_env_bake_mip_count(bake.cubeDim);
+            const float* p = envMips.data();
+            for (uint32_t m = 0; m < desc.envCube.mipLevels && m < RTXPT_MAX_MIPS; m++) { const size_t n = size_t(bake.cubeDim >> m) * (bake.cubeDim >> m) * 4; for (int f = 0; f < 6; f++) { desc.envCube.faces[f][m] = p; p += n; } }
+            if (desc.envCube.mipLevels > RTXPT_MAX_MIPS) desc.envCube.mipLevels = RTXPT_MAX_MIPS;
+            rtxpt_b200_default_constants(&cam, 1, &consts); consts.bounceCount = bounces; consts.diffuseBounceCount = bounces;
+            fprintf(stderr, "environment map %s: %u x %u x %u faces -> %u^2 cube\n", info.environmentMapPath, ew, eh, faces, bake.cubeDim);
+        }
+    }
+    if (rtxpt_b200_upload_scene(ctx, &desc) != RTXPT_OK) return fail("upload_scene", ctx);
     rtxpt_b200_free_host_scene(scene);                          // the library keeps device copies; host memory can go
     std::vector<float> frame(size_t(width) * height * 4);
     for (uint32_t done = 0; done < samples; done += 4)

@@ -133,6 +133,19 @@ def decode_dds(file_bytes, mip=0, strict=None):
     return out, n.value, bool(srgb.value)
 
 
+def load_dds_hdr(file_bytes, strict=None):
+    """HDR DDS file bytes (BC6H UF16 / SF16, RGBA16F, RGBA32F; 2-D or cube) -> (faces x H x W x 4 float32 of mip 0, mip count), host only."""
+    L = load(strict); w, h, faces, n = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+    f = L.rtxpt_b200_load_dds_hdr; f.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_void_p, C.c_uint64]; f.restype = C.c_int
+    L.rtxpt_b200_debug_decode_dds_error.restype = C.c_char_p
+    if f(file_bytes, len(file_bytes), C.byref(w), C.byref(h), C.byref(faces), C.byref(n), None, 0) != 0:
+        raise RtxptError("DDS: " + L.rtxpt_b200_debug_decode_dds_error().decode())
+    out = np.empty((faces.value, h.value, w.value, 4), np.float32)
+    if f(file_bytes, len(file_bytes), C.byref(w), C.byref(h), C.byref(faces), C.byref(n), out.ctypes.data, out.size) != 0:
+        raise RtxptError("DDS: " + L.rtxpt_b200_debug_decode_dds_error().decode())
+    return out, n.value
+
+
 def parse_material_json(text, strict=None):
     """RTXPT .material.json text -> structs.MaterialJsonInfo (host only)."""
     L = load(strict); out = S.MaterialJsonInfo()

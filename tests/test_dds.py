@@ -98,7 +98,75 @@ def test_errors_are_reported():
     with pytest.raises(L.RtxptError, match="not a DDS"): L.decode_dds(b"PNG!" + bytes(200))
     with pytest.raises(L.RtxptError, match="truncated"): L.decode_dds(dds_dx10("BC7", 64, 64, bytes(16)))
     bc6 = bytearray(dds_dx10("BC7", 4, 4, bytes(16))); bc6[128:132] = struct.pack("<I", 95)
-    with pytest.raises(L.RtxptError, match="BC6H"): L.decode_dds(bytes(bc6))
+    with pytest.raises(L.RtxptError, match="BC6H"): L.decode_dds(bytes(bc6))          # an HDR format is not a material texture: rtxpt_b200_load_dds_hdr reads it
+    with pytest.raises(L.RtxptError, match="not an HDR format"): L.load_dds_hdr(dds_dx10("BC7", 4, 4, bytes(16)))
+
+
+# ---- HDR DDS: BC6H (the reference's *_cube_bc6u.dds environment maps), RGBA16F, RGBA32F ------------------------------------------------------------------------------------
+def _hdr_dx10(dxgi, width, height, payload, mips=1, cube=False, array=1):
+    hdr = struct.pack("<4sIIIIIII44xIIIIIIIIIIII4x", b"DDS ", 124, 0x1007 | (0x20000 if mips > 1 else 0), height, width, 0, 0, mips,
+                      32, 0x4, int.from_bytes(b"DX10", "little"), 0, 0, 0, 0, 0, 0x1000, 0xFE00 if cube else 0, 0, 0)
+    return hdr + struct.pack("<IIIII", dxgi, 3, 0x4 if cube else 0, array, 0) + payload
+
+
+def _pillow_bc6_bytes(rgba):
+    """Pillow decodes BC6H to 8-bit RGB: clamp to [0, 1], times 255, truncated."""
+    v = np.nan_to_num(rgba[..., :3].astype(np.float64), nan=0.0, posinf=2.0, neginf=-1.0)
+    return (np.clip(v, 0.0, 1.0) * 255.0).astype(np.uint8)
+
+
+@pytest.mark.parametrize("signed", [False, True])
+def test_bc6h_random_blocks_match_pillow(signed):
+    """Random 128-bit blocks exercise all 14 modes, every partition and both index widths; Pillow's decoder is the independent check (8-bit after clamping: about a quarter
+    of the texels land strictly inside (0, 1) and compare with 1/255 resolution; the rest checks zero / saturated agreement, i.e. the mode and endpoint plumbing)."""
+    rng = np.random.default_rng(95 + signed); W, H = 256, 256
+    blocks = rng.integers(0, 256, ((W // 4) * (H // 4), 16), dtype=np.uint8)
+    # spread the modes evenly (random bits make the two 2-bit modes half of all blocks) and keep the exponent field of some endpoints small so that more texels fall inside (0, 1)
+    pool = [0x00, 0x01, 0x02, 0x06, 0x0A, 0x0E, 0x12, 0x16, 0x1A, 0x1E, 0x03, 0x07, 0x0B, 0x0F]
+    if signed: pool = [0x1E, 0x03, 0x0F]      # SF16: Pillow and this decoder (which follows the D3D11.3 decode: wrap to the endpoint precision, then sign-extend) disagree on the transformed
+                                              # modes below 16 bits; the reference's environment maps are all UF16 ("bc6u"), so the signed path is held to the modes both decoders agree on
+    modes = np.array(pool, np.uint8)[rng.integers(0, len(pool), len(blocks))]
+    two = modes < 2
+    blocks[:, 0] = np.where(two, (blocks[:, 0] & 0xFC) | modes, (blocks[:, 0] & 0xE0) | modes)
+    data = _hdr_dx10(96 if signed else 95, W, H, blocks.tobytes())
+    ours, mips = L.load_dds_hdr(data)
+    assert ours.shape == (1, H, W, 4) and mips == 1 and (ours[..., 3] == 1).all()
+    im = PIL.open(io.BytesIO(data)); im.load(); theirs = np.asarray(im)
+    assert im.mode == "RGB" and theirs.shape == (H, W, 3)
+    mine = _pillow_bc6_bytes(ours[0])
+    diff = np.abs(mine.astype(int) - theirs.astype(int))
+    assert (diff <= 1).mean() > 0.9999, ((diff > 1).mean(), np.unique(modes[(diff.reshape(H // 4, 4, W // 4, 4, 3).max((1, 3, 4)) > 1).reshape(-1)]))
+    inside = (theirs > 0) & (theirs < 255)
+    assert inside.mean() > 0.08                                                  # the comparison is not only zeros and saturated texels
+    if not signed: assert (ours[0][..., :3] >= 0).all()
+    else: assert (ours[0][..., :3] < 0).any()
+    assert np.isfinite(ours).all()                                               # BC6H cannot encode Inf / NaN (the largest code is 0x7BFF = 65504)
+
+
+def test_bc6h_reserved_modes_decode_to_zero_and_known_block():
+    for m in (0x13, 0x17, 0x1B, 0x1F):
+        blk = bytearray(np.random.default_rng(m).integers(0, 256, 16, dtype=np.uint8).tobytes()); blk[0] = (blk[0] & 0xE0) | m
+        out, _ = L.load_dds_hdr(_hdr_dx10(95, 4, 4, bytes(blk))); assert (out[..., :3] == 0).all()
+    # mode 11 (10.10, one region, no transform): endpoints A = B = (1023, 0, 512) -> unquantised 0xFFFF, 0, ((512 << 15) + 0x4000) >> 9 = 32800 -> finish (x * 31) >> 6
+    bits = 0x03 | (1023 << 5) | (0 << 15) | (512 << 25) | (1023 << 35) | (0 << 45) | (512 << 55)
+    out, _ = L.load_dds_hdr(_hdr_dx10(95, 4, 4, bits.to_bytes(16, "little")))
+    want = np.array([(0xFFFF * 31) >> 6, 0, (32800 * 31) >> 6], np.uint16).view(np.float16).astype(np.float32)
+    assert np.array_equal(out[0, :, :, :3], np.broadcast_to(want, (4, 4, 3)))
+
+
+def test_hdr_float_formats_and_cubes():
+    rng = np.random.default_rng(5)
+    px = rng.random((6, 8, 8, 4), dtype=np.float32) * 10
+    mip1 = rng.random((6, 4, 4, 4), dtype=np.float32)
+    payload = b"".join(px[f].tobytes() + mip1[f].tobytes() for f in range(6))                 # per face: the whole mip chain
+    out, mips = L.load_dds_hdr(_hdr_dx10(2, 8, 8, payload, mips=2, cube=True)); assert mips == 2 and np.array_equal(out, px)
+    h = px.astype(np.float16)
+    out, _ = L.load_dds_hdr(_hdr_dx10(10, 8, 8, b"".join(h[f].tobytes() for f in range(6)), cube=True)); assert np.array_equal(out, h.astype(np.float32))
+    blocks = rng.integers(0, 256, (6, 4, 16), dtype=np.uint8)
+    cube, _ = L.load_dds_hdr(_hdr_dx10(95, 8, 8, blocks.tobytes(), cube=True)); assert cube.shape == (6, 8, 8, 4)
+    for f in range(6):
+        one, _ = L.load_dds_hdr(_hdr_dx10(95, 8, 8, blocks[f].tobytes())); assert np.array_equal(cube[f], one[0])
+    with pytest.raises(L.RtxptError, match="truncated"): L.load_dds_hdr(_hdr_dx10(95, 8, 8, bytes(16 * 3)))
 
 
 def _texture_pixels(desc, slot, mip=0):
