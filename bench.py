@@ -203,7 +203,9 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     scene, consts = build_workload()
-    ctx = lib.Context(max_sub_samples_per_launch=SPP, device=local_rank, tile_rank=rank, tile_world=world, tile_size=64)
+    # tuning aid (not a bench mode): RTXPT_BENCH_EMULATE_WORLD=N on one GPU renders rank 0's tile set of an N-GPU job, i.e. what one rank of the strong-scaling run computes per frame
+    emulate = int(os.environ.get("RTXPT_BENCH_EMULATE_WORLD", "0")) if world == 1 else 0
+    ctx = lib.Context(max_sub_samples_per_launch=SPP, device=local_rank, tile_rank=rank if not emulate else 0, tile_world=world if not emulate else emulate, tile_size=64)
     ctx.upload_scene(scene)
     ctx.set_constants(consts)
     owned, padded = ctx.tile_layout()
@@ -302,12 +304,12 @@ def main():
     rays_per_bounce = [int(x) for x in st.raysPerBounce[:BOUNCES + 2]]
     scatter, shadow = int(st.scatterRays), int(st.shadowRays)
     if rank == 0:
-        ctx2 = lib.Context(max_sub_samples_per_launch=SPP, device=local_rank, tile_rank=rank, tile_world=world, tile_size=64, flags=S.CFG_COUNT_TRAVERSAL_STEPS)
+        ctx2 = lib.Context(max_sub_samples_per_launch=SPP, device=local_rank, tile_rank=rank if not emulate else 0, tile_world=world if not emulate else emulate, tile_size=64, flags=S.CFG_COUNT_TRAVERSAL_STEPS)
         ctx2.upload_scene(scene); consts.sampleBaseIndex = (args.warmup + args.steps - 1) * SPP; ctx2.set_constants(consts)
         ctx2.path_trace(0, SPP, True); ctx2.synchronize(); s2 = ctx2.stats(); ctx2.close()
         # per-kernel times: a context with CUDA events around every launch (RTXPT_CFG_TIME_KERNELS runs the kernels back to back, without the
         # shadow/closest overlap of the measured configuration), same frames, 3 warm-up + 1 measured
-        ctx3 = lib.Context(max_sub_samples_per_launch=SPP, device=local_rank, tile_rank=rank, tile_world=world, tile_size=64, flags=S.CFG_TIME_KERNELS)
+        ctx3 = lib.Context(max_sub_samples_per_launch=SPP, device=local_rank, tile_rank=rank if not emulate else 0, tile_world=world if not emulate else emulate, tile_size=64, flags=S.CFG_TIME_KERNELS)
         ctx3.upload_scene(scene)
         for i in range(4):
             consts.sampleBaseIndex = (args.warmup + args.steps - 4 + i) * SPP; ctx3.set_constants(consts); ctx3.path_trace(0, SPP, True)
@@ -357,7 +359,7 @@ def main():
                 "gpu_launches": int(launches * args.steps),
                 "rays_per_frame": rays_per_frame, "rays_per_path": rays_per_frame / (WIDTH * HEIGHT * SPP), "scatter_rays": scatter, "shadow_rays": shadow,
                 "rays_per_iteration": rays_per_bounce, "bvh_build_s": st.bvhBuildSeconds, "bvh_nodes": st.bvhNodeCount, "lights": st.lightCount,
-                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "phases": phases,
+                "emulated_world": emulate or None, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "phases": phases,
                 "config3": (realtime or {}).get("config3") if isinstance(realtime, dict) else None, "realtime": realtime}
         sys.stdout.flush(); os.write(real_stdout, (json.dumps(line) + "\n").encode())
     ctx.close()

@@ -118,8 +118,11 @@ __global__ void __launch_bounds__(256) k_rt_fill_generate(const __grid_constant_
 }
 
 // ---- shade ------------------------------------------------------------------------------------------------------------------------------------------------------
+#ifndef PT_RT_SHADE_CTAS
+#define PT_RT_SHADE_CTAS 3      // resident CTAs of 128 threads per SM: 3 -> up to 170 registers (the kernels use 153-158, no spills)
+#endif
 template <int MODE, bool ANALYTIC_LIGHTS, bool NEEAT = false>
-__global__ void __launch_bounds__(128, 3) k_rt_shade(const __grid_constant__ LaunchParams p)
+__global__ void __launch_bounds__(128, PT_RT_SHADE_CTAS) k_rt_shade(const __grid_constant__ LaunchParams p)
 {
     uint* ctr = p.wf.counters + p.iteration * kCountersPerIter;
     uint* ctrNext = ctr + kCountersPerIter;
@@ -226,12 +229,12 @@ void launchRtBuildGenerate(const LaunchParams& p, const GridConfig& g, cudaStrea
 void launchRtFillGenerate(const LaunchParams& p, const GridConfig& g, cudaStream_t s) { k_rt_fill_generate<<<g.smCount * 4, 256, 0, s>>>(p); }
 void launchRtShadeNeeat(const LaunchParams& p, const GridConfig& g, cudaStream_t s)
 {   // FILL pass with NEE-AT feedback: tile-sampler candidates, MIS against the global table, feedback records for the shadow kernel
-    const int grid = g.smCount * 3;
+    const int grid = g.smCount * PT_RT_SHADE_CTAS;
     if (p.scene.analyticLightCount != 0) k_rt_shade<kModeFillStablePlanes, true, true><<<grid, 128, 0, s>>>(p); else k_rt_shade<kModeFillStablePlanes, false, true><<<grid, 128, 0, s>>>(p);
 }
 void launchRtShade(const LaunchParams& p, const GridConfig& g, bool fill, cudaStream_t s)
 {
-    const int grid = g.smCount * 3;
+    const int grid = g.smCount * PT_RT_SHADE_CTAS;
     if (!fill) { if (p.scene.analyticLightCount != 0) k_rt_shade<kModeBuildStablePlanes, true><<<grid, 128, 0, s>>>(p); else k_rt_shade<kModeBuildStablePlanes, false><<<grid, 128, 0, s>>>(p); }
     else { if (p.scene.analyticLightCount != 0) k_rt_shade<kModeFillStablePlanes, true><<<grid, 128, 0, s>>>(p); else k_rt_shade<kModeFillStablePlanes, false><<<grid, 128, 0, s>>>(p); }
 }
