@@ -1,5 +1,5 @@
 """CPU: the environment-map baking path: the oracle's restatement of EnvMapBaker (oracle/pt_envbake.h) held to what the bake guarantees, and the product's
-pass bodies (rtxpt_b200/csrc/envbake.cuh, compiled for the host by tests/emu) equal to the oracle.  GPU: tests/test_gpu_envbake.py (gpu_unverified)."""
+pass bodies (rtxpt_b200/csrc/envbake.cuh, compiled for the host by tests/emu) equal to the oracle.  GPU: tests/test_gpu_envbake.py (-m gpu)."""
 import ctypes as C
 import numpy as np
 import pytest

@@ -163,10 +163,10 @@ def test_cpp_host_example_without_gpu(product, tmp_path):
     assert r.returncode == 1 and "no CPU fallback" in r.stderr
 
 
-@pytest.mark.gpu_unverified
+@pytest.mark.gpu
 def test_cpp_realtime_example_writes_a_tone_mapped_frame(product, tmp_path):
     """glTF file -> examples/realtime_gltf.cpp (NEE-AT update, stable-plane BUILD/FILL, ReBLUR, tone mapping through the C ABI only) -> PPM: the box is lit, not saturated, and the
-    image differs from a flat fill.  Written after the round's GPU budget ran out - never run on a GPU (scripts/gpu_verify_round2.sh)."""
+    image differs from a flat fill.  First run on a B200 in round 2."""
     import subprocess
     from rtxpt_b200 import scenes
     exe = os.path.join(os.path.dirname(product.LIB_PATH), "realtime_gltf")

@@ -3,12 +3,11 @@ C ABI: realtime path trace -> rtxpt_b200_denoiser_prepare_inputs -> rtxpt_b200_r
 its own history.  Values are fp16 images; the two sides differ by libdevice vs glibc transcendentals (exp, pow, atan, log) in weights, so the bar is agreement within a few fp16
 steps on nearly every pixel plus identical history-length bookkeeping, stated per assert.
 
-NOT YET RUN ON A GPU: written after the round-1 GPU budget was spent.  Every test here is `gpu_unverified` (collected by -m gpu_unverified only) until it has passed on a B200;
-the tolerances are first estimates to be replaced by measured ones."""
+First run on a B200 in round 2 (scripts/gpu_verify_round2.sh, gpu_batch2.sh, gpu_batch3.sh); tolerances marked "measured" come from those runs."""
 import numpy as np
 import pytest
 
-unverified = pytest.mark.gpu_unverified
+unverified = pytest.mark.gpu          # promoted in round 2 after the first green runs on a B200 (the name is kept so that the history of each test stays readable)
 
 
 def _scene(product, strict, W, H):

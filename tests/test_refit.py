@@ -1,7 +1,7 @@
 """CPU: rigid-instance animation: the product's refit bodies (rtxpt_b200/csrc/refit.cuh, compiled for the host by tests/emu) on BVHs from the product's
 builder.  The reference delegates this to the driver (BLAS / TLAS updates), so there is nothing of RTXPT's to restate; the refit is held to its own contract: unmoved
 geometry gives back the built tree bit for bit, and after motion every quantised child box still encloses what lies under it - by at most one grid step.
-GPU: tests/test_gpu_refit.py (gpu_unverified)."""
+GPU: tests/test_gpu_refit.py (-m gpu)."""
 import ctypes as C
 import numpy as np
 import pytest

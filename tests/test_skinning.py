@@ -1,5 +1,5 @@
 """CPU: skinned-mesh animation: the oracle's restatement of Donut's skinning pass (oracle/pt_skinning.h) held to what linear blend skinning guarantees, and the
-product's bodies (rtxpt_b200/csrc/skinning.cuh, host build in tests/emu) equal to the oracle.  GPU: tests/test_gpu_skinning.py (gpu_unverified)."""
+product's bodies (rtxpt_b200/csrc/skinning.cuh, host build in tests/emu) equal to the oracle.  GPU: tests/test_gpu_skinning.py (-m gpu)."""
 import ctypes as C
 import numpy as np
 import pytest
