@@ -42,7 +42,19 @@ PT_HD bool beyondDenoisingRange(const Params& p, int x, int y)
 }
 
 // ---- HitDistReconstruction 5x5: in -> tmp2 ------------------------------------------------------------------------------------------------------------------------
-PT_HD void hitDistReconstructionPixel(const Params& p, const int x, const int y)
+// The 5x5 neighbourhood comes through a tap source: straight from global memory (GlobalTaps: the host build and the border tiles' fallback) or from the CTA's shared-memory
+// tile (reblur_kernels.cu: viewZ, the UNPACKED normal / roughness and the two hit distances of the 20x20 region staged by TMA) - what NRD's PRELOAD_INTO_SMEM does for the same
+// pass (External/Nrd/Shaders/Include/Common.hlsli:143-175): the saving is the 24 normal unpacks and clamped address computations per pixel, not bandwidth.
+struct GlobalTaps
+{
+    const Params& p; int W, H;
+    PT_HD float viewZ(int qx, int qy) const { return viewZAt(p, qx, qy); }                     // callers pass clamped coordinates
+    PT_HD float4 normalRoughness(int qx, int qy) const { float m; return unpackNormalRoughness(p.normalRoughness[size_t(qy) * W + qx], m); }
+    PT_HD float diffHitDist(int qx, int qy) const { return f16tof32(p.inDiff[size_t(qy) * W + qx].y >> 16); }
+    PT_HD float specHitDist(int qx, int qy) const { return f16tof32(p.inSpec[size_t(qy) * W + qx].y >> 16); }
+};
+template <typename Taps>
+PT_HD void hitDistReconstructionBody(const Params& p, const int x, const int y, const Taps& taps)
 {
     RB_PIXEL_PROLOGUE;
     float mid; const float4 nr = unpackNormalRoughness(p.normalRoughness[pix], mid);
@@ -56,15 +68,15 @@ PT_HD void hitDistReconstructionPixel(const Params& p, const int x, const int y)
     for (int j = -2; j <= 2; j++) for (int i = -2; i <= 2; i++)
     {
         if (i == 0 && j == 0) continue;
-        const int qx = clampi(x + i, 0, W - 1), qy = clampi(y + j, 0, H - 1); const size_t q = size_t(qy) * W + qx;
+        const int qx = clampi(x + i, 0, W - 1), qy = clampi(y + j, 0, H - 1);
         const float2 uv = mk2(pixelUv.x + float(i) * rectSizeInv.x, pixelUv.y + float(j) * rectSizeInv.y);
         float w = inScreen(uv) ? 1.0f : 0.0f;
         w *= gaussianWeight(sqrtf(float(i * i + j * j)) * 0.5f);
-        w *= weight(dot3(Nv, reconstructViewPosition(p.frustum, uv, viewZAt(p, qx, qy))), gw.x, gw.y);
-        float ms; const float4 ns = unpackNormalRoughness(p.normalRoughness[q], ms);
+        w *= weight(dot3(Nv, reconstructViewPosition(p.frustum, uv, taps.viewZ(qx, qy))), gw.x, gw.y);
+        const float4 ns = taps.normalRoughness(qx, qy);
         const float angle = acosApprox(dot3(N, xyz(ns)));
         float wx = w * exponentialWeight(angle, diffNormalW, 0.0f), wy = w * exponentialWeight(angle, specNormalW, 0.0f) * exponentialWeight(ns.w * ns.w, rw.x, rw.y);
-        float dx = f16tof32(p.inDiff[q].y >> 16), dy = f16tof32(p.inSpec[q].y >> 16);
+        float dx = taps.diffHitDist(qx, qy), dy = taps.specHitDist(qx, qy);
         if (wx == 0.0f) dx = 0.0f; if (wy == 0.0f) dy = 0.0f;
         wx = dx != 0.0f ? wx : 0.0f; wy = dy != 0.0f ? wy : 0.0f;
         cx += dx * wx; cy += dy * wy; sx += wx; sy += wy;
@@ -72,6 +84,7 @@ PT_HD void hitDistReconstructionPixel(const Params& p, const int x, const int y)
     cx /= fmaxf(sx, kEps); cy /= fmaxf(sy, kEps);
     p.tmp2Diff[pix] = packRGBA16F(make_float4(d.x, d.y, d.z, cx)); p.tmp2Spec[pix] = packRGBA16F(make_float4(s.x, s.y, s.z, cy));
 }
+PT_HD void hitDistReconstructionPixel(const Params& p, const int x, const int y) { const GlobalTaps t{ p, int(p.W), int(p.H) }; hitDistReconstructionBody(p, x, y, t); }
 
 // ---- spatial passes ----------------------------------------------------------------------------------------------------------------------------------------------------
 // MODE 0 PrePass: tmp2 -> tmp1 (+ hit distance for tracking); 1 Blur: tmp1 -> tmp2 (+ viewZ copy into the history); 2 PostBlur: tmp2 -> history (+ normal/roughness copy)
