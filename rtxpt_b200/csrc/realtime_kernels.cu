@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) k_rt_fill_generate(const __grid_constant_
 
 // ---- shade ------------------------------------------------------------------------------------------------------------------------------------------------------
 #ifndef PT_RT_SHADE_CTAS
-#define PT_RT_SHADE_CTAS 3      // resident CTAs of 128 threads per SM: 3 -> up to 170 registers (the kernels use 153-158, no spills)
+#define PT_RT_SHADE_CTAS 4      // resident CTAs of 128 threads per SM.  Measured on a B200 (config-3 frame, trace ms): 3 CTAs (153-158 registers, no spills) 32.7, 4 CTAs (128 registers, 24-88 B spills) 32.0
 #endif
 template <int MODE, bool ANALYTIC_LIGHTS, bool NEEAT = false>
 __global__ void __launch_bounds__(128, PT_RT_SHADE_CTAS) k_rt_shade(const __grid_constant__ LaunchParams p)
