@@ -62,7 +62,7 @@ struct rtxpt_ctx
     bool haveScene = false, haveConstants = false, lightsDirty = true;
     size_t l2PersistBytes = 0, l2WindowMax = 0;
     // measurement knobs, read from the environment once at creation (defaults are the measured optimum on B200, profiles/r1_history.md)
-    struct Tuning { int refillThreshold = 24, waitFlushLanes = 8, traceCtas = 4, shadeCtas = 4, smemNodes = 0, lanes = 1; } tune;
+    struct Tuning { int refillThreshold = 24, waitFlushLanes = 8, traceCtas = 4, shadeCtas = 4, smemNodes = 0, lanes = 1, shadowLpt = 1; } tune; float sceneDiagonal = 0;
     cudaStream_t stream2 = nullptr; cudaEvent_t evShadeDone = nullptr, evShadowDone = nullptr; bool overlapShadow = true;
     // pipeline lanes: the sub-samples of one launch are split into independent wavefronts, each on its own pair of streams, so that the latency-bound tail of every
     // persistent kernel of one lane (its last, longest rays) is filled by the CTAs of the other lanes.  Lane 0 is (caller stream, stream2).
@@ -198,6 +198,7 @@ extern "C" RTXPT_API int rtxpt_b200_create(const RtxptConfig* config, rtxpt_ctx*
     auto envInt = [](const char* name, int def, int lo, int hi) { const char* e = getenv(name); return e ? std::min(hi, std::max(lo, atoi(e))) : def; };
     c->tune.refillThreshold = envInt("RTXPT_REFILL_THRESHOLD", 24, 1, 32); c->tune.waitFlushLanes = envInt("RTXPT_WAIT_FLUSH", 8, 1, 33);
     c->tune.traceCtas = envInt("RTXPT_TRACE_CTAS", 4, 2, 4); c->tune.shadeCtas = envInt("RTXPT_SHADE_CTAS", 4, 3, 5); c->tune.smemNodes = envInt("RTXPT_SMEM_NODES", 0, 0, 1 << 20);
+    c->tune.shadowLpt = envInt("RTXPT_SHADOW_LPT", 1, 0, 1);
     c->tune.lanes = envInt("RTXPT_LANES", 1, 1, rtxpt_ctx::kMaxLanes);          // measured on a B200, 1080p 4 spp: 1 lane 18.61 ms, 2 lanes 18.79, 4 lanes 19.51 (one GPU has enough rays per wavefront; lanes are for small per-rank tile sets)
     cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming);
     for (int l = 1; l < rtxpt_ctx::kMaxLanes; l++) { cudaStreamCreateWithFlags(&c->lanes[l].s, cudaStreamNonBlocking); cudaStreamCreateWithFlags(&c->lanes[l].s2, cudaStreamNonBlocking); }
@@ -421,6 +422,7 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
     Bvh8 bvh;
     buildBvh8(tris, bvh);
     c->bvhBuildSeconds = float(bvh.buildSeconds);
+    { const float dx = bvh.sceneHi[0] - bvh.sceneLo[0], dy = bvh.sceneHi[1] - bvh.sceneLo[1], dz = bvh.sceneHi[2] - bvh.sceneLo[2]; c->sceneDiagonal = tris.empty() ? 0.0f : sqrtf(dx * dx + dy * dy + dz * dz); }
     c->bvhNodeCount = uint32_t(bvh.nodes.size()); c->bvhTriCount = uint32_t(bvh.tris.size());
     cudaStream_t s = c->stream;
     CU(c->dBvhNodes.upload(reinterpret_cast<const uint4*>(bvh.nodes.data()), bvh.nodes.size() * 5, s));
@@ -596,6 +598,7 @@ static void fillParams(rtxpt_ctx* c, LaunchParams& p)
     p.c = c->consts;
     p.flags = c->cfg.flags;
     p.refillThreshold = c->tune.refillThreshold; p.waitFlushLanes = c->tune.waitFlushLanes;
+    p.shadowLongRayT = c->tune.shadowLpt ? 0.25f * c->sceneDiagonal : 3.0e38f;        // 3e38: every record goes to the back, i.e. one queue in reverse order
     p.outputColor = c->outputColor.ptr; p.accumulated = c->accumulated.ptr; p.depth = c->depth.ptr; p.motionVectors = c->motionVectors.ptr; p.throughput = c->throughput.ptr;
     memcpy(p.worldToClip, c->worldToClip, sizeof(p.worldToClip)); p.exportGuides = ((c->cfg.flags & RTXPT_CFG_EXPORT_GUIDES) && c->haveView) ? 1u : 0u;
     // traversal occupancy and the shared-memory BVH prefix are chosen together: B resident CTAs of 256 threads per SM (register budget
@@ -1347,7 +1350,7 @@ extern "C" RTXPT_API int rtxpt_b200_get_stats(rtxpt_ctx* c, RtxptStats* out)
             for (uint32_t l = 0; l < c->lastLanes; l++)        // the lanes of the last batch each counted their own wavefront
             {
                 const uint32_t* k = c->hCounters + size_t(l) * kCounterWords + it * kCountersPerIter;
-                scatter += k[kCtrRayCount]; shadow += k[kCtrShadowCount]; nodes += k[kCtrNodeVisits]; tests += k[kCtrTriTests];
+                scatter += k[kCtrRayCount]; shadow += k[kCtrShadowCount] + k[kCtrShadowShort]; nodes += k[kCtrNodeVisits]; tests += k[kCtrTriTests];
                 snodes += k[kCtrShadowNodeVisits]; stests += k[kCtrShadowTriTests]; raysThisIteration += k[kCtrRayCount];
             }
             if (it < 16) out->raysPerBounce[it] = uint64_t(raysThisIteration * scale);

@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB * kTraceCtaScale) k_trace_
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     uint* ctr = p.wf.counters + p.iteration * kCountersPerIter;
-    const uint count = ctr[kCtrShadowCount];
+    const uint frontCount = ctr[kCtrShadowCount], count = frontCount + ctr[kCtrShadowShort];      // long rays first (wavefront.cuh: appendShadowRecord)
     if (count == 0) return;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smemRaw);
     WarpScratch& ws = reinterpret_cast<WarpScratch*>(smemRaw + 16)[threadIdx.x >> 5];
@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB * kTraceCtaScale) k_trace_
                 if (record >= count) exhausted = true;
                 else
                 {
+                    record = shadowRecordIndex(record, frontCount, p.wf.capacity);
                     const float4 ot = p.wf.shadowOriginTMax[record], dp = p.wf.shadowDirPath[record];
                     slot = __float_as_uint(dp.w);
                     tv.init(p.scene, ws, mk3(ot.x, ot.y, ot.z), mk3(dp.x, dp.y, dp.z), 0.0f, ot.w);

@@ -162,13 +162,9 @@ __global__ void __launch_bounds__(128, PT_RT_SHADE_CTAS) k_rt_shade(const __grid
             appendRay(nextQueue, ctrNext + kCtrRayCount, continues, rayEntry);
             if constexpr (MODE == kModeFillStablePlanes)
             {
-                const uint peers = __ballot_sync(0xFFFFFFFFu, shadow);
+                const uint b = appendShadowRecord(p, ctr, shadow, out.shadow.originTMax.w);
                 if (shadow)
                 {
-                    const uint leader = __ffs(peers) - 1u;
-                    uint b = 0;
-                    if (lane == leader) b = atomicAdd(ctr + kCtrShadowCount, __popc(peers));
-                    b = __shfl_sync(peers, b, leader) + __popc(peers & ((1u << lane) - 1u));
                     p.wf.shadowOriginTMax[b] = out.shadow.originTMax; p.wf.shadowDirPath[b] = out.shadow.dirPath; p.wf.shadowRadiance[b] = out.shadow.radiance;
                     if constexpr (NEEAT) p.naShadowFeedback[b] = out.naRecord;
                 }

@@ -67,15 +67,11 @@ __global__ void __launch_bounds__(128, MINB) k_shade(const __grid_constant__ Lau
                 if (out.emitShadow) shadowCls = 0;
             }
             warpAppend(nextQueue, 0, ctrNext + kCtrRayCount, rayCls, rayEntry);
-            // shadow records: same aggregation, three arrays
+            // shadow records: warp-aggregated, long rays from the front of the three arrays, the rest from the back (appendShadowRecord)
             {
-                const uint peers = __ballot_sync(0xFFFFFFFFu, shadowCls == 0);
+                const uint b = appendShadowRecord(p, ctr, shadowCls == 0, out.shadow.originTMax.w);
                 if (shadowCls == 0)
                 {
-                    const uint leader = __ffs(peers) - 1u;
-                    uint b = 0;
-                    if (lane == leader) b = atomicAdd(ctr + kCtrShadowCount, __popc(peers));
-                    b = __shfl_sync(peers, b, leader) + __popc(peers & ((1u << lane) - 1u));
                     p.wf.shadowOriginTMax[b] = out.shadow.originTMax; p.wf.shadowDirPath[b] = out.shadow.dirPath; p.wf.shadowRadiance[b] = out.shadow.radiance;
                     if constexpr (NEEAT) p.naShadowFeedback[b] = out.naRecord;
                 }

@@ -47,8 +47,9 @@ constexpr int kCtrShadowNodeVisits = kCtrShadowVisible + 1;  // any-hit traversa
 constexpr int kCtrShadowTriTests = kCtrShadowNodeVisits + 1;
 constexpr int kCtrFetchClosest = kCtrShadowTriTests + 1;    // dynamic ray fetch cursors of the persistent traversal warps
 constexpr int kCtrFetchShadow = kCtrFetchClosest + 1;
-static_assert(kCtrFetchShadow < 16, "counter block");
-constexpr int kCountersPerIter = 16;
+constexpr int kCtrShadowShort = kCtrFetchShadow + 1;        // shadow records appended from the END of the record arrays (see appendShadowRecord); kCtrShadowCount counts the ones at the front
+static_assert(kCtrShadowShort < 20, "counter block");
+constexpr int kCountersPerIter = 20;
 
 // realtime mode (stable planes): the reference's u_StablePlanesHeader / u_StablePlanesBuffer / u_StableRadiance / u_SpecularHitT and the
 // realtime fields of PathTracerConstants (StablePlanes.hlsli:82-274, PathTracerShared.h:57-80)
@@ -69,6 +70,12 @@ struct RealtimeParams
     RtxptDenoiserConstants dn; uint dnPlane, dnInitWithStableRadiance;
 };
 
+struct LaunchParams;
+// Shadow records are appended from both ends of the record arrays: rays with a long way to go (tMax above LaunchParams::shadowLongRayT: environment and far-light samples,
+// which walk most of the scene when nothing blocks them) at the front, the rest from the back.  The persistent any-hit kernel fetches front to back, so the longest traversals of a
+// launch start first and its tail - one warp finishing a 100+ node walk while 147 SMs idle - overlaps the bulk of the short rays (longest-processing-time-first).  Index of a record:
+PT_DEVICE uint shadowRecordIndex(uint i, uint frontCount, uint capacity) { return i < frontCount ? i : capacity - 1u - (i - frontCount); }
+
 struct LaunchParams
 {
     SceneView scene;
@@ -81,6 +88,7 @@ struct LaunchParams
     uint flags;
     int refillThreshold;            // dynamic fetch: a warp refills its idle lanes when fewer than this many lanes are still traversing
     int waitFlushLanes;             // a partial group of triangle tests is drained once this many lanes wait for nothing but their results
+    float shadowLongRayT;           // shadow rays with tMax above this are queued at the front (a quarter of the scene diagonal)
     // render targets
     uint2* outputColor;             // RGBA16F, full frame, last sub-sample
     float4* accumulated;            // RGBA32F, full frame
@@ -96,6 +104,20 @@ struct LaunchParams
     uint4* naShadowFeedback;        // per shadow record: light | ssc << 31, feedback weight, reservoir random, Russian roulette outcome had the sample been visible
     uint* naRrFix;                  // per path slot: set by the shadow kernel when the sample was visible, consumed by the next shade of the path
 };
+
+// every lane of the warp calls this; `emit` lanes get the index of their shadow record
+PT_DEVICE uint appendShadowRecord(const LaunchParams& p, uint* ctr, bool emit, float tMax)
+{
+    const uint lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    const bool isLong = emit && tMax > p.shadowLongRayT;
+    const uint longPeers = __ballot_sync(0xFFFFFFFFu, isLong), shortPeers = __ballot_sync(0xFFFFFFFFu, emit && !isLong);
+    uint bl = 0, bs = 0;
+    if (longPeers && lane == __ffs(longPeers) - 1u) bl = atomicAdd(ctr + kCtrShadowCount, __popc(longPeers));
+    if (shortPeers && lane == __ffs(shortPeers) - 1u) bs = atomicAdd(ctr + kCtrShadowShort, __popc(shortPeers));
+    if (longPeers) bl = __shfl_sync(0xFFFFFFFFu, bl, __ffs(longPeers) - 1);
+    if (shortPeers) bs = __shfl_sync(0xFFFFFFFFu, bs, __ffs(shortPeers) - 1);
+    return isLong ? bl + __popc(longPeers & lt) : p.wf.capacity - 1u - (bs + __popc(shortPeers & lt));
+}
 
 // ---- stable-plane addressing (GenericTS, Utils.hlsli:320-362; StablePlanes.hlsli:120-140): host+device so that the denoiser interface's pixel bodies also build for the host ----
 constexpr uint kInvalidBranchID = 0xFFFFFFFFu;
