@@ -116,7 +116,7 @@ void launchReblurFrame(const rb::Params& p, cudaStream_t s)
 {
     const dim3 grid((p.W + 15) / 16, (p.H + 15) / 16), block(16, 16);
     rb::k_rb_classify_tiles<<<grid, block, 0, s>>>(p);
-    static const bool tiled = [] { const char* e = getenv("RTXPT_REBLUR_TILED"); return !e || atoi(e) != 0; }();
+    static const bool tiled = [] { const char* e = getenv("RTXPT_REBLUR_TILED"); return e && atoi(e) != 0; }();          // opt-in until its first green GPU run
     if (tiled)
     {
         rb::HitDistTileMaps maps; memset(&maps, 0, sizeof(maps));
