@@ -141,7 +141,12 @@ typedef struct RtxptBufferDesc {
 enum {
     RTXPT_FORMAT_RGBA8_UNORM = 0,
     RTXPT_FORMAT_RGBA8_SRGB  = 1,   /* sRGB-decoded on fetch, like the reference's per-slot sRGB views (Materials/MaterialsBaker.cpp:63-72) */
-    RTXPT_FORMAT_RGBA32_FLOAT = 2
+    RTXPT_FORMAT_RGBA32_FLOAT = 2,
+    /* Block-compressed textures kept compressed in HBM and decoded by the texture units on fetch, as the reference does (its .dds assets go to D3D block-compressed formats through
+     * Donut's DDSFile.cpp / TextureCache.cpp): mips[] hold the raw 4x4 blocks, rows of ceil(w/4) blocks, 8 (BC1) or 16 (BC2/3/7) bytes each.  4-8x less texture memory and traffic
+     * than the RGBA8 expansion.  The *_SRGB variants decode sRGB -> linear on fetch (base colour / emissive slots, Materials/MaterialsBaker.cpp:63-72). */
+    RTXPT_FORMAT_BC1_UNORM = 3, RTXPT_FORMAT_BC1_SRGB = 4, RTXPT_FORMAT_BC2_UNORM = 5, RTXPT_FORMAT_BC2_SRGB = 6,
+    RTXPT_FORMAT_BC3_UNORM = 7, RTXPT_FORMAT_BC3_SRGB = 8, RTXPT_FORMAT_BC7_UNORM = 9, RTXPT_FORMAT_BC7_SRGB = 10
 };
 #define RTXPT_MAX_MIPS 16
 typedef struct RtxptTextureDesc {
@@ -557,6 +562,9 @@ typedef struct RtxptSceneFileInfo {
     char     startingCamera[64];
     uint32_t modelCount, directionalLightCount; /* directional lights are folded into the environment map by the reference and are not in the light list */
 } RtxptSceneFileInfo;
+/* Loader option (process-wide, default off): keep BC1 / BC2 / BC3 / BC7 .dds textures block-compressed (RTXPT_FORMAT_BC*) instead of expanding them to RGBA8 on the host; BC4 / BC5
+ * (one / two channels) are always expanded, their channel layout differs from what the material code reads. */
+RTXPT_API void rtxpt_b200_loader_keep_block_compression(int enable);
 RTXPT_API int rtxpt_b200_load_gltf(const char* path, rtxpt_host_scene** outScene);
 /* Same, with RTXPT's material files applied on top of the glTF materials the way MaterialsBaker does (Rtxpt/Materials/MaterialsBaker.cpp:707-747, :868-917):
  * for a glTF material <name> of model file <model>.gltf the first existing of <sceneMaterialsDir>/<model>.<name>.material.json, <sceneMaterialsDir>/<name>.material.json,

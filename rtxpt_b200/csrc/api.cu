@@ -22,6 +22,7 @@
 #include <vector>
 
 using namespace pt;
+namespace rtxpt_host { void decodeBlocksToRgba8(uint32_t format, const uint8_t* blocks, uint32_t w, uint32_t h, std::vector<uint8_t>& rgba); }      // dds.cpp
 
 static_assert(sizeof(RtxptGeometryData) == 64, "GeometryData layout");
 static_assert(sizeof(RtxptInstanceData) == 112, "InstanceData layout");
@@ -263,11 +264,29 @@ extern "C" RTXPT_API int rtxpt_b200_destroy(rtxpt_ctx* c)
 }
 
 // ---- textures ----------------------------------------------------------------------------------------------------------------------
+static bool isBlockCompressed(uint32_t format) { return format >= RTXPT_FORMAT_BC1_UNORM && format <= RTXPT_FORMAT_BC7_SRGB; }
 static int createTexture2D(const RtxptTextureDesc& d, DeviceTexture& out)
 {
     if (d.width == 0 || d.height == 0 || d.mipLevels == 0 || d.mipLevels > RTXPT_MAX_MIPS) return fail(RTXPT_ERR_INVALID_ARGUMENT, "bad texture description");
-    const bool isFloat = d.format == RTXPT_FORMAT_RGBA32_FLOAT;
+    if (d.format > RTXPT_FORMAT_BC7_SRGB) return fail(RTXPT_ERR_INVALID_ARGUMENT, "unknown texture format %u", d.format);
+    const bool isFloat = d.format == RTXPT_FORMAT_RGBA32_FLOAT, isBc = isBlockCompressed(d.format);
     cudaChannelFormatDesc fmt = isFloat ? cudaCreateChannelDesc<float4>() : cudaCreateChannelDesc<uchar4>();
+    size_t blockBytes = 0;
+    if (isBc)
+    {   // block-compressed array: the texture units decode BC1 / BC2 / BC3 / BC7 (and sRGB) on fetch, as the reference's TMUs do for its .dds assets
+        if ((d.width & 3u) || (d.height & 3u)) return fail(RTXPT_ERR_INVALID_ARGUMENT, "block-compressed textures need a width and height that are multiples of 4");
+        switch (d.format)
+        {
+        case RTXPT_FORMAT_BC1_UNORM: fmt = cudaCreateChannelDesc<cudaChannelFormatKindUnsignedBlockCompressed1>(); blockBytes = 8; break;
+        case RTXPT_FORMAT_BC1_SRGB:  fmt = cudaCreateChannelDesc<cudaChannelFormatKindUnsignedBlockCompressed1SRGB>(); blockBytes = 8; break;
+        case RTXPT_FORMAT_BC2_UNORM: fmt = cudaCreateChannelDesc<cudaChannelFormatKindUnsignedBlockCompressed2>(); blockBytes = 16; break;
+        case RTXPT_FORMAT_BC2_SRGB:  fmt = cudaCreateChannelDesc<cudaChannelFormatKindUnsignedBlockCompressed2SRGB>(); blockBytes = 16; break;
+        case RTXPT_FORMAT_BC3_UNORM: fmt = cudaCreateChannelDesc<cudaChannelFormatKindUnsignedBlockCompressed3>(); blockBytes = 16; break;
+        case RTXPT_FORMAT_BC3_SRGB:  fmt = cudaCreateChannelDesc<cudaChannelFormatKindUnsignedBlockCompressed3SRGB>(); blockBytes = 16; break;
+        case RTXPT_FORMAT_BC7_UNORM: fmt = cudaCreateChannelDesc<cudaChannelFormatKindUnsignedBlockCompressed7>(); blockBytes = 16; break;
+        default:                     fmt = cudaCreateChannelDesc<cudaChannelFormatKindUnsignedBlockCompressed7SRGB>(); blockBytes = 16; break;
+        }
+    }
     CU(cudaMallocMipmappedArray(&out.array, &fmt, make_cudaExtent(d.width, d.height, 0), d.mipLevels));
     const size_t texel = isFloat ? 16 : 4;
     for (uint32_t m = 0; m < d.mipLevels; m++)
@@ -275,14 +294,15 @@ static int createTexture2D(const RtxptTextureDesc& d, DeviceTexture& out)
         cudaArray_t level; CU(cudaGetMipmappedArrayLevel(&level, out.array, m));
         const uint32_t w = std::max(1u, d.width >> m), h = std::max(1u, d.height >> m);
         if (!d.mips[m]) return fail(RTXPT_ERR_INVALID_ARGUMENT, "texture mip %u has no data", m);
-        CU(cudaMemcpy2DToArray(level, 0, 0, d.mips[m], w * texel, w * texel, h, cudaMemcpyHostToDevice));
+        if (isBc) { const size_t rowBytes = size_t((w + 3) / 4) * blockBytes; CU(cudaMemcpy2DToArray(level, 0, 0, d.mips[m], rowBytes, rowBytes, (h + 3) / 4, cudaMemcpyHostToDevice)); }     // rows of blocks
+        else CU(cudaMemcpy2DToArray(level, 0, 0, d.mips[m], w * texel, w * texel, h, cudaMemcpyHostToDevice));
     }
     cudaResourceDesc res{}; res.resType = cudaResourceTypeMipmappedArray; res.res.mipmap.mipmap = out.array;
     cudaTextureDesc td{};
     td.addressMode[0] = td.addressMode[1] = cudaAddressModeWrap;       // s_MaterialSampler: wrap, trilinear (CommonRenderPasses.cpp:85-86; anisotropy inert under SampleLevel)
     td.filterMode = cudaFilterModeLinear; td.mipmapFilterMode = cudaFilterModeLinear;
     td.readMode = isFloat ? cudaReadModeElementType : cudaReadModeNormalizedFloat;
-    td.sRGB = (d.format == RTXPT_FORMAT_RGBA8_SRGB) ? 1 : 0;
+    td.sRGB = (d.format == RTXPT_FORMAT_RGBA8_SRGB) ? 1 : 0;          // the block-compressed sRGB kinds carry the conversion in the array format
     td.normalizedCoords = 1; td.maxAnisotropy = 1; td.minMipmapLevelClamp = 0; td.maxMipmapLevelClamp = float(d.mipLevels - 1);
     CU(cudaCreateTextureObject(&out.object, &res, &td, nullptr));
     return RTXPT_OK;
@@ -393,6 +413,12 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
     if (tris.size() >= (size_t(1) << 27)) return fail(RTXPT_ERR_INVALID_ARGUMENT, "scene has %zu triangles; the traversal kernels address at most 2^27 - 1", tris.size());
     // opacity masks: 64 two-bit states per alpha-tested triangle, baked from mip 0 of the alpha texture (the reference bakes OMMs for the same geometries, OmmBuildQueue.cpp:30-60)
     std::vector<uint4> masks(maskJobs.size()); uint64_t maskStates[3] = { 0, 0, 0 };
+    std::vector<std::vector<uint8_t>> decodedAlpha(sc->textureCount);          // mip 0 of the block-compressed alpha textures, decoded once for the baker (the device keeps the blocks)
+    for (const MaskJob& j : maskJobs)
+    {
+        const RtxptTextureDesc& td = sc->textures[j.texture];
+        if (isBlockCompressed(td.format) && td.mips[0] && decodedAlpha[j.texture].empty()) rtxpt_host::decodeBlocksToRgba8(td.format, static_cast<const uint8_t*>(td.mips[0]), td.width, td.height, decodedAlpha[j.texture]);
+    }
     {
         const auto t0 = std::chrono::steady_clock::now();
         #pragma omp parallel
@@ -405,7 +431,7 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
                 uint32_t m[4] = { 0xAAAAAAAAu, 0xAAAAAAAAu, 0xAAAAAAAAu, 0xAAAAAAAAu };            // all unknown
                 if (td.mips[0] && td.width && td.height)
                 {
-                    om::AlphaSource a; a.rgba8 = td.format == RTXPT_FORMAT_RGBA32_FLOAT ? nullptr : static_cast<const uint8_t*>(td.mips[0]);
+                    om::AlphaSource a; a.rgba8 = td.format == RTXPT_FORMAT_RGBA32_FLOAT ? nullptr : (isBlockCompressed(td.format) ? decodedAlpha[j.texture].data() : static_cast<const uint8_t*>(td.mips[0]));
                     a.rgba32f = td.format == RTXPT_FORMAT_RGBA32_FLOAT ? static_cast<const float*>(td.mips[0]) : nullptr; a.width = int(td.width); a.height = int(td.height);
                     om::bakeTriangle(a, j.cutoff, j.uv, m, local);
                 }

@@ -279,6 +279,56 @@ DdsImage decodeDds(const uint8_t* data, size_t size, const char* name)
     return img;
 }
 
+// BC1 / BC2 / BC3 / BC7 files handed through without decoding (RTXPT_FORMAT_BC*): the raw blocks of every mip; false for every other format (the caller decodes those)
+struct DdsBlocks { uint32_t width = 0, height = 0, format = 0; bool srgb = false; std::vector<std::vector<uint8_t>> mips; };
+bool extractDdsBlocks(const uint8_t* data, size_t size, const char* name, DdsBlocks& out)
+{
+    if (size < 128 || memcmp(data, "DDS ", 4) != 0 || rd32(data + 4) != 124) return false;
+    out.height = rd32(data + 12); out.width = rd32(data + 16);
+    const uint32_t mipCount = std::max(1u, rd32(data + 28)), pfFlags = rd32(data + 80), fourCC = rd32(data + 84);
+    auto cc = [](const char* s) { return uint32_t(uint8_t(s[0])) | (uint32_t(uint8_t(s[1])) << 8) | (uint32_t(uint8_t(s[2])) << 16) | (uint32_t(uint8_t(s[3])) << 24); };
+    if (!(pfFlags & 0x4)) return false;
+    size_t off = 128; uint32_t fmt = 0;
+    if (fourCC == cc("DX10"))
+    {
+        if (size < 148) return false;
+        off = 148;
+        switch (rd32(data + 128)) { case 70: case 71: fmt = RTXPT_FORMAT_BC1_UNORM; break; case 72: fmt = RTXPT_FORMAT_BC1_UNORM; out.srgb = true; break; case 73: case 74: fmt = RTXPT_FORMAT_BC2_UNORM; break;
+                                    case 75: fmt = RTXPT_FORMAT_BC2_UNORM; out.srgb = true; break; case 76: case 77: fmt = RTXPT_FORMAT_BC3_UNORM; break; case 78: fmt = RTXPT_FORMAT_BC3_UNORM; out.srgb = true; break;
+                                    case 97: case 98: fmt = RTXPT_FORMAT_BC7_UNORM; break; case 99: fmt = RTXPT_FORMAT_BC7_UNORM; out.srgb = true; break; default: return false; }
+    }
+    else if (fourCC == cc("DXT1")) fmt = RTXPT_FORMAT_BC1_UNORM; else if (fourCC == cc("DXT2") || fourCC == cc("DXT3")) fmt = RTXPT_FORMAT_BC2_UNORM; else if (fourCC == cc("DXT4") || fourCC == cc("DXT5")) fmt = RTXPT_FORMAT_BC3_UNORM;
+    else return false;
+    if (!out.width || !out.height || out.width > 32768 || out.height > 32768) failf("DDS '%s': bad dimensions", name);
+    if ((out.width & 3u) || (out.height & 3u)) return false;              // CUDA's block-compressed arrays want whole blocks at mip 0: odd sizes take the decoded path
+    out.format = fmt; const size_t blockBytes = fmt == RTXPT_FORMAT_BC1_UNORM ? 8 : 16;
+    for (uint32_t m = 0; m < mipCount && m < RTXPT_MAX_MIPS; m++)
+    {
+        const uint32_t w = std::max(1u, out.width >> m), h = std::max(1u, out.height >> m); const size_t bytes = size_t((w + 3) / 4) * ((h + 3) / 4) * blockBytes;
+        if (off + bytes > size) failf("DDS '%s': truncated", name);
+        out.mips.emplace_back(data + off, data + off + bytes); off += bytes;
+    }
+    return true;
+}
+// one mip of raw blocks -> RGBA8 (the opacity-mask baker reads the alpha of mip 0 of a texture that stays compressed on the device)
+void decodeBlocksToRgba8(uint32_t format, const uint8_t* blocks, uint32_t w, uint32_t h, std::vector<uint8_t>& rgba)
+{
+    rgba.assign(size_t(w) * h * 4, 0);
+    const uint32_t bw = (w + 3) / 4, bh = (h + 3) / 4; const size_t blockBytes = (format == RTXPT_FORMAT_BC1_UNORM || format == RTXPT_FORMAT_BC1_SRGB) ? 8 : 16;
+    for (uint32_t by = 0; by < bh; by++) for (uint32_t bx = 0; bx < bw; bx++)
+    {
+        const uint8_t* b = blocks + (size_t(by) * bw + bx) * blockBytes; uint8_t px[16][4];
+        switch (format)
+        {
+        case RTXPT_FORMAT_BC1_UNORM: case RTXPT_FORMAT_BC1_SRGB: decodeBc1Color(b, true, px); break;
+        case RTXPT_FORMAT_BC2_UNORM: case RTXPT_FORMAT_BC2_SRGB: decodeBc1Color(b + 8, false, px); for (int i = 0; i < 16; i++) { const uint32_t a = (b[i >> 1] >> ((i & 1) * 4)) & 15; px[i][3] = uint8_t(a * 17); } break;
+        case RTXPT_FORMAT_BC3_UNORM: case RTXPT_FORMAT_BC3_SRGB: { decodeBc1Color(b + 8, false, px); uint8_t a[16]; decodeBc4Channel(b, a); for (int i = 0; i < 16; i++) px[i][3] = a[i]; break; }
+        default: decodeBc7(b, px); break;
+        }
+        for (uint32_t y = 0; y < 4 && by * 4 + y < h; y++) for (uint32_t x = 0; x < 4 && bx * 4 + x < w; x++) memcpy(&rgba[(size_t(by * 4 + y) * w + bx * 4 + x) * 4], px[y * 4 + x], 4);
+    }
+}
+
 // HDR DDS files - what the reference's environment maps are (Assets/EnvironmentMaps/*_cube_bc6u.dds: BC6H_UF16 cubes, loaded by Donut's DDSFile.cpp and fed to
 // EnvMapBaker::Update, Rtxpt/Lighting/Distant/EnvMapBaker.cpp:164-169, :372-375): BC6H UF16 / SF16, RGBA16F, RGBA32F; 2-D or cube; mip 0 of every face as RGBA32F.
 struct HdrImage { uint32_t width = 0, height = 0, faces = 1, mipCount = 1; std::vector<float> rgba; };      // faces back to back, D3D order +x -x +y -y +z -z

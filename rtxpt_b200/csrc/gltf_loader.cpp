@@ -30,6 +30,9 @@ namespace rtxpt_host {
 void materialFromJson(const JValue& j, RtxptMaterialJsonInfo& out);       // material_json.cpp
 struct DdsImage { uint32_t width = 0, height = 0; bool srgb = false; std::vector<std::vector<uint8_t>> mips; };
 DdsImage decodeDds(const uint8_t* data, size_t size, const char* name);   // dds.cpp
+struct DdsBlocks { uint32_t width = 0, height = 0, format = 0; bool srgb = false; std::vector<std::vector<uint8_t>> mips; };
+bool extractDdsBlocks(const uint8_t* data, size_t size, const char* name, DdsBlocks& out);   // dds.cpp: BC1 / BC2 / BC3 / BC7 kept compressed
+bool g_keepBlockCompression = false;                                        // rtxpt_b200_loader_keep_block_compression
 }
 
 namespace {
@@ -301,8 +304,13 @@ struct Loader
     // PNG files get a generated mip chain; DDS files (BC1-5, BC7, RGBA8) are decoded to RGBA8 with the mips they carry (dds.cpp)
     uint32_t registerTexture(const std::string& key, bool srgb, const std::vector<uint8_t>& bytes, const std::string& name)
     {
-        std::vector<std::vector<uint8_t>> mips; uint32_t w, h;
-        if (bytes.size() >= 4 && memcmp(bytes.data(), "DDS ", 4) == 0)
+        std::vector<std::vector<uint8_t>> mips; uint32_t w, h; uint32_t bcFormat = 0;
+        DdsBlocks raw;
+        if (g_keepBlockCompression && extractDdsBlocks(bytes.data(), bytes.size(), name.c_str(), raw))
+        {   // stays block-compressed on the device: the texture units decode it on fetch (include/rtxpt_b200.h RTXPT_FORMAT_BC*)
+            w = raw.width; h = raw.height; mips = std::move(raw.mips); bcFormat = raw.format + (srgb ? 1u : 0u);
+        }
+        else if (bytes.size() >= 4 && memcmp(bytes.data(), "DDS ", 4) == 0)
         {
             DdsImage dds = decodeDds(bytes.data(), bytes.size(), name.c_str());
             w = dds.width; h = dds.height; mips = std::move(dds.mips);
@@ -315,7 +323,7 @@ struct Loader
         }
         if (mips.size() > 16) failf("texture '%s' is larger than 32768 texels per side", name.c_str());
         RtxptTextureDesc d = {};
-        d.width = w; d.height = h; d.mipLevels = uint32_t(mips.size()); d.format = srgb ? RTXPT_FORMAT_RGBA8_SRGB : RTXPT_FORMAT_RGBA8_UNORM;
+        d.width = w; d.height = h; d.mipLevels = uint32_t(mips.size()); d.format = bcFormat ? bcFormat : (srgb ? RTXPT_FORMAT_RGBA8_SRGB : RTXPT_FORMAT_RGBA8_UNORM);
         for (size_t m = 0; m < mips.size(); m++) { out->blobs.push_back(std::move(mips[m])); d.mips[m] = out->blobs.back().data(); }
         const uint32_t slot = uint32_t(out->textures.size()); out->textures.push_back(d); textureSlot[std::make_pair(key, srgb ? 1 : 0)] = slot;
         return slot;
@@ -773,6 +781,7 @@ RTXPT_API int rtxpt_b200_load_gltf_ex(const char* path, const char* materialsDir
     *outScene = scene.release();
     return RTXPT_OK;
 }
+RTXPT_API void rtxpt_b200_loader_keep_block_compression(int enable) { rtxpt_host::g_keepBlockCompression = enable != 0; }
 RTXPT_API int rtxpt_b200_load_gltf(const char* path, rtxpt_host_scene** outScene) { return rtxpt_b200_load_gltf_ex(path, nullptr, nullptr, outScene, nullptr); }
 RTXPT_API const char* rtxpt_b200_load_gltf_error(void) { return g_loaderError.c_str(); }
 RTXPT_API const RtxptSceneDesc* rtxpt_b200_host_scene_desc(const rtxpt_host_scene* scene) { return scene ? &scene->desc : nullptr; }

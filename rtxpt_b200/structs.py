@@ -8,6 +8,7 @@ u32, i32, f32, u64 = C.c_uint32, C.c_int32, C.c_float, C.c_uint64
 MAX_MIPS = 16
 
 FORMAT_RGBA8_UNORM, FORMAT_RGBA8_SRGB, FORMAT_RGBA32_FLOAT = 0, 1, 2
+FORMAT_BC1_UNORM, FORMAT_BC1_SRGB, FORMAT_BC2_UNORM, FORMAT_BC2_SRGB, FORMAT_BC3_UNORM, FORMAT_BC3_SRGB, FORMAT_BC7_UNORM, FORMAT_BC7_SRGB = 3, 4, 5, 6, 7, 8, 9, 10
 SUBINST_FLAG_ALPHA_TESTED = 1 << 16
 SUBINST_FLAG_EXCLUDE_FROM_NEE = 1 << 17
 

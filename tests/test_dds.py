@@ -228,3 +228,77 @@ def test_dds_textures_through_the_scene_loaders(tmp_path):
     tn = g.desc.textures[ns]; assert (tn.width, tn.height, tn.mipLevels, tn.format) == (4, 4, 3, S.FORMAT_RGBA8_UNORM)
     np.testing.assert_array_equal(_texture_pixels(g.desc, ns), nrm)
     g.close(); plain.close()
+
+
+# ---- block-compressed textures kept compressed for the texture units (RTXPT_FORMAT_BC*) --------------------------------------------------------------------------------------
+def _bc_scene(tmp_path, rng, fmt="BC7", size=(64, 64), mips=3):
+    """The textured test scene with its base-colour PNG shadowed by a .dds sibling of random `fmt` blocks (sRGB slot)."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    import gltf_export
+    from test_gltf_loader import _textured_builder
+    d = tmp_path / ("m_" + fmt); d.mkdir()
+    path = gltf_export.export(_textured_builder(), str(d / "scene.gltf"))
+    w, h = size; payload = b""
+    for m in range(mips):
+        mw, mh = max(1, w >> m), max(1, h >> m)
+        blocks = rng.integers(0, 256, (((mw + 3) // 4) * ((mh + 3) // 4), BLOCK_BYTES[fmt]), dtype=np.uint8)
+        if fmt == "BC7": blocks[:, 0] = (blocks[:, 0] & 0x80) | 0x40            # mode 6: RGBA 7.7.7.7 + p-bits, one subset: every block is a smooth gradient (texture filtering stays well conditioned)
+        payload += blocks.tobytes()
+    file_bytes = dds_dx10(fmt, w, h, payload, mips=mips)
+    (d / "scene_tex0.dds").write_bytes(file_bytes)
+    return path, file_bytes
+
+
+def test_loader_keeps_block_compression_when_asked(tmp_path):
+    import ctypes as C
+    from rtxpt_b200 import structs as S
+    lib = L.load(); lib.rtxpt_b200_loader_keep_block_compression.argtypes = [C.c_int]; lib.rtxpt_b200_loader_keep_block_compression.restype = None
+    rng = np.random.default_rng(21)
+    for fmt, want in (("BC7", S.FORMAT_BC7_SRGB), ("BC1", S.FORMAT_BC1_SRGB), ("BC3", S.FORMAT_BC3_SRGB), ("BC2", S.FORMAT_BC2_SRGB)):
+        path, file_bytes = _bc_scene(tmp_path, rng, fmt)
+        try:
+            lib.rtxpt_b200_loader_keep_block_compression(1); g = L.GltfScene(path)
+        finally:
+            lib.rtxpt_b200_loader_keep_block_compression(0)
+        t = g.desc.textures[0]
+        assert (t.width, t.height, t.mipLevels, t.format) == (64, 64, 3, want)                      # the base-colour slot is sRGB: the *_SRGB kind
+        off = 148
+        for m in range(3):
+            n = ((max(1, 64 >> m) + 3) // 4) ** 2 * BLOCK_BYTES[fmt]
+            assert C.string_at(t.mips[m], n) == file_bytes[off:off + n]; off += n                  # the raw blocks, untouched
+        assert g.desc.textures[1].format == S.FORMAT_RGBA8_UNORM                                    # the PNG normal map is still RGBA8
+        g.close()
+        g = L.GltfScene(path); assert g.desc.textures[0].format == S.FORMAT_RGBA8_SRGB; g.close()  # default: expanded on the host
+    # BC4 / BC5 and sizes that are not whole blocks always take the decoded path
+    path, _ = _bc_scene(tmp_path, rng, "BC5")
+    try:
+        lib.rtxpt_b200_loader_keep_block_compression(1); g = L.GltfScene(path); assert g.desc.textures[0].format == S.FORMAT_RGBA8_SRGB; g.close()
+    finally:
+        lib.rtxpt_b200_loader_keep_block_compression(0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", ["BC7", "BC3", "BC1"])
+def test_block_compressed_textures_render_like_their_host_decode(tmp_path, fmt):
+    """The same .dds once expanded to RGBA8 on the host, once kept compressed and decoded by the texture units: BC7 decodes exactly by specification, so the two frames agree to the
+    filter's last bit; BC1 / BC3 colour interpolation may differ by one LSB between hardware and the reference decoder (the documented D3D tolerance)."""
+    import ctypes as C
+    from rtxpt_b200 import scene_builder as sb
+    lib = L.load(); lib.rtxpt_b200_loader_keep_block_compression.argtypes = [C.c_int]; lib.rtxpt_b200_loader_keep_block_compression.restype = None
+    path, _ = _bc_scene(tmp_path, np.random.default_rng(33), fmt, size=(128, 128), mips=5)
+    frames = []
+    for keep in (0, 1):
+        try:
+            lib.rtxpt_b200_loader_keep_block_compression(keep); g = L.GltfScene(path)
+        finally:
+            lib.rtxpt_b200_loader_keep_block_compression(0)
+        cam = sb.bridge_camera(160, 120, pos=(0.0, 1.2, -3.5), direction=(0, -0.15, 1), up=(0, 1, 0), fov_y=0.9)
+        consts = sb.make_constants(160, 120, cam, bounce_count=3, diffuse_bounce_count=3, env_enabled=False)
+        c = L.Context(max_sub_samples_per_launch=4); c.upload_scene(g); c.set_constants(consts)
+        c.path_trace(0, 8, True); c.synchronize(); frames.append(c.readback_accumulated()); c.close(); g.close()
+    a, b = frames
+    assert a[..., :3].mean() > 1e-3 and np.isfinite(b).all()
+    rel = np.abs(a[..., :3] - b[..., :3]) / (np.abs(a[..., :3]) + 1e-2)
+    if fmt == "BC7": assert np.percentile(rel, 99.9) < 2e-3 and abs(a.mean() - b.mean()) < 1e-4 * a.mean()
+    else: assert np.percentile(rel, 99) < 2e-2 and abs(a.mean() - b.mean()) < 5e-3 * a.mean()
