@@ -20,17 +20,18 @@ __global__ void __launch_bounds__(256) k_rb_classify_tiles(const __grid_constant
 }
 __global__ void __launch_bounds__(256) k_rb_hit_dist_reconstruction(const __grid_constant__ Params p) { RB_XY; hitDistReconstructionPixel(p, x, y); }
 
-// ---- tiled HitDistReconstruction: the 20x20 neighbourhood of a 16x16 tile staged in shared memory by four 2-D TMA tensor loads ------------------------------------------------
+// ---- tiled HitDistReconstruction: the neighbourhood of a 16x16 tile (24 x 20 texels, see below) staged in shared memory by four 2-D TMA tensor loads ------------------------------------------------
 // (viewZ R32F, normal/roughness R10G10B10A2 as u32, diffuse and specular radiance + hit distance RGBA16F as u64), one mbarrier, the normals unpacked once per texel instead of
 // once per tap.  TMA fills out-of-image texels with zeros where the pass wants clamped coordinates, so the tiles on the image border - and images whose row pitch is not a
 // multiple of 16 bytes, which TMA cannot address - load their region with ordinary clamped loads; both ways the shared tile holds the same values.
-constexpr int kHdTile = 16, kHdHalo = 2, kHdRegion = kHdTile + 2 * kHdHalo, kHdTexels = kHdRegion * kHdRegion;
+// TMA wants the byte offset of a box's first texel in a row to be a multiple of 16 (measured: a box starting at x = 30 of a 32-bit image raises "illegal instruction", x = 32 loads -
+// scripts/probes/tma_probe2.cu), so the region starts 4 texels left of the tile (16 B for the 32-bit images, 32 B for the 64-bit ones) and is 24 wide: columns 2..21 are the 5x5 taps' reach.
+constexpr int kHdTile = 16, kHdHalo = 2, kHdLeft = 4, kHdRegionW = kHdTile + kHdLeft + 4, kHdRegionH = kHdTile + 2 * kHdHalo, kHdTexels = kHdRegionW * kHdRegionH;
 struct HitDistTileMaps { CUtensorMap viewZ, normalRoughness, diff, spec; uint useTma; };
 struct __align__(128) HitDistTile
 {
-    float viewZ[kHdTexels];                         // 1600 B: every array starts on a 128-byte boundary (TMA destination alignment)
-    uint pad0[16];
-    uint normalRoughness[kHdTexels]; uint pad1[16];
+    float viewZ[kHdTexels];                         // 1920 B each for the 32-bit images, 3840 B for the 64-bit ones: every array starts on a 128-byte boundary (TMA destination alignment)
+    uint normalRoughness[kHdTexels];
     unsigned long long diff[kHdTexels];
     unsigned long long spec[kHdTexels];
     float4 unpacked[kHdTexels];                     // normal.xyz, roughness
@@ -40,7 +41,7 @@ static_assert(offsetof(HitDistTile, normalRoughness) % 128 == 0 && offsetof(HitD
 struct SharedTaps
 {
     const Params& p; const HitDistTile& t; int x0, y0;          // texel (x0, y0) of the image is cell 0 of the region
-    __device__ int cell(int qx, int qy) const { return (qy - y0) * kHdRegion + (qx - x0); }
+    __device__ int cell(int qx, int qy) const { return (qy - y0) * kHdRegionW + (qx - x0); }
     __device__ float viewZ(int qx, int qy) const { return fabsf(t.viewZ[cell(qx, qy)] * p.viewZScale); }
     __device__ float4 normalRoughness(int qx, int qy) const { return t.unpacked[cell(qx, qy)]; }
     __device__ float diffHitDist(int qx, int qy) const { return f16tof32(uint(t.diff[cell(qx, qy)] >> 48)); }
@@ -56,8 +57,8 @@ __global__ void __launch_bounds__(256) k_rb_hit_dist_reconstruction_tiled(const 
     __shared__ HitDistTile tile;
     if (p.tiles[blockIdx.y * p.tilesW + blockIdx.x]) return;                        // sky tile: nothing to reconstruct (uniform over the CTA)
     const int tid = int(threadIdx.y * 16 + threadIdx.x), W = int(p.W), H = int(p.H);
-    const int x0 = int(blockIdx.x) * kHdTile - kHdHalo, y0 = int(blockIdx.y) * kHdTile - kHdHalo;
-    const bool interior = x0 >= 0 && y0 >= 0 && x0 + kHdRegion <= W && y0 + kHdRegion <= H;
+    const int x0 = int(blockIdx.x) * kHdTile - kHdLeft, y0 = int(blockIdx.y) * kHdTile - kHdHalo;
+    const bool interior = x0 >= 0 && y0 >= 0 && x0 + kHdRegionW <= W && y0 + kHdRegionH <= H;
     if (maps.useTma && interior)
     {
         const uint mbarAddr = (uint)__cvta_generic_to_shared(&tile.mbar);
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(256) k_rb_hit_dist_reconstruction_tiled(const 
     {
         for (int c = tid; c < kHdTexels; c += 256)
         {
-            const int qx = clampi(x0 + c % kHdRegion, 0, W - 1), qy = clampi(y0 + c / kHdRegion, 0, H - 1); const size_t q = size_t(qy) * W + qx;
+            const int qx = clampi(x0 + c % kHdRegionW, 0, W - 1), qy = clampi(y0 + c / kHdRegionW, 0, H - 1); const size_t q = size_t(qy) * W + qx;
             tile.viewZ[c] = p.viewZ[q]; tile.normalRoughness[c] = p.normalRoughness[q];
             const uint2 d = p.inDiff[q], s = p.inSpec[q];
             tile.diff[c] = (unsigned long long)d.x | ((unsigned long long)d.y << 32); tile.spec[c] = (unsigned long long)s.x | ((unsigned long long)s.y << 32);
@@ -100,14 +101,14 @@ __global__ void __launch_bounds__(256) k_rb_temporal_stabilization(const __grid_
 
 } // namespace rb
 
-// 2-D tensor map of a row-major W x H image of `elemBytes`-byte texels with a (20 x 20) box; false when TMA cannot address the image (pitch or base not 16-byte aligned)
+// 2-D tensor map of a row-major W x H image of `elemBytes`-byte texels with a (24 x 20) box; false when TMA cannot address the image (pitch or base not 16-byte aligned)
 static bool encodeTileMap(CUtensorMap* out, const void* base, uint32_t W, uint32_t H, uint32_t elemBytes)
 {
     typedef CUresult (*Encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     static Encode encode = [] { void* f = nullptr; cudaDriverEntryPointQueryResult q; return (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) ? (Encode)f : (Encode) nullptr; }();
     if (!encode || (size_t(W) * elemBytes) % 16 != 0 || (reinterpret_cast<uintptr_t>(base) & 15u) != 0) return false;
-    const cuuint64_t dims[2] = { W, H }, strides[1] = { cuuint64_t(W) * elemBytes }; const cuuint32_t box[2] = { rb::kHdRegion, rb::kHdRegion }, estr[2] = { 1, 1 };
+    const cuuint64_t dims[2] = { W, H }, strides[1] = { cuuint64_t(W) * elemBytes }; const cuuint32_t box[2] = { rb::kHdRegionW, rb::kHdRegionH }, estr[2] = { 1, 1 };
     return encode(out, elemBytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -116,7 +117,7 @@ void launchReblurFrame(const rb::Params& p, cudaStream_t s)
 {
     const dim3 grid((p.W + 15) / 16, (p.H + 15) / 16), block(16, 16);
     rb::k_rb_classify_tiles<<<grid, block, 0, s>>>(p);
-    static const bool tiled = [] { const char* e = getenv("RTXPT_REBLUR_TILED"); return e && atoi(e) != 0; }();          // opt-in until its first green GPU run
+    static const bool tiled = [] { const char* e = getenv("RTXPT_REBLUR_TILED"); return !e || atoi(e) != 0; }();
     if (tiled)
     {
         rb::HitDistTileMaps maps; memset(&maps, 0, sizeof(maps));
