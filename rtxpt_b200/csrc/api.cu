@@ -302,7 +302,8 @@ static int createTexture2D(const RtxptTextureDesc& d, DeviceTexture& out)
     td.addressMode[0] = td.addressMode[1] = cudaAddressModeWrap;       // s_MaterialSampler: wrap, trilinear (CommonRenderPasses.cpp:85-86; anisotropy inert under SampleLevel)
     td.filterMode = cudaFilterModeLinear; td.mipmapFilterMode = cudaFilterModeLinear;
     td.readMode = isFloat ? cudaReadModeElementType : cudaReadModeNormalizedFloat;
-    td.sRGB = (d.format == RTXPT_FORMAT_RGBA8_SRGB) ? 1 : 0;          // the block-compressed sRGB kinds carry the conversion in the array format
+    td.sRGB = (d.format == RTXPT_FORMAT_RGBA8_SRGB || d.format == RTXPT_FORMAT_BC1_SRGB || d.format == RTXPT_FORMAT_BC2_SRGB || d.format == RTXPT_FORMAT_BC3_SRGB || d.format == RTXPT_FORMAT_BC7_SRGB) ? 1 : 0;
+    // (measured with scripts/probes/bc_probe.cu: the *SRGB block-compressed kinds are refused without td.sRGB, every block-compressed kind is refused with cudaReadModeElementType)
     td.normalizedCoords = 1; td.maxAnisotropy = 1; td.minMipmapLevelClamp = 0; td.maxMipmapLevelClamp = float(d.mipLevels - 1);
     CU(cudaCreateTextureObject(&out.object, &res, &td, nullptr));
     return RTXPT_OK;

@@ -15,16 +15,16 @@ int main()
         put(v, 7); put(v, 7); put(v, 7); put(v, 7); put(v, 7); put(v, 7); put(a, 7); put(a, 7); put(1, 1); put(1, 1);
         memcpy(&blocks[b * 16], &lo, 8); memcpy(&blocks[b * 16 + 8], &hi, 8);
     }
-    for (int srgb = 0; srgb < 2; srgb++) for (int mode = 0; mode < 2; mode++)
+    for (int srgb = 0; srgb < 2; srgb++) for (int mode = 1; mode < 4; mode++)      // mode bit 0: NormalizedFloat (ElementType is refused for these kinds), bit 1: td.sRGB
     {
         cudaChannelFormatDesc fmt = srgb ? cudaCreateChannelDesc<cudaChannelFormatKindUnsignedBlockCompressed7SRGB>() : cudaCreateChannelDesc<cudaChannelFormatKindUnsignedBlockCompressed7>();
         cudaMipmappedArray_t arr = nullptr; cudaError_t e = cudaMallocMipmappedArray(&arr, &fmt, make_cudaExtent(8, 8, 0), 1);
-        printf("srgb %d readMode %s: malloc %s", srgb, mode ? "NormalizedFloat" : "ElementType", cudaGetErrorString(e)); if (e) { printf("\n"); cudaGetLastError(); continue; }
+        printf("kind %s, readMode %s, td.sRGB %d: malloc %s", srgb ? "BC7SRGB" : "BC7", (mode & 1) ? "NormalizedFloat" : "ElementType", mode >> 1, cudaGetErrorString(e)); if (e) { printf("\n"); cudaGetLastError(); continue; }
         cudaArray_t lvl; cudaGetMipmappedArrayLevel(&lvl, arr, 0);
         e = cudaMemcpy2DToArray(lvl, 0, 0, blocks.data(), 32, 32, 2, cudaMemcpyHostToDevice); printf(", copy %s", cudaGetErrorString(e));
         cudaResourceDesc res{}; res.resType = cudaResourceTypeMipmappedArray; res.res.mipmap.mipmap = arr;
         cudaTextureDesc td{}; td.addressMode[0] = td.addressMode[1] = cudaAddressModeWrap; td.filterMode = cudaFilterModePoint; td.mipmapFilterMode = cudaFilterModePoint;
-        td.readMode = mode ? cudaReadModeNormalizedFloat : cudaReadModeElementType; td.normalizedCoords = 1; td.maxAnisotropy = 1; td.maxMipmapLevelClamp = 0;
+        td.readMode = (mode & 1) ? cudaReadModeNormalizedFloat : cudaReadModeElementType; td.sRGB = mode >> 1; td.normalizedCoords = 1; td.maxAnisotropy = 1; td.maxMipmapLevelClamp = 0;
         cudaTextureObject_t t = 0; e = cudaCreateTextureObject(&t, &res, &td, nullptr); printf(", texture %s", cudaGetErrorString(e));
         if (!e)
         {
