@@ -642,6 +642,14 @@ RTXPT_API const char* rtxpt_b200_debug_decode_dds_error(void);
 RTXPT_API int rtxpt_b200_load_dds_hdr(const void* fileBytes, uint64_t fileSize, uint32_t* outWidth, uint32_t* outHeight, uint32_t* outFaces, uint32_t* outMipCount,
                                       float* outRGBA32F, uint64_t outCapacityFloats);
 
+/* HDR image files by content: OpenEXR (single-part scan-line files; NONE / RLE / ZIPS / ZIP compression; HALF / FLOAT / UINT channels R G B A or Y), Radiance .hdr (RGBE, flat or
+ * run-length coded) and the HDR DDS formats above.  These are the three kinds of file the reference lists as environment-map sources (Rtxpt/Sample.cpp:110-118, read through
+ * External/Donut/src/engine/TextureCache.cpp:200-236); the EXR reader is also how an AccumulatedRadiance dump of an RTXPT run made elsewhere comes in for comparison (BASELINE.md,
+ * scripts/compare_hdr_images.py).  Call with outRGBA32F == NULL for the sizes; rows come back top to bottom as RGBA32F (alpha 1 where the file has none; faces back to back for a
+ * DDS cube, *outFaces = 6).  Errors: rtxpt_b200_load_hdr_image_error. */
+RTXPT_API int rtxpt_b200_load_hdr_image(const void* fileBytes, uint64_t fileSize, uint32_t* outWidth, uint32_t* outHeight, uint32_t* outFaces, float* outRGBA32F, uint64_t outCapacityFloats);
+RTXPT_API const char* rtxpt_b200_load_hdr_image_error(void);
+
 /* Host-only: builds the compressed wide BVH over a triangle soup (9 floats per triangle) and reports its surface-area-heuristic statistics:
  * expected node visits / triangle tests of a random ray that hits the root box.  Used to judge builder changes without a GPU. */
 typedef struct RtxptBvhStats { uint32_t nodeCount, triangleReferenceCount, leafCount, maxDepth; float expectedNodeVisits, expectedTriangleTests, buildSeconds, _pad; } RtxptBvhStats;

@@ -199,6 +199,7 @@ inline bool tileIsSky(const Constants& c, const std::vector<uint8_t>& tiles, int
 inline void hitDistReconstruction(const Constants& c, const Inputs& in, const std::vector<uint8_t>& tiles, const Image4& inDiff, const Image4& inSpec, Image4& outDiff, Image4& outSpec)
 {
     const int BORDER = 2;
+    #pragma omp parallel for schedule(dynamic, 4)          // pixels are independent within a pass (each writes its own outputs only)
     for (int y = 0; y < int(c.H); y++) for (int x = 0; x < int(c.W); x++)
     {
         if (tileIsSky(c, tiles, x, y)) continue;
@@ -249,6 +250,7 @@ inline void spatialPass(const Constants& c, const Inputs& in, const std::vector<
     const float fractionScale = mode == PRE_BLUR ? 2.0f : (mode == BLUR ? 1.0f : 0.5f), radiusScale = mode == POST_BLUR ? 2.0f : 1.0f;
     const Rotator baseRotator = mode == PRE_BLUR ? c.rotatorPre : (mode == BLUR ? c.rotator : c.rotatorPost);       // rotator mode NRD_FRAME: the per-frame rotator as is
     const float2 rectSizeInv = f2(1.0f / float(c.W), 1.0f / float(c.H));
+    #pragma omp parallel for schedule(dynamic, 4)          // pixels are independent within a pass (each writes its own outputs only)
     for (int y = 0; y < int(c.H); y++) for (int x = 0; x < int(c.W); x++)
     {
         if (tileIsSky(c, tiles, x, y)) continue;
@@ -566,6 +568,7 @@ inline void temporalAccumulation(const Constants& c, const FrameMatrices& m, con
         const float px[4] = { origin.x, origin.y, origin.x + 1, origin.y + 1 }; float r[4];
         for (int k = 0; k < 4; k++) r[k] = (px[k] >= 0.0f && px[k] < ((k & 1) ? rectSize.y : rectSize.x)) ? 1.0f : 0.0f;
         return f4(r[0] * r[1], r[2] * r[1], r[0] * r[3], r[2] * r[3]); };       // r.xzxz * r.yyww
+    #pragma omp parallel for schedule(dynamic, 4)          // pixels are independent within a pass (each writes its own outputs only)
     for (int y = 0; y < H; y++) for (int x = 0; x < W; x++)
     {
         if (tileIsSky(c, tiles, x, y)) continue;
@@ -844,6 +847,7 @@ inline void historyFix(const Constants& c, const Inputs& in, const std::vector<u
     const float2 rectSizeInv = f2(1.0f / float(W), 1.0f / float(H));
     auto frames = [&](int x, int y) { const size_t p = (size_t(clampi(y, 0, H - 1)) * W + clampi(x, 0, W - 1)) * 2; return f2(float(data1[p]) / 255.0f * 63.0f, float(data1[p + 1]) / 255.0f * 63.0f); };
     auto fastAt = [&](const std::vector<float>& img, int x, int y) { return img[size_t(clampi(y, 0, H - 1)) * W + clampi(x, 0, W - 1)]; };
+    #pragma omp parallel for schedule(dynamic, 4)          // pixels are independent within a pass (each writes its own outputs only)
     for (int y = 0; y < H; y++) for (int x = 0; x < W; x++)
     {
         if (tileIsSky(c, tiles, x, y)) continue;
@@ -963,6 +967,7 @@ inline void temporalStabilization(const Constants& c, const FrameMatrices& m, co
         const float hc = clampf(history, avg - s, avg + s);
         const float d = fabsf(history - hc) / (std::max(history, hc) + NRD_EPS);
         return 1.0f / (1.0f + d * accumSpeed / magic); };
+    #pragma omp parallel for schedule(dynamic, 4)          // pixels are independent within a pass (each writes its own outputs only)
     for (int y = 0; y < H; y++) for (int x = 0; x < W; x++)
     {
         if (tileIsSky(c, tiles, x, y)) continue;

@@ -467,6 +467,56 @@ def test_config4_4k_window_nested_dielectrics(product, oracle):
 
 
 @pytest.mark.gpu
+def test_config3_full_scene_realtime_neeat_reblur(product, oracle):
+    """BASELINE configs[2] at full size: the 2.8 M-triangle city with delta surfaces (glazed shop fronts, wet street: stable planes 1 / 2 populated), 1920x1080, realtime mode with
+    NEE-AT feedback, then ReBLUR on stable plane 0 - two whole frames, the IEEE build against the oracle, pixel by pixel.  Frame 1 samples lights through the feedback frame 0 left
+    (both sides are handed the oracle's reservoirs, as in test_gpu_neeat.py, so that the comparison is of the path tracer and not of one flipped reservoir); the oracle's ReBLUR
+    denoises the very inputs the product prepared, each side keeping its own history."""
+    from rtxpt_b200 import scenes, scene_builder as sb
+    W, H = 1920, 1080
+    scene, cam = scenes.city_block(width=W, height=H, delta_surfaces=True)
+    consts = sb.make_constants(W, H, cam, bounce_count=6, diffuse_bounce_count=6, env_enabled=True, firefly_threshold=5000.0, nee=True, nee_type=2); consts.NEEATFeedback = 1
+    c = product.Context(max_sub_samples_per_launch=1, strict=True); c.upload_scene(scene); c.set_constants(consts); c.set_view(sb.world_to_clip(cam))
+    o = oracle.Oracle(scene); o.set_constants(consts); o.set_view(sb.world_to_clip(cam)); o.neeat_reset()
+    rt = sb.make_realtime_constants(W, H, cam, bounce_count=6, sub_samples=1); c.set_realtime(rt)
+    k = sb.make_denoiser_constants(cam); rb = oracle.Reblur(); wv, vc = sb.world_to_view(cam), sb.view_to_clip(cam)
+    measured = {}
+    for f in range(2):
+        consts.sampleBaseIndex = f; c.set_constants(consts); o.set_constants(consts)
+        if f > 0: c.neeat_set_feedback(o.neeat_raw(0, np.float32, W * H), o.neeat_raw(1, np.uint32, W * H))
+        o.neeat_update_begin(); c.neeat_update_begin(); c.synchronize()
+        assert np.array_equal(o.neeat_raw(8, np.uint32, 8), c.neeat_raw(8, np.uint32, 8)), f                 # control words: tile grid, proxy count, pixels with feedback
+        r = o.render_realtime(rt)
+        c.path_trace_realtime(True); c.synchronize(); g = c.readback_realtime()
+        same = (g["header"][:3] == r["header"][:3]).all(0)
+        stable = (g["stable_radiance"][same] == r["stable_radiance"][same]).all(-1).mean()
+        d = np.abs(g["merged"] - r["merged"])[same]; scale = np.maximum(r["merged"][same], 0.05); close = (d / scale < 0.05).all(-1).mean()
+        mean_ratio = float(g["merged"].mean() / r["merged"].mean())
+        planes = [float((r["header"][p] != 0xFFFFFFFF).mean()) for p in range(3)]
+        # ReBLUR of plane 0 over the whole frame
+        c.denoiser_prepare_inputs(0, True, k); c.reblur_denoise(0, sb.make_reblur_frame(cam, cam, frame_index=f)); c.synchronize()
+        inputs, out = c.readback_denoiser_inputs(), c.readback_reblur()
+        od, os_, frames = rb.denoise(wv, vc, f, inputs["view_z"], inputs["normal_roughness"], inputs["diff"], inputs["spec"], motion=inputs["motion"], disocclusion_mix=inputs["disocclusion_mix"])
+        surf = inputs["view_z"] < 1e5
+        rbc = {}
+        for name, a, b in (("diff", out["diff"], od), ("spec", out["spec"], os_)):
+            a = a.astype(np.float32)[surf]; b = b.astype(np.float32)[surf]
+            assert np.isfinite(a).all(), (f, name)
+            rbc[name] = float(np.isclose(a, b, rtol=1e-2, atol=2e-3).all(-1).mean())
+        rbc["frames"] = float((np.abs(out["frames"] - frames) < 0.3)[surf].all(-1).mean())
+        measured[f] = dict(same_header=float(same.mean()), stable=float(stable), merged_close=float(close), mean_ratio=mean_ratio, planes=planes, reblur=rbc, surface=float(surf.mean()))
+        print("config3 frame", f, measured[f])
+    rb.close(); c.close(); o.close()
+    for f, m in measured.items():
+        assert m["planes"][1] > 0.2 and m["planes"][2] > 0.02, m                     # the decomposition has work to do in this view
+        assert m["same_header"] > 0.995, (f, m)
+        assert m["stable"] > 0.99, (f, m)
+        assert m["merged_close"] > 0.9, (f, m)                                     # texture filtering (TMU vs software) changes some paths, as in test_realtime_city_matches_oracle
+        assert abs(m["mean_ratio"] - 1) < 0.02, (f, m)
+        assert min(m["reblur"].values()) > 0.97, (f, m)
+
+
+@pytest.mark.gpu
 def test_opacity_masks_do_not_change_hits(product, small_city):
     """The opacity masks (the OMM analogue, rtxpt_b200/csrc/opacity_masks.h) only replace texture fetches whose outcome is certain: closest-hit and any-hit queries through the
     alpha-tested tree canopies, and a whole frame, are bit-identical with the masks baked and with RTXPT_CFG_NO_OPACITY_MASKS; a real share of the micro-triangles is decided."""
