@@ -36,8 +36,8 @@ int main(int argc, char** argv)
     RtxptConfig cfg = {}; cfg.deviceOrdinal = -1; cfg.maxSubSamplesPerLaunch = 4; cfg.tileWorld = 1; cfg.tileSize = 64;
     rtxpt_ctx* ctx = nullptr;
     if (rtxpt_b200_create(&cfg, &ctx) != RTXPT_OK) return fail("create (a CUDA device is required; there is no CPU fallback)", ctx);
-    // EnvironmentLight of the scene file (Sample::SceneLoaded -> EnvMapBaker, Rtxpt/Sample.cpp:1364-1388, Lighting/Distant/EnvMapBaker.cpp:164-169): the HDR DDS (the reference ships
-    // BC6H_UF16 cubes, *_cube_bc6u.dds) is decoded on the host, baked on the GPU into the cube + MIP chain the path tracer samples, and goes up with the scene
+    // EnvironmentLight of the scene file (Sample::SceneLoaded -> EnvMapBaker, Rtxpt/Sample.cpp:1364-1388, Lighting/Distant/EnvMapBaker.cpp:164-169): the HDR file - .dds (the reference ships
+    // BC6H_UF16 cubes, *_cube_bc6u.dds), .exr or .hdr lat-long (Sample.cpp:110-118) - is decoded on the host, baked on the GPU into the cube + MIP chain the path tracer samples, and goes up with the scene
     RtxptSceneDesc desc = *rtxpt_b200_host_scene_desc(scene);
     std::vector<float> envMips; RtxptSceneFileInfo info = {}; rtxpt_b200_host_scene_info(scene, &info);
     if (sceneFile && info.environmentMapPath[0])
@@ -46,13 +46,13 @@ int main(int argc, char** argv)
         const std::string envPath = dir + "/" + info.environmentMapPath;
         std::vector<unsigned char> bytes;
         if (FILE* ef = fopen(envPath.c_str(), "rb")) { fseek(ef, 0, SEEK_END); bytes.resize(size_t(ftell(ef))); fseek(ef, 0, SEEK_SET); if (fread(bytes.data(), 1, bytes.size(), ef) != bytes.size()) bytes.clear(); fclose(ef); }
-        uint32_t ew = 0, eh = 0, faces = 0, emips = 0;
-        if (bytes.empty() || rtxpt_b200_load_dds_hdr(bytes.data(), bytes.size(), &ew, &eh, &faces, &emips, nullptr, 0) != RTXPT_OK)
-            fprintf(stderr, "environment map '%s' not loaded (%s); rendering without it\n", envPath.c_str(), bytes.empty() ? "file missing" : rtxpt_b200_debug_decode_dds_error());
+        uint32_t ew = 0, eh = 0, faces = 0;
+        if (bytes.empty() || rtxpt_b200_load_hdr_image(bytes.data(), bytes.size(), &ew, &eh, &faces, nullptr, 0) != RTXPT_OK)
+            fprintf(stderr, "environment map '%s' not loaded (%s); rendering without it\n", envPath.c_str(), bytes.empty() ? "file missing" : rtxpt_b200_load_hdr_image_error());
         else
         {
             std::vector<float> src(size_t(ew) * eh * 4 * faces);
-            rtxpt_b200_load_dds_hdr(bytes.data(), bytes.size(), &ew, &eh, &faces, &emips, src.data(), src.size());
+            rtxpt_b200_load_hdr_image(bytes.data(), bytes.size(), &ew, &eh, &faces, src.data(), src.size());
             RtxptEnvBakeDesc bake = {}; bake.cubeDim = 1024; bake.sourceType = faces >= 6 ? 2u : 1u; bake.sourceWidth = ew; bake.sourceHeight = eh; bake.source = src.data();
             for (int k = 0; k < 3; k++) bake.scaleColor[k] = info.environmentRadianceScale[k];
             envMips.resize(rtxpt_b200_env_bake_floats(bake.cubeDim));

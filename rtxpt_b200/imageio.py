@@ -26,3 +26,20 @@ def per_pixel_l2(a, b):
 def rel_mse(a, b, eps=1e-2):
     a = np.asarray(a, np.float64)[..., :3]; b = np.asarray(b, np.float64)[..., :3]
     return float((((a - b) ** 2) / (b * b + eps)).mean())
+
+
+def read_pfm(path):
+    """PFM ('PF' RGB or 'Pf' grey, scale < 0 = little endian, bottom row first - what examples/render_gltf.cpp writes) -> H x W x 3 (or H x W) float32, top row first."""
+    with open(path, "rb") as f:
+        kind = f.readline().strip(); w, h = (int(v) for v in f.readline().split()); scale = float(f.readline())
+        if kind not in (b"PF", b"Pf"): raise ValueError("%s: not a PFM file" % path)
+        ch = 3 if kind == b"PF" else 1
+        a = np.frombuffer(f.read(w * h * ch * 4), "<f4" if scale < 0 else ">f4").astype(np.float32)
+    a = a.reshape(h, w, ch)[::-1]
+    return np.ascontiguousarray(a if ch == 3 else a[..., 0])
+
+
+def write_pfm(path, rgb):
+    a = np.asarray(rgb, np.float32)[..., :3]
+    with open(path, "wb") as f:
+        f.write(b"PF\n%d %d\n-1.0\n" % (a.shape[1], a.shape[0])); f.write(np.ascontiguousarray(a[::-1]).astype("<f4").tobytes())

@@ -98,3 +98,14 @@ def test_radiance_hdr(golden):
     assert np.array_equal(out[0, :, :3], np.array([[1.0, 0.5, 0.25], [0, 0, 0], [255.0, 0, 0]], np.float32))
     with pytest.raises(L.RtxptError, match="truncated"): L.load_hdr_image(f[:-3])
     with pytest.raises(L.RtxptError, match="resolution"): L.load_hdr_image(f.replace(b"-Y 1 +X 3", b"+X 3 -Y 1"))
+
+
+def test_compare_script_reads_exr_against_pfm(tmp_path, golden):
+    """scripts/compare_hdr_images.py: an EXR 'reference dump' against our PFM of the same pixels passes the 1e-3 gate, a perturbed one fails it."""
+    import subprocess, sys
+    from rtxpt_b200.imageio import write_pfm, read_pfm
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rgb = golden["rgb"]; p = str(tmp_path / "ours.pfm"); write_pfm(p, rgb); assert np.array_equal(read_pfm(p), rgb)
+    cmd = [sys.executable, os.path.join(root, "scripts", "compare_hdr_images.py"), os.path.join(G, "exr_zip_float.exr")]
+    ok = subprocess.run(cmd + [p], capture_output=True, text=True); assert ok.returncode == 0 and "per-pixel L2 0.000e+00" in ok.stdout, ok.stdout + ok.stderr
+    write_pfm(p, rgb * 1.1 + 0.05); bad = subprocess.run(cmd + [p], capture_output=True, text=True); assert bad.returncode == 1, bad.stdout
