@@ -24,19 +24,7 @@ static const uint NEEAT_TOP_UP_SAMPLES = NEEAT_LOCAL_PROXY_COUNT - NEEAT_WINDOW_
 static const uint LFR_SCREEN_SPACE_COHERENT_FLAG = 0x80000000u;
 static const float LFR_MAX_WEIGHT = 1e12f;
 
-struct MicroRng
-{
-    uint N;
-    static MicroRng make(uint x, uint y, uint seedA, uint seedB)
-    {
-        MicroRng r; r.N = ((x << 16) | y) ^ 0x9e3779b9u;
-        r.N = r.N ^ (seedA + (r.N << 6) + (r.N >> 2));
-        r.N = r.N ^ (seedB + (r.N << 6) + (r.N >> 2));
-        return r;
-    }
-    uint Next() { N ^= N >> 16; N *= 0x21f0aaadu; N ^= N >> 15; N *= 0xf35a2d97u; N ^= N >> 15; return N; }
-    float NextFloat() { return float(Next() >> 8) / 16777216.0f; }
-};
+// MicroRng (Libraries/MicroRng.hlsli): pt_scene.h
 
 inline uint PackMiniListLightAndCount(uint lightIndex, uint counter) { return ((lightIndex & 0x007FFFFFu) << 9) | ((counter - 1) & 0x1FFu); }
 inline uint UnpackMiniListLight(uint v) { return v >> 9; }

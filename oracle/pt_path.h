@@ -480,7 +480,7 @@ inline void HandleHit(const PathTracerCtx& x, PathState& path, float3 rayOrigin,
 {
     const bool build = x.mode == MODE_BUILD_STABLE_PLANES;
     UpdatePathTravelled(path, rayTCurrent);
-    SurfaceData surface = loadSurface(*x.scene, tri.instanceIndex, tri.geometryIndex, tri.primitiveIndex, barycentrics, rayDir, path.rayCone, x.c->texLODBias);
+    SurfaceData surface = loadSurface(*x.scene, tri.instanceIndex, tri.geometryIndex, tri.primitiveIndex, barycentrics, rayDir, path.rayCone, x.c->texLODBias, path.getVertexIndex(), path.id >> 16, path.id & 0xFFFF, x.sampleIndex);
     const uint ndq = x.c->nestedDielectricsQuality;
     if (ndq > 0 && !path.interiorList.isEmpty())
     {   // homogeneous absorption (BridgeDonut:871-887, HomogeneousVolumeSampler::evalTransmittance)
@@ -754,7 +754,7 @@ inline void StablePlanesHandleHit(const PathTracerCtx& x, PathState& path, float
         const bool blockedAtSurface = path.GetMotionVectorSceneLength() != 0;
         const float sceneLengthForMVs = blockedAtSurface ? path.GetMotionVectorSceneLength() : path.sceneLength;
         const float3 virtualWorldPos = camO + camD * sceneLengthForMVs;
-        const float3 worldMotion = f3(0);                  // prevPosW - posW: the scene tables carry no previous transforms (static geometry)
+        const float3 worldMotion = surfaceData.prevPosW - sd.posW;     // actual world-space motion: instance.prevTransform / the previous-position stream (PathTracerStablePlanes.hlsli:286)
         const float3 virtualWorldMotion = mul(imageXform, worldMotion);
         const float3 motionVectors = T.computeMotionVector(virtualWorldPos, virtualWorldPos + virtualWorldMotion);
         float roughness = saturate(surfaceData.bsdf.data.roughness);

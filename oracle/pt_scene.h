@@ -165,6 +165,7 @@ struct SurfaceData      // PathTracerTypes.hlsli:52-94
     float interiorIoR;
     uint neeTriangleLightIndex;
     uint neeAnalyticLightIndex;     // light the hit geometry stands in for (PTMaterialFlags_EnableAsAnalyticLightProxy), else 0xFFFFFFFF
+    float3 prevPosW;                // instance.prevTransform x prevObjectSpacePosition (BridgeDonut:631); read by the BUILD pass's motion vectors only
 };
 
 struct Scene
@@ -198,6 +199,44 @@ struct GeometrySample   // DonutGeometrySample, PathTracerBridgeDonut.hlsli:57-8
     float3 vertexPositions[3]; float2 vertexTexcoords[3];
     float3 objectSpacePosition; float2 texcoord;
     float3 flatNormal, geometryNormal; float4 tangent; bool frontFacing;
+    float3 prevObjectSpacePosition;     // GeomAttr_PrevPosition: last frame's position where the geometry carries a previous-position stream (skinned meshes), else the current one
+    float curvatureWS;                  // TriangleCurvatureApprox_GradN
+};
+
+// PathTracerBridgeDonut.hlsli:104-150: RMS magnitude of the gradient of the (object-space, unit) vertex normals over the world-space triangle, 1 / position units
+inline float TriangleCurvatureApprox_GradN(const float3 vertexPositions[3], const float3 vertexNormals[3], const float* xf)
+{
+    const float eps = 1e-8f;
+    float3 e10 = mul34_vec(xf, vertexPositions[1] - vertexPositions[0]);
+    float e10Len = length(e10);
+    if (e10Len < eps) return 0.0f;
+    float3 e1 = e10 / e10Len;
+    float3 e20 = mul34_vec(xf, vertexPositions[2] - vertexPositions[0]);
+    float u2 = dot(e20, e1);
+    float3 t = e20 - e1 * u2;
+    float tLen = length(t);
+    if (tLen < eps) return 0.0f;
+    float3 e2 = t / tLen;
+    float u1 = e10Len, v2 = dot(e20, e2);
+    float3 dn1 = vertexNormals[1] - vertexNormals[0], dn2 = vertexNormals[2] - vertexNormals[0];
+    float3 a = dn1 / std::max(u1, eps);
+    float denomV = fabsf(v2) < eps ? (v2 >= 0.0f ? eps : -eps) : v2;
+    float3 b = (dn2 - a * u2) / denomV;
+    return sqrtf(dot(a, a) + dot(b, b));
+}
+// Libraries/MicroRng.hlsli:12-58
+struct MicroRng
+{
+    uint N;
+    static MicroRng make(uint x, uint y, uint seedValueA, uint seedValueB)
+    {
+        MicroRng r; r.N = ((x << 16) | y) ^ 0x9e3779b9u;
+        r.N = r.N ^ (seedValueA + (r.N << 6) + (r.N >> 2));
+        r.N = r.N ^ (seedValueB + (r.N << 6) + (r.N >> 2));
+        return r;
+    }
+    uint Next() { N ^= N >> 16; N *= 0x21f0aaadu; N ^= N >> 15; N *= 0xf35a2d97u; N ^= N >> 15; return N; }
+    float NextFloat() { return float(Next() >> 8) / 16777216.0f; }
 };
 
 inline GeometrySample getGeometryFromHit(const Scene& sc, uint instanceIndex, uint geometryIndex, uint triangleIndex, float2 rayBary, float3 rayDirection)
@@ -211,6 +250,12 @@ inline GeometrySample getGeometryFromHit(const Scene& sc, uint instanceIndex, ui
     for (int k = 0; k < 3; k++) idx[k] = sc.load32(g.indexBufferIndex, g.indexOffset + triangleIndex * 12 + k * 4);
     for (int k = 0; k < 3; k++) gs.vertexPositions[k] = sc.loadFloat3(g.vertexBufferIndex, g.positionOffset + idx[k] * 12);
     gs.objectSpacePosition = gs.vertexPositions[0] * bary.x + gs.vertexPositions[1] * bary.y + gs.vertexPositions[2] * bary.z;
+    gs.prevObjectSpacePosition = gs.objectSpacePosition;
+    if (g.prevPositionOffset != ~0u)        // only present for skinned objects (BridgeDonut:187-199)
+    {
+        float3 pv[3]; for (int k = 0; k < 3; k++) pv[k] = sc.loadFloat3(g.vertexBufferIndex, g.prevPositionOffset + idx[k] * 12);
+        gs.prevObjectSpacePosition = pv[0] * bary.x + pv[1] * bary.y + pv[2] * bary.z;
+    }
     if (g.texCoord1Offset != ~0u)
     {
         for (int k = 0; k < 3; k++) gs.vertexTexcoords[k] = sc.loadFloat2(g.vertexBufferIndex, g.texCoord1Offset + idx[k] * 8);
@@ -227,6 +272,7 @@ inline GeometrySample getGeometryFromHit(const Scene& sc, uint instanceIndex, ui
             n[k] = normalize(Unpack_RGB8_SNORM(sc.load32(g.vertexBufferIndex, g.normalOffset + idx[k] * 4)));
             n[k] = FlipIfOpposite(n[k], objectSpaceFlatNormal);
         }
+        gs.curvatureWS = TriangleCurvatureApprox_GradN(gs.vertexPositions, n, xf);
         gs.geometryNormal = n[0] * bary.x + n[1] * bary.y + n[2] * bary.z;
         gs.geometryNormal = SafeNormalize(mul34_vec(xf, gs.geometryNormal));
     }
@@ -376,7 +422,7 @@ inline MaterialProperties sampleGeometryMaterial(const Scene& sc, const Geometry
 
 // Bridge::loadSurface, PathTracerBridgeDonut.hlsli:612-853
 inline SurfaceData loadSurface(const Scene& sc, uint instanceIndex, uint geometryIndex, uint triangleIndex, float2 barycentrics,
-                               float3 rayDir, RayCone rayCone, float texLODBias)
+                               float3 rayDir, RayCone rayCone, float texLODBias, uint pathVertexIndex = 1, uint pixelX = 0, uint pixelY = 0, uint sampleIndex = 0)
 {
     GeometrySample gs = getGeometryFromHit(sc, instanceIndex, geometryIndex, triangleIndex, barycentrics, rayDir);
     float3 posW = mul34_point(gs.instance->transform, gs.objectSpacePosition);
@@ -384,6 +430,7 @@ inline SurfaceData loadSurface(const Scene& sc, uint instanceIndex, uint geometr
     float lambda = rayCone.computeLOD(coneTexLODValue, rayDir, gs.flatNormal, true) + texLODBias;
 
     SurfaceData out = {};
+    out.prevPosW = mul34_point(gs.instance->prevTransform, gs.prevObjectSpacePosition);
     ShadingData& sd = out.sd;
     sd.posW = posW;
     sd.V = -rayDir;
@@ -402,7 +449,19 @@ inline SurfaceData loadSurface(const Scene& sc, uint instanceIndex, uint geometr
     sd.thinSurface = (mat.flags & RTXPT_MATFLAG_ThinSurface) != 0;
     sd.psdExclude = (mat.flags & RTXPT_MATFLAG_PSDExclude) != 0;
     sd.psdDominantDeltaLobeP1 = (mat.flags & 0x0F000000u) >> 24;                                    // PTMaterialFlags_PSDDominantDeltaLobeP1Mask/Shift (BridgeDonut:700)
-    sd.psdBlockMotionVectorsAtSurface = ((mat.flags >> 13) & 3u) == 3u;                              // block type 3 "Full"; the curvature heuristics of types 1/2 (BridgeDonut:704-718) are not restated: treated as Off
+    {   // stopping motion vectors from being calculated behind this surface (BridgeDonut:702-718): 0 Off, 1 AutoLow, 2 AutoHigh (curvature seen through the ray cone), 3 Full
+        const uint blockType = (mat.flags >> 13) & 3u;
+        bool blockMVs = blockType == 3u;
+        if (blockType == 1u || blockType == 2u)
+        {
+            const float projectionTerm = fabsf(dot(rayDir, -sd.N));
+            const float pixelCurvature = (gs.curvatureWS * rayCone.getWidth()) / std::max(projectionTerm, 1e-6f);
+            const float threshold = blockType == 1u ? 0.03f : 0.0005f;
+            MicroRng rng = MicroRng::make(pixelX, pixelY, pathVertexIndex, sampleIndex);
+            blockMVs |= pixelCurvature > ((rng.NextFloat() * 0.9f + 0.3f) * threshold);
+        }
+        sd.psdBlockMotionVectorsAtSurface = blockMVs;
+    }
     adjustShadingNormal(sd, gs.tangent, true, ignoreTangent);
     sd.shadowNoLFadeout = mat.shadowNoLFadeout;
 

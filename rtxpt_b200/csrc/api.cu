@@ -80,7 +80,9 @@ struct rtxpt_ctx
     std::vector<RtxptInstanceData> hInstances; std::vector<uint32_t> bvhLevelStart; DeviceArray<float> dNodeBox;      // rigid-instance animation (refit.cuh)
     // skinned meshes (skinning.cuh): where each (instance, geometry)'s triangles start in gid order, its index range on the device, and the registered bind poses
     std::vector<RtxptGeometryData> hGeometries; std::vector<uint32_t> firstGidOfSubInstance; std::vector<const uint8_t*> hBufferTable; std::vector<uint32_t> maxVertexOfSubInstance;      // largest vertex index each sub-instance's triangles name (skin registration validates against it)
-    struct Skin { uint32_t numVertices = 0, numTriangles = 0, firstGid = 0, flags = 0, numJoints = 0, maxJoint = 0; const uint32_t* dIndices = nullptr;
+    // last frame's object-space corners of geometries with a previous-position stream (scene_device.cuh: prevPosBase / triPrevPos)
+    std::vector<uint32_t> hPrevPosBase; DeviceArray<uint32_t> dPrevPosBase; DeviceArray<float> dTriPrevPos; size_t prevPosTriangles = 0;
+    struct Skin { uint32_t numVertices = 0, numTriangles = 0, firstGid = 0, flags = 0, numJoints = 0, maxJoint = 0, prevPosFirst = 0; const uint32_t* dIndices = nullptr;
                   DeviceArray<float> positions, weights, outPositions, jointMatrices; DeviceArray<uint32_t> normals, tangents, outNormals, outTangents; DeviceArray<unsigned short> jointIndices; };
     std::vector<Skin*> skins;
     uint32_t bvhNodeCount = 0, bvhTriCount = 0; float bvhBuildSeconds = 0;
@@ -230,7 +232,7 @@ extern "C" RTXPT_API int rtxpt_b200_destroy(rtxpt_ctx* c)
     syncContext(c);
     releaseScene(c);
     c->dInstances.release(); c->dGeometries.release(); c->dSubInstances.release(); c->dMaterials.release(); c->dSubInstanceClass.release();
-    c->dBufferTable.release(); c->dTextureTable.release(); c->dBvhNodes.release(); c->dBvhTris.release(); c->dTriInfo.release(); c->dTriShade.release(); c->dNodeBox.release();
+    c->dBufferTable.release(); c->dTextureTable.release(); c->dBvhNodes.release(); c->dBvhTris.release(); c->dTriInfo.release(); c->dTriShade.release(); c->dNodeBox.release(); c->dPrevPosBase.release(); c->dTriPrevPos.release();
     c->dLightsEx.release(); c->dLights.release(); c->dProxyCounters.release(); c->dProxyIndices.release(); c->dEnvLookup.release();
     c->s0.release(); c->s1.release(); c->s2.release(); c->s3.release(); c->s4.release(); c->hits.release();
     c->rayQueue[0].release(); c->rayQueue[1].release(); c->shadeQueue.release();
@@ -350,7 +352,7 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
     releaseScene(c);
     if (sc->materialCount > 0xFFFF || sc->textureCount > 0xFFFF || sc->bufferCount > 0xFFFF) return fail(RTXPT_ERR_UNSUPPORTED, "table sizes exceed the 16-bit indices of SubInstanceData");
     // validate + flatten triangles to world space (gid order: instance, geometry, primitive)
-    std::vector<BuildTriangle> tris; std::vector<uint4> triInfo, triShade; std::vector<uint32_t> firstGid, maxVertex;
+    std::vector<BuildTriangle> tris; std::vector<uint4> triInfo, triShade; std::vector<uint32_t> firstGid, maxVertex, prevPosBase; std::vector<float> triPrevPos;
     struct MaskJob { uint32_t tri, texture, cutoff; float uv[3][2]; }; std::vector<MaskJob> maskJobs;         // alpha-tested triangles that get an opacity mask (opacity_masks.h)
     const bool bakeMasks = !(c->cfg.flags & RTXPT_CFG_NO_OPACITY_MASKS);
     for (uint32_t ii = 0; ii < sc->instanceCount; ii++)
@@ -364,6 +366,8 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
             const uint32_t subIndex = inst.firstGeometryInstanceIndex + gi;
             if (firstGid.size() <= subIndex) firstGid.resize(size_t(subIndex) + 1, 0u);
             firstGid[subIndex] = uint32_t(tris.size());
+            const bool hasPrev = g.prevPositionOffset != ~0u;          // Donut: only skinned geometries carry last frame's positions
+            prevPosBase[subIndex] = hasPrev ? uint32_t(triPrevPos.size() / 9) : 0xFFFFFFFFu;
             if (maxVertex.size() <= subIndex) maxVertex.resize(size_t(subIndex) + 1, 0u);
             const RtxptSubInstanceData& sub = sc->subInstances[subIndex];
             uint32_t flags = subIndex;
@@ -387,6 +391,11 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
                         (hasT && uint64_t(g.tangentOffset) + uint64_t(idx[k]) * 4 + 4 > vbSize)) return fail(RTXPT_ERR_INVALID_ARGUMENT, "vertex attribute exceeds buffer");
                     float v[3]; memcpy(v, vb + g.positionOffset + size_t(idx[k]) * 12, 12);
                     hostXformPoint(inst.transform, v, dst[k]);
+                    if (hasPrev)
+                    {
+                        if (uint64_t(g.prevPositionOffset) + uint64_t(idx[k]) * 12 + 12 > vbSize) return fail(RTXPT_ERR_INVALID_ARGUMENT, "previous-position stream exceeds buffer");
+                        float pv[3]; memcpy(pv, vb + g.prevPositionOffset + size_t(idx[k]) * 12, 12); triPrevPos.insert(triPrevPos.end(), pv, pv + 3);
+                    }
                     uint32_t w[3]; memcpy(w, v, 12); uint32_t nrm = 0, tan = 0, uv[2] = { 0, 0 };
                     if (hasN) memcpy(&nrm, vb + g.normalOffset + size_t(idx[k]) * 4, 4);
                     if (hasT) memcpy(&tan, vb + g.tangentOffset + size_t(idx[k]) * 4, 4);
@@ -456,6 +465,9 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
     CU(c->dBvhTris.upload(reinterpret_cast<const float4*>(bvh.tris.data()), bvh.tris.size() * 3, s));
     CU(c->dTriInfo.upload(triInfo.data(), triInfo.size(), s));
     CU(c->dTriShade.upload(triShade.data(), triShade.size(), s));
+    c->hPrevPosBase = prevPosBase; c->prevPosTriangles = triPrevPos.size() / 9;
+    CU(c->dPrevPosBase.upload(prevPosBase.data(), prevPosBase.size(), s));
+    if (!triPrevPos.empty()) CU(c->dTriPrevPos.upload(triPrevPos.data(), triPrevPos.size(), s)); else c->dTriPrevPos.release();
     if (!masks.empty()) CU(c->dOpacityMasks.upload(masks.data(), masks.size(), s)); else c->dOpacityMasks.release();
     CU(c->dInstances.upload(sc->instances, sc->instanceCount, s));
     c->hInstances.assign(sc->instances, sc->instances + sc->instanceCount); c->bvhLevelStart = bvh.levelStart; c->dNodeBox.release();
@@ -613,7 +625,7 @@ static void fillParams(rtxpt_ctx* c, LaunchParams& p)
     v.instances = c->dInstances.ptr; v.geometries = c->dGeometries.ptr; v.subInstances = c->dSubInstances.ptr; v.materials = c->dMaterials.ptr;
     v.subInstanceClass = c->dSubInstanceClass.ptr; v.materialCount = c->materialCount;
     v.buffers = c->dBufferTable.ptr; v.textures = c->dTextureTable.ptr; v.envCube = c->envCube.object; v.envFaceSize = c->envFaceSize; v.envMipLevels = c->envMipLevels;
-    v.bvhNodes = c->dBvhNodes.ptr; v.bvhTris = c->dBvhTris.ptr; v.triInfo = c->dTriInfo.ptr; v.triShade = c->dTriShade.ptr; v.opacityMasks = c->dOpacityMasks.ptr; v.bvhNodeCount = c->bvhNodeCount; v.bvhTriCount = c->bvhTriCount;
+    v.bvhNodes = c->dBvhNodes.ptr; v.bvhTris = c->dBvhTris.ptr; v.triInfo = c->dTriInfo.ptr; v.triShade = c->dTriShade.ptr; v.opacityMasks = c->dOpacityMasks.ptr; v.prevPosBase = c->dPrevPosBase.ptr; v.triPrevPos = c->dTriPrevPos.ptr; v.bvhNodeCount = c->bvhNodeCount; v.bvhTriCount = c->bvhTriCount;
     v.lightsEx = c->dLightsEx.ptr; v.analyticLightCount = uint32_t(c->lightState.analyticLightsEx.size());
     v.lights = c->dLights.ptr; v.proxyCounters = c->dProxyCounters.ptr; v.proxyIndices = c->dProxyIndices.ptr; v.envLookupMap = c->dEnvLookup.ptr;
     v.lightCount = uint32_t(c->lightState.lights.size()); v.samplingProxyCount = uint32_t(c->lightState.proxyIndices.size()); v.envEnabled = c->lightState.envEnabled ? 1u : 0u;
@@ -1005,6 +1017,24 @@ extern "C" RTXPT_API int rtxpt_b200_skin_register(rtxpt_ctx* c, const RtxptSkinD
     if (e == cudaSuccess) e = sk->outTangents.alloc(d->numVertices);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) { delete sk; CU(e); }
+    {   // last frame's positions for the BUILD pass's motion vectors: a geometry that came without a previous-position stream gets a range now, holding its current corners
+        const uint32_t subIndex = inst.firstGeometryInstanceIndex + d->geometryIndexInInstance;
+        if (c->hPrevPosBase[subIndex] == 0xFFFFFFFFu && sk->numTriangles)
+        {
+            e = syncContext(c);
+            DeviceArray<float> grown;
+            if (e == cudaSuccess) e = grown.alloc((c->prevPosTriangles + sk->numTriangles) * 9);
+            if (e == cudaSuccess && c->prevPosTriangles) e = cudaMemcpy(grown.ptr, c->dTriPrevPos.ptr, c->prevPosTriangles * 36, cudaMemcpyDeviceToDevice);
+            if (e != cudaSuccess) { grown.release(); delete sk; CU(e); }
+            c->dTriPrevPos.release(); c->dTriPrevPos = grown; grown.ptr = nullptr; grown.count = 0;
+            c->hPrevPosBase[subIndex] = uint32_t(c->prevPosTriangles); c->prevPosTriangles += sk->numTriangles;
+            e = cudaMemcpy(c->dPrevPosBase.ptr + subIndex, &c->hPrevPosBase[subIndex], 4, cudaMemcpyHostToDevice);
+            skin::Params ip{}; ip.numTriangles = sk->numTriangles; ip.firstGid = sk->firstGid; ip.triShade = c->dTriShade.ptr; ip.triPrevPos = c->dTriPrevPos.ptr + size_t(c->hPrevPosBase[subIndex]) * 9;
+            if (e == cudaSuccess) { launchSkinInitPrev(ip, s); e = cudaStreamSynchronize(s); }
+            if (e != cudaSuccess) { delete sk; CU(e); }
+        }
+        sk->prevPosFirst = c->hPrevPosBase[subIndex];
+    }
     c->skins.push_back(sk); *outSkinId = uint32_t(c->skins.size() - 1);
     return RTXPT_OK;
 }
@@ -1023,6 +1053,7 @@ extern "C" RTXPT_API int rtxpt_b200_skin_update(rtxpt_ctx* c, uint32_t skinId, c
     p.numVertices = sk.numVertices; p.numTriangles = sk.numTriangles; p.firstGid = sk.firstGid; p.flags = sk.flags;
     p.positions = sk.positions.ptr; p.normals = sk.normals.ptr; p.tangents = sk.tangents.ptr; p.jointIndices = sk.jointIndices.ptr; p.jointWeights = sk.weights.ptr; p.jointMatrices = sk.jointMatrices.ptr;
     p.outPositions = sk.outPositions.ptr; p.outNormals = sk.outNormals.ptr; p.outTangents = sk.outTangents.ptr; p.indices = sk.dIndices; p.triShade = c->dTriShade.ptr;
+    p.triPrevPos = c->dTriPrevPos.ptr + size_t(sk.prevPosFirst) * 9;
     launchSkin(p, s);
     CU(cudaGetLastError());
     return RTXPT_OK;

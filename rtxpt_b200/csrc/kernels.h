@@ -42,6 +42,7 @@ void launchRtShadeNeeat(const LaunchParams& p, const GridConfig& g, cudaStream_t
 void launchTraceShadowRealtimeNeeat(const LaunchParams& p, const GridConfig& g, cudaStream_t s);   // + feedback insertion for visible samples (kernels.cu)
 namespace skin { struct Params; }
 void launchSkin(const skin::Params& p, cudaStream_t s);                 // skinning_kernels.cu
+void launchSkinInitPrev(const skin::Params& p, cudaStream_t s);         // previous-position range of a newly registered skin := the shade records' current corners
 namespace tonemap { struct Params; }
 void launchToneMap(const tonemap::Params& p, const void* src, bool srcIsF32, uint32_t pixelCount, double* partials, float* avgLuminance, uint32_t* dst, cudaStream_t s);      // tonemap_kernels.cu
 namespace refit { struct Params; }

@@ -301,7 +301,7 @@ PT_DEVICE void stablePlanesHandleHit(const LaunchParams& p, PathRegs& path, floa
         const bool blockedAtSurface = mvLength != 0;
         const float sceneLengthForMVs = blockedAtSurface ? mvLength : path.sceneLength;
         const float3 virtualWorldPos = co + cd * sceneLengthForMVs;
-        const float3 virtualWorldMotion = matVec(imageXform, mk3(0.f));          // prevPosW - posW: the scene tables carry no previous transforms (static geometry)
+        const float3 virtualWorldMotion = matVec(imageXform, s.prevPosW - s.posW);      // actual world-space motion (instance.prevTransform / previous-position stream) seen through the stacked reflections (PathTracerStablePlanes.hlsli:286-288)
         const float3 motion = computeMotionVector(p.rt, virtualWorldPos, virtualWorldPos + virtualWorldMotion);
         float roughness = sat(s.bsdf.roughness);
         const float3 worldNormal = norm3(matVec(imageXform, s.N));

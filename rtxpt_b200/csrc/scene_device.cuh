@@ -29,6 +29,10 @@ struct SceneView
     const uint4*                triShade;           // per global triangle id, 6 x uint4 (kTriShadeWords): everything loadSurface gathers per vertex, see below
     const uint4*                opacityMasks;       // per alpha-tested triangle (slot = third w word of its BVH triangle): 64 x 2-bit states, opacity_masks.h
     uint                        bvhNodeCount, bvhTriCount;
+    // last frame's object-space corner positions of the triangles of geometries that carry a previous-position stream (skinned meshes; Donut's prevPositionOffset):
+    // prevPosBase[sub-instance] = first triangle slot in triPrevPos (9 floats per triangle) or 0xFFFFFFFF; read by the BUILD pass's motion vectors only
+    const uint*                 prevPosBase;
+    const float*                triPrevPos;
     // lights
     const LightInfo*            lights;
     const uint*                 proxyCounters;

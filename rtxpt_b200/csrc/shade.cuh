@@ -174,6 +174,7 @@ struct Surface
     uint neeAnalyticLightIndex;     // light this geometry stands in for (PTMaterialFlags_EnableAsAnalyticLightProxy), else kInvalidLight
     // path-space decomposition controls, read by realtime mode only (MaterialHeader, BridgeDonut:699-718)
     bool psdExclude, psdBlockMVs; uint psdDominantDeltaLobeP1;
+    float3 prevPosW;                // BUILD pass only: instance.prevTransform x last frame's object-space position (BridgeDonut:631)
 };
 
 PT_DEVICE float3 safeNormalize(float3 v) { return v * (1.0f / sqrtf(fmaxf(1.175494351e-38f, dot3(v, v)))); }
@@ -186,7 +187,31 @@ PT_DEVICE void computeTangentSpace(Surface& s, float4 tangentW, bool ignoreTange
     else { s.T = perpStark(s.N); s.B = cross3(s.N, s.T); }
 }
 
-PT_DEVICE void loadSurface(const LaunchParams& p, uint gid, float bu, float bv, float3 rayDir, float coneWidth, Surface& s)
+// PathTracerBridgeDonut.hlsli:104-150: RMS magnitude of the gradient of the (object-space, unit) vertex normals over the world-space triangle, 1 / position units
+PT_DEVICE float triangleCurvatureGradN(const float* xf, float3 p0, float3 p1, float3 p2, float3 n0, float3 n1, float3 n2)
+{
+    const float eps = 1e-8f;
+    const float3 e10 = xfVector(xf, p1 - p0);
+    const float e10Len = len3(e10);
+    if (e10Len < eps) return 0.0f;
+    const float3 e1 = e10 / e10Len;
+    const float3 e20 = xfVector(xf, p2 - p0);
+    const float u2 = dot3(e20, e1);
+    const float3 t = e20 - e1 * u2;
+    const float tLen = len3(t);
+    if (tLen < eps) return 0.0f;
+    const float3 e2 = t / tLen;
+    const float v2 = dot3(e20, e2);
+    const float3 a = (n1 - n0) / fmaxf(e10Len, eps);
+    const float denomV = fabsf(v2) < eps ? (v2 >= 0.0f ? eps : -eps) : v2;
+    const float3 b = ((n2 - n0) - a * u2) / denomV;
+    return sqrtf(dot3(a, a) + dot3(b, b));
+}
+
+// MODE: the realtime passes also need the motion-vector controls of the surface (block heuristics: every realtime pass; last frame's position: BUILD pass only); the reference-mode
+// instantiation carries none of that code.  pathId = packed pixel, vertexIndex / sampleIndex seed the heuristic's MicroRng (BridgeDonut:714).
+template <int MODE>
+PT_DEVICE void loadSurface(const LaunchParams& p, uint gid, float bu, float bv, float3 rayDir, float coneWidth, Surface& s, uint pathId = 0, uint vertexIndex = 1, uint sampleIndex = 0)
 {
     const SceneView& sc = p.scene;
     // one contiguous 96-byte record per triangle (scene_device.cuh) instead of the reference's chain of table and vertex fetches (BridgeDonut:152-256)
@@ -208,6 +233,7 @@ PT_DEVICE void loadSurface(const LaunchParams& p, uint gid, float bu, float bv, 
     }
     const float3 objFlat = safeNormalize(cross3(p1 - p0, p2 - p0));
     float3 geometryNormal = mk3(0.f);
+    float curvatureWS = 0.0f;
     if (r5.w & kTriShadeHasNormal)
     {
         float3 n0 = norm3(mk3(unpackSnorm8(r0.w), unpackSnorm8(r0.w >> 8), unpackSnorm8(r0.w >> 16)));
@@ -216,6 +242,7 @@ PT_DEVICE void loadSurface(const LaunchParams& p, uint gid, float bu, float bv, 
         if (dot3(n0, objFlat) < 0) n0 = -n0;
         if (dot3(n1, objFlat) < 0) n1 = -n1;
         if (dot3(n2, objFlat) < 0) n2 = -n2;
+        if (MODE != kModeReference) { const uint blockType = (sc.materials[sc.subInstances[r5.z].GlobalGeometryIndex_PTMaterialDataIndex & 0xFFFF].Flags >> 13) & 3u; if (blockType == 1u || blockType == 2u) curvatureWS = triangleCurvatureGradN(xf, p0, p1, p2, n0, n1, n2); }
         geometryNormal = safeNormalize(xfVector(xf, n0 * b0 + n1 * bu + n2 * bv));
     }
     float4 tangent = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -232,6 +259,17 @@ PT_DEVICE void loadSurface(const LaunchParams& p, uint gid, float bu, float bv, 
     const bool frontFacing = dot3(-rayDir, flatNormal) >= 0.0f;
 
     s.posW = xfPoint(xf, objPos);
+    if (MODE == kModeBuildStablePlanes)
+    {   // GeomAttr_PrevPosition (BridgeDonut:187-199, :631)
+        float3 prevObj = objPos;
+        const uint base = sc.prevPosBase ? __ldg(sc.prevPosBase + r5.z) : 0xFFFFFFFFu;
+        if (base != 0xFFFFFFFFu)
+        {
+            const float* q = sc.triPrevPos + (size_t(base) + (r5.w & kTriShadePrimMask)) * 9;
+            prevObj = mk3(__ldg(q), __ldg(q + 1), __ldg(q + 2)) * b0 + mk3(__ldg(q + 3), __ldg(q + 4), __ldg(q + 5)) * bu + mk3(__ldg(q + 6), __ldg(q + 7), __ldg(q + 8)) * bv;
+        }
+        s.prevPosW = xfPoint(inst.prevTransform, prevObj);
+    }
     // ray-cone LOD: computeRayConeTriangleLODValue + RayCone::computeLOD(moreDetailOnSlopes) + texLODBias
     float lodNoDims;
     {
@@ -319,7 +357,17 @@ PT_DEVICE void loadSurface(const LaunchParams& p, uint gid, float bu, float bv, 
     s.thin = (mflags & RTXPT_MATFLAG_ThinSurface) != 0;
     s.psdExclude = (mflags & RTXPT_MATFLAG_PSDExclude) != 0;
     s.psdDominantDeltaLobeP1 = (mflags & 0x0F000000u) >> 24;
-    s.psdBlockMVs = ((mflags >> 13) & 3u) == 3u;            // block type 3 "Full"; the curvature heuristics of types 1/2 (BridgeDonut:704-718) are treated as Off
+    {   // stopping motion vectors behind this surface (BridgeDonut:702-718): 0 Off, 1 AutoLow, 2 AutoHigh (triangle curvature seen through the ray cone), 3 Full
+        const uint blockType = (mflags >> 13) & 3u;
+        s.psdBlockMVs = blockType == 3u;
+        if (MODE != kModeReference && (blockType == 1u || blockType == 2u))
+        {
+            const float projectionTerm = fabsf(dot3(rayDir, -s.N));
+            const float pixelCurvature = (curvatureWS * coneWidth) / fmaxf(projectionTerm, 1e-6f);
+            neeat::MicroRng rng = neeat::MicroRng::make(pathId >> 16, pathId & 0xFFFFu, vertexIndex, sampleIndex);
+            s.psdBlockMVs = pixelCurvature > ((rng.nextFloat() * 0.9f + 0.3f) * (blockType == 1u ? 0.03f : 0.0005f));
+        }
+    }
     {   // adjustShadingNormal(recomputeTangentSpace = true)
         const float signN = dot3(s.N, s.faceN) >= 0.f ? 1.f : -1.f;
         const float3 Ns = signN * s.N;
@@ -453,7 +501,7 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
     const float rayT = hit.x;
     updatePathTravelled(path, rayT);
     Surface s;
-    loadSurface(p, __float_as_uint(hit.w), hit.y, hit.z, rayDir, path.coneWidth(), s);
+    loadSurface<MODE>(p, __float_as_uint(hit.w), hit.y, hit.z, rayDir, path.coneWidth(), s, path.id, path.vertexIndex(), sampleIndex);
     const uint ndq = p.c.nestedDielectricsQuality;
     if (ndq > 0 && path.interior0 != 0)
     {   // homogeneous absorption through the medium we are in (PathTracer.hlsli:538-547, BridgeDonut:871-887)

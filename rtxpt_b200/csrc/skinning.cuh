@@ -15,6 +15,7 @@ struct Params
     float* outPositions; uint* outNormals; uint* outTangents;   // skinned vertices
     const uint* indices;                                        // 3 per triangle (the geometry's index range)
     uint4* triShade;                                            // 6 x uint4 per source triangle
+    float* triPrevPos;                                          // 9 floats per triangle of this geometry: the corners the records held before this update (BUILD pass motion vectors; Donut's prevPosition stream)
 };
 
 PT_HD uint packSnorm8x(float v) { return uint(int(clampf(v, -1.0f, 1.0f) * 127.0f)) & 0xffu; }          // Pack_R8_SNORM: truncation towards zero
@@ -51,11 +52,19 @@ PT_HD void gatherTriangle(const Params& p, uint t)
     {
         const uint v = p.indices[size_t(t) * 3 + k];
         uint4 r = rec[k];
+        if (p.triPrevPos) { float* q = p.triPrevPos + size_t(t) * 9 + k * 3; q[0] = bitsToFloat(r.x); q[1] = bitsToFloat(r.y); q[2] = bitsToFloat(r.z); }
         r.x = floatBits(p.outPositions[size_t(v) * 3]); r.y = floatBits(p.outPositions[size_t(v) * 3 + 1]); r.z = floatBits(p.outPositions[size_t(v) * 3 + 2]);
         if (p.flags & 2u) r.w = p.outNormals[v];
         rec[k] = r;
         if (p.flags & 4u) { const uint tan = p.outTangents[v]; if (k == 0) rec[4].z = tan; else if (k == 1) rec[4].w = tan; else rec[5].x = tan; }
     }
+}
+
+// previous-position range of a newly registered skin: the corners the shade records hold now (no motion until the first update)
+PT_HD void initPrevTriangle(const Params& p, uint t)
+{
+    const uint4* rec = p.triShade + size_t(p.firstGid + t) * 6;
+    for (int k = 0; k < 3; k++) { float* q = p.triPrevPos + size_t(t) * 9 + k * 3; q[0] = bitsToFloat(rec[k].x); q[1] = bitsToFloat(rec[k].y); q[2] = bitsToFloat(rec[k].z); }
 }
 
 } } // namespace pt::skin

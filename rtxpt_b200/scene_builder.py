@@ -232,11 +232,16 @@ class Scene:
             tan = np.concatenate(tans)
             off_pos, off_uv = 0, nv * 12
             off_nrm, off_tan = off_uv + nv * 8, off_uv + nv * 8 + nv * 4
-            vblob = np.zeros(off_tan + nv * 4, np.uint8)
+            # optional previous-position stream (Donut keeps one for skinned meshes: GeometryData.prevPositionOffset): geometries that give "prev_positions"
+            has_prev = any(g.get("prev_positions") is not None for g in geos); off_prev = off_tan + nv * 4
+            vblob = np.zeros(off_prev + (nv * 12 if has_prev else 0), np.uint8)
+            if has_prev:
+                prev = np.concatenate([np.asarray(g["prev_positions"] if g.get("prev_positions") is not None else g["positions"], np.float32) for g in geos]).astype(np.float32)
+                vblob[off_prev:] = prev.reshape(-1).view(np.uint8)
             vblob[off_pos:off_uv] = pos.reshape(-1).view(np.uint8)
             vblob[off_uv:off_nrm] = np.ascontiguousarray(uvs, np.float32).reshape(-1).view(np.uint8)
             vblob[off_nrm:off_tan] = pack_snorm8_vec3(nrm).view(np.uint8)
-            vblob[off_tan:] = pack_snorm8_vec4(tan).view(np.uint8)
+            vblob[off_tan:off_prev] = pack_snorm8_vec4(tan).view(np.uint8)
             idx_blob = np.ascontiguousarray(idx_blob); self._keep += [idx_blob, vblob]
             self.buffers[2 * mi].data, self.buffers[2 * mi].sizeBytes = idx_blob.ctypes.data, idx_blob.nbytes
             self.buffers[2 * mi + 1].data, self.buffers[2 * mi + 1].sizeBytes = vblob.ctypes.data, vblob.nbytes
@@ -248,7 +253,7 @@ class Scene:
                 d.indexBufferIndex, d.indexOffset = 2 * mi, i0 * 4
                 d.vertexBufferIndex = 2 * mi + 1
                 d.positionOffset = off_pos + v0 * 12
-                d.prevPositionOffset = 0xFFFFFFFF
+                d.prevPositionOffset = (off_prev + v0 * 12) if g.get("prev_positions") is not None else 0xFFFFFFFF
                 d.texCoord1Offset = (off_uv + v0 * 8) if has_uv else 0xFFFFFFFF
                 d.texCoord2Offset = 0xFFFFFFFF
                 d.normalOffset = off_nrm + v0 * 4
@@ -264,7 +269,8 @@ class Scene:
         for ii, (mi, xf) in enumerate(b.instances):
             d = self.instances[ii]
             d.flags, d.firstGeometryInstanceIndex, d.firstGeometryIndex, d.numGeometries = 0, si, mesh_first_geo[mi], len(b.meshes[mi])
-            d.transform[:] = xf.reshape(-1).tolist(); d.prevTransform[:] = xf.reshape(-1).tolist()
+            pxf = getattr(b, "prev_transforms", {}).get(ii, xf)            # last frame's matrix (Donut's InstanceData.prevTransform); default: the instance did not move
+            d.transform[:] = xf.reshape(-1).tolist(); d.prevTransform[:] = np.asarray(pxf, np.float32).reshape(-1).tolist()
             for k, g in enumerate(b.meshes[mi]):
                 s = self.sub_instances[si]
                 mat = b.materials[g["material"]]

@@ -511,9 +511,9 @@ def test_config3_full_scene_realtime_neeat_reblur(product, oracle):
         assert m["planes"][1] > 0.2 and m["planes"][2] > 0.02, m                     # the decomposition has work to do in this view
         assert m["same_header"] > 0.995, (f, m)
         assert m["stable"] > 0.99, (f, m)
-        assert m["merged_close"] > 0.9, (f, m)                                     # texture filtering (TMU vs software) changes some paths, as in test_realtime_city_matches_oracle
+        assert m["merged_close"] > 0.995, (f, m)                                   # measured on a B200: 0.9996 / 0.9995 (texture filtering, TMU vs software, changes a few paths); headers 1.0, stable radiance 0.99998
         assert abs(m["mean_ratio"] - 1) < 0.02, (f, m)
-        assert min(m["reblur"].values()) > 0.97, (f, m)
+        assert min(m["reblur"].values()) > 0.995, (f, m)                           # measured: 1.0 / 1.0 / 1.0 (profiles/r2_config3_parity.log)
 
 
 @pytest.mark.gpu
