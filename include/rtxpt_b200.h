@@ -413,14 +413,16 @@ RTXPT_API int rtxpt_b200_tone_map_pre_exposed_gray(const RtxptToneMappingParams*
 /* ---- Rigid-instance animation (stands in for the per-frame BLAS / TLAS update behind Sample::UpdateAccelStructs and BuildTLAS, Rtxpt/Sample.cpp:1170-1240): new
  * row-major 3x4 matrices for every instance of the uploaded scene; on the stream, the leaf triangles are re-transformed (one thread each) and the 8-wide BVH is refitted bottom-up,
  * level by level, with the builder's own quantisation - unmoved geometry gives back the built nodes bit for bit, topology never changes (quality degrades with large deformation,
- * re-upload then).  The instance table keeps the previous matrices for the BUILD pass's motion vectors.  Emissive triangles are baked into the light list at upload: instances that
- * carry them stay put (or re-upload).  Skinning / vertex animation: not built. */
+ * re-upload then).  The instance table keeps the previous call's matrices as InstanceData.prevTransform: the BUILD pass's motion vectors are those of the moved surface (BridgeDonut:631,
+ * PathTracerStablePlanes.hlsli:282-291); call it every frame, as Sample does its TLAS update, so that an instance that stopped reports no motion.  Emissive triangles are baked into the
+ * light list at upload: instances that carry them stay put (or re-upload). */
 RTXPT_API int rtxpt_b200_update_instance_transforms(rtxpt_ctx* ctx, const float* transforms3x4, uint32_t instanceCount, void* cudaStream);
 /* Skinned meshes (Donut's skinning pass, External/Donut/shaders/skinning_cs.hlsl, which RTXPT runs before its BLAS updates, Sample.cpp:1170-1198): register a geometry's bind pose once
  * (vertex order = the geometry's vertex buffer; normals / tangents snorm8 x 4 as in the vertex buffer, may be NULL; four uint16 joint indices and four float weights per vertex), then per
  * frame hand the joint matrices (row-major 4x4, row vector x matrix, as Donut's t_JointMatrices): the vertices are blended on the stream and the path tracer's per-triangle shade
- * records (object-space positions, normals, tangents) rewritten from them.  Follow with rtxpt_b200_update_instance_transforms to refit the BVH.  Motion vectors of skinned surfaces
- * see the instance motion only (no previous-position stream). */
+ * records (object-space positions, normals, tangents) rewritten from them.  Follow with rtxpt_b200_update_instance_transforms to refit the BVH.  The corners the records held before the
+ * update become the geometry's previous-position stream (Donut's GeometryData.prevPositionOffset, which a scene may also bring along at upload): the BUILD pass's motion vectors of
+ * a skinned surface are prevTransform x previous position - transform x position, as in the reference. */
 typedef struct RtxptSkinDesc {
     uint32_t instanceIndex, geometryIndexInInstance, numVertices, _pad;
     const float* positions; const uint32_t* normals; const uint32_t* tangents; const uint16_t* jointIndices; const float* jointWeights;

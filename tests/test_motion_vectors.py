@@ -12,7 +12,7 @@ def _builder(boxes_prev=None, short_prev_positions=None, block_type=0, curved=Fa
     """Cornell box; boxes_prev: last frame's matrix of the boxes instance; short_prev_positions: previous-position stream of the short box; block_type / curved: a
     sphere with the given PSDBlockMotionVectorsAtSurfaceType in place of nothing (for the heuristics)."""
     from rtxpt_b200 import scenes, scene_builder as sb
-    b = scenes.cornell_builder(delta_surfaces=True)
+    b = scenes.cornell_builder(delta_surfaces=False)         # diffuse boxes: the surface a pixel exports is the box itself (behind a mirror or glass it would be what they show)
     if boxes_prev is not None: b.prev_transforms = {2: np.float32(boxes_prev).reshape(3, 4)}
     if short_prev_positions is not None: b.meshes[b.instances[2][0]][0]["prev_positions"] = short_prev_positions
     if curved:
@@ -76,7 +76,10 @@ def test_oracle_previous_position_stream_and_block_heuristics(oracle):
     scene, cam, consts, o, rt = _pair(oracle, _builder(short_prev_positions=prev)); r = o.render_realtime(rt); o.close()
     mv = r["motion"].astype(np.float32)
     moving = np.abs(mv[..., 0]) > 0.05
-    assert 0.01 < moving.mean() < 0.3 and (mv[..., 0][moving] < 0).mean() > 0.95   # the sheared box moved towards +x: previous screen position is to the left (negative x motion)
+    top = np.float64([1.8, 1.65, 1.7]); (s_prev, _), (s_now, _) = _project(cam, top - np.float64([0.35, 0, 0])), _project(cam, top)
+    want = np.sign(s_prev[0] - s_now[0])                                      # which way a point of the box's top came from on screen
+    assert 0.01 < moving.mean() < 0.3 and (np.sign(mv[..., 0][moving]) == want).mean() > 0.95
+    assert abs(np.abs(mv[..., 0]).max() - abs(s_prev[0] - s_now[0])) < 0.25 * abs(s_prev[0] - s_now[0])       # the top edge moves by about the analytic amount (perspective varies over the box)
     # block types on a curved mirror: Off lets the mirror's reflections define the surface seen (motion vectors / depth of what is reflected), Full stops at the sphere; the
     # automatic modes stop where the triangle's normal gradient x ray-cone width exceeds a threshold jittered by MicroRng: AutoHigh (0.0005) blocks at least where AutoLow (0.03) does
     depth = {}
