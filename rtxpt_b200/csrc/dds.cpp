@@ -200,6 +200,8 @@ float halfBitsToFloat(uint16_t h)
 }
 
 uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+// the header's mip count is untrusted: at most a full chain of the image and RTXPT_MAX_MIPS (so that `width >> m` never shifts by 32 or more)
+uint32_t clampMipCount(uint32_t fromHeader, uint32_t w, uint32_t h) { uint32_t full = 1; for (uint32_t d = std::max(w, h); d > 1; d >>= 1) full++; return std::min(std::min(std::max(1u, fromHeader), full), uint32_t(RTXPT_MAX_MIPS)); }
 enum Fmt { FmtNone, FmtBC1, FmtBC2, FmtBC3, FmtBC4, FmtBC5, FmtBC7, FmtRGBA8, FmtBGRA8 };
 
 } // namespace
@@ -210,7 +212,7 @@ DdsImage decodeDds(const uint8_t* data, size_t size, const char* name)
 {
     if (size < 128 || memcmp(data, "DDS ", 4) != 0 || rd32(data + 4) != 124) failf("'%s' is not a DDS file", name);
     DdsImage img; img.height = rd32(data + 12); img.width = rd32(data + 16);
-    const uint32_t mipCount = std::max(1u, rd32(data + 28)), pfFlags = rd32(data + 80), fourCC = rd32(data + 84);
+    const uint32_t mipCount = clampMipCount(rd32(data + 28), rd32(data + 16), rd32(data + 12)), pfFlags = rd32(data + 80), fourCC = rd32(data + 84);
     size_t off = 128; Fmt fmt = FmtNone;
     auto cc = [](const char* s) { return uint32_t(uint8_t(s[0])) | (uint32_t(uint8_t(s[1])) << 8) | (uint32_t(uint8_t(s[2])) << 16) | (uint32_t(uint8_t(s[3])) << 24); };
     if (pfFlags & 0x4)
@@ -285,7 +287,7 @@ bool extractDdsBlocks(const uint8_t* data, size_t size, const char* name, DdsBlo
 {
     if (size < 128 || memcmp(data, "DDS ", 4) != 0 || rd32(data + 4) != 124) return false;
     out.height = rd32(data + 12); out.width = rd32(data + 16);
-    const uint32_t mipCount = std::max(1u, rd32(data + 28)), pfFlags = rd32(data + 80), fourCC = rd32(data + 84);
+    const uint32_t mipCount = clampMipCount(rd32(data + 28), rd32(data + 16), rd32(data + 12)), pfFlags = rd32(data + 80), fourCC = rd32(data + 84);
     auto cc = [](const char* s) { return uint32_t(uint8_t(s[0])) | (uint32_t(uint8_t(s[1])) << 8) | (uint32_t(uint8_t(s[2])) << 16) | (uint32_t(uint8_t(s[3])) << 24); };
     if (!(pfFlags & 0x4)) return false;
     size_t off = 128; uint32_t fmt = 0;
@@ -335,7 +337,7 @@ struct HdrImage { uint32_t width = 0, height = 0, faces = 1, mipCount = 1; std::
 HdrImage decodeDdsHdr(const uint8_t* data, size_t size, const char* name)
 {
     if (size < 128 || memcmp(data, "DDS ", 4) != 0 || rd32(data + 4) != 124) failf("'%s' is not a DDS file", name);
-    HdrImage img; img.height = rd32(data + 12); img.width = rd32(data + 16); img.mipCount = std::max(1u, rd32(data + 28));
+    HdrImage img; img.height = rd32(data + 12); img.width = rd32(data + 16); img.mipCount = clampMipCount(rd32(data + 28), img.width, img.height);
     const uint32_t pfFlags = rd32(data + 80), fourCC = rd32(data + 84), caps2 = rd32(data + 112);
     auto cc = [](const char* s) { return uint32_t(uint8_t(s[0])) | (uint32_t(uint8_t(s[1])) << 8) | (uint32_t(uint8_t(s[2])) << 16) | (uint32_t(uint8_t(s[3])) << 24); };
     enum { BC6U, BC6S, F16, F32 } fmt; size_t off = 128;

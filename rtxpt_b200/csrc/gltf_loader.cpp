@@ -100,7 +100,12 @@ Image decodePng(const std::vector<uint8_t>& d, const char* name)
     {
         const uint32_t len = be32(&d[off]); const char* type = reinterpret_cast<const char*>(&d[off + 4]); const uint8_t* body = &d[off + 8];
         if (off + 12 + len > d.size()) failf("PNG '%s': truncated chunk", name);
-        if (!memcmp(type, "IHDR", 4)) { img.w = be32(body); img.h = be32(body + 4); depth = body[8]; ctype = body[9]; interlace = body[12]; }
+        if (!memcmp(type, "IHDR", 4))
+        {
+            if (len != 13) failf("PNG '%s': IHDR chunk of %u bytes", name, len);
+            img.w = be32(body); img.h = be32(body + 4); depth = body[8]; ctype = body[9]; interlace = body[12];
+            if (img.w > 32768 || img.h > 32768) failf("PNG '%s': %u x %u is larger than 32768 x 32768", name, img.w, img.h);
+        }
         else if (!memcmp(type, "PLTE", 4)) plte.assign(body, body + len);
         else if (!memcmp(type, "tRNS", 4)) trns.assign(body, body + len);
         else if (!memcmp(type, "IDAT", 4)) idat.insert(idat.end(), body, body + len);
@@ -272,10 +277,19 @@ struct Loader
         const int bvIndex = a.integer("bufferView", -1); if (bvIndex < 0) failf("glTF: accessor %d has no bufferView", index);
         const JValue& bv = arrayItem("bufferViews", bvIndex);
         const int bufIndex = bv.integer("buffer", -1); if (bufIndex < 0 || size_t(bufIndex) >= bufferData.size()) failf("glTF: bufferView %d references a missing buffer", bvIndex);
-        const size_t offset = size_t(bv.number("byteOffset", 0)) + size_t(a.number("byteOffset", 0));
-        r.stride = size_t(bv.number("byteStride", 0)); if (!r.stride) r.stride = compSize * r.components;
+        // offsets, stride and lengths come from an untrusted file: finite, non-negative, inside the bufferView, and checked without wrapping
         const std::vector<uint8_t>& buf = bufferData[size_t(bufIndex)];
-        if (r.count && offset + r.stride * (r.count - 1) + compSize * r.components > buf.size()) failf("glTF: accessor %d reads past the end of buffer %d", index, bufIndex);
+        auto field = [&](const JValue& o, const char* key, double def) { const double v = o.number(key, def); if (!(v >= 0.0) || v > double(buf.size()) || v != std::floor(v)) failf("glTF: accessor %d: '%s' is not a valid byte count", index, key); return size_t(v); };
+        const size_t viewOffset = field(bv, "byteOffset", 0), viewLength = field(bv, "byteLength", double(buf.size() - std::min(buf.size(), viewOffset))), accOffset = field(a, "byteOffset", 0);
+        r.stride = field(bv, "byteStride", 0); if (!r.stride) r.stride = compSize * r.components;
+        if (r.stride < compSize * r.components || r.stride > 252 + compSize * r.components) failf("glTF: accessor %d: byteStride %zu is out of range", index, r.stride);
+        if (viewOffset > buf.size() || viewLength > buf.size() - viewOffset) failf("glTF: bufferView %d lies outside buffer %d", bvIndex, bufIndex);
+        const size_t elem = compSize * r.components;
+        if (r.count)
+        {   // last byte read = accOffset + stride * (count - 1) + elem, within the view
+            if (accOffset > viewLength || elem > viewLength - accOffset || (r.count - 1) > (viewLength - accOffset - elem) / r.stride) failf("glTF: accessor %d reads past the end of bufferView %d", index, bvIndex);
+        }
+        const size_t offset = viewOffset + accOffset;
         r.data = buf.data() + offset;
         return r;
     }

@@ -32,12 +32,15 @@ struct JValue
 };
 struct JParser
 {
-    const char* p; const char* end;
+    const char* p; const char* end; int depth = 0;
+    static constexpr int kMaxDepth = 256;            // nesting limit: a hostile file must not recurse the parser off the stack
+    struct Nest { int& d; explicit Nest(int& dd) : d(dd) { if (++d > kMaxDepth) failf("JSON: nesting deeper than %d levels", kMaxDepth); } ~Nest() { --d; } };
     void ws() { while (p < end && (*p == ' ' || *p == '\n' || *p == '\r' || *p == '\t')) p++; }
     JValue parse() { ws(); JValue v = value(); ws(); return v; }
     JValue value()
     {
         if (p >= end) failf("JSON: unexpected end");
+        Nest nest(depth);
         JValue v;
         switch (*p)
         {
@@ -72,9 +75,12 @@ struct JParser
         case 'n': if (end - p >= 4 && !strncmp(p, "null", 4)) { p += 4; return v; } break;
         default:
         {
-            char* e = nullptr; v.num = strtod(p, &e);
-            if (e == p) break;
-            p = e; v.type = JValue::Number; return v;
+            // the number's characters are copied out first: the input buffer need not be NUL-terminated
+            const char* q = p; while (q < end && q - p < 63 && ((*q >= '0' && *q <= '9') || *q == '-' || *q == '+' || *q == '.' || *q == 'e' || *q == 'E')) q++;
+            char tmp[64]; memcpy(tmp, p, size_t(q - p)); tmp[q - p] = 0;
+            char* e = nullptr; v.num = strtod(tmp, &e);
+            if (e == tmp) break;
+            p += e - tmp; v.type = JValue::Number; return v;
         }
         }
         failf("JSON: unexpected character '%c'", *p);

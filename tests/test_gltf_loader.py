@@ -201,3 +201,37 @@ def test_cpp_host_example_renders_cornell(product, oracle, tmp_path):
         consts.sampleBaseIndex = base; o.set_constants(consts); acc, n = o.render(0, 4, accum=acc, accum_count=n)[:2]
     o.close()
     assert per_pixel_l2(np.concatenate([img, np.ones((96, 96, 1), np.float32)], -1), acc) < 1e-4
+
+
+def test_loaders_refuse_hostile_files(product, tmp_path):
+    """Untrusted input: accessor offsets / strides / counts that would read outside their bufferView, a PNG whose IHDR lies about itself, JSON nested beyond any real scene,
+    a DDS header claiming more mips than the image can have - each refused with a message, none crashes or over-allocates."""
+    import json, struct, zlib
+    b = _textured_builder(); path = gltf_export.export(b, str(tmp_path / "s.gltf")); doc = json.load(open(path))
+    def load_with(mutator, name):
+        d = json.loads(json.dumps(doc)); mutator(d); json.dump(d, open(tmp_path / name, "w")); return product.GltfScene(str(tmp_path / name))
+    pos_acc = doc["meshes"][0]["primitives"][0]["attributes"]["POSITION"]; bv = doc["accessors"][pos_acc]["bufferView"]
+    for mut, match in ((lambda d: d["accessors"][pos_acc].__setitem__("byteOffset", -16), "byteOffset"),
+                       (lambda d: d["accessors"][pos_acc].__setitem__("byteOffset", 1e30), "byteOffset"),
+                       (lambda d: d["bufferViews"][bv].__setitem__("byteStride", 1 << 40), "byteStride"),
+                       (lambda d: d["bufferViews"][bv].__setitem__("byteStride", 4), "byteStride"),
+                       (lambda d: d["bufferViews"][bv].__setitem__("byteLength", 24), "past the end of bufferView"),
+                       (lambda d: d["bufferViews"][bv].__setitem__("byteOffset", 1 << 33), "byteOffset|outside buffer"),
+                       (lambda d: d["accessors"][pos_acc].__setitem__("count", 1 << 30), "past the end")):
+        with pytest.raises(product.RtxptError, match=match): load_with(mut, "hostile.gltf")
+    # JSON nesting
+    deep = tmp_path / "deep.gltf"; deep.write_text("[" * 100000)
+    with pytest.raises(product.RtxptError, match="nesting"): product.GltfScene(str(deep))
+    # PNG: IHDR of the wrong length; absurd dimensions
+    def png(ihdr, extra_len=0):
+        def chunk(t, data): return struct.pack(">I", len(data)) + t + data + struct.pack(">I", zlib.crc32(t + data) & 0xffffffff)
+        return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", ihdr) + chunk(b"IDAT", zlib.compress(b"\0" * 8)) + chunk(b"IEND", b"")
+    tex = [n for n in os.listdir(tmp_path) if n.endswith(".png")][0]
+    (tmp_path / tex).write_bytes(png(struct.pack(">II", 4, 4) + b"\x08"))                      # 9-byte IHDR
+    with pytest.raises(product.RtxptError, match="IHDR"): product.GltfScene(path)
+    (tmp_path / tex).write_bytes(png(struct.pack(">IIBBBBB", 1 << 30, 1 << 30, 8, 6, 0, 0, 0)))
+    with pytest.raises(product.RtxptError, match="larger than"): product.GltfScene(path)
+    # DDS: 2x2 RGBA8 image whose header claims 40 mips decodes as its real chain (2 levels), not 40 shifts
+    from test_dds import dds_dx10
+    data = bytearray(dds_dx10("RGBA8", 2, 2, bytes(16) + bytes(4), mips=2)); data[28:32] = struct.pack("<I", 40)
+    rgba, mips, _ = product.decode_dds(bytes(data)); assert mips == 2 and rgba.shape[:2] == (2, 2)
