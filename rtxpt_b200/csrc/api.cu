@@ -686,7 +686,7 @@ extern "C" RTXPT_API int rtxpt_b200_path_trace(rtxpt_ctx* c, uint32_t firstSubSa
     if (subSampleCount == 0) return RTXPT_OK;
     const bool na = neeatActive(c);
     if (na && (!c->na.allocated || !c->na.frameEnded)) return fail(RTXPT_ERR_INVALID_ARGUMENT, "NEEATFeedback is set: call rtxpt_b200_neeat_update_begin and rtxpt_b200_neeat_update_end before tracing the frame");
-    if (na && c->cfg.tileWorld > 1) return fail(RTXPT_ERR_UNSUPPORTED, "NEE-AT feedback needs every pixel's reservoir on one GPU; the tile partition runs with NEEATFeedback = 0");
+    // tile partition (tileWorld > 1) with feedback: every rank adapts on the tiles it owns - independent global tables, reservoirs of foreign pixels stay empty
     if (na && !(c->cfg.flags & RTXPT_CFG_EXPORT_GUIDES)) return fail(RTXPT_ERR_INVALID_ARGUMENT, "NEE-AT feedback in reference mode reprojects with the exported guides: create the context with RTXPT_CFG_EXPORT_GUIDES");
     cudaStream_t s = pickStream(c, cudaStream);
     LaunchParams p; fillParams(c, p);
@@ -823,7 +823,6 @@ extern "C" RTXPT_API int rtxpt_b200_path_trace_realtime(rtxpt_ctx* c, int mergeN
     cudaStream_t s = pickStream(c, cudaStream);
     const bool na = neeatActive(c);
     if (na && (!c->na.allocated || !c->na.frameBegun)) return fail(RTXPT_ERR_INVALID_ARGUMENT, "NEEATFeedback is set: call rtxpt_b200_neeat_update_begin before tracing the frame");
-    if (na && c->cfg.tileWorld > 1) return fail(RTXPT_ERR_UNSUPPORTED, "NEE-AT feedback needs every pixel's reservoir on one GPU; the tile partition runs with NEEATFeedback = 0");
     LaunchParams p; fillParams(c, p);
     const RtxptRealtimeConstants& r = c->realtime;
     fillRealtimeParams(c, p);
@@ -1459,6 +1458,53 @@ extern "C" RTXPT_API int rtxpt_b200_unpack_all(rtxpt_ctx* c, const void* dSrcAll
     if (c->tableWidth == 0) return fail(RTXPT_ERR_INVALID_ARGUMENT, "constants not set");
     cudaSetDevice(c->device);
     launchUnpackAll((const float4*)dSrcAll, c->allPixelTable.ptr, c->paddedPixelsPerRank * c->cfg.tileWorld, c->tableWidth, c->accumulated.ptr, c->grid, pickStream(c, cudaStream));
+    CU(cudaGetLastError());
+    return RTXPT_OK;
+}
+
+// ---- multi-GPU exchange of the realtime frame's per-pixel images: guides, NRD inputs per plane, output colour ---------------------------------------------
+static int buildExchangeSet(rtxpt_ctx* c, const int* buffers, uint32_t count, ExchangeSet& e)
+{
+    if (!c || !buffers || count == 0 || count > kExchangeMaxImages) return fail(RTXPT_ERR_INVALID_ARGUMENT, "1..%u buffers", kExchangeMaxImages);
+    if (c->tableWidth == 0) return fail(RTXPT_ERR_INVALID_ARGUMENT, "constants not set");
+    const size_t P = size_t(c->tableWidth) * c->tableHeight;
+    memset(&e, 0, sizeof(e)); e.count = count; e.width = c->tableWidth;
+    uint64_t off = 0;
+    for (uint32_t k = 0; k < count; k++)
+    {
+        if (buffers[k] == RTXPT_BUFFER_STABLE_PLANES || buffers[k] == RTXPT_BUFFER_STABLE_PLANES_HEADER) return fail(RTXPT_ERR_INVALID_ARGUMENT, "buffer %d is not a plain per-pixel image", buffers[k]);
+        void* ptr; size_t bytes; const int rc = targetInfo(c, buffers[k], &ptr, &bytes); if (rc != RTXPT_OK) return rc;
+        const size_t bpp = bytes / P;
+        if (bytes != bpp * P || (bpp != 1 && bpp != 4 && bpp != 8 && bpp != 16)) return fail(RTXPT_ERR_INVALID_ARGUMENT, "buffer %d: %zu bytes per pixel cannot be exchanged", buffers[k], bpp);
+        e.image[k] = ptr; e.bytesPerPixel[k] = uint32_t(bpp); e.segmentOffset[k] = off;
+        off += (uint64_t(c->paddedPixelsPerRank) * bpp + 15u) & ~uint64_t(15);
+    }
+    e.bytesPerRank = off;
+    return RTXPT_OK;
+}
+extern "C" RTXPT_API int rtxpt_b200_exchange_bytes(rtxpt_ctx* c, const int* buffers, uint32_t count, size_t* outBytesPerRank)
+{
+    if (!outBytesPerRank) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    ExchangeSet e; const int rc = buildExchangeSet(c, buffers, count, e); if (rc != RTXPT_OK) return rc;
+    *outBytesPerRank = size_t(e.bytesPerRank);
+    return RTXPT_OK;
+}
+extern "C" RTXPT_API int rtxpt_b200_exchange_pack(rtxpt_ctx* c, const int* buffers, uint32_t count, void* dDst, void* cudaStream)
+{
+    if (!dDst) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    ExchangeSet e; const int rc = buildExchangeSet(c, buffers, count, e); if (rc != RTXPT_OK) return rc;
+    cudaSetDevice(c->device);
+    launchExchangePack(e, c->pixelOfSlot.ptr, c->pixelCount, c->paddedPixelsPerRank, dDst, c->grid, pickStream(c, cudaStream));
+    CU(cudaGetLastError());
+    return RTXPT_OK;
+}
+extern "C" RTXPT_API int rtxpt_b200_exchange_unpack(rtxpt_ctx* c, const int* buffers, uint32_t count, const void* dSrcAll, void* cudaStream)
+{
+    if (!dSrcAll) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    ExchangeSet e; const int rc = buildExchangeSet(c, buffers, count, e); if (rc != RTXPT_OK) return rc;
+    if (c->cfg.tileWorld <= 1) return RTXPT_OK;
+    cudaSetDevice(c->device);
+    launchExchangeUnpack(e, c->allPixelTable.ptr, c->paddedPixelsPerRank, c->cfg.tileWorld, c->cfg.tileRank, dSrcAll, c->grid, pickStream(c, cudaStream));
     CU(cudaGetLastError());
     return RTXPT_OK;
 }

@@ -357,6 +357,54 @@ __global__ void k_unpack_all(const float4* __restrict__ srcAll, const uint* __re
         if (id != 0xFFFFFFFFu) image[size_t(id & 0xFFFF) * width + (id >> 16)] = srcAll[i];
     }
 }
+// generic form for the realtime frame (guides, NRD inputs, output colour): up to kExchangeMaxImages full-frame per-pixel images of 1 / 4 / 8 / 16 bytes per pixel; a rank's block
+// holds, image after image, paddedCount elements in slot order (segments start on 16-byte boundaries)
+template <typename T> __device__ __forceinline__ void exchangeCopyPack(const ExchangeSet& e, uint k, uint i, uint id, bool owned, uint8_t* dst)
+{
+    T v{}; if (owned) v = reinterpret_cast<const T*>(e.image[k])[size_t(id & 0xFFFF) * e.width + (id >> 16)];
+    reinterpret_cast<T*>(dst + e.segmentOffset[k])[i] = v;
+}
+__global__ void k_exchange_pack(const __grid_constant__ ExchangeSet e, const uint* __restrict__ pixelOfSlot, uint pixelCount, uint paddedCount, uint8_t* __restrict__ dst)
+{
+    for (uint i = blockIdx.x * blockDim.x + threadIdx.x; i < paddedCount; i += gridDim.x * blockDim.x)
+    {
+        const bool owned = i < pixelCount; const uint id = owned ? pixelOfSlot[i] : 0u;
+        for (uint k = 0; k < e.count; k++)
+            switch (e.bytesPerPixel[k])
+            {
+            case 1: exchangeCopyPack<uint8_t>(e, k, i, id, owned, dst); break;
+            case 4: exchangeCopyPack<uint>(e, k, i, id, owned, dst); break;
+            case 8: exchangeCopyPack<uint2>(e, k, i, id, owned, dst); break;
+            default: exchangeCopyPack<uint4>(e, k, i, id, owned, dst); break;
+            }
+    }
+}
+template <typename T> __device__ __forceinline__ void exchangeCopyUnpack(const ExchangeSet& e, uint k, uint slot, uint id, const uint8_t* src)
+{
+    reinterpret_cast<T*>(e.image[k])[size_t(id & 0xFFFF) * e.width + (id >> 16)] = reinterpret_cast<const T*>(src + e.segmentOffset[k])[slot];
+}
+__global__ void k_exchange_unpack(const __grid_constant__ ExchangeSet e, const uint* __restrict__ allPixelTable, uint paddedCount, uint world, uint skipRank, const uint8_t* __restrict__ srcAll)
+{
+    for (uint i = blockIdx.x * blockDim.x + threadIdx.x; i < paddedCount * world; i += gridDim.x * blockDim.x)
+    {
+        const uint id = allPixelTable[i];
+        const uint rank = i / paddedCount, slot = i - rank * paddedCount;
+        if (id == 0xFFFFFFFFu || rank == skipRank) continue;                 // the rank's own pixels are already in place
+        const uint8_t* src = srcAll + size_t(rank) * e.bytesPerRank;
+        for (uint k = 0; k < e.count; k++)
+            switch (e.bytesPerPixel[k])
+            {
+            case 1: exchangeCopyUnpack<uint8_t>(e, k, slot, id, src); break;
+            case 4: exchangeCopyUnpack<uint>(e, k, slot, id, src); break;
+            case 8: exchangeCopyUnpack<uint2>(e, k, slot, id, src); break;
+            default: exchangeCopyUnpack<uint4>(e, k, slot, id, src); break;
+            }
+    }
+}
+void launchExchangePack(const ExchangeSet& e, const uint32_t* pixelOfSlot, uint32_t pixelCount, uint32_t paddedCount, void* dst, const GridConfig& g, cudaStream_t s)
+{ k_exchange_pack<<<g.smCount * 4, 256, 0, s>>>(e, pixelOfSlot, pixelCount, paddedCount, static_cast<uint8_t*>(dst)); }
+void launchExchangeUnpack(const ExchangeSet& e, const uint32_t* allPixelTable, uint32_t paddedCount, uint32_t world, uint32_t skipRank, const void* srcAll, const GridConfig& g, cudaStream_t s)
+{ k_exchange_unpack<<<g.smCount * 4, 256, 0, s>>>(e, allPixelTable, paddedCount, world, skipRank, static_cast<const uint8_t*>(srcAll)); }
 void launchPackOwned(const float4* image, const uint32_t* pixelOfSlot, uint32_t pixelCount, uint32_t paddedCount, uint32_t width, float4* dst, const GridConfig& g, cudaStream_t s)
 { k_pack_owned<<<g.smCount * 4, 256, 0, s>>>(image, pixelOfSlot, pixelCount, paddedCount, width, dst); }
 void launchUnpackAll(const float4* srcAll, const uint32_t* allPixelTable, uint32_t totalEntries, uint32_t width, float4* image, const GridConfig& g, cudaStream_t s)

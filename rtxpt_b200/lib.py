@@ -41,6 +41,9 @@ _SIGNATURES = {
     "rtxpt_b200_tile_layout": [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)],
     "rtxpt_b200_pack_owned": [C.c_void_p, C.c_void_p, C.c_void_p],
     "rtxpt_b200_unpack_all": [C.c_void_p, C.c_void_p, C.c_void_p],
+    "rtxpt_b200_exchange_bytes": [C.c_void_p, C.POINTER(C.c_int), C.c_uint32, C.POINTER(C.c_size_t)],
+    "rtxpt_b200_exchange_pack": [C.c_void_p, C.POINTER(C.c_int), C.c_uint32, C.c_void_p, C.c_void_p],
+    "rtxpt_b200_exchange_unpack": [C.c_void_p, C.POINTER(C.c_int), C.c_uint32, C.c_void_p, C.c_void_p],
     "rtxpt_b200_trace_rays": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p],
     "rtxpt_b200_trace_rays_device": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32, C.POINTER(C.c_float)],
     "rtxpt_b200_get_lights": [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)],
@@ -454,6 +457,21 @@ class Context:
 
     def unpack_all(self, d_src_all, stream=None):
         _check(self.L.rtxpt_b200_unpack_all(self.h, d_src_all, stream), self.L)
+
+    # ---- multi-GPU exchange of the realtime frame's per-pixel images (rtxpt_b200_exchange_*) ----
+    def _ids(self, buffers):
+        return (C.c_int * len(buffers))(*buffers), len(buffers)
+
+    def exchange_bytes(self, buffers):
+        ids, n = self._ids(buffers); out = C.c_size_t()
+        _check(self.L.rtxpt_b200_exchange_bytes(self.h, ids, n, C.byref(out)), self.L)
+        return out.value
+
+    def exchange_pack(self, buffers, d_dst, stream=None):
+        ids, n = self._ids(buffers); _check(self.L.rtxpt_b200_exchange_pack(self.h, ids, n, d_dst, stream), self.L)
+
+    def exchange_unpack(self, buffers, d_src_all, stream=None):
+        ids, n = self._ids(buffers); _check(self.L.rtxpt_b200_exchange_unpack(self.h, ids, n, d_src_all, stream), self.L)
 
     def trace_rays(self, rays, any_hit=False):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)

@@ -45,3 +45,37 @@ def unpack_all(gathered, tables, padded, image):
         x, y = table >> 16, table & 0xFFFF
         image[y, x] = gathered[r * padded:r * padded + len(table)]
     return image
+
+
+# ---- generic exchange of several per-pixel images (rtxpt_b200_exchange_pack / _unpack): a rank's block holds, image after image, `padded` elements in slot order, every
+# segment starting on a 16-byte boundary
+def exchange_layout(bytes_per_pixel, padded):
+    """(segment offsets, bytes per rank) for images of the given element sizes."""
+    offs, off = [], 0
+    for b in bytes_per_pixel:
+        offs.append(off); off += (padded * b + 15) & ~15
+    return offs, off
+
+
+def exchange_pack(images, table, padded):
+    """images: list of H x W (x C) arrays; returns this rank's block as uint8."""
+    sizes = [int(np.prod(im.shape[2:], dtype=np.int64)) * im.dtype.itemsize for im in images]
+    offs, total = exchange_layout(sizes, padded)
+    out = np.zeros(total, np.uint8); x, y = table >> 16, table & 0xFFFF
+    for im, b, o in zip(images, sizes, offs):
+        seg = np.ascontiguousarray(im[y, x]).view(np.uint8).reshape(-1)
+        out[o:o + len(seg)] = seg
+    return out
+
+
+def exchange_unpack(gathered, tables, padded, images, skip_rank=None):
+    """gathered: world x bytes-per-rank uint8; scatters every rank's pixels (but skip_rank's) into `images` in place."""
+    sizes = [int(np.prod(im.shape[2:], dtype=np.int64)) * im.dtype.itemsize for im in images]
+    offs, total = exchange_layout(sizes, padded); g = np.asarray(gathered, np.uint8).reshape(len(tables), total)
+    for r, table in enumerate(tables):
+        if r == skip_rank: continue
+        x, y = table >> 16, table & 0xFFFF
+        for im, b, o in zip(images, sizes, offs):
+            seg = g[r, o:o + len(table) * b]
+            im[y, x] = seg.view(im.dtype).reshape((len(table),) + im.shape[2:])
+    return images

@@ -3,6 +3,7 @@
 set -u
 mkdir -p gpurun_out
 echo "=== motion vector tests"; timeout 900 python -m pytest tests/test_motion_vectors.py -q -m gpu > gpurun_out/b12_mv.log 2>&1; echo "rc=$?"; tail -n 25 gpurun_out/b12_mv.log | cut -c1-400
+echo "=== config-3 split over two ranks (one GPU)"; timeout 900 python -m pytest tests/test_gpu_realtime.py -q -m gpu -k two_ranks > gpurun_out/b12_split.log 2>&1; echo "rc=$?"; tail -n 25 gpurun_out/b12_split.log | cut -c1-400
 echo "=== gpu suite"; timeout 1800 python -m pytest tests -q -m gpu > gpurun_out/b12_gpu.log 2>&1; echo "rc=$?"; tail -n 15 gpurun_out/b12_gpu.log | cut -c1-400
 echo "=== bench N=1"; timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_n1_b.json 2> gpurun_out/b12_bench.err; echo "rc=$?"; cut -c1-200 gpurun_out/r2_bench_n1_b.json
 echo "=== A/B: next-item prefetch in k_shade (off / L2 / L1), twice each"

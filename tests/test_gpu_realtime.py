@@ -254,3 +254,50 @@ def test_realtime_city_matches_oracle(product, oracle, strict):
     assert (d / scale < 0.05).all(-1).mean() > (0.95 if strict else 0.85)          # texture filtering (TMU vs software) and transcendental differences change some paths
     assert abs(g["merged"].mean() - r["merged"].mean()) < 0.02 * r["merged"].mean()
     c.close(); o.close()
+
+
+@pytest.mark.gpu
+def test_config3_frame_split_over_two_ranks_equals_the_single_gpu_frame(product):
+    """SURVEY §8e for BASELINE configs[2]: two contexts own interleaved 32x32 screen tiles of the frame (both on this GPU; the all-gather is a device copy) and run the recipe of
+    include/rtxpt_b200.h - trace own tiles, exchange guides, per plane { prepare, exchange NRD inputs, ReBLUR on the whole frame, merge }, exchange the output colour, tone map.
+    Without NEE-AT feedback every per-pixel step is deterministic and ReBLUR sees identical inputs: three consecutive frames are bit-identical to one context's frames,
+    in what the denoiser received, what it returned, its history lengths and the tone-mapped image.  With feedback each rank adapts on its own tiles: same mean, finite."""
+    from rtxpt_b200 import scene_builder as sb, scenes, structs as S, realtime_mgpu as M
+    W, H = 160, 128
+    scene, cam = scenes.cornell_box(W, H, delta_surfaces=True)
+    consts = sb.make_constants(W, H, cam, bounce_count=6, diffuse_bounce_count=3)
+    k = sb.make_denoiser_constants(cam); tm = S.make_tone_mapping_params(op=5, auto_exposure=True)
+    def make(rank, world):
+        c = product.Context(max_sub_samples_per_launch=1, tile_rank=rank, tile_world=world, tile_size=32); c.upload_scene(scene); c.set_constants(consts); c.set_view(sb.world_to_clip(cam))
+        c.set_realtime(sb.make_realtime_constants(W, H, cam, bounce_count=6, sub_samples=2)); return c
+    one = make(0, 1); two = [make(0, 2), make(1, 2)]; group = M.LocalGroup(two)
+    for f in range(3):
+        consts.sampleBaseIndex = 2 * f
+        for c in [one] + two: c.set_constants(consts)
+        frame = sb.make_reblur_frame(cam, cam, frame_index=f)
+        one.path_trace_realtime(False); one.denoise_realtime(k, frame); one.tone_map(tm); one.synchronize()
+        moved = M.realtime_frame(group, k, frame, tm)
+        for c in two: c.synchronize()
+        ref = dict(inputs=one.readback_denoiser_inputs(), reblur=one.readback_reblur(), color=one.readback_output_color(), ldr=one.readback_ldr(), guides=one.readback_guides())
+        for c in two:
+            got = dict(inputs=c.readback_denoiser_inputs(), reblur=c.readback_reblur(), color=c.readback_output_color(), ldr=c.readback_ldr(), guides=c.readback_guides())
+            for key in ("inputs", "reblur"):
+                for name in ref[key]: assert ref[key][name].tobytes() == got[key][name].tobytes(), (f, key, name)
+            assert ref["color"].tobytes() == got["color"].tobytes() and ref["ldr"].tobytes() == got["ldr"].tobytes(), f
+            assert ref["guides"][0].tobytes() == got["guides"][0].tobytes()                 # depth: exchanged; motion / throughput stay per rank
+        assert moved == 2 * (two[0].exchange_bytes(M.GUIDES) + 3 * two[0].exchange_bytes(M.NRD_INPUTS) + two[0].exchange_bytes(M.OUTPUT))
+    # with NEE-AT feedback: each rank keeps its own reservoirs and global table
+    consts.NEEATFeedback = 1; means = []
+    for f in range(6):
+        consts.sampleBaseIndex = 100 + 2 * f
+        for c in [one] + two: c.set_constants(consts)
+        frame = sb.make_reblur_frame(cam, cam, frame_index=3 + f)
+        one.neeat_update_begin(); one.path_trace_realtime(False); one.denoise_realtime(k, frame); one.synchronize()
+        M.realtime_frame(group, k, frame, None, feedback=True)
+        for c in two: c.synchronize()
+        a = one.readback_output_color()[..., :3].astype(np.float32); b = two[0].readback_output_color()[..., :3].astype(np.float32)
+        assert np.isfinite(b).all() and two[0].readback_output_color().tobytes() == two[1].readback_output_color().tobytes()
+        means.append((a.mean(), b.mean()))
+    m = np.asarray(means)
+    assert abs(m[:, 1].mean() / m[:, 0].mean() - 1) < 0.03, means
+    for c in [one] + two: c.close()

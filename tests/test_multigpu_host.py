@@ -63,3 +63,37 @@ def test_reference_arm_non_zero_ranks_exit_quietly():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"], env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def _exchange_worker(rank, world, port, w, h, tile, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from rtxpt_b200 import tiles
+    rng = np.random.default_rng(11)                                  # every rank builds the same "truth"; it only owns its tiles of it
+    truth = [rng.random((h, w)).astype(np.float32), rng.integers(0, 255, (h, w), dtype=np.uint8), rng.random((h, w, 4)).astype(np.float16), rng.integers(0, 2 ** 32 - 1, (h, w), dtype=np.uint32)]
+    tables, padded = tiles.gather_layout(w, h, tile, world)
+    x, y = tables[rank] >> 16, tables[rank] & 0xFFFF
+    mine = [np.zeros_like(a) for a in truth]
+    for m, a in zip(mine, truth): m[y, x] = a[y, x]
+    send = torch.from_numpy(tiles.exchange_pack(mine, tables[rank], padded))
+    gathered = torch.empty(world * send.numel(), dtype=torch.uint8)
+    dist.all_gather_into_tensor(gathered, send)
+    tiles.exchange_unpack(gathered.numpy(), tables, padded, mine, skip_rank=rank)
+    q.put((rank, all(np.array_equal(m, a) for m, a in zip(mine, truth)), send.numel()))
+    dist.destroy_process_group()
+
+
+def test_realtime_frame_exchange_layout_world2_gloo():
+    """The generic per-pixel image exchange of the realtime frame (rtxpt_b200_exchange_pack / _unpack; tiles.exchange_* is its host mirror): images of 4, 1, 8 and 4 bytes per
+    pixel, packed tile-wise per rank, one all-gather, scattered back - every rank ends up with the whole of every image."""
+    from rtxpt_b200 import tiles
+    ctx = mp.get_context("spawn"); q = ctx.Queue()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, 2, 29617, 200, 120, 32, q)) for r in range(2)]
+    for p in procs: p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs: p.join(60)
+    assert all(r[1] for r in res)
+    _, padded = tiles.gather_layout(200, 120, 32, 2)
+    offs, total = tiles.exchange_layout([4, 1, 8, 4], padded)
+    assert res[0][2] == total and all(o % 16 == 0 for o in offs)
