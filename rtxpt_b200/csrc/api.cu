@@ -367,6 +367,7 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
             if (firstGid.size() <= subIndex) firstGid.resize(size_t(subIndex) + 1, 0u);
             firstGid[subIndex] = uint32_t(tris.size());
             const bool hasPrev = g.prevPositionOffset != ~0u;          // Donut: only skinned geometries carry last frame's positions
+            if (prevPosBase.size() <= subIndex) prevPosBase.resize(size_t(subIndex) + 1, 0xFFFFFFFFu);
             prevPosBase[subIndex] = hasPrev ? uint32_t(triPrevPos.size() / 9) : 0xFFFFFFFFu;
             if (maxVertex.size() <= subIndex) maxVertex.resize(size_t(subIndex) + 1, 0u);
             const RtxptSubInstanceData& sub = sc->subInstances[subIndex];
@@ -465,6 +466,7 @@ extern "C" RTXPT_API int rtxpt_b200_upload_scene(rtxpt_ctx* c, const RtxptSceneD
     CU(c->dBvhTris.upload(reinterpret_cast<const float4*>(bvh.tris.data()), bvh.tris.size() * 3, s));
     CU(c->dTriInfo.upload(triInfo.data(), triInfo.size(), s));
     CU(c->dTriShade.upload(triShade.data(), triShade.size(), s));
+    prevPosBase.resize(std::max<size_t>(prevPosBase.size(), sc->subInstanceCount), 0xFFFFFFFFu);
     c->hPrevPosBase = prevPosBase; c->prevPosTriangles = triPrevPos.size() / 9;
     CU(c->dPrevPosBase.upload(prevPosBase.data(), prevPosBase.size(), s));
     if (!triPrevPos.empty()) CU(c->dTriPrevPos.upload(triPrevPos.data(), triPrevPos.size(), s)); else c->dTriPrevPos.release();
