@@ -542,13 +542,15 @@ RTXPT_API int rtxpt_b200_unpack_all(rtxpt_ctx* ctx, const void* dSrcAll, void* c
 /* The realtime frame on several GPUs (BASELINE configs[2]).  Every rank traces BUILD / FILL for the screen tiles it owns; what the frame needs of its neighbours is
  * exchanged as packed per-pixel images, one all-gather each, with the calls below (`buffers`: 1..8 RTXPT_BUFFER_* ids of plain per-pixel images of 1 / 4 / 8 / 16 bytes per pixel):
  *   1. rtxpt_b200_path_trace_realtime(ctx, 0, s)                                             own tiles
- *   2. exchange { DEPTH_F32, SPECULAR_HITT_F32 }; rtxpt_b200_denoise_spec_hit_t             the 5x5 guide filter reads across tile borders
+ *   2. exchange { DEPTH_F32, SPECULAR_HITT_F32, STABLE_PLANE_NEIGHBOUR_GUIDES }; rtxpt_b200_denoise_spec_hit_t      the 5x5 guide filter and the disocclusion relaxation of
+ *      prepare_inputs (a pixel's four neighbours: branch ID + packed normal per plane, 24 B per pixel) read across tile borders
  *   3. per plane, last to first: rtxpt_b200_denoiser_prepare_inputs (own tiles); exchange the seven RTXPT_BUFFER_DENOISER_* / COMBINED_HISTORY_CLAMP_RELAX images;
  *      rtxpt_b200_reblur_denoise (whole frame, replicated: every rank keeps the same history); rtxpt_b200_denoiser_final_merge (own tiles)
  *   4. exchange { OUTPUT_COLOR_F16 }; rtxpt_b200_tone_map                                    auto exposure reads the whole frame
  * exchange = rtxpt_b200_exchange_pack into a send buffer of rtxpt_b200_exchange_bytes bytes, ncclAllGather (or torch.distributed.all_gather_into_tensor) into
  * tileWorld x that many bytes, rtxpt_b200_exchange_unpack.  With NEEATFeedback = 0 the assembled frame is bit-identical to the single-GPU frame (tests/test_gpu_multi.py); with
  * feedback every rank adapts on its own tiles (independent global tables, local samplers clamped at screen-tile borders: still unbiased). */
+enum { RTXPT_BUFFER_STABLE_PLANE_NEIGHBOUR_GUIDES = 20 };     /* exchange only: per plane { branch ID, StablePlane::PackedNormal } of every pixel */
 RTXPT_API int rtxpt_b200_exchange_bytes(rtxpt_ctx* ctx, const int* buffers, uint32_t count, size_t* outBytesPerRank);
 RTXPT_API int rtxpt_b200_exchange_pack(rtxpt_ctx* ctx, const int* buffers, uint32_t count, void* dDst, void* cudaStream);
 RTXPT_API int rtxpt_b200_exchange_unpack(rtxpt_ctx* ctx, const int* buffers, uint32_t count, const void* dSrcAllRanks, void* cudaStream);

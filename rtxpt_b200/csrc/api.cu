@@ -1474,6 +1474,12 @@ static int buildExchangeSet(rtxpt_ctx* c, const int* buffers, uint32_t count, Ex
     uint64_t off = 0;
     for (uint32_t k = 0; k < count; k++)
     {
+        if (buffers[k] == RTXPT_BUFFER_STABLE_PLANE_NEIGHBOUR_GUIDES)
+        {   // not an image: per plane the branch ID and the packed normal, gathered from the header layers and the plane records by their own kernels
+            const int rc = checkRealtimeReady(c); if (rc != RTXPT_OK) return rc;
+            e.image[k] = nullptr; e.bytesPerPixel[k] = 24; e.segmentOffset[k] = off; off += (uint64_t(c->paddedPixelsPerRank) * 24 + 15u) & ~uint64_t(15);
+            continue;
+        }
         if (buffers[k] == RTXPT_BUFFER_STABLE_PLANES || buffers[k] == RTXPT_BUFFER_STABLE_PLANES_HEADER) return fail(RTXPT_ERR_INVALID_ARGUMENT, "buffer %d is not a plain per-pixel image", buffers[k]);
         void* ptr; size_t bytes; const int rc = targetInfo(c, buffers[k], &ptr, &bytes); if (rc != RTXPT_OK) return rc;
         const size_t bpp = bytes / P;
@@ -1496,7 +1502,10 @@ extern "C" RTXPT_API int rtxpt_b200_exchange_pack(rtxpt_ctx* c, const int* buffe
     if (!dDst) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
     ExchangeSet e; const int rc = buildExchangeSet(c, buffers, count, e); if (rc != RTXPT_OK) return rc;
     cudaSetDevice(c->device);
-    launchExchangePack(e, c->pixelOfSlot.ptr, c->pixelCount, c->paddedPixelsPerRank, dDst, c->grid, pickStream(c, cudaStream));
+    cudaStream_t s = pickStream(c, cudaStream);
+    launchExchangePack(e, c->pixelOfSlot.ptr, c->pixelCount, c->paddedPixelsPerRank, dDst, c->grid, s);
+    for (uint32_t k = 0; k < e.count; k++)
+        if (!e.image[k]) { LaunchParams p; fillParams(c, p); fillRealtimeParams(c, p); launchRtPackPlaneGuides(p, c->paddedPixelsPerRank, static_cast<uint8_t*>(dDst) + e.segmentOffset[k], c->grid, s); }
     CU(cudaGetLastError());
     return RTXPT_OK;
 }
@@ -1506,7 +1515,10 @@ extern "C" RTXPT_API int rtxpt_b200_exchange_unpack(rtxpt_ctx* c, const int* buf
     ExchangeSet e; const int rc = buildExchangeSet(c, buffers, count, e); if (rc != RTXPT_OK) return rc;
     if (c->cfg.tileWorld <= 1) return RTXPT_OK;
     cudaSetDevice(c->device);
-    launchExchangeUnpack(e, c->allPixelTable.ptr, c->paddedPixelsPerRank, c->cfg.tileWorld, c->cfg.tileRank, dSrcAll, c->grid, pickStream(c, cudaStream));
+    cudaStream_t s = pickStream(c, cudaStream);
+    launchExchangeUnpack(e, c->allPixelTable.ptr, c->paddedPixelsPerRank, c->cfg.tileWorld, c->cfg.tileRank, dSrcAll, c->grid, s);
+    for (uint32_t k = 0; k < e.count; k++)
+        if (!e.image[k]) { LaunchParams p; fillParams(c, p); fillRealtimeParams(c, p); launchRtUnpackPlaneGuides(p, c->allPixelTable.ptr, c->paddedPixelsPerRank, c->cfg.tileWorld, c->cfg.tileRank, dSrcAll, size_t(e.segmentOffset[k]), size_t(e.bytesPerRank), c->grid, s); }
     CU(cudaGetLastError());
     return RTXPT_OK;
 }

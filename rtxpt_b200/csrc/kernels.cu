@@ -370,7 +370,7 @@ __global__ void k_exchange_pack(const __grid_constant__ ExchangeSet e, const uin
     {
         const bool owned = i < pixelCount; const uint id = owned ? pixelOfSlot[i] : 0u;
         for (uint k = 0; k < e.count; k++)
-            switch (e.bytesPerPixel[k])
+            if (e.image[k]) switch (e.bytesPerPixel[k])       // image == NULL: a segment filled by its own kernel (stable-plane neighbour guides)
             {
             case 1: exchangeCopyPack<uint8_t>(e, k, i, id, owned, dst); break;
             case 4: exchangeCopyPack<uint>(e, k, i, id, owned, dst); break;
@@ -392,7 +392,7 @@ __global__ void k_exchange_unpack(const __grid_constant__ ExchangeSet e, const u
         if (id == 0xFFFFFFFFu || rank == skipRank) continue;                 // the rank's own pixels are already in place
         const uint8_t* src = srcAll + size_t(rank) * e.bytesPerRank;
         for (uint k = 0; k < e.count; k++)
-            switch (e.bytesPerPixel[k])
+            if (e.image[k]) switch (e.bytesPerPixel[k])
             {
             case 1: exchangeCopyUnpack<uint8_t>(e, k, slot, id, src); break;
             case 4: exchangeCopyUnpack<uint>(e, k, slot, id, src); break;

@@ -45,6 +45,8 @@ constexpr uint32_t kExchangeMaxImages = 8;
 struct ExchangeSet { void* image[kExchangeMaxImages]; uint32_t bytesPerPixel[kExchangeMaxImages]; uint64_t segmentOffset[kExchangeMaxImages]; uint64_t bytesPerRank; uint32_t count, width; };
 void launchExchangePack(const ExchangeSet& e, const uint32_t* pixelOfSlot, uint32_t pixelCount, uint32_t paddedCount, void* dst, const GridConfig& g, cudaStream_t s);                 // kernels.cu
 void launchExchangeUnpack(const ExchangeSet& e, const uint32_t* allPixelTable, uint32_t paddedCount, uint32_t world, uint32_t skipRank, const void* srcAll, const GridConfig& g, cudaStream_t s);
+void launchRtPackPlaneGuides(const LaunchParams& p, uint32_t paddedCount, void* dst, const GridConfig& g, cudaStream_t s);                                                  // realtime_kernels.cu
+void launchRtUnpackPlaneGuides(const LaunchParams& p, const uint32_t* allPixelTable, uint32_t paddedCount, uint32_t world, uint32_t skipRank, const void* srcAll, size_t segmentOffset, size_t bytesPerRank, const GridConfig& g, cudaStream_t s);
 void launchSkin(const skin::Params& p, cudaStream_t s);                 // skinning_kernels.cu
 void launchSkinInitPrev(const skin::Params& p, cudaStream_t s);         // previous-position range of a newly registered skin := the shade records' current corners
 namespace tonemap { struct Params; }

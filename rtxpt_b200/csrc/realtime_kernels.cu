@@ -217,6 +217,39 @@ __global__ void __launch_bounds__(256) k_dn_spec_hitt(const float* __restrict__ 
     const int x = int(blockIdx.x * 16 + threadIdx.x), y = int(blockIdx.y * 16 + threadIdx.y);
     if (x < W && y < H) dst[size_t(y) * W + x] = specHitTNeighbourhood(src, depth, W, H, x, y);
 }
+// multi-GPU: what ComputeDisocclusionRelaxation reads of a pixel's four neighbours - per plane the branch ID (header layer) and the packed plane normal - travels
+// with the guides, 24 bytes per pixel: segment layout [plane][word][slot], word 0 = branch ID, word 1 = PackedNormal
+__global__ void __launch_bounds__(256) k_rt_pack_plane_guides(const __grid_constant__ LaunchParams p, uint paddedCount, uint* __restrict__ dst)
+{
+    for (uint i = blockIdx.x * blockDim.x + threadIdx.x; i < paddedCount; i += gridDim.x * blockDim.x)
+    {
+        const bool owned = i < p.wf.pixelCount; const uint id = owned ? p.wf.pixelOfSlot[i] : 0u;
+        for (uint plane = 0; plane < kStablePlaneCount; plane++)
+        {
+            uint branch = kInvalidBranchID, normal = 0u;
+            if (owned) { branch = headerWord(p, id, plane); normal = p.rt.planes[planeAddress(p.rt, id, plane)].PackedNormal; }
+            dst[size_t(plane * 2 + 0) * paddedCount + i] = branch; dst[size_t(plane * 2 + 1) * paddedCount + i] = normal;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_rt_unpack_plane_guides(const __grid_constant__ LaunchParams p, const uint* __restrict__ allPixelTable, uint paddedCount, uint world, uint skipRank, const uint8_t* __restrict__ srcAll,
+                                                                size_t segmentOffset, size_t bytesPerRank)
+{
+    for (uint i = blockIdx.x * blockDim.x + threadIdx.x; i < paddedCount * world; i += gridDim.x * blockDim.x)
+    {
+        const uint id = allPixelTable[i]; const uint rank = i / paddedCount, slot = i - rank * paddedCount;
+        if (id == 0xFFFFFFFFu || rank == skipRank) continue;
+        const uint* src = reinterpret_cast<const uint*>(srcAll + size_t(rank) * bytesPerRank + segmentOffset);
+        for (uint plane = 0; plane < kStablePlaneCount; plane++)
+        {
+            headerWord(p, id, plane) = src[size_t(plane * 2 + 0) * paddedCount + slot];
+            p.rt.planes[planeAddress(p.rt, id, plane)].PackedNormal = src[size_t(plane * 2 + 1) * paddedCount + slot];
+        }
+    }
+}
+void launchRtPackPlaneGuides(const LaunchParams& p, uint32_t paddedCount, void* dst, const GridConfig& g, cudaStream_t s) { k_rt_pack_plane_guides<<<g.smCount * 4, 256, 0, s>>>(p, paddedCount, static_cast<uint*>(dst)); }
+void launchRtUnpackPlaneGuides(const LaunchParams& p, const uint32_t* allPixelTable, uint32_t paddedCount, uint32_t world, uint32_t skipRank, const void* srcAll, size_t segmentOffset, size_t bytesPerRank, const GridConfig& g, cudaStream_t s)
+{ k_rt_unpack_plane_guides<<<g.smCount * 4, 256, 0, s>>>(p, allPixelTable, paddedCount, world, skipRank, static_cast<const uint8_t*>(srcAll), segmentOffset, bytesPerRank); }
 void launchDnSpecHitT(const float* src, const float* depth, float* dst, int W, int H, cudaStream_t s) { k_dn_spec_hitt<<<dim3((W + 15) / 16, (H + 15) / 16), dim3(16, 16), 0, s>>>(src, depth, dst, W, H); }
 void launchDnPrepareInputs(const LaunchParams& p, const GridConfig& g, cudaStream_t s) { k_dn_prepare_inputs<<<g.smCount * 4, 256, 0, s>>>(p); }
 void launchDnFinalMerge(const LaunchParams& p, const GridConfig& g, cudaStream_t s) { k_dn_final_merge<<<g.smCount * 4, 256, 0, s>>>(p); }

@@ -1,13 +1,13 @@
 """BASELINE configs[2] (realtime mode + NEE-AT + ReBLUR + tone map) on several GPUs: the frame recipe of include/rtxpt_b200.h ("The realtime frame on several GPUs"), SURVEY.md §8e.
 Every rank traces the screen tiles it owns; three kinds of per-pixel images cross ranks, each as ONE all-gather of packed tiles:
-    guides (depth, specular hit distance) -> per plane the seven NRD input images -> the merged output colour.
+    guides (depth, specular hit distance, per plane branch ID + normal: what the guide filter and the disocclusion relaxation read of a pixel's neighbours) -> per plane the seven NRD input images -> the merged output colour.
 ReBLUR runs on the whole frame on every rank (2.8 ms at 1080p against 32 ms of tracing on one GPU): all ranks feed it the same inputs, so their histories stay identical
 and no history exchange is needed.  `LocalGroup` drives all ranks from one process (contexts on one or several devices, the exchange is a device copy: tests, single-GPU
 emulation); `DistGroup` is one rank of a torchrun job (torch.distributed.all_gather_into_tensor over NCCL)."""
 import numpy as np
 from . import structs as S
 
-GUIDES = [S.BUFFER_DEPTH_F32, S.BUFFER_SPECULAR_HITT_F32]
+GUIDES = [S.BUFFER_DEPTH_F32, S.BUFFER_SPECULAR_HITT_F32, S.BUFFER_STABLE_PLANE_NEIGHBOUR_GUIDES]
 NRD_INPUTS = [S.BUFFER_DENOISER_VIEWSPACE_Z_F32, S.BUFFER_DENOISER_MOTION_VECTORS_F16, S.BUFFER_DENOISER_NORMAL_ROUGHNESS_R10G10B10A2, S.BUFFER_DENOISER_DIFF_RADIANCE_HITDIST_F16,
               S.BUFFER_DENOISER_SPEC_RADIANCE_HITDIST_F16, S.BUFFER_DENOISER_DISOCCLUSION_MIX_R8, S.BUFFER_COMBINED_HISTORY_CLAMP_RELAX_R8]
 OUTPUT = [S.BUFFER_OUTPUT_COLOR_F16]

@@ -38,6 +38,7 @@ STABLE_PLANE_COUNT, STABLE_PLANE_INVALID_BRANCH = 3, 0xFFFFFFFF
  BUFFER_DENOISER_SPEC_RADIANCE_HITDIST_F16, BUFFER_DENOISER_DISOCCLUSION_MIX_R8, BUFFER_COMBINED_HISTORY_CLAMP_RELAX_R8) = 9, 10, 11, 12, 13, 14, 15
 BUFFER_DENOISED_DIFF_RADIANCE_HITDIST_F16, BUFFER_DENOISED_SPEC_RADIANCE_HITDIST_F16, BUFFER_REBLUR_ACCUMULATED_FRAMES_RG8 = 16, 17, 18
 BUFFER_LDR_COLOR_RGBA8 = 19
+BUFFER_STABLE_PLANE_NEIGHBOUR_GUIDES = 20        # exchange only (rtxpt_b200_exchange_*)
 
 
 class GeometryData(C.Structure):
