@@ -48,10 +48,32 @@ def workload_config(n_gpus):
             "cache": "working set per frame (path state 664 MB + scene ~400 MB) exceeds the 126 MB L2; no explicit flush"}
 
 
+def _gpu_uuid(torch, index):
+    """NVML enumerates physical GPUs, CUDA the visible ones: match by UUID."""
+    try: return "GPU-" + str(torch.cuda.get_device_properties(index).uuid)
+    except Exception: return None
+
+
 class ClockSampler:
-    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
-    def __init__(self, index):
-        self.lines, self.proc = [], None
+    """SM clock, power and clock-event reasons of this rank's GPU sampled DURING the timed region (B200_PROFILING.md clocks line).  NVML in a thread of this process (what
+    nvidia-smi itself reads): a looping `nvidia-smi -lms` process needed 70-100+ ms per query on the 8-GPU boxes and held the driver while it enumerated the node - the N=8 timed
+    loop of round 1 / early round 2 measured 6.7 ms per frame against 3.6 ms for the same frames with a host synchronize in between, with ONE clock sample taken
+    (profiles/r2_history.md section 10).  Falls back to nvidia-smi when NVML cannot be loaded."""
+    REASONS = (("hw_slowdown", "HwSlowdown"), ("hw_thermal_slowdown", "HwThermalSlowdown"), ("sw_thermal_slowdown", "SwThermalSlowdown"), ("sw_power_cap", "SwPowerCap"))
+
+    def __init__(self, index, uuid=None, period_s=0.01):
+        self.sm, self.mx, self.reasons, self.proc, self.nvml, self.stop_flag, self.lines, self.source = [], [], set(), None, None, False, [], "nvml"
+        try:
+            import pynvml
+            pynvml.nvmlInit(); self.nvml = pynvml
+            try: self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid if isinstance(uuid, bytes) else str(uuid).encode()) if uuid else pynvml.nvmlDeviceGetHandleByIndex(index)
+            except Exception: self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)); self.period = period_s
+            self.thread = threading.Thread(target=self._poll, daemon=True); self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        self.source = "nvidia-smi"
         q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "50"],
@@ -60,11 +82,28 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))); self.mx.append(self.max_sm)
+                bits = int(get(self.handle))
+                for name, suffix in self.REASONS:
+                    mask = getattr(n, "nvmlClocksEventReason" + suffix, None) or getattr(n, "nvmlClocksThrottleReason" + suffix, 0)
+                    if bits & int(mask): self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True; self.thread.join(1.0)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None, "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -80,7 +119,7 @@ class ClockSampler:
             for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def measured_peak_gbs():
@@ -239,7 +278,7 @@ def main():
     for i in range(args.warmup):
         frame(i)
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank, uuid=_gpu_uuid(torch, local_rank)) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     rays = 0; k_closest = k_shadow = k_shade = k_other = 0.0
     ev0.record()
