@@ -30,6 +30,13 @@ RTXPT_API int rtxpt_b200_mgpu_set_constants(rtxpt_mgpu* m, const RtxptPathTracer
 /* One frame: path_trace on every local context -> pack the owned tiles -> ncclAllGather (grouped over the local devices) -> unpack into every context's full-frame accumulated
  * image.  Asynchronous; exchange = 0 skips the all-gather (1024 spp reference accumulation gathers only at the end, §8e). */
 RTXPT_API int rtxpt_b200_mgpu_render_frame(rtxpt_mgpu* m, uint32_t firstSubSampleIndex, uint32_t subSampleCount, int accumulate, int exchange);
+/* Realtime mode (BASELINE configs[2]) on the same contexts: view / realtime constants go to every local context, then one call renders a frame the way rtxpt_b200.h's "The realtime
+ * frame on several GPUs" lays out - BUILD + FILL on each device's tiles; ncclAllGather (grouped over the local devices) of the guides, of the seven NRD inputs per plane and of
+ * the output colour, packed by tile ownership (rtxpt_b200_exchange_*); ReBLUR on the whole frame on every device; tone mapping when toneMapping != NULL.  neeatFeedback != 0 runs
+ * rtxpt_b200_neeat_update_begin first (the constants must carry NEEATFeedback = 1); every device adapts on its own tiles.  rtxpt_b200_mgpu_last_frame_ms: trace / the rest. */
+RTXPT_API int rtxpt_b200_mgpu_set_view(rtxpt_mgpu* m, const RtxptViewConstants* view);
+RTXPT_API int rtxpt_b200_mgpu_set_realtime(rtxpt_mgpu* m, const RtxptRealtimeConstants* realtime);
+RTXPT_API int rtxpt_b200_mgpu_render_realtime_frame(rtxpt_mgpu* m, const RtxptDenoiserConstants* denoiser, const RtxptReblurFrame* frame, const RtxptToneMappingParams* toneMapping, int neeatFeedback);
 RTXPT_API int rtxpt_b200_mgpu_synchronize(rtxpt_mgpu* m);
 /* Device time of the last render_frame per local device: trace, pack + all-gather + unpack (CUDA events on each device's stream). */
 RTXPT_API int rtxpt_b200_mgpu_last_frame_ms(rtxpt_mgpu* m, uint32_t localIndex, float* outTraceMs, float* outExchangeMs);

@@ -22,9 +22,10 @@ struct Local
 {
     int device = 0; rtxpt_ctx* ctx = nullptr; ncclComm_t comm = nullptr; cudaStream_t stream = nullptr;
     float4* send = nullptr; float4* recv = nullptr; cudaEvent_t ev[3] = { nullptr, nullptr, nullptr }; bool timed = false;
+    uint8_t* xsend = nullptr; uint8_t* xrecv = nullptr; size_t xbytes = 0;        // realtime frame: send / receive blocks of the per-pixel image exchange, grown on demand
 };
 }
-struct rtxpt_mgpu { std::vector<Local> local; uint32_t world = 0; uint32_t padded = 0; bool haveConstants = false; };
+struct rtxpt_mgpu { std::vector<Local> local; uint32_t world = 0; uint32_t padded = 0; bool haveConstants = false; uint32_t activePlanes = RTXPT_STABLE_PLANE_COUNT; };
 
 #define CU_(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(RTXPT_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } while (0)
 #define NC_(x) do { ncclResult_t r_ = (x); if (r_ != ncclSuccess) return fail(RTXPT_ERR_CUDA, "%s: %s", #x, ncclGetErrorString(r_)); } while (0)
@@ -83,7 +84,7 @@ RTXPT_API int rtxpt_b200_mgpu_destroy(rtxpt_mgpu* m)
         cudaSetDevice(l.device);
         if (l.stream) cudaStreamSynchronize(l.stream);
         if (l.comm) ncclCommDestroy(l.comm);
-        if (l.send) cudaFree(l.send); if (l.recv) cudaFree(l.recv);
+        if (l.send) cudaFree(l.send); if (l.recv) cudaFree(l.recv); if (l.xsend) cudaFree(l.xsend); if (l.xrecv) cudaFree(l.xrecv);
         for (cudaEvent_t e : l.ev) if (e) cudaEventDestroy(e);
         if (l.ctx) rtxpt_b200_destroy(l.ctx);
         if (l.stream) cudaStreamDestroy(l.stream);
@@ -135,6 +136,78 @@ RTXPT_API int rtxpt_b200_mgpu_render_frame(rtxpt_mgpu* m, uint32_t firstSubSampl
         for (Local& l : m->local) { CU_(cudaSetDevice(l.device)); RT_(rtxpt_b200_unpack_all(l.ctx, l.recv, l.stream)); }
     }
     for (Local& l : m->local) { CU_(cudaSetDevice(l.device)); CU_(cudaEventRecord(l.ev[2], l.stream)); l.timed = true; }
+    return RTXPT_OK;
+}
+
+// ---- realtime mode (BASELINE configs[2]) on the local devices: the frame recipe of rtxpt_b200.h ("The realtime frame on several GPUs") -----------------------------------------
+RTXPT_API int rtxpt_b200_mgpu_set_view(rtxpt_mgpu* m, const RtxptViewConstants* view)
+{
+    if (!m || !view) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    for (Local& l : m->local) { CU_(cudaSetDevice(l.device)); RT_(rtxpt_b200_set_view(l.ctx, view)); }
+    return RTXPT_OK;
+}
+RTXPT_API int rtxpt_b200_mgpu_set_realtime(rtxpt_mgpu* m, const RtxptRealtimeConstants* realtime)
+{
+    if (!m || !realtime) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    for (Local& l : m->local) { CU_(cudaSetDevice(l.device)); RT_(rtxpt_b200_set_realtime(l.ctx, realtime)); }
+    m->activePlanes = realtime->activeStablePlaneCount;
+    return RTXPT_OK;
+}
+static int exchangeImages(rtxpt_mgpu* m, const int* ids, uint32_t count)
+{
+    if (m->world <= 1) return RTXPT_OK;
+    size_t bytes = 0;
+    for (Local& l : m->local)
+    {
+        CU_(cudaSetDevice(l.device)); RT_(rtxpt_b200_exchange_bytes(l.ctx, ids, count, &bytes));
+        if (l.xbytes < bytes)
+        {
+            CU_(cudaStreamSynchronize(l.stream)); if (l.xsend) cudaFree(l.xsend); if (l.xrecv) cudaFree(l.xrecv); l.xsend = l.xrecv = nullptr; l.xbytes = 0;
+            CU_(cudaMalloc(&l.xsend, bytes)); CU_(cudaMalloc(&l.xrecv, bytes * m->world)); l.xbytes = bytes;
+        }
+        RT_(rtxpt_b200_exchange_pack(l.ctx, ids, count, l.xsend, l.stream));
+    }
+    NC_(ncclGroupStart());
+    for (Local& l : m->local) NC_(ncclAllGather(l.xsend, l.xrecv, bytes, ncclUint8, l.comm, l.stream));
+    NC_(ncclGroupEnd());
+    for (Local& l : m->local) { CU_(cudaSetDevice(l.device)); RT_(rtxpt_b200_exchange_unpack(l.ctx, ids, count, l.xrecv, l.stream)); }
+    return RTXPT_OK;
+}
+RTXPT_API int rtxpt_b200_mgpu_render_realtime_frame(rtxpt_mgpu* m, const RtxptDenoiserConstants* denoiser, const RtxptReblurFrame* frame, const RtxptToneMappingParams* toneMapping, int neeatFeedback)
+{
+    if (!m || !denoiser || !frame) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (!m->haveConstants) return fail(RTXPT_ERR_INVALID_ARGUMENT, "constants not set");
+    static const int guides[] = { RTXPT_BUFFER_DEPTH_F32, RTXPT_BUFFER_SPECULAR_HITT_F32, RTXPT_BUFFER_STABLE_PLANE_NEIGHBOUR_GUIDES };
+    static const int nrdIn[] = { RTXPT_BUFFER_DENOISER_VIEWSPACE_Z_F32, RTXPT_BUFFER_DENOISER_MOTION_VECTORS_F16, RTXPT_BUFFER_DENOISER_NORMAL_ROUGHNESS_R10G10B10A2, RTXPT_BUFFER_DENOISER_DIFF_RADIANCE_HITDIST_F16,
+                                 RTXPT_BUFFER_DENOISER_SPEC_RADIANCE_HITDIST_F16, RTXPT_BUFFER_DENOISER_DISOCCLUSION_MIX_R8, RTXPT_BUFFER_COMBINED_HISTORY_CLAMP_RELAX_R8 };
+    static const int color[] = { RTXPT_BUFFER_OUTPUT_COLOR_F16 };
+    for (Local& l : m->local)
+    {
+        CU_(cudaSetDevice(l.device)); CU_(cudaEventRecord(l.ev[0], l.stream));
+        if (neeatFeedback) RT_(rtxpt_b200_neeat_update_begin(l.ctx, l.stream));
+        RT_(rtxpt_b200_path_trace_realtime(l.ctx, 0, l.stream));
+        CU_(cudaEventRecord(l.ev[1], l.stream));
+    }
+    int rc = exchangeImages(m, guides, 3); if (rc != RTXPT_OK) return rc;
+    for (Local& l : m->local) { CU_(cudaSetDevice(l.device)); RT_(rtxpt_b200_denoise_spec_hit_t(l.ctx, l.stream)); }
+    for (int plane = int(m->activePlanes) - 1; plane >= 0; plane--)
+    {
+        for (Local& l : m->local) { CU_(cudaSetDevice(l.device)); RT_(rtxpt_b200_denoiser_prepare_inputs(l.ctx, uint32_t(plane), plane == int(m->activePlanes) - 1, denoiser, l.stream)); }
+        rc = exchangeImages(m, nrdIn, 7); if (rc != RTXPT_OK) return rc;
+        for (Local& l : m->local)
+        {
+            CU_(cudaSetDevice(l.device));
+            RT_(rtxpt_b200_reblur_denoise(l.ctx, uint32_t(plane), frame, l.stream));                 // whole frame on every device: identical histories
+            RT_(rtxpt_b200_denoiser_final_merge(l.ctx, uint32_t(plane), nullptr, nullptr, l.stream));
+        }
+    }
+    rc = exchangeImages(m, color, 1); if (rc != RTXPT_OK) return rc;
+    for (Local& l : m->local)
+    {
+        CU_(cudaSetDevice(l.device));
+        if (toneMapping) RT_(rtxpt_b200_tone_map(l.ctx, toneMapping, RTXPT_BUFFER_OUTPUT_COLOR_F16, l.stream));
+        CU_(cudaEventRecord(l.ev[2], l.stream)); l.timed = true;
+    }
     return RTXPT_OK;
 }
 

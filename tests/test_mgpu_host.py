@@ -28,7 +28,7 @@ def _lib(product):
 def test_mgpu_library_exports_every_declared_symbol(product):
     src = open(os.path.join(ROOT, "include", "rtxpt_b200_mgpu.h")).read()
     names = sorted(set(re.findall(r"RTXPT_API\s+[\w\s\*]+?\b(rtxpt_b200_mgpu_\w+)\s*\(", src)))
-    assert len(names) == 12, names
+    assert len(names) == 15, names
     L = _lib(product)
     for n in names: assert hasattr(L, n), n
 
@@ -101,3 +101,47 @@ def test_cpp_multigpu_example_writes_the_frame(product, tmp_path):
     r = subprocess.run([exe, str(path), str(out), "1", "96", "96", "8", "3"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     assert "gpu 0: last frame trace" in r.stderr and out.stat().st_size > 96 * 96 * 12
+
+
+def _realtime_with_host(L, product, scene, cam, consts, gpus, frames=2):
+    """The C++ host's realtime frame (rtxpt_b200_mgpu_render_realtime_frame) on `gpus` devices; returns every local context's LDR image and output colour."""
+    from rtxpt_b200 import scene_builder as sb, structs as S
+    for name, args in (("set_view", [C.c_void_p, C.c_void_p]), ("set_realtime", [C.c_void_p, C.c_void_p]), ("render_realtime_frame", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int])):
+        fn = getattr(L, "rtxpt_b200_mgpu_" + name); fn.argtypes = args; fn.restype = C.c_int
+    W, H = consts.imageWidth, consts.imageHeight
+    cfg = S.Config(); cfg.maxSubSamplesPerLaunch = 1; cfg.tileSize = 32; h = C.c_void_p()
+    assert L.rtxpt_b200_mgpu_create(C.byref(cfg), gpus, None, C.byref(h)) == 0, L.rtxpt_b200_mgpu_last_error()
+    assert L.rtxpt_b200_mgpu_upload_scene(h, C.byref(scene.desc)) == 0, L.rtxpt_b200_mgpu_last_error()
+    view = S.ViewConstants(); view.matWorldToClip[:] = [float(x) for x in np.asarray(sb.world_to_clip(cam), np.float32).reshape(16)]
+    rt = sb.make_realtime_constants(W, H, cam, bounce_count=6, sub_samples=2); k = sb.make_denoiser_constants(cam); tm = S.make_tone_mapping_params(op=5, auto_exposure=True)
+    assert L.rtxpt_b200_mgpu_set_constants(h, C.byref(consts)) == 0 and L.rtxpt_b200_mgpu_set_view(h, C.byref(view)) == 0 and L.rtxpt_b200_mgpu_set_realtime(h, C.byref(rt)) == 0, L.rtxpt_b200_mgpu_last_error()
+    for f in range(frames):
+        consts.sampleBaseIndex = 2 * f; frame = sb.make_reblur_frame(cam, cam, frame_index=f)
+        assert L.rtxpt_b200_mgpu_set_constants(h, C.byref(consts)) == 0 and L.rtxpt_b200_mgpu_render_realtime_frame(h, C.byref(k), C.byref(frame), C.byref(tm), 0) == 0, L.rtxpt_b200_mgpu_last_error()
+    assert L.rtxpt_b200_mgpu_synchronize(h) == 0
+    PL = product.load(); out = []
+    for i in range(L.rtxpt_b200_mgpu_local_count(h)):
+        ldr = np.empty((H, W, 4), np.uint8); col = np.empty((H, W, 4), np.float16); ctx = L.rtxpt_b200_mgpu_context(h, i)
+        assert PL.rtxpt_b200_readback(ctx, S.BUFFER_LDR_COLOR_RGBA8, ldr.ctypes.data, ldr.nbytes) == 0 and PL.rtxpt_b200_readback(ctx, S.BUFFER_OUTPUT_COLOR_F16, col.ctypes.data, col.nbytes) == 0
+        out.append((ldr, col))
+    assert L.rtxpt_b200_mgpu_destroy(h) == 0
+    return out
+
+
+@pytest.mark.gpu
+def test_mgpu_realtime_frame_equals_the_single_context(product):
+    """BASELINE configs[2]'s frame through the C++ host: one device reproduces rtxpt_b200_denoise_realtime's frame; with two or more devices every device ends up with that frame."""
+    import torch
+    from rtxpt_b200 import scene_builder as sb, scenes, structs as S
+    W, H = 160, 128
+    scene, cam = scenes.cornell_box(W, H, delta_surfaces=True)
+    consts = sb.make_constants(W, H, cam, bounce_count=6, diffuse_bounce_count=3)
+    c = product.Context(max_sub_samples_per_launch=1, tile_size=32); c.upload_scene(scene); c.set_constants(consts); c.set_view(sb.world_to_clip(cam))
+    c.set_realtime(sb.make_realtime_constants(W, H, cam, bounce_count=6, sub_samples=2)); k = sb.make_denoiser_constants(cam); tm = S.make_tone_mapping_params(op=5, auto_exposure=True)
+    for f in range(2):
+        consts.sampleBaseIndex = 2 * f; c.set_constants(consts)
+        c.path_trace_realtime(False); c.denoise_realtime(k, sb.make_reblur_frame(cam, cam, frame_index=f)); c.tone_map(tm)
+    c.synchronize(); ref_ldr, ref_col = c.readback_ldr(), c.readback_output_color(); c.close()
+    for gpus in sorted({1, min(2, torch.cuda.device_count()), torch.cuda.device_count()}):
+        for ldr, col in _realtime_with_host(_lib(product), product, scene, cam, consts, gpus):
+            assert ldr.tobytes() == ref_ldr.tobytes() and col.tobytes() == ref_col.tobytes(), gpus
