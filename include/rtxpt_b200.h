@@ -460,6 +460,12 @@ RTXPT_API int      rtxpt_b200_bake_env_map(rtxpt_ctx* ctx, const RtxptEnvBakeDes
  * Single GPU: the tile partition does not carry the reservoirs. */
 RTXPT_API int rtxpt_b200_neeat_update_begin(rtxpt_ctx* ctx, void* cudaStream);
 RTXPT_API int rtxpt_b200_neeat_update_end(rtxpt_ctx* ctx, void* cudaStream);
+/* Dynamic analytic lights: replaces the scene's light array (RtxptSceneDesc.lights) - lights that move, change colour / intensity / cone, are added at the end or dropped from the
+ * end keep their identity by position in the array; the library re-bakes its light list (environment nodes, analytic lights, emissive triangles) as LightsBaker::UpdateBegin does
+ * every frame.  With NEE-AT feedback active the reservoirs and tile samplers of the last frame follow the lights through the past -> current index tables of the reference
+ * (LightsBaker.hlsl u_historyRemapPastToCurrent / CurrentToPast: environment nodes through the importance-map lookups, triangles by block offset); a removed light's feedback is
+ * dropped.  Call before rtxpt_b200_neeat_update_begin of the frame.  Emissive geometry and the environment cube stay those of the upload. */
+RTXPT_API int rtxpt_b200_update_lights(rtxpt_ctx* ctx, const RtxptLightDesc* lights, uint32_t lightCount);
 RTXPT_API int rtxpt_b200_neeat_reset(rtxpt_ctx* ctx);                 /* LightsBaker::BakeSettings::ResetFeedback: drop all feedback state */
 /* tests / debugging: what = 0,1 feedback weight / candidate; 2,3 processed; 4,5 half-resolution blend; 6 tile lists; 7 proxy counters; 8 control words; 11 proxy table */
 RTXPT_API int rtxpt_b200_neeat_readback(rtxpt_ctx* ctx, int what, void* dst, size_t dstBytes, size_t* outBytes);

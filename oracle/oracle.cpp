@@ -20,6 +20,7 @@ using namespace orc;
 
 struct OracleCtx
 {
+    RtxptSceneDesc descCopy{}; std::vector<RtxptLightDesc> ownLights;
     Scene scene;
     Bvh2 bvh;
     LightTable lights;
@@ -133,7 +134,8 @@ ORC_API void oracle_bsdf_funcs(const float* in, uint32_t count, float* out)
 ORC_API void* oracle_create(const RtxptSceneDesc* desc)
 {
     OracleCtx* c = new OracleCtx();
-    c->scene.init(desc);
+    c->descCopy = *desc;                 // a private copy of the table of pointers: oracle_set_lights swaps the light array
+    c->scene.init(&c->descCopy);
     auto t0 = std::chrono::steady_clock::now();
     c->bvh.build(c->scene);
     c->bvhBuildSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -149,6 +151,15 @@ ORC_API int oracle_set_constants(void* p, const RtxptPathTracerConstants* consts
     bool rebuildEnv = !c->haveConsts;
     c->consts = *consts; c->haveConsts = true;
     bakeLights(c->scene, c->consts, c->lights, rebuildEnv);
+    return 0;
+}
+
+// the scene's analytic lights changed (rtxpt_b200_update_lights): re-bake the light list; NEE-AT's next update_begin maps last frame's feedback onto it
+ORC_API int oracle_set_lights(void* p, const RtxptLightDesc* lights, uint32_t count)
+{
+    OracleCtx* c = (OracleCtx*)p; if (count && !lights) return -1;
+    c->ownLights.assign(lights, lights + count); c->descCopy.lights = c->ownLights.data(); c->descCopy.lightCount = count;
+    if (c->haveConsts) bakeLights(c->scene, c->consts, c->lights, false);
     return 0;
 }
 

@@ -98,6 +98,10 @@ struct NeeatState
     float globalFeedbackUseWeight = 0, localToGlobalSampleRatio = 0; uint historicTotalLightCount = 0, validFeedbackCount = 0;
     // boosted light weights of this frame (what ComputeWeights stores) and of the last one (u_lightWeights' historic half), their sum in ComputeWeights' order
     std::vector<float> currentWeights, historicWeights; float currentWeightsSum = 0; float frustumPlanes[5][4] = {};
+    // dynamic light lists (LightsBaker.cpp:1086-1225, LightsBaker.hlsl u_historyRemapPastToCurrent / CurrentToPast): what last frame's feedback was indexed by, and this frame's
+    // index tables (empty = the list did not change: identity)
+    struct ListSnapshot { bool valid = false, envEnabled = false; uint analyticCount = 0, triangleCount = 0; std::vector<uint> envNodes, envLookupMap; } past;
+    std::vector<uint> pastToCurrent, currentToPast;
 
     void init(uint w, uint h)
     {
@@ -107,6 +111,7 @@ struct NeeatState
         currentWeights.clear(); historicWeights.clear(); currentWeightsSum = 0;
         updateCounter = 0; jitterF[0] = jitterF[1] = 0; jitter[0] = jitter[1] = jitterPrev[0] = jitterPrev[1] = 0; feedbackBufferFilled = false;
         lastFrameTemporalFeedbackAvailable = lastFrameLocalSamplesAvailable = false; globalFeedbackUseWeight = localToGlobalSampleRatio = 0; historicTotalLightCount = 0;
+        past = ListSnapshot(); pastToCurrent.clear(); currentToPast.clear();
     }
     uint tileBaseAddress(uint tx, uint ty) const { return (tx + ty * tilesX) * NEEAT_LOCAL_PROXY_COUNT; }     // LLSB_ComputeBaseAddress
 };
@@ -145,7 +150,7 @@ inline void InsertFeedbackFromNEE(NeeatState& s, const LightTable& lt, uint px, 
 inline uint RemapPastToCurrent(const NeeatState& s, uint totalLightCount, uint historic)
 {
     if (historic == RTXPT_INVALID_LIGHT_INDEX) return RTXPT_INVALID_LIGHT_INDEX;
-    uint idx = historic < s.historicTotalLightCount ? historic : RTXPT_INVALID_LIGHT_INDEX;        // identity remap of a static light list
+    uint idx = historic < s.historicTotalLightCount ? (s.pastToCurrent.empty() ? historic : s.pastToCurrent[historic]) : RTXPT_INVALID_LIGHT_INDEX;        // LightsBaker.hlsl:1068-1093; no table = unchanged list
     if (idx != RTXPT_INVALID_LIGHT_INDEX && idx >= totalLightCount) idx = RTXPT_INVALID_LIGHT_INDEX;
     return idx;
 }
@@ -250,7 +255,9 @@ inline void ComputeBoostedWeights(NeeatState& s, const LightTable& lt, uint boos
         }
         if (delta)
         {
-            const float historic = i < s.historicWeights.size() ? s.historicWeights[i] : 0.0f;          // identity remap of a static light list
+            float historic = 0.0f;                                                                       // ImportanceBooster, LightsBaker.hlsl:139-141
+            if (s.currentToPast.empty()) historic = i < s.historicWeights.size() ? s.historicWeights[i] : 0.0f;
+            else { const uint h = s.currentToPast[i]; if (h != RTXPT_INVALID_LIGHT_INDEX && h < s.historicWeights.size()) historic = s.historicWeights[h]; }
             const float d = w - historic * 1.1f;
             if (d > 0) w += s.settings.importanceBoostIntensityDeltaMul * d;
         }
@@ -435,8 +442,40 @@ inline void ClearFeedbackHistory(NeeatState& s, const float* depth)
 
 // ---- one frame of LightsBaker around the path tracer -----------------------------------------------------------------------------------------------------------------------------
 // UpdateBegin: before anything of the frame is traced.  Rebuilds lt's global proxy table from the base weights and last frame's feedback.
+// The light list against the one last frame's feedback was indexed by: environment quad-tree nodes map through the importance-map lookups (a past node -> the current node that
+// holds its corner texel, EnvLightsMapPastToCurrent LightsBaker.hlsl:515-538; a current node -> the past node at its corner, :452-463), analytic lights keep their place in the
+// scene's light array (the reference matches them by a hash of the scene object), emissive triangles keep their order behind them (block offsets, :700-711)
+inline void NeeatTrackLightList(NeeatState& s, const LightTable& lt)
+{
+    NeeatState::ListSnapshot now; now.valid = lt.lights.size() >= ENVQT_TOTAL; now.envEnabled = lt.envEnabled; now.analyticCount = lt.analyticLightCount; now.triangleCount = lt.triangleLightCount;
+    now.envNodes.resize(size_t(ENVQT_TOTAL) * 2);
+    for (uint i = 0; i < ENVQT_TOTAL && now.valid; i++) { now.envNodes[2 * i] = lt.lights[i].Direction1; now.envNodes[2 * i + 1] = lt.lights[i].Direction2; }
+    now.envLookupMap = lt.envLookupMap;
+    const NeeatState::ListSnapshot& past = s.past;
+    s.pastToCurrent.clear(); s.currentToPast.clear();
+    const bool changed = past.valid && (past.envEnabled != now.envEnabled || past.analyticCount != now.analyticCount || past.triangleCount != now.triangleCount || past.envNodes != now.envNodes);
+    if (changed && s.feedbackBufferFilled)
+    {
+        const uint E = ENVQT_TOTAL, nPast = past.analyticCount, nCur = now.analyticCount, tPast = past.triangleCount, tCur = now.triangleCount, dimMap = 1024;      // EMISB_IMPORTANCE_MAP_DIM
+        s.pastToCurrent.assign(size_t(E) + nPast + tPast, RTXPT_INVALID_LIGHT_INDEX); s.currentToPast.assign(size_t(E) + nCur + tCur, RTXPT_INVALID_LIGHT_INDEX);
+        if (past.envEnabled && now.envEnabled && past.envLookupMap.size() == size_t(dimMap) * dimMap && now.envLookupMap.size() == past.envLookupMap.size())
+            for (uint i = 0; i < E; i++)
+            {
+                uint dim = past.envNodes[2 * i + 1] >> 16, x = past.envNodes[2 * i] >> 16, y = past.envNodes[2 * i] & 0xFFFFu;
+                if (dim) { const uint ds = dimMap / dim; s.pastToCurrent[i] = now.envLookupMap[size_t(y * ds) * dimMap + x * ds]; }
+                dim = now.envNodes[2 * i + 1] >> 16; x = now.envNodes[2 * i] >> 16; y = now.envNodes[2 * i] & 0xFFFFu;
+                if (dim) { const uint ds = dimMap / dim; s.currentToPast[i] = past.envLookupMap[size_t(y * ds) * dimMap + x * ds]; }
+            }
+        for (uint k = 0; k < nPast; k++) s.pastToCurrent[E + k] = k < nCur ? E + k : RTXPT_INVALID_LIGHT_INDEX;
+        for (uint k = 0; k < nCur; k++) s.currentToPast[E + k] = k < nPast ? E + k : RTXPT_INVALID_LIGHT_INDEX;
+        for (uint t = 0; t < tPast; t++) s.pastToCurrent[E + nPast + t] = t < tCur ? E + nCur + t : RTXPT_INVALID_LIGHT_INDEX;
+        for (uint t = 0; t < tCur; t++) s.currentToPast[E + nCur + t] = t < tPast ? E + nPast + t : RTXPT_INVALID_LIGHT_INDEX;
+    }
+    s.past = std::move(now);
+}
 inline void NeeatUpdateBegin(NeeatState& s, LightTable& lt, uint neeType, uint boostFlags = 0, const float* worldToClip = nullptr)
 {
+    NeeatTrackLightList(s, lt);
     UpdateLocalJitter(s);
     s.updateCounter++;
     const bool lastFrameLocalSamplesAvailable = s.lastFrameTemporalFeedbackAvailable;        // last frame's control data

@@ -60,7 +60,7 @@ struct rtxpt_ctx
     GridConfig grid;
     int maxSmemOptin = 0;
     // scene
-    bool haveScene = false, haveConstants = false, lightsDirty = true;
+    bool haveScene = false, haveConstants = false, lightsDirty = true; uint64_t lightVersion = 0;       // bumped by every re-bake of the light list (uploadLights)
     size_t l2PersistBytes = 0, l2WindowMax = 0;
     // measurement knobs, read from the environment once at creation (defaults are the measured optimum on B200, profiles/r1_history.md)
     struct Tuning { int refillThreshold = 24, waitFlushLanes = 8, traceCtas = 4, shadeCtas = 4, smemNodes = 0, lanes = 1, shadowLpt = 1; } tune; float sceneDiagonal = 0;
@@ -123,9 +123,11 @@ struct rtxpt_ctx
         DeviceArray<float> fbWeight, scratchWeight, blendedWeight, historyDepth, lightWeights; DeviceArray<uint32_t> fbCandidate, scratchCandidate, blendedCandidate, local, counters,
             proxyCounters, proxyOffsets, proxyIndices, samplingProxyCount, scanBlockSums, rrFix; DeviceArray<uint4> shadowFeedback;
         DeviceArray<float> weights[2], weightGroupSums, weightsSum; uint32_t weightPingPong = 0;      // boosted weights: this frame / last frame
+        // dynamic light lists: the list last frame's feedback was indexed by, and this frame's past <-> current index tables (NULL pointers in params while the list stands still)
+        LightListSnapshot snap; uint64_t snapVersion = 0; bool remapActive = false; uint32_t lightCapacity = 0; DeviceArray<uint32_t> pastToCurrent, currentToPast; std::vector<uint32_t> hPastToCurrent, hCurrentToPast;
         void release() { fbWeight.release(); scratchWeight.release(); blendedWeight.release(); historyDepth.release(); lightWeights.release(); fbCandidate.release(); scratchCandidate.release();
                          blendedCandidate.release(); local.release(); counters.release(); proxyCounters.release(); proxyOffsets.release(); proxyIndices.release(); samplingProxyCount.release();
-                         scanBlockSums.release(); rrFix.release(); shadowFeedback.release(); weights[0].release(); weights[1].release(); weightGroupSums.release(); weightsSum.release(); allocated = false; frameBegun = false; frameEnded = false; }
+                         scanBlockSums.release(); rrFix.release(); shadowFeedback.release(); weights[0].release(); weights[1].release(); weightGroupSums.release(); weightsSum.release(); pastToCurrent.release(); currentToPast.release(); snap = LightListSnapshot(); remapActive = false; lightCapacity = 0; allocated = false; frameBegun = false; frameEnded = false; }
     } na;
     DeviceArray<double> tmPartials; DeviceArray<float> tmAvgLuminance; DeviceArray<uint32_t> ldrColor; bool toneMapped = false;      // tone mapping (tonemap.cuh)
     cudaEvent_t evDnStart = nullptr, evDnStop = nullptr; bool denoiseTimed = false;       // around the last rtxpt_b200_denoise_realtime
@@ -600,7 +602,7 @@ static int uploadLights(rtxpt_ctx* c)
     CU(c->dProxyIndices.upload(st.proxyIndices.data(), st.proxyIndices.size(), s));
     CU(c->dEnvLookup.upload(st.envLookupMap.data(), st.envLookupMap.size(), s));
     CU(cudaStreamSynchronize(s));
-    c->lightsDirty = false;
+    c->lightsDirty = false; c->lightVersion++;
     return RTXPT_OK;
 }
 
@@ -1102,16 +1104,19 @@ static int neeatEnsure(rtxpt_ctx* c, cudaStream_t s)
     rtxpt_ctx::Neeat& n = c->na;
     const uint32_t W = c->tableWidth, H = c->tableHeight, L = uint32_t(c->lightState.lights.size());
     if (n.allocated && n.host.W == W && n.host.H == H && n.lightCount == L) return RTXPT_OK;
+    if (n.allocated && n.host.W == W && n.host.H == H && L <= n.lightCapacity) { n.lightCount = L; return RTXPT_OK; }       // the light list changed length: per-light arrays have headroom, the feedback state stays
     CU(syncContext(c)); CU(cudaStreamSynchronize(s));
     n.release(); n.host.reset(W, H); n.lightCount = L;
     const size_t P = size_t(W) * H, B = size_t((W + 1) / 2) * ((H + 1) / 2), T = size_t(neeat::HostState::tilesX(W)) * neeat::HostState::tilesY(H) * neeat::kLocalProxyCount;
-    const size_t proxyCapacity = size_t(neeat::kProxyRatio) * std::max<uint32_t>(L, neeat::kMaxLights / 10) + L;           // every light rounds its share up
+    const uint32_t Lcap = L + 4096u; n.lightCapacity = Lcap;        // headroom for lights added later (rtxpt_b200_update_lights); beyond it the feedback state starts over
+    const size_t proxyCapacity = size_t(neeat::kProxyRatio) * std::max<uint32_t>(Lcap, neeat::kMaxLights / 10) + Lcap;           // every light rounds its share up
     CU(n.fbWeight.alloc(P)); CU(n.scratchWeight.alloc(P)); CU(n.blendedWeight.alloc(B)); CU(n.historyDepth.alloc(P)); CU(n.fbCandidate.alloc(P)); CU(n.scratchCandidate.alloc(P)); CU(n.blendedCandidate.alloc(B));
-    CU(n.local.alloc(T)); CU(n.counters.alloc(size_t(L) + 1)); CU(n.proxyCounters.alloc(L)); CU(n.proxyOffsets.alloc(size_t(L) + 1)); CU(n.proxyIndices.alloc(proxyCapacity)); CU(n.samplingProxyCount.alloc(1));
-    CU(n.scanBlockSums.alloc(1024)); CU(n.lightWeights.alloc(L)); CU(n.rrFix.alloc(c->capacity)); CU(n.shadowFeedback.alloc(c->capacity));
+    CU(n.local.alloc(T)); CU(n.counters.alloc(size_t(Lcap) + 1)); CU(n.proxyCounters.alloc(Lcap)); CU(n.proxyOffsets.alloc(size_t(Lcap) + 1)); CU(n.proxyIndices.alloc(proxyCapacity)); CU(n.samplingProxyCount.alloc(1));
+    CU(n.scanBlockSums.alloc(1024)); CU(n.lightWeights.alloc(Lcap)); CU(n.rrFix.alloc(c->capacity)); CU(n.shadowFeedback.alloc(c->capacity));
+    CU(n.pastToCurrent.alloc(Lcap)); CU(n.currentToPast.alloc(Lcap));
     CU(cudaMemsetAsync(n.rrFix.ptr, 0, size_t(c->capacity) * 4, s));
-    CU(n.weights[0].alloc(L)); CU(n.weights[1].alloc(L)); CU(n.weightGroupSums.alloc((L + 4095) / 4096 + 1)); CU(n.weightsSum.alloc(1)); n.weightPingPong = 0;
-    CU(cudaMemsetAsync(n.weights[0].ptr, 0, size_t(L) * 4, s)); CU(cudaMemsetAsync(n.weights[1].ptr, 0, size_t(L) * 4, s));
+    CU(n.weights[0].alloc(Lcap)); CU(n.weights[1].alloc(Lcap)); CU(n.weightGroupSums.alloc((Lcap + 4095) / 4096 + 1)); CU(n.weightsSum.alloc(1)); n.weightPingPong = 0;
+    CU(cudaMemsetAsync(n.weights[0].ptr, 0, size_t(Lcap) * 4, s)); CU(cudaMemsetAsync(n.weights[1].ptr, 0, size_t(Lcap) * 4, s));
     CU(cudaMemsetAsync(n.fbWeight.ptr, 0, P * 4, s)); CU(cudaMemsetAsync(n.scratchWeight.ptr, 0, P * 4, s)); CU(cudaMemsetAsync(n.blendedWeight.ptr, 0, B * 4, s)); CU(cudaMemsetAsync(n.historyDepth.ptr, 0, P * 4, s));
     CU(cudaMemsetAsync(n.fbCandidate.ptr, 0xFF, P * 4, s)); CU(cudaMemsetAsync(n.scratchCandidate.ptr, 0xFF, P * 4, s)); CU(cudaMemsetAsync(n.blendedCandidate.ptr, 0xFF, B * 4, s));
     CU(cudaMemsetAsync(n.local.ptr, 0, T * 4, s)); CU(cudaMemsetAsync(n.samplingProxyCount.ptr, 0, 4, s));
@@ -1127,7 +1132,31 @@ static void neeatBind(rtxpt_ctx* c)
     p.depth = c->depth.ptr; p.motion = c->motionVectors.ptr;
     p.lightRecords = reinterpret_cast<const uint4*>(c->dLights.ptr); p.curWeights = n.weights[n.weightPingPong].ptr; p.histWeights = n.weights[n.weightPingPong ^ 1u].ptr;
     p.weightGroupSums = n.weightGroupSums.ptr; p.weightsSumDev = n.weightsSum.ptr;
+    p.pastToCurrent = n.remapActive ? n.pastToCurrent.ptr : nullptr; p.currentToPast = n.remapActive ? n.currentToPast.ptr : nullptr;
 }
+// ---- dynamic analytic lights: Donut's scene lights move, dim, appear and disappear between frames; RTXPT re-bakes its light list every frame (LightsBaker::UpdateBegin) ----------
+extern "C" RTXPT_API int rtxpt_b200_update_lights(rtxpt_ctx* c, const RtxptLightDesc* lights, uint32_t count)
+{
+    if (!c || (count && !lights)) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (!c->haveScene) return fail(RTXPT_ERR_NO_SCENE, "no scene uploaded");
+    LightBakeState& st = c->lightState;
+    if (size_t(kEnvQuadLightCount) + count + st.triangleLights.size() >= kMaxLights) return fail(RTXPT_ERR_INVALID_ARGUMENT, "too many lights (%u analytic + %zu emissive triangles)", count, st.triangleLights.size());
+    for (const RtxptSubInstanceData& si : c->hSubInstances)
+        if (si.AnalyticProxyLightIndex != 0xFFFFFFFFu && si.AnalyticProxyLightIndex - kEnvQuadLightCount >= count) return fail(RTXPT_ERR_INVALID_ARGUMENT, "proxy geometry stands in for light %u, %u lights given", si.AnalyticProxyLightIndex - kEnvQuadLightCount, count);
+    cudaSetDevice(c->device);
+    CU(syncContext(c));
+    const int64_t delta = int64_t(count) - int64_t(st.analyticLights.size());
+    LightBaker::setAnalyticLights(lights, count, st);
+    if (delta != 0)
+    {   // the emissive triangles sit behind the analytic lights: their block offsets move with the count
+        for (RtxptSubInstanceData& si : c->hSubInstances) if (si.EmissiveLightMappingOffset != 0xFFFFFFFFu) si.EmissiveLightMappingOffset = uint32_t(int64_t(si.EmissiveLightMappingOffset) + delta);
+        CU(cudaMemcpy(c->dSubInstances.ptr, c->hSubInstances.data(), c->hSubInstances.size() * sizeof(RtxptSubInstanceData), cudaMemcpyHostToDevice));
+    }
+    c->lightsDirty = true;
+    if (c->haveConstants) return uploadLights(c);
+    return RTXPT_OK;
+}
+
 extern "C" RTXPT_API int rtxpt_b200_neeat_reset(rtxpt_ctx* c)
 {
     if (!c) return fail(RTXPT_ERR_INVALID_ARGUMENT, "null context");
@@ -1147,6 +1176,17 @@ extern "C" RTXPT_API int rtxpt_b200_neeat_update_begin(rtxpt_ctx* c, void* cudaS
     rtxpt_ctx::Neeat& n = c->na;
     // the power-based weights follow the light list (uploadLights re-bakes them when the environment or the importance settings change)
     CU(cudaMemcpyAsync(n.lightWeights.ptr, c->lightState.weights.data(), size_t(n.lightCount) * 4, cudaMemcpyHostToDevice, s));
+    // dynamic light list: the feedback of last frame names lights by their index in last frame's list (LightsBaker.cpp:1086-1225)
+    n.remapActive = false;
+    if (n.snap.valid && n.snapVersion != c->lightVersion && n.host.feedbackBufferFilled)
+    {
+        LightBaker::buildRemap(n.snap, c->lightState, n.hPastToCurrent, n.hCurrentToPast);
+        if (n.hPastToCurrent.size() > n.pastToCurrent.count || n.hCurrentToPast.size() > n.currentToPast.count) return fail(RTXPT_ERR_INVALID_ARGUMENT, "light list outgrew the feedback state");
+        CU(cudaMemcpyAsync(n.pastToCurrent.ptr, n.hPastToCurrent.data(), n.hPastToCurrent.size() * 4, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(n.currentToPast.ptr, n.hCurrentToPast.data(), n.hCurrentToPast.size() * 4, cudaMemcpyHostToDevice, s));
+        n.remapActive = true;
+    }
+    if (!n.snap.valid || n.snapVersion != c->lightVersion) { LightBaker::snapshot(c->lightState, n.snap); n.snapVersion = c->lightVersion; }
     neeat::beginFrame(n.host, n.params, c->consts.NEEType, n.lightCount, c->lightState.weightsSum, c->consts.NEEATImportanceBoost, c->haveView ? c->worldToClip : nullptr);
     n.weightPingPong ^= 1u;                 // last frame's boosted weights become the historic ones
     neeatBind(c);

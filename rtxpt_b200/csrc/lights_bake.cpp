@@ -363,18 +363,50 @@ void LightBaker::finalize(const RtxptPathTracerConstants& consts, LightBakeState
     finalizeWeightsAndProxies(consts, st);
 }
 
+void LightBaker::setAnalyticLights(const RtxptLightDesc* lights, uint32_t count, LightBakeState& st)
+{
+    st.analyticLights.clear(); st.analyticLightsEx.clear();
+    for (uint32_t i = 0; i < count && lights; i++)
+    {
+        BakedLight li; BakedLightEx ex; convertAnalyticLight(lights[i], li, ex);
+        st.analyticLights.push_back(li); st.analyticLightsEx.push_back(ex);
+    }
+}
+void LightBaker::snapshot(const LightBakeState& st, LightListSnapshot& out)
+{
+    out.valid = st.lights.size() >= kEnvQuadLightCount; out.envEnabled = st.envEnabled;
+    out.analyticCount = uint32_t(st.analyticLights.size()); out.triangleCount = uint32_t(st.triangleLights.size());
+    out.envNodes.resize(size_t(kEnvQuadLightCount) * 2);
+    for (uint32_t i = 0; i < kEnvQuadLightCount && out.valid; i++) { out.envNodes[2 * i] = st.lights[i].direction1; out.envNodes[2 * i + 1] = st.lights[i].direction2; }
+    out.envLookupMap = st.envLookupMap;
+}
+void LightBaker::buildRemap(const LightListSnapshot& past, const LightBakeState& st, std::vector<uint32_t>& pastToCurrent, std::vector<uint32_t>& currentToPast)
+{
+    const uint32_t E = kEnvQuadLightCount, nPast = past.analyticCount, nCur = uint32_t(st.analyticLights.size()), tPast = past.triangleCount, tCur = uint32_t(st.triangleLights.size());
+    const uint32_t kInvalid = 0xFFFFFFFFu;
+    pastToCurrent.assign(past.total(), kInvalid); currentToPast.assign(size_t(E) + nCur + tCur, kInvalid);
+    const bool envBoth = past.envEnabled && st.envEnabled && past.envLookupMap.size() == size_t(kEnvImportanceMapDim) * kEnvImportanceMapDim && st.envLookupMap.size() == past.envLookupMap.size();
+    if (envBoth)
+        for (uint32_t i = 0; i < E; i++)
+        {   // the node's corner texel looked up in the other frame's importance map (the mapping need not be one to one)
+            uint32_t dim = past.envNodes[2 * i + 1] >> 16, x = past.envNodes[2 * i] >> 16, y = past.envNodes[2 * i] & 0xFFFFu;
+            if (dim) { const uint32_t ds = kEnvImportanceMapDim / dim; pastToCurrent[i] = st.envLookupMap[size_t(y * ds) * kEnvImportanceMapDim + x * ds]; }
+            dim = st.lights[i].direction2 >> 16; x = st.lights[i].direction1 >> 16; y = st.lights[i].direction1 & 0xFFFFu;
+            if (dim) { const uint32_t ds = kEnvImportanceMapDim / dim; currentToPast[i] = past.envLookupMap[size_t(y * ds) * kEnvImportanceMapDim + x * ds]; }
+        }
+    for (uint32_t k = 0; k < nPast; k++) pastToCurrent[E + k] = k < nCur ? E + k : kInvalid;
+    for (uint32_t k = 0; k < nCur; k++) currentToPast[E + k] = k < nPast ? E + k : kInvalid;
+    for (uint32_t t = 0; t < tPast; t++) pastToCurrent[E + nPast + t] = t < tCur ? E + nCur + t : kInvalid;       // emissive geometry is baked at upload: same triangles, shifted block
+    for (uint32_t t = 0; t < tCur; t++) currentToPast[E + nCur + t] = t < tPast ? E + nPast + t : kInvalid;
+}
+
 void LightBaker::prepareScene(const RtxptSceneDesc& scene, std::vector<RtxptSubInstanceData>& subInstances, LightBakeState& st)
 {
     st.hasEnvCube = scene.envCube.faceSize != 0;
     st.envRadianceMips.clear();
     if (st.hasEnvCube) buildEnvRadianceMap(scene.envCube, st);
     // analytic lights sit between the env quad-tree slots and the emissive triangles (LightsBaker.cpp:596-640)
-    st.analyticLights.clear(); st.analyticLightsEx.clear();
-    for (uint32_t i = 0; i < scene.lightCount && scene.lights; i++)
-    {
-        BakedLight li; BakedLightEx ex; convertAnalyticLight(scene.lights[i], li, ex);
-        st.analyticLights.push_back(li); st.analyticLightsEx.push_back(ex);
-    }
+    setAnalyticLights(scene.lights, scene.lights ? scene.lightCount : 0u, st);
     const uint32_t firstTriangleLight = kEnvQuadLightCount + uint32_t(st.analyticLights.size());
     // emissive triangles: one light per triangle of every emissive geometry instance
     st.triangleLights.clear();

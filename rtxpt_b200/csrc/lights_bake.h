@@ -28,8 +28,23 @@ struct LightBakeState
     bool envEnabled = false;
 };
 
+// what NEE-AT's feedback of the last frame was indexed by: enough of that frame's light list to map its indices onto the current list (LightsBaker.cpp:1086-1225)
+struct LightListSnapshot
+{
+    bool valid = false, envEnabled = false; uint32_t analyticCount = 0, triangleCount = 0;
+    std::vector<uint32_t> envNodes;         // per env quad-tree light: direction1 (x << 16 | y), direction2 (dim << 16), interleaved
+    std::vector<uint32_t> envLookupMap;
+    uint32_t total() const { return kEnvQuadLightCount + analyticCount + triangleCount; }
+};
+
 struct LightBaker
 {
+    // the analytic lights of the scene changed (moved, dimmed, added, removed): reconvert them; finalize() rebuilds the list
+    static void setAnalyticLights(const RtxptLightDesc* lights, uint32_t count, LightBakeState& st);
+    static void snapshot(const LightBakeState& st, LightListSnapshot& out);
+    // past -> current and current -> past light indices between the snapshot and the present list: environment nodes through the importance-map lookups (EnvLightsMapPastToCurrent,
+    // LightsBaker.hlsl:440-465, :515-538), analytic lights by their position in the caller's array, emissive triangles by their block offset (:700-711)
+    static void buildRemap(const LightListSnapshot& past, const LightBakeState& st, std::vector<uint32_t>& pastToCurrent, std::vector<uint32_t>& currentToPast);
     static void buildEnvRadianceMap(const RtxptEnvCubeDesc& cube, LightBakeState& st);
     // scene upload: env radiance/importance map, emissive triangle lights; writes EmissiveLightMappingOffset into `subInstances`
     static void prepareScene(const RtxptSceneDesc& scene, std::vector<RtxptSubInstanceData>& subInstances, LightBakeState& st);

@@ -37,6 +37,9 @@ struct Params
     const float* lightWeights; uint* proxyCounters; uint* proxyOffsets; uint* proxyIndices; uint* samplingProxyCount;
     // guides of the frame: depth R32F, screen motion RGBA16F (pixels)
     const float* depth; const uint2* motion;
+    // dynamic light lists (LightsBaker.hlsl: u_historyRemapPastToCurrent / u_historyRemapCurrentToPast): index of last frame's light in this frame's list and back,
+    // kInvalidLight where a light has no counterpart; NULL = the list did not change (identity)
+    const uint* pastToCurrent; const uint* currentToPast;
 };
 
 // single IEEE operations the build flags cannot fuse or approximate (-fmad / -prec-div / -use_fast_math): the baker passes are bit-exact against the oracle
@@ -126,7 +129,7 @@ PT_HD void insertFeedbackFromNEE(const Params& p, uint px, uint py, bool ssc, ui
 PT_HD uint remapPastToCurrent(const Params& p, uint historic)
 {
     if (historic == kInvalidLight) return kInvalidLight;
-    uint idx = historic < p.historicLightCount ? historic : kInvalidLight;
+    uint idx = historic < p.historicLightCount ? (p.pastToCurrent ? p.pastToCurrent[historic] : historic) : kInvalidLight;
     if (idx != kInvalidLight && idx >= p.lightCount) idx = kInvalidLight;
     return idx;
 }
@@ -199,7 +202,9 @@ PT_HD float weightBlock(const Params& p, uint block)
         }
         if ((p.boostFlags & 2u) && p.lastFrameFeedbackAvailable)
         {
-            const float d = fsub_rn(w, fmul_rn(p.histWeights[i], 1.1f));
+            float hist = 0.0f;                                                  // the light's boosted weight of last frame, 0 for a light that was not there (ImportanceBooster, LightsBaker.hlsl:139-141)
+            if (!p.currentToPast) hist = p.histWeights[i]; else { const uint h = p.currentToPast[i]; if (h != kInvalidLight) hist = p.histWeights[h]; }
+            const float d = fsub_rn(w, fmul_rn(hist, 1.1f));
             if (d > 0.0f) w = fadd_rn(w, fmul_rn(p.boostIntensityDeltaMul, d));
         }
         p.curWeights[i] = w;

@@ -41,6 +41,7 @@ _SIGNATURES = {
     "rtxpt_b200_tile_layout": [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)],
     "rtxpt_b200_pack_owned": [C.c_void_p, C.c_void_p, C.c_void_p],
     "rtxpt_b200_unpack_all": [C.c_void_p, C.c_void_p, C.c_void_p],
+    "rtxpt_b200_update_lights": [C.c_void_p, C.c_void_p, C.c_uint32],
     "rtxpt_b200_exchange_bytes": [C.c_void_p, C.POINTER(C.c_int), C.c_uint32, C.POINTER(C.c_size_t)],
     "rtxpt_b200_exchange_pack": [C.c_void_p, C.POINTER(C.c_int), C.c_uint32, C.c_void_p, C.c_void_p],
     "rtxpt_b200_exchange_unpack": [C.c_void_p, C.POINTER(C.c_int), C.c_uint32, C.c_void_p, C.c_void_p],
@@ -374,6 +375,11 @@ class Context:
     def opacity_mask_stats(self):
         st = S.OpacityMaskStats(); _check(self.L.rtxpt_b200_get_opacity_mask_stats(self.h, C.byref(st)), self.L)
         return st
+
+    def update_lights(self, lights):
+        """lights: ctypes array of structs.LightDesc (or None): the scene's analytic lights of this frame (rtxpt_b200_update_lights)."""
+        n = len(lights) if lights is not None else 0
+        _check(self.L.rtxpt_b200_update_lights(self.h, lights if n else None, n), self.L)
 
     def neeat_update_begin(self, stream=None): _check(self.L.rtxpt_b200_neeat_update_begin(self.h, stream), self.L)
 

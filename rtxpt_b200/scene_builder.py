@@ -154,6 +154,19 @@ class SceneBuilder:
         return Scene(self)
 
 
+def make_light_array(lights):
+    """List of light dicts (SceneBuilder.add_point_light / add_spot_light fields) -> ctypes array of RtxptLightDesc: the `lights` of a scene, or of rtxpt_b200_update_lights."""
+    arr = (S.LightDesc * len(lights))()
+    for l, L in zip(arr, lights):
+        l.type = L["type"]; l.position[:] = L["position"]; l.direction[:] = L["direction"]; l.color[:] = L["color"]
+        l.intensity, l.radius, l.innerAngle, l.outerAngle = L["intensity"], L["radius"], L["inner"], L["outer"]
+    return arr
+
+
+def point_light(position, color, intensity, radius):
+    return dict(type=S.LIGHT_POINT, position=position, direction=(0, 0, -1), color=color, intensity=intensity, radius=radius, inner=0.0, outer=0.0)
+
+
 class Scene:
     """Owns the numpy storage behind an RtxptSceneDesc (`.desc`)."""
     def __init__(self, b):
@@ -305,11 +318,7 @@ class Scene:
                 self._keep.append(arr)
                 for f in range(6):
                     d.envCube.faces[f][m] = arr[f].ctypes.data
-        self.lights = (S.LightDesc * max(1, len(b.lights)))()
-        for i, L in enumerate(b.lights):
-            l = self.lights[i]
-            l.type = L["type"]; l.position[:] = L["position"]; l.direction[:] = L["direction"]; l.color[:] = L["color"]
-            l.intensity, l.radius, l.innerAngle, l.outerAngle = L["intensity"], L["radius"], L["inner"], L["outer"]
+        self.lights = make_light_array(b.lights) if b.lights else (S.LightDesc * 1)()
         d.lights, d.lightCount = self.lights, len(b.lights)
         self.desc = d
         self.material_count = len(b.materials)

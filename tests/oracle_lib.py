@@ -132,6 +132,11 @@ class Oracle:
         return accum, n.value, last, primary, st
 
     # ---- NEE-AT temporal feedback (oracle/pt_neeat.h); frame order: set_constants; neeat_update_begin; [render_realtime does update_end after its BUILD pass] or neeat_update_end; render
+    def set_lights(self, lights):
+        """lights: ctypes array of structs.LightDesc (or None / empty): the scene's analytic lights of this frame."""
+        n = len(lights) if lights is not None else 0
+        assert lib().oracle_set_lights(C.c_void_p(self.h), lights if n else None, n) == 0
+
     def neeat_reset(self): assert lib().oracle_neeat_reset(C.c_void_p(self.h)) == 0
 
     def neeat_update_begin(self): assert lib().oracle_neeat_update_begin(C.c_void_p(self.h)) == 0
