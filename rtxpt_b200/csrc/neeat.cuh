@@ -6,7 +6,8 @@
 //   Rtxpt/Shaders/PathTracer/Lighting/LightingAlgorithms.hlsli:654-682 (binary search), Rtxpt/Shaders/Libraries/MicroRng.hlsli:12-60
 //   Rtxpt/Lighting/LightsBaker.hlsl:774-823 (ClearFeedbackHistory), :880-948 (ComputeProxyCounts), :1068-1093, :1095-1181 (PreFilter), :1186-1318 (P0), :1321-1377, :1380-1452 (P1a),
 //     :1456-1528 (P1b), :1531-1610 (FillTile), :1745-1850 (P3: bitonic sort, duplicate ranges)
-// Static light lists only: the past -> current light index remap is the identity with its bounds checks.  PreFilter reads a snapshot of the reservoirs (the reference's in-place
+// Light lists may change between frames (rtxpt_b200_update_lights): Params::pastToCurrent / currentToPast carry the reference's index tables for the one frame that needs them;
+// NULL = unchanged list, the remap is the identity with its bounds checks.  PreFilter reads a snapshot of the reservoirs (the reference's in-place
 // version is racy across thread groups).
 #pragma once
 #include "device_math.cuh"
