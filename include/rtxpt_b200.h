@@ -659,6 +659,11 @@ RTXPT_API int rtxpt_b200_get_lights_ex(rtxpt_ctx* ctx, void* outLightInfoEx, uin
 RTXPT_API int rtxpt_b200_debug_decode_dds(const void* fileBytes, uint64_t fileSize, uint32_t mip, uint32_t* outWidth, uint32_t* outHeight, uint32_t* outMipCount, uint32_t* outSrgb,
                                           uint8_t* outRGBA, uint64_t outCapacity);
 RTXPT_API const char* rtxpt_b200_debug_decode_dds_error(void);
+/* Inspection hook: decodes a baseline / extended-sequential JPEG (8-bit, grey or YCbCr, any sampling factors, restart intervals) held in memory into RGBA8 - the decoder the
+ * glTF loader uses for image/jpeg (the reference: stb_image through Donut's TextureCache).  Progressive, arithmetic-coded, 12-bit and CMYK files are refused with a message.
+ * Call with outRGBA == NULL for the size.  Errors: rtxpt_b200_debug_decode_jpeg_error. */
+RTXPT_API int rtxpt_b200_debug_decode_jpeg(const void* fileBytes, uint64_t fileSize, uint32_t* outWidth, uint32_t* outHeight, uint8_t* outRGBA, uint64_t outCapacity);
+RTXPT_API const char* rtxpt_b200_debug_decode_jpeg_error(void);
 /* HDR DDS files: the reference's environment maps (Assets/EnvironmentMaps/<name>_cube_bc6u.dds - BC6H_UF16 cubes read by Donut's DDSFile.cpp for EnvMapBaker,
  * Rtxpt/Lighting/Distant/EnvMapBaker.cpp:164-169).  BC6H UF16 / SF16, R16G16B16A16_FLOAT, R32G32B32A32_FLOAT; 2-D or cube.  Call with outRGBA32F == NULL for the sizes; then mip 0 of
  * every face comes back as RGBA32F, faces back to back in D3D order (+x -x +y -y +z -z): the `source` of RtxptEnvBakeDesc (sourceType 2).  Errors: rtxpt_b200_debug_decode_dds_error. */

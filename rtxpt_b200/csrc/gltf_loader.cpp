@@ -32,6 +32,8 @@ struct DdsImage { uint32_t width = 0, height = 0; bool srgb = false; std::vector
 DdsImage decodeDds(const uint8_t* data, size_t size, const char* name);   // dds.cpp
 struct DdsBlocks { uint32_t width = 0, height = 0, format = 0; bool srgb = false; std::vector<std::vector<uint8_t>> mips; };
 bool extractDdsBlocks(const uint8_t* data, size_t size, const char* name, DdsBlocks& out);   // dds.cpp: BC1 / BC2 / BC3 / BC7 kept compressed
+struct JpegImage { uint32_t w = 0, h = 0; std::vector<uint8_t> rgba; };
+JpegImage decodeJpeg(const uint8_t* data, size_t size, const char* name);   // jpeg.cpp: baseline / sequential JPEG -> RGBA8
 bool g_keepBlockCompression = false;                                        // rtxpt_b200_loader_keep_block_compression
 }
 
@@ -94,7 +96,7 @@ uint32_t be32(const uint8_t* p) { return (uint32_t(p[0]) << 24) | (uint32_t(p[1]
 Image decodePng(const std::vector<uint8_t>& d, const char* name)
 {
     static const uint8_t sig[8] = { 0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A };
-    if (d.size() < 8 || memcmp(d.data(), sig, 8) != 0) failf("image '%s' is not a PNG (only PNG images are decoded by this loader)", name);
+    if (d.size() < 8 || memcmp(d.data(), sig, 8) != 0) failf("image '%s' is not a PNG (PNG, JPEG and DDS images are decoded by this loader)", name);
     Image img; uint32_t depth = 0, ctype = 0, interlace = 0; std::vector<uint8_t> idat, plte, trns;
     for (size_t off = 8; off + 12 <= d.size();)
     {
@@ -328,6 +330,13 @@ struct Loader
         {
             DdsImage dds = decodeDds(bytes.data(), bytes.size(), name.c_str());
             w = dds.width; h = dds.height; mips = std::move(dds.mips);
+        }
+        else if (bytes.size() >= 2 && bytes[0] == 0xFF && bytes[1] == 0xD8)
+        {   // image/jpeg, the other image format glTF 2.0 allows (jpeg.cpp)
+            JpegImage j = decodeJpeg(bytes.data(), bytes.size(), name.c_str());
+            Image img; img.w = j.w; img.h = j.h; img.rgba = std::move(j.rgba);
+            std::vector<std::pair<uint32_t, uint32_t>> dims;
+            mips = makeMips(img, dims); w = img.w; h = img.h;
         }
         else
         {

@@ -74,7 +74,7 @@ _SIGNATURES = {
     "rtxpt_b200_debug_bsdf": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
     "rtxpt_b200_debug_rng": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
 }
-_LOADER_SYMBOLS = ["rtxpt_b200_load_hdr_image", "rtxpt_b200_load_hdr_image_error", "rtxpt_b200_loader_keep_block_compression", "rtxpt_b200_load_dds_hdr", "rtxpt_b200_host_opacity_micro_index", "rtxpt_b200_camera_matrices", "rtxpt_b200_tone_map_pre_exposed_gray", "rtxpt_b200_debug_build_bvh", "rtxpt_b200_env_bake_mip_count", "rtxpt_b200_env_bake_floats", "rtxpt_b200_load_gltf", "rtxpt_b200_load_gltf_ex", "rtxpt_b200_load_scene_json", "rtxpt_b200_host_scene_info", "rtxpt_b200_load_gltf_error", "rtxpt_b200_host_scene_desc", "rtxpt_b200_host_scene_cameras",
+_LOADER_SYMBOLS = ["rtxpt_b200_debug_decode_jpeg", "rtxpt_b200_debug_decode_jpeg_error", "rtxpt_b200_load_hdr_image", "rtxpt_b200_load_hdr_image_error", "rtxpt_b200_loader_keep_block_compression", "rtxpt_b200_load_dds_hdr", "rtxpt_b200_host_opacity_micro_index", "rtxpt_b200_camera_matrices", "rtxpt_b200_tone_map_pre_exposed_gray", "rtxpt_b200_debug_build_bvh", "rtxpt_b200_env_bake_mip_count", "rtxpt_b200_env_bake_floats", "rtxpt_b200_load_gltf", "rtxpt_b200_load_gltf_ex", "rtxpt_b200_load_scene_json", "rtxpt_b200_host_scene_info", "rtxpt_b200_load_gltf_error", "rtxpt_b200_host_scene_desc", "rtxpt_b200_host_scene_cameras",
                    "rtxpt_b200_host_scene_triangle_count", "rtxpt_b200_free_host_scene", "rtxpt_b200_bridge_camera", "rtxpt_b200_default_constants", "rtxpt_b200_debug_bvh_stats", "rtxpt_b200_parse_material_json", "rtxpt_b200_parse_material_json_error", "rtxpt_b200_debug_decode_dds", "rtxpt_b200_debug_decode_dds_error",
                     "rtxpt_b200_generic_ts_line_stride", "rtxpt_b200_generic_ts_plane_stride", "rtxpt_b200_generic_ts_address"]
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["rtxpt_b200_last_error"] + _LOADER_SYMBOLS)
@@ -135,6 +135,17 @@ def decode_dds(file_bytes, mip=0, strict=None):
     if f(file_bytes, len(file_bytes), mip, C.byref(w), C.byref(h), C.byref(n), C.byref(srgb), out.ctypes.data, out.nbytes) != 0:
         raise RtxptError("DDS: " + L.rtxpt_b200_debug_decode_dds_error().decode())
     return out, n.value, bool(srgb.value)
+
+
+def decode_jpeg(file_bytes, strict=None):
+    """JPEG file bytes -> HxWx4 uint8 RGBA, host only (rtxpt_b200_debug_decode_jpeg: the glTF loader's decoder)."""
+    L = load(strict); w, h = C.c_uint32(), C.c_uint32()
+    f = L.rtxpt_b200_debug_decode_jpeg; f.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_void_p, C.c_uint64]; f.restype = C.c_int
+    L.rtxpt_b200_debug_decode_jpeg_error.restype = C.c_char_p
+    if f(file_bytes, len(file_bytes), C.byref(w), C.byref(h), None, 0) != 0: raise RtxptError("JPEG: " + L.rtxpt_b200_debug_decode_jpeg_error().decode())
+    out = np.empty((h.value, w.value, 4), np.uint8)
+    if f(file_bytes, len(file_bytes), C.byref(w), C.byref(h), out.ctypes.data, out.nbytes) != 0: raise RtxptError("JPEG: " + L.rtxpt_b200_debug_decode_jpeg_error().decode())
+    return out
 
 
 def load_dds_hdr(file_bytes, strict=None):

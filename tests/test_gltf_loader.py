@@ -127,8 +127,11 @@ def test_gltf_loader_errors(product, tmp_path):
     doc3 = json.loads(json.dumps(doc)); doc3["accessors"][0]["sparse"] = {"count": 1}; json.dump(doc3, open(tmp_path / "sparse.gltf", "w"))
     with pytest.raises(product.RtxptError, match="sparse"):
         product.GltfScene(str(tmp_path / "sparse.gltf"))
-    (tmp_path / "s_tex0.png").write_bytes(b"\xff\xd8\xff\xe0 not a png")          # a JPEG where a PNG is expected
+    (tmp_path / "s_tex0.png").write_bytes(b"GIF89a not a png")                      # neither PNG nor JPEG nor DDS
     with pytest.raises(product.RtxptError, match="not a PNG"):
+        product.GltfScene(path)
+    (tmp_path / "s_tex0.png").write_bytes(b"\xff\xd8\xff\xe0 a JPEG signature and nothing behind it")
+    with pytest.raises(product.RtxptError, match="JPEG"):
         product.GltfScene(path)
 
 
