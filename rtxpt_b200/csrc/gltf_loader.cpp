@@ -10,7 +10,7 @@
 // materials forced thin (MaterialsBaker.cpp:543-544), alpha cutoff quantised to 8 bits in SubInstanceData (:990-991).
 // Buffer layout: two bindless buffers per glTF mesh (indices, vertices), one GeometryData per primitive, one InstanceData per node with a mesh
 // in depth-first scene order — the same layout rtxpt_b200/scene_builder.py produces, which the tests compare against byte for byte.
-// Not handled (reported as errors, never silently skipped): sparse accessors, JPEG/KTX images, Draco/meshopt compression, skins, morph targets.
+// Not handled (reported as errors, never silently skipped): sparse accessors, KTX images and progressive JPEGs (PNG, baseline JPEG and DDS are read), Draco/meshopt compression, skins, morph targets.
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
