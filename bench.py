@@ -148,8 +148,9 @@ def ncu_capture(rays_per_iteration):
             rays_captured = sum(rays_per_iteration[:len(rows)])
             ms = sum(r["time_ms"] for r in rows)
             out = {"traffic": captured / frac, "capture_ms": ms, "capture_dram_bytes": captured,
-                   "issue_active": float(np.mean([r["issue_active_pct"] for r in rows])) / 100.0 if "issue_active_pct" in rows[0] else None,
-                   "threads_per_inst": float(np.mean([r["threads_per_inst"] for r in rows])) if "threads_per_inst" in rows[0] else None,
+                   # time-weighted over the captured launches (the last bounces are a few microseconds at single-digit utilisation: a plain mean would describe them)
+                   "issue_active": float(sum(r["issue_active_pct"] * r["time_ms"] for r in rows) / max(ms, 1e-9)) / 100.0 if "issue_active_pct" in rows[0] else None,
+                   "threads_per_inst": float(sum(r["threads_per_inst"] * r["time_ms"] for r in rows) / max(ms, 1e-9)) if "threads_per_inst" in rows[0] else None,
                    "thread_inst_per_ray": (sum(r["warp_insts"] * r["threads_per_inst"] for r in rows) / max(1, rays_captured)) if "warp_insts" in rows[0] else None,
                    "commit": data.get("commit") if isinstance(data, dict) else "round 1 (e38f795 or earlier)",
                    "note": "profiles/%s: %d captured launches = %.0f %% of the frame's scatter rays, scaled to the frame" % (name, len(rows), 100 * frac)}
