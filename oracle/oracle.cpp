@@ -131,6 +131,28 @@ ORC_API void oracle_bsdf_funcs(const float* in, uint32_t count, float* out)
     }
 }
 
+// Utils/Utils.hlsli as the oracle restates it, on the inputs and in the 24-float layout of oracle/ref_kat_bsdf_main.cpp's "utils" mode.  Slots of functions the oracle does
+// not restate (LuminanceClamp, power heuristic, three-way MIS, WeightedAverage, RelativelyEqual, Reinhard: unused by the live path) are NaN.
+ORC_API void oracle_utils_funcs(const float* in, uint32_t count, float* out)
+{
+    const float nan = std::nanf("");
+    for (uint32_t i = 0; i < count; i++)
+    {
+        const float* u = in + size_t(i) * 8; float* o = out + size_t(i) * 24;
+        for (int k = 0; k < 24; k++) o[k] = nan;
+        const float3 dir = normalize(f3(2.0f * u[0] - 1.0f, 2.0f * u[1] - 1.0f, 2.0f * u[2] - 1.0f) + f3(1e-3f, 0.0f, 0.0f));
+        const float n0 = 1.0f + floorf(u[4] * 4.0f), n1 = 1.0f + floorf(u[6] * 4.0f), p0 = u[5] * 3.0f, p1 = u[7] * 3.0f;
+        o[3] = EvalMISBalance(n0, p0, n1, p1);
+        const float2 eo = Encode_Oct(dir); o[6] = eo.x; o[7] = eo.y;
+        const float3 dn = Decode_Oct(f2(u[0], u[1])); o[8] = dn.x; o[9] = dn.y; o[10] = dn.z;
+        const uint p32 = NDirToOctUnorm32(dir); memcpy(&o[11], &p32, 4);
+        const uint q32 = (uint(u[4] * 65534.0f) & 0xffffu) | (uint(u[5] * 65534.0f) << 16); const float3 d32 = OctToNDirUnorm32(q32); o[12] = d32.x; o[13] = d32.y; o[14] = d32.z;
+        const uint p30 = NDirToOctUnorm30(dir); memcpy(&o[15], &p30, 4);
+        const uint q30 = (uint(u[6] * 32767.0f) & 0x7fffu) | ((uint(u[7] * 32767.0f) & 0x7fffu) << 15); const float3 d30 = OctToNDirUnorm30(q30); o[16] = d30.x; o[17] = d30.y; o[18] = d30.z;
+        o[19] = FastSqrt(u[0] * 10.0f); o[20] = FastACos(2.0f * u[1] - 1.0f);
+    }
+}
+
 ORC_API void* oracle_create(const RtxptSceneDesc* desc)
 {
     OracleCtx* c = new OracleCtx();

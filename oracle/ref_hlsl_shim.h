@@ -70,7 +70,7 @@ inline bool operator<=(float16_t a, float16_t b) { return a.v <= b.v; } inline b
 // ---- vectors -----------------------------------------------------------------------------------------------------------------------------------------------------
 template <typename T> struct vec2; template <typename T> struct vec3; template <typename T> struct vec4;
 // a swizzle is a view of the parent's storage: readable as a vector, and (for the non-repeating ones) assignable
-template <typename T, int A, int B> struct swz2 { T d[4]; operator vec2<T>() const; swz2& operator=(const vec2<T>& v); };
+template <typename T, int A, int B> struct swz2 { T d[4]; operator vec2<T>() const; swz2& operator=(const vec2<T>& v); swz2& operator+=(const vec2<T>& v) { d[A] = d[A] + v.x; d[B] = d[B] + v.y; return *this; } };
 template <typename T, int A, int B, int C> struct swz3 { T d[4]; operator vec3<T>() const; swz3& operator=(const vec3<T>& v); };
 
 template <typename T> struct vec2

@@ -25,7 +25,7 @@ static void writeAll(const char* path, const std::vector<float>& v)
 
 int main(int argc, char** argv)
 {
-    if (argc != 4) { fprintf(stderr, "usage: %s bsdf|funcs in.f32 out.f32\n", argv[0]); return 2; }
+    if (argc != 4) { fprintf(stderr, "usage: %s bsdf|funcs|utils in.f32 out.f32\n", argv[0]); return 2; }
     const std::vector<float> in = readAll(argv[2]); std::vector<float> out;
     if (std::string(argv[1]) == "bsdf")
     {
@@ -52,6 +52,26 @@ int main(int argc, char** argv)
             o[32] = nonDelta; o[33] = float(count);
             float3 de, se; b.estimateSpecDiffBSDF(de, se, sd.N, sd.V);
             o[34] = de.x; o[35] = de.y; o[36] = de.z; o[37] = se.x; o[38] = se.y; o[39] = se.z;
+        }
+    }
+    else if (std::string(argv[1]) == "utils")
+    {   // Utils/Utils.hlsli: MIS heuristics, octahedral encodings, luminance clamp, the fast approximations (inputs: 8 uniforms per record; layout shared with oracle_utils_funcs)
+        const size_t n = in.size() / 8; out.assign(n * 24, 0.0f);
+        for (size_t i = 0; i < n; i++)
+        {
+            const float* u = &in[i * 8]; float* o = &out[i * 24];
+            const float3 dir = normalize(float3(2.0f * u[0] - 1.0f, 2.0f * u[1] - 1.0f, 2.0f * u[2] - 1.0f) + float3(1e-3f, 0.0f, 0.0f));
+            const float n0 = 1.0f + floor(u[4] * 4.0f), n1 = 1.0f + floor(u[6] * 4.0f), p0 = u[5] * 3.0f, p1 = u[7] * 3.0f;
+            const float3 lc = LuminanceClamp(float3(u[0], u[1], u[2]) * 4.0f, 0.2f + u[3]); o[0] = lc.x; o[1] = lc.y; o[2] = lc.z;
+            o[3] = EvalMIS(MISHeuristic::Balance, n0, p0, n1, p1); o[4] = EvalMIS(MISHeuristic::PowerTwo, n0, p0, n1, p1); o[5] = EvalMIS(MISHeuristic::Balance, n0, p0, n1, p1, 2.0f, u[3]);
+            const float2 eo = Encode_Oct(dir); o[6] = eo.x; o[7] = eo.y;
+            const float3 dn = Decode_Oct(float2(u[0], u[1])); o[8] = dn.x; o[9] = dn.y; o[10] = dn.z;
+            const uint p32 = NDirToOctUnorm32(dir); memcpy(&o[11], &p32, 4);
+            const uint q32 = (uint(u[4] * 65534.0f) & 0xffffu) | (uint(u[5] * 65534.0f) << 16); const float3 d32 = OctToNDirUnorm32(q32); o[12] = d32.x; o[13] = d32.y; o[14] = d32.z;
+            const uint p30 = NDirToOctUnorm30(dir); memcpy(&o[15], &p30, 4);
+            const uint q30 = (uint(u[6] * 32767.0f) & 0x7fffu) | ((uint(u[7] * 32767.0f) & 0x7fffu) << 15); const float3 d30 = OctToNDirUnorm30(q30); o[16] = d30.x; o[17] = d30.y; o[18] = d30.z;
+            o[19] = FastSqrt(u[0] * 10.0f); o[20] = FastACos(2.0f * u[1] - 1.0f); o[21] = WeightedAverage(u[0], u[1], u[2], u[3]);
+            o[22] = RelativelyEqual(u[0], u[0] * (1.0f + 2e-4f * u[1])) ? 1.0f : 0.0f; o[23] = Reinhard(float3(u[0], u[1], u[2]) * 3.0f).y;
         }
     }
     else

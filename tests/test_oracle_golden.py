@@ -153,3 +153,19 @@ def test_bsdf_golden_file_matches_reference_tree():
     spec = importlib.util.spec_from_file_location("make_bsdf_golden", os.path.join(HERE, "golden", "make_bsdf_golden.py")); m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
     rec, out, u, fout = m.generate(); g = bsdf_golden()
     assert np.array_equal(rec, g["bsdf_in"]) and _same(out, g["bsdf_out"]).all() and np.array_equal(u, g["funcs_in"]) and _same(fout, g["funcs_out"]).all()
+
+
+def test_utils_functions_match_reference_header_golden(oracle):
+    """Utils/Utils.hlsli compiled in place (tests/golden/make_utils_golden.py): the balance heuristic of every MIS weight on the path, the octahedral normal encodings of the
+    stable planes and of the light records (32- and 30-bit packings), FastSqrt / FastACos - the oracle's restatements reproduce the reference's outputs bit for bit (NaN where
+    the reference yields NaN)."""
+    import ctypes as C
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "utils_golden.npz"))
+    u, ref = np.ascontiguousarray(g["utils_in"]), g["utils_out"]
+    L = oracle.lib(); L.oracle_utils_funcs.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]; L.oracle_utils_funcs.restype = None
+    out = np.empty_like(ref); L.oracle_utils_funcs(u.ctypes.data, len(u), out.ctypes.data)
+    restated = [3, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20]      # EvalMIS(Balance); Encode_Oct; Decode_Oct; NDirToOctUnorm32; OctToNDirUnorm32; ..Unorm30 both ways; FastSqrt; FastACos
+    for k in restated:
+        same = (out[:, k].view(np.uint32) == ref[:, k].view(np.uint32)) | (np.isnan(out[:, k]) & np.isnan(ref[:, k]))
+        assert same.all(), (k, int((~same).sum()))
+    assert np.isnan(out[:, [0, 1, 2, 4, 5, 21, 22, 23]]).all()                  # not restated (unused by the live path): LuminanceClamp, power / three-way MIS, WeightedAverage, ...
