@@ -153,6 +153,30 @@ ORC_API void oracle_utils_funcs(const float* in, uint32_t count, float* out)
     }
 }
 
+// PathTracerHelpers.hlsli as the oracle restates it, on the inputs and in the 16-float layout of oracle/ref_kat_bsdf_main.cpp's "helpers" mode (NaN: not restated as a function -
+// the grazing-angle falloff is written inline in HandleNEE, the roughness-based cone growth is unused by the live path)
+ORC_API void oracle_helper_funcs(const float* in, uint32_t count, float* out)
+{
+    const float nan = std::nanf("");
+    for (uint32_t i = 0; i < count; i++)
+    {
+        const float* u = in + size_t(i) * 8; float* o = out + size_t(i) * 16;
+        for (int k = 0; k < 16; k++) o[k] = nan;
+        const float scale = u[6] < 0.25f ? 0.05f : (u[6] < 0.5f ? 1.0f : (u[6] < 0.75f ? 40.0f : 3000.0f));
+        const float3 pos = f3(2.0f * u[0] - 1.0f, 2.0f * u[1] - 1.0f, 2.0f * u[2] - 1.0f) * scale;
+        const float3 nrm = normalize(f3(2.0f * u[3] - 1.0f, 2.0f * u[4] - 1.0f, 2.0f * u[5] - 1.0f) + f3(0.0f, 1e-3f, 0.0f));
+        const float3 ro = ComputeRayOrigin(pos, nrm); o[0] = ro.x; o[1] = ro.y; o[2] = ro.z;
+        const float3 l = normalize(f3(2.0f * u[5] - 1.0f, 2.0f * u[6] - 1.0f, 2.0f * u[7] - 1.0f) + f3(1e-3f, 0.0f, 0.0f));
+        const float from = 0.01f + 0.24f * u[7]; o[3] = saturate((dot(l, nrm) - from) / (2.0f * from));        // HandleNEE's fade-out term (pt_path.h), same expression
+        const float pdf = u[3] < 0.05f ? 0.0f : u[3] * u[3] * 40.0f;
+        o[7] = pdf == 0.0f ? 0.0f : ComputeRayConeSpreadAngleExpansionByScatterPDF(pdf);
+        o[8] = ComputeNewScatterFireflyFilterK(lp(u[4]), pdf, u[5]);
+        const float3 ff = FireflyFilter(f3(lp(u[0] * 8.0f), lp(u[1] * 8.0f), lp(u[2] * 8.0f)), lp(2.0f + u[3]), lp(u[4])); o[9] = ff.x; o[10] = ff.y; o[11] = ff.z;
+        o[12] = FireflyFilterShort(u[0] * 8.0f, 2.0f + u[3], u[4]);
+        o[13] = EvalMISBalance(1.0f, u[5] * 3.0f, 1.0f, u[7] * 3.0f);
+    }
+}
+
 ORC_API void* oracle_create(const RtxptSceneDesc* desc)
 {
     OracleCtx* c = new OracleCtx();

@@ -182,9 +182,11 @@ inline float ComputeNewScatterFireflyFilterK(float currentK, float bouncePDF, fl
 }
 inline float3 FireflyFilter(float3 signalIn, float threshold, float fireflyFilterK)
 {
+    // lpfloat arithmetic: every operation rounds to binary16 (Sample.cpp:1017 compiles the shaders with 16-bit types; pinned by tests/golden/helpers_golden.npz)
+    signalIn = lp(signalIn);                                                          // the parameter is an lpfloat3
     float thr = lp(threshold * fireflyFilterK);
-    float maxR = lp(Average(signalIn));
-    if (maxR > thr) signalIn = lp(signalIn / maxR * thr);
+    float maxR = lp(lp(lp(signalIn.x + signalIn.y) + signalIn.z) / 3.0f);          // Average( lpfloat3 ), Utils.hlsli:63-66
+    if (maxR > thr) signalIn = f3(lp(lp(signalIn.x / maxR) * thr), lp(lp(signalIn.y / maxR) * thr), lp(lp(signalIn.z / maxR) * thr));
     return signalIn;
 }
 inline float FireflyFilterShort(float signalAverage, float threshold, float fireflyFilterK)

@@ -226,5 +226,9 @@ inline uint asuint(float f) { uint u; std::memcpy(&u, &f, 4); return u; } inline
 inline uint3 asuint(float3 v) { return uint3(asuint(v.x), asuint(v.y), asuint(v.z)); }
 inline uint firstbithigh(uint v) { return v ? 31u - uint(__builtin_clz(v)) : 0xFFFFFFFFu; } inline uint firstbitlow(uint v) { return v ? uint(__builtin_ctz(v)) : 0xFFFFFFFFu; }
 inline uint countbits(uint v) { return uint(__builtin_popcount(v)); } inline uint reversebits(uint v) { uint r = 0; for (int i = 0; i < 32; i++) r |= ((v >> i) & 1u) << (31 - i); return r; }
+// int3 pieces of ComputeRayOrigin (PathTracerHelpers.hlsli:29-42): bit casts per component, integer add / negate, per-component select
+inline int3 asint(float3 v) { return int3(asint(v.x), asint(v.y), asint(v.z)); } inline float3 asfloat(int3 v) { return float3(asfloat(v.x), asfloat(v.y), asfloat(v.z)); }
+inline int3 operator+(int3 a, int3 b) { return int3(a.x + b.x, a.y + b.y, a.z + b.z); } inline int3 operator-(int3 a) { return int3(-a.x, -a.y, -a.z); }
+inline int3 select(bool3 c, int3 a, int3 b) { return int3(c.x ? a.x : b.x, c.y ? a.y : b.y, c.z ? a.z : b.z); }
 inline float select(bool c, float a, float b) { return c ? a : b; }
 inline float2 select(bool2 c, float a, float b) { return float2(c.x ? a : b, c.y ? a : b); } inline float3 select(bool3 c, float3 a, float3 b) { return float3(c.x ? a.x : b.x, c.y ? a.y : b.y, c.z ? a.z : b.z); }

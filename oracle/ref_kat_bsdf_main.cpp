@@ -25,7 +25,7 @@ static void writeAll(const char* path, const std::vector<float>& v)
 
 int main(int argc, char** argv)
 {
-    if (argc != 4) { fprintf(stderr, "usage: %s bsdf|funcs|utils in.f32 out.f32\n", argv[0]); return 2; }
+    if (argc != 4) { fprintf(stderr, "usage: %s bsdf|funcs|utils|helpers in.f32 out.f32\n", argv[0]); return 2; }
     const std::vector<float> in = readAll(argv[2]); std::vector<float> out;
     if (std::string(argv[1]) == "bsdf")
     {
@@ -52,6 +52,27 @@ int main(int argc, char** argv)
             o[32] = nonDelta; o[33] = float(count);
             float3 de, se; b.estimateSpecDiffBSDF(de, se, sd.N, sd.V);
             o[34] = de.x; o[35] = de.y; o[36] = de.z; o[37] = se.x; o[38] = se.y; o[39] = se.z;
+        }
+    }
+    else if (std::string(argv[1]) == "helpers")
+    {   // PathTracerHelpers.hlsli:26-66, :155-219: self-intersection offset, grazing-angle falloff, ray-cone growth, firefly filter (layout shared with oracle_helper_funcs)
+        const size_t n = in.size() / 8; out.assign(n * 16, 0.0f);
+        for (size_t i = 0; i < n; i++)
+        {
+            const float* u = &in[i * 8]; float* o = &out[i * 16];
+            const float scale = u[6] < 0.25f ? 0.05f : (u[6] < 0.5f ? 1.0f : (u[6] < 0.75f ? 40.0f : 3000.0f));            // positions inside and outside the |p| < 1/16 switch, up to kilometres
+            const float3 pos = float3(2.0f * u[0] - 1.0f, 2.0f * u[1] - 1.0f, 2.0f * u[2] - 1.0f) * scale;
+            const float3 nrm = normalize(float3(2.0f * u[3] - 1.0f, 2.0f * u[4] - 1.0f, 2.0f * u[5] - 1.0f) + float3(0.0f, 1e-3f, 0.0f));
+            const float3 ro = ComputeRayOrigin(pos, nrm); o[0] = ro.x; o[1] = ro.y; o[2] = ro.z;
+            const float3 l = normalize(float3(2.0f * u[5] - 1.0f, 2.0f * u[6] - 1.0f, 2.0f * u[7] - 1.0f) + float3(1e-3f, 0.0f, 0.0f));
+            const float from = 0.01f + 0.24f * u[7]; o[3] = ComputeLowGrazingAngleFalloff(l, nrm, from, 2.0f * from);
+            o[4] = RoughnessToVariance(u[0]); o[5] = GetAngleFromGGXRoughness(u[1]); o[6] = ComputeRayConeSpreadAngleExpansionByRoughness(u[2]);
+            const float pdf = u[3] < 0.05f ? 0.0f : u[3] * u[3] * 40.0f;
+            o[7] = pdf == 0.0f ? 0.0f : ComputeRayConeSpreadAngleExpansionByScatterPDF(pdf);
+            o[8] = ComputeNewScatterFireflyFilterK(lpfloat(u[4]), pdf, u[5]);
+            const lpfloat3 ff = FireflyFilter(lpfloat3(lpfloat(u[0] * 8.0f), lpfloat(u[1] * 8.0f), lpfloat(u[2] * 8.0f)), lpfloat(2.0f + u[3]), lpfloat(u[4])); o[9] = ff.x; o[10] = ff.y; o[11] = ff.z;
+            o[12] = FireflyFilterShort(u[0] * 8.0f, 2.0f + u[3], u[4]);
+            o[13] = BalanceHeuristic(1.0f, u[5] * 3.0f, 1.0f, u[7] * 3.0f);
         }
     }
     else if (std::string(argv[1]) == "utils")

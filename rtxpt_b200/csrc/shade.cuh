@@ -155,9 +155,11 @@ PT_DEVICE float newFireflyK(float currentK, float bouncePdf, float lobeP)
 }
 PT_DEVICE float3 fireflyFilter(float3 signal, float threshold, float k)
 {
+    // lpfloat arithmetic of the reference: every operation rounds to binary16 (PathTracerHelpers.hlsli:206-212, Utils.hlsli:63-66; pinned by tests/golden/helpers_golden.npz)
+    signal = lp3(signal);                                                           // the parameter is an lpfloat3
     const float thr = lp(threshold * k);
-    const float maxR = lp(average(signal));
-    if (maxR > thr) signal = lp3(signal / maxR * thr);
+    const float maxR = lp(lp(lp(signal.x + signal.y) + signal.z) / 3.0f);
+    if (maxR > thr) signal = mk3(lp(lp(signal.x / maxR) * thr), lp(lp(signal.y / maxR) * thr), lp(lp(signal.z / maxR) * thr));
     return signal;
 }
 

@@ -169,3 +169,19 @@ def test_utils_functions_match_reference_header_golden(oracle):
         same = (out[:, k].view(np.uint32) == ref[:, k].view(np.uint32)) | (np.isnan(out[:, k]) & np.isnan(ref[:, k]))
         assert same.all(), (k, int((~same).sum()))
     assert np.isnan(out[:, [0, 1, 2, 4, 5, 21, 22, 23]]).all()                  # not restated (unused by the live path): LuminanceClamp, power / three-way MIS, WeightedAverage, ...
+
+
+def test_path_tracer_helpers_match_reference_header_golden(oracle):
+    """PathTracerHelpers.hlsli compiled in place (tests/golden/make_helpers_golden.py): the self-intersection offset of every ray origin (ComputeRayOrigin), the grazing-angle
+    fade-out of NEE, the ray-cone growth by scatter pdf, the firefly-filter K update and both firefly filters, the balance heuristic - bit for bit.  (The firefly filter's lpfloat
+    arithmetic rounds to binary16 after EVERY operation; the restatement had rounded once per expression until this vector set caught it: 44 % of the filtered values were off by
+    1-2 fp16 steps.)"""
+    import ctypes as C
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "helpers_golden.npz"))
+    u, ref = np.ascontiguousarray(g["helpers_in"]), g["helpers_out"]
+    L = oracle.lib(); L.oracle_helper_funcs.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]; L.oracle_helper_funcs.restype = None
+    out = np.empty_like(ref); L.oracle_helper_funcs(u.ctypes.data, len(u), out.ctypes.data)
+    for k in (0, 1, 2, 3, 7, 8, 9, 10, 11, 12, 13):
+        same = (out[:, k].view(np.uint32) == ref[:, k].view(np.uint32)) | (np.isnan(out[:, k]) & np.isnan(ref[:, k]))
+        assert same.all(), (k, int((~same).sum()))
+    assert (ref[:, 9:12] != np.float32(u[:, 0:3] * 8).astype(np.float16).astype(np.float32)).any(1).mean() > 0.2       # the filter did clamp a good share of the records
