@@ -177,6 +177,25 @@ ORC_API void oracle_helper_funcs(const float* in, uint32_t count, float* out)
     }
 }
 
+// Lighting/PolymorphicLight.hlsli's emissive-triangle light as the oracle restates it (pt_lights.h), on the inputs and in the layout of ref_kat_bsdf_main.cpp's "lights" mode
+ORC_API void oracle_light_funcs(const float* in, uint32_t count, float* out)
+{
+    for (uint32_t i = 0; i < count; i++)
+    {
+        const float* u = in + size_t(i) * 24; float* o = out + size_t(i) * 24;
+        TriangleLight t; t.base = f3(u[0], u[1], u[2]); t.edge1 = f3(u[3], u[4], u[5]); t.edge2 = f3(u[6], u[7], u[8]); t.radiance = f3(u[9], u[10], u[11]);
+        const PolymorphicLightInfo li = t.Store();
+        const uint words[8] = { asuint(li.Center[0]), asuint(li.Center[1]), asuint(li.Center[2]), li.ColorTypeAndFlags, li.Direction1, li.Direction2, li.Scalars, li.LogRadiance };
+        memcpy(o, words, 32);
+        const TriangleLight r = TriangleLight::Create(li);
+        const float3 viewer = f3(u[14], u[15], u[16]);
+        const PolymorphicLightSample s = r.CalcSample(f2(u[12], u[13]), viewer);
+        o[8] = s.Position.x; o[9] = s.Position.y; o[10] = s.Position.z; o[11] = s.Normal.x; o[12] = s.Normal.y; o[13] = s.Normal.z; o[14] = s.Radiance.x; o[15] = s.Radiance.y; o[16] = s.Radiance.z;
+        o[17] = s.SolidAnglePdf; o[18] = r.CalcSolidAnglePdfForMIS(viewer, s.Position); o[19] = r.GetPower();
+        o[20] = r.edge1.x; o[21] = r.edge1.y; o[22] = r.edge1.z; o[23] = r.surfaceArea;
+    }
+}
+
 ORC_API void* oracle_create(const RtxptSceneDesc* desc)
 {
     OracleCtx* c = new OracleCtx();

@@ -78,9 +78,13 @@ struct TriangleLight
         PackLightColor(radiance, li);
         float3 c = base + ((edge1 + edge2) / 3.0f);
         li.Center[0] = c.x; li.Center[1] = c.y; li.Center[2] = c.z;
-        li.Direction1 = (f32tof16(edge1.x) & 0xffff) | (f32tof16(edge2.x) << 16);
-        li.Direction2 = (f32tof16(edge1.y) & 0xffff) | (f32tof16(edge2.y) << 16);
-        li.Scalars    = (f32tof16(edge1.z) & 0xffff) | (f32tof16(edge2.z) << 16);
+        // PolymorphicLight.hlsli:510-513 keeps the three packed words in a `float3 edges` before they are stored: uint -> float -> uint, i.e. each word is rounded to 24
+        // significant bits and the low bits of edge1's halves are lost (RTXDI's original has `uint3 edges`).  Reproduced as is: these are the records the reference's NEE samples
+        // (pinned by tests/golden/lights_golden.npz, generated from the unmodified header)
+        auto viaFloat = [](uint packed) { const float f = float(packed); return f >= 4294967296.0f ? 0xFFFFFFFFu : uint(f); };
+        li.Direction1 = viaFloat((f32tof16(edge1.x) & 0xffff) | (f32tof16(edge2.x) << 16));
+        li.Direction2 = viaFloat((f32tof16(edge1.y) & 0xffff) | (f32tof16(edge2.y) << 16));
+        li.Scalars    = viaFloat((f32tof16(edge1.z) & 0xffff) | (f32tof16(edge2.z) << 16));
         li.ColorTypeAndFlags |= kLightTypeTriangle << kPolymorphicLightTypeShift;
         return li;
     }

@@ -83,6 +83,7 @@ template <typename T> struct vec2
     template <typename U> explicit vec2(const vec2<U>& o) : x(T(o.x)), y(T(o.y)) {}
     vec2(const vec2& o) : x(o.x), y(o.y) {}
     vec2& operator=(const vec2& o) { x = o.x; y = o.y; return *this; }
+    T& operator[](int i) { return i == 0 ? x : y; } const T& operator[](int i) const { return i == 0 ? x : y; }
 };
 template <typename T> struct vec3
 {
@@ -95,6 +96,7 @@ template <typename T> struct vec3
     template <typename U> vec3(const vec3<U>& o) : x(T(float(o.x))), y(T(float(o.y))), z(T(float(o.z))) {}     // float3 <-> float16_t3 convert implicitly in HLSL
     vec3(const vec3& o) : x(o.x), y(o.y), z(o.z) {}
     vec3& operator=(const vec3& o) { x = o.x; y = o.y; z = o.z; return *this; }
+    T& operator[](int i) { return i == 0 ? x : (i == 1 ? y : z); } const T& operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
 };
 template <typename T> struct vec4
 {
@@ -192,6 +194,7 @@ inline float3 clamp(float3 v, float lo, float hi) { return float3(clamp(v.x, lo,
 inline float3 clamp(float3 v, float3 lo, float3 hi) { return float3(clamp(v.x, lo.x, hi.x), clamp(v.y, lo.y, hi.y), clamp(v.z, lo.z, hi.z)); }
 inline float2 clamp(float2 v, float lo, float hi) { return float2(clamp(v.x, lo, hi), clamp(v.y, lo, hi)); }
 inline float lerp(float a, float b, float t) { return a + (b - a) * t; }            // HLSL lerp: x + s ( y - x )
+inline float smoothstep(float a, float b, float x) { const float t = saturate((x - a) / (b - a)); return t * t * (3.0f - 2.0f * t); }      // HLSL smoothstep
 inline float3 lerp(float3 a, float3 b, float t) { return a + (b - a) * t; } inline float3 lerp(float3 a, float3 b, float3 t) { return a + (b - a) * t; } inline float2 lerp(float2 a, float2 b, float t) { return a + (b - a) * t; }
 inline float mad(float a, float b, float c) { return a * b + c; } inline float3 mad(float3 a, float3 b, float3 c) { return a * b + c; }                   // not fused: "mad" leaves fusing to the compiler; the oracle and product use the unfused form
 inline float rcp(float x) { return 1.0f / x; } inline float rsqrt(float x) { return 1.0f / std::sqrt(x); }
@@ -226,6 +229,11 @@ inline uint asuint(float f) { uint u; std::memcpy(&u, &f, 4); return u; } inline
 inline uint3 asuint(float3 v) { return uint3(asuint(v.x), asuint(v.y), asuint(v.z)); }
 inline uint firstbithigh(uint v) { return v ? 31u - uint(__builtin_clz(v)) : 0xFFFFFFFFu; } inline uint firstbitlow(uint v) { return v ? uint(__builtin_ctz(v)) : 0xFFFFFFFFu; }
 inline uint countbits(uint v) { return uint(__builtin_popcount(v)); } inline uint reversebits(uint v) { uint r = 0; for (int i = 0; i < 32; i++) r |= ((v >> i) & 1u) << (31 - i); return r; }
+// uint3 pieces of TriangleLight::Create / Store (PolymorphicLight.hlsli:478-515): masks, shifts, half conversion per component
+inline uint3 operator&(uint3 a, uint m) { return uint3(a.x & m, a.y & m, a.z & m); } inline uint3 operator>>(uint3 a, int n) { return uint3(a.x >> n, a.y >> n, a.z >> n); }
+inline uint3 operator<<(uint3 a, int n) { return uint3(a.x << n, a.y << n, a.z << n); } inline uint3 operator|(uint3 a, uint3 b) { return uint3(a.x | b.x, a.y | b.y, a.z | b.z); }
+inline float3 f16tof32(uint3 h) { return float3(f16tof32(h.x), f16tof32(h.y), f16tof32(h.z)); } inline uint3 f32tof16(float3 f) { return uint3(f32tof16(f.x), f32tof16(f.y), f32tof16(f.z)); }
+inline float3 asfloat(uint3 v) { float3 r; std::memcpy(&r.x, &v.x, 4); std::memcpy(&r.y, &v.y, 4); std::memcpy(&r.z, &v.z, 4); return r; }
 // int3 pieces of ComputeRayOrigin (PathTracerHelpers.hlsli:29-42): bit casts per component, integer add / negate, per-component select
 inline int3 asint(float3 v) { return int3(asint(v.x), asint(v.y), asint(v.z)); } inline float3 asfloat(int3 v) { return float3(asfloat(v.x), asfloat(v.y), asfloat(v.z)); }
 inline int3 operator+(int3 a, int3 b) { return int3(a.x + b.x, a.y + b.y, a.z + b.z); } inline int3 operator-(int3 a) { return int3(-a.x, -a.y, -a.z); }

@@ -23,9 +23,14 @@ static void writeAll(const char* path, const std::vector<float>& v)
     fwrite(v.data(), 4, v.size(), f); fclose(f);
 }
 
+// EnvironmentQuadLight::ToWorld / ToLocal are left to the application by PolymorphicLight.hlsli (the bridge rotates by the environment-map transform); identity here - the quad-tree
+// lights are not part of these vectors
+float3 EnvironmentQuadLight::ToWorld(float3 localDir) { return localDir; }
+float3 EnvironmentQuadLight::ToLocal(float3 worldDir) { return worldDir; }
+
 int main(int argc, char** argv)
 {
-    if (argc != 4) { fprintf(stderr, "usage: %s bsdf|funcs|utils|helpers in.f32 out.f32\n", argv[0]); return 2; }
+    if (argc != 4) { fprintf(stderr, "usage: %s bsdf|funcs|utils|helpers|lights in.f32 out.f32\n", argv[0]); return 2; }
     const std::vector<float> in = readAll(argv[2]); std::vector<float> out;
     if (std::string(argv[1]) == "bsdf")
     {
@@ -52,6 +57,25 @@ int main(int argc, char** argv)
             o[32] = nonDelta; o[33] = float(count);
             float3 de, se; b.estimateSpecDiffBSDF(de, se, sd.N, sd.V);
             o[34] = de.x; o[35] = de.y; o[36] = de.z; o[37] = se.x; o[38] = se.y; o[39] = se.z;
+        }
+    }
+    else if (std::string(argv[1]) == "lights")
+    {   // Lighting/PolymorphicLight.hlsli: an emissive triangle through TriangleLight::Store (what LightsBaker writes into the light buffer: PackColor, half-packed edges),
+        // TriangleLight::Create (what NEE reads back), CalcSample, CalcSolidAnglePdfForMIS, GetPower.  24 floats in, 24 out (words 0-7: the PolymorphicLightInfo as bit patterns)
+        const size_t n = in.size() / 24; out.assign(n * 24, 0.0f);
+        for (size_t i = 0; i < n; i++)
+        {
+            const float* u = &in[i * 24]; float* o = &out[i * 24];
+            TriangleLight t; t.base = float3(u[0], u[1], u[2]); t.edge1 = float3(u[3], u[4], u[5]); t.edge2 = float3(u[6], u[7], u[8]); t.radiance = float3(u[9], u[10], u[11]);
+            const PolymorphicLightInfoFull full = t.Store(0u);
+            const uint words[8] = { asuint(full.Base.Center.x), asuint(full.Base.Center.y), asuint(full.Base.Center.z), full.Base.ColorTypeAndFlags, full.Base.Direction1, full.Base.Direction2, full.Base.Scalars, full.Base.LogRadiance };
+            memcpy(o, words, 32);
+            const TriangleLight r = TriangleLight::Create(full);
+            const float3 viewer(u[14], u[15], u[16]);
+            const PolymorphicLightSample s = r.CalcSample(float2(u[12], u[13]), viewer);
+            o[8] = s.Position.x; o[9] = s.Position.y; o[10] = s.Position.z; o[11] = s.Normal.x; o[12] = s.Normal.y; o[13] = s.Normal.z; o[14] = s.Radiance.x; o[15] = s.Radiance.y; o[16] = s.Radiance.z;
+            o[17] = s.SolidAnglePdf; o[18] = r.CalcSolidAnglePdfForMIS(viewer, s.Position); o[19] = r.GetPower();
+            o[20] = r.edge1.x; o[21] = r.edge1.y; o[22] = r.edge1.z; o[23] = r.surfaceArea;
         }
     }
     else if (std::string(argv[1]) == "helpers")

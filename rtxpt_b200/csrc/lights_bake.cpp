@@ -453,9 +453,12 @@ void LightBaker::prepareScene(const RtxptSceneDesc& scene, std::vector<RtxptSubI
                 packColor(radiance, li);
                 const V3 c = p[0] + ((e1 + e2) / 3.0f);
                 li.center[0] = c.x; li.center[1] = c.y; li.center[2] = c.z;
-                li.direction1 = (toHalf(e1.x) & 0xffff) | (toHalf(e2.x) << 16);
-                li.direction2 = (toHalf(e1.y) & 0xffff) | (toHalf(e2.y) << 16);
-                li.scalars = (toHalf(e1.z) & 0xffff) | (toHalf(e2.z) << 16);
+                // TriangleLight::Store (PolymorphicLight.hlsli:510-513) passes the packed words through a `float3 edges`: uint -> float -> uint, each word rounded to 24
+                // significant bits (the low bits of edge1's halves are lost).  Reproduced as is - these are the records the reference samples (tests/golden/lights_golden.npz)
+                auto viaFloat = [](uint32_t packed) { const float f = float(packed); return f >= 4294967296.0f ? 0xFFFFFFFFu : uint32_t(f); };
+                li.direction1 = viaFloat((toHalf(e1.x) & 0xffff) | (toHalf(e2.x) << 16));
+                li.direction2 = viaFloat((toHalf(e1.y) & 0xffff) | (toHalf(e2.y) << 16));
+                li.scalars = viaFloat((toHalf(e1.z) & 0xffff) | (toHalf(e2.z) << 16));
                 li.colorTypeAndFlags |= kTypeTriangle << 24;
                 st.triangleLights.push_back(li);
                 st.triangleLightCount++;

@@ -185,3 +185,21 @@ def test_path_tracer_helpers_match_reference_header_golden(oracle):
         same = (out[:, k].view(np.uint32) == ref[:, k].view(np.uint32)) | (np.isnan(out[:, k]) & np.isnan(ref[:, k]))
         assert same.all(), (k, int((~same).sum()))
     assert (ref[:, 9:12] != np.float32(u[:, 0:3] * 8).astype(np.float16).astype(np.float32)).any(1).mean() > 0.2       # the filter did clamp a good share of the records
+
+
+def test_triangle_light_matches_reference_header_golden(oracle):
+    """Lighting/PolymorphicLight.hlsli compiled in place (tests/golden/make_lights_golden.py): TriangleLight::Store - the 32-byte record LightsBaker writes for every emissive
+    triangle (PackColor's log radiance + R8G8B8 colour, centre, half-packed edges) -, Create, CalcSample (uniform triangle sample + ComputeRayOrigin + area -> solid-angle pdf),
+    CalcSolidAnglePdfForMIS and GetPower: the oracle reproduces all of it bit for bit.  This includes a quirk of the reference: Store holds the packed edge words in a `float3`
+    before writing them (uint -> float -> uint), so each word keeps only 24 significant bits and edge1 loses its low mantissa bits; the restatement now does the same."""
+    import ctypes as C
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "lights_golden.npz"))
+    u, ref = np.ascontiguousarray(g["lights_in"]), g["lights_out"]
+    L = oracle.lib(); L.oracle_light_funcs.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]; L.oracle_light_funcs.restype = None
+    out = np.empty_like(ref); L.oracle_light_funcs(u.ctypes.data, len(u), out.ctypes.data)
+    same = (out.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(out) & np.isnan(ref))
+    assert same.all(), same.mean(0)
+    # the quirk is real in these vectors: the stored edge1 differs from the half-rounded input on most records
+    e1 = u[:, 3:6].astype(np.float16).astype(np.float32)
+    rel = np.abs(ref[:, 20:23] - e1) / (np.abs(e1) + 1e-6)
+    assert (ref[:, 20:23] != e1).any(1).mean() > 0.9 and 0.005 < np.median(rel) < 0.03 and np.percentile(rel, 99) < 0.15           # measured: median 1.8 %, 99th percentile 10 % of the component
