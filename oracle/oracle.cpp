@@ -196,6 +196,33 @@ ORC_API void oracle_light_funcs(const float* in, uint32_t count, float* out)
     }
 }
 
+// the analytic sphere / spot light, layout of ref_kat_bsdf_main.cpp's "spheres" mode: the record is assembled with the oracle's packers, then Create / CalcSample / pdf / power
+ORC_API void oracle_sphere_light_funcs(const float* in, uint32_t count, float* out)
+{
+    for (uint32_t i = 0; i < count; i++)
+    {
+        const float* u = in + size_t(i) * 24; float* o = out + size_t(i) * 24;
+        PolymorphicLightInfo li = {}; PolymorphicLightInfoEx ex = {};
+        li.Center[0] = u[0]; li.Center[1] = u[1]; li.Center[2] = u[2]; li.Scalars = f32tof16(u[3]);
+        PackLightColor(f3(u[4], u[5], u[6]), li);
+        li.ColorTypeAndFlags |= kLightTypeSphere << kPolymorphicLightTypeShift;
+        if (u[7] > 0.5f)
+        {
+            li.ColorTypeAndFlags |= kPolymorphicLightShapingEnableBit | (u[8] > 0.5f ? kPolymorphicLightShapingUseMinFalloff : 0u);
+            ex.PrimaryAxis = NDirToOctUnorm32(normalize(f3(u[9], u[10], u[11])));
+            ex.CosConeAngleAndSoftness = f32tof16(u[12]) | (f32tof16(u[13]) << 16);
+        }
+        const uint words[12] = { asuint(li.Center[0]), asuint(li.Center[1]), asuint(li.Center[2]), li.ColorTypeAndFlags, li.Direction1, li.Direction2, li.Scalars, li.LogRadiance, ex.IesProfileIndex, ex.PrimaryAxis, ex.CosConeAngleAndSoftness, ex.UniqueID };
+        memcpy(o, words, 48);
+        const SphereLight s = SphereLight::Create(li, ex);
+        const float3 viewer = f3(u[16], u[17], u[18]);
+        PolymorphicLightSample r = s.CalcSample(f2(u[14], u[15]), viewer);
+        if (r.SolidAnglePdf > 0) r.Radiance = r.Radiance * evaluateLightShaping(s.shaping, viewer, r.Position);       // PolymorphicLight::CalcSample, PolymorphicLight.hlsli:670-673
+        o[12] = r.Position.x; o[13] = r.Position.y; o[14] = r.Position.z; o[15] = r.Normal.x; o[16] = r.Normal.y; o[17] = r.Normal.z; o[18] = r.Radiance.x; o[19] = r.Radiance.y; o[20] = r.Radiance.z;
+        o[21] = r.SolidAnglePdf; o[22] = s.CalcSolidAnglePdfForMIS(viewer); o[23] = s.GetPower();
+    }
+}
+
 ORC_API void* oracle_create(const RtxptSceneDesc* desc)
 {
     OracleCtx* c = new OracleCtx();

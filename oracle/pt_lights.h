@@ -278,7 +278,7 @@ struct SphereLight      // PolymorphicLight.hlsli:93-259
         const float cosThetaMax = sqrtf(std::max(0.0f, 1.0f - sinThetaMax2));
         return 1.0f / (2.0f * K_PI * (1.0f - cosThetaMax));
     }
-    float GetPower() const { return 4 * K_PI * radius * radius * K_PI * Luminance(radiance) * getShapingFluxFactor(shaping); }
+    float GetPower() const { return (4 * K_PI * (radius * radius)) * K_PI * Luminance(radiance) * getShapingFluxFactor(shaping); }        // getSurfaceArea() = 4 pi sq(radius) first (PolymorphicLight.hlsli:224-232)
 };
 
 // Rtxpt/Lighting/LightsBaker.cpp:456-556 (ConvertLight)

@@ -30,7 +30,7 @@ float3 EnvironmentQuadLight::ToLocal(float3 worldDir) { return worldDir; }
 
 int main(int argc, char** argv)
 {
-    if (argc != 4) { fprintf(stderr, "usage: %s bsdf|funcs|utils|helpers|lights in.f32 out.f32\n", argv[0]); return 2; }
+    if (argc != 4) { fprintf(stderr, "usage: %s bsdf|funcs|utils|helpers|lights|spheres in.f32 out.f32\n", argv[0]); return 2; }
     const std::vector<float> in = readAll(argv[2]); std::vector<float> out;
     if (std::string(argv[1]) == "bsdf")
     {
@@ -57,6 +57,35 @@ int main(int argc, char** argv)
             o[32] = nonDelta; o[33] = float(count);
             float3 de, se; b.estimateSpecDiffBSDF(de, se, sd.N, sd.V);
             o[34] = de.x; o[35] = de.y; o[36] = de.z; o[37] = se.x; o[38] = se.y; o[39] = se.z;
+        }
+    }
+    else if (std::string(argv[1]) == "spheres")
+    {   // Lighting/PolymorphicLight.hlsli: the analytic sphere / spot light.  The record is assembled here from the reference's own packers (PackColor, NDirToOctUnorm32, f32tof16:
+        // the host does this in LightsBaker.cpp), then SphereLight::Create, CalcSample (incl. evaluateLightShaping), CalcSolidAnglePdfForMIS, GetPower.  24 floats in, 24 out
+        // (words 0-11: Base + Extended as bit patterns)
+        const size_t n = in.size() / 24; out.assign(n * 24, 0.0f);
+        for (size_t i = 0; i < n; i++)
+        {
+            const float* u = &in[i * 24]; float* o = &out[i * 24];
+            PolymorphicLightInfoFull full = PolymorphicLightInfoFull{}; full.Extended = PolymorphicLightInfoEx::empty();
+            full.Base.Center = float3(u[0], u[1], u[2]); full.Base.ColorTypeAndFlags = 0; full.Base.Direction1 = 0; full.Base.Direction2 = 0; full.Base.LogRadiance = 0;
+            full.Base.Scalars = f32tof16(u[3]);
+            PolymorphicLight::PackColor(float3(u[4], u[5], u[6]), full.Base);
+            full.Base.ColorTypeAndFlags |= uint(PolymorphicLightType::kSphere) << kPolymorphicLightTypeShift;
+            if (u[7] > 0.5f)
+            {   // spot: shaping enabled, axis / cone as the host packs them
+                full.Base.ColorTypeAndFlags |= kPolymorphicLightShapingEnableBit | (u[8] > 0.5f ? kPolymorphicLightShapingUseMinFalloff : 0u);
+                full.Extended.PrimaryAxis = NDirToOctUnorm32(normalize(float3(u[9], u[10], u[11])));
+                full.Extended.CosConeAngleAndSoftness = f32tof16(u[12]) | (f32tof16(u[13]) << 16);
+            }
+            const uint words[12] = { asuint(full.Base.Center.x), asuint(full.Base.Center.y), asuint(full.Base.Center.z), full.Base.ColorTypeAndFlags, full.Base.Direction1, full.Base.Direction2, full.Base.Scalars,
+                                     full.Base.LogRadiance, full.Extended.IesProfileIndex, full.Extended.PrimaryAxis, full.Extended.CosConeAngleAndSoftness, full.Extended.UniqueID };
+            memcpy(o, words, 48);
+            const SphereLight s = SphereLight::Create(full);
+            const float3 viewer(u[16], u[17], u[18]);
+            const PolymorphicLightSample r = PolymorphicLight::CalcSample(full, float2(u[14], u[15]), viewer);       // the dispatcher: SphereLight::CalcSample x evaluateLightShaping
+            o[12] = r.Position.x; o[13] = r.Position.y; o[14] = r.Position.z; o[15] = r.Normal.x; o[16] = r.Normal.y; o[17] = r.Normal.z; o[18] = r.Radiance.x; o[19] = r.Radiance.y; o[20] = r.Radiance.z;
+            o[21] = r.SolidAnglePdf; o[22] = s.CalcSolidAnglePdfForMIS(viewer, r.Position); o[23] = s.GetPower();
         }
     }
     else if (std::string(argv[1]) == "lights")

@@ -308,7 +308,7 @@ static float sphereLightPower(const BakedLight& l, const BakedLightEx& ex)      
         const float cosCone = fromHalf(ex.cosConeAngleAndSoftness & 0xffff), softness = fromHalf(ex.cosConeAngleAndSoftness >> 16);
         shaping = (1.0f - cosCone) * (1.0f + (0.5f - 1.0f) * softness) * 0.5f;
     }
-    return 4 * pi * radius * radius * pi * (rad.x * 0.2126f + rad.y * 0.7152f + rad.z * 0.0722f) * shaping;
+    return (4 * pi * (radius * radius)) * pi * (rad.x * 0.2126f + rad.y * 0.7152f + rad.z * 0.0722f) * shaping;        // getSurfaceArea() = 4 pi sq(radius) first (PolymorphicLight.hlsli:224-232; pinned by tests/golden/lights_golden.npz)
 }
 
 void LightBaker::finalize(const RtxptPathTracerConstants& consts, LightBakeState& st)

@@ -22,3 +22,16 @@ if __name__ == "__main__":
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "lights_golden.npz"), lights_in=u, lights_out=out,
                         source=np.array("Rtxpt/Shaders/PathTracer/Lighting/PolymorphicLight.hlsli at reference commit f08d1c7, compiled as C++ by oracle/Makefile target _ref/ref_kat_bsdf"))
     print(u.shape, out.shape, "nan:", int(np.isnan(out).sum()))
+    # analytic sphere / spot lights (mode "spheres"): record assembled from the reference's own packers, then SphereLight::Create, PolymorphicLight::CalcSample (incl.
+    # evaluateLightShaping), CalcSolidAnglePdfForMIS, GetPower.  in: centre 3, radius, radiance 3, spot?, min-falloff?, axis 3, cos cone, softness, random 2, viewer 3
+    rng = np.random.default_rng(20260927)
+    v = np.zeros((n, 24), np.float32)
+    v[:, 0:3] = (rng.random((n, 3)) - 0.5) * np.float32(40); v[:, 3] = np.float32(0.02) + rng.random(n).astype(np.float32) * np.float32(0.6)
+    v[:, 4:7] = rng.gamma(2.0, 30.0, (n, 3)).astype(np.float32); v[:, 7] = rng.random(n); v[:, 8] = rng.random(n)
+    v[:, 9:12] = rng.normal(size=(n, 3)).astype(np.float32); v[:, 12] = np.cos(np.radians(rng.uniform(5, 80, n))).astype(np.float32); v[:, 13] = np.float32(0.02) + rng.random(n).astype(np.float32) * np.float32(0.3)
+    v[:, 14:16] = rng.random((n, 2)); v[:, 16:19] = (rng.random((n, 3)) - 0.5) * np.float32(60)
+    v[:100, 16:19] = v[:100, 0:3] + np.float32(0.01)                     # viewer inside the sphere
+    sout = run("spheres", v, 24)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "sphere_lights_golden.npz"), spheres_in=v, spheres_out=sout,
+                        source=np.array("Rtxpt/Shaders/PathTracer/Lighting/{PolymorphicLight,LightShaping}.hlsli at reference commit f08d1c7, compiled as C++ by oracle/Makefile target _ref/ref_kat_bsdf"))
+    print(v.shape, sout.shape, "nan:", int(np.isnan(sout).sum()))
