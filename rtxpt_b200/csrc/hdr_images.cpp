@@ -112,7 +112,7 @@ HdrFileImage decodeExr(const uint8_t* data, size_t size)
     static const char* const kNames[] = { "none", "RLE", "ZIPS", "ZIP", "PIZ", "PXR24", "B44", "B44A", "DWAA", "DWAB" };
     if (compression > 3) fail("EXR: %s compression is not supported (NONE, RLE, ZIPS, ZIP are); re-save the file with ZIP", compression < 10 ? kNames[compression] : "this");
     const int64_t w64 = int64_t(dw[2]) - dw[0] + 1, h64 = int64_t(dw[3]) - dw[1] + 1;
-    if (w64 <= 0 || h64 <= 0 || w64 > 32768 || h64 > 32768) fail("EXR: bad dataWindow size");
+    if (w64 <= 0 || h64 <= 0 || w64 > 32768 || h64 > 32768 || w64 * h64 > (int64_t(1) << 28)) fail("EXR: bad dataWindow size (at most 32768 per side and 2^28 pixels)");
     const uint32_t W = uint32_t(w64), H = uint32_t(h64);
     // channel -> RGBA slot; a lone Y channel fills R, G and B.  Layer prefixes ("diffuse.R") are not mapped: the first-part colour channels are what RTXPT's dumps hold.
     std::vector<int> slot(channels.size(), -1); size_t pixelBytes = 0; bool haveY = false, haveRGB = false;
@@ -179,7 +179,7 @@ HdrFileImage decodeRadianceHdr(const uint8_t* data, size_t size)
     if (!rgbe) fail("HDR: no FORMAT line");
     const std::string res = line(); int H = 0, W = 0;
     if (sscanf(res.c_str(), "-Y %d +X %d", &H, &W) != 2) fail("HDR: resolution line '%s' is not supported (-Y h +X w is)", res.c_str());
-    if (W <= 0 || H <= 0 || W > 32768 || H > 32768) fail("HDR: bad dimensions");
+    if (W <= 0 || H <= 0 || W > 32768 || H > 32768 || int64_t(W) * H > (int64_t(1) << 28)) fail("HDR: bad dimensions (at most 32768 per side and 2^28 pixels)");
     HdrFileImage img; img.width = uint32_t(W); img.height = uint32_t(H); img.rgba.resize(size_t(W) * H * 4);
     std::vector<uint8_t> scan(size_t(W) * 4);
     auto put = [&](float* o, const uint8_t* p)

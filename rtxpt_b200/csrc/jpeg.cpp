@@ -141,7 +141,7 @@ JpegImage decodeJpeg(const uint8_t* d, size_t size, const char* name)
             if (n < 6) failf("JPEG '%s': truncated frame header", name);
             if (s[0] != 8) failf("JPEG '%s': %u-bit samples are not supported (8-bit are)", name, unsigned(s[0]));
             height = be16(s + 1); width = be16(s + 3); const int nc = s[5];
-            if (!width || !height || width > 32768 || height > 32768) failf("JPEG '%s': bad dimensions", name);
+            if (!width || !height || width > 32768 || height > 32768 || int64_t(width) * height > (int64_t(1) << 28)) failf("JPEG '%s': bad dimensions (at most 32768 per side and 2^28 pixels)", name);
             if (nc != 1 && nc != 3) failf("JPEG '%s': %d colour components are not supported (grey and YCbCr are)", name, nc);
             if (n < size_t(6 + 3 * nc)) failf("JPEG '%s': truncated frame header", name);
             comps.resize(size_t(nc));
@@ -261,6 +261,7 @@ extern "C" RTXPT_API int rtxpt_b200_debug_decode_jpeg(const void* fileBytes, uin
         if (outRGBA) { if (outCapacity < img.rgba.size()) { g_jpegError = "output buffer too small"; return RTXPT_ERR_INVALID_ARGUMENT; } memcpy(outRGBA, img.rgba.data(), img.rgba.size()); }
     }
     catch (const rtxpt_host::LoadError& e) { g_jpegError = e.msg; return RTXPT_ERR_INVALID_ARGUMENT; }
+    catch (const std::exception& e) { g_jpegError = e.what(); return RTXPT_ERR_INVALID_ARGUMENT; }
     return RTXPT_OK;
 }
 extern "C" RTXPT_API const char* rtxpt_b200_debug_decode_jpeg_error(void) { return g_jpegError.c_str(); }

@@ -109,3 +109,15 @@ def test_compare_script_reads_exr_against_pfm(tmp_path, golden):
     cmd = [sys.executable, os.path.join(root, "scripts", "compare_hdr_images.py"), os.path.join(G, "exr_zip_float.exr")]
     ok = subprocess.run(cmd + [p], capture_output=True, text=True); assert ok.returncode == 0 and "per-pixel L2 0.000e+00" in ok.stdout, ok.stdout + ok.stderr
     write_pfm(p, rgb * 1.1 + 0.05); bad = subprocess.run(cmd + [p], capture_output=True, text=True); assert bad.returncode == 1, bad.stdout
+
+
+def test_hostile_image_sizes_are_refused_before_allocation():
+    """Headers that claim gigapixel images (a 17 GB allocation in RGBA32F) are refused by their size, in all three decoders."""
+    import io
+    from PIL import Image
+    good = bytearray(_file("exr_zip_float.exr")); i = good.find(b"dataWindow\0box2i\0") + len(b"dataWindow\0box2i\0") + 4
+    good[i:i + 16] = struct.pack("<iiii", 0, 0, 32767, 32767)
+    with pytest.raises(L.RtxptError, match="2\\^28|dataWindow"): L.load_hdr_image(bytes(good))
+    with pytest.raises(L.RtxptError, match="2\\^28|dimensions"): L.load_hdr_image(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y 32768 +X 32768\n" + bytes(64))
+    b = io.BytesIO(); Image.new("RGB", (16, 16)).save(b, "JPEG"); j = bytearray(b.getvalue()); k = j.find(b"\xff\xc0"); j[k + 5:k + 9] = struct.pack(">HH", 32768, 32768)
+    with pytest.raises(L.RtxptError, match="2\\^28|dimensions"): L.decode_jpeg(bytes(j))
