@@ -223,6 +223,17 @@ ORC_API void oracle_sphere_light_funcs(const float* in, uint32_t count, float* o
     }
 }
 
+// the six tone-mapping operators as the oracle restates them (pt_tonemap.h), in the layout of ref_kat_bsdf_main.cpp's "tonemap" mode: 8 floats in, rgb + luminance out
+ORC_API void oracle_tonemap_ops(const float* in, uint32_t count, float* out)
+{
+    for (uint32_t i = 0; i < count; i++)
+    {
+        const float* u = in + size_t(i) * 8; float* o = out + size_t(i) * 4;
+        tonemap::Params p; p.op = uint(u[3]); p.whiteMaxLuminance = u[4]; p.whiteScale = u[5];
+        const float3 c = tonemap::toneMapOp(p, f3(u[0], u[1], u[2])); o[0] = c.x; o[1] = c.y; o[2] = c.z; o[3] = tonemap::luminance(f3(u[0], u[1], u[2]));
+    }
+}
+
 ORC_API void* oracle_create(const RtxptSceneDesc* desc)
 {
     OracleCtx* c = new OracleCtx();

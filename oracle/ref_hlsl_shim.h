@@ -159,6 +159,7 @@ struct float2x2 { union { float m[2][2]; struct { float _m00, _m01, _m10, _m11; 
 struct float3x3 { union { float m[3][3]; struct { float _m00, _m01, _m02, _m10, _m11, _m12, _m20, _m21, _m22; }; }; float3x3() {} float3x3(float a, float b, float c, float d, float e, float f, float g, float h, float i) { m[0][0] = a; m[0][1] = b; m[0][2] = c; m[1][0] = d; m[1][1] = e; m[1][2] = f; m[2][0] = g; m[2][1] = h; m[2][2] = i; }
                   float3x3(float3 r0, float3 r1, float3 r2) { m[0][0] = r0.x; m[0][1] = r0.y; m[0][2] = r0.z; m[1][0] = r1.x; m[1][1] = r1.y; m[1][2] = r1.z; m[2][0] = r2.x; m[2][1] = r2.y; m[2][2] = r2.z; }
                   float* operator[](int r) { return m[r]; } const float* operator[](int r) const { return m[r]; } };
+struct float3x4 { float m[3][4]; };          // constant-buffer member of ToneMappingConstants (not used by the pinned operators)
 struct float2x3 { union { float m[2][3]; struct { float _m00, _m01, _m02, _m10, _m11, _m12; }; }; float2x3() {} float2x3(float a, float b, float c, float d, float e, float f) { _m00 = a; _m01 = b; _m02 = c; _m10 = d; _m11 = e; _m12 = f; } float* operator[](int r) { return m[r]; } const float* operator[](int r) const { return m[r]; } };
 typedef float3x3 float16_t3x3;
 inline float2 mul(const float2x2& M, float2 v) { return float2(M.m[0][0] * v.x + M.m[0][1] * v.y, M.m[1][0] * v.x + M.m[1][1] * v.y); }

@@ -28,6 +28,7 @@ filter() {
     -e 's/([(,][[:space:]]*)in[[:space:]]+/\1/g' \
     -e 's/\(([A-Z][A-Za-z0-9_]*)\)[[:space:]]*0([^.0-9a-zA-Z_]|$)/\1{}\2/g' \
     -e 's/\b(radiance|unpackedRadiance)\.xxx\b/float3(\1, \1, \1)/g' \
+    -e 's/float\(0\)\.rrr/float3(0,0,0)/g' \
     -e 's/\b0\.xxx\b/float3(0,0,0)/g' \
     -e 's/\b1\.xxx\b/float3(1,1,1)/g' \
     -e 's/\b_alpha\.xx\b/float2(_alpha, _alpha)/g' \
@@ -51,5 +52,10 @@ for f in Config.h Utils/Math/MathConstants.hlsli Utils/Utils.hlsli:28-67 Utils/U
     *)   echo; echo "#line 1 \"$PT/$f\""; filter "$PT/$f" ;;
   esac
 done
+# the tone-mapping operators (Rtxpt/ToneMapper/ToneMapping.ps.hlsli:31-129: calcLuminance ... toneMap) read a constant buffer: the shared header defines it, a global stands in
+TM=$REF/Rtxpt/ToneMapper
+echo; echo "#line 1 \"$TM/ToneMapping_cb.h\""; filter "$TM/ToneMapping_cb.h"
+echo; echo 'ToneMappingConstants gParams;'
+echo; echo "#line 31 \"$TM/ToneMapping.ps.hlsli\""; filter "$TM/ToneMapping.ps.hlsli" | sed -n '31,129p'
 echo; echo "#line 1 \"$MAIN\""
 cat "$MAIN"

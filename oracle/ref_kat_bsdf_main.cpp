@@ -30,7 +30,7 @@ float3 EnvironmentQuadLight::ToLocal(float3 worldDir) { return worldDir; }
 
 int main(int argc, char** argv)
 {
-    if (argc != 4) { fprintf(stderr, "usage: %s bsdf|funcs|utils|helpers|lights|spheres in.f32 out.f32\n", argv[0]); return 2; }
+    if (argc != 4) { fprintf(stderr, "usage: %s bsdf|funcs|utils|helpers|lights|spheres|tonemap in.f32 out.f32\n", argv[0]); return 2; }
     const std::vector<float> in = readAll(argv[2]); std::vector<float> out;
     if (std::string(argv[1]) == "bsdf")
     {
@@ -57,6 +57,16 @@ int main(int argc, char** argv)
             o[32] = nonDelta; o[33] = float(count);
             float3 de, se; b.estimateSpecDiffBSDF(de, se, sd.N, sd.V);
             o[34] = de.x; o[35] = de.y; o[36] = de.z; o[37] = se.x; o[38] = se.y; o[39] = se.z;
+        }
+    }
+    else if (std::string(argv[1]) == "tonemap")
+    {   // Rtxpt/ToneMapper/ToneMapping.ps.hlsli:31-129: the six operators through toneMap().  8 floats in (rgb, operator, whiteMaxLuminance, whiteScale), 4 out (rgb, luminance)
+        const size_t n = in.size() / 8; out.assign(n * 4, 0.0f);
+        for (size_t i = 0; i < n; i++)
+        {
+            const float* u = &in[i * 8]; float* o = &out[i * 4];
+            gParams.toneMapOperator = uint(u[3]); gParams.whiteMaxLuminance = u[4]; gParams.whiteScale = u[5];
+            const float3 c = toneMap(float3(u[0], u[1], u[2])); o[0] = c.x; o[1] = c.y; o[2] = c.z; o[3] = calcLuminance(float3(u[0], u[1], u[2]));
         }
     }
     else if (std::string(argv[1]) == "spheres")

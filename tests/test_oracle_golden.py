@@ -218,3 +218,17 @@ def test_sphere_light_matches_reference_header_golden(oracle):
     same = (out.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(out) & np.isnan(ref))
     assert same.all(), same.mean(0)
     assert (ref[:, 21] > 0).mean() > 0.9 and (u[:, 7] > 0.5).mean() > 0.3 and ((ref[:, 18:21] == 0).all(1) & (u[:, 7] > 0.5)).mean() > 0.05        # spots exist and some viewers sit outside their cone
+
+
+def test_tone_mapping_operators_match_reference_shader_golden(oracle):
+    """Rtxpt/ToneMapper/ToneMapping.ps.hlsli compiled in place (tests/golden/make_tonemap_golden.py): Linear, Reinhard, ReinhardModified, HejiHableAlu, HableUc2 and Aces through
+    toneMap(), and calcLuminance - the oracle's operators (pt_tonemap.h, which the CUDA tone mapper reproduces byte for byte in tests/test_gpu_tonemap.py) are the reference's
+    bit for bit, NaN for NaN on black input."""
+    import ctypes as C
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "tonemap_golden.npz"))
+    u, ref = np.ascontiguousarray(g["tonemap_in"]), g["tonemap_out"]
+    L = oracle.lib(); L.oracle_tonemap_ops.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]; L.oracle_tonemap_ops.restype = None
+    out = np.empty_like(ref); L.oracle_tonemap_ops(u.ctypes.data, len(u), out.ctypes.data)
+    same = (out.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(out) & np.isnan(ref))
+    assert same.all(), same.mean(0)
+    assert all((u[:, 3] == op).sum() > 300 for op in range(6))
