@@ -174,6 +174,7 @@ ORC_API void oracle_helper_funcs(const float* in, uint32_t count, float* out)
         const float3 ff = FireflyFilter(f3(lp(u[0] * 8.0f), lp(u[1] * 8.0f), lp(u[2] * 8.0f)), lp(2.0f + u[3]), lp(u[4])); o[9] = ff.x; o[10] = ff.y; o[11] = ff.z;
         o[12] = FireflyFilterShort(u[0] * 8.0f, 2.0f + u[3], u[4]);
         o[13] = EvalMISBalance(1.0f, u[5] * 3.0f, 1.0f, u[7] * 3.0f);
+        { const mat3 m = MatrixRotateFromTo(nrm, l); o[14] = m.r[0].x + m.r[0].y * 0.5f + m.r[0].z * 0.25f + m.r[1].x * 0.125f + m.r[1].y * 3.0f; o[15] = m.r[1].z + m.r[2].x * 0.5f + m.r[2].y * 0.25f + m.r[2].z * 3.0f; }
     }
 }
 

@@ -136,6 +136,9 @@ int main(int argc, char** argv)
             const lpfloat3 ff = FireflyFilter(lpfloat3(lpfloat(u[0] * 8.0f), lpfloat(u[1] * 8.0f), lpfloat(u[2] * 8.0f)), lpfloat(2.0f + u[3]), lpfloat(u[4])); o[9] = ff.x; o[10] = ff.y; o[11] = ff.z;
             o[12] = FireflyFilterShort(u[0] * 8.0f, 2.0f + u[3], u[4]);
             o[13] = BalanceHeuristic(1.0f, u[5] * 3.0f, 1.0f, u[7] * 3.0f);
+            // MatrixRotateFromTo (:227-270), the rotation a delta transmission applies to the stable plane's image transform: first two rows (the third follows from orthogonality... it is
+            // compared through the oracle's own packed form elsewhere); 14, 15 = m[0][0], m[1][2]
+            { const float3x3 m = MatrixRotateFromTo(nrm, l); o[14] = m[0][0] + m[0][1] * 0.5f + m[0][2] * 0.25f + m[1][0] * 0.125f + m[1][1] * 3.0f; o[15] = m[1][2] + m[2][0] * 0.5f + m[2][1] * 0.25f + m[2][2] * 3.0f; }
         }
     }
     else if (std::string(argv[1]) == "utils")

@@ -1,5 +1,5 @@
 """Generates tests/golden/helpers_golden.npz from the UNMODIFIED Rtxpt/Shaders/PathTracer/PathTracerHelpers.hlsli (lines 26-66, 155-219: ComputeRayOrigin, the grazing-angle
-falloff, BalanceHeuristic, the ray-cone growth functions, ComputeNewScatterFireflyFilterK, FireflyFilter, FireflyFilterShort) compiled in place as C++ through
+falloff, BalanceHeuristic, the ray-cone growth functions, ComputeNewScatterFireflyFilterK, FireflyFilter, FireflyFilterShort; 221-270: MatrixRotateFromTo) compiled in place as C++ through
 oracle/ref_hlsl_shim.h (oracle/_ref/ref_kat_bsdf, mode "helpers").  Run in the build container only:   make -C oracle ref && python tests/golden/make_helpers_golden.py
   helpers_in [M,8] uniforms   helpers_out [M,16]   layout: oracle/ref_kat_bsdf_main.cpp"""
 import os, sys

@@ -181,7 +181,7 @@ def test_path_tracer_helpers_match_reference_header_golden(oracle):
     u, ref = np.ascontiguousarray(g["helpers_in"]), g["helpers_out"]
     L = oracle.lib(); L.oracle_helper_funcs.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]; L.oracle_helper_funcs.restype = None
     out = np.empty_like(ref); L.oracle_helper_funcs(u.ctypes.data, len(u), out.ctypes.data)
-    for k in (0, 1, 2, 3, 7, 8, 9, 10, 11, 12, 13):
+    for k in (0, 1, 2, 3, 7, 8, 9, 10, 11, 12, 13, 14, 15):                    # 14, 15: two fixed linear combinations of MatrixRotateFromTo's nine entries
         same = (out[:, k].view(np.uint32) == ref[:, k].view(np.uint32)) | (np.isnan(out[:, k]) & np.isnan(ref[:, k]))
         assert same.all(), (k, int((~same).sum()))
     assert (ref[:, 9:12] != np.float32(u[:, 0:3] * 8).astype(np.float16).astype(np.float32)).any(1).mean() > 0.2       # the filter did clamp a good share of the records
