@@ -235,6 +235,24 @@ ORC_API void oracle_tonemap_ops(const float* in, uint32_t count, float* out)
     }
 }
 
+// TexLODHelpers.hlsli as the oracle restates it (pt_scene.h), layout of ref_kat_bsdf_main.cpp's "texlod" mode: 40 floats in, 8 out (slot 6, addToSpreadAngle, is not restated as
+// a function: the path adds to the angle through RayCone::make directly)
+ORC_API void oracle_texlod_funcs(const float* in, uint32_t count, float* out)
+{
+    for (uint32_t i = 0; i < count; i++)
+    {
+        const float* u = in + size_t(i) * 40; float* o = out + size_t(i) * 8;
+        const float3 v[3] = { f3(u[0], u[1], u[2]), f3(u[3], u[4], u[5]), f3(u[6], u[7], u[8]) }; const float2 t[3] = { f2(u[9], u[10]), f2(u[11], u[12]), f2(u[13], u[14]) };
+        const float xf[12] = { u[15], u[16], u[17], 0.0f, u[18], u[19], u[20], 0.0f, u[21], u[22], u[23], 0.0f };
+        o[0] = computeRayConeTriangleLODValue(v, t, xf);
+        RayCone rc = RayCone::make(u[24], u[25]); o[1] = rc.getWidth(); o[2] = rc.getSpreadAngle();
+        rc = rc.propagateDistance(u[26]); o[3] = rc.getWidth();
+        const float3 dir = normalize(f3(u[27], u[28], u[29])), nrm = normalize(f3(u[30], u[31], u[32]));
+        o[4] = rc.computeLOD(o[0], dir, nrm, true); o[5] = rc.computeLOD(o[0], dir, nrm, false);
+        o[6] = RayCone::make(rc.getWidth(), rc.getSpreadAngle() + u[33]).getSpreadAngle(); o[7] = SafeLog2(u[34]);
+    }
+}
+
 ORC_API void* oracle_create(const RtxptSceneDesc* desc)
 {
     OracleCtx* c = new OracleCtx();

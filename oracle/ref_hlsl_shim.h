@@ -6,6 +6,7 @@
 // after every operation" (what a native 16-bit type does), f32tof16 / f16tof32 as IEEE round-to-nearest-even conversions.  Scalar arithmetic is IEEE binary32 without
 // contraction (-ffp-contract=off), the same contract as oracle/*.h, so that agreement between the oracle's restatement and this build is agreement of the formulas.
 #pragma once
+#include <cfloat>
 #include <cmath>
 #include <cstdint>
 #include <cstring>

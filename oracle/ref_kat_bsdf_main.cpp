@@ -30,7 +30,7 @@ float3 EnvironmentQuadLight::ToLocal(float3 worldDir) { return worldDir; }
 
 int main(int argc, char** argv)
 {
-    if (argc != 4) { fprintf(stderr, "usage: %s bsdf|funcs|utils|helpers|lights|spheres|tonemap in.f32 out.f32\n", argv[0]); return 2; }
+    if (argc != 4) { fprintf(stderr, "usage: %s bsdf|funcs|utils|helpers|lights|spheres|tonemap|texlod in.f32 out.f32\n", argv[0]); return 2; }
     const std::vector<float> in = readAll(argv[2]); std::vector<float> out;
     if (std::string(argv[1]) == "bsdf")
     {
@@ -57,6 +57,24 @@ int main(int argc, char** argv)
             o[32] = nonDelta; o[33] = float(count);
             float3 de, se; b.estimateSpecDiffBSDF(de, se, sd.N, sd.V);
             o[34] = de.x; o[35] = de.y; o[36] = de.z; o[37] = se.x; o[38] = se.y; o[39] = se.z;
+        }
+    }
+    else if (std::string(argv[1]) == "texlod")
+    {   // Rendering/Materials/TexLODHelpers.hlsli:40-161: the ray cone (fp16-packed width / spread angle), its propagation, the per-triangle LOD constant and computeLOD - what
+        // every material texture fetch of the path derives its MIP level from.  40 floats in, 8 out
+        const size_t n = in.size() / 40; out.assign(n * 8, 0.0f);
+        for (size_t i = 0; i < n; i++)
+        {
+            const float* u = &in[i * 40]; float* o = &out[i * 8];
+            float3 v[3] = { float3(u[0], u[1], u[2]), float3(u[3], u[4], u[5]), float3(u[6], u[7], u[8]) }; float2 t[3] = { float2(u[9], u[10]), float2(u[11], u[12]), float2(u[13], u[14]) };
+            const float3x3 M(u[15], u[16], u[17], u[18], u[19], u[20], u[21], u[22], u[23]);       // (float3x3)transform; the bridge passes its transpose and multiplies from the left
+            float3x3 Mt; for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) Mt[r][c] = M[c][r];
+            o[0] = computeRayConeTriangleLODValue(v, t, Mt);
+            RayCone rc = RayCone::make(u[24], u[25]); o[1] = rc.getWidth(); o[2] = rc.getSpreadAngle();
+            rc = rc.propagateDistance(u[26]); o[3] = rc.getWidth();
+            const float3 dir = normalize(float3(u[27], u[28], u[29])), nrm = normalize(float3(u[30], u[31], u[32]));
+            o[4] = rc.computeLOD(o[0], dir, nrm, true); o[5] = rc.computeLOD(o[0], dir, nrm, false);
+            rc = rc.addToSpreadAngle(u[33]); o[6] = rc.getSpreadAngle(); o[7] = SafeLog2(u[34]);
         }
     }
     else if (std::string(argv[1]) == "tonemap")

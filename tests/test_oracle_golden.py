@@ -232,3 +232,17 @@ def test_tone_mapping_operators_match_reference_shader_golden(oracle):
     same = (out.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(out) & np.isnan(ref))
     assert same.all(), same.mean(0)
     assert all((u[:, 3] == op).sum() > 300 for op in range(6))
+
+
+def test_ray_cone_texture_lod_matches_reference_header_golden(oracle):
+    """Rendering/Materials/TexLODHelpers.hlsli compiled in place (tests/golden/make_texlod_golden.py): the fp16-packed ray cone, its propagation over a segment, the per-triangle
+    LOD constant (texture-space over world-space area through the instance matrix) and computeLOD with and without the slope term - every material texture fetch of the path
+    takes its MIP level from these; bit for bit, including the clamped logarithm of degenerate texture triangles."""
+    import ctypes as C
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "texlod_golden.npz"))
+    u, ref = np.ascontiguousarray(g["texlod_in"]), g["texlod_out"]
+    L = oracle.lib(); L.oracle_texlod_funcs.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]; L.oracle_texlod_funcs.restype = None
+    out = np.empty_like(ref); L.oracle_texlod_funcs(u.ctypes.data, len(u), out.ctypes.data)
+    same = (out.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(out) & np.isnan(ref))
+    assert same.all(), same.mean(0)
+    assert (ref[:40, 0] < -60).all() and np.isfinite(ref).all()
