@@ -253,6 +253,24 @@ ORC_API void oracle_texlod_funcs(const float* in, uint32_t count, float* out)
     }
 }
 
+// InteriorList.hlsli as the oracle restates it (pt_path.h), layout of ref_kat_bsdf_main.cpp's "interior" mode: 12 crossings per record, 6 values after each
+ORC_API void oracle_interior_list(const float* in, uint32_t count, float* out)
+{
+    for (uint32_t i = 0; i < count; i++)
+    {
+        const float* u = in + size_t(i) * 48; float* o = out + size_t(i) * 72;
+        InteriorList il;
+        for (int k = 0; k < 12; k++)
+        {
+            const uint mat = uint(u[4 * k]), prio = uint(u[4 * k + 1]); const bool entering = u[4 * k + 2] != 0.0f; const uint probe = uint(u[4 * k + 3]);
+            const bool isTrue = il.isTrueIntersection(probe);
+            il.handleIntersection(mat, prio, entering);
+            const uint w[2] = { il.slots[0], il.slots[1] }; memcpy(o + 6 * k, w, 8);
+            o[6 * k + 2] = float(il.getTopNestedPriority()); o[6 * k + 3] = float(int(il.getTopMaterialID())); o[6 * k + 4] = float(int(il.getNextMaterialID())); o[6 * k + 5] = isTrue ? 1.0f : 0.0f;
+        }
+    }
+}
+
 ORC_API void* oracle_create(const RtxptSceneDesc* desc)
 {
     OracleCtx* c = new OracleCtx();

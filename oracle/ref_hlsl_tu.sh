@@ -48,7 +48,7 @@ echo '#define RTXPT_LP_TYPES_USE_16BIT_PRECISION 1      /* Sample.cpp:1017, the 
 echo 'float3 ComputeRayOrigin(float3 pos, float3 normal);      /* PathTracerHelpers.hlsli:29-42: ShadingData.hlsli names it before the helper ranges below define it */'
 for f in Config.h Utils/Math/MathConstants.hlsli Utils/Utils.hlsli:28-67 Utils/Utils.hlsli:68-92 Utils/Utils.hlsli:115-169 Utils/Utils.hlsli:193-198 Utils/Utils.hlsli:392-499 Utils/Utils.hlsli:510-517 Rendering/Materials/BxDFConfig.hlsli Rendering/Materials/LobeType.hlsli Scene/Material/MaterialData.hlsli \
          Utils/ColorHelpers.hlsli Utils/Math/MathHelpers.hlsli Rendering/Materials/Fresnel.hlsli Rendering/Materials/Microfacet.hlsli Rendering/Materials/IBSDF.hlsli \
-         Scene/ShadingData.hlsli Rendering/Materials/BxDF.hlsli Rendering/Materials/StandardBSDF.hlsli PathTracerHelpers.hlsli:26-66 PathTracerHelpers.hlsli:155-219 PathTracerHelpers.hlsli:221-270 Rendering/Materials/TexLODHelpers.hlsli:40-161 Utils/Packing.hlsli:16-51 Utils/Geometry.hlsli Lighting/PolymorphicLightPTConfig.h Lighting/PolymorphicLight.h Lighting/LightShaping.hlsli Lighting/PolymorphicLight.hlsli; do
+         Scene/ShadingData.hlsli Rendering/Materials/BxDF.hlsli Rendering/Materials/StandardBSDF.hlsli PathTracerHelpers.hlsli:26-66 PathTracerHelpers.hlsli:155-219 PathTracerHelpers.hlsli:221-270 Rendering/Materials/TexLODHelpers.hlsli:40-161 Rendering/Materials/InteriorList.hlsli Utils/Packing.hlsli:16-51 Utils/Geometry.hlsli Lighting/PolymorphicLightPTConfig.h Lighting/PolymorphicLight.h Lighting/LightShaping.hlsli Lighting/PolymorphicLight.hlsli; do
   case "$f" in
     *:*) range=${f#*:}; f=${f%%:*}; echo; echo "#line ${range%-*} \"$PT/$f\""; filter "$PT/$f" | sed -n "${range%-*},${range#*-}p" ;;       # a line range of a header whose other parts resist (Utils.hlsli: the lpfloat typedefs, Luminance / Average, LuminanceClamp, the octahedral encodings, EvalMIS, FastSqrt / FastACos, WeightedAverage; not: PackOrthoMatrix (matrix row swizzles; pinned through ref_kat_host instead), the debug text drawing, FastACosLp)
     *)   echo; echo "#line 1 \"$PT/$f\""; filter "$PT/$f" ;;

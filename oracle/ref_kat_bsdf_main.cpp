@@ -30,7 +30,7 @@ float3 EnvironmentQuadLight::ToLocal(float3 worldDir) { return worldDir; }
 
 int main(int argc, char** argv)
 {
-    if (argc != 4) { fprintf(stderr, "usage: %s bsdf|funcs|utils|helpers|lights|spheres|tonemap|texlod in.f32 out.f32\n", argv[0]); return 2; }
+    if (argc != 4) { fprintf(stderr, "usage: %s bsdf|funcs|utils|helpers|lights|spheres|tonemap|texlod|interior in.f32 out.f32\n", argv[0]); return 2; }
     const std::vector<float> in = readAll(argv[2]); std::vector<float> out;
     if (std::string(argv[1]) == "bsdf")
     {
@@ -57,6 +57,24 @@ int main(int argc, char** argv)
             o[32] = nonDelta; o[33] = float(count);
             float3 de, se; b.estimateSpecDiffBSDF(de, se, sd.N, sd.V);
             o[34] = de.x; o[35] = de.y; o[36] = de.z; o[37] = se.x; o[38] = se.y; o[39] = se.z;
+        }
+    }
+    else if (std::string(argv[1]) == "interior")
+    {   // Rendering/Materials/InteriorList.hlsli: the two-slot stack of nested dielectrics.  A record is a sequence of 12 surface crossings (material, nested priority, entering,
+        // probe priority); after each the packed slots and every query are written out (6 values per crossing; slots as bit patterns)
+        const size_t n = in.size() / 48; out.assign(n * 72, 0.0f);
+        for (size_t i = 0; i < n; i++)
+        {
+            const float* u = &in[i * 48]; float* o = &out[i * 72];
+            InteriorList il; il.slots = uint2(0u, 0u);
+            for (int k = 0; k < 12; k++)
+            {
+                const uint mat = uint(u[4 * k]), prio = uint(u[4 * k + 1]); const bool entering = u[4 * k + 2] != 0.0f; const uint probe = uint(u[4 * k + 3]);
+                const bool isTrue = il.isTrueIntersection(probe);                       // asked BEFORE the crossing is committed, as HandleHit does
+                il.handleIntersection(mat, prio, entering);
+                const uint w[2] = { il.slots.x, il.slots.y }; memcpy(o + 6 * k, w, 8);
+                o[6 * k + 2] = float(il.getTopNestedPriority()); o[6 * k + 3] = float(int(il.getTopMaterialID())); o[6 * k + 4] = float(int(il.getNextMaterialID())); o[6 * k + 5] = isTrue ? 1.0f : 0.0f;
+            }
         }
     }
     else if (std::string(argv[1]) == "texlod")

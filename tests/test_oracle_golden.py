@@ -246,3 +246,17 @@ def test_ray_cone_texture_lod_matches_reference_header_golden(oracle):
     same = (out.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(out) & np.isnan(ref))
     assert same.all(), same.mean(0)
     assert (ref[:40, 0] < -60).all() and np.isfinite(ref).all()
+
+
+def test_interior_list_matches_reference_header_golden(oracle):
+    """Rendering/Materials/InteriorList.hlsli compiled in place (tests/golden/make_interior_golden.py): the two-slot stack of nested dielectrics through 12 surface crossings per
+    record - well-formed enter / leave sequences as closed meshes produce them, and random ones (a full stack, leaving a medium that was never entered, priority 0) - slots,
+    top / next material, top priority and the true-intersection test agree after every crossing."""
+    import ctypes as C
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "interior_golden.npz"))
+    u, ref = np.ascontiguousarray(g["interior_in"]), g["interior_out"]
+    L = oracle.lib(); L.oracle_interior_list.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]; L.oracle_interior_list.restype = None
+    out = np.empty_like(ref); L.oracle_interior_list(u.ctypes.data, len(u), out.ctypes.data)
+    assert (out.view(np.uint32) == ref.view(np.uint32)).all()
+    r = ref.reshape(len(u), 12, 6)
+    assert (r[:2000, -1, 0].view(np.uint32) == 0).mean() > 0.5 and (r[..., 5] == 0).mean() > 0.05 and (r[..., 4] >= 0).mean() > 0.2        # stacks unwind; false intersections and two-deep stacks occur
