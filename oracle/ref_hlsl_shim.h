@@ -121,7 +121,7 @@ typedef vec2<float16_t> half2; typedef vec3<float16_t> half3; typedef float16_t 
 typedef vec2<uint> uint2; typedef vec3<uint> uint3; typedef vec4<uint> uint4;
 typedef vec2<int> int2; typedef vec3<int> int3;
 typedef vec2<bool> bool2; typedef vec3<bool> bool3;
-typedef uint16_t uint16_t1; typedef vec2<uint16_t> uint16_t2; typedef vec3<uint16_t> uint16_t3; typedef vec4<uint16_t> uint16_t4;
+typedef uint16_t uint16_t1; typedef vec2<uint> uint16_t2;      /* lpuint2 carries pixel coordinates only: kept 32-bit wide here */ typedef vec3<uint16_t> uint16_t3; typedef vec4<uint16_t> uint16_t4;
 
 // component-wise operators, non-template per type so that swizzle views convert implicitly
 #define RTXPT_SHIM_VEC_OPS(V2, V3, V4, S) \
@@ -242,3 +242,21 @@ inline int3 operator+(int3 a, int3 b) { return int3(a.x + b.x, a.y + b.y, a.z + 
 inline int3 select(bool3 c, int3 a, int3 b) { return int3(c.x ? a.x : b.x, c.y ? a.y : b.y, c.z ? a.z : b.z); }
 inline float select(bool c, float a, float b) { return c ? a : b; }
 inline float2 select(bool2 c, float a, float b) { return float2(c.x ? a : b, c.y ? a : b); } inline float3 select(bool3 c, float3 a, float3 b) { return float3(c.x ? a.x : b.x, c.y ? a.y : b.y, c.z ? a.z : b.z); }
+
+#define row_major        /* HLSL matrix layout qualifier */
+inline void DebugCross(float3, float, float4) {}      // debug drawing hooks of the lighting headers: no-ops
+// ---- resource views over host arrays (Lighting/LightSampler.hlsli, LightingTypes.hlsli): reads outside the bound range return 0 as a D3D buffer / texture does, writes outside
+// are dropped ----------------------------------------------------------------------------------------------------------------------------------------------------------------------
+template <typename T> struct StructuredBuffer { const T* p = nullptr; uint n = 0; T operator[](uint i) const { return i < n ? p[i] : T{}; } };
+template <typename T> struct Buffer { const T* p = nullptr; uint n = 0; T operator[](uint i) const { return i < n ? p[i] : T(0); } };
+template <typename T> struct Texture2D { const T* p = nullptr; uint w = 0, h = 0; T operator[](uint2 c) const { return (c.x < w && c.y < h) ? p[size_t(c.y) * w + c.x] : T(0); }
+    void GetDimensions(uint& ow, uint& oh) const { ow = w; oh = h; } T Load(int3 c) const { return (c.x >= 0 && c.y >= 0 && uint(c.x) < w && uint(c.y) < h) ? p[size_t(c.y) * w + c.x] : T(0); } };
+template <typename T> struct RWTexture3D { T* p = nullptr; mutable T sink = T(0); T& operator[](uint3) const { sink = T(0); return sink; } };
+template <typename T> struct RWTexture2D
+{
+    T* p = nullptr; uint w = 0, h = 0; mutable T sink = T(0);
+    T& operator[](uint2 c) const { if (c.x < w && c.y < h) return p[size_t(c.y) * w + c.x]; sink = T(0); return sink; }
+};
+inline uint2 operator+(uint2 a, uint2 b) { return uint2(a.x + b.x, a.y + b.y); } inline uint2 operator/(uint2 a, uint2 b) { return uint2(a.x / b.x, a.y / b.y); } inline uint2 operator/(uint2 a, uint b) { return uint2(a.x / b, a.y / b); }
+inline uint2 operator*(uint2 a, uint b) { return uint2(a.x * b, a.y * b); } inline uint2 operator*(uint2 a, uint2 b) { return uint2(a.x * b.x, a.y * b.y); } inline uint2 operator-(uint2 a, uint2 b) { return uint2(a.x - b.x, a.y - b.y); }
+inline uint clamp(uint x, int a, uint b) { const uint lo = uint(a); return x < lo ? lo : (x > b ? b : x); } inline uint clamp(uint x, uint a, uint b) { return x < a ? a : (x > b ? b : x); }

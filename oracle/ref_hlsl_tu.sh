@@ -28,7 +28,10 @@ filter() {
     -e 's/([(,][[:space:]]*)in[[:space:]]+/\1/g' \
     -e 's/\(([A-Z][A-Za-z0-9_]*)\)[[:space:]]*0([^.0-9a-zA-Z_]|$)/\1{}\2/g' \
     -e 's/\b(radiance|unpackedRadiance)\.xxx\b/float3(\1, \1, \1)/g' \
-    -e 's/\buniform[[:space:]]+bool\b/bool/g' \
+    -e 's/\buniform[[:space:]]+//g' \
+    -e 's/#ifdef[[:space:]]+__cplusplus/#if 0/' \
+    -e 's/#if[[:space:]]+defined\(__cplusplus\)/#if 0/' \
+    -e 's/\b(RTXPT_LIGHTING_SAMPLING_BUFFER_TILE_SIZE|width)\.xx\b/uint2(\1, \1)/g' \
     -e 's/\bthis\./this->/g' \
     -e 's/float\(0\)\.rrr/float3(0,0,0)/g' \
     -e 's/\b0\.xxx\b/float3(0,0,0)/g' \
@@ -48,7 +51,7 @@ echo '#define RTXPT_LP_TYPES_USE_16BIT_PRECISION 1      /* Sample.cpp:1017, the 
 echo 'float3 ComputeRayOrigin(float3 pos, float3 normal);      /* PathTracerHelpers.hlsli:29-42: ShadingData.hlsli names it before the helper ranges below define it */'
 for f in Config.h Utils/Math/MathConstants.hlsli Utils/Utils.hlsli:28-67 Utils/Utils.hlsli:68-92 Utils/Utils.hlsli:115-169 Utils/Utils.hlsli:193-198 Utils/Utils.hlsli:392-499 Utils/Utils.hlsli:510-517 Rendering/Materials/BxDFConfig.hlsli Rendering/Materials/LobeType.hlsli Scene/Material/MaterialData.hlsli \
          Utils/ColorHelpers.hlsli Utils/Math/MathHelpers.hlsli Rendering/Materials/Fresnel.hlsli Rendering/Materials/Microfacet.hlsli Rendering/Materials/IBSDF.hlsli \
-         Scene/ShadingData.hlsli Rendering/Materials/BxDF.hlsli Rendering/Materials/StandardBSDF.hlsli PathTracerHelpers.hlsli:26-66 PathTracerHelpers.hlsli:155-219 PathTracerHelpers.hlsli:221-270 Rendering/Materials/TexLODHelpers.hlsli:40-161 Rendering/Materials/InteriorList.hlsli Utils/Packing.hlsli:16-51 Utils/Geometry.hlsli Lighting/PolymorphicLightPTConfig.h Lighting/PolymorphicLight.h Lighting/LightShaping.hlsli Lighting/PolymorphicLight.hlsli; do
+         Scene/ShadingData.hlsli Rendering/Materials/BxDF.hlsli Rendering/Materials/StandardBSDF.hlsli PathTracerHelpers.hlsli:26-66 PathTracerHelpers.hlsli:155-219 PathTracerHelpers.hlsli:221-270 Rendering/Materials/TexLODHelpers.hlsli:40-161 Rendering/Materials/InteriorList.hlsli Utils/Packing.hlsli:16-51 Utils/Geometry.hlsli Lighting/PolymorphicLightPTConfig.h Lighting/PolymorphicLight.h Lighting/LightShaping.hlsli Lighting/PolymorphicLight.hlsli Lighting/LightingConfig.h Lighting/LightingTypes.hlsli Lighting/LightingAlgorithms.hlsli Lighting/LightSampler.hlsli; do
   case "$f" in
     *:*) range=${f#*:}; f=${f%%:*}; echo; echo "#line ${range%-*} \"$PT/$f\""; filter "$PT/$f" | sed -n "${range%-*},${range#*-}p" ;;       # a line range of a header whose other parts resist (Utils.hlsli: the lpfloat typedefs, Luminance / Average, LuminanceClamp, the octahedral encodings, EvalMIS, FastSqrt / FastACos, WeightedAverage; not: PackOrthoMatrix (matrix row swizzles; pinned through ref_kat_host instead), the debug text drawing, FastACosLp)
     *)   echo; echo "#line 1 \"$PT/$f\""; filter "$PT/$f" ;;
