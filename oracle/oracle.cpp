@@ -271,6 +271,41 @@ ORC_API void oracle_interior_list(const float* in, uint32_t count, float* out)
     }
 }
 
+// LightSampler.hlsli's sampler side as the oracle restates it (pt_neeat.h, pt_path.h), layout of ref_kat_bsdf_main.cpp's "sampler" mode: one 16-light, 2 x 2-tile scenario and
+// 8 queries per record (680 floats in, 8 x 16 out)
+ORC_API void oracle_sampler_funcs(const float* in, uint32_t count, float* out)
+{
+    for (uint32_t i = 0; i < count; i++)
+    {
+        const float* r = in + size_t(i) * 680; float* o = out + size_t(i) * 128;
+        LightTable lt; lt.samplingProxyCount = uint(r[0]); lt.proxyCounters.resize(16); lt.proxyIndices.resize(64); lt.lights.resize(16);
+        for (int k = 0; k < 16; k++) lt.proxyCounters[k] = uint(r[8 + k]);
+        for (int k = 0; k < 64; k++) lt.proxyIndices[k] = uint(r[24 + k]);
+        NeeatState ns; ns.init(8, 8); ns.jitter[0] = uint(r[1]); ns.jitter[1] = uint(r[2]); ns.localToGlobalSampleRatio = r[5]; ns.settings.screenSpaceVsWorldSpaceThreshold = r[6];
+        memcpy(ns.localSamplingBuffer.data(), r + 88, 512 * sizeof(uint));
+        const uint candidateSampleCount = uint(r[3]), fullSamples = uint(r[4]);
+        for (int q = 0; q < 8; q++)
+        {
+            const float* u = r + 600 + q * 10; float* d = o + q * 16;
+            const uint px = uint(u[0]), py = uint(u[1]), lightIndex = uint(u[3]), flags = uint(u[4]); const bool isSSC = (flags & 1u) != 0;
+            const uint tileAddress = LocalSamplingTilePos(ns, px, py);
+            float pdf = 0; uint idx = SampleGlobal(lt, u[2], pdf); d[0] = float(idx); d[1] = pdf;
+            idx = SampleLocal(ns, tileAddress, u[2], pdf); d[2] = float(idx); d[3] = pdf;
+            d[4] = SampleGlobalPDF(lt, lightIndex); d[5] = SampleLocalPDF(ns, tileAddress, lightIndex);
+            const uint localCount = isSSC ? ComputeCandidateSampleLocalCount(ns.localToGlobalSampleRatio, candidateSampleCount) : 0u, globalCount = candidateSampleCount - localCount;
+            d[6] = float(localCount); d[7] = float(globalCount);
+            d[8] = ComputeLightVsBSDF_MIS_ForBSDF(lt, lightIndex, lp(u[7]), u[8], fullSamples, &ns, (px << 16) | py, isSSC, candidateSampleCount);
+            LightSample s; s.LightIndex = lightIndex; s.SelectionPdf = u[9]; s.SolidAnglePdf = u[8]; s.FromLocalDistribution = (flags & 2u) != 0; s.LightSampleableByBSDF = (flags & 4u) != 0;
+            float thisPdf, otherPdf, thisCount, otherCount; ComputeLightSelectionPdfs(lt, &ns, tileAddress, s, localCount, globalCount, thisPdf, otherPdf, thisCount, otherCount);
+            d[9] = otherPdf; d[10] = thisCount; d[11] = otherCount;
+            d[12] = ComputeLightVsBSDF_MIS_ForLight(s, thisPdf, otherPdf, fullSamples, u[7]);
+            InsertFeedbackFromNEE(ns, lt, px, py, isSSC, lightIndex, u[5], u[6]);
+            d[13] = ns.feedback.weight[py * 8 + px]; memcpy(d + 14, &ns.feedback.candidate[py * 8 + px], 4);
+            d[15] = IsScreenSpaceCoherentHeuristic(ns.settings.screenSpaceVsWorldSpaceThreshold, u[8], u[5]) ? 1.0f : 0.0f;
+        }
+    }
+}
+
 ORC_API void* oracle_create(const RtxptSceneDesc* desc)
 {
     OracleCtx* c = new OracleCtx();

@@ -126,15 +126,16 @@ inline uint SampleLocal(const NeeatState& s, uint tileAddress, float rnd, float&
     return UnpackMiniListLight(v);
 }
 inline float SampleLocalPDF(const NeeatState& s, uint tileAddress, uint lightIndex)
-{   // LocalLightBinarySearch over the sorted tile list
+{   // LocalLightBinarySearch (LightingAlgorithms.hlsli:654-682) over the sorted tile list: exactly 8 steps and NO empty-range test.  A light below every key of the tile walks
+    // left for 7 steps; step 8 then reads the word just BEFORE the tile - the previous tile's last entry (and returns that tile's count if it happens to hold the light), or for
+    // tile 0 address 0x7FFFFFFF, which a D3D typed buffer reads as 0 = "light 0, count 1".  Pinned by tests/golden/sampler_golden.npz; reproduced, not corrected
     uint left = tileAddress, right = tileAddress + NEEAT_LOCAL_PROXY_COUNT - 1;
     for (uint i = 0; i < NEEAT_BINARY_SEARCH_STEPS; i++)
     {
-        const uint mid = (left + right) >> 1; const uint v = s.localSamplingBuffer[mid], key = UnpackMiniListLight(v);
+        const uint mid = (left + right) >> 1; const uint v = mid < s.localSamplingBuffer.size() ? s.localSamplingBuffer[mid] : 0u, key = UnpackMiniListLight(v);
         if (key < lightIndex) left = mid + 1;
-        else if (key > lightIndex) { if (mid == left) return 0.0f; right = mid - 1; }   // empty range: LightingAlgorithms.hlsli:677 would step below the tile (tile 0: index 0xFFFFFFFF, which D3D reads as 0); "not found" is the answer the search means
+        else if (key > lightIndex) right = mid - 1;
         else return float(UnpackMiniListCount(v)) / float(NEEAT_LOCAL_PROXY_COUNT);
-        if (left > right) return 0.0f;
     }
     return 0.0f;
 }

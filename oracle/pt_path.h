@@ -151,6 +151,16 @@ inline float3 envEvalLocal(const PathTracerCtx& x, float3 localDir, float lod)
 // ---- light sampler (global table only) ------------------------------------------------------------------------------------
 inline float SampleGlobalPDF(const LightTable& lt, uint lightIndex) { return float(lt.proxyCounters[lightIndex]) / float(lt.samplingProxyCount); }
 inline float EvalMISBalance(float n0, float p0, float n1, float p1) { float q0 = n0 * p0, q1 = n1 * p1; return saturate(q0 / (q0 + q1)); }   // Utils/Utils.hlsli:407-437
+// LightSampler::SampleGlobal (LightSampler.hlsli:112-122)
+inline uint SampleGlobal(const LightTable& lt, float rnd, float& pdf)
+{
+    const uint M = lt.samplingProxyCount;
+    const uint lightIndex = lt.proxyIndices[std::min(uint(rnd * float(M)), M - 1)];
+    pdf = float(lt.proxyCounters[lightIndex]) / float(M);
+    return lightIndex;
+}
+// LightSampler::IsScreenSpaceCoherentHeuristic (LightSampler.hlsli:45-49)
+inline bool IsScreenSpaceCoherentHeuristic(float threshold, float rayConeWidth, float totalPathLength) { return (rayConeWidth / totalPathLength) < threshold; }
 // neeat / pixel / misInfo: the local sampler the previous vertex drew from (LightSampler.hlsli:318-333: localCount > 0 only for screen-space-coherent vertices)
 inline float ComputeLightVsBSDF_MIS_ForBSDF(const LightTable& lt, uint lightIndex, float bsdfPdf, float solidAnglePdf, uint fullSampleCount, const NeeatState* neeat = nullptr, uint pathId = 0,
                                             bool isSSC = false, uint candidateSampleCount = 0)
@@ -165,6 +175,25 @@ inline float ComputeLightVsBSDF_MIS_ForBSDF(const LightTable& lt, uint lightInde
 
 struct LightSample { float3 Li = f3(0); float Distance = 0; float3 Direction = f3(0); uint LightIndex = 0xFFFFFFFFu; float SelectionPdf = 0, SolidAnglePdf = 0; bool LightSampleableByBSDF = false, FromLocalDistribution = false;
                      bool Valid() const { return Li.x > 0 || Li.y > 0 || Li.z > 0; } };
+// LightSampler::ComputeLightSelectionPdfs (LightSampler.hlsli:245-275): the pdf the OTHER sampler (global vs the pixel's tile) would have picked this light with
+inline void ComputeLightSelectionPdfs(const LightTable& lt, const NeeatState* neeat, uint tileAddress, const LightSample& s, uint localCount, uint globalCount, float& thisPdf, float& otherPdf,
+                                      float& thisCount, float& otherCount)
+{
+    thisPdf = s.SelectionPdf;
+    if (s.FromLocalDistribution) { otherPdf = SampleGlobalPDF(lt, s.LightIndex); thisCount = float(localCount); otherCount = float(globalCount); }
+    else
+    {
+        thisCount = float(globalCount);
+        if (localCount != 0) { otherPdf = SampleLocalPDF(*neeat, tileAddress, s.LightIndex); otherCount = float(localCount); }
+        else { otherPdf = 0; otherCount = 0; }
+    }
+}
+// LightSampler::ComputeLightVsBSDF_MIS_ForLight (LightSampler.hlsli:282-314; LightSamplingMISBoost() == 1)
+inline float ComputeLightVsBSDF_MIS_ForLight(const LightSample& s, float thisPdf, float otherPdf, uint fullSampleCount, float bsdfPdf)
+{
+    const float lightAvgPdf = (thisPdf + otherPdf) * float(fullSampleCount);
+    return EvalMISBalance(1, lightAvgPdf * s.SolidAnglePdf, 1, s.LightSampleableByBSDF ? bsdfPdf : 0.0f);
+}
 
 // ---- firefly filter (PathTracerHelpers.hlsli:183-219) ---------------------------------------------------------------------
 inline float ComputeRayConeSpreadAngleExpansionByScatterPDF(float pdf, float growthFactor = 0.3f)
@@ -377,7 +406,7 @@ inline NEEResult HandleNEE(const PathTracerCtx& x, const PathState& pre, const S
     const uint candidateSampleCount = x.c->NEECandidateSamples;
     const BSDFFrame frame = sd.frame();
     result.BSDFMISInfo.LightSamplingEnabled = true;
-    const bool isSSC = (pre.rayCone.getWidth() / pre.sceneLength) < (x.neeat ? x.neeat->settings.screenSpaceVsWorldSpaceThreshold : 0.3f);      // IsScreenSpaceCoherentHeuristic
+    const bool isSSC = IsScreenSpaceCoherentHeuristic(x.neeat ? x.neeat->settings.screenSpaceVsWorldSpaceThreshold : 0.3f, pre.rayCone.getWidth(), pre.sceneLength);
     result.BSDFMISInfo.LightSamplingIsSSC = isSSC;
     result.BSDFMISInfo.CandidateSamples = candidateSampleCount;
     result.BSDFMISInfo.FullSamples = fullSamples;
@@ -393,10 +422,9 @@ inline NEEResult HandleNEE(const PathTracerCtx& x, const PathState& pre, const S
         {
             const bool sampleIsLocal = i >= globalCount;
             float rnd = sg.Next1D();
-            uint M = lt.samplingProxyCount;
             uint lightIndex; float selectionPdf;
             if (sampleIsLocal) lightIndex = SampleLocal(*x.neeat, tileAddress, rnd, selectionPdf);
-            else { lightIndex = lt.proxyIndices[std::min(uint(rnd * float(M)), M - 1)]; selectionPdf = float(lt.proxyCounters[lightIndex]) / float(M); }
+            else lightIndex = SampleGlobal(lt, rnd, selectionPdf);
             const PolymorphicLightInfo& li = lt.lights[lightIndex];
             float2 interiorRnd; interiorRnd.x = sg.Next1D(); interiorRnd.y = sg.Next1D();
             PolymorphicLightSample ls = {};
@@ -445,13 +473,11 @@ inline NEEResult HandleNEE(const PathTracerCtx& x, const PathState& pre, const S
         {
             float fadeOut = (sd.shadowNoLFadeout > 0) ? saturate((dot(picked.Direction, sd.vertexN) - sd.shadowNoLFadeout) / (2.0f * sd.shadowNoLFadeout)) : 1.0f;
             // ComputeLightSelectionPdfs: the pdf the other sampler would have picked this light with
-            float thisPdf = picked.SelectionPdf, otherPdf = 0, thisCount = float(globalCount);
-            if (picked.FromLocalDistribution) { otherPdf = SampleGlobalPDF(lt, picked.LightIndex); thisCount = float(localCount); }
-            else if (localCount != 0) otherPdf = SampleLocalPDF(*x.neeat, tileAddress, picked.LightIndex);
+            float thisPdf, otherPdf, thisCount, otherCount;
+            ComputeLightSelectionPdfs(lt, x.neeat, tileAddress, picked, localCount, globalCount, thisPdf, otherPdf, thisCount, otherCount);
             float wrsMIS = EvalMISBalance(1, thisPdf, 1, otherPdf) / thisCount;
             float scatterPdfForDir = bsdf.evalPdf(frame, picked.Direction);
-            float lightAvgPdf = (thisPdf + otherPdf) * float(fullSamples);
-            float pathMIS = EvalMISBalance(1, lightAvgPdf * picked.SolidAnglePdf, 1, picked.LightSampleableByBSDF ? scatterPdfForDir : 0.0f);
+            float pathMIS = ComputeLightVsBSDF_MIS_ForLight(picked, thisPdf, otherPdf, fullSamples, scatterPdfForDir);
             float3 Li = picked.Li * (fadeOut * wrsMIS * pathMIS / float(fullSamples));
             float4 bsdfThp = bsdf.eval(frame, picked.Direction);
             float3 radiance = xyz(bsdfThp) * Li;

@@ -30,7 +30,7 @@ float3 EnvironmentQuadLight::ToLocal(float3 worldDir) { return worldDir; }
 
 int main(int argc, char** argv)
 {
-    if (argc != 4) { fprintf(stderr, "usage: %s bsdf|funcs|utils|helpers|lights|spheres|tonemap|texlod|interior in.f32 out.f32\n", argv[0]); return 2; }
+    if (argc != 4) { fprintf(stderr, "usage: %s bsdf|funcs|utils|helpers|lights|spheres|tonemap|texlod|interior|sampler in.f32 out.f32\n", argv[0]); return 2; }
     const std::vector<float> in = readAll(argv[2]); std::vector<float> out;
     if (std::string(argv[1]) == "bsdf")
     {
@@ -74,6 +74,53 @@ int main(int argc, char** argv)
                 il.handleIntersection(mat, prio, entering);
                 const uint w[2] = { il.slots.x, il.slots.y }; memcpy(o + 6 * k, w, 8);
                 o[6 * k + 2] = float(il.getTopNestedPriority()); o[6 * k + 3] = float(int(il.getTopMaterialID())); o[6 * k + 4] = float(int(il.getNextMaterialID())); o[6 * k + 5] = isTrue ? 1.0f : 0.0f;
+            }
+        }
+    }
+    else if (std::string(argv[1]) == "sampler")
+    {   // Lighting/LightSampler.hlsli (+ LightingTypes.hlsli's LightFeedbackReservoir, LightingAlgorithms.hlsli's LocalLightBinarySearch): the NEE-AT sampler side a path
+        // vertex calls.  A record is one small scenario - 16 lights' proxy counters, <= 64 global proxies, 2 x 2 tiles of 128 packed (light, count) tuples, an 8 x 8 cleared
+        // feedback image - and 8 queries run in order against it (the feedback inserts accumulate).  680 floats in (packed words as bit patterns), 8 x 16 out
+        const size_t n = in.size() / 680; out.assign(n * 128, 0.0f);
+        for (size_t i = 0; i < n; i++)
+        {
+            const float* r = &in[i * 680]; float* o = &out[i * 128];
+            LightingControlData cd; memset(&cd, 0, sizeof(cd));
+            cd.TotalLightCount = 16; cd.SamplingProxyCount = uint(r[0]); cd.LocalSamplingTileJitter = uint2(uint(r[1]), uint(r[2])); cd.LocalToGlobalSampleRatio = r[5];
+            cd.LocalSamplingResolution = uint2(2u, 2u); cd.TemporalFeedbackRequired = 1; cd.ScreenSpaceVsWorldSpaceThreshold = r[6];
+            const uint candidateSampleCount = uint(r[3]), fullSamples = uint(r[4]);
+            uint counters[16], indices[64], local[512]; PolymorphicLightInfo lights[16]; PolymorphicLightInfoEx lightsEx[16]; memset(lights, 0, sizeof(lights)); memset(lightsEx, 0, sizeof(lightsEx));
+            for (int k = 0; k < 16; k++) counters[k] = uint(r[8 + k]);
+            for (int k = 0; k < 64; k++) indices[k] = uint(r[24 + k]);
+            memcpy(local, r + 88, sizeof(local));
+            float fbWeight[64]; uint fbCand[64]; uint envLookup[1] = { 0u };
+            for (int k = 0; k < 64; k++) { fbWeight[k] = 0.0f; fbCand[k] = 0xFFFFFFFFu; }
+            StructuredBuffer<LightingControlData> bControl; bControl.p = &cd; bControl.n = 1;
+            StructuredBuffer<PolymorphicLightInfo> bLights; bLights.p = lights; bLights.n = 16;
+            StructuredBuffer<PolymorphicLightInfoEx> bLightsEx; bLightsEx.p = lightsEx; bLightsEx.n = 16;
+            Buffer<uint> bCounters; bCounters.p = counters; bCounters.n = 16;
+            Buffer<uint> bIndices; bIndices.p = indices; bIndices.n = cd.SamplingProxyCount;
+            Buffer<uint> bLocal; bLocal.p = local; bLocal.n = 512;
+            Texture2D<uint> tEnv; tEnv.p = envLookup; tEnv.w = tEnv.h = 1;
+            RWTexture2D<float> tWeight; tWeight.p = fbWeight; tWeight.w = tWeight.h = 8;
+            RWTexture2D<uint> tCand; tCand.p = fbCand; tCand.w = tCand.h = 8;
+            for (int q = 0; q < 8; q++)
+            {
+                const float* u = r + 600 + q * 10; float* d = o + q * 16;
+                const uint2 pixel = uint2((uint)u[0], (uint)u[1]); const uint lightIndex = uint(u[3]); const uint flags = uint(u[4]); const bool isSSC = (flags & 1u) != 0;
+                LightSampler ls = LightSampler::make(bControl, bLights, bLightsEx, bCounters, bIndices, bLocal, tEnv, tWeight, tCand, pixel, isSSC);
+                float pdf = 0; uint idx = ls.SampleGlobal(u[2], pdf); d[0] = float(idx); d[1] = pdf;
+                idx = ls.SampleLocal(u[2], pdf); d[2] = float(idx); d[3] = pdf;
+                d[4] = ls.SampleGlobalPDF(lightIndex); d[5] = ls.SampleLocalPDF(lightIndex);
+                uint localCount = 0, globalCount = 0; ls.GetCandidateSampleCounts(candidateSampleCount, localCount, globalCount); d[6] = float(localCount); d[7] = float(globalCount);
+                d[8] = ls.ComputeLightVsBSDF_MIS_ForBSDF(lightIndex, lpfloat(u[7]), u[8], candidateSampleCount, fullSamples);
+                LightSample s = LightSample::make(); s.LightIndex = lightIndex; s.SelectionPdf = u[9]; s.SolidAnglePdf = u[8]; s.FromLocalDistribution = (flags & 2u) != 0; s.LightSampleableByBSDF = (flags & 4u) != 0;
+                float thisPdf, otherPdf, thisCount, otherCount; ls.ComputeLightSelectionPdfs(s, localCount, globalCount, thisPdf, otherPdf, thisCount, otherCount);
+                d[9] = otherPdf; d[10] = thisCount; d[11] = otherCount;
+                d[12] = ls.ComputeLightVsBSDF_MIS_ForLight(float3(0, 0, 0), s, thisPdf, otherPdf, thisCount, otherCount, candidateSampleCount, fullSamples, u[7]);
+                ls.InsertFeedbackFromNEE(lightIndex, u[5], u[6]);
+                d[13] = fbWeight[pixel.y * 8 + pixel.x]; memcpy(d + 14, &fbCand[pixel.y * 8 + pixel.x], 4);
+                d[15] = LightSampler::IsScreenSpaceCoherentHeuristic(bControl, u[8], u[5]) ? 1.0f : 0.0f;
             }
         }
     }

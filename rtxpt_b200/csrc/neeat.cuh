@@ -105,17 +105,20 @@ PT_HD uint sampleLocal(const Params& p, uint tileAddress, float rnd, float& pdf)
     pdf = float(miniListCount(v)) / float(kLocalProxyCount);
     return miniListLight(v);
 }
+// LocalLightBinarySearch as the reference runs it: exactly 8 steps, no empty-range test.  A light below every key of the tile makes step 8 read the word just before the tile -
+// the previous tile's last entry (whose count comes back if it holds the light) or, for tile 0, address 0x7FFFFFFF, which a D3D typed buffer reads as 0 ("light 0, count 1");
+// the bounds test below is that D3D read.  Pinned against the reference header by tests/golden/sampler_golden.npz (oracle side)
 PT_HD float sampleLocalPdf(const Params& p, uint tileAddress, uint lightIndex)
 {
+    const uint total = p.tilesX * p.tilesY * kLocalProxyCount;
     uint left = tileAddress, right = tileAddress + kLocalProxyCount - 1;
     #pragma unroll
     for (uint i = 0; i < kBinarySearchSteps; i++)
     {
-        const uint mid = (left + right) >> 1; const uint v = p.localSamplingBuffer[mid], key = miniListLight(v);
+        const uint mid = (left + right) >> 1; const uint v = mid < total ? p.localSamplingBuffer[mid] : 0u, key = miniListLight(v);
         if (key < lightIndex) left = mid + 1;
-        else if (key > lightIndex) { if (mid == left) return 0.0f; right = mid - 1; }   // empty range: the reference's `mid - 1` would step below the tile (for tile 0: wrap to 0xFFFFFFFF; D3D returns 0 for that read, a raw pointer faults)
+        else if (key > lightIndex) right = mid - 1;
         else return float(miniListCount(v)) / float(kLocalProxyCount);
-        if (left > right) return 0.0f;
     }
     return 0.0f;
 }

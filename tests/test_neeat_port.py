@@ -58,15 +58,19 @@ def test_feedback_passes_equal_the_oracle(oracle, moving, boost):
         hits += a[2] > 0
     assert 0 < hits < 400                                                                   # the binary search both finds and misses
     st = o.neeat_get()
-    # a light below every key of the tile (light 0 is an environment slot; the lists hold emissive triangles only): the search must stop at the tile's first entry instead of
-    # stepping to `tileAddress - 1` - for tile (0,0) that index wraps to 0xFFFFFFFF, the round-1 GPU fault.  Every tile, both sides, against a brute-force count.
-    lists = st["local"].reshape(st["tiles"][1], st["tiles"][0], 128); jx, jy = st["jitter"]
+    # the binary search, every kind of tile, both sides, against a brute-force count - and, for a light below every key of the tile, against what the reference's search does
+    # (LightingAlgorithms.hlsli:654-682: 8 steps, no empty-range test; pinned by tests/golden/sampler_golden.npz): its last step reads the word just before the tile, i.e. the
+    # previous tile's last entry, or for tile (0,0) address 0x7FFFFFFF, which D3D reads as 0 = "light 0, count 1" (a raw pointer would fault: the round-1 GPU fault)
+    lists = st["local"].reshape(st["tiles"][1], st["tiles"][0], 128); flat = lists.reshape(-1); jx, jy = st["jitter"]
     for px, py in [(0, 0), (7 - jx, 0), (0, 7 - jy), (W - 1, H - 1), (W // 2, H // 2), (8, 0), (0, 8)]:
-        tile = lists[(py + jy) // 8, (px + jx) // 8]; keys = tile >> 9
-        for probe in (0, 1, int(keys.min()) - 1, int(keys.min()), int(keys.max()), int(keys.max()) + 1, n_lights - 1):
+        ty, tx = (py + jy) // 8, (px + jx) // 8; tile = lists[ty, tx]; keys = tile >> 9; base = (tx + ty * st["tiles"][0]) * 128
+        before = int(flat[base - 1]) if base > 0 else 0
+        for probe in (0, 1, int(keys.min()) - 1, int(keys.min()), int(keys.max()), int(keys.max()) + 1, n_lights - 1, before >> 9):
             a = np.zeros(3, np.float32); b = np.zeros(3, np.float32)
             assert Lo.oracle_neeat_sample_local(o.h, px, py, 0.5, probe, a.ctypes.data) == 0 and Le.neeat_emu_sample_local(port.h, px, py, 0.5, probe, b.ctypes.data) == 0
-            assert a[2] == b[2] == np.float32((keys == probe).sum() / 128.0), (px, py, probe, a, b)
+            expect = (keys == probe).sum() / 128.0
+            if probe < int(keys.min()) and (before >> 9) == probe: expect = ((before & 0x1FF) + 1) / 128.0
+            assert a[2] == b[2] == np.float32(expect), (px, py, probe, a, b)
     assert st["available"] and st["valid_feedback"] > 0.3 * W * H
     if moving: assert np.abs(g["motion"][..., 0].astype(np.float32)).mean() > 1.0                # the dolly really exercised reprojection (whole-pixel shifts)
     port.close(); o.close(); guide.close()

@@ -260,3 +260,22 @@ def test_interior_list_matches_reference_header_golden(oracle):
     assert (out.view(np.uint32) == ref.view(np.uint32)).all()
     r = ref.reshape(len(u), 12, 6)
     assert (r[:2000, -1, 0].view(np.uint32) == 0).mean() > 0.5 and (r[..., 5] == 0).mean() > 0.05 and (r[..., 4] >= 0).mean() > 0.2        # stacks unwind; false intersections and two-deep stacks occur
+
+
+def test_light_sampler_matches_reference_header_golden(oracle):
+    """Lighting/LightSampler.hlsli, LightingTypes.hlsli's LightFeedbackReservoir and LightingAlgorithms.hlsli's LocalLightBinarySearch compiled in place with CPU stand-ins for
+    the resource views (tests/golden/make_sampler_golden.py): 1200 scenarios of 16 lights, <= 64 global proxies, 2 x 2 tiles and 8 queries each.  SampleGlobal / SampleLocal,
+    both selection pdfs, the candidate split, the MIS weights on either side, the feedback reservoir after InsertFeedbackFromNEE and the coherence heuristic agree bit for bit -
+    including the binary search's behaviour for a light below every key of the tile (step 8 reads the previous tile's last entry; tile 0 reads out of range = "light 0, 1")."""
+    import ctypes as C
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sampler_golden.npz"))
+    u, ref = np.ascontiguousarray(g["sampler_in"]), g["sampler_out"]
+    L = oracle.lib(); L.oracle_sampler_funcs.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]; L.oracle_sampler_funcs.restype = None
+    out = np.empty_like(ref); L.oracle_sampler_funcs(u.ctypes.data, len(u), out.ctypes.data)
+    same = (out.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(out) & np.isnan(ref))          # 0 / 0 MIS weights (delta lobe against a light without proxies) are NaN on both sides
+    assert same.all()
+    r = ref.reshape(len(u), 8, 16); q = u[:, 600:].reshape(len(u), 8, 10)
+    quirk = r[1100:, [5, 7], 5]                                                                      # the generator's constructed cases: tile 0 / light 0, tile 1 / tile 0's last key
+    assert (quirk[:, 0] == np.float32(1 / 128)).all() and (quirk[:, 1] > 0).all()
+    assert (r[:1100, :, 5] > 0).mean() > 0.3 and (r[:1100, :, 5] == 0).mean() > 0.2 and (r[..., 6] > 0).mean() > 0.2 and (r[..., 13] > 0).mean() > 0.95
+    assert ((r[..., 14].view(np.uint32) & 0x7FFFFFFF) == q[..., 3].astype(np.uint32)).mean() > 0.5      # most inserts win their (mostly empty) reservoir
