@@ -72,7 +72,7 @@ inline bool operator<=(float16_t a, float16_t b) { return a.v <= b.v; } inline b
 template <typename T> struct vec2; template <typename T> struct vec3; template <typename T> struct vec4;
 // a swizzle is a view of the parent's storage: readable as a vector, and (for the non-repeating ones) assignable
 template <typename T, int A, int B> struct swz2 { T d[4]; operator vec2<T>() const; swz2& operator=(const vec2<T>& v); swz2& operator+=(const vec2<T>& v) { d[A] = d[A] + v.x; d[B] = d[B] + v.y; return *this; } };
-template <typename T, int A, int B, int C> struct swz3 { T d[4]; operator vec3<T>() const; swz3& operator=(const vec3<T>& v); };
+template <typename T, int A, int B, int C> struct swz3 { T d[4]; operator vec3<T>() const; swz3& operator=(const vec3<T>& v); swz3& operator+=(const vec3<T>& v) { d[A] = d[A] + v.x; d[B] = d[B] + v.y; d[C] = d[C] + v.z; return *this; } };
 
 template <typename T> struct vec2
 {
@@ -88,12 +88,13 @@ template <typename T> struct vec2
 };
 template <typename T> struct vec3
 {
-    union { struct { T x, y, z; }; struct { T r, g, b; }; swz2<T, 0, 1> xy; swz2<T, 1, 0> yx; swz3<T, 0, 1, 2> xyz; swz3<T, 0, 1, 2> rgb; };
+    union { struct { T x, y, z; }; struct { T r, g, b; }; swz2<T, 0, 1> xy; swz2<T, 1, 0> yx; swz2<T, 1, 2> yz; swz3<T, 0, 1, 2> xyz; swz3<T, 0, 1, 2> rgb; };
     vec3() : x(T(0)), y(T(0)), z(T(0)) {}
     vec3(T s) : x(s), y(s), z(s) {}
     template <typename U, typename std::enable_if<std::is_arithmetic<U>::value && !std::is_same<U, T>::value, int>::type = 0> vec3(U s) : x(T(s)), y(T(s)), z(T(s)) {}      // float3 v = 0;
     vec3(T a, T b, T c) : x(a), y(b), z(c) {}
     vec3(const vec2<T>& a, T c) : x(a.x), y(a.y), z(c) {}
+    vec3(T a, const vec2<T>& b) : x(a), y(b.x), z(b.y) {}
     template <typename U> vec3(const vec3<U>& o) : x(T(float(o.x))), y(T(float(o.y))), z(T(float(o.z))) {}     // float3 <-> float16_t3 convert implicitly in HLSL
     vec3(const vec3& o) : x(o.x), y(o.y), z(o.z) {}
     vec3& operator=(const vec3& o) { x = o.x; y = o.y; z = o.z; return *this; }
@@ -101,14 +102,17 @@ template <typename T> struct vec3
 };
 template <typename T> struct vec4
 {
-    union { struct { T x, y, z, w; }; struct { T r, g, b, a; }; swz2<T, 0, 1> xy; swz3<T, 0, 1, 2> xyz; swz3<T, 0, 1, 2> rgb; swz3<T, 0, 1, 3> xyw; swz3<T, 0, 2, 3> xzw; };
+    union { struct { T x, y, z, w; }; struct { T r, g, b, a; }; swz2<T, 0, 1> xy; swz2<T, 2, 3> zw; swz3<T, 0, 1, 2> xyz; swz3<T, 0, 1, 2> rgb; swz3<T, 0, 1, 3> xyw; swz3<T, 0, 2, 3> xzw; };
     vec4() : x(T(0)), y(T(0)), z(T(0)), w(T(0)) {}
     vec4(T s) : x(s), y(s), z(s), w(s) {}
     vec4(T a, T b, T c, T d) : x(a), y(b), z(c), w(d) {}
     vec4(const vec3<T>& a, T d) : x(a.x), y(a.y), z(a.z), w(d) {}
+    vec4(const vec2<T>& a, const vec2<T>& b) : x(a.x), y(a.y), z(b.x), w(b.y) {}
+    vec4(const vec2<T>& a, T c, T d) : x(a.x), y(a.y), z(c), w(d) {}
     vec4(const vec4& o) : x(o.x), y(o.y), z(o.z), w(o.w) {}
     vec4& operator=(const vec4& o) { x = o.x; y = o.y; z = o.z; w = o.w; return *this; }
     const vec4& xyzw_() const { return *this; }
+    T& operator[](int i) { return i == 0 ? x : (i == 1 ? y : (i == 2 ? z : w)); } const T& operator[](int i) const { return i == 0 ? x : (i == 1 ? y : (i == 2 ? z : w)); }
 };
 template <typename T, int A, int B> swz2<T, A, B>::operator vec2<T>() const { return vec2<T>(d[A], d[B]); }
 template <typename T, int A, int B> swz2<T, A, B>& swz2<T, A, B>::operator=(const vec2<T>& v) { d[A] = v.x; d[B] = v.y; return *this; }
@@ -120,7 +124,7 @@ typedef vec2<float16_t> float16_t2; typedef vec3<float16_t> float16_t3; typedef 
 typedef vec2<float16_t> half2; typedef vec3<float16_t> half3; typedef float16_t half;
 typedef vec2<uint> uint2; typedef vec3<uint> uint3; typedef vec4<uint> uint4;
 typedef vec2<int> int2; typedef vec3<int> int3;
-typedef vec2<bool> bool2; typedef vec3<bool> bool3;
+typedef vec2<bool> bool2; typedef vec3<bool> bool3; typedef vec4<bool> bool4;
 typedef uint16_t uint16_t1; typedef vec2<uint> uint16_t2;      /* lpuint2 carries pixel coordinates only: kept 32-bit wide here */ typedef vec3<uint16_t> uint16_t3; typedef vec4<uint16_t> uint16_t4;
 
 // component-wise operators, non-template per type so that swizzle views convert implicitly
@@ -151,7 +155,9 @@ inline float3 operator+(float16_t3 a, float3 b) { return float3(a) + b; } inline
 inline bool3 operator>(float3 a, float s) { return bool3(a.x > s, a.y > s, a.z > s); } inline bool3 operator>(float16_t3 a, float s) { return bool3(float(a.x) > s, float(a.y) > s, float(a.z) > s); }
 inline bool3 operator<(float3 a, float s) { return bool3(a.x < s, a.y < s, a.z < s); }
 inline bool3 operator>(float3 a, float3 b) { return bool3(a.x > b.x, a.y > b.y, a.z > b.z); }
+inline bool2 operator==(vec2<uint> a, vec2<uint> b) { return bool2(a.x == b.x, a.y == b.y); }
 inline bool2 operator>=(float2 a, float s) { return bool2(a.x >= s, a.y >= s); }
+inline bool3 operator==(float3 a, float s) { return bool3(a.x == s, a.y == s, a.z == s); } inline bool4 operator>(float4 a, int s) { return bool4(a.x > float(s), a.y > float(s), a.z > float(s), a.w > float(s)); } inline bool any(bool4 b) { return b.x || b.y || b.z || b.w; }
 inline bool any(bool3 b) { return b.x || b.y || b.z; } inline bool all(bool3 b) { return b.x && b.y && b.z; } inline bool any(bool2 b) { return b.x || b.y; } inline bool all(bool2 b) { return b.x && b.y; }
 inline bool any(float3 v) { return v.x != 0 || v.y != 0 || v.z != 0; }
 
@@ -160,7 +166,7 @@ struct float2x2 { union { float m[2][2]; struct { float _m00, _m01, _m10, _m11; 
 struct float3x3 { union { float m[3][3]; struct { float _m00, _m01, _m02, _m10, _m11, _m12, _m20, _m21, _m22; }; }; float3x3() {} float3x3(float a, float b, float c, float d, float e, float f, float g, float h, float i) { m[0][0] = a; m[0][1] = b; m[0][2] = c; m[1][0] = d; m[1][1] = e; m[1][2] = f; m[2][0] = g; m[2][1] = h; m[2][2] = i; }
                   float3x3(float3 r0, float3 r1, float3 r2) { m[0][0] = r0.x; m[0][1] = r0.y; m[0][2] = r0.z; m[1][0] = r1.x; m[1][1] = r1.y; m[1][2] = r1.z; m[2][0] = r2.x; m[2][1] = r2.y; m[2][2] = r2.z; }
                   float* operator[](int r) { return m[r]; } const float* operator[](int r) const { return m[r]; } };
-struct float3x4 { float m[3][4]; };          // constant-buffer member of ToneMappingConstants (not used by the pinned operators)
+struct float3x4 { float m[3][4]; explicit operator float3x3() const { return float3x3(m[0][0], m[0][1], m[0][2], m[1][0], m[1][1], m[1][2], m[2][0], m[2][1], m[2][2]); } };          // constant-buffer member of ToneMappingConstants (not used by the pinned operators)
 struct float2x3 { union { float m[2][3]; struct { float _m00, _m01, _m02, _m10, _m11, _m12; }; }; float2x3() {} float2x3(float a, float b, float c, float d, float e, float f) { _m00 = a; _m01 = b; _m02 = c; _m10 = d; _m11 = e; _m12 = f; } float* operator[](int r) { return m[r]; } const float* operator[](int r) const { return m[r]; } };
 typedef float3x3 float16_t3x3;
 inline float2 mul(const float2x2& M, float2 v) { return float2(M.m[0][0] * v.x + M.m[0][1] * v.y, M.m[1][0] * v.x + M.m[1][1] * v.y); }
@@ -194,6 +200,7 @@ inline float clamp(float x, float lo, float hi) { return min(max(x, lo), hi); } 
 inline float clamp(float x, int lo, int hi) { return clamp(x, float(lo), float(hi)); }
 inline float3 clamp(float3 v, float lo, float hi) { return float3(clamp(v.x, lo, hi), clamp(v.y, lo, hi), clamp(v.z, lo, hi)); }
 inline float3 clamp(float3 v, float3 lo, float3 hi) { return float3(clamp(v.x, lo.x, hi.x), clamp(v.y, lo.y, hi.y), clamp(v.z, lo.z, hi.z)); }
+inline float4 clamp(float4 v, float4 lo, float4 hi) { return float4(clamp(v.x, lo.x, hi.x), clamp(v.y, lo.y, hi.y), clamp(v.z, lo.z, hi.z), clamp(v.w, lo.w, hi.w)); }
 inline float2 clamp(float2 v, float lo, float hi) { return float2(clamp(v.x, lo, hi), clamp(v.y, lo, hi)); }
 inline float lerp(float a, float b, float t) { return a + (b - a) * t; }            // HLSL lerp: x + s ( y - x )
 inline float smoothstep(float a, float b, float x) { const float t = saturate((x - a) / (b - a)); return t * t * (3.0f - 2.0f * t); }      // HLSL smoothstep
@@ -234,6 +241,8 @@ inline uint countbits(uint v) { return uint(__builtin_popcount(v)); } inline uin
 // uint3 pieces of TriangleLight::Create / Store (PolymorphicLight.hlsli:478-515): masks, shifts, half conversion per component
 inline uint3 operator&(uint3 a, uint m) { return uint3(a.x & m, a.y & m, a.z & m); } inline uint3 operator>>(uint3 a, int n) { return uint3(a.x >> n, a.y >> n, a.z >> n); }
 inline uint3 operator<<(uint3 a, int n) { return uint3(a.x << n, a.y << n, a.z << n); } inline uint3 operator|(uint3 a, uint3 b) { return uint3(a.x | b.x, a.y | b.y, a.z | b.z); }
+inline float2 f16tof32(uint2 h) { return float2(f16tof32(h.x), f16tof32(h.y)); } inline uint2 f32tof16(float2 f) { return uint2(f32tof16(f.x), f32tof16(f.y)); }
+inline uint2& operator+=(uint2& a, uint2 b) { a.x += b.x; a.y += b.y; return a; }
 inline float3 f16tof32(uint3 h) { return float3(f16tof32(h.x), f16tof32(h.y), f16tof32(h.z)); } inline uint3 f32tof16(float3 f) { return uint3(f32tof16(f.x), f32tof16(f.y), f32tof16(f.z)); }
 inline float3 asfloat(uint3 v) { float3 r; std::memcpy(&r.x, &v.x, 4); std::memcpy(&r.y, &v.y, 4); std::memcpy(&r.z, &v.z, 4); return r; }
 // int3 pieces of ComputeRayOrigin (PathTracerHelpers.hlsli:29-42): bit casts per component, integer add / negate, per-component select
@@ -247,6 +256,19 @@ inline float2 select(bool2 c, float a, float b) { return float2(c.x ? a : b, c.y
 inline void DebugCross(float3, float, float4) {}      // debug drawing hooks of the lighting headers: no-ops
 // ---- resource views over host arrays (Lighting/LightSampler.hlsli, LightingTypes.hlsli): reads outside the bound range return 0 as a D3D buffer / texture does, writes outside
 // are dropped ----------------------------------------------------------------------------------------------------------------------------------------------------------------------
+inline uint InstanceIndex() { return 0u; } inline uint GeometryIndex() { return 0u; } inline uint PrimitiveIndex() { return 0u; }      // DXR intrinsics (only named by a TriangleHit::make overload the path does not call)
+typedef vec4<uint> uint4_shim_;
+inline vec4<uint> operator&(vec4<uint> a, uint m) { return vec4<uint>(a.x & m, a.y & m, a.z & m, a.w & m); } inline vec4<uint> operator>>(vec4<uint> a, int n) { return vec4<uint>(a.x >> n, a.y >> n, a.z >> n, a.w >> n); }
+inline vec4<uint> operator<<(vec4<uint> a, int n) { return vec4<uint>(a.x << n, a.y << n, a.z << n, a.w << n); } inline vec4<uint> operator|(vec4<uint> a, vec4<uint> b) { return vec4<uint>(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w); }
+inline float4 f16tof32(vec4<uint> h) { return float4(f16tof32(h.x), f16tof32(h.y), f16tof32(h.z), f16tof32(h.w)); } inline vec4<uint> f32tof16(float4 f) { return vec4<uint>(f32tof16(f.x), f32tof16(f.y), f32tof16(f.z), f32tof16(f.w)); }
+inline float4 clamp(float4 v, float lo, float hi) { return float4(clamp(v.x, lo, hi), clamp(v.y, lo, hi), clamp(v.z, lo, hi), clamp(v.w, lo, hi)); }
+template <typename T> struct RWStructuredBuffer { T* p = nullptr; uint n = 0; mutable T sink{}; T& operator[](uint i) const { if (i < n) return p[i]; sink = T{}; return sink; } };
+template <typename T> struct RWTexture2DArray { T* p = nullptr; uint w = 0, h = 0, d = 0; mutable T sink = T(0); T& operator[](uint3 c) const { if (c.x < w && c.y < h && c.z < d) return p[(size_t(c.z) * h + c.y) * w + c.x]; sink = T(0); return sink; } };
+struct SamplerState {};
+// a cube map the generator defines analytically: g_shimCubeSample( direction, lod ) (both sides of a golden evaluate the same closed form)
+extern float4 (*g_shimCubeSample)(float3 dir, float lod);
+template <typename T> struct TextureCube { T SampleLevel(SamplerState, float3 dir, float lod) const { return g_shimCubeSample(dir, lod); } };
+struct RayDesc { float3 Origin; float TMin; float3 Direction; float TMax; };     // the D3D built-in
 template <typename T> struct StructuredBuffer { const T* p = nullptr; uint n = 0; T operator[](uint i) const { return i < n ? p[i] : T{}; } };
 template <typename T> struct Buffer { const T* p = nullptr; uint n = 0; T operator[](uint i) const { return i < n ? p[i] : T(0); } };
 template <typename T> struct Texture2D { const T* p = nullptr; uint w = 0, h = 0; T operator[](uint2 c) const { return (c.x < w && c.y < h) ? p[size_t(c.y) * w + c.x] : T(0); }
@@ -259,4 +281,5 @@ template <typename T> struct RWTexture2D
 };
 inline uint2 operator+(uint2 a, uint2 b) { return uint2(a.x + b.x, a.y + b.y); } inline uint2 operator/(uint2 a, uint2 b) { return uint2(a.x / b.x, a.y / b.y); } inline uint2 operator/(uint2 a, uint b) { return uint2(a.x / b, a.y / b); }
 inline uint2 operator*(uint2 a, uint b) { return uint2(a.x * b, a.y * b); } inline uint2 operator*(uint2 a, uint2 b) { return uint2(a.x * b.x, a.y * b.y); } inline uint2 operator-(uint2 a, uint2 b) { return uint2(a.x - b.x, a.y - b.y); }
+inline uint min(uint a, int b) { return a < uint(b) ? a : uint(b); } inline uint max(uint a, int b) { return a > uint(b) ? a : uint(b); } inline uint min(int a, uint b) { return uint(a) < b ? uint(a) : b; }
 inline uint clamp(uint x, int a, uint b) { const uint lo = uint(a); return x < lo ? lo : (x > b ? b : x); } inline uint clamp(uint x, uint a, uint b) { return x < a ? a : (x > b ? b : x); }

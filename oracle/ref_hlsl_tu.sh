@@ -35,10 +35,16 @@ filter() {
     -e 's/\bthis\./this->/g' \
     -e 's/float\(0\)\.rrr/float3(0,0,0)/g' \
     -e 's/\b0\.xxx\b/float3(0,0,0)/g' \
+    -e 's/\b0\.xxxx\b/float4(0,0,0,0)/g' \
+    -e 's/\bHLF_MAX\.xxxx\b/float4(HLF_MAX,HLF_MAX,HLF_MAX,HLF_MAX)/g' \
+    -e 's/\bHLF_MAX\.xxx\b/float3(HLF_MAX,HLF_MAX,HLF_MAX)/g' \
     -e 's/\b1\.xxx\b/float3(1,1,1)/g' \
     -e 's/\b_alpha\.xx\b/float2(_alpha, _alpha)/g' \
     -e 's/\bpackedData\.x\b/packedData/g' \
+    -e 's/\?\(path\.GetBsdfScatterPdf\(\)\):\(0\.0\)/?((float)path.GetBsdfScatterPdf()):(0.0)/' \
+    -e 's/([A-Za-z_.]+\(\))\.xxx\b/float3((float)\1, (float)\1, (float)\1)/g' \
     -e 's/\)\.xxx\b/)/g' \
+    -e 's/\.rgba\b//g' \
     -e 's/\.xyzw\b//g' \
     -e 's/\? 0\.f : dataRoughness/? 0.f : (float)dataRoughness/' \
     -e 's/(^|[^A-Za-z0-9_.])([0-9]+\.[0-9]*([eE][-+]?[0-9]+)?|\.[0-9]+([eE][-+]?[0-9]+)?)([^0-9A-Za-z_.]|$)/\1\2f\5/g' \
@@ -49,12 +55,14 @@ filter() {
 echo '#include "ref_hlsl_shim.h"'
 echo '#define RTXPT_LP_TYPES_USE_16BIT_PRECISION 1      /* Sample.cpp:1017, the default */'
 echo 'float3 ComputeRayOrigin(float3 pos, float3 normal);      /* PathTracerHelpers.hlsli:29-42: ShadingData.hlsli names it before the helper ranges below define it */'
-for f in Config.h Utils/Math/MathConstants.hlsli Utils/Utils.hlsli:28-67 Utils/Utils.hlsli:68-92 Utils/Utils.hlsli:115-169 Utils/Utils.hlsli:193-198 Utils/Utils.hlsli:392-499 Utils/Utils.hlsli:510-517 Rendering/Materials/BxDFConfig.hlsli Rendering/Materials/LobeType.hlsli Scene/Material/MaterialData.hlsli \
+for f in Config.h Utils/Math/MathConstants.hlsli Utils/Utils.hlsli:28-67 Utils/Utils.hlsli:68-92 Utils/Utils.hlsli:115-169 Utils/Utils.hlsli:193-198 Utils/Utils.hlsli:272-370 Utils/Utils.hlsli:392-499 Utils/Utils.hlsli:510-517 Rendering/Materials/BxDFConfig.hlsli Rendering/Materials/LobeType.hlsli Scene/Material/MaterialData.hlsli \
          Utils/ColorHelpers.hlsli Utils/Math/MathHelpers.hlsli Rendering/Materials/Fresnel.hlsli Rendering/Materials/Microfacet.hlsli Rendering/Materials/IBSDF.hlsli \
-         Scene/ShadingData.hlsli Rendering/Materials/BxDF.hlsli Rendering/Materials/StandardBSDF.hlsli PathTracerHelpers.hlsli:26-66 PathTracerHelpers.hlsli:155-219 PathTracerHelpers.hlsli:221-270 Rendering/Materials/TexLODHelpers.hlsli:40-161 Rendering/Materials/InteriorList.hlsli Utils/Packing.hlsli:16-51 Utils/Geometry.hlsli Lighting/PolymorphicLightPTConfig.h Lighting/PolymorphicLight.h Lighting/LightShaping.hlsli Lighting/PolymorphicLight.hlsli Lighting/LightingConfig.h Lighting/LightingTypes.hlsli Lighting/LightingAlgorithms.hlsli Lighting/LightSampler.hlsli; do
+         Scene/ShadingData.hlsli Rendering/Materials/BxDF.hlsli Rendering/Materials/StandardBSDF.hlsli PathTracerHelpers.hlsli:26-66 PathTracerHelpers.hlsli:155-219 PathTracerHelpers.hlsli:221-270 Rendering/Materials/TexLODHelpers.hlsli:40-161 Rendering/Materials/InteriorList.hlsli Utils/Packing.hlsli:16-51 Utils/Packing.hlsli:194-265 Utils/Geometry.hlsli Lighting/PolymorphicLightPTConfig.h Lighting/PolymorphicLight.h Lighting/LightShaping.hlsli Lighting/PolymorphicLight.hlsli Lighting/LightingConfig.h Lighting/LightingTypes.hlsli Lighting/LightingAlgorithms.hlsli Lighting/LightSampler.hlsli PathTracerShared.h Utils/Math/Ray.hlsli Utils/NoiseAndSequences.hlsli:17-18 Utils/NoiseAndSequences.hlsli:58-96 Utils/NoiseAndSequences.hlsli:121-300 Utils/SampleGenerators.hlsli:16-41 Utils/StatelessSampleGenerators.hlsli Utils/SampleGenerators.hlsli:43-112 PathTracerHelpers.hlsli:318-319 Scene/HitInfoType.hlsli Scene/SceneTypes.hlsli Scene/HitInfo.hlsli PathState.hlsli PathPayload.hlsli StablePlanes.hlsli:1-318 StablePlanes.hlsli:336-371 PathTracerDebug.hlsli PathTracerTypes.hlsli:29-220 Lighting/EnvMap.hlsli:23-48 Lighting/EnvMap.hlsli:52-93 Scene/Material/HomogeneousVolumeData.hlsli Rendering/Volumes/HomogeneousVolumeSampler.hlsli local=ref_bridge_stub.h PathTracerNestedDielectrics.hlsli PathTracerStablePlanes.hlsli PathTracerNEE.hlsli PathTracer.hlsli:17-764; do
   case "$f" in
+    local=*) echo; echo "#line 1 \"${f#local=}\""; cat "${f#local=}" ;;
     *:*) range=${f#*:}; f=${f%%:*}; echo; echo "#line ${range%-*} \"$PT/$f\""; filter "$PT/$f" | sed -n "${range%-*},${range#*-}p" ;;       # a line range of a header whose other parts resist (Utils.hlsli: the lpfloat typedefs, Luminance / Average, LuminanceClamp, the octahedral encodings, EvalMIS, FastSqrt / FastACos, WeightedAverage; not: PackOrthoMatrix (matrix row swizzles; pinned through ref_kat_host instead), the debug text drawing, FastACosLp)
-    *)   echo; echo "#line 1 \"$PT/$f\""; filter "$PT/$f" ;;
+    *)   echo; echo "#line 1 \"$PT/$f\""; filter "$PT/$f"
+         if [ "$f" = Config.h ]; then echo; echo '#undef ENABLE_DEBUG_VIZUALISATIONS'; echo '#define ENABLE_DEBUG_VIZUALISATIONS 0   /* the debug overlays (a build switch of Config.h:63) write to UAVs the path does not read */'; fi ;;
   esac
 done
 # the tone-mapping operators (Rtxpt/ToneMapper/ToneMapping.ps.hlsli:31-129: calcLuminance ... toneMap) read a constant buffer: the shared header defines it, a global stands in

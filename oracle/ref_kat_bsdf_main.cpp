@@ -23,15 +23,15 @@ static void writeAll(const char* path, const std::vector<float>& v)
     fwrite(v.data(), 4, v.size(), f); fclose(f);
 }
 
-// EnvironmentQuadLight::ToWorld / ToLocal are left to the application by PolymorphicLight.hlsli (the bridge rotates by the environment-map transform); identity here - the quad-tree
-// lights are not part of these vectors
-float3 EnvironmentQuadLight::ToWorld(float3 localDir) { return localDir; }
-float3 EnvironmentQuadLight::ToLocal(float3 worldDir) { return worldDir; }
+// EnvironmentQuadLight::ToWorld / ToLocal are PathTracerNEE.hlsli's, over Bridge::CreateEnvMap(): the stub bridge's environment transform starts as the identity
+float4 (*g_shimCubeSample)(float3 dir, float lod) = nullptr;
+static void shimIdentityEnv() { memset(&g_bridge.env, 0, sizeof(g_bridge.env)); for (int k = 0; k < 3; k++) g_bridge.env.Transform.m[k][k] = g_bridge.env.InvTransform.m[k][k] = 1.0f; g_bridge.env.ColorMultiplier = float3(1, 1, 1); }
 
 int main(int argc, char** argv)
 {
     if (argc != 4) { fprintf(stderr, "usage: %s bsdf|funcs|utils|helpers|lights|spheres|tonemap|texlod|interior|sampler in.f32 out.f32\n", argv[0]); return 2; }
     const std::vector<float> in = readAll(argv[2]); std::vector<float> out;
+    shimIdentityEnv();
     if (std::string(argv[1]) == "bsdf")
     {
         const size_t n = in.size() / 36; out.assign(n * 40, 0.0f);
