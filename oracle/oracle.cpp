@@ -306,6 +306,67 @@ ORC_API void oracle_sampler_funcs(const float* in, uint32_t count, float* out)
     }
 }
 
+// PathTracer::HandleHit on one path vertex as the oracle restates it (pt_path.h: HandleHitSurface, HandleNEE, GenerateScatterRay, HandleRussianRoulette, nested dielectrics), layout
+// of ref_kat_bsdf_main.cpp's "hit" mode (920 floats in, 64 out).  The scene side is data, as behind the stub bridge there: the surface comes from the record, materials are the
+// IoR / absorption table, a shadow ray is answered by the same function of its bits (ShimVisibilityRule in oracle/ref_bridge_stub.h, restated here).  mode: 0 reference, 2 FILL
+struct HitMirrorVisibility { uint queries = 0; float3 o = f3(0), d = f3(0); float tMax = 0; bool last = false; };
+static bool hitMirrorVisibility(float3 o, float3 d, float tMax, void* user)
+{
+    HitMirrorVisibility& v = *static_cast<HitMirrorVisibility*>(user);
+    const uint h = asuint(o.x) ^ (asuint(o.y) >> 1) ^ (asuint(o.z) >> 2) ^ asuint(d.x) ^ (asuint(d.y) >> 1) ^ (asuint(d.z) >> 2) ^ asuint(tMax);
+    v.queries++; v.o = o; v.d = d; v.tMax = tMax; v.last = (h & 3u) != 0u;
+    return v.last;
+}
+ORC_API void oracle_hit_funcs(const float* in, uint32_t count, float* out, uint32_t mode)
+{
+    for (uint32_t i = 0; i < count; i++)
+    {
+        const float* r = in + size_t(i) * 920; float* o = out + size_t(i) * 64;
+        for (int k = 0; k < 64; k++) o[k] = 0.0f;
+        // surface
+        SurfaceData sf; ShadingData& sd = sf.sd;
+        sd.posW = f3(r[28], r[29], r[30]); sd.faceNCorrected = f3(r[31], r[32], r[33]); sd.V = -f3(r[23], r[24], r[25]); sd.N = f3(r[34], r[35], r[36]); sd.T = f3(r[37], r[38], r[39]);
+        sd.B = f3(r[40], r[41], r[42]); sd.vertexN = f3(r[43], r[44], r[45]); sd.frontFacing = r[46] != 0.0f; sd.nestedPriority = uint(r[47]); sd.activeLobes = uint(r[48]); sd.thinSurface = r[49] != 0.0f;
+        sd.psdExclude = r[50] != 0.0f; sd.psdBlockMotionVectorsAtSurface = r[57] != 0.0f; sd.psdDominantDeltaLobeP1 = uint(r[58]); sd.materialID = uint(r[51]); sd.IoR = r[52]; sd.shadowNoLFadeout = r[53];
+        sd.emission = f3(r[54], r[55], r[56]);
+        const float* b = r + 42;
+        sf.bsdf.data.diffuse = f3(b[18], b[19], b[20]); sf.bsdf.data.roughness = b[21]; sf.bsdf.data.specular = f3(b[22], b[23], b[24]); sf.bsdf.data.metallic = b[25];
+        sf.bsdf.data.transmission = f3(b[26], b[27], b[28]); sf.bsdf.data.diffuseTransmission = b[29]; sf.bsdf.data.specularTransmission = b[30]; sf.bsdf.data.eta = b[31];
+        sf.interiorIoR = r[74]; sf.neeTriangleLightIndex = r[75] < 0 ? 0xFFFFFFFFu : uint(r[75]); sf.neeAnalyticLightIndex = r[76] < 0 ? 0xFFFFFFFFu : uint(r[76]); sf.prevPosW = f3(r[77], r[78], r[79]);
+        // constants, materials
+        RtxptPathTracerConstants c; memset(&c, 0, sizeof(c));
+        c.imageWidth = c.imageHeight = 8; c.bounceCount = uint(r[80]); c.diffuseBounceCount = uint(r[81]); c.NEEEnabled = 1; c.NEEType = 2; c.NEECandidateSamples = uint(r[83]); c.NEEFullSamples = uint(r[84]);
+        c.fireflyFilterThreshold = r[85]; c.enableRussianRoulette = 1; c.enableLDSamplerForBSDF = 1; c.nestedDielectricsQuality = 1; c.EnvironmentMapDiffuseSampleMIPLevel = r[93]; c.NEEATFeedback = 1;
+        for (int k = 0; k < 3; k++) { c.envMap.Transform[k * 4 + k] = 1.0f; c.envMap.InvTransform[k * 4 + k] = 1.0f; c.envMap.ColorMultiplier[k] = 1.0f; }
+        RtxptMaterialData mats[8]; memset(mats, 0, sizeof(mats));
+        for (int m = 0; m < 8; m++) { mats[m].IoR = r[96 + m]; for (int k = 0; k < 3; k++) mats[m].VolumeAttenuationColor[k] = r[104 + 3 * m + k]; mats[m].VolumeAttenuationDistance = r[128 + m]; }
+        RtxptSceneDesc desc; memset(&desc, 0, sizeof(desc)); desc.materials = mats; desc.materialCount = 8;
+        Scene sc; sc.desc = &desc;
+        // lights
+        LightTable lt; lt.samplingProxyCount = uint(r[90]); lt.proxyCounters.resize(16); lt.proxyIndices.resize(64); lt.lights.resize(16); lt.lightsEx.resize(16); lt.exBase = 0; lt.analyticLightCount = 16;
+        for (int k = 0; k < 16; k++) lt.proxyCounters[k] = uint(r[136 + k]);
+        for (int k = 0; k < 64; k++) lt.proxyIndices[k] = uint(r[152 + k]);
+        for (int k = 0; k < 16; k++) { memcpy(&lt.lights[k], r + 728 + 12 * k, 32); memcpy(&lt.lightsEx[k], r + 728 + 12 * k + 8, 16); }
+        NeeatState ns; ns.init(8, 8); ns.jitter[0] = uint(r[88]); ns.jitter[1] = uint(r[89]); ns.localToGlobalSampleRatio = r[86]; ns.settings.screenSpaceVsWorldSpaceThreshold = r[91];
+        ns.temporalFeedbackRequired = r[92] != 0.0f; memcpy(ns.localSamplingBuffer.data(), r + 216, 512 * sizeof(uint));
+        // the vertex
+        HitMirrorVisibility vis;
+        PathTracerCtx x; x.scene = &sc; x.bvh = nullptr; x.lights = &lt; x.c = &c; x.sampleIndex = uint(r[82]); x.stats = nullptr; x.mode = mode; x.neeat = &ns;
+        x.visibilityOverride = hitMirrorVisibility; x.visibilityUser = &vis; x.noisyRadianceAttenuationOverride = r[87];
+        uint payload[20]; memcpy(payload, r, 80);
+        PathState path = unpackPayload(payload); const uint payloadIn14 = payload[14];
+        const float3 rayOrigin = f3(r[20], r[21], r[22]), rayDir = f3(r[23], r[24], r[25]);
+        UpdatePathTravelled(path, r[26]);
+        HandleHitSurface(x, path, rayOrigin, rayDir, r[26], sf);
+        packPayload(path, payload); memcpy(o, payload, 80);
+        o[20] = float(vis.queries); o[21] = vis.o.x; o[22] = vis.o.y; o[23] = vis.o.z; o[24] = vis.d.x; o[25] = vis.d.y; o[26] = vis.d.z; o[27] = vis.tMax; o[28] = vis.last ? 1.0f : 0.0f;
+        const bool rejectedFalseHit = path.getCounter(CTR_RejectedHits) != ((payloadIn14 >> 8) & 0xFFu);
+        if (mode == MODE_REFERENCE && !rejectedFalseHit) { o[29] = 1.0f; o[30] = path.sceneLength; }      // Bridge::ExportSurface( path, surface, path.GetSceneLength() ): once per accepted hit
+        const uint px = (path.id >> 16) & 7u, py = path.id & 7u;
+        o[39] = ns.feedback.weight[py * 8 + px]; memcpy(o + 40, &ns.feedback.candidate[py * 8 + px], 4);
+    }
+}
+
 ORC_API void* oracle_create(const RtxptSceneDesc* desc)
 {
     OracleCtx* c = new OracleCtx();

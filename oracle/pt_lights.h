@@ -348,7 +348,8 @@ struct LightTable
     bool envEnabled = false;
     std::vector<PolymorphicLightInfoEx> lightsEx;      // analytic lights only: light index - ENVQT_TOTAL
     uint analyticLightCount = 0;
-    PolymorphicLightInfoEx exOf(uint lightIndex) const { uint k = lightIndex - ENVQT_TOTAL; return k < analyticLightCount ? lightsEx[k] : PolymorphicLightInfoEx(); }
+    uint exBase = ENVQT_TOTAL;                              // first light with an Extended record (the known-answer mirrors of oracle.cpp index a 16-light table from 0)
+    PolymorphicLightInfoEx exOf(uint lightIndex) const { uint k = lightIndex - exBase; return k < analyticLightCount ? lightsEx[k] : PolymorphicLightInfoEx(); }
     uint importanceMipCount = 0;
     bool IsEmpty() const { return samplingProxyCount == 0; }
 };

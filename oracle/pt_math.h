@@ -66,7 +66,7 @@ inline float4 operator+(float4 a, float4 b) { return {a.x + b.x, a.y + b.y, a.z 
 inline float4 operator*(float4 a, float b)  { return {a.x * b, a.y * b, a.z * b, a.w * b}; }
 inline float3 xyz(float4 a) { return {a.x, a.y, a.z}; }
 
-inline float saturate(float x) { return std::min(std::max(x, 0.0f), 1.0f); }     // NaN -> 0 like HLSL
+inline float saturate(float x) { return std::min(std::max(0.0f, x), 1.0f); }     // NaN -> 0 like HLSL (std::max keeps its FIRST argument when the comparison fails)
 inline float3 saturate(float3 v) { return {saturate(v.x), saturate(v.y), saturate(v.z)}; }
 inline float clampf(float x, float a, float b) { return std::min(std::max(x, a), b); }
 inline float3 clamp3(float3 v, float a, float b) { return {clampf(v.x, a, b), clampf(v.y, a, b), clampf(v.z, a, b)}; }

@@ -115,7 +115,10 @@ struct PathTracerCtx
     const RealtimeTargets* sp = nullptr;
     // NEE-AT temporal feedback + local samplers (pt_neeat.h); null = the global-table-only tier (RtxptPathTracerConstants::NEEATFeedback == 0)
     NeeatState* neeat = nullptr;
-    float noisyRadianceAttenuation() const { return 1.0f / float(sp->rt->subSampleCount); }      // Bridge::getNoisyRadianceAttenuation = invSubSampleCount (BridgeDonut:515-523)
+    // test hook (oracle.cpp's known-answer mirrors): answers a shadow ray instead of the BVH, as the stub bridge of oracle/ref_bridge_stub.h does for the reference's code
+    bool (*visibilityOverride)(float3 origin, float3 dir, float tMax, void* user) = nullptr; void* visibilityUser = nullptr;
+    float noisyRadianceAttenuationOverride = 0.0f;
+    float noisyRadianceAttenuation() const { return noisyRadianceAttenuationOverride != 0.0f ? noisyRadianceAttenuationOverride : 1.0f / float(sp->rt->subSampleCount); }      // Bridge::getNoisyRadianceAttenuation = invSubSampleCount (BridgeDonut:515-523)
 };
 struct GuideOut { float depth; uint throughput; float motion[3]; };
 
@@ -466,8 +469,12 @@ inline NEEResult HandleNEE(const PathTracerCtx& x, const PathState& pre, const S
             float faceSide = dot(sd.N, picked.Direction) >= 0 ? 1.0f : -1.0f;
             float3 o = ComputeRayOrigin(sd.posW, sd.faceNCorrected * faceSide);
             if (x.stats) x.stats->shadowRays++;
-            Hit h = x.bvh->trace(*x.scene, o, picked.Direction, 0.0f, picked.Distance * 0.9985f, true, x.stats ? &x.stats->nodeVisits : nullptr, x.stats ? &x.stats->triTests : nullptr);
-            visible = !h.valid();
+            if (x.visibilityOverride) visible = x.visibilityOverride(o, picked.Direction, picked.Distance * 0.9985f, x.visibilityUser);
+            else
+            {
+                Hit h = x.bvh->trace(*x.scene, o, picked.Direction, 0.0f, picked.Distance * 0.9985f, true, x.stats ? &x.stats->nodeVisits : nullptr, x.stats ? &x.stats->triTests : nullptr);
+                visible = !h.valid();
+            }
         }
         if (visible)
         {
@@ -504,11 +511,17 @@ inline NEEResult HandleNEE(const PathTracerCtx& x, const PathState& pre, const S
 
 // ---- hit (PathTracer.hlsli:505-762) --------------------------------------------------------------------------------------------
 inline void StablePlanesHandleHit(const PathTracerCtx& x, PathState& path, float3 rayOrigin, float3 rayDir, float rayTCurrent, const SurfaceData& surfaceData, bool pathStopping);
+inline void HandleHitSurface(const PathTracerCtx& x, PathState& path, float3 rayOrigin, float3 rayDir, float rayTCurrent, SurfaceData surface);
 inline void HandleHit(const PathTracerCtx& x, PathState& path, float3 rayOrigin, float3 rayDir, float rayTCurrent, const Tri& tri, float2 barycentrics)
 {
-    const bool build = x.mode == MODE_BUILD_STABLE_PLANES;
     UpdatePathTravelled(path, rayTCurrent);
-    SurfaceData surface = loadSurface(*x.scene, tri.instanceIndex, tri.geometryIndex, tri.primitiveIndex, barycentrics, rayDir, path.rayCone, x.c->texLODBias, path.getVertexIndex(), path.id >> 16, path.id & 0xFFFF, x.sampleIndex);
+    HandleHitSurface(x, path, rayOrigin, rayDir, rayTCurrent, loadSurface(*x.scene, tri.instanceIndex, tri.geometryIndex, tri.primitiveIndex, barycentrics, rayDir, path.rayCone, x.c->texLODBias, path.getVertexIndex(),
+                                                                         path.id >> 16, path.id & 0xFFFF, x.sampleIndex));
+}
+// PathTracer::HandleHit after Bridge::loadSurface (PathTracer.hlsli:517-763); the path has been advanced to this vertex (UpdatePathTravelled)
+inline void HandleHitSurface(const PathTracerCtx& x, PathState& path, float3 rayOrigin, float3 rayDir, float rayTCurrent, SurfaceData surface)
+{
+    const bool build = x.mode == MODE_BUILD_STABLE_PLANES;
     const uint ndq = x.c->nestedDielectricsQuality;
     if (ndq > 0 && !path.interiorList.isEmpty())
     {   // homogeneous absorption (BridgeDonut:871-887, HomogeneousVolumeSampler::evalTransmittance)

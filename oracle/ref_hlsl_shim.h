@@ -185,7 +185,7 @@ inline float2x3 mul(const float2x2&, const float2x3&);
 // ---- intrinsics ----------------------------------------------------------------------------------------------------------------------------------------------------
 // scalar overloads spelled out so that HLSL's mixed int / float / double literals resolve to binary32 as they do in the shader
 #define RTXPT_SHIM_MINMAX(F, OP) \
-    inline float F(float a, float b) { return (a OP b) ? a : b; } inline float F(float a, int b) { return F(a, float(b)); } inline float F(int a, float b) { return F(float(a), b); } \
+    inline float F(float a, float b) { return (b != b) ? a : ((a != a) ? b : ((a OP b) ? a : b)); } /* DXIL FMin / FMax: a NaN operand loses */ inline float F(float a, int b) { return F(a, float(b)); } inline float F(int a, float b) { return F(float(a), b); } \
     inline float F(float a, double b) { return F(a, float(b)); } inline float F(double a, float b) { return F(float(a), b); } inline int F(int a, int b) { return (a OP b) ? a : b; } inline uint F(uint a, uint b) { return (a OP b) ? a : b; } \
     inline float F(float16_t a, float b) { return F(float(a), b); } inline float F(float a, float16_t b) { return F(a, float(b)); } inline float16_t F(float16_t a, float16_t b) { return (a.v OP b.v) ? a : b; }
 RTXPT_SHIM_MINMAX(min, <)
@@ -194,7 +194,7 @@ inline float2 min(float2 a, float2 b) { return float2(min(a.x, b.x), min(a.y, b.
 inline float3 min(float3 a, float3 b) { return float3(min(a.x, b.x), min(a.y, b.y), min(a.z, b.z)); } inline float3 max(float3 a, float3 b) { return float3(max(a.x, b.x), max(a.y, b.y), max(a.z, b.z)); }
 inline float3 max(float3 a, float b) { return max(a, float3(b)); } inline float3 min(float3 a, float b) { return min(a, float3(b)); }
 inline float2 max(float2 a, float b) { return max(a, float2(b)); } inline float2 min(float2 a, float b) { return min(a, float2(b)); }
-inline float saturate(float x) { return x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x); } inline float saturate(double x) { return saturate(float(x)); }
+inline float saturate(float x) { return (x != x) ? 0.0f : (x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x)); } /* DXIL Saturate: NaN -> 0 */ inline float saturate(double x) { return saturate(float(x)); }
 inline float3 saturate(float3 v) { return float3(saturate(v.x), saturate(v.y), saturate(v.z)); } inline float2 saturate(float2 v) { return float2(saturate(v.x), saturate(v.y)); }
 inline float clamp(float x, float lo, float hi) { return min(max(x, lo), hi); } inline float clamp(float x, int lo, float hi) { return clamp(x, float(lo), hi); } inline float clamp(float x, float lo, int hi) { return clamp(x, lo, float(hi)); }
 inline float clamp(float x, int lo, int hi) { return clamp(x, float(lo), float(hi)); }

@@ -54,10 +54,29 @@ filter() {
 }
 echo '#include "ref_hlsl_shim.h"'
 echo '#define RTXPT_LP_TYPES_USE_16BIT_PRECISION 1      /* Sample.cpp:1017, the default */'
+# the switches Sample::FillPTPipelineGlobalMacros (Sample.cpp:988-1037) passes to every path-tracer shader, at the UI's defaults (SampleUI.h:181-220); the NEE sample counts stay
+# undefined so that PathTracerNEE.hlsli reads them from the constant buffer (its #ifdef arms are otherwise identical).  PATH_TRACER_MODE comes from the compiler command line
+cat <<'MACROS'
+#define PT_ENABLE_RUSSIAN_ROULETTE 1
+#define PT_NEE_ENABLED 1
+#define PT_USE_RESTIR_DI 0
+#define PT_USE_RESTIR_GI 0
+#define RTXPT_USE_APPROXIMATE_MIS 0
+#define RTXPT_DISCARD_NON_NEE_LIGHTING 0
+#define RTXPT_DISCARD_NEE_LIGHTING 0
+#define RTXPT_FIREFLY_FILTER 1
+#define RTXPT_ACTIVE_STABLE_PLANE_COUNT 3
+#define RTXPT_NESTED_DIELECTRICS_QUALITY 1
+#define RTXPT_ENABLE_LOW_DISCREPANCY_SAMPLER_FOR_BSDF 1
+#define NON_PATH_TRACING_PASS 0
+#ifndef PATH_TRACER_MODE
+#define PATH_TRACER_MODE 0
+#endif
+MACROS
 echo 'float3 ComputeRayOrigin(float3 pos, float3 normal);      /* PathTracerHelpers.hlsli:29-42: ShadingData.hlsli names it before the helper ranges below define it */'
 for f in Config.h Utils/Math/MathConstants.hlsli Utils/Utils.hlsli:28-67 Utils/Utils.hlsli:68-92 Utils/Utils.hlsli:115-169 Utils/Utils.hlsli:193-198 Utils/Utils.hlsli:272-370 Utils/Utils.hlsli:392-499 Utils/Utils.hlsli:510-517 Rendering/Materials/BxDFConfig.hlsli Rendering/Materials/LobeType.hlsli Scene/Material/MaterialData.hlsli \
          Utils/ColorHelpers.hlsli Utils/Math/MathHelpers.hlsli Rendering/Materials/Fresnel.hlsli Rendering/Materials/Microfacet.hlsli Rendering/Materials/IBSDF.hlsli \
-         Scene/ShadingData.hlsli Rendering/Materials/BxDF.hlsli Rendering/Materials/StandardBSDF.hlsli PathTracerHelpers.hlsli:26-66 PathTracerHelpers.hlsli:155-219 PathTracerHelpers.hlsli:221-270 Rendering/Materials/TexLODHelpers.hlsli:40-161 Rendering/Materials/InteriorList.hlsli Utils/Packing.hlsli:16-51 Utils/Packing.hlsli:194-265 Utils/Geometry.hlsli Lighting/PolymorphicLightPTConfig.h Lighting/PolymorphicLight.h Lighting/LightShaping.hlsli Lighting/PolymorphicLight.hlsli Lighting/LightingConfig.h Lighting/LightingTypes.hlsli Lighting/LightingAlgorithms.hlsli Lighting/LightSampler.hlsli PathTracerShared.h Utils/Math/Ray.hlsli Utils/NoiseAndSequences.hlsli:17-18 Utils/NoiseAndSequences.hlsli:58-96 Utils/NoiseAndSequences.hlsli:121-300 Utils/SampleGenerators.hlsli:16-41 Utils/StatelessSampleGenerators.hlsli Utils/SampleGenerators.hlsli:43-112 PathTracerHelpers.hlsli:318-319 Scene/HitInfoType.hlsli Scene/SceneTypes.hlsli Scene/HitInfo.hlsli PathState.hlsli PathPayload.hlsli StablePlanes.hlsli:1-318 StablePlanes.hlsli:336-371 PathTracerDebug.hlsli PathTracerTypes.hlsli:29-220 Lighting/EnvMap.hlsli:23-48 Lighting/EnvMap.hlsli:52-93 Scene/Material/HomogeneousVolumeData.hlsli Rendering/Volumes/HomogeneousVolumeSampler.hlsli local=ref_bridge_stub.h PathTracerNestedDielectrics.hlsli PathTracerStablePlanes.hlsli PathTracerNEE.hlsli PathTracer.hlsli:17-764; do
+         Scene/ShadingData.hlsli Rendering/Materials/BxDF.hlsli Rendering/Materials/StandardBSDF.hlsli PathTracerHelpers.hlsli:26-66 PathTracerHelpers.hlsli:155-219 PathTracerHelpers.hlsli:221-270 Rendering/Materials/TexLODHelpers.hlsli:40-161 Rendering/Materials/InteriorList.hlsli Utils/Packing.hlsli:16-51 Utils/Packing.hlsli:194-265 Utils/Geometry.hlsli Lighting/PolymorphicLightPTConfig.h Lighting/PolymorphicLight.h Lighting/LightShaping.hlsli Lighting/PolymorphicLight.hlsli Lighting/LightingConfig.h Lighting/LightingTypes.hlsli Lighting/LightingAlgorithms.hlsli Lighting/LightSampler.hlsli PathTracerShared.h Utils/Math/Ray.hlsli Utils/NoiseAndSequences.hlsli:17-18 Utils/NoiseAndSequences.hlsli:58-96 Utils/NoiseAndSequences.hlsli:121-300 Utils/SampleGenerators.hlsli:16-41 Utils/StatelessSampleGenerators.hlsli Utils/SampleGenerators.hlsli:43-112 PathTracerHelpers.hlsli:318-319 Scene/HitInfoType.hlsli Scene/SceneTypes.hlsli Scene/HitInfo.hlsli PathState.hlsli PathPayload.hlsli StablePlanes.hlsli:1-318 StablePlanes.hlsli:336-371 PathTracerDebug.hlsli PathTracerTypes.hlsli:29-220 Lighting/EnvMap.hlsli:23-48 Lighting/EnvMap.hlsli:52-93 Scene/Material/HomogeneousVolumeData.hlsli Rendering/Volumes/HomogeneousVolumeSampler.hlsli local=ref_bridge_stub.h PathTracer.hlsli:18-25 PathTracerNestedDielectrics.hlsli PathTracerStablePlanes.hlsli PathTracerNEE.hlsli PathTracer.hlsli:33-764; do
   case "$f" in
     local=*) echo; echo "#line 1 \"${f#local=}\""; cat "${f#local=}" ;;
     *:*) range=${f#*:}; f=${f%%:*}; echo; echo "#line ${range%-*} \"$PT/$f\""; filter "$PT/$f" | sed -n "${range%-*},${range#*-}p" ;;       # a line range of a header whose other parts resist (Utils.hlsli: the lpfloat typedefs, Luminance / Average, LuminanceClamp, the octahedral encodings, EvalMIS, FastSqrt / FastACos, WeightedAverage; not: PackOrthoMatrix (matrix row swizzles; pinned through ref_kat_host instead), the debug text drawing, FastACosLp)

@@ -27,9 +27,74 @@ static void writeAll(const char* path, const std::vector<float>& v)
 float4 (*g_shimCubeSample)(float3 dir, float lod) = nullptr;
 static void shimIdentityEnv() { memset(&g_bridge.env, 0, sizeof(g_bridge.env)); for (int k = 0; k < 3; k++) g_bridge.env.Transform.m[k][k] = g_bridge.env.InvTransform.m[k][k] = 1.0f; g_bridge.env.ColorMultiplier = float3(1, 1, 1); }
 
+
+// ---- "hit" mode: PathTracer::HandleHit / HandleMiss behind the stub bridge (ref_bridge_stub.h) ------------------------------------------------------------------------------------------
+// record layout (floats; words marked * are bit patterns):  0-19* path payload | 20-22 ray origin, 23-25 ray dir, 26 rayTCurrent, 27 miss? | 28-58 surface (posW, faceNCorrected, N, T, B,
+// vertexN, frontFacing, nestedPriority, activeLobes, thinSurface, psdExclude, materialID, IoR, shadowNoLFadeout, emission, psdBlockMotionVectors, psdDominantDeltaLobeP1) | 60-73 BSDF data
+// (order of the "bsdf" mode's words 18-31) | 74 interior IoR, 75 / 76 emissive-triangle / analytic-proxy light (-1: none), 77-79 prevPosW | 80-93 constants | 96-135 materials (IoR,
+// attenuation colour, attenuation distance x 8) | 136-151 proxy counters, 152-215 proxy indices, 216-727* 2 x 2 local tiles, 728-919* 16 light records (Base + Extended)
+static const int kHitIn = 920, kHitOut = 64;
+struct ShimHitScenario
+{
+    LightingControlData cd; uint counters[16], indices[64], local[512]; PolymorphicLightInfo lights[16]; PolymorphicLightInfoEx lightsEx[16]; float fbWeight[64]; uint fbCand[64]; uint envLookup[1];
+    PathTracerConstants pt;
+};
+static float4 shimCube(float3 d, float lod) { const float k = exp2(-lod); return float4((0.5f + 0.5f * d.x) * k, (0.5f + 0.25f * d.y) * k, (0.75f + 0.25f * d.z) * k, 1.0f); }
+static void shimLoadHitScenario(const float* r, ShimHitScenario& S)
+{
+    g_bridge = ShimBridgeScenario(); shimIdentityEnv(); g_shimCubeSample = shimCube;
+    memset(&S.cd, 0, sizeof(S.cd)); memset(&S.pt, 0, sizeof(S.pt)); memset(S.lights, 0, sizeof(S.lights)); memset(S.lightsEx, 0, sizeof(S.lightsEx));
+    // surface
+    ShadingData sd = ShadingData::make();
+    sd.posW = float3(r[28], r[29], r[30]); sd.faceNCorrected = float3(r[31], r[32], r[33]); sd.V = -float3(r[23], r[24], r[25]); sd.N = float3(r[34], r[35], r[36]); sd.T = float3(r[37], r[38], r[39]);
+    sd.B = float3(r[40], r[41], r[42]); sd.vertexN = float3(r[43], r[44], r[45]); sd.frontFacing = r[46] != 0.0f;
+    sd.mtl = MaterialHeader::make(); sd.mtl.setNestedPriority(uint(r[47])); sd.mtl.setActiveLobes(uint(r[48])); sd.mtl.setThinSurface(r[49] != 0.0f); sd.mtl.setPSDExclude(r[50] != 0.0f);
+    sd.mtl.setPSDBlockMotionVectorsAtSurface(r[57] != 0.0f); sd.mtl.setPSDDominantDeltaLobeP1(uint(r[58]));
+    sd.materialID = uint(r[51]); sd.IoR = lpfloat(r[52]); sd.shadowNoLFadeout = lpfloat(r[53]); sd.emission = lpfloat3(lpfloat(r[54]), lpfloat(r[55]), lpfloat(r[56]));
+    const float* b = r + 42;        // the "bsdf" mode's word k sits at k + 42
+    StandardBSDF bsdf = StandardBSDF::make(StandardBSDFData::make(lpfloat3(lpfloat(b[18]), lpfloat(b[19]), lpfloat(b[20])), lpfloat3(lpfloat(b[22]), lpfloat(b[23]), lpfloat(b[24])), lpfloat(b[21]), lpfloat(b[25]),
+                                                                     lpfloat(b[31]), lpfloat3(lpfloat(b[26]), lpfloat(b[27]), lpfloat(b[28])), lpfloat(b[29]), lpfloat(b[30])));
+    const uint neeTri = r[75] < 0 ? 0xFFFFFFFFu : uint(r[75]), neeAna = r[76] < 0 ? 0xFFFFFFFFu : uint(r[76]);
+#if PATH_TRACER_MODE == PATH_TRACER_MODE_BUILD_STABLE_PLANES
+    g_bridge.surface = PathTracer::SurfaceData::make(sd, bsdf, float3(r[77], r[78], r[79]), lpfloat(r[74]), neeTri, neeAna);
+#else
+    g_bridge.surface = PathTracer::SurfaceData::make(sd, bsdf, lpfloat(r[74]), neeTri, neeAna);
+#endif
+    // constants
+    g_bridge.maxBounces = uint(r[80]); g_bridge.maxDiffuseBounces = uint(r[81]); g_bridge.sampleIndex = uint(r[82]); g_bridge.noisyRadianceAttenuation = r[87]; g_bridge.envMipOffset = r[93];
+    S.pt.bounceCount = uint(r[80]); S.pt.diffuseBounceCount = uint(r[81]); S.pt.NEEEnabled = 1; S.pt.NEECandidateSamples = uint(r[83]); S.pt.NEEFullSamples = uint(r[84]); S.pt.fireflyFilterThreshold = r[85];
+    S.pt.invSubSampleCount = r[87]; S.pt.EnvironmentMapDiffuseSampleMIPLevel = r[93];
+    // materials: the bridge's absorption rule (PathTracerBridgeDonut.hlsli:881-887), restated
+    g_bridge.materialCount = 8;
+    for (int m = 0; m < 8; m++)
+    {
+        g_bridge.ior[m] = r[96 + m]; const float dist = max(1e-30f, r[128 + m]);
+        g_bridge.sigmaA[m] = float3(-log(clamp(r[104 + 3 * m], 1e-7f, 1.0f)) / dist, -log(clamp(r[105 + 3 * m], 1e-7f, 1.0f)) / dist, -log(clamp(r[106 + 3 * m], 1e-7f, 1.0f)) / dist);
+    }
+    // lights
+    S.cd.TotalLightCount = 16; S.cd.SamplingProxyCount = uint(r[90]); S.cd.LocalSamplingTileJitter = uint2((uint)r[88], (uint)r[89]); S.cd.LocalToGlobalSampleRatio = r[86];
+    S.cd.LocalSamplingResolution = uint2(2u, 2u); S.cd.TemporalFeedbackRequired = uint(r[92]); S.cd.ScreenSpaceVsWorldSpaceThreshold = r[91];
+    for (int k = 0; k < 16; k++) S.counters[k] = uint(r[136 + k]);
+    for (int k = 0; k < 64; k++) S.indices[k] = uint(r[152 + k]);
+    memcpy(S.local, r + 216, sizeof(S.local));
+    for (int k = 0; k < 16; k++)
+    {
+        uint w[12]; memcpy(w, r + 728 + 12 * k, 48);
+        S.lights[k].Center = float3(asfloat(w[0]), asfloat(w[1]), asfloat(w[2])); S.lights[k].ColorTypeAndFlags = w[3]; S.lights[k].Direction1 = w[4]; S.lights[k].Direction2 = w[5]; S.lights[k].Scalars = w[6];
+        S.lights[k].LogRadiance = w[7]; S.lightsEx[k].IesProfileIndex = w[8]; S.lightsEx[k].PrimaryAxis = w[9]; S.lightsEx[k].CosConeAngleAndSoftness = w[10]; S.lightsEx[k].UniqueID = w[11];
+    }
+    for (int k = 0; k < 64; k++) { S.fbWeight[k] = 0.0f; S.fbCand[k] = 0xFFFFFFFFu; }
+    S.envLookup[0] = 0u;
+    g_bridge.control.p = &S.cd; g_bridge.control.n = 1; g_bridge.lights.p = S.lights; g_bridge.lights.n = 16; g_bridge.lightsEx.p = S.lightsEx; g_bridge.lightsEx.n = 16;
+    g_bridge.proxyCounters.p = S.counters; g_bridge.proxyCounters.n = 16; g_bridge.proxyIndices.p = S.indices; g_bridge.proxyIndices.n = S.cd.SamplingProxyCount; g_bridge.localSampling.p = S.local; g_bridge.localSampling.n = 512;
+    g_bridge.envLookup.p = S.envLookup; g_bridge.envLookup.w = g_bridge.envLookup.h = 1; g_bridge.feedbackWeight.p = S.fbWeight; g_bridge.feedbackWeight.w = g_bridge.feedbackWeight.h = 8;
+    g_bridge.feedbackCandidates.p = S.fbCand; g_bridge.feedbackCandidates.w = g_bridge.feedbackCandidates.h = 8;
+    g_bridge.hasEnvMap = true;
+}
+
 int main(int argc, char** argv)
 {
-    if (argc != 4) { fprintf(stderr, "usage: %s bsdf|funcs|utils|helpers|lights|spheres|tonemap|texlod|interior|sampler in.f32 out.f32\n", argv[0]); return 2; }
+    if (argc != 4) { fprintf(stderr, "usage: %s bsdf|funcs|utils|helpers|lights|spheres|tonemap|texlod|interior|sampler|hit in.f32 out.f32\n", argv[0]); return 2; }
     const std::vector<float> in = readAll(argv[2]); std::vector<float> out;
     shimIdentityEnv();
     if (std::string(argv[1]) == "bsdf")
@@ -123,6 +188,32 @@ int main(int argc, char** argv)
                 d[15] = LightSampler::IsScreenSpaceCoherentHeuristic(bControl, u[8], u[5]) ? 1.0f : 0.0f;
             }
         }
+    }
+    else if (std::string(argv[1]) == "hit")
+    {   // PathTracer::HandleHit / HandleMiss (PathTracer.hlsli:391-763) on one path vertex: the incoming path state, the ray that found the surface, the surface itself (what
+        // Bridge::loadSurface would return) and a small light scenario in; the outgoing path state and everything the call exported out
+        const size_t n = in.size() / kHitIn; out.assign(n * kHitOut, 0.0f);
+        ShimHitScenario* S = new ShimHitScenario();
+        for (size_t i = 0; i < n; i++)
+        {
+            const float* r = &in[i * kHitIn]; float* o = &out[i * kHitOut];
+            shimLoadHitScenario(r, *S);
+            PathPayload payload; memcpy(payload.packed, r, 80);
+            PathState path = PathPayload::unpack(payload);
+            PathTracer::WorkingContext wc; wc.PtConsts = S->pt;
+            const float3 rayOrigin(r[20], r[21], r[22]), rayDir(r[23], r[24], r[25]);
+            if (r[27] != 0.0f) PathTracer::HandleMiss(path, rayOrigin, rayDir, r[26], wc);
+            else PathTracer::HandleHit(path, rayOrigin, rayDir, r[26], float2(0.25f, 0.25f), wc);
+            payload = PathPayload::pack(path); memcpy(o, payload.packed, 80);
+            o[20] = float(g_bridge.visibilityQueries); o[21] = g_bridge.lastVisibilityRay.Origin.x; o[22] = g_bridge.lastVisibilityRay.Origin.y; o[23] = g_bridge.lastVisibilityRay.Origin.z;
+            o[24] = g_bridge.lastVisibilityRay.Direction.x; o[25] = g_bridge.lastVisibilityRay.Direction.y; o[26] = g_bridge.lastVisibilityRay.Direction.z; o[27] = g_bridge.lastVisibilityRay.TMax;
+            o[28] = g_bridge.lastVisibility ? 1.0f : 0.0f; o[29] = float(g_bridge.exportSurfaceCalls); o[30] = g_bridge.exportSceneLength; o[31] = float(g_bridge.exportNonSurfaceCalls);
+            o[32] = g_bridge.exportVirtualPos.x; o[33] = g_bridge.exportVirtualPos.y; o[34] = g_bridge.exportVirtualPos.z; o[35] = float(g_bridge.specHitTStarts); o[36] = float(g_bridge.specHitTStops);
+            o[37] = g_bridge.specHitTStartLength; o[38] = g_bridge.specHitTStopLength;
+            const uint2 px = path.GetPixelPos(); const uint at = (px.y & 7u) * 8u + (px.x & 7u);
+            o[39] = S->fbWeight[at]; memcpy(o + 40, &S->fbCand[at], 4);
+        }
+        delete S;
     }
     else if (std::string(argv[1]) == "texlod")
     {   // Rendering/Materials/TexLODHelpers.hlsli:40-161: the ray cone (fp16-packed width / spread angle), its propagation, the per-triangle LOD constant and computeLOD - what

@@ -279,3 +279,20 @@ def test_light_sampler_matches_reference_header_golden(oracle):
     assert (quirk[:, 0] == np.float32(1 / 128)).all() and (quirk[:, 1] > 0).all()
     assert (r[:1100, :, 5] > 0).mean() > 0.3 and (r[:1100, :, 5] == 0).mean() > 0.2 and (r[..., 6] > 0).mean() > 0.2 and (r[..., 13] > 0).mean() > 0.95
     assert ((r[..., 14].view(np.uint32) & 0x7FFFFFFF) == q[..., 3].astype(np.uint32)).mean() > 0.5      # most inserts win their (mostly empty) reservoir
+
+
+def test_handle_hit_matches_reference_path_tracer_golden(oracle):
+    """PathTracer::HandleHit of the UNMODIFIED PathTracer.hlsli - with PathTracerNEE.hlsli (candidate loop, weighted reservoir, shadow ray, both MIS weights, firefly filter, fp16
+    accumulation, NEE-AT feedback), PathTracerNestedDielectrics.hlsli (false-hit rejection, outside IoR), GenerateScatterRay (BSDF sample, ray cone, bounce counters, firefly K),
+    HandleRussianRoulette, the Sobol / hash sample generators and the 80-byte path payload - compiled in place behind a stub bridge (oracle/ref_bridge_stub.h,
+    tests/golden/make_hit_golden.py).  2000 path vertices: the outgoing payload, the shadow ray and the feedback reservoir the oracle's HandleHitSurface produces are bit-identical."""
+    import ctypes as C
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "hit_golden.npz"))
+    u, ref = np.ascontiguousarray(g["hit_in"]), g["hit_out"]
+    L = oracle.lib(); L.oracle_hit_funcs.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]; L.oracle_hit_funcs.restype = None
+    out = np.empty_like(ref); L.oracle_hit_funcs(u.ctypes.data, len(u), out.ctypes.data, 0)
+    assert (out.view(np.uint32) == ref.view(np.uint32)).all()
+    p, pin = ref[:, :20].view(np.uint32), u[:, :20].view(np.uint32)
+    # the records exercise the paths: one and two shadow rays, occluded and visible, rejected false hits, radiance added, paths ending and going on, feedback written
+    assert np.bincount(ref[:, 20].astype(int), minlength=3)[:3].min() > 300 and 0.3 < ref[:, 28].mean() < 0.6 and (ref[:, 29] == 0).sum() > 20 and (ref[:, 39] > 0).mean() > 0.25
+    assert (p[:, 10:12] != pin[:, 10:12]).any(1).mean() > 0.4 and 0.05 < 1 - ((p[:, 19] >> 10) & 1).mean() < 0.5 and (p[:, 8:10] != pin[:, 8:10]).any(1).mean() > 0.8
