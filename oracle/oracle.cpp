@@ -307,7 +307,7 @@ ORC_API void oracle_sampler_funcs(const float* in, uint32_t count, float* out)
 }
 
 // PathTracer::HandleHit on one path vertex as the oracle restates it (pt_path.h: HandleHitSurface, HandleNEE, GenerateScatterRay, HandleRussianRoulette, nested dielectrics), layout
-// of ref_kat_bsdf_main.cpp's "hit" mode (920 floats in, 64 out).  The scene side is data, as behind the stub bridge there: the surface comes from the record, materials are the
+// of ref_kat_bsdf_main.cpp's "hit" mode (936 floats in, 64 out).  The scene side is data, as behind the stub bridge there: the surface comes from the record, materials are the
 // IoR / absorption table, a shadow ray is answered by the same function of its bits (ShimVisibilityRule in oracle/ref_bridge_stub.h, restated here).  mode: 0 reference, 2 FILL
 struct HitMirrorVisibility { uint queries = 0; float3 o = f3(0), d = f3(0); float tMax = 0; bool last = false; };
 static bool hitMirrorVisibility(float3 o, float3 d, float tMax, void* user)
@@ -321,7 +321,7 @@ ORC_API void oracle_hit_funcs(const float* in, uint32_t count, float* out, uint3
 {
     for (uint32_t i = 0; i < count; i++)
     {
-        const float* r = in + size_t(i) * 920; float* o = out + size_t(i) * 64;
+        const float* r = in + size_t(i) * 936; float* o = out + size_t(i) * 64;
         for (int k = 0; k < 64; k++) o[k] = 0.0f;
         // surface
         SurfaceData sf; ShadingData& sd = sf.sd;
@@ -355,6 +355,19 @@ ORC_API void oracle_hit_funcs(const float* in, uint32_t count, float* out, uint3
         x.visibilityOverride = hitMirrorVisibility; x.visibilityUser = &vis; x.noisyRadianceAttenuationOverride = r[87];
         uint payload[20]; memcpy(payload, r, 80);
         PathState path = unpackPayload(payload); const uint payloadIn14 = payload[14];
+        // FILL: the stable planes of an 8 x 8 image, the pixel's entries from the record
+        const uint pxi = (path.id >> 16) & 7u, pyi = path.id & 7u;
+        std::vector<RtxptStablePlane> planes; std::vector<uint> header; std::vector<float> specHitT; RtxptRealtimeConstants rtc; memset(&rtc, 0, sizeof(rtc)); RealtimeTargets rtt;
+        if (mode != MODE_REFERENCE)
+        {
+            rtt.width = rtt.height = 8; rtt.lineStride = GenericTSComputeLineStride(8, 8); rtt.planeStride = GenericTSComputePlaneStride(8, 8);
+            planes.assign(size_t(3) * rtt.planeStride, RtxptStablePlane{}); header.assign(4 * 64, 0xFFFFFFFFu); specHitT.assign(64, 0.0f);
+            rtt.planes = planes.data(); rtt.header = header.data(); rtt.specularHitT = specHitT.data(); rtc.subSampleCount = 1; rtc.activeStablePlaneCount = 3; rtt.rt = &rtc;
+            for (uint k = 0; k < 4; k++) memcpy(&rtt.hdr(pxi, pyi, k), r + 920 + k, 4);
+            for (uint k = 0; k < 3; k++) memcpy(planes[rtt.PixelToAddress(pxi, pyi, k)].PackedNoisyRadianceAndSpecAvg, r + 924 + 2 * k, 8);
+            specHitT[pyi * 8 + pxi] = r[930];
+            x.sp = &rtt;
+        }
         const float3 rayOrigin = f3(r[20], r[21], r[22]), rayDir = f3(r[23], r[24], r[25]);
         UpdatePathTravelled(path, r[26]);
         HandleHitSurface(x, path, rayOrigin, rayDir, r[26], sf);
@@ -362,6 +375,12 @@ ORC_API void oracle_hit_funcs(const float* in, uint32_t count, float* out, uint3
         o[20] = float(vis.queries); o[21] = vis.o.x; o[22] = vis.o.y; o[23] = vis.o.z; o[24] = vis.d.x; o[25] = vis.d.y; o[26] = vis.d.z; o[27] = vis.tMax; o[28] = vis.last ? 1.0f : 0.0f;
         const bool rejectedFalseHit = path.getCounter(CTR_RejectedHits) != ((payloadIn14 >> 8) & 0xFFu);
         if (mode == MODE_REFERENCE && !rejectedFalseHit) { o[29] = 1.0f; o[30] = path.sceneLength; }      // Bridge::ExportSurface( path, surface, path.GetSceneLength() ): once per accepted hit
+        if (mode != MODE_REFERENCE)
+        {
+            o[37] = specHitT[pyi * 8 + pxi];
+            for (uint k = 0; k < 3; k++) memcpy(o + 41 + 2 * k, planes[rtt.PixelToAddress(pxi, pyi, k)].PackedNoisyRadianceAndSpecAvg, 8);
+            for (uint k = 0; k < 4; k++) memcpy(o + 47 + k, &rtt.hdr(pxi, pyi, k), 4);
+        }
         const uint px = (path.id >> 16) & 7u, py = path.id & 7u;
         o[39] = ns.feedback.weight[py * 8 + px]; memcpy(o + 40, &ns.feedback.candidate[py * 8 + px], 4);
     }

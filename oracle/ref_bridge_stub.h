@@ -23,7 +23,7 @@ struct ShimBridgeScenario
     float3 cameraPos; float3 cameraDirBase, cameraDirDx, cameraDirDy;
     // what the calls exported
     uint visibilityQueries = 0; RayDesc lastVisibilityRay; bool lastVisibility = false;
-    uint exportSurfaceCalls = 0, exportNonSurfaceCalls = 0, specHitTStarts = 0, specHitTStops = 0; float exportSceneLength = 0; float3 exportMotion, exportVirtualPos; float specHitTStartLength = 0, specHitTStopLength = 0;
+    uint exportSurfaceCalls = 0, exportNonSurfaceCalls = 0, specHitTStarts = 0, specHitTStops = 0; float exportSceneLength = 0; float3 exportMotion, exportVirtualPos; float specularHitT = 0;     // u_SpecularHitT of the pixel
 };
 static ShimBridgeScenario g_bridge;
 
@@ -82,6 +82,12 @@ namespace Bridge
     static void ExportSurface(const PathState path, PathTracer::SurfaceData surfaceData, float sceneLength, float3 motionVectors)
     { g_bridge.exportSurfaceCalls++; g_bridge.exportSceneLength = sceneLength; g_bridge.exportMotion = motionVectors; }
     static void ExportNonSurface(const PathState path, float3 virtualWorldPos, float3 motionVectors) { g_bridge.exportNonSurfaceCalls++; g_bridge.exportVirtualPos = virtualWorldPos; g_bridge.exportMotion = motionVectors; }
-    static void ExportSpecHitTStart(const PathState path) { g_bridge.specHitTStarts++; g_bridge.specHitTStartLength = path.GetSceneLength(); }
-    static void ExportSpecHitTStop(const PathState path) { g_bridge.specHitTStops++; g_bridge.specHitTStopLength = path.GetSceneLength(); }
+    // the bridge's bookkeeping (PathTracerBridgeDonut.hlsli:1155-1176), restated: the start stores minus the scene length, the stop turns a negative entry into the distance travelled since
+    static void ExportSpecHitTStart(const PathState path) { g_bridge.specHitTStarts++; g_bridge.specularHitT = -path.GetSceneLength(); }
+    static void ExportSpecHitTStop(const PathState path)
+    {
+        g_bridge.specHitTStops++;
+        const float denoisingSceneLength = g_bridge.specularHitT;
+        if (denoisingSceneLength < 0) g_bridge.specularHitT = max(0.0f, path.GetSceneLength() + denoisingSceneLength);
+    }
 }

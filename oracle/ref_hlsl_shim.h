@@ -242,6 +242,7 @@ inline uint countbits(uint v) { return uint(__builtin_popcount(v)); } inline uin
 inline uint3 operator&(uint3 a, uint m) { return uint3(a.x & m, a.y & m, a.z & m); } inline uint3 operator>>(uint3 a, int n) { return uint3(a.x >> n, a.y >> n, a.z >> n); }
 inline uint3 operator<<(uint3 a, int n) { return uint3(a.x << n, a.y << n, a.z << n); } inline uint3 operator|(uint3 a, uint3 b) { return uint3(a.x | b.x, a.y | b.y, a.z | b.z); }
 inline float2 f16tof32(uint2 h) { return float2(f16tof32(h.x), f16tof32(h.y)); } inline uint2 f32tof16(float2 f) { return uint2(f32tof16(f.x), f32tof16(f.y)); }
+inline float4& operator+=(float4& a, float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; return a; }
 inline uint2& operator+=(uint2& a, uint2 b) { a.x += b.x; a.y += b.y; return a; }
 inline float3 f16tof32(uint3 h) { return float3(f16tof32(h.x), f16tof32(h.y), f16tof32(h.z)); } inline uint3 f32tof16(float3 f) { return uint3(f32tof16(f.x), f32tof16(f.y), f32tof16(f.z)); }
 inline float3 asfloat(uint3 v) { float3 r; std::memcpy(&r.x, &v.x, 4); std::memcpy(&r.y, &v.y, 4); std::memcpy(&r.z, &v.z, 4); return r; }

@@ -45,6 +45,7 @@ filter() {
     -e 's/([A-Za-z_.]+\(\))\.xxx\b/float3((float)\1, (float)\1, (float)\1)/g' \
     -e 's/\)\.xxx\b/)/g' \
     -e 's/\.rgba\b//g' \
+    -e 's/CommitPixel\( const PathState path/CommitPixel( PathState path/' \
     -e 's/\.xyzw\b//g' \
     -e 's/\? 0\.f : dataRoughness/? 0.f : (float)dataRoughness/' \
     -e 's/(^|[^A-Za-z0-9_.])([0-9]+\.[0-9]*([eE][-+]?[0-9]+)?|\.[0-9]+([eE][-+]?[0-9]+)?)([^0-9A-Za-z_.]|$)/\1\2f\5/g' \

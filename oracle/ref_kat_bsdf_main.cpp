@@ -32,12 +32,14 @@ static void shimIdentityEnv() { memset(&g_bridge.env, 0, sizeof(g_bridge.env)); 
 // record layout (floats; words marked * are bit patterns):  0-19* path payload | 20-22 ray origin, 23-25 ray dir, 26 rayTCurrent, 27 miss? | 28-58 surface (posW, faceNCorrected, N, T, B,
 // vertexN, frontFacing, nestedPriority, activeLobes, thinSurface, psdExclude, materialID, IoR, shadowNoLFadeout, emission, psdBlockMotionVectors, psdDominantDeltaLobeP1) | 60-73 BSDF data
 // (order of the "bsdf" mode's words 18-31) | 74 interior IoR, 75 / 76 emissive-triangle / analytic-proxy light (-1: none), 77-79 prevPosW | 80-93 constants | 96-135 materials (IoR,
-// attenuation colour, attenuation distance x 8) | 136-151 proxy counters, 152-215 proxy indices, 216-727* 2 x 2 local tiles, 728-919* 16 light records (Base + Extended)
-static const int kHitIn = 920, kHitOut = 64;
+// attenuation colour, attenuation distance x 8) | 136-151 proxy counters, 152-215 proxy indices, 216-727* 2 x 2 local tiles, 728-919* 16 light records (Base + Extended) | FILL mode: 920-923* the pixel's stable-plane header (3 branch ids, first-hit length | dominant index), 924-929* the three planes'
+// packed noisy radiance, 930 the pixel's specular hit distance
+static const int kHitIn = 936, kHitOut = 64;
 struct ShimHitScenario
 {
     LightingControlData cd; uint counters[16], indices[64], local[512]; PolymorphicLightInfo lights[16]; PolymorphicLightInfoEx lightsEx[16]; float fbWeight[64]; uint fbCand[64]; uint envLookup[1];
     PathTracerConstants pt;
+    uint spHeader[4 * 64]; StablePlane spPlanes[3 * 256]; float4 spRadiance[64];
 };
 static float4 shimCube(float3 d, float lod) { const float k = exp2(-lod); return float4((0.5f + 0.5f * d.x) * k, (0.5f + 0.25f * d.y) * k, (0.75f + 0.25f * d.z) * k, 1.0f); }
 static void shimLoadHitScenario(const float* r, ShimHitScenario& S)
@@ -201,6 +203,17 @@ int main(int argc, char** argv)
             PathPayload payload; memcpy(payload.packed, r, 80);
             PathState path = PathPayload::unpack(payload);
             PathTracer::WorkingContext wc; wc.PtConsts = S->pt;
+#if PATH_TRACER_MODE != PATH_TRACER_MODE_REFERENCE
+            // the stable planes of an 8 x 8 image; the record carries the pixel's own entries
+            const uint2 pixelIn = PathPayload::unpack(payload).GetPixelPos(); const uint pxi = pixelIn.x & 7u, pyi = pixelIn.y & 7u;
+            wc.PtConsts.imageWidth = wc.PtConsts.imageHeight = 8; wc.PtConsts.genericTSLineStride = GenericTSComputeLineStride(8, 8); wc.PtConsts.genericTSPlaneStride = GenericTSComputePlaneStride(8, 8);
+            memset(S->spHeader, 0xFF, sizeof(S->spHeader)); memset(S->spPlanes, 0, sizeof(S->spPlanes)); memset(S->spRadiance, 0, sizeof(S->spRadiance));
+            RWTexture2DArray<uint> hdr; hdr.p = S->spHeader; hdr.w = hdr.h = 8; hdr.d = 4; RWStructuredBuffer<StablePlane> planes; planes.p = S->spPlanes; planes.n = 3 * 256; RWTexture2D<float4> rad; rad.p = S->spRadiance; rad.w = rad.h = 8;
+            wc.StablePlanes = StablePlanesContext::make(hdr, planes, rad, wc.PtConsts);
+            for (uint k = 0; k < 4; k++) memcpy(&S->spHeader[(k * 8 + pyi) * 8 + pxi], r + 920 + k, 4);
+            for (uint k = 0; k < 3; k++) memcpy(&S->spPlanes[wc.StablePlanes.PixelToAddress(uint2(pxi, pyi), k)].PackedNoisyRadianceAndSpecAvg, r + 924 + 2 * k, 8);
+            g_bridge.specularHitT = r[930];
+#endif
             const float3 rayOrigin(r[20], r[21], r[22]), rayDir(r[23], r[24], r[25]);
             if (r[27] != 0.0f) PathTracer::HandleMiss(path, rayOrigin, rayDir, r[26], wc);
             else PathTracer::HandleHit(path, rayOrigin, rayDir, r[26], float2(0.25f, 0.25f), wc);
@@ -209,7 +222,11 @@ int main(int argc, char** argv)
             o[24] = g_bridge.lastVisibilityRay.Direction.x; o[25] = g_bridge.lastVisibilityRay.Direction.y; o[26] = g_bridge.lastVisibilityRay.Direction.z; o[27] = g_bridge.lastVisibilityRay.TMax;
             o[28] = g_bridge.lastVisibility ? 1.0f : 0.0f; o[29] = float(g_bridge.exportSurfaceCalls); o[30] = g_bridge.exportSceneLength; o[31] = float(g_bridge.exportNonSurfaceCalls);
             o[32] = g_bridge.exportVirtualPos.x; o[33] = g_bridge.exportVirtualPos.y; o[34] = g_bridge.exportVirtualPos.z; o[35] = float(g_bridge.specHitTStarts); o[36] = float(g_bridge.specHitTStops);
-            o[37] = g_bridge.specHitTStartLength; o[38] = g_bridge.specHitTStopLength;
+            o[37] = g_bridge.specularHitT;
+#if PATH_TRACER_MODE != PATH_TRACER_MODE_REFERENCE
+            for (uint k = 0; k < 3; k++) memcpy(o + 41 + 2 * k, &S->spPlanes[wc.StablePlanes.PixelToAddress(uint2(pxi, pyi), k)].PackedNoisyRadianceAndSpecAvg, 8);
+            for (uint k = 0; k < 4; k++) memcpy(o + 47 + k, &S->spHeader[(k * 8 + pyi) * 8 + pxi], 4);
+#endif
             const uint2 px = path.GetPixelPos(); const uint at = (px.y & 7u) * 8u + (px.x & 7u);
             o[39] = S->fbWeight[at]; memcpy(o + 40, &S->fbCand[at], 4);
         }

@@ -17,8 +17,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from bsdf_records import make_records  # noqa: E402
 
 
-def run(mode, arr, width):
-    exe = os.path.join(ROOT, "oracle", "_ref", "ref_kat_bsdf")
+def run(mode, arr, width, exe="ref_kat_bsdf"):
+    exe = os.path.join(ROOT, "oracle", "_ref", exe)
     with tempfile.TemporaryDirectory() as d:
         a, b = os.path.join(d, "in.f32"), os.path.join(d, "out.f32")
         np.ascontiguousarray(arr, np.float32).tofile(a)

@@ -38,8 +38,8 @@ def light_records(rng, n, around):
     return rec
 
 
-def make(rng, n, slots_pool):
-    r = np.zeros((n, 920), np.float32)
+def make(rng, n, slots_pool, fill=False):
+    r = np.zeros((n, 936), np.float32)
     b = make_records(rng, n); V, N, T, B = b[:, 0:3], b[:, 3:6], b[:, 6:9], b[:, 9:12]
     ray_dir = -V; t = np.exp(rng.uniform(-2, 3, n)).astype(np.float32); origin = ((rng.random((n, 3)) - 0.5) * 40).astype(np.float32); pos = origin + ray_dir * t[:, None]
     r[:, 20:23], r[:, 23:26], r[:, 26] = origin, ray_dir, t
@@ -53,6 +53,7 @@ def make(rng, n, slots_pool):
     em = rng.random(n) < 0.3; r[em, 54:57] = f16(rng.gamma(2.0, 2.0, (int(em.sum()), 3)))
     r[:, 57] = rng.random(n) < 0.1; r[:, 58] = rng.integers(0, 3, n)
     r[:, 60:74] = b[:, 18:32]
+    if fill: r[rng.random(n) < 0.45, 63] = np.float16(0.02)        # delta lobes (mirrors, clear glass): what the stable planes follow
     ior = f16(np.where(rng.random(n) < 0.7, 1.5, 1.0 + rng.random(n) * 1.2)); r[:, 74] = ior
     r[:, 75] = np.where(em & (rng.random(n) < 0.8), rng.integers(0, 12, n), -1); r[:, 76] = np.where(rng.random(n) < 0.15, rng.integers(12, 16, n), -1)
     r[:, 77:80] = pos + rng.normal(size=(n, 3)).astype(np.float32) * np.float32(0.01)
@@ -89,7 +90,23 @@ def make(rng, n, slots_pool):
     flags = np.full(n, PF["active"] | PF["hit"], np.uint32)
     for name, prob in (("transmission", 0.2), ("specular", 0.4), ("delta", 0.2), ("inside", 0.3), ("terminateNext", 0.15), ("deltaOnlyPath", 0.4), ("deltaTransmissionPath", 0.1), ("baseScatterDiff", 0.4)):
         flags |= (rng.random(n) < prob).astype(np.uint32) * np.uint32(PF[name])
-    p[:, 19] = (flags << 10) | rng.integers(0, 7, n).astype(np.uint32)
+    vertex = rng.integers(0, 7, n).astype(np.uint32)
+    if fill:
+        # FILL pass: the path tracks the delta tree of the BUILD pass.  The pixel's header holds three plane branch ids - often the id the path will have after this scatter (stable
+        # branch id << 2 | delta lobe), so that landing on a plane (commit of the noisy radiance, plane switch, dominant flag) happens - and the planes hold earlier radiance
+        for name, prob in (("onPlane", 0.5), ("onBranch", 0.6), ("specHitTQueued", 0.3), ("onDominant", 0.5)): flags |= (rng.random(n) < prob).astype(np.uint32) * np.uint32(PF[name])
+        flags |= rng.integers(0, 3, n).astype(np.uint32) << 14                                    # stable plane index
+        branch = np.where(rng.random(n) < 0.5, 1, rng.integers(1, 1 << 10, n)).astype(np.uint32); p[:, 15] = branch
+        hdr = np.full((n, 4), 0xFFFFFFFF, np.uint32)
+        for k in range(3):
+            kind = rng.random(n); lobe = rng.integers(0, 3, n).astype(np.uint32)
+            hdr[:, k] = np.where(kind < 0.45, (branch << 2) | lobe, np.where(kind < 0.7, ((branch << 2) | lobe) << 2 | rng.integers(0, 3, n).astype(np.uint32), np.where(kind < 0.85, rng.integers(1, 1 << 12, n).astype(np.uint32), 0xFFFFFFFF)))
+        hdr[:, 3] = (np.exp(rng.uniform(-1, 4, n)).astype(np.float32).view(np.uint32) & np.uint32(0xFFFFFFFC)) | rng.integers(0, 3, n).astype(np.uint32)
+        r[:, 920:924] = hdr.view(np.float32)
+        rad = rng.gamma(1.0, 0.5, (n, 3, 4)).astype(np.float32) * (rng.random((n, 3, 1)) < 0.6); rad[rng.random((n, 3)) < 0.15, 0:2] = 0     # r = g = 0 with b > 0: the commit's "both words non-zero" test
+        r[:, 924:930] = np.stack([h16(rad[..., 0]) | (h16(rad[..., 1]) << 16), h16(rad[..., 2]) | (h16(rad[..., 3]) << 16)], axis=-1).reshape(n, 6).view(np.float32)
+        r[:, 930] = np.where(rng.random(n) < 0.5, -np.exp(rng.uniform(-3, 4, n)), np.where(rng.random(n) < 0.5, 0, np.exp(rng.uniform(-3, 3, n))))
+    p[:, 19] = (flags << 10) | vertex
     r[:, 0:20] = p.view(np.float32)
     return r
 
@@ -97,9 +114,10 @@ def make(rng, n, slots_pool):
 if __name__ == "__main__":
     rng = np.random.default_rng(777)
     g = np.load(os.path.join(ROOT, "tests", "golden", "interior_golden.npz")); slots = g["interior_out"].reshape(-1, 12, 6)[:, :, 0:2].reshape(-1, 2).view(np.uint32); slots = slots[(slots != 0).any(1)]
-    u = make(rng, 2000, slots)
+    u = make(rng, 1500, slots)
     out = run("hit", u, 64)
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "hit_golden.npz"), hit_in=u, hit_out=out,
-                        source=np.array("Rtxpt/Shaders/PathTracer/{PathTracer,PathTracerNEE,PathTracerNestedDielectrics,PathState,PathPayload}.hlsli + Utils/SampleGenerators.hlsli at reference commit f08d1c7, "
-                                        "compiled as C++ by oracle/Makefile target _ref/ref_kat_bsdf behind oracle/ref_bridge_stub.h"))
-    print(u.shape, out.shape, "nan:", int(np.isnan(out).sum()), os.path.getsize(os.path.join(ROOT, "tests", "golden", "hit_golden.npz")))
+    src = "Rtxpt/Shaders/PathTracer/{PathTracer,PathTracerNEE,PathTracerNestedDielectrics,PathTracerStablePlanes,StablePlanes,PathState,PathPayload}.hlsli + Utils/SampleGenerators.hlsli at reference commit f08d1c7, compiled as C++ by oracle/Makefile targets _ref/ref_kat_bsdf (PATH_TRACER_MODE 0) and _ref/ref_kat_pt_fill (2) behind oracle/ref_bridge_stub.h"
+    uf = make(np.random.default_rng(778), 1500, slots, fill=True)
+    outf = run("hit", uf, 64, exe="ref_kat_pt_fill")
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "hit_golden.npz"), hit_in=u, hit_out=out, fill_in=uf, fill_out=outf, source=np.array(src))
+    print(u.shape, out.shape, uf.shape, outf.shape, os.path.getsize(os.path.join(ROOT, "tests", "golden", "hit_golden.npz")))

@@ -285,14 +285,21 @@ def test_handle_hit_matches_reference_path_tracer_golden(oracle):
     """PathTracer::HandleHit of the UNMODIFIED PathTracer.hlsli - with PathTracerNEE.hlsli (candidate loop, weighted reservoir, shadow ray, both MIS weights, firefly filter, fp16
     accumulation, NEE-AT feedback), PathTracerNestedDielectrics.hlsli (false-hit rejection, outside IoR), GenerateScatterRay (BSDF sample, ray cone, bounce counters, firefly K),
     HandleRussianRoulette, the Sobol / hash sample generators and the 80-byte path payload - compiled in place behind a stub bridge (oracle/ref_bridge_stub.h,
-    tests/golden/make_hit_golden.py).  2000 path vertices: the outgoing payload, the shadow ray and the feedback reservoir the oracle's HandleHitSurface produces are bit-identical."""
+    tests/golden/make_hit_golden.py), once as the reference-mode shader and once as the FILL pass (PathTracerStablePlanes.hlsli's StablePlanesOnScatter, StablePlanes.hlsli's
+    CommitDenoiserRadiance, the specular hit distance, attenuated noisy radiance).  1500 path vertices each: the outgoing payload, the shadow ray, the feedback reservoir, the planes'
+    noisy radiance and the hit distance the oracle's HandleHitSurface produces are bit-identical."""
     import ctypes as C
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "hit_golden.npz"))
-    u, ref = np.ascontiguousarray(g["hit_in"]), g["hit_out"]
     L = oracle.lib(); L.oracle_hit_funcs.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]; L.oracle_hit_funcs.restype = None
-    out = np.empty_like(ref); L.oracle_hit_funcs(u.ctypes.data, len(u), out.ctypes.data, 0)
-    assert (out.view(np.uint32) == ref.view(np.uint32)).all()
-    p, pin = ref[:, :20].view(np.uint32), u[:, :20].view(np.uint32)
-    # the records exercise the paths: one and two shadow rays, occluded and visible, rejected false hits, radiance added, paths ending and going on, feedback written
-    assert np.bincount(ref[:, 20].astype(int), minlength=3)[:3].min() > 300 and 0.3 < ref[:, 28].mean() < 0.6 and (ref[:, 29] == 0).sum() > 20 and (ref[:, 39] > 0).mean() > 0.25
-    assert (p[:, 10:12] != pin[:, 10:12]).any(1).mean() > 0.4 and 0.05 < 1 - ((p[:, 19] >> 10) & 1).mean() < 0.5 and (p[:, 8:10] != pin[:, 8:10]).any(1).mean() > 0.8
+    for key, mode in (("hit", 0), ("fill", 2)):
+        u, ref = np.ascontiguousarray(g[key + "_in"]), g[key + "_out"]
+        out = np.empty_like(ref); L.oracle_hit_funcs(u.ctypes.data, len(u), out.ctypes.data, mode)
+        same = out.view(np.uint32) == ref.view(np.uint32); same[:, 35:37] = True            # 35, 36: how often the bridge's ExportSpecHitTStart / Stop were called (not mirrored)
+        assert same.all(), (key, np.argwhere(~same)[:8])
+        p, pin = ref[:, :20].view(np.uint32), u[:, :20].view(np.uint32)
+        # the records exercise the paths: one and two shadow rays, occluded and visible, rejected false hits, radiance added, paths ending and going on, feedback written
+        assert np.bincount(ref[:, 20].astype(int), minlength=3)[:3].min() > 200 and 0.3 < ref[:, 28].mean() < 0.6 and (ref[:, 39] > 0).mean() > 0.25
+        assert (p[:, 10:12] != pin[:, 10:12]).any(1).mean() > 0.3 and 0.05 < 1 - ((p[:, 19] >> 10) & 1).mean() < 0.5 and (p[:, 8:10] != pin[:, 8:10]).any(1).mean() > 0.8
+        if mode == 0: assert (ref[:, 29] == 0).sum() > 15                                   # rejected false hits export nothing
+        else:   # landing on a stable plane commits the path's radiance into it; specular hit distances start and stop
+            assert (ref[:, 41:47].view(np.uint32) != u[:, 924:930].view(np.uint32)).any(1).sum() > 40 and (ref[:, 37] != u[:, 930]).sum() > 150 and ref[:, 35].sum() > 60
