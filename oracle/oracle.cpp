@@ -307,9 +307,16 @@ ORC_API void oracle_sampler_funcs(const float* in, uint32_t count, float* out)
 }
 
 // PathTracer::HandleHit on one path vertex as the oracle restates it (pt_path.h: HandleHitSurface, HandleNEE, GenerateScatterRay, HandleRussianRoulette, nested dielectrics), layout
-// of ref_kat_bsdf_main.cpp's "hit" mode (936 floats in, 64 out).  The scene side is data, as behind the stub bridge there: the surface comes from the record, materials are the
+// of ref_kat_bsdf_main.cpp's "hit" mode (960 floats in, 128 out).  The scene side is data, as behind the stub bridge there: the surface comes from the record, materials are the
 // IoR / absorption table, a shadow ray is answered by the same function of its bits (ShimVisibilityRule in oracle/ref_bridge_stub.h, restated here).  mode: 0 reference, 2 FILL
 struct HitMirrorVisibility { uint queries = 0; float3 o = f3(0), d = f3(0); float tMax = 0; bool last = false; };
+struct HitMirrorCamera { float3 pos, base, dx, dy; };
+static void hitMirrorCameraRay(uint px, uint py, float3& origin, float3& dir, void* user)
+{
+    const HitMirrorCamera& c = *static_cast<const HitMirrorCamera*>(user);
+    origin = c.pos; dir = normalize(c.base + c.dx * float(px) + c.dy * float(py));
+}
+static float3 hitMirrorMotionVector(float3 posW, float3 prevPosW) { return (prevPosW - posW) * 0.5f; }
 static bool hitMirrorVisibility(float3 o, float3 d, float tMax, void* user)
 {
     HitMirrorVisibility& v = *static_cast<HitMirrorVisibility*>(user);
@@ -321,8 +328,8 @@ ORC_API void oracle_hit_funcs(const float* in, uint32_t count, float* out, uint3
 {
     for (uint32_t i = 0; i < count; i++)
     {
-        const float* r = in + size_t(i) * 936; float* o = out + size_t(i) * 64;
-        for (int k = 0; k < 64; k++) o[k] = 0.0f;
+        const float* r = in + size_t(i) * 960; float* o = out + size_t(i) * 128;
+        for (int k = 0; k < 128; k++) o[k] = 0.0f;
         // surface
         SurfaceData sf; ShadingData& sd = sf.sd;
         sd.posW = f3(r[28], r[29], r[30]); sd.faceNCorrected = f3(r[31], r[32], r[33]); sd.V = -f3(r[23], r[24], r[25]); sd.N = f3(r[34], r[35], r[36]); sd.T = f3(r[37], r[38], r[39]);
@@ -357,7 +364,8 @@ ORC_API void oracle_hit_funcs(const float* in, uint32_t count, float* out, uint3
         PathState path = unpackPayload(payload); const uint payloadIn14 = payload[14];
         // FILL: the stable planes of an 8 x 8 image, the pixel's entries from the record
         const uint pxi = (path.id >> 16) & 7u, pyi = path.id & 7u;
-        std::vector<RtxptStablePlane> planes; std::vector<uint> header; std::vector<float> specHitT; RtxptRealtimeConstants rtc; memset(&rtc, 0, sizeof(rtc)); RealtimeTargets rtt;
+        std::vector<RtxptStablePlane> planes; std::vector<uint> header, throughput; std::vector<float> specHitT, depth; std::vector<uint16_t> stableRadiance, motion; RtxptRealtimeConstants rtc; memset(&rtc, 0, sizeof(rtc)); RealtimeTargets rtt;
+        HitMirrorCamera cam; const float identity[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
         if (mode != MODE_REFERENCE)
         {
             rtt.width = rtt.height = 8; rtt.lineStride = GenericTSComputeLineStride(8, 8); rtt.planeStride = GenericTSComputePlaneStride(8, 8);
@@ -366,6 +374,12 @@ ORC_API void oracle_hit_funcs(const float* in, uint32_t count, float* out, uint3
             for (uint k = 0; k < 4; k++) memcpy(&rtt.hdr(pxi, pyi, k), r + 920 + k, 4);
             for (uint k = 0; k < 3; k++) memcpy(planes[rtt.PixelToAddress(pxi, pyi, k)].PackedNoisyRadianceAndSpecAvg, r + 924 + 2 * k, 8);
             specHitT[pyi * 8 + pxi] = r[930];
+            stableRadiance.assign(64 * 4, 0); motion.assign(64 * 4, 0); depth.assign(64, -1.0f); throughput.assign(64, 0u);
+            rtt.stableRadiance = stableRadiance.data(); rtt.motionVectors = motion.data(); rtt.depth = depth.data(); rtt.throughput = throughput.data();
+            for (int k = 0; k < 4; k++) stableRadiance[(pyi * 8 + pxi) * 4 + k] = uint16_t(f32tof16(r[946 + k]));
+            rtc.maxStablePlaneVertexDepth = uint(r[943]); rtc.allowPrimarySurfaceReplacement = uint(r[944]);
+            cam.pos = f3(r[931], r[932], r[933]); cam.base = f3(r[934], r[935], r[936]); cam.dx = f3(r[937], r[938], r[939]); cam.dy = f3(r[940], r[941], r[942]);
+            x.cameraRayOverride = hitMirrorCameraRay; x.cameraRayUser = &cam; rtt.motionVectorOverride = hitMirrorMotionVector; x.worldToClip = identity;
             x.sp = &rtt;
         }
         const float3 rayOrigin = f3(r[20], r[21], r[22]), rayDir = f3(r[23], r[24], r[25]);
@@ -380,6 +394,9 @@ ORC_API void oracle_hit_funcs(const float* in, uint32_t count, float* out, uint3
             o[37] = specHitT[pyi * 8 + pxi];
             for (uint k = 0; k < 3; k++) memcpy(o + 41 + 2 * k, planes[rtt.PixelToAddress(pxi, pyi, k)].PackedNoisyRadianceAndSpecAvg, 8);
             for (uint k = 0; k < 4; k++) memcpy(o + 47 + k, &rtt.hdr(pxi, pyi, k), 4);
+            for (int k = 0; k < 4; k++) o[52 + k] = f16tof32(stableRadiance[(pyi * 8 + pxi) * 4 + k]);
+            for (uint k = 0; k < 3; k++) memcpy(o + 56 + 20 * k, &planes[rtt.PixelToAddress(pxi, pyi, k)], 80);
+            if (mode == MODE_BUILD_STABLE_PLANES) o[29] = depth[pyi * 8 + pxi] != -1.0f ? 1.0f : 0.0f;        // Bridge::ExportSurface from the dominant base plane
         }
         const uint px = (path.id >> 16) & 7u, py = path.id & 7u;
         o[39] = ns.feedback.weight[py * 8 + px]; memcpy(o + 40, &ns.feedback.candidate[py * 8 + px], 4);

@@ -117,6 +117,7 @@ struct PathTracerCtx
     NeeatState* neeat = nullptr;
     // test hook (oracle.cpp's known-answer mirrors): answers a shadow ray instead of the BVH, as the stub bridge of oracle/ref_bridge_stub.h does for the reference's code
     bool (*visibilityOverride)(float3 origin, float3 dir, float tMax, void* user) = nullptr; void* visibilityUser = nullptr;
+    void (*cameraRayOverride)(uint px, uint py, float3& origin, float3& dir, void* user) = nullptr; void* cameraRayUser = nullptr;
     float noisyRadianceAttenuationOverride = 0.0f;
     float noisyRadianceAttenuation() const { return noisyRadianceAttenuationOverride != 0.0f ? noisyRadianceAttenuationOverride : 1.0f / float(sp->rt->subSampleCount); }      // Bridge::getNoisyRadianceAttenuation = invSubSampleCount (BridgeDonut:515-523)
 };
@@ -230,6 +231,7 @@ inline float FireflyFilterShort(float signalAverage, float threshold, float fire
 // ---- camera (BridgeDonut:543-564, PathTracerHelpers.hlsli:126-153) ---------------------------------------------------------
 inline void computeCameraRay(const PathTracerCtx& x, uint px, uint py, float3& origin, float3& dir)
 {
+    if (x.cameraRayOverride) { x.cameraRayOverride(px, py, origin, dir, x.cameraRayUser); return; }
     const RtxptCameraData& cam = x.c->camera;
     SampleSequenceGenerator sg = SampleSequenceGenerator::make(SampleGeneratorVertexBase::make((px << 16) | py, 0, x.sampleIndex));
     float r0 = sg.Next1D(), r1 = sg.Next1D();

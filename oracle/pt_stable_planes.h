@@ -183,8 +183,10 @@ struct RealtimeTargets
         for (uint i = 1; i < std::min(activePlaneCount(), cStablePlaneCount); i++) if (GetBranchID(px, py, i) == cStablePlaneInvalidBranchID) availablePlanes[availableCount++] = int(i);
     }
     // Bridge::computeMotionVector
+    float3 (*motionVectorOverride)(float3 posW, float3 prevPosW) = nullptr;       // test hook (oracle.cpp's known-answer mirrors): the stub bridge's closed form
     float3 computeMotionVector(float3 posW, float3 prevPosW) const
     {
+        if (motionVectorOverride) return motionVectorOverride(posW, prevPosW);
         auto xf = [](const float* M, float3 p, float out[4]) { for (int c = 0; c < 4; c++) out[c] = ((p.x * M[c] + p.y * M[4 + c]) + p.z * M[8 + c]) + M[12 + c]; };
         float clip[4], prev[4]; xf(rt->matWorldToClipNoOffset, posW, clip); xf(rt->prevMatWorldToClipNoOffset, prevPosW, prev);
         const float cx = clip[0] / clip[3], cy = clip[1] / clip[3], pxx = prev[0] / prev[3], pyy = prev[1] / prev[3];

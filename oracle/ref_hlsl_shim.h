@@ -168,7 +168,26 @@ struct float3x3 { union { float m[3][3]; struct { float _m00, _m01, _m02, _m10, 
                   float* operator[](int r) { return m[r]; } const float* operator[](int r) const { return m[r]; } };
 struct float3x4 { float m[3][4]; explicit operator float3x3() const { return float3x3(m[0][0], m[0][1], m[0][2], m[1][0], m[1][1], m[1][2], m[2][0], m[2][1], m[2][2]); } };          // constant-buffer member of ToneMappingConstants (not used by the pinned operators)
 struct float2x3 { union { float m[2][3]; struct { float _m00, _m01, _m02, _m10, _m11, _m12; }; }; float2x3() {} float2x3(float a, float b, float c, float d, float e, float f) { _m00 = a; _m01 = b; _m02 = c; _m10 = d; _m11 = e; _m12 = f; } float* operator[](int r) { return m[r]; } const float* operator[](int r) const { return m[r]; } };
-typedef float3x3 float16_t3x3;
+// a half matrix: elements are binary16 values.  How DXC lowers a product of two half matrices (which adds are fused, in which order, at which width) cannot be observed here;
+// the shim computes the products in binary32 and rounds each element of the result once - the convention the oracle and the product follow (pt_path.h: SplitDeltaPath)
+struct float16_t3x3
+{
+    float m[3][3];
+    float16_t3x3() {}
+    explicit float16_t3x3(const float3x3& a) { for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) m[r][c] = f16tof32(f32tof16(a.m[r][c])); }
+    float16_t3x3(float3 r0, float3 r1, float3 r2) { const float3 rows[3] = { r0, r1, r2 }; for (int r = 0; r < 3; r++) { m[r][0] = f16tof32(f32tof16(rows[r].x)); m[r][1] = f16tof32(f32tof16(rows[r].y)); m[r][2] = f16tof32(f32tof16(rows[r].z)); } }
+    float16_t3x3(float a, float b, float c, float d, float e, float f, float g, float h, float i) { const float v[9] = { a, b, c, d, e, f, g, h, i }; for (int k = 0; k < 9; k++) m[k / 3][k % 3] = f16tof32(f32tof16(v[k])); }
+    operator float3x3() const { float3x3 o; for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) o.m[r][c] = m[r][c]; return o; }
+};
+inline float16_t3x3 mul(const float16_t3x3& A, const float16_t3x3& B)
+{
+    float16_t3x3 o; for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) o.m[r][c] = f16tof32(f32tof16(A.m[r][0] * B.m[0][c] + A.m[r][1] * B.m[1][c] + A.m[r][2] * B.m[2][c]));
+    return o;
+}
+inline float3x3 mul(const float3x3& A, const float3x3& B) { float3x3 o; for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) o.m[r][c] = A.m[r][0] * B.m[0][c] + A.m[r][1] * B.m[1][c] + A.m[r][2] * B.m[2][c]; return o; }
+inline float3x3 mul(const float3x3& A, const float16_t3x3& B) { return mul(A, float3x3(B)); }      // the half matrix is promoted
+inline float16_t3x3 transpose(const float16_t3x3& A) { float16_t3x3 o; for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) o.m[r][c] = A.m[c][r]; return o; }
+inline float3 shimRow(const float3x3& M, int r) { return float3(M.m[r][0], M.m[r][1], M.m[r][2]); } inline void shimSetRow(float3x3& M, int r, float3 v) { M.m[r][0] = v.x; M.m[r][1] = v.y; M.m[r][2] = v.z; }
 inline float2 mul(const float2x2& M, float2 v) { return float2(M.m[0][0] * v.x + M.m[0][1] * v.y, M.m[1][0] * v.x + M.m[1][1] * v.y); }
 inline float3 mul(const float3x3& M, float3 v) { return float3(M.m[0][0] * v.x + M.m[0][1] * v.y + M.m[0][2] * v.z, M.m[1][0] * v.x + M.m[1][1] * v.y + M.m[1][2] * v.z, M.m[2][0] * v.x + M.m[2][1] * v.y + M.m[2][2] * v.z); }
 inline float3 mul(float3 v, const float3x3& M) { return float3(v.x * M.m[0][0] + v.y * M.m[1][0] + v.z * M.m[2][0], v.x * M.m[0][1] + v.y * M.m[1][1] + v.z * M.m[2][1], v.x * M.m[0][2] + v.y * M.m[1][2] + v.z * M.m[2][2]); }

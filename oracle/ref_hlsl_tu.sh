@@ -34,6 +34,13 @@ filter() {
     -e 's/\b(RTXPT_LIGHTING_SAMPLING_BUFFER_TILE_SIZE|width)\.xx\b/uint2(\1, \1)/g' \
     -e 's/\bthis\./this->/g' \
     -e 's/float\(0\)\.rrr/float3(0,0,0)/g' \
+    -e 's/1\.#INF/asfloat(0x7F800000u)/g' \
+    -e 's/DeltaLobe deltaLobes\[cMaxDeltaLobes\]; uint deltaLobeCount;/DeltaLobe deltaLobes[cMaxDeltaLobes]; int deltaLobeCount;/' \
+    -e 's/\b([0-9]+\.[0-9]+)\.xxx\b/float3(\1, \1, \1)/g' \
+    -e 's/\b(kNRDMinReflectance|kNRDMaxReflectance)\.xxx\b/float3(\1, \1, \1)/g' \
+    -e 's/\bxform\[([0-2])\]\.xyz\b/shimRow(xform, \1)/g' \
+    -e 's/^([[:space:]]*)xform\[([0-2])\] = (.*);/\1shimSetRow(xform, \2, \3);/' \
+    -e 's/\bxform\[([0-2])\]([,)[:space:]])/shimRow(xform, \1)\2/g' \
     -e 's/\b0\.xxx\b/float3(0,0,0)/g' \
     -e 's/\b0\.xxxx\b/float4(0,0,0,0)/g' \
     -e 's/\bHLF_MAX\.xxxx\b/float4(HLF_MAX,HLF_MAX,HLF_MAX,HLF_MAX)/g' \
@@ -75,7 +82,7 @@ cat <<'MACROS'
 #endif
 MACROS
 echo 'float3 ComputeRayOrigin(float3 pos, float3 normal);      /* PathTracerHelpers.hlsli:29-42: ShadingData.hlsli names it before the helper ranges below define it */'
-for f in Config.h Utils/Math/MathConstants.hlsli Utils/Utils.hlsli:28-67 Utils/Utils.hlsli:68-92 Utils/Utils.hlsli:115-169 Utils/Utils.hlsli:193-198 Utils/Utils.hlsli:272-370 Utils/Utils.hlsli:392-499 Utils/Utils.hlsli:510-517 Rendering/Materials/BxDFConfig.hlsli Rendering/Materials/LobeType.hlsli Scene/Material/MaterialData.hlsli \
+for f in Config.h Utils/Math/MathConstants.hlsli Utils/Utils.hlsli:28-67 Utils/Utils.hlsli:68-92 Utils/Utils.hlsli:115-169 Utils/Utils.hlsli:170-192 Utils/Utils.hlsli:193-198 Utils/Utils.hlsli:272-370 Utils/Utils.hlsli:392-499 Utils/Utils.hlsli:510-517 Rendering/Materials/BxDFConfig.hlsli Rendering/Materials/LobeType.hlsli Scene/Material/MaterialData.hlsli \
          Utils/ColorHelpers.hlsli Utils/Math/MathHelpers.hlsli Rendering/Materials/Fresnel.hlsli Rendering/Materials/Microfacet.hlsli Rendering/Materials/IBSDF.hlsli \
          Scene/ShadingData.hlsli Rendering/Materials/BxDF.hlsli Rendering/Materials/StandardBSDF.hlsli PathTracerHelpers.hlsli:26-66 PathTracerHelpers.hlsli:155-219 PathTracerHelpers.hlsli:221-270 Rendering/Materials/TexLODHelpers.hlsli:40-161 Rendering/Materials/InteriorList.hlsli Utils/Packing.hlsli:16-51 Utils/Packing.hlsli:194-265 Utils/Geometry.hlsli Lighting/PolymorphicLightPTConfig.h Lighting/PolymorphicLight.h Lighting/LightShaping.hlsli Lighting/PolymorphicLight.hlsli Lighting/LightingConfig.h Lighting/LightingTypes.hlsli Lighting/LightingAlgorithms.hlsli Lighting/LightSampler.hlsli PathTracerShared.h Utils/Math/Ray.hlsli Utils/NoiseAndSequences.hlsli:17-18 Utils/NoiseAndSequences.hlsli:58-96 Utils/NoiseAndSequences.hlsli:121-300 Utils/SampleGenerators.hlsli:16-41 Utils/StatelessSampleGenerators.hlsli Utils/SampleGenerators.hlsli:43-112 PathTracerHelpers.hlsli:318-319 Scene/HitInfoType.hlsli Scene/SceneTypes.hlsli Scene/HitInfo.hlsli PathState.hlsli PathPayload.hlsli StablePlanes.hlsli:1-318 StablePlanes.hlsli:336-371 PathTracerDebug.hlsli PathTracerTypes.hlsli:29-220 Lighting/EnvMap.hlsli:23-48 Lighting/EnvMap.hlsli:52-93 Scene/Material/HomogeneousVolumeData.hlsli Rendering/Volumes/HomogeneousVolumeSampler.hlsli local=ref_bridge_stub.h PathTracer.hlsli:18-25 PathTracerNestedDielectrics.hlsli PathTracerStablePlanes.hlsli PathTracerNEE.hlsli PathTracer.hlsli:33-764; do
   case "$f" in

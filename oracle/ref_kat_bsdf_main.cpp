@@ -33,8 +33,9 @@ static void shimIdentityEnv() { memset(&g_bridge.env, 0, sizeof(g_bridge.env)); 
 // vertexN, frontFacing, nestedPriority, activeLobes, thinSurface, psdExclude, materialID, IoR, shadowNoLFadeout, emission, psdBlockMotionVectors, psdDominantDeltaLobeP1) | 60-73 BSDF data
 // (order of the "bsdf" mode's words 18-31) | 74 interior IoR, 75 / 76 emissive-triangle / analytic-proxy light (-1: none), 77-79 prevPosW | 80-93 constants | 96-135 materials (IoR,
 // attenuation colour, attenuation distance x 8) | 136-151 proxy counters, 152-215 proxy indices, 216-727* 2 x 2 local tiles, 728-919* 16 light records (Base + Extended) | FILL mode: 920-923* the pixel's stable-plane header (3 branch ids, first-hit length | dominant index), 924-929* the three planes'
-// packed noisy radiance, 930 the pixel's specular hit distance
-static const int kHitIn = 936, kHitOut = 64;
+// packed noisy radiance, 930 the pixel's specular hit distance | BUILD mode: 931-942 the stub camera (position, direction at pixel 0, per-pixel steps), 943 maxStablePlaneVertexDepth,
+// 944 allowPrimarySurfaceReplacement, 945 stablePlanesSplitStopThreshold, 946-949 the pixel's stable radiance (RGBA16F values)
+static const int kHitIn = 960, kHitOut = 128;
 struct ShimHitScenario
 {
     LightingControlData cd; uint counters[16], indices[64], local[512]; PolymorphicLightInfo lights[16]; PolymorphicLightInfoEx lightsEx[16]; float fbWeight[64]; uint fbCand[64]; uint envLookup[1];
@@ -211,8 +212,12 @@ int main(int argc, char** argv)
             RWTexture2DArray<uint> hdr; hdr.p = S->spHeader; hdr.w = hdr.h = 8; hdr.d = 4; RWStructuredBuffer<StablePlane> planes; planes.p = S->spPlanes; planes.n = 3 * 256; RWTexture2D<float4> rad; rad.p = S->spRadiance; rad.w = rad.h = 8;
             wc.StablePlanes = StablePlanesContext::make(hdr, planes, rad, wc.PtConsts);
             for (uint k = 0; k < 4; k++) memcpy(&S->spHeader[(k * 8 + pyi) * 8 + pxi], r + 920 + k, 4);
-            for (uint k = 0; k < 3; k++) memcpy(&S->spPlanes[wc.StablePlanes.PixelToAddress(uint2(pxi, pyi), k)].PackedNoisyRadianceAndSpecAvg, r + 924 + 2 * k, 8);
+            for (uint k = 0; k < 3; k++) { uint w[2]; memcpy(w, r + 924 + 2 * k, 8); S->spPlanes[wc.StablePlanes.PixelToAddress(uint2(pxi, pyi), k)].PackedNoisyRadianceAndSpecAvg = uint2(w[0], w[1]); }
             g_bridge.specularHitT = r[930];
+            g_bridge.cameraPos = float3(r[931], r[932], r[933]); g_bridge.cameraDirBase = float3(r[934], r[935], r[936]); g_bridge.cameraDirDx = float3(r[937], r[938], r[939]); g_bridge.cameraDirDy = float3(r[940], r[941], r[942]);
+            wc.PtConsts.maxStablePlaneVertexDepth = uint(r[943]); wc.PtConsts.allowPrimarySurfaceReplacement = uint(r[944]); wc.PtConsts.stablePlanesSplitStopThreshold = r[945];
+            wc.StablePlanes.PTConstants = wc.PtConsts;
+            S->spRadiance[pyi * 8 + pxi] = float4(r[946], r[947], r[948], r[949]);
 #endif
             const float3 rayOrigin(r[20], r[21], r[22]), rayDir(r[23], r[24], r[25]);
             if (r[27] != 0.0f) PathTracer::HandleMiss(path, rayOrigin, rayDir, r[26], wc);
@@ -224,8 +229,19 @@ int main(int argc, char** argv)
             o[32] = g_bridge.exportVirtualPos.x; o[33] = g_bridge.exportVirtualPos.y; o[34] = g_bridge.exportVirtualPos.z; o[35] = float(g_bridge.specHitTStarts); o[36] = float(g_bridge.specHitTStops);
             o[37] = g_bridge.specularHitT;
 #if PATH_TRACER_MODE != PATH_TRACER_MODE_REFERENCE
-            for (uint k = 0; k < 3; k++) memcpy(o + 41 + 2 * k, &S->spPlanes[wc.StablePlanes.PixelToAddress(uint2(pxi, pyi), k)].PackedNoisyRadianceAndSpecAvg, 8);
+            for (uint k = 0; k < 3; k++) { const uint2 w = S->spPlanes[wc.StablePlanes.PixelToAddress(uint2(pxi, pyi), k)].PackedNoisyRadianceAndSpecAvg; memcpy(o + 41 + 2 * k, &w.x, 4); memcpy(o + 42 + 2 * k, &w.y, 4); }
             for (uint k = 0; k < 4; k++) memcpy(o + 47 + k, &S->spHeader[(k * 8 + pyi) * 8 + pxi], 4);
+            // the stable radiance target is RGBA16F: the format conversion of the UAV store, which the stand-in texture does not have, is applied here
+            { const float4 sr = S->spRadiance[pyi * 8 + pxi]; o[52] = f16tof32(f32tof16(sr.x)); o[53] = f16tof32(f32tof16(sr.y)); o[54] = f16tof32(f32tof16(sr.z)); o[55] = f16tof32(f32tof16(sr.w)); }
+            for (uint k = 0; k < 3; k++)
+            {   // the 80-byte record, member by member (the shim's vector types are wider than their HLSL counterparts)
+                const StablePlane& sp = S->spPlanes[wc.StablePlanes.PixelToAddress(uint2(pxi, pyi), k)];
+                const uint w[20] = { asuint(sp.RayOrigin.x), asuint(sp.RayOrigin.y), asuint(sp.RayOrigin.z), asuint(sp.LastRayTCurrent), asuint(sp.RayDir.x), asuint(sp.RayDir.y), asuint(sp.RayDir.z), asuint(sp.SceneLength),
+                                     sp.PackedThpAndMVs.x, sp.PackedThpAndMVs.y, sp.PackedThpAndMVs.z, sp.VertexIndexAndRoughness, sp.DenoiserPackedBSDFEstimate.x, sp.DenoiserPackedBSDFEstimate.y, sp.DenoiserPackedBSDFEstimate.z,
+                                     sp.PackedNormal, sp.PackedNoisyRadianceAndSpecAvg.x, sp.PackedNoisyRadianceAndSpecAvg.y, sp.FlagsAndVertexIndex, sp.PackedCounters };
+                memcpy(o + 56 + 20 * k, w, 80);
+            }
+            o[117] = g_bridge.exportMotion.x; o[118] = g_bridge.exportMotion.y; o[119] = g_bridge.exportMotion.z;
 #endif
             const uint2 px = path.GetPixelPos(); const uint at = (px.y & 7u) * 8u + (px.x & 7u);
             o[39] = S->fbWeight[at]; memcpy(o + 40, &S->fbCand[at], 4);

@@ -38,8 +38,8 @@ def light_records(rng, n, around):
     return rec
 
 
-def make(rng, n, slots_pool, fill=False):
-    r = np.zeros((n, 936), np.float32)
+def make(rng, n, slots_pool, fill=False, build=False):
+    r = np.zeros((n, 960), np.float32)
     b = make_records(rng, n); V, N, T, B = b[:, 0:3], b[:, 3:6], b[:, 6:9], b[:, 9:12]
     ray_dir = -V; t = np.exp(rng.uniform(-2, 3, n)).astype(np.float32); origin = ((rng.random((n, 3)) - 0.5) * 40).astype(np.float32); pos = origin + ray_dir * t[:, None]
     r[:, 20:23], r[:, 23:26], r[:, 26] = origin, ray_dir, t
@@ -53,7 +53,10 @@ def make(rng, n, slots_pool, fill=False):
     em = rng.random(n) < 0.3; r[em, 54:57] = f16(rng.gamma(2.0, 2.0, (int(em.sum()), 3)))
     r[:, 57] = rng.random(n) < 0.1; r[:, 58] = rng.integers(0, 3, n)
     r[:, 60:74] = b[:, 18:32]
-    if fill: r[rng.random(n) < 0.45, 63] = np.float16(0.02)        # delta lobes (mirrors, clear glass): what the stable planes follow
+    if build:
+        pure = rng.random(n) < 0.4       # mirrors and clear glass: no non-delta lobe at all, the case in which a path keeps walking the delta tree (plane 0: primary surface replacement)
+        r[pure, 60:63] = 0; r[pure, 63] = np.float16(0.02); r[pure, 71] = 0; glass = pure & (rng.random(n) < 0.5); r[glass, 72] = 1.0; r[glass, 49] = rng.random(int(glass.sum())) < 0.3
+    if fill or build: r[rng.random(n) < (0.6 if build else 0.45), 63] = np.float16(0.02)        # delta lobes (mirrors, clear glass): what the stable planes follow
     ior = f16(np.where(rng.random(n) < 0.7, 1.5, 1.0 + rng.random(n) * 1.2)); r[:, 74] = ior
     r[:, 75] = np.where(em & (rng.random(n) < 0.8), rng.integers(0, 12, n), -1); r[:, 76] = np.where(rng.random(n) < 0.15, rng.integers(12, 16, n), -1)
     r[:, 77:80] = pos + rng.normal(size=(n, 3)).astype(np.float32) * np.float32(0.01)
@@ -106,6 +109,17 @@ def make(rng, n, slots_pool, fill=False):
         rad = rng.gamma(1.0, 0.5, (n, 3, 4)).astype(np.float32) * (rng.random((n, 3, 1)) < 0.6); rad[rng.random((n, 3)) < 0.15, 0:2] = 0     # r = g = 0 with b > 0: the commit's "both words non-zero" test
         r[:, 924:930] = np.stack([h16(rad[..., 0]) | (h16(rad[..., 1]) << 16), h16(rad[..., 2]) | (h16(rad[..., 3]) << 16)], axis=-1).reshape(n, 6).view(np.float32)
         r[:, 930] = np.where(rng.random(n) < 0.5, -np.exp(rng.uniform(-3, 4, n)), np.where(rng.random(n) < 0.5, 0, np.exp(rng.uniform(-3, 3, n))))
+    if build:
+        # BUILD pass: the delta tree is explored plane by plane.  Words 10-11 of the payload hold the packed image transform (two 30-bit octahedral rows + handedness), word 17 the scene
+        # length at which motion vectors were blocked (mostly 0 = not blocked), word 18 nothing; the header says which planes are free (invalid id), enqueued or taken
+        p[:, 10] = rng.integers(0, 1 << 30, n); p[:, 11] = rng.integers(0, 1 << 30, n).astype(np.uint32) | (rng.integers(0, 2, n).astype(np.uint32) << 31)
+        p[:, 17] = np.where(rng.random(n) < 0.75, 0, np.exp(rng.uniform(-2, 3, n))).astype(np.float32).view(np.uint32); p[:, 18] = 0
+        cur = rng.integers(0, 3, n).astype(np.uint32); flags |= cur << 14; flags |= (rng.random(n) < 0.6).astype(np.uint32) * np.uint32(PF["onDominant"])
+        p[:, 15] = np.where(rng.random(n) < 0.4, 1, rng.integers(1, 1 << 10, n)).astype(np.uint32)
+        kind = rng.random((n, 3)); hdr = np.where(kind < 0.6, 0xFFFFFFFF, np.where(kind < 0.8, 0xFFFFFFFE, rng.integers(1, 1 << 12, (n, 3)))).astype(np.uint32); hdr[np.arange(n), cur] = 0
+        r[:, 920:923] = hdr.view(np.float32); r[:, 923] = ((np.exp(rng.uniform(-1, 4, n)).astype(np.float32).view(np.uint32) & np.uint32(0xFFFFFFFC)) | rng.integers(0, 3, n).astype(np.uint32)).view(np.float32)
+        r[:, 931:934] = (rng.random((n, 3)) - 0.5) * 20; d = rng.normal(size=(n, 3)); r[:, 934:937] = d / np.linalg.norm(d, axis=1, keepdims=True); r[:, 937:943] = rng.normal(size=(n, 6)) * 0.01
+        r[:, 943] = rng.integers(1, 10, n); r[:, 944] = rng.random(n) < 0.7; r[:, 945] = 0.95; r[:, 946:949] = f16(rng.gamma(1.0, 0.5, (n, 3)) * (rng.random((n, 1)) < 0.5))
     p[:, 19] = (flags << 10) | vertex
     r[:, 0:20] = p.view(np.float32)
     return r
@@ -114,10 +128,12 @@ def make(rng, n, slots_pool, fill=False):
 if __name__ == "__main__":
     rng = np.random.default_rng(777)
     g = np.load(os.path.join(ROOT, "tests", "golden", "interior_golden.npz")); slots = g["interior_out"].reshape(-1, 12, 6)[:, :, 0:2].reshape(-1, 2).view(np.uint32); slots = slots[(slots != 0).any(1)]
-    u = make(rng, 1500, slots)
-    out = run("hit", u, 64)
-    src = "Rtxpt/Shaders/PathTracer/{PathTracer,PathTracerNEE,PathTracerNestedDielectrics,PathTracerStablePlanes,StablePlanes,PathState,PathPayload}.hlsli + Utils/SampleGenerators.hlsli at reference commit f08d1c7, compiled as C++ by oracle/Makefile targets _ref/ref_kat_bsdf (PATH_TRACER_MODE 0) and _ref/ref_kat_pt_fill (2) behind oracle/ref_bridge_stub.h"
-    uf = make(np.random.default_rng(778), 1500, slots, fill=True)
-    outf = run("hit", uf, 64, exe="ref_kat_pt_fill")
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "hit_golden.npz"), hit_in=u, hit_out=out, fill_in=uf, fill_out=outf, source=np.array(src))
-    print(u.shape, out.shape, uf.shape, outf.shape, os.path.getsize(os.path.join(ROOT, "tests", "golden", "hit_golden.npz")))
+    u = make(rng, 1200, slots)
+    out = run("hit", u, 128)
+    src = "Rtxpt/Shaders/PathTracer/{PathTracer,PathTracerNEE,PathTracerNestedDielectrics,PathTracerStablePlanes,StablePlanes,PathState,PathPayload}.hlsli + Utils/SampleGenerators.hlsli at reference commit f08d1c7, compiled as C++ by oracle/Makefile targets _ref/ref_kat_bsdf (PATH_TRACER_MODE 0), _ref/ref_kat_pt_build (1) and _ref/ref_kat_pt_fill (2) behind oracle/ref_bridge_stub.h"
+    uf = make(np.random.default_rng(778), 1200, slots, fill=True)
+    outf = run("hit", uf, 128, exe="ref_kat_pt_fill")
+    ub = make(np.random.default_rng(779), 1200, slots, build=True)
+    outb = run("hit", ub, 128, exe="ref_kat_pt_build")
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "hit_golden.npz"), hit_in=u, hit_out=out, fill_in=uf, fill_out=outf, build_in=ub, build_out=outb, source=np.array(src))
+    print(u.shape, out.shape, uf.shape, outf.shape, ub.shape, outb.shape, os.path.getsize(os.path.join(ROOT, "tests", "golden", "hit_golden.npz")))

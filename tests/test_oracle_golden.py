@@ -285,21 +285,30 @@ def test_handle_hit_matches_reference_path_tracer_golden(oracle):
     """PathTracer::HandleHit of the UNMODIFIED PathTracer.hlsli - with PathTracerNEE.hlsli (candidate loop, weighted reservoir, shadow ray, both MIS weights, firefly filter, fp16
     accumulation, NEE-AT feedback), PathTracerNestedDielectrics.hlsli (false-hit rejection, outside IoR), GenerateScatterRay (BSDF sample, ray cone, bounce counters, firefly K),
     HandleRussianRoulette, the Sobol / hash sample generators and the 80-byte path payload - compiled in place behind a stub bridge (oracle/ref_bridge_stub.h,
-    tests/golden/make_hit_golden.py), once as the reference-mode shader and once as the FILL pass (PathTracerStablePlanes.hlsli's StablePlanesOnScatter, StablePlanes.hlsli's
-    CommitDenoiserRadiance, the specular hit distance, attenuated noisy radiance).  1500 path vertices each: the outgoing payload, the shadow ray, the feedback reservoir, the planes'
-    noisy radiance and the hit distance the oracle's HandleHitSurface produces are bit-identical."""
+    tests/golden/make_hit_golden.py) three times, as the three shaders RTXPT compiles it into:
+      reference mode;
+      the BUILD pass (PathTracerStablePlanes.hlsli's StablePlanesHandleHit: delta-lobe enumeration, plane allocation, SplitDeltaPath with the accumulated image transform,
+        StablePlanes.hlsli's StoreStablePlane / StoreExplorationStart packing, dominant plane, stable radiance);
+      the FILL pass (StablePlanesOnScatter, CommitDenoiserRadiance, the specular hit distance, attenuated noisy radiance).
+    1200 path vertices each: the outgoing payload, the shadow ray, the feedback reservoir, the pixel's three stable planes (all 80 bytes), its header and stable radiance and the hit
+    distance the oracle's HandleHitSurface produces are bit-identical."""
     import ctypes as C
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "hit_golden.npz"))
     L = oracle.lib(); L.oracle_hit_funcs.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]; L.oracle_hit_funcs.restype = None
-    for key, mode in (("hit", 0), ("fill", 2)):
+    for key, mode in (("hit", 0), ("build", 1), ("fill", 2)):
         u, ref = np.ascontiguousarray(g[key + "_in"]), g[key + "_out"]
         out = np.empty_like(ref); L.oracle_hit_funcs(u.ctypes.data, len(u), out.ctypes.data, mode)
         same = out.view(np.uint32) == ref.view(np.uint32); same[:, 35:37] = True            # 35, 36: how often the bridge's ExportSpecHitTStart / Stop were called (not mirrored)
+        if mode == 1: same[:, 30] = True; same[:, 117:120] = True                           # what Bridge::ExportSurface was handed (the stub records it; the planes hold the same values packed)
         assert same.all(), (key, np.argwhere(~same)[:8])
-        p, pin = ref[:, :20].view(np.uint32), u[:, :20].view(np.uint32)
-        # the records exercise the paths: one and two shadow rays, occluded and visible, rejected false hits, radiance added, paths ending and going on, feedback written
-        assert np.bincount(ref[:, 20].astype(int), minlength=3)[:3].min() > 200 and 0.3 < ref[:, 28].mean() < 0.6 and (ref[:, 39] > 0).mean() > 0.25
-        assert (p[:, 10:12] != pin[:, 10:12]).any(1).mean() > 0.3 and 0.05 < 1 - ((p[:, 19] >> 10) & 1).mean() < 0.5 and (p[:, 8:10] != pin[:, 8:10]).any(1).mean() > 0.8
-        if mode == 0: assert (ref[:, 29] == 0).sum() > 15                                   # rejected false hits export nothing
-        else:   # landing on a stable plane commits the path's radiance into it; specular hit distances start and stop
-            assert (ref[:, 41:47].view(np.uint32) != u[:, 924:930].view(np.uint32)).any(1).sum() > 40 and (ref[:, 37] != u[:, 930]).sum() > 150 and ref[:, 35].sum() > 60
+        p, pin, R, U = ref[:, :20].view(np.uint32), u[:, :20].view(np.uint32), ref.view(np.uint32), u.view(np.uint32)
+        if mode != 1:   # one and two shadow rays, occluded and visible, radiance added, paths ending and going on, feedback written
+            assert np.bincount(ref[:, 20].astype(int), minlength=3)[:3].min() > 150 and 0.3 < ref[:, 28].mean() < 0.6 and (ref[:, 39] > 0).mean() > 0.25
+            assert (p[:, 10:12] != pin[:, 10:12]).any(1).mean() > 0.3 and 0.05 < 1 - ((p[:, 19] >> 10) & 1).mean() < 0.5 and (p[:, 8:10] != pin[:, 8:10]).any(1).mean() > 0.8
+        if mode == 0: assert (ref[:, 29] == 0).sum() > 10                                   # rejected false hits export nothing
+        if mode == 2:   # landing on a stable plane commits the path's radiance into it; specular hit distances start and stop
+            assert (R[:, 41:47] != U[:, 924:930]).any(1).sum() > 30 and (ref[:, 37] != u[:, 930]).sum() > 120 and ref[:, 35].sum() > 50
+        if mode == 1:   # planes enqueued for later exploration, paths that keep walking the delta tree (new branch id, turned image transform), base planes stored, stable emission
+            hin, hout = U[:, 920:924], R[:, 47:51]
+            assert ((hout[:, :3] == 0xFFFFFFFE) & (hin[:, :3] != 0xFFFFFFFE)).any(1).mean() > 0.1 and (R[:, 15] != U[:, 15]).mean() > 0.05 and (R[:, 10:12] != U[:, 10:12]).any(1).mean() > 0.03
+            assert 1 - ((R[:, 19] >> 10) & 1).mean() > 0.7 and (ref[:, 52:55] != u[:, 946:949]).any(1).mean() > 0.15 and 0.3 < ref[:, 29].mean() < 0.8
