@@ -306,10 +306,41 @@ ORC_API void oracle_sampler_funcs(const float* in, uint32_t count, float* out)
     }
 }
 
+// the environment-quad light, layout of ref_kat_bsdf_main.cpp's "envquads" mode: Store, Create, the sample HandleNEE draws from it (pt_path.h), pdf, power
+ORC_API void oracle_envquad_light_funcs(const float* in, uint32_t count, float* out)
+{
+    for (uint32_t i = 0; i < count; i++)
+    {
+        const float* u = in + size_t(i) * 24; float* o = out + size_t(i) * 24;
+        EnvironmentQuadLight e; e.NodeX = uint(u[0]); e.NodeY = uint(u[1]); e.NodeDim = uint(u[2]); e.Weight = u[3]; e.Radiance = f3(u[4], u[5], u[6]);
+        const PolymorphicLightInfo li = e.Store();
+        uint words[12] = {}; memcpy(words, &li, 32); words[11] = uint(u[7]);
+        memcpy(o, words, 48);
+        RtxptPathTracerConstants c; memset(&c, 0, sizeof(c));
+        const bool rotated = u[8] != 0.0f || u[9] != 0.0f || u[10] != 0.0f;
+        for (int a = 0; a < 3; a++) for (int k = 0; k < 3; k++) { const float v = rotated ? u[8 + 3 * a + k] : (a == k ? 1.0f : 0.0f); c.envMap.Transform[a * 4 + k] = v; c.envMap.InvTransform[k * 4 + a] = v; }
+        PathTracerCtx x; x.c = &c;
+        const EnvironmentQuadLight q = EnvironmentQuadLight::Create(li);
+        const float3 viewer = f3(u[19], u[20], u[21]);
+        const float2 subTexelPos = f2((float(q.NodeX) + u[17]) / float(q.NodeDim), (float(q.NodeY) + u[18]) / float(q.NodeDim));
+        const float3 worldDir = envToWorld(x, oct_to_ndir_equal_area_unorm(subTexelPos));
+        const float3 position = viewer + worldDir * DISTANT_LIGHT_DISTANCE, normal = -worldDir;
+        o[12] = position.x; o[13] = position.y; o[14] = position.z; o[15] = normal.x; o[16] = normal.y; o[17] = normal.z; o[18] = q.Radiance.x; o[19] = q.Radiance.y; o[20] = q.Radiance.z;
+        o[21] = q.SolidAnglePdf(); o[22] = q.SolidAnglePdf(); o[23] = q.Weight;
+    }
+}
+
 // PathTracer::HandleHit on one path vertex as the oracle restates it (pt_path.h: HandleHitSurface, HandleNEE, GenerateScatterRay, HandleRussianRoulette, nested dielectrics), layout
 // of ref_kat_bsdf_main.cpp's "hit" mode (960 floats in, 128 out).  The scene side is data, as behind the stub bridge there: the surface comes from the record, materials are the
 // IoR / absorption table, a shadow ray is answered by the same function of its bits (ShimVisibilityRule in oracle/ref_bridge_stub.h, restated here).  mode: 0 reference, 2 FILL
 struct HitMirrorVisibility { uint queries = 0; float3 o = f3(0), d = f3(0); float tMax = 0; bool last = false; };
+static float3 hitMirrorEnvCube(float3 d, float lod) { const float k = exp2f(-lod); return f3((0.5f + 0.5f * d.x) * k, (0.5f + 0.25f * d.y) * k, (0.75f + 0.25f * d.z) * k); }
+static const std::vector<uint>& hitMirrorEnvLookup()
+{
+    static std::vector<uint> m;
+    if (m.empty()) { m.resize(size_t(IMPORTANCE_MAP_DIM) * IMPORTANCE_MAP_DIM); for (uint y = 0; y < IMPORTANCE_MAP_DIM; y++) for (uint x = 0; x < IMPORTANCE_MAP_DIM; x++) m[size_t(y) * IMPORTANCE_MAP_DIM + x] = ((x >> 6) + (y >> 6) * 3u) & 3u; }
+    return m;
+}
 struct HitMirrorCamera { float3 pos, base, dx, dy; };
 static void hitMirrorCameraRay(uint px, uint py, float3& origin, float3& dir, void* user)
 {
@@ -344,7 +375,8 @@ ORC_API void oracle_hit_funcs(const float* in, uint32_t count, float* out, uint3
         RtxptPathTracerConstants c; memset(&c, 0, sizeof(c));
         c.imageWidth = c.imageHeight = 8; c.bounceCount = uint(r[80]); c.diffuseBounceCount = uint(r[81]); c.NEEEnabled = 1; c.NEEType = 2; c.NEECandidateSamples = uint(r[83]); c.NEEFullSamples = uint(r[84]);
         c.fireflyFilterThreshold = r[85]; c.enableRussianRoulette = 1; c.enableLDSamplerForBSDF = 1; c.nestedDielectricsQuality = 1; c.EnvironmentMapDiffuseSampleMIPLevel = r[93]; c.NEEATFeedback = 1;
-        for (int k = 0; k < 3; k++) { c.envMap.Transform[k * 4 + k] = 1.0f; c.envMap.InvTransform[k * 4 + k] = 1.0f; c.envMap.ColorMultiplier[k] = 1.0f; }
+        for (int a = 0; a < 3; a++) for (int k = 0; k < 3; k++) { c.envMap.Transform[a * 4 + k] = r[950 + 3 * a + k]; c.envMap.InvTransform[k * 4 + a] = r[950 + 3 * a + k]; }
+        for (int k = 0; k < 3; k++) c.envMap.ColorMultiplier[k] = r[959];
         RtxptMaterialData mats[8]; memset(mats, 0, sizeof(mats));
         for (int m = 0; m < 8; m++) { mats[m].IoR = r[96 + m]; for (int k = 0; k < 3; k++) mats[m].VolumeAttenuationColor[k] = r[104 + 3 * m + k]; mats[m].VolumeAttenuationDistance = r[128 + m]; }
         RtxptSceneDesc desc; memset(&desc, 0, sizeof(desc)); desc.materials = mats; desc.materialCount = 8;
@@ -354,12 +386,13 @@ ORC_API void oracle_hit_funcs(const float* in, uint32_t count, float* out, uint3
         for (int k = 0; k < 16; k++) lt.proxyCounters[k] = uint(r[136 + k]);
         for (int k = 0; k < 64; k++) lt.proxyIndices[k] = uint(r[152 + k]);
         for (int k = 0; k < 16; k++) { memcpy(&lt.lights[k], r + 728 + 12 * k, 32); memcpy(&lt.lightsEx[k], r + 728 + 12 * k + 8, 16); }
+        lt.envEnabled = true; lt.envLookupMap = hitMirrorEnvLookup();
         NeeatState ns; ns.init(8, 8); ns.jitter[0] = uint(r[88]); ns.jitter[1] = uint(r[89]); ns.localToGlobalSampleRatio = r[86]; ns.settings.screenSpaceVsWorldSpaceThreshold = r[91];
         ns.temporalFeedbackRequired = r[92] != 0.0f; memcpy(ns.localSamplingBuffer.data(), r + 216, 512 * sizeof(uint));
         // the vertex
         HitMirrorVisibility vis;
         PathTracerCtx x; x.scene = &sc; x.bvh = nullptr; x.lights = &lt; x.c = &c; x.sampleIndex = uint(r[82]); x.stats = nullptr; x.mode = mode; x.neeat = &ns;
-        x.visibilityOverride = hitMirrorVisibility; x.visibilityUser = &vis; x.noisyRadianceAttenuationOverride = r[87];
+        x.envEvalOverride = hitMirrorEnvCube; x.visibilityOverride = hitMirrorVisibility; x.visibilityUser = &vis; x.noisyRadianceAttenuationOverride = r[87];
         uint payload[20]; memcpy(payload, r, 80);
         PathState path = unpackPayload(payload); const uint payloadIn14 = payload[14];
         // FILL: the stable planes of an 8 x 8 image, the pixel's entries from the record
@@ -383,12 +416,14 @@ ORC_API void oracle_hit_funcs(const float* in, uint32_t count, float* out, uint3
             x.sp = &rtt;
         }
         const float3 rayOrigin = f3(r[20], r[21], r[22]), rayDir = f3(r[23], r[24], r[25]);
-        UpdatePathTravelled(path, r[26]);
-        HandleHitSurface(x, path, rayOrigin, rayDir, r[26], sf);
+        if (r[27] != 0.0f) HandleMiss(x, path, rayDir, r[26]);          // the payload's origin is the ray's
+        else { UpdatePathTravelled(path, r[26]); HandleHitSurface(x, path, rayOrigin, rayDir, r[26], sf); }
         packPayload(path, payload); memcpy(o, payload, 80);
         o[20] = float(vis.queries); o[21] = vis.o.x; o[22] = vis.o.y; o[23] = vis.o.z; o[24] = vis.d.x; o[25] = vis.d.y; o[26] = vis.d.z; o[27] = vis.tMax; o[28] = vis.last ? 1.0f : 0.0f;
         const bool rejectedFalseHit = path.getCounter(CTR_RejectedHits) != ((payloadIn14 >> 8) & 0xFFu);
-        if (mode == MODE_REFERENCE && !rejectedFalseHit) { o[29] = 1.0f; o[30] = path.sceneLength; }      // Bridge::ExportSurface( path, surface, path.GetSceneLength() ): once per accepted hit
+        const bool miss = r[27] != 0.0f;
+        if (mode == MODE_REFERENCE && miss) { const float3 v = rayOrigin + rayDir * r[26]; o[31] = 1.0f; o[32] = v.x; o[33] = v.y; o[34] = v.z; }      // Bridge::ExportNonSurface( path, rayOrigin + rayDir * rayTCurrent )
+        if (mode == MODE_REFERENCE && !miss && !rejectedFalseHit) { o[29] = 1.0f; o[30] = path.sceneLength; }      // Bridge::ExportSurface( path, surface, path.GetSceneLength() ): once per accepted hit
         if (mode != MODE_REFERENCE)
         {
             o[37] = specHitT[pyi * 8 + pxi];
@@ -396,7 +431,7 @@ ORC_API void oracle_hit_funcs(const float* in, uint32_t count, float* out, uint3
             for (uint k = 0; k < 4; k++) memcpy(o + 47 + k, &rtt.hdr(pxi, pyi, k), 4);
             for (int k = 0; k < 4; k++) o[52 + k] = f16tof32(stableRadiance[(pyi * 8 + pxi) * 4 + k]);
             for (uint k = 0; k < 3; k++) memcpy(o + 56 + 20 * k, &planes[rtt.PixelToAddress(pxi, pyi, k)], 80);
-            if (mode == MODE_BUILD_STABLE_PLANES) o[29] = depth[pyi * 8 + pxi] != -1.0f ? 1.0f : 0.0f;        // Bridge::ExportSurface from the dominant base plane
+            if (mode == MODE_BUILD_STABLE_PLANES) o[miss ? 31 : 29] = depth[pyi * 8 + pxi] != -1.0f ? 1.0f : 0.0f;        // Bridge::ExportSurface / ExportNonSurface from the dominant base plane
         }
         const uint px = (path.id >> 16) & 7u, py = path.id & 7u;
         o[39] = ns.feedback.weight[py * 8 + px]; memcpy(o + 40, &ns.feedback.candidate[py * 8 + px], 4);

@@ -118,6 +118,7 @@ struct PathTracerCtx
     // test hook (oracle.cpp's known-answer mirrors): answers a shadow ray instead of the BVH, as the stub bridge of oracle/ref_bridge_stub.h does for the reference's code
     bool (*visibilityOverride)(float3 origin, float3 dir, float tMax, void* user) = nullptr; void* visibilityUser = nullptr;
     void (*cameraRayOverride)(uint px, uint py, float3& origin, float3& dir, void* user) = nullptr; void* cameraRayUser = nullptr;
+    float3 (*envEvalOverride)(float3 localDir, float lod) = nullptr;       // stands in for the environment cube map (before the colour multiplier)
     float noisyRadianceAttenuationOverride = 0.0f;
     float noisyRadianceAttenuation() const { return noisyRadianceAttenuationOverride != 0.0f ? noisyRadianceAttenuationOverride : 1.0f / float(sp->rt->subSampleCount); }      // Bridge::getNoisyRadianceAttenuation = invSubSampleCount (BridgeDonut:515-523)
 };
@@ -149,6 +150,7 @@ inline float3 envToLocal(const PathTracerCtx& x, float3 d) { return mul_vec_33of
 inline float3 envToWorld(const PathTracerCtx& x, float3 d) { return mul_vec_33of34(d, x.c->envMap.Transform); }
 inline float3 envEvalLocal(const PathTracerCtx& x, float3 localDir, float lod)
 {
+    if (x.envEvalOverride) return x.envEvalOverride(localDir, lod) * f3(x.c->envMap.ColorMultiplier[0], x.c->envMap.ColorMultiplier[1], x.c->envMap.ColorMultiplier[2]);
     return x.scene->env.sampleLevel(localDir, lod) * f3(x.c->envMap.ColorMultiplier[0], x.c->envMap.ColorMultiplier[1], x.c->envMap.ColorMultiplier[2]);
 }
 

@@ -34,7 +34,7 @@ static void shimIdentityEnv() { memset(&g_bridge.env, 0, sizeof(g_bridge.env)); 
 // (order of the "bsdf" mode's words 18-31) | 74 interior IoR, 75 / 76 emissive-triangle / analytic-proxy light (-1: none), 77-79 prevPosW | 80-93 constants | 96-135 materials (IoR,
 // attenuation colour, attenuation distance x 8) | 136-151 proxy counters, 152-215 proxy indices, 216-727* 2 x 2 local tiles, 728-919* 16 light records (Base + Extended) | FILL mode: 920-923* the pixel's stable-plane header (3 branch ids, first-hit length | dominant index), 924-929* the three planes'
 // packed noisy radiance, 930 the pixel's specular hit distance | BUILD mode: 931-942 the stub camera (position, direction at pixel 0, per-pixel steps), 943 maxStablePlaneVertexDepth,
-// 944 allowPrimarySurfaceReplacement, 945 stablePlanesSplitStopThreshold, 946-949 the pixel's stable radiance (RGBA16F values)
+// 944 allowPrimarySurfaceReplacement, 945 stablePlanesSplitStopThreshold, 946-949 the pixel's stable radiance (RGBA16F values) | 950-958 the environment map's rotation (rows), 959 its intensity
 static const int kHitIn = 960, kHitOut = 128;
 struct ShimHitScenario
 {
@@ -87,17 +87,23 @@ static void shimLoadHitScenario(const float* r, ShimHitScenario& S)
         S.lights[k].LogRadiance = w[7]; S.lightsEx[k].IesProfileIndex = w[8]; S.lightsEx[k].PrimaryAxis = w[9]; S.lightsEx[k].CosConeAngleAndSoftness = w[10]; S.lightsEx[k].UniqueID = w[11];
     }
     for (int k = 0; k < 64; k++) { S.fbWeight[k] = 0.0f; S.fbCand[k] = 0xFFFFFFFFu; }
-    S.envLookup[0] = 0u;
+    // the environment lookup map (direction -> environment-quad light): 1024 x 1024 texels of the equal-area octahedral map, in 64-texel blocks over lights 0-3 (what the record's first
+    // four lights are when it has environment quads)
+    static std::vector<uint> envLookup1024;
+    if (envLookup1024.empty()) { envLookup1024.resize(1024 * 1024); for (uint y = 0; y < 1024; y++) for (uint x = 0; x < 1024; x++) envLookup1024[y * 1024 + x] = ((x >> 6) + (y >> 6) * 3u) & 3u; }
+    memset(&g_bridge.env, 0, sizeof(g_bridge.env));
+    for (int a = 0; a < 3; a++) for (int c = 0; c < 3; c++) { g_bridge.env.Transform.m[a][c] = r[950 + 3 * a + c]; g_bridge.env.InvTransform.m[c][a] = r[950 + 3 * a + c]; }
+    g_bridge.env.ColorMultiplier = float3(r[959], r[959], r[959]); g_bridge.env.Enabled = 1.0f;
     g_bridge.control.p = &S.cd; g_bridge.control.n = 1; g_bridge.lights.p = S.lights; g_bridge.lights.n = 16; g_bridge.lightsEx.p = S.lightsEx; g_bridge.lightsEx.n = 16;
     g_bridge.proxyCounters.p = S.counters; g_bridge.proxyCounters.n = 16; g_bridge.proxyIndices.p = S.indices; g_bridge.proxyIndices.n = S.cd.SamplingProxyCount; g_bridge.localSampling.p = S.local; g_bridge.localSampling.n = 512;
-    g_bridge.envLookup.p = S.envLookup; g_bridge.envLookup.w = g_bridge.envLookup.h = 1; g_bridge.feedbackWeight.p = S.fbWeight; g_bridge.feedbackWeight.w = g_bridge.feedbackWeight.h = 8;
+    g_bridge.envLookup.p = envLookup1024.data(); g_bridge.envLookup.w = g_bridge.envLookup.h = 1024; g_bridge.feedbackWeight.p = S.fbWeight; g_bridge.feedbackWeight.w = g_bridge.feedbackWeight.h = 8;
     g_bridge.feedbackCandidates.p = S.fbCand; g_bridge.feedbackCandidates.w = g_bridge.feedbackCandidates.h = 8;
     g_bridge.hasEnvMap = true;
 }
 
 int main(int argc, char** argv)
 {
-    if (argc != 4) { fprintf(stderr, "usage: %s bsdf|funcs|utils|helpers|lights|spheres|tonemap|texlod|interior|sampler|hit in.f32 out.f32\n", argv[0]); return 2; }
+    if (argc != 4) { fprintf(stderr, "usage: %s bsdf|funcs|utils|helpers|lights|spheres|tonemap|texlod|interior|sampler|hit|envquads in.f32 out.f32\n", argv[0]); return 2; }
     const std::vector<float> in = readAll(argv[2]); std::vector<float> out;
     shimIdentityEnv();
     if (std::string(argv[1]) == "bsdf")
@@ -247,6 +253,27 @@ int main(int argc, char** argv)
             o[39] = S->fbWeight[at]; memcpy(o + 40, &S->fbCand[at], 4);
         }
         delete S;
+    }
+    else if (std::string(argv[1]) == "envquads")
+    {   // Lighting/PolymorphicLight.hlsli: an environment-quad light (a node of the quad tree over the equal-area octahedral environment map) through EnvironmentQuadLight::Store, Create,
+        // CalcSample (through the environment rotation words 8-16 give; identity when all zero), CalcSolidAnglePdfForMIS, GetPower.  24 floats in, 24 out (words 0-11: the record)
+        const size_t n = in.size() / 24; out.assign(n * 24, 0.0f);
+        for (size_t i = 0; i < n; i++)
+        {
+            const float* u = &in[i * 24]; float* o = &out[i * 24];
+            EnvironmentQuadLight e; e.NodeX = uint(u[0]); e.NodeY = uint(u[1]); e.NodeDim = uint(u[2]); e.Weight = u[3]; e.Radiance = float3(u[4], u[5], u[6]);
+            const PolymorphicLightInfoFull full = e.Store(uint(u[7]));
+            const uint words[12] = { asuint(full.Base.Center.x), asuint(full.Base.Center.y), asuint(full.Base.Center.z), full.Base.ColorTypeAndFlags, full.Base.Direction1, full.Base.Direction2, full.Base.Scalars,
+                                     full.Base.LogRadiance, full.Extended.IesProfileIndex, full.Extended.PrimaryAxis, full.Extended.CosConeAngleAndSoftness, full.Extended.UniqueID };
+            memcpy(o, words, 48);
+            shimIdentityEnv();
+            if (u[8] != 0.0f || u[9] != 0.0f || u[10] != 0.0f) for (int a = 0; a < 3; a++) for (int c = 0; c < 3; c++) { g_bridge.env.Transform.m[a][c] = u[8 + 3 * a + c]; g_bridge.env.InvTransform.m[c][a] = u[8 + 3 * a + c]; }
+            const float3 viewer(u[19], u[20], u[21]);
+            const PolymorphicLightSample r = PolymorphicLight::CalcSample(full, float2(u[17], u[18]), viewer);
+            o[12] = r.Position.x; o[13] = r.Position.y; o[14] = r.Position.z; o[15] = r.Normal.x; o[16] = r.Normal.y; o[17] = r.Normal.z; o[18] = r.Radiance.x; o[19] = r.Radiance.y; o[20] = r.Radiance.z;
+            const EnvironmentQuadLight c = EnvironmentQuadLight::Create(full);
+            o[21] = r.SolidAnglePdf; o[22] = c.CalcSolidAnglePdfForMIS(viewer, r.Position); o[23] = c.GetPower();
+        }
     }
     else if (std::string(argv[1]) == "texlod")
     {   // Rendering/Materials/TexLODHelpers.hlsli:40-161: the ray cone (fp16-packed width / spread angle), its propagation, the per-triangle LOD constant and computeLOD - what

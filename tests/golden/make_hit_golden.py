@@ -23,13 +23,33 @@ PF = dict(active=1 << 0, hit=1 << 1, transmission=1 << 2, specular=1 << 3, delta
           onPlane=1 << 16, onBranch=1 << 17, baseScatterDiff=1 << 18, specHitTQueued=1 << 19, onDominant=1 << 20)
 
 
+def rotations(rng, n):
+    q = rng.normal(size=(n, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True); w, x, y, z = q.T
+    R = np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w), 2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w), 2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], axis=1)
+    return R.astype(np.float32)
+
+
+def envquad_inputs(rng, n, rot=None):
+    """the "envquads" mode's input: node x, y, dimension (4 .. 256), weight, radiance, id, rotation (zeros = identity), random 2, viewer 3"""
+    u = np.zeros((n, 24), np.float32); dim = 2 ** rng.integers(2, 9, n); u[:, 2] = dim; u[:, 0] = rng.integers(0, dim); u[:, 1] = rng.integers(0, dim)
+    u[:, 3] = rng.gamma(2.0, 2.0, n); u[:, 4:7] = rng.gamma(2.0, 1.5, (n, 3)); u[:, 7] = rng.integers(0, 1 << 20, n)
+    if rot is not None: u[:, 8:17] = rot
+    u[:, 17:19] = rng.random((n, 2)); u[:, 19:22] = (rng.random((n, 3)) - 0.5) * 40
+    return u
+
+
 def light_records(rng, n, around):
-    """n x 16 lights x 12 words: 12 emissive triangles and 4 sphere / spot lights placed around the shaded points"""
+    """n x 16 lights x 12 words: 4 environment quads, 8 emissive triangles and 4 sphere / spot lights placed around the shaded points"""
     rec = np.zeros((n, 16, 12), np.uint32)
+    rec[:, :4, :] = run("envquads", envquad_inputs(rng, n * 4), 24)[:, :12].view(np.uint32).reshape(n, 4, 12)
+    return rec, 4
+
+
+def light_records_rest(rng, n, around, rec):
     u = np.zeros((n * 12, 24), np.float32); c = np.repeat(around, 12, axis=0)
     u[:, 0:3] = c + rng.normal(size=(n * 12, 3)).astype(np.float32) * np.float32(6); u[:, 3:6] = (rng.random((n * 12, 3)) - 0.5) * np.float32(3); u[:, 6:9] = (rng.random((n * 12, 3)) - 0.5) * np.float32(3)
     u[:, 9:12] = rng.gamma(2.0, 4.0, (n * 12, 3)).astype(np.float32)
-    rec[:, :12, :8] = run("lights", u, 24)[:, :8].view(np.uint32).reshape(n, 12, 8)
+    rec[:, 4:12, :8] = run("lights", u, 24)[:, :8].view(np.uint32).reshape(n, 12, 8)[:, :8]
     v = np.zeros((n * 4, 24), np.float32); c = np.repeat(around, 4, axis=0)
     v[:, 0:3] = c + rng.normal(size=(n * 4, 3)).astype(np.float32) * np.float32(5); v[:, 3] = np.float32(0.05) + rng.random(n * 4).astype(np.float32) * np.float32(0.5)
     v[:, 4:7] = rng.gamma(2.0, 30.0, (n * 4, 3)).astype(np.float32); v[:, 7] = rng.random(n * 4); v[:, 8] = rng.random(n * 4)
@@ -58,7 +78,7 @@ def make(rng, n, slots_pool, fill=False, build=False):
         r[pure, 60:63] = 0; r[pure, 63] = np.float16(0.02); r[pure, 71] = 0; glass = pure & (rng.random(n) < 0.5); r[glass, 72] = 1.0; r[glass, 49] = rng.random(int(glass.sum())) < 0.3
     if fill or build: r[rng.random(n) < (0.6 if build else 0.45), 63] = np.float16(0.02)        # delta lobes (mirrors, clear glass): what the stable planes follow
     ior = f16(np.where(rng.random(n) < 0.7, 1.5, 1.0 + rng.random(n) * 1.2)); r[:, 74] = ior
-    r[:, 75] = np.where(em & (rng.random(n) < 0.8), rng.integers(0, 12, n), -1); r[:, 76] = np.where(rng.random(n) < 0.15, rng.integers(12, 16, n), -1)
+    r[:, 75] = np.where(em & (rng.random(n) < 0.8), rng.integers(4, 12, n), -1); r[:, 76] = np.where(rng.random(n) < 0.15, rng.integers(12, 16, n), -1)
     r[:, 77:80] = pos + rng.normal(size=(n, 3)).astype(np.float32) * np.float32(0.01)
     # constants
     r[:, 80] = rng.integers(1, 9, n); r[:, 81] = rng.integers(0, 5, n); r[:, 82] = rng.integers(0, 4096, n); r[:, 83] = rng.integers(1, 9, n); r[:, 84] = rng.integers(1, 3, n)
@@ -69,7 +89,9 @@ def make(rng, n, slots_pool, fill=False, build=False):
     r[:, 96:104] = f16(np.where(rng.random((n, 8)) < 0.6, 1.5, 1.0 + rng.random((n, 8)) * 1.2)); r[:, 104:128] = rng.random((n, 24)) ** 0.3; r[:, 104:107] = 0.0   # material 0: black absorber (the 1e-7 clamp)
     r[:, 128:136] = np.exp(rng.uniform(-3, 3, (n, 8))); r[:, 129] = 0.0                                                                                                   # material 1: zero distance (the 1e-30 clamp)
     # light scenario
-    lights = light_records(rng, n, pos); r[:, 728:920] = lights.reshape(n, 192).view(np.float32)
+    lights, _ = light_records(rng, n, pos); lights = light_records_rest(rng, n, pos, lights); r[:, 728:920] = lights.reshape(n, 192).view(np.float32)
+    r[:, 950:959] = rotations(rng, n); r[:, 959] = np.float32(0.5) + rng.random(n).astype(np.float32) * 2
+    r[:, 27] = rng.random(n) < 0.25                                                          # a quarter of the rays leave the scene: HandleMiss
     for i in range(n):
         counters = rng.integers(0, 9, 16) * (rng.random(16) < 0.8)
         if counters.sum() == 0: counters[rng.integers(0, 16)] = 3
@@ -128,6 +150,9 @@ def make(rng, n, slots_pool, fill=False, build=False):
 if __name__ == "__main__":
     rng = np.random.default_rng(777)
     g = np.load(os.path.join(ROOT, "tests", "golden", "interior_golden.npz")); slots = g["interior_out"].reshape(-1, 12, 6)[:, :, 0:2].reshape(-1, 2).view(np.uint32); slots = slots[(slots != 0).any(1)]
+    e = envquad_inputs(np.random.default_rng(776), 2000, rotations(np.random.default_rng(775), 2000)); e[:200, 8:17] = 0
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "envquad_lights_golden.npz"), envquads_in=e, envquads_out=run("envquads", e, 24),
+                        source=np.array("Rtxpt/Shaders/PathTracer/Lighting/PolymorphicLight.hlsli (EnvironmentQuadLight) at reference commit f08d1c7, compiled as C++ by oracle/Makefile target _ref/ref_kat_bsdf"))
     u = make(rng, 1200, slots)
     out = run("hit", u, 128)
     src = "Rtxpt/Shaders/PathTracer/{PathTracer,PathTracerNEE,PathTracerNestedDielectrics,PathTracerStablePlanes,StablePlanes,PathState,PathPayload}.hlsli + Utils/SampleGenerators.hlsli at reference commit f08d1c7, compiled as C++ by oracle/Makefile targets _ref/ref_kat_bsdf (PATH_TRACER_MODE 0), _ref/ref_kat_pt_build (1) and _ref/ref_kat_pt_fill (2) behind oracle/ref_bridge_stub.h"

@@ -290,7 +290,8 @@ def test_handle_hit_matches_reference_path_tracer_golden(oracle):
       the BUILD pass (PathTracerStablePlanes.hlsli's StablePlanesHandleHit: delta-lobe enumeration, plane allocation, SplitDeltaPath with the accumulated image transform,
         StablePlanes.hlsli's StoreStablePlane / StoreExplorationStart packing, dominant plane, stable radiance);
       the FILL pass (StablePlanesOnScatter, CommitDenoiserRadiance, the specular hit distance, attenuated noisy radiance).
-    1200 path vertices each: the outgoing payload, the shadow ray, the feedback reservoir, the pixel's three stable planes (all 80 bytes), its header and stable radiance and the hit
+    1200 path vertices each, a quarter of them rays that leave the scene (HandleMiss: environment lookup, MIS against the environment-quad light, StablePlanesHandleMiss), lights of all
+    three kinds in the NEE-AT tables: the outgoing payload, the shadow ray, the feedback reservoir, the pixel's three stable planes (all 80 bytes), its header and stable radiance and the hit
     distance the oracle's HandleHitSurface produces are bit-identical."""
     import ctypes as C
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "hit_golden.npz"))
@@ -299,16 +300,32 @@ def test_handle_hit_matches_reference_path_tracer_golden(oracle):
         u, ref = np.ascontiguousarray(g[key + "_in"]), g[key + "_out"]
         out = np.empty_like(ref); L.oracle_hit_funcs(u.ctypes.data, len(u), out.ctypes.data, mode)
         same = out.view(np.uint32) == ref.view(np.uint32); same[:, 35:37] = True            # 35, 36: how often the bridge's ExportSpecHitTStart / Stop were called (not mirrored)
-        if mode == 1: same[:, 30] = True; same[:, 117:120] = True                           # what Bridge::ExportSurface was handed (the stub records it; the planes hold the same values packed)
+        if mode == 1: same[:, 30] = True; same[:, 32:35] = True; same[:, 117:120] = True    # what Bridge::ExportSurface / ExportNonSurface were handed (the stub records it; the planes hold the same values packed)
         assert same.all(), (key, np.argwhere(~same)[:8])
-        p, pin, R, U = ref[:, :20].view(np.uint32), u[:, :20].view(np.uint32), ref.view(np.uint32), u.view(np.uint32)
+        R, U = ref.view(np.uint32), u.view(np.uint32); p, pin = R[:, :20], U[:, :20]
+        hitv = u[:, 27] == 0; missv = ~hitv
+        assert 200 < missv.sum() < 400 and ((R[missv, 19] >> 10) & 1).max() == 0                # a miss ends the path
+        if mode != 1: assert (R[missv, 10:12] != U[missv, 10:12]).any(1).mean() > 0.3            # ... and adds the environment's radiance
+        else: assert (R[missv, 47:50] != U[missv, 920:923]).any(1).all()                         # ... BUILD stores the sky as a plane
         if mode != 1:   # one and two shadow rays, occluded and visible, radiance added, paths ending and going on, feedback written
-            assert np.bincount(ref[:, 20].astype(int), minlength=3)[:3].min() > 150 and 0.3 < ref[:, 28].mean() < 0.6 and (ref[:, 39] > 0).mean() > 0.25
-            assert (p[:, 10:12] != pin[:, 10:12]).any(1).mean() > 0.3 and 0.05 < 1 - ((p[:, 19] >> 10) & 1).mean() < 0.5 and (p[:, 8:10] != pin[:, 8:10]).any(1).mean() > 0.8
-        if mode == 0: assert (ref[:, 29] == 0).sum() > 10                                   # rejected false hits export nothing
+            assert np.bincount(ref[:, 20].astype(int), minlength=3)[1:3].min() > 150 and 0.25 < ref[:, 28].mean() < 0.6 and (ref[:, 39] > 0).mean() > 0.2
+            assert (p[hitv, 10:12] != pin[hitv, 10:12]).any(1).mean() > 0.3 and 0.05 < 1 - ((p[hitv, 19] >> 10) & 1).mean() < 0.5 and (p[hitv, 8:10] != pin[hitv, 8:10]).any(1).mean() > 0.8
+        if mode == 0: assert (ref[hitv, 29] == 0).sum() > 8                                 # rejected false hits export nothing
         if mode == 2:   # landing on a stable plane commits the path's radiance into it; specular hit distances start and stop
             assert (R[:, 41:47] != U[:, 924:930]).any(1).sum() > 30 and (ref[:, 37] != u[:, 930]).sum() > 120 and ref[:, 35].sum() > 50
         if mode == 1:   # planes enqueued for later exploration, paths that keep walking the delta tree (new branch id, turned image transform), base planes stored, stable emission
             hin, hout = U[:, 920:924], R[:, 47:51]
             assert ((hout[:, :3] == 0xFFFFFFFE) & (hin[:, :3] != 0xFFFFFFFE)).any(1).mean() > 0.1 and (R[:, 15] != U[:, 15]).mean() > 0.05 and (R[:, 10:12] != U[:, 10:12]).any(1).mean() > 0.03
             assert 1 - ((R[:, 19] >> 10) & 1).mean() > 0.7 and (ref[:, 52:55] != u[:, 946:949]).any(1).mean() > 0.15 and 0.3 < ref[:, 29].mean() < 0.8
+
+
+def test_environment_quad_light_matches_reference_header_golden(oracle):
+    """Lighting/PolymorphicLight.hlsli's EnvironmentQuadLight compiled in place (tests/golden/make_hit_golden.py, mode "envquads"): Store (the record of a quad-tree node over the
+    equal-area octahedral environment map), Create, the sample NEE draws from a node through the environment's rotation, its solid-angle pdf and power - bit for bit."""
+    import ctypes as C
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "envquad_lights_golden.npz"))
+    u, ref = np.ascontiguousarray(g["envquads_in"]), g["envquads_out"]
+    L = oracle.lib(); L.oracle_envquad_light_funcs.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]; L.oracle_envquad_light_funcs.restype = None
+    out = np.empty_like(ref); L.oracle_envquad_light_funcs(u.ctypes.data, len(u), out.ctypes.data)
+    assert (out.view(np.uint32) == ref.view(np.uint32)).all()
+    assert np.allclose(np.linalg.norm(ref[:, 15:18], axis=1), 1, atol=1e-4) and (ref[:, 21] == (u[:, 2] ** 2 / np.float32(4 * np.pi)).astype(np.float32)).mean() > 0.9
