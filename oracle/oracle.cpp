@@ -331,7 +331,7 @@ ORC_API void oracle_envquad_light_funcs(const float* in, uint32_t count, float* 
 }
 
 // PathTracer::HandleHit on one path vertex as the oracle restates it (pt_path.h: HandleHitSurface, HandleNEE, GenerateScatterRay, HandleRussianRoulette, nested dielectrics), layout
-// of ref_kat_bsdf_main.cpp's "hit" mode (960 floats in, 128 out).  The scene side is data, as behind the stub bridge there: the surface comes from the record, materials are the
+// of ref_kat_bsdf_main.cpp's "hit" mode (1024 floats in, 128 out).  The scene side is data, as behind the stub bridge there: the surface comes from the record, materials are the
 // IoR / absorption table, a shadow ray is answered by the same function of its bits (ShimVisibilityRule in oracle/ref_bridge_stub.h, restated here).  mode: 0 reference, 2 FILL
 struct HitMirrorVisibility { uint queries = 0; float3 o = f3(0), d = f3(0); float tMax = 0; bool last = false; };
 static float3 hitMirrorEnvCube(float3 d, float lod) { const float k = exp2f(-lod); return f3((0.5f + 0.5f * d.x) * k, (0.5f + 0.25f * d.y) * k, (0.75f + 0.25f * d.z) * k); }
@@ -359,7 +359,7 @@ ORC_API void oracle_hit_funcs(const float* in, uint32_t count, float* out, uint3
 {
     for (uint32_t i = 0; i < count; i++)
     {
-        const float* r = in + size_t(i) * 960; float* o = out + size_t(i) * 128;
+        const float* r = in + size_t(i) * 1024; float* o = out + size_t(i) * 128;
         for (int k = 0; k < 128; k++) o[k] = 0.0f;
         // surface
         SurfaceData sf; ShadingData& sd = sf.sd;
@@ -407,6 +407,7 @@ ORC_API void oracle_hit_funcs(const float* in, uint32_t count, float* out, uint3
             for (uint k = 0; k < 4; k++) memcpy(&rtt.hdr(pxi, pyi, k), r + 920 + k, 4);
             for (uint k = 0; k < 3; k++) memcpy(planes[rtt.PixelToAddress(pxi, pyi, k)].PackedNoisyRadianceAndSpecAvg, r + 924 + 2 * k, 8);
             specHitT[pyi * 8 + pxi] = r[930];
+            if (r[27] >= 3.0f) for (uint k = 0; k < 3; k++) memcpy(&planes[rtt.PixelToAddress(pxi, pyi, k)], r + 960 + 20 * k, 80);
             stableRadiance.assign(64 * 4, 0); motion.assign(64 * 4, 0); depth.assign(64, -1.0f); throughput.assign(64, 0u);
             rtt.stableRadiance = stableRadiance.data(); rtt.motionVectors = motion.data(); rtt.depth = depth.data(); rtt.throughput = throughput.data();
             for (int k = 0; k < 4; k++) stableRadiance[(pyi * 8 + pxi) * 4 + k] = uint16_t(f32tof16(r[946 + k]));
@@ -416,14 +417,19 @@ ORC_API void oracle_hit_funcs(const float* in, uint32_t count, float* out, uint3
             x.sp = &rtt;
         }
         const float3 rayOrigin = f3(r[20], r[21], r[22]), rayDir = f3(r[23], r[24], r[25]);
-        if (r[27] != 0.0f) HandleMiss(x, path, rayDir, r[26]);          // the payload's origin is the ray's
-        else { UpdatePathTravelled(path, r[26]); HandleHitSurface(x, path, rayOrigin, rayDir, r[26], sf); }
+        float tMin = 0.0f, tMax = 0.0f;
+        if (r[27] == 1.0f) HandleMiss(x, path, rayDir, r[26]);          // the payload's origin is the ray's
+        else if (r[27] == 0.0f) { UpdatePathTravelled(path, r[26]); HandleHitSurface(x, path, rayOrigin, rayDir, r[26], sf); }
+        else if (r[27] == 2.0f) path = EmptyPathInitialize(x, path.id >> 16, path.id & 0xFFFF, r[1020]);
+        else if (r[27] == 3.0f) { path = EmptyPathInitialize(x, path.id >> 16, path.id & 0xFFFF, r[1020]); tMax = kMaxRayTravel; FirstHitFromVBuffer(x, path, tMin, tMax); }
+        else if (r[27] == 4.0f) postProcessHit(x, path);
+        o[120] = tMin; o[121] = tMax;
         packPayload(path, payload); memcpy(o, payload, 80);
         o[20] = float(vis.queries); o[21] = vis.o.x; o[22] = vis.o.y; o[23] = vis.o.z; o[24] = vis.d.x; o[25] = vis.d.y; o[26] = vis.d.z; o[27] = vis.tMax; o[28] = vis.last ? 1.0f : 0.0f;
         const bool rejectedFalseHit = path.getCounter(CTR_RejectedHits) != ((payloadIn14 >> 8) & 0xFFu);
-        const bool miss = r[27] != 0.0f;
+        const bool miss = r[27] == 1.0f, vertexOp = r[27] <= 1.0f;
         if (mode == MODE_REFERENCE && miss) { const float3 v = rayOrigin + rayDir * r[26]; o[31] = 1.0f; o[32] = v.x; o[33] = v.y; o[34] = v.z; }      // Bridge::ExportNonSurface( path, rayOrigin + rayDir * rayTCurrent )
-        if (mode == MODE_REFERENCE && !miss && !rejectedFalseHit) { o[29] = 1.0f; o[30] = path.sceneLength; }      // Bridge::ExportSurface( path, surface, path.GetSceneLength() ): once per accepted hit
+        if (mode == MODE_REFERENCE && vertexOp && !miss && !rejectedFalseHit) { o[29] = 1.0f; o[30] = path.sceneLength; }      // Bridge::ExportSurface( path, surface, path.GetSceneLength() ): once per accepted hit
         if (mode != MODE_REFERENCE)
         {
             o[37] = specHitT[pyi * 8 + pxi];

@@ -642,20 +642,38 @@ inline void HandleHitSurface(const PathTracerCtx& x, PathState& path, float3 ray
     if (shouldTerminate) path.setFlag(PF_terminateAtNextBounce);
 }
 
-// ---- one pixel, one sample (PathTracerSample.hlsl:201-256): returns L.rgb as stored to u_OutputColor (RGBA16F) -------------------
-struct PixelResult { float rgb[3]; float primaryT; uint primaryTri; float primaryU, primaryV; };
-
-inline PixelResult tracePixel(const PathTracerCtx& x, uint px, uint py)
+// PathTracer::EmptyPathInitialize (PathTracer.hlsli:45-92) for the pass x.mode names; the primary ray is set by the caller (SetupPathPrimaryRay)
+inline PathState EmptyPathInitialize(const PathTracerCtx& x, uint px, uint py, float pixelConeSpreadAngle)
 {
     PathState path;
     path.id = (px << 16) | py;
     path.SetThp(f3(1));
     path.setFlag(PF_active); path.setFlag(PF_deltaOnlyPath, true);
-    path.rayCone = RayCone::make(0, x.c->camera.PixelConeSpreadAngle);
-    path.SetL(f4(0, 0, 0, 0));
-    path.SetFireflyFilterK_BsdfScatterPdf(1.0f, 0.0f);
-    path.SetPackedMISInfo_ThpRuRuCorrection(NEEBSDFMISInfo().Pack16bit(), 1.0f);
+    path.rayCone = RayCone::make(0, pixelConeSpreadAngle);
+    if (x.mode == MODE_BUILD_STABLE_PLANES)
+    {
+        path.SetImageXform(identity3());
+        path.setFlag(PF_stablePlaneOnDominantBranch, true);
+        path.SetMotionVectorSceneLength(0);
+    }
+    else
+    {
+        path.SetL(f4(0, 0, 0, 0));
+        path.SetFireflyFilterK_BsdfScatterPdf(1.0f, 0.0f);
+        path.SetPackedMISInfo_ThpRuRuCorrection(NEEBSDFMISInfo().Pack16bit(), 1.0f);
+    }
+    path.setStablePlaneIndex(0);
+    path.stableBranchID = 1;
     if (HasFinishedSurfaceBounces(x, path.getVertexIndex() + 1, path.getCounter(CTR_DiffuseBounces))) path.setFlag(PF_terminateAtNextBounce);
+    return path;
+}
+
+// ---- one pixel, one sample (PathTracerSample.hlsl:201-256): returns L.rgb as stored to u_OutputColor (RGBA16F) -------------------
+struct PixelResult { float rgb[3]; float primaryT; uint primaryTri; float primaryU, primaryV; };
+
+inline PixelResult tracePixel(const PathTracerCtx& x, uint px, uint py)
+{
+    PathState path = EmptyPathInitialize(x, px, py, x.c->camera.PixelConeSpreadAngle);
     computeCameraRay(x, px, py, path.origin, path.dir);
 
     PixelResult out = {}; out.primaryT = -1.0f; out.primaryTri = 0xFFFFFFFFu;
@@ -885,60 +903,22 @@ inline void StablePlanesOnScatter(const PathTracerCtx& x, PathState& path, const
 
 struct RealtimeStats { uint64_t rays = 0; };
 
-// RayGen of the BUILD pass for one pixel
-inline void buildStablePlanesPixel(const PathTracerCtx& x, uint px, uint py)
+// postProcessHit of the BUILD pass (PathTracerSample.hlsl:96-113): a finished path continues with the pixel's next enqueued branch, if any
+inline void postProcessHit(const PathTracerCtx& x, PathState& path)
 {
-    const RealtimeTargets& T = *x.sp;
-    PathState path;
-    path.id = (px << 16) | py;
-    path.SetThp(f3(1));
-    path.setFlag(PF_active); path.setFlag(PF_deltaOnlyPath, true);
-    path.rayCone = RayCone::make(0, x.c->camera.PixelConeSpreadAngle);
-    path.SetImageXform(identity3());
-    path.setFlag(PF_stablePlaneOnDominantBranch, true);
-    path.SetMotionVectorSceneLength(0);
-    path.setStablePlaneIndex(0);
-    path.stableBranchID = 1;
-    if (HasFinishedSurfaceBounces(x, path.getVertexIndex() + 1, path.getCounter(CTR_DiffuseBounces))) path.setFlag(PF_terminateAtNextBounce);
-    computeCameraRay(x, px, py, path.origin, path.dir);
-    T.StartPixel(px, py); T.ExportSurfaceInit(px, py);
-    while (path.isActive())
+    const RealtimeTargets& T = *x.sp; const uint px = path.id >> 16, py = path.id & 0xFFFF;
+    int next;
+    if (!path.isActive() && (next = T.FindNextToExplore(px, py, path.getStablePlaneIndex() + 1)) != -1)
     {
-        const float3 o = path.origin, d = path.dir;
-        if (x.stats) x.stats->scatterRays++;
-        Hit h = x.bvh->trace(*x.scene, o, d, 0.0f, kMaxRayTravel, false, x.stats ? &x.stats->nodeVisits : nullptr, x.stats ? &x.stats->triTests : nullptr);
-        if (!h.valid()) HandleMiss(x, path, d, kMaxRayTravel);
-        else HandleHit(x, path, o, d, h.t, x.bvh->tris[h.triId], f2(h.u, h.v));
-        // postProcessHit: continue with the next enqueued branch of this pixel
-        int next;
-        if (!path.isActive() && (next = T.FindNextToExplore(px, py, path.getStablePlaneIndex() + 1)) != -1)
-        {
-            uint payload[20]; memcpy(payload, &T.planes[T.PixelToAddress(px, py, uint(next))], 80);
-            T.SetBranchID(px, py, uint(next), cStablePlaneJustStartedID);
-            path = unpackPayload(payload);
-        }
+        uint payload[20]; memcpy(payload, &T.planes[T.PixelToAddress(px, py, uint(next))], 80);          // ExplorationStart
+        T.SetBranchID(px, py, uint(next), cStablePlaneJustStartedID);
+        path = unpackPayload(payload);
     }
 }
-
-// RayGen of the FILL pass for one pixel and one sub-sample (x.sampleIndex = sampleBaseIndex + subSampleIndex)
-inline void fillStablePlanesPixel(const PathTracerCtx& x, uint px, uint py)
+// FirstHitFromVBuffer( path, 0 ) of the FILL pass (PathTracerSample.hlsl:33-93): the path restarts from stable plane 0; tMin / tMax bracket the surface the plane stands on
+inline void FirstHitFromVBuffer(const PathTracerCtx& x, PathState& path, float& tMin, float& tMax)
 {
-    const RealtimeTargets& T = *x.sp;
-    PathState path;
-    path.id = (px << 16) | py;
-    path.SetThp(f3(1));
-    path.setFlag(PF_active); path.setFlag(PF_deltaOnlyPath, true);
-    path.rayCone = RayCone::make(0, x.c->camera.PixelConeSpreadAngle);
-    path.SetL(f4(0, 0, 0, 0));
-    path.SetFireflyFilterK_BsdfScatterPdf(1.0f, 0.0f);
-    path.SetPackedMISInfo_ThpRuRuCorrection(NEEBSDFMISInfo().Pack16bit(), 1.0f);
-    path.setStablePlaneIndex(0);
-    path.stableBranchID = 1;
-    if (HasFinishedSurfaceBounces(x, path.getVertexIndex() + 1, path.getCounter(CTR_DiffuseBounces))) path.setFlag(PF_terminateAtNextBounce);
-    computeCameraRay(x, px, py, path.origin, path.dir);
-
-    // FirstHitFromVBuffer(path, 0): restart from stable plane 0
-    float tMin = 0, tMax = kMaxRayTravel;
+    const RealtimeTargets& T = *x.sp; const uint px = path.id >> 16, py = path.id & 0xFFFF;
     {
         const RtxptStablePlane& sp = T.planes[T.PixelToAddress(px, py, 0)];
         const uint stableBranchID = T.GetBranchID(px, py, 0);
@@ -962,6 +942,34 @@ inline void fillStablePlanesPixel(const PathTracerCtx& x, uint px, uint py)
         path.sceneLength = std::min(path.sceneLength + sceneLength, kMaxRayTravel);
         if (isMiss) HandleMiss(x, path, path.dir, sceneLength);
     }
+}
+
+// RayGen of the BUILD pass for one pixel
+inline void buildStablePlanesPixel(const PathTracerCtx& x, uint px, uint py)
+{
+    const RealtimeTargets& T = *x.sp;
+    PathState path = EmptyPathInitialize(x, px, py, x.c->camera.PixelConeSpreadAngle);
+    computeCameraRay(x, px, py, path.origin, path.dir);
+    T.StartPixel(px, py); T.ExportSurfaceInit(px, py);
+    while (path.isActive())
+    {
+        const float3 o = path.origin, d = path.dir;
+        if (x.stats) x.stats->scatterRays++;
+        Hit h = x.bvh->trace(*x.scene, o, d, 0.0f, kMaxRayTravel, false, x.stats ? &x.stats->nodeVisits : nullptr, x.stats ? &x.stats->triTests : nullptr);
+        if (!h.valid()) HandleMiss(x, path, d, kMaxRayTravel);
+        else HandleHit(x, path, o, d, h.t, x.bvh->tris[h.triId], f2(h.u, h.v));
+        postProcessHit(x, path);
+    }
+}
+
+// RayGen of the FILL pass for one pixel and one sub-sample (x.sampleIndex = sampleBaseIndex + subSampleIndex)
+inline void fillStablePlanesPixel(const PathTracerCtx& x, uint px, uint py)
+{
+    const RealtimeTargets& T = *x.sp;
+    PathState path = EmptyPathInitialize(x, px, py, x.c->camera.PixelConeSpreadAngle);
+    computeCameraRay(x, px, py, path.origin, path.dir);
+    float tMin = 0, tMax = kMaxRayTravel;
+    FirstHitFromVBuffer(x, path, tMin, tMax);
     while (path.isActive())
     {
         const float3 o = path.origin, d = path.dir;

@@ -97,5 +97,9 @@ TM=$REF/Rtxpt/ToneMapper
 echo; echo "#line 1 \"$TM/ToneMapping_cb.h\""; filter "$TM/ToneMapping_cb.h"
 echo; echo 'ToneMappingConstants gParams;'
 echo; echo "#line 31 \"$TM/ToneMapping.ps.hlsli\""; filter "$TM/ToneMapping.ps.hlsli" | sed -n '31,129p'
+# the per-pixel driver's own logic (Rtxpt/Shaders/PathTracerSample.hlsl): FirstHitFromVBuffer (FILL: restart from stable plane 0) and postProcessHit (BUILD: next enqueued branch);
+# the ray-generation loop around them only alternates nextHit and postProcessHit
+SH=$REF/Rtxpt/Shaders
+echo; echo "#line 33 \"$SH/PathTracerSample.hlsl\""; filter "$SH/PathTracerSample.hlsl" | sed -n '33,113p'
 echo; echo "#line 1 \"$MAIN\""
 cat "$MAIN"

@@ -34,8 +34,9 @@ static void shimIdentityEnv() { memset(&g_bridge.env, 0, sizeof(g_bridge.env)); 
 // (order of the "bsdf" mode's words 18-31) | 74 interior IoR, 75 / 76 emissive-triangle / analytic-proxy light (-1: none), 77-79 prevPosW | 80-93 constants | 96-135 materials (IoR,
 // attenuation colour, attenuation distance x 8) | 136-151 proxy counters, 152-215 proxy indices, 216-727* 2 x 2 local tiles, 728-919* 16 light records (Base + Extended) | FILL mode: 920-923* the pixel's stable-plane header (3 branch ids, first-hit length | dominant index), 924-929* the three planes'
 // packed noisy radiance, 930 the pixel's specular hit distance | BUILD mode: 931-942 the stub camera (position, direction at pixel 0, per-pixel steps), 943 maxStablePlaneVertexDepth,
-// 944 allowPrimarySurfaceReplacement, 945 stablePlanesSplitStopThreshold, 946-949 the pixel's stable radiance (RGBA16F values) | 950-958 the environment map's rotation (rows), 959 its intensity
-static const int kHitIn = 960, kHitOut = 128;
+// 944 allowPrimarySurfaceReplacement, 945 stablePlanesSplitStopThreshold, 946-949 the pixel's stable radiance (RGBA16F values) | 950-958 the environment map's rotation (rows), 959 its intensity | 960-1019* the pixel's three stable planes (ops 3, 4), 1020 the pixel cone spread angle (op 2)
+// word 27 selects the call: 0 HandleHit, 1 HandleMiss, 2 EmptyPathInitialize, 3 FirstHitFromVBuffer (FILL binary), 4 postProcessHit (BUILD binary)
+static const int kHitIn = 1024, kHitOut = 128;
 struct ShimHitScenario
 {
     LightingControlData cd; uint counters[16], indices[64], local[512]; PolymorphicLightInfo lights[16]; PolymorphicLightInfoEx lightsEx[16]; float fbWeight[64]; uint fbCand[64]; uint envLookup[1];
@@ -220,14 +221,30 @@ int main(int argc, char** argv)
             for (uint k = 0; k < 4; k++) memcpy(&S->spHeader[(k * 8 + pyi) * 8 + pxi], r + 920 + k, 4);
             for (uint k = 0; k < 3; k++) { uint w[2]; memcpy(w, r + 924 + 2 * k, 8); S->spPlanes[wc.StablePlanes.PixelToAddress(uint2(pxi, pyi), k)].PackedNoisyRadianceAndSpecAvg = uint2(w[0], w[1]); }
             g_bridge.specularHitT = r[930];
+            if (r[27] >= 3.0f) for (uint k = 0; k < 3; k++)
+            {   // ops 3, 4 read whole planes: a stored base plane (FirstHitFromVBuffer) or an enqueued path (postProcessHit: StablePlane::UnpackCustomPayload is member by member too)
+                uint w[20]; memcpy(w, r + 960 + 20 * k, 80); StablePlane& sp = S->spPlanes[wc.StablePlanes.PixelToAddress(uint2(pxi, pyi), k)];
+                sp.RayOrigin = float3(asfloat(w[0]), asfloat(w[1]), asfloat(w[2])); sp.LastRayTCurrent = asfloat(w[3]); sp.RayDir = float3(asfloat(w[4]), asfloat(w[5]), asfloat(w[6])); sp.SceneLength = asfloat(w[7]);
+                sp.PackedThpAndMVs = uint3(w[8], w[9], w[10]); sp.VertexIndexAndRoughness = w[11]; sp.DenoiserPackedBSDFEstimate = uint3(w[12], w[13], w[14]); sp.PackedNormal = w[15];
+                sp.PackedNoisyRadianceAndSpecAvg = uint2(w[16], w[17]); sp.FlagsAndVertexIndex = w[18]; sp.PackedCounters = w[19];
+            }
             g_bridge.cameraPos = float3(r[931], r[932], r[933]); g_bridge.cameraDirBase = float3(r[934], r[935], r[936]); g_bridge.cameraDirDx = float3(r[937], r[938], r[939]); g_bridge.cameraDirDy = float3(r[940], r[941], r[942]);
             wc.PtConsts.maxStablePlaneVertexDepth = uint(r[943]); wc.PtConsts.allowPrimarySurfaceReplacement = uint(r[944]); wc.PtConsts.stablePlanesSplitStopThreshold = r[945];
             wc.StablePlanes.PTConstants = wc.PtConsts;
             S->spRadiance[pyi * 8 + pxi] = float4(r[946], r[947], r[948], r[949]);
 #endif
             const float3 rayOrigin(r[20], r[21], r[22]), rayDir(r[23], r[24], r[25]);
-            if (r[27] != 0.0f) PathTracer::HandleMiss(path, rayOrigin, rayDir, r[26], wc);
-            else PathTracer::HandleHit(path, rayOrigin, rayDir, r[26], float2(0.25f, 0.25f), wc);
+            float2 tMinMax = float2(0.0f, 0.0f);
+            if (r[27] == 1.0f) PathTracer::HandleMiss(path, rayOrigin, rayDir, r[26], wc);
+            else if (r[27] == 0.0f) PathTracer::HandleHit(path, rayOrigin, rayDir, r[26], float2(0.25f, 0.25f), wc);
+            else if (r[27] == 2.0f) path = PathTracer::EmptyPathInitialize(path.GetPixelPos(), r[1020]);
+#if PATH_TRACER_MODE == PATH_TRACER_MODE_FILL_STABLE_PLANES
+            else if (r[27] == 3.0f) { path = PathTracer::EmptyPathInitialize(path.GetPixelPos(), r[1020]); tMinMax = FirstHitFromVBuffer(path, 0, wc); }
+#endif
+#if PATH_TRACER_MODE == PATH_TRACER_MODE_BUILD_STABLE_PLANES
+            else if (r[27] == 4.0f) postProcessHit(path, wc);
+#endif
+            o[120] = tMinMax.x; o[121] = tMinMax.y;
             payload = PathPayload::pack(path); memcpy(o, payload.packed, 80);
             o[20] = float(g_bridge.visibilityQueries); o[21] = g_bridge.lastVisibilityRay.Origin.x; o[22] = g_bridge.lastVisibilityRay.Origin.y; o[23] = g_bridge.lastVisibilityRay.Origin.z;
             o[24] = g_bridge.lastVisibilityRay.Direction.x; o[25] = g_bridge.lastVisibilityRay.Direction.y; o[26] = g_bridge.lastVisibilityRay.Direction.z; o[27] = g_bridge.lastVisibilityRay.TMax;

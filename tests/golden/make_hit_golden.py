@@ -59,7 +59,7 @@ def light_records_rest(rng, n, around, rec):
 
 
 def make(rng, n, slots_pool, fill=False, build=False):
-    r = np.zeros((n, 960), np.float32)
+    r = np.zeros((n, 1024), np.float32)
     b = make_records(rng, n); V, N, T, B = b[:, 0:3], b[:, 3:6], b[:, 6:9], b[:, 9:12]
     ray_dir = -V; t = np.exp(rng.uniform(-2, 3, n)).astype(np.float32); origin = ((rng.random((n, 3)) - 0.5) * 40).astype(np.float32); pos = origin + ray_dir * t[:, None]
     r[:, 20:23], r[:, 23:26], r[:, 26] = origin, ray_dir, t
@@ -153,12 +153,26 @@ if __name__ == "__main__":
     e = envquad_inputs(np.random.default_rng(776), 2000, rotations(np.random.default_rng(775), 2000)); e[:200, 8:17] = 0
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "envquad_lights_golden.npz"), envquads_in=e, envquads_out=run("envquads", e, 24),
                         source=np.array("Rtxpt/Shaders/PathTracer/Lighting/PolymorphicLight.hlsli (EnvironmentQuadLight) at reference commit f08d1c7, compiled as C++ by oracle/Makefile target _ref/ref_kat_bsdf"))
-    u = make(rng, 1200, slots)
+    def with_ops(u, n_init, seed):
+        """op 2 (EmptyPathInitialize) on the first n_init records: only the pixel, the cone spread angle and the bounce limits (0 ends the path at the first vertex) matter"""
+        r2 = np.random.default_rng(seed); u[:n_init, 27] = 2; u[:n_init, 1020] = np.exp(r2.uniform(-9, -5, n_init)); u[:n_init // 4, 80] = 0
+        return u
+
+    u = with_ops(make(rng, 1200, slots), 60, 1)
     out = run("hit", u, 128)
-    src = "Rtxpt/Shaders/PathTracer/{PathTracer,PathTracerNEE,PathTracerNestedDielectrics,PathTracerStablePlanes,StablePlanes,PathState,PathPayload}.hlsli + Utils/SampleGenerators.hlsli at reference commit f08d1c7, compiled as C++ by oracle/Makefile targets _ref/ref_kat_bsdf (PATH_TRACER_MODE 0), _ref/ref_kat_pt_build (1) and _ref/ref_kat_pt_fill (2) behind oracle/ref_bridge_stub.h"
-    uf = make(np.random.default_rng(778), 1200, slots, fill=True)
-    outf = run("hit", uf, 128, exe="ref_kat_pt_fill")
-    ub = make(np.random.default_rng(779), 1200, slots, build=True)
+    src = "Rtxpt/Shaders/PathTracer/{PathTracer,PathTracerNEE,PathTracerNestedDielectrics,PathTracerStablePlanes,StablePlanes,PathState,PathPayload}.hlsli + Utils/SampleGenerators.hlsli + Rtxpt/Shaders/PathTracerSample.hlsl:33-113 at reference commit f08d1c7, compiled as C++ by oracle/Makefile targets _ref/ref_kat_bsdf (PATH_TRACER_MODE 0), _ref/ref_kat_pt_build (1) and _ref/ref_kat_pt_fill (2) behind oracle/ref_bridge_stub.h"
+    ub = with_ops(make(np.random.default_rng(779), 1200, slots, build=True), 60, 2)
     outb = run("hit", ub, 128, exe="ref_kat_pt_build")
+    # op 4 (postProcessHit): what the BUILD records above left behind - the pixel's header with planes enqueued for exploration, the three planes, the path as it ended
+    U, O = ub.view(np.uint32), outb.view(np.uint32); enq = np.where((O[:, 47:50] == 0xFFFFFFFE).any(1) & (ub[:, 27] <= 1))[0]; r4 = np.random.default_rng(3); pick = r4.choice(enq, 200)
+    u4 = ub[pick].copy(); u4[:, 27] = 4; u4[:, 0:20] = outb[pick, 0:20]; u4[:, 920:924] = outb[pick, 47:51]; u4[:, 960:1020] = outb[pick, 56:116]
+    flip = r4.random(200) < 0.25; u4.view(np.uint32)[flip, 19] |= np.uint32(1 << 10)                    # a path that is still active explores nothing
+    ub = np.concatenate([ub, u4]); outb = np.concatenate([outb, run("hit", u4, 128, exe="ref_kat_pt_build")])
+    uf = with_ops(make(np.random.default_rng(778), 1200, slots, fill=True), 60, 3)
+    # op 3 (FirstHitFromVBuffer): the FILL pass restarts from plane 0 as the BUILD records above stored it - surfaces and sky (scene length +inf: the miss is handled inline)
+    base = np.where((O[:1200, 47] != 0xFFFFFFFF) & (O[:1200, 47] != 0xFFFFFFFE) & (O[:1200, 47] != 0) & (ub[:1200, 27] <= 1))[0]; r3 = np.random.default_rng(4); pick = r3.choice(base, 240)
+    u3 = uf[:240].copy(); u3[:, 27] = 3; u3[:, 920:924] = outb[pick, 47:51]; u3[:, 960:1020] = outb[pick, 56:116]; u3[:, 1020] = np.exp(r3.uniform(-9, -5, 240))
+    uf = np.concatenate([uf[240:], u3, uf[:240]])[:1200 + 240]
+    outf = run("hit", uf, 128, exe="ref_kat_pt_fill")
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "hit_golden.npz"), hit_in=u, hit_out=out, fill_in=uf, fill_out=outf, build_in=ub, build_out=outb, source=np.array(src))
     print(u.shape, out.shape, uf.shape, outf.shape, ub.shape, outb.shape, os.path.getsize(os.path.join(ROOT, "tests", "golden", "hit_golden.npz")))
