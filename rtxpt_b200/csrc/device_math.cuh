@@ -7,7 +7,9 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 
+#ifndef PT_DEVICE      // tests/emu/shade_host_emu.cu builds the shading functions for the host (test infrastructure): it defines PT_DEVICE as __host__ __device__ before this header
 #define PT_DEVICE __device__ __forceinline__
+#endif
 #define PT_HD __host__ __device__ __forceinline__
 
 namespace pt {

@@ -40,8 +40,14 @@ PT_DEVICE float3 sampleEnvCube(const SceneView& sc, float3 v, float lod)
     const float4 c = tex2DLayeredLod<float4>(sc.envCube, (s / m + 1.0f) * 0.5f, (t / m + 1.0f) * 0.5f, face, level);
     return mk3(c.x, c.y, c.z);
 }
+#ifdef PT_HOST_EMU     // tests/emu/shade_host_emu.cu (test infrastructure): the environment cube and the triangle gather are what the golden vectors' stub bridge supplies as data
+__host__ __device__ float3 emuEnvCube(float3 localDir, float lod);
+#endif
 PT_DEVICE float3 envEvalLocal(const LaunchParams& p, float3 localDir, float lod)     // EnvMap::EvalLocal, Lighting/EnvMap.hlsli:84-87
 {
+#ifdef PT_HOST_EMU
+    return emuEnvCube(localDir, lod) * mk3(p.c.envMap.ColorMultiplier[0], p.c.envMap.ColorMultiplier[1], p.c.envMap.ColorMultiplier[2]);
+#endif
     return sampleEnvCube(p.scene, localDir, lod) * mk3(p.c.envMap.ColorMultiplier[0], p.c.envMap.ColorMultiplier[1], p.c.envMap.ColorMultiplier[2]);
 }
 
@@ -179,6 +185,9 @@ struct Surface
     float3 prevPosW;                // BUILD pass only: instance.prevTransform x last frame's object-space position (BridgeDonut:631)
 };
 
+#ifdef PT_HOST_EMU
+__host__ __device__ void emuLoadSurface(Surface& s);
+#endif
 PT_DEVICE float3 safeNormalize(float3 v) { return v * (1.0f / sqrtf(fmaxf(1.175494351e-38f, dot3(v, v)))); }
 PT_DEVICE void computeTangentSpace(Surface& s, float4 tangentW, bool ignoreTangent)
 {
@@ -503,7 +512,11 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
     const float rayT = hit.x;
     updatePathTravelled(path, rayT);
     Surface s;
+#ifdef PT_HOST_EMU
+    emuLoadSurface(s);
+#else
     loadSurface<MODE>(p, __float_as_uint(hit.w), hit.y, hit.z, rayDir, path.coneWidth(), s, path.id, path.vertexIndex(), sampleIndex);
+#endif
     const uint ndq = p.c.nestedDielectricsQuality;
     if (ndq > 0 && path.interior0 != 0)
     {   // homogeneous absorption through the medium we are in (PathTracer.hlsli:538-547, BridgeDonut:871-887)
@@ -716,8 +729,10 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
             for (uint i = 0; i < kPrefetch; i++)
                 if (i < globalCount)
                 {
+#ifdef __CUDA_ARCH__    // (the host build of tests/emu/shade_host_emu.cu has no PTX)
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(p.scene.lights + preLight[i]));
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(proxyCounters + preLight[i]));
+#endif
                 }
         }
         #pragma unroll 1
@@ -837,9 +852,10 @@ PT_DEVICE void shadeHit(const LaunchParams& p, PathRegs& path, uint slot, float4
         {   // had the light sample been visible, rrRnd is the feedback reservoir's number and roulette gets the next one: keep that outcome for the shadow kernel to publish
             if (out.emitShadow && p.na.temporalFeedbackRequired)
             {
-                const bool altTerminate = finished || (uniformSG.next() < prob);
+                // (roulette runs - and, when it lets the path live, stores its correction - even on a path the bounce limit already ends: PathTracer.hlsli:756-760)
+                const bool altRoulette = uniformSG.next() < prob, altTerminate = finished || altRoulette;
                 out.naRecord = make_uint4(naFeedback, __float_as_uint(naFeedbackWeight), __float_as_uint(rrRnd),
-                                          0x80000000u | (altTerminate ? 0x40000000u : 0u) | (altTerminate ? f32tof16(path.ruRuCorrection()) : f32tof16(1.0f / (1.0f - prob))));
+                                          0x80000000u | (altTerminate ? 0x40000000u : 0u) | (altRoulette ? f32tof16(path.ruRuCorrection()) : f32tof16(1.0f / (1.0f - prob))));
             }
         }
         if (rrRnd < prob) shouldTerminate = true;

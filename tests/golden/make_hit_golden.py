@@ -81,7 +81,7 @@ def make(rng, n, slots_pool, fill=False, build=False):
     r[:, 75] = np.where(em & (rng.random(n) < 0.8), rng.integers(4, 12, n), -1); r[:, 76] = np.where(rng.random(n) < 0.15, rng.integers(12, 16, n), -1)
     r[:, 77:80] = pos + rng.normal(size=(n, 3)).astype(np.float32) * np.float32(0.01)
     # constants
-    r[:, 80] = rng.integers(1, 9, n); r[:, 81] = rng.integers(0, 5, n); r[:, 82] = rng.integers(0, 4096, n); r[:, 83] = rng.integers(1, 9, n); r[:, 84] = rng.integers(1, 3, n)
+    r[:, 80] = rng.integers(1, 9, n); r[:, 81] = rng.integers(0, 5, n); r[:, 82] = rng.integers(0, 4096, n); r[:, 83] = rng.integers(1, 9, n); r[:, 84] = np.where(rng.random(n) < 0.75, 1, 2)      # NEEFullSamples: 1 is RTXPT's default (and what the CUDA tier supports)
     r[:, 85] = np.float32(2.0) + rng.random(n).astype(np.float32) * 8;      # never 0: the binary is built with RTXPT_FIREFLY_FILTER = 1, and the application passes threshold 0 only together with the macro off
     r[:, 86] = rng.choice(np.float32([0.0, 0.35, 0.65, 1.0]), n); r[:, 87] = rng.choice(np.float32([1.0, 0.5, 0.25]), n)
     r[:, 88:90] = rng.integers(0, 8, (n, 2)); r[:, 91] = 0.3; r[:, 92] = rng.random(n) < 0.85; r[:, 93] = rng.choice(np.float32([0.0, 1.0, 2.5]), n)
@@ -92,6 +92,7 @@ def make(rng, n, slots_pool, fill=False, build=False):
     lights, _ = light_records(rng, n, pos); lights = light_records_rest(rng, n, pos, lights); r[:, 728:920] = lights.reshape(n, 192).view(np.float32)
     r[:, 950:959] = rotations(rng, n); r[:, 959] = np.float32(0.5) + rng.random(n).astype(np.float32) * 2
     r[:, 27] = rng.random(n) < 0.25                                                          # a quarter of the rays leave the scene: HandleMiss
+    r[r[:, 27] == 1, 26] = 1e15                                                              # ... with rayTCurrent = kMaxRayTravel, as nextHit passes it (PathTracerSample.hlsl:127)
     for i in range(n):
         counters = rng.integers(0, 9, 16) * (rng.random(16) < 0.8)
         if counters.sum() == 0: counters[rng.integers(0, 16)] = 3

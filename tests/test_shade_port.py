@@ -1,0 +1,40 @@
+"""The CUDA source of the shading kernel held to the reference's own shader code on the CPU.
+
+tests/emu/shade_host_emu.cu (test infrastructure, never linked into the product) compiles rtxpt_b200/csrc/shade.cuh - shadeHit / shadeMiss with bsdf.cuh, the NEE-AT sampler of
+neeat.cuh and the sample generators of device_math.cuh, the very functions k_shade wraps - for the host, and runs them on the records of tests/golden/hit_golden.npz: path vertices whose
+expected outcome was produced by the UNMODIFIED Rtxpt/Shaders/PathTracer/PathTracer.hlsli (HandleHit / HandleMiss with PathTracerNEE.hlsli, PathTracerNestedDielectrics.hlsli, the
+sample generators ...) compiled in place behind a stub bridge (tests/golden/make_hit_golden.py).  The surface a hit loads and the environment cube are what that bridge supplies (hooks
+under PT_HOST_EMU in shade.cuh); the shadow kernel's half of ProcessLightSample (radiance into L, feedback reservoir, Russian-roulette outcome of a visible sample) is applied by the
+emulation as kernels.cu does.  What only the GPU build has - libdevice's transcendental functions, fast-math in the default build, the wavefront's queues - stays with the -m gpu tests."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lib():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "emu"), "-s", "_build/libshade_emu.so"], check=True)
+    L = C.CDLL(os.path.join(ROOT, "tests", "emu", "_build", "libshade_emu.so"))
+    L.shade_emu_reference_vertex.argtypes = [C.c_void_p, C.c_void_p]; L.shade_emu_reference_vertex.restype = C.c_int
+    return L
+
+
+def test_shade_kernel_source_matches_reference_path_tracer_golden():
+    """Reference mode with NEE-AT feedback: every hit with NEEFullSamples = 1 (what this tier supports; rtxpt_b200_set_constants refuses more) and every miss of the golden - the outgoing
+    80-byte path state (all words but stableBranchID, which carries the sample index in reference mode), the shadow ray and its answer, the pixel's feedback reservoir - bit for bit."""
+    L = _lib()
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hit_golden.npz"))
+    u, ref = np.ascontiguousarray(g["hit_in"]), g["hit_out"]
+    out = np.zeros_like(ref); ran = np.zeros(len(u), bool)
+    for i in range(len(u)): ran[i] = L.shade_emu_reference_vertex(u[i].ctypes.data, out[i].ctypes.data) == 0
+    hits = ran & (u[:, 27] == 0) & (u[:, 84] == 1); misses = ran & (u[:, 27] == 1)
+    assert hits.sum() > 400 and misses.sum() > 200
+    cols = [c for c in range(20) if c != 15] + list(range(20, 29)) + [39, 40]
+    R, O = ref.view(np.uint32)[:, cols], out.view(np.uint32)[:, cols]
+    same = R == O
+    assert same[hits].all(), np.argwhere(~same[hits])[:8]
+    assert same[misses].all(), np.argwhere(~same[misses])[:8]
+    # the hits took every turn: shadow rays seen and blocked, feedback written, false hits rejected, paths ended by the bounce limit and by roulette
+    assert 0.25 < ref[hits, 28].mean() < 0.7 and (ref[hits, 39] > 0).mean() > 0.2 and (ref[hits, 20] > 0).mean() > 0.5
