@@ -148,6 +148,9 @@ PT_DEVICE void accumulateStableRadiance(const LaunchParams& p, uint id, float3 r
 }
 PT_DEVICE float3 computeMotionVector(const RealtimeParams& rt, float3 posW, float3 prevPosW)
 {
+#ifdef PT_HOST_EMU
+    return emuMotionVector(posW, prevPosW);
+#endif
     const float* M = rt.worldToClipNoOffset; const float* Q = rt.prevWorldToClipNoOffset;
     const float cx = ((posW.x * M[0] + posW.y * M[4]) + posW.z * M[8]) + M[12], cy = ((posW.x * M[1] + posW.y * M[5]) + posW.z * M[9]) + M[13], cw = ((posW.x * M[3] + posW.y * M[7]) + posW.z * M[11]) + M[15];
     const float qx = ((prevPosW.x * Q[0] + prevPosW.y * Q[4]) + prevPosW.z * Q[8]) + Q[12], qy = ((prevPosW.x * Q[1] + prevPosW.y * Q[5]) + prevPosW.z * Q[9]) + Q[13], qw = ((prevPosW.x * Q[3] + prevPosW.y * Q[7]) + prevPosW.z * Q[11]) + Q[15];

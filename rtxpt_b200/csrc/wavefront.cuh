@@ -230,8 +230,15 @@ struct PathRegs             // one path's state in registers
 constexpr uint kCtrDiffuseBounces = 0, kCtrRejectedHits = 1, kCtrBouncesFromStablePlane = 2;
 
 // Bridge::computeCameraRay + ComputeRayThinlens (BridgeDonut:543-564, PathTracerHelpers.hlsli:126-153): camera ray of pixel `id` for sample `sampleIndex`
+#ifdef PT_HOST_EMU     // tests/emu/shade_host_emu.cu (test infrastructure): the camera and the motion-vector projection are the golden vectors' stub bridge's closed forms
+__host__ __device__ void emuCameraRay(uint id, float3& origin, float3& dir);
+__host__ __device__ float3 emuMotionVector(float3 posW, float3 prevPosW);
+#endif
 PT_HD void computeCameraRay(const RtxptPathTracerConstants& c, uint id, uint sampleIndex, float3& origin, float3& dir)
 {
+#ifdef PT_HOST_EMU
+    emuCameraRay(id, origin, dir); return;
+#endif
     const RtxptCameraData& cam = c.camera;
     const uint px = id >> 16, py = id & 0xFFFF;
     UniformSeq sg = UniformSeq::make(vertexBaseHash(id, 0), sampleIndex, 0u);

@@ -56,6 +56,14 @@ __host__ __device__ void pt::emuLoadSurface(Surface& s) {
 #endif
 }
 __host__ __device__ float3 pt::emuEnvCube(float3 d, float lod) { const float k = exp2f(-lod); return mk3((0.5f + 0.5f * d.x) * k, (0.5f + 0.25f * d.y) * k, (0.75f + 0.25f * d.z) * k); }
+static thread_local float3 gCamPos, gCamBase, gCamDx, gCamDy;
+__host__ __device__ void pt::emuCameraRay(uint id, float3& origin, float3& dir)
+{
+#ifndef __CUDA_ARCH__
+    const float3 d = gCamBase + gCamDx * float(id >> 16) + gCamDy * float(id & 0xFFFFu); origin = gCamPos; dir = d * (1.0f / sqrtf(dot3(d, d)));
+#endif
+}
+__host__ __device__ float3 pt::emuMotionVector(float3 posW, float3 prevPosW) { return (prevPosW - posW) * 0.5f; }
 static bool visibilityRule(float4 o, float4 d)
 {   // ShimVisibilityRule of oracle/ref_bridge_stub.h
     const uint32_t h = emu::f2u(o.x) ^ (emu::f2u(o.y) >> 1) ^ (emu::f2u(o.z) >> 2) ^ emu::f2u(d.x) ^ (emu::f2u(d.y) >> 1) ^ (emu::f2u(d.z) >> 2) ^ emu::f2u(o.w);
@@ -71,8 +79,9 @@ static const std::vector<uint32_t>& envLookup()
 // One path vertex of the reference-mode shade kernel with NEE-AT (k_shade<.., true, true, true>: shadeHit / shadeMiss) followed by what k_trace_shadow does with the vertex's
 // shadow record (kernels.cu:190-222: radiance into L, feedback reservoir, the Russian-roulette outcome of a visible sample, which the path's next shadeHit applies - applied here),
 // on records of tests/golden/hit_golden.npz (layout: oracle/ref_kat_bsdf_main.cpp, "hit" mode; ops 0 and 1).  Returns 0, or -1 for a record this path does not cover.
-extern "C" int shade_emu_reference_vertex(const float* r, float* o)
+template <int MODE> static int shadeVertex(const float* r, float* o)
 {
+    constexpr bool kRealtime = MODE != kModeReference, kNeeat = MODE != kModeBuildStablePlanes;     // k_shade< .., NEEAT >, k_rt_shade< BUILD, .. >, k_rt_shade< FILL, .., NEEAT >
     for (int k = 0; k < 128; k++) o[k] = 0.0f;
     if (r[27] > 1.0f) return -1;
     LaunchParams p; memset(&p, 0, sizeof(p));
@@ -109,15 +118,32 @@ extern "C" int shade_emu_reference_vertex(const float* r, float* o)
     p.na.screenSpaceVsWorldSpaceThreshold = r[91]; p.na.temporalFeedbackRequired = uint(r[92]); p.na.fbWeight = fbWeight; p.na.fbCandidate = fbCand; p.na.localSamplingBuffer = local;
     p.na.proxyCounters = counters; p.na.proxyIndices = indices; p.na.samplingProxyCount = &proxyCount;
     uint32_t rrFix[1] = { 0u }; p.naRrFix = rrFix;
+    // realtime passes: the stable planes of an 8 x 8 image, the pixel's entries from the record; the stub bridge's camera
+    const uint32_t pid = emu::f2u(r[3]), px = (pid >> 16) & 7u, py = pid & 7u;
+    RtxptStablePlane planes[3 * 64]; uint32_t header[4 * 64]; uint2 stableRadiance[64]; float specHitT[64], depth[64]; uint2 motion[64]; uint32_t throughput[64];
+    if (kRealtime)
+    {
+        memset(planes, 0, sizeof(planes)); memset(header, 0xFF, sizeof(header)); memset(stableRadiance, 0, sizeof(stableRadiance)); memset(motion, 0, sizeof(motion)); memset(throughput, 0, sizeof(throughput));
+        for (int k = 0; k < 64; k++) { specHitT[k] = 0.0f; depth[k] = -1.0f; }
+        p.rt.planes = planes; p.rt.header = header; p.rt.stableRadiance = stableRadiance; p.rt.specularHitT = specHitT; p.rt.lineStride = 8; p.rt.planeStride = 64; p.rt.activePlaneCount = 3;
+        p.rt.maxVertexDepth = uint(r[943]); p.rt.allowPSR = uint(r[944]); p.rt.attenuation = r[87]; p.depth = depth; p.motionVectors = motion; p.throughput = throughput;
+        for (int k = 0; k < 16; k += 5) p.worldToClip[k] = 1.0f;
+        for (uint32_t k = 0; k < 4; k++) memcpy(&header[(k * 8 + py) * 8 + px], r + 920 + k, 4);
+        for (uint32_t k = 0; k < 3; k++) memcpy(planes[planeAddress(p.rt, (px << 16) | py, k)].PackedNoisyRadianceAndSpecAvg, r + 924 + 2 * k, 8);
+        specHitT[py * 8 + px] = r[930];
+        stableRadiance[py * 8 + px] = make_uint2(f32tof16(r[946]) | (f32tof16(r[947]) << 16), f32tof16(r[948]) | (f32tof16(r[949]) << 16));
+        gCamPos = mk3(r[931], r[932], r[933]); gCamBase = mk3(r[934], r[935], r[936]); gCamDx = mk3(r[937], r[938], r[939]); gCamDy = mk3(r[940], r[941], r[942]);
+        p.firstSampleIndex = uint(r[82]);
+    }
     // the path: the 80-byte payload in the order of wavefront.cuh's five state words (the stableBranchID word carries the sample index in reference mode)
     uint32_t w[20]; memcpy(w, r, 80);
     PathRegs path;
     path.origin = mk3(emu::u2f(w[0]), emu::u2f(w[1]), emu::u2f(w[2])); path.id = w[3]; path.dir = mk3(emu::u2f(w[4]), emu::u2f(w[5]), emu::u2f(w[6])); path.sceneLength = emu::u2f(w[7]);
     path.thpXY = w[8]; path.thpZ = w[9]; path.lXY = w[10]; path.lZW = w[11]; path.interior0 = w[12]; path.interior1 = w[13]; path.packedCounters = w[14]; path.rayCone = w[16];
-    path.pack0 = w[17]; path.pack1 = w[18]; path.flagsAndVertexIndex = w[19]; path.sampleIndex = uint(r[82]);
+    path.pack0 = w[17]; path.pack1 = w[18]; path.flagsAndVertexIndex = w[19]; path.sampleIndex = kRealtime ? w[15] : uint(r[82]);
     HitOutputs out; out.continuePath = false; out.emitShadow = false; out.naRecord = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
-    if (r[27] == 1.0f) shadeMiss<false, kModeReference, true>(p, path);
-    else shadeHit<false, true, kModeReference, true>(p, path, 0u, make_float4(r[26], 0.25f, 0.25f, 0.0f), out);
+    if (r[27] == 1.0f) shadeMiss<false, MODE, kNeeat>(p, path);
+    else shadeHit<false, true, MODE, kNeeat>(p, path, 0u, make_float4(r[26], 0.25f, 0.25f, 0.0f), out);
     // k_trace_shadow's half of ProcessLightSample
     if (out.emitShadow)
     {
@@ -130,7 +156,13 @@ extern "C" int shade_emu_reference_vertex(const float* r, float* o)
             const float rx = f16tof32(rad.x & 0x7FFFu), ry = f16tof32((rad.x >> 16) & 0x7FFFu), rz = f16tof32(rad.y), rw = f16tof32(rad.y >> 16);
             if (rx > 0 || ry > 0 || rz > 0 || rw > 0)
             {
-                const float lx = f16tof32(path.lXY) + rx, ly = f16tof32(path.lXY >> 16) + ry, lz = f16tof32(path.lZW) + rz, lw = f16tof32(path.lZW >> 16);
+                float lx, ly, lz, lw;
+                if (kRealtime)
+                {
+                    const float a = p.rt.attenuation, spec = (rad.x & 0x00008000u) ? rw : ((rad.x & 0x80000000u) ? (rx + ry + rz) / 3.0f : 0.0f);
+                    lx = f16tof32(path.lXY) + rx * a; ly = f16tof32(path.lXY >> 16) + ry * a; lz = f16tof32(path.lZW) + rz * a; lw = f16tof32(path.lZW >> 16) + spec * a;
+                }
+                else { lx = f16tof32(path.lXY) + rx; ly = f16tof32(path.lXY >> 16) + ry; lz = f16tof32(path.lZW) + rz; lw = f16tof32(path.lZW >> 16); }
                 path.lXY = packHalf2NoClamp(clampf(lx, 0.f, kHalfMax), clampf(ly, 0.f, kHalfMax)); path.lZW = packHalf2NoClamp(clampf(lz, 0.f, kHalfMax), clampf(lw, 0.f, kHalfMax));
             }
             const uint4 fb = out.naRecord;
@@ -142,9 +174,20 @@ extern "C" int shade_emu_reference_vertex(const float* r, float* o)
         }
     }
     uint32_t q[20] = { emu::f2u(path.origin.x), emu::f2u(path.origin.y), emu::f2u(path.origin.z), path.id, emu::f2u(path.dir.x), emu::f2u(path.dir.y), emu::f2u(path.dir.z), emu::f2u(path.sceneLength),
-                       path.thpXY, path.thpZ, path.lXY, path.lZW, path.interior0, path.interior1, path.packedCounters, w[15], path.rayCone, path.pack0, path.pack1, path.flagsAndVertexIndex };
+                       path.thpXY, path.thpZ, path.lXY, path.lZW, path.interior0, path.interior1, path.packedCounters, kRealtime ? path.sampleIndex : w[15], path.rayCone, path.pack0, path.pack1, path.flagsAndVertexIndex };
     memcpy(o, q, 80);
+    if (kRealtime)
+    {
+        o[37] = specHitT[py * 8 + px];
+        for (uint32_t k = 0; k < 3; k++) { const RtxptStablePlane& sp = planes[planeAddress(p.rt, (px << 16) | py, k)]; memcpy(o + 41 + 2 * k, sp.PackedNoisyRadianceAndSpecAvg, 8); memcpy(o + 56 + 20 * k, &sp, 80); }
+        for (uint32_t k = 0; k < 4; k++) memcpy(o + 47 + k, &header[(k * 8 + py) * 8 + px], 4);
+        const uint2 sr = stableRadiance[py * 8 + px]; o[52] = f16tof32(sr.x); o[53] = f16tof32(sr.x >> 16); o[54] = f16tof32(sr.y); o[55] = f16tof32(sr.y >> 16);
+        if (MODE == kModeBuildStablePlanes) o[r[27] == 1.0f ? 31 : 29] = depth[py * 8 + px] != -1.0f ? 1.0f : 0.0f;
+    }
     const uint32_t at = (path.id & 7u) * 8 + ((path.id >> 16) & 7u);
     o[39] = fbWeight[at]; memcpy(o + 40, &fbCand[at], 4);
     return 0;
 }
+extern "C" int shade_emu_reference_vertex(const float* r, float* o) { return shadeVertex<kModeReference>(r, o); }
+extern "C" int shade_emu_build_vertex(const float* r, float* o) { return shadeVertex<kModeBuildStablePlanes>(r, o); }
+extern "C" int shade_emu_fill_vertex(const float* r, float* o) { return shadeVertex<kModeFillStablePlanes>(r, o); }

@@ -17,24 +17,49 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _lib():
     subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "emu"), "-s", "_build/libshade_emu.so"], check=True)
     L = C.CDLL(os.path.join(ROOT, "tests", "emu", "_build", "libshade_emu.so"))
-    L.shade_emu_reference_vertex.argtypes = [C.c_void_p, C.c_void_p]; L.shade_emu_reference_vertex.restype = C.c_int
+    for f in (L.shade_emu_reference_vertex, L.shade_emu_build_vertex, L.shade_emu_fill_vertex): f.argtypes = [C.c_void_p, C.c_void_p]; f.restype = C.c_int
     return L
 
 
+def _run(fn, u, ref):
+    out = np.zeros_like(ref); ran = np.zeros(len(u), bool)
+    for i in range(len(u)): ran[i] = fn(u[i].ctypes.data, out[i].ctypes.data) == 0
+    return out, ran
+
+
+PAYLOAD = list(range(20)); SHADOW = list(range(20, 29)); FEEDBACK = [39, 40]
+
+
 def test_shade_kernel_source_matches_reference_path_tracer_golden():
-    """Reference mode with NEE-AT feedback: every hit with NEEFullSamples = 1 (what this tier supports; rtxpt_b200_set_constants refuses more) and every miss of the golden - the outgoing
-    80-byte path state (all words but stableBranchID, which carries the sample index in reference mode), the shadow ray and its answer, the pixel's feedback reservoir - bit for bit."""
+    """Reference mode with NEE-AT feedback (k_shade< .., NEEAT >): every hit with NEEFullSamples = 1 (what this tier supports; rtxpt_b200_set_constants refuses more) and every miss of
+    the golden - the outgoing 80-byte path state (all words but stableBranchID, which carries the sample index in reference mode), the shadow ray and its answer, the pixel's feedback
+    reservoir - bit for bit."""
     L = _lib()
     g = np.load(os.path.join(ROOT, "tests", "golden", "hit_golden.npz"))
     u, ref = np.ascontiguousarray(g["hit_in"]), g["hit_out"]
-    out = np.zeros_like(ref); ran = np.zeros(len(u), bool)
-    for i in range(len(u)): ran[i] = L.shade_emu_reference_vertex(u[i].ctypes.data, out[i].ctypes.data) == 0
+    out, ran = _run(L.shade_emu_reference_vertex, u, ref)
     hits = ran & (u[:, 27] == 0) & (u[:, 84] == 1); misses = ran & (u[:, 27] == 1)
-    assert hits.sum() > 400 and misses.sum() > 200
-    cols = [c for c in range(20) if c != 15] + list(range(20, 29)) + [39, 40]
-    R, O = ref.view(np.uint32)[:, cols], out.view(np.uint32)[:, cols]
-    same = R == O
+    assert hits.sum() > 500 and misses.sum() > 200
+    cols = [c for c in PAYLOAD if c != 15] + SHADOW + FEEDBACK
+    same = ref.view(np.uint32)[:, cols] == out.view(np.uint32)[:, cols]
     assert same[hits].all(), np.argwhere(~same[hits])[:8]
     assert same[misses].all(), np.argwhere(~same[misses])[:8]
     # the hits took every turn: shadow rays seen and blocked, feedback written, false hits rejected, paths ended by the bounce limit and by roulette
     assert 0.25 < ref[hits, 28].mean() < 0.7 and (ref[hits, 39] > 0).mean() > 0.2 and (ref[hits, 20] > 0).mean() > 0.5
+
+
+def test_realtime_shade_kernel_source_matches_reference_path_tracer_golden():
+    """The realtime passes (k_rt_shade< BUILD >, k_rt_shade< FILL, .., NEEAT >: realtime.cuh's stablePlanesHandleHit / HandleMiss / OnScatter, splitDeltaPath, storeStablePlane,
+    storeExplorationStart, commitDenoiserRadiance, the specular hit distance) against the same shader code compiled as the BUILD and FILL shaders: the outgoing path state (all 20
+    words), the pixel's three 80-byte stable planes, header, stable radiance, hit distance, shadow ray and feedback reservoir - bit for bit, hits and misses."""
+    L = _lib()
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hit_golden.npz"))
+    for key, fn, cols, single in (("build", L.shade_emu_build_vertex, PAYLOAD + [29, 31] + list(range(47, 51)) + list(range(52, 56)) + list(range(56, 116)), False),
+                                  ("fill", L.shade_emu_fill_vertex, PAYLOAD + SHADOW + [37] + FEEDBACK + list(range(41, 51)), True)):
+        u, ref = np.ascontiguousarray(g[key + "_in"]), g[key + "_out"]
+        out, ran = _run(fn, u, ref)
+        hits = ran & (u[:, 27] == 0) & ((u[:, 84] == 1) | (not single)); misses = ran & (u[:, 27] == 1)      # BUILD does no NEE: every record applies
+        assert hits.sum() > 600 and misses.sum() > 200
+        same = ref.view(np.uint32)[:, cols] == out.view(np.uint32)[:, cols]
+        assert same[hits].all(), (key, np.argwhere(~same[hits])[:8])
+        assert same[misses].all(), (key, np.argwhere(~same[misses])[:8])
