@@ -191,3 +191,22 @@ template <int MODE> static int shadeVertex(const float* r, float* o)
 extern "C" int shade_emu_reference_vertex(const float* r, float* o) { return shadeVertex<kModeReference>(r, o); }
 extern "C" int shade_emu_build_vertex(const float* r, float* o) { return shadeVertex<kModeBuildStablePlanes>(r, o); }
 extern "C" int shade_emu_fill_vertex(const float* r, float* o) { return shadeVertex<kModeFillStablePlanes>(r, o); }
+
+// k_debug_bsdf's body (shade_kernels.cu) on the host: StandardBSDF eval / evalPdf / sample / getLobes of bsdf.cuh on the records of tests/golden/bsdf_golden.npz (36 floats in, 16 out)
+extern "C" void shade_emu_bsdf(const float* in, uint32_t count, float* out)
+{
+    for (uint32_t i = 0; i < count; i++)
+    {
+        const float* r = in + size_t(i) * 36; float* o = out + size_t(i) * 16;
+        BsdfParams d;
+        d.diffuse = mk3(r[18], r[19], r[20]); d.roughness = r[21]; d.specular = mk3(r[22], r[23], r[24]); d.metallic = r[25];
+        d.transmission = mk3(r[26], r[27], r[28]); d.diffuseTransmission = r[29]; d.specularTransmission = r[30]; d.eta = r[31];
+        BsdfSetup b; b.init(mk3(r[6], r[7], r[8]), mk3(r[9], r[10], r[11]), mk3(r[3], r[4], r[5]), mk3(r[0], r[1], r[2]), r[32] != 0.0f, d);
+        const float3 wo = mk3(r[12], r[13], r[14]);
+        const float4 e = b.eval(wo);
+        o[0] = e.x; o[1] = e.y; o[2] = e.z; o[3] = e.w; o[4] = b.pdf(wo);
+        BsdfSample s; const bool valid = b.sample(r[15], r[16], r[17], s);
+        o[5] = valid ? 1.0f : 0.0f; o[6] = s.wo.x; o[7] = s.wo.y; o[8] = s.wo.z; o[9] = s.pdf; o[10] = s.weight.x; o[11] = s.weight.y; o[12] = s.weight.z;
+        o[13] = float(s.lobe); o[14] = s.lobeP; o[15] = float(bsdfLobes(d));
+    }
+}
