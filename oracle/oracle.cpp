@@ -382,11 +382,12 @@ ORC_API void oracle_hit_funcs(const float* in, uint32_t count, float* out, uint3
         RtxptSceneDesc desc; memset(&desc, 0, sizeof(desc)); desc.materials = mats; desc.materialCount = 8;
         Scene sc; sc.desc = &desc;
         // lights
-        LightTable lt; lt.samplingProxyCount = uint(r[90]); lt.proxyCounters.resize(16); lt.proxyIndices.resize(64); lt.lights.resize(16); lt.lightsEx.resize(16); lt.exBase = 0; lt.analyticLightCount = 16;
+        static thread_local LightTable lt;      // (kept across records: its 1024 x 1024 environment lookup map is filled once)
+        lt.samplingProxyCount = uint(r[90]); lt.proxyCounters.resize(16); lt.proxyIndices.resize(64); lt.lights.resize(16); lt.lightsEx.resize(16); lt.exBase = 0; lt.analyticLightCount = 16;
         for (int k = 0; k < 16; k++) lt.proxyCounters[k] = uint(r[136 + k]);
         for (int k = 0; k < 64; k++) lt.proxyIndices[k] = uint(r[152 + k]);
         for (int k = 0; k < 16; k++) { memcpy(&lt.lights[k], r + 728 + 12 * k, 32); memcpy(&lt.lightsEx[k], r + 728 + 12 * k + 8, 16); }
-        lt.envEnabled = true; lt.envLookupMap = hitMirrorEnvLookup();
+        lt.envEnabled = true; if (lt.envLookupMap.empty()) lt.envLookupMap = hitMirrorEnvLookup();
         NeeatState ns; ns.init(8, 8); ns.jitter[0] = uint(r[88]); ns.jitter[1] = uint(r[89]); ns.localToGlobalSampleRatio = r[86]; ns.settings.screenSpaceVsWorldSpaceThreshold = r[91];
         ns.temporalFeedbackRequired = r[92] != 0.0f; memcpy(ns.localSamplingBuffer.data(), r + 216, 512 * sizeof(uint));
         // the vertex

@@ -60,7 +60,7 @@ static thread_local float3 gCamPos, gCamBase, gCamDx, gCamDy;
 __host__ __device__ void pt::emuCameraRay(uint id, float3& origin, float3& dir)
 {
 #ifndef __CUDA_ARCH__
-    const float3 d = gCamBase + gCamDx * float(id >> 16) + gCamDy * float(id & 0xFFFFu); origin = gCamPos; dir = d * (1.0f / sqrtf(dot3(d, d)));
+    const float3 d = gCamBase + gCamDx * float(id >> 16) + gCamDy * float(id & 0xFFFFu); origin = gCamPos; dir = d / sqrtf(dot3(d, d));       // normalize( ) as the stub bridge spells it: x / length( x )
 #endif
 }
 __host__ __device__ float3 pt::emuMotionVector(float3 posW, float3 prevPosW) { return (prevPosW - posW) * 0.5f; }
@@ -208,5 +208,14 @@ extern "C" void shade_emu_bsdf(const float* in, uint32_t count, float* out)
         BsdfSample s; const bool valid = b.sample(r[15], r[16], r[17], s);
         o[5] = valid ? 1.0f : 0.0f; o[6] = s.wo.x; o[7] = s.wo.y; o[8] = s.wo.z; o[9] = s.pdf; o[10] = s.weight.x; o[11] = s.weight.y; o[12] = s.weight.z;
         o[13] = float(s.lobe); o[14] = s.lobeP; o[15] = float(bsdfLobes(d));
+    }
+}
+// batch form: `count` records of 1024 floats, 128 floats out each; status[i] = 0 where the record was run
+extern "C" void shade_emu_vertices(const float* in, uint32_t count, float* out, int32_t* status, uint32_t mode)
+{
+    for (uint32_t i = 0; i < count; i++)
+    {
+        const float* r = in + size_t(i) * 1024; float* o = out + size_t(i) * 128;
+        status[i] = mode == 0 ? shadeVertex<kModeReference>(r, o) : (mode == 1 ? shadeVertex<kModeBuildStablePlanes>(r, o) : shadeVertex<kModeFillStablePlanes>(r, o));
     }
 }

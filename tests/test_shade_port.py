@@ -76,3 +76,25 @@ def test_bsdf_source_matches_reference_header_golden():
     all_lobes = u[:, 33] == 255
     same = (out.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(out) & np.isnan(ref))
     assert all_lobes.sum() > 3800 and same[all_lobes].all(), np.argwhere(~same[all_lobes])[:8]
+
+
+def test_shade_kernel_source_agrees_with_oracle_on_recombined_vertices(oracle):
+    """Beyond the golden's own records: 60 000 vertices per pass made by recombining the golden's parts (a path with its ray and surface; constants; medium table; light scenario;
+    plane header; environment - each from a different record, counters / roulette words swapped in) - new situations the reference binary never saw, on which the oracle (which
+    reproduces the reference on the golden) and the host build of the CUDA source must still agree on every word."""
+    L = _lib(); L.shade_emu_vertices.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]; L.shade_emu_vertices.restype = None
+    O = oracle.lib(); O.oracle_hit_funcs.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]; O.oracle_hit_funcs.restype = None
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hit_golden.npz"))
+    n = 60000
+    for key, mode, cols in (("hit", 0, [c for c in PAYLOAD if c != 15] + SHADOW + FEEDBACK), ("build", 1, PAYLOAD + [29, 31] + list(range(47, 51)) + list(range(52, 56)) + list(range(56, 116))),
+                            ("fill", 2, PAYLOAD + SHADOW + [37] + FEEDBACK + list(range(41, 51)))):
+        rng = np.random.default_rng(100 + mode); u = g[key + "_in"]; u = u[u[:, 27] <= 1]; pick = lambda: rng.integers(0, len(u), n)
+        r = u[pick()].copy()
+        for lo, hi in ((80, 96), (96, 136), (136, 920), (920, 950), (950, 960)): r[:, lo:hi] = u[pick(), lo:hi]
+        for w in (14, 17, 18): q = pick(); sel = rng.random(n) < 0.5; r[sel, w] = u[q[sel], w]
+        r = np.ascontiguousarray(r)
+        a = np.zeros((n, 128), np.float32); st = np.zeros(n, np.int32); L.shade_emu_vertices(r.ctypes.data, n, a.ctypes.data, st.ctypes.data, mode)
+        b = np.zeros((n, 128), np.float32); O.oracle_hit_funcs(r.ctypes.data, n, b.ctypes.data, mode)
+        run = (st == 0) & ((r[:, 84] == 1) | (mode == 1) | (r[:, 27] == 1))
+        same = a.view(np.uint32)[:, cols] == b.view(np.uint32)[:, cols]
+        assert run.sum() > 0.7 * n and same[run].all(), (key, np.argwhere(~same[run])[:8])
