@@ -306,6 +306,40 @@ ORC_API void oracle_sampler_funcs(const float* in, uint32_t count, float* out)
     }
 }
 
+// NEE-AT's feedback passes as the oracle restates them (pt_neeat.h), layout of oracle/ref_kat_baker_main.cpp (3056 floats in, 3089 out): P0, P1a, P1b, P2 (FillTile) and
+// ClearFeedbackHistory on a 16 x 16 image with 3 x 3 tiles, in UpdateEnd's order
+ORC_API void oracle_baker_feedback(const float* in, uint32_t count, float* out)
+{
+    for (uint32_t i = 0; i < count; i++)
+    {
+        const float* r = in + size_t(i) * 3056; float* o = out + size_t(i) * 3089;
+        const uint W = 16, H = 16, P = W * H;
+        NeeatState s; s.init(W, H);
+        const uint total = uint(r[0]); s.historicTotalLightCount = uint(r[1]); s.updateCounter = uint(r[2]); s.jitter[0] = uint(r[3]); s.jitter[1] = uint(r[4]); s.jitterPrev[0] = uint(r[5]); s.jitterPrev[1] = uint(r[6]);
+        s.lastFrameTemporalFeedbackAvailable = r[7] != 0.0f; s.lastFrameLocalSamplesAvailable = r[8] != 0.0f;
+        s.settings.depthDisocclusionThreshold = r[10]; s.settings.enableMotionReprojection = r[11] != 0.0f; s.settings.reservoirHistoryDropoff = r[12];
+        LightTable lt; lt.lights.resize(total); lt.samplingProxyCount = uint(r[9]); lt.proxyIndices.resize(64); for (int k = 0; k < 64; k++) lt.proxyIndices[k] = uint(r[48 + k]);
+        s.pastToCurrent.resize(32); memcpy(s.pastToCurrent.data(), r + 32, 64); for (int k = 16; k < 32; k++) s.pastToCurrent[k] = RTXPT_INVALID_LIGHT_INDEX;
+        memcpy(s.feedback.weight.data(), r + 112, P * 4); memcpy(s.feedback.candidate.data(), r + 368, P * 4); memcpy(s.historyDepth.data(), r + 624, P * 4);
+        std::vector<float> depth(r + 880, r + 880 + P); std::vector<uint16_t> motion(size_t(P) * 4, 0);
+        for (uint k = 0; k < P; k++) { motion[4 * k] = uint16_t(f32tof16(r[1136 + 3 * k])); motion[4 * k + 1] = uint16_t(f32tof16(r[1137 + 3 * k])); motion[4 * k + 2] = uint16_t(f32tof16(r[1138 + 3 * k])); }
+        memcpy(s.localSamplingBuffer.data(), r + 1904, 1152 * 4);
+        ProcessFeedbackHistoryP0(s, total);
+        memcpy(o, s.feedback.weight.data(), P * 4); memcpy(o + 256, s.feedback.candidate.data(), P * 4); for (uint k = 0; k < 17; k++) o[512 + k] = k <= total ? float(s.feedbackCounters[k]) : 0.0f;
+        ProcessFeedbackHistoryP1a(s, lt, depth.data(), motion.data());
+        memcpy(o + 529, s.blended.weight.data(), 64 * 4); memcpy(o + 593, s.blended.candidate.data(), 64 * 4);
+        ProcessFeedbackHistoryP1b(s, lt, depth.data(), motion.data());
+        memcpy(o + 657, s.scratch.weight.data(), P * 4); memcpy(o + 913, s.scratch.candidate.data(), P * 4);
+        for (uint ty = 0; ty < 3; ty++) for (uint tx = 0; tx < 3; tx++)
+        {
+            uint list[NEEAT_LOCAL_PROXY_COUNT]; FillTile(s, tx, ty, list);
+            for (uint k = 0; k < NEEAT_LOCAL_PROXY_COUNT; k++) { const uint w = PackMiniListLightAndCount(list[k], 1); memcpy(o + 1169 + s.tileBaseAddress(tx, ty) + k, &w, 4); }
+        }
+        ClearFeedbackHistory(s, depth.data());
+        memcpy(o + 2321, s.feedback.weight.data(), P * 4); memcpy(o + 2577, s.feedback.candidate.data(), P * 4); memcpy(o + 2833, s.historyDepth.data(), P * 4);
+    }
+}
+
 // the environment-quad light, layout of ref_kat_bsdf_main.cpp's "envquads" mode: Store, Create, the sample HandleNEE draws from it (pt_path.h), pdf, power
 ORC_API void oracle_envquad_light_funcs(const float* in, uint32_t count, float* out)
 {

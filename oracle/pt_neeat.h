@@ -382,12 +382,12 @@ inline void ProcessFeedbackHistoryP1b(NeeatState& s, const LightTable& lt, const
 }
 
 // P2 (FillTile): the 8x8 window of full-resolution candidates + 64 top-up picks from the blended image around the tile; P3: sort by light, merge duplicates into counts
-inline void ProcessFeedbackHistoryP2P3(NeeatState& s)
+// FillTile (LightsBaker.hlsl:1531-1598): the 128 candidates of one tile in the order the reference writes them, before P3 sorts them
+inline void FillTile(const NeeatState& s, uint tx, uint ty, uint list[NEEAT_LOCAL_PROXY_COUNT])
 {
     const int W = int(s.W), H = int(s.H);
-    for (uint ty = 0; ty < s.tilesY; ty++) for (uint tx = 0; tx < s.tilesX; tx++)
     {
-        uint list[NEEAT_LOCAL_PROXY_COUNT]; uint n = 0;
+        uint n = 0;
         const int margin = int(NEEAT_WINDOW_SIZE - NEEAT_TILE_SIZE) / 2;
         const int cellX = int(tx * NEEAT_TILE_SIZE) - int(s.jitter[0]), cellY = int(ty * NEEAT_TILE_SIZE) - int(s.jitter[1]);
         for (int x = 0; x < int(NEEAT_WINDOW_SIZE); x++) for (int y = 0; y < int(NEEAT_WINDOW_SIZE); y++)
@@ -403,6 +403,13 @@ inline void ProcessFeedbackHistoryP2P3(NeeatState& s)
             int px = int(centerX + ox + 0.5f), py = int(centerY + oy + 0.5f); MirrorCoord(px, py, W, H);
             list[n++] = s.blended.candidate[size_t(py / int(NEEAT_EARLY_FEEDBACK_TILE_SIZE)) * s.blended.W + px / int(NEEAT_EARLY_FEEDBACK_TILE_SIZE)];
         }
+    }
+}
+inline void ProcessFeedbackHistoryP2P3(NeeatState& s)
+{
+    for (uint ty = 0; ty < s.tilesY; ty++) for (uint tx = 0; tx < s.tilesX; tx++)
+    {
+        uint list[NEEAT_LOCAL_PROXY_COUNT]; FillTile(s, tx, ty, list);
         // P3: keys are the 23-bit light indices the tuples carry (PackMiniListLightAndCount masks the index); ascending sort, then every entry gets the run length of its key
         for (uint i = 0; i < NEEAT_LOCAL_PROXY_COUNT; i++) list[i] = UnpackMiniListLight(PackMiniListLightAndCount(list[i], 1));
         std::sort(list, list + NEEAT_LOCAL_PROXY_COUNT);

@@ -81,7 +81,9 @@ template <typename T> struct vec2
     vec2(T s) : x(s), y(s) {}
     template <typename U, typename std::enable_if<std::is_arithmetic<U>::value && !std::is_same<U, T>::value, int>::type = 0> vec2(U s) : x(T(s)), y(T(s)) {}
     vec2(T a, T b) : x(a), y(b) {}
-    template <typename U> explicit vec2(const vec2<U>& o) : x(T(o.x)), y(T(o.y)) {}
+    template <typename U, typename std::enable_if<!(std::is_integral<U>::value && std::is_integral<T>::value), int>::type = 0> explicit vec2(const vec2<U>& o) : x(T(o.x)), y(T(o.y)) {}
+    template <typename U, typename std::enable_if<std::is_integral<U>::value && std::is_integral<T>::value && !std::is_same<U, T>::value, int>::type = 0> vec2(const vec2<U>& o) : x(T(o.x)), y(T(o.y)) {}      // int2 <-> uint2: implicit in HLSL
+    template <typename U, int A, int B> explicit vec2(const swz2<U, A, B>& s) : x(T(s.d[A])), y(T(s.d[B])) {}
     vec2(const vec2& o) : x(o.x), y(o.y) {}
     vec2& operator=(const vec2& o) { x = o.x; y = o.y; return *this; }
     T& operator[](int i) { return i == 0 ? x : y; } const T& operator[](int i) const { return i == 0 ? x : y; }
@@ -270,6 +272,7 @@ inline int3 asint(float3 v) { return int3(asint(v.x), asint(v.y), asint(v.z)); }
 inline int3 operator+(int3 a, int3 b) { return int3(a.x + b.x, a.y + b.y, a.z + b.z); } inline int3 operator-(int3 a) { return int3(-a.x, -a.y, -a.z); }
 inline int3 select(bool3 c, int3 a, int3 b) { return int3(c.x ? a.x : b.x, c.y ? a.y : b.y, c.z ? a.z : b.z); }
 inline float select(bool c, float a, float b) { return c ? a : b; }
+inline int2 select(bool2 c, int2 a, int2 b) { return int2(c.x ? a.x : b.x, c.y ? a.y : b.y); }
 inline float2 select(bool2 c, float a, float b) { return float2(c.x ? a : b, c.y ? a : b); } inline float3 select(bool3 c, float3 a, float3 b) { return float3(c.x ? a.x : b.x, c.y ? a.y : b.y, c.z ? a.z : b.z); }
 
 #define row_major        /* HLSL matrix layout qualifier */
@@ -288,18 +291,58 @@ struct SamplerState {};
 // a cube map the generator defines analytically: g_shimCubeSample( direction, lod ) (both sides of a golden evaluate the same closed form)
 extern float4 (*g_shimCubeSample)(float3 dir, float lod);
 template <typename T> struct TextureCube { T SampleLevel(SamplerState, float3 dir, float lod) const { return g_shimCubeSample(dir, lod); } };
+// compute-shader resources and intrinsics of the baker passes (Rtxpt/Lighting/LightsBaker.hlsl).  A pass whose threads do not talk to each other is run one thread after the other:
+// barriers are then no-ops and a wave is one lane wide (the generator only runs such passes - the others are compiled, not called)
+template <typename T> struct RWBuffer { T* p = nullptr; uint n = 0; mutable T sink = T(0); T& operator[](uint i) const { if (i < n) return p[i]; sink = T(0); return sink; } };
+struct RWByteAddressBuffer
+{
+    uint* p = nullptr; uint bytes = 0;
+    uint Load(uint a) const { return a + 4 <= bytes ? p[a >> 2] : 0u; } void Store(uint a, uint v) const { if (a + 4 <= bytes) p[a >> 2] = v; }
+    template <typename T> T Load(uint a) const { T t; std::memset(&t, 0, sizeof(T)); if (a + sizeof(T) <= bytes) std::memcpy(&t, reinterpret_cast<const char*>(p) + a, sizeof(T)); return t; }
+    template <typename T> void Store(uint a, const T& t) const { if (a + sizeof(T) <= bytes) std::memcpy(reinterpret_cast<char*>(p) + a, &t, sizeof(T)); }
+    void InterlockedAdd(uint a, uint v, uint& old) const { old = Load(a); Store(a, old + v); } void InterlockedAdd(uint a, uint v) const { Store(a, Load(a) + v); }
+    void InterlockedCompareExchange(uint a, uint cmp, uint v, uint& old) const { old = Load(a); if (old == cmp) Store(a, v); }
+};
+inline void GroupMemoryBarrierWithGroupSync() {} inline void GroupMemoryBarrier() {} inline void DeviceMemoryBarrier() {} inline void AllMemoryBarrier() {}
+template <typename T, typename U> inline void InterlockedAdd(T& dst, U v) { dst = dst + T(v); } template <typename T, typename U> inline void InterlockedAdd(T& dst, U v, T& old) { old = dst; dst = dst + T(v); }
+template <typename T, typename U> inline void InterlockedMax(T& dst, U v) { if (T(v) > dst) dst = T(v); } template <typename T, typename U> inline void InterlockedMin(T& dst, U v) { if (T(v) < dst) dst = T(v); }
+template <typename T, typename U> inline void InterlockedOr(T& dst, U v) { dst = dst | T(v); }
+template <typename T, typename U, typename V> inline void InterlockedCompareExchange(T& dst, U cmp, V v, T& old) { old = dst; if (dst == T(cmp)) dst = T(v); }
+template <typename T> inline T WaveActiveMax(T v) { return v; } template <typename T> inline T WaveActiveMin(T v) { return v; } template <typename T> inline T WaveActiveSum(T v) { return v; }
+template <typename T> inline T WavePrefixSum(T) { return T(0); } template <typename T> inline T WaveReadLaneFirst(T v) { return v; } template <typename T> inline T WaveReadLaneAt(T v, uint) { return v; }
+inline bool WaveIsFirstLane() { return true; } inline uint WaveGetLaneIndex() { return 0u; } inline uint WaveGetLaneCount() { return 1u; } inline uint WaveActiveCountBits(bool b) { return b ? 1u : 0u; }
+inline uint WavePrefixCountBits(bool) { return 0u; } inline bool WaveActiveAnyTrue(bool b) { return b; } inline bool WaveActiveAllTrue(bool b) { return b; }
+inline vec4<uint> WaveActiveBallot(bool b) { return vec4<uint>(b ? 1u : 0u, 0u, 0u, 0u); } template <typename T> inline vec4<uint> WaveMatch(T) { return vec4<uint>(1u, 0u, 0u, 0u); }
+inline uint WaveMultiPrefixCountBits(bool, vec4<uint>) { return 0u; } inline vec4<uint> countbits(vec4<uint> m) { return vec4<uint>(uint(__builtin_popcount(m.x)), uint(__builtin_popcount(m.y)), uint(__builtin_popcount(m.z)), uint(__builtin_popcount(m.w))); }
 struct RayDesc { float3 Origin; float TMin; float3 Direction; float TMax; };     // the D3D built-in
 template <typename T> struct StructuredBuffer { const T* p = nullptr; uint n = 0; T operator[](uint i) const { return i < n ? p[i] : T{}; } };
 template <typename T> struct Buffer { const T* p = nullptr; uint n = 0; T operator[](uint i) const { return i < n ? p[i] : T(0); } };
-template <typename T> struct Texture2D { const T* p = nullptr; uint w = 0, h = 0; T operator[](uint2 c) const { return (c.x < w && c.y < h) ? p[size_t(c.y) * w + c.x] : T(0); }
+template <typename T> struct Texture2D { const T* p = nullptr; uint w = 0, h = 0; T operator[](uint2 c) const { return (c.x < w && c.y < h) ? p[size_t(c.y) * w + c.x] : T(0); } T operator[](int2 c) const { return (*this)[uint2(uint(c.x), uint(c.y))]; }
     void GetDimensions(uint& ow, uint& oh) const { ow = w; oh = h; } T Load(int3 c) const { return (c.x >= 0 && c.y >= 0 && uint(c.x) < w && uint(c.y) < h) ? p[size_t(c.y) * w + c.x] : T(0); } };
 template <typename T> struct RWTexture3D { T* p = nullptr; mutable T sink = T(0); T& operator[](uint3) const { sink = T(0); return sink; } };
 template <typename T> struct RWTexture2D
 {
     T* p = nullptr; uint w = 0, h = 0; mutable T sink = T(0);
     T& operator[](uint2 c) const { if (c.x < w && c.y < h) return p[size_t(c.y) * w + c.x]; sink = T(0); return sink; }
+    T& operator[](int2 c) const { return (*this)[uint2(uint(c.x), uint(c.y))]; }
 };
 inline uint2 operator+(uint2 a, uint2 b) { return uint2(a.x + b.x, a.y + b.y); } inline uint2 operator/(uint2 a, uint2 b) { return uint2(a.x / b.x, a.y / b.y); } inline uint2 operator/(uint2 a, uint b) { return uint2(a.x / b, a.y / b); }
 inline uint2 operator*(uint2 a, uint b) { return uint2(a.x * b, a.y * b); } inline uint2 operator*(uint2 a, uint2 b) { return uint2(a.x * b.x, a.y * b.y); } inline uint2 operator-(uint2 a, uint2 b) { return uint2(a.x - b.x, a.y - b.y); }
 inline uint min(uint a, int b) { return a < uint(b) ? a : uint(b); } inline uint max(uint a, int b) { return a > uint(b) ? a : uint(b); } inline uint min(int a, uint b) { return uint(a) < b ? uint(a) : b; }
+// int2 / uint2 mix freely in HLSL (the baker's pixel arithmetic): results take the left operand's type here, comparisons are per component
+inline int2 toInt2(uint2 v) { return int2(int(v.x), int(v.y)); } inline uint2 toUint2(int2 v) { return uint2(uint(v.x), uint(v.y)); }
+inline int2 operator+(int2 a, int2 b) { return int2(a.x + b.x, a.y + b.y); } inline int2 operator-(int2 a, int2 b) { return int2(a.x - b.x, a.y - b.y); } inline int2 operator*(int2 a, int2 b) { return int2(a.x * b.x, a.y * b.y); }
+inline int2 operator/(int2 a, int2 b) { return int2(a.x / b.x, a.y / b.y); } inline int2 operator*(int2 a, int b) { return int2(a.x * b, a.y * b); } inline int2 operator*(int a, int2 b) { return int2(a * b.x, a * b.y); }
+inline int2 operator/(int2 a, int b) { return int2(a.x / b, a.y / b); } inline int2 operator+(int2 a, int b) { return int2(a.x + b, a.y + b); } inline int2 operator-(int2 a, int b) { return int2(a.x - b, a.y - b); }
+inline int2 operator-(int2 a) { return int2(-a.x, -a.y); } inline int2 operator+(int2 a, uint2 b) { return a + toInt2(b); } inline int2 operator-(int2 a, uint2 b) { return a - toInt2(b); }
+inline uint2 operator-(uint2 a, int2 b) { return uint2(a.x - uint(b.x), a.y - uint(b.y)); } inline uint2 operator+(uint2 a, int2 b) { return uint2(a.x + uint(b.x), a.y + uint(b.y)); }
+inline uint2 operator+(uint2 a, uint b) { return uint2(a.x + b, a.y + b); } inline uint2 operator-(uint2 a, uint b) { return uint2(a.x - b, a.y - b); } inline uint2 operator%(uint2 a, uint b) { return uint2(a.x % b, a.y % b); }
+inline uint2 operator>>(uint2 a, uint b) { return uint2(a.x >> b, a.y >> b); } inline uint2 operator<<(uint2 a, uint b) { return uint2(a.x << b, a.y << b); } inline uint2 operator&(uint2 a, uint b) { return uint2(a.x & b, a.y & b); }
+inline bool2 operator>=(int2 a, int b) { return bool2(a.x >= b, a.y >= b); } inline bool2 operator<(int2 a, int2 b) { return bool2(a.x < b.x, a.y < b.y); } inline bool2 operator>=(int2 a, int2 b) { return bool2(a.x >= b.x, a.y >= b.y); }
+inline bool2 operator<(int2 a, uint2 b) { return bool2(a.x < int(b.x), a.y < int(b.y)); } inline bool2 operator>=(uint2 a, int2 b) { return bool2(int(a.x) >= b.x, int(a.y) >= b.y); }
+inline bool2 operator>=(uint2 a, uint2 b) { return bool2(a.x >= b.x, a.y >= b.y); } inline bool2 operator<(uint2 a, uint2 b) { return bool2(a.x < b.x, a.y < b.y); } inline bool2 operator<(uint2 a, int2 b) { return bool2(int(a.x) < b.x, int(a.y) < b.y); }
+inline bool2 operator==(int2 a, int2 b) { return bool2(a.x == b.x, a.y == b.y); } inline bool2 operator!=(uint2 a, uint2 b) { return bool2(a.x != b.x, a.y != b.y); }
+inline bool2 operator&&(bool2 a, bool2 b) { return bool2(a.x && b.x, a.y && b.y); } inline bool2 operator&(bool2 a, bool2 b) { return bool2(a.x && b.x, a.y && b.y); }
+inline float max(float a, uint b) { return max(a, float(b)); } inline float min(float a, uint b) { return min(a, float(b)); }
+inline int2 min(int2 a, int2 b) { return int2(min(a.x, b.x), min(a.y, b.y)); } inline int2 max(int2 a, int2 b) { return int2(max(a.x, b.x), max(a.y, b.y)); } inline int2 clamp(int2 v, int2 lo, int2 hi) { return min(max(v, lo), hi); }
 inline uint clamp(uint x, int a, uint b) { const uint lo = uint(a); return x < lo ? lo : (x > b ? b : x); } inline uint clamp(uint x, uint a, uint b) { return x < a ? a : (x > b ? b : x); }

@@ -333,3 +333,22 @@ def test_environment_quad_light_matches_reference_header_golden(oracle):
     out = np.empty_like(ref); L.oracle_envquad_light_funcs(u.ctypes.data, len(u), out.ctypes.data)
     assert (out.view(np.uint32) == ref.view(np.uint32)).all()
     assert np.allclose(np.linalg.norm(ref[:, 15:18], axis=1), 1, atol=1e-4) and (ref[:, 21] == (u[:, 2] ** 2 / np.float32(4 * np.pi)).astype(np.float32)).mean() > 0.9
+
+
+def test_neeat_feedback_passes_match_reference_lights_baker_golden(oracle):
+    """NEE-AT's frame-end passes of the UNMODIFIED Rtxpt/Lighting/LightsBaker.hlsl compiled in place (tests/golden/make_baker_golden.py, oracle/_ref/ref_kat_baker; the passes whose
+    threads are independent, run one thread after the other): ProcessFeedbackHistoryP0 (remap to this frame's light list, per-light usage counters, world-space candidates stripped),
+    P1a (the half-resolution blend through depth / motion reprojection), P1b (full-resolution reservoirs: reprojected + blended, holes filled from last frame's tile or the global
+    table), P2 / FillTile (the 8 x 8 window + 64 top-up picks per tile) and ClearFeedbackHistory (the faded seed of next frame's reservoirs, history depth).  200 frames on a 16 x 16
+    image, 16 lights: every reservoir, counter, tile entry and depth the oracle's passes produce is bit-identical."""
+    import ctypes as C
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "baker_golden.npz"))
+    u, ref = np.ascontiguousarray(g["baker_in"]), g["baker_out"]
+    L = oracle.lib(); L.oracle_baker_feedback.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]; L.oracle_baker_feedback.restype = None
+    out = np.zeros_like(ref); L.oracle_baker_feedback(u.ctypes.data, len(u), out.ctypes.data)
+    same = out.view(np.uint32) == ref.view(np.uint32)
+    assert same.all(), np.argwhere(~same)[:8]
+    R, U = ref.view(np.uint32), u.view(np.uint32)
+    # P0 strips and remaps, the reprojection both finds and loses its pixel, holes get filled, the seed keeps part of the history
+    assert 0.3 < ((R[:, 256:512] == 0xFFFFFFFF) & (U[:, 368:624] != 0xFFFFFFFF)).mean() < 0.7 and 0.3 < (ref[:, 657:913] > 0).mean() < 0.7 and (R[:, 913:1169] != 0xFFFFFFFF).all()
+    assert (ref[:, 2321:2577] > 0).mean() > 0.4 and (ref[:, 512:529].sum(1) == 256).all()
