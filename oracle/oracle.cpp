@@ -306,13 +306,13 @@ ORC_API void oracle_sampler_funcs(const float* in, uint32_t count, float* out)
     }
 }
 
-// NEE-AT's feedback passes as the oracle restates them (pt_neeat.h), layout of oracle/ref_kat_baker_main.cpp (3056 floats in, 3089 out): P0, P1a, P1b, P2 (FillTile) and
-// ClearFeedbackHistory on a 16 x 16 image with 3 x 3 tiles, in UpdateEnd's order
+// NEE-AT's feedback passes as the oracle restates them (pt_neeat.h), layout of oracle/ref_kat_baker_main.cpp (3056 floats in, 4241 out): P0, P1a, P1b, P2 (FillTile),
+// ClearFeedbackHistory and P3 (the sorted lists with their run lengths) on a 16 x 16 image with 3 x 3 tiles, in UpdateEnd's order
 ORC_API void oracle_baker_feedback(const float* in, uint32_t count, float* out)
 {
     for (uint32_t i = 0; i < count; i++)
     {
-        const float* r = in + size_t(i) * 3056; float* o = out + size_t(i) * 3089;
+        const float* r = in + size_t(i) * 3056; float* o = out + size_t(i) * 4241;
         const uint W = 16, H = 16, P = W * H;
         NeeatState s; s.init(W, H);
         const uint total = uint(r[0]); s.historicTotalLightCount = uint(r[1]); s.updateCounter = uint(r[2]); s.jitter[0] = uint(r[3]); s.jitter[1] = uint(r[4]); s.jitterPrev[0] = uint(r[5]); s.jitterPrev[1] = uint(r[6]);
@@ -337,6 +337,8 @@ ORC_API void oracle_baker_feedback(const float* in, uint32_t count, float* out)
         }
         ClearFeedbackHistory(s, depth.data());
         memcpy(o + 2321, s.feedback.weight.data(), P * 4); memcpy(o + 2577, s.feedback.candidate.data(), P * 4); memcpy(o + 2833, s.historyDepth.data(), P * 4);
+        ProcessFeedbackHistoryP2P3(s);      // (reads the scratch and blended images, which ClearFeedbackHistory left alone)
+        memcpy(o + 3089, s.localSamplingBuffer.data(), 1152 * 4);
     }
 }
 

@@ -303,7 +303,11 @@ struct RWByteAddressBuffer
     void InterlockedAdd(uint a, uint v, uint& old) const { old = Load(a); Store(a, old + v); } void InterlockedAdd(uint a, uint v) const { Store(a, Load(a) + v); }
     void InterlockedCompareExchange(uint a, uint cmp, uint v, uint& old) const { old = Load(a); if (old == cmp) Store(a, v); }
 };
-inline void GroupMemoryBarrierWithGroupSync() {} inline void GroupMemoryBarrier() {} inline void DeviceMemoryBarrier() {} inline void AllMemoryBarrier() {}
+// a pass that synchronises its thread group is run on real threads by the generator (one group at a time, `groupshared` = statics): it points g_shimGroupBarrier at a barrier for the
+// group's thread count; everywhere else the pointer is null and the barrier is a no-op
+#include <pthread.h>
+static pthread_barrier_t* g_shimGroupBarrier = nullptr;
+inline void GroupMemoryBarrierWithGroupSync() { if (g_shimGroupBarrier) pthread_barrier_wait(g_shimGroupBarrier); } inline void GroupMemoryBarrier() {} inline void DeviceMemoryBarrier() {} inline void AllMemoryBarrier() {}
 template <typename T, typename U> inline void InterlockedAdd(T& dst, U v) { dst = dst + T(v); } template <typename T, typename U> inline void InterlockedAdd(T& dst, U v, T& old) { old = dst; dst = dst + T(v); }
 template <typename T, typename U> inline void InterlockedMax(T& dst, U v) { if (T(v) > dst) dst = T(v); } template <typename T, typename U> inline void InterlockedMin(T& dst, U v) { if (T(v) < dst) dst = T(v); }
 template <typename T, typename U> inline void InterlockedOr(T& dst, U v) { dst = dst | T(v); }

@@ -7,9 +7,11 @@
 // record (3056 floats; words marked * are bit patterns): 0-31 header | 32-47* past-to-current table (16) | 48-111 global proxies (64) | 112-367 feedback total weight (16 x 16),
 // 368-623* feedback candidates | 624-879 history depth | 880-1135 depth | 1136-1903 motion vectors (xyz per pixel) | 1904-3055* last frame's local sampling buffer (3 x 3 tiles x 128)
 // out (3089 floats): feedback weight / candidates after P0 (512), counters (17) | blended after P1a (64 + 64) | scratch after P1b (512) | tile lists after P2, unsorted (1152) |
-// feedback after ClearFeedbackHistory (512), history depth (256)
+// feedback after ClearFeedbackHistory (512), history depth (256) | tile lists after P3 (1152): ProcessFeedbackHistoryP3 synchronises its 64 threads (bitonic sort in group-shared
+// memory), so every tile runs on 64 real threads with a barrier behind GroupMemoryBarrierWithGroupSync
 #include <cstdio>
 #include <vector>
+#include <thread>
 static std::vector<float> readAll(const char* path) { std::vector<float> v; FILE* f = fopen(path, "rb"); if (!f) { perror(path); exit(1); } fseek(f, 0, SEEK_END); v.resize(size_t(ftell(f)) / 4); fseek(f, 0, SEEK_SET); if (fread(v.data(), 4, v.size(), f) != v.size()) exit(1); fclose(f); return v; }
 float4 (*g_shimCubeSample)(float3 dir, float lod) = nullptr;
 
@@ -17,7 +19,7 @@ float4 (*g_shimCubeSample)(float3 dir, float lod) = nullptr;
 int main(int argc, char** argv)
 {
     if (argc != 4 || std::string(argv[1]) != "feedback") { fprintf(stderr, "usage: %s feedback in.f32 out.f32\n", argv[0]); return 2; }
-    const std::vector<float> in = readAll(argv[2]); const int kIn = 3056, kOut = 3089; const size_t n = in.size() / kIn; std::vector<float> out(n * kOut, 0.0f);
+    const std::vector<float> in = readAll(argv[2]); const int kIn = 3056, kOut = 4241; const size_t n = in.size() / kIn; std::vector<float> out(n * kOut, 0.0f);
     const uint W = 16, H = 16, P = W * H, LW = 8, LH = 8, TX = 3, TY = 3;
     for (size_t i = 0; i < n; i++)
     {
@@ -52,6 +54,15 @@ int main(int argc, char** argv)
         memcpy(o + 1169, local.data(), 1152 * 4);
         for (uint y = 0; y < H; y++) for (uint x = 0; x < W; x++) ClearFeedbackHistory(uint2(x, y));
         memcpy(o + 2321, fbW.data(), P * 4); memcpy(o + 2577, fbC.data(), P * 4); memcpy(o + 2833, histDepth.data(), P * 4);
+        for (uint ty = 0; ty < TY; ty++) for (uint tx = 0; tx < TX; tx++)
+        {
+            pthread_barrier_t barrier; pthread_barrier_init(&barrier, nullptr, 64); g_shimGroupBarrier = &barrier;
+            std::vector<std::thread> threads;
+            for (uint t = 0; t < 64; t++) threads.emplace_back([=]() { ProcessFeedbackHistoryP3(uint3(tx, ty, 0u), uint3(t, 0u, 0u)); });
+            for (auto& th : threads) th.join();
+            g_shimGroupBarrier = nullptr; pthread_barrier_destroy(&barrier);
+        }
+        memcpy(o + 3089, local.data(), 1152 * 4);
     }
     FILE* f = fopen(argv[3], "wb"); if (!f) { perror(argv[3]); return 1; } fwrite(out.data(), 4, out.size(), f); fclose(f);
     return 0;

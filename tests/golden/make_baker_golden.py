@@ -1,7 +1,7 @@
 """Generates tests/golden/baker_golden.npz from the UNMODIFIED Rtxpt/Lighting/LightsBaker.hlsl (NEE-AT's feedback passes ProcessFeedbackHistoryP0, P1a, P1b, P2 / FillTile and
 ClearFeedbackHistory - the passes whose threads are independent) compiled in place as C++ through oracle/ref_hlsl_shim.h (oracle/_ref/ref_kat_baker).  Run in the build container only:
     make -C oracle ref && python tests/golden/make_baker_golden.py
-  baker_in [M,3056], baker_out [M,3089]: layouts in oracle/ref_kat_baker_main.cpp.  One record = one frame end on a 16 x 16 image (3 x 3 tiles, 8 x 8 blended image, 16 lights):
+  baker_in [M,3056], baker_out [M,4241]: layouts in oracle/ref_kat_baker_main.cpp.  One record = one frame end on a 16 x 16 image (3 x 3 tiles, 8 x 8 blended image, 16 lights):
   the reservoirs NEE filled, last frame's depth, this frame's depth and motion vectors, last frame's tile lists, the global proxies, a past-to-current light table."""
 import os, sys
 import numpy as np
@@ -32,7 +32,7 @@ if __name__ == "__main__":
         hd = np.exp(rng.uniform(0, 3, P)).astype(np.float32); r[i, 624:880] = hd; d = hd * np.where(rng.random(P) < 0.8, 1 + rng.normal(0, 0.05, P), rng.uniform(1.6, 3, P)); r[i, 880:1136] = d.astype(np.float32)
         mv = np.zeros((P, 3), np.float32); mv[:, :2] = np.float16(rng.normal(0, 2.5, (P, 2)) * (rng.random((P, 1)) < 0.7)); mv[:, 2] = np.float16(rng.normal(0, 0.1, P)); r[i, 1136:1904] = mv.reshape(-1)
         tiles = np.stack([pack_tile(rng.choice(rng.choice(hist, rng.integers(1, min(hist, 8) + 1), replace=False), 128)) for _ in range(9)]); r[i, 1904:3056] = tiles.reshape(-1).view(np.float32)
-    out = run("feedback", r, 3089, exe="ref_kat_baker")
+    out = run("feedback", r, 4241, exe="ref_kat_baker")
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "baker_golden.npz"), baker_in=r, baker_out=out,
-                        source=np.array("Rtxpt/Lighting/LightsBaker.hlsl (ProcessFeedbackHistoryP0 / P1a / P1b / P2, ClearFeedbackHistory) at reference commit f08d1c7, compiled as C++ by oracle/Makefile target _ref/ref_kat_baker"))
+                        source=np.array("Rtxpt/Lighting/LightsBaker.hlsl (ProcessFeedbackHistoryP0 / P1a / P1b / P2 / P3, ClearFeedbackHistory) at reference commit f08d1c7, compiled as C++ by oracle/Makefile target _ref/ref_kat_baker"))
     print(r.shape, out.shape, "nan:", int(np.isnan(out).sum()), os.path.getsize(os.path.join(ROOT, "tests", "golden", "baker_golden.npz")))

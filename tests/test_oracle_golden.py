@@ -336,10 +336,11 @@ def test_environment_quad_light_matches_reference_header_golden(oracle):
 
 
 def test_neeat_feedback_passes_match_reference_lights_baker_golden(oracle):
-    """NEE-AT's frame-end passes of the UNMODIFIED Rtxpt/Lighting/LightsBaker.hlsl compiled in place (tests/golden/make_baker_golden.py, oracle/_ref/ref_kat_baker; the passes whose
-    threads are independent, run one thread after the other): ProcessFeedbackHistoryP0 (remap to this frame's light list, per-light usage counters, world-space candidates stripped),
+    """NEE-AT's frame-end passes of the UNMODIFIED Rtxpt/Lighting/LightsBaker.hlsl compiled in place (tests/golden/make_baker_golden.py, oracle/_ref/ref_kat_baker; the passes of
+    LightsBaker::UpdateEnd but PreFilter, whose in-place update races across thread groups): ProcessFeedbackHistoryP0 (remap to this frame's light list, per-light usage counters, world-space candidates stripped),
     P1a (the half-resolution blend through depth / motion reprojection), P1b (full-resolution reservoirs: reprojected + blended, holes filled from last frame's tile or the global
-    table), P2 / FillTile (the 8 x 8 window + 64 top-up picks per tile) and ClearFeedbackHistory (the faded seed of next frame's reservoirs, history depth).  200 frames on a 16 x 16
+    table), P2 / FillTile (the 8 x 8 window + 64 top-up picks per tile), P3 (the bitonic sort in group-shared memory and the duplicate counts - run on 64 real threads with a barrier behind
+    GroupMemoryBarrierWithGroupSync) and ClearFeedbackHistory (the faded seed of next frame's reservoirs, history depth).  200 frames on a 16 x 16
     image, 16 lights: every reservoir, counter, tile entry and depth the oracle's passes produce is bit-identical."""
     import ctypes as C
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "baker_golden.npz"))
@@ -352,3 +353,4 @@ def test_neeat_feedback_passes_match_reference_lights_baker_golden(oracle):
     # P0 strips and remaps, the reprojection both finds and loses its pixel, holes get filled, the seed keeps part of the history
     assert 0.3 < ((R[:, 256:512] == 0xFFFFFFFF) & (U[:, 368:624] != 0xFFFFFFFF)).mean() < 0.7 and 0.3 < (ref[:, 657:913] > 0).mean() < 0.7 and (R[:, 913:1169] != 0xFFFFFFFF).all()
     assert (ref[:, 2321:2577] > 0).mean() > 0.4 and (ref[:, 512:529].sum(1) == 256).all()
+    lists = R[:, 3089:4241].reshape(-1, 128); assert (np.diff((lists >> 9).astype(np.int64), axis=1) >= 0).all() and ((lists & 0x1FF) > 0).mean() > 0.9       # sorted, duplicates counted
