@@ -342,6 +342,26 @@ ORC_API void oracle_baker_feedback(const float* in, uint32_t count, float* out)
     }
 }
 
+// ComputeProxyCounts as the oracle restates it (pt_neeat.h: RebuildGlobalProxies), layout of ref_kat_baker_main.cpp's "counts" mode (64 floats in, 40 out)
+ORC_API void oracle_baker_counts(const float* in, uint32_t count, float* out)
+{
+    for (uint32_t i = 0; i < count; i++)
+    {
+        const float* r = in + size_t(i) * 64; float* o = out + size_t(i) * 40;
+        for (int k = 0; k < 40; k++) o[k] = 0.0f;
+        const uint n = uint(r[0]);
+        NeeatState s; s.lastFrameTemporalFeedbackAvailable = r[1] != 0.0f; s.globalFeedbackUseWeight = r[3]; s.currentWeightsSum = r[5];
+        s.currentWeights.assign(r + 8, r + 8 + n); s.feedbackCounters.resize(n + 1); for (uint k = 0; k <= n; k++) s.feedbackCounters[k] = uint(r[24 + k]);
+        s.validFeedbackCount = uint(r[2]) - s.feedbackCounters[n];
+        LightTable lt; lt.lights.resize(n); lt.proxyCounters.resize(n);
+        RebuildGlobalProxies(s, lt, uint(r[4]) == 0 ? 0u : 2u);
+        uint offset = 0;
+        for (uint k = 0; k < n; k++) { o[k] = float(lt.proxyCounters[k]); o[17 + k] = float(offset); offset += lt.proxyCounters[k]; }
+        for (uint k = n; k < 16; k++) o[k] = r[24 + k];      // the slots behind the lights keep what they held (slot n: reservoirs without a light)
+        o[16] = float(lt.samplingProxyCount); o[33] = float(offset);
+    }
+}
+
 // the environment-quad light, layout of ref_kat_bsdf_main.cpp's "envquads" mode: Store, Create, the sample HandleNEE draws from it (pt_path.h), pdf, power
 ORC_API void oracle_envquad_light_funcs(const float* in, uint32_t count, float* out)
 {

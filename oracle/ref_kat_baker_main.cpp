@@ -3,7 +3,7 @@
 // talk to each other - ProcessFeedbackHistoryP0, P1a, P1b, P2 (FillTile), ClearFeedbackHistory - one thread after the other, in LightsBaker::UpdateEnd's order
 // (LightsBaker.cpp:1331-1418); barriers are no-ops, a wave is one lane (P0's WaveMatch counting degenerates to one atomic add per pixel: same counters).  Not run: PreFilter and
 // P3 (group-shared tiles, bitonic sort across a thread group), the proxy-table passes.
-//   usage: ref_kat_baker feedback in.f32 out.f32
+//   usage: ref_kat_baker feedback|counts in.f32 out.f32
 // record (3056 floats; words marked * are bit patterns): 0-31 header | 32-47* past-to-current table (16) | 48-111 global proxies (64) | 112-367 feedback total weight (16 x 16),
 // 368-623* feedback candidates | 624-879 history depth | 880-1135 depth | 1136-1903 motion vectors (xyz per pixel) | 1904-3055* last frame's local sampling buffer (3 x 3 tiles x 128)
 // out (3089 floats): feedback weight / candidates after P0 (512), counters (17) | blended after P1a (64 + 64) | scratch after P1b (512) | tile lists after P2, unsorted (1152) |
@@ -18,7 +18,34 @@ float4 (*g_shimCubeSample)(float3 dir, float lod) = nullptr;
 
 int main(int argc, char** argv)
 {
-    if (argc != 4 || std::string(argv[1]) != "feedback") { fprintf(stderr, "usage: %s feedback in.f32 out.f32\n", argv[0]); return 2; }
+    if (argc != 4 || (std::string(argv[1]) != "feedback" && std::string(argv[1]) != "counts")) { fprintf(stderr, "usage: %s feedback|counts in.f32 out.f32\n", argv[0]); return 2; }
+    if (std::string(argv[1]) == "counts")
+    {   // ComputeProxyCounts (LightsBaker.hlsl:880-948, UpdateBegin): how many global sampling proxies every light gets from its power-based weight blended with last frame's usage
+        // counters.  One thread per light in a group of 128 that synchronises once (thread 0 then sums the group): real threads, as for P3.
+        // record (64 floats): 0 light count (<= 16), 1 LastFrameTemporalFeedbackAvailable, 2 TotalMaxFeedbackCount, 3 GlobalFeedbackUseWeight, 4 ImportanceSamplingType, 5 weights sum,
+        // 8-23 weights, 24-40 usage counters (the last: reservoirs without a light)   out (40 floats): 0-15 proxy counters, 16 SamplingProxyCount, 17-32 offsets inside the group, 33 group total
+        const std::vector<float> in = readAll(argv[2]); const size_t n = in.size() / 64; std::vector<float> out(n * 40, 0.0f);
+        for (size_t i = 0; i < n; i++)
+        {
+            const float* r = &in[i * 64]; float* o = &out[i * 40];
+            LightingControlData cd; memset(&cd, 0, sizeof(cd));
+            const uint count = uint(r[0]); cd.TotalLightCount = count; cd.LastFrameTemporalFeedbackAvailable = uint(r[1]); cd.TotalMaxFeedbackCount = uint(r[2]); cd.GlobalFeedbackUseWeight = r[3];
+            cd.ImportanceSamplingType = uint(r[4]); memcpy(&cd.WeightsSumUINT, r + 5, 4);
+            std::vector<float> weights(r + 8, r + 24); std::vector<uint> counters(32, 0u), scratchList(32, 0u), proxies(64, 0u);
+            for (int k = 0; k < 17; k++) counters[k] = uint(r[24 + k]);
+            u_controlBuffer.p = &cd; u_controlBuffer.n = 1; u_lightWeights.p = weights.data(); u_lightWeights.n = 16; u_perLightProxyCounters.p = counters.data(); u_perLightProxyCounters.n = 32;
+            u_scratchList.p = scratchList.data(); u_scratchList.n = 32; u_lightSamplingProxies.p = proxies.data(); u_lightSamplingProxies.n = 64;
+            pthread_barrier_t barrier; pthread_barrier_init(&barrier, nullptr, count); g_shimGroupBarrier = &barrier;       // threads past the light count leave before the barrier
+            std::vector<std::thread> threads;
+            for (uint t = 0; t < 128; t++) threads.emplace_back([=]() { ComputeProxyCounts(t, t); });
+            for (auto& th : threads) th.join();
+            g_shimGroupBarrier = nullptr; pthread_barrier_destroy(&barrier);
+            for (int k = 0; k < 16; k++) { o[k] = float(counters[k]); o[17 + k] = float(scratchList[k]); }
+            o[16] = float(cd.SamplingProxyCount); o[33] = float(proxies[1]);
+        }
+        FILE* f = fopen(argv[3], "wb"); if (!f) { perror(argv[3]); return 1; } fwrite(out.data(), 4, out.size(), f); fclose(f);
+        return 0;
+    }
     const std::vector<float> in = readAll(argv[2]); const int kIn = 3056, kOut = 4241; const size_t n = in.size() / kIn; std::vector<float> out(n * kOut, 0.0f);
     const uint W = 16, H = 16, P = W * H, LW = 8, LH = 8, TX = 3, TY = 3;
     for (size_t i = 0; i < n; i++)

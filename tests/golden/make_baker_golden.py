@@ -33,6 +33,15 @@ if __name__ == "__main__":
         mv = np.zeros((P, 3), np.float32); mv[:, :2] = np.float16(rng.normal(0, 2.5, (P, 2)) * (rng.random((P, 1)) < 0.7)); mv[:, 2] = np.float16(rng.normal(0, 0.1, P)); r[i, 1136:1904] = mv.reshape(-1)
         tiles = np.stack([pack_tile(rng.choice(rng.choice(hist, rng.integers(1, min(hist, 8) + 1), replace=False), 128)) for _ in range(9)]); r[i, 1904:3056] = tiles.reshape(-1).view(np.float32)
     out = run("feedback", r, 4241, exe="ref_kat_baker")
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "baker_golden.npz"), baker_in=r, baker_out=out,
+    # ComputeProxyCounts (mode "counts"): light count, feedback available?, total feedback slots, use weight, sampling type, weights (some zero, some huge), usage counters
+    c = np.zeros((1000, 64), np.float32)
+    for i in range(len(c)):
+        k = rng.integers(1, 17); c[i, 0] = k; c[i, 1] = rng.random() < 0.8; c[i, 3] = rng.choice(np.float32([0.0, 0.25, 0.75, 1.0])); c[i, 4] = 0 if rng.random() < 0.1 else 2
+        w = (rng.gamma(0.7, 3.0, k) * (rng.random(k) < 0.85)).astype(np.float32); w[rng.random(k) < 0.05] *= np.float32(1e4)
+        if w.sum() == 0: w[0] = 1
+        c[i, 8:8 + k] = w; c[i, 5] = np.add.reduce(w, dtype=np.float32)
+        use = rng.integers(0, 60, k + 1); c[i, 24:25 + k] = use; c[i, 2] = use.sum() if rng.random() < 0.9 else use[k]           # (the last case: no valid feedback at all)
+    cout = run("counts", c, 40, exe="ref_kat_baker")
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "baker_golden.npz"), baker_in=r, baker_out=out, counts_in=c, counts_out=cout,
                         source=np.array("Rtxpt/Lighting/LightsBaker.hlsl (ProcessFeedbackHistoryP0 / P1a / P1b / P2 / P3, ClearFeedbackHistory) at reference commit f08d1c7, compiled as C++ by oracle/Makefile target _ref/ref_kat_baker"))
     print(r.shape, out.shape, "nan:", int(np.isnan(out).sum()), os.path.getsize(os.path.join(ROOT, "tests", "golden", "baker_golden.npz")))

@@ -354,3 +354,16 @@ def test_neeat_feedback_passes_match_reference_lights_baker_golden(oracle):
     assert 0.3 < ((R[:, 256:512] == 0xFFFFFFFF) & (U[:, 368:624] != 0xFFFFFFFF)).mean() < 0.7 and 0.3 < (ref[:, 657:913] > 0).mean() < 0.7 and (R[:, 913:1169] != 0xFFFFFFFF).all()
     assert (ref[:, 2321:2577] > 0).mean() > 0.4 and (ref[:, 512:529].sum(1) == 256).all()
     lists = R[:, 3089:4241].reshape(-1, 128); assert (np.diff((lists >> 9).astype(np.int64), axis=1) >= 0).all() and ((lists & 0x1FF) > 0).mean() > 0.9       # sorted, duplicates counted
+
+
+def test_neeat_proxy_counts_match_reference_lights_baker_golden(oracle):
+    """ComputeProxyCounts of the UNMODIFIED LightsBaker.hlsl (UpdateBegin: every light's share of the global sampling proxies from its weight blended with last frame's usage
+    counters; one thread per light, a group barrier, thread 0 sums - run on real threads): 1000 light lists incl. unused lights, a light 10^4 times brighter than the rest (the
+    per-light cap), uniform sampling, no valid feedback at all.  Counters, offsets and the total are bit-identical with the oracle's RebuildGlobalProxies."""
+    import ctypes as C
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "baker_golden.npz"))
+    u, ref = np.ascontiguousarray(g["counts_in"]), g["counts_out"]
+    L = oracle.lib(); L.oracle_baker_counts.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]; L.oracle_baker_counts.restype = None
+    out = np.zeros_like(ref); L.oracle_baker_counts(u.ctypes.data, len(u), out.ctypes.data)
+    assert (out.view(np.uint32) == ref.view(np.uint32)).all()
+    assert (ref[:, :16] == 262143).sum() > 100 and (ref[:, 16] == ref[:, 33]).all() and (ref[u[:, 4] == 0, :16].max() <= 60)
