@@ -2,9 +2,11 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may build, load or call this library.
 // The product (rtxpt_b200/) never links it.
 //
-// Parity status: RNG / packing are pinned against the reference's own C++ halves (oracle/_ref, tests/golden/); everything that
-// depends on the DXR driver (BVH, traversal, intersection), TMU filtering or fp16 shader arithmetic is "parity unpinned" — the
-// reference ships no runnable golden data for it.
+// Parity status: RNG / packing are pinned against the reference's own C++ halves, and the path tracer's HLSL (material model, lights, NEE-AT sampler and frame-end passes,
+// PathTracer::HandleHit / HandleMiss in all three passes, the per-pixel driver steps) against golden vectors made by compiling those headers in place as C++ (oracle/_ref,
+// tests/golden/): the oracle_*_funcs / oracle_hit_funcs / oracle_baker_* mirrors below are what tests/test_oracle_golden.py compares.  Everything that depends on
+// the DXR driver (BVH, traversal, intersection) or on TMU filtering, the Donut bridge's scene access, the environment bake and ReBLUR stay "parity unpinned" — the reference
+// ships no runnable golden data for them.
 #include "pt_path.h"
 #include "reblur.h"
 #include "pt_envbake.h"

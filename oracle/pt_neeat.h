@@ -9,6 +9,8 @@
 //     :1745-1850 (P3: bitonic sort + duplicate counting)
 //   Rtxpt/Lighting/LightsBaker.cpp:943-962 (R2 tile jitter), :985-1070 (control data of a frame), :1203-1225 (PreFilter, P0 order), :1331-1418 (UpdateEnd: P1a, P1b, P2, P3, clear)
 //   Rtxpt/Lighting/LightsBaker.h:62-63, :240-255 (defaults), Rtxpt/Shaders/PathTracer/Lighting/LightingConfig.h (tile 8, window 8, 128 local proxies, early-feedback tile 2)
+// Pinned: the sampler side by tests/golden/sampler_golden.npz; P0, P1a, P1b, P2, P3, ClearFeedbackHistory and ComputeProxyCounts by tests/golden/baker_golden.npz
+// (LightSampler.hlsli / LightsBaker.hlsl compiled in place).  PreFilter, the importance boosters, the proxy fill and the light-list tracking are restatements.
 // Scope: light lists may change between frames (NeeatTrackLightList builds the past <-> current index tables; an unchanged list is the identity remap with its bounds checks), importance boosters off except the pre-filter merge (default on),
 // debug views omitted.  ProcessFeedbackHistoryPreFilter is racy across thread groups in the reference (a group's margin may read texels another group has already
 // rewritten); here every pixel reads the reservoirs as they were before the pass.

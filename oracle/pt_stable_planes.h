@@ -6,7 +6,8 @@
 //   Rtxpt/Shaders/PathTracer/PathTracerHelpers.hlsli:227-262 (MatrixRotateFromTo)
 //   Rtxpt/Shaders/PathTracerBridgeDonut.hlsli:890-909 (computeMotionVector), :1096-1175 (guide export)
 // Branch-ID helpers and GenericTS addressing are pinned against the reference's own C++ halves of the same headers (oracle/_ref/ref_kat_host,
-// tests/golden/host_golden.json); everything else here is "parity unpinned" like the rest of the shading path.
+// tests/golden/host_golden.json); the plane packing, exploration payloads and the BUILD / FILL logic that uses them are pinned through tests/golden/hit_golden.npz
+// (StablePlanes.hlsli and PathTracerStablePlanes.hlsli compiled in place).  computeMotionVector and the guide export restate the Donut bridge (unpinned).
 #pragma once
 #include <vector>
 #include "pt_math.h"
