@@ -8,6 +8,9 @@
 //   Rtxpt/Shaders/PathTracer/PathTracerNestedDielectrics.hlsli:24-131, Rendering/Materials/InteriorList.hlsli:28-246
 //   Rtxpt/Shaders/PathTracerBridgeDonut.hlsli:543-564 (camera ray)
 //   Rtxpt/Shaders/PathTracer/Lighting/LightSampler.hlsli (global sampling + MIS), Lighting/EnvMap.hlsli:84-87
+// Pinned: HandleHitSurface, HandleMiss, EmptyPathInitialize, FirstHitFromVBuffer and postProcessHit reproduce tests/golden/hit_golden.npz - whole calls of the
+// reference's PathTracer::HandleHit / HandleMiss and driver steps compiled in place for the reference, BUILD and FILL passes - bit for bit.  The hooks of PathTracerCtx
+// (visibilityOverride, cameraRayOverride, envEvalOverride) exist for that comparison: they stand where the golden's stub bridge supplies data.
 #pragma once
 #include "pt_scene.h"
 #include "pt_bvh.h"
